@@ -1,0 +1,180 @@
+/* reverie_b200.h -- C ABI of libreverie_b200.so: the B200-native KKW (MPC-in-the-head) prover/verifier core.
+ *
+ * Drop-in boundary for trailofbits/reverie 0.3.2 (all citations relative to the reference repository root):
+ *   Proof::new(circuit, wit_gf2, wit_z64, wire_counts) -> Proof      src/proof/mod.rs:119-222
+ *   Proof::verify(&self, circuit, wire_counts) -> bool               src/proof/mod.rs:224-307
+ * A Rust maintainer binds these entry points with a ~40-line `extern "C"` block; the proof bytes
+ * crossing the boundary are exactly `bincode::serialize(&Proof)` (src/proof/mod.rs:40-66, src/main.rs:84).
+ *
+ * Plain pointers and sizes only.  Every call is synchronous unless its name ends in `_async`.  Nothing unwinds across
+ * the boundary: the reference's panics become negative error codes.  There is no CPU fallback: without a CUDA device
+ * every compute entry point returns RV_E_CUDA.
+ */
+#ifndef REVERIE_B200_H
+#define REVERIE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- protocol constants: src/lib.rs:17-38, src/crypto/prg.rs:9, src/crypto/hash.rs:8 ---- */
+#define RV_PLAYERS 8
+#define RV_PACKED 8
+#define RV_TOTAL_REPS 256
+#define RV_ONLINE_REPS 40
+#define RV_PREPROCESSING_REPS (RV_TOTAL_REPS - RV_ONLINE_REPS)
+#define RV_PACKED_REPS (RV_TOTAL_REPS / RV_PACKED)
+#define RV_KEY_SIZE 16
+#define RV_HASH_SIZE 32
+
+/* ---- circuit: mcircuit::{Operation, CombineOperation} as matched by the reference's interpreter
+ *      (src/interpreter/single.rs:106-156, src/interpreter/combine.rs:120-132), flattened to a 24-byte POD. ---- */
+enum rv_domain { RV_GF2 = 0, RV_Z64 = 1, RV_B2A = 2 /* dst = z64 wire, a = lowest of 64 gf2 wires */,
+                 RV_SIZE_HINT = 3 /* a = z64 cells, b = gf2 cells */ };
+enum rv_opcode {
+    RV_INPUT = 0,       /* Input(dst)            */
+    RV_RANDOM = 1,      /* Random(dst)           */
+    RV_ADD = 2,         /* Add(dst, a, b)        */
+    RV_ADDC = 3,        /* AddConst(dst, a, imm) */
+    RV_SUB = 4,         /* Sub(dst, a, b)        */
+    RV_SUBC = 5,        /* SubConst(dst, a, imm) */
+    RV_MUL = 6,         /* Mul(dst, a, b)        */
+    RV_MULC = 7,        /* MulConst(dst, a, imm) */
+    RV_ASSERT_ZERO = 8, /* AssertZero(a)         */
+    RV_CONST = 9        /* Const(dst, imm)       */
+};
+typedef struct rv_op {
+    uint8_t domain;  /* enum rv_domain */
+    uint8_t opcode;  /* enum rv_opcode (ignored for RV_B2A / RV_SIZE_HINT) */
+    uint16_t pad;
+    uint32_t dst, a, b;
+    uint64_t imm;    /* GF(2): bit 0; Z64: the full word */
+} rv_op;
+
+/* ---- errors (the reference panics here) ---- */
+enum rv_status {
+    RV_OK = 0,
+    RV_E_WITNESS_INVALID = -1, /* an AssertZero failed            src/transcript/prover.rs:221-228 */
+    RV_E_WITNESS_SHORT = -2,   /* ran out of witness elements     src/transcript/prover.rs:190     */
+    RV_E_FORMAT = -3,          /* malformed proof bytes           src/algebra/gf2/share.rs:158-164 */
+    RV_E_ARG = -4,             /* bad argument / wire index out of range for the given wire_counts */
+    RV_E_CUDA = -5,            /* CUDA runtime failure or no device */
+    RV_E_NOMEM = -6,
+    RV_E_UNSUPPORTED = -7      /* op set not yet accelerated (reported at compile time, never silently degraded) */
+};
+
+typedef struct rv_circuit rv_circuit; /* a compiled circuit: device-resident gate tables, reusable across proofs  */
+typedef struct rv_session rv_session; /* one in-flight prove: device buffers + stream                              */
+
+/* Per-thread message for the last non-OK status returned on this thread. */
+const char *rv_last_error(void);
+/* Library/ABI version string, e.g. "reverie-b200 0.1 (sm_100a)". */
+const char *rv_version(void);
+/* Number of visible CUDA devices (0 without a GPU; never fails). */
+int rv_device_count(void);
+/* Select the CUDA device used by objects created afterwards on this thread (default 0). */
+int rv_set_device(int device);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Circuit compilation.  Stands for the `Arc<Vec<CombineOperation>>` argument of Proof::new / Proof::verify
+ * (src/proof/mod.rs:120,224): compile once, share read-only across any number of proofs and threads.
+ * wire counts are passed in the reference's own tuple order (z64, gf2)  -- src/proof/mod.rs:125,232.
+ * ------------------------------------------------------------------------------------------------------------- */
+int rv_circuit_compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, rv_circuit **out);
+void rv_circuit_free(rv_circuit *c);
+
+typedef struct rv_circuit_stats {
+    uint64_t n_ops;
+    uint64_t n_and;          /* GF(2) Mul gates                                   */
+    uint64_t n_inputs;       /* GF(2) witness bits consumed                       */
+    uint64_t n_assert;       /* GF(2) AssertZero                                  */
+    uint64_t n_masks;        /* GF(2) PRG masks drawn per (rep, player)           */
+    uint64_t n_linear;       /* materialised linear (XOR) mask nodes              */
+    uint64_t value_depth;    /* levels of the plaintext plane                     */
+    uint64_t linear_depth;   /* levels of the mask plane                          */
+    uint64_t online_bytes;   /* bytes hashed per repetition, online stream        */
+    uint64_t pre_bytes;      /* bytes hashed per repetition, preprocessing stream */
+    uint64_t algorithmic_bytes; /* SURVEY.md 8(d) HBM bytes for one proof (all 256 reps) */
+    uint64_t device_bytes;   /* device memory held by the compiled tables         */
+} rv_circuit_stats;
+int rv_circuit_get_stats(const rv_circuit *c, rv_circuit_stats *out);
+
+/* Debug/test tap: copy one compiled table to the host (tests/ re-executes the tables in numpy).  `what` is one of
+ * the RV_TAB_* ids; call with buf == NULL to obtain the byte length. */
+enum rv_table { RV_TAB_VGATES = 0, RV_TAB_VLEVELS = 1, RV_TAB_LGATES = 2, RV_TAB_LLEVELS = 3, RV_TAB_ITEMS = 4,
+                RV_TAB_RECON_POS = 5, RV_TAB_INPUT_POS = 6, RV_TAB_INPUT_VID = 7 };
+int rv_circuit_export(const rv_circuit *c, int what, void *buf, size_t *len);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Proof::new  (src/proof/mod.rs:119-222).
+ *   wit_gf2: one byte per GF(2) witness element (0/1), consumed in Input order  (src/transcript/prover.rs:181-199)
+ *   wit_z64: one u64 per Z64 witness element
+ *   seeds:   256 x 16 bytes, repetition r at seeds[16r..16r+16) -- replaces the OsRng draw at src/proof/mod.rs:131-134
+ *            so that proofs are reproducible; NULL = draw from the OS RNG like the reference.
+ *   *proof:  library-allocated bincode bytes of `Proof`; release with rv_free.
+ * ------------------------------------------------------------------------------------------------------------- */
+int rv_prove(const rv_circuit *c, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64, size_t n_z64,
+             const uint8_t *seeds, uint8_t **proof, size_t *proof_len);
+
+/* Proof::verify  (src/proof/mod.rs:224-307).  Returns 1 accept / 0 reject / <0 error.
+ * *okay (optional) receives the AND of the online verifiers' zero_check flags, which the reference computes
+ * (src/transcript/verifier/online.rs:176-178) but never reads. */
+int rv_verify(const rv_circuit *c, const uint8_t *proof, size_t proof_len, int *okay);
+
+/* One-shot forms with the exact argument shape of the reference API (compile + run + free). */
+int rv_proof_new(const rv_op *ops, size_t n_ops, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64,
+                 size_t n_z64, size_t z64_cells, size_t gf2_cells, const uint8_t *seeds, uint8_t **proof,
+                 size_t *proof_len);
+int rv_proof_verify(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, const uint8_t *proof,
+                    size_t proof_len);
+
+void rv_free(void *p);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Phase-split proving, for sharding the 32 packed instances (src/proof/mod.rs:127-157) across GPUs and for
+ * measuring with inputs resident in HBM.  A session owns a CUDA stream and all device buffers of one proof shard.
+ *
+ *   rv_session_create   shard = packed instances [first_instance, first_instance + n_instances)
+ *   rv_session_upload   host -> device copy of witness + this shard's seeds (pinned staging, async on the stream)
+ *   rv_session_commit   the closure at src/proof/mod.rs:129-156 for every instance of the shard, entirely on the
+ *                       device; leaves n_instances*8 repetition hashes in device memory
+ *   rv_session_hashes   device -> host copy of those hashes (n_instances * 8 * 32 bytes); synchronises
+ *   rv_session_open     src/proof/mod.rs:160-196 given all 256 repetition hashes (the all-gather result, instance-major
+ *                       order); computes comm + challenge on the device and extracts this shard's openings
+ *   rv_session_fetch    device -> host: comm (32 B) and this shard's openings as a relocatable blob
+ *   rv_proof_assemble   src/proof/mod.rs:200-221: concatenates shard blobs (any order) into the bincode `Proof`
+ * ------------------------------------------------------------------------------------------------------------- */
+int rv_session_create(const rv_circuit *c, int first_instance, int n_instances, rv_session **out);
+void rv_session_free(rv_session *s);
+int rv_session_upload(rv_session *s, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64, size_t n_z64,
+                      const uint8_t *seeds /* all 256 x 16, or NULL = OS RNG */);
+int rv_session_commit(rv_session *s);                                   /* async on the session stream */
+int rv_session_hashes(rv_session *s, uint8_t *rep_hashes);              /* synchronises                */
+int rv_session_open(rv_session *s, const uint8_t *all_rep_hashes);      /* async; NULL = own hashes (single shard) */
+int rv_session_fetch(rv_session *s, uint8_t comm[RV_HASH_SIZE], uint8_t **part, size_t *part_len); /* synchronises */
+int rv_session_sync(rv_session *s);
+int rv_proof_assemble(const uint8_t comm[RV_HASH_SIZE], const uint8_t *const *parts, const size_t *part_lens,
+                      int n_parts, uint8_t **proof, size_t *proof_len);
+/* cudaStream_t of the session (as void*), so callers can bracket work with their own CUDA events. */
+void *rv_session_stream(rv_session *s);
+
+/* Per-kernel device timing (CUDA events on the session stream).  Enable, run, then read back
+ * `n` (name, total ms, launches) triples accumulated since the last reset. */
+typedef struct rv_kernel_time {
+    char name[32];
+    double ms;
+    uint64_t launches;
+    uint64_t algorithmic_bytes; /* SURVEY.md 8(d) bytes attributed to this kernel, summed over launches */
+} rv_kernel_time;
+int rv_session_timing(rv_session *s, int enable);
+int rv_session_kernel_times(rv_session *s, rv_kernel_time *out, int max_out, int reset);
+/* Kernels launched on this session since creation (the bench's `gpu_launches`). */
+uint64_t rv_session_launch_count(const rv_session *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REVERIE_B200_H */

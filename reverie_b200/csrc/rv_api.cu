@@ -1,0 +1,592 @@
+// rv_api.cu -- the extern "C" boundary (include/reverie_b200.h): circuit handles, sessions, prove / verify.
+// Host orchestration only; every byte of proof data is produced by the kernels in rv_kernels.cu.
+#include <cuda_runtime.h>
+#include <sys/random.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "rv_kernels.cuh"
+#include "rv_planes.cuh"
+
+using namespace rv;
+
+// ---------------------------------------------------------------------------------------------------------------------
+//  errors
+// ---------------------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string &msg) {
+    g_err = msg;
+    return code;
+}
+#define CU(call)                                                                                                     \
+    do {                                                                                                             \
+        cudaError_t e_ = (call);                                                                                     \
+        if (e_ != cudaSuccess) return fail(RV_E_CUDA, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+    } while (0)
+
+extern "C" const char *rv_last_error(void) { return g_err.c_str(); }
+extern "C" const char *rv_version(void) { return "reverie-b200 0.1 (sm_100a)"; }
+extern "C" int rv_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+static thread_local int g_device = 0;
+extern "C" int rv_set_device(int device) {
+    if (device < 0 || device >= rv_device_count()) return fail(RV_E_CUDA, "no such CUDA device");
+    g_device = device;
+    CU(cudaSetDevice(device));
+    return RV_OK;
+}
+extern "C" void rv_free(void *p) { free(p); }
+
+// ---------------------------------------------------------------------------------------------------------------------
+//  circuit
+// ---------------------------------------------------------------------------------------------------------------------
+struct rv_circuit {
+    Program prog;
+    DevProgram dev;
+    std::vector<void *> allocs;
+    std::vector<uint32_t> mul_pos;
+    int device = 0;
+    uint64_t device_bytes = 0;
+    uint32_t z64_empty_hash[8];  // B3("")
+    uint32_t z64_rep_hash[8];    // Transcript::hash of an empty Z64 transcript: H(B3("") || B3(""))
+};
+
+template <typename T>
+static int upload(rv_circuit *c, const std::vector<T> &v, const T **out) {
+    *out = nullptr;
+    const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    void *d = nullptr;
+    CU(cudaMalloc(&d, bytes));
+    c->allocs.push_back(d);
+    c->device_bytes += bytes;
+    if (!v.empty()) CU(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *out = reinterpret_cast<const T *>(d);
+    return RV_OK;
+}
+
+extern "C" void rv_circuit_free(rv_circuit *c) {
+    if (!c) return;
+    for (void *p : c->allocs) cudaFree(p);
+    delete c;
+}
+
+extern "C" int rv_circuit_compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, rv_circuit **out) {
+    if (!out) return fail(RV_E_ARG, "out is NULL");
+    *out = nullptr;
+    rv_circuit *c = new (std::nothrow) rv_circuit();
+    if (!c) return fail(RV_E_NOMEM, "out of memory");
+    std::string err;
+    int rc;
+    try {
+        rc = compile(ops, n_ops, z64_cells, gf2_cells, c->prog, err);
+    } catch (const std::bad_alloc &) {
+        delete c;
+        return fail(RV_E_NOMEM, "out of host memory while compiling the circuit");
+    }
+    if (rc != RV_OK) {
+        delete c;
+        return fail(rc, err);
+    }
+    Program &P = c->prog;
+    for (uint32_t t = 0; t < P.n_online; t++)
+        if (P.items[t].kind == ITEM_MUL) c->mul_pos.push_back(t);
+    {
+        uint32_t e[8];
+        b3_chunk_cv(nullptr, 0, 0, true, e);
+        memcpy(c->z64_empty_hash, e, 32);
+        b3_hash64(e, e, c->z64_rep_hash);
+    }
+    // Device tables.  Without a device the handle still carries the host tables (stats / export for the CPU test-suite),
+    // but it cannot prove or verify: there is no CPU fallback and rv_session_create reports RV_E_CUDA.
+    if (rv_device_count() == 0) {
+        c->device = -1;
+        *out = c;
+        return RV_OK;
+    }
+    c->device = g_device;
+    cudaSetDevice(c->device);
+    DevProgram &D = c->dev;
+    if ((rc = upload(c, P.vgates, &D.vgates)) || (rc = upload(c, P.vlevel_off, &D.vlevel_off)) || (rc = upload(c, P.lgates, &D.lgates)) ||
+        (rc = upload(c, P.llevel_off, &D.llevel_off)) || (rc = upload(c, P.items, &D.items)) || (rc = upload(c, c->mul_pos, &D.mul_pos)) ||
+        (rc = upload(c, P.recon_pos, &D.recon_pos)) || (rc = upload(c, P.input_pos, &D.input_pos)) ||
+        (rc = upload(c, P.input_vid, &D.input_vid))) {
+        rv_circuit_free(c);
+        return rc;
+    }
+    D.n_vgates = (uint32_t)P.vgates.size();
+    D.n_vlevels = (uint32_t)P.vlevel_off.size() - 1;
+    D.n_lgates = (uint32_t)P.lgates.size();
+    D.n_llevels = (uint32_t)P.llevel_off.size() - 1;
+    D.n_masks = P.n_masks;
+    D.n_rows = P.n_rows;
+    D.n_vals = P.n_vals;
+    D.n_online = P.n_online;
+    D.n_pre = P.n_pre;
+    D.n_inputs = (uint32_t)P.n_inputs;
+    D.n_recon = (uint32_t)P.recon_pos.size();
+    *out = c;
+    return RV_OK;
+}
+
+extern "C" int rv_circuit_get_stats(const rv_circuit *c, rv_circuit_stats *o) {
+    if (!c || !o) return fail(RV_E_ARG, "NULL argument");
+    const Program &P = c->prog;
+    o->n_ops = P.n_ops;
+    o->n_and = P.n_and;
+    o->n_inputs = P.n_inputs;
+    o->n_assert = P.n_assert;
+    o->n_masks = P.n_masks;
+    o->n_linear = P.n_lin;
+    o->value_depth = P.vlevel_off.size() - 1;
+    o->linear_depth = P.llevel_off.size() - 1;
+    o->online_bytes = P.n_online;
+    o->pre_bytes = P.n_pre;
+    o->algorithmic_bytes = P.algorithmic_bytes;
+    o->device_bytes = c->device_bytes;
+    return RV_OK;
+}
+
+extern "C" int rv_circuit_export(const rv_circuit *c, int what, void *buf, size_t *len) {
+    if (!c || !len) return fail(RV_E_ARG, "NULL argument");
+    const Program &P = c->prog;
+    const void *src = nullptr;
+    size_t n = 0;
+    switch (what) {
+        case RV_TAB_VGATES: src = P.vgates.data(); n = P.vgates.size() * sizeof(VGate); break;
+        case RV_TAB_VLEVELS: src = P.vlevel_off.data(); n = P.vlevel_off.size() * 4; break;
+        case RV_TAB_LGATES: src = P.lgates.data(); n = P.lgates.size() * sizeof(LGate); break;
+        case RV_TAB_LLEVELS: src = P.llevel_off.data(); n = P.llevel_off.size() * 4; break;
+        case RV_TAB_ITEMS: src = P.items.data(); n = P.items.size() * sizeof(Item); break;
+        case RV_TAB_RECON_POS: src = P.recon_pos.data(); n = P.recon_pos.size() * 4; break;
+        case RV_TAB_INPUT_POS: src = P.input_pos.data(); n = P.input_pos.size() * 4; break;
+        case RV_TAB_INPUT_VID: src = P.input_vid.data(); n = P.input_vid.size() * 4; break;
+        default: return fail(RV_E_ARG, "unknown table id");
+    }
+    if (buf) {
+        if (*len < n) return fail(RV_E_ARG, "buffer too small");
+        if (n) memcpy(buf, src, n);
+    }
+    *len = n;
+    return RV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+//  session
+// ---------------------------------------------------------------------------------------------------------------------
+static size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+struct KTimer {
+    std::string name;
+    double ms = 0;
+    uint64_t launches = 0, bytes = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+struct rv_session {
+    const rv_circuit *c = nullptr;
+    uint32_t first_instance = 0, npi = 0, nreps = 0, first_rep = 0;
+    cudaStream_t st = nullptr, st_val = nullptr;
+    bool own_stream = true;
+    cudaEvent_t ev_upload = nullptr, ev_vals = nullptr;
+    // device buffers
+    uint8_t *d_wit = nullptr, *d_seeds = nullptr, *d_pkeys = nullptr, *d_vals = nullptr;
+    uint32_t *d_ks = nullptr, *d_lane_mask = nullptr;
+    uint64_t *d_rows = nullptr;
+    uint8_t *d_on = nullptr, *d_pre = nullptr;
+    size_t pitch_on = 0, pitch_pre = 0;
+    uint32_t *d_cv_on = nullptr, *d_cv_pre = nullptr, n_chunks_on = 1, n_chunks_pre = 1;
+    uint8_t *d_on_hash = nullptr, *d_rep_hash = nullptr, *d_all_hashes = nullptr, *d_comm = nullptr, *d_omit = nullptr;
+    uint16_t *d_rank = nullptr;
+    uint32_t *d_zconst = nullptr;  // [0..8) B3(""), [8..16) H(B3("")||B3(""))
+    int *d_bad = nullptr;
+    uint8_t *d_proof = nullptr;
+    size_t proof_len = 0;
+    uint32_t len_recons = 0, len_corrs = 0, len_inputs = 0;
+    // pinned host staging
+    uint8_t *h_in = nullptr;   // witness || seeds(256*16)
+    uint8_t *h_out = nullptr;  // proof || bad(4) || comm(32)
+    size_t h_in_bytes = 0;
+    std::vector<void *> allocs;
+    bool timing = false;
+    std::vector<KTimer> timers;
+    uint64_t launches = 0;
+    bool committed = false, opened = false;
+};
+
+template <typename T>
+static int dalloc(rv_session *s, T **p, size_t count) {
+    void *d = nullptr;
+    const size_t bytes = std::max<size_t>(count, 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(&d, bytes);
+    if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? RV_E_NOMEM : RV_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    s->allocs.push_back(d);
+    *p = reinterpret_cast<T *>(d);
+    return RV_OK;
+}
+
+extern "C" void rv_session_free(rv_session *s) {
+    if (!s) return;
+    cudaSetDevice(s->c->device);
+    if (s->st) cudaStreamSynchronize(s->st);
+    if (s->st_val) cudaStreamSynchronize(s->st_val);
+    for (auto &t : s->timers)
+        for (auto &p : t.pending) {
+            cudaEventDestroy(p.first);
+            cudaEventDestroy(p.second);
+        }
+    for (void *p : s->allocs) cudaFree(p);
+    if (s->h_in) cudaFreeHost(s->h_in);
+    if (s->h_out) cudaFreeHost(s->h_out);
+    if (s->ev_upload) cudaEventDestroy(s->ev_upload);
+    if (s->ev_vals) cudaEventDestroy(s->ev_vals);
+    if (s->st && s->own_stream) cudaStreamDestroy(s->st);
+    if (s->st_val) cudaStreamDestroy(s->st_val);
+    delete s;
+}
+
+extern "C" int rv_session_create(const rv_circuit *c, int first_instance, int n_instances, rv_session **out) {
+    if (!c || !out) return fail(RV_E_ARG, "NULL argument");
+    *out = nullptr;
+    if (first_instance < 0 || n_instances <= 0 || first_instance + n_instances > RV_PACKED_REPS)
+        return fail(RV_E_ARG, "shard must be a non-empty range of the 32 packed instances");
+    if (c->device < 0) return fail(RV_E_CUDA, "no CUDA device: reverie-b200 has no CPU fallback");
+    CU(cudaSetDevice(c->device));
+    rv_session *s = new (std::nothrow) rv_session();
+    if (!s) return fail(RV_E_NOMEM, "out of memory");
+    s->c = c;
+    s->first_instance = (uint32_t)first_instance;
+    s->npi = (uint32_t)n_instances;
+    s->nreps = 8 * s->npi;
+    s->first_rep = 8 * s->first_instance;
+    const Program &P = c->prog;
+    int rc = RV_OK;
+    auto bail = [&](int code) {
+        rv_session_free(s);
+        return code;
+    };
+    if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&s->st_val, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_upload, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&s->ev_vals, cudaEventDisableTiming) != cudaSuccess)
+        return bail(fail(RV_E_CUDA, "stream/event creation failed"));
+    s->pitch_on = round_up(std::max<size_t>(P.n_online, 1), 64);
+    s->pitch_pre = round_up(std::max<size_t>(P.n_pre, 1), 64);
+    s->n_chunks_on = P.n_online == 0 ? 1 : (P.n_online + 1023) / 1024;
+    s->n_chunks_pre = P.n_pre == 0 ? 1 : (P.n_pre + 1023) / 1024;
+    s->len_recons = (uint32_t)(P.recon_pos.size() / 8 + 1);  // floor(n/8)+1: the residue group is always flushed (gf2/share.rs:131-138)
+    s->len_corrs = P.n_pre / 8 + 1;
+    s->len_inputs = (uint32_t)(P.n_inputs / 8 + 1);
+    s->proof_len = ProofLayout{s->len_recons, s->len_corrs, s->len_inputs}.total();
+    if ((rc = dalloc(s, &s->d_wit, P.n_inputs)) || (rc = dalloc(s, &s->d_seeds, (size_t)s->nreps * 16)) ||
+        (rc = dalloc(s, &s->d_pkeys, (size_t)s->nreps * 128)) || (rc = dalloc(s, &s->d_vals, round_up(P.n_vals, 16))) ||
+        (rc = dalloc(s, &s->d_ks, (size_t)2 * s->npi * 1408)) || (rc = dalloc(s, &s->d_lane_mask, 2 * s->npi)) ||
+        (rc = dalloc(s, &s->d_rows, (size_t)P.n_rows * s->npi)) || (rc = dalloc(s, &s->d_on, s->pitch_on * s->nreps)) ||
+        (rc = dalloc(s, &s->d_pre, s->pitch_pre * s->nreps)) || (rc = dalloc(s, &s->d_cv_on, (size_t)s->n_chunks_on * s->nreps * 8)) ||
+        (rc = dalloc(s, &s->d_cv_pre, (size_t)s->n_chunks_pre * s->nreps * 8)) || (rc = dalloc(s, &s->d_on_hash, (size_t)s->nreps * 32)) ||
+        (rc = dalloc(s, &s->d_rep_hash, (size_t)s->nreps * 32)) || (rc = dalloc(s, &s->d_all_hashes, RV_TOTAL_REPS * 32)) ||
+        (rc = dalloc(s, &s->d_comm, 32)) || (rc = dalloc(s, &s->d_omit, RV_TOTAL_REPS)) || (rc = dalloc(s, &s->d_rank, RV_TOTAL_REPS)) ||
+        (rc = dalloc(s, &s->d_zconst, 16)) || (rc = dalloc(s, &s->d_bad, 1)) || (rc = dalloc(s, &s->d_proof, s->proof_len)))
+        return bail(rc);
+    s->h_in_bytes = round_up(P.n_inputs, 16) + RV_TOTAL_REPS * 16;
+    if (cudaMallocHost(&s->h_in, s->h_in_bytes) != cudaSuccess || cudaMallocHost(&s->h_out, s->proof_len + 64) != cudaSuccess)
+        return bail(fail(RV_E_NOMEM, "pinned host allocation failed"));
+    uint32_t zc[16];
+    memcpy(zc, c->z64_empty_hash, 32);
+    memcpy(zc + 8, c->z64_rep_hash, 32);
+    if (cudaMemcpy(s->d_zconst, zc, 64, cudaMemcpyHostToDevice) != cudaSuccess) return bail(fail(RV_E_CUDA, "cudaMemcpy failed"));
+    *out = s;
+    return RV_OK;
+}
+
+extern "C" void *rv_session_stream(rv_session *s) { return s ? (void *)s->st : nullptr; }
+extern "C" uint64_t rv_session_launch_count(const rv_session *s) { return s ? s->launches : 0; }
+extern "C" int rv_session_sync(rv_session *s) {
+    if (!s) return fail(RV_E_ARG, "NULL session");
+    CU(cudaStreamSynchronize(s->st));
+    return RV_OK;
+}
+
+// ---- per-kernel timing ---------------------------------------------------------------------------------------------
+struct Scope {
+    rv_session *s;
+    KTimer *t = nullptr;
+    cudaEvent_t a = nullptr, b = nullptr;
+    Scope(rv_session *s_, const char *name, uint64_t bytes, uint64_t n_launches = 1) : s(s_) {
+        s->launches += n_launches;
+        if (!s->timing) return;
+        for (auto &k : s->timers)
+            if (k.name == name) t = &k;
+        if (!t) {
+            s->timers.push_back(KTimer());
+            t = &s->timers.back();
+            t->name = name;
+        }
+        t->launches += n_launches;
+        t->bytes += bytes;
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+        cudaEventRecord(a, s->st);
+    }
+    ~Scope() {
+        if (!t) return;
+        cudaEventRecord(b, s->st);
+        t->pending.push_back({a, b});
+    }
+};
+
+extern "C" int rv_session_timing(rv_session *s, int enable) {
+    if (!s) return fail(RV_E_ARG, "NULL session");
+    s->timing = enable != 0;
+    return RV_OK;
+}
+
+extern "C" int rv_session_kernel_times(rv_session *s, rv_kernel_time *out, int max_out, int reset) {
+    if (!s) return fail(RV_E_ARG, "NULL session");
+    CU(cudaStreamSynchronize(s->st));
+    int n = 0;
+    for (auto &t : s->timers) {
+        for (auto &p : t.pending) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, p.first, p.second);
+            t.ms += ms;
+            cudaEventDestroy(p.first);
+            cudaEventDestroy(p.second);
+        }
+        t.pending.clear();
+        if (out && n < max_out) {
+            memset(&out[n], 0, sizeof(rv_kernel_time));
+            strncpy(out[n].name, t.name.c_str(), sizeof(out[n].name) - 1);
+            out[n].ms = t.ms;
+            out[n].launches = t.launches;
+            out[n].algorithmic_bytes = t.bytes;
+        }
+        n++;
+    }
+    if (reset) s->timers.clear();
+    return n;
+}
+
+// ---- upload / commit / open / fetch ----------------------------------------------------------------------------------
+extern "C" int rv_session_upload(rv_session *s, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64, size_t n_z64,
+                                 const uint8_t *seeds) {
+    (void)wit_z64;
+    (void)n_z64;
+    if (!s) return fail(RV_E_ARG, "NULL session");
+    const Program &P = s->c->prog;
+    if (n_gf2 < P.n_inputs) return fail(RV_E_WITNESS_SHORT, "witness is too short");  // prover.rs:190
+    if (P.n_inputs && !wit_gf2) return fail(RV_E_ARG, "wit_gf2 is NULL");
+    CU(cudaSetDevice(s->c->device));
+    CU(cudaStreamSynchronize(s->st));  // the staging buffer may still be in flight from a previous proof
+    const size_t woff = round_up(P.n_inputs, 16);
+    if (P.n_inputs) memcpy(s->h_in, wit_gf2, P.n_inputs);
+    uint8_t *hs = s->h_in + woff;
+    if (seeds) memcpy(hs, seeds, RV_TOTAL_REPS * 16);
+    else {  // OsRng, src/proof/mod.rs:131-134
+        size_t got = 0;
+        while (got < RV_TOTAL_REPS * 16) {
+            ssize_t r = getrandom(hs + got, RV_TOTAL_REPS * 16 - got, 0);
+            if (r <= 0) return fail(RV_E_ARG, "getrandom failed");
+            got += (size_t)r;
+        }
+    }
+    if (P.n_inputs) CU(cudaMemcpyAsync(s->d_wit, s->h_in, P.n_inputs, cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemcpyAsync(s->d_seeds, hs + (size_t)s->first_rep * 16, (size_t)s->nreps * 16, cudaMemcpyHostToDevice, s->st));
+    CU(cudaEventRecord(s->ev_upload, s->st));
+    s->committed = s->opened = false;
+    return RV_OK;
+}
+
+extern "C" int rv_session_commit(rv_session *s) {
+    if (!s) return fail(RV_E_ARG, "NULL session");
+    const rv_circuit *c = s->c;
+    const Program &P = c->prog;
+    const DevProgram &D = c->dev;
+    CU(cudaSetDevice(c->device));
+    const uint32_t nslices = 2 * s->npi;
+    // value plane on its own stream: it depends only on the witness and overlaps the whole mask pipeline
+    CU(cudaStreamWaitEvent(s->st_val, s->ev_upload, 0));
+    launch_values(D, s->d_wit, s->d_vals, s->st_val);
+    s->launches++;
+    CU(cudaEventRecord(s->ev_vals, s->st_val));
+    CU(cudaMemsetAsync(s->d_bad, 0, sizeof(int), s->st));
+    CU(cudaMemsetAsync(s->d_rows + (size_t)P.zero_row() * s->npi, 0, (size_t)s->npi * 8, s->st));
+    {
+        Scope k(s, "key_setup", 0);
+        launch_key_setup(s->d_seeds, nullptr, nullptr, nullptr, nslices, s->d_ks, s->d_lane_mask, s->d_pkeys, s->st);
+    }
+    {
+        Scope k(s, "mask_gen", (uint64_t)P.n_masks * s->npi * 8);
+        launch_mask_gen(s->d_ks, s->d_lane_mask, nslices, P.n_masks, s->d_rows, s->st);
+    }
+    if (D.n_llevels) {
+        const double avg_width = (double)D.n_lgates / D.n_llevels;
+        Scope k(s, "linear", (uint64_t)P.n_lin * s->npi * 8 * 3, avg_width < 4096.0 ? 1 : D.n_llevels);
+        launch_linear(D, P.llevel_off.data(), s->d_rows, s->npi, s->st);
+    }
+    CU(cudaStreamWaitEvent(s->st, s->ev_vals, 0));
+    {
+        // per Mul: 4 row reads + 2 stream bytes per rep (online) and 3 row reads + 1 byte per rep (pre)
+        Scope k(s, "items", ((uint64_t)P.n_and * 7 + P.n_inputs + P.n_assert) * s->npi * 8 + ((uint64_t)P.n_online + P.n_pre) * s->nreps, 2);
+        launch_items(D, s->d_rows, s->npi, s->d_vals, s->d_on, s->pitch_on, s->d_pre, s->pitch_pre, s->d_bad, s->st);
+    }
+    {
+        Scope k(s, "chunk_cv", ((uint64_t)P.n_online + P.n_pre) * s->nreps, 2);
+        launch_chunk_cv(s->d_on, s->pitch_on, P.n_online, s->nreps, s->d_cv_on, s->st);
+        launch_chunk_cv(s->d_pre, s->pitch_pre, P.n_pre, s->nreps, s->d_cv_pre, s->st);
+    }
+    {
+        Scope k(s, "rep_hash", ((uint64_t)s->n_chunks_on + s->n_chunks_pre) * s->nreps * 32);
+        launch_rep_hash(s->d_cv_on, s->n_chunks_on, s->d_cv_pre, s->n_chunks_pre, s->d_zconst + 8, s->nreps, s->d_on_hash, s->d_rep_hash, s->st);
+    }
+    CU(cudaGetLastError());
+    s->committed = true;
+    return RV_OK;
+}
+
+extern "C" int rv_session_hashes(rv_session *s, uint8_t *rep_hashes) {
+    if (!s || !rep_hashes) return fail(RV_E_ARG, "NULL argument");
+    if (!s->committed) return fail(RV_E_ARG, "rv_session_commit has not run");
+    CU(cudaSetDevice(s->c->device));
+    CU(cudaMemcpyAsync(rep_hashes, s->d_rep_hash, (size_t)s->nreps * 32, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaStreamSynchronize(s->st));
+    return RV_OK;
+}
+
+extern "C" int rv_session_open(rv_session *s, const uint8_t *all_rep_hashes) {
+    if (!s) return fail(RV_E_ARG, "NULL session");
+    if (!s->committed) return fail(RV_E_ARG, "rv_session_commit has not run");
+    const rv_circuit *c = s->c;
+    const DevProgram &D = c->dev;
+    CU(cudaSetDevice(c->device));
+    const uint8_t *hashes = s->d_all_hashes;
+    if (all_rep_hashes) {
+        cudaPointerAttributes at;
+        const bool on_device = cudaPointerGetAttributes(&at, all_rep_hashes) == cudaSuccess && at.type == cudaMemoryTypeDevice;
+        cudaGetLastError();
+        CU(cudaMemcpyAsync(s->d_all_hashes, all_rep_hashes, RV_TOTAL_REPS * 32, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s->st));
+    } else {
+        if (s->npi != RV_PACKED_REPS) return fail(RV_E_ARG, "a partial shard needs the all-gathered repetition hashes");
+        hashes = s->d_rep_hash;
+    }
+    {
+        Scope k(s, "challenge", RV_TOTAL_REPS * 32);
+        launch_challenge(hashes, s->d_comm, s->d_omit, s->d_rank, s->st);
+    }
+    CU(cudaMemsetAsync(s->d_proof, 0, s->proof_len, s->st));
+    {
+        Scope k(s, "extract", s->proof_len);
+        ExtractArgs a;
+        a.on = s->d_on;
+        a.pre = s->d_pre;
+        a.pitch_on = s->pitch_on;
+        a.pitch_pre = s->pitch_pre;
+        a.on_hash = s->d_on_hash;
+        a.pkeys = s->d_pkeys;
+        a.seeds = s->d_seeds;
+        a.comm = s->d_comm;
+        a.omit_of_rep = s->d_omit;
+        a.rank_of_rep = s->d_rank;
+        a.z64_empty_hash = s->d_zconst;
+        a.first_rep = s->first_rep;
+        a.nreps = s->nreps;
+        a.len_recons = s->len_recons;
+        a.len_corrs = s->len_corrs;
+        a.len_inputs = s->len_inputs;
+        a.proof = s->d_proof;
+        launch_extract(D, a, s->st);
+    }
+    CU(cudaMemcpyAsync(s->h_out, s->d_proof, s->proof_len, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(s->h_out + s->proof_len, s->d_bad, 4, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(s->h_out + s->proof_len + 4, s->d_comm, 32, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaGetLastError());
+    s->opened = true;
+    return RV_OK;
+}
+
+extern "C" int rv_session_fetch(rv_session *s, uint8_t comm[RV_HASH_SIZE], uint8_t **part, size_t *part_len) {
+    if (!s || !part || !part_len) return fail(RV_E_ARG, "NULL argument");
+    if (!s->opened) return fail(RV_E_ARG, "rv_session_open has not run");
+    CU(cudaSetDevice(s->c->device));
+    CU(cudaStreamSynchronize(s->st));
+    int bad;
+    memcpy(&bad, s->h_out + s->proof_len, 4);
+    if (bad) return fail(RV_E_WITNESS_INVALID, "witness is invalid!");  // prover.rs:223
+    uint8_t *p = (uint8_t *)malloc(s->proof_len);
+    if (!p) return fail(RV_E_NOMEM, "out of memory");
+    memcpy(p, s->h_out, s->proof_len);
+    if (comm) memcpy(comm, s->h_out + s->proof_len + 4, 32);
+    *part = p;
+    *part_len = s->proof_len;
+    return RV_OK;
+}
+
+// Shard blobs are full-length proofs with only the shard's entries filled in (zero elsewhere); entries never overlap,
+// so the assembly of src/proof/mod.rs:200-221 is a byte-wise OR.
+extern "C" int rv_proof_assemble(const uint8_t comm[RV_HASH_SIZE], const uint8_t *const *parts, const size_t *part_lens, int n_parts,
+                                 uint8_t **proof, size_t *proof_len) {
+    if (!parts || !part_lens || n_parts <= 0 || !proof || !proof_len) return fail(RV_E_ARG, "bad argument");
+    const size_t n = part_lens[0];
+    for (int i = 1; i < n_parts; i++)
+        if (part_lens[i] != n) return fail(RV_E_FORMAT, "shard blobs differ in length");
+    if (n < 32) return fail(RV_E_FORMAT, "shard blob too short");
+    uint8_t *p = (uint8_t *)calloc(n, 1);
+    if (!p) return fail(RV_E_NOMEM, "out of memory");
+    for (int i = 0; i < n_parts; i++)
+        for (size_t k = 0; k < n; k++) p[k] |= parts[i][k];
+    if (comm) memcpy(p, comm, 32);
+    *proof = p;
+    *proof_len = n;
+    return RV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+//  Proof::new / Proof::verify
+// ---------------------------------------------------------------------------------------------------------------------
+extern "C" int rv_prove(const rv_circuit *c, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64, size_t n_z64,
+                        const uint8_t *seeds, uint8_t **proof, size_t *proof_len) {
+    if (!c || !proof || !proof_len) return fail(RV_E_ARG, "NULL argument");
+    rv_session *s = nullptr;
+    int rc = rv_session_create(c, 0, RV_PACKED_REPS, &s);
+    if (rc) return rc;
+    if ((rc = rv_session_upload(s, wit_gf2, n_gf2, wit_z64, n_z64, seeds)) == RV_OK && (rc = rv_session_commit(s)) == RV_OK &&
+        (rc = rv_session_open(s, nullptr)) == RV_OK)
+        rc = rv_session_fetch(s, nullptr, proof, proof_len);
+    rv_session_free(s);
+    return rc;
+}
+
+extern "C" int rv_verify(const rv_circuit *c, const uint8_t *proof, size_t proof_len, int *okay) {
+    (void)c;
+    (void)proof;
+    (void)proof_len;
+    (void)okay;
+    return fail(RV_E_UNSUPPORTED, "rv_verify: not implemented yet");
+}
+
+extern "C" int rv_proof_new(const rv_op *ops, size_t n_ops, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64, size_t n_z64,
+                            size_t z64_cells, size_t gf2_cells, const uint8_t *seeds, uint8_t **proof, size_t *proof_len) {
+    rv_circuit *c = nullptr;
+    int rc = rv_circuit_compile(ops, n_ops, z64_cells, gf2_cells, &c);
+    if (rc) return rc;
+    rc = rv_prove(c, wit_gf2, n_gf2, wit_z64, n_z64, seeds, proof, proof_len);
+    rv_circuit_free(c);
+    return rc;
+}
+
+extern "C" int rv_proof_verify(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, const uint8_t *proof, size_t proof_len) {
+    rv_circuit *c = nullptr;
+    int rc = rv_circuit_compile(ops, n_ops, z64_cells, gf2_cells, &c);
+    if (rc) return rc;
+    rc = rv_verify(c, proof, proof_len, nullptr);
+    rv_circuit_free(c);
+    return rc;
+}

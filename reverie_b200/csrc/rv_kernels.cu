@@ -1,0 +1,488 @@
+// rv_kernels.cu -- the sm_100a kernels of the KKW prover.  Compiled with -gencode arch=compute_100a,code=sm_100a.
+// Integer / bitwise work only: no tensor cores.  See DESIGN.md section 5 for the roofline of each kernel.
+#include <cuda_pipeline.h>
+
+#include "rv_kernels.cuh"
+#include "rv_planes.cuh"
+
+namespace rv {
+
+// =====================================================================================================================
+//  K1  key setup: one warp per slice (32 PRG streams = 4 repetitions x 8 players = one u32 half of a share word)
+// =====================================================================================================================
+// Lane q owns the stream that lives at bit q of the slice word: stream index 31-q = 8*rep_in_slice + player.
+// Slice w: packed instance w/2; odd w = high u32 (repetitions 0..3), even w = low u32 (repetitions 4..7).
+__global__ void __launch_bounds__(128) k_key_setup(const uint8_t *__restrict__ seeds, const uint8_t *__restrict__ pkeys_in,
+                                                   const uint8_t *__restrict__ mode, const uint8_t *__restrict__ omit, uint32_t nslices,
+                                                   uint32_t *__restrict__ ks, uint32_t *__restrict__ lane_mask, uint8_t *__restrict__ pkeys_out) {
+    const uint32_t lane = threadIdx.x & 31, w = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (w >= nslices) return;
+    const uint32_t rep = slice_rep(w, lane), p = slice_player(lane);
+    uint32_t rk[44];
+    const bool active = key_setup_stream(rep, p, seeds, pkeys_in, mode, omit, pkeys_out, rk);
+    const uint32_t am = __ballot_sync(0xffffffffu, active);
+    if (lane == 0) lane_mask[w] = am;
+    // bitslice: plane k of round R = bit k of the 128-bit little-endian round key, gathered over the 32 lanes
+#pragma unroll 1
+    for (int q = 0; q < 44; q++) {
+        const uint32_t word = rk[q];
+        uint32_t mine = 0;
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+            const uint32_t b = __ballot_sync(0xffffffffu, (word >> i) & 1u);
+            if (lane == (uint32_t)i) mine = b;
+        }
+        ks[(size_t)w * 1408 + q * 32 + lane] = mine;
+    }
+}
+
+void launch_key_setup(const uint8_t *seeds, const uint8_t *pkeys_in, const uint8_t *mode, const uint8_t *omit, uint32_t nslices,
+                      uint32_t *ks, uint32_t *lane_mask, uint8_t *pkeys_out, cudaStream_t st) {
+    k_key_setup<<<(nslices + 3) / 4, 128, 0, st>>>(seeds, pkeys_in, mode, omit, nslices, ks, lane_mask, pkeys_out);
+}
+
+// =====================================================================================================================
+//  K2  mask generation: bitsliced AES-128-CTR, thread = (slice, counter block)
+// =====================================================================================================================
+constexpr int MG_SLICES = 8;    // slices per CTA (their round keys live in shared memory: 8 x 5632 B = 44 KB)
+constexpr int MG_COUNTERS = 16; // counter blocks per CTA
+constexpr int MG_THREADS = MG_SLICES * MG_COUNTERS;
+
+struct SmemRoundKeys {
+    const uint4 *base;  // [(round*32 + plane/4)][slice] uint4
+    uint32_t sl;
+    __device__ __forceinline__ uint4 quad(int round, int g) const { return base[(round * 32 + g) * MG_SLICES + sl]; }
+};
+
+// Same dataflow as bs_aes128_ctr_block (rv_aes_bs.cuh), with the round-key planes fetched four at a time (LDS.128).
+__device__ __forceinline__ void aes_ctr_block_smem(uint64_t ctr, const SmemRoundKeys &rk, uint32_t *s) {
+#pragma unroll
+    for (int g = 0; g < 32; g++) {
+        const uint4 k4 = rk.quad(0, g);
+        const uint32_t kk[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const int k = 4 * g + i, B = k >> 3, b = k & 7;
+            uint32_t in = 0;
+            if (B >= 8) in = 0u - (uint32_t)((ctr >> (8 * (15 - B) + b)) & 1);
+            s[k] = in ^ kk[i];
+        }
+    }
+#pragma unroll 1
+    for (int round = 1; round <= 10; round++) {
+#pragma unroll
+        for (int B = 0; B < 16; B++) bs_sbox<uint32_t>(s + 8 * B, 0xFFFFFFFFu);
+        uint32_t t[128];
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int b = 0; b < 8; b++) t[8 * (4 * c + r) + b] = s[8 * (4 * ((c + r) & 3) + r) + b];
+        if (round < 10) {
+#pragma unroll
+            for (int c = 0; c < 4; c++) bs_mix_column<uint32_t>(t + 32 * c, t + 32 * c + 8, t + 32 * c + 16, t + 32 * c + 24, s + 32 * c);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 128; k++) s[k] = t[k];
+        }
+#pragma unroll
+        for (int g = 0; g < 32; g++) {
+            const uint4 k4 = rk.quad(round, g);
+            s[4 * g + 0] ^= k4.x;
+            s[4 * g + 1] ^= k4.y;
+            s[4 * g + 2] ^= k4.z;
+            s[4 * g + 3] ^= k4.w;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(MG_THREADS) k_mask_gen(const uint32_t *__restrict__ ks, const uint32_t *__restrict__ lane_mask,
+                                                         uint32_t nslices, uint32_t n_masks, uint32_t *__restrict__ rows32) {
+    __shared__ uint4 sk[11 * 32 * MG_SLICES];
+    const uint32_t w0 = blockIdx.y * MG_SLICES;
+    {
+        uint32_t *sk32 = reinterpret_cast<uint32_t *>(sk);
+        for (uint32_t idx = threadIdx.x; idx < MG_SLICES * 1408; idx += MG_THREADS) {
+            const uint32_t sl = idx / 1408, e = idx % 1408;
+            const uint32_t v = (w0 + sl < nslices) ? ks[(size_t)(w0 + sl) * 1408 + e] : 0u;
+            sk32[((e >> 2) * MG_SLICES + sl) * 4 + (e & 3)] = v;
+        }
+    }
+    __syncthreads();
+    const uint32_t sl = threadIdx.x % MG_SLICES, w = w0 + sl;
+    const uint64_t j = (uint64_t)blockIdx.x * MG_COUNTERS + threadIdx.x / MG_SLICES;
+    if (w >= nslices || j * 128 >= n_masks) return;
+    uint32_t s[128];
+    SmemRoundKeys rk{sk, sl};
+    aes_ctr_block_smem(j, rk, s);
+    const uint32_t lm = lane_mask[w];
+#pragma unroll
+    for (int k = 0; k < 128; k++) {
+        const uint64_t i = plane_to_mask_index(j, k);
+        if (i < n_masks) rows32[i * nslices + w] = s[k] & lm;
+    }
+}
+
+void launch_mask_gen(const uint32_t *ks, const uint32_t *lane_mask, uint32_t nslices, uint32_t n_masks, uint64_t *rows, cudaStream_t st) {
+    if (n_masks == 0) return;
+    const uint32_t n_blocks = (n_masks + 127) / 128;
+    dim3 grid((n_blocks + MG_COUNTERS - 1) / MG_COUNTERS, (nslices + MG_SLICES - 1) / MG_SLICES);
+    k_mask_gen<<<grid, MG_THREADS, 0, st>>>(ks, lane_mask, nslices, n_masks, reinterpret_cast<uint32_t *>(rows));
+}
+
+// =====================================================================================================================
+//  K0  value plane: plaintext evaluation, one CTA, level-synchronous; gate descriptors double-buffered through
+//      shared memory with cp.async; wire values in shared memory when they fit.
+// =====================================================================================================================
+constexpr int VP_THREADS = 256;
+constexpr int VP_CHUNK = 1024;  // gates per staging buffer (16 KB)
+
+template <bool SMEM_VALS>
+__global__ void __launch_bounds__(VP_THREADS) k_values(const VGate *__restrict__ gates, const uint32_t *__restrict__ level_off,
+                                                       uint32_t n_levels, uint32_t n_gates, const uint32_t *__restrict__ input_vid,
+                                                       const uint8_t *__restrict__ wit, uint32_t n_inputs, uint8_t *__restrict__ vals_g,
+                                                       uint32_t n_vals) {
+    extern __shared__ __align__(16) uint8_t smem[];
+    VGate *sbuf = reinterpret_cast<VGate *>(smem);                // [2][VP_CHUNK]
+    uint8_t *vals = SMEM_VALS ? smem + 2 * VP_CHUNK * sizeof(VGate) : vals_g;
+    const uint32_t tid = threadIdx.x;
+
+    auto load_chunk = [&](uint32_t c) {
+        const uint32_t base = c * VP_CHUNK;
+        VGate *dst = sbuf + (c & 1) * VP_CHUNK;
+        for (uint32_t i = tid; i < VP_CHUNK; i += VP_THREADS)
+            if (base + i < n_gates) __pipeline_memcpy_async(dst + i, gates + base + i, sizeof(VGate));
+        __pipeline_commit();
+    };
+    load_chunk(0);
+    load_chunk(1);
+    if (tid == 0) vals[0] = 0;
+    for (uint32_t k = tid; k < n_inputs; k += VP_THREADS) vals[input_vid[k]] = wit[k] & 1;
+    __pipeline_wait_prior(1);
+    __syncthreads();
+
+    uint32_t cur = 0;  // chunk being consumed
+    uint32_t s = n_levels ? level_off[0] : 0;
+    for (uint32_t l = 0; l < n_levels; l++) {
+        const uint32_t e = level_off[l + 1];
+        while (s < e) {
+            const uint32_t cbase = cur * VP_CHUNK, cend = min(e, cbase + VP_CHUNK);
+            const VGate *buf = sbuf + (cur & 1) * VP_CHUNK;
+            for (uint32_t g = s + tid; g < cend; g += VP_THREADS) {
+                const VGate gt = buf[g - cbase];
+                const uint32_t a = vals[gt.a >> 1] ^ (gt.a & 1), b = vals[gt.b >> 1] ^ (gt.b & 1);
+                vals[gt.dst] = (uint8_t)((gt.op ? (a & b) : (a ^ b)) & 1);
+            }
+            s = cend;
+            if (s == (cur + 1) * VP_CHUNK && s < n_gates) {  // staging buffer exhausted: refill it, move to the other one
+                __syncthreads();
+                load_chunk(cur + 2);
+                cur++;
+                __pipeline_wait_prior(1);
+                __syncthreads();
+            }
+        }
+        __syncthreads();
+    }
+    if (SMEM_VALS) {
+        for (uint32_t i = tid; i < n_vals; i += VP_THREADS) vals_g[i] = vals[i];
+    }
+}
+
+size_t launch_values(const DevProgram &P, const uint8_t *wit, uint8_t *vals, cudaStream_t st) {
+    const size_t stage = 2 * VP_CHUNK * sizeof(VGate);
+    const size_t want = stage + ((P.n_vals + 15) & ~15u);
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_values<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(k_values<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        configured = true;
+    }
+    if (want <= 227 * 1024) {
+        k_values<true><<<1, VP_THREADS, want, st>>>(P.vgates, P.vlevel_off, P.n_vlevels, P.n_vgates, P.input_vid, wit, P.n_inputs, vals, P.n_vals);
+        return want;
+    }
+    k_values<false><<<1, VP_THREADS, stage, st>>>(P.vgates, P.vlevel_off, P.n_vlevels, P.n_vgates, P.input_vid, wit, P.n_inputs, vals, P.n_vals);
+    return stage;
+}
+
+// =====================================================================================================================
+//  K3  mask plane: row[dst] = row[a] ^ row[b], level by level
+// =====================================================================================================================
+constexpr int LIN_THREADS = 256;
+
+// deep / narrow networks: one CTA per packed instance walks all levels (CTA barrier only; columns are independent)
+__global__ void __launch_bounds__(LIN_THREADS) k_linear_cta(const LGate *__restrict__ gates, const uint32_t *__restrict__ level_off,
+                                                            uint32_t n_levels, uint64_t *rows, uint32_t npi) {
+    const uint32_t pi = blockIdx.x, tid = threadIdx.x;
+    uint32_t s = level_off[0];
+    LGate nxt = (s + tid < level_off[n_levels]) ? gates[s + tid] : LGate{0, 0, 0, 0};
+    for (uint32_t l = 0; l < n_levels; l++) {
+        const uint32_t e = level_off[l + 1];
+        LGate cur = nxt;
+        if (e + tid < level_off[n_levels]) nxt = gates[e + tid];  // prefetch the next level's first descriptor
+        for (uint32_t g = s + tid; g < e; g += LIN_THREADS) {
+            if (g != s + tid) cur = gates[g];
+            rows[(size_t)cur.dst * npi + pi] = rows[(size_t)cur.a * npi + pi] ^ rows[(size_t)cur.b * npi + pi];
+        }
+        s = e;
+        __syncthreads();
+    }
+}
+
+// wide levels: one launch per level, thread = (gate, packed instance)
+__global__ void __launch_bounds__(256) k_linear_level(const LGate *__restrict__ gates, uint32_t n, uint64_t *rows, uint32_t npi) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t g = gid / npi;
+    const uint32_t pi = (uint32_t)(gid % npi);
+    if (g >= n) return;
+    const LGate gt = gates[g];
+    rows[(size_t)gt.dst * npi + pi] = rows[(size_t)gt.a * npi + pi] ^ rows[(size_t)gt.b * npi + pi];
+}
+
+int launch_linear(const DevProgram &P, const uint32_t *off_host, uint64_t *rows, uint32_t npi, cudaStream_t st) {
+    if (P.n_llevels == 0) return 0;
+    // per-level launches pay ~3 us each; the CTA walker pays ~0.4 us per level but uses only npi SMs
+    const double avg_width = (double)P.n_lgates / P.n_llevels;
+    if (avg_width < 4096.0) {
+        k_linear_cta<<<npi, LIN_THREADS, 0, st>>>(P.lgates, P.llevel_off, P.n_llevels, rows, npi);
+        return 1;
+    }
+    for (uint32_t l = 0; l < P.n_llevels; l++) {
+        const uint32_t n = off_host[l + 1] - off_host[l];
+        const uint64_t threads = (uint64_t)n * npi;
+        k_linear_level<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P.lgates + off_host[l], n, rows, npi);
+    }
+    return (int)P.n_llevels;
+}
+
+// =====================================================================================================================
+//  K4  item plane: thread = (8 consecutive stream positions, packed instance); 8x8 byte transpose in registers so each
+//      repetition's 8 stream bytes leave as one aligned 64-bit store
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) k_items_online(const Item *__restrict__ items, uint32_t n_online, const uint64_t *__restrict__ rows,
+                                                      uint32_t npi, const uint8_t *__restrict__ vals, uint8_t *__restrict__ on, size_t pitch,
+                                                      int *bad) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t pi = (uint32_t)(gid % npi);
+    const uint64_t t0 = (gid / npi) * 8;
+    if (t0 >= n_online) return;
+    uint64_t W[8], out[8];
+    int flag = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        W[i] = 0;
+        if (t0 + i < n_online) W[i] = prover_online_word(items[t0 + i], rows, npi, pi, vals, &flag);
+    }
+    if (flag && pi == 0) atomicOr(bad, 1);
+    words_to_stream_bytes(W, out);
+#pragma unroll
+    for (int r = 0; r < 8; r++) *reinterpret_cast<uint64_t *>(on + (size_t)(8 * pi + r) * pitch + t0) = out[r];
+}
+
+__global__ void __launch_bounds__(256) k_items_pre(const Item *__restrict__ items, const uint32_t *__restrict__ mul_pos, uint32_t n_pre,
+                                                   const uint64_t *__restrict__ rows, uint32_t npi, uint8_t *__restrict__ pre, size_t pitch) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t pi = (uint32_t)(gid % npi);
+    const uint64_t j0 = (gid / npi) * 8;
+    if (j0 >= n_pre) return;
+    uint64_t W[8], out[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        W[i] = 0;
+        if (j0 + i < n_pre) W[i] = pre_word(items[mul_pos[j0 + i]], rows, npi, pi);
+    }
+    words_to_stream_bytes(W, out);
+#pragma unroll
+    for (int r = 0; r < 8; r++) *reinterpret_cast<uint64_t *>(pre + (size_t)(8 * pi + r) * pitch + j0) = out[r];
+}
+
+void launch_items(const DevProgram &P, const uint64_t *rows, uint32_t npi, const uint8_t *vals, uint8_t *on, size_t pitch_on,
+                  uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st) {
+    if (P.n_online) {
+        const uint64_t threads = (uint64_t)((P.n_online + 7) / 8) * npi;
+        k_items_online<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P.items, P.n_online, rows, npi, vals, on, pitch_on, bad);
+    }
+    if (P.n_pre) {
+        const uint64_t threads = (uint64_t)((P.n_pre + 7) / 8) * npi;
+        k_items_pre<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P.items, P.mul_pos, P.n_pre, rows, npi, pre, pitch_pre);
+    }
+}
+
+// =====================================================================================================================
+//  K5  transcript hashing
+// =====================================================================================================================
+// thread = (repetition, chunk): chaining value of one 1 KiB chunk
+__global__ void __launch_bounds__(128) k_chunk_cv(const uint8_t *__restrict__ stream, size_t pitch, uint32_t len, uint32_t n_chunks,
+                                                  uint32_t nreps, uint32_t *__restrict__ cvs) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t chunk = (uint32_t)(gid % n_chunks), rep = (uint32_t)(gid / n_chunks);
+    if (rep >= nreps) return;
+    const uint32_t off = chunk * 1024u;
+    const uint32_t clen = min(1024u, len - off);
+    uint32_t cv[8];
+    b3_chunk_cv(reinterpret_cast<const uint32_t *>(stream + (size_t)rep * pitch + off), clen, chunk, n_chunks == 1, cv);
+    uint32_t *dst = cvs + ((size_t)rep * n_chunks + chunk) * 8;
+#pragma unroll
+    for (int i = 0; i < 8; i++) dst[i] = cv[i];
+}
+
+void launch_chunk_cv(const uint8_t *stream, size_t pitch, uint32_t len, uint32_t nreps, uint32_t *cvs, cudaStream_t st) {
+    const uint32_t n_chunks = len == 0 ? 1 : (len + 1023) / 1024;
+    const uint64_t threads = (uint64_t)n_chunks * nreps;
+    k_chunk_cv<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(stream, pitch, len, n_chunks, nreps, cvs);
+}
+
+// BLAKE3 tree over n chunk CVs, in place: adjacent pairs merge, an odd tail is carried up unchanged (this reproduces
+// the spec's left-heavy tree).  The root lands in cvs[0..8).  Block-cooperative.
+__device__ void tree_reduce(uint32_t *cvs, uint32_t n) {
+    const uint32_t T = blockDim.x, tid = threadIdx.x;
+    while (n > 1) {
+        const uint32_t pairs = n / 2, outn = (n + 1) / 2;
+        const bool root = (n == 2);
+        for (uint32_t base = 0; base < outn; base += T) {
+            const uint32_t p = base + tid;
+            uint32_t res[8];
+            bool have = false;
+            if (p < pairs) {
+                uint32_t l[8], r[8];
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    l[i] = cvs[(size_t)(2 * p) * 8 + i];
+                    r[i] = cvs[(size_t)(2 * p + 1) * 8 + i];
+                }
+                b3_parent_cv(l, r, root, res);
+                have = true;
+            } else if (p < outn) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) res[i] = cvs[(size_t)(2 * p) * 8 + i];
+                have = true;
+            }
+            __syncthreads();
+            if (have) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) cvs[(size_t)p * 8 + i] = res[i];
+            }
+            __syncthreads();
+        }
+        n = outn;
+    }
+}
+
+// CTA = one repetition: roots of both streams, then the joins of Transcript::hash (src/transcript/mod.rs:77-96) and
+// CombineInstance::hash (src/interpreter/combine.rs:104-118).
+__global__ void __launch_bounds__(128) k_rep_hash(uint32_t *cv_on, uint32_t n_chunks_on, uint32_t *cv_pre, uint32_t n_chunks_pre,
+                                                  const uint32_t *__restrict__ z64_hash, uint8_t *__restrict__ on_hash,
+                                                  uint8_t *__restrict__ rep_hash) {
+    const uint32_t rep = blockIdx.x;
+    uint32_t *on = cv_on + (size_t)rep * n_chunks_on * 8, *pre = cv_pre + (size_t)rep * n_chunks_pre * 8;
+    tree_reduce(on, n_chunks_on);
+    tree_reduce(pre, n_chunks_pre);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t h_on[8], h_pre[8], z[8], out[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            h_on[i] = on[i];
+            h_pre[i] = pre[i];
+            z[i] = z64_hash[i];
+        }
+        rep_join(h_on, h_pre, z, out);
+        uint32_t *d0 = reinterpret_cast<uint32_t *>(on_hash + (size_t)rep * 32), *d1 = reinterpret_cast<uint32_t *>(rep_hash + (size_t)rep * 32);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            d0[i] = h_on[i];
+            d1[i] = out[i];
+        }
+    }
+}
+
+void launch_rep_hash(uint32_t *cv_on, uint32_t n_chunks_on, uint32_t *cv_pre, uint32_t n_chunks_pre, const uint32_t *z64_hash,
+                     uint32_t nreps, uint8_t *on_hash, uint8_t *rep_hash, cudaStream_t st) {
+    k_rep_hash<<<nreps, 128, 0, st>>>(cv_on, n_chunks_on, cv_pre, n_chunks_pre, z64_hash, on_hash, rep_hash);
+}
+
+// =====================================================================================================================
+//  K6  comm + Fiat-Shamir challenge: one warp
+// =====================================================================================================================
+__global__ void __launch_bounds__(32) k_challenge(const uint8_t *__restrict__ all_hashes, uint8_t *__restrict__ comm,
+                                                  uint8_t *__restrict__ omit_of_rep, uint16_t *__restrict__ rank_of_rep) {
+    __shared__ uint32_t cv[8][8];
+    __shared__ uint32_t xof[32][16];
+    __shared__ uint8_t omit[RV_TOTAL_REPS];
+    const uint32_t lane = threadIdx.x;
+    // combine_hashes (src/proof/mod.rs:102-108): BLAKE3 of 256 x 32 B = 8 chunks
+    if (lane < 8) {
+        uint32_t c[8];
+        b3_chunk_cv(reinterpret_cast<const uint32_t *>(all_hashes + 1024 * lane), 1024, lane, false, c);
+        for (int i = 0; i < 8; i++) cv[lane][i] = c[i];
+    }
+    __syncwarp();
+    for (uint32_t n = 8; n > 1; n >>= 1) {
+        uint32_t res[8];
+        if (lane < n / 2) b3_parent_cv(cv[2 * lane], cv[2 * lane + 1], n == 2, res);
+        __syncwarp();
+        if (lane < n / 2)
+            for (int i = 0; i < 8; i++) cv[lane][i] = res[i];
+        __syncwarp();
+    }
+    if (lane < 8) reinterpret_cast<uint32_t *>(comm)[lane] = cv[0][lane];
+    for (uint32_t i = lane; i < RV_TOTAL_REPS; i += 32) omit[i] = RV_PLAYERS;
+    uint32_t m[16];
+    challenge_block(cv[0], m);
+    __shared__ int distinct;
+    if (lane == 0) distinct = 0;
+    __syncwarp();
+    for (uint32_t round = 0; round < 64; round++) {
+        uint32_t o[16];
+        challenge_xof_block(m, (uint64_t)round * 32 + lane, o);
+        for (int i = 0; i < 16; i++) xof[lane][i] = o[i];
+        __syncwarp();
+        if (lane == 0)
+            for (int b = 0; b < 32 && distinct < RV_ONLINE_REPS; b++) challenge_consume(xof[b], omit, &distinct);
+        __syncwarp();
+        if (distinct >= RV_ONLINE_REPS) break;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        uint16_t n_on = 0, n_pre = 0;
+        for (int i = 0; i < RV_TOTAL_REPS; i++) {
+            omit_of_rep[i] = omit[i];
+            rank_of_rep[i] = (omit[i] < RV_PLAYERS) ? n_on++ : n_pre++;
+        }
+    }
+}
+
+void launch_challenge(const uint8_t *all_hashes, uint8_t *comm, uint8_t *omit_of_rep, uint16_t *rank_of_rep, cudaStream_t st) {
+    k_challenge<<<1, 32, 0, st>>>(all_hashes, comm, omit_of_rep, rank_of_rep);
+}
+
+// =====================================================================================================================
+//  K7  extraction: CTA = one repetition of the shard; writes its entry of the bincode `Proof` in place
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) k_extract(const uint32_t *__restrict__ recon_pos, const uint32_t *__restrict__ input_pos,
+                                                 uint32_t n_recon, uint32_t n_pre, uint32_t n_inputs, ExtractArgs a) {
+    const uint32_t lrep = blockIdx.x, rep = a.first_rep + lrep;
+    ProofLayout L{a.len_recons, a.len_corrs, a.len_inputs};
+    ExtractView v;
+    v.on = a.on + (size_t)lrep * a.pitch_on;
+    v.pre = a.pre + (size_t)lrep * a.pitch_pre;
+    v.on_hash = a.on_hash + (size_t)lrep * 32;
+    v.pkeys = a.pkeys + (size_t)lrep * 128;
+    v.seed = a.seeds + (size_t)lrep * 16;
+    v.comm = a.comm;
+    v.z64_empty_hash = a.z64_empty_hash;
+    v.recon_pos = recon_pos;
+    v.input_pos = input_pos;
+    v.n_recon = n_recon;
+    v.n_pre = n_pre;
+    v.n_inputs = n_inputs;
+    extract_entry(L, v, rep, a.omit_of_rep[rep], a.rank_of_rep[rep], threadIdx.x, blockDim.x, a.proof);
+}
+
+void launch_extract(const DevProgram &P, const ExtractArgs &a, cudaStream_t st) {
+    k_extract<<<a.nreps, 256, 0, st>>>(P.recon_pos, P.input_pos, P.n_recon, P.n_pre, P.n_inputs, a);
+}
+
+}  // namespace rv

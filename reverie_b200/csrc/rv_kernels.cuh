@@ -1,0 +1,62 @@
+// rv_kernels.cuh -- launchers of the sm_100a kernels (definitions in rv_kernels.cu).  Host-callable, all asynchronous on
+// the given stream.  Nothing here falls back to the CPU.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "rv_compile.h"
+
+namespace rv {
+
+// compiled tables resident in device memory
+struct DevProgram {
+    const VGate *vgates = nullptr;
+    const uint32_t *vlevel_off = nullptr;  // n_vlevels + 1
+    const LGate *lgates = nullptr;
+    const uint32_t *llevel_off = nullptr;  // n_llevels + 1
+    const Item *items = nullptr;
+    const uint32_t *mul_pos = nullptr;    // j -> online position of the j-th Mul
+    const uint32_t *recon_pos = nullptr;  // k -> online position of the k-th reconstruct()
+    const uint32_t *input_pos = nullptr;  // k -> online position of the k-th input()
+    const uint32_t *input_vid = nullptr;  // k -> value id
+    uint32_t n_vgates = 0, n_vlevels = 0, n_lgates = 0, n_llevels = 0;
+    uint32_t n_masks = 0, n_rows = 0, n_vals = 0, n_online = 0, n_pre = 0, n_inputs = 0, n_recon = 0;
+    uint32_t max_llevel_width = 0;
+};
+
+// K1  seeds -> player keys -> bitsliced round keys (src/transcript/mod.rs:99-106, src/crypto/prg.rs:16-20)
+void launch_key_setup(const uint8_t *seeds, const uint8_t *pkeys_in, const uint8_t *mode, const uint8_t *omit, uint32_t nslices,
+                      uint32_t *ks, uint32_t *lane_mask, uint8_t *pkeys_out, cudaStream_t st);
+// K2  AES-CTR mask generation straight into the share tensor (src/generator/share.rs:54-65)
+void launch_mask_gen(const uint32_t *ks, const uint32_t *lane_mask, uint32_t nslices, uint32_t n_masks, uint64_t *rows, cudaStream_t st);
+// K0  value plane (plaintext evaluation; one CTA, level-synchronous).  Returns the dynamic smem it asked for.
+size_t launch_values(const DevProgram &P, const uint8_t *wit, uint8_t *vals, cudaStream_t st);
+// K3  mask plane (XOR network over the share tensor)
+int launch_linear(const DevProgram &P, const uint32_t *llevel_off_host, uint64_t *rows, uint32_t npi, cudaStream_t st);
+// K4  item plane: the two hash streams of every repetition
+void launch_items(const DevProgram &P, const uint64_t *rows, uint32_t npi, const uint8_t *vals, uint8_t *on, size_t pitch_on,
+                  uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st);
+// K5  BLAKE3 chunk chaining values of `nreps` streams, then per-repetition tree + joins
+void launch_chunk_cv(const uint8_t *stream, size_t pitch, uint32_t len, uint32_t nreps, uint32_t *cvs, cudaStream_t st);
+void launch_rep_hash(uint32_t *cv_on, uint32_t n_chunks_on, uint32_t *cv_pre, uint32_t n_chunks_pre, const uint32_t *z64_hash,
+                     uint32_t nreps, uint8_t *on_hash, uint8_t *rep_hash, cudaStream_t st);
+// K6  comm = H(256 rep hashes); Fiat-Shamir challenge (src/proof/mod.rs:74-108)
+void launch_challenge(const uint8_t *all_hashes, uint8_t *comm, uint8_t *omit_of_rep, uint16_t *rank_of_rep, cudaStream_t st);
+// K7  openings -> bincode bytes of `Proof` (src/transcript/prover.rs:57-175, src/proof/mod.rs:40-66,200-221)
+struct ExtractArgs {
+    const uint8_t *on, *pre;
+    size_t pitch_on, pitch_pre;
+    const uint8_t *on_hash;      // [nreps][32]
+    const uint8_t *pkeys;        // [nreps][8][16]
+    const uint8_t *seeds;        // [nreps][16]
+    const uint8_t *comm;         // [32]
+    const uint8_t *omit_of_rep;  // [256]
+    const uint16_t *rank_of_rep; // [256]
+    const uint32_t *z64_empty_hash;  // B3("")
+    uint32_t first_rep, nreps;
+    uint32_t len_recons, len_corrs, len_inputs;  // packed byte lengths
+    uint8_t *proof;
+};
+void launch_extract(const DevProgram &P, const ExtractArgs &a, cudaStream_t st);
+
+}  // namespace rv

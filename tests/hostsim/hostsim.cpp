@@ -1,0 +1,195 @@
+// tests/hostsim/hostsim.cpp -- TEST INFRASTRUCTURE ONLY.  Replays the device pipeline on the CPU, thread by thread, by
+// calling the very same __host__ __device__ bodies the CUDA kernels call (csrc/rv_planes.cuh, rv_aes_bs.cuh,
+// rv_blake3.cuh) on the tables produced by the product's circuit compiler.  It lets the CPU-only test-suite pin the
+// kernels' arithmetic, bit orders and proof layout against the oracle before any GPU time is spent.  The product never
+// links this file.
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../reverie_b200/csrc/rv_planes.cuh"
+
+using namespace rv;
+
+static std::string g_err;
+extern "C" const char *hs_last_error() { return g_err.c_str(); }
+
+// the pairwise-with-carry tree of k_rep_hash / tree_reduce, serial
+static void tree_root(std::vector<uint32_t> &cvs, uint32_t n) {
+    while (n > 1) {
+        const uint32_t pairs = n / 2, outn = (n + 1) / 2;
+        const bool root = n == 2;
+        std::vector<uint32_t> nxt(outn * 8);
+        for (uint32_t p = 0; p < outn; p++) {
+            if (p < pairs) b3_parent_cv(&cvs[2 * p * 8], &cvs[(2 * p + 1) * 8], root, &nxt[p * 8]);
+            else memcpy(&nxt[p * 8], &cvs[2 * p * 8], 32);
+        }
+        cvs.swap(nxt);
+        n = outn;
+    }
+}
+
+static void stream_hash(const uint8_t *data, uint32_t len, uint32_t out[8]) {
+    const uint32_t n_chunks = len == 0 ? 1 : (len + 1023) / 1024;
+    std::vector<uint32_t> cvs(n_chunks * 8);
+    std::vector<uint32_t> buf(256);
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        const uint32_t off = c * 1024, clen = std::min<uint32_t>(1024, len - off);
+        memset(buf.data(), 0, 1024);
+        if (clen) memcpy(buf.data(), data + off, clen);
+        b3_chunk_cv(buf.data(), clen, c, n_chunks == 1, &cvs[c * 8]);
+    }
+    tree_root(cvs, n_chunks);
+    memcpy(out, cvs.data(), 32);
+}
+
+extern "C" void hs_blake3(const uint8_t *data, uint32_t len, uint8_t out[32]) {
+    uint32_t h[8];
+    stream_hash(data, len, h);
+    memcpy(out, h, 32);
+}
+
+extern "C" void hs_aes128_encrypt(const uint8_t key[16], const uint8_t in[16], uint8_t out[16]) {
+    uint32_t k[4], rk[44], i4[4], o4[4];
+    memcpy(k, key, 16);
+    memcpy(i4, in, 16);
+    aes128_expand_key(k, rk);
+    aes128_encrypt_block(rk, i4, o4);
+    memcpy(out, o4, 16);
+}
+
+// rows of the share tensor for `npi` packed instances starting at first_instance: the K1 + K2 kernels
+static void gen_masks(const uint8_t *seeds_shard, const uint8_t *pkeys_in, const uint8_t *mode, const uint8_t *omit, uint32_t npi,
+                      uint32_t n_masks, std::vector<uint64_t> &rows, std::vector<uint8_t> &pkeys) {
+    const uint32_t nslices = 2 * npi;
+    std::vector<uint32_t> ks((size_t)nslices * 1408, 0), lane_mask(nslices, 0);
+    pkeys.assign((size_t)npi * 8 * 128, 0);
+    for (uint32_t w = 0; w < nslices; w++)
+        for (uint32_t q = 0; q < 32; q++) {  // lane q of the warp
+            uint32_t rk[44];
+            const bool active = key_setup_stream(slice_rep(w, q), slice_player(q), seeds_shard, pkeys_in, mode, omit, pkeys.data(), rk);
+            if (active) lane_mask[w] |= 1u << q;
+            for (int qq = 0; qq < 44; qq++)
+                for (int i = 0; i < 32; i++)
+                    if ((rk[qq] >> i) & 1) ks[(size_t)w * 1408 + qq * 32 + i] |= 1u << q;  // __ballot_sync
+        }
+    uint32_t *rows32 = reinterpret_cast<uint32_t *>(rows.data());
+    const uint64_t n_blocks = ((uint64_t)n_masks + 127) / 128;
+    for (uint32_t w = 0; w < nslices; w++)
+        for (uint64_t j = 0; j < n_blocks; j++) {
+            uint32_t s[128];
+            const uint32_t *k = &ks[(size_t)w * 1408];
+            bs_aes128_ctr_block(j, [k](int round, int plane) { return k[round * 128 + plane]; }, s);
+            for (int p = 0; p < 128; p++) {
+                const uint64_t i = plane_to_mask_index(j, p);
+                if (i < n_masks) rows32[i * nslices + w] = s[p] & lane_mask[w];
+            }
+        }
+}
+
+extern "C" void hs_gf2_masks(const uint8_t *seeds8, const uint8_t *omit8, uint64_t *out, uint32_t n) {
+    std::vector<uint64_t> rows((size_t)n + 1, 0);
+    std::vector<uint8_t> pkeys;
+    uint8_t om[8];
+    for (int i = 0; i < 8; i++) om[i] = omit8 ? omit8[i] : 8;
+    gen_masks(seeds8, nullptr, nullptr, om, 1, n, rows, pkeys);
+    memcpy(out, rows.data(), (size_t)n * 8);
+}
+
+// Proof::new on the CPU through the kernel bodies.  rep_hashes (optional): 256*32 bytes.
+extern "C" int hs_prove(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, const uint8_t *wit, size_t n_wit,
+                        const uint8_t *seeds, uint8_t **proof, size_t *proof_len, uint8_t *rep_hashes) {
+    Program P;
+    int rc = compile(ops, n_ops, z64_cells, gf2_cells, P, g_err);
+    if (rc) return rc;
+    if (n_wit < P.n_inputs) return RV_E_WITNESS_SHORT;
+    const uint32_t npi = 32, nreps = 256;
+    // K1 + K2
+    std::vector<uint64_t> rows((size_t)P.n_rows * npi, 0);
+    std::vector<uint8_t> pkeys;
+    gen_masks(seeds, nullptr, nullptr, nullptr, npi, P.n_masks, rows, pkeys);
+    // K0
+    std::vector<uint8_t> vals(P.n_vals, 0);
+    for (size_t k = 0; k < P.n_inputs; k++) vals[P.input_vid[k]] = wit[k] & 1;
+    for (const VGate &g : P.vgates) {
+        const uint32_t a = vals[g.a >> 1] ^ (g.a & 1), b = vals[g.b >> 1] ^ (g.b & 1);
+        vals[g.dst] = (uint8_t)((g.op ? (a & b) : (a ^ b)) & 1);
+    }
+    // K3
+    for (const LGate &g : P.lgates)
+        for (uint32_t pi = 0; pi < npi; pi++) rows[(size_t)g.dst * npi + pi] = rows[(size_t)g.a * npi + pi] ^ rows[(size_t)g.b * npi + pi];
+    // K4
+    const size_t pitch_on = (std::max<size_t>(P.n_online, 1) + 63) / 64 * 64, pitch_pre = (std::max<size_t>(P.n_pre, 1) + 63) / 64 * 64;
+    std::vector<uint8_t> on(pitch_on * nreps, 0), pre(pitch_pre * nreps, 0);
+    std::vector<uint32_t> mul_pos;
+    for (uint32_t t = 0; t < P.n_online; t++)
+        if (P.items[t].kind == ITEM_MUL) mul_pos.push_back(t);
+    int bad = 0;
+    for (uint32_t pi = 0; pi < npi; pi++) {
+        for (uint64_t t0 = 0; t0 < P.n_online; t0 += 8) {
+            uint64_t W[8], out[8];
+            for (int i = 0; i < 8; i++) W[i] = (t0 + i < P.n_online) ? prover_online_word(P.items[t0 + i], rows.data(), npi, pi, vals.data(), &bad) : 0;
+            words_to_stream_bytes(W, out);
+            for (int r = 0; r < 8; r++) memcpy(&on[(size_t)(8 * pi + r) * pitch_on + t0], &out[r], 8);
+        }
+        for (uint64_t j0 = 0; j0 < P.n_pre; j0 += 8) {
+            uint64_t W[8], out[8];
+            for (int i = 0; i < 8; i++) W[i] = (j0 + i < P.n_pre) ? pre_word(P.items[mul_pos[j0 + i]], rows.data(), npi, pi) : 0;
+            words_to_stream_bytes(W, out);
+            for (int r = 0; r < 8; r++) memcpy(&pre[(size_t)(8 * pi + r) * pitch_pre + j0], &out[r], 8);
+        }
+    }
+    if (bad) return RV_E_WITNESS_INVALID;
+    // K5
+    uint32_t empty[8], zrep[8];
+    b3_chunk_cv(nullptr, 0, 0, true, empty);
+    b3_hash64(empty, empty, zrep);
+    std::vector<uint32_t> on_hash(nreps * 8), rep_hash(nreps * 8);
+    for (uint32_t r = 0; r < nreps; r++) {
+        uint32_t h_pre[8];
+        stream_hash(&on[(size_t)r * pitch_on], P.n_online, &on_hash[r * 8]);
+        stream_hash(&pre[(size_t)r * pitch_pre], P.n_pre, h_pre);
+        rep_join(&on_hash[r * 8], h_pre, zrep, &rep_hash[r * 8]);
+    }
+    if (rep_hashes) memcpy(rep_hashes, rep_hash.data(), nreps * 32);
+    // K6
+    uint32_t comm[8], m[16];
+    stream_hash(reinterpret_cast<const uint8_t *>(rep_hash.data()), nreps * 32, comm);
+    challenge_block(comm, m);
+    uint8_t omit[256];
+    uint16_t rank[256];
+    memset(omit, RV_PLAYERS, sizeof omit);
+    int distinct = 0;
+    for (uint64_t t = 0; distinct < RV_ONLINE_REPS; t++) {
+        uint32_t o[16];
+        challenge_xof_block(m, t, o);
+        challenge_consume(o, omit, &distinct);
+    }
+    uint16_t n_on = 0, n_pre = 0;
+    for (int i = 0; i < 256; i++) rank[i] = omit[i] < RV_PLAYERS ? n_on++ : n_pre++;
+    // K7
+    ProofLayout L{(uint32_t)(P.recon_pos.size() / 8 + 1), P.n_pre / 8 + 1, (uint32_t)(P.n_inputs / 8 + 1)};
+    uint8_t *out = (uint8_t *)calloc(L.total(), 1);
+    for (uint32_t r = 0; r < nreps; r++) {
+        ExtractView v;
+        v.on = &on[(size_t)r * pitch_on];
+        v.pre = &pre[(size_t)r * pitch_pre];
+        v.on_hash = reinterpret_cast<const uint8_t *>(&on_hash[r * 8]);
+        v.pkeys = &pkeys[(size_t)r * 128];
+        v.seed = seeds + (size_t)r * 16;
+        v.comm = reinterpret_cast<const uint8_t *>(comm);
+        v.z64_empty_hash = empty;
+        v.recon_pos = P.recon_pos.data();
+        v.input_pos = P.input_pos.data();
+        v.n_recon = (uint32_t)P.recon_pos.size();
+        v.n_pre = P.n_pre;
+        v.n_inputs = (uint32_t)P.n_inputs;
+        for (uint32_t tid = 0; tid < 4; tid++) extract_entry(L, v, r, omit[r], rank[r], tid, 4, out);
+    }
+    *proof = out;
+    *proof_len = L.total();
+    return RV_OK;
+}
+
+extern "C" void hs_free(void *p) { free(p); }
