@@ -1,0 +1,101 @@
+"""ctypes binding of libreverie_b200.so (include/reverie_b200.h).  Importing this module never touches a GPU; the first
+compute call does.  If the shared library is missing it is built in-tree with nvcc (reverie_b200/_build.py); if that
+fails the import error is loud -- there is no Python or CPU fallback for any compute entry point."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import _build
+
+RV_OK, E_WITNESS_INVALID, E_WITNESS_SHORT, E_FORMAT, E_ARG, E_CUDA, E_NOMEM, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6, -7
+TOTAL_REPS, ONLINE_REPS, PACKED_REPS, PLAYERS = 256, 40, 32, 8
+
+
+class CircuitStats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in (
+        "n_ops", "n_and", "n_inputs", "n_assert", "n_masks", "n_linear", "value_depth", "linear_depth", "online_bytes",
+        "pre_bytes", "algorithmic_bytes", "device_bytes")]
+
+
+class KernelTime(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("ms", C.c_double), ("launches", C.c_uint64), ("algorithmic_bytes", C.c_uint64)]
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB if os.path.exists(_build.LIB) and not _build._stale() else _build.build()
+    L = C.CDLL(path)
+    vp, sz, i32 = C.c_void_p, C.c_size_t, C.c_int
+    pp, psz = C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)
+    sigs = {
+        "rv_last_error": ([], C.c_char_p),
+        "rv_version": ([], C.c_char_p),
+        "rv_device_count": ([], i32),
+        "rv_set_device": ([i32], i32),
+        "rv_circuit_compile": ([vp, sz, sz, sz, pp], i32),
+        "rv_circuit_free": ([vp], None),
+        "rv_circuit_get_stats": ([vp, C.POINTER(CircuitStats)], i32),
+        "rv_circuit_export": ([vp, i32, vp, psz], i32),
+        "rv_prove": ([vp, vp, sz, vp, sz, vp, pp, psz], i32),
+        "rv_verify": ([vp, vp, sz, C.POINTER(i32)], i32),
+        "rv_proof_new": ([vp, sz, vp, sz, vp, sz, sz, sz, vp, pp, psz], i32),
+        "rv_proof_verify": ([vp, sz, sz, sz, vp, sz], i32),
+        "rv_free": ([vp], None),
+        "rv_session_create": ([vp, i32, i32, pp], i32),
+        "rv_session_free": ([vp], None),
+        "rv_session_upload": ([vp, vp, sz, vp, sz, vp], i32),
+        "rv_session_commit": ([vp], i32),
+        "rv_session_hashes": ([vp, vp], i32),
+        "rv_session_open": ([vp, vp], i32),
+        "rv_session_fetch": ([vp, vp, pp, psz], i32),
+        "rv_session_sync": ([vp], i32),
+        "rv_proof_assemble": ([vp, C.POINTER(vp), psz, i32, pp, psz], i32),
+        "rv_session_stream": ([vp], vp),
+        "rv_session_timing": ([vp, i32], i32),
+        "rv_session_kernel_times": ([vp, C.POINTER(KernelTime), i32, i32], i32),
+        "rv_session_launch_count": ([vp], C.c_uint64),
+    }
+    for name, (args, res) in sigs.items():
+        fn = getattr(L, name)  # AttributeError here = the library does not export what include/reverie_b200.h declares
+        fn.argtypes, fn.restype = args, res
+    _lib = L
+    return L
+
+
+EXPORTED = (
+    "rv_last_error rv_version rv_device_count rv_set_device rv_circuit_compile rv_circuit_free rv_circuit_get_stats "
+    "rv_circuit_export rv_prove rv_verify rv_proof_new rv_proof_verify rv_free rv_session_create rv_session_free "
+    "rv_session_upload rv_session_commit rv_session_hashes rv_session_open rv_session_fetch rv_session_sync "
+    "rv_proof_assemble rv_session_stream rv_session_timing rv_session_kernel_times rv_session_launch_count"
+).split()
+
+
+class ReverieError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"[rv_status {code}] {msg}")
+        self.code = code
+
+
+class WitnessError(ReverieError):
+    """The reference's panics 'witness is invalid!' / 'witness is too short' (src/transcript/prover.rs:190,223)."""
+
+
+class FormatError(ReverieError):
+    """Malformed proof bytes (the reference panics on these, e.g. src/algebra/gf2/share.rs:158-164)."""
+
+
+def check(rc: int) -> int:
+    if rc >= 0:
+        return rc
+    msg = (lib().rv_last_error() or b"").decode()
+    if rc in (E_WITNESS_INVALID, E_WITNESS_SHORT):
+        raise WitnessError(rc, msg)
+    if rc == E_FORMAT:
+        raise FormatError(rc, msg)
+    raise ReverieError(rc, msg)

@@ -1,0 +1,205 @@
+"""Host-side mirror of the reference's public API for the KKW hot path.
+
+    reverie (Rust)                                              here
+    Proof::new(circuit, wit_gf2, wit_z64, wire_counts)     ->   Proof.new(circuit, wit_gf2, wit_z64, wire_counts[, seeds])
+    proof.verify(circuit, wire_counts) -> bool             ->   proof.verify(circuit, wire_counts) -> bool
+    bincode::serialize(&proof) / deserialize               ->   proof.serialize() / Proof.deserialize(bytes)
+
+(src/proof/mod.rs:119-124,224; src/main.rs:74,84,103,108).  `circuit` is either a numpy array of packed op records
+(reverie_b200.circuits.OP_DTYPE) or a `Circuit`, the compiled, device-resident form that plays the role of the
+reference's `Arc<Vec<CombineOperation>>`: build it once, prove many times.  Everything runs on the GPU through the C ABI
+(include/reverie_b200.h); nothing here computes proof data on the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _native as N
+from .circuits import OP_DTYPE
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+def _seeds_arr(seeds) -> Optional[np.ndarray]:
+    if seeds is None:
+        return None
+    b = b"".join(seeds) if not isinstance(seeds, (bytes, bytearray, np.ndarray)) else bytes(seeds)
+    if len(b) != N.TOTAL_REPS * 16:
+        raise ValueError("seeds must be 256 x 16 bytes")
+    return np.frombuffer(b, dtype=np.uint8)
+
+
+class Circuit:
+    """A compiled circuit (rv_circuit).  wire_counts = (z64_cells, gf2_cells), the reference's tuple order
+    (src/proof/mod.rs:125)."""
+
+    def __init__(self, ops: np.ndarray, wire_counts: Tuple[int, int]):
+        self.ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+        self.wire_counts = (int(wire_counts[0]), int(wire_counts[1]))
+        h = C.c_void_p()
+        N.check(N.lib().rv_circuit_compile(_ptr(self.ops), self.ops.size, self.wire_counts[0], self.wire_counts[1], C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            N.lib().rv_circuit_free(h)
+
+    @property
+    def handle(self):
+        return self._h
+
+    def stats(self) -> dict:
+        st = N.CircuitStats()
+        N.check(N.lib().rv_circuit_get_stats(self._h, C.byref(st)))
+        return {n: int(getattr(st, n)) for n, _ in st._fields_}
+
+    def export(self, what: int, dtype) -> np.ndarray:
+        n = C.c_size_t(0)
+        N.check(N.lib().rv_circuit_export(self._h, what, None, C.byref(n)))
+        buf = np.zeros(n.value, dtype=np.uint8)
+        N.check(N.lib().rv_circuit_export(self._h, what, _ptr(buf), C.byref(n)))
+        return buf.view(dtype)
+
+
+def _as_circuit(circuit, wire_counts) -> Circuit:
+    if isinstance(circuit, Circuit):
+        if wire_counts is not None and tuple(wire_counts) != circuit.wire_counts:
+            raise ValueError("wire_counts differ from the ones the circuit was compiled with")
+        return circuit
+    return Circuit(circuit, wire_counts)
+
+
+def _take(out: C.c_void_p, n: C.c_size_t) -> bytes:
+    b = C.string_at(out, n.value)
+    N.lib().rv_free(out)
+    return b
+
+
+class Session:
+    """One proof shard in flight (rv_session): packed instances [first, first + count) of the 32
+    (src/proof/mod.rs:127-157).  Used directly for multi-GPU sharding and for device-resident timing."""
+
+    def __init__(self, circuit: Circuit, first_instance: int = 0, n_instances: int = N.PACKED_REPS):
+        self.circuit = circuit
+        h = C.c_void_p()
+        N.check(N.lib().rv_session_create(circuit.handle, first_instance, n_instances, C.byref(h)))
+        self._h = h
+        self.first_instance, self.n_instances = first_instance, n_instances
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            N.lib().rv_session_free(h)
+
+    def upload(self, wit_gf2, wit_z64=(), seeds=None):
+        self._wg = np.ascontiguousarray(np.asarray(wit_gf2, dtype=np.uint8))
+        self._wz = np.ascontiguousarray(np.asarray(wit_z64, dtype=np.uint64))
+        self._sd = _seeds_arr(seeds)
+        N.check(N.lib().rv_session_upload(self._h, _ptr(self._wg), self._wg.size, _ptr(self._wz), self._wz.size, _ptr(self._sd)))
+
+    def commit(self):
+        N.check(N.lib().rv_session_commit(self._h))
+
+    def hashes(self) -> bytes:
+        out = np.zeros(self.n_instances * 8 * 32, dtype=np.uint8)
+        N.check(N.lib().rv_session_hashes(self._h, _ptr(out)))
+        return out.tobytes()
+
+    def open(self, all_rep_hashes=None):
+        """all_rep_hashes: 256*32 bytes (host bytes / numpy) or an int device pointer; None = own hashes (single shard)."""
+        if all_rep_hashes is None:
+            p = None
+        elif isinstance(all_rep_hashes, int):
+            p = C.c_void_p(all_rep_hashes)
+        else:
+            self._ah = np.frombuffer(bytes(all_rep_hashes), dtype=np.uint8)
+            if self._ah.size != N.TOTAL_REPS * 32:
+                raise ValueError("need 256 x 32 bytes of repetition hashes")
+            p = _ptr(self._ah)
+        N.check(N.lib().rv_session_open(self._h, p))
+
+    def fetch(self) -> Tuple[bytes, bytes]:
+        comm = np.zeros(32, dtype=np.uint8)
+        out, n = C.c_void_p(), C.c_size_t()
+        N.check(N.lib().rv_session_fetch(self._h, _ptr(comm), C.byref(out), C.byref(n)))
+        return comm.tobytes(), _take(out, n)
+
+    def sync(self):
+        N.check(N.lib().rv_session_sync(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(N.lib().rv_session_stream(self._h) or 0)
+
+    def timing(self, enable: bool):
+        N.check(N.lib().rv_session_timing(self._h, int(enable)))
+
+    def kernel_times(self, reset: bool = True) -> list:
+        arr = (N.KernelTime * 32)()
+        n = N.check(N.lib().rv_session_kernel_times(self._h, arr, 32, int(reset)))
+        return [dict(name=arr[i].name.decode(), ms=arr[i].ms, launches=int(arr[i].launches), algorithmic_bytes=int(arr[i].algorithmic_bytes))
+                for i in range(min(n, 32))]
+
+    @property
+    def launch_count(self) -> int:
+        return int(N.lib().rv_session_launch_count(self._h))
+
+
+def assemble(comm: bytes, parts: Sequence[bytes]) -> bytes:
+    """src/proof/mod.rs:200-221 for shard blobs produced by Session.fetch()."""
+    bufs = [np.frombuffer(p, dtype=np.uint8) for p in parts]
+    ptrs = (C.c_void_p * len(bufs))(*[b.ctypes.data for b in bufs])
+    lens = (C.c_size_t * len(bufs))(*[b.size for b in bufs])
+    cm = np.frombuffer(comm, dtype=np.uint8)
+    out, n = C.c_void_p(), C.c_size_t()
+    N.check(N.lib().rv_proof_assemble(_ptr(cm), ptrs, lens, len(bufs), C.byref(out), C.byref(n)))
+    return _take(out, n)
+
+
+class Proof:
+    """The bincode bytes of the reference's `Proof` struct (src/proof/mod.rs:40-66)."""
+
+    def __init__(self, data: bytes):
+        self.data = bytes(data)
+
+    @staticmethod
+    def new(circuit, wit_gf2, wit_z64=(), wire_counts=None, seeds=None) -> "Proof":
+        """Proof::new (src/proof/mod.rs:119-222).  `seeds` (256 x 16 bytes) replaces the OsRng draw at :131-134 so a
+        proof can be reproduced; None draws from the OS RNG like the reference."""
+        c = _as_circuit(circuit, wire_counts)
+        wg = np.ascontiguousarray(np.asarray(wit_gf2, dtype=np.uint8))
+        wz = np.ascontiguousarray(np.asarray(wit_z64, dtype=np.uint64))
+        sd = _seeds_arr(seeds)
+        out, n = C.c_void_p(), C.c_size_t()
+        N.check(N.lib().rv_prove(c.handle, _ptr(wg), wg.size, _ptr(wz), wz.size, _ptr(sd), C.byref(out), C.byref(n)))
+        return Proof(_take(out, n))
+
+    def verify(self, circuit, wire_counts=None) -> bool:
+        """Proof::verify (src/proof/mod.rs:224-307)."""
+        c = _as_circuit(circuit, wire_counts)
+        buf = np.frombuffer(self.data, dtype=np.uint8)
+        okay = C.c_int(1)
+        return N.check(N.lib().rv_verify(c.handle, _ptr(buf), buf.size, C.byref(okay))) == 1
+
+    def serialize(self) -> bytes:
+        return self.data
+
+    @staticmethod
+    def deserialize(data: bytes) -> "Proof":
+        return Proof(data)
+
+    @property
+    def comm(self) -> bytes:
+        return self.data[:32]
+
+    def __len__(self):
+        return len(self.data)
+
+    def __eq__(self, other):
+        return isinstance(other, Proof) and self.data == other.data
