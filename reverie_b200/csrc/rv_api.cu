@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -60,6 +61,9 @@ struct rv_circuit {
     uint64_t device_bytes = 0;
     uint32_t z64_empty_hash[8];  // B3("")
     uint32_t z64_rep_hash[8];    // Transcript::hash of an empty Z64 transcript: H(B3("") || B3(""))
+    // idle full-shard sessions kept for rv_prove, so that back-to-back proofs reuse their device buffers
+    mutable std::mutex pool_mu;
+    mutable std::vector<rv_session *> pool;
 };
 
 template <typename T>
@@ -77,6 +81,8 @@ static int upload(rv_circuit *c, const std::vector<T> &v, const T **out) {
 
 extern "C" void rv_circuit_free(rv_circuit *c) {
     if (!c) return;
+    for (rv_session *s : c->pool) rv_session_free(s);
+    c->pool.clear();
     for (void *p : c->allocs) cudaFree(p);
     delete c;
 }
@@ -198,7 +204,7 @@ struct rv_session {
     uint32_t first_instance = 0, npi = 0, nreps = 0, first_rep = 0;
     cudaStream_t st = nullptr, st_val = nullptr;
     bool own_stream = true;
-    cudaEvent_t ev_upload = nullptr, ev_vals = nullptr;
+    cudaEvent_t ev_upload = nullptr, ev_vals = nullptr, ev_items = nullptr;
     // device buffers
     uint8_t *d_wit = nullptr, *d_seeds = nullptr, *d_pkeys = nullptr, *d_vals = nullptr;
     uint32_t *d_ks = nullptr, *d_lane_mask = nullptr;
@@ -221,7 +227,7 @@ struct rv_session {
     bool timing = false;
     std::vector<KTimer> timers;
     uint64_t launches = 0;
-    bool committed = false, opened = false;
+    bool committed = false, opened = false, ever_committed = false;
 };
 
 template <typename T>
@@ -250,6 +256,7 @@ extern "C" void rv_session_free(rv_session *s) {
     if (s->h_out) cudaFreeHost(s->h_out);
     if (s->ev_upload) cudaEventDestroy(s->ev_upload);
     if (s->ev_vals) cudaEventDestroy(s->ev_vals);
+    if (s->ev_items) cudaEventDestroy(s->ev_items);
     if (s->st && s->own_stream) cudaStreamDestroy(s->st);
     if (s->st_val) cudaStreamDestroy(s->st_val);
     delete s;
@@ -276,7 +283,8 @@ extern "C" int rv_session_create(const rv_circuit *c, int first_instance, int n_
         return code;
     };
     if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&s->st_val, cudaStreamNonBlocking) != cudaSuccess ||
-        cudaEventCreateWithFlags(&s->ev_upload, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&s->ev_vals, cudaEventDisableTiming) != cudaSuccess)
+        cudaEventCreateWithFlags(&s->ev_upload, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&s->ev_vals, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&s->ev_items, cudaEventDisableTiming) != cudaSuccess)
         return bail(fail(RV_E_CUDA, "stream/event creation failed"));
     s->pitch_on = round_up(std::max<size_t>(P.n_online, 1), 64);
     s->pitch_pre = round_up(std::max<size_t>(P.n_pre, 1), 64);
@@ -320,7 +328,8 @@ struct Scope {
     rv_session *s;
     KTimer *t = nullptr;
     cudaEvent_t a = nullptr, b = nullptr;
-    Scope(rv_session *s_, const char *name, uint64_t bytes, uint64_t n_launches = 1) : s(s_) {
+    cudaStream_t stream;
+    Scope(rv_session *s_, const char *name, uint64_t bytes, uint64_t n_launches = 1, cudaStream_t on = nullptr) : s(s_), stream(on ? on : s_->st) {
         s->launches += n_launches;
         if (!s->timing) return;
         for (auto &k : s->timers)
@@ -334,11 +343,11 @@ struct Scope {
         t->bytes += bytes;
         cudaEventCreate(&a);
         cudaEventCreate(&b);
-        cudaEventRecord(a, s->st);
+        cudaEventRecord(a, stream);
     }
     ~Scope() {
         if (!t) return;
-        cudaEventRecord(b, s->st);
+        cudaEventRecord(b, stream);
         t->pending.push_back({a, b});
     }
 };
@@ -352,6 +361,7 @@ extern "C" int rv_session_timing(rv_session *s, int enable) {
 extern "C" int rv_session_kernel_times(rv_session *s, rv_kernel_time *out, int max_out, int reset) {
     if (!s) return fail(RV_E_ARG, "NULL session");
     CU(cudaStreamSynchronize(s->st));
+    CU(cudaStreamSynchronize(s->st_val));
     int n = 0;
     for (auto &t : s->timers) {
         for (auto &p : t.pending) {
@@ -414,8 +424,11 @@ extern "C" int rv_session_commit(rv_session *s) {
     const uint32_t nslices = 2 * s->npi;
     // value plane on its own stream: it depends only on the witness and overlaps the whole mask pipeline
     CU(cudaStreamWaitEvent(s->st_val, s->ev_upload, 0));
-    launch_values(D, s->d_wit, s->d_vals, s->st_val);
-    s->launches++;
+    if (s->ever_committed) CU(cudaStreamWaitEvent(s->st_val, s->ev_items, 0));  // the previous proof's item plane still reads d_vals
+    {
+        Scope k(s, "values", (uint64_t)D.n_vgates * sizeof(VGate), 1, s->st_val);
+        launch_values(D, s->d_wit, s->d_vals, s->st_val);
+    }
     CU(cudaEventRecord(s->ev_vals, s->st_val));
     CU(cudaMemsetAsync(s->d_bad, 0, sizeof(int), s->st));
     CU(cudaMemsetAsync(s->d_rows + (size_t)P.zero_row() * s->npi, 0, (size_t)s->npi * 8, s->st));
@@ -438,6 +451,7 @@ extern "C" int rv_session_commit(rv_session *s) {
         Scope k(s, "items", ((uint64_t)P.n_and * 7 + P.n_inputs + P.n_assert) * s->npi * 8 + ((uint64_t)P.n_online + P.n_pre) * s->nreps, 2);
         launch_items(D, s->d_rows, s->npi, s->d_vals, s->d_on, s->pitch_on, s->d_pre, s->pitch_pre, s->d_bad, s->st);
     }
+    CU(cudaEventRecord(s->ev_items, s->st));
     {
         Scope k(s, "chunk_cv", ((uint64_t)P.n_online + P.n_pre) * s->nreps, 2);
         launch_chunk_cv(s->d_on, s->pitch_on, P.n_online, s->nreps, s->d_cv_on, s->st);
@@ -448,7 +462,7 @@ extern "C" int rv_session_commit(rv_session *s) {
         launch_rep_hash(s->d_cv_on, s->n_chunks_on, s->d_cv_pre, s->n_chunks_pre, s->d_zconst + 8, s->nreps, s->d_on_hash, s->d_rep_hash, s->st);
     }
     CU(cudaGetLastError());
-    s->committed = true;
+    s->committed = s->ever_committed = true;
     return RV_OK;
 }
 
@@ -555,12 +569,25 @@ extern "C" int rv_prove(const rv_circuit *c, const uint8_t *wit_gf2, size_t n_gf
                         const uint8_t *seeds, uint8_t **proof, size_t *proof_len) {
     if (!c || !proof || !proof_len) return fail(RV_E_ARG, "NULL argument");
     rv_session *s = nullptr;
-    int rc = rv_session_create(c, 0, RV_PACKED_REPS, &s);
-    if (rc) return rc;
+    {
+        std::lock_guard<std::mutex> g(c->pool_mu);
+        if (!c->pool.empty()) {
+            s = c->pool.back();
+            c->pool.pop_back();
+        }
+    }
+    int rc = RV_OK;
+    if (!s && (rc = rv_session_create(c, 0, RV_PACKED_REPS, &s))) return rc;
     if ((rc = rv_session_upload(s, wit_gf2, n_gf2, wit_z64, n_z64, seeds)) == RV_OK && (rc = rv_session_commit(s)) == RV_OK &&
         (rc = rv_session_open(s, nullptr)) == RV_OK)
         rc = rv_session_fetch(s, nullptr, proof, proof_len);
-    rv_session_free(s);
+    if (rc == RV_E_CUDA) {
+        rv_session_free(s);
+        return rc;
+    }
+    std::lock_guard<std::mutex> g(c->pool_mu);
+    if (c->pool.size() < 4) c->pool.push_back(s);
+    else rv_session_free(s);
     return rc;
 }
 
