@@ -127,14 +127,25 @@ RV_HD uint32_t sub_word(uint32_t w) {
     return r;
 }
 
+struct NetlistSubWord {  // S-box from the netlist: no table, no memory
+    RV_HD uint32_t operator()(uint32_t w) const { return sub_word(w); }
+};
+struct TableSubWord {  // S-box from a 256-byte table (shared memory on the device)
+    const uint8_t *t;
+    RV_HD uint32_t operator()(uint32_t w) const {
+        return (uint32_t)t[w & 0xff] | ((uint32_t)t[(w >> 8) & 0xff] << 8) | ((uint32_t)t[(w >> 16) & 0xff] << 16) | ((uint32_t)t[w >> 24] << 24);
+    }
+};
+
 // Key expansion (FIPS-197 5.2).  Words are little-endian loads of the key bytes: byte 0 of a word is its low byte.
-RV_HD void aes128_expand_key(const uint32_t key[4], uint32_t rk[44]) {
+template <typename SW = NetlistSubWord>
+RV_HD void aes128_expand_key(const uint32_t key[4], uint32_t rk[44], SW sw = SW()) {
     const uint32_t rcon[10] = {0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40, 0x80, 0x1b, 0x36};
     for (int i = 0; i < 4; i++) rk[i] = key[i];
     for (int i = 4; i < 44; i += 4) {
         uint32_t t = rk[i - 1];
         t = (t >> 8) | (t << 24);  // RotWord on a little-endian word
-        t = sub_word(t) ^ rcon[i / 4 - 1];
+        t = sw(t) ^ rcon[i / 4 - 1];
         rk[i] = rk[i - 4] ^ t;
         rk[i + 1] = rk[i - 3] ^ rk[i];
         rk[i + 2] = rk[i - 2] ^ rk[i + 1];
@@ -148,11 +159,12 @@ RV_HD uint32_t xtime4(uint32_t w) {  // xtime on 4 packed bytes
 }
 
 // One AES-128 block, scalar.  Column c of the state is word c (row r in byte r).
-RV_HD void aes128_encrypt_block(const uint32_t rk[44], const uint32_t in[4], uint32_t out[4]) {
+template <typename SW = NetlistSubWord>
+RV_HD void aes128_encrypt_block(const uint32_t rk[44], const uint32_t in[4], uint32_t out[4], SW sw = SW()) {
     uint32_t s[4] = {in[0] ^ rk[0], in[1] ^ rk[1], in[2] ^ rk[2], in[3] ^ rk[3]};
     for (int round = 1; round <= 10; round++) {
         uint32_t t[4];
-        for (int c = 0; c < 4; c++) t[c] = sub_word(s[c]);
+        for (int c = 0; c < 4; c++) t[c] = sw(s[c]);
         uint32_t u[4];
         for (int c = 0; c < 4; c++)  // ShiftRows: row r of column c comes from column c + r
             u[c] = (t[c] & 0x000000ffu) | (t[(c + 1) & 3] & 0x0000ff00u) | (t[(c + 2) & 3] & 0x00ff0000u) | (t[(c + 3) & 3] & 0xff000000u);

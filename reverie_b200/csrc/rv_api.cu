@@ -126,7 +126,8 @@ extern "C" int rv_circuit_compile(const rv_op *ops, size_t n_ops, size_t z64_cel
     if ((rc = upload(c, P.vgates, &D.vgates)) || (rc = upload(c, P.vlevel_off, &D.vlevel_off)) || (rc = upload(c, P.lgates, &D.lgates)) ||
         (rc = upload(c, P.llevel_off, &D.llevel_off)) || (rc = upload(c, P.items, &D.items)) || (rc = upload(c, c->mul_pos, &D.mul_pos)) ||
         (rc = upload(c, P.recon_pos, &D.recon_pos)) || (rc = upload(c, P.input_pos, &D.input_pos)) ||
-        (rc = upload(c, P.input_vid, &D.input_vid))) {
+        (rc = upload(c, P.input_vid, &D.input_vid)) || (rc = upload(c, P.vm, &D.vm)) || (rc = upload(c, P.vm_level_off, &D.vm_level_off)) ||
+        (rc = upload(c, P.luts, &D.luts)) || (rc = upload(c, P.lut_level_off, &D.lut_level_off))) {
         rv_circuit_free(c);
         return rc;
     }
@@ -134,6 +135,11 @@ extern "C" int rv_circuit_compile(const rv_op *ops, size_t n_ops, size_t z64_cel
     D.n_vlevels = (uint32_t)P.vlevel_off.size() - 1;
     D.n_lgates = (uint32_t)P.lgates.size();
     D.n_llevels = (uint32_t)P.llevel_off.size() - 1;
+    D.n_luts = (uint32_t)P.luts.size();
+    D.n_lut_levels = P.lut_level_off.empty() ? 0 : (uint32_t)P.lut_level_off.size() - 1;
+    D.n_vm = (uint32_t)P.vm.size();
+    D.n_vm_levels = P.vm_level_off.empty() ? 0 : (uint32_t)P.vm_level_off.size() - 1;
+    D.vm_cells = P.vm_cells;
     D.n_masks = P.n_masks;
     D.n_rows = P.n_rows;
     D.n_vals = P.n_vals;
@@ -154,7 +160,7 @@ extern "C" int rv_circuit_get_stats(const rv_circuit *c, rv_circuit_stats *o) {
     o->n_assert = P.n_assert;
     o->n_masks = P.n_masks;
     o->n_linear = P.n_lin;
-    o->value_depth = P.vlevel_off.size() - 1;
+    o->value_depth = P.lut_depth;
     o->linear_depth = P.llevel_off.size() - 1;
     o->online_bytes = P.n_online;
     o->pre_bytes = P.n_pre;
@@ -426,7 +432,7 @@ extern "C" int rv_session_commit(rv_session *s) {
     CU(cudaStreamWaitEvent(s->st_val, s->ev_upload, 0));
     if (s->ever_committed) CU(cudaStreamWaitEvent(s->st_val, s->ev_items, 0));  // the previous proof's item plane still reads d_vals
     {
-        Scope k(s, "values", (uint64_t)D.n_vgates * sizeof(VGate), 1, s->st_val);
+        Scope k(s, "values", (uint64_t)D.n_luts * sizeof(LutInstr), 1, s->st_val);
         launch_values(D, s->d_wit, s->d_vals, s->st_val);
     }
     CU(cudaEventRecord(s->ev_vals, s->st_val));
@@ -443,7 +449,7 @@ extern "C" int rv_session_commit(rv_session *s) {
     if (D.n_llevels) {
         const double avg_width = (double)D.n_lgates / D.n_llevels;
         Scope k(s, "linear", (uint64_t)P.n_lin * s->npi * 8 * 3, avg_width < 4096.0 ? 1 : D.n_llevels);
-        launch_linear(D, P.llevel_off.data(), s->d_rows, s->npi, s->st);
+        launch_linear(D, P.llevel_off.data(), s->d_rows, s->npi, s->st, nullptr);
     }
     CU(cudaStreamWaitEvent(s->st, s->ev_vals, 0));
     {
@@ -453,9 +459,8 @@ extern "C" int rv_session_commit(rv_session *s) {
     }
     CU(cudaEventRecord(s->ev_items, s->st));
     {
-        Scope k(s, "chunk_cv", ((uint64_t)P.n_online + P.n_pre) * s->nreps, 2);
-        launch_chunk_cv(s->d_on, s->pitch_on, P.n_online, s->nreps, s->d_cv_on, s->st);
-        launch_chunk_cv(s->d_pre, s->pitch_pre, P.n_pre, s->nreps, s->d_cv_pre, s->st);
+        Scope k(s, "chunk_cv", ((uint64_t)P.n_online + P.n_pre) * s->nreps, 1);
+        launch_chunk_cv2(s->d_on, s->pitch_on, P.n_online, s->d_cv_on, s->d_pre, s->pitch_pre, P.n_pre, s->d_cv_pre, s->nreps, s->st);
     }
     {
         Scope k(s, "rep_hash", ((uint64_t)s->n_chunks_on + s->n_chunks_pre) * s->nreps * 32);

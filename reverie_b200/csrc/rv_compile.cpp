@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cstring>
+#include <initializer_list>
 
 namespace rv {
 namespace {
@@ -20,6 +21,278 @@ struct Cell {
 // algorithmic HBM bytes per gate over all 256 repetitions, plus the 16-byte descriptor
 constexpr uint64_t B_AND = 2048 + 16, B_XOR = 1536 + 16, B_UNARY = 1024 + 16, B_INPUT = 768 + 16, B_ASSERT = 768 + 16,
                    B_LEAF = 512 + 16;
+
+// Mask-plane VM: the XOR network re-expressed over a small pool of shared-memory cells so that the dependent chain of
+// the level-synchronous walk is LDS -> XOR -> STS instead of L2 round trips.  Fresh rows are brought into cells by
+// asynchronous LOADs issued VM_DELTA levels early; only rows that the item plane reads are written back (`row`).
+// Cells are assigned by a linear scan over levels: a cell is free again one level after its value's last use.
+void build_mask_vm(Program &P) {
+    P.vm.clear();
+    P.vm_level_off.clear();
+    P.vm_cells = 0;
+    const uint32_t depth = (uint32_t)P.llevel_off.size() - 1;
+    if (depth == 0) return;
+    const uint32_t n_rows = P.n_rows, n_masks = P.n_masks, n_lin = P.n_lin;
+    const uint32_t NEVER = 0xFFFFFFFFu;
+    std::vector<uint32_t> first(n_rows, NEVER), last(n_rows, 0);
+    std::vector<uint8_t> exported(n_rows, 0);
+    for (uint32_t l = 0; l < depth; l++)
+        for (uint32_t g = P.llevel_off[l]; g < P.llevel_off[l + 1]; g++)
+            for (uint32_t r : {P.lgates[g].a, P.lgates[g].b}) {
+                if (first[r] == NEVER) first[r] = l + 1;
+                last[r] = l + 1;
+            }
+    for (const Item &it : P.items) {
+        if (it.kind == ITEM_MUL) exported[it.ra] = exported[it.rb] = 1;
+        else if (it.kind == ITEM_ASSERT) exported[it.ra] = 1;
+    }
+    // VM level of an original level L (1-based) is L + VM_DELTA - 1; the LOAD of a fresh row first used at L sits at L - 1.
+    const uint32_t n_levels = depth + VM_DELTA;
+    std::vector<uint32_t> cnt(n_levels + 1, 0);
+    for (uint32_t r = 0; r < n_masks; r++)
+        if (first[r] != NEVER) cnt[first[r] - 1]++;
+    for (uint32_t l = 0; l < depth; l++) cnt[l + VM_DELTA] += P.llevel_off[l + 1] - P.llevel_off[l];
+    P.vm_level_off.assign(n_levels + 1, 0);
+    for (uint32_t l = 0; l < n_levels; l++) P.vm_level_off[l + 1] = P.vm_level_off[l] + cnt[l];
+    P.vm.resize(P.vm_level_off[n_levels]);
+    std::vector<uint32_t> cursor(P.vm_level_off.begin(), P.vm_level_off.end() - 1);
+    // provisional instructions hold rows; cells are assigned in the scan below
+    for (uint32_t r = 0; r < n_masks; r++)
+        if (first[r] != NEVER) P.vm[cursor[first[r] - 1]++] = VmInstr{VM_LOAD, r, 0, 0};
+    for (uint32_t l = 0; l < depth; l++)
+        for (uint32_t g = P.llevel_off[l]; g < P.llevel_off[l + 1]; g++)
+            P.vm[cursor[l + VM_DELTA]++] = VmInstr{P.lgates[g].dst, P.lgates[g].a, P.lgates[g].b, 0};
+    std::vector<uint32_t> cell_of(n_rows, VM_NONE);
+    std::vector<std::vector<uint32_t>> free_at(n_levels + 2);
+    std::vector<uint32_t> free_list;
+    uint32_t n_cells = 0;
+    auto alloc = [&]() -> uint32_t {
+        if (!free_list.empty()) {
+            uint32_t c = free_list.back();
+            free_list.pop_back();
+            return c;
+        }
+        return n_cells++;
+    };
+    for (uint32_t l = 0; l < n_levels; l++) {
+        for (uint32_t c : free_at[l]) free_list.push_back(c);
+        free_at[l].clear();
+        free_at[l].shrink_to_fit();
+        for (uint32_t k = P.vm_level_off[l]; k < P.vm_level_off[l + 1]; k++) {
+            VmInstr &in = P.vm[k];
+            if (in.dst == VM_LOAD) {
+                const uint32_t r = in.a, c = alloc();
+                cell_of[r] = c;
+                free_at[last[r] + VM_DELTA].push_back(c);  // last use at VM level last + DELTA - 1
+                in.dst = VM_LOAD | c;
+            } else {
+                const uint32_t r = in.dst;
+                in.a = cell_of[in.a];
+                in.b = cell_of[in.b];
+                in.row = exported[r] ? r : VM_NONE;
+                if (first[r] != NEVER) {
+                    const uint32_t c = alloc();
+                    cell_of[r] = c;
+                    free_at[last[r] + VM_DELTA].push_back(c);
+                    in.dst = c;
+                } else {
+                    in.dst = VM_NONE;
+                }
+            }
+        }
+    }
+    (void)n_lin;
+    P.vm_cells = n_cells;
+}
+
+// Split levels wider than `maxw` into consecutive sub-levels (always legal: instructions of a level are independent).
+static void split_levels(std::vector<uint32_t> &off, uint32_t maxw) {
+    if (off.size() < 2) return;
+    std::vector<uint32_t> out;
+    out.push_back(off[0]);
+    for (size_t l = 0; l + 1 < off.size(); l++) {
+        uint32_t s = off[l];
+        const uint32_t e = off[l + 1];
+        while (e - s > maxw) {
+            s += maxw;
+            out.push_back(s);
+        }
+        out.push_back(e);
+    }
+    off.swap(out);
+}
+
+// ---- value-plane technology mapping: K-feasible cuts, depth first (the FPGA "priority cuts" scheme) ------------------
+constexpr int LUT_K = 6, CUTS_PER_NODE = 6;
+struct Cut {
+    uint32_t leaf[LUT_K];
+    uint8_t n;
+    uint32_t depth;
+};
+
+static bool merge_cuts(const Cut &a, const Cut &b, Cut &o) {
+    int i = 0, j = 0, n = 0;
+    while (i < a.n || j < b.n) {
+        uint32_t v;
+        if (j >= b.n || (i < a.n && a.leaf[i] < b.leaf[j])) v = a.leaf[i++];
+        else if (i >= a.n || b.leaf[j] < a.leaf[i]) v = b.leaf[j++];
+        else {
+            v = a.leaf[i];
+            i++;
+            j++;
+        }
+        if (n == LUT_K) return false;
+        o.leaf[n++] = v;
+    }
+    o.n = (uint8_t)n;
+    return true;
+}
+
+void build_value_luts(Program &P, const std::vector<VGate> &vg /* creation (topological) order */, bool map) {
+    const uint32_t n_vals = P.n_vals;
+    std::vector<uint32_t> gate_of(n_vals, 0xFFFFFFFFu);  // vid -> index into vg, or none for leaves (inputs, constant)
+    for (uint32_t g = 0; g < vg.size(); g++) gate_of[vg[g].dst] = g;
+    std::vector<uint8_t> required(n_vals, 0);
+    for (const Item &it : P.items) {
+        required[it.va >> 1] = 1;
+        if (it.kind == ITEM_MUL) required[it.vb >> 1] = 1;
+    }
+    std::vector<uint32_t> depth(n_vals, 0);
+    std::vector<Cut> best(vg.size());  // chosen cut per gate
+    if (map) {
+        std::vector<Cut> cuts((size_t)vg.size() * CUTS_PER_NODE);
+        std::vector<uint8_t> ncuts(vg.size(), 0);
+        auto cut_set = [&](uint32_t vid, Cut *tmp, int &n) {  // the node's stored cuts plus its trivial cut
+            n = 0;
+            if (vid == 0) {  // the constant contributes no leaf
+                tmp[n].n = 0;
+                tmp[n].depth = 0;
+                n++;
+                return;
+            }
+            const uint32_t g = gate_of[vid];
+            if (g != 0xFFFFFFFFu)
+                for (int i = 0; i < ncuts[g]; i++) tmp[n++] = cuts[(size_t)g * CUTS_PER_NODE + i];
+            tmp[n].n = 1;
+            tmp[n].leaf[0] = vid;
+            tmp[n].depth = 0;
+            n++;
+        };
+        Cut ca[CUTS_PER_NODE + 1], cb[CUTS_PER_NODE + 1], cand[(CUTS_PER_NODE + 1) * (CUTS_PER_NODE + 1)];
+        for (uint32_t g = 0; g < vg.size(); g++) {
+            int na, nb, nc = 0;
+            cut_set(vg[g].a >> 1, ca, na);
+            cut_set(vg[g].b >> 1, cb, nb);
+            for (int i = 0; i < na; i++)
+                for (int j = 0; j < nb; j++) {
+                    Cut &o = cand[nc];
+                    if (!merge_cuts(ca[i], cb[j], o)) continue;
+                    uint32_t d = 0;
+                    for (int k = 0; k < o.n; k++) d = std::max(d, depth[o.leaf[k]]);
+                    o.depth = d + 1;
+                    bool dup = false;
+                    for (int k = 0; k < nc && !dup; k++) dup = cand[k].n == o.n && std::memcmp(cand[k].leaf, o.leaf, o.n * 4) == 0;
+                    if (!dup) nc++;
+                }
+            std::sort(cand, cand + nc, [](const Cut &x, const Cut &y) { return x.depth != y.depth ? x.depth < y.depth : x.n < y.n; });
+            const int keep = std::min(nc, CUTS_PER_NODE);
+            for (int i = 0; i < keep; i++) cuts[(size_t)g * CUTS_PER_NODE + i] = cand[i];
+            ncuts[g] = (uint8_t)keep;
+            best[g] = cand[0];
+            depth[vg[g].dst] = cand[0].depth;
+        }
+    } else {
+        for (uint32_t g = 0; g < vg.size(); g++) {
+            Cut c;
+            c.n = 0;
+            uint32_t a = vg[g].a >> 1, b = vg[g].b >> 1;
+            if (a > b) std::swap(a, b);
+            if (a) c.leaf[c.n++] = a;
+            if (b && b != a) c.leaf[c.n++] = b;
+            uint32_t d = 0;
+            for (int k = 0; k < c.n; k++) d = std::max(d, depth[c.leaf[k]]);
+            c.depth = d + 1;
+            best[g] = c;
+            depth[vg[g].dst] = c.depth;
+        }
+    }
+    // cover: walk backwards from the values the item plane reads
+    for (size_t g = vg.size(); g-- > 0;) {
+        if (!required[vg[g].dst]) continue;
+        for (int k = 0; k < best[g].n; k++) required[best[g].leaf[k]] = 1;
+    }
+    // final levels (over the chosen cover) and truth tables
+    static const uint64_t PAT[6] = {0xAAAAAAAAAAAAAAAAull, 0xCCCCCCCCCCCCCCCCull, 0xF0F0F0F0F0F0F0F0ull,
+                                    0xFF00FF00FF00FF00ull, 0xFFFF0000FFFF0000ull, 0xFFFFFFFF00000000ull};
+    std::vector<uint32_t> level(n_vals, 0), stamp(n_vals, 0);
+    std::vector<uint64_t> tmp(n_vals, 0);
+    std::vector<LutInstr> luts;
+    std::vector<uint32_t> lut_level;
+    std::vector<uint32_t> stack;
+    uint32_t epoch = 0, max_level = 0;
+    for (uint32_t g = 0; g < vg.size(); g++) {
+        const uint32_t out = vg[g].dst;
+        if (!required[out]) continue;
+        const Cut &c = best[g];
+        epoch++;
+        uint32_t lv = 0;
+        for (int k = 0; k < c.n; k++) {
+            stamp[c.leaf[k]] = epoch;
+            tmp[c.leaf[k]] = PAT[k];
+            lv = std::max(lv, level[c.leaf[k]]);
+        }
+        stamp[0] = epoch;
+        tmp[0] = 0;
+        // evaluate the cone bottom-up with an explicit stack (post-order)
+        stack.clear();
+        stack.push_back(out);
+        while (!stack.empty()) {
+            const uint32_t v = stack.back();
+            if (stamp[v] == epoch) {
+                stack.pop_back();
+                continue;
+            }
+            const VGate &gt = vg[gate_of[v]];
+            const uint32_t a = gt.a >> 1, b = gt.b >> 1;
+            const bool ra = stamp[a] == epoch, rb = stamp[b] == epoch;
+            if (ra && rb) {
+                const uint64_t x = tmp[a] ^ (0ull - (gt.a & 1)), y = tmp[b] ^ (0ull - (gt.b & 1));
+                tmp[v] = gt.op ? (x & y) : (x ^ y);
+                stamp[v] = epoch;
+                stack.pop_back();
+            } else {
+                if (!ra) stack.push_back(a);
+                if (!rb) stack.push_back(b);
+            }
+        }
+        LutInstr li;
+        li.dst = out;
+        for (int k = 0; k < 6; k++) li.in[k] = k < c.n ? c.leaf[k] : 0;
+        li.pad = 0;
+        li.pad2 = 0;
+        li.tt = tmp[out];
+        level[out] = lv + 1;
+        max_level = std::max(max_level, lv + 1);
+        luts.push_back(li);
+        lut_level.push_back(lv + 1);
+    }
+    // counting sort by level
+    P.lut_depth = max_level;
+    P.lut_level_off.assign(max_level + 1, 0);
+    std::vector<uint32_t> cursor(max_level + 2, 0);
+    for (uint32_t l : lut_level) cursor[l]++;
+    uint32_t run = 0;
+    for (uint32_t l = 1; l <= max_level; l++) {
+        const uint32_t c = cursor[l];
+        cursor[l] = run;
+        P.lut_level_off[l - 1] = run;
+        run += c;
+    }
+    P.lut_level_off[max_level] = run;
+    P.luts.resize(luts.size());
+    for (size_t i = 0; i < luts.size(); i++) P.luts[cursor[lut_level[i]]++] = luts[i];
+    split_levels(P.lut_level_off, LUT_LEVEL_MAX);
+}
 
 }  // namespace
 
@@ -225,6 +498,9 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
             if (it.kind == ITEM_MUL) it.rb = row_of(it.rb);
         }
     }
+    build_mask_vm(P);
+    split_levels(P.vm_level_off, VM_LEVEL_MAX);
+    build_value_luts(P, vg, vg.size() <= LUT_MAP_MAX_GATES);
     // ---- value plane: counting sort by level (value ids keep their creation order) ----
     {
         uint32_t depth = 0;

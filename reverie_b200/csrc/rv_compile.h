@@ -33,6 +33,28 @@ struct VGate {
 struct LGate {
     uint32_t dst, a, b, pad;
 };
+// mask-plane VM instruction (shared-memory cells; see build_mask_vm):
+//   XOR : cell[dst] = cell[a] ^ cell[b]; if (row != VM_NONE) rows[row] = that value        (dst may be VM_NONE)
+//   LOAD: cell[dst & ~VM_LOAD] <- rows[a]   asynchronously, `VM_DELTA` levels ahead of its first use
+struct VmInstr {
+    uint32_t dst, a, b, row;
+};
+constexpr uint32_t VM_LOAD = 0x80000000u, VM_NONE = 0x7FFFFFFFu;
+constexpr int VM_DELTA = 8;  // prefetch distance in levels (L2 latency / per-level time)
+
+// value-plane LUT instruction: v[dst] = tt >> (v[in0] | v[in1]<<1 | ... | v[in5]<<5) & 1.  Unused inputs name value 0
+// (the constant 0).  Produced by the depth-oriented K=6 cut mapper (build_value_luts), which collapses cones of 2-input
+// gates -- e.g. two full-adder stages of a ripple carry -- into one lookup, so the level count of the plane drops.
+struct LutInstr {
+    uint32_t dst;
+    uint32_t in[6];
+    uint32_t pad;
+    uint64_t tt;
+    uint64_t pad2;  // 48 bytes = three 16-byte ring units
+};
+constexpr uint32_t LUT_LEVEL_MAX = 256;   // levels are split so that none holds more instructions (one ring chunk)
+constexpr uint32_t VM_LEVEL_MAX = 1024;
+
 enum ItemKind : uint32_t { ITEM_INPUT = 0, ITEM_MUL = 1, ITEM_ASSERT = 2 };
 // one byte of the online stream per repetition (and, for Mul, one byte of the preprocessing stream)
 struct Item {
@@ -45,7 +67,7 @@ struct Item {
     uint32_t j;     // MUL: position in the preprocessing stream; INPUT: witness index
     uint32_t pad;
 };
-static_assert(sizeof(VGate) == 16 && sizeof(LGate) == 16 && sizeof(Item) == 32, "POD layout");
+static_assert(sizeof(VGate) == 16 && sizeof(LGate) == 16 && sizeof(VmInstr) == 16 && sizeof(LutInstr) == 48 && sizeof(Item) == 32, "POD layout");
 
 struct Program {
     // GF(2) side
@@ -60,6 +82,12 @@ struct Program {
     std::vector<uint32_t> vlevel_off;   // value_depth + 1 offsets into vgates
     std::vector<LGate> lgates;          // sorted by level; dst rows are n_masks + position
     std::vector<uint32_t> llevel_off;   // linear_depth + 1 offsets into lgates
+    std::vector<LutInstr> luts;         // value-plane program, sorted by level
+    std::vector<uint32_t> lut_level_off;
+    uint32_t lut_depth = 0;             // levels before splitting wide ones
+    std::vector<VmInstr> vm;            // mask-plane VM program, sorted by VM level (= level + VM_DELTA - 1)
+    std::vector<uint32_t> vm_level_off; // linear_depth + VM_DELTA + 1 offsets into vm (empty when there are no lgates)
+    uint32_t vm_cells = 0;              // shared-memory cells the program needs (one lane word each)
     std::vector<Item> items;            // online-stream order
     std::vector<uint32_t> recon_pos;    // online positions of the reconstruct() calls (Mul, AssertZero), in order
     std::vector<uint32_t> input_pos;    // online positions of the input() calls, in order
@@ -71,5 +99,8 @@ struct Program {
 
 // Returns RV_OK or a negative rv_status; `err` receives a human-readable reason.
 int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, Program &out, std::string &err);
+
+// Gate-count limit above which the value plane keeps 2-input "LUTs" (the mapper's cut sets cost ~250 bytes per gate).
+constexpr size_t LUT_MAP_MAX_GATES = 8u << 20;
 
 }  // namespace rv

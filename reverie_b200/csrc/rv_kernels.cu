@@ -2,6 +2,8 @@
 // Integer / bitwise work only: no tensor cores.  See DESIGN.md section 5 for the roofline of each kernel.
 #include <cuda_pipeline.h>
 
+#include <algorithm>
+
 #include "rv_kernels.cuh"
 #include "rv_planes.cuh"
 
@@ -15,11 +17,18 @@ namespace rv {
 __global__ void __launch_bounds__(128) k_key_setup(const uint8_t *__restrict__ seeds, const uint8_t *__restrict__ pkeys_in,
                                                    const uint8_t *__restrict__ mode, const uint8_t *__restrict__ omit, uint32_t nslices,
                                                    uint32_t *__restrict__ ks, uint32_t *__restrict__ lane_mask, uint8_t *__restrict__ pkeys_out) {
+    __shared__ uint32_t sbox32[64];  // the S-box as a byte table, built from the netlist (4 entries per thread)
+    if (threadIdx.x < 64) {
+        const uint32_t b = 4 * threadIdx.x;
+        sbox32[threadIdx.x] = sub_word(b | ((b + 1) << 8) | ((b + 2) << 16) | ((b + 3) << 24));
+    }
+    __syncthreads();
+    const TableSubWord sw{reinterpret_cast<const uint8_t *>(sbox32)};
     const uint32_t lane = threadIdx.x & 31, w = blockIdx.x * 4 + (threadIdx.x >> 5);
     if (w >= nslices) return;
     const uint32_t rep = slice_rep(w, lane), p = slice_player(lane);
     uint32_t rk[44];
-    const bool active = key_setup_stream(rep, p, seeds, pkeys_in, mode, omit, pkeys_out, rk);
+    const bool active = key_setup_stream(rep, p, seeds, pkeys_in, mode, omit, pkeys_out, rk, sw);
     const uint32_t am = __ballot_sync(0xffffffffu, active);
     if (lane == 0) lane_mask[w] = am;
     // bitslice: plane k of round R = bit k of the 128-bit little-endian round key, gathered over the 32 lanes
@@ -45,7 +54,7 @@ void launch_key_setup(const uint8_t *seeds, const uint8_t *pkeys_in, const uint8
 //  K2  mask generation: bitsliced AES-128-CTR, thread = (slice, counter block)
 // =====================================================================================================================
 constexpr int MG_SLICES = 8;    // slices per CTA (their round keys live in shared memory: 8 x 5632 B = 44 KB)
-constexpr int MG_COUNTERS = 16; // counter blocks per CTA
+constexpr int MG_COUNTERS = 8;  // counter blocks per CTA (64 threads: fine-grained CTAs balance the 148 SMs)
 constexpr int MG_THREADS = MG_SLICES * MG_COUNTERS;
 
 struct SmemRoundKeys {
@@ -132,87 +141,233 @@ void launch_mask_gen(const uint32_t *ks, const uint32_t *lane_mask, uint32_t nsl
 }
 
 // =====================================================================================================================
-//  K0  value plane: plaintext evaluation, one CTA, level-synchronous; gate descriptors double-buffered through
-//      shared memory with cp.async; wire values in shared memory when they fit.
+//  Instruction ring: a level-sorted program streamed global -> shared memory with 1-D bulk async copies (TMA,
+//  cp.async.bulk + mbarrier complete_tx), RING_NB chunks in flight.  Thread 0 issues; every thread consumes.
 // =====================================================================================================================
-constexpr int VP_THREADS = 256;
-constexpr int VP_CHUNK = 1024;  // gates per staging buffer (16 KB)
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 
-template <bool SMEM_VALS>
-__global__ void __launch_bounds__(VP_THREADS) k_values(const VGate *__restrict__ gates, const uint32_t *__restrict__ level_off,
-                                                       uint32_t n_levels, uint32_t n_gates, const uint32_t *__restrict__ input_vid,
-                                                       const uint8_t *__restrict__ wit, uint32_t n_inputs, uint8_t *__restrict__ vals_g,
-                                                       uint32_t n_vals) {
-    extern __shared__ __align__(16) uint8_t smem[];
-    VGate *sbuf = reinterpret_cast<VGate *>(smem);                // [2][VP_CHUNK]
-    uint8_t *vals = SMEM_VALS ? smem + 2 * VP_CHUNK * sizeof(VGate) : vals_g;
-    const uint32_t tid = threadIdx.x;
+constexpr size_t SMEM_DYN_CAP = 226 * 1024;  // of the 227 KB a CTA may opt into; the rest covers static __shared__
+constexpr int RING_NB = 3;
 
-    auto load_chunk = [&](uint32_t c) {
-        const uint32_t base = c * VP_CHUNK;
-        VGate *dst = sbuf + (c & 1) * VP_CHUNK;
-        for (uint32_t i = tid; i < VP_CHUNK; i += VP_THREADS)
-            if (base + i < n_gates) __pipeline_memcpy_async(dst + i, gates + base + i, sizeof(VGate));
-        __pipeline_commit();
-    };
-    load_chunk(0);
-    load_chunk(1);
-    if (tid == 0) vals[0] = 0;
-    for (uint32_t k = tid; k < n_inputs; k += VP_THREADS) vals[input_vid[k]] = wit[k] & 1;
-    __pipeline_wait_prior(1);
-    __syncthreads();
+// UNITS = 16-byte units per instruction, CHUNK = instructions per chunk (= the widest level the compiler emits)
+template <int UNITS, int CHUNK>
+struct InstrRing {
+    static constexpr size_t CHUNK_BYTES = (size_t)UNITS * 16 * CHUNK;
+    static constexpr size_t BYTES = RING_NB * CHUNK_BYTES + 64;
+    uint4 *buf;          // [RING_NB][CHUNK][UNITS]
+    uint64_t *bars;      // [RING_NB]
+    const uint4 *src;
+    uint32_t n;          // instructions in the program
+    uint32_t next_issue; // thread 0: next chunk to request
+    uint32_t ready;      // per thread: chunks [0, ready) are known to have landed
 
-    uint32_t cur = 0;  // chunk being consumed
-    uint32_t s = n_levels ? level_off[0] : 0;
-    for (uint32_t l = 0; l < n_levels; l++) {
-        const uint32_t e = level_off[l + 1];
-        while (s < e) {
-            const uint32_t cbase = cur * VP_CHUNK, cend = min(e, cbase + VP_CHUNK);
-            const VGate *buf = sbuf + (cur & 1) * VP_CHUNK;
-            for (uint32_t g = s + tid; g < cend; g += VP_THREADS) {
-                const VGate gt = buf[g - cbase];
-                const uint32_t a = vals[gt.a >> 1] ^ (gt.a & 1), b = vals[gt.b >> 1] ^ (gt.b & 1);
-                vals[gt.dst] = (uint8_t)((gt.op ? (a & b) : (a ^ b)) & 1);
-            }
-            s = cend;
-            if (s == (cur + 1) * VP_CHUNK && s < n_gates) {  // staging buffer exhausted: refill it, move to the other one
-                __syncthreads();
-                load_chunk(cur + 2);
-                cur++;
-                __pipeline_wait_prior(1);
-                __syncthreads();
-            }
+    __device__ __forceinline__ void issue(uint32_t c) {
+        const uint32_t first = c * CHUNK;
+        if (first >= n) return;
+        const uint32_t bytes = min((uint32_t)CHUNK, n - first) * UNITS * 16;
+        uint64_t *bar = bars + (c % RING_NB);
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(reinterpret_cast<uint8_t *>(buf) + (size_t)(c % RING_NB) * CHUNK_BYTES, src + (size_t)first * UNITS, bytes, bar);
+    }
+    // All threads call; includes a CTA barrier.
+    __device__ void init(uint8_t *smem, const void *program, uint32_t n_instr) {
+        buf = reinterpret_cast<uint4 *>(smem);
+        bars = reinterpret_cast<uint64_t *>(smem + RING_NB * CHUNK_BYTES);
+        src = reinterpret_cast<const uint4 *>(program);
+        n = n_instr;
+        next_issue = 0;
+        ready = 0;
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < RING_NB; i++) mbar_init(bars + i, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
+        if (threadIdx.x == 0)
+            for (; next_issue < RING_NB; next_issue++) issue(next_issue);
     }
+    // Thread 0, when every instruction below `consumed` has been read by everyone: the buffers of chunks lying entirely
+    // below it are refilled.  Afterwards chunks up to consumed / CHUNK + RING_NB - 1 have been requested.
+    __device__ __forceinline__ void advance(uint32_t consumed) {
+        while ((next_issue - RING_NB + 1) * CHUNK <= consumed && next_issue * CHUNK < n) issue(next_issue++);
+    }
+    // Uniform wait: EVERY thread that will read the ring must have called this for every chunk in order (never skipping
+    // one), otherwise a lagging thread could test a stale mbarrier phase.  Chunks [0, c] are complete on return.
+    __device__ __forceinline__ void wait_upto(uint32_t c) {
+        while (ready <= c) {
+            uint64_t *bar = bars + (ready % RING_NB);
+            const uint32_t parity = (ready / RING_NB) & 1;
+            while (!mbar_try_wait(bar, parity)) {
+            }
+            ready++;
+        }
+    }
+    __device__ __forceinline__ uint4 at(uint32_t g, int unit = 0) const {
+        return buf[((size_t)((g / CHUNK) % RING_NB) * CHUNK + (g % CHUNK)) * UNITS + unit];
+    }
+};
+
+// =====================================================================================================================
+//  K0  value plane: the mapped LUT program (rv_compile.cpp, build_value_luts), one CTA, level-synchronous.  Values live
+//      in shared memory (or global when they do not fit).  Levels of <= VP_NARROW instructions are run by warp 0 alone
+//      with __syncwarp instead of a CTA barrier; the compiler never emits a level wider than one ring chunk.
+// =====================================================================================================================
+constexpr int VP_THREADS = 256;
+constexpr int VP_NARROW = 128;
+using LutRing = InstrRing<3, LUT_LEVEL_MAX>;
+static_assert(VP_THREADS >= (int)LUT_LEVEL_MAX, "one instruction per thread in wide levels");
+
+template <bool SMEM_VALS>
+__global__ void __launch_bounds__(VP_THREADS) k_values(const LutInstr *__restrict__ prog, const uint32_t *__restrict__ level_off,
+                                                       uint32_t n_levels, uint32_t n_instr, const uint32_t *__restrict__ input_vid,
+                                                       const uint8_t *__restrict__ wit, uint32_t n_inputs, uint8_t *__restrict__ vals_g,
+                                                       uint32_t n_vals, uint32_t levels_in_smem) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    __shared__ uint32_t warp0_ready;
+    LutRing ring;
+    ring.init(smem, prog, n_instr);
+    uint32_t *soff = reinterpret_cast<uint32_t *>(smem + LutRing::BYTES);
+    uint8_t *vals = SMEM_VALS ? smem + LutRing::BYTES + ((size_t)(levels_in_smem + 1) * 4 + 15) / 16 * 16 : vals_g;
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t i = tid; i <= levels_in_smem; i += VP_THREADS) soff[i] = level_off[i];
+    if (tid == 0) vals[0] = 0;
+    for (uint32_t k = tid; k < n_inputs; k += VP_THREADS) vals[input_vid[k]] = wit[k] & 1;
+    __syncthreads();
+    const uint32_t *off = levels_in_smem == n_levels ? soff : level_off;
+
+    auto exec = [&](uint32_t g) {
+        const uint4 u0 = ring.at(g, 0), u1 = ring.at(g, 1), u2 = ring.at(g, 2);  // {dst,in0,in1,in2} {in3,in4,in5,-} {tt}
+        const uint32_t idx = (uint32_t)vals[u0.y] | ((uint32_t)vals[u0.z] << 1) | ((uint32_t)vals[u0.w] << 2) | ((uint32_t)vals[u1.x] << 3) |
+                             ((uint32_t)vals[u1.y] << 4) | ((uint32_t)vals[u1.z] << 5);
+        const uint64_t tt = ((uint64_t)u2.y << 32) | u2.x;
+        vals[u0.x] = (uint8_t)((tt >> idx) & 1);
+    };
+    bool synced = true;  // "a CTA barrier separates us from the previous level's writes"
+    for (uint32_t l = 0; l < n_levels; l++) {
+        const uint32_t s = off[l], e = off[l + 1];
+        if (e == s) continue;
+        if (e - s <= VP_NARROW) {  // narrow level: warp 0 only, warp-synchronous; the other warps run ahead to the next wide level
+            if (tid < 32) {
+                if (tid == 0) ring.advance(s);
+                ring.wait_upto((e - 1) / LUT_LEVEL_MAX);
+                for (uint32_t g = s + tid; g < e; g += 32) exec(g);
+                __syncwarp();
+            }
+            synced = false;
+        } else {
+            if (!synced) {  // hand the ring position of warp 0 to everyone (see InstrRing::wait_upto)
+                if (tid == 0) warp0_ready = ring.ready;
+                __syncthreads();
+                ring.ready = max(ring.ready, warp0_ready);
+            }
+            if (tid == 0) ring.advance(s);
+            ring.wait_upto((e - 1) / LUT_LEVEL_MAX);
+            if (s + tid < e) exec(s + tid);
+            __syncthreads();
+            synced = true;
+        }
+    }
+    __syncthreads();
     if (SMEM_VALS) {
         for (uint32_t i = tid; i < n_vals; i += VP_THREADS) vals_g[i] = vals[i];
     }
 }
 
 size_t launch_values(const DevProgram &P, const uint8_t *wit, uint8_t *vals, cudaStream_t st) {
-    const size_t stage = 2 * VP_CHUNK * sizeof(VGate);
-    const size_t want = stage + ((P.n_vals + 15) & ~15u);
+    // dynamic shared memory available to one CTA: 227 KB minus the kernels' few static bytes
+    const size_t cap = SMEM_DYN_CAP;
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(k_values<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        cudaFuncSetAttribute(k_values<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(k_values<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
+        cudaFuncSetAttribute(k_values<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
         configured = true;
     }
-    if (want <= 227 * 1024) {
-        k_values<true><<<1, VP_THREADS, want, st>>>(P.vgates, P.vlevel_off, P.n_vlevels, P.n_vgates, P.input_vid, wit, P.n_inputs, vals, P.n_vals);
+    const size_t lvl_bytes = ((size_t)(P.n_lut_levels + 1) * 4 + 15) / 16 * 16;
+    const size_t want = LutRing::BYTES + lvl_bytes + ((P.n_vals + 15) & ~15u);
+    if (want <= cap) {
+        k_values<true><<<1, VP_THREADS, want, st>>>(P.luts, P.lut_level_off, P.n_lut_levels, P.n_luts, P.input_vid, wit, P.n_inputs, vals, P.n_vals, P.n_lut_levels);
         return want;
     }
-    k_values<false><<<1, VP_THREADS, stage, st>>>(P.vgates, P.vlevel_off, P.n_vlevels, P.n_vgates, P.input_vid, wit, P.n_inputs, vals, P.n_vals);
-    return stage;
+    const uint32_t lv = LutRing::BYTES + lvl_bytes <= cap ? P.n_lut_levels : 0;
+    const size_t sm = LutRing::BYTES + (lv ? lvl_bytes : 16);
+    k_values<false><<<1, VP_THREADS, sm, st>>>(P.luts, P.lut_level_off, P.n_lut_levels, P.n_luts, P.input_vid, wit, P.n_inputs, vals, P.n_vals, lv);
+    return sm;
 }
 
 // =====================================================================================================================
 //  K3  mask plane: row[dst] = row[a] ^ row[b], level by level
 // =====================================================================================================================
 constexpr int LIN_THREADS = 256;
+constexpr int VM_THREADS = 256;
 
-// deep / narrow networks: one CTA per packed instance walks all levels (CTA barrier only; columns are independent)
+// (a) VM over shared-memory cells: one CTA per slice (u32 lane word = 4 repetitions x 8 players).  The dependent chain
+//     per level is LDS -> XOR -> STS -> barrier; fresh rows arrive through cp.async LOADs issued VM_DELTA levels early;
+//     only rows the item plane needs are written back to the share tensor.
+using VmRing = InstrRing<1, VM_LEVEL_MAX>;
+
+__global__ void __launch_bounds__(VM_THREADS) k_mask_vm(const VmInstr *__restrict__ prog, const uint32_t *__restrict__ level_off,
+                                                        uint32_t n_levels, uint32_t n_instr, uint32_t *rows32, uint32_t nslices) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    VmRing ring;
+    ring.init(smem, prog, n_instr);
+    uint32_t *soff = reinterpret_cast<uint32_t *>(smem + VmRing::BYTES);
+    uint32_t *cells = soff + ((n_levels + 1 + 3) & ~3u);
+    const uint32_t tid = threadIdx.x, w = blockIdx.x;
+    for (uint32_t i = tid; i <= n_levels; i += VM_THREADS) soff[i] = level_off[i];
+    __syncthreads();
+    auto exec = [&](const uint4 in) {  // {dst, a, b, row}
+        if (in.x & VM_LOAD) {
+            __pipeline_memcpy_async(cells + (in.x & ~VM_LOAD), rows32 + (size_t)in.y * nslices + w, 4);
+        } else {
+            const uint32_t v = cells[in.y] ^ cells[in.z];
+            if (in.x != VM_NONE) cells[in.x] = v;
+            if (in.w != VM_NONE) rows32[(size_t)in.w * nslices + w] = v;
+        }
+    };
+    // Software pipeline: while level l executes, the bounds of level l+2 and this thread's first instruction of level
+    // l+1 are already on their way into registers, so the per-level dependent chain is LDS(cells) -> XOR -> STS -> barrier.
+    uint32_t s = soff[0], e = soff[1], e2 = soff[min(2u, n_levels)];
+    if (e2) ring.wait_upto((e2 - 1) / VM_LEVEL_MAX);
+    const uint4 nop = make_uint4(VM_NONE, 0, 0, VM_NONE);
+    uint4 cur = (s + tid < e) ? ring.at(s + tid) : nop;
+    for (uint32_t l = 0; l < n_levels; l++) {
+        const uint32_t e3 = soff[min(l + 3, n_levels)];
+        const uint4 nxt = (e + tid < e2) ? ring.at(e + tid) : nop;
+        if (s + tid < e) exec(cur);
+        for (uint32_t g = s + tid + VM_THREADS; g < e; g += VM_THREADS) exec(ring.at(g));
+        __pipeline_commit();
+        __pipeline_wait_prior(VM_DELTA - 1);
+        __syncthreads();
+        if (tid == 0) ring.advance(e);
+        if (e3 > e2) ring.wait_upto((e3 - 1) / VM_LEVEL_MAX);
+        s = e;
+        e = e2;
+        e2 = e3;
+        cur = nxt;
+    }
+}
+
+// (b) fallback for networks whose live set does not fit in shared memory: one CTA per packed instance walks all levels
+//     over the share tensor itself (CTA barrier only; columns are independent)
 __global__ void __launch_bounds__(LIN_THREADS) k_linear_cta(const LGate *__restrict__ gates, const uint32_t *__restrict__ level_off,
                                                             uint32_t n_levels, uint64_t *rows, uint32_t npi) {
     const uint32_t pi = blockIdx.x, tid = threadIdx.x;
@@ -231,7 +386,7 @@ __global__ void __launch_bounds__(LIN_THREADS) k_linear_cta(const LGate *__restr
     }
 }
 
-// wide levels: one launch per level, thread = (gate, packed instance)
+// (c) wide levels: one launch per level, thread = (gate, packed instance)
 __global__ void __launch_bounds__(256) k_linear_level(const LGate *__restrict__ gates, uint32_t n, uint64_t *rows, uint32_t npi) {
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t g = gid / npi;
@@ -241,20 +396,33 @@ __global__ void __launch_bounds__(256) k_linear_level(const LGate *__restrict__ 
     rows[(size_t)gt.dst * npi + pi] = rows[(size_t)gt.a * npi + pi] ^ rows[(size_t)gt.b * npi + pi];
 }
 
-int launch_linear(const DevProgram &P, const uint32_t *off_host, uint64_t *rows, uint32_t npi, cudaStream_t st) {
+int launch_linear(const DevProgram &P, const uint32_t *off_host, uint64_t *rows, uint32_t npi, cudaStream_t st, int *which) {
+    if (which) *which = -1;
     if (P.n_llevels == 0) return 0;
-    // per-level launches pay ~3 us each; the CTA walker pays ~0.4 us per level but uses only npi SMs
     const double avg_width = (double)P.n_lgates / P.n_llevels;
-    if (avg_width < 4096.0) {
-        k_linear_cta<<<npi, LIN_THREADS, 0, st>>>(P.lgates, P.llevel_off, P.n_llevels, rows, npi);
+    if (avg_width >= 4096.0) {  // wide: per-level launches (~3 us each) keep every SM busy
+        if (which) *which = 2;
+        for (uint32_t l = 0; l < P.n_llevels; l++) {
+            const uint32_t n = off_host[l + 1] - off_host[l];
+            const uint64_t threads = (uint64_t)n * npi;
+            k_linear_level<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P.lgates + off_host[l], n, rows, npi);
+        }
+        return (int)P.n_llevels;
+    }
+    const size_t vm_smem = VmRing::BYTES + (size_t)((P.n_vm_levels + 1 + 3) & ~3u) * 4 + (size_t)P.vm_cells * 4;
+    if (P.n_vm && vm_smem <= SMEM_DYN_CAP) {
+        static bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(k_mask_vm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DYN_CAP);
+            configured = true;
+        }
+        if (which) *which = 0;
+        k_mask_vm<<<2 * npi, VM_THREADS, vm_smem, st>>>(P.vm, P.vm_level_off, P.n_vm_levels, P.n_vm, reinterpret_cast<uint32_t *>(rows), 2 * npi);
         return 1;
     }
-    for (uint32_t l = 0; l < P.n_llevels; l++) {
-        const uint32_t n = off_host[l + 1] - off_host[l];
-        const uint64_t threads = (uint64_t)n * npi;
-        k_linear_level<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P.lgates + off_host[l], n, rows, npi);
-    }
-    return (int)P.n_llevels;
+    if (which) *which = 1;
+    k_linear_cta<<<npi, LIN_THREADS, 0, st>>>(P.lgates, P.llevel_off, P.n_llevels, rows, npi);
+    return 1;
 }
 
 // =====================================================================================================================
@@ -313,25 +481,74 @@ void launch_items(const DevProgram &P, const uint64_t *rows, uint32_t npi, const
 // =====================================================================================================================
 //  K5  transcript hashing
 // =====================================================================================================================
-// thread = (repetition, chunk): chaining value of one 1 KiB chunk
-__global__ void __launch_bounds__(128) k_chunk_cv(const uint8_t *__restrict__ stream, size_t pitch, uint32_t len, uint32_t n_chunks,
-                                                  uint32_t nreps, uint32_t *__restrict__ cvs) {
-    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t chunk = (uint32_t)(gid % n_chunks), rep = (uint32_t)(gid / n_chunks);
-    if (rep >= nreps) return;
-    const uint32_t off = chunk * 1024u;
-    const uint32_t clen = min(1024u, len - off);
-    uint32_t cv[8];
-    b3_chunk_cv(reinterpret_cast<const uint32_t *>(stream + (size_t)rep * pitch + off), clen, chunk, n_chunks == 1, cv);
-    uint32_t *dst = cvs + ((size_t)rep * n_chunks + chunk) * 8;
-#pragma unroll
-    for (int i = 0; i < 8; i++) dst[i] = cv[i];
+// thread = (stream, repetition, chunk): chaining value of one 1 KiB chunk.  Full 64-byte blocks are fetched as four
+// 16-byte loads, one block ahead of the compression that consumes them.
+struct ChunkJob {
+    const uint8_t *stream;
+    size_t pitch;
+    uint32_t len, n_chunks;
+    uint32_t *cvs;
+};
+
+__device__ __forceinline__ void load_block(const uint4 *p, uint32_t m[16]) {
+    const uint4 a = p[0], b = p[1], c = p[2], d = p[3];
+    m[0] = a.x; m[1] = a.y; m[2] = a.z; m[3] = a.w;
+    m[4] = b.x; m[5] = b.y; m[6] = b.z; m[7] = b.w;
+    m[8] = c.x; m[9] = c.y; m[10] = c.z; m[11] = c.w;
+    m[12] = d.x; m[13] = d.y; m[14] = d.z; m[15] = d.w;
 }
 
-void launch_chunk_cv(const uint8_t *stream, size_t pitch, uint32_t len, uint32_t nreps, uint32_t *cvs, cudaStream_t st) {
-    const uint32_t n_chunks = len == 0 ? 1 : (len + 1023) / 1024;
-    const uint64_t threads = (uint64_t)n_chunks * nreps;
-    k_chunk_cv<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(stream, pitch, len, n_chunks, nreps, cvs);
+__global__ void __launch_bounds__(64) k_chunk_cv(ChunkJob j0, ChunkJob j1, uint32_t nreps) {
+    const ChunkJob &J = blockIdx.y == 0 ? j0 : j1;
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t chunk = (uint32_t)(gid % J.n_chunks), rep = (uint32_t)(gid / J.n_chunks);
+    if (rep >= nreps) return;
+    const uint32_t off = chunk * 1024u;
+    const uint32_t clen = min(1024u, J.len - off);
+    const bool root = J.n_chunks == 1;
+    const uint8_t *base = J.stream + (size_t)rep * J.pitch + off;
+    uint32_t cv[8];
+    b3_iv(cv);
+    const uint32_t n_blocks = clen == 0 ? 1 : (clen + 63) / 64;
+    const uint32_t n_full = clen / 64;  // blocks read with plain vector loads (the pitch is a multiple of 64)
+    uint32_t m[16], nx[16];
+    if (n_full) load_block(reinterpret_cast<const uint4 *>(base), nx);
+    for (uint32_t b = 0; b < n_blocks; b++) {
+        uint32_t blen = 64;
+        if (b < n_full) {
+#pragma unroll
+            for (int i = 0; i < 16; i++) m[i] = nx[i];
+            if (b + 1 < n_full) load_block(reinterpret_cast<const uint4 *>(base + 64 * (b + 1)), nx);
+        } else {  // the ragged tail block (or the single empty block)
+            blen = clen - 64 * b;
+            const uint32_t *w = reinterpret_cast<const uint32_t *>(base + 64 * b);
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                uint32_t v = 0;
+                if (4u * i < blen) {
+                    v = w[i];
+                    if (blen - 4 * i < 4) v &= (1u << (8 * (blen - 4 * i))) - 1u;
+                }
+                m[i] = v;
+            }
+        }
+        uint32_t flags = (b == 0 ? B3_CHUNK_START : 0) | (b + 1 == n_blocks ? B3_CHUNK_END : 0);
+        if (root && b + 1 == n_blocks) flags |= B3_ROOT;
+        b3_compress_cv(cv, m, chunk, blen, flags);
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(J.cvs + ((size_t)rep * J.n_chunks + chunk) * 8);
+    dst[0] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
+    dst[1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
+}
+
+static uint32_t n_chunks_of(uint32_t len) { return len == 0 ? 1 : (len + 1023) / 1024; }
+
+void launch_chunk_cv2(const uint8_t *on, size_t pitch_on, uint32_t len_on, uint32_t *cv_on, const uint8_t *pre, size_t pitch_pre,
+                      uint32_t len_pre, uint32_t *cv_pre, uint32_t nreps, cudaStream_t st) {
+    ChunkJob j0{on, pitch_on, len_on, n_chunks_of(len_on), cv_on}, j1{pre, pitch_pre, len_pre, n_chunks_of(len_pre), cv_pre};
+    const uint64_t threads = (uint64_t)std::max(j0.n_chunks, j1.n_chunks) * nreps;
+    dim3 grid((unsigned)((threads + 63) / 64), 2);
+    k_chunk_cv<<<grid, 64, 0, st>>>(j0, j1, nreps);
 }
 
 // BLAKE3 tree over n chunk CVs, in place: adjacent pairs merge, an odd tail is carried up unchanged (this reproduces

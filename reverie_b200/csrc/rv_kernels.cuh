@@ -19,6 +19,12 @@ struct DevProgram {
     const uint32_t *recon_pos = nullptr;  // k -> online position of the k-th reconstruct()
     const uint32_t *input_pos = nullptr;  // k -> online position of the k-th input()
     const uint32_t *input_vid = nullptr;  // k -> value id
+    const LutInstr *luts = nullptr;        // value-plane LUT program
+    const uint32_t *lut_level_off = nullptr;
+    uint32_t n_luts = 0, n_lut_levels = 0;
+    const VmInstr *vm = nullptr;           // mask-plane VM program (empty when the circuit has no Add/Sub on masks)
+    const uint32_t *vm_level_off = nullptr;
+    uint32_t n_vm = 0, n_vm_levels = 0, vm_cells = 0;
     uint32_t n_vgates = 0, n_vlevels = 0, n_lgates = 0, n_llevels = 0;
     uint32_t n_masks = 0, n_rows = 0, n_vals = 0, n_online = 0, n_pre = 0, n_inputs = 0, n_recon = 0;
     uint32_t max_llevel_width = 0;
@@ -32,12 +38,14 @@ void launch_mask_gen(const uint32_t *ks, const uint32_t *lane_mask, uint32_t nsl
 // K0  value plane (plaintext evaluation; one CTA, level-synchronous).  Returns the dynamic smem it asked for.
 size_t launch_values(const DevProgram &P, const uint8_t *wit, uint8_t *vals, cudaStream_t st);
 // K3  mask plane (XOR network over the share tensor)
-int launch_linear(const DevProgram &P, const uint32_t *llevel_off_host, uint64_t *rows, uint32_t npi, cudaStream_t st);
+//     returns the number of kernel launches; *which (optional) names the variant: 0 VM (smem cells), 1 CTA walker, 2 per level
+int launch_linear(const DevProgram &P, const uint32_t *llevel_off_host, uint64_t *rows, uint32_t npi, cudaStream_t st, int *which = nullptr);
 // K4  item plane: the two hash streams of every repetition
 void launch_items(const DevProgram &P, const uint64_t *rows, uint32_t npi, const uint8_t *vals, uint8_t *on, size_t pitch_on,
                   uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st);
 // K5  BLAKE3 chunk chaining values of `nreps` streams, then per-repetition tree + joins
-void launch_chunk_cv(const uint8_t *stream, size_t pitch, uint32_t len, uint32_t nreps, uint32_t *cvs, cudaStream_t st);
+void launch_chunk_cv2(const uint8_t *on, size_t pitch_on, uint32_t len_on, uint32_t *cv_on, const uint8_t *pre, size_t pitch_pre,
+                      uint32_t len_pre, uint32_t *cv_pre, uint32_t nreps, cudaStream_t st);
 void launch_rep_hash(uint32_t *cv_on, uint32_t n_chunks_on, uint32_t *cv_pre, uint32_t n_chunks_pre, const uint32_t *z64_hash,
                      uint32_t nreps, uint8_t *on_hash, uint8_t *rep_hash, cudaStream_t st);
 // K6  comm = H(256 rep hashes); Fiat-Shamir challenge (src/proof/mod.rs:74-108)

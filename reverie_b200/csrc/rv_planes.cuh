@@ -104,8 +104,9 @@ RV_HD uint32_t slice_player(uint32_t q) { return (31 - q) & 7; }
 // Player key of (rep, p) and its AES round keys.  mode[rep]==1: the key is given (verifier, online.rs:25-121); otherwise
 // it is block p of AES-CTR(seed[rep]) (expand_seed, src/transcript/mod.rs:99-106).  Returns "stream is active" (the
 // omitted player's tape stays zero, src/generator/batch.rs:31-34) and writes the OpenOnline.seeds entry (prover.rs:126-127).
+template <typename SW = NetlistSubWord>
 RV_HD bool key_setup_stream(uint32_t rep, uint32_t p, const uint8_t *seeds, const uint8_t *pkeys_in, const uint8_t *mode,
-                            const uint8_t *omit, uint8_t *pkeys_out, uint32_t rk[44]) {
+                            const uint8_t *omit, uint8_t *pkeys_out, uint32_t rk[44], SW sw = SW()) {
     uint32_t key[4];
     if (mode != nullptr && mode[rep] == 1) {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(pkeys_in + ((size_t)rep * 8 + p) * 16);
@@ -113,14 +114,14 @@ RV_HD bool key_setup_stream(uint32_t rep, uint32_t p, const uint8_t *seeds, cons
     } else {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(seeds + (size_t)rep * 16);
         uint32_t sk[4] = {src[0], src[1], src[2], src[3]}, in[4];
-        aes128_expand_key(sk, rk);
+        aes128_expand_key(sk, rk, sw);
         ctr_block_words(p, in);
-        aes128_encrypt_block(rk, in, key);
+        aes128_encrypt_block(rk, in, key, sw);
     }
     const bool active = !(omit != nullptr && omit[rep] == p);
     uint32_t *dst = reinterpret_cast<uint32_t *>(pkeys_out + ((size_t)rep * 8 + p) * 16);
     for (int i = 0; i < 4; i++) dst[i] = active ? key[i] : 0u;
-    aes128_expand_key(key, rk);
+    aes128_expand_key(key, rk, sw);
     return active;
 }
 

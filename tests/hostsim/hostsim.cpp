@@ -193,3 +193,93 @@ extern "C" int hs_prove(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t
 }
 
 extern "C" void hs_free(void *p) { free(p); }
+
+// Executes the mask-plane VM program (build_mask_vm) on random fresh rows with cell reuse exactly as scheduled and
+// compares every exported row against the plain XOR network.  LOADs are applied at their issue level, the earliest the
+// asynchronous copy may land.  Returns 0 on success; *n_cells receives the cell count.
+extern "C" int hs_check_vm(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, uint32_t *n_cells, uint32_t *n_instr) {
+    Program P;
+    int rc = compile(ops, n_ops, z64_cells, gf2_cells, P, g_err);
+    if (rc) return rc;
+    *n_cells = P.vm_cells;
+    *n_instr = (uint32_t)P.vm.size();
+    std::vector<uint32_t> rows(P.n_rows, 0), ref;
+    uint32_t x = 12345;
+    for (uint32_t r = 0; r < P.n_masks; r++) rows[r] = (x = x * 1664525u + 1013904223u);
+    ref = rows;
+    for (const LGate &g : P.lgates) ref[g.dst] = ref[g.a] ^ ref[g.b];
+    std::vector<uint32_t> cells(P.vm_cells + 1, 0xDEADBEEF);
+    std::vector<uint8_t> exported(P.n_rows, 0);
+    const uint32_t n_levels = P.vm_level_off.empty() ? 0 : (uint32_t)P.vm_level_off.size() - 1;
+    for (uint32_t l = 0; l < n_levels; l++) {
+        // reads of a level happen before its writes become visible to OTHER instructions of the same level: emulate by
+        // computing all results first
+        std::vector<std::pair<uint32_t, uint32_t>> writes;
+        for (uint32_t k = P.vm_level_off[l]; k < P.vm_level_off[l + 1]; k++) {
+            const VmInstr &in = P.vm[k];
+            if (in.dst & VM_LOAD) writes.push_back({in.dst & ~VM_LOAD, rows[in.a]});
+            else {
+                const uint32_t v = cells[in.a] ^ cells[in.b];
+                if (in.dst != VM_NONE) writes.push_back({in.dst, v});
+                if (in.row != VM_NONE) {
+                    rows[in.row] = v;
+                    exported[in.row] = 1;
+                }
+            }
+        }
+        for (auto &w : writes) cells[w.first] = w.second;
+    }
+    for (const Item &it : P.items) {
+        const uint32_t rr[2] = {it.ra, it.kind == ITEM_MUL ? it.rb : it.ra};
+        for (uint32_t r : rr) {
+            if (r >= P.n_masks && r != P.zero_row() && !exported[r]) { g_err = "item operand row never exported"; return -100; }
+            if (rows[r] != ref[r]) { g_err = "VM row mismatch at row " + std::to_string(r); return -101; }
+        }
+    }
+    return 0;
+}
+
+// Evaluates the value plane twice -- plain 2-input gates vs. the mapped LUT program -- on `n_trials` random witnesses and
+// checks every value the item plane reads.  Returns 0 on success; stats: [n_luts, lut_levels(after split), lut_depth, plain_depth].
+extern "C" int hs_check_luts(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, int n_trials, uint32_t *stats) {
+    Program P;
+    int rc = compile(ops, n_ops, z64_cells, gf2_cells, P, g_err);
+    if (rc) return rc;
+    stats[0] = (uint32_t)P.luts.size();
+    stats[1] = (uint32_t)P.lut_level_off.size() - 1;
+    stats[2] = P.lut_depth;
+    stats[3] = (uint32_t)P.vlevel_off.size() - 1;
+    uint32_t x = 777;
+    for (int t = 0; t < n_trials; t++) {
+        std::vector<uint8_t> a(P.n_vals, 0), b(P.n_vals, 0xEE);
+        b[0] = 0;
+        for (size_t k = 0; k < P.n_inputs; k++) {
+            x = x * 1664525u + 1013904223u;
+            a[P.input_vid[k]] = b[P.input_vid[k]] = (x >> 16) & 1;
+        }
+        for (const VGate &g : P.vgates) {
+            const uint32_t u = a[g.a >> 1] ^ (g.a & 1), v = a[g.b >> 1] ^ (g.b & 1);
+            a[g.dst] = (uint8_t)((g.op ? (u & v) : (u ^ v)) & 1);
+        }
+        // level by level; within a level reads must not see the level's own writes
+        for (size_t l = 0; l + 1 < P.lut_level_off.size(); l++) {
+            std::vector<std::pair<uint32_t, uint8_t>> w;
+            for (uint32_t i = P.lut_level_off[l]; i < P.lut_level_off[l + 1]; i++) {
+                const LutInstr &li = P.luts[i];
+                uint32_t idx = 0;
+                for (int k = 0; k < 6; k++) {
+                    if (b[li.in[k]] > 1) { g_err = "LUT reads a value that was never written"; return -200; }
+                    idx |= (uint32_t)b[li.in[k]] << k;
+                }
+                w.push_back({li.dst, (uint8_t)((li.tt >> idx) & 1)});
+            }
+            for (auto &p : w) b[p.first] = p.second;
+        }
+        for (const Item &it : P.items) {
+            const uint32_t vv[2] = {it.va >> 1, it.kind == ITEM_MUL ? it.vb >> 1 : it.va >> 1};
+            for (uint32_t v : vv)
+                if (a[v] != b[v]) { g_err = "LUT value mismatch at vid " + std::to_string(v); return -201; }
+        }
+    }
+    return 0;
+}
