@@ -126,8 +126,7 @@ extern "C" int rv_circuit_compile(const rv_op *ops, size_t n_ops, size_t z64_cel
     if ((rc = upload(c, P.vgates, &D.vgates)) || (rc = upload(c, P.vlevel_off, &D.vlevel_off)) || (rc = upload(c, P.lgates, &D.lgates)) ||
         (rc = upload(c, P.llevel_off, &D.llevel_off)) || (rc = upload(c, P.items, &D.items)) || (rc = upload(c, c->mul_pos, &D.mul_pos)) ||
         (rc = upload(c, P.recon_pos, &D.recon_pos)) || (rc = upload(c, P.input_pos, &D.input_pos)) ||
-        (rc = upload(c, P.input_vid, &D.input_vid)) || (rc = upload(c, P.vm, &D.vm)) || (rc = upload(c, P.vm_level_off, &D.vm_level_off)) ||
-        (rc = upload(c, P.luts, &D.luts)) || (rc = upload(c, P.lut_level_off, &D.lut_level_off))) {
+        (rc = upload(c, P.input_vid, &D.input_vid)) || (rc = upload(c, P.vm_steps, &D.vm_steps)) || (rc = upload(c, P.lut_steps, &D.lut_steps))) {
         rv_circuit_free(c);
         return rc;
     }
@@ -135,10 +134,8 @@ extern "C" int rv_circuit_compile(const rv_op *ops, size_t n_ops, size_t z64_cel
     D.n_vlevels = (uint32_t)P.vlevel_off.size() - 1;
     D.n_lgates = (uint32_t)P.lgates.size();
     D.n_llevels = (uint32_t)P.llevel_off.size() - 1;
-    D.n_luts = (uint32_t)P.luts.size();
-    D.n_lut_levels = P.lut_level_off.empty() ? 0 : (uint32_t)P.lut_level_off.size() - 1;
-    D.n_vm = (uint32_t)P.vm.size();
-    D.n_vm_levels = P.vm_level_off.empty() ? 0 : (uint32_t)P.vm_level_off.size() - 1;
+    D.n_lut_steps = P.n_lut_steps;
+    D.n_vm_steps = P.n_vm_steps;
     D.vm_cells = P.vm_cells;
     D.n_masks = P.n_masks;
     D.n_rows = P.n_rows;
@@ -301,7 +298,7 @@ extern "C" int rv_session_create(const rv_circuit *c, int first_instance, int n_
     s->len_inputs = (uint32_t)(P.n_inputs / 8 + 1);
     s->proof_len = ProofLayout{s->len_recons, s->len_corrs, s->len_inputs}.total();
     if ((rc = dalloc(s, &s->d_wit, P.n_inputs)) || (rc = dalloc(s, &s->d_seeds, (size_t)s->nreps * 16)) ||
-        (rc = dalloc(s, &s->d_pkeys, (size_t)s->nreps * 128)) || (rc = dalloc(s, &s->d_vals, round_up(P.n_vals, 16))) ||
+        (rc = dalloc(s, &s->d_pkeys, (size_t)s->nreps * 128)) || (rc = dalloc(s, &s->d_vals, round_up((size_t)P.n_vals + 1, 16))) ||
         (rc = dalloc(s, &s->d_ks, (size_t)2 * s->npi * 1408)) || (rc = dalloc(s, &s->d_lane_mask, 2 * s->npi)) ||
         (rc = dalloc(s, &s->d_rows, (size_t)P.n_rows * s->npi)) || (rc = dalloc(s, &s->d_on, s->pitch_on * s->nreps)) ||
         (rc = dalloc(s, &s->d_pre, s->pitch_pre * s->nreps)) || (rc = dalloc(s, &s->d_cv_on, (size_t)s->n_chunks_on * s->nreps * 8)) ||
@@ -432,7 +429,7 @@ extern "C" int rv_session_commit(rv_session *s) {
     CU(cudaStreamWaitEvent(s->st_val, s->ev_upload, 0));
     if (s->ever_committed) CU(cudaStreamWaitEvent(s->st_val, s->ev_items, 0));  // the previous proof's item plane still reads d_vals
     {
-        Scope k(s, "values", (uint64_t)D.n_luts * sizeof(LutInstr), 1, s->st_val);
+        Scope k(s, "values", (uint64_t)P.luts.size() * sizeof(LutInstr), 1, s->st_val);
         launch_values(D, s->d_wit, s->d_vals, s->st_val);
     }
     CU(cudaEventRecord(s->ev_vals, s->st_val));

@@ -294,6 +294,63 @@ void build_value_luts(Program &P, const std::vector<VGate> &vg /* creation (topo
     split_levels(P.lut_level_off, LUT_LEVEL_MAX);
 }
 
+// ---- step streams (see rv_compile.h) ---------------------------------------------------------------------------------
+static void emit_vm_steps(Program &P) {
+    P.vm_steps.clear();
+    P.n_vm_steps = 0;
+    if (P.vm.empty()) return;
+    const uint32_t scratch = P.vm_cells;  // one extra cell absorbs the writes of empty slots and of export-only XORs
+    const VmInstr nop{scratch, scratch, scratch, VM_ROW_NONE};
+    const size_t n_levels = P.vm_level_off.size() - 1;
+    for (size_t l = 0; l < n_levels; l++) {
+        const uint32_t s = P.vm_level_off[l], e = P.vm_level_off[l + 1];
+        if (e == s) continue;
+        const uint32_t steps = (e - s + VM_STEP - 1) / VM_STEP;
+        for (uint32_t k = 0; k < steps; k++) {
+            const bool last = k + 1 == steps;
+            const bool chunk_end = (P.n_vm_steps + 1) % VM_STEPS_PER_CHUNK == 0;
+            for (uint32_t t = 0; t < VM_STEP; t++) {
+                const uint32_t g = s + k * VM_STEP + t;
+                VmInstr o = nop;
+                if (g < e) {
+                    const VmInstr &in = P.vm[g];
+                    if (in.dst & VM_LOAD) o = VmInstr{VM_F_LOAD | (in.dst & ~VM_LOAD), in.a, 0, VM_ROW_NONE};
+                    else o = VmInstr{in.dst == VM_NONE ? scratch : in.dst, in.a, in.b, in.row == VM_NONE ? VM_ROW_NONE : in.row};
+                }
+                if (last || chunk_end) o.dst |= VM_F_BAR;
+                P.vm_steps.push_back(o);
+            }
+            P.n_vm_steps++;
+        }
+    }
+}
+
+static void emit_lut_steps(Program &P) {
+    P.lut_steps.clear();
+    P.n_lut_steps = 0;
+    if (P.luts.empty()) return;
+    LutInstr nop;
+    std::memset(&nop, 0, sizeof nop);
+    nop.dst = P.n_vals;  // scratch value slot
+    const size_t n_levels = P.lut_level_off.size() - 1;
+    for (size_t l = 0; l < n_levels; l++) {
+        const uint32_t s = P.lut_level_off[l], e = P.lut_level_off[l + 1];
+        if (e == s) continue;
+        const uint32_t steps = (e - s + LUT_STEP - 1) / LUT_STEP;
+        for (uint32_t k = 0; k < steps; k++) {
+            const bool last = k + 1 == steps;
+            const bool chunk_end = (P.n_lut_steps + 1) % LUT_STEPS_PER_CHUNK == 0;
+            for (uint32_t t = 0; t < LUT_STEP; t++) {
+                const uint32_t g = s + k * LUT_STEP + t;
+                LutInstr o = g < e ? P.luts[g] : nop;
+                o.pad = (last || chunk_end) ? LUT_F_BAR : 0;
+                P.lut_steps.push_back(o);
+            }
+            P.n_lut_steps++;
+        }
+    }
+}
+
 }  // namespace
 
 int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, Program &P, std::string &err) {
@@ -501,6 +558,8 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
     build_mask_vm(P);
     split_levels(P.vm_level_off, VM_LEVEL_MAX);
     build_value_luts(P, vg, vg.size() <= LUT_MAP_MAX_GATES);
+    emit_vm_steps(P);
+    emit_lut_steps(P);
     // ---- value plane: counting sort by level (value ids keep their creation order) ----
     {
         uint32_t depth = 0;

@@ -52,8 +52,18 @@ struct LutInstr {
     uint64_t tt;
     uint64_t pad2;  // 48 bytes = three 16-byte ring units
 };
-constexpr uint32_t LUT_LEVEL_MAX = 256;   // levels are split so that none holds more instructions (one ring chunk)
+constexpr uint32_t LUT_LEVEL_MAX = 256;   // levels are split so that none holds more instructions
 constexpr uint32_t VM_LEVEL_MAX = 1024;
+
+// Device form of both programs: a dense "VLIW" stream of STEPS.  Every thread of the CTA executes exactly one slot per
+// step (empty slots are harmless no-ops on a scratch cell), so the device loop needs no level table, no bounds checks and
+// no inner loops -- the per-level dependent chain is what bounds these kernels, and it is paid in instructions per warp.
+//   mask VM : step = VM_STEP slots of 16 bytes; word 0 = dst cell | flags
+//   LUT     : step = LUT_STEP slots of 48 bytes; `pad` = flags
+// STEP_BAR on a slot means "CTA barrier after this step" (set on every slot of the last step of a level and of a chunk).
+constexpr uint32_t VM_STEP = 256, VM_STEPS_PER_CHUNK = 4, LUT_STEP = 128, LUT_STEPS_PER_CHUNK = 2;
+constexpr uint32_t VM_F_LOAD = 0x80000000u, VM_F_BAR = 0x40000000u, VM_CELL_MASK = 0x00FFFFFFu, VM_ROW_NONE = 0xFFFFFFFFu;
+constexpr uint32_t LUT_F_BAR = 1u;
 
 enum ItemKind : uint32_t { ITEM_INPUT = 0, ITEM_MUL = 1, ITEM_ASSERT = 2 };
 // one byte of the online stream per repetition (and, for Mul, one byte of the preprocessing stream)
@@ -88,6 +98,10 @@ struct Program {
     std::vector<VmInstr> vm;            // mask-plane VM program, sorted by VM level (= level + VM_DELTA - 1)
     std::vector<uint32_t> vm_level_off; // linear_depth + VM_DELTA + 1 offsets into vm (empty when there are no lgates)
     uint32_t vm_cells = 0;              // shared-memory cells the program needs (one lane word each)
+    std::vector<VmInstr> vm_steps;      // padded device stream of the mask VM (n_vm_steps * VM_STEP slots); cell vm_cells = scratch
+    uint32_t n_vm_steps = 0;
+    std::vector<LutInstr> lut_steps;    // padded device stream of the value plane (n_lut_steps * LUT_STEP slots); value n_vals = scratch
+    uint32_t n_lut_steps = 0;
     std::vector<Item> items;            // online-stream order
     std::vector<uint32_t> recon_pos;    // online positions of the reconstruct() calls (Mul, AssertZero), in order
     std::vector<uint32_t> input_pos;    // online positions of the input() calls, in order

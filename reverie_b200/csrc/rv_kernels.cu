@@ -167,124 +167,91 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 }
 
 constexpr size_t SMEM_DYN_CAP = 226 * 1024;  // of the 227 KB a CTA may opt into; the rest covers static __shared__
-constexpr int RING_NB = 3;
+constexpr int RING_NB = 4;                     // chunks in flight (power of two)
 
-// UNITS = 16-byte units per instruction, CHUNK = instructions per chunk (= the widest level the compiler emits)
-template <int UNITS, int CHUNK>
-struct InstrRing {
-    static constexpr size_t CHUNK_BYTES = (size_t)UNITS * 16 * CHUNK;
+// CHUNK_BYTES of program per chunk.  Every thread calls begin_chunk(c) for c = 0, 1, 2, ... in order (uniformly), and a
+// CTA barrier separates the last read of chunk c-1 from begin_chunk(c): the host compiler forces one at every chunk end.
+template <size_t CHUNK_BYTES>
+struct ChunkStream {
     static constexpr size_t BYTES = RING_NB * CHUNK_BYTES + 64;
-    uint4 *buf;          // [RING_NB][CHUNK][UNITS]
-    uint64_t *bars;      // [RING_NB]
-    const uint4 *src;
-    uint32_t n;          // instructions in the program
-    uint32_t next_issue; // thread 0: next chunk to request
-    uint32_t ready;      // per thread: chunks [0, ready) are known to have landed
+    uint8_t *buf;
+    uint64_t *bars;
+    const uint8_t *src;
+    size_t total;  // program bytes
 
     __device__ __forceinline__ void issue(uint32_t c) {
-        const uint32_t first = c * CHUNK;
-        if (first >= n) return;
-        const uint32_t bytes = min((uint32_t)CHUNK, n - first) * UNITS * 16;
+        const size_t first = (size_t)c * CHUNK_BYTES;
+        if (first >= total) return;
+        const uint32_t bytes = (uint32_t)min((size_t)CHUNK_BYTES, total - first);
         uint64_t *bar = bars + (c % RING_NB);
         mbar_expect_tx(bar, bytes);
-        bulk_g2s(reinterpret_cast<uint8_t *>(buf) + (size_t)(c % RING_NB) * CHUNK_BYTES, src + (size_t)first * UNITS, bytes, bar);
+        bulk_g2s(buf + (size_t)(c % RING_NB) * CHUNK_BYTES, src + first, bytes, bar);
     }
-    // All threads call; includes a CTA barrier.
-    __device__ void init(uint8_t *smem, const void *program, uint32_t n_instr) {
-        buf = reinterpret_cast<uint4 *>(smem);
+    __device__ void init(uint8_t *smem, const void *program, size_t program_bytes) {  // all threads; includes a CTA barrier
+        buf = smem;
         bars = reinterpret_cast<uint64_t *>(smem + RING_NB * CHUNK_BYTES);
-        src = reinterpret_cast<const uint4 *>(program);
-        n = n_instr;
-        next_issue = 0;
-        ready = 0;
+        src = reinterpret_cast<const uint8_t *>(program);
+        total = program_bytes;
         if (threadIdx.x == 0) {
             for (int i = 0; i < RING_NB; i++) mbar_init(bars + i, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
         if (threadIdx.x == 0)
-            for (; next_issue < RING_NB; next_issue++) issue(next_issue);
+            for (uint32_t c = 0; c < RING_NB; c++) issue(c);
     }
-    // Thread 0, when every instruction below `consumed` has been read by everyone: the buffers of chunks lying entirely
-    // below it are refilled.  Afterwards chunks up to consumed / CHUNK + RING_NB - 1 have been requested.
-    __device__ __forceinline__ void advance(uint32_t consumed) {
-        while ((next_issue - RING_NB + 1) * CHUNK <= consumed && next_issue * CHUNK < n) issue(next_issue++);
-    }
-    // Uniform wait: EVERY thread that will read the ring must have called this for every chunk in order (never skipping
-    // one), otherwise a lagging thread could test a stale mbarrier phase.  Chunks [0, c] are complete on return.
-    __device__ __forceinline__ void wait_upto(uint32_t c) {
-        while (ready <= c) {
-            uint64_t *bar = bars + (ready % RING_NB);
-            const uint32_t parity = (ready / RING_NB) & 1;
-            while (!mbar_try_wait(bar, parity)) {
-            }
-            ready++;
+    // Returns the chunk's shared-memory image.  Thread 0 also re-arms the buffer that chunk c-1 occupied.
+    __device__ __forceinline__ const uint8_t *begin_chunk(uint32_t c) {
+        if (threadIdx.x == 0 && c >= 1) issue(c + RING_NB - 1);
+        uint64_t *bar = bars + (c % RING_NB);
+        const uint32_t parity = (c / RING_NB) & 1;
+        while (!mbar_try_wait(bar, parity)) {
         }
-    }
-    __device__ __forceinline__ uint4 at(uint32_t g, int unit = 0) const {
-        return buf[((size_t)((g / CHUNK) % RING_NB) * CHUNK + (g % CHUNK)) * UNITS + unit];
+        return buf + (size_t)(c % RING_NB) * CHUNK_BYTES;
     }
 };
 
 // =====================================================================================================================
-//  K0  value plane: the mapped LUT program (rv_compile.cpp, build_value_luts), one CTA, level-synchronous.  Values live
-//      in shared memory (or global when they do not fit).  Levels of <= VP_NARROW instructions are run by warp 0 alone
-//      with __syncwarp instead of a CTA barrier; the compiler never emits a level wider than one ring chunk.
+//  K0  value plane: the mapped LUT program as a step stream (rv_compile.h), one CTA of LUT_STEP threads, one slot per
+//      thread per step.  Values live in shared memory (or global when they do not fit).
 // =====================================================================================================================
-constexpr int VP_THREADS = 256;
-constexpr int VP_NARROW = 128;
-using LutRing = InstrRing<3, LUT_LEVEL_MAX>;
-static_assert(VP_THREADS >= (int)LUT_LEVEL_MAX, "one instruction per thread in wide levels");
+constexpr int VP_THREADS = LUT_STEP;
+using LutStream = ChunkStream<(size_t)LUT_STEPS_PER_CHUNK * LUT_STEP * sizeof(LutInstr)>;
 
 template <bool SMEM_VALS>
-__global__ void __launch_bounds__(VP_THREADS) k_values(const LutInstr *__restrict__ prog, const uint32_t *__restrict__ level_off,
-                                                       uint32_t n_levels, uint32_t n_instr, const uint32_t *__restrict__ input_vid,
+__global__ void __launch_bounds__(VP_THREADS) k_values(const LutInstr *__restrict__ prog, uint32_t n_steps, const uint32_t *__restrict__ input_vid,
                                                        const uint8_t *__restrict__ wit, uint32_t n_inputs, uint8_t *__restrict__ vals_g,
-                                                       uint32_t n_vals, uint32_t levels_in_smem) {
+                                                       uint32_t n_vals) {
     extern __shared__ __align__(128) uint8_t smem[];
-    __shared__ uint32_t warp0_ready;
-    LutRing ring;
-    ring.init(smem, prog, n_instr);
-    uint32_t *soff = reinterpret_cast<uint32_t *>(smem + LutRing::BYTES);
-    uint8_t *vals = SMEM_VALS ? smem + LutRing::BYTES + ((size_t)(levels_in_smem + 1) * 4 + 15) / 16 * 16 : vals_g;
+    LutStream stream;
+    stream.init(smem, prog, (size_t)n_steps * LUT_STEP * sizeof(LutInstr));
+    uint8_t *vals = SMEM_VALS ? smem + LutStream::BYTES : vals_g;  // slot n_vals is the scratch target of empty slots
     const uint32_t tid = threadIdx.x;
-    for (uint32_t i = tid; i <= levels_in_smem; i += VP_THREADS) soff[i] = level_off[i];
     if (tid == 0) vals[0] = 0;
     for (uint32_t k = tid; k < n_inputs; k += VP_THREADS) vals[input_vid[k]] = wit[k] & 1;
     __syncthreads();
-    const uint32_t *off = levels_in_smem == n_levels ? soff : level_off;
-
-    auto exec = [&](uint32_t g) {
-        const uint4 u0 = ring.at(g, 0), u1 = ring.at(g, 1), u2 = ring.at(g, 2);  // {dst,in0,in1,in2} {in3,in4,in5,-} {tt}
-        const uint32_t idx = (uint32_t)vals[u0.y] | ((uint32_t)vals[u0.z] << 1) | ((uint32_t)vals[u0.w] << 2) | ((uint32_t)vals[u1.x] << 3) |
-                             ((uint32_t)vals[u1.y] << 4) | ((uint32_t)vals[u1.z] << 5);
-        const uint64_t tt = ((uint64_t)u2.y << 32) | u2.x;
-        vals[u0.x] = (uint8_t)((tt >> idx) & 1);
-    };
-    bool synced = true;  // "a CTA barrier separates us from the previous level's writes"
-    for (uint32_t l = 0; l < n_levels; l++) {
-        const uint32_t s = off[l], e = off[l + 1];
-        if (e == s) continue;
-        if (e - s <= VP_NARROW) {  // narrow level: warp 0 only, warp-synchronous; the other warps run ahead to the next wide level
-            if (tid < 32) {
-                if (tid == 0) ring.advance(s);
-                ring.wait_upto((e - 1) / LUT_LEVEL_MAX);
-                for (uint32_t g = s + tid; g < e; g += 32) exec(g);
-                __syncwarp();
+    const uint32_t n_chunks = (n_steps + LUT_STEPS_PER_CHUNK - 1) / LUT_STEPS_PER_CHUNK;
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        const uint4 *img = reinterpret_cast<const uint4 *>(stream.begin_chunk(c));
+        const uint32_t nst = min((uint32_t)LUT_STEPS_PER_CHUNK, n_steps - c * LUT_STEPS_PER_CHUNK);
+        uint4 u[LUT_STEPS_PER_CHUNK][3];
+#pragma unroll
+        for (int k = 0; k < (int)LUT_STEPS_PER_CHUNK; k++)
+            if (k < (int)nst) {
+                const uint4 *p = img + ((size_t)k * LUT_STEP + tid) * 3;
+                u[k][0] = p[0];  // {dst, in0, in1, in2}
+                u[k][1] = p[1];  // {in3, in4, in5, flags}
+                u[k][2] = p[2];  // {tt lo, tt hi, -, -}
             }
-            synced = false;
-        } else {
-            if (!synced) {  // hand the ring position of warp 0 to everyone (see InstrRing::wait_upto)
-                if (tid == 0) warp0_ready = ring.ready;
-                __syncthreads();
-                ring.ready = max(ring.ready, warp0_ready);
+#pragma unroll
+        for (int k = 0; k < (int)LUT_STEPS_PER_CHUNK; k++)
+            if (k < (int)nst) {
+                const uint32_t idx = (uint32_t)vals[u[k][0].y] | ((uint32_t)vals[u[k][0].z] << 1) | ((uint32_t)vals[u[k][0].w] << 2) |
+                                     ((uint32_t)vals[u[k][1].x] << 3) | ((uint32_t)vals[u[k][1].y] << 4) | ((uint32_t)vals[u[k][1].z] << 5);
+                const uint64_t tt = ((uint64_t)u[k][2].y << 32) | u[k][2].x;
+                vals[u[k][0].x] = (uint8_t)((tt >> idx) & 1);
+                if (u[k][1].w & LUT_F_BAR) __syncthreads();
             }
-            if (tid == 0) ring.advance(s);
-            ring.wait_upto((e - 1) / LUT_LEVEL_MAX);
-            if (s + tid < e) exec(s + tid);
-            __syncthreads();
-            synced = true;
-        }
     }
     __syncthreads();
     if (SMEM_VALS) {
@@ -293,7 +260,6 @@ __global__ void __launch_bounds__(VP_THREADS) k_values(const LutInstr *__restric
 }
 
 size_t launch_values(const DevProgram &P, const uint8_t *wit, uint8_t *vals, cudaStream_t st) {
-    // dynamic shared memory available to one CTA: 227 KB minus the kernels' few static bytes
     const size_t cap = SMEM_DYN_CAP;
     static bool configured = false;
     if (!configured) {
@@ -301,16 +267,13 @@ size_t launch_values(const DevProgram &P, const uint8_t *wit, uint8_t *vals, cud
         cudaFuncSetAttribute(k_values<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
         configured = true;
     }
-    const size_t lvl_bytes = ((size_t)(P.n_lut_levels + 1) * 4 + 15) / 16 * 16;
-    const size_t want = LutRing::BYTES + lvl_bytes + ((P.n_vals + 15) & ~15u);
+    const size_t want = LutStream::BYTES + (((size_t)P.n_vals + 1 + 15) & ~(size_t)15);
     if (want <= cap) {
-        k_values<true><<<1, VP_THREADS, want, st>>>(P.luts, P.lut_level_off, P.n_lut_levels, P.n_luts, P.input_vid, wit, P.n_inputs, vals, P.n_vals, P.n_lut_levels);
+        k_values<true><<<1, VP_THREADS, want, st>>>(P.lut_steps, P.n_lut_steps, P.input_vid, wit, P.n_inputs, vals, P.n_vals);
         return want;
     }
-    const uint32_t lv = LutRing::BYTES + lvl_bytes <= cap ? P.n_lut_levels : 0;
-    const size_t sm = LutRing::BYTES + (lv ? lvl_bytes : 16);
-    k_values<false><<<1, VP_THREADS, sm, st>>>(P.luts, P.lut_level_off, P.n_lut_levels, P.n_luts, P.input_vid, wit, P.n_inputs, vals, P.n_vals, lv);
-    return sm;
+    k_values<false><<<1, VP_THREADS, LutStream::BYTES, st>>>(P.lut_steps, P.n_lut_steps, P.input_vid, wit, P.n_inputs, vals, P.n_vals);
+    return LutStream::BYTES;
 }
 
 // =====================================================================================================================
@@ -319,50 +282,41 @@ size_t launch_values(const DevProgram &P, const uint8_t *wit, uint8_t *vals, cud
 constexpr int LIN_THREADS = 256;
 constexpr int VM_THREADS = 256;
 
-// (a) VM over shared-memory cells: one CTA per slice (u32 lane word = 4 repetitions x 8 players).  The dependent chain
-//     per level is LDS -> XOR -> STS -> barrier; fresh rows arrive through cp.async LOADs issued VM_DELTA levels early;
-//     only rows the item plane needs are written back to the share tensor.
-using VmRing = InstrRing<1, VM_LEVEL_MAX>;
+// (a) VM over shared-memory cells: one CTA per slice (u32 lane word = 4 repetitions x 8 players), one slot per thread per
+//     step.  The dependent chain per level is LDS -> XOR -> STS -> barrier; fresh rows arrive through cp.async LOADs issued
+//     VM_DELTA levels early; only rows the item plane needs are written back to the share tensor.
+using VmStream = ChunkStream<(size_t)VM_STEPS_PER_CHUNK * VM_STEP * sizeof(VmInstr)>;
+static_assert(VM_THREADS == (int)VM_STEP, "one slot per thread");
 
-__global__ void __launch_bounds__(VM_THREADS) k_mask_vm(const VmInstr *__restrict__ prog, const uint32_t *__restrict__ level_off,
-                                                        uint32_t n_levels, uint32_t n_instr, uint32_t *rows32, uint32_t nslices) {
+__global__ void __launch_bounds__(VM_THREADS) k_mask_vm(const VmInstr *__restrict__ prog, uint32_t n_steps, uint32_t *rows32, uint32_t nslices) {
     extern __shared__ __align__(128) uint8_t smem[];
-    VmRing ring;
-    ring.init(smem, prog, n_instr);
-    uint32_t *soff = reinterpret_cast<uint32_t *>(smem + VmRing::BYTES);
-    uint32_t *cells = soff + ((n_levels + 1 + 3) & ~3u);
+    VmStream stream;
+    stream.init(smem, prog, (size_t)n_steps * VM_STEP * sizeof(VmInstr));
+    uint32_t *cells = reinterpret_cast<uint32_t *>(smem + VmStream::BYTES);
     const uint32_t tid = threadIdx.x, w = blockIdx.x;
-    for (uint32_t i = tid; i <= n_levels; i += VM_THREADS) soff[i] = level_off[i];
-    __syncthreads();
-    auto exec = [&](const uint4 in) {  // {dst, a, b, row}
-        if (in.x & VM_LOAD) {
-            __pipeline_memcpy_async(cells + (in.x & ~VM_LOAD), rows32 + (size_t)in.y * nslices + w, 4);
-        } else {
-            const uint32_t v = cells[in.y] ^ cells[in.z];
-            if (in.x != VM_NONE) cells[in.x] = v;
-            if (in.w != VM_NONE) rows32[(size_t)in.w * nslices + w] = v;
-        }
-    };
-    // Software pipeline: while level l executes, the bounds of level l+2 and this thread's first instruction of level
-    // l+1 are already on their way into registers, so the per-level dependent chain is LDS(cells) -> XOR -> STS -> barrier.
-    uint32_t s = soff[0], e = soff[1], e2 = soff[min(2u, n_levels)];
-    if (e2) ring.wait_upto((e2 - 1) / VM_LEVEL_MAX);
-    const uint4 nop = make_uint4(VM_NONE, 0, 0, VM_NONE);
-    uint4 cur = (s + tid < e) ? ring.at(s + tid) : nop;
-    for (uint32_t l = 0; l < n_levels; l++) {
-        const uint32_t e3 = soff[min(l + 3, n_levels)];
-        const uint4 nxt = (e + tid < e2) ? ring.at(e + tid) : nop;
-        if (s + tid < e) exec(cur);
-        for (uint32_t g = s + tid + VM_THREADS; g < e; g += VM_THREADS) exec(ring.at(g));
-        __pipeline_commit();
-        __pipeline_wait_prior(VM_DELTA - 1);
-        __syncthreads();
-        if (tid == 0) ring.advance(e);
-        if (e3 > e2) ring.wait_upto((e3 - 1) / VM_LEVEL_MAX);
-        s = e;
-        e = e2;
-        e2 = e3;
-        cur = nxt;
+    const uint32_t n_chunks = (n_steps + VM_STEPS_PER_CHUNK - 1) / VM_STEPS_PER_CHUNK;
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        const uint4 *img = reinterpret_cast<const uint4 *>(stream.begin_chunk(c));
+        const uint32_t nst = min((uint32_t)VM_STEPS_PER_CHUNK, n_steps - c * VM_STEPS_PER_CHUNK);
+        uint4 ins[VM_STEPS_PER_CHUNK];
+#pragma unroll
+        for (int k = 0; k < (int)VM_STEPS_PER_CHUNK; k++)
+            if (k < (int)nst) ins[k] = img[k * VM_STEP + tid];
+#pragma unroll
+        for (int k = 0; k < (int)VM_STEPS_PER_CHUNK; k++)
+            if (k < (int)nst) {
+                const uint4 in = ins[k];  // {dst | flags, a, b, row}
+                if (in.x & VM_F_LOAD) {
+                    __pipeline_memcpy_async(cells + (in.x & VM_CELL_MASK), rows32 + (size_t)in.y * nslices + w, 4);
+                } else {
+                    const uint32_t v = cells[in.y] ^ cells[in.z];
+                    cells[in.x & VM_CELL_MASK] = v;
+                    if (in.w != VM_ROW_NONE) rows32[(size_t)in.w * nslices + w] = v;
+                }
+                __pipeline_commit();
+                __pipeline_wait_prior(VM_DELTA - 1);
+                if (in.x & VM_F_BAR) __syncthreads();
+            }
     }
 }
 
@@ -409,15 +363,15 @@ int launch_linear(const DevProgram &P, const uint32_t *off_host, uint64_t *rows,
         }
         return (int)P.n_llevels;
     }
-    const size_t vm_smem = VmRing::BYTES + (size_t)((P.n_vm_levels + 1 + 3) & ~3u) * 4 + (size_t)P.vm_cells * 4;
-    if (P.n_vm && vm_smem <= SMEM_DYN_CAP) {
+    const size_t vm_smem = VmStream::BYTES + ((size_t)P.vm_cells + 1) * 4;
+    if (P.n_vm_steps && P.vm_cells < VM_CELL_MASK && vm_smem <= SMEM_DYN_CAP) {
         static bool configured = false;
         if (!configured) {
             cudaFuncSetAttribute(k_mask_vm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DYN_CAP);
             configured = true;
         }
         if (which) *which = 0;
-        k_mask_vm<<<2 * npi, VM_THREADS, vm_smem, st>>>(P.vm, P.vm_level_off, P.n_vm_levels, P.n_vm, reinterpret_cast<uint32_t *>(rows), 2 * npi);
+        k_mask_vm<<<2 * npi, VM_THREADS, vm_smem, st>>>(P.vm_steps, P.n_vm_steps, reinterpret_cast<uint32_t *>(rows), 2 * npi);
         return 1;
     }
     if (which) *which = 1;

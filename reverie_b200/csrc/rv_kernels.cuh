@@ -19,12 +19,10 @@ struct DevProgram {
     const uint32_t *recon_pos = nullptr;  // k -> online position of the k-th reconstruct()
     const uint32_t *input_pos = nullptr;  // k -> online position of the k-th input()
     const uint32_t *input_vid = nullptr;  // k -> value id
-    const LutInstr *luts = nullptr;        // value-plane LUT program
-    const uint32_t *lut_level_off = nullptr;
-    uint32_t n_luts = 0, n_lut_levels = 0;
-    const VmInstr *vm = nullptr;           // mask-plane VM program (empty when the circuit has no Add/Sub on masks)
-    const uint32_t *vm_level_off = nullptr;
-    uint32_t n_vm = 0, n_vm_levels = 0, vm_cells = 0;
+    const LutInstr *lut_steps = nullptr;   // value-plane step stream (n_lut_steps * LUT_STEP slots)
+    uint32_t n_lut_steps = 0;
+    const VmInstr *vm_steps = nullptr;     // mask-plane VM step stream (n_vm_steps * VM_STEP slots); empty without Add/Sub
+    uint32_t n_vm_steps = 0, vm_cells = 0;
     uint32_t n_vgates = 0, n_vlevels = 0, n_lgates = 0, n_llevels = 0;
     uint32_t n_masks = 0, n_rows = 0, n_vals = 0, n_online = 0, n_pre = 0, n_inputs = 0, n_recon = 0;
     uint32_t max_llevel_width = 0;
