@@ -93,8 +93,11 @@ typedef struct rv_circuit_stats {
     uint64_t n_assert;       /* GF(2) AssertZero                                  */
     uint64_t n_masks;        /* GF(2) PRG masks drawn per (rep, player)           */
     uint64_t n_linear;       /* materialised linear (XOR) mask nodes              */
-    uint64_t value_depth;    /* levels of the plaintext plane                     */
-    uint64_t linear_depth;   /* levels of the mask plane                          */
+    uint64_t value_depth;    /* levels of the plaintext plane after LUT mapping   */
+    uint64_t linear_depth;   /* levels of the mask plane after XOR-cut mapping    */
+    uint64_t plain_value_depth;   /* ... of the circuit's own 2-input gates       */
+    uint64_t plain_linear_depth;
+    uint64_t n_luts, n_lut_steps, n_vm_steps, vm_cells; /* sizes of the device programs */
     uint64_t online_bytes;   /* bytes hashed per repetition, online stream        */
     uint64_t pre_bytes;      /* bytes hashed per repetition, preprocessing stream */
     uint64_t algorithmic_bytes; /* SURVEY.md 8(d) HBM bytes for one proof (all 256 reps) */
@@ -104,7 +107,7 @@ int rv_circuit_get_stats(const rv_circuit *c, rv_circuit_stats *out);
 
 /* Debug/test tap: copy one compiled table to the host (tests/ re-executes the tables in numpy).  `what` is one of
  * the RV_TAB_* ids; call with buf == NULL to obtain the byte length. */
-enum rv_table { RV_TAB_VGATES = 0, RV_TAB_VLEVELS = 1, RV_TAB_LGATES = 2, RV_TAB_LLEVELS = 3, RV_TAB_ITEMS = 4,
+enum rv_table { RV_TAB_VGATES = 0, RV_TAB_LUTS = 1, RV_TAB_XGATES = 2, RV_TAB_XLEVELS = 3, RV_TAB_ITEMS = 4,
                 RV_TAB_RECON_POS = 5, RV_TAB_INPUT_POS = 6, RV_TAB_INPUT_VID = 7 };
 int rv_circuit_export(const rv_circuit *c, int what, void *buf, size_t *len);
 

@@ -14,8 +14,9 @@ TOTAL_REPS, ONLINE_REPS, PACKED_REPS, PLAYERS = 256, 40, 32, 8
 
 class CircuitStats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in (
-        "n_ops", "n_and", "n_inputs", "n_assert", "n_masks", "n_linear", "value_depth", "linear_depth", "online_bytes",
-        "pre_bytes", "algorithmic_bytes", "device_bytes")]
+        "n_ops", "n_and", "n_inputs", "n_assert", "n_masks", "n_linear", "value_depth", "linear_depth", "plain_value_depth",
+        "plain_linear_depth", "n_luts", "n_lut_steps", "n_vm_steps", "vm_cells", "online_bytes", "pre_bytes", "algorithmic_bytes",
+        "device_bytes")]
 
 
 class KernelTime(C.Structure):

@@ -123,20 +123,18 @@ extern "C" int rv_circuit_compile(const rv_op *ops, size_t n_ops, size_t z64_cel
     c->device = g_device;
     cudaSetDevice(c->device);
     DevProgram &D = c->dev;
-    if ((rc = upload(c, P.vgates, &D.vgates)) || (rc = upload(c, P.vlevel_off, &D.vlevel_off)) || (rc = upload(c, P.lgates, &D.lgates)) ||
-        (rc = upload(c, P.llevel_off, &D.llevel_off)) || (rc = upload(c, P.items, &D.items)) || (rc = upload(c, c->mul_pos, &D.mul_pos)) ||
-        (rc = upload(c, P.recon_pos, &D.recon_pos)) || (rc = upload(c, P.input_pos, &D.input_pos)) ||
+    if ((rc = upload(c, P.xgates, &D.xgates)) || (rc = upload(c, P.xlevel_off, &D.xlevel_off)) || (rc = upload(c, P.items, &D.items)) ||
+        (rc = upload(c, c->mul_pos, &D.mul_pos)) || (rc = upload(c, P.recon_pos, &D.recon_pos)) || (rc = upload(c, P.input_pos, &D.input_pos)) ||
         (rc = upload(c, P.input_vid, &D.input_vid)) || (rc = upload(c, P.vm_steps, &D.vm_steps)) || (rc = upload(c, P.lut_steps, &D.lut_steps))) {
         rv_circuit_free(c);
         return rc;
     }
-    D.n_vgates = (uint32_t)P.vgates.size();
-    D.n_vlevels = (uint32_t)P.vlevel_off.size() - 1;
-    D.n_lgates = (uint32_t)P.lgates.size();
-    D.n_llevels = (uint32_t)P.llevel_off.size() - 1;
+    D.n_xgates = (uint32_t)P.xgates.size();
+    D.n_llevels = (uint32_t)P.xlevel_off.size() - 1;
     D.n_lut_steps = P.n_lut_steps;
     D.n_vm_steps = P.n_vm_steps;
     D.vm_cells = P.vm_cells;
+    D.n_lin = P.n_lin;
     D.n_masks = P.n_masks;
     D.n_rows = P.n_rows;
     D.n_vals = P.n_vals;
@@ -157,8 +155,14 @@ extern "C" int rv_circuit_get_stats(const rv_circuit *c, rv_circuit_stats *o) {
     o->n_assert = P.n_assert;
     o->n_masks = P.n_masks;
     o->n_linear = P.n_lin;
-    o->value_depth = P.lut_depth;
-    o->linear_depth = P.llevel_off.size() - 1;
+    o->value_depth = P.lut_level_off.empty() ? 0 : P.lut_level_off.size() - 1;
+    o->linear_depth = P.xlevel_off.size() - 1;
+    o->plain_value_depth = P.plain_value_depth;
+    o->plain_linear_depth = P.plain_linear_depth;
+    o->n_luts = P.n_lut_steps ? P.lut_steps.size() : 0;
+    o->n_lut_steps = P.n_lut_steps;
+    o->n_vm_steps = P.n_vm_steps;
+    o->vm_cells = P.vm_cells;
     o->online_bytes = P.n_online;
     o->pre_bytes = P.n_pre;
     o->algorithmic_bytes = P.algorithmic_bytes;
@@ -173,9 +177,9 @@ extern "C" int rv_circuit_export(const rv_circuit *c, int what, void *buf, size_
     size_t n = 0;
     switch (what) {
         case RV_TAB_VGATES: src = P.vgates.data(); n = P.vgates.size() * sizeof(VGate); break;
-        case RV_TAB_VLEVELS: src = P.vlevel_off.data(); n = P.vlevel_off.size() * 4; break;
-        case RV_TAB_LGATES: src = P.lgates.data(); n = P.lgates.size() * sizeof(LGate); break;
-        case RV_TAB_LLEVELS: src = P.llevel_off.data(); n = P.llevel_off.size() * 4; break;
+        case RV_TAB_LUTS: src = P.luts.data(); n = P.luts.size() * sizeof(LutInstr); break;
+        case RV_TAB_XGATES: src = P.xgates.data(); n = P.xgates.size() * sizeof(XGate); break;
+        case RV_TAB_XLEVELS: src = P.xlevel_off.data(); n = P.xlevel_off.size() * 4; break;
         case RV_TAB_ITEMS: src = P.items.data(); n = P.items.size() * sizeof(Item); break;
         case RV_TAB_RECON_POS: src = P.recon_pos.data(); n = P.recon_pos.size() * 4; break;
         case RV_TAB_INPUT_POS: src = P.input_pos.data(); n = P.input_pos.size() * 4; break;
@@ -212,6 +216,8 @@ struct rv_session {
     uint8_t *d_wit = nullptr, *d_seeds = nullptr, *d_pkeys = nullptr, *d_vals = nullptr;
     uint32_t *d_ks = nullptr, *d_lane_mask = nullptr;
     uint64_t *d_rows = nullptr;
+    uint32_t *d_fresh_sm = nullptr, *d_exp_sm = nullptr;  // slice-major staging of the mask VM
+    size_t pitch_fresh = 0, pitch_exp = 0;
     uint8_t *d_on = nullptr, *d_pre = nullptr;
     size_t pitch_on = 0, pitch_pre = 0;
     uint32_t *d_cv_on = nullptr, *d_cv_pre = nullptr, n_chunks_on = 1, n_chunks_pre = 1;
@@ -297,6 +303,11 @@ extern "C" int rv_session_create(const rv_circuit *c, int first_instance, int n_
     s->len_corrs = P.n_pre / 8 + 1;
     s->len_inputs = (uint32_t)(P.n_inputs / 8 + 1);
     s->proof_len = ProofLayout{s->len_recons, s->len_corrs, s->len_inputs}.total();
+    if (linear_uses_vm(c->dev)) {
+        s->pitch_fresh = round_up((size_t)P.n_masks + 128, 128);
+        s->pitch_exp = round_up((size_t)P.n_lin + 32, 32);
+        if ((rc = dalloc(s, &s->d_fresh_sm, s->pitch_fresh * 2 * s->npi)) || (rc = dalloc(s, &s->d_exp_sm, s->pitch_exp * 2 * s->npi))) return bail(rc);
+    }
     if ((rc = dalloc(s, &s->d_wit, P.n_inputs)) || (rc = dalloc(s, &s->d_seeds, (size_t)s->nreps * 16)) ||
         (rc = dalloc(s, &s->d_pkeys, (size_t)s->nreps * 128)) || (rc = dalloc(s, &s->d_vals, round_up((size_t)P.n_vals + 1, 16))) ||
         (rc = dalloc(s, &s->d_ks, (size_t)2 * s->npi * 1408)) || (rc = dalloc(s, &s->d_lane_mask, 2 * s->npi)) ||
@@ -429,7 +440,7 @@ extern "C" int rv_session_commit(rv_session *s) {
     CU(cudaStreamWaitEvent(s->st_val, s->ev_upload, 0));
     if (s->ever_committed) CU(cudaStreamWaitEvent(s->st_val, s->ev_items, 0));  // the previous proof's item plane still reads d_vals
     {
-        Scope k(s, "values", (uint64_t)P.luts.size() * sizeof(LutInstr), 1, s->st_val);
+        Scope k(s, "values", (uint64_t)P.lut_steps.size() * sizeof(LutInstr), 1, s->st_val);
         launch_values(D, s->d_wit, s->d_vals, s->st_val);
     }
     CU(cudaEventRecord(s->ev_vals, s->st_val));
@@ -441,12 +452,12 @@ extern "C" int rv_session_commit(rv_session *s) {
     }
     {
         Scope k(s, "mask_gen", (uint64_t)P.n_masks * s->npi * 8);
-        launch_mask_gen(s->d_ks, s->d_lane_mask, nslices, P.n_masks, s->d_rows, s->st);
+        launch_mask_gen(s->d_ks, s->d_lane_mask, nslices, P.n_masks, s->d_rows, s->d_fresh_sm, s->pitch_fresh, s->st);
     }
     if (D.n_llevels) {
-        const double avg_width = (double)D.n_lgates / D.n_llevels;
-        Scope k(s, "linear", (uint64_t)P.n_lin * s->npi * 8 * 3, avg_width < 4096.0 ? 1 : D.n_llevels);
-        launch_linear(D, P.llevel_off.data(), s->d_rows, s->npi, s->st, nullptr);
+        const double avg_width = (double)D.n_xgates / D.n_llevels;
+        Scope k(s, "linear", (uint64_t)P.n_lin * s->npi * 8 * 3, avg_width < 4096.0 ? (s->d_fresh_sm ? 2 : 1) : D.n_llevels);
+        launch_linear(D, P.xlevel_off.data(), s->d_rows, s->npi, s->d_fresh_sm, s->pitch_fresh, s->d_exp_sm, s->pitch_exp, s->st, nullptr);
     }
     CU(cudaStreamWaitEvent(s->st, s->ev_vals, 0));
     {

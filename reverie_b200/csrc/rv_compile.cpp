@@ -12,6 +12,7 @@ constexpr uint32_t ZERO_MID = 0xFFFFFFFFu;  // "the all-zero mask" until row num
 constexpr uint32_t LIN_BASE = 0x80000000u;  // provisional ids of linear nodes: LIN_BASE + creation index
 constexpr uint32_t VREF_ZERO = 0;           // vid 0, not negated
 constexpr uint32_t VREF_ONE = 1;            // vid 0, negated
+constexpr uint32_t NONE32 = 0xFFFFFFFFu;
 
 struct Cell {
     uint32_t vref;  // value id << 1 | negate
@@ -22,115 +23,29 @@ struct Cell {
 constexpr uint64_t B_AND = 2048 + 16, B_XOR = 1536 + 16, B_UNARY = 1024 + 16, B_INPUT = 768 + 16, B_ASSERT = 768 + 16,
                    B_LEAF = 512 + 16;
 
-// Mask-plane VM: the XOR network re-expressed over a small pool of shared-memory cells so that the dependent chain of
-// the level-synchronous walk is LDS -> XOR -> STS instead of L2 round trips.  Fresh rows are brought into cells by
-// asynchronous LOADs issued VM_DELTA levels early; only rows that the item plane reads are written back (`row`).
-// Cells are assigned by a linear scan over levels: a cell is free again one level after its value's last use.
-void build_mask_vm(Program &P) {
-    P.vm.clear();
-    P.vm_level_off.clear();
-    P.vm_cells = 0;
-    const uint32_t depth = (uint32_t)P.llevel_off.size() - 1;
-    if (depth == 0) return;
-    const uint32_t n_rows = P.n_rows, n_masks = P.n_masks, n_lin = P.n_lin;
-    const uint32_t NEVER = 0xFFFFFFFFu;
-    std::vector<uint32_t> first(n_rows, NEVER), last(n_rows, 0);
-    std::vector<uint8_t> exported(n_rows, 0);
-    for (uint32_t l = 0; l < depth; l++)
-        for (uint32_t g = P.llevel_off[l]; g < P.llevel_off[l + 1]; g++)
-            for (uint32_t r : {P.lgates[g].a, P.lgates[g].b}) {
-                if (first[r] == NEVER) first[r] = l + 1;
-                last[r] = l + 1;
-            }
-    for (const Item &it : P.items) {
-        if (it.kind == ITEM_MUL) exported[it.ra] = exported[it.rb] = 1;
-        else if (it.kind == ITEM_ASSERT) exported[it.ra] = 1;
-    }
-    // VM level of an original level L (1-based) is L + VM_DELTA - 1; the LOAD of a fresh row first used at L sits at L - 1.
-    const uint32_t n_levels = depth + VM_DELTA;
-    std::vector<uint32_t> cnt(n_levels + 1, 0);
-    for (uint32_t r = 0; r < n_masks; r++)
-        if (first[r] != NEVER) cnt[first[r] - 1]++;
-    for (uint32_t l = 0; l < depth; l++) cnt[l + VM_DELTA] += P.llevel_off[l + 1] - P.llevel_off[l];
-    P.vm_level_off.assign(n_levels + 1, 0);
-    for (uint32_t l = 0; l < n_levels; l++) P.vm_level_off[l + 1] = P.vm_level_off[l] + cnt[l];
-    P.vm.resize(P.vm_level_off[n_levels]);
-    std::vector<uint32_t> cursor(P.vm_level_off.begin(), P.vm_level_off.end() - 1);
-    // provisional instructions hold rows; cells are assigned in the scan below
-    for (uint32_t r = 0; r < n_masks; r++)
-        if (first[r] != NEVER) P.vm[cursor[first[r] - 1]++] = VmInstr{VM_LOAD, r, 0, 0};
-    for (uint32_t l = 0; l < depth; l++)
-        for (uint32_t g = P.llevel_off[l]; g < P.llevel_off[l + 1]; g++)
-            P.vm[cursor[l + VM_DELTA]++] = VmInstr{P.lgates[g].dst, P.lgates[g].a, P.lgates[g].b, 0};
-    std::vector<uint32_t> cell_of(n_rows, VM_NONE);
-    std::vector<std::vector<uint32_t>> free_at(n_levels + 2);
-    std::vector<uint32_t> free_list;
-    uint32_t n_cells = 0;
-    auto alloc = [&]() -> uint32_t {
-        if (!free_list.empty()) {
-            uint32_t c = free_list.back();
-            free_list.pop_back();
-            return c;
-        }
-        return n_cells++;
-    };
-    for (uint32_t l = 0; l < n_levels; l++) {
-        for (uint32_t c : free_at[l]) free_list.push_back(c);
-        free_at[l].clear();
-        free_at[l].shrink_to_fit();
-        for (uint32_t k = P.vm_level_off[l]; k < P.vm_level_off[l + 1]; k++) {
-            VmInstr &in = P.vm[k];
-            if (in.dst == VM_LOAD) {
-                const uint32_t r = in.a, c = alloc();
-                cell_of[r] = c;
-                free_at[last[r] + VM_DELTA].push_back(c);  // last use at VM level last + DELTA - 1
-                in.dst = VM_LOAD | c;
-            } else {
-                const uint32_t r = in.dst;
-                in.a = cell_of[in.a];
-                in.b = cell_of[in.b];
-                in.row = exported[r] ? r : VM_NONE;
-                if (first[r] != NEVER) {
-                    const uint32_t c = alloc();
-                    cell_of[r] = c;
-                    free_at[last[r] + VM_DELTA].push_back(c);
-                    in.dst = c;
-                } else {
-                    in.dst = VM_NONE;
-                }
-            }
-        }
-    }
-    (void)n_lin;
-    P.vm_cells = n_cells;
-}
-
-// Split levels wider than `maxw` into consecutive sub-levels (always legal: instructions of a level are independent).
-static void split_levels(std::vector<uint32_t> &off, uint32_t maxw) {
-    if (off.size() < 2) return;
-    std::vector<uint32_t> out;
-    out.push_back(off[0]);
-    for (size_t l = 0; l + 1 < off.size(); l++) {
-        uint32_t s = off[l];
-        const uint32_t e = off[l + 1];
-        while (e - s > maxw) {
-            s += maxw;
-            out.push_back(s);
-        }
-        out.push_back(e);
-    }
-    off.swap(out);
-}
-
-// ---- value-plane technology mapping: K-feasible cuts, depth first (the FPGA "priority cuts" scheme) ------------------
-constexpr int LUT_K = 6, CUTS_PER_NODE = 6;
+// =====================================================================================================================
+//  Technology mapping: K-feasible cuts, depth first (the FPGA "priority cuts" scheme), shared by both planes.
+//  A network is a topologically ordered list of 2-input gates over node ids; id 0 is the constant 0 and is free.
+// =====================================================================================================================
+constexpr int MAP_K = 6, CUTS_PER_NODE = 6;
+struct MGate {
+    uint32_t out, a, b;  // a, b = id << 1 | negate
+    uint32_t op;         // 0 xor, 1 and
+};
+struct MNode {  // one mapped node: out = f(leaf[0..n)), f given by its truth table over the leaves
+    uint32_t out;
+    uint32_t leaf[MAP_K];
+    uint32_t n;
+    uint32_t level;
+    uint64_t tt;
+};
 struct Cut {
-    uint32_t leaf[LUT_K];
+    uint32_t leaf[MAP_K];
     uint8_t n;
     uint32_t depth;
 };
 
-static bool merge_cuts(const Cut &a, const Cut &b, Cut &o) {
+bool merge_cuts(const Cut &a, const Cut &b, Cut &o) {
     int i = 0, j = 0, n = 0;
     while (i < a.n || j < b.n) {
         uint32_t v;
@@ -141,48 +56,44 @@ static bool merge_cuts(const Cut &a, const Cut &b, Cut &o) {
             i++;
             j++;
         }
-        if (n == LUT_K) return false;
+        if (n == MAP_K) return false;
         o.leaf[n++] = v;
     }
     o.n = (uint8_t)n;
     return true;
 }
 
-void build_value_luts(Program &P, const std::vector<VGate> &vg /* creation (topological) order */, bool map) {
-    const uint32_t n_vals = P.n_vals;
-    std::vector<uint32_t> gate_of(n_vals, 0xFFFFFFFFu);  // vid -> index into vg, or none for leaves (inputs, constant)
-    for (uint32_t g = 0; g < vg.size(); g++) gate_of[vg[g].dst] = g;
-    std::vector<uint8_t> required(n_vals, 0);
-    for (const Item &it : P.items) {
-        required[it.va >> 1] = 1;
-        if (it.kind == ITEM_MUL) required[it.vb >> 1] = 1;
-    }
-    std::vector<uint32_t> depth(n_vals, 0);
-    std::vector<Cut> best(vg.size());  // chosen cut per gate
+// `required` marks the nodes some consumer outside the network reads; on return it also marks every leaf the chosen
+// cover uses.  With map == false every gate keeps its own two inputs as its cut (no collapsing).
+void map_network(uint32_t n_ids, const std::vector<MGate> &g, std::vector<uint8_t> &required, bool map, std::vector<MNode> &out) {
+    std::vector<uint32_t> gate_of(n_ids, NONE32);
+    for (uint32_t i = 0; i < g.size(); i++) gate_of[g[i].out] = i;
+    std::vector<uint32_t> depth(n_ids, 0);
+    std::vector<Cut> best(g.size());
     if (map) {
-        std::vector<Cut> cuts((size_t)vg.size() * CUTS_PER_NODE);
-        std::vector<uint8_t> ncuts(vg.size(), 0);
-        auto cut_set = [&](uint32_t vid, Cut *tmp, int &n) {  // the node's stored cuts plus its trivial cut
+        std::vector<Cut> cuts((size_t)g.size() * CUTS_PER_NODE);
+        std::vector<uint8_t> ncuts(g.size(), 0);
+        auto cut_set = [&](uint32_t id, Cut *tmp, int &n) {  // the node's stored cuts plus its trivial cut
             n = 0;
-            if (vid == 0) {  // the constant contributes no leaf
+            if (id == 0) {  // the constant contributes no leaf
                 tmp[n].n = 0;
                 tmp[n].depth = 0;
                 n++;
                 return;
             }
-            const uint32_t g = gate_of[vid];
-            if (g != 0xFFFFFFFFu)
-                for (int i = 0; i < ncuts[g]; i++) tmp[n++] = cuts[(size_t)g * CUTS_PER_NODE + i];
+            const uint32_t gi = gate_of[id];
+            if (gi != NONE32)
+                for (int i = 0; i < ncuts[gi]; i++) tmp[n++] = cuts[(size_t)gi * CUTS_PER_NODE + i];
             tmp[n].n = 1;
-            tmp[n].leaf[0] = vid;
+            tmp[n].leaf[0] = id;
             tmp[n].depth = 0;
             n++;
         };
         Cut ca[CUTS_PER_NODE + 1], cb[CUTS_PER_NODE + 1], cand[(CUTS_PER_NODE + 1) * (CUTS_PER_NODE + 1)];
-        for (uint32_t g = 0; g < vg.size(); g++) {
+        for (uint32_t gi = 0; gi < g.size(); gi++) {
             int na, nb, nc = 0;
-            cut_set(vg[g].a >> 1, ca, na);
-            cut_set(vg[g].b >> 1, cb, nb);
+            cut_set(g[gi].a >> 1, ca, na);
+            cut_set(g[gi].b >> 1, cb, nb);
             for (int i = 0; i < na; i++)
                 for (int j = 0; j < nb; j++) {
                     Cut &o = cand[nc];
@@ -196,44 +107,43 @@ void build_value_luts(Program &P, const std::vector<VGate> &vg /* creation (topo
                 }
             std::sort(cand, cand + nc, [](const Cut &x, const Cut &y) { return x.depth != y.depth ? x.depth < y.depth : x.n < y.n; });
             const int keep = std::min(nc, CUTS_PER_NODE);
-            for (int i = 0; i < keep; i++) cuts[(size_t)g * CUTS_PER_NODE + i] = cand[i];
-            ncuts[g] = (uint8_t)keep;
-            best[g] = cand[0];
-            depth[vg[g].dst] = cand[0].depth;
+            for (int i = 0; i < keep; i++) cuts[(size_t)gi * CUTS_PER_NODE + i] = cand[i];
+            ncuts[gi] = (uint8_t)keep;
+            best[gi] = cand[0];
+            depth[g[gi].out] = cand[0].depth;
         }
     } else {
-        for (uint32_t g = 0; g < vg.size(); g++) {
+        for (uint32_t gi = 0; gi < g.size(); gi++) {
             Cut c;
             c.n = 0;
-            uint32_t a = vg[g].a >> 1, b = vg[g].b >> 1;
+            uint32_t a = g[gi].a >> 1, b = g[gi].b >> 1;
             if (a > b) std::swap(a, b);
             if (a) c.leaf[c.n++] = a;
             if (b && b != a) c.leaf[c.n++] = b;
             uint32_t d = 0;
             for (int k = 0; k < c.n; k++) d = std::max(d, depth[c.leaf[k]]);
             c.depth = d + 1;
-            best[g] = c;
-            depth[vg[g].dst] = c.depth;
+            best[gi] = c;
+            depth[g[gi].out] = c.depth;
         }
     }
-    // cover: walk backwards from the values the item plane reads
-    for (size_t g = vg.size(); g-- > 0;) {
-        if (!required[vg[g].dst]) continue;
-        for (int k = 0; k < best[g].n; k++) required[best[g].leaf[k]] = 1;
+    // cover: walk backwards from the required nodes
+    for (size_t gi = g.size(); gi-- > 0;) {
+        if (!required[g[gi].out]) continue;
+        for (int k = 0; k < best[gi].n; k++) required[best[gi].leaf[k]] = 1;
     }
-    // final levels (over the chosen cover) and truth tables
+    // levels over the chosen cover and truth tables (cone simulated on the 64 input patterns at once)
     static const uint64_t PAT[6] = {0xAAAAAAAAAAAAAAAAull, 0xCCCCCCCCCCCCCCCCull, 0xF0F0F0F0F0F0F0F0ull,
                                     0xFF00FF00FF00FF00ull, 0xFFFF0000FFFF0000ull, 0xFFFFFFFF00000000ull};
-    std::vector<uint32_t> level(n_vals, 0), stamp(n_vals, 0);
-    std::vector<uint64_t> tmp(n_vals, 0);
-    std::vector<LutInstr> luts;
-    std::vector<uint32_t> lut_level;
+    std::vector<uint32_t> level(n_ids, 0), stamp(n_ids, 0);
+    std::vector<uint64_t> tmp(n_ids, 0);
     std::vector<uint32_t> stack;
-    uint32_t epoch = 0, max_level = 0;
-    for (uint32_t g = 0; g < vg.size(); g++) {
-        const uint32_t out = vg[g].dst;
-        if (!required[out]) continue;
-        const Cut &c = best[g];
+    uint32_t epoch = 0;
+    out.clear();
+    for (uint32_t gi = 0; gi < g.size(); gi++) {
+        const uint32_t o = g[gi].out;
+        if (!required[o]) continue;
+        const Cut &c = best[gi];
         epoch++;
         uint32_t lv = 0;
         for (int k = 0; k < c.n; k++) {
@@ -243,16 +153,15 @@ void build_value_luts(Program &P, const std::vector<VGate> &vg /* creation (topo
         }
         stamp[0] = epoch;
         tmp[0] = 0;
-        // evaluate the cone bottom-up with an explicit stack (post-order)
         stack.clear();
-        stack.push_back(out);
-        while (!stack.empty()) {
+        stack.push_back(o);
+        while (!stack.empty()) {  // post-order evaluation of the cone
             const uint32_t v = stack.back();
             if (stamp[v] == epoch) {
                 stack.pop_back();
                 continue;
             }
-            const VGate &gt = vg[gate_of[v]];
+            const MGate &gt = g[gate_of[v]];
             const uint32_t a = gt.a >> 1, b = gt.b >> 1;
             const bool ra = stamp[a] == epoch, rb = stamp[b] == epoch;
             if (ra && rb) {
@@ -265,58 +174,154 @@ void build_value_luts(Program &P, const std::vector<VGate> &vg /* creation (topo
                 if (!rb) stack.push_back(b);
             }
         }
-        LutInstr li;
-        li.dst = out;
-        for (int k = 0; k < 6; k++) li.in[k] = k < c.n ? c.leaf[k] : 0;
-        li.pad = 0;
-        li.pad2 = 0;
-        li.tt = tmp[out];
-        level[out] = lv + 1;
-        max_level = std::max(max_level, lv + 1);
-        luts.push_back(li);
-        lut_level.push_back(lv + 1);
+        MNode m;
+        m.out = o;
+        m.n = c.n;
+        for (int k = 0; k < MAP_K; k++) m.leaf[k] = k < c.n ? c.leaf[k] : 0;
+        m.level = lv + 1;
+        m.tt = tmp[o];
+        level[o] = lv + 1;
+        out.push_back(m);
     }
-    // counting sort by level
-    P.lut_depth = max_level;
-    P.lut_level_off.assign(max_level + 1, 0);
-    std::vector<uint32_t> cursor(max_level + 2, 0);
-    for (uint32_t l : lut_level) cursor[l]++;
+}
+
+// counting sort of mapped nodes by level; returns offsets (levels 1..depth -> [off[l-1], off[l]))
+std::vector<uint32_t> sort_by_level(const std::vector<MNode> &nodes, std::vector<uint32_t> &order) {
+    uint32_t depth = 0;
+    for (const MNode &m : nodes) depth = std::max(depth, m.level);
+    std::vector<uint32_t> cnt(depth + 2, 0), off(depth + 1, 0);
+    for (const MNode &m : nodes) cnt[m.level]++;
     uint32_t run = 0;
-    for (uint32_t l = 1; l <= max_level; l++) {
-        const uint32_t c = cursor[l];
+    std::vector<uint32_t> cursor(depth + 1, 0);
+    for (uint32_t l = 1; l <= depth; l++) {
         cursor[l] = run;
-        P.lut_level_off[l - 1] = run;
-        run += c;
+        off[l - 1] = run;
+        run += cnt[l];
     }
-    P.lut_level_off[max_level] = run;
-    P.luts.resize(luts.size());
-    for (size_t i = 0; i < luts.size(); i++) P.luts[cursor[lut_level[i]]++] = luts[i];
-    split_levels(P.lut_level_off, LUT_LEVEL_MAX);
+    off[depth] = run;
+    order.resize(nodes.size());
+    for (uint32_t i = 0; i < nodes.size(); i++) order[i] = cursor[nodes[i].level]++;  // position of node i in level order
+    return off;
+}
+
+// =====================================================================================================================
+//  Mask-plane VM: the mapped XOR network re-expressed over a small pool of shared-memory cells so that the dependent
+//  chain of the level-synchronous walk is LDS -> XOR -> STS instead of L2 round trips.  Fresh rows are brought into cells
+//  by asynchronous LOADs issued VM_DELTA levels early; only rows that the item plane reads are written back (`row`).
+//  Cells are assigned by a linear scan over levels: a cell is free again one level after its value's last use.
+// =====================================================================================================================
+void build_mask_vm(Program &P) {
+    P.vm.clear();
+    P.vm_level_off.clear();
+    P.vm_cells = 0;
+    const uint32_t depth = (uint32_t)P.xlevel_off.size() - 1;
+    if (depth == 0) return;
+    const uint32_t n_rows = P.n_rows, n_masks = P.n_masks, zero = P.zero_row();
+    std::vector<uint32_t> first(n_rows, NONE32), last(n_rows, 0);
+    std::vector<uint8_t> exported(n_rows, 0);
+    for (uint32_t l = 0; l < depth; l++)
+        for (uint32_t gi = P.xlevel_off[l]; gi < P.xlevel_off[l + 1]; gi++)
+            for (uint32_t r : P.xgates[gi].in) {
+                if (r == zero) continue;
+                if (first[r] == NONE32) first[r] = l + 1;
+                last[r] = l + 1;
+            }
+    for (const Item &it : P.items) {
+        if (it.kind == ITEM_MUL) exported[it.ra] = exported[it.rb] = 1;
+        else if (it.kind == ITEM_ASSERT) exported[it.ra] = 1;
+    }
+    // VM level of an original level L (1-based) is L + VM_DELTA - 1; the LOAD of a fresh row first used at L sits at L - 1.
+    const uint32_t n_levels = depth + VM_DELTA;
+    std::vector<uint32_t> cnt(n_levels + 1, 0);
+    for (uint32_t r = 0; r < n_masks; r++)
+        if (first[r] != NONE32) cnt[first[r] - 1]++;
+    for (uint32_t l = 0; l < depth; l++) cnt[l + VM_DELTA] += P.xlevel_off[l + 1] - P.xlevel_off[l];
+    P.vm_level_off.assign(n_levels + 1, 0);
+    for (uint32_t l = 0; l < n_levels; l++) P.vm_level_off[l + 1] = P.vm_level_off[l] + cnt[l];
+    P.vm.resize(P.vm_level_off[n_levels]);
+    std::vector<uint32_t> cursor(P.vm_level_off.begin(), P.vm_level_off.end() - 1);
+    // provisional instructions hold rows; cells are assigned in the scan below.  Cell 0 is the constant zero.
+    VmInstr blank;
+    std::memset(&blank, 0, sizeof blank);
+    for (uint32_t r = 0; r < n_masks; r++)
+        if (first[r] != NONE32) {
+            VmInstr in = blank;
+            in.dst = VM_F_LOAD;
+            in.in[0] = r;
+            in.row = VM_ROW_NONE;
+            P.vm[cursor[first[r] - 1]++] = in;
+        }
+    for (uint32_t l = 0; l < depth; l++)
+        for (uint32_t gi = P.xlevel_off[l]; gi < P.xlevel_off[l + 1]; gi++) {
+            VmInstr in = blank;
+            in.dst = P.xgates[gi].dst;
+            for (int k = 0; k < 6; k++) in.in[k] = P.xgates[gi].in[k];
+            P.vm[cursor[l + VM_DELTA]++] = in;
+        }
+    std::vector<uint32_t> cell_of(n_rows, NONE32);
+    cell_of[zero] = 0;
+    std::vector<std::vector<uint32_t>> free_at(n_levels + 2);
+    std::vector<uint32_t> free_list;
+    uint32_t n_cells = 1;  // cell 0 = zero
+    auto alloc = [&]() -> uint32_t {
+        if (!free_list.empty()) {
+            uint32_t c = free_list.back();
+            free_list.pop_back();
+            return c;
+        }
+        return n_cells++;
+    };
+    for (uint32_t l = 0; l < n_levels; l++) {
+        for (uint32_t c : free_at[l]) free_list.push_back(c);
+        std::vector<uint32_t>().swap(free_at[l]);
+        for (uint32_t k = P.vm_level_off[l]; k < P.vm_level_off[l + 1]; k++) {
+            VmInstr &in = P.vm[k];
+            if (in.dst == VM_F_LOAD) {
+                const uint32_t r = in.in[0], c = alloc();
+                cell_of[r] = c;
+                free_at[last[r] + VM_DELTA].push_back(c);  // last use at VM level last + DELTA - 1
+                in.dst = VM_F_LOAD | c;
+            } else {
+                const uint32_t r = in.dst;
+                for (int q = 0; q < 6; q++) in.in[q] = cell_of[in.in[q]];
+                in.row = exported[r] ? r : VM_ROW_NONE;
+                if (first[r] != NONE32) {
+                    const uint32_t c = alloc();
+                    cell_of[r] = c;
+                    free_at[last[r] + VM_DELTA].push_back(c);
+                    in.dst = c;
+                } else {
+                    in.dst = VM_CELL_MASK;  // no consumer in the network: resolved to the scratch cell when the steps are emitted
+                }
+            }
+        }
+    }
+    P.vm_cells = n_cells;
 }
 
 // ---- step streams (see rv_compile.h) ---------------------------------------------------------------------------------
-static void emit_vm_steps(Program &P) {
+void emit_vm_steps(Program &P) {
     P.vm_steps.clear();
     P.n_vm_steps = 0;
     if (P.vm.empty()) return;
     const uint32_t scratch = P.vm_cells;  // one extra cell absorbs the writes of empty slots and of export-only XORs
-    const VmInstr nop{scratch, scratch, scratch, VM_ROW_NONE};
+    VmInstr nop;
+    std::memset(&nop, 0, sizeof nop);  // XOR of six zero cells
+    nop.dst = scratch;
+    nop.row = VM_ROW_NONE;
+    // Every VM level becomes at least one step, even an empty one: the device waits for a LOAD by counting cp.async groups
+    // (one per step), so a LOAD must stay at least VM_DELTA steps ahead of its first use.
     const size_t n_levels = P.vm_level_off.size() - 1;
     for (size_t l = 0; l < n_levels; l++) {
         const uint32_t s = P.vm_level_off[l], e = P.vm_level_off[l + 1];
-        if (e == s) continue;
-        const uint32_t steps = (e - s + VM_STEP - 1) / VM_STEP;
+        const uint32_t steps = std::max<uint32_t>(1, (e - s + VM_STEP - 1) / VM_STEP);
         for (uint32_t k = 0; k < steps; k++) {
             const bool last = k + 1 == steps;
             const bool chunk_end = (P.n_vm_steps + 1) % VM_STEPS_PER_CHUNK == 0;
             for (uint32_t t = 0; t < VM_STEP; t++) {
-                const uint32_t g = s + k * VM_STEP + t;
-                VmInstr o = nop;
-                if (g < e) {
-                    const VmInstr &in = P.vm[g];
-                    if (in.dst & VM_LOAD) o = VmInstr{VM_F_LOAD | (in.dst & ~VM_LOAD), in.a, 0, VM_ROW_NONE};
-                    else o = VmInstr{in.dst == VM_NONE ? scratch : in.dst, in.a, in.b, in.row == VM_NONE ? VM_ROW_NONE : in.row};
-                }
+                const uint32_t gi = s + k * VM_STEP + t;
+                VmInstr o = gi < e ? P.vm[gi] : nop;
+                if (!(o.dst & VM_F_LOAD) && (o.dst & VM_CELL_MASK) == VM_CELL_MASK) o.dst = scratch;
                 if (last || chunk_end) o.dst |= VM_F_BAR;
                 P.vm_steps.push_back(o);
             }
@@ -325,7 +330,7 @@ static void emit_vm_steps(Program &P) {
     }
 }
 
-static void emit_lut_steps(Program &P) {
+void emit_lut_steps(Program &P) {
     P.lut_steps.clear();
     P.n_lut_steps = 0;
     if (P.luts.empty()) return;
@@ -341,8 +346,8 @@ static void emit_lut_steps(Program &P) {
             const bool last = k + 1 == steps;
             const bool chunk_end = (P.n_lut_steps + 1) % LUT_STEPS_PER_CHUNK == 0;
             for (uint32_t t = 0; t < LUT_STEP; t++) {
-                const uint32_t g = s + k * LUT_STEP + t;
-                LutInstr o = g < e ? P.luts[g] : nop;
+                const uint32_t gi = s + k * LUT_STEP + t;
+                LutInstr o = gi < e ? P.luts[gi] : nop;
                 o.pad = (last || chunk_end) ? LUT_F_BAR : 0;
                 P.lut_steps.push_back(o);
             }
@@ -361,10 +366,10 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
         return RV_E_ARG;
     }
     std::vector<Cell> cells(gf2_cells, Cell{VREF_ZERO, ZERO_MID});
-    std::vector<uint32_t> vlevel(1, 0);  // per value id
-    std::vector<uint32_t> llevel;        // per linear node (creation order)
-    std::vector<VGate> vg;               // creation order
-    std::vector<LGate> lg;               // creation order, provisional ids
+    std::vector<uint32_t> vlevel(1, 0);  // per value id (plain 2-input depth, for the stats)
+    std::vector<uint32_t> llevel;        // per linear node (plain depth)
+    std::vector<MGate> vg;               // value network, topological; ids = value ids
+    std::vector<MGate> lg;               // mask network, topological; provisional ids (see mask_id below)
     uint64_t n_masks = 0;
 
     auto mid_level = [&](uint32_t mid) -> uint32_t { return (mid != ZERO_MID && mid >= LIN_BASE) ? llevel[mid - LIN_BASE] : 0; };
@@ -426,7 +431,7 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
                 else if ((A.vref >> 1) == (B.vref >> 1)) R.vref = neg;  // x ^ x (^1)
                 else {
                     uint32_t vid = new_val(1 + std::max(vlevel[A.vref >> 1], vlevel[B.vref >> 1]));
-                    vg.push_back(VGate{vid, A.vref & ~1u, B.vref & ~1u, 0});
+                    vg.push_back(MGate{vid, A.vref & ~1u, B.vref & ~1u, 0});
                     R.vref = (vid << 1) | neg;
                 }
                 // mask
@@ -440,7 +445,7 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
                     }
                     uint32_t id = LIN_BASE + (uint32_t)lg.size();
                     llevel.push_back(1 + std::max(mid_level(A.mid), mid_level(B.mid)));
-                    lg.push_back(LGate{id, A.mid, B.mid, 0});
+                    lg.push_back(MGate{id, A.mid, B.mid, 0});  // provisional ids; renumbered below
                     R.mid = id;
                 }
                 cells[op.dst] = R;
@@ -478,7 +483,7 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
                 else if (va == vb) R.vref = VREF_ZERO;  // x & ~x
                 else {
                     uint32_t vid = new_val(1 + std::max(vlevel[va], vlevel[vb]));
-                    vg.push_back(VGate{vid, A.vref, B.vref, 1});
+                    vg.push_back(MGate{vid, A.vref, B.vref, 1});
                     R.vref = vid << 1;
                 }
                 cells[op.dst] = R;
@@ -512,72 +517,106 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
             return RV_E_UNSUPPORTED;
         }
     }
+    std::vector<Cell>().swap(cells);
 
     P.n_masks = (uint32_t)n_masks;
-    P.n_lin = (uint32_t)lg.size();
-    if ((uint64_t)P.n_masks + P.n_lin + 1 >= LIN_BASE) {
-        err = "circuit too large for 32-bit row indices";
-        return RV_E_UNSUPPORTED;
-    }
-    P.n_rows = P.n_masks + P.n_lin + 1;
     P.n_vals = (uint32_t)vlevel.size();
     P.n_online = (uint32_t)P.items.size();
     P.n_pre = (uint32_t)P.n_and;
+    for (uint32_t l : vlevel) P.plain_value_depth = std::max(P.plain_value_depth, l);
+    for (uint32_t l : llevel) P.plain_linear_depth = std::max(P.plain_linear_depth, l);
+    const bool small = n_ops <= (4u << 20);  // debug tables only where tests can use them
 
-    // ---- mask plane: counting sort by level; final row of a linear node = n_masks + its rank ----
+    // ---- mask plane: map the XOR network, number the rows -----------------------------------------------------------
     {
-        uint32_t depth = 0;
-        for (uint32_t l : llevel) depth = std::max(depth, l);
-        P.llevel_off.assign(depth + 1, 0);
-        for (uint32_t l : llevel) P.llevel_off[l]++;  // level l >= 1 counted at index l, shifted below
-        // offsets: level l (1..depth) occupies [off[l-1], off[l])
-        uint32_t run = 0;
-        std::vector<uint32_t> start(depth + 1, 0);
-        for (uint32_t l = 1; l <= depth; l++) {
-            start[l] = run;
-            run += P.llevel_off[l];
+        // mapper ids: 0 = zero mask, 1 + i = fresh PRG mask i, 1 + n_masks + k = linear node k
+        const uint32_t n_lin_all = (uint32_t)lg.size();
+        if ((uint64_t)P.n_masks + n_lin_all + 2 >= LIN_BASE) {
+            err = "circuit too large for 32-bit row indices";
+            return RV_E_UNSUPPORTED;
         }
-        for (uint32_t l = 0; l < depth; l++) P.llevel_off[l] = start[l + 1];
-        P.llevel_off[depth] = run;
-        std::vector<uint32_t> rank(lg.size());
-        std::vector<uint32_t> cursor(start);
-        for (size_t n = 0; n < lg.size(); n++) rank[n] = cursor[llevel[n]]++;
-        const uint32_t zero_row = P.zero_row();
-        auto row_of = [&](uint32_t mid) -> uint32_t {
-            if (mid == ZERO_MID) return zero_row;
-            if (mid >= LIN_BASE) return P.n_masks + rank[mid - LIN_BASE];
-            return mid;
+        auto mask_id = [&](uint32_t mid) -> uint32_t {
+            if (mid == ZERO_MID) return 0;
+            if (mid >= LIN_BASE) return 1 + P.n_masks + (mid - LIN_BASE);
+            return 1 + mid;
         };
-        P.lgates.resize(lg.size());
-        for (size_t n = 0; n < lg.size(); n++) P.lgates[rank[n]] = LGate{row_of(lg[n].dst), row_of(lg[n].a), row_of(lg[n].b), 0};
+        for (MGate &g : lg) {
+            g.out = mask_id(g.out);
+            g.a = mask_id(g.a) << 1;
+            g.b = mask_id(g.b) << 1;
+        }
+        const uint32_t n_ids = 1 + P.n_masks + n_lin_all;
+        std::vector<uint8_t> required(n_ids, 0);
+        for (const Item &it : P.items) {
+            required[mask_id(it.ra)] = 1;
+            if (it.kind == ITEM_MUL) required[mask_id(it.rb)] = 1;
+        }
+        std::vector<MNode> nodes;
+        map_network(n_ids, lg, required, lg.size() <= LUT_MAP_MAX_GATES, nodes);
+        std::vector<MGate>().swap(lg);
+        std::vector<uint32_t> order;
+        P.xlevel_off = sort_by_level(nodes, order);
+        P.n_lin = (uint32_t)nodes.size();
+        P.n_rows = P.n_masks + P.n_lin + 1;
+        const uint32_t zero_row = P.zero_row();
+        std::vector<uint32_t> row_of_lin(n_lin_all, NONE32);  // linear node k -> row (only for materialised nodes)
+        for (uint32_t i = 0; i < nodes.size(); i++) row_of_lin[nodes[i].out - 1 - P.n_masks] = P.n_masks + order[i];
+        auto row_of_id = [&](uint32_t id) -> uint32_t {
+            if (id == 0) return zero_row;
+            if (id <= P.n_masks) return id - 1;
+            return row_of_lin[id - 1 - P.n_masks];
+        };
+        P.xgates.resize(nodes.size());
+        for (uint32_t i = 0; i < nodes.size(); i++) {
+            XGate x;
+            x.dst = P.n_masks + order[i];
+            x.pad = 0;
+            int q = 0;
+            for (uint32_t k = 0; k < nodes[i].n; k++)
+                if ((nodes[i].tt >> (1u << k)) & 1) x.in[q++] = row_of_id(nodes[i].leaf[k]);  // leaves that cancel (x ^ x) drop out
+            for (; q < 6; q++) x.in[q] = zero_row;
+            P.xgates[order[i]] = x;
+        }
         for (Item &it : P.items) {
-            it.ra = row_of(it.ra);
-            if (it.kind == ITEM_MUL) it.rb = row_of(it.rb);
+            it.ra = row_of_id(mask_id(it.ra));
+            if (it.kind == ITEM_MUL) it.rb = row_of_id(mask_id(it.rb));
         }
     }
     build_mask_vm(P);
-    split_levels(P.vm_level_off, VM_LEVEL_MAX);
-    build_value_luts(P, vg, vg.size() <= LUT_MAP_MAX_GATES);
     emit_vm_steps(P);
-    emit_lut_steps(P);
-    // ---- value plane: counting sort by level (value ids keep their creation order) ----
-    {
-        uint32_t depth = 0;
-        for (const VGate &g : vg) depth = std::max(depth, vlevel[g.dst]);
-        std::vector<uint32_t> cnt(depth + 2, 0);
-        for (const VGate &g : vg) cnt[vlevel[g.dst]]++;
-        P.vlevel_off.assign(depth + 1, 0);
-        uint32_t run = 0;
-        std::vector<uint32_t> cursor(depth + 1, 0);
-        for (uint32_t l = 1; l <= depth; l++) {
-            cursor[l] = run;
-            run += cnt[l];
-            P.vlevel_off[l - 1] = cursor[l];
-        }
-        P.vlevel_off[depth] = run;
-        P.vgates.resize(vg.size());
-        for (const VGate &g : vg) P.vgates[cursor[vlevel[g.dst]]++] = g;
+    if (!small) {
+        std::vector<VmInstr>().swap(P.vm);
+        std::vector<uint32_t>().swap(P.vm_level_off);
     }
+
+    // ---- value plane: map to 6-input LUTs --------------------------------------------------------------------------
+    {
+        std::vector<uint8_t> required(P.n_vals, 0);
+        for (const Item &it : P.items) {
+            required[it.va >> 1] = 1;
+            if (it.kind == ITEM_MUL) required[it.vb >> 1] = 1;
+        }
+        std::vector<MNode> nodes;
+        map_network(P.n_vals, vg, required, vg.size() <= LUT_MAP_MAX_GATES, nodes);
+        if (small) {
+            P.vgates.resize(vg.size());
+            for (size_t i = 0; i < vg.size(); i++) P.vgates[i] = VGate{vg[i].out, vg[i].a, vg[i].b, vg[i].op};
+        }
+        std::vector<MGate>().swap(vg);
+        std::vector<uint32_t> order;
+        P.lut_level_off = sort_by_level(nodes, order);
+        P.luts.resize(nodes.size());
+        for (uint32_t i = 0; i < nodes.size(); i++) {
+            LutInstr li;
+            std::memset(&li, 0, sizeof li);
+            li.dst = nodes[i].out;
+            for (int k = 0; k < 6; k++) li.in[k] = nodes[i].leaf[k];
+            li.tt = nodes[i].tt;
+            P.luts[order[i]] = li;
+        }
+    }
+    emit_lut_steps(P);
+    if (!small) std::vector<LutInstr>().swap(P.luts);
     return RV_OK;
 }
 

@@ -29,17 +29,23 @@ namespace rv {
 struct VGate {
     uint32_t dst, a, b, op;
 };
-// mask-plane gate: row[dst] = row[a] ^ row[b]   (rows of the share tensor, 8 bytes per packed instance)
-struct LGate {
-    uint32_t dst, a, b, pad;
+// mask-plane gate after cut mapping: row[dst] = XOR of row[in[0..5]] (unused inputs name the all-zero row).  The same
+// K=6 cut mapper that shortens the value plane collapses XOR chains here (a ripple carry's running XOR of AND outputs
+// becomes one 6-input gate per five links), so the linear depth of SHA-256 drops from 557 to ~1/5.
+struct XGate {
+    uint32_t dst;
+    uint32_t in[6];
+    uint32_t pad;
 };
 // mask-plane VM instruction (shared-memory cells; see build_mask_vm):
-//   XOR : cell[dst] = cell[a] ^ cell[b]; if (row != VM_NONE) rows[row] = that value        (dst may be VM_NONE)
-//   LOAD: cell[dst & ~VM_LOAD] <- rows[a]   asynchronously, `VM_DELTA` levels ahead of its first use
+//   XOR : v = XOR of cell[in[0..5]]; cell[dst] = v; if (row != VM_ROW_NONE) rows[row] = v
+//   LOAD: cell[dst] <- rows[in[0]]   asynchronously, `VM_DELTA` levels ahead of its first use
 struct VmInstr {
-    uint32_t dst, a, b, row;
+    uint32_t dst;  // cell | VM_F_* flags
+    uint32_t in[6];
+    uint32_t row;
+    uint32_t pad[4];  // 48 bytes = three 16-byte units
 };
-constexpr uint32_t VM_LOAD = 0x80000000u, VM_NONE = 0x7FFFFFFFu;
 constexpr int VM_DELTA = 8;  // prefetch distance in levels (L2 latency / per-level time)
 
 // value-plane LUT instruction: v[dst] = tt >> (v[in0] | v[in1]<<1 | ... | v[in5]<<5) & 1.  Unused inputs name value 0
@@ -52,16 +58,14 @@ struct LutInstr {
     uint64_t tt;
     uint64_t pad2;  // 48 bytes = three 16-byte ring units
 };
-constexpr uint32_t LUT_LEVEL_MAX = 256;   // levels are split so that none holds more instructions
-constexpr uint32_t VM_LEVEL_MAX = 1024;
 
 // Device form of both programs: a dense "VLIW" stream of STEPS.  Every thread of the CTA executes exactly one slot per
 // step (empty slots are harmless no-ops on a scratch cell), so the device loop needs no level table, no bounds checks and
 // no inner loops -- the per-level dependent chain is what bounds these kernels, and it is paid in instructions per warp.
-//   mask VM : step = VM_STEP slots of 16 bytes; word 0 = dst cell | flags
+//   mask VM : step = VM_STEP slots of 48 bytes; word 0 = dst cell | flags
 //   LUT     : step = LUT_STEP slots of 48 bytes; `pad` = flags
 // STEP_BAR on a slot means "CTA barrier after this step" (set on every slot of the last step of a level and of a chunk).
-constexpr uint32_t VM_STEP = 256, VM_STEPS_PER_CHUNK = 4, LUT_STEP = 128, LUT_STEPS_PER_CHUNK = 2;
+constexpr uint32_t VM_STEP = 256, VM_STEPS_PER_CHUNK = 2, LUT_STEP = 128, LUT_STEPS_PER_CHUNK = 2;
 constexpr uint32_t VM_F_LOAD = 0x80000000u, VM_F_BAR = 0x40000000u, VM_CELL_MASK = 0x00FFFFFFu, VM_ROW_NONE = 0xFFFFFFFFu;
 constexpr uint32_t LUT_F_BAR = 1u;
 
@@ -77,27 +81,26 @@ struct Item {
     uint32_t j;     // MUL: position in the preprocessing stream; INPUT: witness index
     uint32_t pad;
 };
-static_assert(sizeof(VGate) == 16 && sizeof(LGate) == 16 && sizeof(VmInstr) == 16 && sizeof(LutInstr) == 48 && sizeof(Item) == 32, "POD layout");
+static_assert(sizeof(VGate) == 16 && sizeof(XGate) == 32 && sizeof(VmInstr) == 48 && sizeof(LutInstr) == 48 && sizeof(Item) == 32, "POD layout");
 
 struct Program {
     // GF(2) side
     uint64_t n_ops = 0, n_and = 0, n_inputs = 0, n_assert = 0;
     uint32_t n_masks = 0;   // fresh PRG masks per (rep, player)
-    uint32_t n_lin = 0;     // linear nodes
+    uint32_t n_lin = 0;     // materialised (mapped) linear nodes
     uint32_t n_rows = 0;    // n_masks + n_lin + 1; the last row is all-zero
     uint32_t n_vals = 1;    // value ids; vid 0 is the constant 0
     uint32_t n_online = 0;  // == items.size()
     uint32_t n_pre = 0;     // == n_and
-    std::vector<VGate> vgates;          // sorted by level
-    std::vector<uint32_t> vlevel_off;   // value_depth + 1 offsets into vgates
-    std::vector<LGate> lgates;          // sorted by level; dst rows are n_masks + position
-    std::vector<uint32_t> llevel_off;   // linear_depth + 1 offsets into lgates
-    std::vector<LutInstr> luts;         // value-plane program, sorted by level
+    std::vector<VGate> vgates;          // plain 2-input value gates in topological order (debug/tests; dropped for huge circuits)
+    std::vector<XGate> xgates;          // mapped XOR network, sorted by level; dst rows are n_masks + position
+    std::vector<uint32_t> xlevel_off;   // linear_depth + 1 offsets into xgates
+    std::vector<LutInstr> luts;         // mapped value-plane program, sorted by level
     std::vector<uint32_t> lut_level_off;
-    uint32_t lut_depth = 0;             // levels before splitting wide ones
-    std::vector<VmInstr> vm;            // mask-plane VM program, sorted by VM level (= level + VM_DELTA - 1)
-    std::vector<uint32_t> vm_level_off; // linear_depth + VM_DELTA + 1 offsets into vm (empty when there are no lgates)
-    uint32_t vm_cells = 0;              // shared-memory cells the program needs (one lane word each)
+    std::vector<VmInstr> vm;            // mask-plane VM program over cells, sorted by VM level (= level + VM_DELTA - 1)
+    std::vector<uint32_t> vm_level_off;
+    uint32_t vm_cells = 0;              // shared-memory cells the program needs (one lane word each), excluding the scratch cell
+    uint32_t plain_value_depth = 0, plain_linear_depth = 0;  // depths before mapping (reported in the stats)
     std::vector<VmInstr> vm_steps;      // padded device stream of the mask VM (n_vm_steps * VM_STEP slots); cell vm_cells = scratch
     uint32_t n_vm_steps = 0;
     std::vector<LutInstr> lut_steps;    // padded device stream of the value plane (n_lut_steps * LUT_STEP slots); value n_vals = scratch

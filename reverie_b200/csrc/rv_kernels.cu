@@ -107,7 +107,8 @@ __device__ __forceinline__ void aes_ctr_block_smem(uint64_t ctr, const SmemRound
 }
 
 __global__ void __launch_bounds__(MG_THREADS) k_mask_gen(const uint32_t *__restrict__ ks, const uint32_t *__restrict__ lane_mask,
-                                                         uint32_t nslices, uint32_t n_masks, uint32_t *__restrict__ rows32) {
+                                                         uint32_t nslices, uint32_t n_masks, uint32_t *__restrict__ rows32,
+                                                         uint32_t *__restrict__ fresh_sm, size_t pitch_sm) {
     __shared__ uint4 sk[11 * 32 * MG_SLICES];
     const uint32_t w0 = blockIdx.y * MG_SLICES;
     {
@@ -131,13 +132,22 @@ __global__ void __launch_bounds__(MG_THREADS) k_mask_gen(const uint32_t *__restr
         const uint64_t i = plane_to_mask_index(j, k);
         if (i < n_masks) rows32[i * nslices + w] = s[k] & lm;
     }
+    if (fresh_sm != nullptr) {  // slice-major copy for the mask VM: this thread's 128 masks are 512 contiguous bytes
+        uint4 *dst = reinterpret_cast<uint4 *>(fresh_sm + (size_t)w * pitch_sm + j * 128);
+#pragma unroll
+        for (int q = 0; q < 32; q++) {  // masks 4q..4q+3 = byte q/2, bits 7-(4q%8) downwards: planes 8B+7-b
+            const int B = q >> 1, hi = (q & 1) ? 3 : 7;
+            dst[q] = make_uint4(s[8 * B + hi] & lm, s[8 * B + hi - 1] & lm, s[8 * B + hi - 2] & lm, s[8 * B + hi - 3] & lm);
+        }
+    }
 }
 
-void launch_mask_gen(const uint32_t *ks, const uint32_t *lane_mask, uint32_t nslices, uint32_t n_masks, uint64_t *rows, cudaStream_t st) {
+void launch_mask_gen(const uint32_t *ks, const uint32_t *lane_mask, uint32_t nslices, uint32_t n_masks, uint64_t *rows, uint32_t *fresh_sm,
+                     size_t pitch_sm, cudaStream_t st) {
     if (n_masks == 0) return;
     const uint32_t n_blocks = (n_masks + 127) / 128;
     dim3 grid((n_blocks + MG_COUNTERS - 1) / MG_COUNTERS, (nslices + MG_SLICES - 1) / MG_SLICES);
-    k_mask_gen<<<grid, MG_THREADS, 0, st>>>(ks, lane_mask, nslices, n_masks, reinterpret_cast<uint32_t *>(rows));
+    k_mask_gen<<<grid, MG_THREADS, 0, st>>>(ks, lane_mask, nslices, n_masks, reinterpret_cast<uint32_t *>(rows), fresh_sm, pitch_sm);
 }
 
 // =====================================================================================================================
@@ -280,7 +290,7 @@ size_t launch_values(const DevProgram &P, const uint8_t *wit, uint8_t *vals, cud
 //  K3  mask plane: row[dst] = row[a] ^ row[b], level by level
 // =====================================================================================================================
 constexpr int LIN_THREADS = 256;
-constexpr int VM_THREADS = 256;
+constexpr int VM_THREADS = VM_STEP;
 
 // (a) VM over shared-memory cells: one CTA per slice (u32 lane word = 4 repetitions x 8 players), one slot per thread per
 //     step.  The dependent chain per level is LDS -> XOR -> STS -> barrier; fresh rows arrive through cp.async LOADs issued
@@ -288,94 +298,128 @@ constexpr int VM_THREADS = 256;
 using VmStream = ChunkStream<(size_t)VM_STEPS_PER_CHUNK * VM_STEP * sizeof(VmInstr)>;
 static_assert(VM_THREADS == (int)VM_STEP, "one slot per thread");
 
-__global__ void __launch_bounds__(VM_THREADS) k_mask_vm(const VmInstr *__restrict__ prog, uint32_t n_steps, uint32_t *rows32, uint32_t nslices) {
+__global__ void __launch_bounds__(VM_THREADS) k_mask_vm(const VmInstr *__restrict__ prog, uint32_t n_steps, const uint32_t *__restrict__ fresh_sm,
+                                                        size_t pitch_fresh, uint32_t *__restrict__ exp_sm, size_t pitch_exp, uint32_t n_masks) {
     extern __shared__ __align__(128) uint8_t smem[];
     VmStream stream;
     stream.init(smem, prog, (size_t)n_steps * VM_STEP * sizeof(VmInstr));
     uint32_t *cells = reinterpret_cast<uint32_t *>(smem + VmStream::BYTES);
     const uint32_t tid = threadIdx.x, w = blockIdx.x;
+    // Global traffic is slice-major on both sides, so a warp's 32 accesses fall into a few 128-byte lines: LOADs of a level
+    // are sorted by row, exported rows are numbered in program order.  (Row-major, each lane would touch its own 256-byte
+    // row and the kernel would be bound by L1 request rate.)
+    const uint32_t *src = fresh_sm + (size_t)w * pitch_fresh;
+    uint32_t *dst = exp_sm + (size_t)w * pitch_exp;
+    if (tid == 0) cells[0] = 0;  // cell 0 is the constant zero (first read happens after the first barrier)
     const uint32_t n_chunks = (n_steps + VM_STEPS_PER_CHUNK - 1) / VM_STEPS_PER_CHUNK;
     for (uint32_t c = 0; c < n_chunks; c++) {
         const uint4 *img = reinterpret_cast<const uint4 *>(stream.begin_chunk(c));
         const uint32_t nst = min((uint32_t)VM_STEPS_PER_CHUNK, n_steps - c * VM_STEPS_PER_CHUNK);
-        uint4 ins[VM_STEPS_PER_CHUNK];
-#pragma unroll
-        for (int k = 0; k < (int)VM_STEPS_PER_CHUNK; k++)
-            if (k < (int)nst) ins[k] = img[k * VM_STEP + tid];
+        uint4 u[VM_STEPS_PER_CHUNK][2];
 #pragma unroll
         for (int k = 0; k < (int)VM_STEPS_PER_CHUNK; k++)
             if (k < (int)nst) {
-                const uint4 in = ins[k];  // {dst | flags, a, b, row}
-                if (in.x & VM_F_LOAD) {
-                    __pipeline_memcpy_async(cells + (in.x & VM_CELL_MASK), rows32 + (size_t)in.y * nslices + w, 4);
+                const uint4 *p = img + ((size_t)k * VM_STEP + tid) * 3;
+                u[k][0] = p[0];  // {dst | flags, in0, in1, in2}
+                u[k][1] = p[1];  // {in3, in4, in5, row}
+            }
+#pragma unroll
+        for (int k = 0; k < (int)VM_STEPS_PER_CHUNK; k++)
+            if (k < (int)nst) {
+                const uint4 a = u[k][0], b = u[k][1];
+                if (a.x & VM_F_LOAD) {
+                    __pipeline_memcpy_async(cells + (a.x & VM_CELL_MASK), src + a.y, 4);
                 } else {
-                    const uint32_t v = cells[in.y] ^ cells[in.z];
-                    cells[in.x & VM_CELL_MASK] = v;
-                    if (in.w != VM_ROW_NONE) rows32[(size_t)in.w * nslices + w] = v;
+                    const uint32_t v = cells[a.y] ^ cells[a.z] ^ cells[a.w] ^ cells[b.x] ^ cells[b.y] ^ cells[b.z];
+                    cells[a.x & VM_CELL_MASK] = v;
+                    if (b.w != VM_ROW_NONE) dst[b.w - n_masks] = v;
                 }
                 __pipeline_commit();
                 __pipeline_wait_prior(VM_DELTA - 1);
-                if (in.x & VM_F_BAR) __syncthreads();
+                if (a.x & VM_F_BAR) __syncthreads();
             }
     }
 }
 
 // (b) fallback for networks whose live set does not fit in shared memory: one CTA per packed instance walks all levels
 //     over the share tensor itself (CTA barrier only; columns are independent)
-__global__ void __launch_bounds__(LIN_THREADS) k_linear_cta(const LGate *__restrict__ gates, const uint32_t *__restrict__ level_off,
+__device__ __forceinline__ uint64_t xor6(const uint64_t *rows, const XGate &g, uint32_t npi, uint32_t pi) {
+    uint64_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 6; k++) v ^= rows[(size_t)g.in[k] * npi + pi];
+    return v;
+}
+
+__global__ void __launch_bounds__(LIN_THREADS) k_linear_cta(const XGate *__restrict__ gates, const uint32_t *__restrict__ level_off,
                                                             uint32_t n_levels, uint64_t *rows, uint32_t npi) {
     const uint32_t pi = blockIdx.x, tid = threadIdx.x;
-    uint32_t s = level_off[0];
-    LGate nxt = (s + tid < level_off[n_levels]) ? gates[s + tid] : LGate{0, 0, 0, 0};
     for (uint32_t l = 0; l < n_levels; l++) {
-        const uint32_t e = level_off[l + 1];
-        LGate cur = nxt;
-        if (e + tid < level_off[n_levels]) nxt = gates[e + tid];  // prefetch the next level's first descriptor
+        const uint32_t s = level_off[l], e = level_off[l + 1];
         for (uint32_t g = s + tid; g < e; g += LIN_THREADS) {
-            if (g != s + tid) cur = gates[g];
-            rows[(size_t)cur.dst * npi + pi] = rows[(size_t)cur.a * npi + pi] ^ rows[(size_t)cur.b * npi + pi];
+            const XGate gt = gates[g];
+            rows[(size_t)gt.dst * npi + pi] = xor6(rows, gt, npi, pi);
         }
-        s = e;
         __syncthreads();
     }
 }
 
 // (c) wide levels: one launch per level, thread = (gate, packed instance)
-__global__ void __launch_bounds__(256) k_linear_level(const LGate *__restrict__ gates, uint32_t n, uint64_t *rows, uint32_t npi) {
+__global__ void __launch_bounds__(256) k_linear_level(const XGate *__restrict__ gates, uint32_t n, uint64_t *rows, uint32_t npi) {
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t g = gid / npi;
     const uint32_t pi = (uint32_t)(gid % npi);
     if (g >= n) return;
-    const LGate gt = gates[g];
-    rows[(size_t)gt.dst * npi + pi] = rows[(size_t)gt.a * npi + pi] ^ rows[(size_t)gt.b * npi + pi];
+    const XGate gt = gates[g];
+    rows[(size_t)gt.dst * npi + pi] = xor6(rows, gt, npi, pi);
 }
 
-int launch_linear(const DevProgram &P, const uint32_t *off_host, uint64_t *rows, uint32_t npi, cudaStream_t st, int *which) {
+// exp_sm [nslices][pitch] (u32, slice-major, written by the VM) -> rows[n_masks + e][nslices] (row-major, read by the item plane)
+__global__ void __launch_bounds__(256) k_export_transpose(const uint32_t *__restrict__ exp_sm, size_t pitch, uint32_t n_lin, uint32_t nslices,
+                                                          uint32_t *__restrict__ rows32_lin) {
+    __shared__ uint32_t tile[64][33];
+    const uint32_t e0 = blockIdx.x * 32, lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+    for (uint32_t sl = wrp; sl < nslices; sl += 8) tile[sl][lane] = (e0 + lane < n_lin) ? exp_sm[(size_t)sl * pitch + e0 + lane] : 0u;
+    __syncthreads();
+    for (uint32_t idx = threadIdx.x; idx < 32 * nslices; idx += 256) {
+        const uint32_t r = idx / nslices, sl = idx % nslices;
+        if (e0 + r < n_lin) rows32_lin[(size_t)(e0 + r) * nslices + sl] = tile[sl][r];
+    }
+}
+
+static size_t vm_smem_bytes(const DevProgram &P) { return VmStream::BYTES + ((size_t)P.vm_cells + 1) * 4; }
+bool linear_uses_vm(const DevProgram &P) {
+    if (P.n_llevels == 0 || (double)P.n_xgates / P.n_llevels >= 4096.0) return false;
+    return P.n_vm_steps && P.vm_cells < VM_CELL_MASK && vm_smem_bytes(P) <= SMEM_DYN_CAP;
+}
+
+int launch_linear(const DevProgram &P, const uint32_t *off_host, uint64_t *rows, uint32_t npi, const uint32_t *fresh_sm, size_t pitch_fresh,
+                  uint32_t *exp_sm, size_t pitch_exp, cudaStream_t st, int *which) {
     if (which) *which = -1;
     if (P.n_llevels == 0) return 0;
-    const double avg_width = (double)P.n_lgates / P.n_llevels;
+    const double avg_width = (double)P.n_xgates / P.n_llevels;
     if (avg_width >= 4096.0) {  // wide: per-level launches (~3 us each) keep every SM busy
         if (which) *which = 2;
         for (uint32_t l = 0; l < P.n_llevels; l++) {
             const uint32_t n = off_host[l + 1] - off_host[l];
             const uint64_t threads = (uint64_t)n * npi;
-            k_linear_level<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P.lgates + off_host[l], n, rows, npi);
+            k_linear_level<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P.xgates + off_host[l], n, rows, npi);
         }
         return (int)P.n_llevels;
     }
-    const size_t vm_smem = VmStream::BYTES + ((size_t)P.vm_cells + 1) * 4;
-    if (P.n_vm_steps && P.vm_cells < VM_CELL_MASK && vm_smem <= SMEM_DYN_CAP) {
+    if (linear_uses_vm(P) && fresh_sm && exp_sm) {
         static bool configured = false;
         if (!configured) {
             cudaFuncSetAttribute(k_mask_vm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DYN_CAP);
             configured = true;
         }
         if (which) *which = 0;
-        k_mask_vm<<<2 * npi, VM_THREADS, vm_smem, st>>>(P.vm_steps, P.n_vm_steps, reinterpret_cast<uint32_t *>(rows), 2 * npi);
-        return 1;
+        k_mask_vm<<<2 * npi, VM_THREADS, vm_smem_bytes(P), st>>>(P.vm_steps, P.n_vm_steps, fresh_sm, pitch_fresh, exp_sm, pitch_exp, P.n_masks);
+        k_export_transpose<<<(P.n_lin + 31) / 32, 256, 0, st>>>(exp_sm, pitch_exp, P.n_lin, 2 * npi,
+                                                                reinterpret_cast<uint32_t *>(rows) + (size_t)P.n_masks * 2 * npi);
+        return 2;
     }
     if (which) *which = 1;
-    k_linear_cta<<<npi, LIN_THREADS, 0, st>>>(P.lgates, P.llevel_off, P.n_llevels, rows, npi);
+    k_linear_cta<<<npi, LIN_THREADS, 0, st>>>(P.xgates, P.xlevel_off, P.n_llevels, rows, npi);
     return 1;
 }
 

@@ -10,10 +10,8 @@ namespace rv {
 
 // compiled tables resident in device memory
 struct DevProgram {
-    const VGate *vgates = nullptr;
-    const uint32_t *vlevel_off = nullptr;  // n_vlevels + 1
-    const LGate *lgates = nullptr;
-    const uint32_t *llevel_off = nullptr;  // n_llevels + 1
+    const XGate *xgates = nullptr;         // mapped XOR network (global-memory fallback of the mask plane)
+    const uint32_t *xlevel_off = nullptr;  // n_llevels + 1
     const Item *items = nullptr;
     const uint32_t *mul_pos = nullptr;    // j -> online position of the j-th Mul
     const uint32_t *recon_pos = nullptr;  // k -> online position of the k-th reconstruct()
@@ -23,7 +21,8 @@ struct DevProgram {
     uint32_t n_lut_steps = 0;
     const VmInstr *vm_steps = nullptr;     // mask-plane VM step stream (n_vm_steps * VM_STEP slots); empty without Add/Sub
     uint32_t n_vm_steps = 0, vm_cells = 0;
-    uint32_t n_vgates = 0, n_vlevels = 0, n_lgates = 0, n_llevels = 0;
+    uint32_t n_xgates = 0, n_llevels = 0;
+    uint32_t n_lin = 0;
     uint32_t n_masks = 0, n_rows = 0, n_vals = 0, n_online = 0, n_pre = 0, n_inputs = 0, n_recon = 0;
     uint32_t max_llevel_width = 0;
 };
@@ -32,12 +31,17 @@ struct DevProgram {
 void launch_key_setup(const uint8_t *seeds, const uint8_t *pkeys_in, const uint8_t *mode, const uint8_t *omit, uint32_t nslices,
                       uint32_t *ks, uint32_t *lane_mask, uint8_t *pkeys_out, cudaStream_t st);
 // K2  AES-CTR mask generation straight into the share tensor (src/generator/share.rs:54-65)
-void launch_mask_gen(const uint32_t *ks, const uint32_t *lane_mask, uint32_t nslices, uint32_t n_masks, uint64_t *rows, cudaStream_t st);
+//     also writes the slice-major copy `fresh_sm` [nslices][pitch_sm] (u32) that the mask VM loads from (nullptr = skip)
+void launch_mask_gen(const uint32_t *ks, const uint32_t *lane_mask, uint32_t nslices, uint32_t n_masks, uint64_t *rows, uint32_t *fresh_sm,
+                     size_t pitch_sm, cudaStream_t st);
 // K0  value plane (plaintext evaluation; one CTA, level-synchronous).  Returns the dynamic smem it asked for.
 size_t launch_values(const DevProgram &P, const uint8_t *wit, uint8_t *vals, cudaStream_t st);
 // K3  mask plane (XOR network over the share tensor)
 //     returns the number of kernel launches; *which (optional) names the variant: 0 VM (smem cells), 1 CTA walker, 2 per level
-int launch_linear(const DevProgram &P, const uint32_t *llevel_off_host, uint64_t *rows, uint32_t npi, cudaStream_t st, int *which = nullptr);
+//     fresh_sm / exp_sm: slice-major staging buffers of the VM variant ([2*npi][pitch] u32 each)
+int launch_linear(const DevProgram &P, const uint32_t *llevel_off_host, uint64_t *rows, uint32_t npi, const uint32_t *fresh_sm, size_t pitch_fresh,
+                  uint32_t *exp_sm, size_t pitch_exp, cudaStream_t st, int *which = nullptr);
+bool linear_uses_vm(const DevProgram &P);
 // K4  item plane: the two hash streams of every repetition
 void launch_items(const DevProgram &P, const uint64_t *rows, uint32_t npi, const uint8_t *vals, uint8_t *on, size_t pitch_on,
                   uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st);

@@ -117,8 +117,12 @@ extern "C" int hs_prove(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t
         vals[g.dst] = (uint8_t)((g.op ? (a & b) : (a ^ b)) & 1);
     }
     // K3
-    for (const LGate &g : P.lgates)
-        for (uint32_t pi = 0; pi < npi; pi++) rows[(size_t)g.dst * npi + pi] = rows[(size_t)g.a * npi + pi] ^ rows[(size_t)g.b * npi + pi];
+    for (const XGate &g : P.xgates)
+        for (uint32_t pi = 0; pi < npi; pi++) {
+            uint64_t v = 0;
+            for (int k = 0; k < 6; k++) v ^= rows[(size_t)g.in[k] * npi + pi];
+            rows[(size_t)g.dst * npi + pi] = v;
+        }
     // K4
     const size_t pitch_on = (std::max<size_t>(P.n_online, 1) + 63) / 64 * 64, pitch_pre = (std::max<size_t>(P.n_pre, 1) + 63) / 64 * 64;
     std::vector<uint8_t> on(pitch_on * nreps, 0), pre(pitch_pre * nreps, 0);
@@ -194,97 +198,9 @@ extern "C" int hs_prove(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t
 
 extern "C" void hs_free(void *p) { free(p); }
 
-// Executes the mask-plane VM program (build_mask_vm) on random fresh rows with cell reuse exactly as scheduled and
-// compares every exported row against the plain XOR network.  LOADs are applied at their issue level, the earliest the
-// asynchronous copy may land.  Returns 0 on success; *n_cells receives the cell count.
-extern "C" int hs_check_vm(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, uint32_t *n_cells, uint32_t *n_instr) {
-    Program P;
-    int rc = compile(ops, n_ops, z64_cells, gf2_cells, P, g_err);
-    if (rc) return rc;
-    *n_cells = P.vm_cells;
-    *n_instr = (uint32_t)P.vm.size();
-    std::vector<uint32_t> rows(P.n_rows, 0), ref;
-    uint32_t x = 12345;
-    for (uint32_t r = 0; r < P.n_masks; r++) rows[r] = (x = x * 1664525u + 1013904223u);
-    ref = rows;
-    for (const LGate &g : P.lgates) ref[g.dst] = ref[g.a] ^ ref[g.b];
-    std::vector<uint32_t> cells(P.vm_cells + 1, 0xDEADBEEF);
-    std::vector<uint8_t> exported(P.n_rows, 0);
-    const uint32_t n_levels = P.vm_level_off.empty() ? 0 : (uint32_t)P.vm_level_off.size() - 1;
-    for (uint32_t l = 0; l < n_levels; l++) {
-        // reads of a level happen before its writes become visible to OTHER instructions of the same level: emulate by
-        // computing all results first
-        std::vector<std::pair<uint32_t, uint32_t>> writes;
-        for (uint32_t k = P.vm_level_off[l]; k < P.vm_level_off[l + 1]; k++) {
-            const VmInstr &in = P.vm[k];
-            if (in.dst & VM_LOAD) writes.push_back({in.dst & ~VM_LOAD, rows[in.a]});
-            else {
-                const uint32_t v = cells[in.a] ^ cells[in.b];
-                if (in.dst != VM_NONE) writes.push_back({in.dst, v});
-                if (in.row != VM_NONE) {
-                    rows[in.row] = v;
-                    exported[in.row] = 1;
-                }
-            }
-        }
-        for (auto &w : writes) cells[w.first] = w.second;
-    }
-    for (const Item &it : P.items) {
-        const uint32_t rr[2] = {it.ra, it.kind == ITEM_MUL ? it.rb : it.ra};
-        for (uint32_t r : rr) {
-            if (r >= P.n_masks && r != P.zero_row() && !exported[r]) { g_err = "item operand row never exported"; return -100; }
-            if (rows[r] != ref[r]) { g_err = "VM row mismatch at row " + std::to_string(r); return -101; }
-        }
-    }
-    return 0;
-}
-
-// Evaluates the value plane twice -- plain 2-input gates vs. the mapped LUT program -- on `n_trials` random witnesses and
-// checks every value the item plane reads.  Returns 0 on success; stats: [n_luts, lut_levels(after split), lut_depth, plain_depth].
-extern "C" int hs_check_luts(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, int n_trials, uint32_t *stats) {
-    Program P;
-    int rc = compile(ops, n_ops, z64_cells, gf2_cells, P, g_err);
-    if (rc) return rc;
-    stats[0] = (uint32_t)P.luts.size();
-    stats[1] = (uint32_t)P.lut_level_off.size() - 1;
-    stats[2] = P.lut_depth;
-    stats[3] = (uint32_t)P.vlevel_off.size() - 1;
-    uint32_t x = 777;
-    for (int t = 0; t < n_trials; t++) {
-        std::vector<uint8_t> a(P.n_vals, 0), b(P.n_vals, 0xEE);
-        b[0] = 0;
-        for (size_t k = 0; k < P.n_inputs; k++) {
-            x = x * 1664525u + 1013904223u;
-            a[P.input_vid[k]] = b[P.input_vid[k]] = (x >> 16) & 1;
-        }
-        for (const VGate &g : P.vgates) {
-            const uint32_t u = a[g.a >> 1] ^ (g.a & 1), v = a[g.b >> 1] ^ (g.b & 1);
-            a[g.dst] = (uint8_t)((g.op ? (u & v) : (u ^ v)) & 1);
-        }
-        // level by level; within a level reads must not see the level's own writes
-        for (size_t l = 0; l + 1 < P.lut_level_off.size(); l++) {
-            std::vector<std::pair<uint32_t, uint8_t>> w;
-            for (uint32_t i = P.lut_level_off[l]; i < P.lut_level_off[l + 1]; i++) {
-                const LutInstr &li = P.luts[i];
-                uint32_t idx = 0;
-                for (int k = 0; k < 6; k++) {
-                    if (b[li.in[k]] > 1) { g_err = "LUT reads a value that was never written"; return -200; }
-                    idx |= (uint32_t)b[li.in[k]] << k;
-                }
-                w.push_back({li.dst, (uint8_t)((li.tt >> idx) & 1)});
-            }
-            for (auto &p : w) b[p.first] = p.second;
-        }
-        for (const Item &it : P.items) {
-            const uint32_t vv[2] = {it.va >> 1, it.kind == ITEM_MUL ? it.vb >> 1 : it.va >> 1};
-            for (uint32_t v : vv)
-                if (a[v] != b[v]) { g_err = "LUT value mismatch at vid " + std::to_string(v); return -201; }
-        }
-    }
-    return 0;
-}
-
-// The same two checks on the padded device step streams (what the kernels actually execute).
+// Replays the padded device step streams of both planes (what the kernels actually execute) against the plain networks:
+// the mask VM on random fresh rows vs. the unmapped... mapped XOR gates, the LUT stream on random witnesses vs. the circuit's
+// own 2-input gates.  stats: [n_vm_steps, n_lut_steps, vm_cells, n_luts].
 extern "C" int hs_check_steps(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, uint32_t *stats) {
     Program P;
     int rc = compile(ops, n_ops, z64_cells, gf2_cells, P, g_err);
@@ -293,6 +209,9 @@ extern "C" int hs_check_steps(const rv_op *ops, size_t n_ops, size_t z64_cells, 
     stats[1] = P.n_lut_steps;
     stats[2] = P.vm_cells;
     stats[3] = (uint32_t)P.luts.size();
+    stats[4] = (uint32_t)P.xlevel_off.size() - 1;
+    stats[5] = (uint32_t)P.lut_level_off.size() - 1;
+    stats[6] = P.n_lin;
     if (P.vm_steps.size() != (size_t)P.n_vm_steps * VM_STEP || P.lut_steps.size() != (size_t)P.n_lut_steps * LUT_STEP) { g_err = "stream size"; return -300; }
     // --- mask VM ---
     {
@@ -300,8 +219,13 @@ extern "C" int hs_check_steps(const rv_op *ops, size_t n_ops, size_t z64_cells, 
         uint32_t x = 99;
         for (uint32_t r = 0; r < P.n_masks; r++) rows[r] = (x = x * 1664525u + 1013904223u);
         ref = rows;
-        for (const LGate &g : P.lgates) ref[g.dst] = ref[g.a] ^ ref[g.b];
+        for (const XGate &g : P.xgates) {
+            uint32_t v = 0;
+            for (int k = 0; k < 6; k++) v ^= ref[g.in[k]];
+            ref[g.dst] = v;
+        }
         std::vector<uint32_t> cells(P.vm_cells + 1, 0xDEADBEEF);
+        cells[0] = 0;
         std::vector<std::pair<uint32_t, uint32_t>> writes;  // writes become visible at the next barrier at the latest;
         for (uint32_t st = 0; st < P.n_vm_steps; st++) {    // applying them per step is the most adversarial legal order
             writes.clear();
@@ -310,9 +234,10 @@ extern "C" int hs_check_steps(const rv_op *ops, size_t n_ops, size_t z64_cells, 
                 const VmInstr &in = P.vm_steps[(size_t)st * VM_STEP + t];
                 bar = (in.dst & VM_F_BAR) != 0;
                 if (((P.vm_steps[(size_t)st * VM_STEP].dst & VM_F_BAR) != 0) != bar) { g_err = "non-uniform barrier flag"; return -301; }
-                if (in.dst & VM_F_LOAD) writes.push_back({in.dst & VM_CELL_MASK, rows[in.a]});
+                if (in.dst & VM_F_LOAD) writes.push_back({in.dst & VM_CELL_MASK, rows[in.in[0]]});
                 else {
-                    const uint32_t v = cells[in.a] ^ cells[in.b];
+                    uint32_t v = 0;
+                    for (int k = 0; k < 6; k++) v ^= cells[in.in[k]];
                     writes.push_back({in.dst & VM_CELL_MASK, v});
                     if (in.row != VM_ROW_NONE) rows[in.row] = v;
                 }
