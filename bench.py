@@ -6,9 +6,13 @@ For N > 1 the driver launches it under torchrun, one rank per GPU; the 32 packed
 sharded 32/N per rank and the only exchange is the all-gather of the 256 x 32-byte repetition hashes
 (src/proof/mod.rs:160-171) -> strong scaling (the proof is the same for every N).
 
-A step = one `Proof::new` of the workload circuit (default: SHA-256 compression, SURVEY.md 8(d) config 2).
-  value  device-resident: witness + seeds already in HBM, commit + open on the session stream, CUDA events per step
-  e2e    host buffers in, proof bytes out, through the public API (Proof.new -> rv_prove), copies inside the timed region
+A step = one batch of B independent `Proof::new` calls on the workload circuit (default: SHA-256 compression, SURVEY.md
+8(d) config 2; B = --batch, default 8) issued together, the way a proving service sees concurrent requests; B = 1 gives the
+single-proof latency, which is also reported.  The CPU arm (--impl reference) proves the same B proofs per step.
+  value  device-resident: witnesses + seeds already in HBM; per step the B sessions' commit + open run on their own CUDA
+         streams, forked from / joined into one timing stream that carries the CUDA-event pair of the step
+  e2e    host buffers in, proof bytes out, through the public API (B threads calling Proof.new -> rv_prove), all
+         host<->device copies inside the timed region
 """
 from __future__ import annotations
 
@@ -36,17 +40,17 @@ def make_workload(name: str):
 
     if name == "sha256":
         ops, wit, wc = C.sha256_abc_case()
-        return ops, wit, wc, "GF(2) SHA-256 compression circuit (generated Bristol-style: 22573 AND / 93666 XOR / 2147 INV, 768 inputs, 256 output asserts), 256 reps x 8 players, 1 proof per step"
+        return ops, wit, wc, "GF(2) SHA-256 compression circuit (generated Bristol-style: 22573 AND / 93666 XOR / 2147 INV, 768 inputs, 256 output asserts), 256 reps x 8 players"
     if name.startswith("flat"):
         n = int(name[4:])
         ops, wc = C.flat_mul_circuit(n)
-        return ops, np.array([1, 1], dtype=np.uint8), wc, f"GF(2) flat circuit: 2 inputs + {n} x Mul(2,0,1) (src/proof/mod.rs:322-329 scaled), 1 proof per step"
+        return ops, np.array([1, 1], dtype=np.uint8), wc, f"GF(2) flat circuit: 2 inputs + {n} x Mul(2,0,1) (src/proof/mod.rs:322-329 scaled)"
     if name.startswith("layered"):
         n = int(name[7:])
         width = min(1 << 20, max(1024, n // 16))
         ops, nw = C.layered_and_circuit(width, n)
         wit = np.random.default_rng(0).integers(0, 2, size=width).astype(np.uint8)
-        return ops, wit, (0, nw), f"GF(2) layered circuit: {width} inputs + {n} ANDs in layers of {width}, 1 proof per step"
+        return ops, wit, (0, nw), f"GF(2) layered circuit: {width} inputs + {n} ANDs in layers of {width}"
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -128,20 +132,22 @@ def run_reference(args, rank, world):
     import orc
 
     cores = min(os.cpu_count() or 1, 32)
+    B = args.batch
     for _ in range(max(args.warmup, 1)):
         orc.prove(ops, wit, [], wc, seeds, n_threads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        rc, _ = orc.prove(ops, wit, [], wc, seeds, n_threads=cores)
-        assert rc == 0
+        for _b in range(B):
+            rc, _ = orc.prove(ops, wit, [], wc, seeds, n_threads=cores)
+            assert rc == 0
     dt = time.perf_counter() - t0
-    v = n_and * args.steps / dt
+    v = n_and * B * args.steps / dt
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
-        "data": "synthetic", "config": {"workload": desc, "parallelism": f"{cores} host threads over 32 packed instances"},
+        "data": "synthetic", "config": {"workload": desc, "batch": B, "parallelism": f"{cores} host threads over 32 packed instances, proofs of a batch one after the other"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} whole proofs; C restatement of the reference's dataflow (oracle/c): the Rust reference cannot be built here (no cargo/rustc)"},
+                         "sample": f"{args.steps * B} whole proofs; C restatement of the reference's dataflow (oracle/c): the Rust reference cannot be built here (no cargo/rustc)"},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -154,6 +160,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sha256")
+    ap.add_argument("--batch", type=int, default=8, help="independent proofs per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -184,10 +191,12 @@ def main():
     st = circ.stats()
     n_and = st["n_and"]
     per = 32 // world
-    sess = rb.Session(circ, rank * per, per)
-    stream = torch.cuda.ExternalStream(sess.stream)
+    B = max(1, args.batch)
+    sessions = [rb.Session(circ, rank * per, per) for _ in range(B)]
+    streams = [torch.cuda.ExternalStream(x.stream) for x in sessions]
+    timing_stream = torch.cuda.Stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    gathered = torch.empty(256 * 32, dtype=torch.uint8, device="cuda")
+    gathered = [torch.empty(256 * 32, dtype=torch.uint8, device="cuda") for _ in range(B)]
 
     def barrier():
         if world > 1:
@@ -195,79 +204,112 @@ def main():
         torch.cuda.synchronize()
 
     def step_device():
-        """commit + open with inputs resident in HBM; the all-gather of repetition hashes when sharded."""
-        sess.commit()
+        """B proofs: commit + open with inputs resident in HBM; the all-gather of repetition hashes when sharded."""
+        for x in sessions:
+            x.commit()
         if world > 1:
-            mine = torch.frombuffer(bytearray(sess.hashes()), dtype=torch.uint8).cuda()
-            dist.all_gather_into_tensor(gathered, mine)
+            for b, x in enumerate(sessions):
+                mine = torch.frombuffer(bytearray(x.hashes()), dtype=torch.uint8).cuda()
+                dist.all_gather_into_tensor(gathered[b], mine)
             torch.cuda.synchronize()
-            sess.open(gathered.data_ptr())
+            for b, x in enumerate(sessions):
+                x.open(gathered[b].data_ptr())
         else:
-            sess.open()
+            for x in sessions:
+                x.open()
 
     def timed_device(k: int):
         tot = 0.0
         for _ in range(k):
-            with torch.cuda.stream(stream):
+            with torch.cuda.stream(timing_stream):
                 flush.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
-            a.record(stream)
+            a.record(timing_stream)
+            for st_ in streams:  # fork
+                st_.wait_event(a)
             step_device()
-            b.record(stream)
+            for st_ in streams:  # join
+                e = torch.cuda.Event()
+                e.record(st_)
+                timing_stream.wait_event(e)
+            b.record(timing_stream)
             barrier()
             tot += a.elapsed_time(b)
         return tot  # ms
 
-    sess.upload(wit, (), seeds)
+    for x in sessions:
+        x.upload(wit, (), seeds)
     for _ in range(args.warmup):
         step_device()
-    sess.sync()
-    launches0 = sess.launch_count
+    for x in sessions:
+        x.sync()
+    sess = sessions[0]
+    launches0 = sum(x.launch_count for x in sessions)
     sampler = ClockSampler(local_rank)
     sampler.start()
     ms_total = timed_device(args.steps)
-    launches = sess.launch_count - launches0
+    launches = sum(x.launch_count for x in sessions) - launches0
     clocks = sampler.stop()
     if world > 1:
         t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     comm, part = sess.fetch()
-    value = n_and * args.steps / (ms_total * 1e-3)
+    value = n_and * B * args.steps / (ms_total * 1e-3)
+
+    # single-proof device latency (B = 1), same rules
+    lat_ms = None
+    if world == 1:
+        keep_s, keep_st = sessions, streams
+        sessions, streams = sessions[:1], streams[:1]
+        lat_ms = timed_device(max(5, min(args.steps, 20))) / max(5, min(args.steps, 20))
+        sessions, streams = keep_s, keep_st
 
     # ---- end to end through the public API (host buffers, copies inside the timed region) ----
     e2e = None
     single_latency_ms = None
     if world == 1:
+        from concurrent.futures import ThreadPoolExecutor
+
+        pool = ThreadPoolExecutor(max_workers=B)
+
+        def one(_):
+            return rb.Proof.new(circ, wit, (), seeds=seeds)
+
         for _ in range(args.warmup):
-            proof = rb.Proof.new(circ, wit, (), seeds=seeds)
+            proofs = list(pool.map(one, range(B)))
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            proof = rb.Proof.new(circ, wit, (), seeds=seeds)
+            proofs = list(pool.map(one, range(B)))
         dt = time.perf_counter() - t0
-        e2e_v = n_and * args.steps / dt
-        single_latency_ms = dt / args.steps * 1e3
-        d2h = len(proof) + 36
+        e2e_v = n_and * B * args.steps / dt
+        proof = proofs[0]
+        t0 = time.perf_counter()
+        for _ in range(10):
+            one(0)
+        single_latency_ms = (time.perf_counter() - t0) / 10 * 1e3
+        d2h = B * (len(proof) + 36)
     else:
         def step_e2e():
-            sess.upload(wit, (), seeds)
+            for x in sessions:
+                x.upload(wit, (), seeds)
             step_device()
-            return sess.fetch()
+            return [x.fetch() for x in sessions]
         for _ in range(args.warmup):
             step_e2e()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            c_, p_ = step_e2e()
+            outs = step_e2e()
         barrier()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_v = n_and * args.steps / float(t.item())
-        d2h = len(p_) + 36 + per * 8 * 32
-    e2e = {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": st["n_inputs"] + per * 8 * 16 + (256 * 32 if world > 1 else 0), "d2h_bytes_per_step": d2h}
+        e2e_v = n_and * B * args.steps / float(t.item())
+        d2h = B * (len(outs[0][1]) + 36 + per * 8 * 32)
+    e2e = {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": B * (st["n_inputs"] + per * 8 * 16 + (256 * 32 if world > 1 else 0)), "d2h_bytes_per_step": d2h}
 
     # ---- per-kernel device times -> roofline of the dominant kernel (rank 0) ----
     roofline, kernels = None, None
@@ -275,8 +317,11 @@ def main():
     if rank == 0:
         sess.timing(True)
         reps = max(5, min(args.steps, 20))
+        keep_s = sessions
+        sessions = sessions[:1]
         for _ in range(reps):
             step_device()
+        sessions = keep_s
         kt = sess.kernel_times()
         sess.timing(False)
         kernels = {k["name"]: {"us_per_step": k["ms"] * 1e3 / reps, "launches_per_step": k["launches"] // reps,
@@ -288,9 +333,9 @@ def main():
         ach = bytes_per_launch / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
         roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                     "peak_source": peak_src, "us_per_launch": per_launch_s * 1e6,
-                    "path": {"algorithmic_bytes_per_step": st["algorithmic_bytes"], "achieved": st["algorithmic_bytes"] / (ms_total / args.steps * 1e-3) / 1e9,
-                             "frac": st["algorithmic_bytes"] / (ms_total / args.steps * 1e-3) / 1e9 / peak,
-                             "note": "SURVEY.md 8(d) bytes of the whole proof / device time per step"}}
+                    "path": {"algorithmic_bytes_per_step": st["algorithmic_bytes"], "achieved": B * st["algorithmic_bytes"] / (ms_total / args.steps * 1e-3) / 1e9,
+                             "frac": B * st["algorithmic_bytes"] / (ms_total / args.steps * 1e-3) / 1e9 / peak,
+                             "note": "SURVEY.md 8(d) bytes of the B proofs of a step / device time per step"}}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -303,11 +348,11 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
-            "config": {"workload": desc, "parallelism": f"{per} packed instances (= {per * 8} repetitions) per GPU",
+            "config": {"workload": desc, "batch": B, "parallelism": f"{per} packed instances (= {per * 8} repetitions) per GPU, {B} proofs in flight per step",
                        "l2": "256 MiB memset between timed steps (outside the per-step CUDA-event pair)",
-                       "timing": "CUDA events on the library's stream, one pair per step, summed over K steps"},
+                       "timing": "one CUDA-event pair per step on a timing stream that forks to / joins the B session streams, summed over K steps"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "kernels": kernels, "single_proof_latency_ms": single_latency_ms, "circuit": {k: st[k] for k in ("n_and", "n_ops", "value_depth", "linear_depth")},
+            "kernels": kernels, "single_proof_latency_ms": {"device": lat_ms, "e2e": single_latency_ms}, "circuit": {k: st[k] for k in ("n_and", "n_ops", "value_depth", "linear_depth")},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

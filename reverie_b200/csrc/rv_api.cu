@@ -599,7 +599,7 @@ extern "C" int rv_prove(const rv_circuit *c, const uint8_t *wit_gf2, size_t n_gf
         return rc;
     }
     std::lock_guard<std::mutex> g(c->pool_mu);
-    if (c->pool.size() < 4) c->pool.push_back(s);
+    if (c->pool.size() < 32) c->pool.push_back(s);
     else rv_session_free(s);
     return rc;
 }
