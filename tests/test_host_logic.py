@@ -1,0 +1,126 @@
+"""CPU tests of the product's host logic: the C-ABI library loads and exports every declared symbol, the circuit compiler's
+outputs (replayed on the CPU through the kernels' own __host__ __device__ bodies, tests/hostsim) reproduce the oracle's
+proof bytes, error codes, and the golden fixtures.  No compute entry point is called here (no GPU)."""
+import ctypes as C
+import hashlib
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import orc
+from reverie_b200 import _native as N
+from reverie_b200 import circuits as CI
+from tests import hostsim
+from tests.test_gpu_parity import _random_circuit
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "reverie_b200.h")).read()
+    declared = set(re.findall(r"\b(rv_[a-z0-9_]+)\s*\(", hdr))
+    declared -= {"rv_status", "rv_domain", "rv_opcode", "rv_table"}
+    lib = C.CDLL(N._build.LIB if os.path.exists(N._build.LIB) else N._build.build())
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/reverie_b200.h but not exported"
+    assert set(N.EXPORTED) == declared
+    assert b"sm_100a" in N.lib().rv_version()
+
+
+def test_no_gpu_means_loud_failure_not_fallback():
+    import reverie_b200 as rb
+
+    if N.lib().rv_device_count() > 0:
+        pytest.skip("a GPU is present")
+    ops, wc = CI.flat_mul_circuit(3)
+    with pytest.raises(rb.ReverieError) as e:
+        rb.Proof.new(ops, [1, 1], (), wc)
+    assert e.value.code == N.E_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_compile_stats_and_errors():
+    import reverie_b200 as rb
+
+    ops, wit, wc = CI.sha256_abc_case()
+    st = rb.Circuit(ops, wc).stats()
+    assert st["n_and"] == 22573 and st["n_inputs"] == 768 and st["n_assert"] == 256 and st["n_masks"] == 768 + 2 * 22573
+    assert st["online_bytes"] == 768 + 22573 + 256 and st["pre_bytes"] == 22573
+    assert st["plain_value_depth"] > 5000 and st["value_depth"] < st["plain_value_depth"] // 3  # the LUT mapper
+    assert st["plain_linear_depth"] > 500 and st["linear_depth"] < st["plain_linear_depth"] // 3  # the XOR-cut mapper
+    # AND 2048, XOR 1536, unary 1024, Input/Assert 768 (+16 descriptor each)
+    oc = ops["opcode"]
+    want = ((oc == CI.MUL).sum() * 2064 + (oc == CI.ADD).sum() * 1552 + (oc == CI.ADDC).sum() * 1040 + (oc == CI.INPUT).sum() * 784 +
+            (oc == CI.ASSERT_ZERO).sum() * 784)
+    assert st["algorithmic_bytes"] == int(want)
+    bad = ops.copy()
+    bad["a"][1000] = wc[1] + 5
+    with pytest.raises(rb.ReverieError) as e:
+        rb.Circuit(bad, wc)
+    assert e.value.code == N.E_ARG
+    z = np.zeros(1, dtype=CI.OP_DTYPE)
+    z["domain"], z["opcode"] = CI.Z64, CI.INPUT
+    with pytest.raises(rb.ReverieError) as e:
+        rb.Circuit(z, (4, 4))
+    assert e.value.code == N.E_UNSUPPORTED  # reported, never silently degraded
+    r = np.zeros(1, dtype=CI.OP_DTYPE)
+    r["opcode"] = CI.RANDOM
+    with pytest.raises(rb.ReverieError) as e:
+        rb.Circuit(r, (0, 4))
+    assert e.value.code == N.E_UNSUPPORTED
+
+
+def _check_steps(ops, wc):
+    L = hostsim.lib()
+    L.hs_check_steps.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.POINTER(C.c_uint32)]
+    ops = np.ascontiguousarray(ops)
+    st = (C.c_uint32 * 8)()
+    rc = L.hs_check_steps(ops.ctypes.data_as(C.c_void_p), ops.size, wc[0], wc[1], st)
+    assert rc == 0, L.hs_last_error()
+    return list(st)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_kernel_bodies_reproduce_oracle_proofs(seed, default_seeds):
+    """compile -> (same code the kernels run, on the CPU) -> proof bytes == oracle; plus the padded device streams."""
+    rng = np.random.default_rng(seed)
+    ops, wit, wc = _random_circuit(rng, int(rng.integers(1, 40)), int(rng.integers(1, 3000)))
+    rc, want, hashes = orc.prove(ops, wit, [], wc, default_seeds, want_hashes=True)
+    rc2, got, h2 = hostsim.prove(ops, wit, wc, default_seeds)
+    assert rc == 0 and rc2 == 0 and h2 == hashes and got == want
+    _check_steps(ops, wc)
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 8, 9, 1023, 1024, 1025, 3000])
+def test_kernel_bodies_flat_lengths(n, default_seeds):
+    ops, wc = CI.flat_mul_circuit(n)
+    rc, want = orc.prove(ops, [1, 0], [], wc, default_seeds)
+    rc2, got, _ = hostsim.prove(ops, [1, 0], wc, default_seeds)
+    assert rc == 0 and rc2 == 0 and got == want
+
+
+def test_kernel_bodies_sha256_and_streams(default_seeds):
+    ops, wit, wc = CI.sha256_abc_case()
+    rc2, got, _ = hostsim.prove(ops, wit, wc, default_seeds)
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "proofs.json")))["cases"]["sha256_abc"]
+    assert rc2 == 0 and hashlib.sha256(got).hexdigest() == gold["proof_sha256"] and len(got) == gold["proof_len"]
+    st = _check_steps(ops, wc)
+    assert st[0] > 0 and st[1] > 0
+    bad = wit.copy()
+    bad[7] ^= 1
+    assert hostsim.prove(ops, bad, wc, default_seeds)[0] == N.E_WITNESS_INVALID
+    assert hostsim.prove(ops, wit[:5], wc, default_seeds)[0] == N.E_WITNESS_SHORT
+
+
+def test_oracle_matches_golden_fixtures(default_seeds):
+    """tests/golden/proofs.json (made by tests/golden/make_golden.py) pins the oracle itself."""
+    from tests.golden.make_golden import cases
+
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "proofs.json")))["cases"]
+    for name, (ops, wit, wc) in cases().items():
+        rc, pb, hashes = orc.prove(ops, wit, [], wc, default_seeds, want_hashes=True)
+        g = gold[name]
+        assert rc == 0 and len(pb) == g["proof_len"] and hashlib.sha256(pb).hexdigest() == g["proof_sha256"], name
+        assert pb[:32].hex() == g["comm"] and hashlib.sha256(hashes).hexdigest() == g["rep_hashes_sha256"], name
