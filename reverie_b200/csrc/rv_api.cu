@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 
+#include "rv_bincode.h"
 #include "rv_kernels.cuh"
 #include "rv_planes.cuh"
 
@@ -57,6 +58,8 @@ struct rv_circuit {
     DevProgram dev;
     std::vector<void *> allocs;
     std::vector<uint32_t> mul_pos;
+    std::vector<uint32_t> recon_idx;  // online item -> index among the reconstruct() calls (verifier)
+    std::vector<uint32_t> vleaf_ids;  // u-plane value ids of the verifier's leaves: inputs then kappas
     int device = 0;
     uint64_t device_bytes = 0;
     uint32_t z64_empty_hash[8];  // B3("")
@@ -107,6 +110,12 @@ extern "C" int rv_circuit_compile(const rv_op *ops, size_t n_ops, size_t z64_cel
     Program &P = c->prog;
     for (uint32_t t = 0; t < P.n_online; t++)
         if (P.items[t].kind == ITEM_MUL) c->mul_pos.push_back(t);
+    c->recon_idx.assign(P.n_online, 0);
+    for (uint32_t k = 0; k < P.recon_pos.size(); k++) c->recon_idx[P.recon_pos[k]] = k;
+    if (P.has_verify) {
+        c->vleaf_ids = P.input_uid;
+        c->vleaf_ids.insert(c->vleaf_ids.end(), P.kappa_uid.begin(), P.kappa_uid.end());
+    }
     {
         uint32_t e[8];
         b3_chunk_cv(nullptr, 0, 0, true, e);
@@ -125,13 +134,17 @@ extern "C" int rv_circuit_compile(const rv_op *ops, size_t n_ops, size_t z64_cel
     DevProgram &D = c->dev;
     if ((rc = upload(c, P.xgates, &D.xgates)) || (rc = upload(c, P.xlevel_off, &D.xlevel_off)) || (rc = upload(c, P.items, &D.items)) ||
         (rc = upload(c, c->mul_pos, &D.mul_pos)) || (rc = upload(c, P.recon_pos, &D.recon_pos)) || (rc = upload(c, P.input_pos, &D.input_pos)) ||
-        (rc = upload(c, P.input_vid, &D.input_vid)) || (rc = upload(c, P.vm_steps, &D.vm_steps)) || (rc = upload(c, P.lut_steps, &D.lut_steps))) {
+        (rc = upload(c, P.input_vid, &D.input_vid)) || (rc = upload(c, P.vm_steps, &D.vm_steps)) || (rc = upload(c, P.lut_steps, &D.lut_steps)) || (rc = upload(c, P.vlut_steps, &D.vlut_steps)) ||
+        (rc = upload(c, c->vleaf_ids, &D.vleaf_ids)) || (rc = upload(c, P.item_ua, &D.item_ua)) || (rc = upload(c, P.item_ub, &D.item_ub)) ||
+        (rc = upload(c, c->recon_idx, &D.recon_idx))) {
         rv_circuit_free(c);
         return rc;
     }
     D.n_xgates = (uint32_t)P.xgates.size();
     D.n_llevels = (uint32_t)P.xlevel_off.size() - 1;
     D.n_lut_steps = P.n_lut_steps;
+    D.n_vlut_steps = P.n_vlut_steps;
+    D.n_uvals = P.n_uvals;
     D.n_vm_steps = P.n_vm_steps;
     D.vm_cells = P.vm_cells;
     D.n_lin = P.n_lin;
@@ -227,6 +240,12 @@ struct rv_session {
     int *d_bad = nullptr;
     uint8_t *d_proof = nullptr;
     size_t proof_len = 0;
+    // verifier-only buffers (allocated on first rv_verify)
+    uint8_t *d_vin = nullptr, *h_vin = nullptr;  // one staging blob: see VerifyLayout
+    size_t vin_bytes = 0;
+    uint8_t *d_leaf_vals = nullptr, *d_uvals = nullptr;
+    size_t leaf_pitch = 0, upitch = 0;
+    uint8_t *h_vout = nullptr;  // rep hashes (8 KB) + not_okay
     uint32_t len_recons = 0, len_corrs = 0, len_inputs = 0;
     // pinned host staging
     uint8_t *h_in = nullptr;   // witness || seeds(256*16)
@@ -263,6 +282,8 @@ extern "C" void rv_session_free(rv_session *s) {
     for (void *p : s->allocs) cudaFree(p);
     if (s->h_in) cudaFreeHost(s->h_in);
     if (s->h_out) cudaFreeHost(s->h_out);
+    if (s->h_vin) cudaFreeHost(s->h_vin);
+    if (s->h_vout) cudaFreeHost(s->h_vout);
     if (s->ev_upload) cudaEventDestroy(s->ev_upload);
     if (s->ev_vals) cudaEventDestroy(s->ev_vals);
     if (s->ev_items) cudaEventDestroy(s->ev_items);
@@ -441,7 +462,7 @@ extern "C" int rv_session_commit(rv_session *s) {
     if (s->ever_committed) CU(cudaStreamWaitEvent(s->st_val, s->ev_items, 0));  // the previous proof's item plane still reads d_vals
     {
         Scope k(s, "values", (uint64_t)P.lut_steps.size() * sizeof(LutInstr), 1, s->st_val);
-        launch_values(D, s->d_wit, s->d_vals, s->st_val);
+        launch_values(D.lut_steps, D.n_lut_steps, D.input_vid, s->d_wit, 0, D.n_inputs, s->d_vals, 0, D.n_vals, 1, s->st_val);
     }
     CU(cudaEventRecord(s->ev_vals, s->st_val));
     CU(cudaMemsetAsync(s->d_bad, 0, sizeof(int), s->st));
@@ -468,11 +489,11 @@ extern "C" int rv_session_commit(rv_session *s) {
     CU(cudaEventRecord(s->ev_items, s->st));
     {
         Scope k(s, "chunk_cv", ((uint64_t)P.n_online + P.n_pre) * s->nreps, 1);
-        launch_chunk_cv2(s->d_on, s->pitch_on, P.n_online, s->d_cv_on, s->d_pre, s->pitch_pre, P.n_pre, s->d_cv_pre, s->nreps, s->st);
+        launch_chunk_cv2(s->d_on, s->pitch_on, P.n_online, s->d_cv_on, s->nreps, s->d_pre, s->pitch_pre, P.n_pre, s->d_cv_pre, s->nreps, s->st);
     }
     {
         Scope k(s, "rep_hash", ((uint64_t)s->n_chunks_on + s->n_chunks_pre) * s->nreps * 32);
-        launch_rep_hash(s->d_cv_on, s->n_chunks_on, s->d_cv_pre, s->n_chunks_pre, s->d_zconst + 8, s->nreps, s->d_on_hash, s->d_rep_hash, s->st);
+        launch_rep_hash(s->d_cv_on, s->n_chunks_on, s->d_cv_pre, s->n_chunks_pre, s->d_zconst, s->nreps, s->d_on_hash, s->d_rep_hash, s->st);
     }
     CU(cudaGetLastError());
     s->committed = s->ever_committed = true;
@@ -604,12 +625,152 @@ extern "C" int rv_prove(const rv_circuit *c, const uint8_t *wit_gf2, size_t n_gf
     return rc;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+//  Proof::verify (src/proof/mod.rs:224-307)
+// ---------------------------------------------------------------------------------------------------------------------
+static int verify_on_session(rv_session *s, const uint8_t *proof, size_t proof_len, const PDomain &g, const PDomain &z, int *okay, int *accept) {
+    const rv_circuit *c = s->c;
+    const Program &P = c->prog;
+    const DevProgram &D = c->dev;
+    constexpr uint32_t NON = RV_ONLINE_REPS, NPRE = RV_PREPROCESSING_REPS, NPI_ON = RV_ONLINE_REPS / 8;
+    // ---- staging blob: [seeds 256x16][pkeys 256x128][mode 256][omit 256][VOpen x40][on_given 216x32][z_on_given 216x32][proof bytes] ----
+    const size_t o_seeds = 0, o_pkeys = o_seeds + 256 * 16, o_mode = o_pkeys + 256 * 128, o_omit = o_mode + 256, o_opens = o_omit + 256,
+                 o_ong = o_opens + NON * sizeof(VOpen), o_zg = o_ong + NPRE * 32, o_proof = round_up(o_zg + NPRE * 32, 16);
+    const size_t need = o_proof + round_up(proof_len, 16);
+    if (s->vin_bytes < need) {
+        if (s->h_vin) cudaFreeHost(s->h_vin);
+        s->h_vin = nullptr;
+        CU(cudaMallocHost(&s->h_vin, need));
+        int rc = dalloc(s, &s->d_vin, need);
+        if (rc) return rc;
+        s->vin_bytes = need;
+    }
+    if (!s->d_leaf_vals) {
+        s->leaf_pitch = round_up((size_t)P.n_inputs + P.n_pre + 16, 16);
+        s->upitch = round_up((size_t)P.n_uvals + 16, 16);
+        int rc;
+        if ((rc = dalloc(s, &s->d_leaf_vals, s->leaf_pitch * NON)) || (rc = dalloc(s, &s->d_uvals, s->upitch * NON))) return rc;
+        CU(cudaMallocHost(&s->h_vout, RV_TOTAL_REPS * 32 + 16));
+    }
+    CU(cudaStreamSynchronize(s->st));
+    uint8_t *h = s->h_vin;
+    memset(h, 0, o_proof);
+    VOpen *opens = reinterpret_cast<VOpen *>(h + o_opens);
+    for (uint32_t k = 0; k < NON; k++) {  // opened repetitions occupy slots 0..39 in proof order (src/proof/mod.rs:234-246)
+        const POnline &o = g.online[k];
+        memcpy(h + o_pkeys + (size_t)k * 128, proof + o.keys, 128);
+        h[o_mode + k] = 1;
+        h[o_omit + k] = o.omit;
+        const POnline &first = g.online[k & ~7u];  // the pack's first repetition fixes how many elements are unpacked
+        opens[k] = VOpen{(uint32_t)(o_proof + o.recons.off), (uint32_t)(o_proof + o.corrs.off), (uint32_t)(o_proof + o.inputs.off),
+                         (uint32_t)first.recons.len, (uint32_t)first.corrs.len, (uint32_t)first.inputs.len, o.omit, 0};
+    }
+    for (uint32_t k = 0; k < NPRE; k++) {  // then the 216 preprocessing repetitions
+        memcpy(h + o_seeds + (size_t)(NON + k) * 16, proof + g.pre[k].seed, 16);
+        h[o_omit + NON + k] = RV_PLAYERS;
+        memcpy(h + o_ong + (size_t)k * 32, proof + g.pre[k].comm_online, 32);
+        memcpy(h + o_zg + (size_t)k * 32, proof + z.pre[k].comm_online, 32);
+    }
+    memcpy(h + o_proof, proof, proof_len);
+    uint8_t *dv = s->d_vin;
+    CU(cudaMemcpyAsync(dv, h, need, cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemsetAsync(s->d_bad, 0, sizeof(int), s->st));
+    CU(cudaMemsetAsync(s->d_rows + (size_t)P.zero_row() * s->npi, 0, (size_t)s->npi * 8, s->st));
+    const uint32_t nslices = 2 * s->npi;
+    const VOpen *d_opens = reinterpret_cast<const VOpen *>(dv + o_opens);
+    {
+        Scope k(s, "v.key_setup", 0);
+        launch_key_setup(dv + o_seeds, dv + o_pkeys, dv + o_mode, dv + o_omit, nslices, s->d_ks, s->d_lane_mask, s->d_pkeys, s->st);
+    }
+    {
+        Scope k(s, "v.mask_gen", (uint64_t)P.n_masks * s->npi * 8);
+        launch_mask_gen(s->d_ks, s->d_lane_mask, nslices, P.n_masks, s->d_rows, s->d_fresh_sm, s->pitch_fresh, s->st);
+    }
+    if (D.n_llevels) {
+        Scope k(s, "v.linear", (uint64_t)P.n_lin * s->npi * 8 * 3, 2);
+        launch_linear(D, P.xlevel_off.data(), s->d_rows, s->npi, s->d_fresh_sm, s->pitch_fresh, s->d_exp_sm, s->pitch_exp, s->st, nullptr);
+    }
+    {
+        Scope k(s, "v.leaves", 0);
+        launch_verify_leaves(D, d_opens, dv, s->d_rows, s->npi, NON, s->d_leaf_vals, s->leaf_pitch, s->st);
+    }
+    {
+        Scope k(s, "v.values", (uint64_t)P.vlut_steps.size() * sizeof(LutInstr));
+        launch_values(D.vlut_steps, D.n_vlut_steps, D.vleaf_ids, s->d_leaf_vals, s->leaf_pitch, D.n_inputs + D.n_pre, s->d_uvals, s->upitch, D.n_uvals, NON, s->st);
+    }
+    {
+        Scope k(s, "v.items", 0, 3);
+        launch_items_pre_range(D, s->d_rows, s->npi, NPI_ON, s->d_pre, s->pitch_pre, s->st);
+        launch_verify_items(D, d_opens, dv, s->d_rows, s->npi, NPI_ON, s->d_uvals, s->upitch, s->d_on, s->pitch_on, s->d_pre, s->pitch_pre, s->d_bad, s->st);
+    }
+    {
+        Scope k(s, "v.chunk_cv", 0);
+        launch_chunk_cv2(s->d_on, s->pitch_on, P.n_online, s->d_cv_on, NON, s->d_pre, s->pitch_pre, P.n_pre, s->d_cv_pre, s->nreps, s->st);
+    }
+    {
+        Scope k(s, "v.rep_hash", 0);
+        launch_rep_hash(s->d_cv_on, s->n_chunks_on, s->d_cv_pre, s->n_chunks_pre, s->d_zconst, s->nreps, s->d_on_hash, s->d_rep_hash, s->st, NON,
+                        dv + o_ong, dv + o_zg);
+    }
+    CU(cudaMemcpyAsync(s->h_vout, s->d_rep_hash, RV_TOTAL_REPS * 32, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(s->h_vout + RV_TOTAL_REPS * 32, s->d_bad, 4, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(s->st));
+    s->committed = s->opened = false;
+    s->ever_committed = true;
+    // re-interleave into original repetition order using the challenge derived from the claimed comm (src/proof/mod.rs:292-302)
+    uint8_t omit_of_rep[RV_TOTAL_REPS], ordered[RV_TOTAL_REPS * 32];
+    host_challenge(proof, omit_of_rep);
+    size_t on = 0, pre = NON;
+    for (int i = 0; i < RV_TOTAL_REPS; i++) memcpy(ordered + 32 * i, s->h_vout + 32 * (omit_of_rep[i] < RV_PLAYERS ? on++ : pre++), 32);
+    uint32_t comm2[8];
+    host_hash(ordered, sizeof ordered, comm2);
+    int bad;
+    memcpy(&bad, s->h_vout + RV_TOTAL_REPS * 32, 4);
+    if (okay) *okay = bad ? 0 : 1;
+    *accept = memcmp(comm2, proof, 32) == 0 ? 1 : 0;  // src/proof/mod.rs:305-306
+    return RV_OK;
+}
+
 extern "C" int rv_verify(const rv_circuit *c, const uint8_t *proof, size_t proof_len, int *okay) {
-    (void)c;
-    (void)proof;
-    (void)proof_len;
-    (void)okay;
-    return fail(RV_E_UNSUPPORTED, "rv_verify: not implemented yet");
+    if (!c || (!proof && proof_len)) return fail(RV_E_ARG, "NULL argument");
+    if (!c->prog.has_verify) return fail(RV_E_UNSUPPORTED, "verification tables are only built for circuits of at most 4M ops");
+    if (proof_len < 32) return fail(RV_E_FORMAT, "proof shorter than its commitment");
+    PDomain g, z;
+    size_t pos = 32;
+    if (!parse_domain(proof, proof_len, pos, g) || !parse_domain(proof, proof_len, pos, z) || pos != proof_len)
+        return fail(RV_E_FORMAT, "malformed proof bytes");
+    if (okay) *okay = 1;
+    // check_format, src/proof/mod.rs:110-114,225-230
+    if (g.online.size() != RV_ONLINE_REPS || g.pre.size() != RV_PREPROCESSING_REPS || z.online.size() != RV_ONLINE_REPS || z.pre.size() != RV_PREPROCESSING_REPS)
+        return 0;
+    for (uint32_t k = 0; k < RV_ONLINE_REPS; k++) {
+        if (g.online[k].omit >= RV_PLAYERS || z.online[k].omit >= RV_PLAYERS) return fail(RV_E_FORMAT, "omitted player out of range");
+        const POnline &first = g.online[k & ~7u], &o = g.online[k];
+        // unpack_selected asserts equal lengths (src/algebra/gf2/share.rs:158-164); ReconGF2::unpack indexes every lane up to the
+        // first lane's length (src/algebra/gf2/recon.rs:241-259)
+        if (o.recons.len != first.recons.len || o.corrs.len < first.corrs.len || o.inputs.len < first.inputs.len)
+            return fail(RV_E_FORMAT, "ragged packed lengths inside a pack of 8 openings");
+    }
+    rv_session *s = nullptr;
+    {
+        std::lock_guard<std::mutex> lk(c->pool_mu);
+        if (!c->pool.empty()) {
+            s = c->pool.back();
+            c->pool.pop_back();
+        }
+    }
+    int rc = RV_OK, accept = 0;
+    if (!s && (rc = rv_session_create(c, 0, RV_PACKED_REPS, &s))) return rc;
+    rc = verify_on_session(s, proof, proof_len, g, z, okay, &accept);
+    if (rc == RV_E_CUDA) {
+        rv_session_free(s);
+        return rc;
+    }
+    std::lock_guard<std::mutex> lk(c->pool_mu);
+    if (c->pool.size() < 32) c->pool.push_back(s);
+    else rv_session_free(s);
+    return rc == RV_OK ? accept : rc;
 }
 
 extern "C" int rv_proof_new(const rv_op *ops, size_t n_ops, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64, size_t n_z64,

@@ -17,6 +17,7 @@ constexpr uint32_t NONE32 = 0xFFFFFFFFu;
 struct Cell {
     uint32_t vref;  // value id << 1 | negate
     uint32_t mid;   // fresh PRG index, LIN_BASE + linear node, or ZERO_MID
+    uint32_t uref;  // u-plane (online verifier) value ref
 };
 
 // algorithmic HBM bytes per gate over all 256 repetitions, plus the 16-byte descriptor
@@ -330,31 +331,76 @@ void emit_vm_steps(Program &P) {
     }
 }
 
-void emit_lut_steps(Program &P) {
-    P.lut_steps.clear();
-    P.n_lut_steps = 0;
-    if (P.luts.empty()) return;
+void emit_lut_steps(const std::vector<LutInstr> &luts, const std::vector<uint32_t> &level_off, uint32_t scratch, std::vector<LutInstr> &steps,
+                    uint32_t &n_steps) {
+    steps.clear();
+    n_steps = 0;
+    if (luts.empty()) return;
     LutInstr nop;
     std::memset(&nop, 0, sizeof nop);
-    nop.dst = P.n_vals;  // scratch value slot
-    const size_t n_levels = P.lut_level_off.size() - 1;
+    nop.dst = scratch;  // scratch value slot
+    const size_t n_levels = level_off.size() - 1;
     for (size_t l = 0; l < n_levels; l++) {
-        const uint32_t s = P.lut_level_off[l], e = P.lut_level_off[l + 1];
+        const uint32_t s = level_off[l], e = level_off[l + 1];
         if (e == s) continue;
-        const uint32_t steps = (e - s + LUT_STEP - 1) / LUT_STEP;
-        for (uint32_t k = 0; k < steps; k++) {
-            const bool last = k + 1 == steps;
-            const bool chunk_end = (P.n_lut_steps + 1) % LUT_STEPS_PER_CHUNK == 0;
+        const uint32_t cnt = (e - s + LUT_STEP - 1) / LUT_STEP;
+        for (uint32_t k = 0; k < cnt; k++) {
+            const bool last = k + 1 == cnt;
+            const bool chunk_end = (n_steps + 1) % LUT_STEPS_PER_CHUNK == 0;
             for (uint32_t t = 0; t < LUT_STEP; t++) {
                 const uint32_t gi = s + k * LUT_STEP + t;
-                LutInstr o = gi < e ? P.luts[gi] : nop;
+                LutInstr o = gi < e ? luts[gi] : nop;
                 o.pad = (last || chunk_end) ? LUT_F_BAR : 0;
-                P.lut_steps.push_back(o);
+                steps.push_back(o);
             }
-            P.n_lut_steps++;
+            n_steps++;
         }
     }
 }
+
+// network -> level-sorted LUT list + level offsets
+void map_to_luts(uint32_t n_ids, std::vector<MGate> &net, std::vector<uint8_t> &required, std::vector<LutInstr> &luts, std::vector<uint32_t> &level_off) {
+    std::vector<MNode> nodes;
+    map_network(n_ids, net, required, net.size() <= LUT_MAP_MAX_GATES, nodes);
+    std::vector<uint32_t> order;
+    level_off = sort_by_level(nodes, order);
+    luts.resize(nodes.size());
+    for (uint32_t i = 0; i < nodes.size(); i++) {
+        LutInstr li;
+        std::memset(&li, 0, sizeof li);
+        li.dst = nodes[i].out;
+        for (int k = 0; k < 6; k++) li.in[k] = nodes[i].leaf[k];
+        li.tt = nodes[i].tt;
+        luts[order[i]] = li;
+    }
+}
+
+// Value algebra shared by the prover's plaintext plane and the verifier's u-plane: constant folding on refs.
+struct ValueNet {
+    std::vector<MGate> g;
+    uint32_t n_ids = 1;  // id 0 = constant 0
+    uint32_t fresh() { return n_ids++; }
+    uint32_t vxor(uint32_t a, uint32_t b) {
+        const uint32_t neg = (a ^ b) & 1;
+        if ((a >> 1) == 0) return b ^ (a & 1);
+        if ((b >> 1) == 0) return a ^ (b & 1);
+        if ((a >> 1) == (b >> 1)) return neg;
+        const uint32_t id = fresh();
+        g.push_back(MGate{id, a & ~1u, b & ~1u, 0});
+        return (id << 1) | neg;
+    }
+    uint32_t vand(uint32_t a, uint32_t b) {
+        const uint32_t va = a >> 1, vb = b >> 1;
+        if (va == 0 && vb == 0) return (a & b) & 1;
+        if (va == 0) return (a & 1) ? b : 0u;
+        if (vb == 0) return (b & 1) ? a : 0u;
+        if (a == b) return a;
+        if (va == vb) return 0u;  // x & ~x
+        const uint32_t id = fresh();
+        g.push_back(MGate{id, a, b, 1});
+        return id << 1;
+    }
+};
 
 }  // namespace
 
@@ -365,7 +411,9 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
         err = "ops is NULL";
         return RV_E_ARG;
     }
-    std::vector<Cell> cells(gf2_cells, Cell{VREF_ZERO, ZERO_MID});
+    std::vector<Cell> cells(gf2_cells, Cell{VREF_ZERO, ZERO_MID, VREF_ZERO});
+    ValueNet un;  // u-plane network (built only while the circuit stays small)
+    const bool want_verify = n_ops <= (4u << 20);
     std::vector<uint32_t> vlevel(1, 0);  // per value id (plain 2-input depth, for the stats)
     std::vector<uint32_t> llevel;        // per linear node (plain depth)
     std::vector<MGate> vg;               // value network, topological; ids = value ids
@@ -385,7 +433,7 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
     for (size_t i = 0; i < n_ops; i++) {
         const rv_op &op = ops[i];
         if (op.domain == RV_SIZE_HINT) {  // src/interpreter/combine.rs:122-129
-            if (cells.size() < op.b) cells.resize(op.b, Cell{VREF_ZERO, ZERO_MID});
+            if (cells.size() < op.b) cells.resize(op.b, Cell{VREF_ZERO, ZERO_MID, VREF_ZERO});
             if (z64_cells < op.a) z64_cells = op.a;
             continue;
         }
@@ -408,7 +456,14 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
                 P.input_pos.push_back((uint32_t)P.items.size());
                 P.items.push_back(it);
                 P.input_vid.push_back(vid);
-                cells[op.dst] = Cell{vid << 1, (uint32_t)n_masks};
+                uint32_t uid = 0;
+                if (want_verify) {
+                    uid = un.fresh();
+                    P.input_uid.push_back(uid);
+                    P.item_ua.push_back(uid << 1);
+                    P.item_ub.push_back(0);
+                }
+                cells[op.dst] = Cell{vid << 1, (uint32_t)n_masks, uid << 1};
                 n_masks += 1;
                 P.n_inputs++;
                 P.algorithmic_bytes += B_INPUT;
@@ -448,6 +503,7 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
                     lg.push_back(MGate{id, A.mid, B.mid, 0});  // provisional ids; renumbered below
                     R.mid = id;
                 }
+                R.uref = want_verify ? un.vxor(A.uref, B.uref) : 0;
                 cells[op.dst] = R;
                 P.algorithmic_bytes += B_XOR;
                 break;
@@ -457,13 +513,14 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
                 if (op.dst >= nc || op.a >= nc) return bad_wire(i);
                 Cell R = cells[op.a];
                 R.vref ^= c;
+                R.uref ^= c;
                 cells[op.dst] = R;
                 P.algorithmic_bytes += B_UNARY;
                 break;
             }
             case RV_MULC: {  // src/interpreter/single.rs:97-104
                 if (op.dst >= nc || op.a >= nc) return bad_wire(i);
-                cells[op.dst] = c ? cells[op.a] : Cell{VREF_ZERO, ZERO_MID};
+                cells[op.dst] = c ? cells[op.a] : Cell{VREF_ZERO, ZERO_MID, VREF_ZERO};
                 P.algorithmic_bytes += B_UNARY;
                 break;
             }
@@ -486,6 +543,14 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
                     vg.push_back(MGate{vid, A.vref, B.vref, 1});
                     R.vref = vid << 1;
                 }
+                R.uref = 0;
+                if (want_verify) {  // u_out = u_a & u_b ^ kappa_j  
+                    const uint32_t kid = un.fresh();
+                    P.kappa_uid.push_back(kid);
+                    P.item_ua.push_back(A.uref);
+                    P.item_ub.push_back(B.uref);
+                    R.uref = un.vxor(un.vand(A.uref, B.uref), kid << 1);
+                }
                 cells[op.dst] = R;
                 n_masks += 2;
                 P.n_and++;
@@ -498,13 +563,17 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
                 Item it{ITEM_ASSERT, A.mid, 0, 0, A.vref, 0, 0, 0};
                 P.recon_pos.push_back((uint32_t)P.items.size());
                 P.items.push_back(it);
+                if (want_verify) {
+                    P.item_ua.push_back(A.uref);
+                    P.item_ub.push_back(0);
+                }
                 P.n_assert++;
                 P.algorithmic_bytes += B_ASSERT;
                 break;
             }
             case RV_CONST: {  // src/interpreter/single.rs:151-155
                 if (op.dst >= nc) return bad_wire(i);
-                cells[op.dst] = Cell{c ? VREF_ONE : VREF_ZERO, ZERO_MID};
+                cells[op.dst] = Cell{c ? VREF_ONE : VREF_ZERO, ZERO_MID, c ? VREF_ONE : VREF_ZERO};
                 P.algorithmic_bytes += B_LEAF;
                 break;
             }
@@ -596,27 +665,30 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
             required[it.va >> 1] = 1;
             if (it.kind == ITEM_MUL) required[it.vb >> 1] = 1;
         }
-        std::vector<MNode> nodes;
-        map_network(P.n_vals, vg, required, vg.size() <= LUT_MAP_MAX_GATES, nodes);
         if (small) {
             P.vgates.resize(vg.size());
             for (size_t i = 0; i < vg.size(); i++) P.vgates[i] = VGate{vg[i].out, vg[i].a, vg[i].b, vg[i].op};
         }
+        map_to_luts(P.n_vals, vg, required, P.luts, P.lut_level_off);
         std::vector<MGate>().swap(vg);
-        std::vector<uint32_t> order;
-        P.lut_level_off = sort_by_level(nodes, order);
-        P.luts.resize(nodes.size());
-        for (uint32_t i = 0; i < nodes.size(); i++) {
-            LutInstr li;
-            std::memset(&li, 0, sizeof li);
-            li.dst = nodes[i].out;
-            for (int k = 0; k < 6; k++) li.in[k] = nodes[i].leaf[k];
-            li.tt = nodes[i].tt;
-            P.luts[order[i]] = li;
-        }
     }
-    emit_lut_steps(P);
+    emit_lut_steps(P.luts, P.lut_level_off, P.n_vals, P.lut_steps, P.n_lut_steps);
     if (!small) std::vector<LutInstr>().swap(P.luts);
+
+    // ---- online verifier's u-plane ---------------------------------------------------------------------------------
+    if (want_verify) {
+        P.n_uvals = un.n_ids;
+        std::vector<uint8_t> required(P.n_uvals, 0);
+        for (size_t t = 0; t < P.items.size(); t++) {
+            required[P.item_ua[t] >> 1] = 1;
+            required[P.item_ub[t] >> 1] = 1;
+        }
+        std::vector<LutInstr> luts;
+        std::vector<uint32_t> off;
+        map_to_luts(P.n_uvals, un.g, required, luts, off);
+        emit_lut_steps(luts, off, P.n_uvals, P.vlut_steps, P.n_vlut_steps);
+        P.has_verify = true;
+    }
     return RV_OK;
 }
 

@@ -105,6 +105,13 @@ struct Program {
     uint32_t n_vm_steps = 0;
     std::vector<LutInstr> lut_steps;    // padded device stream of the value plane (n_lut_steps * LUT_STEP slots); value n_vals = scratch
     uint32_t n_lut_steps = 0;
+    // online-verifier value plane ("u-plane"): same circuit, every Mul is (a & b) ^ kappa_j with kappa_j a leaf
+    std::vector<LutInstr> vlut_steps;   // padded device stream; value n_uvals = scratch
+    uint32_t n_vlut_steps = 0, n_uvals = 0;
+    std::vector<uint32_t> input_uid;    // witness index -> u-plane value id
+    std::vector<uint32_t> kappa_uid;    // Mul index j -> u-plane value id of its kappa leaf
+    std::vector<uint32_t> item_ua, item_ub;  // per online item: u-plane refs (id << 1 | negate) of the operands / asserted wire
+    bool has_verify = false;            // built only for circuits of <= 4M ops
     std::vector<Item> items;            // online-stream order
     std::vector<uint32_t> recon_pos;    // online positions of the reconstruct() calls (Mul, AssertZero), in order
     std::vector<uint32_t> input_pos;    // online positions of the input() calls, in order

@@ -228,17 +228,21 @@ struct ChunkStream {
 constexpr int VP_THREADS = LUT_STEP;
 using LutStream = ChunkStream<(size_t)LUT_STEPS_PER_CHUNK * LUT_STEP * sizeof(LutInstr)>;
 
+// CTA b evaluates instance b: leaves leaf_vals[b * leaf_pitch + k] -> value id leaf_ids[k]; results to vals_g + b * vals_pitch.
+// Prover: one instance, leaves = the witness bits.  Online verifier: one instance per opened repetition (u-plane).
 template <bool SMEM_VALS>
-__global__ void __launch_bounds__(VP_THREADS) k_values(const LutInstr *__restrict__ prog, uint32_t n_steps, const uint32_t *__restrict__ input_vid,
-                                                       const uint8_t *__restrict__ wit, uint32_t n_inputs, uint8_t *__restrict__ vals_g,
-                                                       uint32_t n_vals) {
+__global__ void __launch_bounds__(VP_THREADS) k_values(const LutInstr *__restrict__ prog, uint32_t n_steps, const uint32_t *__restrict__ leaf_ids,
+                                                       const uint8_t *__restrict__ leaf_vals, size_t leaf_pitch, uint32_t n_leaves,
+                                                       uint8_t *__restrict__ vals_out, size_t vals_pitch, uint32_t n_vals) {
     extern __shared__ __align__(128) uint8_t smem[];
     LutStream stream;
     stream.init(smem, prog, (size_t)n_steps * LUT_STEP * sizeof(LutInstr));
+    uint8_t *vals_g = vals_out + (size_t)blockIdx.x * vals_pitch;
+    const uint8_t *wit = leaf_vals + (size_t)blockIdx.x * leaf_pitch;
     uint8_t *vals = SMEM_VALS ? smem + LutStream::BYTES : vals_g;  // slot n_vals is the scratch target of empty slots
     const uint32_t tid = threadIdx.x;
     if (tid == 0) vals[0] = 0;
-    for (uint32_t k = tid; k < n_inputs; k += VP_THREADS) vals[input_vid[k]] = wit[k] & 1;
+    for (uint32_t k = tid; k < n_leaves; k += VP_THREADS) vals[leaf_ids[k]] = wit[k] & 1;
     __syncthreads();
     const uint32_t n_chunks = (n_steps + LUT_STEPS_PER_CHUNK - 1) / LUT_STEPS_PER_CHUNK;
     for (uint32_t c = 0; c < n_chunks; c++) {
@@ -269,7 +273,8 @@ __global__ void __launch_bounds__(VP_THREADS) k_values(const LutInstr *__restric
     }
 }
 
-size_t launch_values(const DevProgram &P, const uint8_t *wit, uint8_t *vals, cudaStream_t st) {
+size_t launch_values(const LutInstr *steps, uint32_t n_steps, const uint32_t *leaf_ids, const uint8_t *leaf_vals, size_t leaf_pitch,
+                     uint32_t n_leaves, uint8_t *vals, size_t vals_pitch, uint32_t n_vals, uint32_t n_instances, cudaStream_t st) {
     const size_t cap = SMEM_DYN_CAP;
     static bool configured = false;
     if (!configured) {
@@ -277,12 +282,12 @@ size_t launch_values(const DevProgram &P, const uint8_t *wit, uint8_t *vals, cud
         cudaFuncSetAttribute(k_values<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
         configured = true;
     }
-    const size_t want = LutStream::BYTES + (((size_t)P.n_vals + 1 + 15) & ~(size_t)15);
+    const size_t want = LutStream::BYTES + (((size_t)n_vals + 1 + 15) & ~(size_t)15);
     if (want <= cap) {
-        k_values<true><<<1, VP_THREADS, want, st>>>(P.lut_steps, P.n_lut_steps, P.input_vid, wit, P.n_inputs, vals, P.n_vals);
+        k_values<true><<<n_instances, VP_THREADS, want, st>>>(steps, n_steps, leaf_ids, leaf_vals, leaf_pitch, n_leaves, vals, vals_pitch, n_vals);
         return want;
     }
-    k_values<false><<<1, VP_THREADS, LutStream::BYTES, st>>>(P.lut_steps, P.n_lut_steps, P.input_vid, wit, P.n_inputs, vals, P.n_vals);
+    k_values<false><<<n_instances, VP_THREADS, LutStream::BYTES, st>>>(steps, n_steps, leaf_ids, leaf_vals, leaf_pitch, n_leaves, vals, vals_pitch, n_vals);
     return LutStream::BYTES;
 }
 
@@ -448,10 +453,11 @@ __global__ void __launch_bounds__(256) k_items_online(const Item *__restrict__ i
 }
 
 __global__ void __launch_bounds__(256) k_items_pre(const Item *__restrict__ items, const uint32_t *__restrict__ mul_pos, uint32_t n_pre,
-                                                   const uint64_t *__restrict__ rows, uint32_t npi, uint8_t *__restrict__ pre, size_t pitch) {
+                                                   const uint64_t *__restrict__ rows, uint32_t npi, uint8_t *__restrict__ pre, size_t pitch,
+                                                   uint32_t first_pi) {
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t pi = (uint32_t)(gid % npi);
-    const uint64_t j0 = (gid / npi) * 8;
+    const uint32_t pi = first_pi + (uint32_t)(gid % (npi - first_pi));
+    const uint64_t j0 = (gid / (npi - first_pi)) * 8;
     if (j0 >= n_pre) return;
     uint64_t W[8], out[8];
 #pragma unroll
@@ -472,8 +478,15 @@ void launch_items(const DevProgram &P, const uint64_t *rows, uint32_t npi, const
     }
     if (P.n_pre) {
         const uint64_t threads = (uint64_t)((P.n_pre + 7) / 8) * npi;
-        k_items_pre<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P.items, P.mul_pos, P.n_pre, rows, npi, pre, pitch_pre);
+        k_items_pre<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P.items, P.mul_pos, P.n_pre, rows, npi, pre, pitch_pre, 0);
     }
+}
+
+// verifier, preprocessing repetitions: recompute the corrections from the seeds (src/transcript/verifier/preprocess.rs:66-69)
+void launch_items_pre_range(const DevProgram &P, const uint64_t *rows, uint32_t npi, uint32_t first_pi, uint8_t *pre, size_t pitch_pre, cudaStream_t st) {
+    if (!P.n_pre || first_pi >= npi) return;
+    const uint64_t threads = (uint64_t)((P.n_pre + 7) / 8) * (npi - first_pi);
+    k_items_pre<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P.items, P.mul_pos, P.n_pre, rows, npi, pre, pitch_pre, first_pi);
 }
 
 // =====================================================================================================================
@@ -484,7 +497,7 @@ void launch_items(const DevProgram &P, const uint64_t *rows, uint32_t npi, const
 struct ChunkJob {
     const uint8_t *stream;
     size_t pitch;
-    uint32_t len, n_chunks;
+    uint32_t len, n_chunks, nreps;
     uint32_t *cvs;
 };
 
@@ -496,11 +509,11 @@ __device__ __forceinline__ void load_block(const uint4 *p, uint32_t m[16]) {
     m[12] = d.x; m[13] = d.y; m[14] = d.z; m[15] = d.w;
 }
 
-__global__ void __launch_bounds__(64) k_chunk_cv(ChunkJob j0, ChunkJob j1, uint32_t nreps) {
+__global__ void __launch_bounds__(64) k_chunk_cv(ChunkJob j0, ChunkJob j1) {
     const ChunkJob &J = blockIdx.y == 0 ? j0 : j1;
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t chunk = (uint32_t)(gid % J.n_chunks), rep = (uint32_t)(gid / J.n_chunks);
-    if (rep >= nreps) return;
+    if (rep >= J.nreps) return;
     const uint32_t off = chunk * 1024u;
     const uint32_t clen = min(1024u, J.len - off);
     const bool root = J.n_chunks == 1;
@@ -541,12 +554,13 @@ __global__ void __launch_bounds__(64) k_chunk_cv(ChunkJob j0, ChunkJob j1, uint3
 
 static uint32_t n_chunks_of(uint32_t len) { return len == 0 ? 1 : (len + 1023) / 1024; }
 
-void launch_chunk_cv2(const uint8_t *on, size_t pitch_on, uint32_t len_on, uint32_t *cv_on, const uint8_t *pre, size_t pitch_pre,
-                      uint32_t len_pre, uint32_t *cv_pre, uint32_t nreps, cudaStream_t st) {
-    ChunkJob j0{on, pitch_on, len_on, n_chunks_of(len_on), cv_on}, j1{pre, pitch_pre, len_pre, n_chunks_of(len_pre), cv_pre};
-    const uint64_t threads = (uint64_t)std::max(j0.n_chunks, j1.n_chunks) * nreps;
+void launch_chunk_cv2(const uint8_t *on, size_t pitch_on, uint32_t len_on, uint32_t *cv_on, uint32_t nreps_on, const uint8_t *pre, size_t pitch_pre,
+                      uint32_t len_pre, uint32_t *cv_pre, uint32_t nreps_pre, cudaStream_t st) {
+    ChunkJob j0{on, pitch_on, len_on, n_chunks_of(len_on), nreps_on, cv_on}, j1{pre, pitch_pre, len_pre, n_chunks_of(len_pre), nreps_pre, cv_pre};
+    const uint64_t threads = std::max((uint64_t)j0.n_chunks * nreps_on, (uint64_t)j1.n_chunks * nreps_pre);
+    if (threads == 0) return;
     dim3 grid((unsigned)((threads + 63) / 64), 2);
-    k_chunk_cv<<<grid, 64, 0, st>>>(j0, j1, nreps);
+    k_chunk_cv<<<grid, 64, 0, st>>>(j0, j1);
 }
 
 // BLAKE3 tree over n chunk CVs, in place: adjacent pairs merge, an odd tail is carried up unchanged (this reproduces
@@ -587,21 +601,38 @@ __device__ void tree_reduce(uint32_t *cvs, uint32_t n) {
 
 // CTA = one repetition: roots of both streams, then the joins of Transcript::hash (src/transcript/mod.rs:77-96) and
 // CombineInstance::hash (src/interpreter/combine.rs:104-118).
+// Verifier: repetitions >= first_pre take their online hash from the proof (VerifierTranscriptPreprocess::online_hash,
+// src/transcript/verifier/preprocess.rs:54-56) -- `on_given` / `z_on_given` hold those 32-byte values per such repetition.
 __global__ void __launch_bounds__(128) k_rep_hash(uint32_t *cv_on, uint32_t n_chunks_on, uint32_t *cv_pre, uint32_t n_chunks_pre,
-                                                  const uint32_t *__restrict__ z64_hash, uint8_t *__restrict__ on_hash,
-                                                  uint8_t *__restrict__ rep_hash) {
+                                                  const uint32_t *__restrict__ zconst, uint8_t *__restrict__ on_hash,
+                                                  uint8_t *__restrict__ rep_hash, uint32_t first_pre, const uint8_t *__restrict__ on_given,
+                                                  const uint8_t *__restrict__ z_on_given) {
     const uint32_t rep = blockIdx.x;
+    const bool given = rep >= first_pre;
     uint32_t *on = cv_on + (size_t)rep * n_chunks_on * 8, *pre = cv_pre + (size_t)rep * n_chunks_pre * 8;
-    tree_reduce(on, n_chunks_on);
+    if (!given) tree_reduce(on, n_chunks_on);
     tree_reduce(pre, n_chunks_pre);
     __syncthreads();
     if (threadIdx.x == 0) {
         uint32_t h_on[8], h_pre[8], z[8], out[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            h_on[i] = on[i];
             h_pre[i] = pre[i];
-            z[i] = z64_hash[i];
+            z[i] = zconst[8 + i];  // H(B3("") || B3("")): the empty Z64 transcript of a prover / online-verifier repetition
+        }
+        if (given) {
+            const uint8_t *g = on_given + (size_t)(rep - first_pre) * 32, *zg = z_on_given + (size_t)(rep - first_pre) * 32;
+            uint32_t zon[8], e[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                h_on[i] = (uint32_t)g[4 * i] | ((uint32_t)g[4 * i + 1] << 8) | ((uint32_t)g[4 * i + 2] << 16) | ((uint32_t)g[4 * i + 3] << 24);
+                zon[i] = (uint32_t)zg[4 * i] | ((uint32_t)zg[4 * i + 1] << 8) | ((uint32_t)zg[4 * i + 2] << 16) | ((uint32_t)zg[4 * i + 3] << 24);
+                e[i] = zconst[i];  // B3(""): the (empty) Z64 preprocessing stream
+            }
+            b3_hash64(e, zon, z);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) h_on[i] = on[i];
         }
         rep_join(h_on, h_pre, z, out);
         uint32_t *d0 = reinterpret_cast<uint32_t *>(on_hash + (size_t)rep * 32), *d1 = reinterpret_cast<uint32_t *>(rep_hash + (size_t)rep * 32);
@@ -613,9 +644,92 @@ __global__ void __launch_bounds__(128) k_rep_hash(uint32_t *cv_on, uint32_t n_ch
     }
 }
 
-void launch_rep_hash(uint32_t *cv_on, uint32_t n_chunks_on, uint32_t *cv_pre, uint32_t n_chunks_pre, const uint32_t *z64_hash,
-                     uint32_t nreps, uint8_t *on_hash, uint8_t *rep_hash, cudaStream_t st) {
-    k_rep_hash<<<nreps, 128, 0, st>>>(cv_on, n_chunks_on, cv_pre, n_chunks_pre, z64_hash, on_hash, rep_hash);
+void launch_rep_hash(uint32_t *cv_on, uint32_t n_chunks_on, uint32_t *cv_pre, uint32_t n_chunks_pre, const uint32_t *zconst, uint32_t nreps,
+                     uint8_t *on_hash, uint8_t *rep_hash, cudaStream_t st, uint32_t first_pre, const uint8_t *on_given, const uint8_t *z_on_given) {
+    k_rep_hash<<<nreps, 128, 0, st>>>(cv_on, n_chunks_on, cv_pre, n_chunks_pre, zconst, on_hash, rep_hash, first_pre, on_given, z_on_given);
+}
+
+// =====================================================================================================================
+//  Online verifier kernels (src/transcript/verifier/online.rs): u-plane leaves, the item plane with the proof's data
+// =====================================================================================================================
+// thread = (leaf, opened repetition).  Leaves 0..n_inputs-1 are the inputs, n_inputs.. the kappa of every Mul.
+__global__ void __launch_bounds__(256) k_verify_leaves(const Item *__restrict__ items, const uint32_t *__restrict__ input_pos,
+                                                       const uint32_t *__restrict__ mul_pos, const uint32_t *__restrict__ recon_idx,
+                                                       uint32_t n_inputs, uint32_t n_and, const VOpen *__restrict__ opens,
+                                                       const uint8_t *__restrict__ proof, const uint64_t *__restrict__ rows, uint32_t npi,
+                                                       uint32_t n_slots, uint8_t *__restrict__ leaf_vals, size_t leaf_pitch) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t leaf = (uint32_t)(gid % (n_inputs + n_and)), slot = (uint32_t)(gid / (n_inputs + n_and));
+    if (slot >= n_slots) return;
+    uint8_t v;
+    if (leaf < n_inputs) v = verify_leaf_input(items[input_pos[leaf]], leaf, opens[slot], proof, rows, npi, slot);
+    else {
+        const uint32_t t = mul_pos[leaf - n_inputs];
+        v = verify_leaf_kappa(items[t], recon_idx[t], opens[slot], proof, rows, npi, slot);
+    }
+    leaf_vals[(size_t)slot * leaf_pitch + leaf] = v;
+}
+
+// thread = (8 consecutive online positions, packed instance of opened repetitions)
+__global__ void __launch_bounds__(256) k_verify_items_online(const Item *__restrict__ items, const uint32_t *__restrict__ item_ua,
+                                                             const uint32_t *__restrict__ item_ub, const uint32_t *__restrict__ recon_idx,
+                                                             uint32_t n_online, const VOpen *__restrict__ opens, const uint8_t *__restrict__ proof,
+                                                             const uint64_t *__restrict__ rows, uint32_t npi, uint32_t npi_online,
+                                                             const uint8_t *__restrict__ uvals, size_t upitch, uint8_t *__restrict__ on, size_t pitch,
+                                                             int *not_okay) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t pi = (uint32_t)(gid % npi_online);
+    const uint64_t t0 = (gid / npi_online) * 8;
+    if (t0 >= n_online) return;
+    uint64_t W[8], out[8];
+    int flag = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        W[i] = 0;
+        const uint32_t t = (uint32_t)t0 + i;
+        if (t < n_online) W[i] = verify_online_word(items[t], t, item_ua[t], item_ub[t], recon_idx[t], opens, proof, rows, npi, pi, uvals, upitch, &flag);
+    }
+    if (flag) atomicOr(not_okay, 1);
+    words_to_stream_bytes(W, out);
+#pragma unroll
+    for (int r = 0; r < 8; r++) *reinterpret_cast<uint64_t *>(on + (size_t)(8 * pi + r) * pitch + t0) = out[r];
+}
+
+// thread = (8 consecutive Mul indices, packed instance of opened repetitions): the proof's corrections as stream bytes
+__global__ void __launch_bounds__(256) k_verify_items_pre(uint32_t n_pre, const VOpen *__restrict__ opens, const uint8_t *__restrict__ proof,
+                                                          uint32_t npi_online, uint8_t *__restrict__ pre, size_t pitch) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t pi = (uint32_t)(gid % npi_online);
+    const uint64_t j0 = (gid / npi_online) * 8;
+    if (j0 >= n_pre) return;
+    uint64_t W[8], out[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) W[i] = (j0 + i < n_pre) ? verify_pre_word((uint32_t)j0 + i, opens, proof, pi) : 0;
+    words_to_stream_bytes(W, out);
+#pragma unroll
+    for (int r = 0; r < 8; r++) *reinterpret_cast<uint64_t *>(pre + (size_t)(8 * pi + r) * pitch + j0) = out[r];
+}
+
+void launch_verify_leaves(const DevProgram &P, const VOpen *opens, const uint8_t *proof, const uint64_t *rows, uint32_t npi, uint32_t n_slots,
+                          uint8_t *leaf_vals, size_t leaf_pitch, cudaStream_t st) {
+    const uint64_t threads = (uint64_t)(P.n_inputs + P.n_pre) * n_slots;
+    if (!threads) return;
+    k_verify_leaves<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P.items, P.input_pos, P.mul_pos, P.recon_idx, P.n_inputs, P.n_pre, opens, proof, rows,
+                                                                        npi, n_slots, leaf_vals, leaf_pitch);
+}
+
+void launch_verify_items(const DevProgram &P, const VOpen *opens, const uint8_t *proof, const uint64_t *rows, uint32_t npi, uint32_t npi_online,
+                         const uint8_t *uvals, size_t upitch, uint8_t *on, size_t pitch_on, uint8_t *pre, size_t pitch_pre, int *not_okay,
+                         cudaStream_t st) {
+    if (P.n_online) {
+        const uint64_t threads = (uint64_t)((P.n_online + 7) / 8) * npi_online;
+        k_verify_items_online<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P.items, P.item_ua, P.item_ub, P.recon_idx, P.n_online, opens, proof, rows, npi,
+                                                                                  npi_online, uvals, upitch, on, pitch_on, not_okay);
+    }
+    if (P.n_pre) {
+        const uint64_t threads = (uint64_t)((P.n_pre + 7) / 8) * npi_online;
+        k_verify_items_pre<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P.n_pre, opens, proof, npi_online, pre, pitch_pre);
+    }
 }
 
 // =====================================================================================================================

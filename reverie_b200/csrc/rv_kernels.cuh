@@ -19,6 +19,11 @@ struct DevProgram {
     const uint32_t *input_vid = nullptr;  // k -> value id
     const LutInstr *lut_steps = nullptr;   // value-plane step stream (n_lut_steps * LUT_STEP slots)
     uint32_t n_lut_steps = 0;
+    // online verifier (absent for circuits of more than 4M ops)
+    const LutInstr *vlut_steps = nullptr;  // u-plane step stream
+    uint32_t n_vlut_steps = 0, n_uvals = 0;
+    const uint32_t *vleaf_ids = nullptr;   // [n_inputs + n_and]: u-plane value id of every input, then of every Mul's kappa
+    const uint32_t *item_ua = nullptr, *item_ub = nullptr, *recon_idx = nullptr;  // per online item
     const VmInstr *vm_steps = nullptr;     // mask-plane VM step stream (n_vm_steps * VM_STEP slots); empty without Add/Sub
     uint32_t n_vm_steps = 0, vm_cells = 0;
     uint32_t n_xgates = 0, n_llevels = 0;
@@ -35,7 +40,8 @@ void launch_key_setup(const uint8_t *seeds, const uint8_t *pkeys_in, const uint8
 void launch_mask_gen(const uint32_t *ks, const uint32_t *lane_mask, uint32_t nslices, uint32_t n_masks, uint64_t *rows, uint32_t *fresh_sm,
                      size_t pitch_sm, cudaStream_t st);
 // K0  value plane (plaintext evaluation; one CTA, level-synchronous).  Returns the dynamic smem it asked for.
-size_t launch_values(const DevProgram &P, const uint8_t *wit, uint8_t *vals, cudaStream_t st);
+size_t launch_values(const LutInstr *steps, uint32_t n_steps, const uint32_t *leaf_ids, const uint8_t *leaf_vals, size_t leaf_pitch,
+                     uint32_t n_leaves, uint8_t *vals, size_t vals_pitch, uint32_t n_vals, uint32_t n_instances, cudaStream_t st);
 // K3  mask plane (XOR network over the share tensor)
 //     returns the number of kernel launches; *which (optional) names the variant: 0 VM (smem cells), 1 CTA walker, 2 per level
 //     fresh_sm / exp_sm: slice-major staging buffers of the VM variant ([2*npi][pitch] u32 each)
@@ -46,10 +52,20 @@ bool linear_uses_vm(const DevProgram &P);
 void launch_items(const DevProgram &P, const uint64_t *rows, uint32_t npi, const uint8_t *vals, uint8_t *on, size_t pitch_on,
                   uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st);
 // K5  BLAKE3 chunk chaining values of `nreps` streams, then per-repetition tree + joins
-void launch_chunk_cv2(const uint8_t *on, size_t pitch_on, uint32_t len_on, uint32_t *cv_on, const uint8_t *pre, size_t pitch_pre,
-                      uint32_t len_pre, uint32_t *cv_pre, uint32_t nreps, cudaStream_t st);
-void launch_rep_hash(uint32_t *cv_on, uint32_t n_chunks_on, uint32_t *cv_pre, uint32_t n_chunks_pre, const uint32_t *z64_hash,
-                     uint32_t nreps, uint8_t *on_hash, uint8_t *rep_hash, cudaStream_t st);
+void launch_chunk_cv2(const uint8_t *on, size_t pitch_on, uint32_t len_on, uint32_t *cv_on, uint32_t nreps_on, const uint8_t *pre, size_t pitch_pre,
+                      uint32_t len_pre, uint32_t *cv_pre, uint32_t nreps_pre, cudaStream_t st);
+//     zconst: [0..8) B3(""), [8..16) H(B3("") || B3("")).  Verifier: repetitions >= first_pre use the proof's online hashes.
+void launch_rep_hash(uint32_t *cv_on, uint32_t n_chunks_on, uint32_t *cv_pre, uint32_t n_chunks_pre, const uint32_t *zconst, uint32_t nreps,
+                     uint8_t *on_hash, uint8_t *rep_hash, cudaStream_t st, uint32_t first_pre = 0xFFFFFFFFu, const uint8_t *on_given = nullptr,
+                     const uint8_t *z_on_given = nullptr);
+// online verifier (src/transcript/verifier/online.rs)
+struct VOpen;
+void launch_verify_leaves(const DevProgram &P, const VOpen *opens, const uint8_t *proof, const uint64_t *rows, uint32_t npi, uint32_t n_slots,
+                          uint8_t *leaf_vals, size_t leaf_pitch, cudaStream_t st);
+void launch_verify_items(const DevProgram &P, const VOpen *opens, const uint8_t *proof, const uint64_t *rows, uint32_t npi, uint32_t npi_online,
+                         const uint8_t *uvals, size_t upitch, uint8_t *on, size_t pitch_on, uint8_t *pre, size_t pitch_pre, int *not_okay,
+                         cudaStream_t st);
+void launch_items_pre_range(const DevProgram &P, const uint64_t *rows, uint32_t npi, uint32_t first_pi, uint8_t *pre, size_t pitch_pre, cudaStream_t st);
 // K6  comm = H(256 rep hashes); Fiat-Shamir challenge (src/proof/mod.rs:74-108)
 void launch_challenge(const uint8_t *all_hashes, uint8_t *comm, uint8_t *omit_of_rep, uint16_t *rank_of_rep, cudaStream_t st);
 // K7  openings -> bincode bytes of `Proof` (src/transcript/prover.rs:57-175, src/proof/mod.rs:40-66,200-221)

@@ -95,6 +95,88 @@ RV_HD uint64_t pre_word(const Item &it, const uint64_t *rows, uint32_t npi, uint
     return (a & b) ^ c;
 }
 
+// ---- online verifier (src/transcript/verifier/online.rs:25-182) -------------------------------------------------------
+// One opened repetition's packed proof fields inside the uploaded proof bytes.  `eff_*` are the byte counts the reference's
+// unpack actually reads for this repetition's pack of 8 (the length of the pack's FIRST repetition, src/algebra/gf2/recon.rs
+// :241-259, gf2/share.rs:151-208); elements past the end read as zero (`unwrap_or_default`, online.rs:124,163,171).
+struct VOpen {
+    uint32_t off_recons, off_corrs, off_inputs;
+    uint32_t eff_recons, eff_corrs, eff_inputs;
+    uint32_t omit, pad;
+};
+
+// element e of a packed bit vector, first element = MSB of byte 0 (gf2/share.rs:66-85, gf2/recon.rs:127-148)
+RV_HD uint32_t packed_bit(const uint8_t *p, uint32_t eff_bytes, uint32_t e) {
+    return (e >> 3) < eff_bytes ? (uint32_t)(p[e >> 3] >> (7 - (e & 7))) & 1u : 0u;
+}
+// parity of the (non-omitted) player bits of repetition `rep` (0..7 within the word)
+RV_HD uint32_t rho_bit(uint64_t share_word, uint32_t rep) { return (uint32_t)(gf2_reconstruct(share_word) >> (8 * (7 - rep))) & 1u; }
+
+// u-plane leaves of opened repetition `slot`: u = corr ^ rho.
+//   input k : u = inputs[k] ^ rho(mask)                                               (online.rs:123-130)
+//   Mul   j : kappa = rho_a*rho_b ^ rho_ab ^ msg ^ delta, msg = the omitted player's broadcast bit, delta = proof correction
+RV_HD uint8_t verify_leaf_input(const Item &it, uint32_t k, const VOpen &o, const uint8_t *proof, const uint64_t *rows, uint32_t npi, uint32_t slot) {
+    const uint32_t c = packed_bit(proof + o.off_inputs, o.eff_inputs, k);
+    return (uint8_t)(c ^ rho_bit(rows[(size_t)it.ra * npi + (slot >> 3)], slot & 7));
+}
+RV_HD uint8_t verify_leaf_kappa(const Item &it, uint32_t recon_idx, const VOpen &o, const uint8_t *proof, const uint64_t *rows, uint32_t npi,
+                                uint32_t slot) {
+    const uint32_t pi = slot >> 3, r = slot & 7;
+    const uint32_t ra = rho_bit(rows[(size_t)it.ra * npi + pi], r), rb = rho_bit(rows[(size_t)it.rb * npi + pi], r);
+    const uint32_t rab = rho_bit(rows[(size_t)it.k * npi + pi], r);
+    const uint32_t msg = packed_bit(proof + o.off_recons, o.eff_recons, recon_idx);
+    const uint32_t delta = packed_bit(proof + o.off_corrs, o.eff_corrs, it.j);
+    return (uint8_t)((ra & rb) ^ rab ^ msg ^ delta);
+}
+
+// The packed online word of item t for packed instance `pi` of opened repetitions (slots 8pi..8pi+7).
+//   uvals: u-plane values, repetition `slot` at uvals + slot * upitch; ua/ub: the item's u-plane refs.
+// *not_okay is OR-ed with 1 when an AssertZero sees a non-zero value (online.rs:176-178; unused by Proof::verify).
+RV_HD uint64_t verify_online_word(const Item &it, uint32_t t, uint32_t ua, uint32_t ub, uint32_t recon_idx, const VOpen *opens,
+                                  const uint8_t *proof, const uint64_t *rows, uint32_t npi, uint32_t pi, const uint8_t *uvals, size_t upitch,
+                                  int *not_okay) {
+    (void)t;
+    uint64_t Va = 0, Vb = 0, msgw = 0, inw = 0;
+#pragma unroll
+    for (uint32_t r = 0; r < 8; r++) {
+        const uint32_t slot = 8 * pi + r;
+        const VOpen &o = opens[slot];
+        const uint8_t *uv = uvals + (size_t)slot * upitch;
+        const uint64_t byte = 0xFFull << (8 * (7 - r));
+        if (it.kind == ITEM_INPUT) {
+            if (packed_bit(proof + o.off_inputs, o.eff_inputs, it.j)) inw |= byte;
+        } else {
+            const uint32_t msg = packed_bit(proof + o.off_recons, o.eff_recons, recon_idx);
+            msgw |= (uint64_t)msg << (63 - (8 * r + o.omit));  // the omitted player's share of the broadcast (online.rs:140-160)
+            const uint32_t a = val_of(uv, ua);
+            if (a) Va |= byte;
+            if (it.kind == ITEM_MUL) {
+                if (val_of(uv, ub)) Vb |= byte;
+            } else if (a ^ msg) {
+                *not_okay |= 1;
+            }
+        }
+    }
+    if (it.kind == ITEM_INPUT) return inw;  // the masked input from the proof is hashed as is (online.rs:126-127)
+    const uint64_t la = rows[(size_t)it.ra * npi + pi];
+    if (it.kind == ITEM_ASSERT) return la ^ msgw;
+    const uint64_t lb = rows[(size_t)it.rb * npi + pi];
+    const uint64_t mab = rows[(size_t)it.k * npi + pi], mnew = rows[(size_t)(it.k + 1) * npi + pi];
+    const uint64_t ca = Va ^ gf2_reconstruct(la), cb = Vb ^ gf2_reconstruct(lb);  // corr = u ^ rho
+    return (lb & ca) ^ (la & cb) ^ mab ^ mnew ^ msgw;
+}
+
+// Preprocessing-stream word of opened repetitions: the proof's corrections, one 0x00/0xFF byte per repetition (online.rs:169-174).
+RV_HD uint64_t verify_pre_word(uint32_t j, const VOpen *opens, const uint8_t *proof, uint32_t pi) {
+    uint64_t w = 0;
+#pragma unroll
+    for (uint32_t r = 0; r < 8; r++) {
+        const VOpen &o = opens[8 * pi + r];
+        if (packed_bit(proof + o.off_corrs, o.eff_corrs, j)) w |= 0xFFull << (8 * (7 - r));
+    }
+    return w;
+}
+
 // ---- key setup -------------------------------------------------------------------------------------------------------
 // Slice w covers packed instance w/2; odd w = the high u32 of the share word (repetitions 0..3), even w = the low u32
 // (repetitions 4..7).  Bit q of a slice word belongs to stream index 31-q = 8*(rep within slice) + player.

@@ -285,3 +285,114 @@ extern "C" int hs_check_steps(const rv_op *ops, size_t n_ops, size_t z64_cells, 
     }
     return 0;
 }
+
+// Proof::verify on the CPU through the kernel bodies (mirrors verify_on_session in csrc/rv_api.cu).
+// Returns 1 accept / 0 reject / <0 error; rep_hashes (optional, 256*32) receives the hashes in ORIGINAL repetition order.
+#include "../../reverie_b200/csrc/rv_bincode.h"
+extern "C" int hs_verify(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, const uint8_t *proof, size_t proof_len, int *okay,
+                         uint8_t *rep_hashes) {
+    Program P;
+    int rc = compile(ops, n_ops, z64_cells, gf2_cells, P, g_err);
+    if (rc) return rc;
+    if (proof_len < 32) return RV_E_FORMAT;
+    PDomain g, z;
+    size_t pos = 32;
+    if (!parse_domain(proof, proof_len, pos, g) || !parse_domain(proof, proof_len, pos, z) || pos != proof_len) return RV_E_FORMAT;
+    if (g.online.size() != 40 || g.pre.size() != 216 || z.online.size() != 40 || z.pre.size() != 216) return 0;
+    const uint32_t npi = 32, NON = 40;
+    std::vector<uint8_t> seeds(256 * 16, 0), pkeys_in(256 * 128, 0), mode(256, 0), omit(256, 8);
+    std::vector<VOpen> opens(NON);
+    for (uint32_t k = 0; k < NON; k++) {
+        const POnline &o = g.online[k], &first = g.online[k & ~7u];
+        if (o.omit >= 8 || z.online[k].omit >= 8) return RV_E_FORMAT;
+        if (o.recons.len != first.recons.len || o.corrs.len < first.corrs.len || o.inputs.len < first.inputs.len) return RV_E_FORMAT;
+        memcpy(&pkeys_in[k * 128], proof + o.keys, 128);
+        mode[k] = 1;
+        omit[k] = o.omit;
+        opens[k] = VOpen{(uint32_t)o.recons.off, (uint32_t)o.corrs.off, (uint32_t)o.inputs.off, (uint32_t)first.recons.len,
+                         (uint32_t)first.corrs.len, (uint32_t)first.inputs.len, o.omit, 0};
+    }
+    for (uint32_t k = 0; k < 216; k++) memcpy(&seeds[(NON + k) * 16], proof + g.pre[k].seed, 16);
+    std::vector<uint64_t> rows((size_t)P.n_rows * npi, 0);
+    std::vector<uint8_t> pkeys;
+    gen_masks(seeds.data(), pkeys_in.data(), mode.data(), omit.data(), npi, P.n_masks, rows, pkeys);
+    for (const XGate &x : P.xgates)
+        for (uint32_t pi = 0; pi < npi; pi++) {
+            uint64_t v = 0;
+            for (int k = 0; k < 6; k++) v ^= rows[(size_t)x.in[k] * npi + pi];
+            rows[(size_t)x.dst * npi + pi] = v;
+        }
+    std::vector<uint32_t> mul_pos, recon_idx(P.n_online, 0);
+    for (uint32_t t = 0; t < P.n_online; t++)
+        if (P.items[t].kind == ITEM_MUL) mul_pos.push_back(t);
+    for (uint32_t k = 0; k < P.recon_pos.size(); k++) recon_idx[P.recon_pos[k]] = k;
+    // u-plane of the 40 opened repetitions
+    const size_t upitch = (size_t)P.n_uvals + 1;
+    std::vector<uint8_t> uvals(upitch * NON, 0);
+    for (uint32_t s = 0; s < NON; s++) {
+        uint8_t *uv = &uvals[s * upitch];
+        for (uint32_t k = 0; k < P.n_inputs; k++) uv[P.input_uid[k]] = verify_leaf_input(P.items[P.input_pos[k]], k, opens[s], proof, rows.data(), npi, s);
+        for (uint32_t j = 0; j < P.n_pre; j++) uv[P.kappa_uid[j]] = verify_leaf_kappa(P.items[mul_pos[j]], recon_idx[mul_pos[j]], opens[s], proof, rows.data(), npi, s);
+        for (uint32_t st = 0; st < P.n_vlut_steps; st++)
+            for (uint32_t t = 0; t < LUT_STEP; t++) {
+                const LutInstr &li = P.vlut_steps[(size_t)st * LUT_STEP + t];
+                uint32_t idx = 0;
+                for (int k = 0; k < 6; k++) idx |= (uint32_t)uv[li.in[k]] << k;
+                uv[li.dst] = (uint8_t)((li.tt >> idx) & 1);
+            }
+    }
+    const size_t pitch_on = (std::max<size_t>(P.n_online, 1) + 63) / 64 * 64, pitch_pre = (std::max<size_t>(P.n_pre, 1) + 63) / 64 * 64;
+    std::vector<uint8_t> on(pitch_on * 256, 0), pre(pitch_pre * 256, 0);
+    int not_okay = 0;
+    for (uint32_t pi = 0; pi < npi; pi++) {
+        if (pi < NON / 8)
+            for (uint64_t t0 = 0; t0 < P.n_online; t0 += 8) {
+                uint64_t W[8], out[8];
+                for (int i = 0; i < 8; i++) {
+                    const uint32_t t = (uint32_t)t0 + i;
+                    W[i] = t < P.n_online ? verify_online_word(P.items[t], t, P.item_ua[t], P.item_ub[t], recon_idx[t], opens.data(), proof, rows.data(), npi, pi,
+                                                               uvals.data(), upitch, &not_okay)
+                                          : 0;
+                }
+                words_to_stream_bytes(W, out);
+                for (int r = 0; r < 8; r++) memcpy(&on[(size_t)(8 * pi + r) * pitch_on + t0], &out[r], 8);
+            }
+        for (uint64_t j0 = 0; j0 < P.n_pre; j0 += 8) {
+            uint64_t W[8], out[8];
+            for (int i = 0; i < 8; i++) {
+                const uint32_t j = (uint32_t)j0 + i;
+                W[i] = j >= P.n_pre ? 0 : (pi < NON / 8 ? verify_pre_word(j, opens.data(), proof, pi) : pre_word(P.items[mul_pos[j]], rows.data(), npi, pi));
+            }
+            words_to_stream_bytes(W, out);
+            for (int r = 0; r < 8; r++) memcpy(&pre[(size_t)(8 * pi + r) * pitch_pre + j0], &out[r], 8);
+        }
+    }
+    uint32_t empty[8], zrep[8];
+    b3_chunk_cv(nullptr, 0, 0, true, empty);
+    b3_hash64(empty, empty, zrep);
+    std::vector<uint8_t> slot_hash(256 * 32);
+    for (uint32_t s = 0; s < 256; s++) {
+        uint32_t h_on[8], h_pre[8], zz[8], out[8];
+        stream_hash(&pre[(size_t)s * pitch_pre], P.n_pre, h_pre);
+        if (s < NON) {
+            stream_hash(&on[(size_t)s * pitch_on], P.n_online, h_on);
+            memcpy(zz, zrep, 32);
+        } else {
+            uint32_t zon[8];
+            memcpy(h_on, proof + g.pre[s - NON].comm_online, 32);
+            memcpy(zon, proof + z.pre[s - NON].comm_online, 32);
+            b3_hash64(empty, zon, zz);
+        }
+        rep_join(h_on, h_pre, zz, out);
+        memcpy(&slot_hash[s * 32], out, 32);
+    }
+    uint8_t omit_of_rep[256], ordered[256 * 32];
+    host_challenge(proof, omit_of_rep);
+    size_t a = 0, b = NON;
+    for (int i = 0; i < 256; i++) memcpy(ordered + 32 * i, &slot_hash[32 * (omit_of_rep[i] < 8 ? a++ : b++)], 32);
+    if (rep_hashes) memcpy(rep_hashes, ordered, sizeof ordered);
+    uint32_t comm2[8];
+    host_hash(ordered, sizeof ordered, comm2);
+    if (okay) *okay = not_okay ? 0 : 1;
+    return memcmp(comm2, proof, 32) == 0 ? 1 : 0;
+}

@@ -152,3 +152,86 @@ def test_os_rng_seeds_verify(rb):
     p2 = rb.Proof.new(ops, wit, (), wc).serialize()
     assert p1 != p2
     assert orc.verify(ops, wc, p1)[0] == 1 and orc.verify(ops, wc, p2)[0] == 1
+
+
+# ---- Proof::verify on the GPU (src/proof/mod.rs:224-307) ------------------------------------------------------------------
+def _verify_both(rb, circ, ops, wc, blob):
+    """(ours, oracle) verdicts: 1 accept / 0 reject / <0 error."""
+    import orc
+    from reverie_b200 import _native as N
+
+    want = orc.verify(ops, wc, blob)[0]
+    try:
+        got = 1 if rb.Proof(blob).verify(circ) else 0
+    except rb.ReverieError as e:
+        got = e.code
+    if want < 0:
+        want = N.E_FORMAT
+    return got, want
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_verify_accepts_and_rejects_like_the_oracle(rb, default_seeds, seed):
+    import orc
+
+    rng = np.random.default_rng(50 + seed)
+    ops, wit, wc = _random_circuit(rng, int(rng.integers(1, 40)), int(rng.integers(1, 3000)))
+    circ = rb.Circuit(ops, wc)
+    blob = rb.Proof.new(circ, wit, (), seeds=default_seeds).serialize()
+    assert _verify_both(rb, circ, ops, wc, blob) == (1, 1)
+    assert rb.Proof(orc.prove(ops, wit, [], wc, default_seeds)[1]).verify(circ)  # the oracle's proof bytes, our verifier
+    for pos in [0, 31, 32, 40, 41, 170, 171, len(blob) // 2, len(blob) - 1] + [int(x) for x in rng.integers(32, len(blob), size=12)]:
+        bad = bytearray(blob)
+        bad[pos] ^= 1 << int(rng.integers(0, 8))
+        got, want = _verify_both(rb, circ, ops, wc, bytes(bad))
+        assert got == want, f"byte {pos}: ours {got}, oracle {want}"
+    for cut in (1, 7, 48, 1000):
+        assert _verify_both(rb, circ, ops, wc, blob[:-cut])[0] == -3  # truncated -> RV_E_FORMAT
+    assert _verify_both(rb, circ, ops, wc, blob + b"\x00")[0] == -3
+
+
+def test_verify_sha256_and_flat_lengths(rb, default_seeds):
+    from reverie_b200 import circuits as C
+
+    ops, wit, wc = C.sha256_abc_case()
+    circ = rb.Circuit(ops, wc)
+    blob = rb.Proof.new(circ, wit, (), seeds=default_seeds).serialize()
+    assert rb.Proof(blob).verify(circ)
+    bad = bytearray(blob)
+    bad[100000] ^= 0x20
+    assert not rb.Proof(bytes(bad)).verify(circ)
+    for n in (0, 1, 7, 8, 9, 1025):
+        ops, wc = C.flat_mul_circuit(n)
+        circ = rb.Circuit(ops, wc)
+        blob = rb.Proof.new(circ, [1, 0], (), seeds=default_seeds).serialize()
+        assert rb.Proof(blob).verify(circ), n
+        other = rb.Proof.new(circ, [1, 1], (), seeds=default_seeds).serialize()
+        assert rb.Proof(other).verify(circ)
+        mixed = blob[:32] + other[32:]  # commitment of one proof, openings of another
+        assert not rb.Proof(mixed).verify(circ), n
+
+
+def test_verify_wrong_circuit_rejects(rb, default_seeds):
+    rng = np.random.default_rng(77)
+    ops, wit, wc = _random_circuit(rng, 16, 600)
+    blob = rb.Proof.new(ops, wit, (), wc, seeds=default_seeds).serialize()
+    ops2 = ops.copy()
+    k = int(np.where(ops2["opcode"] == 6)[0][3])
+    ops2["opcode"][k] = 2  # one Mul becomes an Add: stream lengths change -> hashes differ
+    got, want = _verify_both(rb, rb.Circuit(ops2, wc), ops2, wc, blob)
+    assert got == want and got != 1
+
+
+def test_golden_fixtures(rb, default_seeds):
+    """GPU proofs against tests/golden/proofs.json (no oracle run involved)."""
+    import hashlib
+    import json
+    import os
+
+    from tests.golden.make_golden import cases
+
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "proofs.json")))["cases"]
+    for name, (ops, wit, wc) in cases().items():
+        blob = rb.Proof.new(ops, wit, (), wc, seeds=default_seeds).serialize()
+        assert len(blob) == gold[name]["proof_len"] and hashlib.sha256(blob).hexdigest() == gold[name]["proof_sha256"], name
+        assert blob[:32].hex() == gold[name]["comm"], name
