@@ -157,6 +157,8 @@ int rv_session_upload(rv_session *s, const uint8_t *wit_gf2, size_t n_gf2, const
 int rv_session_commit(rv_session *s);                                   /* async on the session stream */
 int rv_session_hashes(rv_session *s, uint8_t *rep_hashes);              /* synchronises                */
 int rv_session_open(rv_session *s, const uint8_t *all_rep_hashes);      /* async; NULL = own hashes (single shard) */
+int rv_session_prove(rv_session *s);                                    /* async: commit + open(own hashes) of a full shard as
+                                                                           one CUDA graph launch after the first, eager, call */
 int rv_session_fetch(rv_session *s, uint8_t comm[RV_HASH_SIZE], uint8_t **part, size_t *part_len); /* synchronises */
 int rv_session_sync(rv_session *s);
 int rv_proof_assemble(const uint8_t comm[RV_HASH_SIZE], const uint8_t *const *parts, const size_t *part_lens,

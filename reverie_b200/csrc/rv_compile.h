@@ -39,14 +39,14 @@ struct XGate {
 };
 // mask-plane VM instruction (shared-memory cells; see build_mask_vm):
 //   XOR : v = XOR of cell[in[0..5]]; cell[dst] = v; if (row != VM_ROW_NONE) rows[row] = v
-//   LOAD: cell[dst] <- rows[in[0]]   asynchronously, `VM_DELTA` levels ahead of its first use
+//   LOAD: cell[dst] <- rows[in[0]]   asynchronously, `VM_DELTA` levels ahead of its first use (one cp.async group per level)
 struct VmInstr {
     uint32_t dst;  // cell | VM_F_* flags
     uint32_t in[6];
     uint32_t row;
     uint32_t pad[4];  // 48 bytes = three 16-byte units
 };
-constexpr int VM_DELTA = 8;  // prefetch distance in levels (L2 latency / per-level time)
+constexpr int VM_DELTA = 2;  // prefetch distance in levels: a LOAD issued during level L-2 is awaited at the end of level L-1
 
 // value-plane LUT instruction: v[dst] = tt >> (v[in0] | v[in1]<<1 | ... | v[in5]<<5) & 1.  Unused inputs name value 0
 // (the constant 0).  Produced by the depth-oriented K=6 cut mapper (build_value_luts), which collapses cones of 2-input
@@ -66,7 +66,8 @@ struct LutInstr {
 //   LUT     : step = LUT_STEP slots of 48 bytes; `pad` = flags
 // STEP_BAR on a slot means "CTA barrier after this step" (set on every slot of the last step of a level and of a chunk).
 constexpr uint32_t VM_STEP = 512, VM_STEPS_PER_CHUNK = 1, LUT_STEP = 128, LUT_STEPS_PER_CHUNK = 2;
-constexpr uint32_t VM_F_LOAD = 0x80000000u, VM_F_BAR = 0x40000000u, VM_CELL_MASK = 0x00FFFFFFu, VM_ROW_NONE = 0xFFFFFFFFu;
+constexpr uint32_t VM_F_LOAD = 0x80000000u, VM_F_BAR = 0x40000000u, VM_F_LEVEL_END = 0x20000000u, VM_CELL_MASK = 0x00FFFFFFu,
+                   VM_ROW_NONE = 0xFFFFFFFFu;
 constexpr uint32_t LUT_F_BAR = 1u;
 
 enum ItemKind : uint32_t { ITEM_INPUT = 0, ITEM_MUL = 1, ITEM_ASSERT = 2 };

@@ -177,11 +177,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 }
 
 constexpr size_t SMEM_DYN_CAP = 226 * 1024;  // of the 227 KB a CTA may opt into; the rest covers static __shared__
-constexpr int RING_NB = 4;                     // chunks in flight (power of two)
 
 // CHUNK_BYTES of program per chunk.  Every thread calls begin_chunk(c) for c = 0, 1, 2, ... in order (uniformly), and a
 // CTA barrier separates the last read of chunk c-1 from begin_chunk(c): the host compiler forces one at every chunk end.
-template <size_t CHUNK_BYTES>
+template <size_t CHUNK_BYTES, int RING_NB>  // RING_NB chunks in flight
 struct ChunkStream {
     static constexpr size_t BYTES = RING_NB * CHUNK_BYTES + 64;
     uint8_t *buf;
@@ -226,7 +225,7 @@ struct ChunkStream {
 //      thread per step.  Values live in shared memory (or global when they do not fit).
 // =====================================================================================================================
 constexpr int VP_THREADS = LUT_STEP;
-using LutStream = ChunkStream<(size_t)LUT_STEPS_PER_CHUNK * LUT_STEP * sizeof(LutInstr)>;
+using LutStream = ChunkStream<(size_t)LUT_STEPS_PER_CHUNK * LUT_STEP * sizeof(LutInstr), 4>;
 
 // CTA b evaluates instance b: leaves leaf_vals[b * leaf_pitch + k] -> value id leaf_ids[k]; results to vals_g + b * vals_pitch.
 // Prover: one instance, leaves = the witness bits.  Online verifier: one instance per opened repetition (u-plane).
@@ -300,7 +299,7 @@ constexpr int VM_THREADS = VM_STEP;
 // (a) VM over shared-memory cells: one CTA per slice (u32 lane word = 4 repetitions x 8 players), one slot per thread per
 //     step.  The dependent chain per level is LDS -> XOR -> STS -> barrier; fresh rows arrive through cp.async LOADs issued
 //     VM_DELTA levels early; only rows the item plane needs are written back to the share tensor.
-using VmStream = ChunkStream<(size_t)VM_STEPS_PER_CHUNK * VM_STEP * sizeof(VmInstr)>;
+using VmStream = ChunkStream<(size_t)VM_STEPS_PER_CHUNK * VM_STEP * sizeof(VmInstr), 3>;  // 72 KB: two CTAs per SM stay possible
 static_assert(VM_THREADS == (int)VM_STEP, "one slot per thread");
 
 __global__ void __launch_bounds__(VM_THREADS) k_mask_vm(const VmInstr *__restrict__ prog, uint32_t n_steps, const uint32_t *__restrict__ fresh_sm,
@@ -339,8 +338,10 @@ __global__ void __launch_bounds__(VM_THREADS) k_mask_vm(const VmInstr *__restric
                     cells[a.x & VM_CELL_MASK] = v;
                     if (b.w != VM_ROW_NONE) dst[b.w - n_masks] = v;
                 }
-                __pipeline_commit();
-                __pipeline_wait_prior(VM_DELTA - 1);
+                if (a.x & VM_F_LEVEL_END) {  // one cp.async group per level; LOADs of level L-2 are complete before level L starts
+                    __pipeline_commit();
+                    __pipeline_wait_prior(VM_DELTA - 1);
+                }
                 if (a.x & VM_F_BAR) __syncthreads();
             }
     }

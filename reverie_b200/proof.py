@@ -124,6 +124,10 @@ class Session:
             p = _ptr(self._ah)
         N.check(N.lib().rv_session_open(self._h, p))
 
+    def prove(self):
+        """commit + open (own hashes) of a full shard, asynchronously; one CUDA graph launch after the first call."""
+        N.check(N.lib().rv_session_prove(self._h))
+
     def fetch(self) -> Tuple[bytes, bytes]:
         comm = np.zeros(32, dtype=np.uint8)
         out, n = C.c_void_p(), C.c_size_t()

@@ -213,8 +213,8 @@ extern "C" int hs_check_steps(const rv_op *ops, size_t n_ops, size_t z64_cells, 
     stats[5] = (uint32_t)P.lut_level_off.size() - 1;
     stats[6] = P.n_lin;
     if (P.vm_steps.size() != (size_t)P.n_vm_steps * VM_STEP || P.lut_steps.size() != (size_t)P.n_lut_steps * LUT_STEP) { g_err = "stream size"; return -300; }
-    // --- mask VM ---
-    {
+    // --- mask VM: once with every LOAD landing immediately, once landing as late as the cp.async group wait allows ---
+    for (int late = 0; late < 2; late++) {
         std::vector<uint32_t> rows(P.n_rows, 0), ref;
         uint32_t x = 99;
         for (uint32_t r = 0; r < P.n_masks; r++) rows[r] = (x = x * 1664525u + 1013904223u);
@@ -226,16 +226,21 @@ extern "C" int hs_check_steps(const rv_op *ops, size_t n_ops, size_t z64_cells, 
         }
         std::vector<uint32_t> cells(P.vm_cells + 1, 0xDEADBEEF);
         cells[0] = 0;
-        std::vector<std::pair<uint32_t, uint32_t>> writes;  // writes become visible at the next barrier at the latest;
-        for (uint32_t st = 0; st < P.n_vm_steps; st++) {    // applying them per step is the most adversarial legal order
+        std::vector<std::pair<uint32_t, uint32_t>> writes;
+        std::vector<std::pair<uint32_t, uint32_t>> pending[2];  // [0]: issued in the current level, [1]: in the previous one
+        for (uint32_t st = 0; st < P.n_vm_steps; st++) {
             writes.clear();
-            bool bar = false;
+            bool bar = false, level_end = false;
             for (uint32_t t = 0; t < VM_STEP; t++) {
                 const VmInstr &in = P.vm_steps[(size_t)st * VM_STEP + t];
                 bar = (in.dst & VM_F_BAR) != 0;
+                level_end = (in.dst & VM_F_LEVEL_END) != 0;
                 if (((P.vm_steps[(size_t)st * VM_STEP].dst & VM_F_BAR) != 0) != bar) { g_err = "non-uniform barrier flag"; return -301; }
-                if (in.dst & VM_F_LOAD) writes.push_back({in.dst & VM_CELL_MASK, rows[in.in[0]]});
-                else {
+                if ((in.dst & VM_F_LEVEL_END) && !bar) { g_err = "level end without barrier"; return -305; }
+                if (in.dst & VM_F_LOAD) {
+                    if (late) pending[0].push_back({in.dst & VM_CELL_MASK, rows[in.in[0]]});
+                    else writes.push_back({in.dst & VM_CELL_MASK, rows[in.in[0]]});
+                } else {
                     uint32_t v = 0;
                     for (int k = 0; k < 6; k++) v ^= cells[in.in[k]];
                     writes.push_back({in.dst & VM_CELL_MASK, v});
@@ -244,11 +249,16 @@ extern "C" int hs_check_steps(const rv_op *ops, size_t n_ops, size_t z64_cells, 
             }
             if ((st + 1) % VM_STEPS_PER_CHUNK == 0 && !bar) { g_err = "missing barrier at chunk end"; return -302; }
             for (auto &w : writes) cells[w.first] = w.second;
+            if (level_end) {  // commit; wait_prior(VM_DELTA - 1): everything but the newest group has landed
+                for (auto &w : pending[1]) cells[w.first] = w.second;
+                pending[1].swap(pending[0]);
+                pending[0].clear();
+            }
         }
         for (const Item &it : P.items) {
             const uint32_t rr[2] = {it.ra, it.kind == ITEM_MUL ? it.rb : it.ra};
             for (uint32_t r : rr)
-                if (rows[r] != ref[r]) { g_err = "VM step stream: row mismatch at row " + std::to_string(r); return -303; }
+                if (rows[r] != ref[r]) { g_err = "VM step stream: row mismatch at row " + std::to_string(r) + (late ? " (late LOADs)" : ""); return -303; }
         }
     }
     // --- LUT stream ---

@@ -27,6 +27,6 @@ for k in s.kernel_times():
 s.timing(False)
 t = time.time()
 for it in range(20):
-    s.upload(wit, (), seeds); s.commit(); s.open(); s.fetch()
+    s.upload(wit, (), seeds); s.prove(); s.fetch()
 dt = (time.time() - t) / 20
 print("steady e2e ms/proof", dt * 1e3, "AND/s", circ.stats()["n_and"] / dt)
