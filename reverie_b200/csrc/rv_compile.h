@@ -65,7 +65,7 @@ struct LutInstr {
 //   mask VM : step = VM_STEP slots of 48 bytes; word 0 = dst cell | flags
 //   LUT     : step = LUT_STEP slots of 48 bytes; `pad` = flags
 // STEP_BAR on a slot means "CTA barrier after this step" (set on every slot of the last step of a level and of a chunk).
-constexpr uint32_t VM_STEP = 512, VM_STEPS_PER_CHUNK = 1, LUT_STEP = 128, LUT_STEPS_PER_CHUNK = 2;
+constexpr uint32_t VM_STEP = 512, VM_STEPS_PER_CHUNK = 2, LUT_STEP = 128, LUT_STEPS_PER_CHUNK = 8;
 constexpr uint32_t VM_F_LOAD = 0x80000000u, VM_F_BAR = 0x40000000u, VM_F_LEVEL_END = 0x20000000u, VM_CELL_MASK = 0x00FFFFFFu,
                    VM_ROW_NONE = 0xFFFFFFFFu;
 constexpr uint32_t LUT_F_BAR = 1u;

@@ -180,52 +180,68 @@ constexpr size_t SMEM_DYN_CAP = 226 * 1024;  // of the 227 KB a CTA may opt into
 
 // CHUNK_BYTES of program per chunk.  Every thread calls begin_chunk(c) for c = 0, 1, 2, ... in order (uniformly), and a
 // CTA barrier separates the last read of chunk c-1 from begin_chunk(c): the host compiler forces one at every chunk end.
-template <size_t CHUNK_BYTES, int RING_NB>  // RING_NB chunks in flight
+// All bookkeeping is 32-bit and precomputed: the per-chunk cost sits on the critical path of the level-synchronous kernels.
+template <uint32_t CHUNK_BYTES, int RING_NB>  // RING_NB chunks in flight
 struct ChunkStream {
-    static constexpr size_t BYTES = RING_NB * CHUNK_BYTES + 64;
-    uint8_t *buf;
-    uint64_t *bars;
+    static constexpr size_t BYTES = (size_t)RING_NB * CHUNK_BYTES + 64;
+    uint32_t buf_s, bars_s;  // shared-space addresses
     const uint8_t *src;
-    size_t total;  // program bytes
+    uint32_t n_chunks, last_bytes;
 
-    __device__ __forceinline__ void issue(uint32_t c) {
-        const size_t first = (size_t)c * CHUNK_BYTES;
-        if (first >= total) return;
-        const uint32_t bytes = (uint32_t)min((size_t)CHUNK_BYTES, total - first);
-        uint64_t *bar = bars + (c % RING_NB);
-        mbar_expect_tx(bar, bytes);
-        bulk_g2s(buf + (size_t)(c % RING_NB) * CHUNK_BYTES, src + first, bytes, bar);
+    __device__ __forceinline__ void issue(uint32_t c) {  // c < n_chunks
+        const uint32_t bytes = c + 1 == n_chunks ? last_bytes : CHUNK_BYTES;
+        const uint32_t slot = c % RING_NB, bar = bars_s + 8 * slot;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(buf_s + slot * CHUNK_BYTES),
+                     "l"(src + (size_t)c * CHUNK_BYTES), "r"(bytes), "r"(bar)
+                     : "memory");
     }
-    __device__ void init(uint8_t *smem, const void *program, size_t program_bytes) {  // all threads; includes a CTA barrier
-        buf = smem;
-        bars = reinterpret_cast<uint64_t *>(smem + RING_NB * CHUNK_BYTES);
+    __device__ void init(uint8_t *smem, const void *program, uint32_t chunks, uint32_t last_chunk_bytes) {  // all threads; has a CTA barrier
+        buf_s = smem_u32(smem);
+        bars_s = buf_s + RING_NB * CHUNK_BYTES;
         src = reinterpret_cast<const uint8_t *>(program);
-        total = program_bytes;
+        n_chunks = chunks;
+        last_bytes = last_chunk_bytes;
         if (threadIdx.x == 0) {
-            for (int i = 0; i < RING_NB; i++) mbar_init(bars + i, 1);
+            for (int i = 0; i < RING_NB; i++) mbar_init(reinterpret_cast<uint64_t *>(smem + RING_NB * CHUNK_BYTES) + i, 1);
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         __syncthreads();
         if (threadIdx.x == 0)
-            for (uint32_t c = 0; c < RING_NB; c++) issue(c);
+            for (uint32_t c = 0; c < RING_NB && c < n_chunks; c++) issue(c);
     }
-    // Returns the chunk's shared-memory image.  Thread 0 also re-arms the buffer that chunk c-1 occupied.
-    __device__ __forceinline__ const uint8_t *begin_chunk(uint32_t c) {
-        if (threadIdx.x == 0 && c >= 1) issue(c + RING_NB - 1);
-        uint64_t *bar = bars + (c % RING_NB);
-        const uint32_t parity = (c / RING_NB) & 1;
-        while (!mbar_try_wait(bar, parity)) {
-        }
-        return buf + (size_t)(c % RING_NB) * CHUNK_BYTES;
+    // Returns the shared-space address of the chunk's image.  Thread 0 also re-arms the buffer that chunk c-1 occupied.
+    __device__ __forceinline__ uint32_t begin_chunk(uint32_t c) {
+        if (threadIdx.x == 0 && c >= 1 && c + RING_NB - 1 < n_chunks) issue(c + RING_NB - 1);
+        const uint32_t slot = c % RING_NB, bar = bars_s + 8 * slot, parity = (c / RING_NB) & 1;
+        uint32_t ok;
+        do {
+            asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(ok)
+                         : "r"(bar), "r"(parity)
+                         : "memory");
+        } while (!ok);
+        return buf_s + slot * CHUNK_BYTES;
     }
 };
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
 
 // =====================================================================================================================
 //  K0  value plane: the mapped LUT program as a step stream (rv_compile.h), one CTA of LUT_STEP threads, one slot per
 //      thread per step.  Values live in shared memory (or global when they do not fit).
 // =====================================================================================================================
 constexpr int VP_THREADS = LUT_STEP;
-using LutStream = ChunkStream<(size_t)LUT_STEPS_PER_CHUNK * LUT_STEP * sizeof(LutInstr), 4>;
+constexpr uint32_t LUT_CHUNK_BYTES = LUT_STEPS_PER_CHUNK * LUT_STEP * (uint32_t)sizeof(LutInstr);
+using LutStream = ChunkStream<LUT_CHUNK_BYTES, 2>;
 
 // CTA b evaluates instance b: leaves leaf_vals[b * leaf_pitch + k] -> value id leaf_ids[k]; results to vals_g + b * vals_pitch.
 // Prover: one instance, leaves = the witness bits.  Online verifier: one instance per opened repetition (u-plane).
@@ -234,41 +250,47 @@ __global__ void __launch_bounds__(VP_THREADS) k_values(const LutInstr *__restric
                                                        const uint8_t *__restrict__ leaf_vals, size_t leaf_pitch, uint32_t n_leaves,
                                                        uint8_t *__restrict__ vals_out, size_t vals_pitch, uint32_t n_vals) {
     extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t n_chunks = (n_steps + LUT_STEPS_PER_CHUNK - 1) / LUT_STEPS_PER_CHUNK;
     LutStream stream;
-    stream.init(smem, prog, (size_t)n_steps * LUT_STEP * sizeof(LutInstr));
+    stream.init(smem, prog, n_chunks, (n_steps - (n_chunks ? n_chunks - 1 : 0) * LUT_STEPS_PER_CHUNK) * LUT_STEP * (uint32_t)sizeof(LutInstr));
     uint8_t *vals_g = vals_out + (size_t)blockIdx.x * vals_pitch;
     const uint8_t *wit = leaf_vals + (size_t)blockIdx.x * leaf_pitch;
-    uint8_t *vals = SMEM_VALS ? smem + LutStream::BYTES : vals_g;  // slot n_vals is the scratch target of empty slots
+    // values: slot n_vals is the scratch target of empty slots.  In shared memory they are addressed as smem[BYTES + id] so
+    // that every access is a plain LDS/STS with an immediate offset (no generic-address arithmetic in the hot loop).
+    auto ld = [&](uint32_t id) -> uint32_t { return SMEM_VALS ? (uint32_t)smem[LutStream::BYTES + id] : (uint32_t)vals_g[id]; };
+    auto st = [&](uint32_t id, uint32_t v) {
+        if (SMEM_VALS) smem[LutStream::BYTES + id] = (uint8_t)v;
+        else vals_g[id] = (uint8_t)v;
+    };
     const uint32_t tid = threadIdx.x;
-    if (tid == 0) vals[0] = 0;
-    for (uint32_t k = tid; k < n_leaves; k += VP_THREADS) vals[leaf_ids[k]] = wit[k] & 1;
+    if (tid == 0) st(0, 0);
+    for (uint32_t k = tid; k < n_leaves; k += VP_THREADS) st(leaf_ids[k], wit[k] & 1);
     __syncthreads();
-    const uint32_t n_chunks = (n_steps + LUT_STEPS_PER_CHUNK - 1) / LUT_STEPS_PER_CHUNK;
     for (uint32_t c = 0; c < n_chunks; c++) {
-        const uint4 *img = reinterpret_cast<const uint4 *>(stream.begin_chunk(c));
+        const uint32_t img = stream.begin_chunk(c) + tid * (uint32_t)sizeof(LutInstr);
         const uint32_t nst = min((uint32_t)LUT_STEPS_PER_CHUNK, n_steps - c * LUT_STEPS_PER_CHUNK);
-        uint4 u[LUT_STEPS_PER_CHUNK][3];
+        uint4 u0[LUT_STEPS_PER_CHUNK], u1[LUT_STEPS_PER_CHUNK];
+        uint2 u2[LUT_STEPS_PER_CHUNK];
 #pragma unroll
         for (int k = 0; k < (int)LUT_STEPS_PER_CHUNK; k++)
             if (k < (int)nst) {
-                const uint4 *p = img + ((size_t)k * LUT_STEP + tid) * 3;
-                u[k][0] = p[0];  // {dst, in0, in1, in2}
-                u[k][1] = p[1];  // {in3, in4, in5, flags}
-                u[k][2] = p[2];  // {tt lo, tt hi, -, -}
+                const uint32_t p = img + k * LUT_STEP * (uint32_t)sizeof(LutInstr);
+                u0[k] = lds128(p);       // {dst, in0, in1, in2}
+                u1[k] = lds128(p + 16);  // {in3, in4, in5, flags}
+                u2[k] = lds64(p + 32);   // {tt lo, tt hi}
             }
 #pragma unroll
         for (int k = 0; k < (int)LUT_STEPS_PER_CHUNK; k++)
             if (k < (int)nst) {
-                const uint32_t idx = (uint32_t)vals[u[k][0].y] | ((uint32_t)vals[u[k][0].z] << 1) | ((uint32_t)vals[u[k][0].w] << 2) |
-                                     ((uint32_t)vals[u[k][1].x] << 3) | ((uint32_t)vals[u[k][1].y] << 4) | ((uint32_t)vals[u[k][1].z] << 5);
-                const uint64_t tt = ((uint64_t)u[k][2].y << 32) | u[k][2].x;
-                vals[u[k][0].x] = (uint8_t)((tt >> idx) & 1);
-                if (u[k][1].w & LUT_F_BAR) __syncthreads();
+                const uint32_t idx = ld(u0[k].y) | (ld(u0[k].z) << 1) | (ld(u0[k].w) << 2) | (ld(u1[k].x) << 3) | (ld(u1[k].y) << 4) | (ld(u1[k].z) << 5);
+                const uint64_t tt = ((uint64_t)u2[k].y << 32) | u2[k].x;
+                st(u0[k].x, (uint32_t)(tt >> idx) & 1u);
+                if (u1[k].w & LUT_F_BAR) __syncthreads();
             }
     }
     __syncthreads();
     if (SMEM_VALS) {
-        for (uint32_t i = tid; i < n_vals; i += VP_THREADS) vals_g[i] = vals[i];
+        for (uint32_t i = tid; i < n_vals; i += VP_THREADS) vals_g[i] = smem[LutStream::BYTES + i];
     }
 }
 
@@ -299,44 +321,45 @@ constexpr int VM_THREADS = VM_STEP;
 // (a) VM over shared-memory cells: one CTA per slice (u32 lane word = 4 repetitions x 8 players), one slot per thread per
 //     step.  The dependent chain per level is LDS -> XOR -> STS -> barrier; fresh rows arrive through cp.async LOADs issued
 //     VM_DELTA levels early; only rows the item plane needs are written back to the share tensor.
-using VmStream = ChunkStream<(size_t)VM_STEPS_PER_CHUNK * VM_STEP * sizeof(VmInstr), 3>;  // 72 KB: two CTAs per SM stay possible
+constexpr uint32_t VM_CHUNK_BYTES = VM_STEPS_PER_CHUNK * VM_STEP * (uint32_t)sizeof(VmInstr);
+using VmStream = ChunkStream<VM_CHUNK_BYTES, 2>;
 static_assert(VM_THREADS == (int)VM_STEP, "one slot per thread");
 
 __global__ void __launch_bounds__(VM_THREADS) k_mask_vm(const VmInstr *__restrict__ prog, uint32_t n_steps, const uint32_t *__restrict__ fresh_sm,
                                                         size_t pitch_fresh, uint32_t *__restrict__ exp_sm, size_t pitch_exp, uint32_t n_masks) {
     extern __shared__ __align__(128) uint8_t smem[];
+    const uint32_t n_chunks = (n_steps + VM_STEPS_PER_CHUNK - 1) / VM_STEPS_PER_CHUNK;
     VmStream stream;
-    stream.init(smem, prog, (size_t)n_steps * VM_STEP * sizeof(VmInstr));
-    uint32_t *cells = reinterpret_cast<uint32_t *>(smem + VmStream::BYTES);
+    stream.init(smem, prog, n_chunks, (n_steps - (n_chunks ? n_chunks - 1 : 0) * VM_STEPS_PER_CHUNK) * VM_STEP * (uint32_t)sizeof(VmInstr));
+    uint32_t *cells = reinterpret_cast<uint32_t *>(smem + VmStream::BYTES);  // indexed as a shared array: LDS/STS [R.X4 + imm]
     const uint32_t tid = threadIdx.x, w = blockIdx.x;
     // Global traffic is slice-major on both sides, so a warp's 32 accesses fall into a few 128-byte lines: LOADs of a level
     // are sorted by row, exported rows are numbered in program order.  (Row-major, each lane would touch its own 256-byte
     // row and the kernel would be bound by L1 request rate.)
     const uint32_t *src = fresh_sm + (size_t)w * pitch_fresh;
-    uint32_t *dst = exp_sm + (size_t)w * pitch_exp;
+    uint32_t *dst = exp_sm + (size_t)w * pitch_exp - n_masks;
     if (tid == 0) cells[0] = 0;  // cell 0 is the constant zero (first read happens after the first barrier)
-    const uint32_t n_chunks = (n_steps + VM_STEPS_PER_CHUNK - 1) / VM_STEPS_PER_CHUNK;
     for (uint32_t c = 0; c < n_chunks; c++) {
-        const uint4 *img = reinterpret_cast<const uint4 *>(stream.begin_chunk(c));
+        const uint32_t img = stream.begin_chunk(c) + tid * (uint32_t)sizeof(VmInstr);
         const uint32_t nst = min((uint32_t)VM_STEPS_PER_CHUNK, n_steps - c * VM_STEPS_PER_CHUNK);
-        uint4 u[VM_STEPS_PER_CHUNK][2];
+        uint4 u0[VM_STEPS_PER_CHUNK], u1[VM_STEPS_PER_CHUNK];
 #pragma unroll
         for (int k = 0; k < (int)VM_STEPS_PER_CHUNK; k++)
             if (k < (int)nst) {
-                const uint4 *p = img + ((size_t)k * VM_STEP + tid) * 3;
-                u[k][0] = p[0];  // {dst | flags, in0, in1, in2}
-                u[k][1] = p[1];  // {in3, in4, in5, row}
+                const uint32_t p = img + k * VM_STEP * (uint32_t)sizeof(VmInstr);
+                u0[k] = lds128(p);       // {dst | flags, in0, in1, in2}
+                u1[k] = lds128(p + 16);  // {in3, in4, in5, row}
             }
 #pragma unroll
         for (int k = 0; k < (int)VM_STEPS_PER_CHUNK; k++)
             if (k < (int)nst) {
-                const uint4 a = u[k][0], b = u[k][1];
+                const uint4 a = u0[k], b = u1[k];
                 if (a.x & VM_F_LOAD) {
                     __pipeline_memcpy_async(cells + (a.x & VM_CELL_MASK), src + a.y, 4);
                 } else {
                     const uint32_t v = cells[a.y] ^ cells[a.z] ^ cells[a.w] ^ cells[b.x] ^ cells[b.y] ^ cells[b.z];
                     cells[a.x & VM_CELL_MASK] = v;
-                    if (b.w != VM_ROW_NONE) dst[b.w - n_masks] = v;
+                    if (b.w != VM_ROW_NONE) dst[b.w] = v;
                 }
                 if (a.x & VM_F_LEVEL_END) {  // one cp.async group per level; LOADs of level L-2 are complete before level L starts
                     __pipeline_commit();
