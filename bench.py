@@ -38,19 +38,29 @@ UNIT = "AND-gates/s"
 def make_workload(name: str):
     from reverie_b200 import circuits as C
 
+    nz = np.zeros(0, dtype=np.uint64)
+    zw = np.array([0x0123456789ABCDEF, 0xFEDCBA9876543210], dtype=np.uint64)
+    if name.startswith("z64mul"):
+        n = int(name[6:])
+        ops, nw = C.z64_mul_circuit(n)
+        return ops, np.zeros(0, dtype=np.uint8), zw, (nw, 0), f"Z64 synthetic arithmetic circuit: 2 inputs + {n} x Mul over a 1024-cell register file (SURVEY.md 8(d) config 3), 256 reps x 8 players"
+    if name.startswith("z64flat"):
+        n = int(name[7:])
+        ops, wc = C.flat_mul_circuit(n, domain=C.Z64)
+        return ops, np.zeros(0, dtype=np.uint8), zw, wc, f"Z64 flat circuit: 2 inputs + {n} x Mul(2,0,1) (src/proof/mod.rs:322-329 over Z64)"
     if name == "sha256":
         ops, wit, wc = C.sha256_abc_case()
-        return ops, wit, wc, "GF(2) SHA-256 compression circuit (generated Bristol-style: 22573 AND / 93666 XOR / 2147 INV, 768 inputs, 256 output asserts), 256 reps x 8 players"
+        return ops, wit, nz, wc, "GF(2) SHA-256 compression circuit (generated Bristol-style: 22573 AND / 93666 XOR / 2147 INV, 768 inputs, 256 output asserts), 256 reps x 8 players"
     if name.startswith("flat"):
         n = int(name[4:])
         ops, wc = C.flat_mul_circuit(n)
-        return ops, np.array([1, 1], dtype=np.uint8), wc, f"GF(2) flat circuit: 2 inputs + {n} x Mul(2,0,1) (src/proof/mod.rs:322-329 scaled)"
+        return ops, np.array([1, 1], dtype=np.uint8), nz, wc, f"GF(2) flat circuit: 2 inputs + {n} x Mul(2,0,1) (src/proof/mod.rs:322-329 scaled)"
     if name.startswith("layered"):
         n = int(name[7:])
         width = min(1 << 20, max(1024, n // 16))
         ops, nw = C.layered_and_circuit(width, n)
         wit = np.random.default_rng(0).integers(0, 2, size=width).astype(np.uint8)
-        return ops, wit, (0, nw), f"GF(2) layered circuit: {width} inputs + {n} ANDs in layers of {width}"
+        return ops, wit, nz, (0, nw), f"GF(2) layered circuit: {width} inputs + {n} ANDs in layers of {width}"
     raise SystemExit(f"unknown workload {name}")
 
 
@@ -108,16 +118,16 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_port_run(ops, wit, wc, seeds, min_seconds: float, min_proofs: int):
+def cpu_port_run(ops, wit, wz, wc, seeds, min_seconds: float, min_proofs: int):
     """The CPU restatement of the reference's dataflow (oracle/c, `kind: port`), all host threads (capped at 32 like the
     reference's rayon fan-out over packed instances)."""
     import orc
 
     cores = min(os.cpu_count() or 1, 32)
-    orc.prove(ops, wit, [], wc, seeds, n_threads=cores)  # warm
+    orc.prove(ops, wit, wz, wc, seeds, n_threads=cores)  # warm
     n, t0 = 0, time.perf_counter()
     while n < min_proofs or time.perf_counter() - t0 < min_seconds:
-        rc, _ = orc.prove(ops, wit, [], wc, seeds, n_threads=cores)
+        rc, _ = orc.prove(ops, wit, wz, wc, seeds, n_threads=cores)
         assert rc == 0
         n += 1
     return n, time.perf_counter() - t0, cores
@@ -126,7 +136,7 @@ def cpu_port_run(ops, wit, wc, seeds, min_seconds: float, min_proofs: int):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    ops, wit, wc, desc = make_workload(args.workload)
+    ops, wit, wz, wc, desc = make_workload(args.workload)
     n_and = int((ops["opcode"] == 6).sum())
     seeds = default_seeds()
     import orc
@@ -134,11 +144,11 @@ def run_reference(args, rank, world):
     cores = min(os.cpu_count() or 1, 32)
     B = args.batch
     for _ in range(max(args.warmup, 1)):
-        orc.prove(ops, wit, [], wc, seeds, n_threads=cores)
+        orc.prove(ops, wit, wz, wc, seeds, n_threads=cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         for _b in range(B):
-            rc, _ = orc.prove(ops, wit, [], wc, seeds, n_threads=cores)
+            rc, _ = orc.prove(ops, wit, wz, wc, seeds, n_threads=cores)
             assert rc == 0
     dt = time.perf_counter() - t0
     v = n_and * B * args.steps / dt
@@ -153,6 +163,13 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def set_metric(workload: str):
+    """The headline metric is BASELINE.json's (GF(2) AND gates); a Z64 workload reports its multiplication gates instead."""
+    global METRIC, UNIT
+    if workload.startswith("z64"):
+        METRIC, UNIT = "KKW prover MUL-gates/sec (Z64, 128-bit sec)", "MUL-gates/s"
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -163,6 +180,7 @@ def main():
     ap.add_argument("--batch", type=int, default=8, help="independent proofs per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    set_metric(args.workload)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -185,11 +203,11 @@ def main():
     if 32 % world:
         raise SystemExit("world size must divide the 32 packed instances")
 
-    ops, wit, wc, desc = make_workload(args.workload)
+    ops, wit, wz, wc, desc = make_workload(args.workload)
     seeds = default_seeds()
     circ = rb.Circuit(ops, wc)
     st = circ.stats()
-    n_and = st["n_and"]
+    n_and = st["n_and"] + st["z64_mul"]  # multiplication gates of either domain
     per = 32 // world
     B = max(1, args.batch)
     sessions = [rb.Session(circ, rank * per, per) for _ in range(B)]
@@ -243,7 +261,7 @@ def main():
         return tot  # ms
 
     for x in sessions:
-        x.upload(wit, (), seeds)
+        x.upload(wit, wz, seeds)
     for _ in range(args.warmup):
         step_device()
     for x in sessions:
@@ -279,7 +297,7 @@ def main():
         pool = ThreadPoolExecutor(max_workers=B)
 
         def one(_):
-            return rb.Proof.new(circ, wit, (), seeds=seeds)
+            return rb.Proof.new(circ, wit, wz, seeds=seeds)
 
         for _ in range(args.warmup):
             proofs = list(pool.map(one, range(B)))
@@ -298,7 +316,7 @@ def main():
     else:
         def step_e2e():
             for x in sessions:
-                x.upload(wit, (), seeds)
+                x.upload(wit, wz, seeds)
             step_device()
             return [x.fetch() for x in sessions]
         for _ in range(args.warmup):
@@ -313,7 +331,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_v = n_and * B * args.steps / float(t.item())
         d2h = B * (len(outs[0][1]) + 36 + per * 8 * 32)
-    e2e = {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": B * (st["n_inputs"] + per * 8 * 16 + (256 * 32 if world > 1 else 0)), "d2h_bytes_per_step": d2h}
+    e2e = {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": B * (st["n_inputs"] + 8 * st["z64_inputs"] + per * 8 * 16 + (256 * 32 if world > 1 else 0)), "d2h_bytes_per_step": d2h}
 
     # ---- per-kernel device times -> roofline of the dominant kernel (rank 0) ----
     roofline, kernels = None, None
@@ -343,7 +361,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n, secs, cores = cpu_port_run(ops, wit, wc, seeds, 10.0, 3)
+        n, secs, cores = cpu_port_run(ops, wit, wz, wc, seeds, 10.0, 1)
         cpu = {"value": n_and * n / secs, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{n} whole proofs of the same workload in {secs:.1f} s; C restatement of the reference's dataflow (oracle/c), threads over the 32 packed instances"}
 
@@ -356,7 +374,7 @@ def main():
                        "l2": "256 MiB memset between timed steps (outside the per-step CUDA-event pair)",
                        "timing": "one CUDA-event pair per step on a timing stream that forks to / joins the B session streams, summed over K steps"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "kernels": kernels, "single_proof_latency_ms": {"device": lat_ms, "e2e": single_latency_ms}, "circuit": {k: st[k] for k in ("n_and", "n_ops", "value_depth", "linear_depth")},
+            "kernels": kernels, "single_proof_latency_ms": {"device": lat_ms, "e2e": single_latency_ms}, "circuit": {k: st[k] for k in ("n_and", "n_ops", "value_depth", "linear_depth", "z64_mul", "z64_value_depth")},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

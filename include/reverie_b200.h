@@ -63,7 +63,7 @@ enum rv_status {
     RV_E_ARG = -4,             /* bad argument / wire index out of range for the given wire_counts */
     RV_E_CUDA = -5,            /* CUDA runtime failure or no device */
     RV_E_NOMEM = -6,
-    RV_E_UNSUPPORTED = -7      /* op set not yet accelerated (reported at compile time, never silently degraded) */
+    RV_E_UNSUPPORTED = -7      /* op not yet accelerated: Random, B2A (reported at compile time, never silently degraded) */
 };
 
 typedef struct rv_circuit rv_circuit; /* a compiled circuit: device-resident gate tables, reusable across proofs  */
@@ -102,6 +102,16 @@ typedef struct rv_circuit_stats {
     uint64_t pre_bytes;      /* bytes hashed per repetition, preprocessing stream */
     uint64_t algorithmic_bytes; /* SURVEY.md 8(d) HBM bytes for one proof (all 256 reps) */
     uint64_t device_bytes;   /* device memory held by the compiled tables         */
+    /* Z64 domain (src/algebra/z64) */
+    uint64_t z64_mul;           /* Z64 Mul gates                                  */
+    uint64_t z64_inputs;        /* Z64 witness elements consumed                  */
+    uint64_t z64_assert;
+    uint64_t z64_masks;         /* Z64 PRG masks drawn per (rep, player)          */
+    uint64_t z64_linear;        /* materialised Z64 linear mask nodes             */
+    uint64_t z64_value_depth;   /* levels of the Z64 plaintext plane              */
+    uint64_t z64_linear_depth;
+    uint64_t z64_online_bytes;  /* bytes hashed per repetition, Z64 online stream */
+    uint64_t z64_pre_bytes;
 } rv_circuit_stats;
 int rv_circuit_get_stats(const rv_circuit *c, rv_circuit_stats *out);
 

@@ -14,6 +14,7 @@
 #include "rv_bincode.h"
 #include "rv_kernels.cuh"
 #include "rv_planes.cuh"
+#include "rv_zplanes.cuh"
 
 using namespace rv;
 
@@ -60,6 +61,8 @@ struct rv_circuit {
     std::vector<uint32_t> mul_pos;
     std::vector<uint32_t> recon_idx;  // online item -> index among the reconstruct() calls (verifier)
     std::vector<uint32_t> vleaf_ids;  // u-plane value ids of the verifier's leaves: inputs then kappas
+    DevZProgram zdev;
+    std::vector<uint32_t> z_input_item;  // k -> item index of the k-th Z64 input()
     int device = 0;
     uint64_t device_bytes = 0;
     uint32_t z64_empty_hash[8];  // B3("")
@@ -140,6 +143,31 @@ extern "C" int rv_circuit_compile(const rv_op *ops, size_t n_ops, size_t z64_cel
         rv_circuit_free(c);
         return rc;
     }
+    if (P.z.any()) {
+        const ZProgram &Z = P.z;
+        DevZProgram &DZ = c->zdev;
+        for (uint32_t t = 0; t < Z.items.size(); t++)
+            if (Z.items[t].kind == ITEM_INPUT) c->z_input_item.push_back(t);
+        if ((rc = upload(c, Z.vprog, &DZ.vprog)) || (rc = upload(c, Z.vlevel_off, &DZ.vlevel_off)) || (rc = upload(c, Z.lin, &DZ.lin)) ||
+            (rc = upload(c, Z.items, &DZ.items)) || (rc = upload(c, Z.leaf_ids, &DZ.leaf_ids)) || (rc = upload(c, Z.recon_off, &DZ.recon_off)) ||
+            (rc = upload(c, Z.input_off, &DZ.input_off)) || (rc = upload(c, Z.mul_pos, &DZ.mul_pos)) || (rc = upload(c, Z.recon_idx, &DZ.recon_idx)) ||
+            (rc = upload(c, c->z_input_item, &DZ.input_item))) {
+            rv_circuit_free(c);
+            return rc;
+        }
+        DZ.n_vlevels = Z.vlevel_off.empty() ? 0 : (uint32_t)Z.vlevel_off.size() - 1;
+        DZ.n_llevels = Z.llevel_off.empty() ? 0 : (uint32_t)Z.llevel_off.size() - 1;
+        DZ.n_items = (uint32_t)Z.items.size();
+        DZ.n_mul = (uint32_t)Z.n_mul;
+        DZ.n_inputs = (uint32_t)Z.n_inputs;
+        DZ.n_recon = (uint32_t)Z.recon_off.size();
+        DZ.n_leaves = (uint32_t)Z.leaf_ids.size();
+        DZ.n_masks = Z.n_masks;
+        DZ.n_rows = Z.n_rows;
+        DZ.n_vals = Z.n_vals;
+        DZ.on_bytes = (uint32_t)Z.on_bytes;
+        DZ.pre_bytes = (uint32_t)Z.pre_bytes;
+    }
     D.n_xgates = (uint32_t)P.xgates.size();
     D.n_llevels = (uint32_t)P.xlevel_off.size() - 1;
     D.n_lut_steps = P.n_lut_steps;
@@ -180,6 +208,16 @@ extern "C" int rv_circuit_get_stats(const rv_circuit *c, rv_circuit_stats *o) {
     o->pre_bytes = P.n_pre;
     o->algorithmic_bytes = P.algorithmic_bytes;
     o->device_bytes = c->device_bytes;
+    const ZProgram &Z = P.z;
+    o->z64_mul = Z.n_mul;
+    o->z64_inputs = Z.n_inputs;
+    o->z64_assert = Z.n_assert;
+    o->z64_masks = Z.n_masks;
+    o->z64_linear = Z.n_lin;
+    o->z64_value_depth = Z.vlevel_off.empty() ? 0 : Z.vlevel_off.size() - 1;
+    o->z64_linear_depth = Z.llevel_off.empty() ? 0 : Z.llevel_off.size() - 1;
+    o->z64_online_bytes = Z.on_bytes;
+    o->z64_pre_bytes = Z.pre_bytes;
     return RV_OK;
 }
 
@@ -243,6 +281,17 @@ struct rv_session {
     int *d_bad = nullptr;
     uint8_t *d_proof = nullptr;
     size_t proof_len = 0;
+    // Z64 domain (allocated only when the circuit has Z64 ops)
+    bool has_z = false;
+    size_t zrowlen = 0;  // 64 * npi
+    uint64_t *d_zrows = nullptr, *d_zleaf = nullptr, *d_zvals = nullptr;
+    uint8_t *d_zon = nullptr, *d_zpre = nullptr;
+    size_t pitch_zon = 0, pitch_zpre = 0;
+    uint32_t *d_zcv_on = nullptr, *d_zcv_pre = nullptr, n_chunks_zon = 1, n_chunks_zpre = 1, *d_zrep = nullptr;
+    uint8_t *d_zon_hash = nullptr;
+    uint32_t len_zrecons = 0, len_zcorrs = 0, len_zinputs = 0;
+    uint64_t *d_zleaf_v = nullptr, *d_zuvals = nullptr;  // verifier: [40][pitch]
+    size_t zleaf_pitch = 0, zupitch = 0;
     // verifier-only buffers (allocated on first rv_verify)
     uint8_t *d_vin = nullptr, *h_vin = nullptr;  // one staging blob: see VerifyLayout
     size_t vin_bytes = 0;
@@ -325,7 +374,30 @@ extern "C" int rv_session_create(const rv_circuit *c, int first_instance, int n_
     s->len_recons = (uint32_t)(P.recon_pos.size() / 8 + 1);  // floor(n/8)+1: the residue group is always flushed (gf2/share.rs:131-138)
     s->len_corrs = P.n_pre / 8 + 1;
     s->len_inputs = (uint32_t)(P.n_inputs / 8 + 1);
-    s->proof_len = ProofLayout{s->len_recons, s->len_corrs, s->len_inputs}.total();
+    const ZProgram &Z = P.z;
+    s->has_z = Z.any();
+    if (s->has_z) {
+        s->len_zrecons = (uint32_t)(8 * Z.recon_off.size());  // exactly 8 n bytes: src/algebra/z64/share.rs:37-49, recon.rs:46-66
+        s->len_zcorrs = (uint32_t)(8 * Z.n_mul);
+        s->len_zinputs = (uint32_t)(8 * Z.n_inputs);
+    }
+    s->proof_len = ProofLayout{s->len_recons, s->len_corrs, s->len_inputs, s->len_zrecons, s->len_zcorrs, s->len_zinputs}.total();
+    if (s->has_z) {
+        s->zrowlen = (size_t)64 * s->npi;
+        s->pitch_zon = round_up(std::max<size_t>(Z.on_bytes, 1), 64);
+        s->pitch_zpre = round_up(std::max<size_t>(Z.pre_bytes, 1), 64);
+        s->n_chunks_zon = Z.on_bytes == 0 ? 1 : (uint32_t)((Z.on_bytes + 1023) / 1024);
+        s->n_chunks_zpre = Z.pre_bytes == 0 ? 1 : (uint32_t)((Z.pre_bytes + 1023) / 1024);
+        if ((rc = dalloc(s, &s->d_zrows, (size_t)Z.n_rows * s->zrowlen)) || (rc = dalloc(s, &s->d_zleaf, Z.leaf_ids.size())) ||
+            (rc = dalloc(s, &s->d_zvals, (size_t)Z.n_vals + 1)) || (rc = dalloc(s, &s->d_zon, s->pitch_zon * s->nreps)) ||
+            (rc = dalloc(s, &s->d_zpre, s->pitch_zpre * s->nreps)) || (rc = dalloc(s, &s->d_zcv_on, (size_t)s->n_chunks_zon * s->nreps * 8)) ||
+            (rc = dalloc(s, &s->d_zcv_pre, (size_t)s->n_chunks_zpre * s->nreps * 8)) || (rc = dalloc(s, &s->d_zrep, (size_t)s->nreps * 8)) ||
+            (rc = dalloc(s, &s->d_zon_hash, (size_t)s->nreps * 32)))
+            return bail(rc);
+        if (cudaMemset(s->d_zleaf, 0, std::max<size_t>(Z.leaf_ids.size(), 1) * 8) != cudaSuccess ||
+            cudaMemset(s->d_zrows + (size_t)Z.zero_row() * s->zrowlen, 0, s->zrowlen * 8) != cudaSuccess)
+            return bail(fail(RV_E_CUDA, "cudaMemset failed"));
+    }
     if (linear_uses_vm(c->dev)) {
         s->pitch_fresh = round_up((size_t)P.n_masks + 128, 128);
         s->pitch_exp = round_up((size_t)P.n_lin + 32, 32);
@@ -341,7 +413,7 @@ extern "C" int rv_session_create(const rv_circuit *c, int first_instance, int n_
         (rc = dalloc(s, &s->d_comm, 32)) || (rc = dalloc(s, &s->d_omit, RV_TOTAL_REPS)) || (rc = dalloc(s, &s->d_rank, RV_TOTAL_REPS)) ||
         (rc = dalloc(s, &s->d_zconst, 16)) || (rc = dalloc(s, &s->d_bad, 1)) || (rc = dalloc(s, &s->d_proof, s->proof_len)))
         return bail(rc);
-    s->h_in_bytes = round_up(P.n_inputs, 16) + RV_TOTAL_REPS * 16;
+    s->h_in_bytes = round_up(P.n_inputs, 16) + RV_TOTAL_REPS * 16 + 8 * (size_t)Z.n_inputs;
     if (cudaMallocHost(&s->h_in, s->h_in_bytes) != cudaSuccess || cudaMallocHost(&s->h_out, s->proof_len + 64) != cudaSuccess)
         return bail(fail(RV_E_NOMEM, "pinned host allocation failed"));
     uint32_t zc[16];
@@ -425,12 +497,10 @@ extern "C" int rv_session_kernel_times(rv_session *s, rv_kernel_time *out, int m
 // ---- upload / commit / open / fetch ----------------------------------------------------------------------------------
 extern "C" int rv_session_upload(rv_session *s, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64, size_t n_z64,
                                  const uint8_t *seeds) {
-    (void)wit_z64;
-    (void)n_z64;
     if (!s) return fail(RV_E_ARG, "NULL session");
     const Program &P = s->c->prog;
-    if (n_gf2 < P.n_inputs) return fail(RV_E_WITNESS_SHORT, "witness is too short");  // prover.rs:190
-    if (P.n_inputs && !wit_gf2) return fail(RV_E_ARG, "wit_gf2 is NULL");
+    if (n_gf2 < P.n_inputs || n_z64 < P.z.n_inputs) return fail(RV_E_WITNESS_SHORT, "witness is too short");  // prover.rs:190
+    if ((P.n_inputs && !wit_gf2) || (P.z.n_inputs && !wit_z64)) return fail(RV_E_ARG, "witness pointer is NULL");
     CU(cudaSetDevice(s->c->device));
     CU(cudaStreamSynchronize(s->st));  // the staging buffer may still be in flight from a previous proof
     const size_t woff = round_up(P.n_inputs, 16);
@@ -446,6 +516,11 @@ extern "C" int rv_session_upload(rv_session *s, const uint8_t *wit_gf2, size_t n
         }
     }
     if (P.n_inputs) CU(cudaMemcpyAsync(s->d_wit, s->h_in, P.n_inputs, cudaMemcpyHostToDevice, s->st));
+    if (P.z.n_inputs) {  // the Z64 witness fills the first leaves of the value plane; the kappa leaves after it stay zero
+        uint8_t *hz = hs + RV_TOTAL_REPS * 16;
+        memcpy(hz, wit_z64, 8 * (size_t)P.z.n_inputs);
+        CU(cudaMemcpyAsync(s->d_zleaf, hz, 8 * (size_t)P.z.n_inputs, cudaMemcpyHostToDevice, s->st));
+    }
     CU(cudaMemcpyAsync(s->d_seeds, hs + (size_t)s->first_rep * 16, (size_t)s->nreps * 16, cudaMemcpyHostToDevice, s->st));
     s->committed = s->opened = false;
     return RV_OK;
@@ -467,6 +542,11 @@ extern "C" int rv_session_commit(rv_session *s) {
         Scope k(s, "values", (uint64_t)P.lut_steps.size() * sizeof(LutInstr), 1, s->st_val);
         launch_values(D.lut_steps, D.n_lut_steps, D.input_vid, s->d_wit, 0, D.n_inputs, s->d_vals, 0, D.n_vals, 1, s->st_val);
     }
+    const DevZProgram &DZ = c->zdev;
+    if (s->has_z) {
+        Scope k(s, "z.values", (uint64_t)P.z.vprog.size() * sizeof(ZInstr), 1, s->st_val);
+        launch_zvalues(DZ, s->d_zleaf, 0, s->d_zvals, 0, 1, s->st_val);
+    }
     CU(cudaEventRecord(s->ev_vals, s->st_val));
     CU(cudaMemsetAsync(s->d_bad, 0, sizeof(int), s->st));
     CU(cudaMemsetAsync(s->d_rows + (size_t)P.zero_row() * s->npi, 0, (size_t)s->npi * 8, s->st));
@@ -483,7 +563,33 @@ extern "C" int rv_session_commit(rv_session *s) {
         Scope k(s, "linear", (uint64_t)P.n_lin * s->npi * 8 * 3, avg_width < 4096.0 ? (s->d_fresh_sm ? 2 : 1) : D.n_llevels);
         launch_linear(D, P.xlevel_off.data(), s->d_rows, s->npi, s->d_fresh_sm, s->pitch_fresh, s->d_exp_sm, s->pitch_exp, s->st, nullptr);
     }
+    if (s->has_z) {
+        {
+            Scope k(s, "z.mask_gen", (uint64_t)P.z.n_masks * s->zrowlen * 8);
+            launch_zmask_gen(s->d_ks, s->d_lane_mask, nslices, P.z.n_masks, s->d_zrows, s->zrowlen, s->st);
+        }
+        if (DZ.n_llevels) {
+            Scope k(s, "z.linear", (uint64_t)P.z.n_lin * s->zrowlen * 8 * 3, DZ.n_llevels);
+            launch_zlinear(DZ, P.z.llevel_off.data(), s->d_zrows, (uint32_t)s->zrowlen, s->st);
+        }
+    }
     CU(cudaStreamWaitEvent(s->st, s->ev_vals, 0));
+    if (s->has_z) {
+        {
+            // per Mul: 4 row segments of 64 B read, 64 + 8 stream bytes written, per repetition; pre: 3 segments + 8 bytes
+            Scope k(s, "z.items", ((uint64_t)P.z.n_mul * (7 * 64 + 72) + P.z.n_inputs * 72 + P.z.n_assert * 128) * s->nreps, 2);
+            launch_zitems(DZ, s->d_zrows, s->zrowlen, s->nreps, s->d_zvals, s->d_zon, s->pitch_zon, s->d_zpre, s->pitch_zpre, s->d_bad, s->st);
+        }
+        {
+            Scope k(s, "z.chunk_cv", (P.z.on_bytes + P.z.pre_bytes) * s->nreps, 1);
+            launch_chunk_cv2(s->d_zon, s->pitch_zon, (uint32_t)P.z.on_bytes, s->d_zcv_on, s->nreps, s->d_zpre, s->pitch_zpre, (uint32_t)P.z.pre_bytes,
+                             s->d_zcv_pre, s->nreps, s->st);
+        }
+        {
+            Scope k(s, "z.rep_hash", ((uint64_t)s->n_chunks_zon + s->n_chunks_zpre) * s->nreps * 32);
+            launch_zrep_hash(s->d_zcv_on, s->n_chunks_zon, s->d_zcv_pre, s->n_chunks_zpre, s->nreps, s->d_zon_hash, s->d_zrep, s->st);
+        }
+    }
     {
         // per Mul: 4 row reads + 2 stream bytes per rep (online) and 3 row reads + 1 byte per rep (pre)
         Scope k(s, "items", ((uint64_t)P.n_and * 7 + P.n_inputs + P.n_assert) * s->npi * 8 + ((uint64_t)P.n_online + P.n_pre) * s->nreps, 2);
@@ -495,7 +601,8 @@ extern "C" int rv_session_commit(rv_session *s) {
     }
     {
         Scope k(s, "rep_hash", ((uint64_t)s->n_chunks_on + s->n_chunks_pre) * s->nreps * 32);
-        launch_rep_hash(s->d_cv_on, s->n_chunks_on, s->d_cv_pre, s->n_chunks_pre, s->d_zconst, s->nreps, s->d_on_hash, s->d_rep_hash, s->st);
+        launch_rep_hash(s->d_cv_on, s->n_chunks_on, s->d_cv_pre, s->n_chunks_pre, s->d_zconst, s->nreps, s->d_on_hash, s->d_rep_hash, s->st, 0xFFFFFFFFu,
+                        nullptr, nullptr, s->has_z ? s->d_zrep : nullptr);
     }
     CU(cudaGetLastError());
     s->committed = s->ever_committed = true;
@@ -551,8 +658,29 @@ extern "C" int rv_session_open(rv_session *s, const uint8_t *all_rep_hashes) {
         a.len_recons = s->len_recons;
         a.len_corrs = s->len_corrs;
         a.len_inputs = s->len_inputs;
+        a.len_zrecons = s->len_zrecons;
+        a.len_zcorrs = s->len_zcorrs;
+        a.len_zinputs = s->len_zinputs;
+        a.z_on_hash = s->has_z ? s->d_zon_hash : nullptr;
         a.proof = s->d_proof;
         launch_extract(D, a, s->st);
+    }
+    if (s->has_z) {
+        Scope k(s, "z.extract", (uint64_t)RV_ONLINE_REPS * (s->len_zrecons + s->len_zcorrs + s->len_zinputs));
+        const ProofLayout L{s->len_recons, s->len_corrs, s->len_inputs, s->len_zrecons, s->len_zcorrs, s->len_zinputs};
+        ZExtractArgs a;
+        a.on = s->d_zon;
+        a.pre = s->d_zpre;
+        a.pitch_on = s->pitch_zon;
+        a.pitch_pre = s->pitch_zpre;
+        a.omit_of_rep = s->d_omit;
+        a.rank_of_rep = s->d_rank;
+        a.first_rep = s->first_rep;
+        a.nreps = s->nreps;
+        a.z_base = L.z_base();
+        a.sz_on_z = L.sz_on_z();
+        a.proof = s->d_proof;
+        launch_zextract(c->zdev, a, s->st);
     }
     CU(cudaMemcpyAsync(s->h_out, s->d_proof, s->proof_len, cudaMemcpyDeviceToHost, s->st));
     CU(cudaMemcpyAsync(s->h_out + s->proof_len, s->d_bad, 4, cudaMemcpyDeviceToHost, s->st));
@@ -674,8 +802,12 @@ static int verify_on_session(rv_session *s, const uint8_t *proof, size_t proof_l
     const DevProgram &D = c->dev;
     constexpr uint32_t NON = RV_ONLINE_REPS, NPRE = RV_PREPROCESSING_REPS, NPI_ON = RV_ONLINE_REPS / 8;
     // ---- staging blob: [seeds 256x16][pkeys 256x128][mode 256][omit 256][VOpen x40][on_given 216x32][z_on_given 216x32][proof bytes] ----
+    // Z64 (only when the circuit has Z64 ops): [ZOpen x40][z seeds 256x16][z pkeys 256x128][z omit 256] -- the Z64 openings carry their
+    // own keys and unopened player (src/proof/mod.rs:262-280); an honest proof repeats the GF(2) ones
     const size_t o_seeds = 0, o_pkeys = o_seeds + 256 * 16, o_mode = o_pkeys + 256 * 128, o_omit = o_mode + 256, o_opens = o_omit + 256,
-                 o_ong = o_opens + NON * sizeof(VOpen), o_zg = o_ong + NPRE * 32, o_proof = round_up(o_zg + NPRE * 32, 16);
+                 o_ong = o_opens + NON * sizeof(VOpen), o_zg = o_ong + NPRE * 32, o_zopens = round_up(o_zg + NPRE * 32, 16),
+                 o_zseeds = o_zopens + NON * sizeof(ZOpen), o_zpkeys = o_zseeds + 256 * 16, o_zomit = o_zpkeys + 256 * 128,
+                 o_proof = round_up(o_zomit + 256, 16);
     const size_t need = o_proof + round_up(proof_len, 16);
     if (s->vin_bytes < need) {
         if (s->h_vin) cudaFreeHost(s->h_vin);
@@ -690,6 +822,11 @@ static int verify_on_session(rv_session *s, const uint8_t *proof, size_t proof_l
         s->upitch = round_up((size_t)P.n_uvals + 16, 16);
         int rc;
         if ((rc = dalloc(s, &s->d_leaf_vals, s->leaf_pitch * NON)) || (rc = dalloc(s, &s->d_uvals, s->upitch * NON))) return rc;
+        if (s->has_z) {
+            s->zleaf_pitch = P.z.leaf_ids.size() + 1;
+            s->zupitch = (size_t)P.z.n_vals + 1;
+            if ((rc = dalloc(s, &s->d_zleaf_v, s->zleaf_pitch * NON)) || (rc = dalloc(s, &s->d_zuvals, s->zupitch * NON))) return rc;
+        }
         CU(cudaMallocHost(&s->h_vout, RV_TOTAL_REPS * 32 + 16));
     }
     CU(cudaStreamSynchronize(s->st));
@@ -710,6 +847,24 @@ static int verify_on_session(rv_session *s, const uint8_t *proof, size_t proof_l
         h[o_omit + NON + k] = RV_PLAYERS;
         memcpy(h + o_ong + (size_t)k * 32, proof + g.pre[k].comm_online, 32);
         memcpy(h + o_zg + (size_t)k * 32, proof + z.pre[k].comm_online, 32);
+    }
+    bool z_own_keys = false;
+    if (s->has_z) {
+        ZOpen *zopens = reinterpret_cast<ZOpen *>(h + o_zopens);
+        for (uint32_t k = 0; k < NON; k++) {
+            const POnline &o = z.online[k], &first = z.online[k & ~7u];
+            zopens[k] = ZOpen{o_proof + o.recons.off, o_proof + o.corrs.off, o_proof + o.inputs.off, (uint32_t)(first.recons.len / 8),
+                              (uint32_t)(first.corrs.len / 8), (uint32_t)(first.inputs.len / 8), (uint32_t)o.recons.len, (uint32_t)o.corrs.len,
+                              (uint32_t)o.inputs.len, o.omit, 0};
+            memcpy(h + o_zpkeys + (size_t)k * 128, proof + o.keys, 128);
+            h[o_zomit + k] = o.omit;
+            if (o.omit != g.online[k].omit || memcmp(proof + o.keys, proof + g.online[k].keys, 128) != 0) z_own_keys = true;
+        }
+        for (uint32_t k = 0; k < NPRE; k++) {
+            memcpy(h + o_zseeds + (size_t)(NON + k) * 16, proof + z.pre[k].seed, 16);
+            h[o_zomit + NON + k] = RV_PLAYERS;
+            if (memcmp(proof + z.pre[k].seed, proof + g.pre[k].seed, 16) != 0) z_own_keys = true;
+        }
     }
     memcpy(h + o_proof, proof, proof_len);
     uint8_t *dv = s->d_vin;
@@ -747,10 +902,49 @@ static int verify_on_session(rv_session *s, const uint8_t *proof, size_t proof_l
         Scope k(s, "v.chunk_cv", 0);
         launch_chunk_cv2(s->d_on, s->pitch_on, P.n_online, s->d_cv_on, NON, s->d_pre, s->pitch_pre, P.n_pre, s->d_cv_pre, s->nreps, s->st);
     }
+    if (s->has_z) {  // the Z64 instances of src/proof/mod.rs:262-280 (online) and :247-260 (preprocessing)
+        const DevZProgram &DZ = c->zdev;
+        const ZOpen *d_zopens = reinterpret_cast<const ZOpen *>(dv + o_zopens);
+        if (z_own_keys) {  // a (dishonest) proof whose Z64 openings name other keys: the reference would use them, so do we
+            Scope k(s, "v.z.key_setup", 0);
+            launch_key_setup(dv + o_zseeds, dv + o_zpkeys, dv + o_mode, dv + o_zomit, nslices, s->d_ks, s->d_lane_mask, s->d_pkeys, s->st);
+        }
+        {
+            Scope k(s, "v.z.mask_gen", (uint64_t)P.z.n_masks * s->zrowlen * 8);
+            launch_zmask_gen(s->d_ks, s->d_lane_mask, nslices, P.z.n_masks, s->d_zrows, s->zrowlen, s->st);
+        }
+        if (DZ.n_llevels) {
+            Scope k(s, "v.z.linear", 0, DZ.n_llevels);
+            launch_zlinear(DZ, P.z.llevel_off.data(), s->d_zrows, (uint32_t)s->zrowlen, s->st);
+        }
+        {
+            Scope k(s, "v.z.leaves", 0);
+            launch_zverify_leaves(DZ, d_zopens, dv, s->d_zrows, s->zrowlen, NON, s->d_zleaf_v, s->zleaf_pitch, s->st);
+        }
+        {
+            Scope k(s, "v.z.values", 0);
+            launch_zvalues(DZ, s->d_zleaf_v, s->zleaf_pitch, s->d_zuvals, s->zupitch, NON, s->st);
+        }
+        {
+            Scope k(s, "v.z.items", 0, 3);
+            launch_zitems_pre_range(DZ, s->d_zrows, s->zrowlen, NON, s->nreps, s->d_zpre, s->pitch_zpre, s->st);
+            launch_zverify_items(DZ, d_zopens, dv, s->d_zrows, s->zrowlen, NON, s->d_zuvals, s->zupitch, s->d_zon, s->pitch_zon, s->d_zpre, s->pitch_zpre,
+                                 s->d_bad, s->st);
+        }
+        {
+            Scope k(s, "v.z.chunk_cv", 0);
+            launch_chunk_cv2(s->d_zon, s->pitch_zon, (uint32_t)P.z.on_bytes, s->d_zcv_on, NON, s->d_zpre, s->pitch_zpre, (uint32_t)P.z.pre_bytes, s->d_zcv_pre,
+                             s->nreps, s->st);
+        }
+        {
+            Scope k(s, "v.z.rep_hash", 0);
+            launch_zrep_hash(s->d_zcv_on, s->n_chunks_zon, s->d_zcv_pre, s->n_chunks_zpre, s->nreps, s->d_zon_hash, s->d_zrep, s->st, NON, dv + o_zg);
+        }
+    }
     {
         Scope k(s, "v.rep_hash", 0);
         launch_rep_hash(s->d_cv_on, s->n_chunks_on, s->d_cv_pre, s->n_chunks_pre, s->d_zconst, s->nreps, s->d_on_hash, s->d_rep_hash, s->st, NON,
-                        dv + o_ong, dv + o_zg);
+                        dv + o_ong, dv + o_zg, s->has_z ? s->d_zrep : nullptr);
     }
     CU(cudaMemcpyAsync(s->h_vout, s->d_rep_hash, RV_TOTAL_REPS * 32, cudaMemcpyDeviceToHost, s->st));
     CU(cudaMemcpyAsync(s->h_vout + RV_TOTAL_REPS * 32, s->d_bad, 4, cudaMemcpyDeviceToHost, s->st));

@@ -403,6 +403,240 @@ struct ValueNet {
     }
 };
 
+
+// =====================================================================================================================
+//  Z64 domain front end (see rv_compile.h).  Cells carry (value id, mask row, coefficient); rows are provisional ids until
+//  finish() sorts the linear nodes by level.
+// =====================================================================================================================
+constexpr uint64_t ZB_WIRE = (512 + 64) * 32;  // one Z64 wire over all 256 repetitions = share 512 B + corr 64 B per instance
+constexpr uint64_t ZB_MUL = 73728 + 16, ZB_BIN = 3 * ZB_WIRE + 16, ZB_UNARY = 2 * ZB_WIRE + 16, ZB_INPUT = ZB_WIRE + 2048 + 16,
+                   ZB_ASSERT = ZB_WIRE + 16384 + 16, ZB_LEAF = ZB_WIRE + 16;
+
+struct ZCell {
+    uint32_t vid;
+    uint32_t mid;   // fresh index, LIN_BASE + node, or ZERO_MID
+    uint64_t coef;  // wire mask = coef * row
+};
+
+struct ZBuilder {
+    ZProgram &Z;
+    std::vector<ZCell> cells;
+    std::vector<uint32_t> vlevel;  // per value id
+    std::vector<uint32_t> llevel;  // per linear node
+    std::vector<ZLin> lin;         // provisional ids
+    std::vector<ZInstr> prog;      // creation order
+    std::vector<uint32_t> kappa_ids;
+    std::vector<uint32_t> input_ids;
+    uint64_t n_masks = 0;
+    uint64_t alg_bytes = 0;
+
+    explicit ZBuilder(ZProgram &z, size_t n_cells) : Z(z), cells(n_cells, ZCell{0, ZERO_MID, 0}), vlevel(1, 0) {}
+
+    uint32_t mid_level(uint32_t mid) const { return (mid != ZERO_MID && mid >= LIN_BASE) ? llevel[mid - LIN_BASE] : 0; }
+    uint32_t new_val(uint32_t level) {
+        vlevel.push_back(level);
+        return (uint32_t)(vlevel.size() - 1);
+    }
+    uint32_t emit(uint32_t op, uint32_t a, uint32_t b, uint32_t c, uint64_t imm) {
+        const uint32_t lv = 1 + std::max(vlevel[a], std::max(vlevel[b], vlevel[c]));
+        const uint32_t id = new_val(lv);
+        prog.push_back(ZInstr{op, id, a, b, c, 0, imm});
+        return id;
+    }
+    static bool is_zero(const ZCell &c) { return c.mid == ZERO_MID || c.coef == 0; }
+
+    // returns RV_OK or an error; `i` is the op index for messages
+    int step(const rv_op &op, size_t i, std::string &err) {
+        const size_t nc = cells.size();
+        auto bad_wire = [&]() {
+            err = "op " + std::to_string(i) + ": Z64 wire index out of range for the given wire_counts";
+            return (int)RV_E_ARG;
+        };
+        const uint64_t c = op.imm;  // u64 -> Recon broadcast, src/algebra/z64/recon.rs:123-129
+        switch (op.opcode) {
+            case RV_INPUT: {  // src/transcript/prover.rs:181-199
+                if (op.dst >= nc) return bad_wire();
+                const uint32_t vid = new_val(0);
+                ZItem it{ITEM_INPUT, (uint32_t)n_masks, 0, 0, vid, 0, (uint32_t)input_ids.size(), (uint32_t)Z.on_bytes, 1, 0};
+                Z.input_off.push_back((uint32_t)Z.on_bytes);
+                Z.recon_idx.push_back(0);
+                Z.items.push_back(it);
+                input_ids.push_back(vid);
+                cells[op.dst] = ZCell{vid, (uint32_t)n_masks, 1};
+                n_masks += 1;
+                Z.on_bytes += 8;
+                Z.n_inputs++;
+                alg_bytes += ZB_INPUT;
+                break;
+            }
+            case RV_RANDOM:
+                err = "op " + std::to_string(i) + ": Random is not accelerated yet";
+                return RV_E_UNSUPPORTED;
+            case RV_ADD:
+            case RV_SUB: {  // src/interpreter/single.rs:71-85
+                if (op.dst >= nc || op.a >= nc || op.b >= nc) return bad_wire();
+                const ZCell A = cells[op.a];
+                ZCell B = cells[op.b];
+                const bool sub = op.opcode == RV_SUB;
+                if (sub) B.coef = 0 - B.coef;
+                ZCell R;
+                R.vid = emit(sub ? ZV_SUB : ZV_ADD, A.vid, B.vid, 0, 0);
+                if (is_zero(A) && is_zero(B)) R.mid = ZERO_MID, R.coef = 0;
+                else if (is_zero(A)) R.mid = B.mid, R.coef = B.coef;
+                else if (is_zero(B)) R.mid = A.mid, R.coef = A.coef;
+                else if (A.mid == B.mid) {
+                    R.mid = A.mid;
+                    R.coef = A.coef + B.coef;
+                    if (R.coef == 0) R.mid = ZERO_MID;
+                } else {
+                    if (lin.size() >= LIN_BASE - 2) {
+                        err = "too many Z64 linear nodes";
+                        return RV_E_UNSUPPORTED;
+                    }
+                    const uint32_t id = LIN_BASE + (uint32_t)lin.size();
+                    llevel.push_back(1 + std::max(mid_level(A.mid), mid_level(B.mid)));
+                    lin.push_back(ZLin{id, A.mid, B.mid, 0, A.coef, B.coef});
+                    R.mid = id;
+                    R.coef = 1;
+                }
+                cells[op.dst] = R;
+                alg_bytes += ZB_BIN;
+                break;
+            }
+            case RV_ADDC:
+            case RV_SUBC: {  // src/interpreter/single.rs:87-95: only the correction changes
+                if (op.dst >= nc || op.a >= nc) return bad_wire();
+                ZCell R = cells[op.a];
+                R.vid = emit(ZV_ADDC, R.vid, 0, 0, op.opcode == RV_ADDC ? c : 0 - c);
+                cells[op.dst] = R;
+                alg_bytes += ZB_UNARY;
+                break;
+            }
+            case RV_MULC: {  // src/interpreter/single.rs:97-104: mask and correction are both scaled
+                if (op.dst >= nc || op.a >= nc) return bad_wire();
+                ZCell R = cells[op.a];
+                R.vid = emit(ZV_MULC, R.vid, 0, 0, c);
+                R.coef *= c;
+                if (R.coef == 0) R.mid = ZERO_MID;
+                cells[op.dst] = R;
+                alg_bytes += ZB_UNARY;
+                break;
+            }
+            case RV_MUL: {  // src/interpreter/single.rs:25-69
+                if (op.dst >= nc || op.a >= nc || op.b >= nc) return bad_wire();
+                const ZCell A = cells[op.a], B = cells[op.b];
+                ZItem it{ITEM_MUL, A.mid, B.mid, (uint32_t)n_masks, A.vid, B.vid, (uint32_t)Z.n_mul, (uint32_t)Z.on_bytes,
+                         is_zero(A) ? 0 : A.coef, is_zero(B) ? 0 : B.coef};
+                Z.recon_off.push_back((uint32_t)Z.on_bytes);
+                Z.recon_idx.push_back((uint32_t)Z.recon_off.size() - 1);
+                Z.mul_pos.push_back((uint32_t)Z.items.size());
+                Z.items.push_back(it);
+                const uint32_t kid = new_val(0);  // kappa leaf: 0 in the prover
+                kappa_ids.push_back(kid);
+                ZCell R;
+                R.vid = emit(ZV_MUL, A.vid, B.vid, kid, 0);
+                R.mid = (uint32_t)n_masks + 1;  // mask_new
+                R.coef = 1;
+                cells[op.dst] = R;
+                n_masks += 2;
+                Z.on_bytes += 64;
+                Z.pre_bytes += 8;
+                Z.n_mul++;
+                alg_bytes += ZB_MUL;
+                break;
+            }
+            case RV_ASSERT_ZERO: {  // src/interpreter/single.rs:140-147
+                if (op.a >= nc) return bad_wire();
+                const ZCell A = cells[op.a];
+                ZItem it{ITEM_ASSERT, A.mid, 0, 0, A.vid, 0, 0, (uint32_t)Z.on_bytes, is_zero(A) ? 0 : A.coef, 0};
+                Z.recon_off.push_back((uint32_t)Z.on_bytes);
+                Z.recon_idx.push_back((uint32_t)Z.recon_off.size() - 1);
+                Z.items.push_back(it);
+                Z.on_bytes += 64;
+                Z.n_assert++;
+                alg_bytes += ZB_ASSERT;
+                break;
+            }
+            case RV_CONST: {  // src/interpreter/single.rs:151-155
+                if (op.dst >= nc) return bad_wire();
+                cells[op.dst] = ZCell{emit(ZV_CONST, 0, 0, 0, c), ZERO_MID, 0};
+                alg_bytes += ZB_LEAF;
+                break;
+            }
+            default:
+                err = "op " + std::to_string(i) + ": unknown opcode";
+                return RV_E_ARG;
+        }
+        if (n_masks >= LIN_BASE - 2 || Z.on_bytes >= 0xFFFFFF00ull || vlevel.size() >= 0x7FFFFFF0ull) {
+            err = "Z64 circuit too large for 32-bit table indices / stream offsets";
+            return RV_E_UNSUPPORTED;
+        }
+        return RV_OK;
+    }
+
+    void finish() {
+        Z.n_masks = (uint32_t)n_masks;
+        Z.n_lin = (uint32_t)lin.size();
+        Z.n_rows = Z.n_masks + Z.n_lin + 1;
+        Z.n_vals = (uint32_t)vlevel.size();
+        Z.leaf_ids = input_ids;
+        Z.leaf_ids.insert(Z.leaf_ids.end(), kappa_ids.begin(), kappa_ids.end());
+        // value program by level (counting sort; stable, so creation order is kept inside a level)
+        {
+            uint32_t depth = 0;
+            for (const ZInstr &in : prog) depth = std::max(depth, vlevel[in.dst]);
+            Z.vlevel_off.assign(depth + 1, 0);
+            std::vector<uint32_t> cnt(depth + 2, 0);
+            for (const ZInstr &in : prog) cnt[vlevel[in.dst]]++;
+            uint32_t run = 0;
+            std::vector<uint32_t> cur(depth + 1, 0);
+            for (uint32_t l = 1; l <= depth; l++) {
+                cur[l] = run;
+                Z.vlevel_off[l - 1] = run;
+                run += cnt[l];
+            }
+            Z.vlevel_off[depth] = run;
+            Z.vprog.resize(prog.size());
+            for (const ZInstr &in : prog) Z.vprog[cur[vlevel[in.dst]]++] = in;
+            std::vector<ZInstr>().swap(prog);
+        }
+        // linear nodes by level; final row numbers
+        {
+            uint32_t depth = 0;
+            for (uint32_t l : llevel) depth = std::max(depth, l);
+            Z.llevel_off.assign(depth + 1, 0);
+            std::vector<uint32_t> cnt(depth + 2, 0), cur(depth + 1, 0), row_of(lin.size());
+            for (uint32_t l : llevel) cnt[l]++;
+            uint32_t run = 0;
+            for (uint32_t l = 1; l <= depth; l++) {
+                cur[l] = run;
+                Z.llevel_off[l - 1] = run;
+                run += cnt[l];
+            }
+            Z.llevel_off[depth] = run;
+            for (size_t k = 0; k < lin.size(); k++) row_of[k] = Z.n_masks + cur[llevel[k]]++;
+            const uint32_t zero = Z.zero_row();
+            auto row = [&](uint32_t mid) -> uint32_t {
+                if (mid == ZERO_MID) return zero;
+                if (mid >= LIN_BASE) return row_of[mid - LIN_BASE];
+                return mid;
+            };
+            Z.lin.resize(lin.size());
+            for (size_t k = 0; k < lin.size(); k++) {
+                ZLin n = lin[k];
+                n.dst = row_of[k];
+                n.a = row(n.a);
+                n.b = row(n.b);
+                Z.lin[n.dst - Z.n_masks] = n;
+            }
+            for (ZItem &it : Z.items) {
+                it.ra = it.ca == 0 && it.kind != ITEM_INPUT ? zero : row(it.ra);
+                if (it.kind == ITEM_MUL) it.rb = it.cb == 0 ? zero : row(it.rb);
+            }
+        }
+    }
+};
+
 }  // namespace
 
 int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, Program &P, std::string &err) {
@@ -421,6 +655,8 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
     std::vector<MGate> lg;               // mask network, topological; provisional ids (see mask_id below)
     uint64_t n_masks = 0;
 
+    ZBuilder zb(P.z, z64_cells);
+
     auto mid_level = [&](uint32_t mid) -> uint32_t { return (mid != ZERO_MID && mid >= LIN_BASE) ? llevel[mid - LIN_BASE] : 0; };
     auto new_val = [&](uint32_t level) -> uint32_t {
         vlevel.push_back(level);
@@ -438,9 +674,16 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
             if (z64_cells < op.a) z64_cells = op.a;
             continue;
         }
-        if (op.domain == RV_Z64 || op.domain == RV_B2A) {
+        if (op.domain == RV_Z64) {
             P.uses_z64 = true;
-            err = "op " + std::to_string(i) + ": Z64 / B2A operations are not accelerated yet";
+            if (zb.cells.size() < z64_cells) zb.cells.resize(z64_cells, ZCell{0, ZERO_MID, 0});
+            const int zrc = zb.step(op, i, err);
+            if (zrc != RV_OK) return zrc;
+            continue;
+        }
+        if (op.domain == RV_B2A) {
+            P.uses_z64 = true;
+            err = "op " + std::to_string(i) + ": B2A conversions are not accelerated yet";
             return RV_E_UNSUPPORTED;
         }
         if (op.domain != RV_GF2) {
@@ -588,6 +831,8 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
         }
     }
     std::vector<Cell>().swap(cells);
+    zb.finish();
+    P.algorithmic_bytes += zb.alg_bytes;
 
     P.n_masks = (uint32_t)n_masks;
     P.n_vals = (uint32_t)vlevel.size();

@@ -84,6 +84,63 @@ struct Item {
 };
 static_assert(sizeof(VGate) == 16 && sizeof(XGate) == 32 && sizeof(VmInstr) == 48 && sizeof(LutInstr) == 48 && sizeof(Item) == 32, "POD layout");
 
+// =====================================================================================================================
+//  Z64 domain (src/algebra/z64/*): the same three planes over the ring Z_2^64.
+//    value plane  one u64 per wire, shared by all repetitions (corr = value - reconstruct(mask) holds here too: for Mul,
+//                 corr_out = (a + c1)(b + c2) - reconstruct(mask_new), src/interpreter/single.rs:25-69)
+//    mask plane   512 bytes per wire per packed instance ([8 reps][8 players] u64); Add/Sub/MulConst keep a wire's mask a
+//                 Z_2^64-linear combination of fresh PRG masks, carried as (row, coefficient) so MulConst costs nothing
+//    item plane   Input: 8 bytes of online stream per repetition; Mul / AssertZero: 64 bytes (the 8 players' shares,
+//                 src/algebra/z64/share.rs:100-108); Mul: 8 bytes of preprocessing stream (src/algebra/z64/recon.rs:131-137)
+//  The same value program serves the online verifier: every Mul is v[a] * v[b] + v[kappa], with the kappa leaves zero in
+//  the prover and rho_ab - rho_a * rho_b + msg + delta in the verifier.
+// =====================================================================================================================
+enum ZvOp : uint32_t { ZV_ADD = 0, ZV_SUB = 1, ZV_MUL = 2 /* v[a] * v[b] + v[c] */, ZV_ADDC = 3 /* v[a] + imm */, ZV_MULC = 4 /* v[a] * imm */,
+                       ZV_CONST = 5 /* imm */ };
+struct ZInstr {
+    uint32_t op, dst, a, b, c, pad;
+    uint64_t imm;
+};
+// mask-plane node: zrow[dst] = ca * zrow[a] + cb * zrow[b]  (element-wise over the 64 * npi shares of a row)
+struct ZLin {
+    uint32_t dst, a, b, pad;
+    uint64_t ca, cb;
+};
+struct ZItem {
+    uint32_t kind;  // ItemKind
+    uint32_t ra;    // row of operand a's mask (INPUT: the fresh mask; ASSERT: the wire's mask)
+    uint32_t rb;    // MUL: row of operand b's mask
+    uint32_t k;     // MUL: fresh-mask index of mask_ab (mask_new = k + 1)
+    uint32_t va;    // value id of operand a / the input / the asserted wire
+    uint32_t vb;    // MUL: value id of operand b
+    uint32_t j;     // MUL: index among the Muls (preprocessing stream offset 8 j); INPUT: witness index
+    uint32_t off;   // byte offset in the online stream
+    uint64_t ca;    // wire mask = ca * zrow[ra]
+    uint64_t cb;
+};
+static_assert(sizeof(ZInstr) == 32 && sizeof(ZLin) == 32 && sizeof(ZItem) == 48, "POD layout");
+
+struct ZProgram {
+    uint64_t n_mul = 0, n_inputs = 0, n_assert = 0;
+    uint32_t n_masks = 0;  // fresh Z64 PRG masks per (rep, player): mask i = LE u64 at byte 8 i of the stream (z64/batch.rs:25-30)
+    uint32_t n_lin = 0;    // linear nodes
+    uint32_t n_rows = 1;   // n_masks + n_lin + 1 (the last row is all-zero)
+    uint32_t n_vals = 1;   // value ids; id 0 is the constant 0
+    std::vector<ZInstr> vprog;          // sorted by level
+    std::vector<uint32_t> vlevel_off;   // value_depth + 1 offsets
+    std::vector<ZLin> lin;              // sorted by level; dst rows are n_masks + position
+    std::vector<uint32_t> llevel_off;
+    std::vector<ZItem> items;           // online-stream order
+    std::vector<uint32_t> leaf_ids;     // value ids of the leaves: inputs (witness order), then one kappa per Mul
+    std::vector<uint32_t> recon_off;    // online byte offset of the k-th reconstruct() (Mul, AssertZero)
+    std::vector<uint32_t> input_off;    // online byte offset of the k-th input()
+    std::vector<uint32_t> mul_pos;      // j -> item index
+    std::vector<uint32_t> recon_idx;    // item index -> index among the reconstruct() calls
+    uint64_t on_bytes = 0, pre_bytes = 0;  // per repetition
+    bool any() const { return !items.empty() || n_masks != 0; }
+    uint32_t zero_row() const { return n_rows - 1; }
+};
+
 struct Program {
     // GF(2) side
     uint64_t n_ops = 0, n_and = 0, n_inputs = 0, n_assert = 0;
@@ -119,6 +176,7 @@ struct Program {
     std::vector<uint32_t> input_vid;    // witness index -> value id
     uint64_t algorithmic_bytes = 0;
     bool uses_z64 = false;
+    ZProgram z;
     uint32_t zero_row() const { return n_rows - 1; }
 };
 

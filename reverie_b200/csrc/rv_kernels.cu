@@ -5,6 +5,7 @@
 #include <algorithm>
 
 #include "rv_kernels.cuh"
+#include "rv_maskgen.cuh"
 #include "rv_planes.cuh"
 
 namespace rv {
@@ -53,72 +54,12 @@ void launch_key_setup(const uint8_t *seeds, const uint8_t *pkeys_in, const uint8
 // =====================================================================================================================
 //  K2  mask generation: bitsliced AES-128-CTR, thread = (slice, counter block)
 // =====================================================================================================================
-constexpr int MG_SLICES = 8;    // slices per CTA (their round keys live in shared memory: 8 x 5632 B = 44 KB)
-constexpr int MG_COUNTERS = 8;  // counter blocks per CTA (64 threads: fine-grained CTAs balance the 148 SMs)
-constexpr int MG_THREADS = MG_SLICES * MG_COUNTERS;
-
-struct SmemRoundKeys {
-    const uint4 *base;  // [(round*32 + plane/4)][slice] uint4
-    uint32_t sl;
-    __device__ __forceinline__ uint4 quad(int round, int g) const { return base[(round * 32 + g) * MG_SLICES + sl]; }
-};
-
-// Same dataflow as bs_aes128_ctr_block (rv_aes_bs.cuh), with the round-key planes fetched four at a time (LDS.128).
-__device__ __forceinline__ void aes_ctr_block_smem(uint64_t ctr, const SmemRoundKeys &rk, uint32_t *s) {
-#pragma unroll
-    for (int g = 0; g < 32; g++) {
-        const uint4 k4 = rk.quad(0, g);
-        const uint32_t kk[4] = {k4.x, k4.y, k4.z, k4.w};
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int k = 4 * g + i, B = k >> 3, b = k & 7;
-            uint32_t in = 0;
-            if (B >= 8) in = 0u - (uint32_t)((ctr >> (8 * (15 - B) + b)) & 1);
-            s[k] = in ^ kk[i];
-        }
-    }
-#pragma unroll 1
-    for (int round = 1; round <= 10; round++) {
-#pragma unroll
-        for (int B = 0; B < 16; B++) bs_sbox<uint32_t>(s + 8 * B, 0xFFFFFFFFu);
-        uint32_t t[128];
-#pragma unroll
-        for (int c = 0; c < 4; c++)
-#pragma unroll
-            for (int r = 0; r < 4; r++)
-#pragma unroll
-                for (int b = 0; b < 8; b++) t[8 * (4 * c + r) + b] = s[8 * (4 * ((c + r) & 3) + r) + b];
-        if (round < 10) {
-#pragma unroll
-            for (int c = 0; c < 4; c++) bs_mix_column<uint32_t>(t + 32 * c, t + 32 * c + 8, t + 32 * c + 16, t + 32 * c + 24, s + 32 * c);
-        } else {
-#pragma unroll
-            for (int k = 0; k < 128; k++) s[k] = t[k];
-        }
-#pragma unroll
-        for (int g = 0; g < 32; g++) {
-            const uint4 k4 = rk.quad(round, g);
-            s[4 * g + 0] ^= k4.x;
-            s[4 * g + 1] ^= k4.y;
-            s[4 * g + 2] ^= k4.z;
-            s[4 * g + 3] ^= k4.w;
-        }
-    }
-}
-
 __global__ void __launch_bounds__(MG_THREADS) k_mask_gen(const uint32_t *__restrict__ ks, const uint32_t *__restrict__ lane_mask,
                                                          uint32_t nslices, uint32_t n_masks, uint32_t *__restrict__ rows32,
                                                          uint32_t *__restrict__ fresh_sm, size_t pitch_sm) {
     __shared__ uint4 sk[11 * 32 * MG_SLICES];
     const uint32_t w0 = blockIdx.y * MG_SLICES;
-    {
-        uint32_t *sk32 = reinterpret_cast<uint32_t *>(sk);
-        for (uint32_t idx = threadIdx.x; idx < MG_SLICES * 1408; idx += MG_THREADS) {
-            const uint32_t sl = idx / 1408, e = idx % 1408;
-            const uint32_t v = (w0 + sl < nslices) ? ks[(size_t)(w0 + sl) * 1408 + e] : 0u;
-            sk32[((e >> 2) * MG_SLICES + sl) * 4 + (e & 3)] = v;
-        }
-    }
+    load_round_keys(sk, ks, w0, nslices);
     __syncthreads();
     const uint32_t sl = threadIdx.x % MG_SLICES, w = w0 + sl;
     const uint64_t j = (uint64_t)blockIdx.x * MG_COUNTERS + threadIdx.x / MG_SLICES;
@@ -630,7 +571,7 @@ __device__ void tree_reduce(uint32_t *cvs, uint32_t n) {
 __global__ void __launch_bounds__(128) k_rep_hash(uint32_t *cv_on, uint32_t n_chunks_on, uint32_t *cv_pre, uint32_t n_chunks_pre,
                                                   const uint32_t *__restrict__ zconst, uint8_t *__restrict__ on_hash,
                                                   uint8_t *__restrict__ rep_hash, uint32_t first_pre, const uint8_t *__restrict__ on_given,
-                                                  const uint8_t *__restrict__ z_on_given) {
+                                                  const uint8_t *__restrict__ z_on_given, const uint32_t *__restrict__ zrep) {
     const uint32_t rep = blockIdx.x;
     const bool given = rep >= first_pre;
     uint32_t *on = cv_on + (size_t)rep * n_chunks_on * 8, *pre = cv_pre + (size_t)rep * n_chunks_pre * 8;
@@ -653,10 +594,14 @@ __global__ void __launch_bounds__(128) k_rep_hash(uint32_t *cv_on, uint32_t n_ch
                 zon[i] = (uint32_t)zg[4 * i] | ((uint32_t)zg[4 * i + 1] << 8) | ((uint32_t)zg[4 * i + 2] << 16) | ((uint32_t)zg[4 * i + 3] << 24);
                 e[i] = zconst[i];  // B3(""): the (empty) Z64 preprocessing stream
             }
-            b3_hash64(e, zon, z);
+            if (zrep == nullptr) b3_hash64(e, zon, z);
         } else {
 #pragma unroll
             for (int i = 0; i < 8; i++) h_on[i] = on[i];
+        }
+        if (zrep != nullptr) {  // the circuit has Z64 ops: k_zrep_hash computed this repetition's Z64 transcript hash
+#pragma unroll
+            for (int i = 0; i < 8; i++) z[i] = zrep[(size_t)rep * 8 + i];
         }
         rep_join(h_on, h_pre, z, out);
         uint32_t *d0 = reinterpret_cast<uint32_t *>(on_hash + (size_t)rep * 32), *d1 = reinterpret_cast<uint32_t *>(rep_hash + (size_t)rep * 32);
@@ -669,8 +614,46 @@ __global__ void __launch_bounds__(128) k_rep_hash(uint32_t *cv_on, uint32_t n_ch
 }
 
 void launch_rep_hash(uint32_t *cv_on, uint32_t n_chunks_on, uint32_t *cv_pre, uint32_t n_chunks_pre, const uint32_t *zconst, uint32_t nreps,
-                     uint8_t *on_hash, uint8_t *rep_hash, cudaStream_t st, uint32_t first_pre, const uint8_t *on_given, const uint8_t *z_on_given) {
-    k_rep_hash<<<nreps, 128, 0, st>>>(cv_on, n_chunks_on, cv_pre, n_chunks_pre, zconst, on_hash, rep_hash, first_pre, on_given, z_on_given);
+                     uint8_t *on_hash, uint8_t *rep_hash, cudaStream_t st, uint32_t first_pre, const uint8_t *on_given, const uint8_t *z_on_given,
+                     const uint32_t *zrep) {
+    k_rep_hash<<<nreps, 128, 0, st>>>(cv_on, n_chunks_on, cv_pre, n_chunks_pre, zconst, on_hash, rep_hash, first_pre, on_given, z_on_given, zrep);
+}
+
+// Z64 transcript of one repetition (CTA): Transcript::hash = H(B3(pre) || B3(on)), src/transcript/mod.rs:77-96
+__global__ void __launch_bounds__(256) k_zrep_hash(uint32_t *cv_on, uint32_t n_chunks_on, uint32_t *cv_pre, uint32_t n_chunks_pre,
+                                                   uint8_t *__restrict__ zon_hash, uint32_t *__restrict__ zrep, uint32_t first_pre,
+                                                   const uint8_t *__restrict__ z_on_given) {
+    const uint32_t rep = blockIdx.x;
+    const bool given = rep >= first_pre;
+    uint32_t *on = cv_on + (size_t)rep * n_chunks_on * 8, *pre = cv_pre + (size_t)rep * n_chunks_pre * 8;
+    if (!given) tree_reduce(on, n_chunks_on);
+    tree_reduce(pre, n_chunks_pre);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t h_on[8], h_pre[8], out[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) h_pre[i] = pre[i];
+        if (given) {
+            const uint8_t *g = z_on_given + (size_t)(rep - first_pre) * 32;
+#pragma unroll
+            for (int i = 0; i < 8; i++) h_on[i] = (uint32_t)g[4 * i] | ((uint32_t)g[4 * i + 1] << 8) | ((uint32_t)g[4 * i + 2] << 16) | ((uint32_t)g[4 * i + 3] << 24);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; i++) h_on[i] = on[i];
+        }
+        b3_hash64(h_pre, h_on, out);
+        uint32_t *d0 = reinterpret_cast<uint32_t *>(zon_hash + (size_t)rep * 32);
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            d0[i] = h_on[i];
+            zrep[(size_t)rep * 8 + i] = out[i];
+        }
+    }
+}
+
+void launch_zrep_hash(uint32_t *cv_on, uint32_t n_chunks_on, uint32_t *cv_pre, uint32_t n_chunks_pre, uint32_t nreps, uint8_t *zon_hash,
+                      uint32_t *zrep, cudaStream_t st, uint32_t first_pre, const uint8_t *z_on_given) {
+    k_zrep_hash<<<nreps, 256, 0, st>>>(cv_on, n_chunks_on, cv_pre, n_chunks_pre, zon_hash, zrep, first_pre, z_on_given);
 }
 
 // =====================================================================================================================
@@ -817,7 +800,7 @@ void launch_challenge(const uint8_t *all_hashes, uint8_t *comm, uint8_t *omit_of
 __global__ void __launch_bounds__(256) k_extract(const uint32_t *__restrict__ recon_pos, const uint32_t *__restrict__ input_pos,
                                                  uint32_t n_recon, uint32_t n_pre, uint32_t n_inputs, ExtractArgs a) {
     const uint32_t lrep = blockIdx.x, rep = a.first_rep + lrep;
-    ProofLayout L{a.len_recons, a.len_corrs, a.len_inputs};
+    ProofLayout L{a.len_recons, a.len_corrs, a.len_inputs, a.len_zrecons, a.len_zcorrs, a.len_zinputs};
     ExtractView v;
     v.on = a.on + (size_t)lrep * a.pitch_on;
     v.pre = a.pre + (size_t)lrep * a.pitch_pre;
@@ -826,6 +809,7 @@ __global__ void __launch_bounds__(256) k_extract(const uint32_t *__restrict__ re
     v.seed = a.seeds + (size_t)lrep * 16;
     v.comm = a.comm;
     v.z64_empty_hash = a.z64_empty_hash;
+    v.z_on_hash = a.z_on_hash ? a.z_on_hash + (size_t)lrep * 32 : nullptr;
     v.recon_pos = recon_pos;
     v.input_pos = input_pos;
     v.n_recon = n_recon;

@@ -32,6 +32,19 @@ struct DevProgram {
     uint32_t max_llevel_width = 0;
 };
 
+// compiled Z64 tables resident in device memory (rv_compile.h: ZProgram)
+struct DevZProgram {
+    const ZInstr *vprog = nullptr;
+    const uint32_t *vlevel_off = nullptr;
+    const ZLin *lin = nullptr;
+    const ZItem *items = nullptr;
+    const uint32_t *leaf_ids = nullptr, *recon_off = nullptr, *input_off = nullptr, *mul_pos = nullptr, *recon_idx = nullptr;
+    const uint32_t *input_item = nullptr;  // k -> item index of the k-th input()
+    uint32_t n_vlevels = 0, n_llevels = 0, n_items = 0, n_mul = 0, n_inputs = 0, n_recon = 0, n_leaves = 0;
+    uint32_t n_masks = 0, n_rows = 1, n_vals = 1;
+    uint32_t on_bytes = 0, pre_bytes = 0;
+};
+
 // K1  seeds -> player keys -> bitsliced round keys (src/transcript/mod.rs:99-106, src/crypto/prg.rs:16-20)
 void launch_key_setup(const uint8_t *seeds, const uint8_t *pkeys_in, const uint8_t *mode, const uint8_t *omit, uint32_t nslices,
                       uint32_t *ks, uint32_t *lane_mask, uint8_t *pkeys_out, cudaStream_t st);
@@ -57,7 +70,11 @@ void launch_chunk_cv2(const uint8_t *on, size_t pitch_on, uint32_t len_on, uint3
 //     zconst: [0..8) B3(""), [8..16) H(B3("") || B3("")).  Verifier: repetitions >= first_pre use the proof's online hashes.
 void launch_rep_hash(uint32_t *cv_on, uint32_t n_chunks_on, uint32_t *cv_pre, uint32_t n_chunks_pre, const uint32_t *zconst, uint32_t nreps,
                      uint8_t *on_hash, uint8_t *rep_hash, cudaStream_t st, uint32_t first_pre = 0xFFFFFFFFu, const uint8_t *on_given = nullptr,
-                     const uint8_t *z_on_given = nullptr);
+                     const uint8_t *z_on_given = nullptr, const uint32_t *zrep = nullptr);
+//     Z64 transcript of every repetition: roots of its two streams -> zon_hash[rep] (32 B) and zrep[rep] = H(B3(pre) || B3(on))
+//     (src/transcript/mod.rs:77-96); feeds launch_rep_hash's `zrep`.  Repetitions >= first_pre take the proof's online hash.
+void launch_zrep_hash(uint32_t *cv_on, uint32_t n_chunks_on, uint32_t *cv_pre, uint32_t n_chunks_pre, uint32_t nreps, uint8_t *zon_hash,
+                      uint32_t *zrep, cudaStream_t st, uint32_t first_pre = 0xFFFFFFFFu, const uint8_t *z_on_given = nullptr);
 // online verifier (src/transcript/verifier/online.rs)
 struct VOpen;
 void launch_verify_leaves(const DevProgram &P, const VOpen *opens, const uint8_t *proof, const uint64_t *rows, uint32_t npi, uint32_t n_slots,
@@ -79,10 +96,39 @@ struct ExtractArgs {
     const uint8_t *omit_of_rep;  // [256]
     const uint16_t *rank_of_rep; // [256]
     const uint32_t *z64_empty_hash;  // B3("")
+    const uint8_t *z_on_hash = nullptr;  // [nreps][32] BLAKE3 of the Z64 online streams (nullptr: no Z64 ops)
     uint32_t first_rep, nreps;
     uint32_t len_recons, len_corrs, len_inputs;  // packed byte lengths
+    uint32_t len_zrecons = 0, len_zcorrs = 0, len_zinputs = 0;
     uint8_t *proof;
 };
 void launch_extract(const DevProgram &P, const ExtractArgs &a, cudaStream_t st);
+
+// ---- Z64 domain (rv_z64.cu) ------------------------------------------------------------------------------------------
+struct ZOpen;
+void launch_zmask_gen(const uint32_t *ks, const uint32_t *lane_mask, uint32_t nslices, uint32_t n_masks, uint64_t *zrows, size_t rowlen,
+                      cudaStream_t st);
+int launch_zlinear(const DevZProgram &Z, const uint32_t *llevel_off_host, uint64_t *zrows, uint32_t rowlen, cudaStream_t st);
+void launch_zvalues(const DevZProgram &Z, const uint64_t *leaf_vals, size_t leaf_pitch, uint64_t *vals, size_t vals_pitch, uint32_t n_instances,
+                    cudaStream_t st);
+void launch_zitems(const DevZProgram &Z, const uint64_t *zrows, size_t rowlen, uint32_t nreps, const uint64_t *vals, uint8_t *on, size_t pitch_on,
+                   uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st);
+void launch_zitems_pre_range(const DevZProgram &Z, const uint64_t *zrows, size_t rowlen, uint32_t first_rep, uint32_t nreps, uint8_t *pre,
+                             size_t pitch_pre, cudaStream_t st);
+void launch_zverify_leaves(const DevZProgram &Z, const ZOpen *opens, const uint8_t *proof, const uint64_t *zrows, size_t rowlen, uint32_t n_slots,
+                           uint64_t *leaf_vals, size_t leaf_pitch, cudaStream_t st);
+void launch_zverify_items(const DevZProgram &Z, const ZOpen *opens, const uint8_t *proof, const uint64_t *zrows, size_t rowlen, uint32_t n_slots,
+                          const uint64_t *uvals, size_t upitch, uint8_t *on, size_t pitch_on, uint8_t *pre, size_t pitch_pre, int *not_okay,
+                          cudaStream_t st);
+struct ZExtractArgs {
+    const uint8_t *on, *pre;
+    size_t pitch_on, pitch_pre;
+    const uint8_t *omit_of_rep;   // [256]
+    const uint16_t *rank_of_rep;  // [256]
+    uint32_t first_rep, nreps;
+    size_t z_base, sz_on_z;       // ProofLayout::z_base(), ::sz_on_z()
+    uint8_t *proof;
+};
+void launch_zextract(const DevZProgram &Z, const ZExtractArgs &a, cudaStream_t st);
 
 }  // namespace rv

@@ -256,8 +256,9 @@ RV_HD uint8_t pack_bits_byte(const uint8_t *stream, const uint32_t *pos, uint32_
 // ---- bincode `Proof` layout (src/proof/mod.rs:40-66; bincode 1.3 default: LE, u64 lengths, fixed arrays inline) ----
 struct ProofLayout {
     uint32_t len_recons, len_corrs, len_inputs;
+    uint32_t len_zrecons = 0, len_zcorrs = 0, len_zinputs = 0;  // Z64 packs are exactly 8 n bytes (src/algebra/z64/share.rs:37-49, recon.rs:46-66)
     RV_HD size_t sz_on_g() const { return 1 + 128 + 24 + (size_t)len_recons + len_corrs + len_inputs; }
-    RV_HD size_t sz_on_z() const { return 1 + 128 + 24; }
+    RV_HD size_t sz_on_z() const { return 1 + 128 + 24 + (size_t)len_zrecons + len_zcorrs + len_zinputs; }
     RV_HD size_t g_base() const { return 32; }
     RV_HD size_t g_pre_base() const { return g_base() + 8 + RV_ONLINE_REPS * sz_on_g(); }
     RV_HD size_t z_base() const { return g_pre_base() + 8 + RV_PREPROCESSING_REPS * (size_t)48; }
@@ -276,6 +277,7 @@ struct ExtractView {
     const uint8_t *seed;           // [16]
     const uint8_t *comm;           // [32]
     const uint32_t *z64_empty_hash;
+    const uint8_t *z_on_hash = nullptr;  // [32] BLAKE3 of this repetition's Z64 online stream; nullptr = the stream is empty
     const uint32_t *recon_pos, *input_pos;
     uint32_t n_recon, n_pre, n_inputs;
 };
@@ -299,9 +301,9 @@ RV_HD void extract_entry(const ProofLayout &L, const ExtractView &v, uint32_t re
             put_u64le(e + 129, L.len_recons);
             put_u64le(e + 137 + L.len_recons, L.len_corrs);
             put_u64le(e + 145 + L.len_recons + L.len_corrs, L.len_inputs);
-            put_u64le(z + 129, 0);
-            put_u64le(z + 137, 0);
-            put_u64le(z + 145, 0);
+            put_u64le(z + 129, L.len_zrecons);  // the Z64 vectors themselves are copied by k_zextract
+            put_u64le(z + 137 + L.len_zrecons, L.len_zcorrs);
+            put_u64le(z + 145 + L.len_zrecons + L.len_zcorrs, L.len_zinputs);
         }
         for (uint32_t i = tid; i < 128; i += nt) {  // OpenOnline.seeds with the unopened player's key zeroed
             const uint8_t b = (i / 16 == omit) ? 0 : v.pkeys[i];
@@ -323,7 +325,7 @@ RV_HD void extract_entry(const ProofLayout &L, const ExtractView &v, uint32_t re
                 z[i] = v.seed[i];
             } else {
                 e[i] = v.on_hash[i - 16];
-                z[i] = (uint8_t)(v.z64_empty_hash[(i - 16) / 4] >> (8 * ((i - 16) & 3)));
+                z[i] = v.z_on_hash ? v.z_on_hash[i - 16] : (uint8_t)(v.z64_empty_hash[(i - 16) / 4] >> (8 * ((i - 16) & 3)));
             }
         }
     }

@@ -1,0 +1,230 @@
+// rv_z64.cu -- sm_100a kernels of the Z64 domain (src/algebra/z64/*, the Z64 instance of src/interpreter/single.rs and of
+// the three transcripts).  Integer work only.  Layouts: rv_zplanes.cuh.
+#include <algorithm>
+
+#include "rv_kernels.cuh"
+#include "rv_maskgen.cuh"
+#include "rv_zplanes.cuh"
+
+namespace rv {
+
+// =====================================================================================================================
+//  ZK2  Z64 mask generation: the same bitsliced AES-128-CTR as the GF(2) generator (thread = slice x counter block), then
+//       four 32x32 bit transposes turn the 128 planes back into each stream's 16 keystream bytes = Z64 masks 2j, 2j+1
+//       (src/algebra/z64/batch.rs:25-30, src/algebra/z64/domain.rs:64-83).  A thread stores 2 x 256 contiguous bytes.
+// =====================================================================================================================
+__global__ void __launch_bounds__(MG_THREADS) k_zmask_gen(const uint32_t *__restrict__ ks, const uint32_t *__restrict__ lane_mask, uint32_t nslices,
+                                                          uint32_t n_masks, uint64_t *__restrict__ zrows, size_t rowlen) {
+    __shared__ uint4 sk[11 * 32 * MG_SLICES];
+    const uint32_t w0 = blockIdx.y * MG_SLICES;
+    load_round_keys(sk, ks, w0, nslices);
+    __syncthreads();
+    const uint32_t sl = threadIdx.x % MG_SLICES, w = w0 + sl;
+    const uint64_t j = (uint64_t)blockIdx.x * MG_COUNTERS + threadIdx.x / MG_SLICES;
+    if (w >= nslices || 2 * j >= n_masks) return;
+    uint32_t s[128];
+    SmemRoundKeys rk{sk, sl};
+    aes_ctr_block_smem(j, rk, s);
+    const uint32_t lm = lane_mask[w];
+    const uint32_t base = zrow_index(w, 0);
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        if (2 * j + h >= n_masks) break;
+        uint32_t lo[32], hi[32];
+        planes_to_mask_words(s, lm, h, lo, hi);
+        uint4 *dst = reinterpret_cast<uint4 *>(zrows + (size_t)(2 * j + h) * rowlen + base);
+#pragma unroll
+        for (int q = 0; q < 16; q++) dst[q] = make_uint4(lo[2 * q], hi[2 * q], lo[2 * q + 1], hi[2 * q + 1]);
+    }
+}
+
+void launch_zmask_gen(const uint32_t *ks, const uint32_t *lane_mask, uint32_t nslices, uint32_t n_masks, uint64_t *zrows, size_t rowlen,
+                      cudaStream_t st) {
+    if (n_masks == 0) return;
+    const uint32_t n_blocks = (n_masks + 1) / 2;
+    dim3 grid((n_blocks + MG_COUNTERS - 1) / MG_COUNTERS, (nslices + MG_SLICES - 1) / MG_SLICES);
+    k_zmask_gen<<<grid, MG_THREADS, 0, st>>>(ks, lane_mask, nslices, n_masks, zrows, rowlen);
+}
+
+// =====================================================================================================================
+//  ZK3  mask plane: zrow[dst] = ca * zrow[a] + cb * zrow[b], one launch per level, thread = (node, element)
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) k_zlinear_level(const ZLin *__restrict__ lin, uint32_t n, uint64_t *zrows, uint32_t rowlen) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t g = gid / rowlen;
+    const uint32_t e = (uint32_t)(gid % rowlen);
+    if (g >= n) return;
+    const ZLin nd = lin[g];
+    zrows[(size_t)nd.dst * rowlen + e] = nd.ca * zrows[(size_t)nd.a * rowlen + e] + nd.cb * zrows[(size_t)nd.b * rowlen + e];
+}
+
+int launch_zlinear(const DevZProgram &Z, const uint32_t *llevel_off_host, uint64_t *zrows, uint32_t rowlen, cudaStream_t st) {
+    for (uint32_t l = 0; l < Z.n_llevels; l++) {
+        const uint32_t n = llevel_off_host[l + 1] - llevel_off_host[l];
+        const uint64_t threads = (uint64_t)n * rowlen;
+        k_zlinear_level<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(Z.lin + llevel_off_host[l], n, zrows, rowlen);
+    }
+    return (int)Z.n_llevels;
+}
+
+// =====================================================================================================================
+//  ZK0  value plane: level-synchronous walk of the u64 program by one CTA per instance (prover: 1; verifier: one per
+//       opened repetition).  The next level's instructions are fetched before the barrier that ends the current one.
+// =====================================================================================================================
+constexpr int ZV_THREADS = 256;
+__global__ void __launch_bounds__(ZV_THREADS) k_zvalues(const ZInstr *__restrict__ prog, const uint32_t *__restrict__ level_off, uint32_t n_levels,
+                                                        const uint32_t *__restrict__ leaf_ids, const uint64_t *__restrict__ leaf_vals,
+                                                        size_t leaf_pitch, uint32_t n_leaves, uint64_t *vals_out, size_t vals_pitch) {
+    uint64_t *v = vals_out + (size_t)blockIdx.x * vals_pitch;
+    const uint64_t *lv = leaf_vals + (size_t)blockIdx.x * leaf_pitch;
+    const uint32_t tid = threadIdx.x;
+    if (tid == 0) v[0] = 0;
+    for (uint32_t k = tid; k < n_leaves; k += ZV_THREADS) v[leaf_ids[k]] = lv[k];
+    if (n_levels == 0) return;
+    uint32_t s = level_off[0], e = level_off[1];
+    ZInstr nx;
+    bool have = s + tid < e;
+    if (have) nx = prog[s + tid];
+    __syncthreads();
+    for (uint32_t l = 0; l < n_levels; l++) {
+        const uint32_t e_next = l + 1 < n_levels ? level_off[l + 2] : e;
+        uint32_t g = s + tid;
+        ZInstr in = nx;
+        const bool had = have;
+        have = e + tid < e_next;
+        if (have) nx = prog[e + tid];  // prefetch: does not depend on this level's values
+        if (had) {
+            v[in.dst] = z_exec(in, v);
+            for (g += ZV_THREADS; g < e; g += ZV_THREADS) {
+                in = prog[g];
+                v[in.dst] = z_exec(in, v);
+            }
+        }
+        __syncthreads();
+        s = e;
+        e = e_next;
+    }
+}
+
+void launch_zvalues(const DevZProgram &Z, const uint64_t *leaf_vals, size_t leaf_pitch, uint64_t *vals, size_t vals_pitch, uint32_t n_instances,
+                    cudaStream_t st) {
+    k_zvalues<<<n_instances, ZV_THREADS, 0, st>>>(Z.vprog, Z.vlevel_off, Z.n_vlevels, Z.leaf_ids, leaf_vals, leaf_pitch, Z.n_leaves, vals, vals_pitch);
+}
+
+// =====================================================================================================================
+//  ZK4  item plane.  thread = (item, repetition); a CTA = 32 consecutive items x the 8 repetitions of one packed instance
+//       (repetition fastest), so a warp reads each operand row as 512 contiguous bytes and appends 256 contiguous bytes
+//       to each of its 8 streams.
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) k_zitems_online(const ZItem *__restrict__ items, uint32_t n_items, const uint64_t *__restrict__ zrows,
+                                                       size_t rowlen, const uint64_t *__restrict__ vals, uint8_t *__restrict__ on, size_t pitch,
+                                                       int *bad) {
+    const uint32_t t = blockIdx.x * 32 + (threadIdx.x >> 3), rep = 8 * blockIdx.y + (threadIdx.x & 7);
+    if (t >= n_items) return;
+    int flag = 0;
+    z_prover_online(items[t], zrows, rowlen, rep, vals, on + (size_t)rep * pitch, &flag);
+    if (flag && rep == 0) atomicOr(bad, 1);
+}
+
+__global__ void __launch_bounds__(256) k_zitems_pre(const ZItem *__restrict__ items, const uint32_t *__restrict__ mul_pos, uint32_t n_mul,
+                                                    const uint64_t *__restrict__ zrows, size_t rowlen, uint8_t *__restrict__ pre, size_t pitch,
+                                                    uint32_t first_rep) {
+    const uint32_t j = blockIdx.x * 32 + (threadIdx.x >> 3), rep = first_rep + 8 * blockIdx.y + (threadIdx.x & 7);
+    if (j >= n_mul) return;
+    put64(pre + (size_t)rep * pitch + 8ull * j, z_pre_word(items[mul_pos[j]], zrows, rowlen, rep));
+}
+
+void launch_zitems(const DevZProgram &Z, const uint64_t *zrows, size_t rowlen, uint32_t nreps, const uint64_t *vals, uint8_t *on, size_t pitch_on,
+                   uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st) {
+    if (Z.n_items) k_zitems_online<<<dim3((Z.n_items + 31) / 32, nreps / 8), 256, 0, st>>>(Z.items, Z.n_items, zrows, rowlen, vals, on, pitch_on, bad);
+    if (Z.n_mul) k_zitems_pre<<<dim3((Z.n_mul + 31) / 32, nreps / 8), 256, 0, st>>>(Z.items, Z.mul_pos, Z.n_mul, zrows, rowlen, pre, pitch_pre, 0);
+}
+
+void launch_zitems_pre_range(const DevZProgram &Z, const uint64_t *zrows, size_t rowlen, uint32_t first_rep, uint32_t nreps, uint8_t *pre,
+                             size_t pitch_pre, cudaStream_t st) {
+    if (!Z.n_mul || first_rep >= nreps) return;
+    k_zitems_pre<<<dim3((Z.n_mul + 31) / 32, (nreps - first_rep) / 8), 256, 0, st>>>(Z.items, Z.mul_pos, Z.n_mul, zrows, rowlen, pre, pitch_pre, first_rep);
+}
+
+// =====================================================================================================================
+//  online verifier
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) k_zverify_leaves(const ZItem *__restrict__ items, const uint32_t *__restrict__ input_item,
+                                                        const uint32_t *__restrict__ mul_pos, const uint32_t *__restrict__ recon_idx,
+                                                        uint32_t n_inputs, uint32_t n_mul, const ZOpen *__restrict__ opens,
+                                                        const uint8_t *__restrict__ proof, const uint64_t *__restrict__ zrows, size_t rowlen,
+                                                        uint64_t *__restrict__ leaf_vals, size_t leaf_pitch) {
+    const uint32_t leaf = blockIdx.x * 32 + (threadIdx.x >> 3), slot = 8 * blockIdx.y + (threadIdx.x & 7);
+    if (leaf >= n_inputs + n_mul) return;
+    uint64_t v;
+    if (leaf < n_inputs) v = z_verify_leaf_input(items[input_item[leaf]], leaf, opens[slot], proof, zrows, rowlen, slot);
+    else {
+        const uint32_t t = mul_pos[leaf - n_inputs];
+        v = z_verify_leaf_kappa(items[t], recon_idx[t], opens[slot], proof, zrows, rowlen, slot);
+    }
+    leaf_vals[(size_t)slot * leaf_pitch + leaf] = v;
+}
+
+__global__ void __launch_bounds__(256) k_zverify_items_online(const ZItem *__restrict__ items, const uint32_t *__restrict__ recon_idx, uint32_t n_items,
+                                                              const ZOpen *__restrict__ opens, const uint8_t *__restrict__ proof,
+                                                              const uint64_t *__restrict__ zrows, size_t rowlen, const uint64_t *__restrict__ uvals,
+                                                              size_t upitch, uint8_t *__restrict__ on, size_t pitch, int *not_okay) {
+    const uint32_t t = blockIdx.x * 32 + (threadIdx.x >> 3), slot = 8 * blockIdx.y + (threadIdx.x & 7);
+    if (t >= n_items) return;
+    int flag = 0;
+    z_verify_online(items[t], recon_idx[t], opens[slot], proof, zrows, rowlen, slot, uvals + (size_t)slot * upitch, on + (size_t)slot * pitch, &flag);
+    if (flag) atomicOr(not_okay, 1);
+}
+
+// preprocessing stream of an opened repetition = the proof's corrections (online.rs:169-174)
+__global__ void __launch_bounds__(256) k_zverify_items_pre(uint32_t n_mul, const ZOpen *__restrict__ opens, const uint8_t *__restrict__ proof,
+                                                           uint8_t *__restrict__ pre, size_t pitch) {
+    const uint32_t j = blockIdx.x * 32 + (threadIdx.x >> 3), slot = 8 * blockIdx.y + (threadIdx.x & 7);
+    if (j >= n_mul) return;
+    const ZOpen &o = opens[slot];
+    put64(pre + (size_t)slot * pitch + 8ull * j, z_packed(proof, o.off_corrs, o.n_corrs, o.len_corrs, j));
+}
+
+void launch_zverify_leaves(const DevZProgram &Z, const ZOpen *opens, const uint8_t *proof, const uint64_t *zrows, size_t rowlen, uint32_t n_slots,
+                           uint64_t *leaf_vals, size_t leaf_pitch, cudaStream_t st) {
+    if (!Z.n_leaves) return;
+    k_zverify_leaves<<<dim3((Z.n_leaves + 31) / 32, n_slots / 8), 256, 0, st>>>(Z.items, Z.input_item, Z.mul_pos, Z.recon_idx, Z.n_inputs, Z.n_mul, opens, proof,
+                                                                             zrows, rowlen, leaf_vals, leaf_pitch);
+}
+
+void launch_zverify_items(const DevZProgram &Z, const ZOpen *opens, const uint8_t *proof, const uint64_t *zrows, size_t rowlen, uint32_t n_slots,
+                          const uint64_t *uvals, size_t upitch, uint8_t *on, size_t pitch_on, uint8_t *pre, size_t pitch_pre, int *not_okay,
+                          cudaStream_t st) {
+    if (Z.n_items)
+        k_zverify_items_online<<<dim3((Z.n_items + 31) / 32, n_slots / 8), 256, 0, st>>>(Z.items, Z.recon_idx, Z.n_items, opens, proof, zrows, rowlen, uvals,
+                                                                                      upitch, on, pitch_on, not_okay);
+    if (Z.n_mul) k_zverify_items_pre<<<dim3((Z.n_mul + 31) / 32, n_slots / 8), 256, 0, st>>>(Z.n_mul, opens, proof, pre, pitch_pre);
+}
+
+// =====================================================================================================================
+//  ZK7  extraction of the Z64 vectors of the opened repetitions (src/transcript/prover.rs:57-175 with
+//       src/algebra/z64/share.rs:37-49 and recon.rs:46-66): thread = one byte, so the unaligned proof bytes leave coalesced.
+//       grid.y = repetition of the shard, grid.x covers the 8 * (n_recon + n_mul + n_inputs) bytes of its three vectors.
+// =====================================================================================================================
+__global__ void __launch_bounds__(256) k_zextract(const uint32_t *__restrict__ recon_off, const uint32_t *__restrict__ input_off, uint32_t n_recon,
+                                                  uint32_t n_mul, uint32_t n_inputs, ZExtractArgs a) {
+    const uint32_t lrep = blockIdx.y, rep = a.first_rep + lrep;
+    const uint32_t omit = a.omit_of_rep[rep];
+    if (omit >= RV_PLAYERS) return;
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t nr = 8ull * n_recon, nc = 8ull * n_mul, ni = 8ull * n_inputs;
+    if (i >= nr + nc + ni) return;
+    const uint8_t *on = a.on + (size_t)lrep * a.pitch_on, *pre = a.pre + (size_t)lrep * a.pitch_pre;
+    uint8_t *z = a.proof + a.z_base + 8 + (size_t)a.rank_of_rep[rep] * a.sz_on_z;
+    if (i < nr) z[137 + i] = on[recon_off[i >> 3] + 8 * omit + (i & 7)];
+    else if (i < nr + nc) z[145 + i] = pre[i - nr];
+    else z[153 + i] = on[input_off[(i - nr - nc) >> 3] + ((i - nr - nc) & 7)];
+}
+
+void launch_zextract(const DevZProgram &Z, const ZExtractArgs &a, cudaStream_t st) {
+    const uint64_t bytes = 8ull * ((uint64_t)Z.n_recon + Z.n_mul + Z.n_inputs);
+    if (!bytes) return;
+    k_zextract<<<dim3((unsigned)((bytes + 255) / 256), a.nreps), 256, 0, st>>>(Z.recon_off, Z.input_off, Z.n_recon, Z.n_mul, Z.n_inputs, a);
+}
+
+}  // namespace rv

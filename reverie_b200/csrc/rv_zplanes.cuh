@@ -1,0 +1,161 @@
+// rv_zplanes.cuh -- per-thread bodies of the Z64 kernels (__host__ __device__: tests/hostsim replays them on the CPU; the
+// product only runs them inside the CUDA kernels of rv_z64.cu).
+//
+// Data layout in HBM for a shard of `npi` packed instances (nreps = 8 npi repetitions):
+//   zrows   u64 [n_zrows][64 * npi]   Z64 share tensor: row = one mask (fresh PRG mask, linear node, or the zero row);
+//                                     element 64*pi + 8*r + p = the reference's ShareZ64.pack[r][p] of instance pi
+//                                     (src/algebra/z64/share.rs:10-13).  One (row, repetition) = 64 contiguous bytes.
+//   zvals   u64 [n_zvals]             value plane (one per opened repetition in the verifier)
+//   zon     u8  [nreps][pitch]        online hash stream of every repetition: 8 bytes per Input (LE corr,
+//                                     src/algebra/z64/recon.rs:131-137), 64 bytes per Mul / AssertZero (8 players x LE u64,
+//                                     src/algebra/z64/share.rs:100-108)
+//   zpre    u8  [nreps][pitch]        preprocessing hash stream: 8 bytes per Mul
+#pragma once
+#include <stdint.h>
+
+#include "rv_planes.cuh"
+
+namespace rv {
+
+// 32x32 bit-matrix transpose in registers (Hacker's Delight 7-3): new a[i] bit b = old a[31-b] bit 31-i.
+RV_HD void transpose32(uint32_t a[32]) {
+    uint32_t m = 0x0000FFFFu;
+#pragma unroll
+    for (int j = 16; j != 0; j >>= 1, m ^= (m << j)) {
+#pragma unroll
+        for (int k = 0; k < 32; k = (k + j + 1) & ~j) {
+            const uint32_t t = (a[k] ^ (a[k | j] >> j)) & m;
+            a[k] ^= t;
+            a[k | j] ^= (t << j);
+        }
+    }
+}
+
+// Bitsliced AES planes of counter block j for one slice (plane 8B+b = keystream byte B, bit b; lane bit q = stream 31-q)
+// -> Z64 mask 2j+h of each of the 32 streams as (lo[sigma], hi[sigma]), sigma = 8*(rep within slice) + player: the little-endian
+// u64 at keystream byte 8h of the block (src/algebra/z64/batch.rs:25-30).  Streams whose bit is clear in lane_mask (the
+// verifier's unopened player, src/generator/batch.rs:31-34) read as zero.
+RV_HD void planes_to_mask_words(const uint32_t s[128], uint32_t lane_mask, int h, uint32_t lo[32], uint32_t hi[32]) {
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+        lo[k] = s[64 * h + 31 - k] & lane_mask;
+        hi[k] = s[64 * h + 32 + 31 - k] & lane_mask;
+    }
+    transpose32(lo);
+    transpose32(hi);
+}
+
+// element index of (slice w, stream sigma) inside a zrow
+RV_HD uint32_t zrow_index(uint32_t w, uint32_t sigma) { return 64 * (w >> 1) + ((w & 1) ? 0u : 32u) + sigma; }
+
+RV_HD uint64_t zsum8(const uint64_t *p) { return p[0] + p[1] + p[2] + p[3] + p[4] + p[5] + p[6] + p[7]; }
+RV_HD void put64(uint8_t *p, uint64_t v) { *reinterpret_cast<uint64_t *>(p) = v; }  // all stream offsets are multiples of 8
+RV_HD uint64_t get64_unaligned(const uint8_t *p) {
+    uint64_t v = 0;
+    for (int i = 0; i < 8; i++) v |= (uint64_t)p[i] << (8 * i);
+    return v;
+}
+
+// ---- prover ---------------------------------------------------------------------------------------------------------
+// One online item of repetition `rep` (index inside the shard): src/interpreter/single.rs:25-69,140-147,
+// src/transcript/prover.rs:181-232.  `stream` = this repetition's online stream.
+RV_HD void z_prover_online(const ZItem &it, const uint64_t *zrows, size_t rowlen, uint32_t rep, const uint64_t *vals, uint8_t *stream, int *bad) {
+    const uint64_t *A = zrows + (size_t)it.ra * rowlen + 8 * rep;
+    uint8_t *dst = stream + it.off;
+    if (it.kind == ITEM_INPUT) {
+        put64(dst, vals[it.va] - zsum8(A));  // corr = w - reconstruct(mask), prover.rs:186-195
+        return;
+    }
+    uint64_t a[8];
+#pragma unroll
+    for (int p = 0; p < 8; p++) a[p] = it.ca * A[p];
+    if (it.kind == ITEM_ASSERT) {
+        if (vals[it.va] != 0) *bad |= 1;
+#pragma unroll
+        for (int p = 0; p < 8; p++) put64(dst + 8 * p, a[p]);
+        return;
+    }
+    const uint64_t *B = zrows + (size_t)it.rb * rowlen + 8 * rep;
+    const uint64_t *AB = zrows + (size_t)it.k * rowlen + 8 * rep, *NW = zrows + (size_t)(it.k + 1) * rowlen + 8 * rep;
+    uint64_t b[8];
+#pragma unroll
+    for (int p = 0; p < 8; p++) b[p] = it.cb * B[p];
+    const uint64_t c1 = vals[it.va] - zsum8(a), c2 = vals[it.vb] - zsum8(b);  // corr = value - reconstruct(mask)
+#pragma unroll
+    for (int p = 0; p < 8; p++) put64(dst + 8 * p, b[p] * c1 + a[p] * c2 + AB[p] - NW[p]);  // single.rs:41-45
+}
+
+// delta = a * b - c on reconstructed masks (single.rs:35-39)
+RV_HD uint64_t z_pre_word(const ZItem &it, const uint64_t *zrows, size_t rowlen, uint32_t rep) {
+    const uint64_t a = it.ca * zsum8(zrows + (size_t)it.ra * rowlen + 8 * rep), b = it.cb * zsum8(zrows + (size_t)it.rb * rowlen + 8 * rep);
+    return a * b - zsum8(zrows + (size_t)it.k * rowlen + 8 * rep);
+}
+
+// ---- online verifier (src/transcript/verifier/online.rs; unpacking src/algebra/z64/share.rs:51-91, recon.rs:68-107) ----
+// n_* = element counts taken from the FIRST repetition of the pack of 8; len_* = this repetition's own byte lengths: an
+// element past n reads as the default (zero), a missing 8-byte chunk inside n reads as zero.
+struct ZOpen {
+    uint64_t off_recons, off_corrs, off_inputs;
+    uint32_t n_recons, n_corrs, n_inputs;
+    uint32_t len_recons, len_corrs, len_inputs;
+    uint32_t omit, pad;
+};
+RV_HD uint64_t z_packed(const uint8_t *proof, uint64_t off, uint32_t n, uint32_t len, uint32_t e) {
+    return (e < n && 8ull * e + 8 <= len) ? get64_unaligned(proof + off + 8ull * e) : 0ull;
+}
+
+// u-plane leaves of opened repetition `slot`: u = corr + rho, rho = sum of the opened players' mask shares
+RV_HD uint64_t z_verify_leaf_input(const ZItem &it, uint32_t k, const ZOpen &o, const uint8_t *proof, const uint64_t *zrows, size_t rowlen, uint32_t slot) {
+    return z_packed(proof, o.off_inputs, o.n_inputs, o.len_inputs, k) + zsum8(zrows + (size_t)it.ra * rowlen + 8 * slot);
+}
+// kappa = rho_ab - rho_a * rho_b + msg + delta
+RV_HD uint64_t z_verify_leaf_kappa(const ZItem &it, uint32_t recon_idx, const ZOpen &o, const uint8_t *proof, const uint64_t *zrows, size_t rowlen,
+                                   uint32_t slot) {
+    const uint64_t ra = it.ca * zsum8(zrows + (size_t)it.ra * rowlen + 8 * slot), rb = it.cb * zsum8(zrows + (size_t)it.rb * rowlen + 8 * slot);
+    const uint64_t rab = zsum8(zrows + (size_t)it.k * rowlen + 8 * slot);
+    return rab - ra * rb + z_packed(proof, o.off_recons, o.n_recons, o.len_recons, recon_idx) + z_packed(proof, o.off_corrs, o.n_corrs, o.len_corrs, it.j);
+}
+
+RV_HD void z_verify_online(const ZItem &it, uint32_t recon_idx, const ZOpen &o, const uint8_t *proof, const uint64_t *zrows, size_t rowlen, uint32_t slot,
+                           const uint64_t *uvals, uint8_t *stream, int *not_okay) {
+    uint8_t *dst = stream + it.off;
+    if (it.kind == ITEM_INPUT) {  // the masked input from the proof is hashed as is (online.rs:123-130)
+        put64(dst, z_packed(proof, o.off_inputs, o.n_inputs, o.len_inputs, it.j));
+        return;
+    }
+    const uint64_t msg = z_packed(proof, o.off_recons, o.n_recons, o.len_recons, recon_idx);  // the unopened player's broadcast (online.rs:140-160)
+    const uint64_t *A = zrows + (size_t)it.ra * rowlen + 8 * slot;
+    uint64_t a[8], s[8];
+#pragma unroll
+    for (int p = 0; p < 8; p++) a[p] = it.ca * A[p];
+    if (it.kind == ITEM_ASSERT) {
+#pragma unroll
+        for (int p = 0; p < 8; p++) s[p] = a[p];
+        if (uvals[it.va] + msg != 0) *not_okay |= 1;  // corr + reconstruct(mask + msg) = u + msg
+    } else {
+        const uint64_t *B = zrows + (size_t)it.rb * rowlen + 8 * slot;
+        const uint64_t *AB = zrows + (size_t)it.k * rowlen + 8 * slot, *NW = zrows + (size_t)(it.k + 1) * rowlen + 8 * slot;
+        uint64_t b[8];
+#pragma unroll
+        for (int p = 0; p < 8; p++) b[p] = it.cb * B[p];
+        const uint64_t c1 = uvals[it.va] - zsum8(a), c2 = uvals[it.vb] - zsum8(b);  // corr = u - rho
+#pragma unroll
+        for (int p = 0; p < 8; p++) s[p] = b[p] * c1 + a[p] * c2 + AB[p] - NW[p];
+    }
+#pragma unroll
+    for (int p = 0; p < 8; p++) put64(dst + 8 * p, s[p] + (p == (int)o.omit ? msg : 0ull));
+}
+
+// value-plane instruction
+RV_HD uint64_t z_exec(const ZInstr &in, const uint64_t *v) {
+    switch (in.op) {
+        case ZV_ADD: return v[in.a] + v[in.b];
+        case ZV_SUB: return v[in.a] - v[in.b];
+        case ZV_MUL: return v[in.a] * v[in.b] + v[in.c];
+        case ZV_ADDC: return v[in.a] + in.imm;
+        case ZV_MULC: return v[in.a] * in.imm;
+        default: return in.imm;
+    }
+}
+
+}  // namespace rv

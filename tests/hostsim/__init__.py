@@ -15,12 +15,12 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        deps = _SRC + [os.path.join(_ROOT, "reverie_b200", "csrc", f) for f in ("rv_planes.cuh", "rv_aes_bs.cuh", "rv_blake3.cuh", "rv_compile.h")]
+        deps = _SRC + [os.path.join(_ROOT, "reverie_b200", "csrc", f) for f in ("rv_planes.cuh", "rv_zplanes.cuh", "rv_aes_bs.cuh", "rv_blake3.cuh", "rv_compile.h", "rv_bincode.h")]
         if not os.path.exists(_LIB) or any(os.path.getmtime(d) > os.path.getmtime(_LIB) for d in deps):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", _LIB] + _SRC)
         L = C.CDLL(_LIB)
         sz = C.c_size_t
-        L.hs_prove.argtypes = [C.c_void_p, sz, sz, sz, C.c_void_p, sz, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(sz), C.c_void_p]
+        L.hs_prove.argtypes = [C.c_void_p, sz, sz, sz, C.c_void_p, sz, C.c_void_p, sz, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(sz), C.c_void_p]
         L.hs_prove.restype = C.c_int
         L.hs_free.argtypes = [C.c_void_p]
         L.hs_blake3.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
@@ -35,13 +35,14 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
 
 
-def prove(ops, wit, wire_counts, seeds: bytes):
+def prove(ops, wit, wire_counts, seeds: bytes, wit_z64=()):
     ops = np.ascontiguousarray(ops)
     w = np.ascontiguousarray(np.asarray(wit, dtype=np.uint8))
+    wz = np.ascontiguousarray(np.asarray(wit_z64, dtype=np.uint64))
     sd = np.frombuffer(seeds, dtype=np.uint8)
     out, n = C.c_void_p(), C.c_size_t()
     hashes = np.zeros(256 * 32, dtype=np.uint8)
-    rc = lib().hs_prove(_p(ops), ops.size, wire_counts[0], wire_counts[1], _p(w), w.size, _p(sd), C.byref(out), C.byref(n), _p(hashes))
+    rc = lib().hs_prove(_p(ops), ops.size, wire_counts[0], wire_counts[1], _p(w), w.size, _p(wz), wz.size, _p(sd), C.byref(out), C.byref(n), _p(hashes))
     if rc != 0:
         return rc, None, None
     proof = C.string_at(out, n.value)
@@ -67,3 +68,16 @@ def gf2_masks(seeds8: bytes, omit, n: int) -> np.ndarray:
     o = np.asarray(omit, dtype=np.uint8)
     lib().hs_gf2_masks(_p(np.frombuffer(seeds8, dtype=np.uint8)), _p(o), _p(out), n)
     return out
+
+
+def verify(ops, wire_counts, proof: bytes):
+    """-> (rc, okay, rep_hashes): rc 1 accept / 0 reject / <0 error, through the verifier kernels' bodies."""
+    L = lib()
+    L.hs_verify.argtypes = [C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.c_void_p]
+    L.hs_verify.restype = C.c_int
+    ops = np.ascontiguousarray(ops)
+    pb = np.frombuffer(proof, dtype=np.uint8)
+    okay = C.c_int(1)
+    hashes = np.zeros(256 * 32, dtype=np.uint8)
+    rc = L.hs_verify(_p(ops), ops.size, wire_counts[0], wire_counts[1], _p(pb), pb.size, C.byref(okay), _p(hashes))
+    return rc, bool(okay.value), hashes.tobytes()

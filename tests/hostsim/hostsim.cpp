@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "../../reverie_b200/csrc/rv_planes.cuh"
+#include "../../reverie_b200/csrc/rv_zplanes.cuh"
 
 using namespace rv;
 
@@ -60,8 +61,11 @@ extern "C" void hs_aes128_encrypt(const uint8_t key[16], const uint8_t in[16], u
 }
 
 // rows of the share tensor for `npi` packed instances starting at first_instance: the K1 + K2 kernels
+struct SimKeys {
+    std::vector<uint32_t> ks, lane_mask;
+};
 static void gen_masks(const uint8_t *seeds_shard, const uint8_t *pkeys_in, const uint8_t *mode, const uint8_t *omit, uint32_t npi,
-                      uint32_t n_masks, std::vector<uint64_t> &rows, std::vector<uint8_t> &pkeys) {
+                      uint32_t n_masks, std::vector<uint64_t> &rows, std::vector<uint8_t> &pkeys, SimKeys *keep = nullptr) {
     const uint32_t nslices = 2 * npi;
     std::vector<uint32_t> ks((size_t)nslices * 1408, 0), lane_mask(nslices, 0);
     pkeys.assign((size_t)npi * 8 * 128, 0);
@@ -86,6 +90,39 @@ static void gen_masks(const uint8_t *seeds_shard, const uint8_t *pkeys_in, const
                 if (i < n_masks) rows32[i * nslices + w] = s[p] & lane_mask[w];
             }
         }
+    if (keep) {
+        keep->ks.swap(ks);
+        keep->lane_mask.swap(lane_mask);
+    }
+}
+
+// k_zmask_gen + k_zlinear_level
+static void gen_zrows(const SimKeys &K, uint32_t npi, const ZProgram &Z, std::vector<uint64_t> &zrows) {
+    const uint32_t nslices = 2 * npi;
+    const size_t rowlen = (size_t)64 * npi;
+    zrows.assign((size_t)Z.n_rows * rowlen, 0);
+    const uint64_t n_blocks = ((uint64_t)Z.n_masks + 1) / 2;
+    for (uint32_t w = 0; w < nslices; w++)
+        for (uint64_t j = 0; j < n_blocks; j++) {
+            uint32_t s[128];
+            const uint32_t *k = &K.ks[(size_t)w * 1408];
+            bs_aes128_ctr_block(j, [k](int round, int plane) { return k[round * 128 + plane]; }, s);
+            for (int h = 0; h < 2; h++) {
+                if (2 * j + h >= Z.n_masks) break;
+                uint32_t lo[32], hi[32];
+                planes_to_mask_words(s, K.lane_mask[w], h, lo, hi);
+                uint64_t *dst = &zrows[(size_t)(2 * j + h) * rowlen + zrow_index(w, 0)];
+                for (int q = 0; q < 32; q++) dst[q] = ((uint64_t)hi[q] << 32) | lo[q];
+            }
+        }
+    for (const ZLin &n : Z.lin)
+        for (size_t e = 0; e < rowlen; e++) zrows[(size_t)n.dst * rowlen + e] = n.ca * zrows[(size_t)n.a * rowlen + e] + n.cb * zrows[(size_t)n.b * rowlen + e];
+}
+
+static void z_values(const ZProgram &Z, const uint64_t *leaves, uint64_t *v) {
+    v[0] = 0;
+    for (size_t k = 0; k < Z.leaf_ids.size(); k++) v[Z.leaf_ids[k]] = leaves[k];
+    for (const ZInstr &in : Z.vprog) v[in.dst] = z_exec(in, v);
 }
 
 extern "C" void hs_gf2_masks(const uint8_t *seeds8, const uint8_t *omit8, uint64_t *out, uint32_t n) {
@@ -99,16 +136,42 @@ extern "C" void hs_gf2_masks(const uint8_t *seeds8, const uint8_t *omit8, uint64
 
 // Proof::new on the CPU through the kernel bodies.  rep_hashes (optional): 256*32 bytes.
 extern "C" int hs_prove(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, const uint8_t *wit, size_t n_wit,
-                        const uint8_t *seeds, uint8_t **proof, size_t *proof_len, uint8_t *rep_hashes) {
+                        const uint64_t *wit_z, size_t n_wit_z, const uint8_t *seeds, uint8_t **proof, size_t *proof_len, uint8_t *rep_hashes) {
     Program P;
     int rc = compile(ops, n_ops, z64_cells, gf2_cells, P, g_err);
     if (rc) return rc;
-    if (n_wit < P.n_inputs) return RV_E_WITNESS_SHORT;
+    if (n_wit < P.n_inputs || n_wit_z < P.z.n_inputs) return RV_E_WITNESS_SHORT;
+    const ZProgram &Z = P.z;
     const uint32_t npi = 32, nreps = 256;
     // K1 + K2
     std::vector<uint64_t> rows((size_t)P.n_rows * npi, 0);
     std::vector<uint8_t> pkeys;
-    gen_masks(seeds, nullptr, nullptr, nullptr, npi, P.n_masks, rows, pkeys);
+    SimKeys K;
+    gen_masks(seeds, nullptr, nullptr, nullptr, npi, P.n_masks, rows, pkeys, &K);
+    // Z64: masks, value plane, item plane, stream hashes
+    const size_t rowlen = (size_t)64 * npi;
+    const size_t pitch_zon = (std::max<size_t>(Z.on_bytes, 1) + 63) / 64 * 64, pitch_zpre = (std::max<size_t>(Z.pre_bytes, 1) + 63) / 64 * 64;
+    std::vector<uint8_t> zon, zpre;
+    std::vector<uint32_t> zon_hash(nreps * 8), zrep(nreps * 8);
+    int zbad = 0;
+    if (Z.any()) {
+        std::vector<uint64_t> zrows;
+        gen_zrows(K, npi, Z, zrows);
+        std::vector<uint64_t> leaves(Z.leaf_ids.size(), 0), zvals((size_t)Z.n_vals + 1, 0);
+        for (size_t k = 0; k < Z.n_inputs; k++) leaves[k] = wit_z[k];
+        z_values(Z, leaves.data(), zvals.data());
+        zon.assign(pitch_zon * nreps, 0);
+        zpre.assign(pitch_zpre * nreps, 0);
+        for (uint32_t rep = 0; rep < nreps; rep++) {
+            for (const ZItem &it : Z.items) z_prover_online(it, zrows.data(), rowlen, rep, zvals.data(), &zon[(size_t)rep * pitch_zon], &zbad);
+            for (uint32_t j = 0; j < Z.n_mul; j++) put64(&zpre[(size_t)rep * pitch_zpre + 8ull * j], z_pre_word(Z.items[Z.mul_pos[j]], zrows.data(), rowlen, rep));
+            uint32_t h_pre[8];
+            stream_hash(&zon[(size_t)rep * pitch_zon], (uint32_t)Z.on_bytes, &zon_hash[rep * 8]);
+            stream_hash(&zpre[(size_t)rep * pitch_zpre], (uint32_t)Z.pre_bytes, h_pre);
+            b3_hash64(h_pre, &zon_hash[rep * 8], &zrep[rep * 8]);
+        }
+    }
+    if (zbad) return RV_E_WITNESS_INVALID;
     // K0
     std::vector<uint8_t> vals(P.n_vals, 0);
     for (size_t k = 0; k < P.n_inputs; k++) vals[P.input_vid[k]] = wit[k] & 1;
@@ -146,15 +209,15 @@ extern "C" int hs_prove(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t
     }
     if (bad) return RV_E_WITNESS_INVALID;
     // K5
-    uint32_t empty[8], zrep[8];
+    uint32_t empty[8], zrep0[8];
     b3_chunk_cv(nullptr, 0, 0, true, empty);
-    b3_hash64(empty, empty, zrep);
+    b3_hash64(empty, empty, zrep0);
     std::vector<uint32_t> on_hash(nreps * 8), rep_hash(nreps * 8);
     for (uint32_t r = 0; r < nreps; r++) {
         uint32_t h_pre[8];
         stream_hash(&on[(size_t)r * pitch_on], P.n_online, &on_hash[r * 8]);
         stream_hash(&pre[(size_t)r * pitch_pre], P.n_pre, h_pre);
-        rep_join(&on_hash[r * 8], h_pre, zrep, &rep_hash[r * 8]);
+        rep_join(&on_hash[r * 8], h_pre, Z.any() ? &zrep[r * 8] : zrep0, &rep_hash[r * 8]);
     }
     if (rep_hashes) memcpy(rep_hashes, rep_hash.data(), nreps * 32);
     // K6
@@ -174,7 +237,23 @@ extern "C" int hs_prove(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t
     for (int i = 0; i < 256; i++) rank[i] = omit[i] < RV_PLAYERS ? n_on++ : n_pre++;
     // K7
     ProofLayout L{(uint32_t)(P.recon_pos.size() / 8 + 1), P.n_pre / 8 + 1, (uint32_t)(P.n_inputs / 8 + 1)};
+    if (Z.any()) {
+        L.len_zrecons = (uint32_t)(8 * Z.recon_off.size());
+        L.len_zcorrs = (uint32_t)(8 * Z.n_mul);
+        L.len_zinputs = (uint32_t)(8 * Z.n_inputs);
+    }
     uint8_t *out = (uint8_t *)calloc(L.total(), 1);
+    for (uint32_t r = 0; r < nreps && Z.any(); r++) {  // k_zextract, byte by byte
+        if (omit[r] >= RV_PLAYERS) continue;
+        const uint8_t *zo = &zon[(size_t)r * pitch_zon], *zp = &zpre[(size_t)r * pitch_zpre];
+        uint8_t *z = out + L.z_base() + 8 + (size_t)rank[r] * L.sz_on_z();
+        const uint64_t nr = 8ull * Z.recon_off.size(), nc = 8ull * Z.n_mul, ni = 8ull * Z.n_inputs;
+        for (uint64_t i = 0; i < nr + nc + ni; i++) {
+            if (i < nr) z[137 + i] = zo[Z.recon_off[i >> 3] + 8 * omit[r] + (i & 7)];
+            else if (i < nr + nc) z[145 + i] = zp[i - nr];
+            else z[153 + i] = zo[Z.input_off[(i - nr - nc) >> 3] + ((i - nr - nc) & 7)];
+        }
+    }
     for (uint32_t r = 0; r < nreps; r++) {
         ExtractView v;
         v.on = &on[(size_t)r * pitch_on];
@@ -184,6 +263,7 @@ extern "C" int hs_prove(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t
         v.seed = seeds + (size_t)r * 16;
         v.comm = reinterpret_cast<const uint8_t *>(comm);
         v.z64_empty_hash = empty;
+        v.z_on_hash = Z.any() ? reinterpret_cast<const uint8_t *>(&zon_hash[r * 8]) : nullptr;
         v.recon_pos = P.recon_pos.data();
         v.input_pos = P.input_pos.data();
         v.n_recon = (uint32_t)P.recon_pos.size();
@@ -325,7 +405,63 @@ extern "C" int hs_verify(const rv_op *ops, size_t n_ops, size_t z64_cells, size_
     for (uint32_t k = 0; k < 216; k++) memcpy(&seeds[(NON + k) * 16], proof + g.pre[k].seed, 16);
     std::vector<uint64_t> rows((size_t)P.n_rows * npi, 0);
     std::vector<uint8_t> pkeys;
-    gen_masks(seeds.data(), pkeys_in.data(), mode.data(), omit.data(), npi, P.n_masks, rows, pkeys);
+    SimKeys K;
+    gen_masks(seeds.data(), pkeys_in.data(), mode.data(), omit.data(), npi, P.n_masks, rows, pkeys, &K);
+    // ---- Z64 instances (mirrors the has_z block of verify_on_session) ----
+    const ZProgram &Z = P.z;
+    std::vector<uint32_t> zrep_slot(256 * 8, 0);
+    int z_not_okay = 0;
+    if (Z.any()) {
+        std::vector<ZOpen> zopens(NON);
+        std::vector<uint8_t> zseeds(256 * 16, 0), zpkeys_in(256 * 128, 0), zomit(256, 8);
+        bool own = false;
+        for (uint32_t k = 0; k < NON; k++) {
+            const POnline &o = z.online[k], &first = z.online[k & ~7u];
+            zopens[k] = ZOpen{o.recons.off, o.corrs.off, o.inputs.off, (uint32_t)(first.recons.len / 8), (uint32_t)(first.corrs.len / 8),
+                              (uint32_t)(first.inputs.len / 8), (uint32_t)o.recons.len, (uint32_t)o.corrs.len, (uint32_t)o.inputs.len, o.omit, 0};
+            memcpy(&zpkeys_in[k * 128], proof + o.keys, 128);
+            zomit[k] = o.omit;
+            if (o.omit != g.online[k].omit || memcmp(proof + o.keys, proof + g.online[k].keys, 128) != 0) own = true;
+        }
+        for (uint32_t k = 0; k < 216; k++) {
+            memcpy(&zseeds[(NON + k) * 16], proof + z.pre[k].seed, 16);
+            if (memcmp(proof + z.pre[k].seed, proof + g.pre[k].seed, 16) != 0) own = true;
+        }
+        SimKeys KZ;
+        if (own) {
+            std::vector<uint64_t> dummy(1, 0);
+            std::vector<uint8_t> pk2;
+            gen_masks(zseeds.data(), zpkeys_in.data(), mode.data(), zomit.data(), npi, 0, dummy, pk2, &KZ);
+        }
+        const size_t rowlen = (size_t)64 * npi;
+        std::vector<uint64_t> zrows;
+        gen_zrows(own ? KZ : K, npi, Z, zrows);
+        const size_t pitch_zon = (std::max<size_t>(Z.on_bytes, 1) + 63) / 64 * 64, pitch_zpre = (std::max<size_t>(Z.pre_bytes, 1) + 63) / 64 * 64;
+        std::vector<uint8_t> zon(pitch_zon * 256, 0), zpre(pitch_zpre * 256, 0);
+        std::vector<uint64_t> leaves(Z.leaf_ids.size() + 1), uv((size_t)Z.n_vals + 1);
+        std::vector<uint32_t> input_item;
+        for (uint32_t t = 0; t < Z.items.size(); t++)
+            if (Z.items[t].kind == ITEM_INPUT) input_item.push_back(t);
+        for (uint32_t slot = 0; slot < 256; slot++) {
+            uint32_t h_on[8], h_pre[8];
+            if (slot < NON) {
+                for (uint32_t k = 0; k < Z.n_inputs; k++) leaves[k] = z_verify_leaf_input(Z.items[input_item[k]], k, zopens[slot], proof, zrows.data(), rowlen, slot);
+                for (uint32_t j = 0; j < Z.n_mul; j++)
+                    leaves[Z.n_inputs + j] = z_verify_leaf_kappa(Z.items[Z.mul_pos[j]], Z.recon_idx[Z.mul_pos[j]], zopens[slot], proof, zrows.data(), rowlen, slot);
+                z_values(Z, leaves.data(), uv.data());
+                for (uint32_t t = 0; t < Z.items.size(); t++)
+                    z_verify_online(Z.items[t], Z.recon_idx[t], zopens[slot], proof, zrows.data(), rowlen, slot, uv.data(), &zon[(size_t)slot * pitch_zon], &z_not_okay);
+                for (uint32_t j = 0; j < Z.n_mul; j++)
+                    put64(&zpre[(size_t)slot * pitch_zpre + 8ull * j], z_packed(proof, zopens[slot].off_corrs, zopens[slot].n_corrs, zopens[slot].len_corrs, j));
+                stream_hash(&zon[(size_t)slot * pitch_zon], (uint32_t)Z.on_bytes, h_on);
+            } else {
+                for (uint32_t j = 0; j < Z.n_mul; j++) put64(&zpre[(size_t)slot * pitch_zpre + 8ull * j], z_pre_word(Z.items[Z.mul_pos[j]], zrows.data(), rowlen, slot));
+                memcpy(h_on, proof + z.pre[slot - NON].comm_online, 32);
+            }
+            stream_hash(&zpre[(size_t)slot * pitch_zpre], (uint32_t)Z.pre_bytes, h_pre);
+            b3_hash64(h_pre, h_on, &zrep_slot[slot * 8]);
+        }
+    }
     for (const XGate &x : P.xgates)
         for (uint32_t pi = 0; pi < npi; pi++) {
             uint64_t v = 0;
@@ -393,6 +529,7 @@ extern "C" int hs_verify(const rv_op *ops, size_t n_ops, size_t z64_cells, size_
             memcpy(zon, proof + z.pre[s - NON].comm_online, 32);
             b3_hash64(empty, zon, zz);
         }
+        if (Z.any()) memcpy(zz, &zrep_slot[s * 8], 32);
         rep_join(h_on, h_pre, zz, out);
         memcpy(&slot_hash[s * 32], out, 32);
     }
@@ -403,6 +540,6 @@ extern "C" int hs_verify(const rv_op *ops, size_t n_ops, size_t z64_cells, size_
     if (rep_hashes) memcpy(rep_hashes, ordered, sizeof ordered);
     uint32_t comm2[8];
     host_hash(ordered, sizeof ordered, comm2);
-    if (okay) *okay = not_okay ? 0 : 1;
+    if (okay) *okay = (not_okay || z_not_okay) ? 0 : 1;
     return memcmp(comm2, proof, 32) == 0 ? 1 : 0;
 }

@@ -235,3 +235,79 @@ def test_golden_fixtures(rb, default_seeds):
         blob = rb.Proof.new(ops, wit, (), wc, seeds=default_seeds).serialize()
         assert len(blob) == gold[name]["proof_len"] and hashlib.sha256(blob).hexdigest() == gold[name]["proof_sha256"], name
         assert blob[:32].hex() == gold[name]["comm"], name
+
+
+# ---- Z64 domain (src/algebra/z64/*) and mixed circuits --------------------------------------------------------------------
+def _check_z(rb, ops, gwit, zwit, wc, seeds):
+    import orc
+
+    rc, want = orc.prove(ops, gwit, zwit, wc, seeds)
+    assert rc == 0
+    got = rb.Proof.new(ops, gwit, zwit, wc, seeds=seeds).serialize()
+    assert len(got) == len(want)
+    assert got == want, "first differing byte at %d" % next(i for i in range(len(want)) if got[i] != want[i])
+    return got
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_z64_random_circuits_prove_and_verify(rb, default_seeds, seed):
+    import orc
+    from tests._zgen import random_z_circuit
+
+    rng = np.random.default_rng(2000 + seed)
+    ops, gwit, zwit, wc = random_z_circuit(rng, int(rng.integers(1, 8)), int(rng.integers(0, 1200)), n_cells=int(rng.integers(4, 64)),
+                                           with_gf2=seed % 2 == 1)
+    blob = _check_z(rb, ops, gwit, zwit, wc, default_seeds)
+    circ = rb.Circuit(ops, wc)
+    assert _verify_both(rb, circ, ops, wc, blob) == (1, 1)
+    for pos in [len(blob) // 2, len(blob) - 60, len(blob) - 20000] + [int(x) for x in rng.integers(32, len(blob), size=10)]:
+        bad = bytearray(blob)
+        bad[pos] ^= 1 << int(rng.integers(0, 8))
+        got, want = _verify_both(rb, circ, ops, wc, bytes(bad))
+        assert got == want, f"byte {pos}: ours {got}, oracle {want}"
+
+
+@pytest.mark.parametrize("n_mul", [0, 1, 15, 16, 17, 127, 128, 129, 2000])
+def test_z64_flat_and_config3_lengths(rb, default_seeds, n_mul):
+    """BLAKE3 chunk boundaries of the 64-byte-per-Mul online stream and the 8-byte-per-Mul preprocessing stream; the
+    reference-shaped flat circuit (src/proof/mod.rs:322-329 over Z64) and SURVEY.md 8(d) config 3's register-file shape."""
+    from reverie_b200 import circuits as C
+    from tests._zgen import Z64_WITNESS
+
+    ops, wc = C.flat_mul_circuit(n_mul, domain=C.Z64)
+    blob = _check_z(rb, ops, (), Z64_WITNESS, wc, default_seeds)
+    assert rb.Proof(blob).verify(rb.Circuit(ops, wc))
+    ops, nw = C.z64_mul_circuit(n_mul)
+    blob = _check_z(rb, ops, (), Z64_WITNESS, (nw, 0), default_seeds)
+    assert rb.Proof(blob).verify(rb.Circuit(ops, (nw, 0)))
+
+
+def test_z64_witness_errors_and_sharding(rb, default_seeds):
+    import orc
+    from reverie_b200 import circuits as C
+    from tests._zgen import random_z_circuit
+
+    b = C.Builder(C.Z64)
+    x = b.input()
+    b.assert_zero(b.addc(b.mul(x, x), 5))
+    with pytest.raises(rb.WitnessError) as e:
+        rb.Proof.new(b.ops(), (), [3], (b.n_wires, 0), seeds=default_seeds)
+    assert e.value.code == -1
+    with pytest.raises(rb.WitnessError) as e:
+        rb.Proof.new(b.ops(), (), [], (b.n_wires, 0), seeds=default_seeds)
+    assert e.value.code == -2
+    rng = np.random.default_rng(31)
+    ops, gwit, zwit, wc = random_z_circuit(rng, 5, 700, with_gf2=True)
+    rc, want = orc.prove(ops, gwit, zwit, wc, default_seeds)
+    circ = rb.Circuit(ops, wc)
+    for G in (2, 8):
+        per = 32 // G
+        sess = [rb.Session(circ, g * per, per) for g in range(G)]
+        for s in sess:
+            s.upload(gwit, zwit, default_seeds)
+            s.commit()
+        allh = b"".join(s.hashes() for s in sess)
+        for s in sess:
+            s.open(allh)
+        parts = [s.fetch() for s in sess]
+        assert rb.assemble(parts[0][0], [p for _, p in parts]) == want, f"G={G}"

@@ -61,9 +61,9 @@ def test_compile_stats_and_errors():
         rb.Circuit(bad, wc)
     assert e.value.code == N.E_ARG
     z = np.zeros(1, dtype=CI.OP_DTYPE)
-    z["domain"], z["opcode"] = CI.Z64, CI.INPUT
+    z["domain"], z["dst"], z["a"] = CI.B2A, 0, 0
     with pytest.raises(rb.ReverieError) as e:
-        rb.Circuit(z, (4, 4))
+        rb.Circuit(z, (4, 64))
     assert e.value.code == N.E_UNSUPPORTED  # reported, never silently degraded
     r = np.zeros(1, dtype=CI.OP_DTYPE)
     r["opcode"] = CI.RANDOM
@@ -124,3 +124,44 @@ def test_oracle_matches_golden_fixtures(default_seeds):
         g = gold[name]
         assert rc == 0 and len(pb) == g["proof_len"] and hashlib.sha256(pb).hexdigest() == g["proof_sha256"], name
         assert pb[:32].hex() == g["comm"] and hashlib.sha256(hashes).hexdigest() == g["rep_hashes_sha256"], name
+
+
+# ---- Z64 domain: the kernels' bodies (csrc/rv_zplanes.cuh) replayed on the CPU vs. the oracle --------------------------
+@pytest.mark.parametrize("seed", range(8))
+def test_z64_kernel_bodies_prove_and_verify(seed, default_seeds):
+    from tests._zgen import random_z_circuit
+
+    rng = np.random.default_rng(1000 + seed)
+    ops, gwit, wit, wc = random_z_circuit(rng, int(rng.integers(1, 6)), int(rng.integers(0, 160)), with_gf2=seed % 2 == 1)
+    rc, want, hashes = orc.prove(ops, gwit, wit, wc, default_seeds, want_hashes=True)
+    rc2, got, h2 = hostsim.prove(ops, gwit, wc, default_seeds, wit_z64=wit)
+    assert rc == 0 and rc2 == 0 and h2 == hashes and got == want
+    v, vo = hostsim.verify(ops, wc, want), orc.verify(ops, wc, want, want_hashes=True)
+    assert v[0] == 1 and vo[0] == 1 and v[2] == vo[2]
+    for pos in [len(want) // 2, len(want) - 60] + [int(x) for x in rng.integers(32, len(want), size=4)]:
+        t = bytearray(want)
+        t[pos] ^= 1 << int(rng.integers(0, 8))
+        v, vo = hostsim.verify(ops, wc, bytes(t)), orc.verify(ops, wc, bytes(t), want_hashes=True)
+        assert (v[0] < 0) == (vo[0] < 0), pos
+        if v[0] >= 0:
+            assert v[0] == vo[0] and v[2] == vo[2], pos
+
+
+def test_z64_config3_shape_and_errors(default_seeds):
+    """SURVEY.md 8(d) config 3 at a size the CPU replays in seconds, the reference-shaped flat variant, and the witness panics."""
+    from tests._zgen import Z64_WITNESS
+
+    ops, nw = CI.z64_mul_circuit(300)
+    rc, want = orc.prove(ops, [], Z64_WITNESS, (nw, 0), default_seeds)
+    rc2, got, _ = hostsim.prove(ops, [], (nw, 0), default_seeds, wit_z64=Z64_WITNESS)
+    assert rc == 0 and rc2 == 0 and got == want
+    ops, wc = CI.flat_mul_circuit(129, domain=CI.Z64)
+    rc, want = orc.prove(ops, [], Z64_WITNESS, wc, default_seeds)
+    rc2, got, _ = hostsim.prove(ops, [], wc, default_seeds, wit_z64=Z64_WITNESS)
+    assert rc == 0 and rc2 == 0 and got == want
+    assert hostsim.prove(ops, [], wc, default_seeds, wit_z64=Z64_WITNESS[:1])[0] == N.E_WITNESS_SHORT
+    b = CI.Builder(CI.Z64)
+    x = b.input()
+    b.assert_zero(b.addc(x, 5))
+    assert hostsim.prove(b.ops(), [], (b.n_wires, 0), default_seeds, wit_z64=[7])[0] == N.E_WITNESS_INVALID
+    assert hostsim.prove(b.ops(), [], (b.n_wires, 0), default_seeds, wit_z64=[(1 << 64) - 5])[0] == 0
