@@ -277,7 +277,6 @@ def main():
         t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-    comm, part = sess.fetch()
     value = n_and * B * args.steps / (ms_total * 1e-3)
 
     # single-proof device latency (B = 1), same rules
@@ -287,6 +286,42 @@ def main():
         sessions, streams = sessions[:1], streams[:1]
         lat_ms = timed_device(max(5, min(args.steps, 20))) / max(5, min(args.steps, 20))
         sessions, streams = keep_s, keep_st
+
+    # ---- per-kernel device times -> roofline of the dominant kernel (rank 0) ----
+    roofline, kernels = None, None
+    peak, peak_src = load_peaks()
+    if rank == 0:
+        sess.timing(True)
+        reps = max(5, min(args.steps, 20))
+        keep_s = sessions
+        sessions = sessions[:1]
+        for _ in range(reps):
+            step_device()
+        sessions = keep_s
+        kt = sess.kernel_times()
+        sess.timing(False)
+        comm, part = sess.fetch()
+        kernels = {k["name"]: {"us_per_step": k["ms"] * 1e3 / reps, "launches_per_step": k["launches"] // reps,
+                               "algorithmic_bytes_per_step": k["algorithmic_bytes"] // reps} for k in kt}
+        main_stream = [k for k in kt if k["name"] != "values"]
+        top = max(kt, key=lambda k: k["ms"])
+        per_launch_s = top["ms"] * 1e-3 / max(top["launches"], 1)
+        bytes_per_launch = top["algorithmic_bytes"] / max(top["launches"], 1)
+        ach = bytes_per_launch / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                    "peak_source": peak_src, "us_per_launch": per_launch_s * 1e6,
+                    "path": {"algorithmic_bytes_per_step": st["algorithmic_bytes"], "achieved": B * st["algorithmic_bytes"] / (ms_total / args.steps * 1e-3) / 1e9,
+                             "frac": B * st["algorithmic_bytes"] / (ms_total / args.steps * 1e-3) / 1e9 / peak,
+                             "note": "SURVEY.md 8(d) bytes of the B proofs of a step / device time per step"}}
+
+    big = st["n_masks"] * 256 + st["z64_masks"] * 16384 > (8 << 30)  # a session of this circuit holds tens of GB: one at a time
+    if big and world == 1:
+        del sess, x
+        sessions.clear()
+        streams.clear()
+        import gc
+
+        gc.collect()
 
     # ---- end to end through the public API (host buffers, copies inside the timed region) ----
     e2e = None
@@ -333,37 +368,17 @@ def main():
         d2h = B * (len(outs[0][1]) + 36 + per * 8 * 32)
     e2e = {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": B * (st["n_inputs"] + 8 * st["z64_inputs"] + per * 8 * 16 + (256 * 32 if world > 1 else 0)), "d2h_bytes_per_step": d2h}
 
-    # ---- per-kernel device times -> roofline of the dominant kernel (rank 0) ----
-    roofline, kernels = None, None
-    peak, peak_src = load_peaks()
-    if rank == 0:
-        sess.timing(True)
-        reps = max(5, min(args.steps, 20))
-        keep_s = sessions
-        sessions = sessions[:1]
-        for _ in range(reps):
-            step_device()
-        sessions = keep_s
-        kt = sess.kernel_times()
-        sess.timing(False)
-        kernels = {k["name"]: {"us_per_step": k["ms"] * 1e3 / reps, "launches_per_step": k["launches"] // reps,
-                               "algorithmic_bytes_per_step": k["algorithmic_bytes"] // reps} for k in kt}
-        main_stream = [k for k in kt if k["name"] != "values"]
-        top = max(kt, key=lambda k: k["ms"])
-        per_launch_s = top["ms"] * 1e-3 / max(top["launches"], 1)
-        bytes_per_launch = top["algorithmic_bytes"] / max(top["launches"], 1)
-        ach = bytes_per_launch / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
-        roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
-                    "peak_source": peak_src, "us_per_launch": per_launch_s * 1e6,
-                    "path": {"algorithmic_bytes_per_step": st["algorithmic_bytes"], "achieved": B * st["algorithmic_bytes"] / (ms_total / args.steps * 1e-3) / 1e9,
-                             "frac": B * st["algorithmic_bytes"] / (ms_total / args.steps * 1e-3) / 1e9 / peak,
-                             "note": "SURVEY.md 8(d) bytes of the B proofs of a step / device time per step"}}
-
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n, secs, cores = cpu_port_run(ops, wit, wz, wc, seeds, 10.0, 1)
-        cpu = {"value": n_and * n / secs, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n} whole proofs of the same workload in {secs:.1f} s; C restatement of the reference's dataflow (oracle/c), threads over the 32 packed instances"}
+        c_ops, c_wit, c_wz, c_wc, c_n, c_note = ops, wit, wz, wc, n_and, "whole proofs of the same workload"
+        if n_and > 4 * 10**6:  # bounded sample: the same circuit family at a size the CPU finishes in seconds
+            small = args.workload.rstrip("0123456789") + str(2 * 10**6 if args.workload.startswith("z64") is False else 2 * 10**5)
+            c_ops, c_wit, c_wz, c_wc, _ = make_workload(small)
+            c_n = int((c_ops["opcode"] == 6).sum())
+            c_note = f"whole proofs of the same circuit family at {c_n} multiplication gates ({small})"
+        n, secs, cores = cpu_port_run(c_ops, c_wit, c_wz, c_wc, seeds, 10.0, 1)
+        cpu = {"value": c_n * n / secs, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n} {c_note} in {secs:.1f} s; C restatement of the reference's dataflow (oracle/c), threads over the 32 packed instances"}
 
     if rank == 0:
         line = {

@@ -180,6 +180,37 @@ RV_HD void aes128_encrypt_block(const uint32_t rk[44], const uint32_t in[4], uin
     for (int c = 0; c < 4; c++) out[c] = s[c];
 }
 
+// ---- T-table AES (one block per thread, natural byte order) for the Z64 mask generator -------------------------------
+// Te0[x] = (2 s, s, s, 3 s) with s = S[x], row r of the column in byte r; Te_r = rotl(Te0, 8 r).  `tab(r, x)` returns Te_r[x]
+// (on the device: a bank-private copy per lane, so the 32 lookups of a warp never conflict).
+RV_HD uint32_t te0_entry(uint32_t sbox_byte) {
+    const uint32_t s1 = sbox_byte & 0xff, s2 = ((s1 << 1) ^ ((s1 >> 7) * 0x1bu)) & 0xff, s3 = s2 ^ s1;
+    return s2 | (s1 << 8) | (s1 << 16) | (s3 << 24);
+}
+template <typename TAB>  // tab(t, w, b) = Te_t[byte b of w]
+RV_HD void tt_aes128_encrypt(const uint32_t rk[44], uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3, TAB tab, uint32_t out[4]) {
+    s0 ^= rk[0];
+    s1 ^= rk[1];
+    s2 ^= rk[2];
+    s3 ^= rk[3];
+#pragma unroll
+    for (int round = 1; round < 10; round++) {  // new column c = Te0[row 0 of col c] ^ Te1[row 1 of col c+1] ^ Te2[row 2 of col c+2] ^ Te3[row 3 of col c+3]
+        const uint32_t t0 = tab(0, s0, 0) ^ tab(1, s1, 1) ^ tab(2, s2, 2) ^ tab(3, s3, 3) ^ rk[4 * round + 0];
+        const uint32_t t1 = tab(0, s1, 0) ^ tab(1, s2, 1) ^ tab(2, s3, 2) ^ tab(3, s0, 3) ^ rk[4 * round + 1];
+        const uint32_t t2 = tab(0, s2, 0) ^ tab(1, s3, 1) ^ tab(2, s0, 2) ^ tab(3, s1, 3) ^ rk[4 * round + 2];
+        const uint32_t t3 = tab(0, s3, 0) ^ tab(1, s0, 1) ^ tab(2, s1, 2) ^ tab(3, s2, 3) ^ rk[4 * round + 3];
+        s0 = t0;
+        s1 = t1;
+        s2 = t2;
+        s3 = t3;
+    }
+    // last round: SubBytes + ShiftRows only; S[x] sits in byte 0 of Te2, byte 1 of Te3, byte 2 of Te0, byte 3 of Te1
+    out[0] = ((tab(2, s0, 0) & 0x000000ffu) | (tab(3, s1, 1) & 0x0000ff00u) | (tab(0, s2, 2) & 0x00ff0000u) | (tab(1, s3, 3) & 0xff000000u)) ^ rk[40];
+    out[1] = ((tab(2, s1, 0) & 0x000000ffu) | (tab(3, s2, 1) & 0x0000ff00u) | (tab(0, s3, 2) & 0x00ff0000u) | (tab(1, s0, 3) & 0xff000000u)) ^ rk[41];
+    out[2] = ((tab(2, s2, 0) & 0x000000ffu) | (tab(3, s3, 1) & 0x0000ff00u) | (tab(0, s0, 2) & 0x00ff0000u) | (tab(1, s1, 3) & 0xff000000u)) ^ rk[42];
+    out[3] = ((tab(2, s3, 0) & 0x000000ffu) | (tab(3, s0, 1) & 0x0000ff00u) | (tab(0, s1, 2) & 0x00ff0000u) | (tab(1, s2, 3) & 0xff000000u)) ^ rk[43];
+}
+
 // CTR block j of the reference's PRG as little-endian state words: bytes 8..15 = BE64(j).
 RV_HD void ctr_block_words(uint64_t j, uint32_t in[4]) {
     const uint32_t hi = (uint32_t)(j >> 32), lo = (uint32_t)j;

@@ -63,7 +63,7 @@ struct rv_circuit {
     std::vector<uint32_t> vleaf_ids;  // u-plane value ids of the verifier's leaves: inputs then kappas
     DevZProgram zdev;
     std::vector<uint32_t> z_input_item;  // k -> item index of the k-th Z64 input()
-    int device = 0;
+    int device = 0, n_sms = 148;
     uint64_t device_bytes = 0;
     uint32_t z64_empty_hash[8];  // B3("")
     uint32_t z64_rep_hash[8];    // Transcript::hash of an empty Z64 transcript: H(B3("") || B3(""))
@@ -134,6 +134,7 @@ extern "C" int rv_circuit_compile(const rv_op *ops, size_t n_ops, size_t z64_cel
     }
     c->device = g_device;
     cudaSetDevice(c->device);
+    cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, c->device);
     DevProgram &D = c->dev;
     if ((rc = upload(c, P.xgates, &D.xgates)) || (rc = upload(c, P.xlevel_off, &D.xlevel_off)) || (rc = upload(c, P.items, &D.items)) ||
         (rc = upload(c, c->mul_pos, &D.mul_pos)) || (rc = upload(c, P.recon_pos, &D.recon_pos)) || (rc = upload(c, P.input_pos, &D.input_pos)) ||
@@ -171,6 +172,13 @@ extern "C" int rv_circuit_compile(const rv_op *ops, size_t n_ops, size_t z64_cel
     D.n_xgates = (uint32_t)P.xgates.size();
     D.n_llevels = (uint32_t)P.xlevel_off.size() - 1;
     D.n_lut_steps = P.n_lut_steps;
+    if (P.values_wide) {
+        if ((rc = upload(c, P.luts, &D.luts))) {
+            rv_circuit_free(c);
+            return rc;
+        }
+        D.n_lut_levels = (uint32_t)P.lut_level_off.size() - 1;
+    }
     D.n_vlut_steps = P.n_vlut_steps;
     D.n_uvals = P.n_uvals;
     D.n_vm_steps = P.n_vm_steps;
@@ -200,7 +208,7 @@ extern "C" int rv_circuit_get_stats(const rv_circuit *c, rv_circuit_stats *o) {
     o->linear_depth = P.xlevel_off.size() - 1;
     o->plain_value_depth = P.plain_value_depth;
     o->plain_linear_depth = P.plain_linear_depth;
-    o->n_luts = P.n_lut_steps ? P.lut_steps.size() : 0;
+    o->n_luts = P.values_wide ? P.luts.size() : (P.n_lut_steps ? P.lut_steps.size() : 0);
     o->n_lut_steps = P.n_lut_steps;
     o->n_vm_steps = P.n_vm_steps;
     o->vm_cells = P.vm_cells;
@@ -270,7 +278,7 @@ struct rv_session {
     uint8_t *d_wit = nullptr, *d_seeds = nullptr, *d_pkeys = nullptr, *d_vals = nullptr;
     uint32_t *d_ks = nullptr, *d_lane_mask = nullptr;
     uint64_t *d_rows = nullptr;
-    uint32_t *d_fresh_sm = nullptr, *d_exp_sm = nullptr;  // slice-major staging of the mask VM
+    uint64_t *d_fresh_sm = nullptr, *d_exp_sm = nullptr;  // instance-major staging of the mask VM
     size_t pitch_fresh = 0, pitch_exp = 0;
     uint8_t *d_on = nullptr, *d_pre = nullptr;
     size_t pitch_on = 0, pitch_pre = 0;
@@ -285,6 +293,7 @@ struct rv_session {
     bool has_z = false;
     size_t zrowlen = 0;  // 64 * npi
     uint64_t *d_zrows = nullptr, *d_zleaf = nullptr, *d_zvals = nullptr;
+    uint32_t *d_rk_plain = nullptr;  // [45][64 * npi]: plain round keys of every PRG stream for the T-table Z64 generator
     uint8_t *d_zon = nullptr, *d_zpre = nullptr;
     size_t pitch_zon = 0, pitch_zpre = 0;
     uint32_t *d_zcv_on = nullptr, *d_zcv_pre = nullptr, n_chunks_zon = 1, n_chunks_zpre = 1, *d_zrep = nullptr;
@@ -367,8 +376,8 @@ extern "C" int rv_session_create(const rv_circuit *c, int first_instance, int n_
     if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&s->st_val, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&s->ev_vals, cudaEventDisableTiming) != cudaSuccess)
         return bail(fail(RV_E_CUDA, "stream/event creation failed"));
-    s->pitch_on = round_up(std::max<size_t>(P.n_online, 1), 64);
-    s->pitch_pre = round_up(std::max<size_t>(P.n_pre, 1), 64);
+    s->pitch_on = round_up(std::max<size_t>(P.n_online, 1), 2048);  // whole tiles of the item plane (k_items_tile: T <= 2048)
+    s->pitch_pre = round_up(std::max<size_t>(P.n_pre, 1), 2048);
     s->n_chunks_on = P.n_online == 0 ? 1 : (P.n_online + 1023) / 1024;
     s->n_chunks_pre = P.n_pre == 0 ? 1 : (P.n_pre + 1023) / 1024;
     s->len_recons = (uint32_t)(P.recon_pos.size() / 8 + 1);  // floor(n/8)+1: the residue group is always flushed (gf2/share.rs:131-138)
@@ -401,11 +410,11 @@ extern "C" int rv_session_create(const rv_circuit *c, int first_instance, int n_
     if (linear_uses_vm(c->dev)) {
         s->pitch_fresh = round_up((size_t)P.n_masks + 128, 128);
         s->pitch_exp = round_up((size_t)P.n_lin + 32, 32);
-        if ((rc = dalloc(s, &s->d_fresh_sm, s->pitch_fresh * 2 * s->npi)) || (rc = dalloc(s, &s->d_exp_sm, s->pitch_exp * 2 * s->npi))) return bail(rc);
+        if ((rc = dalloc(s, &s->d_fresh_sm, s->pitch_fresh * s->npi)) || (rc = dalloc(s, &s->d_exp_sm, s->pitch_exp * s->npi))) return bail(rc);
     }
     if ((rc = dalloc(s, &s->d_wit, P.n_inputs)) || (rc = dalloc(s, &s->d_seeds, (size_t)s->nreps * 16)) ||
         (rc = dalloc(s, &s->d_pkeys, (size_t)s->nreps * 128)) || (rc = dalloc(s, &s->d_vals, round_up((size_t)P.n_vals + 1, 16))) ||
-        (rc = dalloc(s, &s->d_ks, (size_t)2 * s->npi * 1408)) || (rc = dalloc(s, &s->d_lane_mask, 2 * s->npi)) ||
+        (rc = dalloc(s, &s->d_ks, (size_t)2 * s->npi * 1408)) || (rc = dalloc(s, &s->d_rk_plain, (size_t)45 * 64 * s->npi)) || (rc = dalloc(s, &s->d_lane_mask, 2 * s->npi)) ||
         (rc = dalloc(s, &s->d_rows, (size_t)P.n_rows * s->npi)) || (rc = dalloc(s, &s->d_on, s->pitch_on * s->nreps)) ||
         (rc = dalloc(s, &s->d_pre, s->pitch_pre * s->nreps)) || (rc = dalloc(s, &s->d_cv_on, (size_t)s->n_chunks_on * s->nreps * 8)) ||
         (rc = dalloc(s, &s->d_cv_pre, (size_t)s->n_chunks_pre * s->nreps * 8)) || (rc = dalloc(s, &s->d_on_hash, (size_t)s->nreps * 32)) ||
@@ -538,7 +547,10 @@ extern "C" int rv_session_commit(rv_session *s) {
     // makes the whole proof capturable as one CUDA graph.
     CU(cudaEventRecord(s->ev_fork, s->st));
     CU(cudaStreamWaitEvent(s->st_val, s->ev_fork, 0));
-    {
+    if (P.values_wide) {
+        Scope k(s, "values", (uint64_t)P.luts.size() * sizeof(LutInstr), 1 + D.n_lut_levels, s->st_val);
+        launch_values_wide(D, P.lut_level_off.data(), s->d_wit, s->d_vals, s->st_val);
+    } else {
         Scope k(s, "values", (uint64_t)P.lut_steps.size() * sizeof(LutInstr), 1, s->st_val);
         launch_values(D.lut_steps, D.n_lut_steps, D.input_vid, s->d_wit, 0, D.n_inputs, s->d_vals, 0, D.n_vals, 1, s->st_val);
     }
@@ -552,11 +564,11 @@ extern "C" int rv_session_commit(rv_session *s) {
     CU(cudaMemsetAsync(s->d_rows + (size_t)P.zero_row() * s->npi, 0, (size_t)s->npi * 8, s->st));
     {
         Scope k(s, "key_setup", 0);
-        launch_key_setup(s->d_seeds, nullptr, nullptr, nullptr, nslices, s->d_ks, s->d_lane_mask, s->d_pkeys, s->st);
+        launch_key_setup(s->d_seeds, nullptr, nullptr, nullptr, nslices, s->d_ks, s->d_lane_mask, s->d_pkeys, s->st, s->d_rk_plain);
     }
     {
         Scope k(s, "mask_gen", (uint64_t)P.n_masks * s->npi * 8);
-        launch_mask_gen(s->d_ks, s->d_lane_mask, nslices, P.n_masks, s->d_rows, s->d_fresh_sm, s->pitch_fresh, s->st);
+        launch_mask_gen_tt(s->d_rk_plain, nslices, P.n_masks, s->d_rows, s->d_fresh_sm, s->pitch_fresh, c->n_sms, s->st);
     }
     if (D.n_llevels) {
         const double avg_width = (double)D.n_xgates / D.n_llevels;
@@ -566,7 +578,7 @@ extern "C" int rv_session_commit(rv_session *s) {
     if (s->has_z) {
         {
             Scope k(s, "z.mask_gen", (uint64_t)P.z.n_masks * s->zrowlen * 8);
-            launch_zmask_gen(s->d_ks, s->d_lane_mask, nslices, P.z.n_masks, s->d_zrows, s->zrowlen, s->st);
+            launch_zmask_gen_tt(s->d_rk_plain, (uint32_t)s->zrowlen, P.z.n_masks, s->d_zrows, c->n_sms, s->st);
         }
         if (DZ.n_llevels) {
             Scope k(s, "z.linear", (uint64_t)P.z.n_lin * s->zrowlen * 8 * 3, DZ.n_llevels);
@@ -875,11 +887,11 @@ static int verify_on_session(rv_session *s, const uint8_t *proof, size_t proof_l
     const VOpen *d_opens = reinterpret_cast<const VOpen *>(dv + o_opens);
     {
         Scope k(s, "v.key_setup", 0);
-        launch_key_setup(dv + o_seeds, dv + o_pkeys, dv + o_mode, dv + o_omit, nslices, s->d_ks, s->d_lane_mask, s->d_pkeys, s->st);
+        launch_key_setup(dv + o_seeds, dv + o_pkeys, dv + o_mode, dv + o_omit, nslices, s->d_ks, s->d_lane_mask, s->d_pkeys, s->st, s->d_rk_plain);
     }
     {
         Scope k(s, "v.mask_gen", (uint64_t)P.n_masks * s->npi * 8);
-        launch_mask_gen(s->d_ks, s->d_lane_mask, nslices, P.n_masks, s->d_rows, s->d_fresh_sm, s->pitch_fresh, s->st);
+        launch_mask_gen_tt(s->d_rk_plain, nslices, P.n_masks, s->d_rows, s->d_fresh_sm, s->pitch_fresh, c->n_sms, s->st);
     }
     if (D.n_llevels) {
         Scope k(s, "v.linear", (uint64_t)P.n_lin * s->npi * 8 * 3, 2);
@@ -907,11 +919,11 @@ static int verify_on_session(rv_session *s, const uint8_t *proof, size_t proof_l
         const ZOpen *d_zopens = reinterpret_cast<const ZOpen *>(dv + o_zopens);
         if (z_own_keys) {  // a (dishonest) proof whose Z64 openings name other keys: the reference would use them, so do we
             Scope k(s, "v.z.key_setup", 0);
-            launch_key_setup(dv + o_zseeds, dv + o_zpkeys, dv + o_mode, dv + o_zomit, nslices, s->d_ks, s->d_lane_mask, s->d_pkeys, s->st);
+            launch_key_setup(dv + o_zseeds, dv + o_zpkeys, dv + o_mode, dv + o_zomit, nslices, s->d_ks, s->d_lane_mask, s->d_pkeys, s->st, s->d_rk_plain);
         }
         {
             Scope k(s, "v.z.mask_gen", (uint64_t)P.z.n_masks * s->zrowlen * 8);
-            launch_zmask_gen(s->d_ks, s->d_lane_mask, nslices, P.z.n_masks, s->d_zrows, s->zrowlen, s->st);
+            launch_zmask_gen_tt(s->d_rk_plain, (uint32_t)s->zrowlen, P.z.n_masks, s->d_zrows, c->n_sms, s->st);
         }
         if (DZ.n_llevels) {
             Scope k(s, "v.z.linear", 0, DZ.n_llevels);

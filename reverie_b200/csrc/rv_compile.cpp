@@ -232,6 +232,10 @@ void build_mask_vm(Program &P) {
         else if (it.kind == ITEM_ASSERT) exported[it.ra] = 1;
     }
     // VM level of an original level L (1-based) is L + VM_DELTA - 1; the LOAD of a fresh row first used at L sits at L - 1.
+    struct Tmp {  // provisional instruction: rows until the scan below assigns cells
+        uint32_t dst, in[6];
+        bool load;
+    };
     const uint32_t n_levels = depth + VM_DELTA;
     std::vector<uint32_t> cnt(n_levels + 1, 0);
     for (uint32_t r = 0; r < n_masks; r++)
@@ -239,25 +243,22 @@ void build_mask_vm(Program &P) {
     for (uint32_t l = 0; l < depth; l++) cnt[l + VM_DELTA] += P.xlevel_off[l + 1] - P.xlevel_off[l];
     P.vm_level_off.assign(n_levels + 1, 0);
     for (uint32_t l = 0; l < n_levels; l++) P.vm_level_off[l + 1] = P.vm_level_off[l] + cnt[l];
-    P.vm.resize(P.vm_level_off[n_levels]);
+    std::vector<Tmp> tmp(P.vm_level_off[n_levels]);
     std::vector<uint32_t> cursor(P.vm_level_off.begin(), P.vm_level_off.end() - 1);
-    // provisional instructions hold rows; cells are assigned in the scan below.  Cell 0 is the constant zero.
-    VmInstr blank;
-    std::memset(&blank, 0, sizeof blank);
     for (uint32_t r = 0; r < n_masks; r++)
         if (first[r] != NONE32) {
-            VmInstr in = blank;
-            in.dst = VM_F_LOAD;
-            in.in[0] = r;
-            in.row = VM_ROW_NONE;
-            P.vm[cursor[first[r] - 1]++] = in;
+            Tmp t{};
+            t.load = true;
+            t.in[0] = r;
+            tmp[cursor[first[r] - 1]++] = t;
         }
     for (uint32_t l = 0; l < depth; l++)
         for (uint32_t gi = P.xlevel_off[l]; gi < P.xlevel_off[l + 1]; gi++) {
-            VmInstr in = blank;
-            in.dst = P.xgates[gi].dst;
-            for (int k = 0; k < 6; k++) in.in[k] = P.xgates[gi].in[k];
-            P.vm[cursor[l + VM_DELTA]++] = in;
+            Tmp t{};
+            t.load = false;
+            t.dst = P.xgates[gi].dst;
+            for (int k = 0; k < 6; k++) t.in[k] = P.xgates[gi].in[k];
+            tmp[cursor[l + VM_DELTA]++] = t;
         }
     std::vector<uint32_t> cell_of(n_rows, NONE32);
     cell_of[zero] = 0;
@@ -272,29 +273,41 @@ void build_mask_vm(Program &P) {
         }
         return n_cells++;
     };
+    P.vm.resize(tmp.size());
     for (uint32_t l = 0; l < n_levels; l++) {
         for (uint32_t c : free_at[l]) free_list.push_back(c);
         std::vector<uint32_t>().swap(free_at[l]);
         for (uint32_t k = P.vm_level_off[l]; k < P.vm_level_off[l + 1]; k++) {
-            VmInstr &in = P.vm[k];
-            if (in.dst == VM_F_LOAD) {
-                const uint32_t r = in.in[0], c = alloc();
+            const Tmp &t = tmp[k];
+            VmInstr out;
+            std::memset(&out, 0, sizeof out);
+            if (t.load) {
+                const uint32_t r = t.in[0], c = alloc();
                 cell_of[r] = c;
                 free_at[last[r] + VM_DELTA].push_back(c);  // last use at VM level last + DELTA - 1
-                in.dst = VM_F_LOAD | c;
+                out.flags = (uint16_t)VM_F_LOAD;
+                out.dst = (uint16_t)c;
+                out.row = r;
             } else {
-                const uint32_t r = in.dst;
-                for (int q = 0; q < 6; q++) in.in[q] = cell_of[in.in[q]];
-                in.row = exported[r] ? r : VM_ROW_NONE;
+                const uint32_t r = t.dst;
+                for (int q = 0; q < 6; q++) out.in[q] = (uint16_t)cell_of[t.in[q]];
+                out.row = exported[r] ? r : VM_ROW_NONE;
                 if (first[r] != NONE32) {
                     const uint32_t c = alloc();
                     cell_of[r] = c;
                     free_at[last[r] + VM_DELTA].push_back(c);
-                    in.dst = c;
+                    out.dst = (uint16_t)c;
                 } else {
-                    in.dst = VM_CELL_MASK;  // no consumer in the network: resolved to the scratch cell when the steps are emitted
+                    out.dst = (uint16_t)VM_CELL_MASK;  // no consumer in the network: resolved to the scratch cell when the steps are emitted
                 }
             }
+            P.vm[k] = out;
+        }
+        if (n_cells >= VM_CELL_MASK) {  // 16-bit cell ids: such a network does not fit in shared memory anyway; use the fallbacks
+            P.vm.clear();
+            P.vm_level_off.clear();
+            P.vm_cells = 0;
+            return;
         }
     }
     P.vm_cells = n_cells;
@@ -308,7 +321,7 @@ void emit_vm_steps(Program &P) {
     const uint32_t scratch = P.vm_cells;  // one extra cell absorbs the writes of empty slots and of export-only XORs
     VmInstr nop;
     std::memset(&nop, 0, sizeof nop);  // XOR of six zero cells
-    nop.dst = scratch;
+    nop.dst = (uint16_t)scratch;
     nop.row = VM_ROW_NONE;
     // Every VM level becomes at least one step, even an empty one: the device waits for a LOAD by counting cp.async groups
     // (one per level, committed at the level's last step), so a LOAD must stay VM_DELTA levels ahead of its first use.
@@ -322,9 +335,9 @@ void emit_vm_steps(Program &P) {
             for (uint32_t t = 0; t < VM_STEP; t++) {
                 const uint32_t gi = s + k * VM_STEP + t;
                 VmInstr o = gi < e ? P.vm[gi] : nop;
-                if (!(o.dst & VM_F_LOAD) && (o.dst & VM_CELL_MASK) == VM_CELL_MASK) o.dst = scratch;
-                if (last || chunk_end) o.dst |= VM_F_BAR;
-                if (last) o.dst |= VM_F_LEVEL_END;
+                if (!(o.flags & VM_F_LOAD) && o.dst == VM_CELL_MASK) o.dst = (uint16_t)scratch;
+                if (last || chunk_end) o.flags |= (uint16_t)VM_F_BAR;
+                if (last) o.flags |= (uint16_t)VM_F_LEVEL_END;
                 P.vm_steps.push_back(o);
             }
             P.n_vm_steps++;
@@ -928,8 +941,11 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
         map_to_luts(P.n_vals, vg, required, P.luts, P.lut_level_off);
         std::vector<MGate>().swap(vg);
     }
-    emit_lut_steps(P.luts, P.lut_level_off, P.n_vals, P.lut_steps, P.n_lut_steps);
-    if (!small) std::vector<LutInstr>().swap(P.luts);
+    P.values_wide = P.lut_level_off.size() > 1 && P.luts.size() / (P.lut_level_off.size() - 1) >= WIDE_LEVEL;
+    if (!P.values_wide) {
+        emit_lut_steps(P.luts, P.lut_level_off, P.n_vals, P.lut_steps, P.n_lut_steps);
+        if (!small) std::vector<LutInstr>().swap(P.luts);
+    }
 
     // ---- online verifier's u-plane ---------------------------------------------------------------------------------
     if (want_verify) {

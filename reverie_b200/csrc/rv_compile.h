@@ -37,14 +37,15 @@ struct XGate {
     uint32_t in[6];
     uint32_t pad;
 };
-// mask-plane VM instruction (shared-memory cells; see build_mask_vm):
-//   XOR : v = XOR of cell[in[0..5]]; cell[dst] = v; if (row != VM_ROW_NONE) rows[row] = v
-//   LOAD: cell[dst] <- rows[in[0]]   asynchronously, `VM_DELTA` levels ahead of its first use (one cp.async group per level)
+// mask-plane VM instruction (shared-memory cells; see build_mask_vm).  20 bytes: the instruction stream is re-read by every
+// CTA (one per packed instance), so its size is what bounds the kernel.
+//   XOR : v = XOR of cell[in[0..5]]; cell[dst] = v; if (row != VM_ROW_NONE) exported[row - n_masks] = v
+//   LOAD: cell[dst] <- fresh row `row`   asynchronously, `VM_DELTA` levels ahead of its first use (one cp.async group per level)
 struct VmInstr {
-    uint32_t dst;  // cell | VM_F_* flags
-    uint32_t in[6];
     uint32_t row;
-    uint32_t pad[4];  // 48 bytes = three 16-byte units
+    uint16_t dst;    // cell
+    uint16_t flags;  // VM_F_*
+    uint16_t in[6];  // cells
 };
 constexpr int VM_DELTA = 2;  // prefetch distance in levels: a LOAD issued during level L-2 is awaited at the end of level L-1
 
@@ -62,11 +63,11 @@ struct LutInstr {
 // Device form of both programs: a dense "VLIW" stream of STEPS.  Every thread of the CTA executes exactly one slot per
 // step (empty slots are harmless no-ops on a scratch cell), so the device loop needs no level table, no bounds checks and
 // no inner loops -- the per-level dependent chain is what bounds these kernels, and it is paid in instructions per warp.
-//   mask VM : step = VM_STEP slots of 48 bytes; word 0 = dst cell | flags
+//   mask VM : step = VM_STEP slots of 20 bytes
 //   LUT     : step = LUT_STEP slots of 48 bytes; `pad` = flags
 // STEP_BAR on a slot means "CTA barrier after this step" (set on every slot of the last step of a level and of a chunk).
 constexpr uint32_t VM_STEP = 512, VM_STEPS_PER_CHUNK = 2, LUT_STEP = 128, LUT_STEPS_PER_CHUNK = 8;
-constexpr uint32_t VM_F_LOAD = 0x80000000u, VM_F_BAR = 0x40000000u, VM_F_LEVEL_END = 0x20000000u, VM_CELL_MASK = 0x00FFFFFFu,
+constexpr uint32_t VM_F_LOAD = 1u, VM_F_BAR = 2u, VM_F_LEVEL_END = 4u, VM_CELL_MASK = 0xFFFFu /* also "no cell yet" */,
                    VM_ROW_NONE = 0xFFFFFFFFu;
 constexpr uint32_t LUT_F_BAR = 1u;
 
@@ -82,7 +83,7 @@ struct Item {
     uint32_t j;     // MUL: position in the preprocessing stream; INPUT: witness index
     uint32_t pad;
 };
-static_assert(sizeof(VGate) == 16 && sizeof(XGate) == 32 && sizeof(VmInstr) == 48 && sizeof(LutInstr) == 48 && sizeof(Item) == 32, "POD layout");
+static_assert(sizeof(VGate) == 16 && sizeof(XGate) == 32 && sizeof(VmInstr) == 20 && sizeof(LutInstr) == 48 && sizeof(Item) == 32, "POD layout");
 
 // =====================================================================================================================
 //  Z64 domain (src/algebra/z64/*): the same three planes over the ring Z_2^64.
@@ -155,7 +156,7 @@ struct Program {
     std::vector<uint32_t> xlevel_off;   // linear_depth + 1 offsets into xgates
     std::vector<LutInstr> luts;         // mapped value-plane program, sorted by level
     std::vector<uint32_t> lut_level_off;
-    std::vector<VmInstr> vm;            // mask-plane VM program over cells, sorted by VM level (= level + VM_DELTA - 1)
+    std::vector<VmInstr> vm;            // mask-plane VM program over cells, sorted by VM level (= level + VM_DELTA - 1); empty if it needs > 65534 cells
     std::vector<uint32_t> vm_level_off;
     uint32_t vm_cells = 0;              // shared-memory cells the program needs (one lane word each), excluding the scratch cell
     uint32_t plain_value_depth = 0, plain_linear_depth = 0;  // depths before mapping (reported in the stats)
@@ -163,6 +164,7 @@ struct Program {
     uint32_t n_vm_steps = 0;
     std::vector<LutInstr> lut_steps;    // padded device stream of the value plane (n_lut_steps * LUT_STEP slots); value n_vals = scratch
     uint32_t n_lut_steps = 0;
+    bool values_wide = false;           // levels average >= WIDE_LEVEL gates: `luts` runs one grid-wide launch per level instead of the step stream
     // online-verifier value plane ("u-plane"): same circuit, every Mul is (a & b) ^ kappa_j with kappa_j a leaf
     std::vector<LutInstr> vlut_steps;   // padded device stream; value n_uvals = scratch
     uint32_t n_vlut_steps = 0, n_uvals = 0;
@@ -182,6 +184,8 @@ struct Program {
 
 // Returns RV_OK or a negative rv_status; `err` receives a human-readable reason.
 int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, Program &out, std::string &err);
+
+constexpr uint32_t WIDE_LEVEL = 4096;
 
 // Gate-count limit above which the value plane keeps 2-input "LUTs" (the mapper's cut sets cost ~250 bytes per gate).
 constexpr size_t LUT_MAP_MAX_GATES = 8u << 20;

@@ -17,7 +17,8 @@ namespace rv {
 // Slice w: packed instance w/2; odd w = high u32 (repetitions 0..3), even w = low u32 (repetitions 4..7).
 __global__ void __launch_bounds__(128) k_key_setup(const uint8_t *__restrict__ seeds, const uint8_t *__restrict__ pkeys_in,
                                                    const uint8_t *__restrict__ mode, const uint8_t *__restrict__ omit, uint32_t nslices,
-                                                   uint32_t *__restrict__ ks, uint32_t *__restrict__ lane_mask, uint8_t *__restrict__ pkeys_out) {
+                                                   uint32_t *__restrict__ ks, uint32_t *__restrict__ lane_mask, uint8_t *__restrict__ pkeys_out,
+                                                   uint32_t *__restrict__ rk_plain) {
     __shared__ uint32_t sbox32[64];  // the S-box as a byte table, built from the netlist (4 entries per thread)
     if (threadIdx.x < 64) {
         const uint32_t b = 4 * threadIdx.x;
@@ -32,6 +33,12 @@ __global__ void __launch_bounds__(128) k_key_setup(const uint8_t *__restrict__ s
     const bool active = key_setup_stream(rep, p, seeds, pkeys_in, mode, omit, pkeys_out, rk, sw);
     const uint32_t am = __ballot_sync(0xffffffffu, active);
     if (lane == 0) lane_mask[w] = am;
+    if (rk_plain != nullptr) {  // Z64 generator: plain round keys, [44][streams] (+ row 44: stream is active), stream = 8 * rep + player
+        const uint32_t ns = nslices * 32, sidx = 8 * rep + p;
+#pragma unroll 1
+        for (int q = 0; q < 44; q++) rk_plain[(size_t)q * ns + sidx] = rk[q];
+        rk_plain[(size_t)44 * ns + sidx] = active ? 0xFFFFFFFFu : 0u;
+    }
     // bitslice: plane k of round R = bit k of the 128-bit little-endian round key, gathered over the 32 lanes
 #pragma unroll 1
     for (int q = 0; q < 44; q++) {
@@ -47,8 +54,8 @@ __global__ void __launch_bounds__(128) k_key_setup(const uint8_t *__restrict__ s
 }
 
 void launch_key_setup(const uint8_t *seeds, const uint8_t *pkeys_in, const uint8_t *mode, const uint8_t *omit, uint32_t nslices,
-                      uint32_t *ks, uint32_t *lane_mask, uint8_t *pkeys_out, cudaStream_t st) {
-    k_key_setup<<<(nslices + 3) / 4, 128, 0, st>>>(seeds, pkeys_in, mode, omit, nslices, ks, lane_mask, pkeys_out);
+                      uint32_t *ks, uint32_t *lane_mask, uint8_t *pkeys_out, cudaStream_t st, uint32_t *rk_plain) {
+    k_key_setup<<<(nslices + 3) / 4, 128, 0, st>>>(seeds, pkeys_in, mode, omit, nslices, ks, lane_mask, pkeys_out, rk_plain);
 }
 
 // =====================================================================================================================
@@ -56,7 +63,7 @@ void launch_key_setup(const uint8_t *seeds, const uint8_t *pkeys_in, const uint8
 // =====================================================================================================================
 __global__ void __launch_bounds__(MG_THREADS) k_mask_gen(const uint32_t *__restrict__ ks, const uint32_t *__restrict__ lane_mask,
                                                          uint32_t nslices, uint32_t n_masks, uint32_t *__restrict__ rows32,
-                                                         uint32_t *__restrict__ fresh_sm, size_t pitch_sm) {
+                                                         uint64_t *__restrict__ fresh_pm, size_t pitch_pm) {
     __shared__ uint4 sk[11 * 32 * MG_SLICES];
     const uint32_t w0 = blockIdx.y * MG_SLICES;
     load_round_keys(sk, ks, w0, nslices);
@@ -70,25 +77,148 @@ __global__ void __launch_bounds__(MG_THREADS) k_mask_gen(const uint32_t *__restr
     const uint32_t lm = lane_mask[w];
 #pragma unroll
     for (int k = 0; k < 128; k++) {
+        s[k] &= lm;
         const uint64_t i = plane_to_mask_index(j, k);
-        if (i < n_masks) rows32[i * nslices + w] = s[k] & lm;
+        if (i < n_masks) rows32[i * nslices + w] = s[k];
     }
-    if (fresh_sm != nullptr) {  // slice-major copy for the mask VM: this thread's 128 masks are 512 contiguous bytes
-        uint4 *dst = reinterpret_cast<uint4 *>(fresh_sm + (size_t)w * pitch_sm + j * 128);
+    if (fresh_pm != nullptr) {
+        // Instance-major copy for the mask VM: fresh_pm[pi][i] = the whole u64 share word.  The two slices of an instance sit
+        // in adjacent lanes (even w = low half, odd w = high half); they swap halves of their 128 masks by shuffle so that each
+        // lane stores 64 complete words = 512 contiguous bytes.  (Pairs exit together above: same j, nslices is even.)
+        const uint32_t act = __activemask(), odd = w & 1;
+        uint4 *dst = reinterpret_cast<uint4 *>(fresh_pm + (size_t)(w >> 1) * pitch_pm + j * 128 + 64 * odd);
 #pragma unroll
-        for (int q = 0; q < 32; q++) {  // masks 4q..4q+3 = byte q/2, bits 7-(4q%8) downwards: planes 8B+7-b
-            const int B = q >> 1, hi = (q & 1) ? 3 : 7;
-            dst[q] = make_uint4(s[8 * B + hi] & lm, s[8 * B + hi - 1] & lm, s[8 * B + hi - 2] & lm, s[8 * B + hi - 3] & lm);
+        for (int q = 0; q < 32; q++) {  // masks m = 2q, 2q+1 of this lane's half; mask m of the block = plane 8 (m / 8) + 7 - m % 8
+            uint32_t mine[2], theirs[2];
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int m = 2 * q + h, p_lo = 8 * (m >> 3) + 7 - (m & 7), p_hi = 8 * ((m + 64) >> 3) + 7 - (m & 7);
+                const uint32_t send = odd ? s[p_lo] : s[p_hi];  // what the partner stores
+                theirs[h] = __shfl_xor_sync(act, send, 1);
+                mine[h] = odd ? s[p_hi] : s[p_lo];
+            }
+            dst[q] = odd ? make_uint4(theirs[0], mine[0], theirs[1], mine[1]) : make_uint4(mine[0], theirs[0], mine[1], theirs[1]);
         }
     }
 }
 
-void launch_mask_gen(const uint32_t *ks, const uint32_t *lane_mask, uint32_t nslices, uint32_t n_masks, uint64_t *rows, uint32_t *fresh_sm,
-                     size_t pitch_sm, cudaStream_t st) {
+void launch_mask_gen(const uint32_t *ks, const uint32_t *lane_mask, uint32_t nslices, uint32_t n_masks, uint64_t *rows, uint64_t *fresh_pm,
+                     size_t pitch_pm, cudaStream_t st) {
     if (n_masks == 0) return;
     const uint32_t n_blocks = (n_masks + 127) / 128;
     dim3 grid((n_blocks + MG_COUNTERS - 1) / MG_COUNTERS, (nslices + MG_SLICES - 1) / MG_SLICES);
-    k_mask_gen<<<grid, MG_THREADS, 0, st>>>(ks, lane_mask, nslices, n_masks, reinterpret_cast<uint32_t *>(rows), fresh_sm, pitch_sm);
+    k_mask_gen<<<grid, MG_THREADS, 0, st>>>(ks, lane_mask, nslices, n_masks, reinterpret_cast<uint32_t *>(rows), fresh_pm, pitch_pm);
+}
+
+// ---- T-table variant (the default).  A warp = one slice: lane q runs AES-128 for the PRG stream that lives at bit q of the
+//      slice word (its 44 round-key words in registers), one counter block at a time, with Te0 / Te2 replicated once per
+//      shared-memory bank (64 KB; Te1 / Te3 are byte rotations), so the 160 data-dependent lookups per block never conflict.
+//      Five shuffle-exchange stages per keystream word then transpose the warp's 32 x 128 keystream bits into the 128 share
+//      words of the slice (what the reference's AVX2 movemask transpose produces, src/algebra/gf2/domain.rs:66-173), and a
+//      small shared-memory tile regroups the CTA's 16 slices so every mask row leaves as one 64-byte segment.
+//      Cost per block and lane: ~190 LDS/SHFL + ~380 ALU-pipe instructions, against ~640 LOP3 bitsliced.
+constexpr int GT_SLICES = 16, GT_THREADS = 32 * GT_SLICES, GT_TILE_PITCH = 20;  // tile row = 16 slice words + pad (16-byte aligned rows)
+constexpr size_t GT_SMEM = 2 * 256 * 32 * 4 + 128 * GT_TILE_PITCH * 4;
+struct SmemTe02 {
+    const uint8_t *base;  // entry x at byte 256 x: [0, 128) = Te0[x] once per lane, [128, 256) = Te2[x]
+    uint32_t lane4;
+    __device__ __forceinline__ uint32_t operator()(int t, uint32_t w, int b) const {
+        const uint32_t off = __byte_perm(w, lane4, 0x7604 | (b << 4));  // (byte b of w) << 8 | 4 * lane
+        const uint32_t v = *reinterpret_cast<const uint32_t *>(base + (t >> 1) * 128 + off);
+        return (t & 1) ? __byte_perm(v, v, 0x2103) : v;  // Te1 = rotl(Te0, 8), Te3 = rotl(Te2, 8)
+    }
+};
+// 32 x 32 bit transpose across the lanes of a warp: result bit q of lane l = input bit l of lane q.
+__device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, uint32_t lane) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const uint32_t m = d == 16 ? 0x0000FFFFu : d == 8 ? 0x00FF00FFu : d == 4 ? 0x0F0F0F0Fu : d == 2 ? 0x33333333u : 0x55555555u;
+        const uint32_t y = __shfl_xor_sync(0xffffffffu, x, d);
+        x = (lane & d) ? ((x & ~m) | ((y >> d) & m)) : ((x & m) | ((y << d) & ~m));
+    }
+    return x;
+}
+
+__global__ void __launch_bounds__(GT_THREADS, 1) k_mask_gen_tt(const uint32_t *__restrict__ rk_plain, uint32_t nslices, uint32_t n_masks,
+                                                               uint32_t blocks_per_cta, uint32_t *__restrict__ rows32,
+                                                               uint64_t *__restrict__ fresh_pm, size_t pitch_pm) {
+    extern __shared__ __align__(16) uint32_t gt_smem[];
+    uint32_t *te = gt_smem, *tile = gt_smem + 2 * 256 * 32;
+    __shared__ uint32_t sbox32[64];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
+    if (tid < 64) {
+        const uint32_t b = 4 * tid;
+        sbox32[tid] = sub_word(b | ((b + 1) << 8) | ((b + 2) << 16) | ((b + 3) << 24));
+    }
+    __syncthreads();
+    for (uint32_t e = tid; e < 256 * 32; e += GT_THREADS) {
+        const uint32_t x = e >> 5, l = e & 31, t0 = te0_entry(reinterpret_cast<const uint8_t *>(sbox32)[x]);
+        te[x * 64 + l] = t0;
+        te[x * 64 + 32 + l] = (t0 << 16) | (t0 >> 16);
+    }
+    const uint32_t w0 = blockIdx.y * GT_SLICES, w = w0 + wv, nstreams = nslices * 32;
+    const bool live = w < nslices;
+    uint32_t rk[44], act = 0;
+    if (live) {
+        const uint32_t sidx = 8 * slice_rep(w, lane) + slice_player(lane);
+#pragma unroll
+        for (int q = 0; q < 44; q++) rk[q] = rk_plain[(size_t)q * nstreams + sidx];
+        act = rk_plain[(size_t)44 * nstreams + sidx];
+    }
+    __syncthreads();
+    const SmemTe02 tab{reinterpret_cast<const uint8_t *>(te), 4 * lane};
+    const uint32_t n_blocks = (n_masks + 127) / 128;
+    const uint32_t j_end = min(n_blocks, (blockIdx.x + 1) * blocks_per_cta);
+#pragma unroll 1
+    for (uint32_t j = blockIdx.x * blocks_per_cta; j < j_end; j++) {
+        if (live) {
+            uint32_t in[4], o[4];
+            ctr_block_words(j, in);
+            tt_aes128_encrypt(rk, in[0], in[1], in[2], in[3], tab, o);
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                // lane now holds plane k = 32 g + lane of the slice = keystream byte B = k / 8, bit b = k % 8 -> mask 8 B + 7 - b of the block
+                const uint32_t t = warp_transpose32(o[g] & act, lane);
+                const uint32_t k = 32 * g + lane, m = (k & ~7u) | (7 - (k & 7));
+                tile[m * GT_TILE_PITCH + wv] = t;
+            }
+        }
+        __syncthreads();
+        {  // row-major share tensor: thread = (mask of the block, 4 slices) -> one 16-byte store; a row's 16 slices = 64 contiguous bytes
+            const uint32_t m = tid >> 2, q4 = 4 * (tid & 3);
+            const uint64_t i = (uint64_t)j * 128 + m;
+            if (i < n_masks && w0 + q4 < nslices) {
+                const uint4 v = *reinterpret_cast<const uint4 *>(tile + m * GT_TILE_PITCH + q4);
+                *reinterpret_cast<uint4 *>(rows32 + i * nslices + w0 + q4) = v;
+            }
+        }
+        if (fresh_pm != nullptr) {  // instance-major copy for the mask VM: 8 instances x 128 masks, u64 each
+#pragma unroll
+            for (uint32_t e = tid; e < 8 * 128; e += GT_THREADS) {
+                const uint32_t p = e >> 7, m = e & 127;
+                if (w0 + 2 * p < nslices) {
+                    const uint2 v = *reinterpret_cast<const uint2 *>(tile + m * GT_TILE_PITCH + 2 * p);
+                    fresh_pm[(size_t)((w0 >> 1) + p) * pitch_pm + (uint64_t)j * 128 + m] = ((uint64_t)v.y << 32) | v.x;
+                }
+            }
+        }
+        __syncthreads();
+    }
+}
+
+void launch_mask_gen_tt(const uint32_t *rk_plain, uint32_t nslices, uint32_t n_masks, uint64_t *rows, uint64_t *fresh_pm, size_t pitch_pm, int n_sms,
+                        cudaStream_t st) {
+    if (n_masks == 0) return;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_mask_gen_tt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM);
+        configured = true;
+    }
+    const uint32_t n_blocks = (n_masks + 127) / 128, gy = (nslices + GT_SLICES - 1) / GT_SLICES;
+    const uint32_t want_x = std::max(1u, (uint32_t)n_sms / gy);  // about one CTA per SM for a single small proof
+    const uint32_t per = std::min(64u, std::max(4u, (n_blocks + want_x - 1) / want_x));
+    dim3 grid((n_blocks + per - 1) / per, gy);
+    k_mask_gen_tt<<<grid, GT_THREADS, GT_SMEM, st>>>(rk_plain, nslices, n_masks, per, reinterpret_cast<uint32_t *>(rows), fresh_pm, pitch_pm);
 }
 
 // =====================================================================================================================
@@ -253,60 +383,93 @@ size_t launch_values(const LutInstr *steps, uint32_t n_steps, const uint32_t *le
     return LutStream::BYTES;
 }
 
+// Wide circuits: thread = one LUT of the level; values in global memory (L2-resident between the per-level launches).
+__global__ void __launch_bounds__(256) k_values_leaves(const uint32_t *__restrict__ leaf_ids, const uint8_t *__restrict__ wit, uint32_t n_leaves,
+                                                       uint8_t *__restrict__ vals) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k == 0) vals[0] = 0;
+    if (k < n_leaves) vals[leaf_ids[k]] = wit[k] & 1;
+}
+__global__ void __launch_bounds__(256) k_values_level(const LutInstr *__restrict__ luts, uint32_t n, uint8_t *vals) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const LutInstr li = luts[g];
+    const uint32_t idx = (uint32_t)vals[li.in[0]] | ((uint32_t)vals[li.in[1]] << 1) | ((uint32_t)vals[li.in[2]] << 2) | ((uint32_t)vals[li.in[3]] << 3) |
+                         ((uint32_t)vals[li.in[4]] << 4) | ((uint32_t)vals[li.in[5]] << 5);
+    vals[li.dst] = (uint8_t)((li.tt >> idx) & 1);
+}
+
+int launch_values_wide(const DevProgram &P, const uint32_t *off_host, const uint8_t *wit, uint8_t *vals, cudaStream_t st) {
+    k_values_leaves<<<(std::max(P.n_inputs, 1u) + 255) / 256, 256, 0, st>>>(P.input_vid, wit, P.n_inputs, vals);
+    for (uint32_t l = 0; l < P.n_lut_levels; l++) {
+        const uint32_t n = off_host[l + 1] - off_host[l];
+        if (n) k_values_level<<<(n + 255) / 256, 256, 0, st>>>(P.luts + off_host[l], n, vals);
+    }
+    return 1 + (int)P.n_lut_levels;
+}
+
 // =====================================================================================================================
 //  K3  mask plane: row[dst] = row[a] ^ row[b], level by level
 // =====================================================================================================================
 constexpr int LIN_THREADS = 256;
 constexpr int VM_THREADS = VM_STEP;
 
-// (a) VM over shared-memory cells: one CTA per slice (u32 lane word = 4 repetitions x 8 players), one slot per thread per
-//     step.  The dependent chain per level is LDS -> XOR -> STS -> barrier; fresh rows arrive through cp.async LOADs issued
-//     VM_DELTA levels early; only rows the item plane needs are written back to the share tensor.
+// (a) VM over shared-memory cells: one CTA per packed instance (cell = the u64 share word: 8 repetitions x 8 players), one
+//     slot per thread per step.  The dependent chain per level is LDS -> XOR -> STS -> barrier; fresh rows arrive through
+//     cp.async LOADs issued VM_DELTA levels early; only rows the item plane needs are written back.  Every CTA streams the
+//     whole program from L2, so the 20-byte instruction (16-bit cell ids) is what sets the pace.
 constexpr uint32_t VM_CHUNK_BYTES = VM_STEPS_PER_CHUNK * VM_STEP * (uint32_t)sizeof(VmInstr);
 using VmStream = ChunkStream<VM_CHUNK_BYTES, 2>;
 static_assert(VM_THREADS == (int)VM_STEP, "one slot per thread");
+static_assert(VM_CHUNK_BYTES % 16 == 0 && (VM_STEP * sizeof(VmInstr)) % 16 == 0, "bulk copies move multiples of 16 bytes");
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
 
-__global__ void __launch_bounds__(VM_THREADS) k_mask_vm(const VmInstr *__restrict__ prog, uint32_t n_steps, const uint32_t *__restrict__ fresh_sm,
-                                                        size_t pitch_fresh, uint32_t *__restrict__ exp_sm, size_t pitch_exp, uint32_t n_masks) {
+__global__ void __launch_bounds__(VM_THREADS) k_mask_vm(const VmInstr *__restrict__ prog, uint32_t n_steps, const uint64_t *__restrict__ fresh_pm,
+                                                        size_t pitch_fresh, uint64_t *__restrict__ exp_pm, size_t pitch_exp, uint32_t n_masks) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t n_chunks = (n_steps + VM_STEPS_PER_CHUNK - 1) / VM_STEPS_PER_CHUNK;
     VmStream stream;
     stream.init(smem, prog, n_chunks, (n_steps - (n_chunks ? n_chunks - 1 : 0) * VM_STEPS_PER_CHUNK) * VM_STEP * (uint32_t)sizeof(VmInstr));
-    uint32_t *cells = reinterpret_cast<uint32_t *>(smem + VmStream::BYTES);  // indexed as a shared array: LDS/STS [R.X4 + imm]
-    const uint32_t tid = threadIdx.x, w = blockIdx.x;
-    // Global traffic is slice-major on both sides, so a warp's 32 accesses fall into a few 128-byte lines: LOADs of a level
+    uint64_t *cells = reinterpret_cast<uint64_t *>(smem + VmStream::BYTES);
+    const uint32_t tid = threadIdx.x, pi = blockIdx.x;
+    // Global traffic is instance-major on both sides, so a warp's 32 accesses fall into a few 128-byte lines: LOADs of a level
     // are sorted by row, exported rows are numbered in program order.  (Row-major, each lane would touch its own 256-byte
     // row and the kernel would be bound by L1 request rate.)
-    const uint32_t *src = fresh_sm + (size_t)w * pitch_fresh;
-    uint32_t *dst = exp_sm + (size_t)w * pitch_exp - n_masks;
+    const uint64_t *src = fresh_pm + (size_t)pi * pitch_fresh;
+    uint64_t *dst = exp_pm + (size_t)pi * pitch_exp - n_masks;
     if (tid == 0) cells[0] = 0;  // cell 0 is the constant zero (first read happens after the first barrier)
     for (uint32_t c = 0; c < n_chunks; c++) {
-        const uint32_t img = stream.begin_chunk(c) + tid * (uint32_t)sizeof(VmInstr);
+        const uint32_t img = stream.begin_chunk(c) + tid * (uint32_t)sizeof(VmInstr);  // 5-word stride: conflict-free LDS.32
         const uint32_t nst = min((uint32_t)VM_STEPS_PER_CHUNK, n_steps - c * VM_STEPS_PER_CHUNK);
-        uint4 u0[VM_STEPS_PER_CHUNK], u1[VM_STEPS_PER_CHUNK];
+        uint32_t u[VM_STEPS_PER_CHUNK][5];
 #pragma unroll
         for (int k = 0; k < (int)VM_STEPS_PER_CHUNK; k++)
             if (k < (int)nst) {
                 const uint32_t p = img + k * VM_STEP * (uint32_t)sizeof(VmInstr);
-                u0[k] = lds128(p);       // {dst | flags, in0, in1, in2}
-                u1[k] = lds128(p + 16);  // {in3, in4, in5, row}
+#pragma unroll
+                for (int q = 0; q < 5; q++) u[k][q] = lds32(p + 4 * q);  // {row, dst | flags << 16, in0 | in1 << 16, in2 | in3 << 16, in4 | in5 << 16}
             }
 #pragma unroll
         for (int k = 0; k < (int)VM_STEPS_PER_CHUNK; k++)
             if (k < (int)nst) {
-                const uint4 a = u0[k], b = u1[k];
-                if (a.x & VM_F_LOAD) {
-                    __pipeline_memcpy_async(cells + (a.x & VM_CELL_MASK), src + a.y, 4);
+                const uint32_t row = u[k][0], d = u[k][1] & 0xFFFFu, fl = u[k][1] >> 16;
+                if (fl & VM_F_LOAD) {
+                    __pipeline_memcpy_async(cells + d, src + row, 8);
                 } else {
-                    const uint32_t v = cells[a.y] ^ cells[a.z] ^ cells[a.w] ^ cells[b.x] ^ cells[b.y] ^ cells[b.z];
-                    cells[a.x & VM_CELL_MASK] = v;
-                    if (b.w != VM_ROW_NONE) dst[b.w] = v;
+                    const uint64_t v = cells[u[k][2] & 0xFFFFu] ^ cells[u[k][2] >> 16] ^ cells[u[k][3] & 0xFFFFu] ^ cells[u[k][3] >> 16] ^
+                                       cells[u[k][4] & 0xFFFFu] ^ cells[u[k][4] >> 16];
+                    cells[d] = v;
+                    if (row != VM_ROW_NONE) dst[row] = v;
                 }
-                if (a.x & VM_F_LEVEL_END) {  // one cp.async group per level; LOADs of level L-2 are complete before level L starts
+                if (fl & VM_F_LEVEL_END) {  // one cp.async group per level; LOADs of level L-2 are complete before level L starts
                     __pipeline_commit();
                     __pipeline_wait_prior(VM_DELTA - 1);
                 }
-                if (a.x & VM_F_BAR) __syncthreads();
+                if (fl & VM_F_BAR) __syncthreads();
             }
     }
 }
@@ -343,27 +506,27 @@ __global__ void __launch_bounds__(256) k_linear_level(const XGate *__restrict__ 
     rows[(size_t)gt.dst * npi + pi] = xor6(rows, gt, npi, pi);
 }
 
-// exp_sm [nslices][pitch] (u32, slice-major, written by the VM) -> rows[n_masks + e][nslices] (row-major, read by the item plane)
-__global__ void __launch_bounds__(256) k_export_transpose(const uint32_t *__restrict__ exp_sm, size_t pitch, uint32_t n_lin, uint32_t nslices,
-                                                          uint32_t *__restrict__ rows32_lin) {
-    __shared__ uint32_t tile[64][33];
+// exp_pm [npi][pitch] (instance-major, written by the VM) -> rows[n_masks + e][npi] (row-major, read by the item plane)
+__global__ void __launch_bounds__(256) k_export_transpose(const uint64_t *__restrict__ exp_pm, size_t pitch, uint32_t n_lin, uint32_t npi,
+                                                          uint64_t *__restrict__ rows_lin) {
+    __shared__ uint64_t tile[32][33];
     const uint32_t e0 = blockIdx.x * 32, lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    for (uint32_t sl = wrp; sl < nslices; sl += 8) tile[sl][lane] = (e0 + lane < n_lin) ? exp_sm[(size_t)sl * pitch + e0 + lane] : 0u;
+    for (uint32_t p = wrp; p < npi; p += 8) tile[p][lane] = (e0 + lane < n_lin) ? exp_pm[(size_t)p * pitch + e0 + lane] : 0ull;
     __syncthreads();
-    for (uint32_t idx = threadIdx.x; idx < 32 * nslices; idx += 256) {
-        const uint32_t r = idx / nslices, sl = idx % nslices;
-        if (e0 + r < n_lin) rows32_lin[(size_t)(e0 + r) * nslices + sl] = tile[sl][r];
+    for (uint32_t idx = threadIdx.x; idx < 32 * npi; idx += 256) {
+        const uint32_t r = idx / npi, p = idx % npi;
+        if (e0 + r < n_lin) rows_lin[(size_t)(e0 + r) * npi + p] = tile[p][r];
     }
 }
 
-static size_t vm_smem_bytes(const DevProgram &P) { return VmStream::BYTES + ((size_t)P.vm_cells + 1) * 4; }
+static size_t vm_smem_bytes(const DevProgram &P) { return VmStream::BYTES + ((size_t)P.vm_cells + 1) * 8; }
 bool linear_uses_vm(const DevProgram &P) {
     if (P.n_llevels == 0 || (double)P.n_xgates / P.n_llevels >= 4096.0) return false;
     return P.n_vm_steps && P.vm_cells < VM_CELL_MASK && vm_smem_bytes(P) <= SMEM_DYN_CAP;
 }
 
-int launch_linear(const DevProgram &P, const uint32_t *off_host, uint64_t *rows, uint32_t npi, const uint32_t *fresh_sm, size_t pitch_fresh,
-                  uint32_t *exp_sm, size_t pitch_exp, cudaStream_t st, int *which) {
+int launch_linear(const DevProgram &P, const uint32_t *off_host, uint64_t *rows, uint32_t npi, const uint64_t *fresh_sm, size_t pitch_fresh,
+                  uint64_t *exp_sm, size_t pitch_exp, cudaStream_t st, int *which) {
     if (which) *which = -1;
     if (P.n_llevels == 0) return 0;
     const double avg_width = (double)P.n_xgates / P.n_llevels;
@@ -383,9 +546,8 @@ int launch_linear(const DevProgram &P, const uint32_t *off_host, uint64_t *rows,
             configured = true;
         }
         if (which) *which = 0;
-        k_mask_vm<<<2 * npi, VM_THREADS, vm_smem_bytes(P), st>>>(P.vm_steps, P.n_vm_steps, fresh_sm, pitch_fresh, exp_sm, pitch_exp, P.n_masks);
-        k_export_transpose<<<(P.n_lin + 31) / 32, 256, 0, st>>>(exp_sm, pitch_exp, P.n_lin, 2 * npi,
-                                                                reinterpret_cast<uint32_t *>(rows) + (size_t)P.n_masks * 2 * npi);
+        k_mask_vm<<<npi, VM_THREADS, vm_smem_bytes(P), st>>>(P.vm_steps, P.n_vm_steps, fresh_sm, pitch_fresh, exp_sm, pitch_exp, P.n_masks);
+        k_export_transpose<<<(P.n_lin + 31) / 32, 256, 0, st>>>(exp_sm, pitch_exp, P.n_lin, npi, rows + (size_t)P.n_masks * npi);
         return 2;
     }
     if (which) *which = 1;
@@ -397,26 +559,6 @@ int launch_linear(const DevProgram &P, const uint32_t *off_host, uint64_t *rows,
 //  K4  item plane: thread = (8 consecutive stream positions, packed instance); 8x8 byte transpose in registers so each
 //      repetition's 8 stream bytes leave as one aligned 64-bit store
 // =====================================================================================================================
-__global__ void __launch_bounds__(256) k_items_online(const Item *__restrict__ items, uint32_t n_online, const uint64_t *__restrict__ rows,
-                                                      uint32_t npi, const uint8_t *__restrict__ vals, uint8_t *__restrict__ on, size_t pitch,
-                                                      int *bad) {
-    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t pi = (uint32_t)(gid % npi);
-    const uint64_t t0 = (gid / npi) * 8;
-    if (t0 >= n_online) return;
-    uint64_t W[8], out[8];
-    int flag = 0;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        W[i] = 0;
-        if (t0 + i < n_online) W[i] = prover_online_word(items[t0 + i], rows, npi, pi, vals, &flag);
-    }
-    if (flag && pi == 0) atomicOr(bad, 1);
-    words_to_stream_bytes(W, out);
-#pragma unroll
-    for (int r = 0; r < 8; r++) *reinterpret_cast<uint64_t *>(on + (size_t)(8 * pi + r) * pitch + t0) = out[r];
-}
-
 __global__ void __launch_bounds__(256) k_items_pre(const Item *__restrict__ items, const uint32_t *__restrict__ mul_pos, uint32_t n_pre,
                                                    const uint64_t *__restrict__ rows, uint32_t npi, uint8_t *__restrict__ pre, size_t pitch,
                                                    uint32_t first_pi) {
@@ -435,16 +577,53 @@ __global__ void __launch_bounds__(256) k_items_pre(const Item *__restrict__ item
     for (int r = 0; r < 8; r++) *reinterpret_cast<uint64_t *>(pre + (size_t)(8 * pi + r) * pitch + j0) = out[r];
 }
 
+// Tiled item plane (prover).  A CTA computes a tile of T consecutive stream positions for every repetition of the shard:
+// lane = (packed instance, position group of 8) so that each mask row is read as one contiguous run of npi * 8 bytes; the
+// 8x8 byte transposes happen in registers (words_to_stream_bytes); the tile is staged in shared memory (row = repetition,
+// pitch T + 8 bytes: 64-bit stores of consecutive instances fall into distinct banks) and leaves as whole 128-byte lines
+// of each repetition's stream.  PRE selects the preprocessing stream (one byte per Mul) instead of the online stream.
+constexpr int IT_THREADS = 256;
+template <bool PRE>
+__global__ void __launch_bounds__(IT_THREADS) k_items_tile(const Item *__restrict__ items, const uint32_t *__restrict__ mul_pos, uint32_t n,
+                                                          const uint64_t *__restrict__ rows, uint32_t npi, const uint8_t *__restrict__ vals,
+                                                          uint8_t *__restrict__ out, size_t pitch, uint32_t T, int *bad) {
+    extern __shared__ __align__(16) uint8_t tile[];
+    const uint32_t tid = threadIdx.x, pi = tid % npi, pg0 = tid / npi, pg_step = IT_THREADS / npi;
+    const uint32_t tp = T + 8;  // tile pitch in bytes
+    const uint64_t T0 = (uint64_t)blockIdx.x * T;
+    int flag = 0;
+    for (uint32_t g = pg0; g < T / 8; g += pg_step) {
+        const uint64_t t0 = T0 + 8ull * g;
+        uint64_t W[8], o[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            W[i] = 0;
+            if (t0 + i < n) W[i] = PRE ? pre_word(items[mul_pos[t0 + i]], rows, npi, pi) : prover_online_word(items[t0 + i], rows, npi, pi, vals, &flag);
+        }
+        words_to_stream_bytes(W, o);
+#pragma unroll
+        for (int r = 0; r < 8; r++) *reinterpret_cast<uint64_t *>(tile + (size_t)(r * npi + pi) * tp + 8 * g) = o[r];
+    }
+    if (!PRE && flag && pi == 0) atomicOr(bad, 1);
+    __syncthreads();
+    // write-out: one warp per tile row, 128 bytes (32 lanes x u32) per step
+    const uint32_t lane = tid & 31, wrp = tid >> 5, nrows = 8 * npi;
+    for (uint32_t row = wrp; row < nrows; row += IT_THREADS / 32) {
+        const uint32_t r = row / npi, p = row % npi;
+        uint8_t *dst = out + (size_t)(8 * p + r) * pitch + T0;
+        const uint8_t *src = tile + (size_t)row * tp;
+        for (uint32_t c = 4 * lane; c < T; c += 128) *reinterpret_cast<uint32_t *>(dst + c) = *reinterpret_cast<const uint32_t *>(src + c);
+    }
+}
+
+static uint32_t items_tile(uint32_t npi) { return std::max(128u, 8u * IT_THREADS / npi); }
+
 void launch_items(const DevProgram &P, const uint64_t *rows, uint32_t npi, const uint8_t *vals, uint8_t *on, size_t pitch_on,
                   uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st) {
-    if (P.n_online) {
-        const uint64_t threads = (uint64_t)((P.n_online + 7) / 8) * npi;
-        k_items_online<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P.items, P.n_online, rows, npi, vals, on, pitch_on, bad);
-    }
-    if (P.n_pre) {
-        const uint64_t threads = (uint64_t)((P.n_pre + 7) / 8) * npi;
-        k_items_pre<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P.items, P.mul_pos, P.n_pre, rows, npi, pre, pitch_pre, 0);
-    }
+    const uint32_t T = items_tile(npi);
+    const size_t smem = (size_t)8 * npi * (T + 8);
+    if (P.n_online) k_items_tile<false><<<(P.n_online + T - 1) / T, IT_THREADS, smem, st>>>(P.items, nullptr, P.n_online, rows, npi, vals, on, pitch_on, T, bad);
+    if (P.n_pre) k_items_tile<true><<<(P.n_pre + T - 1) / T, IT_THREADS, smem, st>>>(P.items, P.mul_pos, P.n_pre, rows, npi, nullptr, pre, pitch_pre, T, nullptr);
 }
 
 // verifier, preprocessing repetitions: recompute the corrections from the seeds (src/transcript/verifier/preprocess.rs:66-69)
@@ -815,11 +994,15 @@ __global__ void __launch_bounds__(256) k_extract(const uint32_t *__restrict__ re
     v.n_recon = n_recon;
     v.n_pre = n_pre;
     v.n_inputs = n_inputs;
-    extract_entry(L, v, rep, a.omit_of_rep[rep], a.rank_of_rep[rep], threadIdx.x, blockDim.x, a.proof);
+    // grid.y CTAs share one repetition: the packed vectors of a big circuit are megabytes per opened repetition
+    if (a.omit_of_rep[rep] >= RV_PLAYERS && blockIdx.y != 0) return;
+    extract_entry(L, v, rep, a.omit_of_rep[rep], a.rank_of_rep[rep], threadIdx.x + blockDim.x * blockIdx.y, blockDim.x * gridDim.y, a.proof);
 }
 
 void launch_extract(const DevProgram &P, const ExtractArgs &a, cudaStream_t st) {
-    k_extract<<<a.nreps, 256, 0, st>>>(P.recon_pos, P.input_pos, P.n_recon, P.n_pre, P.n_inputs, a);
+    const uint32_t bytes = a.len_recons + a.len_corrs + a.len_inputs;
+    const uint32_t ny = std::min(64u, std::max(1u, bytes / 4096));
+    k_extract<<<dim3(a.nreps, ny), 256, 0, st>>>(P.recon_pos, P.input_pos, P.n_recon, P.n_pre, P.n_inputs, a);
 }
 
 }  // namespace rv

@@ -46,6 +46,78 @@ void launch_zmask_gen(const uint32_t *ks, const uint32_t *lane_mask, uint32_t ns
     k_zmask_gen<<<grid, MG_THREADS, 0, st>>>(ks, lane_mask, nslices, n_masks, zrows, rowlen);
 }
 
+// ---- T-table variant: thread = one PRG stream (its 44 round-key words in registers), looping over counter blocks; a warp =
+//      32 consecutive streams, so every mask leaves as one 256-byte row segment.  The four 1 KB Te tables are replicated
+//      once per shared-memory bank (128 KB): lane l only ever reads words = l (mod 32), so the 32 data-dependent lookups
+//      of a warp are conflict-free and the generator is bound by the LDS pipe (160 lookups per block) instead of the
+//      ~640 LOP3 per block of the bitsliced form (whose planes would need transposing back for Z64 anyway).
+constexpr int ZT_THREADS = 512, ZT_BLOCKS_PER_TASK = 64;
+// Shared-memory image: entry x of table t at byte (t >> 1) * 65536 + x * 256 + (t & 1) * 128 + 4 * lane.  The 256-byte entry
+// stride makes the data-dependent part of the address a single PRMT: (byte b of w) << 8 | 4 * lane.
+struct SmemTe {
+    const uint8_t *base;  // the table image (uniform)
+    uint32_t lane4;       // 4 * lane
+    __device__ __forceinline__ uint32_t operator()(int t, uint32_t w, int b) const {
+        const uint32_t off = __byte_perm(w, lane4, 0x7604 | (b << 4));
+        return *reinterpret_cast<const uint32_t *>(base + (t >> 1) * 65536 + (t & 1) * 128 + off);
+    }
+};
+
+__global__ void __launch_bounds__(ZT_THREADS, 1) k_zmask_gen_tt(const uint32_t *__restrict__ rk_plain, uint32_t nstreams, uint32_t n_masks,
+                                                                uint64_t *__restrict__ zrows) {
+    extern __shared__ __align__(16) uint32_t te[];  // [4][256][32]
+    __shared__ uint32_t sbox32[64];
+    const uint32_t tid = threadIdx.x, lane = tid & 31;
+    if (tid < 64) {
+        const uint32_t b = 4 * tid;
+        sbox32[tid] = sub_word(b | ((b + 1) << 8) | ((b + 2) << 16) | ((b + 3) << 24));
+    }
+    __syncthreads();
+    for (uint32_t e = tid; e < 256 * 32; e += ZT_THREADS) {
+        const uint32_t x = e >> 5, l = e & 31, t0 = te0_entry(reinterpret_cast<const uint8_t *>(sbox32)[x]);
+        te[x * 64 + l] = t0;
+        te[x * 64 + 32 + l] = (t0 << 8) | (t0 >> 24);
+        te[16384 + x * 64 + l] = (t0 << 16) | (t0 >> 16);
+        te[16384 + x * 64 + 32 + l] = (t0 << 24) | (t0 >> 8);
+    }
+    __syncthreads();
+    const SmemTe tab{reinterpret_cast<const uint8_t *>(te), 4 * lane};
+    const uint32_t n_sg = nstreams / 32, n_blocks = (n_masks + 1) / 2;
+    const uint32_t n_ranges = (n_blocks + ZT_BLOCKS_PER_TASK - 1) / ZT_BLOCKS_PER_TASK;
+    const uint64_t n_tasks = (uint64_t)n_sg * n_ranges;
+    constexpr uint32_t WARPS = ZT_THREADS / 32;
+    for (uint64_t task = (uint64_t)blockIdx.x * WARPS + (tid >> 5); task < n_tasks; task += (uint64_t)gridDim.x * WARPS) {
+        const uint32_t sidx = (uint32_t)(task % n_sg) * 32 + lane, range = (uint32_t)(task / n_sg);
+        uint32_t rk[44];
+#pragma unroll
+        for (int q = 0; q < 44; q++) rk[q] = rk_plain[(size_t)q * nstreams + sidx];
+        const uint32_t act = rk_plain[(size_t)44 * nstreams + sidx];
+        const uint32_t j_end = min(n_blocks, (range + 1) * ZT_BLOCKS_PER_TASK);
+#pragma unroll 1
+        for (uint32_t j = range * ZT_BLOCKS_PER_TASK; j < j_end; j++) {
+            uint32_t in[4], o[4];
+            ctr_block_words(j, in);
+            tt_aes128_encrypt(rk, in[0], in[1], in[2], in[3], tab, o);
+            uint64_t *dst = zrows + (size_t)(2 * j) * nstreams + sidx;
+            dst[0] = ((uint64_t)(o[1] & act) << 32) | (o[0] & act);
+            if (2 * j + 1 < n_masks) dst[nstreams] = ((uint64_t)(o[3] & act) << 32) | (o[2] & act);
+        }
+    }
+}
+
+void launch_zmask_gen_tt(const uint32_t *rk_plain, uint32_t nstreams, uint32_t n_masks, uint64_t *zrows, int n_sms, cudaStream_t st) {
+    if (n_masks == 0) return;
+    static bool configured = false;
+    if (!configured) {
+        cudaFuncSetAttribute(k_zmask_gen_tt, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 256 * 32 * 4);
+        configured = true;
+    }
+    const uint32_t n_blocks = (n_masks + 1) / 2, n_ranges = (n_blocks + ZT_BLOCKS_PER_TASK - 1) / ZT_BLOCKS_PER_TASK;
+    const uint64_t n_tasks = (uint64_t)(nstreams / 32) * n_ranges;
+    const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)n_sms, (n_tasks + ZT_THREADS / 32 - 1) / (ZT_THREADS / 32));
+    k_zmask_gen_tt<<<grid, ZT_THREADS, 4 * 256 * 32 * 4, st>>>(rk_plain, nstreams, n_masks, zrows);
+}
+
 // =====================================================================================================================
 //  ZK3  mask plane: zrow[dst] = ca * zrow[a] + cb * zrow[b], one launch per level, thread = (node, element)
 // =====================================================================================================================

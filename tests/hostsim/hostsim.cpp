@@ -313,17 +313,18 @@ extern "C" int hs_check_steps(const rv_op *ops, size_t n_ops, size_t z64_cells, 
             bool bar = false, level_end = false;
             for (uint32_t t = 0; t < VM_STEP; t++) {
                 const VmInstr &in = P.vm_steps[(size_t)st * VM_STEP + t];
-                bar = (in.dst & VM_F_BAR) != 0;
-                level_end = (in.dst & VM_F_LEVEL_END) != 0;
-                if (((P.vm_steps[(size_t)st * VM_STEP].dst & VM_F_BAR) != 0) != bar) { g_err = "non-uniform barrier flag"; return -301; }
-                if ((in.dst & VM_F_LEVEL_END) && !bar) { g_err = "level end without barrier"; return -305; }
-                if (in.dst & VM_F_LOAD) {
-                    if (late) pending[0].push_back({in.dst & VM_CELL_MASK, rows[in.in[0]]});
-                    else writes.push_back({in.dst & VM_CELL_MASK, rows[in.in[0]]});
+                bar = (in.flags & VM_F_BAR) != 0;
+                level_end = (in.flags & VM_F_LEVEL_END) != 0;
+                if (((P.vm_steps[(size_t)st * VM_STEP].flags & VM_F_BAR) != 0) != bar) { g_err = "non-uniform barrier flag"; return -301; }
+                if ((in.flags & VM_F_LEVEL_END) && !bar) { g_err = "level end without barrier"; return -305; }
+                if (in.dst > P.vm_cells) { g_err = "cell id out of range"; return -306; }
+                if (in.flags & VM_F_LOAD) {
+                    if (late) pending[0].push_back({in.dst, rows[in.row]});
+                    else writes.push_back({in.dst, rows[in.row]});
                 } else {
                     uint32_t v = 0;
                     for (int k = 0; k < 6; k++) v ^= cells[in.in[k]];
-                    writes.push_back({in.dst & VM_CELL_MASK, v});
+                    writes.push_back({in.dst, v});
                     if (in.row != VM_ROW_NONE) rows[in.row] = v;
                 }
             }
@@ -354,6 +355,12 @@ extern "C" int hs_check_steps(const rv_op *ops, size_t n_ops, size_t z64_cells, 
             a[g.dst] = (uint8_t)((g.op ? (u & v) : (u ^ v)) & 1);
         }
         std::vector<std::pair<uint32_t, uint8_t>> w;
+        if (P.values_wide)  // k_values_level: one launch per level over the level-sorted list
+            for (const LutInstr &li : P.luts) {
+                uint32_t idx = 0;
+                for (int k = 0; k < 6; k++) idx |= (uint32_t)b[li.in[k]] << k;
+                b[li.dst] = (uint8_t)((li.tt >> idx) & 1);
+            }
         for (uint32_t st = 0; st < P.n_lut_steps; st++) {
             w.clear();
             for (uint32_t t = 0; t < LUT_STEP; t++) {

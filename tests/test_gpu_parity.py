@@ -311,3 +311,16 @@ def test_z64_witness_errors_and_sharding(rb, default_seeds):
             s.open(allh)
         parts = [s.fetch() for s in sess]
         assert rb.assemble(parts[0][0], [p for _, p in parts]) == want, f"G={G}"
+
+
+def test_wide_layered_circuit(rb, default_seeds):
+    """SURVEY.md 8(d) config 5(ii) at a size the oracle finishes in seconds: wide levels take the per-level value-plane launches."""
+    from reverie_b200 import circuits as C
+
+    width, n_and = 8192, 40000
+    ops, nw = C.layered_and_circuit(width, n_and)
+    wit = np.random.default_rng(0).integers(0, 2, size=width).astype(np.uint8)
+    circ = rb.Circuit(ops, (0, nw))
+    assert circ.stats()["n_lut_steps"] == 0 and circ.stats()["n_luts"] > 0  # the wide path is the one that runs
+    blob = _check(rb, ops, wit, (0, nw), default_seeds)
+    assert rb.Proof(blob).verify(circ)

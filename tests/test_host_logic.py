@@ -165,3 +165,10 @@ def test_z64_config3_shape_and_errors(default_seeds):
     b.assert_zero(b.addc(x, 5))
     assert hostsim.prove(b.ops(), [], (b.n_wires, 0), default_seeds, wit_z64=[7])[0] == N.E_WITNESS_INVALID
     assert hostsim.prove(b.ops(), [], (b.n_wires, 0), default_seeds, wit_z64=[(1 << 64) - 5])[0] == 0
+
+
+def test_wide_layered_circuit_bodies(default_seeds):
+    ops, nw = CI.layered_and_circuit(8192, 30000)
+    wit = np.random.default_rng(0).integers(0, 2, size=8192).astype(np.uint8)
+    st = _check_steps(ops, (0, nw))
+    assert st[1] == 0 and st[3] > 0  # no step stream: the per-level launches run the level-sorted LUT list
