@@ -177,7 +177,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sha256")
-    ap.add_argument("--batch", type=int, default=8, help="independent proofs per step")
+    ap.add_argument("--batch", type=int, default=32, help="independent proofs per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     set_metric(args.workload)
@@ -192,14 +192,16 @@ def main():
     import torch.distributed as dist
 
     import reverie_b200 as rb
-    from reverie_b200 import _native
+    from reverie_b200 import _native, sharding
 
     if not torch.cuda.is_available() or _native.lib().rv_device_count() < 1:
         raise SystemExit("bench.py needs a CUDA device: reverie_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     _native.check(_native.lib().rv_set_device(local_rank))
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        import datetime
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=120))
     if 32 % world:
         raise SystemExit("world size must divide the 32 packed instances")
 
@@ -214,7 +216,9 @@ def main():
     streams = [torch.cuda.ExternalStream(x.stream) for x in sessions]
     timing_stream = torch.cuda.Stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    gathered = [torch.empty(256 * 32, dtype=torch.uint8, device="cuda") for _ in range(B)]
+    recv_bufs = {}  # session -> (receive tensor over the session's own all-gather buffer, send tensor over its hashes, address, event)
+    sessions_all = list(sessions)
+    gather_stream, gathered_ev = torch.cuda.Stream(), torch.cuda.Event()
 
     def barrier():
         if world > 1:
@@ -229,16 +233,23 @@ def main():
             return
         for x in sessions:
             x.commit()
-        if world > 1:
-            for b, x in enumerate(sessions):
-                mine = torch.frombuffer(bytearray(x.hashes()), dtype=torch.uint8).cuda()
-                dist.all_gather_into_tensor(gathered[b], mine)
-            torch.cuda.synchronize()
-            for b, x in enumerate(sessions):
-                x.open(gathered[b].data_ptr())
-        else:
-            for x in sessions:
-                x.open()
+        # the one exchange of the protocol (src/proof/mod.rs:160-171): NCCL all-gather of the repetition hashes, device to
+        # device into each session's own receive buffer -- no host round trip.  The B proofs of a step share ONE NCCL group
+        # launch: their streams join a gather stream and fork again.
+        if not recv_bufs:
+            for x in sessions_all:
+                r = x.all_hashes_device()
+                recv_bufs[x] = (torch.as_tensor(r, device="cuda"), torch.as_tensor(x.hashes_device(), device="cuda"), r.ptr, torch.cuda.Event())
+        for b, x in enumerate(sessions):
+            ev = recv_bufs[x][3]
+            ev.record(streams[b])
+            gather_stream.wait_event(ev)
+        with torch.cuda.stream(gather_stream):
+            sharding.all_gather_hashes_batched([recv_bufs[x][0] for x in sessions], [recv_bufs[x][1] for x in sessions])
+            gathered_ev.record(gather_stream)
+        for b, x in enumerate(sessions):
+            streams[b].wait_event(gathered_ev)
+            x.open(recv_bufs[x][2])
 
     def timed_device(k: int):
         tot = 0.0
@@ -290,26 +301,30 @@ def main():
     # ---- per-kernel device times -> roofline of the dominant kernel (rank 0) ----
     roofline, kernels = None, None
     peak, peak_src = load_peaks()
+    reps = max(5, min(args.steps, 20))
     if rank == 0:
         sess.timing(True)
-        reps = max(5, min(args.steps, 20))
-        keep_s = sessions
-        sessions = sessions[:1]
-        for _ in range(reps):
-            step_device()
-        sessions = keep_s
+    keep_s = sessions
+    sessions = sessions[:1]
+    for _ in range(reps):  # every rank runs the steps (they contain the all-gather); only rank 0 brackets its kernels with events
+        step_device()
+    sessions = keep_s
+    sess.sync()
+    if rank == 0:
         kt = sess.kernel_times()
         sess.timing(False)
         comm, part = sess.fetch()
         kernels = {k["name"]: {"us_per_step": k["ms"] * 1e3 / reps, "launches_per_step": k["launches"] // reps,
                                "algorithmic_bytes_per_step": k["algorithmic_bytes"] // reps} for k in kt}
-        main_stream = [k for k in kt if k["name"] != "values"]
-        top = max(kt, key=lambda k: k["ms"])
+        # the dominant kernel of the critical stream; the plaintext value planes run on a side stream, overlapped with mask generation
+        main_stream = [k for k in kt if k["name"] not in ("values", "z.values")] or kt
+        top = max(main_stream, key=lambda k: k["ms"])
         per_launch_s = top["ms"] * 1e-3 / max(top["launches"], 1)
         bytes_per_launch = top["algorithmic_bytes"] / max(top["launches"], 1)
         ach = bytes_per_launch / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
         roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                     "peak_source": peak_src, "us_per_launch": per_launch_s * 1e6,
+                    "per_kernel_frac": {k["name"]: (k["algorithmic_bytes"] / max(k["ms"], 1e-9) / 1e6) / peak for k in kt},
                     "path": {"algorithmic_bytes_per_step": st["algorithmic_bytes"], "achieved": B * st["algorithmic_bytes"] / (ms_total / args.steps * 1e-3) / 1e9,
                              "frac": B * st["algorithmic_bytes"] / (ms_total / args.steps * 1e-3) / 1e9 / peak,
                              "note": "SURVEY.md 8(d) bytes of the B proofs of a step / device time per step"}}
@@ -318,6 +333,7 @@ def main():
     if big and world == 1:
         del sess, x
         sessions.clear()
+        sessions_all.clear()
         streams.clear()
         import gc
 
@@ -353,13 +369,14 @@ def main():
             for x in sessions:
                 x.upload(wit, wz, seeds)
             step_device()
-            return [x.fetch() for x in sessions]
+            outs = [x.fetch() for x in sessions]
+            return outs, [sharding.gather_parts(c, p) for c, p in outs]  # rank 0 ends up with the B assembled proofs
         for _ in range(args.warmup):
             step_e2e()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            outs = step_e2e()
+            outs, proofs = step_e2e()
         barrier()
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")

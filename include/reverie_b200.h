@@ -164,9 +164,15 @@ int rv_session_create(const rv_circuit *c, int first_instance, int n_instances, 
 void rv_session_free(rv_session *s);
 int rv_session_upload(rv_session *s, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64, size_t n_z64,
                       const uint8_t *seeds /* all 256 x 16, or NULL = OS RNG */);
-int rv_session_commit(rv_session *s);                                   /* async on the session stream */
+int rv_session_commit(rv_session *s);                                   /* async on the session stream; one CUDA graph launch after the first call */
 int rv_session_hashes(rv_session *s, uint8_t *rep_hashes);              /* synchronises                */
-int rv_session_open(rv_session *s, const uint8_t *all_rep_hashes);      /* async; NULL = own hashes (single shard) */
+/* Device pointer to this shard's n_instances * 8 * 32 bytes of repetition hashes: valid once rv_session_commit has been
+ * enqueued, to be read by work ordered after it on the session stream (e.g. an NCCL all-gather launched on that stream). */
+const void *rv_session_hashes_device(rv_session *s);
+/* Device buffer of 256 x 32 bytes owned by the session: gather all repetition hashes straight into it (e.g. as the NCCL
+ * receive buffer) and pass the same pointer to rv_session_open -- no copy, and the open phase replays as one CUDA graph. */
+void *rv_session_all_hashes_device(rv_session *s);
+int rv_session_open(rv_session *s, const uint8_t *all_rep_hashes);      /* async; host or device pointer; NULL = own hashes (single shard) */
 int rv_session_prove(rv_session *s);                                    /* async: commit + open(own hashes) of a full shard as
                                                                            one CUDA graph launch after the first, eager, call */
 int rv_session_fetch(rv_session *s, uint8_t comm[RV_HASH_SIZE], uint8_t **part, size_t *part_len); /* synchronises */

@@ -271,15 +271,17 @@ struct rv_session {
     cudaStream_t st = nullptr, st_val = nullptr;
     bool own_stream = true;
     cudaEvent_t ev_fork = nullptr, ev_vals = nullptr;
-    cudaGraphExec_t graph_prove = nullptr;  // commit + open of a full-shard session as one launch
-    int prove_calls = 0;
-    uint64_t kernels_per_proof = 0, graph_launches_per_proof = 0;
+    // CUDA graphs: after one eager run a phase is captured once and replayed as a single launch
+    struct GraphSlot {
+        cudaGraphExec_t exec = nullptr;
+        int calls = 0;
+        uint64_t kernels = 0;
+    } g_prove /* commit + open of a full shard */, g_commit, g_open /* open from the session's own all-gather buffer */;
     // device buffers
     uint8_t *d_wit = nullptr, *d_seeds = nullptr, *d_pkeys = nullptr, *d_vals = nullptr;
-    uint32_t *d_ks = nullptr, *d_lane_mask = nullptr;
     uint64_t *d_rows = nullptr;
-    uint64_t *d_fresh_sm = nullptr, *d_exp_sm = nullptr;  // instance-major staging of the mask VM
-    size_t pitch_fresh = 0, pitch_exp = 0;
+    uint64_t *d_fresh_sm = nullptr;  // instance-major copy of the fresh masks for the mask VM
+    size_t pitch_fresh = 0;
     uint8_t *d_on = nullptr, *d_pre = nullptr;
     size_t pitch_on = 0, pitch_pre = 0;
     uint32_t *d_cv_on = nullptr, *d_cv_pre = nullptr, n_chunks_on = 1, n_chunks_pre = 1;
@@ -346,7 +348,8 @@ extern "C" void rv_session_free(rv_session *s) {
     if (s->h_vin) cudaFreeHost(s->h_vin);
     if (s->h_vout) cudaFreeHost(s->h_vout);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
-    if (s->graph_prove) cudaGraphExecDestroy(s->graph_prove);
+    for (rv_session::GraphSlot *g : {&s->g_prove, &s->g_commit, &s->g_open})
+        if (g->exec) cudaGraphExecDestroy(g->exec);
     if (s->ev_vals) cudaEventDestroy(s->ev_vals);
     if (s->st && s->own_stream) cudaStreamDestroy(s->st);
     if (s->st_val) cudaStreamDestroy(s->st_val);
@@ -409,12 +412,11 @@ extern "C" int rv_session_create(const rv_circuit *c, int first_instance, int n_
     }
     if (linear_uses_vm(c->dev)) {
         s->pitch_fresh = round_up((size_t)P.n_masks + 128, 128);
-        s->pitch_exp = round_up((size_t)P.n_lin + 32, 32);
-        if ((rc = dalloc(s, &s->d_fresh_sm, s->pitch_fresh * s->npi)) || (rc = dalloc(s, &s->d_exp_sm, s->pitch_exp * s->npi))) return bail(rc);
+        if ((rc = dalloc(s, &s->d_fresh_sm, s->pitch_fresh * s->npi))) return bail(rc);
     }
     if ((rc = dalloc(s, &s->d_wit, P.n_inputs)) || (rc = dalloc(s, &s->d_seeds, (size_t)s->nreps * 16)) ||
         (rc = dalloc(s, &s->d_pkeys, (size_t)s->nreps * 128)) || (rc = dalloc(s, &s->d_vals, round_up((size_t)P.n_vals + 1, 16))) ||
-        (rc = dalloc(s, &s->d_ks, (size_t)2 * s->npi * 1408)) || (rc = dalloc(s, &s->d_rk_plain, (size_t)45 * 64 * s->npi)) || (rc = dalloc(s, &s->d_lane_mask, 2 * s->npi)) ||
+        (rc = dalloc(s, &s->d_rk_plain, (size_t)45 * 64 * s->npi)) || 
         (rc = dalloc(s, &s->d_rows, (size_t)P.n_rows * s->npi)) || (rc = dalloc(s, &s->d_on, s->pitch_on * s->nreps)) ||
         (rc = dalloc(s, &s->d_pre, s->pitch_pre * s->nreps)) || (rc = dalloc(s, &s->d_cv_on, (size_t)s->n_chunks_on * s->nreps * 8)) ||
         (rc = dalloc(s, &s->d_cv_pre, (size_t)s->n_chunks_pre * s->nreps * 8)) || (rc = dalloc(s, &s->d_on_hash, (size_t)s->nreps * 32)) ||
@@ -535,8 +537,40 @@ extern "C" int rv_session_upload(rv_session *s, const uint8_t *wit_gf2, size_t n
     return RV_OK;
 }
 
-extern "C" int rv_session_commit(rv_session *s) {
-    if (!s) return fail(RV_E_ARG, "NULL session");
+// Runs `body` (a sequence of asynchronous launches on the session's streams) eagerly the first time and whenever per-kernel
+// timing is on; the second plain call captures it into a CUDA graph, later calls replay that graph with one launch.
+template <typename F>
+static int run_graphed(rv_session *s, rv_session::GraphSlot &g, F &&body) {
+    int rc;
+    if (s->timing || g.calls == 0) {
+        g.calls++;
+        const uint64_t before = s->launches;
+        rc = body();
+        g.kernels = s->launches - before;
+        return rc;
+    }
+    if (!g.exec) {
+        cudaGraph_t graph = nullptr;
+        const uint64_t before = s->launches;
+        CU(cudaStreamBeginCapture(s->st, cudaStreamCaptureModeThreadLocal));
+        rc = body();
+        cudaError_t e = cudaStreamEndCapture(s->st, &graph);
+        s->launches = before;
+        if (rc != RV_OK || e != cudaSuccess) {
+            if (graph) cudaGraphDestroy(graph);
+            cudaGetLastError();
+            return rc != RV_OK ? rc : fail(RV_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
+        }
+        e = cudaGraphInstantiate(&g.exec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return fail(RV_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+    }
+    CU(cudaGraphLaunch(g.exec, s->st));
+    s->launches += g.kernels;
+    return RV_OK;
+}
+
+static int commit_body(rv_session *s) {
     const rv_circuit *c = s->c;
     const Program &P = c->prog;
     const DevProgram &D = c->dev;
@@ -564,7 +598,7 @@ extern "C" int rv_session_commit(rv_session *s) {
     CU(cudaMemsetAsync(s->d_rows + (size_t)P.zero_row() * s->npi, 0, (size_t)s->npi * 8, s->st));
     {
         Scope k(s, "key_setup", 0);
-        launch_key_setup(s->d_seeds, nullptr, nullptr, nullptr, nslices, s->d_ks, s->d_lane_mask, s->d_pkeys, s->st, s->d_rk_plain);
+        launch_key_setup(s->d_seeds, nullptr, nullptr, nullptr, nslices, s->d_pkeys, s->d_rk_plain, s->st);
     }
     {
         Scope k(s, "mask_gen", (uint64_t)P.n_masks * s->npi * 8);
@@ -572,8 +606,8 @@ extern "C" int rv_session_commit(rv_session *s) {
     }
     if (D.n_llevels) {
         const double avg_width = (double)D.n_xgates / D.n_llevels;
-        Scope k(s, "linear", (uint64_t)P.n_lin * s->npi * 8 * 3, avg_width < 4096.0 ? (s->d_fresh_sm ? 2 : 1) : D.n_llevels);
-        launch_linear(D, P.xlevel_off.data(), s->d_rows, s->npi, s->d_fresh_sm, s->pitch_fresh, s->d_exp_sm, s->pitch_exp, s->st, nullptr);
+        Scope k(s, "linear", (uint64_t)P.n_lin * s->npi * 8 * 3, avg_width < 4096.0 ? 1 : D.n_llevels);
+        launch_linear(D, P.xlevel_off.data(), s->d_rows, s->npi, s->d_fresh_sm, s->pitch_fresh, s->st, nullptr);
     }
     if (s->has_z) {
         {
@@ -617,8 +651,15 @@ extern "C" int rv_session_commit(rv_session *s) {
                         nullptr, nullptr, s->has_z ? s->d_zrep : nullptr);
     }
     CU(cudaGetLastError());
-    s->committed = s->ever_committed = true;
     return RV_OK;
+}
+
+extern "C" int rv_session_commit(rv_session *s) {
+    if (!s) return fail(RV_E_ARG, "NULL session");
+    CU(cudaSetDevice(s->c->device));
+    const int rc = run_graphed(s, s->g_commit, [&] { return commit_body(s); });
+    if (rc == RV_OK) s->committed = s->ever_committed = true;
+    return rc;
 }
 
 extern "C" int rv_session_hashes(rv_session *s, uint8_t *rep_hashes) {
@@ -630,14 +671,17 @@ extern "C" int rv_session_hashes(rv_session *s, uint8_t *rep_hashes) {
     return RV_OK;
 }
 
-extern "C" int rv_session_open(rv_session *s, const uint8_t *all_rep_hashes) {
-    if (!s) return fail(RV_E_ARG, "NULL session");
-    if (!s->committed) return fail(RV_E_ARG, "rv_session_commit has not run");
+extern "C" const void *rv_session_hashes_device(rv_session *s) { return (s && s->committed) ? s->d_rep_hash : nullptr; }
+
+extern "C" void *rv_session_all_hashes_device(rv_session *s) { return s ? s->d_all_hashes : nullptr; }
+
+static int open_body(rv_session *s, const uint8_t *all_rep_hashes) {
     const rv_circuit *c = s->c;
     const DevProgram &D = c->dev;
-    CU(cudaSetDevice(c->device));
     const uint8_t *hashes = s->d_all_hashes;
-    if (all_rep_hashes) {
+    if (all_rep_hashes == s->d_all_hashes) {
+        // gathered in place (rv_session_all_hashes_device): nothing to copy
+    } else if (all_rep_hashes) {
         cudaPointerAttributes at;
         const bool on_device = cudaPointerGetAttributes(&at, all_rep_hashes) == cudaSuccess && at.type == cudaMemoryTypeDevice;
         cudaGetLastError();
@@ -698,8 +742,18 @@ extern "C" int rv_session_open(rv_session *s, const uint8_t *all_rep_hashes) {
     CU(cudaMemcpyAsync(s->h_out + s->proof_len, s->d_bad, 4, cudaMemcpyDeviceToHost, s->st));
     CU(cudaMemcpyAsync(s->h_out + s->proof_len + 4, s->d_comm, 32, cudaMemcpyDeviceToHost, s->st));
     CU(cudaGetLastError());
-    s->opened = true;
     return RV_OK;
+}
+
+extern "C" int rv_session_open(rv_session *s, const uint8_t *all_rep_hashes) {
+    if (!s) return fail(RV_E_ARG, "NULL session");
+    if (!s->committed) return fail(RV_E_ARG, "rv_session_commit has not run");
+    CU(cudaSetDevice(s->c->device));
+    int rc;
+    if (all_rep_hashes == s->d_all_hashes) rc = run_graphed(s, s->g_open, [&] { return open_body(s, all_rep_hashes); });
+    else rc = open_body(s, all_rep_hashes);  // caller-owned buffer: its address may change from call to call
+    if (rc == RV_OK) s->opened = true;
+    return rc;
 }
 
 // commit + open(own hashes) of a full-shard session.  After one eager run the sequence (12 kernels on two streams, memsets,
@@ -708,37 +762,12 @@ extern "C" int rv_session_prove(rv_session *s) {
     if (!s) return fail(RV_E_ARG, "NULL session");
     if (s->npi != RV_PACKED_REPS) return fail(RV_E_ARG, "rv_session_prove needs a full shard");
     CU(cudaSetDevice(s->c->device));
-    int rc;
-    if (s->timing || s->prove_calls == 0) {
-        s->prove_calls++;
-        const uint64_t before = s->launches;
-        if ((rc = rv_session_commit(s)) != RV_OK) return rc;
-        rc = rv_session_open(s, nullptr);
-        s->kernels_per_proof = s->launches - before;
-        return rc;
-    }
-    if (!s->graph_prove) {
-        cudaGraph_t g = nullptr;
-        const uint64_t launches_before = s->launches;
-        CU(cudaStreamBeginCapture(s->st, cudaStreamCaptureModeThreadLocal));
-        rc = rv_session_commit(s);
-        if (rc == RV_OK) rc = rv_session_open(s, nullptr);
-        cudaError_t e = cudaStreamEndCapture(s->st, &g);
-        if (rc != RV_OK || e != cudaSuccess) {
-            if (g) cudaGraphDestroy(g);
-            cudaGetLastError();
-            return rc != RV_OK ? rc : fail(RV_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
-        }
-        s->launches = launches_before;
-        e = cudaGraphInstantiate(&s->graph_prove, g, 0);
-        cudaGraphDestroy(g);
-        if (e != cudaSuccess) return fail(RV_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
-        s->graph_launches_per_proof = 13;
-    }
-    CU(cudaGraphLaunch(s->graph_prove, s->st));
-    s->launches += s->kernels_per_proof;
-    s->committed = s->opened = s->ever_committed = true;
-    return RV_OK;
+    const int rc = run_graphed(s, s->g_prove, [&] {
+        const int r = commit_body(s);
+        return r != RV_OK ? r : open_body(s, nullptr);
+    });
+    if (rc == RV_OK) s->committed = s->opened = s->ever_committed = true;
+    return rc;
 }
 
 extern "C" int rv_session_fetch(rv_session *s, uint8_t comm[RV_HASH_SIZE], uint8_t **part, size_t *part_len) {
@@ -887,7 +916,7 @@ static int verify_on_session(rv_session *s, const uint8_t *proof, size_t proof_l
     const VOpen *d_opens = reinterpret_cast<const VOpen *>(dv + o_opens);
     {
         Scope k(s, "v.key_setup", 0);
-        launch_key_setup(dv + o_seeds, dv + o_pkeys, dv + o_mode, dv + o_omit, nslices, s->d_ks, s->d_lane_mask, s->d_pkeys, s->st, s->d_rk_plain);
+        launch_key_setup(dv + o_seeds, dv + o_pkeys, dv + o_mode, dv + o_omit, nslices, s->d_pkeys, s->d_rk_plain, s->st);
     }
     {
         Scope k(s, "v.mask_gen", (uint64_t)P.n_masks * s->npi * 8);
@@ -895,7 +924,7 @@ static int verify_on_session(rv_session *s, const uint8_t *proof, size_t proof_l
     }
     if (D.n_llevels) {
         Scope k(s, "v.linear", (uint64_t)P.n_lin * s->npi * 8 * 3, 2);
-        launch_linear(D, P.xlevel_off.data(), s->d_rows, s->npi, s->d_fresh_sm, s->pitch_fresh, s->d_exp_sm, s->pitch_exp, s->st, nullptr);
+        launch_linear(D, P.xlevel_off.data(), s->d_rows, s->npi, s->d_fresh_sm, s->pitch_fresh, s->st, nullptr);
     }
     {
         Scope k(s, "v.leaves", 0);
@@ -919,7 +948,7 @@ static int verify_on_session(rv_session *s, const uint8_t *proof, size_t proof_l
         const ZOpen *d_zopens = reinterpret_cast<const ZOpen *>(dv + o_zopens);
         if (z_own_keys) {  // a (dishonest) proof whose Z64 openings name other keys: the reference would use them, so do we
             Scope k(s, "v.z.key_setup", 0);
-            launch_key_setup(dv + o_zseeds, dv + o_zpkeys, dv + o_mode, dv + o_zomit, nslices, s->d_ks, s->d_lane_mask, s->d_pkeys, s->st, s->d_rk_plain);
+            launch_key_setup(dv + o_zseeds, dv + o_zpkeys, dv + o_mode, dv + o_zomit, nslices, s->d_pkeys, s->d_rk_plain, s->st);
         }
         {
             Scope k(s, "v.z.mask_gen", (uint64_t)P.z.n_masks * s->zrowlen * 8);

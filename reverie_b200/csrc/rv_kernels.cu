@@ -5,7 +5,6 @@
 #include <algorithm>
 
 #include "rv_kernels.cuh"
-#include "rv_maskgen.cuh"
 #include "rv_planes.cuh"
 
 namespace rv {
@@ -15,10 +14,11 @@ namespace rv {
 // =====================================================================================================================
 // Lane q owns the stream that lives at bit q of the slice word: stream index 31-q = 8*rep_in_slice + player.
 // Slice w: packed instance w/2; odd w = high u32 (repetitions 0..3), even w = low u32 (repetitions 4..7).
+// Output: rk_plain [45][32 * nslices] -- the 44 round-key words of every stream (stream = 8 * rep + player) and a row of
+// all-ones / zero "stream is active" words (the verifier's unopened player stays zero, src/generator/batch.rs:31-34).
 __global__ void __launch_bounds__(128) k_key_setup(const uint8_t *__restrict__ seeds, const uint8_t *__restrict__ pkeys_in,
                                                    const uint8_t *__restrict__ mode, const uint8_t *__restrict__ omit, uint32_t nslices,
-                                                   uint32_t *__restrict__ ks, uint32_t *__restrict__ lane_mask, uint8_t *__restrict__ pkeys_out,
-                                                   uint32_t *__restrict__ rk_plain) {
+                                                   uint8_t *__restrict__ pkeys_out, uint32_t *__restrict__ rk_plain) {
     __shared__ uint32_t sbox32[64];  // the S-box as a byte table, built from the netlist (4 entries per thread)
     if (threadIdx.x < 64) {
         const uint32_t b = 4 * threadIdx.x;
@@ -31,86 +31,21 @@ __global__ void __launch_bounds__(128) k_key_setup(const uint8_t *__restrict__ s
     const uint32_t rep = slice_rep(w, lane), p = slice_player(lane);
     uint32_t rk[44];
     const bool active = key_setup_stream(rep, p, seeds, pkeys_in, mode, omit, pkeys_out, rk, sw);
-    const uint32_t am = __ballot_sync(0xffffffffu, active);
-    if (lane == 0) lane_mask[w] = am;
-    if (rk_plain != nullptr) {  // Z64 generator: plain round keys, [44][streams] (+ row 44: stream is active), stream = 8 * rep + player
-        const uint32_t ns = nslices * 32, sidx = 8 * rep + p;
-#pragma unroll 1
-        for (int q = 0; q < 44; q++) rk_plain[(size_t)q * ns + sidx] = rk[q];
-        rk_plain[(size_t)44 * ns + sidx] = active ? 0xFFFFFFFFu : 0u;
-    }
-    // bitslice: plane k of round R = bit k of the 128-bit little-endian round key, gathered over the 32 lanes
-#pragma unroll 1
-    for (int q = 0; q < 44; q++) {
-        const uint32_t word = rk[q];
-        uint32_t mine = 0;
+    const uint32_t ns = nslices * 32, sidx = 8 * rep + p;
 #pragma unroll
-        for (int i = 0; i < 32; i++) {
-            const uint32_t b = __ballot_sync(0xffffffffu, (word >> i) & 1u);
-            if (lane == (uint32_t)i) mine = b;
-        }
-        ks[(size_t)w * 1408 + q * 32 + lane] = mine;
-    }
+    for (int q = 0; q < 44; q++) rk_plain[(size_t)q * ns + sidx] = rk[q];
+    rk_plain[(size_t)44 * ns + sidx] = active ? 0xFFFFFFFFu : 0u;
 }
 
 void launch_key_setup(const uint8_t *seeds, const uint8_t *pkeys_in, const uint8_t *mode, const uint8_t *omit, uint32_t nslices,
-                      uint32_t *ks, uint32_t *lane_mask, uint8_t *pkeys_out, cudaStream_t st, uint32_t *rk_plain) {
-    k_key_setup<<<(nslices + 3) / 4, 128, 0, st>>>(seeds, pkeys_in, mode, omit, nslices, ks, lane_mask, pkeys_out, rk_plain);
+                      uint8_t *pkeys_out, uint32_t *rk_plain, cudaStream_t st) {
+    k_key_setup<<<(nslices + 3) / 4, 128, 0, st>>>(seeds, pkeys_in, mode, omit, nslices, pkeys_out, rk_plain);
 }
 
 // =====================================================================================================================
-//  K2  mask generation: bitsliced AES-128-CTR, thread = (slice, counter block)
+//  K2  mask generation: AES-128-CTR of every PRG stream, transposed into packed share words
 // =====================================================================================================================
-__global__ void __launch_bounds__(MG_THREADS) k_mask_gen(const uint32_t *__restrict__ ks, const uint32_t *__restrict__ lane_mask,
-                                                         uint32_t nslices, uint32_t n_masks, uint32_t *__restrict__ rows32,
-                                                         uint64_t *__restrict__ fresh_pm, size_t pitch_pm) {
-    __shared__ uint4 sk[11 * 32 * MG_SLICES];
-    const uint32_t w0 = blockIdx.y * MG_SLICES;
-    load_round_keys(sk, ks, w0, nslices);
-    __syncthreads();
-    const uint32_t sl = threadIdx.x % MG_SLICES, w = w0 + sl;
-    const uint64_t j = (uint64_t)blockIdx.x * MG_COUNTERS + threadIdx.x / MG_SLICES;
-    if (w >= nslices || j * 128 >= n_masks) return;
-    uint32_t s[128];
-    SmemRoundKeys rk{sk, sl};
-    aes_ctr_block_smem(j, rk, s);
-    const uint32_t lm = lane_mask[w];
-#pragma unroll
-    for (int k = 0; k < 128; k++) {
-        s[k] &= lm;
-        const uint64_t i = plane_to_mask_index(j, k);
-        if (i < n_masks) rows32[i * nslices + w] = s[k];
-    }
-    if (fresh_pm != nullptr) {
-        // Instance-major copy for the mask VM: fresh_pm[pi][i] = the whole u64 share word.  The two slices of an instance sit
-        // in adjacent lanes (even w = low half, odd w = high half); they swap halves of their 128 masks by shuffle so that each
-        // lane stores 64 complete words = 512 contiguous bytes.  (Pairs exit together above: same j, nslices is even.)
-        const uint32_t act = __activemask(), odd = w & 1;
-        uint4 *dst = reinterpret_cast<uint4 *>(fresh_pm + (size_t)(w >> 1) * pitch_pm + j * 128 + 64 * odd);
-#pragma unroll
-        for (int q = 0; q < 32; q++) {  // masks m = 2q, 2q+1 of this lane's half; mask m of the block = plane 8 (m / 8) + 7 - m % 8
-            uint32_t mine[2], theirs[2];
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                const int m = 2 * q + h, p_lo = 8 * (m >> 3) + 7 - (m & 7), p_hi = 8 * ((m + 64) >> 3) + 7 - (m & 7);
-                const uint32_t send = odd ? s[p_lo] : s[p_hi];  // what the partner stores
-                theirs[h] = __shfl_xor_sync(act, send, 1);
-                mine[h] = odd ? s[p_hi] : s[p_lo];
-            }
-            dst[q] = odd ? make_uint4(theirs[0], mine[0], theirs[1], mine[1]) : make_uint4(mine[0], theirs[0], mine[1], theirs[1]);
-        }
-    }
-}
-
-void launch_mask_gen(const uint32_t *ks, const uint32_t *lane_mask, uint32_t nslices, uint32_t n_masks, uint64_t *rows, uint64_t *fresh_pm,
-                     size_t pitch_pm, cudaStream_t st) {
-    if (n_masks == 0) return;
-    const uint32_t n_blocks = (n_masks + 127) / 128;
-    dim3 grid((n_blocks + MG_COUNTERS - 1) / MG_COUNTERS, (nslices + MG_SLICES - 1) / MG_SLICES);
-    k_mask_gen<<<grid, MG_THREADS, 0, st>>>(ks, lane_mask, nslices, n_masks, reinterpret_cast<uint32_t *>(rows), fresh_pm, pitch_pm);
-}
-
-// ---- T-table variant (the default).  A warp = one slice: lane q runs AES-128 for the PRG stream that lives at bit q of the
+// T-table AES.  A warp = one slice: lane q runs AES-128 for the PRG stream that lives at bit q of the
 //      slice word (its 44 round-key words in registers), one counter block at a time, with Te0 / Te2 replicated once per
 //      shared-memory bank (64 KB; Te1 / Te3 are byte rotations), so the 160 data-dependent lookups per block never conflict.
 //      Five shuffle-exchange stages per keystream word then transpose the warp's 32 x 128 keystream bits into the 128 share
@@ -429,18 +364,18 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
 }
 
 __global__ void __launch_bounds__(VM_THREADS) k_mask_vm(const VmInstr *__restrict__ prog, uint32_t n_steps, const uint64_t *__restrict__ fresh_pm,
-                                                        size_t pitch_fresh, uint64_t *__restrict__ exp_pm, size_t pitch_exp, uint32_t n_masks) {
+                                                        size_t pitch_fresh, uint64_t *__restrict__ rows, uint32_t npi) {
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t n_chunks = (n_steps + VM_STEPS_PER_CHUNK - 1) / VM_STEPS_PER_CHUNK;
     VmStream stream;
     stream.init(smem, prog, n_chunks, (n_steps - (n_chunks ? n_chunks - 1 : 0) * VM_STEPS_PER_CHUNK) * VM_STEP * (uint32_t)sizeof(VmInstr));
     uint64_t *cells = reinterpret_cast<uint64_t *>(smem + VmStream::BYTES);
     const uint32_t tid = threadIdx.x, pi = blockIdx.x;
-    // Global traffic is instance-major on both sides, so a warp's 32 accesses fall into a few 128-byte lines: LOADs of a level
-    // are sorted by row, exported rows are numbered in program order.  (Row-major, each lane would touch its own 256-byte
-    // row and the kernel would be bound by L1 request rate.)
+    // LOADs read the instance-major copy of the fresh masks, so a warp's 32 requests (sorted by row inside a level) fall into a
+    // few 128-byte lines.  Exported rows go straight into the row-major share tensor as 8-byte stores: the tensor of a
+    // VM-sized circuit lives in L2, which merges the 32 instances' pieces of a row before the item plane reads it.
     const uint64_t *src = fresh_pm + (size_t)pi * pitch_fresh;
-    uint64_t *dst = exp_pm + (size_t)pi * pitch_exp - n_masks;
+    uint64_t *dst = rows + pi;
     if (tid == 0) cells[0] = 0;  // cell 0 is the constant zero (first read happens after the first barrier)
     for (uint32_t c = 0; c < n_chunks; c++) {
         const uint32_t img = stream.begin_chunk(c) + tid * (uint32_t)sizeof(VmInstr);  // 5-word stride: conflict-free LDS.32
@@ -463,7 +398,7 @@ __global__ void __launch_bounds__(VM_THREADS) k_mask_vm(const VmInstr *__restric
                     const uint64_t v = cells[u[k][2] & 0xFFFFu] ^ cells[u[k][2] >> 16] ^ cells[u[k][3] & 0xFFFFu] ^ cells[u[k][3] >> 16] ^
                                        cells[u[k][4] & 0xFFFFu] ^ cells[u[k][4] >> 16];
                     cells[d] = v;
-                    if (row != VM_ROW_NONE) dst[row] = v;
+                    if (row != VM_ROW_NONE) dst[(size_t)row * npi] = v;
                 }
                 if (fl & VM_F_LEVEL_END) {  // one cp.async group per level; LOADs of level L-2 are complete before level L starts
                     __pipeline_commit();
@@ -506,19 +441,6 @@ __global__ void __launch_bounds__(256) k_linear_level(const XGate *__restrict__ 
     rows[(size_t)gt.dst * npi + pi] = xor6(rows, gt, npi, pi);
 }
 
-// exp_pm [npi][pitch] (instance-major, written by the VM) -> rows[n_masks + e][npi] (row-major, read by the item plane)
-__global__ void __launch_bounds__(256) k_export_transpose(const uint64_t *__restrict__ exp_pm, size_t pitch, uint32_t n_lin, uint32_t npi,
-                                                          uint64_t *__restrict__ rows_lin) {
-    __shared__ uint64_t tile[32][33];
-    const uint32_t e0 = blockIdx.x * 32, lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-    for (uint32_t p = wrp; p < npi; p += 8) tile[p][lane] = (e0 + lane < n_lin) ? exp_pm[(size_t)p * pitch + e0 + lane] : 0ull;
-    __syncthreads();
-    for (uint32_t idx = threadIdx.x; idx < 32 * npi; idx += 256) {
-        const uint32_t r = idx / npi, p = idx % npi;
-        if (e0 + r < n_lin) rows_lin[(size_t)(e0 + r) * npi + p] = tile[p][r];
-    }
-}
-
 static size_t vm_smem_bytes(const DevProgram &P) { return VmStream::BYTES + ((size_t)P.vm_cells + 1) * 8; }
 bool linear_uses_vm(const DevProgram &P) {
     if (P.n_llevels == 0 || (double)P.n_xgates / P.n_llevels >= 4096.0) return false;
@@ -526,7 +448,7 @@ bool linear_uses_vm(const DevProgram &P) {
 }
 
 int launch_linear(const DevProgram &P, const uint32_t *off_host, uint64_t *rows, uint32_t npi, const uint64_t *fresh_sm, size_t pitch_fresh,
-                  uint64_t *exp_sm, size_t pitch_exp, cudaStream_t st, int *which) {
+                  cudaStream_t st, int *which) {
     if (which) *which = -1;
     if (P.n_llevels == 0) return 0;
     const double avg_width = (double)P.n_xgates / P.n_llevels;
@@ -539,16 +461,15 @@ int launch_linear(const DevProgram &P, const uint32_t *off_host, uint64_t *rows,
         }
         return (int)P.n_llevels;
     }
-    if (linear_uses_vm(P) && fresh_sm && exp_sm) {
+    if (linear_uses_vm(P) && fresh_sm) {
         static bool configured = false;
         if (!configured) {
             cudaFuncSetAttribute(k_mask_vm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DYN_CAP);
             configured = true;
         }
         if (which) *which = 0;
-        k_mask_vm<<<npi, VM_THREADS, vm_smem_bytes(P), st>>>(P.vm_steps, P.n_vm_steps, fresh_sm, pitch_fresh, exp_sm, pitch_exp, P.n_masks);
-        k_export_transpose<<<(P.n_lin + 31) / 32, 256, 0, st>>>(exp_sm, pitch_exp, P.n_lin, npi, rows + (size_t)P.n_masks * npi);
-        return 2;
+        k_mask_vm<<<npi, VM_THREADS, vm_smem_bytes(P), st>>>(P.vm_steps, P.n_vm_steps, fresh_sm, pitch_fresh, rows, npi);
+        return 1;
     }
     if (which) *which = 1;
     k_linear_cta<<<npi, LIN_THREADS, 0, st>>>(P.xgates, P.xlevel_off, P.n_llevels, rows, npi);

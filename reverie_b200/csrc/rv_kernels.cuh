@@ -47,16 +47,13 @@ struct DevZProgram {
     uint32_t on_bytes = 0, pre_bytes = 0;
 };
 
-// K1  seeds -> player keys -> bitsliced round keys (src/transcript/mod.rs:99-106, src/crypto/prg.rs:16-20)
+// K1  seeds -> player keys -> AES round keys (src/transcript/mod.rs:99-106, src/crypto/prg.rs:16-20)
+//     rk_plain: [45][32 * nslices] u32 -- the 44 round-key words of every stream (stream = 8 * rep + player), then a row of
+//     all-ones / zero "stream is active" words
 void launch_key_setup(const uint8_t *seeds, const uint8_t *pkeys_in, const uint8_t *mode, const uint8_t *omit, uint32_t nslices,
-                      uint32_t *ks, uint32_t *lane_mask, uint8_t *pkeys_out, cudaStream_t st, uint32_t *rk_plain = nullptr);
-//     rk_plain (optional, Z64 circuits): [45][32 * nslices] u32 -- the 44 plain round-key words of every stream (stream = 8 * rep +
-//     player) and a row of all-ones / zero "stream is active" words, for the T-table generator
-// K2  AES-CTR mask generation straight into the share tensor (src/generator/share.rs:54-65)
+                      uint8_t *pkeys_out, uint32_t *rk_plain, cudaStream_t st);
+// K2  AES-CTR mask generation straight into the share tensor (src/generator/share.rs:54-65, src/algebra/gf2/domain.rs:66-173)
 //     also writes the instance-major copy `fresh_pm` [npi][pitch_pm] (u64) that the mask VM loads from (nullptr = skip)
-void launch_mask_gen(const uint32_t *ks, const uint32_t *lane_mask, uint32_t nslices, uint32_t n_masks, uint64_t *rows, uint64_t *fresh_pm,
-                     size_t pitch_pm, cudaStream_t st);
-//     T-table generator (default): same outputs from the plain round keys written by launch_key_setup(..., rk_plain)
 void launch_mask_gen_tt(const uint32_t *rk_plain, uint32_t nslices, uint32_t n_masks, uint64_t *rows, uint64_t *fresh_pm, size_t pitch_pm, int n_sms,
                         cudaStream_t st);
 // K0  value plane (plaintext evaluation; one CTA, level-synchronous).  Returns the dynamic smem it asked for.
@@ -66,9 +63,9 @@ size_t launch_values(const LutInstr *steps, uint32_t n_steps, const uint32_t *le
 int launch_values_wide(const DevProgram &P, const uint32_t *lut_level_off_host, const uint8_t *wit, uint8_t *vals, cudaStream_t st);
 // K3  mask plane (XOR network over the share tensor)
 //     returns the number of kernel launches; *which (optional) names the variant: 0 VM (smem cells), 1 CTA walker, 2 per level
-//     fresh_pm / exp_pm: instance-major staging buffers of the VM variant ([npi][pitch] u64 each)
+//     fresh_pm: instance-major copy of the fresh masks for the VM variant ([npi][pitch] u64)
 int launch_linear(const DevProgram &P, const uint32_t *llevel_off_host, uint64_t *rows, uint32_t npi, const uint64_t *fresh_pm, size_t pitch_fresh,
-                  uint64_t *exp_pm, size_t pitch_exp, cudaStream_t st, int *which = nullptr);
+                  cudaStream_t st, int *which = nullptr);
 bool linear_uses_vm(const DevProgram &P);
 // K4  item plane: the two hash streams of every repetition
 void launch_items(const DevProgram &P, const uint64_t *rows, uint32_t npi, const uint8_t *vals, uint8_t *on, size_t pitch_on,
@@ -115,8 +112,6 @@ void launch_extract(const DevProgram &P, const ExtractArgs &a, cudaStream_t st);
 
 // ---- Z64 domain (rv_z64.cu) ------------------------------------------------------------------------------------------
 struct ZOpen;
-void launch_zmask_gen(const uint32_t *ks, const uint32_t *lane_mask, uint32_t nslices, uint32_t n_masks, uint64_t *zrows, size_t rowlen,
-                      cudaStream_t st);  // bitsliced variant (kept for cross-checking the T-table generator)
 void launch_zmask_gen_tt(const uint32_t *rk_plain, uint32_t nstreams, uint32_t n_masks, uint64_t *zrows, int n_sms, cudaStream_t st);
 int launch_zlinear(const DevZProgram &Z, const uint32_t *llevel_off_host, uint64_t *zrows, uint32_t rowlen, cudaStream_t st);
 void launch_zvalues(const DevZProgram &Z, const uint64_t *leaf_vals, size_t leaf_pitch, uint64_t *vals, size_t vals_pitch, uint32_t n_instances,

@@ -3,50 +3,15 @@
 #include <algorithm>
 
 #include "rv_kernels.cuh"
-#include "rv_maskgen.cuh"
 #include "rv_zplanes.cuh"
 
 namespace rv {
 
 // =====================================================================================================================
-//  ZK2  Z64 mask generation: the same bitsliced AES-128-CTR as the GF(2) generator (thread = slice x counter block), then
-//       four 32x32 bit transposes turn the 128 planes back into each stream's 16 keystream bytes = Z64 masks 2j, 2j+1
-//       (src/algebra/z64/batch.rs:25-30, src/algebra/z64/domain.rs:64-83).  A thread stores 2 x 256 contiguous bytes.
+//  ZK2  Z64 mask generation (src/algebra/z64/batch.rs:25-30, src/algebra/z64/domain.rs:64-83): mask i of a stream is the
+//       little-endian u64 at keystream byte 8 i, i.e. AES block j = masks 2j, 2j+1 in natural byte order.
 // =====================================================================================================================
-__global__ void __launch_bounds__(MG_THREADS) k_zmask_gen(const uint32_t *__restrict__ ks, const uint32_t *__restrict__ lane_mask, uint32_t nslices,
-                                                          uint32_t n_masks, uint64_t *__restrict__ zrows, size_t rowlen) {
-    __shared__ uint4 sk[11 * 32 * MG_SLICES];
-    const uint32_t w0 = blockIdx.y * MG_SLICES;
-    load_round_keys(sk, ks, w0, nslices);
-    __syncthreads();
-    const uint32_t sl = threadIdx.x % MG_SLICES, w = w0 + sl;
-    const uint64_t j = (uint64_t)blockIdx.x * MG_COUNTERS + threadIdx.x / MG_SLICES;
-    if (w >= nslices || 2 * j >= n_masks) return;
-    uint32_t s[128];
-    SmemRoundKeys rk{sk, sl};
-    aes_ctr_block_smem(j, rk, s);
-    const uint32_t lm = lane_mask[w];
-    const uint32_t base = zrow_index(w, 0);
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        if (2 * j + h >= n_masks) break;
-        uint32_t lo[32], hi[32];
-        planes_to_mask_words(s, lm, h, lo, hi);
-        uint4 *dst = reinterpret_cast<uint4 *>(zrows + (size_t)(2 * j + h) * rowlen + base);
-#pragma unroll
-        for (int q = 0; q < 16; q++) dst[q] = make_uint4(lo[2 * q], hi[2 * q], lo[2 * q + 1], hi[2 * q + 1]);
-    }
-}
-
-void launch_zmask_gen(const uint32_t *ks, const uint32_t *lane_mask, uint32_t nslices, uint32_t n_masks, uint64_t *zrows, size_t rowlen,
-                      cudaStream_t st) {
-    if (n_masks == 0) return;
-    const uint32_t n_blocks = (n_masks + 1) / 2;
-    dim3 grid((n_blocks + MG_COUNTERS - 1) / MG_COUNTERS, (nslices + MG_SLICES - 1) / MG_SLICES);
-    k_zmask_gen<<<grid, MG_THREADS, 0, st>>>(ks, lane_mask, nslices, n_masks, zrows, rowlen);
-}
-
-// ---- T-table variant: thread = one PRG stream (its 44 round-key words in registers), looping over counter blocks; a warp =
+//      T-table AES: thread = one PRG stream (its 44 round-key words in registers), looping over counter blocks; a warp =
 //      32 consecutive streams, so every mask leaves as one 256-byte row segment.  The four 1 KB Te tables are replicated
 //      once per shared-memory bank (128 KB): lane l only ever reads words = l (mod 32), so the 32 data-dependent lookups
 //      of a warp are conflict-free and the generator is bound by the LDS pipe (160 lookups per block) instead of the

@@ -48,7 +48,25 @@ RV_HD void planes_to_mask_words(const uint32_t s[128], uint32_t lane_mask, int h
 // element index of (slice w, stream sigma) inside a zrow
 RV_HD uint32_t zrow_index(uint32_t w, uint32_t sigma) { return 64 * (w >> 1) + ((w & 1) ? 0u : 32u) + sigma; }
 
-RV_HD uint64_t zsum8(const uint64_t *p) { return p[0] + p[1] + p[2] + p[3] + p[4] + p[5] + p[6] + p[7]; }
+// one (row, repetition) segment = 8 players x u64 = 64 bytes, 64-byte aligned: four 16-byte loads
+struct alignas(16) ZPair {
+    uint64_t x, y;
+};
+RV_HD void zload8(const uint64_t *p, uint64_t v[8]) {
+    const ZPair *q = reinterpret_cast<const ZPair *>(p);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const ZPair t = q[i];
+        v[2 * i] = t.x;
+        v[2 * i + 1] = t.y;
+    }
+}
+RV_HD uint64_t zsum8v(const uint64_t v[8]) { return v[0] + v[1] + v[2] + v[3] + v[4] + v[5] + v[6] + v[7]; }
+RV_HD uint64_t zsum8(const uint64_t *p) {
+    uint64_t v[8];
+    zload8(p, v);
+    return zsum8v(v);
+}
 RV_HD void put64(uint8_t *p, uint64_t v) { *reinterpret_cast<uint64_t *>(p) = v; }  // all stream offsets are multiples of 8
 RV_HD uint64_t get64_unaligned(const uint8_t *p) {
     uint64_t v = 0;
@@ -67,8 +85,9 @@ RV_HD void z_prover_online(const ZItem &it, const uint64_t *zrows, size_t rowlen
         return;
     }
     uint64_t a[8];
+    zload8(A, a);
 #pragma unroll
-    for (int p = 0; p < 8; p++) a[p] = it.ca * A[p];
+    for (int p = 0; p < 8; p++) a[p] *= it.ca;
     if (it.kind == ITEM_ASSERT) {
         if (vals[it.va] != 0) *bad |= 1;
 #pragma unroll
@@ -77,12 +96,15 @@ RV_HD void z_prover_online(const ZItem &it, const uint64_t *zrows, size_t rowlen
     }
     const uint64_t *B = zrows + (size_t)it.rb * rowlen + 8 * rep;
     const uint64_t *AB = zrows + (size_t)it.k * rowlen + 8 * rep, *NW = zrows + (size_t)(it.k + 1) * rowlen + 8 * rep;
-    uint64_t b[8];
+    uint64_t b[8], ab[8], nw[8];
+    zload8(B, b);
+    zload8(AB, ab);
+    zload8(NW, nw);
 #pragma unroll
-    for (int p = 0; p < 8; p++) b[p] = it.cb * B[p];
-    const uint64_t c1 = vals[it.va] - zsum8(a), c2 = vals[it.vb] - zsum8(b);  // corr = value - reconstruct(mask)
+    for (int p = 0; p < 8; p++) b[p] *= it.cb;
+    const uint64_t c1 = vals[it.va] - zsum8v(a), c2 = vals[it.vb] - zsum8v(b);  // corr = value - reconstruct(mask)
 #pragma unroll
-    for (int p = 0; p < 8; p++) put64(dst + 8 * p, b[p] * c1 + a[p] * c2 + AB[p] - NW[p]);  // single.rs:41-45
+    for (int p = 0; p < 8; p++) put64(dst + 8 * p, b[p] * c1 + a[p] * c2 + ab[p] - nw[p]);  // single.rs:41-45
 }
 
 // delta = a * b - c on reconstructed masks (single.rs:35-39)
@@ -126,8 +148,9 @@ RV_HD void z_verify_online(const ZItem &it, uint32_t recon_idx, const ZOpen &o, 
     const uint64_t msg = z_packed(proof, o.off_recons, o.n_recons, o.len_recons, recon_idx);  // the unopened player's broadcast (online.rs:140-160)
     const uint64_t *A = zrows + (size_t)it.ra * rowlen + 8 * slot;
     uint64_t a[8], s[8];
+    zload8(A, a);
 #pragma unroll
-    for (int p = 0; p < 8; p++) a[p] = it.ca * A[p];
+    for (int p = 0; p < 8; p++) a[p] *= it.ca;
     if (it.kind == ITEM_ASSERT) {
 #pragma unroll
         for (int p = 0; p < 8; p++) s[p] = a[p];
@@ -135,12 +158,15 @@ RV_HD void z_verify_online(const ZItem &it, uint32_t recon_idx, const ZOpen &o, 
     } else {
         const uint64_t *B = zrows + (size_t)it.rb * rowlen + 8 * slot;
         const uint64_t *AB = zrows + (size_t)it.k * rowlen + 8 * slot, *NW = zrows + (size_t)(it.k + 1) * rowlen + 8 * slot;
-        uint64_t b[8];
+        uint64_t b[8], ab[8], nw[8];
+        zload8(B, b);
+        zload8(AB, ab);
+        zload8(NW, nw);
 #pragma unroll
-        for (int p = 0; p < 8; p++) b[p] = it.cb * B[p];
-        const uint64_t c1 = uvals[it.va] - zsum8(a), c2 = uvals[it.vb] - zsum8(b);  // corr = u - rho
+        for (int p = 0; p < 8; p++) b[p] *= it.cb;
+        const uint64_t c1 = uvals[it.va] - zsum8v(a), c2 = uvals[it.vb] - zsum8v(b);  // corr = u - rho
 #pragma unroll
-        for (int p = 0; p < 8; p++) s[p] = b[p] * c1 + a[p] * c2 + AB[p] - NW[p];
+        for (int p = 0; p < 8; p++) s[p] = b[p] * c1 + a[p] * c2 + ab[p] - nw[p];
     }
 #pragma unroll
     for (int p = 0; p < 8; p++) put64(dst + 8 * p, s[p] + (p == (int)o.omit ? msg : 0ull));

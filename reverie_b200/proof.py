@@ -111,6 +111,32 @@ class Session:
         N.check(N.lib().rv_session_hashes(self._h, _ptr(out)))
         return out.tobytes()
 
+    def hashes_device(self):
+        """The shard's repetition hashes in device memory as an object exposing __cuda_array_interface__ (uint8,
+        n_instances * 256 bytes), e.g. `torch.as_tensor(s.hashes_device(), device="cuda")` for an NCCL all-gather on the
+        session stream -- no host round trip."""
+        ptr = int(N.lib().rv_session_hashes_device(self._h) or 0)
+        if not ptr:
+            raise N.ReverieError(N.E_ARG, "rv_session_commit has not run")
+        n = self.n_instances * 8 * 32
+
+        class _Dev:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+        return _Dev()
+
+    def all_hashes_device(self):
+        """The session's own 256 x 32-byte receive buffer for the all-gather (__cuda_array_interface__); pass its address to
+        open() afterwards: no copy, and the open phase replays as one CUDA graph."""
+        ptr = int(N.lib().rv_session_all_hashes_device(self._h) or 0)
+
+        class _Dev:
+            __cuda_array_interface__ = {"shape": (N.TOTAL_REPS * 32,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+        d = _Dev()
+        d.ptr = ptr
+        return d
+
     def open(self, all_rep_hashes=None):
         """all_rep_hashes: 256*32 bytes (host bytes / numpy) or an int device pointer; None = own hashes (single shard)."""
         if all_rep_hashes is None:

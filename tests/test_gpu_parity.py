@@ -324,3 +324,22 @@ def test_wide_layered_circuit(rb, default_seeds):
     assert circ.stats()["n_lut_steps"] == 0 and circ.stats()["n_luts"] > 0  # the wide path is the one that runs
     blob = _check(rb, ops, wit, (0, nw), default_seeds)
     assert rb.Proof(blob).verify(circ)
+
+
+def test_multi_gpu_nccl_sharded_prove(rb):
+    """One process per GPU over NCCL: needs >= 2 GPUs on the box; the proof must not depend on the sharding."""
+    import os
+    import subprocess
+    import sys
+
+    from reverie_b200 import _native
+
+    n = _native.lib().rv_device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    world = 2 if n < 4 else (4 if n < 8 else 8)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+                          "--master-port", "29533", os.path.join(root, "tests", "_mgpu_worker.py")], capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert res.stdout.count("mgpu ok") == 2
