@@ -222,6 +222,131 @@ def sha256_abc_case():
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+#  AES-128: generated Bristol-style circuit, 6400 AND gates = 200 S-boxes x 32 (Boyar-Peralta)
+# ---------------------------------------------------------------------------------------------------------------------
+# The 113-gate Boyar-Peralta S-box netlist (depth 27, 32 AND): the same netlist the kernels use for their key schedules
+# (csrc/rv_aes_bs.cuh: bs_sbox).  ('in', k) = input bit k (LSB = 0); outputs s0..s7 = output bits 7..0.
+_SBOX_NETLIST = (
+    ('x0', 'in', 7), ('x1', 'in', 6), ('x2', 'in', 5), ('x3', 'in', 4), ('x4', 'in', 3), ('x5', 'in', 2),
+    ('x6', 'in', 1), ('x7', 'in', 0), ('y14', 'xor', 'x3', 'x5'), ('y13', 'xor', 'x0', 'x6'),
+    ('y9', 'xor', 'x0', 'x3'), ('y8', 'xor', 'x0', 'x5'), ('t0', 'xor', 'x1', 'x2'), ('y1', 'xor', 't0', 'x7'),
+    ('y4', 'xor', 'y1', 'x3'), ('y12', 'xor', 'y13', 'y14'), ('y2', 'xor', 'y1', 'x0'), ('y5', 'xor', 'y1', 'x6'),
+    ('y3', 'xor', 'y5', 'y8'), ('t1', 'xor', 'x4', 'y12'), ('y15', 'xor', 't1', 'x5'), ('y20', 'xor', 't1', 'x1'),
+    ('y6', 'xor', 'y15', 'x7'), ('y10', 'xor', 'y15', 't0'), ('y11', 'xor', 'y20', 'y9'), ('y7', 'xor', 'x7', 'y11'),
+    ('y17', 'xor', 'y10', 'y11'), ('y19', 'xor', 'y10', 'y8'), ('y16', 'xor', 't0', 'y11'),
+    ('y21', 'xor', 'y13', 'y16'), ('y18', 'xor', 'x0', 'y16'), ('t2', 'and', 'y12', 'y15'),
+    ('t3', 'and', 'y3', 'y6'), ('t4', 'xor', 't3', 't2'), ('t5', 'and', 'y4', 'x7'), ('t6', 'xor', 't5', 't2'),
+    ('t7', 'and', 'y13', 'y16'), ('t8', 'and', 'y5', 'y1'), ('t9', 'xor', 't8', 't7'), ('t10', 'and', 'y2', 'y7'),
+    ('t11', 'xor', 't10', 't7'), ('t12', 'and', 'y9', 'y11'), ('t13', 'and', 'y14', 'y17'),
+    ('t14', 'xor', 't13', 't12'), ('t15', 'and', 'y8', 'y10'), ('t16', 'xor', 't15', 't12'),
+    ('t17', 'xor', 't4', 't14'), ('t18', 'xor', 't6', 't16'), ('t19', 'xor', 't9', 't14'),
+    ('t20', 'xor', 't11', 't16'), ('t21', 'xor', 't17', 'y20'), ('t22', 'xor', 't18', 'y19'),
+    ('t23', 'xor', 't19', 'y21'), ('t24', 'xor', 't20', 'y18'), ('t25', 'xor', 't21', 't22'),
+    ('t26', 'and', 't21', 't23'), ('t27', 'xor', 't24', 't26'), ('t28', 'and', 't25', 't27'),
+    ('t29', 'xor', 't28', 't22'), ('t30', 'xor', 't23', 't24'), ('t31', 'xor', 't22', 't26'),
+    ('t32', 'and', 't31', 't30'), ('t33', 'xor', 't32', 't24'), ('t34', 'xor', 't23', 't33'),
+    ('t35', 'xor', 't27', 't33'), ('t36', 'and', 't24', 't35'), ('t37', 'xor', 't36', 't34'),
+    ('t38', 'xor', 't27', 't36'), ('t39', 'and', 't29', 't38'), ('t40', 'xor', 't25', 't39'),
+    ('t41', 'xor', 't40', 't37'), ('t42', 'xor', 't29', 't33'), ('t43', 'xor', 't29', 't40'),
+    ('t44', 'xor', 't33', 't37'), ('t45', 'xor', 't42', 't41'), ('z0', 'and', 't44', 'y15'),
+    ('z1', 'and', 't37', 'y6'), ('z2', 'and', 't33', 'x7'), ('z3', 'and', 't43', 'y16'), ('z4', 'and', 't40', 'y1'),
+    ('z5', 'and', 't29', 'y7'), ('z6', 'and', 't42', 'y11'), ('z7', 'and', 't45', 'y17'),
+    ('z8', 'and', 't41', 'y10'), ('z9', 'and', 't44', 'y12'), ('z10', 'and', 't37', 'y3'),
+    ('z11', 'and', 't33', 'y4'), ('z12', 'and', 't43', 'y13'), ('z13', 'and', 't40', 'y5'),
+    ('z14', 'and', 't29', 'y2'), ('z15', 'and', 't42', 'y9'), ('z16', 'and', 't45', 'y14'),
+    ('z17', 'and', 't41', 'y8'), ('t46', 'xor', 'z15', 'z16'), ('t47', 'xor', 'z10', 'z11'),
+    ('t48', 'xor', 'z5', 'z13'), ('t49', 'xor', 'z9', 'z10'), ('t50', 'xor', 'z2', 'z12'),
+    ('t51', 'xor', 'z2', 'z5'), ('t52', 'xor', 'z7', 'z8'), ('t53', 'xor', 'z0', 'z3'), ('t54', 'xor', 'z6', 'z7'),
+    ('t55', 'xor', 'z16', 'z17'), ('t56', 'xor', 'z12', 't48'), ('t57', 'xor', 't50', 't53'),
+    ('t58', 'xor', 'z4', 't46'), ('t59', 'xor', 'z3', 't54'), ('t60', 'xor', 't46', 't57'),
+    ('t61', 'xor', 'z14', 't57'), ('t62', 'xor', 't52', 't58'), ('t63', 'xor', 't49', 't58'),
+    ('t64', 'xor', 'z4', 't59'), ('t65', 'xor', 't61', 't62'), ('t66', 'xor', 'z1', 't63'),
+    ('s0', 'xor', 't59', 't63'), ('s6', 'xnor', 't56', 't62'), ('s7', 'xnor', 't48', 't60'),
+    ('t67', 'xor', 't64', 't65'), ('s3', 'xor', 't53', 't66'), ('s4', 'xor', 't51', 't66'),
+    ('s5', 'xor', 't47', 't65'), ('s1', 'xnor', 't64', 's3'), ('s2', 'xnor', 't55', 't67'),
+)
+_SBOX_OUT = ("s7", "s6", "s5", "s4", "s3", "s2", "s1", "s0")  # output bit 0 (LSB) .. bit 7
+
+
+def _sbox(b: Builder, x: Sequence[int]) -> List[int]:
+    """x: 8 wires, LSB first -> 8 wires of S[x]."""
+    v = {}
+    for name, kind, *args in _SBOX_NETLIST:
+        if kind == "in":
+            v[name] = x[args[0]]
+        elif kind == "and":
+            v[name] = b.mul(v[args[0]], v[args[1]])
+        else:
+            w = v[args[0]]
+            for a in args[1:]:
+                w = b.add(w, v[a])
+            v[name] = b.addc(w, 1) if kind == "xnor" else w
+    return [v[n] for n in _SBOX_OUT]
+
+
+def _xtime(b: Builder, x: Sequence[int]) -> List[int]:
+    """multiplication by 2 in GF(2^8) mod x^8+x^4+x^3+x+1, on 8 wires (LSB first): linear."""
+    return [x[7], b.add(x[0], x[7]), x[1], b.add(x[2], x[7]), b.add(x[3], x[7]), x[4], x[5], x[6]]
+
+
+def _xor_bytes(b: Builder, x, y):
+    return [b.add(p, q) for p, q in zip(x, y)]
+
+
+def aes128_circuit(expected_ciphertext: bytes | None = None):
+    """AES-128 encryption of one block.  Inputs (256 `Input` ops): key bytes 0..15 then plaintext bytes 0..15, each byte
+    LSB first.  With `expected_ciphertext` every output bit gets AddConst + AssertZero (the statement "I know a key that
+    maps this plaintext to this ciphertext" when the plaintext is public ... here both are witness, as in SURVEY config 1).
+    Returns (ops, n_wires, out_wires) with out_wires = ciphertext bytes 0..15, LSB first."""
+    b = Builder()
+    key = [[b.input() for _ in range(8)] for _ in range(16)]
+    st = [[b.input() for _ in range(8)] for _ in range(16)]
+    rcon = [0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40, 0x80, 0x1B, 0x36]
+    rk = [list(key)]
+    for r in range(10):  # FIPS-197 5.2: w[i] = w[i-4] ^ (SubWord(RotWord(w[i-1])) ^ Rcon) for i % 4 == 0
+        prev = rk[-1]
+        t = [_sbox(b, prev[12 + ((k + 1) & 3)]) for k in range(4)]
+        t[0] = [b.addc(w, 1) if (rcon[r] >> i) & 1 else w for i, w in enumerate(t[0])]
+        nxt = [None] * 16
+        for k in range(4):
+            nxt[k] = _xor_bytes(b, prev[k], t[k])
+        for c in range(1, 4):
+            for k in range(4):
+                nxt[4 * c + k] = _xor_bytes(b, prev[4 * c + k], nxt[4 * (c - 1) + k])
+        rk.append(nxt)
+    st = [_xor_bytes(b, st[i], rk[0][i]) for i in range(16)]
+    for r in range(1, 11):
+        sb = [_sbox(b, st[i]) for i in range(16)]
+        sh = [sb[4 * ((c + rr) & 3) + rr] for c in range(4) for rr in range(4)]  # ShiftRows: state[row + 4 col]
+        if r < 10:
+            mc = [None] * 16
+            for c in range(4):
+                a = sh[4 * c : 4 * c + 4]
+                for rr in range(4):  # out_r = xtime(a_r ^ a_{r+1}) ^ a_{r+1} ^ a_{r+2} ^ a_{r+3}
+                    x = _xtime(b, _xor_bytes(b, a[rr], a[(rr + 1) & 3]))
+                    mc[4 * c + rr] = _xor_bytes(b, _xor_bytes(b, x, a[(rr + 1) & 3]), _xor_bytes(b, a[(rr + 2) & 3], a[(rr + 3) & 3]))
+            sh = mc
+        st = [_xor_bytes(b, sh[i], rk[r][i]) for i in range(16)]
+    out_wires = [w for byte in st for w in byte]
+    if expected_ciphertext is not None:
+        for i, w in enumerate(out_wires):
+            b.assert_zero(b.addc(w, (expected_ciphertext[i // 8] >> (i % 8)) & 1))
+    return b.ops(), b.n_wires, out_wires
+
+
+def aes128_witness(key: bytes, pt: bytes) -> np.ndarray:
+    return np.array([(byte >> i) & 1 for byte in key + pt for i in range(8)], dtype=np.uint8)
+
+
+def aes128_fips197_case():
+    """FIPS-197 Appendix C.1: key 00..0f, plaintext 00 11 .. ff, ciphertext 69c4e0d86a7b0430d8cdb78070b4c55a."""
+    key, pt = bytes(range(16)), bytes(0x11 * i for i in range(16))
+    ct = bytes.fromhex("69c4e0d86a7b0430d8cdb78070b4c55a")
+    ops, nw, _ = aes128_circuit(ct)
+    return ops, aes128_witness(key, pt), (0, nw)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 #  Bristol-Fashion text format  ->  ops     (SURVEY.md 8(f)1)
 # ---------------------------------------------------------------------------------------------------------------------
 def parse_bristol_fashion(text: str, expected_outputs: Sequence[int] | None = None):
@@ -336,6 +461,30 @@ def z64_mul_circuit(n_mul: int) -> Tuple[np.ndarray, int]:
     ops["a"][2:] = ((i * 7) % m).astype(np.uint32)
     ops["b"][2:] = ((i * 13 + 1) % m).astype(np.uint32)
     return ops, 1024
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+#  .rvops program files: magic, (z64_cells, gf2_cells), then the packed 24-byte rv_op records
+# ---------------------------------------------------------------------------------------------------------------------
+RVOPS_MAGIC = b"RVOPS\x00\x01\x00"
+
+
+def save_ops(path: str, ops: np.ndarray, wire_counts: Tuple[int, int]) -> None:
+    with open(path, "wb") as f:
+        f.write(RVOPS_MAGIC)
+        f.write(struct.pack("<QQQ", int(wire_counts[0]), int(wire_counts[1]), len(ops)))
+        f.write(np.ascontiguousarray(ops, dtype=OP_DTYPE).tobytes())
+
+
+def load_ops(path: str) -> Tuple[np.ndarray, Tuple[int, int]]:
+    with open(path, "rb") as f:
+        if f.read(8) != RVOPS_MAGIC:
+            raise ValueError("not an .rvops file")
+        z, g, n = struct.unpack("<QQQ", f.read(24))
+        ops = np.frombuffer(f.read(), dtype=OP_DTYPE)
+    if len(ops) != n:
+        raise ValueError("truncated .rvops file")
+    return ops.copy(), (int(z), int(g))
 
 
 # ---------------------------------------------------------------------------------------------------------------------

@@ -32,7 +32,24 @@ def cases():
         rng = np.random.default_rng(1000 + seed)
         out[f"random_{seed}"] = _random_circuit(rng, int(rng.integers(1, 40)), int(rng.integers(1, 2000)))
     out["sha256_abc"] = C.sha256_abc_case()
+    out["aes128_fips197"] = C.aes128_fips197_case()
     out["empty"] = (np.zeros(0, dtype=C.OP_DTYPE), np.zeros(0, dtype=np.uint8), (0, 0))
+    return out
+
+
+def zcases():
+    """Z64 / mixed-domain cases: name -> (ops, wit_gf2, wit_z64, wire_counts)."""
+    from tests._zgen import Z64_WITNESS, random_z_circuit
+
+    out = {}
+    none = np.zeros(0, dtype=np.uint8)
+    for n in (0, 1, 16, 129):
+        ops, wc = C.flat_mul_circuit(n, domain=C.Z64)
+        out[f"z64_flat_{n}"] = (ops, none, Z64_WITNESS, wc)
+    ops, nw = C.z64_mul_circuit(500)  # SURVEY.md 8(d) config 3 at test size
+    out["z64_config3_500"] = (ops, none, Z64_WITNESS, (nw, 0))
+    for seed in (0, 1):
+        out[f"z64_random_{seed}"] = random_z_circuit(np.random.default_rng(3000 + seed), 4, 300, with_gf2=seed == 1)
     return out
 
 
@@ -50,6 +67,17 @@ def main():
         golden["cases"][name] = {"n_ops": int(len(ops)), "proof_len": len(pb), "proof_sha256": hashlib.sha256(pb).hexdigest(),
                                  "comm": pb[:32].hex(), "rep_hashes_sha256": hashlib.sha256(hashes).hexdigest()}
         print(name, golden["cases"][name])
+    golden["zcases"] = {}
+    for name, (ops, gwit, zwit, wc) in zcases().items():
+        rc, pb, hashes = orc.prove(ops, gwit, zwit, wc, seeds, want_hashes=True)
+        assert rc == 0, name
+        if len(ops) <= 400:
+            p = R.prove(orc.ops_to_tuples(ops), [int(x) for x in gwit], [int(x) for x in zwit], wc, seed_list)
+            assert R.serialize(p) == pb, name
+        assert orc.verify(ops, wc, pb)[0] == 1, name
+        golden["zcases"][name] = {"n_ops": int(len(ops)), "proof_len": len(pb), "proof_sha256": hashlib.sha256(pb).hexdigest(),
+                                  "comm": pb[:32].hex(), "rep_hashes_sha256": hashlib.sha256(hashes).hexdigest()}
+        print(name, golden["zcases"][name])
     with open(os.path.join(ROOT, "tests", "golden", "proofs.json"), "w") as f:
         json.dump(golden, f, indent=1, sort_keys=True)
 

@@ -235,6 +235,27 @@ def test_golden_fixtures(rb, default_seeds):
         blob = rb.Proof.new(ops, wit, (), wc, seeds=default_seeds).serialize()
         assert len(blob) == gold[name]["proof_len"] and hashlib.sha256(blob).hexdigest() == gold[name]["proof_sha256"], name
         assert blob[:32].hex() == gold[name]["comm"], name
+    from tests.golden.make_golden import zcases
+
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "proofs.json")))["zcases"]
+    for name, (ops, gwit, zwit, wc) in zcases().items():
+        blob = rb.Proof.new(ops, gwit, zwit, wc, seeds=default_seeds).serialize()
+        assert len(blob) == gold[name]["proof_len"] and hashlib.sha256(blob).hexdigest() == gold[name]["proof_sha256"], name
+
+
+def test_aes128_config1(rb, default_seeds):
+    """AES-128 (6400 AND), FIPS-197 C.1 witness: prove parity, verify, reject a wrong key."""
+    from reverie_b200 import circuits as C
+
+    ops, wit, wc = C.aes128_fips197_case()
+    circ = rb.Circuit(ops, wc)
+    assert circ.stats()["n_and"] == 6400
+    blob = _check(rb, ops, wit, wc, default_seeds)
+    assert _verify_both(rb, circ, ops, wc, blob) == (1, 1)
+    bad = wit.copy()
+    bad[17] ^= 1
+    with pytest.raises(rb.WitnessError):
+        rb.Proof.new(circ, bad, (), seeds=default_seeds)
 
 
 # ---- Z64 domain (src/algebra/z64/*) and mixed circuits --------------------------------------------------------------------
@@ -343,3 +364,26 @@ def test_multi_gpu_nccl_sharded_prove(rb):
                           "--master-port", "29533", os.path.join(root, "tests", "_mgpu_worker.py")], capture_output=True, text=True, timeout=600, cwd=root)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert res.stdout.count("mgpu ok") == 2
+
+
+def test_cli_prove_verify_roundtrip(rb, tmp_path):
+    """python -m reverie_b200 --operation prove / verify / oneshot-zk (src/main.rs:57-165); the oracle accepts the proof file."""
+    import orc
+    from reverie_b200 import __main__ as cli, circuits as C
+
+    ops, wit, wc = C.aes128_fips197_case()
+    prog, w, pf = tmp_path / "aes.rvops", tmp_path / "aes.wit", tmp_path / "aes.proof"
+    C.save_ops(str(prog), ops, wc)
+    w.write_text("".join(str(int(b)) for b in wit))
+    assert cli.main(["--operation", "prove", "--program-path", str(prog), "--witness-path", str(w), "--proof-path", str(pf)]) == 0
+    assert orc.verify(ops, wc, pf.read_bytes())[0] == 1
+    assert cli.main(["--operation", "verify", "--program-path", str(prog), "--proof-path", str(pf)]) == 0
+    blob = bytearray(pf.read_bytes())
+    blob[5000] ^= 4
+    pf.write_bytes(bytes(blob))
+    assert cli.main(["--operation", "verify", "--program-path", str(prog), "--proof-path", str(pf)]) == 255
+    assert cli.main(["--operation", "oneshot-zk", "--program-path", str(prog), "--witness-path", str(w)]) == 0
+    bad = wit.copy()
+    bad[3] ^= 1
+    w.write_text("".join(str(int(b)) for b in bad))
+    assert cli.main(["--operation", "oneshot-zk", "--program-path", str(prog), "--witness-path", str(w)]) == 255

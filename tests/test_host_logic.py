@@ -124,6 +124,39 @@ def test_oracle_matches_golden_fixtures(default_seeds):
         g = gold[name]
         assert rc == 0 and len(pb) == g["proof_len"] and hashlib.sha256(pb).hexdigest() == g["proof_sha256"], name
         assert pb[:32].hex() == g["comm"] and hashlib.sha256(hashes).hexdigest() == g["rep_hashes_sha256"], name
+    from tests.golden.make_golden import zcases
+
+    gold = json.load(open(os.path.join(ROOT, "tests", "golden", "proofs.json")))["zcases"]
+    for name, (ops, gwit, zwit, wc) in zcases().items():
+        rc, pb, hashes = orc.prove(ops, gwit, zwit, wc, default_seeds, want_hashes=True)
+        g = gold[name]
+        assert rc == 0 and len(pb) == g["proof_len"] and hashlib.sha256(pb).hexdigest() == g["proof_sha256"], name
+        assert pb[:32].hex() == g["comm"] and hashlib.sha256(hashes).hexdigest() == g["rep_hashes_sha256"], name
+
+
+def test_aes128_circuit_fips197(default_seeds):
+    """generated AES-128 circuit (6400 AND = 200 Boyar-Peralta S-boxes) against FIPS-197 C.1, and the
+    kernels' bodies against the oracle on it."""
+    ops, wit, wc = CI.aes128_fips197_case()
+    assert int((ops["opcode"] == CI.MUL).sum()) == 6400 and int((ops["opcode"] == CI.INPUT).sum()) == 256
+    assert CI.evaluate_gf2(ops, wit, wc[1])[1]
+    ops2, nw, outs = CI.aes128_circuit()
+    vals, _ = CI.evaluate_gf2(ops2, wit, nw)
+    ct = bytes(sum(int(vals[outs[8 * i + b]]) << b for b in range(8)) for i in range(16))
+    assert ct.hex() == "69c4e0d86a7b0430d8cdb78070b4c55a"
+    key, pt = bytes(range(1, 17)), b"reverie-b200 aes"
+    from cryptography.hazmat.primitives.ciphers import Cipher, algorithms, modes
+
+    want = Cipher(algorithms.AES(key), modes.ECB()).encryptor().update(pt)
+    vals, _ = CI.evaluate_gf2(ops2, CI.aes128_witness(key, pt), nw)
+    assert bytes(sum(int(vals[outs[8 * i + b]]) << b for b in range(8)) for i in range(16)) == want
+    rc, want_proof = orc.prove(ops, wit, [], wc, default_seeds)
+    rc2, got, _ = hostsim.prove(ops, wit, wc, default_seeds)
+    assert rc == 0 and rc2 == 0 and got == want_proof
+    assert hostsim.verify(ops, wc, want_proof)[0] == 1 and orc.verify(ops, wc, want_proof)[0] == 1
+    bad = wit.copy()
+    bad[200] ^= 1
+    assert hostsim.prove(ops, bad, wc, default_seeds)[0] == N.E_WITNESS_INVALID
 
 
 # ---- Z64 domain: the kernels' bodies (csrc/rv_zplanes.cuh) replayed on the CPU vs. the oracle --------------------------
@@ -172,3 +205,35 @@ def test_wide_layered_circuit_bodies(default_seeds):
     wit = np.random.default_rng(0).integers(0, 2, size=8192).astype(np.uint8)
     st = _check_steps(ops, (0, nw))
     assert st[1] == 0 and st[3] > 0  # no step stream: the per-level launches run the level-sorted LUT list
+
+
+def test_cli_program_witness_formats(tmp_path, capsys):
+    """The reference CLI's file handling (src/main.rs:167-273, src/witness.rs:17-34): ASCII witness with junk bytes skipped,
+    .rvops and Bristol-Fashion programs, cleartext `oneshot`."""
+    from reverie_b200 import __main__ as cli
+
+    ops, wit, wc = CI.sha256_abc_case()
+    prog = tmp_path / "sha.rvops"
+    CI.save_ops(str(prog), ops, wc)
+    o2, wc2 = CI.load_ops(str(prog))
+    assert (o2 == ops).all() and wc2 == wc
+    w = tmp_path / "w.txt"
+    w.write_text("# witness\n" + " ".join(str(int(b)) for b in wit) + "\nxyz\n")
+    assert (cli.load_witness(str(w))[-len(wit):] == wit).all() is not None
+    w.write_text(" ".join(str(int(b)) for b in wit) + "\n")
+    assert (cli.load_witness(str(w)) == wit).all()
+    assert cli.main(["--operation", "oneshot", "--program-path", str(prog), "--witness-path", str(w)]) == 0
+    bad = wit.copy()
+    bad[0] ^= 1
+    w.write_text("".join(str(int(b)) for b in bad))
+    assert cli.main(["--operation", "oneshot", "--program-path", str(prog), "--witness-path", str(w)]) == 255
+    # Bristol-Fashion program with pinned outputs: a 1-bit full adder
+    bf = tmp_path / "fa.txt"
+    bf.write_text("5 8\n3 1 1 1\n2 1 1\n\n2 1 0 1 3 XOR\n2 1 3 2 6 XOR\n2 1 0 1 4 AND\n2 1 3 2 5 AND\n2 1 4 5 7 XOR\n")
+    pops, pwc = cli.load_program(str(bf), "01")  # a=1,b=1,c=0 -> sum 0, carry 1
+    assert pwc[0] == 0 and int((pops["opcode"] == CI.ASSERT_ZERO).sum()) == 2
+    w.write_text("1 1 0")
+    assert cli.main(["--operation", "oneshot", "--program-path", str(bf), "--witness-path", str(w), "--assert-outputs", "01"]) == 0
+    assert cli.main(["--operation", "oneshot", "--program-path", str(bf), "--witness-path", str(w), "--assert-outputs", "11"]) == 255
+    assert cli.main(["--operation", "version_info"]) == 0
+    assert "reverie-b200" in capsys.readouterr().out
