@@ -118,6 +118,7 @@ extern "C" int rv_circuit_compile(const rv_op *ops, size_t n_ops, size_t z64_cel
     if (P.has_verify) {
         c->vleaf_ids = P.input_uid;
         c->vleaf_ids.insert(c->vleaf_ids.end(), P.kappa_uid.begin(), P.kappa_uid.end());
+        c->vleaf_ids.insert(c->vleaf_ids.end(), P.rand_uid.begin(), P.rand_uid.end());
     }
     {
         uint32_t e[8];
@@ -140,10 +141,14 @@ extern "C" int rv_circuit_compile(const rv_op *ops, size_t n_ops, size_t z64_cel
         (rc = upload(c, c->mul_pos, &D.mul_pos)) || (rc = upload(c, P.recon_pos, &D.recon_pos)) || (rc = upload(c, P.input_pos, &D.input_pos)) ||
         (rc = upload(c, P.input_vid, &D.input_vid)) || (rc = upload(c, P.vm_steps, &D.vm_steps)) || (rc = upload(c, P.lut_steps, &D.lut_steps)) || (rc = upload(c, P.vlut_steps, &D.vlut_steps)) ||
         (rc = upload(c, c->vleaf_ids, &D.vleaf_ids)) || (rc = upload(c, P.item_ua, &D.item_ua)) || (rc = upload(c, P.item_ub, &D.item_ub)) ||
-        (rc = upload(c, c->recon_idx, &D.recon_idx))) {
+        (rc = upload(c, c->recon_idx, &D.recon_idx)) || (rc = upload(c, P.tgates, &D.tgates)) || (rc = upload(c, P.tlevel_off, &D.tlevel_off)) ||
+        (rc = upload(c, P.rand_row, &D.rand_row)) || (rc = upload(c, P.b2a_vrefs, &D.b2a_vrefs)) || (rc = upload(c, P.b2a_urefs, &D.b2a_urefs))) {
         rv_circuit_free(c);
         return rc;
     }
+    D.n_tlevels = P.tlevel_off.empty() ? 0 : (uint32_t)P.tlevel_off.size() - 1;
+    D.n_tvals = P.n_tvals;
+    D.n_rand = (uint32_t)P.rand_row.size();
     if (P.z.any()) {
         const ZProgram &Z = P.z;
         DevZProgram &DZ = c->zdev;
@@ -159,7 +164,7 @@ extern "C" int rv_circuit_compile(const rv_op *ops, size_t n_ops, size_t z64_cel
         DZ.n_vlevels = Z.vlevel_off.empty() ? 0 : (uint32_t)Z.vlevel_off.size() - 1;
         DZ.n_llevels = Z.llevel_off.empty() ? 0 : (uint32_t)Z.llevel_off.size() - 1;
         DZ.n_items = (uint32_t)Z.items.size();
-        DZ.n_mul = (uint32_t)Z.n_mul;
+        DZ.n_corr = (uint32_t)Z.n_corr;
         DZ.n_inputs = (uint32_t)Z.n_inputs;
         DZ.n_recon = (uint32_t)Z.recon_off.size();
         DZ.n_leaves = (uint32_t)Z.leaf_ids.size();
@@ -279,6 +284,7 @@ struct rv_session {
     } g_prove /* commit + open of a full shard */, g_commit, g_open /* open from the session's own all-gather buffer */;
     // device buffers
     uint8_t *d_wit = nullptr, *d_seeds = nullptr, *d_pkeys = nullptr, *d_vals = nullptr;
+    uint64_t *d_tvals = nullptr;  // tainted plane [n_tvals][npi]
     uint64_t *d_rows = nullptr;
     uint64_t *d_fresh_sm = nullptr;  // instance-major copy of the fresh masks for the mask VM
     size_t pitch_fresh = 0;
@@ -390,7 +396,7 @@ extern "C" int rv_session_create(const rv_circuit *c, int first_instance, int n_
     s->has_z = Z.any();
     if (s->has_z) {
         s->len_zrecons = (uint32_t)(8 * Z.recon_off.size());  // exactly 8 n bytes: src/algebra/z64/share.rs:37-49, recon.rs:46-66
-        s->len_zcorrs = (uint32_t)(8 * Z.n_mul);
+        s->len_zcorrs = (uint32_t)(8 * Z.n_corr);
         s->len_zinputs = (uint32_t)(8 * Z.n_inputs);
     }
     s->proof_len = ProofLayout{s->len_recons, s->len_corrs, s->len_inputs, s->len_zrecons, s->len_zcorrs, s->len_zinputs}.total();
@@ -416,7 +422,7 @@ extern "C" int rv_session_create(const rv_circuit *c, int first_instance, int n_
     }
     if ((rc = dalloc(s, &s->d_wit, P.n_inputs)) || (rc = dalloc(s, &s->d_seeds, (size_t)s->nreps * 16)) ||
         (rc = dalloc(s, &s->d_pkeys, (size_t)s->nreps * 128)) || (rc = dalloc(s, &s->d_vals, round_up((size_t)P.n_vals + 1, 16))) ||
-        (rc = dalloc(s, &s->d_rk_plain, (size_t)45 * 64 * s->npi)) || 
+        (rc = dalloc(s, &s->d_rk_plain, (size_t)45 * 64 * s->npi)) || (rc = dalloc(s, &s->d_tvals, (size_t)P.n_tvals * s->npi)) || 
         (rc = dalloc(s, &s->d_rows, (size_t)P.n_rows * s->npi)) || (rc = dalloc(s, &s->d_on, s->pitch_on * s->nreps)) ||
         (rc = dalloc(s, &s->d_pre, s->pitch_pre * s->nreps)) || (rc = dalloc(s, &s->d_cv_on, (size_t)s->n_chunks_on * s->nreps * 8)) ||
         (rc = dalloc(s, &s->d_cv_pre, (size_t)s->n_chunks_pre * s->nreps * 8)) || (rc = dalloc(s, &s->d_on_hash, (size_t)s->nreps * 32)) ||
@@ -591,7 +597,7 @@ static int commit_body(rv_session *s) {
     const DevZProgram &DZ = c->zdev;
     if (s->has_z) {
         Scope k(s, "z.values", (uint64_t)P.z.vprog.size() * sizeof(ZInstr), 1, s->st_val);
-        launch_zvalues(DZ, s->d_zleaf, 0, s->d_zvals, 0, 1, s->st_val);
+        launch_zvalues(DZ, s->d_zleaf, 0, s->d_zvals, 0, 1, s->d_vals, D.b2a_vrefs, s->st_val);
     }
     CU(cudaEventRecord(s->ev_vals, s->st_val));
     CU(cudaMemsetAsync(s->d_bad, 0, sizeof(int), s->st));
@@ -624,7 +630,7 @@ static int commit_body(rv_session *s) {
         {
             // per Mul: 4 row segments of 64 B read, 64 + 8 stream bytes written, per repetition; pre: 3 segments + 8 bytes
             Scope k(s, "z.items", ((uint64_t)P.z.n_mul * (7 * 64 + 72) + P.z.n_inputs * 72 + P.z.n_assert * 128) * s->nreps, 2);
-            launch_zitems(DZ, s->d_zrows, s->zrowlen, s->nreps, s->d_zvals, s->d_zon, s->pitch_zon, s->d_zpre, s->pitch_zpre, s->d_bad, s->st);
+            launch_zitems(DZ, s->d_zrows, s->zrowlen, s->nreps, s->d_zvals, s->d_rows, s->d_zon, s->pitch_zon, s->d_zpre, s->pitch_zpre, s->d_bad, s->st);
         }
         {
             Scope k(s, "z.chunk_cv", (P.z.on_bytes + P.z.pre_bytes) * s->nreps, 1);
@@ -639,7 +645,8 @@ static int commit_body(rv_session *s) {
     {
         // per Mul: 4 row reads + 2 stream bytes per rep (online) and 3 row reads + 1 byte per rep (pre)
         Scope k(s, "items", ((uint64_t)P.n_and * 7 + P.n_inputs + P.n_assert) * s->npi * 8 + ((uint64_t)P.n_online + P.n_pre) * s->nreps, 2);
-        launch_items(D, s->d_rows, s->npi, s->d_vals, s->d_on, s->pitch_on, s->d_pre, s->pitch_pre, s->d_bad, s->st);
+        if (D.n_tlevels) launch_tainted(D, s->d_rows, s->npi, s->d_vals, s->d_tvals, s->st);
+        launch_items(D, s->d_rows, s->npi, s->d_vals, s->d_tvals, s->d_on, s->pitch_on, s->d_pre, s->pitch_pre, s->d_bad, s->st);
     }
     {
         Scope k(s, "chunk_cv", ((uint64_t)P.n_online + P.n_pre) * s->nreps, 1);
@@ -859,7 +866,7 @@ static int verify_on_session(rv_session *s, const uint8_t *proof, size_t proof_l
         s->vin_bytes = need;
     }
     if (!s->d_leaf_vals) {
-        s->leaf_pitch = round_up((size_t)P.n_inputs + P.n_pre + 16, 16);
+        s->leaf_pitch = round_up((size_t)P.n_inputs + P.n_pre + P.rand_row.size() + 16, 16);
         s->upitch = round_up((size_t)P.n_uvals + 16, 16);
         int rc;
         if ((rc = dalloc(s, &s->d_leaf_vals, s->leaf_pitch * NON)) || (rc = dalloc(s, &s->d_uvals, s->upitch * NON))) return rc;
@@ -932,7 +939,8 @@ static int verify_on_session(rv_session *s, const uint8_t *proof, size_t proof_l
     }
     {
         Scope k(s, "v.values", (uint64_t)P.vlut_steps.size() * sizeof(LutInstr));
-        launch_values(D.vlut_steps, D.n_vlut_steps, D.vleaf_ids, s->d_leaf_vals, s->leaf_pitch, D.n_inputs + D.n_pre, s->d_uvals, s->upitch, D.n_uvals, NON, s->st);
+        launch_values(D.vlut_steps, D.n_vlut_steps, D.vleaf_ids, s->d_leaf_vals, s->leaf_pitch, D.n_inputs + D.n_pre + D.n_rand, s->d_uvals, s->upitch, D.n_uvals, NON,
+                      s->st);
     }
     {
         Scope k(s, "v.items", 0, 3);
@@ -960,15 +968,15 @@ static int verify_on_session(rv_session *s, const uint8_t *proof, size_t proof_l
         }
         {
             Scope k(s, "v.z.leaves", 0);
-            launch_zverify_leaves(DZ, d_zopens, dv, s->d_zrows, s->zrowlen, NON, s->d_zleaf_v, s->zleaf_pitch, s->st);
+            launch_zverify_leaves(DZ, d_zopens, dv, s->d_zrows, s->zrowlen, NON, s->d_zleaf_v, s->zleaf_pitch, d_opens, s->d_uvals, s->upitch, D.b2a_urefs, s->st);
         }
         {
             Scope k(s, "v.z.values", 0);
-            launch_zvalues(DZ, s->d_zleaf_v, s->zleaf_pitch, s->d_zuvals, s->zupitch, NON, s->st);
+            launch_zvalues(DZ, s->d_zleaf_v, s->zleaf_pitch, s->d_zuvals, s->zupitch, NON, nullptr, nullptr, s->st);
         }
         {
             Scope k(s, "v.z.items", 0, 3);
-            launch_zitems_pre_range(DZ, s->d_zrows, s->zrowlen, NON, s->nreps, s->d_zpre, s->pitch_zpre, s->st);
+            launch_zitems_pre_range(DZ, s->d_zrows, s->zrowlen, NON, s->nreps, s->d_rows, s->d_zpre, s->pitch_zpre, s->st);
             launch_zverify_items(DZ, d_zopens, dv, s->d_zrows, s->zrowlen, NON, s->d_zuvals, s->zupitch, s->d_zon, s->pitch_zon, s->d_zpre, s->pitch_zpre,
                                  s->d_bad, s->st);
         }

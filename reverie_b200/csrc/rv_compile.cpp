@@ -229,7 +229,7 @@ void build_mask_vm(Program &P) {
             }
     for (const Item &it : P.items) {
         if (it.kind == ITEM_MUL) exported[it.ra] = exported[it.rb] = 1;
-        else if (it.kind == ITEM_ASSERT) exported[it.ra] = 1;
+        else if (it.kind != ITEM_INPUT) exported[it.ra] = 1;
     }
     // VM level of an original level L (1-based) is L + VM_DELTA - 1; the LOAD of a fresh row first used at L sits at L - 1.
     struct Tmp {  // provisional instruction: rows until the scan below assigns cells
@@ -538,7 +538,7 @@ struct ZBuilder {
             case RV_MUL: {  // src/interpreter/single.rs:25-69
                 if (op.dst >= nc || op.a >= nc || op.b >= nc) return bad_wire();
                 const ZCell A = cells[op.a], B = cells[op.b];
-                ZItem it{ITEM_MUL, A.mid, B.mid, (uint32_t)n_masks, A.vid, B.vid, (uint32_t)Z.n_mul, (uint32_t)Z.on_bytes,
+                ZItem it{ITEM_MUL, A.mid, B.mid, (uint32_t)n_masks, A.vid, B.vid, (uint32_t)Z.n_corr, (uint32_t)Z.on_bytes,
                          is_zero(A) ? 0 : A.coef, is_zero(B) ? 0 : B.coef};
                 Z.recon_off.push_back((uint32_t)Z.on_bytes);
                 Z.recon_idx.push_back((uint32_t)Z.recon_off.size() - 1);
@@ -555,6 +555,7 @@ struct ZBuilder {
                 Z.on_bytes += 64;
                 Z.pre_bytes += 8;
                 Z.n_mul++;
+                Z.n_corr++;
                 alg_bytes += ZB_MUL;
                 break;
             }
@@ -585,6 +586,26 @@ struct ZBuilder {
             return RV_E_UNSUPPORTED;
         }
         return RV_OK;
+    }
+
+    // The Z64 half of a B2A conversion (src/interpreter/combine.rs:148-158,208-218): a fresh Z64 mask, the correction
+    // r - reconstruct(mask) into the preprocessing stream (r = the 64 fresh GF(2) wires' per-repetition plaintext), and the
+    // output wire Wire{mask: -z64_mask, corr: recon - corr}.  g0 = first of the 64 fresh GF(2) rows, grecon0 = index of the
+    // first of the 64 GF(2) reconstruct() calls.
+    void b2a(uint32_t dst, uint32_t g0, uint32_t grecon0) {
+        const uint32_t idx = (uint32_t)Z.n_b2a;
+        ZItem it{ITEM_B2A, g0, 0, (uint32_t)n_masks, idx, grecon0, (uint32_t)Z.n_corr, (uint32_t)Z.on_bytes, 1, 0};
+        Z.recon_idx.push_back(0);
+        Z.mul_pos.push_back((uint32_t)Z.items.size());
+        Z.items.push_back(it);
+        const uint32_t leaf = new_val(0);  // verifier: u of the output wire; prover: 0
+        kappa_ids.push_back(leaf);
+        cells[dst] = ZCell{emit(ZV_B2A, 0, 0, leaf, 0), (uint32_t)n_masks, 0 - (uint64_t)1};
+        prog.back().a = idx;  // `a` names the conversion, not a value id
+        n_masks += 1;
+        Z.pre_bytes += 8;
+        Z.n_b2a++;
+        Z.n_corr++;
     }
 
     void finish() {
@@ -643,6 +664,7 @@ struct ZBuilder {
                 Z.lin[n.dst - Z.n_masks] = n;
             }
             for (ZItem &it : Z.items) {
+                if (it.kind == ITEM_B2A) continue;  // ra names GF(2) rows there
                 it.ra = it.ca == 0 && it.kind != ITEM_INPUT ? zero : row(it.ra);
                 if (it.kind == ITEM_MUL) it.rb = it.cb == 0 ? zero : row(it.rb);
             }
@@ -664,10 +686,11 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
     const bool want_verify = n_ops <= (4u << 20);
     std::vector<uint32_t> vlevel(1, 0);  // per value id (plain 2-input depth, for the stats)
     std::vector<uint32_t> llevel;        // per linear node (plain depth)
+    std::vector<uint32_t> tlevel;        // per tainted value
     std::vector<MGate> vg;               // value network, topological; ids = value ids
     std::vector<MGate> lg;               // mask network, topological; provisional ids (see mask_id below)
+    std::vector<TGate> tg;               // tainted plane, creation order
     uint64_t n_masks = 0;
-
     ZBuilder zb(P.z, z64_cells);
 
     auto mid_level = [&](uint32_t mid) -> uint32_t { return (mid != ZERO_MID && mid >= LIN_BASE) ? llevel[mid - LIN_BASE] : 0; };
@@ -679,25 +702,142 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
         err = "op " + std::to_string(i) + ": wire index out of range for the given wire_counts";
         return RV_E_ARG;
     };
+    auto tainted = [](uint32_t vref) { return (vref & VREF_TAINT) != 0; };
+    auto t_level = [&](uint32_t vref) -> uint32_t { return tainted(vref) ? tlevel[(vref & ~VREF_TAINT) >> 1] : 0; };
+    auto new_tval = [&](uint32_t op, uint32_t a, uint32_t b) -> uint32_t {  // returns the (non-negated) ref
+        const uint32_t tid = (uint32_t)tlevel.size();
+        tlevel.push_back(op == T_LEAF ? 1 : 1 + std::max(t_level(a), t_level(b)));
+        tg.push_back(TGate{op, tid, a, b});
+        return VREF_TAINT | (tid << 1);
+    };
+    // ---- value algebra on refs: shared plaintext (constant folding as before) or tainted (per repetition) ----
+    auto v_xor = [&](uint32_t a, uint32_t b) -> uint32_t {
+        const uint32_t neg = (a ^ b) & 1;
+        if (!tainted(a) && (a >> 1) == 0) return b ^ (a & 1);
+        if (!tainted(b) && (b >> 1) == 0) return a ^ (b & 1);
+        if ((a & ~1u) == (b & ~1u)) return neg;  // x ^ x (^1)
+        if (tainted(a) || tainted(b)) return new_tval(T_XOR, a & ~1u, b & ~1u) | neg;
+        const uint32_t vid = new_val(1 + std::max(vlevel[a >> 1], vlevel[b >> 1]));
+        vg.push_back(MGate{vid, a & ~1u, b & ~1u, 0});
+        return (vid << 1) | neg;
+    };
+    auto v_and = [&](uint32_t a, uint32_t b) -> uint32_t {
+        if (!tainted(a) && (a >> 1) == 0) return (a & 1) ? b : VREF_ZERO;
+        if (!tainted(b) && (b >> 1) == 0) return (b & 1) ? a : VREF_ZERO;
+        if (a == b) return a;
+        if ((a & ~1u) == (b & ~1u)) return VREF_ZERO;  // x & ~x
+        if (tainted(a) || tainted(b)) return new_tval(T_AND, a, b);
+        const uint32_t vid = new_val(1 + std::max(vlevel[a >> 1], vlevel[b >> 1]));
+        vg.push_back(MGate{vid, a, b, 1});
+        return vid << 1;
+    };
+    // ---- cell-level gates (shared by the op loop and by the adder inside B2A) ----
+    auto cell_xor = [&](const Cell &A, const Cell &B, Cell &R) -> int {  // src/interpreter/single.rs:71-85
+        R.vref = v_xor(A.vref, B.vref);
+        if (A.mid == ZERO_MID) R.mid = B.mid;
+        else if (B.mid == ZERO_MID) R.mid = A.mid;
+        else if (A.mid == B.mid) R.mid = ZERO_MID;
+        else {
+            if (lg.size() >= LIN_BASE - 1) {
+                err = "too many linear nodes";
+                return RV_E_UNSUPPORTED;
+            }
+            const uint32_t id = LIN_BASE + (uint32_t)lg.size();
+            llevel.push_back(1 + std::max(mid_level(A.mid), mid_level(B.mid)));
+            lg.push_back(MGate{id, A.mid, B.mid, 0});  // provisional ids; renumbered below
+            R.mid = id;
+        }
+        R.uref = want_verify ? un.vxor(A.uref, B.uref) : 0;
+        return RV_OK;
+    };
+    auto cell_and = [&](const Cell &A, const Cell &B, Cell &R) {  // src/interpreter/single.rs:25-69
+        Item it{ITEM_MUL, A.mid, B.mid, (uint32_t)n_masks, A.vref, B.vref, (uint32_t)P.n_and, 0};
+        P.recon_pos.push_back((uint32_t)P.items.size());
+        P.items.push_back(it);
+        R.mid = (uint32_t)n_masks + 1;  // mask_new
+        R.vref = v_and(A.vref, B.vref);
+        R.uref = 0;
+        if (want_verify) {  // u_out = u_a & u_b ^ kappa_j  
+            const uint32_t kid = un.fresh();
+            P.kappa_uid.push_back(kid);
+            P.item_ua.push_back(A.uref);
+            P.item_ub.push_back(B.uref);
+            R.uref = un.vxor(un.vand(A.uref, B.uref), kid << 1);
+        }
+        n_masks += 2;
+        P.n_and++;
+        P.algorithmic_bytes += B_AND;
+    };
+    auto cell_random = [&](Cell &R) {  // Wire{mask: fresh, corr: 0}: value = reconstruct(mask), src/interpreter/single.rs:148-150
+        R.mid = (uint32_t)n_masks;
+        R.vref = new_tval(T_LEAF, (uint32_t)n_masks, 0);
+        R.uref = 0;
+        if (want_verify) {  // corr = 0  =>  u = rho(mask): a leaf computed from the opened players' shares
+            const uint32_t uid = un.fresh();
+            P.rand_row.push_back((uint32_t)n_masks);
+            P.rand_uid.push_back(uid);
+            R.uref = uid << 1;
+        }
+        n_masks += 1;
+    };
+    auto push_recon = [&](const Cell &A, uint32_t kind) {  // reconstruct(mask): one online byte per repetition, recorded for the opening
+        Item it{kind, A.mid, 0, 0, A.vref, 0, 0, 0};
+        P.recon_pos.push_back((uint32_t)P.items.size());
+        P.items.push_back(it);
+        if (want_verify) {
+            P.item_ua.push_back(A.uref);
+            P.item_ub.push_back(0);
+        }
+    };
 
     for (size_t i = 0; i < n_ops; i++) {
         const rv_op &op = ops[i];
         if (op.domain == RV_SIZE_HINT) {  // src/interpreter/combine.rs:122-129
             if (cells.size() < op.b) cells.resize(op.b, Cell{VREF_ZERO, ZERO_MID, VREF_ZERO});
             if (z64_cells < op.a) z64_cells = op.a;
+            if (zb.cells.size() < z64_cells) zb.cells.resize(z64_cells, ZCell{0, ZERO_MID, 0});
             continue;
         }
         if (op.domain == RV_Z64) {
             P.uses_z64 = true;
-            if (zb.cells.size() < z64_cells) zb.cells.resize(z64_cells, ZCell{0, ZERO_MID, 0});
             const int zrc = zb.step(op, i, err);
             if (zrc != RV_OK) return zrc;
             continue;
         }
-        if (op.domain == RV_B2A) {
+        if (op.domain == RV_B2A) {  // src/interpreter/combine.rs:132-219: z64[dst] <- the 64 GF(2) wires a .. a+63, LSB first
             P.uses_z64 = true;
-            err = "op " + std::to_string(i) + ": B2A conversions are not accelerated yet";
-            return RV_E_UNSUPPORTED;
+            if (op.dst >= zb.cells.size() || (uint64_t)op.a + 64 > cells.size()) return bad_wire(i);
+            Cell rnd[64], src[64], res[64];
+            const uint32_t g0 = (uint32_t)n_masks;
+            for (int k = 0; k < 64; k++) cell_random(rnd[k]);  // 64 fresh GF(2) masks, then the Z64 mask + correction (combine.rs:139-158)
+            for (int k = 0; k < 64; k++) {
+                src[k] = cells[op.a + k];
+                if (tainted(src[k].vref)) {
+                    err = "op " + std::to_string(i) + ": B2A of wires that depend on Random / another B2A's fresh bits is not accelerated yet";
+                    return RV_E_UNSUPPORTED;
+                }
+                P.b2a_vrefs.push_back(src[k].vref);
+            }
+            // add_64 (combine.rs:39-93): ripple adder, 63 ANDs, no carry out
+            Cell carry, ac, bc, acbc, t;
+            int rc2;
+            cell_and(rnd[0], src[0], carry);
+            if ((rc2 = cell_xor(rnd[0], src[0], res[0]))) return rc2;
+            for (int k = 1; k < 63; k++) {
+                if ((rc2 = cell_xor(rnd[k], carry, ac)) || (rc2 = cell_xor(src[k], carry, bc))) return rc2;
+                cell_and(ac, bc, acbc);
+                if ((rc2 = cell_xor(ac, src[k], res[k])) || (rc2 = cell_xor(acbc, carry, t))) return rc2;
+                carry = t;
+            }
+            if ((rc2 = cell_xor(rnd[63], src[63], t)) || (rc2 = cell_xor(carry, t, res[63]))) return rc2;
+            const uint32_t grecon0 = (uint32_t)P.recon_pos.size();
+            for (int k = 0; k < 64; k++) {  // recon_gf2_to_z64 over the sum: 64 reconstruct() calls (combine.rs:204-207)
+                push_recon(res[k], ITEM_RECON);
+                P.b2a_urefs.push_back(res[k].uref);
+            }
+            zb.b2a(op.dst, g0, grecon0);
+            P.algorithmic_bytes += 64 * B_LEAF + 63 * B_AND + 189 * B_XOR + 64 * B_ASSERT + ZB_MUL;
+            continue;
         }
         if (op.domain != RV_GF2) {
             err = "op " + std::to_string(i) + ": unknown domain";
@@ -726,41 +866,21 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
                 P.algorithmic_bytes += B_INPUT;
                 break;
             }
-            case RV_RANDOM:
-                // Wire{mask: fresh, corr: 0}: the wire's value differs per repetition, so the shared value plane does
-                // not apply.  Never silently degraded: reported here.
-                err = "op " + std::to_string(i) + ": Random is not accelerated yet";
-                return RV_E_UNSUPPORTED;
+            case RV_RANDOM: {
+                if (op.dst >= nc) return bad_wire(i);
+                Cell R;
+                cell_random(R);
+                cells[op.dst] = R;
+                P.algorithmic_bytes += B_LEAF;
+                break;
+            }
             case RV_ADD:
             case RV_SUB: {  // src/interpreter/single.rs:71-85: mask and correction add component-wise
                 if (op.dst >= nc || op.a >= nc || op.b >= nc) return bad_wire(i);
                 const Cell A = cells[op.a], B = cells[op.b];
                 Cell R;
-                // value
-                const uint32_t neg = (A.vref ^ B.vref) & 1;
-                if ((A.vref >> 1) == 0) R.vref = B.vref ^ (A.vref & 1);
-                else if ((B.vref >> 1) == 0) R.vref = A.vref ^ (B.vref & 1);
-                else if ((A.vref >> 1) == (B.vref >> 1)) R.vref = neg;  // x ^ x (^1)
-                else {
-                    uint32_t vid = new_val(1 + std::max(vlevel[A.vref >> 1], vlevel[B.vref >> 1]));
-                    vg.push_back(MGate{vid, A.vref & ~1u, B.vref & ~1u, 0});
-                    R.vref = (vid << 1) | neg;
-                }
-                // mask
-                if (A.mid == ZERO_MID) R.mid = B.mid;
-                else if (B.mid == ZERO_MID) R.mid = A.mid;
-                else if (A.mid == B.mid) R.mid = ZERO_MID;
-                else {
-                    if (lg.size() >= LIN_BASE - 1) {
-                        err = "too many linear nodes";
-                        return RV_E_UNSUPPORTED;
-                    }
-                    uint32_t id = LIN_BASE + (uint32_t)lg.size();
-                    llevel.push_back(1 + std::max(mid_level(A.mid), mid_level(B.mid)));
-                    lg.push_back(MGate{id, A.mid, B.mid, 0});  // provisional ids; renumbered below
-                    R.mid = id;
-                }
-                R.uref = want_verify ? un.vxor(A.uref, B.uref) : 0;
+                const int rc2 = cell_xor(A, B, R);
+                if (rc2) return rc2;
                 cells[op.dst] = R;
                 P.algorithmic_bytes += B_XOR;
                 break;
@@ -784,46 +904,14 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
             case RV_MUL: {  // src/interpreter/single.rs:25-69
                 if (op.dst >= nc || op.a >= nc || op.b >= nc) return bad_wire(i);
                 const Cell A = cells[op.a], B = cells[op.b];
-                Item it{ITEM_MUL, A.mid, B.mid, (uint32_t)n_masks, A.vref, B.vref, (uint32_t)P.n_and, 0};
-                P.recon_pos.push_back((uint32_t)P.items.size());
-                P.items.push_back(it);
                 Cell R;
-                R.mid = (uint32_t)n_masks + 1;  // mask_new
-                const uint32_t va = A.vref >> 1, vb = B.vref >> 1;
-                if (va == 0 && vb == 0) R.vref = (A.vref & B.vref) & 1;
-                else if (va == 0) R.vref = (A.vref & 1) ? B.vref : VREF_ZERO;
-                else if (vb == 0) R.vref = (B.vref & 1) ? A.vref : VREF_ZERO;
-                else if (A.vref == B.vref) R.vref = A.vref;
-                else if (va == vb) R.vref = VREF_ZERO;  // x & ~x
-                else {
-                    uint32_t vid = new_val(1 + std::max(vlevel[va], vlevel[vb]));
-                    vg.push_back(MGate{vid, A.vref, B.vref, 1});
-                    R.vref = vid << 1;
-                }
-                R.uref = 0;
-                if (want_verify) {  // u_out = u_a & u_b ^ kappa_j  
-                    const uint32_t kid = un.fresh();
-                    P.kappa_uid.push_back(kid);
-                    P.item_ua.push_back(A.uref);
-                    P.item_ub.push_back(B.uref);
-                    R.uref = un.vxor(un.vand(A.uref, B.uref), kid << 1);
-                }
+                cell_and(A, B, R);
                 cells[op.dst] = R;
-                n_masks += 2;
-                P.n_and++;
-                P.algorithmic_bytes += B_AND;
                 break;
             }
             case RV_ASSERT_ZERO: {  // src/interpreter/single.rs:140-147
                 if (op.a >= nc) return bad_wire(i);
-                const Cell A = cells[op.a];
-                Item it{ITEM_ASSERT, A.mid, 0, 0, A.vref, 0, 0, 0};
-                P.recon_pos.push_back((uint32_t)P.items.size());
-                P.items.push_back(it);
-                if (want_verify) {
-                    P.item_ua.push_back(A.uref);
-                    P.item_ub.push_back(0);
-                }
+                push_recon(cells[op.a], ITEM_ASSERT);
                 P.n_assert++;
                 P.algorithmic_bytes += B_ASSERT;
                 break;
@@ -838,10 +926,29 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
                 err = "op " + std::to_string(i) + ": unknown opcode";
                 return RV_E_ARG;
         }
-        if (n_masks >= LIN_BASE - 2 || P.items.size() >= 0xFFFFFFF0ull || vlevel.size() >= 0x7FFFFFF0ull) {
+        if (n_masks >= LIN_BASE - 130 || P.items.size() >= 0xFFFFFF00ull || vlevel.size() >= 0x3FFFFFF0ull || tlevel.size() >= 0x3FFFFFF0ull) {
             err = "circuit too large for 32-bit table indices";
             return RV_E_UNSUPPORTED;
         }
+    }
+    // tainted plane by level
+    {
+        uint32_t depth = 0;
+        for (uint32_t l : tlevel) depth = std::max(depth, l);
+        P.n_tvals = (uint32_t)tlevel.size();
+        P.tlevel_off.assign(depth + 1, 0);
+        std::vector<uint32_t> cnt(depth + 2, 0), cur(depth + 1, 0);
+        for (uint32_t l : tlevel) cnt[l]++;
+        uint32_t run = 0;
+        for (uint32_t l = 1; l <= depth; l++) {
+            cur[l] = run;
+            P.tlevel_off[l - 1] = run;
+            run += cnt[l];
+        }
+        P.tlevel_off[depth] = run;
+        P.tgates.resize(tg.size());
+        for (const TGate &g : tg) P.tgates[cur[tlevel[g.dst]]++] = g;
+        std::vector<TGate>().swap(tg);
     }
     std::vector<Cell>().swap(cells);
     zb.finish();
@@ -930,10 +1037,19 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
     // ---- value plane: map to 6-input LUTs --------------------------------------------------------------------------
     {
         std::vector<uint8_t> required(P.n_vals, 0);
+        auto need = [&](uint32_t vref) {
+            if (!(vref & VREF_TAINT)) required[vref >> 1] = 1;
+        };
         for (const Item &it : P.items) {
-            required[it.va >> 1] = 1;
-            if (it.kind == ITEM_MUL) required[it.vb >> 1] = 1;
+            need(it.va);
+            if (it.kind == ITEM_MUL) need(it.vb);
         }
+        for (const TGate &g : P.tgates)
+            if (g.op != T_LEAF) {
+                need(g.a);
+                need(g.b);
+            }
+        for (uint32_t r : P.b2a_vrefs) need(r);
         if (small) {
             P.vgates.resize(vg.size());
             for (size_t i = 0; i < vg.size(); i++) P.vgates[i] = VGate{vg[i].out, vg[i].a, vg[i].b, vg[i].op};

@@ -71,7 +71,19 @@ constexpr uint32_t VM_F_LOAD = 1u, VM_F_BAR = 2u, VM_F_LEVEL_END = 4u, VM_CELL_M
                    VM_ROW_NONE = 0xFFFFFFFFu;
 constexpr uint32_t LUT_F_BAR = 1u;
 
-enum ItemKind : uint32_t { ITEM_INPUT = 0, ITEM_MUL = 1, ITEM_ASSERT = 2 };
+enum ItemKind : uint32_t { ITEM_INPUT = 0, ITEM_MUL = 1, ITEM_ASSERT = 2,
+                           ITEM_RECON = 3 /* GF(2): reconstruct() without a zero check (B2A result bits, src/interpreter/combine.rs:204-207) */,
+                           ITEM_B2A = 3 /* Z64 item list: the correction of a B2A conversion (src/interpreter/combine.rs:150-158) */ };
+
+// Per-repetition ("tainted") values.  `Random` and the 64 fresh wires of a B2A conversion have corr = 0, so their plaintext
+// is reconstruct(mask): different in every repetition (src/interpreter/single.rs:148-150, combine.rs:139-147).  Everything
+// computed from them lives in the tainted plane: one Recon-format u64 per packed instance (byte r = 0x00 / 0xFF for rep r).
+// A value ref with VREF_TAINT set names tainted value (ref >> 1) & 0x3FFFFFFF; bit 0 is still "negate".
+constexpr uint32_t VREF_TAINT = 0x80000000u;
+enum TOp : uint32_t { T_XOR = 0, T_AND = 1, T_LEAF = 2 /* a = fresh mask row: value = reconstruct(row) */ };
+struct TGate {
+    uint32_t op, dst, a, b;  // a, b: value refs (tainted or shared)
+};
 // one byte of the online stream per repetition (and, for Mul, one byte of the preprocessing stream)
 struct Item {
     uint32_t kind;  // ItemKind
@@ -83,7 +95,7 @@ struct Item {
     uint32_t j;     // MUL: position in the preprocessing stream; INPUT: witness index
     uint32_t pad;
 };
-static_assert(sizeof(VGate) == 16 && sizeof(XGate) == 32 && sizeof(VmInstr) == 20 && sizeof(LutInstr) == 48 && sizeof(Item) == 32, "POD layout");
+static_assert(sizeof(TGate) == 16 && sizeof(VGate) == 16 && sizeof(XGate) == 32 && sizeof(VmInstr) == 20 && sizeof(LutInstr) == 48 && sizeof(Item) == 32, "POD layout");
 
 // =====================================================================================================================
 //  Z64 domain (src/algebra/z64/*): the same three planes over the ring Z_2^64.
@@ -97,7 +109,7 @@ static_assert(sizeof(VGate) == 16 && sizeof(XGate) == 32 && sizeof(VmInstr) == 2
 //  the prover and rho_ab - rho_a * rho_b + msg + delta in the verifier.
 // =====================================================================================================================
 enum ZvOp : uint32_t { ZV_ADD = 0, ZV_SUB = 1, ZV_MUL = 2 /* v[a] * v[b] + v[c] */, ZV_ADDC = 3 /* v[a] + imm */, ZV_MULC = 4 /* v[a] * imm */,
-                       ZV_CONST = 5 /* imm */ };
+                       ZV_CONST = 5 /* imm */, ZV_B2A = 6 /* v[c] + (prover: the 64 source bits of conversion `a` packed LSB first) */ };
 struct ZInstr {
     uint32_t op, dst, a, b, c, pad;
     uint64_t imm;
@@ -109,20 +121,21 @@ struct ZLin {
 };
 struct ZItem {
     uint32_t kind;  // ItemKind
-    uint32_t ra;    // row of operand a's mask (INPUT: the fresh mask; ASSERT: the wire's mask)
+    uint32_t ra;    // row of operand a's mask (INPUT: the fresh mask; ASSERT: the wire's mask); B2A: first of the 64 fresh GF(2) rows
     uint32_t rb;    // MUL: row of operand b's mask
-    uint32_t k;     // MUL: fresh-mask index of mask_ab (mask_new = k + 1)
-    uint32_t va;    // value id of operand a / the input / the asserted wire
-    uint32_t vb;    // MUL: value id of operand b
-    uint32_t j;     // MUL: index among the Muls (preprocessing stream offset 8 j); INPUT: witness index
-    uint32_t off;   // byte offset in the online stream
+    uint32_t k;     // MUL: fresh-mask index of mask_ab (mask_new = k + 1); B2A: the fresh Z64 mask
+    uint32_t va;    // value id of operand a / the input / the asserted wire; B2A: index of the conversion (side tables)
+    uint32_t vb;    // MUL: value id of operand b; B2A: index of its first GF(2) reconstruct()
+    uint32_t j;     // MUL / B2A: index among the corrections (preprocessing stream offset 8 j); INPUT: witness index
+    uint32_t off;   // byte offset in the online stream (B2A: none)
     uint64_t ca;    // wire mask = ca * zrow[ra]
     uint64_t cb;
 };
 static_assert(sizeof(ZInstr) == 32 && sizeof(ZLin) == 32 && sizeof(ZItem) == 48, "POD layout");
 
 struct ZProgram {
-    uint64_t n_mul = 0, n_inputs = 0, n_assert = 0;
+    uint64_t n_mul = 0, n_inputs = 0, n_assert = 0, n_b2a = 0;
+    uint64_t n_corr = 0;   // corrections = Mul + B2A: 8 bytes of preprocessing stream each
     uint32_t n_masks = 0;  // fresh Z64 PRG masks per (rep, player): mask i = LE u64 at byte 8 i of the stream (z64/batch.rs:25-30)
     uint32_t n_lin = 0;    // linear nodes
     uint32_t n_rows = 1;   // n_masks + n_lin + 1 (the last row is all-zero)
@@ -132,10 +145,10 @@ struct ZProgram {
     std::vector<ZLin> lin;              // sorted by level; dst rows are n_masks + position
     std::vector<uint32_t> llevel_off;
     std::vector<ZItem> items;           // online-stream order
-    std::vector<uint32_t> leaf_ids;     // value ids of the leaves: inputs (witness order), then one kappa per Mul
+    std::vector<uint32_t> leaf_ids;     // value ids of the leaves: inputs (witness order), then one per correction (Mul: kappa; B2A: u of its output)
     std::vector<uint32_t> recon_off;    // online byte offset of the k-th reconstruct() (Mul, AssertZero)
     std::vector<uint32_t> input_off;    // online byte offset of the k-th input()
-    std::vector<uint32_t> mul_pos;      // j -> item index
+    std::vector<uint32_t> mul_pos;      // correction j -> item index (Mul or B2A)
     std::vector<uint32_t> recon_idx;    // item index -> index among the reconstruct() calls
     uint64_t on_bytes = 0, pre_bytes = 0;  // per repetition
     bool any() const { return !items.empty() || n_masks != 0; }
@@ -172,6 +185,14 @@ struct Program {
     std::vector<uint32_t> kappa_uid;    // Mul index j -> u-plane value id of its kappa leaf
     std::vector<uint32_t> item_ua, item_ub;  // per online item: u-plane refs (id << 1 | negate) of the operands / asserted wire
     bool has_verify = false;            // built only for circuits of <= 4M ops
+    std::vector<TGate> tgates;          // tainted plane, sorted by level
+    std::vector<uint32_t> tlevel_off;
+    uint32_t n_tvals = 0;
+    std::vector<uint32_t> rand_row;     // k-th random leaf of the verifier's u-plane -> its fresh mask row (u = rho(row))
+    std::vector<uint32_t> rand_uid;     //                                            -> its u-plane value id
+    // B2A conversions (src/interpreter/combine.rs:132-219), 64 entries each
+    std::vector<uint32_t> b2a_vrefs;    // plaintext value refs of the 64 source wires (prover: the Z64 value is their packing)
+    std::vector<uint32_t> b2a_urefs;    // u-plane refs of the 64 result wires (verifier)
     std::vector<Item> items;            // online-stream order
     std::vector<uint32_t> recon_pos;    // online positions of the reconstruct() calls (Mul, AssertZero), in order
     std::vector<uint32_t> input_pos;    // online positions of the input() calls, in order

@@ -507,7 +507,8 @@ constexpr int IT_THREADS = 256;
 template <bool PRE>
 __global__ void __launch_bounds__(IT_THREADS) k_items_tile(const Item *__restrict__ items, const uint32_t *__restrict__ mul_pos, uint32_t n,
                                                           const uint64_t *__restrict__ rows, uint32_t npi, const uint8_t *__restrict__ vals,
-                                                          uint8_t *__restrict__ out, size_t pitch, uint32_t T, int *bad) {
+                                                          const uint64_t *__restrict__ tvals, uint8_t *__restrict__ out, size_t pitch, uint32_t T,
+                                                          int *bad) {
     extern __shared__ __align__(16) uint8_t tile[];
     const uint32_t tid = threadIdx.x, pi = tid % npi, pg0 = tid / npi, pg_step = IT_THREADS / npi;
     const uint32_t tp = T + 8;  // tile pitch in bytes
@@ -519,13 +520,13 @@ __global__ void __launch_bounds__(IT_THREADS) k_items_tile(const Item *__restric
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             W[i] = 0;
-            if (t0 + i < n) W[i] = PRE ? pre_word(items[mul_pos[t0 + i]], rows, npi, pi) : prover_online_word(items[t0 + i], rows, npi, pi, vals, &flag);
+            if (t0 + i < n) W[i] = PRE ? pre_word(items[mul_pos[t0 + i]], rows, npi, pi) : prover_online_word(items[t0 + i], rows, npi, pi, vals, tvals, &flag);
         }
         words_to_stream_bytes(W, o);
 #pragma unroll
         for (int r = 0; r < 8; r++) *reinterpret_cast<uint64_t *>(tile + (size_t)(r * npi + pi) * tp + 8 * g) = o[r];
     }
-    if (!PRE && flag && pi == 0) atomicOr(bad, 1);
+    if (!PRE && flag) atomicOr(bad, 1);
     __syncthreads();
     // write-out: one warp per tile row, 128 bytes (32 lanes x u32) per step
     const uint32_t lane = tid & 31, wrp = tid >> 5, nrows = 8 * npi;
@@ -539,12 +540,32 @@ __global__ void __launch_bounds__(IT_THREADS) k_items_tile(const Item *__restric
 
 static uint32_t items_tile(uint32_t npi) { return std::max(128u, 8u * IT_THREADS / npi); }
 
-void launch_items(const DevProgram &P, const uint64_t *rows, uint32_t npi, const uint8_t *vals, uint8_t *on, size_t pitch_on,
+void launch_items(const DevProgram &P, const uint64_t *rows, uint32_t npi, const uint8_t *vals, const uint64_t *tvals, uint8_t *on, size_t pitch_on,
                   uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st) {
     const uint32_t T = items_tile(npi);
     const size_t smem = (size_t)8 * npi * (T + 8);
-    if (P.n_online) k_items_tile<false><<<(P.n_online + T - 1) / T, IT_THREADS, smem, st>>>(P.items, nullptr, P.n_online, rows, npi, vals, on, pitch_on, T, bad);
-    if (P.n_pre) k_items_tile<true><<<(P.n_pre + T - 1) / T, IT_THREADS, smem, st>>>(P.items, P.mul_pos, P.n_pre, rows, npi, nullptr, pre, pitch_pre, T, nullptr);
+    if (P.n_online)
+        k_items_tile<false><<<(P.n_online + T - 1) / T, IT_THREADS, smem, st>>>(P.items, nullptr, P.n_online, rows, npi, vals, tvals, on, pitch_on, T, bad);
+    if (P.n_pre)
+        k_items_tile<true><<<(P.n_pre + T - 1) / T, IT_THREADS, smem, st>>>(P.items, P.mul_pos, P.n_pre, rows, npi, nullptr, nullptr, pre, pitch_pre, T, nullptr);
+}
+
+// Tainted plane: CTA = one packed instance (columns are independent), level-synchronous with CTA barriers only.
+__global__ void __launch_bounds__(256) k_tainted(const TGate *__restrict__ gates, const uint32_t *__restrict__ level_off, uint32_t n_levels,
+                                                 const uint64_t *__restrict__ rows, uint32_t npi, const uint8_t *__restrict__ vals, uint64_t *tvals) {
+    const uint32_t pi = blockIdx.x;
+    for (uint32_t l = 0; l < n_levels; l++) {
+        const uint32_t e = level_off[l + 1];
+        for (uint32_t g = level_off[l] + threadIdx.x; g < e; g += blockDim.x) {
+            const TGate gt = gates[g];
+            tvals[(size_t)gt.dst * npi + pi] = tainted_eval(gt, rows, npi, pi, vals, tvals);
+        }
+        __syncthreads();
+    }
+}
+
+void launch_tainted(const DevProgram &P, const uint64_t *rows, uint32_t npi, const uint8_t *vals, uint64_t *tvals, cudaStream_t st) {
+    if (P.n_tlevels) k_tainted<<<npi, 256, 0, st>>>(P.tgates, P.tlevel_off, P.n_tlevels, rows, npi, vals, tvals);
 }
 
 // verifier, preprocessing repetitions: recompute the corrections from the seeds (src/transcript/verifier/preprocess.rs:66-69)
@@ -762,14 +783,17 @@ void launch_zrep_hash(uint32_t *cv_on, uint32_t n_chunks_on, uint32_t *cv_pre, u
 // thread = (leaf, opened repetition).  Leaves 0..n_inputs-1 are the inputs, n_inputs.. the kappa of every Mul.
 __global__ void __launch_bounds__(256) k_verify_leaves(const Item *__restrict__ items, const uint32_t *__restrict__ input_pos,
                                                        const uint32_t *__restrict__ mul_pos, const uint32_t *__restrict__ recon_idx,
-                                                       uint32_t n_inputs, uint32_t n_and, const VOpen *__restrict__ opens,
-                                                       const uint8_t *__restrict__ proof, const uint64_t *__restrict__ rows, uint32_t npi,
-                                                       uint32_t n_slots, uint8_t *__restrict__ leaf_vals, size_t leaf_pitch) {
+                                                       uint32_t n_inputs, uint32_t n_and, const uint32_t *__restrict__ rand_row, uint32_t n_rand,
+                                                       const VOpen *__restrict__ opens, const uint8_t *__restrict__ proof,
+                                                       const uint64_t *__restrict__ rows, uint32_t npi, uint32_t n_slots,
+                                                       uint8_t *__restrict__ leaf_vals, size_t leaf_pitch) {
     const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t leaf = (uint32_t)(gid % (n_inputs + n_and)), slot = (uint32_t)(gid / (n_inputs + n_and));
+    const uint32_t n_leaves = n_inputs + n_and + n_rand;
+    const uint32_t leaf = (uint32_t)(gid % n_leaves), slot = (uint32_t)(gid / n_leaves);
     if (slot >= n_slots) return;
     uint8_t v;
     if (leaf < n_inputs) v = verify_leaf_input(items[input_pos[leaf]], leaf, opens[slot], proof, rows, npi, slot);
+    else if (leaf >= n_inputs + n_and) v = verify_leaf_random(rand_row[leaf - n_inputs - n_and], rows, npi, slot);
     else {
         const uint32_t t = mul_pos[leaf - n_inputs];
         v = verify_leaf_kappa(items[t], recon_idx[t], opens[slot], proof, rows, npi, slot);
@@ -819,10 +843,10 @@ __global__ void __launch_bounds__(256) k_verify_items_pre(uint32_t n_pre, const 
 
 void launch_verify_leaves(const DevProgram &P, const VOpen *opens, const uint8_t *proof, const uint64_t *rows, uint32_t npi, uint32_t n_slots,
                           uint8_t *leaf_vals, size_t leaf_pitch, cudaStream_t st) {
-    const uint64_t threads = (uint64_t)(P.n_inputs + P.n_pre) * n_slots;
+    const uint64_t threads = (uint64_t)(P.n_inputs + P.n_pre + P.n_rand) * n_slots;
     if (!threads) return;
-    k_verify_leaves<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P.items, P.input_pos, P.mul_pos, P.recon_idx, P.n_inputs, P.n_pre, opens, proof, rows,
-                                                                        npi, n_slots, leaf_vals, leaf_pitch);
+    k_verify_leaves<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(P.items, P.input_pos, P.mul_pos, P.recon_idx, P.n_inputs, P.n_pre, P.rand_row, P.n_rand,
+                                                                        opens, proof, rows, npi, n_slots, leaf_vals, leaf_pitch);
 }
 
 void launch_verify_items(const DevProgram &P, const VOpen *opens, const uint8_t *proof, const uint64_t *rows, uint32_t npi, uint32_t npi_online,

@@ -32,6 +32,13 @@ struct DevProgram {
     uint32_t n_lin = 0;
     uint32_t n_masks = 0, n_rows = 0, n_vals = 0, n_online = 0, n_pre = 0, n_inputs = 0, n_recon = 0;
     uint32_t max_llevel_width = 0;
+    // tainted plane (Random / B2A): per-repetition plaintext words
+    const TGate *tgates = nullptr;
+    const uint32_t *tlevel_off = nullptr;
+    uint32_t n_tlevels = 0, n_tvals = 0;
+    const uint32_t *rand_row = nullptr;  // verifier: fresh mask row of every random leaf of the u-plane
+    uint32_t n_rand = 0;
+    const uint32_t *b2a_vrefs = nullptr, *b2a_urefs = nullptr;  // 64 per conversion
 };
 
 // compiled Z64 tables resident in device memory (rv_compile.h: ZProgram)
@@ -42,7 +49,7 @@ struct DevZProgram {
     const ZItem *items = nullptr;
     const uint32_t *leaf_ids = nullptr, *recon_off = nullptr, *input_off = nullptr, *mul_pos = nullptr, *recon_idx = nullptr;
     const uint32_t *input_item = nullptr;  // k -> item index of the k-th input()
-    uint32_t n_vlevels = 0, n_llevels = 0, n_items = 0, n_mul = 0, n_inputs = 0, n_recon = 0, n_leaves = 0;
+    uint32_t n_vlevels = 0, n_llevels = 0, n_items = 0, n_corr = 0 /* Mul + B2A */, n_inputs = 0, n_recon = 0, n_leaves = 0;
     uint32_t n_masks = 0, n_rows = 1, n_vals = 1;
     uint32_t on_bytes = 0, pre_bytes = 0;
 };
@@ -68,7 +75,9 @@ int launch_linear(const DevProgram &P, const uint32_t *llevel_off_host, uint64_t
                   cudaStream_t st, int *which = nullptr);
 bool linear_uses_vm(const DevProgram &P);
 // K4  item plane: the two hash streams of every repetition
-void launch_items(const DevProgram &P, const uint64_t *rows, uint32_t npi, const uint8_t *vals, uint8_t *on, size_t pitch_on,
+//     tvals: tainted plane [n_tvals][npi] (launch_tainted), read by items whose operands depend on Random / B2A fresh wires
+void launch_tainted(const DevProgram &P, const uint64_t *rows, uint32_t npi, const uint8_t *vals, uint64_t *tvals, cudaStream_t st);
+void launch_items(const DevProgram &P, const uint64_t *rows, uint32_t npi, const uint8_t *vals, const uint64_t *tvals, uint8_t *on, size_t pitch_on,
                   uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st);
 // K5  BLAKE3 chunk chaining values of `nreps` streams, then per-repetition tree + joins
 void launch_chunk_cv2(const uint8_t *on, size_t pitch_on, uint32_t len_on, uint32_t *cv_on, uint32_t nreps_on, const uint8_t *pre, size_t pitch_pre,
@@ -114,14 +123,18 @@ void launch_extract(const DevProgram &P, const ExtractArgs &a, cudaStream_t st);
 struct ZOpen;
 void launch_zmask_gen_tt(const uint32_t *rk_plain, uint32_t nstreams, uint32_t n_masks, uint64_t *zrows, int n_sms, cudaStream_t st);
 int launch_zlinear(const DevZProgram &Z, const uint32_t *llevel_off_host, uint64_t *zrows, uint32_t rowlen, cudaStream_t st);
+//     gvals / b2a_vrefs: GF(2) value plane and B2A source refs (prover); nullptr in the verifier
 void launch_zvalues(const DevZProgram &Z, const uint64_t *leaf_vals, size_t leaf_pitch, uint64_t *vals, size_t vals_pitch, uint32_t n_instances,
-                    cudaStream_t st);
-void launch_zitems(const DevZProgram &Z, const uint64_t *zrows, size_t rowlen, uint32_t nreps, const uint64_t *vals, uint8_t *on, size_t pitch_on,
-                   uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st);
-void launch_zitems_pre_range(const DevZProgram &Z, const uint64_t *zrows, size_t rowlen, uint32_t first_rep, uint32_t nreps, uint8_t *pre,
-                             size_t pitch_pre, cudaStream_t st);
+                    const uint8_t *gvals, const uint32_t *b2a_vrefs, cudaStream_t st);
+//     grows: the GF(2) share tensor [row][npi] (B2A corrections read the 64 fresh GF(2) rows of the conversion)
+void launch_zitems(const DevZProgram &Z, const uint64_t *zrows, size_t rowlen, uint32_t nreps, const uint64_t *vals, const uint64_t *grows, uint8_t *on,
+                   size_t pitch_on, uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st);
+void launch_zitems_pre_range(const DevZProgram &Z, const uint64_t *zrows, size_t rowlen, uint32_t first_rep, uint32_t nreps, const uint64_t *grows,
+                             uint8_t *pre, size_t pitch_pre, cudaStream_t st);
+//     gopens / guvals / b2a_urefs: the GF(2) openings, u-plane and B2A result refs (leaves of B2A outputs)
 void launch_zverify_leaves(const DevZProgram &Z, const ZOpen *opens, const uint8_t *proof, const uint64_t *zrows, size_t rowlen, uint32_t n_slots,
-                           uint64_t *leaf_vals, size_t leaf_pitch, cudaStream_t st);
+                           uint64_t *leaf_vals, size_t leaf_pitch, const VOpen *gopens, const uint8_t *guvals, size_t gupitch,
+                           const uint32_t *b2a_urefs, cudaStream_t st);
 void launch_zverify_items(const DevZProgram &Z, const ZOpen *opens, const uint8_t *proof, const uint64_t *zrows, size_t rowlen, uint32_t n_slots,
                           const uint64_t *uvals, size_t upitch, uint8_t *on, size_t pitch_on, uint8_t *pre, size_t pitch_pre, int *not_okay,
                           cudaStream_t st);

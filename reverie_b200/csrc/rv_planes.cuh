@@ -66,25 +66,38 @@ RV_HD void words_to_stream_bytes(const uint64_t W[8], uint64_t out[8]) {
 }
 
 RV_HD uint32_t val_of(const uint8_t *vals, uint32_t vref) { return (uint32_t)(vals[vref >> 1] ^ (vref & 1)) & 1u; }
+// The plaintext of a wire as a Recon-format word of packed instance pi (byte r = 0x00 / 0xFF for repetition r): shared by
+// all repetitions (value plane), or per repetition (tainted plane: wires that depend on Random / B2A fresh bits).
+RV_HD uint64_t val_word(const uint8_t *vals, const uint64_t *tvals, uint32_t npi, uint32_t pi, uint32_t vref) {
+    if (vref & VREF_TAINT) return tvals[(size_t)((vref & ~VREF_TAINT) >> 1) * npi + pi] ^ (0ull - (uint64_t)(vref & 1));
+    return 0ull - (uint64_t)val_of(vals, vref);
+}
+// One gate of the tainted plane for packed instance pi.
+RV_HD uint64_t tainted_eval(const TGate &g, const uint64_t *rows, uint32_t npi, uint32_t pi, const uint8_t *vals, const uint64_t *tvals) {
+    if (g.op == T_LEAF) return gf2_reconstruct(rows[(size_t)g.a * npi + pi]);  // corr = 0: value = reconstruct(mask)
+    const uint64_t a = val_word(vals, tvals, npi, pi, g.a), b = val_word(vals, tvals, npi, pi, g.b);
+    return g.op == T_AND ? (a & b) : (a ^ b);
+}
 
 // ---- item plane, prover ------------------------------------------------------------------------------------------
 // The packed word one online item contributes (src/transcript/prover.rs:181-232, src/interpreter/single.rs:25-69,140-147).
 // *bad is OR-ed with 1 when an AssertZero sees a non-zero plaintext (the reference's `assert!`, prover.rs:221-228).
-RV_HD uint64_t prover_online_word(const Item &it, const uint64_t *rows, uint32_t npi, uint32_t pi, const uint8_t *vals, int *bad) {
+RV_HD uint64_t prover_online_word(const Item &it, const uint64_t *rows, uint32_t npi, uint32_t pi, const uint8_t *vals, const uint64_t *tvals,
+                                  int *bad) {
     if (it.kind == ITEM_MUL) {
         const uint64_t la = rows[(size_t)it.ra * npi + pi], lb = rows[(size_t)it.rb * npi + pi];
         const uint64_t mab = rows[(size_t)it.k * npi + pi], mnew = rows[(size_t)(it.k + 1) * npi + pi];
         // corr = value - reconstruct(mask)   (src/interpreter/mod.rs:17-19)
-        const uint64_t ca = (0ull - val_of(vals, it.va)) ^ gf2_reconstruct(la);
-        const uint64_t cb = (0ull - val_of(vals, it.vb)) ^ gf2_reconstruct(lb);
+        const uint64_t ca = val_word(vals, tvals, npi, pi, it.va) ^ gf2_reconstruct(la);
+        const uint64_t cb = val_word(vals, tvals, npi, pi, it.vb) ^ gf2_reconstruct(lb);
         return (lb & ca) ^ (la & cb) ^ mab ^ mnew;  // the broadcast share `s`, single.rs:41-45
     }
     if (it.kind == ITEM_INPUT) {
         const uint64_t m = rows[(size_t)it.ra * npi + pi];
         return (0ull - val_of(vals, it.va)) ^ gf2_reconstruct(m);  // masked input, prover.rs:186-195
     }
-    if (val_of(vals, it.va)) *bad |= 1;
-    return rows[(size_t)it.ra * npi + pi];  // AssertZero broadcasts the wire's mask shares, single.rs:143-144
+    if (it.kind == ITEM_ASSERT && val_word(vals, tvals, npi, pi, it.va) != 0) *bad |= 1;
+    return rows[(size_t)it.ra * npi + pi];  // AssertZero / B2A reconstruct() broadcast the wire's mask shares, single.rs:143-144
 }
 
 // The correction word of the j-th Mul: delta = a*b - c on reconstructed masks (single.rs:35-39).
@@ -119,6 +132,10 @@ RV_HD uint8_t verify_leaf_input(const Item &it, uint32_t k, const VOpen &o, cons
     const uint32_t c = packed_bit(proof + o.off_inputs, o.eff_inputs, k);
     return (uint8_t)(c ^ rho_bit(rows[(size_t)it.ra * npi + (slot >> 3)], slot & 7));
 }
+// Random / B2A fresh wire: corr = 0, so u = rho(mask)
+RV_HD uint8_t verify_leaf_random(uint32_t row, const uint64_t *rows, uint32_t npi, uint32_t slot) {
+    return (uint8_t)rho_bit(rows[(size_t)row * npi + (slot >> 3)], slot & 7);
+}
 RV_HD uint8_t verify_leaf_kappa(const Item &it, uint32_t recon_idx, const VOpen &o, const uint8_t *proof, const uint64_t *rows, uint32_t npi,
                                 uint32_t slot) {
     const uint32_t pi = slot >> 3, r = slot & 7;
@@ -152,14 +169,14 @@ RV_HD uint64_t verify_online_word(const Item &it, uint32_t t, uint32_t ua, uint3
             if (a) Va |= byte;
             if (it.kind == ITEM_MUL) {
                 if (val_of(uv, ub)) Vb |= byte;
-            } else if (a ^ msg) {
+            } else if (it.kind == ITEM_ASSERT && (a ^ msg)) {
                 *not_okay |= 1;
             }
         }
     }
     if (it.kind == ITEM_INPUT) return inw;  // the masked input from the proof is hashed as is (online.rs:126-127)
     const uint64_t la = rows[(size_t)it.ra * npi + pi];
-    if (it.kind == ITEM_ASSERT) return la ^ msgw;
+    if (it.kind != ITEM_MUL) return la ^ msgw;  // AssertZero / B2A reconstruct()
     const uint64_t lb = rows[(size_t)it.rb * npi + pi];
     const uint64_t mab = rows[(size_t)it.k * npi + pi], mnew = rows[(size_t)(it.k + 1) * npi + pi];
     const uint64_t ca = Va ^ gf2_reconstruct(la), cb = Vb ^ gf2_reconstruct(lb);  // corr = u ^ rho

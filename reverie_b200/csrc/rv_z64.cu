@@ -111,7 +111,8 @@ int launch_zlinear(const DevZProgram &Z, const uint32_t *llevel_off_host, uint64
 constexpr int ZV_THREADS = 256;
 __global__ void __launch_bounds__(ZV_THREADS) k_zvalues(const ZInstr *__restrict__ prog, const uint32_t *__restrict__ level_off, uint32_t n_levels,
                                                         const uint32_t *__restrict__ leaf_ids, const uint64_t *__restrict__ leaf_vals,
-                                                        size_t leaf_pitch, uint32_t n_leaves, uint64_t *vals_out, size_t vals_pitch) {
+                                                        size_t leaf_pitch, uint32_t n_leaves, uint64_t *vals_out, size_t vals_pitch,
+                                                        const uint8_t *__restrict__ gvals, const uint32_t *__restrict__ b2a_vrefs) {
     uint64_t *v = vals_out + (size_t)blockIdx.x * vals_pitch;
     const uint64_t *lv = leaf_vals + (size_t)blockIdx.x * leaf_pitch;
     const uint32_t tid = threadIdx.x;
@@ -131,10 +132,10 @@ __global__ void __launch_bounds__(ZV_THREADS) k_zvalues(const ZInstr *__restrict
         have = e + tid < e_next;
         if (have) nx = prog[e + tid];  // prefetch: does not depend on this level's values
         if (had) {
-            v[in.dst] = z_exec(in, v);
+            v[in.dst] = z_exec(in, v, gvals, b2a_vrefs);
             for (g += ZV_THREADS; g < e; g += ZV_THREADS) {
                 in = prog[g];
-                v[in.dst] = z_exec(in, v);
+                v[in.dst] = z_exec(in, v, gvals, b2a_vrefs);
             }
         }
         __syncthreads();
@@ -144,8 +145,9 @@ __global__ void __launch_bounds__(ZV_THREADS) k_zvalues(const ZInstr *__restrict
 }
 
 void launch_zvalues(const DevZProgram &Z, const uint64_t *leaf_vals, size_t leaf_pitch, uint64_t *vals, size_t vals_pitch, uint32_t n_instances,
-                    cudaStream_t st) {
-    k_zvalues<<<n_instances, ZV_THREADS, 0, st>>>(Z.vprog, Z.vlevel_off, Z.n_vlevels, Z.leaf_ids, leaf_vals, leaf_pitch, Z.n_leaves, vals, vals_pitch);
+                    const uint8_t *gvals, const uint32_t *b2a_vrefs, cudaStream_t st) {
+    k_zvalues<<<n_instances, ZV_THREADS, 0, st>>>(Z.vprog, Z.vlevel_off, Z.n_vlevels, Z.leaf_ids, leaf_vals, leaf_pitch, Z.n_leaves, vals, vals_pitch, gvals,
+                                                  b2a_vrefs);
 }
 
 // =====================================================================================================================
@@ -164,23 +166,24 @@ __global__ void __launch_bounds__(256) k_zitems_online(const ZItem *__restrict__
 }
 
 __global__ void __launch_bounds__(256) k_zitems_pre(const ZItem *__restrict__ items, const uint32_t *__restrict__ mul_pos, uint32_t n_mul,
-                                                    const uint64_t *__restrict__ zrows, size_t rowlen, uint8_t *__restrict__ pre, size_t pitch,
-                                                    uint32_t first_rep) {
+                                                    const uint64_t *__restrict__ zrows, size_t rowlen, const uint64_t *__restrict__ grows,
+                                                    uint8_t *__restrict__ pre, size_t pitch, uint32_t first_rep) {
     const uint32_t j = blockIdx.x * 32 + (threadIdx.x >> 3), rep = first_rep + 8 * blockIdx.y + (threadIdx.x & 7);
     if (j >= n_mul) return;
-    put64(pre + (size_t)rep * pitch + 8ull * j, z_pre_word(items[mul_pos[j]], zrows, rowlen, rep));
+    put64(pre + (size_t)rep * pitch + 8ull * j, z_pre_word(items[mul_pos[j]], zrows, rowlen, rep, grows, (uint32_t)(rowlen / 64)));
 }
 
-void launch_zitems(const DevZProgram &Z, const uint64_t *zrows, size_t rowlen, uint32_t nreps, const uint64_t *vals, uint8_t *on, size_t pitch_on,
-                   uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st) {
+void launch_zitems(const DevZProgram &Z, const uint64_t *zrows, size_t rowlen, uint32_t nreps, const uint64_t *vals, const uint64_t *grows, uint8_t *on,
+                   size_t pitch_on, uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st) {
     if (Z.n_items) k_zitems_online<<<dim3((Z.n_items + 31) / 32, nreps / 8), 256, 0, st>>>(Z.items, Z.n_items, zrows, rowlen, vals, on, pitch_on, bad);
-    if (Z.n_mul) k_zitems_pre<<<dim3((Z.n_mul + 31) / 32, nreps / 8), 256, 0, st>>>(Z.items, Z.mul_pos, Z.n_mul, zrows, rowlen, pre, pitch_pre, 0);
+    if (Z.n_corr) k_zitems_pre<<<dim3((Z.n_corr + 31) / 32, nreps / 8), 256, 0, st>>>(Z.items, Z.mul_pos, Z.n_corr, zrows, rowlen, grows, pre, pitch_pre, 0);
 }
 
-void launch_zitems_pre_range(const DevZProgram &Z, const uint64_t *zrows, size_t rowlen, uint32_t first_rep, uint32_t nreps, uint8_t *pre,
-                             size_t pitch_pre, cudaStream_t st) {
-    if (!Z.n_mul || first_rep >= nreps) return;
-    k_zitems_pre<<<dim3((Z.n_mul + 31) / 32, (nreps - first_rep) / 8), 256, 0, st>>>(Z.items, Z.mul_pos, Z.n_mul, zrows, rowlen, pre, pitch_pre, first_rep);
+void launch_zitems_pre_range(const DevZProgram &Z, const uint64_t *zrows, size_t rowlen, uint32_t first_rep, uint32_t nreps, const uint64_t *grows,
+                             uint8_t *pre, size_t pitch_pre, cudaStream_t st) {
+    if (!Z.n_corr || first_rep >= nreps) return;
+    k_zitems_pre<<<dim3((Z.n_corr + 31) / 32, (nreps - first_rep) / 8), 256, 0, st>>>(Z.items, Z.mul_pos, Z.n_corr, zrows, rowlen, grows, pre, pitch_pre,
+                                                                                       first_rep);
 }
 
 // =====================================================================================================================
@@ -190,14 +193,17 @@ __global__ void __launch_bounds__(256) k_zverify_leaves(const ZItem *__restrict_
                                                         const uint32_t *__restrict__ mul_pos, const uint32_t *__restrict__ recon_idx,
                                                         uint32_t n_inputs, uint32_t n_mul, const ZOpen *__restrict__ opens,
                                                         const uint8_t *__restrict__ proof, const uint64_t *__restrict__ zrows, size_t rowlen,
-                                                        uint64_t *__restrict__ leaf_vals, size_t leaf_pitch) {
+                                                        uint64_t *__restrict__ leaf_vals, size_t leaf_pitch, const VOpen *__restrict__ gopens,
+                                                        const uint8_t *__restrict__ guvals, size_t gupitch, const uint32_t *__restrict__ b2a_urefs) {
     const uint32_t leaf = blockIdx.x * 32 + (threadIdx.x >> 3), slot = 8 * blockIdx.y + (threadIdx.x & 7);
     if (leaf >= n_inputs + n_mul) return;
     uint64_t v;
     if (leaf < n_inputs) v = z_verify_leaf_input(items[input_item[leaf]], leaf, opens[slot], proof, zrows, rowlen, slot);
     else {
         const uint32_t t = mul_pos[leaf - n_inputs];
-        v = z_verify_leaf_kappa(items[t], recon_idx[t], opens[slot], proof, zrows, rowlen, slot);
+        if (items[t].kind == ITEM_B2A)
+            v = z_verify_leaf_b2a(items[t], opens[slot], gopens[slot], proof, zrows, rowlen, slot, guvals + (size_t)slot * gupitch, b2a_urefs);
+        else v = z_verify_leaf_kappa(items[t], recon_idx[t], opens[slot], proof, zrows, rowlen, slot);
     }
     leaf_vals[(size_t)slot * leaf_pitch + leaf] = v;
 }
@@ -223,10 +229,11 @@ __global__ void __launch_bounds__(256) k_zverify_items_pre(uint32_t n_mul, const
 }
 
 void launch_zverify_leaves(const DevZProgram &Z, const ZOpen *opens, const uint8_t *proof, const uint64_t *zrows, size_t rowlen, uint32_t n_slots,
-                           uint64_t *leaf_vals, size_t leaf_pitch, cudaStream_t st) {
+                           uint64_t *leaf_vals, size_t leaf_pitch, const VOpen *gopens, const uint8_t *guvals, size_t gupitch,
+                           const uint32_t *b2a_urefs, cudaStream_t st) {
     if (!Z.n_leaves) return;
-    k_zverify_leaves<<<dim3((Z.n_leaves + 31) / 32, n_slots / 8), 256, 0, st>>>(Z.items, Z.input_item, Z.mul_pos, Z.recon_idx, Z.n_inputs, Z.n_mul, opens, proof,
-                                                                             zrows, rowlen, leaf_vals, leaf_pitch);
+    k_zverify_leaves<<<dim3((Z.n_leaves + 31) / 32, n_slots / 8), 256, 0, st>>>(Z.items, Z.input_item, Z.mul_pos, Z.recon_idx, Z.n_inputs, Z.n_corr, opens, proof,
+                                                                             zrows, rowlen, leaf_vals, leaf_pitch, gopens, guvals, gupitch, b2a_urefs);
 }
 
 void launch_zverify_items(const DevZProgram &Z, const ZOpen *opens, const uint8_t *proof, const uint64_t *zrows, size_t rowlen, uint32_t n_slots,
@@ -235,7 +242,7 @@ void launch_zverify_items(const DevZProgram &Z, const ZOpen *opens, const uint8_
     if (Z.n_items)
         k_zverify_items_online<<<dim3((Z.n_items + 31) / 32, n_slots / 8), 256, 0, st>>>(Z.items, Z.recon_idx, Z.n_items, opens, proof, zrows, rowlen, uvals,
                                                                                       upitch, on, pitch_on, not_okay);
-    if (Z.n_mul) k_zverify_items_pre<<<dim3((Z.n_mul + 31) / 32, n_slots / 8), 256, 0, st>>>(Z.n_mul, opens, proof, pre, pitch_pre);
+    if (Z.n_corr) k_zverify_items_pre<<<dim3((Z.n_corr + 31) / 32, n_slots / 8), 256, 0, st>>>(Z.n_corr, opens, proof, pre, pitch_pre);
 }
 
 // =====================================================================================================================
@@ -259,9 +266,9 @@ __global__ void __launch_bounds__(256) k_zextract(const uint32_t *__restrict__ r
 }
 
 void launch_zextract(const DevZProgram &Z, const ZExtractArgs &a, cudaStream_t st) {
-    const uint64_t bytes = 8ull * ((uint64_t)Z.n_recon + Z.n_mul + Z.n_inputs);
+    const uint64_t bytes = 8ull * ((uint64_t)Z.n_recon + Z.n_corr + Z.n_inputs);
     if (!bytes) return;
-    k_zextract<<<dim3((unsigned)((bytes + 255) / 256), a.nreps), 256, 0, st>>>(Z.recon_off, Z.input_off, Z.n_recon, Z.n_mul, Z.n_inputs, a);
+    k_zextract<<<dim3((unsigned)((bytes + 255) / 256), a.nreps), 256, 0, st>>>(Z.recon_off, Z.input_off, Z.n_recon, Z.n_corr, Z.n_inputs, a);
 }
 
 }  // namespace rv

@@ -78,6 +78,7 @@ RV_HD uint64_t get64_unaligned(const uint8_t *p) {
 // One online item of repetition `rep` (index inside the shard): src/interpreter/single.rs:25-69,140-147,
 // src/transcript/prover.rs:181-232.  `stream` = this repetition's online stream.
 RV_HD void z_prover_online(const ZItem &it, const uint64_t *zrows, size_t rowlen, uint32_t rep, const uint64_t *vals, uint8_t *stream, int *bad) {
+    if (it.kind == ITEM_B2A) return;  // a conversion only appends to the preprocessing stream
     const uint64_t *A = zrows + (size_t)it.ra * rowlen + 8 * rep;
     uint8_t *dst = stream + it.off;
     if (it.kind == ITEM_INPUT) {
@@ -107,8 +108,17 @@ RV_HD void z_prover_online(const ZItem &it, const uint64_t *zrows, size_t rowlen
     for (int p = 0; p < 8; p++) put64(dst + 8 * p, b[p] * c1 + a[p] * c2 + ab[p] - nw[p]);  // single.rs:41-45
 }
 
-// delta = a * b - c on reconstructed masks (single.rs:35-39)
-RV_HD uint64_t z_pre_word(const ZItem &it, const uint64_t *zrows, size_t rowlen, uint32_t rep) {
+// B2A: the per-repetition plaintext of the 64 fresh GF(2) wires g0 .. g0+63 (corr = 0: value = parity of the mask shares),
+// wire i = bit i (src/interpreter/combine.rs:19-36).  grows = the GF(2) share tensor [row][npi].
+RV_HD uint64_t b2a_random_value(const uint64_t *grows, uint32_t npi, uint32_t g0, uint32_t rep) {
+    const uint32_t pi = rep >> 3, sh = 8 * (7 - (rep & 7));
+    uint64_t r = 0;
+    for (uint32_t i = 0; i < 64; i++) r |= ((gf2_reconstruct(grows[(size_t)(g0 + i) * npi + pi]) >> sh) & 1ull) << i;
+    return r;
+}
+// Mul: delta = a * b - c on reconstructed masks (single.rs:35-39).  B2A: r - reconstruct(z64_mask) (combine.rs:150-158).
+RV_HD uint64_t z_pre_word(const ZItem &it, const uint64_t *zrows, size_t rowlen, uint32_t rep, const uint64_t *grows, uint32_t npi) {
+    if (it.kind == ITEM_B2A) return b2a_random_value(grows, npi, it.ra, rep) - zsum8(zrows + (size_t)it.k * rowlen + 8 * rep);
     const uint64_t a = it.ca * zsum8(zrows + (size_t)it.ra * rowlen + 8 * rep), b = it.cb * zsum8(zrows + (size_t)it.rb * rowlen + 8 * rep);
     return a * b - zsum8(zrows + (size_t)it.k * rowlen + 8 * rep);
 }
@@ -138,8 +148,20 @@ RV_HD uint64_t z_verify_leaf_kappa(const ZItem &it, uint32_t recon_idx, const ZO
     return rab - ra * rb + z_packed(proof, o.off_recons, o.n_recons, o.len_recons, recon_idx) + z_packed(proof, o.off_corrs, o.n_corrs, o.len_corrs, it.j);
 }
 
+// B2A output wire of an opened repetition: mask = -z64_mask, corr = recon - corr_j with recon = the 64 reconstructed result bits
+// (u_i ^ msg_i, as in AssertZero) and corr_j from the proof, so u = corr + rho(mask) (src/interpreter/combine.rs:204-218).
+//   guv: the repetition's GF(2) u-plane; go: its GF(2) opening; urefs: the 64 result wires' u-plane refs
+RV_HD uint64_t z_verify_leaf_b2a(const ZItem &it, const ZOpen &o, const VOpen &go, const uint8_t *proof, const uint64_t *zrows, size_t rowlen,
+                                 uint32_t slot, const uint8_t *guv, const uint32_t *urefs) {
+    uint64_t recon = 0;
+    for (uint32_t i = 0; i < 64; i++)
+        recon |= (uint64_t)(val_of(guv, urefs[64 * it.va + i]) ^ packed_bit(proof + go.off_recons, go.eff_recons, it.vb + i)) << i;
+    return recon - z_packed(proof, o.off_corrs, o.n_corrs, o.len_corrs, it.j) - zsum8(zrows + (size_t)it.k * rowlen + 8 * slot);
+}
+
 RV_HD void z_verify_online(const ZItem &it, uint32_t recon_idx, const ZOpen &o, const uint8_t *proof, const uint64_t *zrows, size_t rowlen, uint32_t slot,
                            const uint64_t *uvals, uint8_t *stream, int *not_okay) {
+    if (it.kind == ITEM_B2A) return;
     uint8_t *dst = stream + it.off;
     if (it.kind == ITEM_INPUT) {  // the masked input from the proof is hashed as is (online.rs:123-130)
         put64(dst, z_packed(proof, o.off_inputs, o.n_inputs, o.len_inputs, it.j));
@@ -172,9 +194,16 @@ RV_HD void z_verify_online(const ZItem &it, uint32_t recon_idx, const ZOpen &o, 
     for (int p = 0; p < 8; p++) put64(dst + 8 * p, s[p] + (p == (int)o.omit ? msg : 0ull));
 }
 
-// value-plane instruction
-RV_HD uint64_t z_exec(const ZInstr &in, const uint64_t *v) {
+// value-plane instruction.  gvals / b2a_vrefs: the GF(2) value plane and the conversions' source refs (prover; nullptr in the
+// verifier, whose B2A outputs are leaves computed by z_verify_leaf_b2a).
+RV_HD uint64_t z_exec(const ZInstr &in, const uint64_t *v, const uint8_t *gvals, const uint32_t *b2a_vrefs) {
     switch (in.op) {
+        case ZV_B2A: {
+            uint64_t x = 0;
+            if (gvals != nullptr)
+                for (uint32_t i = 0; i < 64; i++) x |= (uint64_t)val_of(gvals, b2a_vrefs[64 * in.a + i]) << i;
+            return v[in.c] + x;
+        }
         case ZV_ADD: return v[in.a] + v[in.b];
         case ZV_SUB: return v[in.a] - v[in.b];
         case ZV_MUL: return v[in.a] * v[in.b] + v[in.c];

@@ -74,3 +74,82 @@ def random_z_circuit(rng, n_in, n_ops, n_cells=24, with_gf2=False, n_asserts=3):
 
 
 Z64_WITNESS = np.array([0x0123456789ABCDEF, 0xFEDCBA9876543210], dtype=np.uint64)
+
+
+def random_mixed_circuit(rng, n_b2a=2, n_random=3, n_gf2_ops=60, n_z_ops=20):
+    """GF(2) circuit with `Random` wires and B2A conversions feeding a Z64 tail (src/interpreter/combine.rs:132-219).
+    -> (ops, wit_gf2, wit_z64, wire_counts); witness valid by construction."""
+    recs = []
+    n_g = 64 * n_b2a + 40
+    gv = [None] * n_g  # plaintext bit, or None when the wire depends on a Random (per-repetition value)
+    gwit = []
+
+    def emit(d, op, dst=0, a=0, b=0, imm=0):
+        recs.append((d, op, 0, dst, a, b, imm & M64))
+
+    n_in = 64 * n_b2a + 8
+    for k in range(n_in):
+        bit = int(rng.integers(0, 2))
+        gwit.append(bit)
+        gv[k] = bit
+        emit(CI.GF2, CI.INPUT, k)
+    scratch = list(range(n_in, n_g))
+    for w in scratch:
+        gv[w] = 0
+    rnd = []
+    for k in range(n_random):
+        w = scratch[k]
+        emit(CI.GF2, CI.RANDOM, w)
+        gv[w] = None
+        rnd.append(w)
+    for _ in range(n_gf2_ops):  # gates over the scratch wires and inputs, some touching the Random wires
+        d = int(rng.choice(scratch[n_random:]))
+        a, b = int(rng.integers(0, n_g)), int(rng.integers(0, n_g))
+        if rng.random() < 0.5:
+            emit(CI.GF2, CI.MUL, d, a, b)
+            gv[d] = None if (gv[a] is None or gv[b] is None) and not (gv[a] == 0 or gv[b] == 0) else (gv[a] & gv[b] if gv[a] is not None and gv[b] is not None else 0)
+        else:
+            emit(CI.GF2, CI.ADD, d, a, b)
+            gv[d] = None if gv[a] is None or gv[b] is None else gv[a] ^ gv[b]
+    for w in rnd:  # r ^ r = 0 in every repetition
+        d = scratch[-1]
+        emit(CI.GF2, CI.ADD, d, w, w)
+        emit(CI.GF2, CI.ASSERT_ZERO, 0, d)
+        gv[d] = 0
+    for w in scratch[n_random:-1]:
+        if gv[w] == 0 and rng.random() < 0.3:
+            emit(CI.GF2, CI.ASSERT_ZERO, 0, w)
+    # B2A of input words, then a Z64 tail
+    n_z = n_b2a + 6
+    zv = [0] * n_z
+    for k in range(n_b2a):
+        recs.append((CI.B2A, 0, 0, k, 64 * k, 0, 0))
+        zv[k] = sum(gwit[64 * k + i] << i for i in range(64))
+    zwit = []
+    w = int(rng.integers(0, 1 << 63))
+    zwit.append(w)
+    zv[n_b2a] = w
+    emit(CI.Z64, CI.INPUT, n_b2a)
+    for _ in range(n_z_ops):
+        d = int(rng.integers(n_b2a + 1, n_z))
+        a, b = int(rng.integers(0, n_z)), int(rng.integers(0, n_z))
+        k = int(rng.integers(0, 4))
+        if k == 0:
+            emit(CI.Z64, CI.ADD, d, a, b)
+            zv[d] = (zv[a] + zv[b]) & M64
+        elif k == 1:
+            emit(CI.Z64, CI.SUB, d, a, b)
+            zv[d] = (zv[a] - zv[b]) & M64
+        elif k == 2:
+            emit(CI.Z64, CI.MUL, d, a, b)
+            zv[d] = (zv[a] * zv[b]) & M64
+        else:
+            c = int(rng.integers(0, 1 << 62)) * 2 + 1
+            emit(CI.Z64, CI.MULC, d, a, 0, c)
+            zv[d] = (zv[a] * c) & M64
+    for a in range(n_z):
+        d = n_z - 1
+        emit(CI.Z64, CI.SUBC, d, a, 0, zv[a])
+        emit(CI.Z64, CI.ASSERT_ZERO, 0, d)
+        zv[d] = 0
+    return np.array(recs, dtype=CI.OP_DTYPE), np.array(gwit, dtype=np.uint8), np.array(zwit, dtype=np.uint64), (n_z, n_g)

@@ -119,10 +119,10 @@ static void gen_zrows(const SimKeys &K, uint32_t npi, const ZProgram &Z, std::ve
         for (size_t e = 0; e < rowlen; e++) zrows[(size_t)n.dst * rowlen + e] = n.ca * zrows[(size_t)n.a * rowlen + e] + n.cb * zrows[(size_t)n.b * rowlen + e];
 }
 
-static void z_values(const ZProgram &Z, const uint64_t *leaves, uint64_t *v) {
+static void z_values(const ZProgram &Z, const uint64_t *leaves, uint64_t *v, const uint8_t *gvals, const uint32_t *b2a_vrefs) {
     v[0] = 0;
     for (size_t k = 0; k < Z.leaf_ids.size(); k++) v[Z.leaf_ids[k]] = leaves[k];
-    for (const ZInstr &in : Z.vprog) v[in.dst] = z_exec(in, v);
+    for (const ZInstr &in : Z.vprog) v[in.dst] = z_exec(in, v, gvals, b2a_vrefs);
 }
 
 extern "C" void hs_gf2_masks(const uint8_t *seeds8, const uint8_t *omit8, uint64_t *out, uint32_t n) {
@@ -148,30 +148,6 @@ extern "C" int hs_prove(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t
     std::vector<uint8_t> pkeys;
     SimKeys K;
     gen_masks(seeds, nullptr, nullptr, nullptr, npi, P.n_masks, rows, pkeys, &K);
-    // Z64: masks, value plane, item plane, stream hashes
-    const size_t rowlen = (size_t)64 * npi;
-    const size_t pitch_zon = (std::max<size_t>(Z.on_bytes, 1) + 63) / 64 * 64, pitch_zpre = (std::max<size_t>(Z.pre_bytes, 1) + 63) / 64 * 64;
-    std::vector<uint8_t> zon, zpre;
-    std::vector<uint32_t> zon_hash(nreps * 8), zrep(nreps * 8);
-    int zbad = 0;
-    if (Z.any()) {
-        std::vector<uint64_t> zrows;
-        gen_zrows(K, npi, Z, zrows);
-        std::vector<uint64_t> leaves(Z.leaf_ids.size(), 0), zvals((size_t)Z.n_vals + 1, 0);
-        for (size_t k = 0; k < Z.n_inputs; k++) leaves[k] = wit_z[k];
-        z_values(Z, leaves.data(), zvals.data());
-        zon.assign(pitch_zon * nreps, 0);
-        zpre.assign(pitch_zpre * nreps, 0);
-        for (uint32_t rep = 0; rep < nreps; rep++) {
-            for (const ZItem &it : Z.items) z_prover_online(it, zrows.data(), rowlen, rep, zvals.data(), &zon[(size_t)rep * pitch_zon], &zbad);
-            for (uint32_t j = 0; j < Z.n_mul; j++) put64(&zpre[(size_t)rep * pitch_zpre + 8ull * j], z_pre_word(Z.items[Z.mul_pos[j]], zrows.data(), rowlen, rep));
-            uint32_t h_pre[8];
-            stream_hash(&zon[(size_t)rep * pitch_zon], (uint32_t)Z.on_bytes, &zon_hash[rep * 8]);
-            stream_hash(&zpre[(size_t)rep * pitch_zpre], (uint32_t)Z.pre_bytes, h_pre);
-            b3_hash64(h_pre, &zon_hash[rep * 8], &zrep[rep * 8]);
-        }
-    }
-    if (zbad) return RV_E_WITNESS_INVALID;
     // K0
     std::vector<uint8_t> vals(P.n_vals, 0);
     for (size_t k = 0; k < P.n_inputs; k++) vals[P.input_vid[k]] = wit[k] & 1;
@@ -186,6 +162,35 @@ extern "C" int hs_prove(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t
             for (int k = 0; k < 6; k++) v ^= rows[(size_t)g.in[k] * npi + pi];
             rows[(size_t)g.dst * npi + pi] = v;
         }
+    // tainted plane (k_tainted): per-repetition plaintext of everything that depends on Random / B2A fresh wires
+    std::vector<uint64_t> tvals((size_t)P.n_tvals * npi + 1, 0);
+    for (const TGate &g : P.tgates)
+        for (uint32_t pi = 0; pi < npi; pi++) tvals[(size_t)g.dst * npi + pi] = tainted_eval(g, rows.data(), npi, pi, vals.data(), tvals.data());
+    // Z64: masks, value plane, item plane, stream hashes
+    const size_t rowlen = (size_t)64 * npi;
+    const size_t pitch_zon = (std::max<size_t>(Z.on_bytes, 1) + 63) / 64 * 64, pitch_zpre = (std::max<size_t>(Z.pre_bytes, 1) + 63) / 64 * 64;
+    std::vector<uint8_t> zon, zpre;
+    std::vector<uint32_t> zon_hash(nreps * 8), zrep(nreps * 8);
+    int zbad = 0;
+    if (Z.any()) {
+        std::vector<uint64_t> zrows;
+        gen_zrows(K, npi, Z, zrows);
+        std::vector<uint64_t> leaves(Z.leaf_ids.size(), 0), zvals((size_t)Z.n_vals + 1, 0);
+        for (size_t k = 0; k < Z.n_inputs; k++) leaves[k] = wit_z[k];
+        z_values(Z, leaves.data(), zvals.data(), vals.data(), P.b2a_vrefs.data());
+        zon.assign(pitch_zon * nreps, 0);
+        zpre.assign(pitch_zpre * nreps, 0);
+        for (uint32_t rep = 0; rep < nreps; rep++) {
+            for (const ZItem &it : Z.items) z_prover_online(it, zrows.data(), rowlen, rep, zvals.data(), &zon[(size_t)rep * pitch_zon], &zbad);
+            for (uint32_t j = 0; j < Z.n_corr; j++)
+                put64(&zpre[(size_t)rep * pitch_zpre + 8ull * j], z_pre_word(Z.items[Z.mul_pos[j]], zrows.data(), rowlen, rep, rows.data(), npi));
+            uint32_t h_pre[8];
+            stream_hash(&zon[(size_t)rep * pitch_zon], (uint32_t)Z.on_bytes, &zon_hash[rep * 8]);
+            stream_hash(&zpre[(size_t)rep * pitch_zpre], (uint32_t)Z.pre_bytes, h_pre);
+            b3_hash64(h_pre, &zon_hash[rep * 8], &zrep[rep * 8]);
+        }
+    }
+    if (zbad) return RV_E_WITNESS_INVALID;
     // K4
     const size_t pitch_on = (std::max<size_t>(P.n_online, 1) + 63) / 64 * 64, pitch_pre = (std::max<size_t>(P.n_pre, 1) + 63) / 64 * 64;
     std::vector<uint8_t> on(pitch_on * nreps, 0), pre(pitch_pre * nreps, 0);
@@ -196,7 +201,7 @@ extern "C" int hs_prove(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t
     for (uint32_t pi = 0; pi < npi; pi++) {
         for (uint64_t t0 = 0; t0 < P.n_online; t0 += 8) {
             uint64_t W[8], out[8];
-            for (int i = 0; i < 8; i++) W[i] = (t0 + i < P.n_online) ? prover_online_word(P.items[t0 + i], rows.data(), npi, pi, vals.data(), &bad) : 0;
+            for (int i = 0; i < 8; i++) W[i] = (t0 + i < P.n_online) ? prover_online_word(P.items[t0 + i], rows.data(), npi, pi, vals.data(), tvals.data(), &bad) : 0;
             words_to_stream_bytes(W, out);
             for (int r = 0; r < 8; r++) memcpy(&on[(size_t)(8 * pi + r) * pitch_on + t0], &out[r], 8);
         }
@@ -239,7 +244,7 @@ extern "C" int hs_prove(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t
     ProofLayout L{(uint32_t)(P.recon_pos.size() / 8 + 1), P.n_pre / 8 + 1, (uint32_t)(P.n_inputs / 8 + 1)};
     if (Z.any()) {
         L.len_zrecons = (uint32_t)(8 * Z.recon_off.size());
-        L.len_zcorrs = (uint32_t)(8 * Z.n_mul);
+        L.len_zcorrs = (uint32_t)(8 * Z.n_corr);
         L.len_zinputs = (uint32_t)(8 * Z.n_inputs);
     }
     uint8_t *out = (uint8_t *)calloc(L.total(), 1);
@@ -247,7 +252,7 @@ extern "C" int hs_prove(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t
         if (omit[r] >= RV_PLAYERS) continue;
         const uint8_t *zo = &zon[(size_t)r * pitch_zon], *zp = &zpre[(size_t)r * pitch_zpre];
         uint8_t *z = out + L.z_base() + 8 + (size_t)rank[r] * L.sz_on_z();
-        const uint64_t nr = 8ull * Z.recon_off.size(), nc = 8ull * Z.n_mul, ni = 8ull * Z.n_inputs;
+        const uint64_t nr = 8ull * Z.recon_off.size(), nc = 8ull * Z.n_corr, ni = 8ull * Z.n_inputs;
         for (uint64_t i = 0; i < nr + nc + ni; i++) {
             if (i < nr) z[137 + i] = zo[Z.recon_off[i >> 3] + 8 * omit[r] + (i & 7)];
             else if (i < nr + nc) z[145 + i] = zp[i - nr];
@@ -414,6 +419,32 @@ extern "C" int hs_verify(const rv_op *ops, size_t n_ops, size_t z64_cells, size_
     std::vector<uint8_t> pkeys;
     SimKeys K;
     gen_masks(seeds.data(), pkeys_in.data(), mode.data(), omit.data(), npi, P.n_masks, rows, pkeys, &K);
+    for (const XGate &x : P.xgates)
+        for (uint32_t pi = 0; pi < npi; pi++) {
+            uint64_t v = 0;
+            for (int k = 0; k < 6; k++) v ^= rows[(size_t)x.in[k] * npi + pi];
+            rows[(size_t)x.dst * npi + pi] = v;
+        }
+    std::vector<uint32_t> mul_pos, recon_idx(P.n_online, 0);
+    for (uint32_t t = 0; t < P.n_online; t++)
+        if (P.items[t].kind == ITEM_MUL) mul_pos.push_back(t);
+    for (uint32_t k = 0; k < P.recon_pos.size(); k++) recon_idx[P.recon_pos[k]] = k;
+    // u-plane of the 40 opened repetitions
+    const size_t upitch = (size_t)P.n_uvals + 1;
+    std::vector<uint8_t> uvals(upitch * NON, 0);
+    for (uint32_t s = 0; s < NON; s++) {
+        uint8_t *uv = &uvals[s * upitch];
+        for (uint32_t k = 0; k < P.n_inputs; k++) uv[P.input_uid[k]] = verify_leaf_input(P.items[P.input_pos[k]], k, opens[s], proof, rows.data(), npi, s);
+        for (uint32_t j = 0; j < P.n_pre; j++) uv[P.kappa_uid[j]] = verify_leaf_kappa(P.items[mul_pos[j]], recon_idx[mul_pos[j]], opens[s], proof, rows.data(), npi, s);
+        for (uint32_t k = 0; k < P.rand_uid.size(); k++) uv[P.rand_uid[k]] = verify_leaf_random(P.rand_row[k], rows.data(), npi, s);
+        for (uint32_t st = 0; st < P.n_vlut_steps; st++)
+            for (uint32_t t = 0; t < LUT_STEP; t++) {
+                const LutInstr &li = P.vlut_steps[(size_t)st * LUT_STEP + t];
+                uint32_t idx = 0;
+                for (int k = 0; k < 6; k++) idx |= (uint32_t)uv[li.in[k]] << k;
+                uv[li.dst] = (uint8_t)((li.tt >> idx) & 1);
+            }
+    }
     // ---- Z64 instances (mirrors the has_z block of verify_on_session) ----
     const ZProgram &Z = P.z;
     std::vector<uint32_t> zrep_slot(256 * 8, 0);
@@ -453,46 +484,26 @@ extern "C" int hs_verify(const rv_op *ops, size_t n_ops, size_t z64_cells, size_
             uint32_t h_on[8], h_pre[8];
             if (slot < NON) {
                 for (uint32_t k = 0; k < Z.n_inputs; k++) leaves[k] = z_verify_leaf_input(Z.items[input_item[k]], k, zopens[slot], proof, zrows.data(), rowlen, slot);
-                for (uint32_t j = 0; j < Z.n_mul; j++)
-                    leaves[Z.n_inputs + j] = z_verify_leaf_kappa(Z.items[Z.mul_pos[j]], Z.recon_idx[Z.mul_pos[j]], zopens[slot], proof, zrows.data(), rowlen, slot);
-                z_values(Z, leaves.data(), uv.data());
+                for (uint32_t j = 0; j < Z.n_corr; j++) {
+                    const ZItem &it = Z.items[Z.mul_pos[j]];
+                    leaves[Z.n_inputs + j] = it.kind == ITEM_B2A ? z_verify_leaf_b2a(it, zopens[slot], opens[slot], proof, zrows.data(), rowlen, slot,
+                                                                                     &uvals[slot * upitch], P.b2a_urefs.data())
+                                                                 : z_verify_leaf_kappa(it, Z.recon_idx[Z.mul_pos[j]], zopens[slot], proof, zrows.data(), rowlen, slot);
+                }
+                z_values(Z, leaves.data(), uv.data(), nullptr, nullptr);
                 for (uint32_t t = 0; t < Z.items.size(); t++)
                     z_verify_online(Z.items[t], Z.recon_idx[t], zopens[slot], proof, zrows.data(), rowlen, slot, uv.data(), &zon[(size_t)slot * pitch_zon], &z_not_okay);
-                for (uint32_t j = 0; j < Z.n_mul; j++)
+                for (uint32_t j = 0; j < Z.n_corr; j++)
                     put64(&zpre[(size_t)slot * pitch_zpre + 8ull * j], z_packed(proof, zopens[slot].off_corrs, zopens[slot].n_corrs, zopens[slot].len_corrs, j));
                 stream_hash(&zon[(size_t)slot * pitch_zon], (uint32_t)Z.on_bytes, h_on);
             } else {
-                for (uint32_t j = 0; j < Z.n_mul; j++) put64(&zpre[(size_t)slot * pitch_zpre + 8ull * j], z_pre_word(Z.items[Z.mul_pos[j]], zrows.data(), rowlen, slot));
+                for (uint32_t j = 0; j < Z.n_corr; j++)
+                    put64(&zpre[(size_t)slot * pitch_zpre + 8ull * j], z_pre_word(Z.items[Z.mul_pos[j]], zrows.data(), rowlen, slot, rows.data(), npi));
                 memcpy(h_on, proof + z.pre[slot - NON].comm_online, 32);
             }
             stream_hash(&zpre[(size_t)slot * pitch_zpre], (uint32_t)Z.pre_bytes, h_pre);
             b3_hash64(h_pre, h_on, &zrep_slot[slot * 8]);
         }
-    }
-    for (const XGate &x : P.xgates)
-        for (uint32_t pi = 0; pi < npi; pi++) {
-            uint64_t v = 0;
-            for (int k = 0; k < 6; k++) v ^= rows[(size_t)x.in[k] * npi + pi];
-            rows[(size_t)x.dst * npi + pi] = v;
-        }
-    std::vector<uint32_t> mul_pos, recon_idx(P.n_online, 0);
-    for (uint32_t t = 0; t < P.n_online; t++)
-        if (P.items[t].kind == ITEM_MUL) mul_pos.push_back(t);
-    for (uint32_t k = 0; k < P.recon_pos.size(); k++) recon_idx[P.recon_pos[k]] = k;
-    // u-plane of the 40 opened repetitions
-    const size_t upitch = (size_t)P.n_uvals + 1;
-    std::vector<uint8_t> uvals(upitch * NON, 0);
-    for (uint32_t s = 0; s < NON; s++) {
-        uint8_t *uv = &uvals[s * upitch];
-        for (uint32_t k = 0; k < P.n_inputs; k++) uv[P.input_uid[k]] = verify_leaf_input(P.items[P.input_pos[k]], k, opens[s], proof, rows.data(), npi, s);
-        for (uint32_t j = 0; j < P.n_pre; j++) uv[P.kappa_uid[j]] = verify_leaf_kappa(P.items[mul_pos[j]], recon_idx[mul_pos[j]], opens[s], proof, rows.data(), npi, s);
-        for (uint32_t st = 0; st < P.n_vlut_steps; st++)
-            for (uint32_t t = 0; t < LUT_STEP; t++) {
-                const LutInstr &li = P.vlut_steps[(size_t)st * LUT_STEP + t];
-                uint32_t idx = 0;
-                for (int k = 0; k < 6; k++) idx |= (uint32_t)uv[li.in[k]] << k;
-                uv[li.dst] = (uint8_t)((li.tt >> idx) & 1);
-            }
     }
     const size_t pitch_on = (std::max<size_t>(P.n_online, 1) + 63) / 64 * 64, pitch_pre = (std::max<size_t>(P.n_pre, 1) + 63) / 64 * 64;
     std::vector<uint8_t> on(pitch_on * 256, 0), pre(pitch_pre * 256, 0);

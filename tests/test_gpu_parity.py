@@ -387,3 +387,24 @@ def test_cli_prove_verify_roundtrip(rb, tmp_path):
     bad[3] ^= 1
     w.write_text("".join(str(int(b)) for b in bad))
     assert cli.main(["--operation", "oneshot-zk", "--program-path", str(prog), "--witness-path", str(w)]) == 255
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_random_and_b2a(rb, default_seeds, seed):
+    """Random wires and B2A conversions (src/interpreter/single.rs:148-150, combine.rs:132-219): prove and verify parity, tampering."""
+    from tests._zgen import random_mixed_circuit
+
+    rng = np.random.default_rng(5000 + seed)
+    ops, gwit, zwit, wc = random_mixed_circuit(rng, n_b2a=1 + seed % 3, n_random=seed % 4, n_gf2_ops=200, n_z_ops=60)
+    blob = _check_z(rb, ops, gwit, zwit, wc, default_seeds)
+    circ = rb.Circuit(ops, wc)
+    assert _verify_both(rb, circ, ops, wc, blob) == (1, 1)
+    for pos in [len(blob) // 2, len(blob) // 3, len(blob) - 5000] + [int(x) for x in rng.integers(32, len(blob), size=8)]:
+        bad = bytearray(blob)
+        bad[pos] ^= 1 << int(rng.integers(0, 8))
+        got, want = _verify_both(rb, circ, ops, wc, bytes(bad))
+        assert got == want, f"byte {pos}: ours {got}, oracle {want}"
+    badw = gwit.copy()
+    badw[3] ^= 1
+    with pytest.raises(rb.WitnessError):
+        rb.Proof.new(circ, badw, zwit, seeds=default_seeds)

@@ -60,16 +60,17 @@ def test_compile_stats_and_errors():
     with pytest.raises(rb.ReverieError) as e:
         rb.Circuit(bad, wc)
     assert e.value.code == N.E_ARG
-    z = np.zeros(1, dtype=CI.OP_DTYPE)
-    z["domain"], z["dst"], z["a"] = CI.B2A, 0, 0
+    # the one construct not accelerated yet is reported, never silently degraded: B2A of per-repetition (Random-derived) bits
+    z = np.zeros(65, dtype=CI.OP_DTYPE)
+    z["opcode"][:64] = CI.RANDOM
+    z["dst"][:64] = np.arange(64)
+    z["domain"][64], z["dst"][64], z["a"][64] = CI.B2A, 0, 0
     with pytest.raises(rb.ReverieError) as e:
         rb.Circuit(z, (4, 64))
-    assert e.value.code == N.E_UNSUPPORTED  # reported, never silently degraded
-    r = np.zeros(1, dtype=CI.OP_DTYPE)
-    r["opcode"] = CI.RANDOM
-    with pytest.raises(rb.ReverieError) as e:
-        rb.Circuit(r, (0, 4))
     assert e.value.code == N.E_UNSUPPORTED
+    with pytest.raises(rb.ReverieError) as e:  # B2A source wires out of range
+        rb.Circuit(z[64:], (4, 63))
+    assert e.value.code == N.E_ARG
 
 
 def _check_steps(ops, wc):
@@ -237,3 +238,45 @@ def test_cli_program_witness_formats(tmp_path, capsys):
     assert cli.main(["--operation", "oneshot", "--program-path", str(bf), "--witness-path", str(w), "--assert-outputs", "11"]) == 255
     assert cli.main(["--operation", "version_info"]) == 0
     assert "reverie-b200" in capsys.readouterr().out
+
+
+# ---- Random and B2A (src/interpreter/single.rs:148-150, src/interpreter/combine.rs:132-219): tainted plane, cross-domain leaves ----
+@pytest.mark.parametrize("seed", range(6))
+def test_random_and_b2a_kernel_bodies(seed, default_seeds):
+    from tests._zgen import random_mixed_circuit
+
+    rng = np.random.default_rng(4000 + seed)
+    ops, gwit, zwit, wc = random_mixed_circuit(rng, n_b2a=seed % 3, n_random=(seed + 1) % 4)
+    rc, want, hashes = orc.prove(ops, gwit, zwit, wc, default_seeds, want_hashes=True)
+    rc2, got, h2 = hostsim.prove(ops, gwit, wc, default_seeds, wit_z64=zwit)
+    assert rc == 0 and rc2 == 0 and h2 == hashes and got == want
+    v, vo = hostsim.verify(ops, wc, want), orc.verify(ops, wc, want, want_hashes=True)
+    assert v[0] == 1 and vo[0] == 1 and v[2] == vo[2]
+    for pos in [len(want) // 2, len(want) // 3, len(want) - 5000] + [int(x) for x in rng.integers(32, len(want), size=3)]:
+        t = bytearray(want)
+        t[pos] ^= 1 << int(rng.integers(0, 8))
+        v, vo = hostsim.verify(ops, wc, bytes(t)), orc.verify(ops, wc, bytes(t), want_hashes=True)
+        assert (v[0] < 0) == (vo[0] < 0) and (v[0] < 0 or (v[0] == vo[0] and v[2] == vo[2])), pos
+    if seed % 3:  # a wrong source bit changes the converted Z64 value: the Z64 AssertZero must fail
+        bad = gwit.copy()
+        bad[5] ^= 1
+        assert hostsim.prove(ops, bad, wc, default_seeds, wit_z64=zwit)[0] == N.E_WITNESS_INVALID
+        assert orc.prove(ops, bad, zwit, wc, default_seeds)[0] == orc.E_WITNESS_INVALID
+
+
+def test_reference_e2e_case_b2a(default_seeds):
+    """The reference's only end-to-end test circuit (src/proof/mod.rs:397-427): 64 GF(2) inputs, B2A, Z64 arithmetic, AssertZero."""
+    recs = [(CI.GF2, CI.INPUT, 0, i, 0, 0, 0) for i in range(64)]
+    recs.append((CI.B2A, 0, 0, 0, 0, 0, 0))
+    recs.append((CI.Z64, CI.INPUT, 0, 1, 0, 0, 0))
+    recs.append((CI.Z64, CI.MUL, 0, 2, 0, 1, 0))
+    x, y = 0x0123456789ABCDEF, 0x1111111111111111
+    recs.append((CI.Z64, CI.SUBC, 0, 3, 2, 0, (x * y) & ((1 << 64) - 1)))
+    recs.append((CI.Z64, CI.ASSERT_ZERO, 0, 0, 3, 0, 0))
+    ops = np.array(recs, dtype=CI.OP_DTYPE)
+    gwit = np.array([(x >> i) & 1 for i in range(64)], dtype=np.uint8)
+    rc, want = orc.prove(ops, gwit, [y], (4, 64), default_seeds)
+    rc2, got, _ = hostsim.prove(ops, gwit, (4, 64), default_seeds, wit_z64=[y])
+    assert rc == 0 and rc2 == 0 and got == want
+    assert hostsim.verify(ops, (4, 64), want)[0] == 1
+    assert hostsim.prove(ops, gwit, (4, 64), default_seeds, wit_z64=[y + 1])[0] == N.E_WITNESS_INVALID
