@@ -341,6 +341,7 @@ def main():
 
     # ---- end to end through the public API (host buffers, copies inside the timed region) ----
     e2e = None
+    verify = None
     single_latency_ms = None
     if world == 1:
         from concurrent.futures import ThreadPoolExecutor
@@ -364,6 +365,22 @@ def main():
             one(0)
         single_latency_ms = (time.perf_counter() - t0) / 10 * 1e3
         d2h = B * (len(proof) + 36)
+        # Proof::verify through the same API ("also reported"); tables exist for circuits of <= 4M ops
+        if st["n_ops"] <= (4 << 20):
+            def vfy(_):
+                return proof.verify(circ)
+
+            assert all(pool.map(vfy, range(B)))
+            nv = max(2, args.steps // 4)
+            t0 = time.perf_counter()
+            for _ in range(nv):
+                oks = list(pool.map(vfy, range(B)))
+            dtv = time.perf_counter() - t0
+            t0 = time.perf_counter()
+            for _ in range(5):
+                vfy(0)
+            verify = {"value": n_and * B * nv / dtv, "unit": UNIT, "accepted": bool(all(oks)), "single_proof_ms": (time.perf_counter() - t0) / 5 * 1e3,
+                      "note": "Proof.verify end to end (proof bytes in host memory), B verifications in flight"}
     else:
         def step_e2e():
             for x in sessions:
@@ -405,7 +422,7 @@ def main():
             "config": {"workload": desc, "batch": B, "parallelism": f"{per} packed instances (= {per * 8} repetitions) per GPU, {B} proofs in flight per step",
                        "l2": "256 MiB memset between timed steps (outside the per-step CUDA-event pair)",
                        "timing": "one CUDA-event pair per step on a timing stream that forks to / joins the B session streams, summed over K steps"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+            "clocks": clocks, "e2e": e2e, "verify": verify, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "kernels": kernels, "single_proof_latency_ms": {"device": lat_ms, "e2e": single_latency_ms}, "circuit": {k: st[k] for k in ("n_and", "n_ops", "value_depth", "linear_depth", "z64_mul", "z64_value_depth")},
         }
         print(json.dumps(line), flush=True)

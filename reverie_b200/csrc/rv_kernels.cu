@@ -52,7 +52,8 @@ void launch_key_setup(const uint8_t *seeds, const uint8_t *pkeys_in, const uint8
 //      words of the slice (what the reference's AVX2 movemask transpose produces, src/algebra/gf2/domain.rs:66-173), and a
 //      small shared-memory tile regroups the CTA's 16 slices so every mask row leaves as one 64-byte segment.
 //      Cost per block and lane: ~190 LDS/SHFL + ~380 ALU-pipe instructions, against ~640 LOP3 bitsliced.
-constexpr int GT_SLICES = 16, GT_THREADS = 32 * GT_SLICES, GT_TILE_PITCH = 20;  // tile row = 16 slice words + pad (16-byte aligned rows)
+constexpr int GT_SLICES = 16, GT_THREADS = 32 * GT_SLICES, GT_TILE_PITCH = GT_SLICES + 4;  // tile row = the CTA's slice words + pad (16-byte aligned rows)
+constexpr int GT_QUADS = GT_SLICES / 4;  // 16-byte pieces of a tile row
 constexpr size_t GT_SMEM = 2 * 256 * 32 * 4 + 128 * GT_TILE_PITCH * 4;
 struct SmemTe02 {
     const uint8_t *base;  // entry x at byte 256 x: [0, 128) = Te0[x] once per lane, [128, 256) = Te2[x]
@@ -120,16 +121,18 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_mask_gen_tt(const uint32_t *_
         }
         __syncthreads();
         {  // row-major share tensor: thread = (mask of the block, 4 slices) -> one 16-byte store; a row's 16 slices = 64 contiguous bytes
-            const uint32_t m = tid >> 2, q4 = 4 * (tid & 3);
-            const uint64_t i = (uint64_t)j * 128 + m;
-            if (i < n_masks && w0 + q4 < nslices) {
-                const uint4 v = *reinterpret_cast<const uint4 *>(tile + m * GT_TILE_PITCH + q4);
-                *reinterpret_cast<uint4 *>(rows32 + i * nslices + w0 + q4) = v;
+            for (uint32_t e = tid; e < 128 * GT_QUADS; e += GT_THREADS) {
+                const uint32_t m = e / GT_QUADS, q4 = 4 * (e % GT_QUADS);
+                const uint64_t i = (uint64_t)j * 128 + m;
+                if (i < n_masks && w0 + q4 < nslices) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(tile + m * GT_TILE_PITCH + q4);
+                    *reinterpret_cast<uint4 *>(rows32 + i * nslices + w0 + q4) = v;
+                }
             }
         }
         if (fresh_pm != nullptr) {  // instance-major copy for the mask VM: 8 instances x 128 masks, u64 each
 #pragma unroll
-            for (uint32_t e = tid; e < 8 * 128; e += GT_THREADS) {
+            for (uint32_t e = tid; e < (GT_SLICES / 2) * 128; e += GT_THREADS) {
                 const uint32_t p = e >> 7, m = e & 127;
                 if (w0 + 2 * p < nslices) {
                     const uint2 v = *reinterpret_cast<const uint2 *>(tile + m * GT_TILE_PITCH + 2 * p);
