@@ -179,6 +179,9 @@ def main():
     ap.add_argument("--workload", default="sha256")
     ap.add_argument("--batch", type=int, default=32, help="independent proofs per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shard", default="reps", choices=["reps", "proofs"],
+                    help="N > 1: 'reps' shards the 32 packed instances of every proof over the ranks with the NCCL all-gather of repetition "
+                         "hashes (BASELINE config 4, strong scaling); 'proofs' gives every rank its own whole proofs (no collective, weak scaling)")
     args = ap.parse_args()
     set_metric(args.workload)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -210,9 +213,11 @@ def main():
     circ = rb.Circuit(ops, wc)
     st = circ.stats()
     n_and = st["n_and"] + st["z64_mul"]  # multiplication gates of either domain
-    per = 32 // world
+    st_proof_len = 0
+    by_proofs = world > 1 and args.shard == "proofs"
+    per = 32 if by_proofs else 32 // world
     B = max(1, args.batch)
-    sessions = [rb.Session(circ, rank * per, per) for _ in range(B)]
+    sessions = [rb.Session(circ, 0 if by_proofs else rank * per, per) for _ in range(B)]
     streams = [torch.cuda.ExternalStream(x.stream) for x in sessions]
     timing_stream = torch.cuda.Stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
@@ -227,7 +232,7 @@ def main():
 
     def step_device():
         """B proofs: commit + open with inputs resident in HBM; the all-gather of repetition hashes when sharded."""
-        if world == 1:
+        if world == 1 or by_proofs:
             for x in sessions:
                 x.prove()
             return
@@ -273,6 +278,7 @@ def main():
 
     for x in sessions:
         x.upload(wit, wz, seeds)
+    st_proof_len = len(torch.as_tensor(sessions[0].proof_device(), device="cuda"))
     for _ in range(args.warmup):
         step_device()
     for x in sessions:
@@ -288,7 +294,8 @@ def main():
         t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
-    value = n_and * B * args.steps / (ms_total * 1e-3)
+    n_jobs = B * (world if by_proofs else 1)  # proofs completed per step by the whole job
+    value = n_and * n_jobs * args.steps / (ms_total * 1e-3)
 
     # single-proof device latency (B = 1), same rules
     lat_ms = None
@@ -386,8 +393,11 @@ def main():
             for x in sessions:
                 x.upload(wit, wz, seeds)
             step_device()
-            outs = [x.fetch() for x in sessions]
-            return outs, [sharding.gather_parts(c, p) for c, p in outs]  # rank 0 ends up with the B assembled proofs
+            if by_proofs:
+                outs = [x.fetch() for x in sessions]
+                return outs, [p for _, p in outs]  # every rank holds its own whole proofs
+            proofs = sharding.reduce_proofs(sessions)  # one NCCL reduce: rank 0 ends up with the B assembled proofs in host memory
+            return [(None, proofs[0] if proofs else b"")], proofs
         for _ in range(args.warmup):
             step_e2e()
         barrier()
@@ -398,8 +408,8 @@ def main():
         dt = time.perf_counter() - t0
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_v = n_and * B * args.steps / float(t.item())
-        d2h = B * (len(outs[0][1]) + 36 + per * 8 * 32)
+        e2e_v = n_and * n_jobs * args.steps / float(t.item())
+        d2h = B * (st_proof_len + 36)
     e2e = {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": B * (st["n_inputs"] + 8 * st["z64_inputs"] + per * 8 * 16 + (256 * 32 if world > 1 else 0)), "d2h_bytes_per_step": d2h}
 
     cpu = None
@@ -417,9 +427,10 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u64",
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak" if by_proofs else "strong", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
-            "config": {"workload": desc, "batch": B, "parallelism": f"{per} packed instances (= {per * 8} repetitions) per GPU, {B} proofs in flight per step",
+            "config": {"workload": desc, "batch": B, "parallelism": (f"whole proofs per GPU, {B} proofs in flight per GPU per step, no collective" if by_proofs else
+                                                                      f"{per} packed instances (= {per * 8} repetitions) per GPU, {B} proofs in flight per step, NCCL all-gather of the repetition hashes"),
                        "l2": "256 MiB memset between timed steps (outside the per-step CUDA-event pair)",
                        "timing": "one CUDA-event pair per step on a timing stream that forks to / joins the B session streams, summed over K steps"},
             "clocks": clocks, "e2e": e2e, "verify": verify, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,

@@ -177,6 +177,12 @@ int rv_session_prove(rv_session *s);                                    /* async
                                                                            one CUDA graph launch after the first, eager, call */
 int rv_session_fetch(rv_session *s, uint8_t comm[RV_HASH_SIZE], uint8_t **part, size_t *part_len); /* synchronises */
 int rv_session_sync(rv_session *s);
+/* Synchronises and reports the proof's status without copying it: RV_OK, or RV_E_WITNESS_INVALID if an AssertZero failed. */
+int rv_session_status(rv_session *s);
+/* The shard's openings in device memory (the full-length proof buffer, zero outside the shard's entries), valid after
+ * rv_session_open: lets a multi-GPU caller combine the shards on the device (their non-zero bytes are disjoint, so an
+ * NCCL sum-reduce of the byte buffers is the assembly of src/proof/mod.rs:200-221). */
+int rv_session_proof_device(rv_session *s, void **ptr, size_t *len);
 int rv_proof_assemble(const uint8_t comm[RV_HASH_SIZE], const uint8_t *const *parts, const size_t *part_lens,
                       int n_parts, uint8_t **proof, size_t *proof_len);
 /* cudaStream_t of the session (as void*), so callers can bracket work with their own CUDA events. */

@@ -794,6 +794,24 @@ extern "C" int rv_session_fetch(rv_session *s, uint8_t comm[RV_HASH_SIZE], uint8
     return RV_OK;
 }
 
+extern "C" int rv_session_status(rv_session *s) {
+    if (!s) return fail(RV_E_ARG, "NULL session");
+    if (!s->opened) return fail(RV_E_ARG, "rv_session_open has not run");
+    CU(cudaSetDevice(s->c->device));
+    CU(cudaStreamSynchronize(s->st));
+    int bad;
+    memcpy(&bad, s->h_out + s->proof_len, 4);
+    if (bad) return fail(RV_E_WITNESS_INVALID, "witness is invalid!");  // prover.rs:223
+    return RV_OK;
+}
+
+extern "C" int rv_session_proof_device(rv_session *s, void **ptr, size_t *len) {
+    if (!s || !ptr || !len) return fail(RV_E_ARG, "NULL argument");
+    *ptr = s->d_proof;
+    *len = s->proof_len;
+    return RV_OK;
+}
+
 // Shard blobs are full-length proofs with only the shard's entries filled in (zero elsewhere); entries never overlap,
 // so the assembly of src/proof/mod.rs:200-221 is a byte-wise OR.
 extern "C" int rv_proof_assemble(const uint8_t comm[RV_HASH_SIZE], const uint8_t *const *parts, const size_t *part_lens, int n_parts,

@@ -163,6 +163,20 @@ class Session:
     def sync(self):
         N.check(N.lib().rv_session_sync(self._h))
 
+    def status(self):
+        """Synchronise and raise WitnessError if an AssertZero failed, without copying the proof."""
+        N.check(N.lib().rv_session_status(self._h))
+
+    def proof_device(self):
+        """The shard's full-length proof buffer in device memory (__cuda_array_interface__, uint8)."""
+        ptr, n = C.c_void_p(), C.c_size_t()
+        N.check(N.lib().rv_session_proof_device(self._h, C.byref(ptr), C.byref(n)))
+
+        class _Dev:
+            __cuda_array_interface__ = {"shape": (n.value,), "typestr": "|u1", "data": (ptr.value, False), "version": 2}
+
+        return _Dev()
+
     @property
     def stream(self) -> int:
         return int(N.lib().rv_session_stream(self._h) or 0)

@@ -78,6 +78,28 @@ def gather_parts(comm: bytes, part: bytes, group=None, dst: int = 0) -> Optional
     return assemble(comm, parts) if rank == dst else None
 
 
+def reduce_proofs(sessions, group=None, dst: int = 0):
+    """Assemble the proofs of several sharded sessions on the device: the shard buffers of one proof are zero outside their
+    own entries, so a sum-reduce of the bytes IS the concatenation of src/proof/mod.rs:200-221.  One NCCL reduce for all
+    sessions; returns the list of proof bytes on `dst`, None elsewhere.  Raises WitnessError if any shard saw a failed assert."""
+    import torch
+    import torch.distributed as dist
+
+    for s in sessions:
+        s.status()
+    parts = [torch.as_tensor(s.proof_device(), device="cuda") for s in sessions]
+    buf = torch.cat(parts)
+    dist.reduce(buf, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    if dist.get_rank(group) != dst:
+        return None
+    host = buf.cpu().numpy()
+    out, pos = [], 0
+    for p in parts:
+        out.append(host[pos:pos + p.numel()].tobytes())
+        pos += p.numel()
+    return out
+
+
 def prove_sharded(circuit, wit_gf2, wit_z64=(), seeds=None, group=None, session=None) -> Optional[bytes]:
     """Proof::new over all ranks of `group` (NCCL, one GPU per rank).  `seeds` must be the same 256 x 16 bytes on every rank
     (rank 0 may draw them and broadcast).  Returns the proof on rank 0."""
@@ -97,5 +119,5 @@ def prove_sharded(circuit, wit_gf2, wit_z64=(), seeds=None, group=None, session=
     with torch.cuda.stream(torch.cuda.ExternalStream(s.stream)):
         all_gather_hashes_into(torch.as_tensor(recv, device="cuda"), torch.as_tensor(s.hashes_device(), device="cuda"), group)
     s.open(recv.ptr)
-    comm, part = s.fetch()
-    return gather_parts(comm, part, group)
+    out = reduce_proofs([s], group)
+    return out[0] if out is not None else None
