@@ -49,7 +49,50 @@ extern "C" int rv_set_device(int device) {
     CU(cudaSetDevice(device));
     return RV_OK;
 }
-extern "C" void rv_free(void *p) { free(p); }
+// Large proofs (hundreds of MB for Z64 / 10^8-gate circuits) are returned in pinned host buffers the device copies into
+// directly; rv_free recognises them and parks up to a few in a pool, because pinning a gigabyte costs more than proving.
+static std::mutex g_pin_mu;
+static std::vector<std::pair<void *, size_t>> g_pin_live, g_pin_free;
+static constexpr size_t PIN_THRESHOLD = 4u << 20, PIN_POOL_MAX = 4;
+static void *pinned_get(size_t bytes) {
+    {
+        std::lock_guard<std::mutex> g(g_pin_mu);
+        for (size_t i = 0; i < g_pin_free.size(); i++)
+            if (g_pin_free[i].second >= bytes && g_pin_free[i].second <= 2 * bytes) {
+                auto e = g_pin_free[i];
+                g_pin_free.erase(g_pin_free.begin() + i);
+                g_pin_live.push_back(e);
+                return e.first;
+            }
+    }
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> g(g_pin_mu);
+    g_pin_live.push_back({p, bytes});
+    return p;
+}
+extern "C" void rv_free(void *p) {
+    if (!p) return;
+    {
+        std::lock_guard<std::mutex> g(g_pin_mu);
+        for (size_t i = 0; i < g_pin_live.size(); i++)
+            if (g_pin_live[i].first == p) {
+                auto e = g_pin_live[i];
+                g_pin_live.erase(g_pin_live.begin() + i);
+                if (g_pin_free.size() < PIN_POOL_MAX) {
+                    g_pin_free.push_back(e);
+                    return;
+                }
+                p = nullptr;
+                cudaFreeHost(e.first);
+                return;
+            }
+    }
+    free(p);
+}
 
 // ---------------------------------------------------------------------------------------------------------------------
 //  circuit
@@ -318,7 +361,9 @@ struct rv_session {
     uint32_t len_recons = 0, len_corrs = 0, len_inputs = 0;
     // pinned host staging
     uint8_t *h_in = nullptr;   // witness || seeds(256*16)
-    uint8_t *h_out = nullptr;  // proof || bad(4) || comm(32)
+    uint8_t *h_out = nullptr;  // proof || bad(4) || comm(32); big proofs (>= PIN_THRESHOLD) skip the proof part: rv_session_fetch copies
+                               // them from d_proof straight into the pinned buffer it returns
+    size_t out_off = 0;        // offset of bad / comm inside h_out
     size_t h_in_bytes = 0;
     std::vector<void *> allocs;
     bool timing = false;
@@ -431,7 +476,7 @@ extern "C" int rv_session_create(const rv_circuit *c, int first_instance, int n_
         (rc = dalloc(s, &s->d_zconst, 16)) || (rc = dalloc(s, &s->d_bad, 1)) || (rc = dalloc(s, &s->d_proof, s->proof_len)))
         return bail(rc);
     s->h_in_bytes = round_up(P.n_inputs, 16) + RV_TOTAL_REPS * 16 + 8 * (size_t)Z.n_inputs;
-    if (cudaMallocHost(&s->h_in, s->h_in_bytes) != cudaSuccess || cudaMallocHost(&s->h_out, s->proof_len + 64) != cudaSuccess)
+    if (cudaMallocHost(&s->h_in, s->h_in_bytes) != cudaSuccess || cudaMallocHost(&s->h_out, (s->out_off = s->proof_len >= PIN_THRESHOLD ? 0 : s->proof_len) + 64) != cudaSuccess)
         return bail(fail(RV_E_NOMEM, "pinned host allocation failed"));
     uint32_t zc[16];
     memcpy(zc, c->z64_empty_hash, 32);
@@ -745,9 +790,9 @@ static int open_body(rv_session *s, const uint8_t *all_rep_hashes) {
         a.proof = s->d_proof;
         launch_zextract(c->zdev, a, s->st);
     }
-    CU(cudaMemcpyAsync(s->h_out, s->d_proof, s->proof_len, cudaMemcpyDeviceToHost, s->st));
-    CU(cudaMemcpyAsync(s->h_out + s->proof_len, s->d_bad, 4, cudaMemcpyDeviceToHost, s->st));
-    CU(cudaMemcpyAsync(s->h_out + s->proof_len + 4, s->d_comm, 32, cudaMemcpyDeviceToHost, s->st));
+    if (s->out_off) CU(cudaMemcpyAsync(s->h_out, s->d_proof, s->proof_len, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(s->h_out + s->out_off, s->d_bad, 4, cudaMemcpyDeviceToHost, s->st));
+    CU(cudaMemcpyAsync(s->h_out + s->out_off + 4, s->d_comm, 32, cudaMemcpyDeviceToHost, s->st));
     CU(cudaGetLastError());
     return RV_OK;
 }
@@ -783,12 +828,24 @@ extern "C" int rv_session_fetch(rv_session *s, uint8_t comm[RV_HASH_SIZE], uint8
     CU(cudaSetDevice(s->c->device));
     CU(cudaStreamSynchronize(s->st));
     int bad;
-    memcpy(&bad, s->h_out + s->proof_len, 4);
+    memcpy(&bad, s->h_out + s->out_off, 4);
     if (bad) return fail(RV_E_WITNESS_INVALID, "witness is invalid!");  // prover.rs:223
-    uint8_t *p = (uint8_t *)malloc(s->proof_len);
-    if (!p) return fail(RV_E_NOMEM, "out of memory");
-    memcpy(p, s->h_out, s->proof_len);
-    if (comm) memcpy(comm, s->h_out + s->proof_len + 4, 32);
+    uint8_t *p;
+    if (s->out_off) {
+        p = (uint8_t *)malloc(s->proof_len);
+        if (!p) return fail(RV_E_NOMEM, "out of memory");
+        memcpy(p, s->h_out, s->proof_len);
+    } else {  // big proof: device -> the returned pinned buffer, no staging copy
+        p = (uint8_t *)pinned_get(s->proof_len);
+        if (!p) return fail(RV_E_NOMEM, "pinned host allocation failed");
+        cudaError_t e = cudaMemcpyAsync(p, s->d_proof, s->proof_len, cudaMemcpyDeviceToHost, s->st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
+        if (e != cudaSuccess) {
+            rv_free(p);
+            return fail(RV_E_CUDA, std::string("proof copy: ") + cudaGetErrorString(e));
+        }
+    }
+    if (comm) memcpy(comm, s->h_out + s->out_off + 4, 32);
     *part = p;
     *part_len = s->proof_len;
     return RV_OK;
@@ -800,7 +857,7 @@ extern "C" int rv_session_status(rv_session *s) {
     CU(cudaSetDevice(s->c->device));
     CU(cudaStreamSynchronize(s->st));
     int bad;
-    memcpy(&bad, s->h_out + s->proof_len, 4);
+    memcpy(&bad, s->h_out + s->out_off, 4);
     if (bad) return fail(RV_E_WITNESS_INVALID, "witness is invalid!");  // prover.rs:223
     return RV_OK;
 }

@@ -75,10 +75,22 @@ def _as_circuit(circuit, wire_counts) -> Circuit:
     return Circuit(circuit, wire_counts)
 
 
-def _take(out: C.c_void_p, n: C.c_size_t) -> bytes:
-    b = C.string_at(out, n.value)
-    N.lib().rv_free(out)
-    return b
+_ZERO_COPY_FROM = 4 << 20
+
+
+def _take(out: C.c_void_p, n: C.c_size_t):
+    """Library-allocated bytes -> Python.  Small results are copied into `bytes`; big ones (proofs of Z64 / 10^8-gate circuits
+    run to a gigabyte) stay in the library's pinned buffer, wrapped as a read-only numpy view that frees it when collected."""
+    if n.value < _ZERO_COPY_FROM:
+        b = C.string_at(out, n.value)
+        N.lib().rv_free(out)
+        return b
+    import weakref
+
+    arr = np.ctypeslib.as_array(C.cast(out, C.POINTER(C.c_uint8)), shape=(n.value,))
+    arr.flags.writeable = False
+    weakref.finalize(arr, N.lib().rv_free, C.c_void_p(out.value))
+    return arr
 
 
 class Session:
@@ -154,7 +166,7 @@ class Session:
         """commit + open (own hashes) of a full shard, asynchronously; one CUDA graph launch after the first call."""
         N.check(N.lib().rv_session_prove(self._h))
 
-    def fetch(self) -> Tuple[bytes, bytes]:
+    def fetch(self):
         comm = np.zeros(32, dtype=np.uint8)
         out, n = C.c_void_p(), C.c_size_t()
         N.check(N.lib().rv_session_fetch(self._h, _ptr(comm), C.byref(out), C.byref(n)))
@@ -209,8 +221,14 @@ def assemble(comm: bytes, parts: Sequence[bytes]) -> bytes:
 class Proof:
     """The bincode bytes of the reference's `Proof` struct (src/proof/mod.rs:40-66)."""
 
-    def __init__(self, data: bytes):
-        self.data = bytes(data)
+    def __init__(self, data):
+        self._buf = data if isinstance(data, (bytes, np.ndarray)) else bytes(data)
+
+    @property
+    def data(self) -> bytes:
+        if not isinstance(self._buf, bytes):
+            return self._buf.tobytes()
+        return self._buf
 
     @staticmethod
     def new(circuit, wit_gf2, wit_z64=(), wire_counts=None, seeds=None) -> "Proof":
@@ -227,7 +245,7 @@ class Proof:
     def verify(self, circuit, wire_counts=None) -> bool:
         """Proof::verify (src/proof/mod.rs:224-307)."""
         c = _as_circuit(circuit, wire_counts)
-        buf = np.frombuffer(self.data, dtype=np.uint8)
+        buf = self._buf if isinstance(self._buf, np.ndarray) else np.frombuffer(self._buf, dtype=np.uint8)
         okay = C.c_int(1)
         return N.check(N.lib().rv_verify(c.handle, _ptr(buf), buf.size, C.byref(okay))) == 1
 
@@ -240,10 +258,10 @@ class Proof:
 
     @property
     def comm(self) -> bytes:
-        return self.data[:32]
+        return bytes(self._buf[:32])
 
     def __len__(self):
-        return len(self.data)
+        return len(self._buf)
 
     def __eq__(self, other):
         return isinstance(other, Proof) and self.data == other.data
