@@ -221,56 +221,55 @@ def main():
     streams = [torch.cuda.ExternalStream(x.stream) for x in sessions]
     timing_stream = torch.cuda.Stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    recv_bufs = {}  # session -> (receive tensor over the session's own all-gather buffer, send tensor over its hashes, address, event)
-    sessions_all = list(sessions)
-    gather_stream, gathered_ev = torch.cuda.Stream(), torch.cuda.Event()
+    recv_bufs = {}  # session -> (receive tensor over the session's own all-gather buffer, send tensor over its hashes)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # The B sessions of a step are driven as one rv_batch: each phase (commit / open / prove) of all of them is ONE CUDA
+    # graph launch on the leader's stream; the sessions' own streams fork from it and join back inside the graph.
+    batches = {}
+
+    def batch_of(sess_list):
+        key = len(sess_list)
+        if key not in batches:
+            bt = rb.Batch(sess_list)
+            batches[key] = (bt, torch.cuda.ExternalStream(bt.stream))
+        return batches[key]
+
     def step_device():
         """B proofs: commit + open with inputs resident in HBM; the all-gather of repetition hashes when sharded."""
+        bt, lead = batch_of(sessions)
         if world == 1 or by_proofs:
-            for x in sessions:
-                x.prove()
+            bt.prove()
             return
-        for x in sessions:
-            x.commit()
+        bt.commit()
         # the one exchange of the protocol (src/proof/mod.rs:160-171): NCCL all-gather of the repetition hashes, device to
-        # device into each session's own receive buffer -- no host round trip.  The B proofs of a step share ONE NCCL group
-        # launch: their streams join a gather stream and fork again.
-        if not recv_bufs:
-            for x in sessions_all:
-                r = x.all_hashes_device()
-                recv_bufs[x] = (torch.as_tensor(r, device="cuda"), torch.as_tensor(x.hashes_device(), device="cuda"), r.ptr, torch.cuda.Event())
-        for b, x in enumerate(sessions):
-            ev = recv_bufs[x][3]
-            ev.record(streams[b])
-            gather_stream.wait_event(ev)
-        with torch.cuda.stream(gather_stream):
+        # device from each session's hash buffer into its own receive buffer, ONE NCCL group launch for the B proofs in
+        # flight, enqueued on the leader's stream between the two graphs -- no host round trip, no synchronisation
+        for x in sessions:
+            if x not in recv_bufs:
+                recv_bufs[x] = (torch.as_tensor(x.all_hashes_device(), device="cuda"), torch.as_tensor(x.hashes_device(), device="cuda"))
+        with torch.cuda.stream(lead):
             sharding.all_gather_hashes_batched([recv_bufs[x][0] for x in sessions], [recv_bufs[x][1] for x in sessions])
-            gathered_ev.record(gather_stream)
-        for b, x in enumerate(sessions):
-            streams[b].wait_event(gathered_ev)
-            x.open(recv_bufs[x][2])
+        bt.open()
 
     def timed_device(k: int):
         tot = 0.0
+        _, lead = batch_of(sessions)
         for _ in range(k):
             with torch.cuda.stream(timing_stream):
                 flush.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             barrier()
             a.record(timing_stream)
-            for st_ in streams:  # fork
-                st_.wait_event(a)
+            lead.wait_event(a)
             step_device()
-            for st_ in streams:  # join
-                e = torch.cuda.Event()
-                e.record(st_)
-                timing_stream.wait_event(e)
+            e = torch.cuda.Event()
+            e.record(lead)
+            timing_stream.wait_event(e)
             b.record(timing_stream)
             barrier()
             tot += a.elapsed_time(b)
@@ -302,6 +301,8 @@ def main():
     if world == 1:
         keep_s, keep_st = sessions, streams
         sessions, streams = sessions[:1], streams[:1]
+        for _ in range(3):  # eager run, graph capture, first replay
+            step_device()
         lat_ms = timed_device(max(5, min(args.steps, 20))) / max(5, min(args.steps, 20))
         sessions, streams = keep_s, keep_st
 
@@ -339,8 +340,9 @@ def main():
     big = st["n_masks"] * 256 + st["z64_masks"] * 16384 > (8 << 30)  # a session of this circuit holds tens of GB: one at a time
     if big and world == 1:
         del sess, x
+        batches.clear()
+        recv_bufs.clear()
         sessions.clear()
-        sessions_all.clear()
         streams.clear()
         import gc
 
@@ -432,7 +434,7 @@ def main():
             "config": {"workload": desc, "batch": B, "parallelism": (f"whole proofs per GPU, {B} proofs in flight per GPU per step, no collective" if by_proofs else
                                                                       f"{per} packed instances (= {per * 8} repetitions) per GPU, {B} proofs in flight per step, NCCL all-gather of the repetition hashes"),
                        "l2": "256 MiB memset between timed steps (outside the per-step CUDA-event pair)",
-                       "timing": "one CUDA-event pair per step on a timing stream that forks to / joins the B session streams, summed over K steps"},
+                       "timing": "one CUDA-event pair per step on a timing stream that forks to / joins the batch leader's stream (the B session streams fork from / join it inside the CUDA graph), summed over K steps"},
             "clocks": clocks, "e2e": e2e, "verify": verify, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
             "kernels": kernels, "single_proof_latency_ms": {"device": lat_ms, "e2e": single_latency_ms}, "circuit": {k: st[k] for k in ("n_and", "n_ops", "value_depth", "linear_depth", "z64_mul", "z64_value_depth")},
         }

@@ -188,6 +188,22 @@ int rv_proof_assemble(const uint8_t comm[RV_HASH_SIZE], const uint8_t *const *pa
 /* cudaStream_t of the session (as void*), so callers can bracket work with their own CUDA events. */
 void *rv_session_stream(rv_session *s);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Batches: several sessions of ONE circuit (proofs in flight, e.g. the requests a proving service has queued) driven as a
+ * unit.  A phase of all of them is a single CUDA graph launch on the leader's stream (sessions[0]); the sessions' own
+ * streams fork from it and join back inside the graph.  While bound to a batch a session must be driven through the batch
+ * calls; rv_session_upload / _fetch / _status / _hashes_device / _all_hashes_device still address it individually and are
+ * ordered on the leader's stream (rv_batch_stream), which is also where the caller enqueues the all-gather between
+ * rv_batch_commit and rv_batch_open.  rv_batch_open reads every session's own rv_session_all_hashes_device buffer.
+ * ------------------------------------------------------------------------------------------------------------- */
+typedef struct rv_batch rv_batch;
+int rv_batch_create(rv_session *const *sessions, int n, rv_batch **out);
+void rv_batch_free(rv_batch *b);        /* unbinds the sessions; does not free them */
+int rv_batch_commit(rv_batch *b);       /* async */
+int rv_batch_open(rv_batch *b);         /* async */
+int rv_batch_prove(rv_batch *b);        /* async: commit + open(own hashes), full shards only */
+void *rv_batch_stream(rv_batch *b);     /* cudaStream_t of the leader */
+
 /* Per-kernel device timing (CUDA events on the session stream).  Enable, run, then read back
  * `n` (name, total ms, launches) triples accumulated since the last reset. */
 typedef struct rv_kernel_time {

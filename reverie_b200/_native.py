@@ -62,6 +62,12 @@ def lib() -> C.CDLL:
         "rv_session_sync": ([vp], i32),
         "rv_session_status": ([vp], i32),
         "rv_session_proof_device": ([vp, pp, psz], i32),
+        "rv_batch_create": ([C.POINTER(vp), i32, pp], i32),
+        "rv_batch_free": ([vp], None),
+        "rv_batch_commit": ([vp], i32),
+        "rv_batch_open": ([vp], i32),
+        "rv_batch_prove": ([vp], i32),
+        "rv_batch_stream": ([vp], vp),
         "rv_proof_assemble": ([vp, C.POINTER(vp), psz, i32, pp, psz], i32),
         "rv_session_stream": ([vp], vp),
         "rv_session_timing": ([vp, i32], i32),
@@ -79,7 +85,7 @@ EXPORTED = (
     "rv_last_error rv_version rv_device_count rv_set_device rv_circuit_compile rv_circuit_free rv_circuit_get_stats "
     "rv_circuit_export rv_prove rv_verify rv_proof_new rv_proof_verify rv_free rv_session_create rv_session_free "
     "rv_session_upload rv_session_commit rv_session_hashes rv_session_hashes_device rv_session_all_hashes_device rv_session_open rv_session_prove rv_session_fetch rv_session_sync rv_session_status rv_session_proof_device "
-    "rv_proof_assemble rv_session_stream rv_session_timing rv_session_kernel_times rv_session_launch_count"
+    "rv_proof_assemble rv_batch_create rv_batch_free rv_batch_commit rv_batch_open rv_batch_prove rv_batch_stream rv_session_stream rv_session_timing rv_session_kernel_times rv_session_launch_count"
 ).split()
 
 

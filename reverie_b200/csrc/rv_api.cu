@@ -370,7 +370,11 @@ struct rv_session {
     std::vector<KTimer> timers;
     uint64_t launches = 0;
     bool committed = false, opened = false, ever_committed = false;
+    // batching (rv_batch): host-initiated work of a bound session goes to the leader's stream; the phases fork from / join into it
+    rv_session *lead = nullptr;
+    cudaEvent_t ev_bjoin = nullptr;
 };
+static cudaStream_t host_stream(const rv_session *s) { return s->lead ? s->lead->st : s->st; }
 
 template <typename T>
 static int dalloc(rv_session *s, T **p, size_t count) {
@@ -399,6 +403,7 @@ extern "C" void rv_session_free(rv_session *s) {
     if (s->h_vin) cudaFreeHost(s->h_vin);
     if (s->h_vout) cudaFreeHost(s->h_vout);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_bjoin) cudaEventDestroy(s->ev_bjoin);
     for (rv_session::GraphSlot *g : {&s->g_prove, &s->g_commit, &s->g_open})
         if (g->exec) cudaGraphExecDestroy(g->exec);
     if (s->ev_vals) cudaEventDestroy(s->ev_vals);
@@ -486,11 +491,11 @@ extern "C" int rv_session_create(const rv_circuit *c, int first_instance, int n_
     return RV_OK;
 }
 
-extern "C" void *rv_session_stream(rv_session *s) { return s ? (void *)s->st : nullptr; }
+extern "C" void *rv_session_stream(rv_session *s) { return s ? (void *)host_stream(s) : nullptr; }
 extern "C" uint64_t rv_session_launch_count(const rv_session *s) { return s ? s->launches : 0; }
 extern "C" int rv_session_sync(rv_session *s) {
     if (!s) return fail(RV_E_ARG, "NULL session");
-    CU(cudaStreamSynchronize(s->st));
+    CU(cudaStreamSynchronize(host_stream(s)));
     return RV_OK;
 }
 
@@ -564,7 +569,8 @@ extern "C" int rv_session_upload(rv_session *s, const uint8_t *wit_gf2, size_t n
     if (n_gf2 < P.n_inputs || n_z64 < P.z.n_inputs) return fail(RV_E_WITNESS_SHORT, "witness is too short");  // prover.rs:190
     if ((P.n_inputs && !wit_gf2) || (P.z.n_inputs && !wit_z64)) return fail(RV_E_ARG, "witness pointer is NULL");
     CU(cudaSetDevice(s->c->device));
-    CU(cudaStreamSynchronize(s->st));  // the staging buffer may still be in flight from a previous proof
+    cudaStream_t hst = host_stream(s);
+    CU(cudaStreamSynchronize(hst));  // the staging buffer may still be in flight from a previous proof
     const size_t woff = round_up(P.n_inputs, 16);
     if (P.n_inputs) memcpy(s->h_in, wit_gf2, P.n_inputs);
     uint8_t *hs = s->h_in + woff;
@@ -577,13 +583,13 @@ extern "C" int rv_session_upload(rv_session *s, const uint8_t *wit_gf2, size_t n
             got += (size_t)r;
         }
     }
-    if (P.n_inputs) CU(cudaMemcpyAsync(s->d_wit, s->h_in, P.n_inputs, cudaMemcpyHostToDevice, s->st));
+    if (P.n_inputs) CU(cudaMemcpyAsync(s->d_wit, s->h_in, P.n_inputs, cudaMemcpyHostToDevice, hst));
     if (P.z.n_inputs) {  // the Z64 witness fills the first leaves of the value plane; the kappa leaves after it stay zero
         uint8_t *hz = hs + RV_TOTAL_REPS * 16;
         memcpy(hz, wit_z64, 8 * (size_t)P.z.n_inputs);
-        CU(cudaMemcpyAsync(s->d_zleaf, hz, 8 * (size_t)P.z.n_inputs, cudaMemcpyHostToDevice, s->st));
+        CU(cudaMemcpyAsync(s->d_zleaf, hz, 8 * (size_t)P.z.n_inputs, cudaMemcpyHostToDevice, hst));
     }
-    CU(cudaMemcpyAsync(s->d_seeds, hs + (size_t)s->first_rep * 16, (size_t)s->nreps * 16, cudaMemcpyHostToDevice, s->st));
+    CU(cudaMemcpyAsync(s->d_seeds, hs + (size_t)s->first_rep * 16, (size_t)s->nreps * 16, cudaMemcpyHostToDevice, hst));
     s->committed = s->opened = false;
     return RV_OK;
 }
@@ -718,8 +724,8 @@ extern "C" int rv_session_hashes(rv_session *s, uint8_t *rep_hashes) {
     if (!s || !rep_hashes) return fail(RV_E_ARG, "NULL argument");
     if (!s->committed) return fail(RV_E_ARG, "rv_session_commit has not run");
     CU(cudaSetDevice(s->c->device));
-    CU(cudaMemcpyAsync(rep_hashes, s->d_rep_hash, (size_t)s->nreps * 32, cudaMemcpyDeviceToHost, s->st));
-    CU(cudaStreamSynchronize(s->st));
+    CU(cudaMemcpyAsync(rep_hashes, s->d_rep_hash, (size_t)s->nreps * 32, cudaMemcpyDeviceToHost, host_stream(s)));
+    CU(cudaStreamSynchronize(host_stream(s)));
     return RV_OK;
 }
 
@@ -822,11 +828,111 @@ extern "C" int rv_session_prove(rv_session *s) {
     return rc;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+//  rv_batch: several sessions of one circuit driven as one unit -- a phase of ALL of them is one CUDA graph launch on the
+//  leader's stream (the sessions' own streams fork from it and join back inside the graph), so a proving service with many
+//  small proofs in flight pays three launches per step instead of three per proof.
+// ---------------------------------------------------------------------------------------------------------------------
+struct rv_batch {
+    std::vector<rv_session *> ss;
+    rv_session::GraphSlot g[3];  // commit, open, prove
+    cudaEvent_t ev_fork = nullptr;
+};
+
+extern "C" int rv_batch_create(rv_session *const *ss, int n, rv_batch **out) {
+    if (!ss || n <= 0 || !out) return fail(RV_E_ARG, "bad argument");
+    for (int i = 0; i < n; i++) {
+        if (!ss[i] || ss[i]->c != ss[0]->c) return fail(RV_E_ARG, "the sessions of a batch must share one circuit");
+        if (i && ss[i]->lead && ss[i]->lead != ss[0]) return fail(RV_E_ARG, "session already belongs to another batch");
+    }
+    rv_batch *b = new (std::nothrow) rv_batch();
+    if (!b) return fail(RV_E_NOMEM, "out of memory");
+    CU(cudaSetDevice(ss[0]->c->device));
+    if (cudaEventCreateWithFlags(&b->ev_fork, cudaEventDisableTiming) != cudaSuccess) {
+        delete b;
+        return fail(RV_E_CUDA, "event creation failed");
+    }
+    for (int i = 0; i < n; i++) {
+        rv_session *s = ss[i];
+        if (i) {
+            CU(cudaStreamSynchronize(s->st));
+            s->lead = ss[0];
+            if (!s->ev_bjoin && cudaEventCreateWithFlags(&s->ev_bjoin, cudaEventDisableTiming) != cudaSuccess) return fail(RV_E_CUDA, "event creation failed");
+        }
+        b->ss.push_back(s);
+    }
+    *out = b;
+    return RV_OK;
+}
+
+extern "C" void rv_batch_free(rv_batch *b) {
+    if (!b) return;
+    if (!b->ss.empty()) {
+        cudaSetDevice(b->ss[0]->c->device);
+        cudaStreamSynchronize(b->ss[0]->st);
+    }
+    for (size_t i = 1; i < b->ss.size(); i++) b->ss[i]->lead = nullptr;
+    for (auto &g : b->g)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    if (b->ev_fork) cudaEventDestroy(b->ev_fork);
+    delete b;
+}
+
+static int batch_run(rv_batch *b, int kind) {
+    rv_session *lead = b->ss[0];
+    CU(cudaSetDevice(lead->c->device));
+    if (kind == 1)
+        for (rv_session *s : b->ss)
+            if (!s->committed) return fail(RV_E_ARG, "rv_batch_commit has not run");
+    if (kind == 2)
+        for (rv_session *s : b->ss)
+            if (s->npi != RV_PACKED_REPS) return fail(RV_E_ARG, "rv_batch_prove needs full shards");
+    bool timing = false;
+    std::vector<uint64_t> before;
+    for (rv_session *s : b->ss) {
+        timing |= s->timing;
+        before.push_back(s->launches);
+    }
+    const bool keep = lead->timing;
+    lead->timing = timing;  // any session being timed keeps the whole phase eager
+    const int rc = run_graphed(lead, b->g[kind], [&] {
+        if (cudaEventRecord(b->ev_fork, lead->st) != cudaSuccess) return fail(RV_E_CUDA, "cudaEventRecord failed");
+        for (size_t i = 1; i < b->ss.size(); i++)
+            if (cudaStreamWaitEvent(b->ss[i]->st, b->ev_fork, 0) != cudaSuccess) return fail(RV_E_CUDA, "cudaStreamWaitEvent failed");
+        for (rv_session *s : b->ss) {
+            int r = RV_OK;
+            if (kind != 1) r = commit_body(s);
+            if (r == RV_OK && kind != 0) r = open_body(s, kind == 1 ? s->d_all_hashes : nullptr);
+            if (r != RV_OK) return r;
+        }
+        for (size_t i = 1; i < b->ss.size(); i++) {
+            rv_session *f = b->ss[i];
+            if (cudaEventRecord(f->ev_bjoin, f->st) != cudaSuccess || cudaStreamWaitEvent(lead->st, f->ev_bjoin, 0) != cudaSuccess)
+                return fail(RV_E_CUDA, "stream join failed");
+        }
+        return (int)RV_OK;
+    });
+    lead->timing = keep;
+    if (rc != RV_OK) return rc;
+    const uint64_t per = b->g[kind].kernels;  // the leader's own launches of this phase = every session's (same circuit)
+    for (size_t i = 0; i < b->ss.size(); i++) {
+        rv_session *s = b->ss[i];
+        s->launches = before[i] + per;
+        if (kind != 1) s->committed = s->ever_committed = true;
+        if (kind != 0) s->opened = true;
+    }
+    return RV_OK;
+}
+extern "C" int rv_batch_commit(rv_batch *b) { return b ? batch_run(b, 0) : fail(RV_E_ARG, "NULL batch"); }
+extern "C" int rv_batch_open(rv_batch *b) { return b ? batch_run(b, 1) : fail(RV_E_ARG, "NULL batch"); }
+extern "C" int rv_batch_prove(rv_batch *b) { return b ? batch_run(b, 2) : fail(RV_E_ARG, "NULL batch"); }
+extern "C" void *rv_batch_stream(rv_batch *b) { return b ? (void *)b->ss[0]->st : nullptr; }
+
 extern "C" int rv_session_fetch(rv_session *s, uint8_t comm[RV_HASH_SIZE], uint8_t **part, size_t *part_len) {
     if (!s || !part || !part_len) return fail(RV_E_ARG, "NULL argument");
     if (!s->opened) return fail(RV_E_ARG, "rv_session_open has not run");
     CU(cudaSetDevice(s->c->device));
-    CU(cudaStreamSynchronize(s->st));
+    CU(cudaStreamSynchronize(host_stream(s)));
     int bad;
     memcpy(&bad, s->h_out + s->out_off, 4);
     if (bad) return fail(RV_E_WITNESS_INVALID, "witness is invalid!");  // prover.rs:223
@@ -838,8 +944,8 @@ extern "C" int rv_session_fetch(rv_session *s, uint8_t comm[RV_HASH_SIZE], uint8
     } else {  // big proof: device -> the returned pinned buffer, no staging copy
         p = (uint8_t *)pinned_get(s->proof_len);
         if (!p) return fail(RV_E_NOMEM, "pinned host allocation failed");
-        cudaError_t e = cudaMemcpyAsync(p, s->d_proof, s->proof_len, cudaMemcpyDeviceToHost, s->st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(s->st);
+        cudaError_t e = cudaMemcpyAsync(p, s->d_proof, s->proof_len, cudaMemcpyDeviceToHost, host_stream(s));
+        if (e == cudaSuccess) e = cudaStreamSynchronize(host_stream(s));
         if (e != cudaSuccess) {
             rv_free(p);
             return fail(RV_E_CUDA, std::string("proof copy: ") + cudaGetErrorString(e));
@@ -855,7 +961,7 @@ extern "C" int rv_session_status(rv_session *s) {
     if (!s) return fail(RV_E_ARG, "NULL session");
     if (!s->opened) return fail(RV_E_ARG, "rv_session_open has not run");
     CU(cudaSetDevice(s->c->device));
-    CU(cudaStreamSynchronize(s->st));
+    CU(cudaStreamSynchronize(host_stream(s)));
     int bad;
     memcpy(&bad, s->h_out + s->out_off, 4);
     if (bad) return fail(RV_E_WITNESS_INVALID, "witness is invalid!");  // prover.rs:223

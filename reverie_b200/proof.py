@@ -207,6 +207,36 @@ class Session:
         return int(N.lib().rv_session_launch_count(self._h))
 
 
+class Batch:
+    """Several sessions of one circuit driven as a unit (rv_batch): each phase of all of them is one CUDA graph launch on the
+    leader's stream.  Keep the sessions alive for as long as the batch."""
+
+    def __init__(self, sessions: Sequence["Session"]):
+        self.sessions = list(sessions)
+        arr = (C.c_void_p * len(self.sessions))(*[s._h for s in self.sessions])
+        h = C.c_void_p()
+        N.check(N.lib().rv_batch_create(arr, len(self.sessions), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            N.lib().rv_batch_free(h)
+
+    def commit(self):
+        N.check(N.lib().rv_batch_commit(self._h))
+
+    def open(self):
+        N.check(N.lib().rv_batch_open(self._h))
+
+    def prove(self):
+        N.check(N.lib().rv_batch_prove(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(N.lib().rv_batch_stream(self._h) or 0)
+
+
 def assemble(comm: bytes, parts: Sequence[bytes]) -> bytes:
     """src/proof/mod.rs:200-221 for shard blobs produced by Session.fetch()."""
     bufs = [np.frombuffer(p, dtype=np.uint8) for p in parts]

@@ -37,6 +37,28 @@ def main():
             assert rc == 0 and proof == want, f"{name}: sharded proof over {world} GPUs differs from the oracle"
             assert rb.Proof(proof).verify(circ)
             print(f"mgpu ok: {name} on {world} GPUs, {len(proof)} bytes", flush=True)
+    # two proofs in flight as one rv_batch: commit graph -> one NCCL group launch for both all-gathers -> open graph -> one reduce
+    name, ops, gwit, zwit, wc = cases[0]
+    circ = rb.Circuit(ops, wc)
+    first, count = sharding.shard_of(rank, world)
+    sess = [rb.Session(circ, first, count) for _ in range(2)]
+    seeds2 = bytes(reversed(seeds))
+    batch = rb.Batch(sess)
+    lead = torch.cuda.ExternalStream(batch.stream)
+    for rnd in range(3):
+        sess[0].upload(gwit, zwit, seeds)
+        sess[1].upload(gwit, zwit, seeds2)
+        batch.commit()
+        with torch.cuda.stream(lead):
+            sharding.all_gather_hashes_batched([torch.as_tensor(s.all_hashes_device(), device="cuda") for s in sess],
+                                               [torch.as_tensor(s.hashes_device(), device="cuda") for s in sess])
+        batch.open()
+        proofs = sharding.reduce_proofs(sess)
+        if rank == 0:
+            assert proofs[0] == orc.prove(ops, gwit, zwit, wc, seeds)[1] and proofs[1] == orc.prove(ops, gwit, zwit, wc, seeds2)[1], rnd
+    if rank == 0:
+        print(f"mgpu ok: batch of 2 on {world} GPUs", flush=True)
+    del batch
     dist.barrier()
     dist.destroy_process_group()
 

@@ -363,7 +363,7 @@ def test_multi_gpu_nccl_sharded_prove(rb):
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
                           "--master-port", "29533", os.path.join(root, "tests", "_mgpu_worker.py")], capture_output=True, text=True, timeout=600, cwd=root)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
-    assert res.stdout.count("mgpu ok") == 2
+    assert res.stdout.count("mgpu ok") == 3
 
 
 def test_cli_prove_verify_roundtrip(rb, tmp_path):
@@ -408,3 +408,33 @@ def test_random_and_b2a(rb, default_seeds, seed):
     badw[3] ^= 1
     with pytest.raises(rb.WitnessError):
         rb.Proof.new(circ, badw, zwit, seeds=default_seeds)
+
+
+def test_batch_of_sessions_one_graph_per_phase(rb, default_seeds):
+    """rv_batch: several proofs in flight driven as one unit (one CUDA graph launch per phase); replays stay bit-exact, a
+    bad witness in one session is reported for that session only."""
+    import orc
+    from reverie_b200 import circuits as C
+
+    ops, wit, wc = C.aes128_fips197_case()
+    rc, want = orc.prove(ops, wit, [], wc, default_seeds)
+    rng = np.random.default_rng(3)
+    seeds2 = rng.integers(0, 256, size=256 * 16, dtype=np.uint8).tobytes()
+    rc, want2 = orc.prove(ops, wit, [], wc, seeds2)
+    circ = rb.Circuit(ops, wc)
+    sess = [rb.Session(circ) for _ in range(3)]
+    batch = rb.Batch(sess)
+    for rnd in range(4):  # eager, capture, replay, replay
+        for k, s in enumerate(sess):
+            s.upload(wit, (), seeds2 if (k + rnd) % 2 else default_seeds)
+        batch.prove()
+        for k, s in enumerate(sess):
+            assert s.fetch()[1] == (want2 if (k + rnd) % 2 else want), (rnd, k)
+    bad = wit.copy()
+    bad[9] ^= 1
+    sess[1].upload(bad, (), default_seeds)
+    batch.prove()
+    assert sess[0].fetch()[1] in (want, want2) and sess[2].fetch()[1] in (want, want2)
+    with pytest.raises(rb.WitnessError):
+        sess[1].fetch()
+    del batch
