@@ -156,12 +156,12 @@ void launch_zvalues(const DevZProgram &Z, const uint64_t *leaf_vals, size_t leaf
 //       to each of its 8 streams.
 // =====================================================================================================================
 __global__ void __launch_bounds__(256) k_zitems_online(const ZItem *__restrict__ items, uint32_t n_items, const uint64_t *__restrict__ zrows,
-                                                       size_t rowlen, const uint64_t *__restrict__ vals, uint8_t *__restrict__ on, size_t pitch,
-                                                       int *bad) {
+                                                       size_t rowlen, const uint64_t *__restrict__ vals, const uint64_t *__restrict__ grows,
+                                                       uint8_t *__restrict__ on, size_t pitch, uint8_t *__restrict__ pre, size_t pitch_pre, int *bad) {
     const uint32_t t = blockIdx.x * 32 + (threadIdx.x >> 3), rep = 8 * blockIdx.y + (threadIdx.x & 7);
     if (t >= n_items) return;
     int flag = 0;
-    z_prover_online(items[t], zrows, rowlen, rep, vals, on + (size_t)rep * pitch, &flag);
+    z_prover_online(items[t], zrows, rowlen, rep, vals, on + (size_t)rep * pitch, &flag, pre + (size_t)rep * pitch_pre, grows, (uint32_t)(rowlen / 64));
     if (flag && rep == 0) atomicOr(bad, 1);
 }
 
@@ -175,8 +175,9 @@ __global__ void __launch_bounds__(256) k_zitems_pre(const ZItem *__restrict__ it
 
 void launch_zitems(const DevZProgram &Z, const uint64_t *zrows, size_t rowlen, uint32_t nreps, const uint64_t *vals, const uint64_t *grows, uint8_t *on,
                    size_t pitch_on, uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st) {
-    if (Z.n_items) k_zitems_online<<<dim3((Z.n_items + 31) / 32, nreps / 8), 256, 0, st>>>(Z.items, Z.n_items, zrows, rowlen, vals, on, pitch_on, bad);
-    if (Z.n_corr) k_zitems_pre<<<dim3((Z.n_corr + 31) / 32, nreps / 8), 256, 0, st>>>(Z.items, Z.mul_pos, Z.n_corr, zrows, rowlen, grows, pre, pitch_pre, 0);
+    // one pass fills both streams: a Mul's preprocessing word needs the operand segments its online word has just loaded
+    if (Z.n_items)
+        k_zitems_online<<<dim3((Z.n_items + 31) / 32, nreps / 8), 256, 0, st>>>(Z.items, Z.n_items, zrows, rowlen, vals, grows, on, pitch_on, pre, pitch_pre, bad);
 }
 
 void launch_zitems_pre_range(const DevZProgram &Z, const uint64_t *zrows, size_t rowlen, uint32_t first_rep, uint32_t nreps, const uint64_t *grows,
@@ -247,28 +248,57 @@ void launch_zverify_items(const DevZProgram &Z, const ZOpen *opens, const uint8_
 
 // =====================================================================================================================
 //  ZK7  extraction of the Z64 vectors of the opened repetitions (src/transcript/prover.rs:57-175 with
-//       src/algebra/z64/share.rs:37-49 and recon.rs:46-66): thread = one byte, so the unaligned proof bytes leave coalesced.
-//       grid.y = repetition of the shard, grid.x covers the 8 * (n_recon + n_mul + n_inputs) bytes of its three vectors.
+//       src/algebra/z64/share.rs:37-49 and recon.rs:46-66).  The vectors sit at arbitrary byte alignment inside the bincode
+//       proof, so a thread writes one ALIGNED 8-byte word of the destination, spliced from the two elements that straddle
+//       it; only the first and last word of a vector fall back to byte stores (their other bytes belong to neighbours).
+//       grid.y = repetition of the shard, grid.x covers the n + 1 words of each of the three vectors.
 // =====================================================================================================================
+template <typename F>
+__device__ __forceinline__ void put_spliced(uint8_t *D, uint64_t n, uint64_t w, F src) {  // w in [0, n]
+    if (n == 0) return;
+    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(D) & 7);
+    if (a == 0) {
+        if (w < n) *reinterpret_cast<uint64_t *>(D + 8 * w) = src(w);
+        return;
+    }
+    uint8_t *D0 = D - a;
+    if (w == 0) {
+        const uint64_t v = src(0);
+        for (uint32_t i = a; i < 8; i++) D0[i] = (uint8_t)(v >> (8 * (i - a)));
+    } else if (w == n) {
+        const uint64_t v = src(n - 1) >> (8 * (8 - a));
+        for (uint32_t i = 0; i < a; i++) D0[8 * n + i] = (uint8_t)(v >> (8 * i));
+    } else {
+        *reinterpret_cast<uint64_t *>(D0 + 8 * w) = (src(w - 1) >> (8 * (8 - a))) | (src(w) << (8 * a));
+    }
+}
+
 __global__ void __launch_bounds__(256) k_zextract(const uint32_t *__restrict__ recon_off, const uint32_t *__restrict__ input_off, uint32_t n_recon,
-                                                  uint32_t n_mul, uint32_t n_inputs, ZExtractArgs a) {
+                                                  uint32_t n_corr, uint32_t n_inputs, ZExtractArgs a) {
     const uint32_t lrep = blockIdx.y, rep = a.first_rep + lrep;
     const uint32_t omit = a.omit_of_rep[rep];
     if (omit >= RV_PLAYERS) return;
-    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const uint64_t nr = 8ull * n_recon, nc = 8ull * n_mul, ni = 8ull * n_inputs;
-    if (i >= nr + nc + ni) return;
+    uint64_t w = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint8_t *on = a.on + (size_t)lrep * a.pitch_on, *pre = a.pre + (size_t)lrep * a.pitch_pre;
     uint8_t *z = a.proof + a.z_base + 8 + (size_t)a.rank_of_rep[rep] * a.sz_on_z;
-    if (i < nr) z[137 + i] = on[recon_off[i >> 3] + 8 * omit + (i & 7)];
-    else if (i < nr + nc) z[145 + i] = pre[i - nr];
-    else z[153 + i] = on[input_off[(i - nr - nc) >> 3] + ((i - nr - nc) & 7)];
+    const uint64_t nr = n_recon, nc = n_corr, ni = n_inputs;
+    if (w <= nr) {  // recons: the unopened player's u64 of every broadcast share
+        put_spliced(z + 137, nr, w, [&](uint64_t e) { return *reinterpret_cast<const uint64_t *>(on + recon_off[e] + 8 * omit); });
+        return;
+    }
+    w -= nr + 1;
+    if (w <= nc) {  // corrs: the preprocessing stream itself
+        put_spliced(z + 145 + 8 * nr, nc, w, [&](uint64_t e) { return *reinterpret_cast<const uint64_t *>(pre + 8 * e); });
+        return;
+    }
+    w -= nc + 1;
+    if (w <= ni) put_spliced(z + 153 + 8 * (nr + nc), ni, w, [&](uint64_t e) { return *reinterpret_cast<const uint64_t *>(on + input_off[e]); });
 }
 
 void launch_zextract(const DevZProgram &Z, const ZExtractArgs &a, cudaStream_t st) {
-    const uint64_t bytes = 8ull * ((uint64_t)Z.n_recon + Z.n_corr + Z.n_inputs);
-    if (!bytes) return;
-    k_zextract<<<dim3((unsigned)((bytes + 255) / 256), a.nreps), 256, 0, st>>>(Z.recon_off, Z.input_off, Z.n_recon, Z.n_corr, Z.n_inputs, a);
+    const uint64_t words = (uint64_t)Z.n_recon + Z.n_corr + Z.n_inputs + 3;
+    if (words == 3) return;
+    k_zextract<<<dim3((unsigned)((words + 255) / 256), a.nreps), 256, 0, st>>>(Z.recon_off, Z.input_off, Z.n_recon, Z.n_corr, Z.n_inputs, a);
 }
 
 }  // namespace rv

@@ -77,8 +77,14 @@ RV_HD uint64_t get64_unaligned(const uint8_t *p) {
 // ---- prover ---------------------------------------------------------------------------------------------------------
 // One online item of repetition `rep` (index inside the shard): src/interpreter/single.rs:25-69,140-147,
 // src/transcript/prover.rs:181-232.  `stream` = this repetition's online stream.
-RV_HD void z_prover_online(const ZItem &it, const uint64_t *zrows, size_t rowlen, uint32_t rep, const uint64_t *vals, uint8_t *stream, int *bad) {
-    if (it.kind == ITEM_B2A) return;  // a conversion only appends to the preprocessing stream
+RV_HD uint64_t z_pre_word(const ZItem &it, const uint64_t *zrows, size_t rowlen, uint32_t rep, const uint64_t *grows, uint32_t npi);
+// `pre` (optional) = this repetition's preprocessing stream: the prover fills both streams in one pass over the operands.
+RV_HD void z_prover_online(const ZItem &it, const uint64_t *zrows, size_t rowlen, uint32_t rep, const uint64_t *vals, uint8_t *stream, int *bad,
+                           uint8_t *pre = nullptr, const uint64_t *grows = nullptr, uint32_t npi = 0) {
+    if (it.kind == ITEM_B2A) {  // a conversion only appends to the preprocessing stream
+        if (pre) put64(pre + 8ull * it.j, z_pre_word(it, zrows, rowlen, rep, grows, npi));
+        return;
+    }
     const uint64_t *A = zrows + (size_t)it.ra * rowlen + 8 * rep;
     uint8_t *dst = stream + it.off;
     if (it.kind == ITEM_INPUT) {
@@ -103,9 +109,11 @@ RV_HD void z_prover_online(const ZItem &it, const uint64_t *zrows, size_t rowlen
     zload8(NW, nw);
 #pragma unroll
     for (int p = 0; p < 8; p++) b[p] *= it.cb;
-    const uint64_t c1 = vals[it.va] - zsum8v(a), c2 = vals[it.vb] - zsum8v(b);  // corr = value - reconstruct(mask)
+    const uint64_t sa = zsum8v(a), sb = zsum8v(b);
+    const uint64_t c1 = vals[it.va] - sa, c2 = vals[it.vb] - sb;  // corr = value - reconstruct(mask)
 #pragma unroll
     for (int p = 0; p < 8; p++) put64(dst + 8 * p, b[p] * c1 + a[p] * c2 + ab[p] - nw[p]);  // single.rs:41-45
+    if (pre) put64(pre + 8ull * it.j, sa * sb - zsum8v(ab));                                   // delta = a * b - c, single.rs:35-39
 }
 
 // B2A: the per-repetition plaintext of the 64 fresh GF(2) wires g0 .. g0+63 (corr = 0: value = parity of the mask shares),

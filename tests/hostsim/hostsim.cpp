@@ -181,9 +181,8 @@ extern "C" int hs_prove(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t
         zon.assign(pitch_zon * nreps, 0);
         zpre.assign(pitch_zpre * nreps, 0);
         for (uint32_t rep = 0; rep < nreps; rep++) {
-            for (const ZItem &it : Z.items) z_prover_online(it, zrows.data(), rowlen, rep, zvals.data(), &zon[(size_t)rep * pitch_zon], &zbad);
-            for (uint32_t j = 0; j < Z.n_corr; j++)
-                put64(&zpre[(size_t)rep * pitch_zpre + 8ull * j], z_pre_word(Z.items[Z.mul_pos[j]], zrows.data(), rowlen, rep, rows.data(), npi));
+            for (const ZItem &it : Z.items)  // k_zitems_online: both streams in one pass
+                z_prover_online(it, zrows.data(), rowlen, rep, zvals.data(), &zon[(size_t)rep * pitch_zon], &zbad, &zpre[(size_t)rep * pitch_zpre], rows.data(), npi);
             uint32_t h_pre[8];
             stream_hash(&zon[(size_t)rep * pitch_zon], (uint32_t)Z.on_bytes, &zon_hash[rep * 8]);
             stream_hash(&zpre[(size_t)rep * pitch_zpre], (uint32_t)Z.pre_bytes, h_pre);
