@@ -70,6 +70,24 @@ def default_seeds() -> bytes:
     return b"".join(R.default_seeds())
 
 
+# bench kernel label -> kernel(s) in the committed ncu capture (profiles/r1c_traffic.json; DRAM bytes per launch)
+NCU_NAMES = {"linear": ["k_mask_vm"], "mask_gen": ["k_mask_gen_tt"], "items": ["k_items_tile<0>", "k_items_tile<1>"], "chunk_cv": ["k_chunk_cv"],
+             "values": ["k_values<1>"], "rep_hash": ["k_rep_hash"], "extract": ["k_extract"], "challenge": ["k_challenge"], "key_setup": ["k_key_setup"],
+             "z.mask_gen": ["k_zmask_gen_tt"], "z.items": ["k_zitems_online"], "z.values": ["k_zvalues"], "z.extract": ["k_zextract"]}
+
+
+def ncu_traffic(workload: str, label: str):
+    """DRAM bytes per launch of the kernel behind `label`, from the committed `ncu --set full` capture of the same workload
+    (None when that workload / kernel was not captured)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1c_traffic.json")) as f:
+            w = json.load(f)["workloads"].get(workload)
+        vals = [w[k]["dram_bytes_per_launch"] for k in NCU_NAMES.get(label, [])]
+        return sum(vals) / len(vals) if vals else None
+    except Exception:
+        return None
+
+
 def load_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -330,7 +348,8 @@ def main():
         per_launch_s = top["ms"] * 1e-3 / max(top["launches"], 1)
         bytes_per_launch = top["algorithmic_bytes"] / max(top["launches"], 1)
         ach = bytes_per_launch / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
-        roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                    "traffic": ncu_traffic(args.workload, top["name"]),
                     "peak_source": peak_src, "us_per_launch": per_launch_s * 1e6,
                     "per_kernel_frac": {k["name"]: (k["algorithmic_bytes"] / max(k["ms"], 1e-9) / 1e6) / peak for k in kt},
                     "path": {"algorithmic_bytes_per_step": st["algorithmic_bytes"], "achieved": B * st["algorithmic_bytes"] / (ms_total / args.steps * 1e-3) / 1e9,
