@@ -54,12 +54,16 @@ void launch_key_setup(const uint8_t *seeds, const uint8_t *pkeys_in, const uint8
 //      Cost per block and lane: ~190 LDS/SHFL + ~380 ALU-pipe instructions, against ~640 LOP3 bitsliced.
 constexpr int GT_SLICES = 16, GT_THREADS = 32 * GT_SLICES, GT_TILE_PITCH = GT_SLICES + 4;  // tile row = the CTA's slice words + pad (16-byte aligned rows)
 constexpr int GT_QUADS = GT_SLICES / 4;  // 16-byte pieces of a tile row
-constexpr size_t GT_SMEM = 2 * 256 * 32 * 4 + 128 * GT_TILE_PITCH * 4;
-struct SmemTe02 {
-    const uint8_t *base;  // entry x at byte 256 x: [0, 128) = Te0[x] once per lane, [128, 256) = Te2[x]
+constexpr size_t GT_TILE_BYTES = 128 * GT_TILE_PITCH * 4;
+// FOUR = false: Te0 / Te2 in 64 KB (Te1 / Te3 by PRMT rotation): leaves room for a mask-VM CTA on the same SM -- small proofs
+// in flight.  FOUR = true: all four tables (128 KB), 72 fewer ALU instructions per block -- circuits big enough to own the chip.
+template <bool FOUR>
+struct SmemTe {
+    const uint8_t *base;  // entry x at byte 256 x: [0, 128) = Te0[x] once per lane, [128, 256) = Te2[x]; FOUR: Te1 / Te3 64 KB further
     uint32_t lane4;
     __device__ __forceinline__ uint32_t operator()(int t, uint32_t w, int b) const {
         const uint32_t off = __byte_perm(w, lane4, 0x7604 | (b << 4));  // (byte b of w) << 8 | 4 * lane
+        if (FOUR) return *reinterpret_cast<const uint32_t *>(base + (t & 1) * 65536 + (t >> 1) * 128 + off);
         const uint32_t v = *reinterpret_cast<const uint32_t *>(base + (t >> 1) * 128 + off);
         return (t & 1) ? __byte_perm(v, v, 0x2103) : v;  // Te1 = rotl(Te0, 8), Te3 = rotl(Te2, 8)
     }
@@ -75,11 +79,12 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, uint32_t lane) 
     return x;
 }
 
+template <bool FOUR>
 __global__ void __launch_bounds__(GT_THREADS, 1) k_mask_gen_tt(const uint32_t *__restrict__ rk_plain, uint32_t nslices, uint32_t n_masks,
                                                                uint32_t blocks_per_cta, uint32_t *__restrict__ rows32,
                                                                uint64_t *__restrict__ fresh_pm, size_t pitch_pm) {
     extern __shared__ __align__(16) uint32_t gt_smem[];
-    uint32_t *te = gt_smem, *tile = gt_smem + 2 * 256 * 32;
+    uint32_t *te = gt_smem, *tile = gt_smem + (FOUR ? 4 : 2) * 256 * 32;
     __shared__ uint32_t sbox32[64];
     const uint32_t tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
     if (tid < 64) {
@@ -91,6 +96,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_mask_gen_tt(const uint32_t *_
         const uint32_t x = e >> 5, l = e & 31, t0 = te0_entry(reinterpret_cast<const uint8_t *>(sbox32)[x]);
         te[x * 64 + l] = t0;
         te[x * 64 + 32 + l] = (t0 << 16) | (t0 >> 16);
+        if (FOUR) {
+            te[16384 + x * 64 + l] = (t0 << 8) | (t0 >> 24);
+            te[16384 + x * 64 + 32 + l] = (t0 << 24) | (t0 >> 8);
+        }
     }
     const uint32_t w0 = blockIdx.y * GT_SLICES, w = w0 + wv, nstreams = nslices * 32;
     const bool live = w < nslices;
@@ -102,7 +111,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_mask_gen_tt(const uint32_t *_
         act = rk_plain[(size_t)44 * nstreams + sidx];
     }
     __syncthreads();
-    const SmemTe02 tab{reinterpret_cast<const uint8_t *>(te), 4 * lane};
+    const SmemTe<FOUR> tab{reinterpret_cast<const uint8_t *>(te), 4 * lane};
     const uint32_t n_blocks = (n_masks + 127) / 128;
     const uint32_t j_end = min(n_blocks, (blockIdx.x + 1) * blocks_per_cta);
 #pragma unroll 1
@@ -147,16 +156,21 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_mask_gen_tt(const uint32_t *_
 void launch_mask_gen_tt(const uint32_t *rk_plain, uint32_t nslices, uint32_t n_masks, uint64_t *rows, uint64_t *fresh_pm, size_t pitch_pm, int n_sms,
                         cudaStream_t st) {
     if (n_masks == 0) return;
+    constexpr size_t SMEM2 = 2 * 256 * 32 * 4 + GT_TILE_BYTES, SMEM4 = 4 * 256 * 32 * 4 + GT_TILE_BYTES;
     static bool configured = false;
     if (!configured) {
-        cudaFuncSetAttribute(k_mask_gen_tt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GT_SMEM);
+        cudaFuncSetAttribute(k_mask_gen_tt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM2);
+        cudaFuncSetAttribute(k_mask_gen_tt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM4);
         configured = true;
     }
     const uint32_t n_blocks = (n_masks + 127) / 128, gy = (nslices + GT_SLICES - 1) / GT_SLICES;
     const uint32_t want_x = std::max(1u, (uint32_t)n_sms / gy);  // about one CTA per SM for a single small proof
     const uint32_t per = std::min(64u, std::max(4u, (n_blocks + want_x - 1) / want_x));
     dim3 grid((n_blocks + per - 1) / per, gy);
-    k_mask_gen_tt<<<grid, GT_THREADS, GT_SMEM, st>>>(rk_plain, nslices, n_masks, per, reinterpret_cast<uint32_t *>(rows), fresh_pm, pitch_pm);
+    if ((uint64_t)n_blocks * gy >= 64ull * n_sms)  // enough work for many waves: the mask generator owns the chip
+        k_mask_gen_tt<true><<<grid, GT_THREADS, SMEM4, st>>>(rk_plain, nslices, n_masks, per, reinterpret_cast<uint32_t *>(rows), fresh_pm, pitch_pm);
+    else
+        k_mask_gen_tt<false><<<grid, GT_THREADS, SMEM2, st>>>(rk_plain, nslices, n_masks, per, reinterpret_cast<uint32_t *>(rows), fresh_pm, pitch_pm);
 }
 
 // =====================================================================================================================

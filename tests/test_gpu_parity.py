@@ -438,3 +438,20 @@ def test_batch_of_sessions_one_graph_per_phase(rb, default_seeds):
     with pytest.raises(rb.WitnessError):
         sess[1].fetch()
     del batch
+
+
+def test_large_flat_circuit_paths(rb, default_seeds):
+    """7x10^5 ANDs: the four-table mask generator (circuits with many waves of work), the pinned zero-copy proof return
+    (proofs >= 4 MB) and multi-CTA extraction, all against the oracle's bytes."""
+    import orc
+    from reverie_b200 import circuits as C
+
+    ops, wc = C.flat_mul_circuit(700000)
+    rc, want = orc.prove(ops, [1, 1], [], wc, default_seeds)
+    assert rc == 0 and len(want) > (4 << 20)
+    circ = rb.Circuit(ops, wc)
+    for _ in range(2):  # second proof: pooled pinned buffer, graph replay
+        p = rb.Proof.new(circ, [1, 1], (), seeds=default_seeds)
+        assert len(p) == len(want) and p.serialize() == want
+    assert p.verify(circ)
+    del p
