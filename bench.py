@@ -393,8 +393,9 @@ def main():
             one(0)
         single_latency_ms = (time.perf_counter() - t0) / 10 * 1e3
         d2h = B * (len(proof) + 36)
-        # Proof::verify through the same API ("also reported"); tables exist for circuits of <= 4M ops
-        if st["n_ops"] <= (4 << 20):
+        # Proof::verify through the same API ("also reported"); bounded to circuits whose verifier tables
+        # (kappa leaves + u-plane of 40 repetitions) fit next to a prover session
+        if st["n_ops"] <= (32 << 20):
             def vfy(_):
                 return proof.verify(circ)
 

@@ -228,6 +228,13 @@ extern "C" int rv_circuit_compile(const rv_op *ops, size_t n_ops, size_t z64_cel
         D.n_lut_levels = (uint32_t)P.lut_level_off.size() - 1;
     }
     D.n_vlut_steps = P.n_vlut_steps;
+    if (P.verify_wide) {
+        if ((rc = upload(c, P.vluts, &D.vluts))) {
+            rv_circuit_free(c);
+            return rc;
+        }
+        D.n_vlut_levels = (uint32_t)P.vlut_level_off.size() - 1;
+    }
     D.n_uvals = P.n_uvals;
     D.n_vm_steps = P.n_vm_steps;
     D.vm_cells = P.vm_cells;
@@ -1120,7 +1127,10 @@ static int verify_on_session(rv_session *s, const uint8_t *proof, size_t proof_l
     }
     {
         Scope k(s, "v.values", (uint64_t)P.vlut_steps.size() * sizeof(LutInstr));
-        launch_values(D.vlut_steps, D.n_vlut_steps, D.vleaf_ids, s->d_leaf_vals, s->leaf_pitch, D.n_inputs + D.n_pre + D.n_rand, s->d_uvals, s->upitch, D.n_uvals, NON,
+        if (P.verify_wide)
+            launch_uvalues_wide(D, P.vlut_level_off.data(), s->d_leaf_vals, s->leaf_pitch, D.n_inputs + D.n_pre + D.n_rand, s->d_uvals, s->upitch, NON, s->st);
+        else
+            launch_values(D.vlut_steps, D.n_vlut_steps, D.vleaf_ids, s->d_leaf_vals, s->leaf_pitch, D.n_inputs + D.n_pre + D.n_rand, s->d_uvals, s->upitch, D.n_uvals, NON,
                       s->st);
     }
     {
@@ -1198,7 +1208,7 @@ static int verify_on_session(rv_session *s, const uint8_t *proof, size_t proof_l
 
 extern "C" int rv_verify(const rv_circuit *c, const uint8_t *proof, size_t proof_len, int *okay) {
     if (!c || (!proof && proof_len)) return fail(RV_E_ARG, "NULL argument");
-    if (!c->prog.has_verify) return fail(RV_E_UNSUPPORTED, "verification tables are only built for circuits of at most 4M ops");
+    if (!c->prog.has_verify) return fail(RV_E_UNSUPPORTED, "verification tables are only built for circuits of at most 2^28 ops");
     if (proof_len < 32) return fail(RV_E_FORMAT, "proof shorter than its commitment");
     PDomain g, z;
     size_t pos = 32;

@@ -683,7 +683,7 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
     }
     std::vector<Cell> cells(gf2_cells, Cell{VREF_ZERO, ZERO_MID, VREF_ZERO});
     ValueNet un;  // u-plane network (built only while the circuit stays small)
-    const bool want_verify = n_ops <= (4u << 20);
+    const bool want_verify = n_ops <= VERIFY_MAX_OPS;
     std::vector<uint32_t> vlevel(1, 0);  // per value id (plain 2-input depth, for the stats)
     std::vector<uint32_t> llevel;        // per linear node (plain depth)
     std::vector<uint32_t> tlevel;        // per tainted value
@@ -1071,10 +1071,13 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
             required[P.item_ua[t] >> 1] = 1;
             required[P.item_ub[t] >> 1] = 1;
         }
-        std::vector<LutInstr> luts;
-        std::vector<uint32_t> off;
-        map_to_luts(P.n_uvals, un.g, required, luts, off);
-        emit_lut_steps(luts, off, P.n_uvals, P.vlut_steps, P.n_vlut_steps);
+        map_to_luts(P.n_uvals, un.g, required, P.vluts, P.vlut_level_off);
+        std::vector<MGate>().swap(un.g);
+        P.verify_wide = P.vlut_level_off.size() > 1 && P.vluts.size() / (P.vlut_level_off.size() - 1) >= WIDE_LEVEL;
+        if (!P.verify_wide) {
+            emit_lut_steps(P.vluts, P.vlut_level_off, P.n_uvals, P.vlut_steps, P.n_vlut_steps);
+            std::vector<LutInstr>().swap(P.vluts);
+        }
         P.has_verify = true;
     }
     return RV_OK;

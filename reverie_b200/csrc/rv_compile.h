@@ -184,7 +184,10 @@ struct Program {
     std::vector<uint32_t> input_uid;    // witness index -> u-plane value id
     std::vector<uint32_t> kappa_uid;    // Mul index j -> u-plane value id of its kappa leaf
     std::vector<uint32_t> item_ua, item_ub;  // per online item: u-plane refs (id << 1 | negate) of the operands / asserted wire
-    bool has_verify = false;            // built only for circuits of <= 4M ops
+    std::vector<LutInstr> vluts;        // wide circuits (verify_wide): the level-sorted u-plane LUT list, one launch per level
+    std::vector<uint32_t> vlut_level_off;
+    bool verify_wide = false;
+    bool has_verify = false;            // built for circuits of <= VERIFY_MAX_OPS ops
     std::vector<TGate> tgates;          // tainted plane, sorted by level
     std::vector<uint32_t> tlevel_off;
     uint32_t n_tvals = 0;
@@ -207,6 +210,7 @@ struct Program {
 int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, Program &out, std::string &err);
 
 constexpr uint32_t WIDE_LEVEL = 4096;
+constexpr size_t VERIFY_MAX_OPS = (size_t)1 << 28;  // the verifier's tables cost ~200 bytes of host memory per gate while compiling
 
 // Gate-count limit above which the value plane keeps 2-input "LUTs" (the mapper's cut sets cost ~250 bytes per gate).
 constexpr size_t LUT_MAP_MAX_GATES = 8u << 20;

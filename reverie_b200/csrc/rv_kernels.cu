@@ -360,6 +360,33 @@ int launch_values_wide(const DevProgram &P, const uint32_t *off_host, const uint
     return 1 + (int)P.n_lut_levels;
 }
 
+__global__ void __launch_bounds__(256) k_uvalues_leaves(const uint32_t *__restrict__ leaf_ids, const uint8_t *__restrict__ leaf_vals, size_t leaf_pitch,
+                                                        uint32_t n_leaves, uint8_t *__restrict__ uvals, size_t upitch) {
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    uint8_t *v = uvals + (size_t)blockIdx.y * upitch;
+    if (k == 0) v[0] = 0;
+    if (k < n_leaves) v[leaf_ids[k]] = leaf_vals[(size_t)blockIdx.y * leaf_pitch + k] & 1;
+}
+__global__ void __launch_bounds__(256) k_uvalues_level(const LutInstr *__restrict__ luts, uint32_t n, uint8_t *uvals, size_t upitch) {
+    const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    uint8_t *v = uvals + (size_t)blockIdx.y * upitch;
+    const LutInstr li = luts[g];
+    const uint32_t idx = (uint32_t)v[li.in[0]] | ((uint32_t)v[li.in[1]] << 1) | ((uint32_t)v[li.in[2]] << 2) | ((uint32_t)v[li.in[3]] << 3) |
+                         ((uint32_t)v[li.in[4]] << 4) | ((uint32_t)v[li.in[5]] << 5);
+    v[li.dst] = (uint8_t)((li.tt >> idx) & 1);
+}
+
+int launch_uvalues_wide(const DevProgram &P, const uint32_t *off_host, const uint8_t *leaf_vals, size_t leaf_pitch, uint32_t n_leaves, uint8_t *uvals,
+                        size_t upitch, uint32_t n_instances, cudaStream_t st) {
+    k_uvalues_leaves<<<dim3((std::max(n_leaves, 1u) + 255) / 256, n_instances), 256, 0, st>>>(P.vleaf_ids, leaf_vals, leaf_pitch, n_leaves, uvals, upitch);
+    for (uint32_t l = 0; l < P.n_vlut_levels; l++) {
+        const uint32_t n = off_host[l + 1] - off_host[l];
+        if (n) k_uvalues_level<<<dim3((n + 255) / 256, n_instances), 256, 0, st>>>(P.vluts + off_host[l], n, uvals, upitch);
+    }
+    return 1 + (int)P.n_vlut_levels;
+}
+
 // =====================================================================================================================
 //  K3  mask plane: row[dst] = row[a] ^ row[b], level by level
 // =====================================================================================================================

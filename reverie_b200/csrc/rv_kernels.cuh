@@ -24,6 +24,8 @@ struct DevProgram {
     // online verifier (absent for circuits of more than 4M ops)
     const LutInstr *vlut_steps = nullptr;  // u-plane step stream
     uint32_t n_vlut_steps = 0, n_uvals = 0;
+    const LutInstr *vluts = nullptr;       // wide circuits: level-sorted u-plane LUT list
+    uint32_t n_vlut_levels = 0;
     const uint32_t *vleaf_ids = nullptr;   // [n_inputs + n_and]: u-plane value id of every input, then of every Mul's kappa
     const uint32_t *item_ua = nullptr, *item_ub = nullptr, *recon_idx = nullptr;  // per online item
     const VmInstr *vm_steps = nullptr;     // mask-plane VM step stream (n_vm_steps * VM_STEP slots); empty without Add/Sub
@@ -68,6 +70,9 @@ size_t launch_values(const LutInstr *steps, uint32_t n_steps, const uint32_t *le
                      uint32_t n_leaves, uint8_t *vals, size_t vals_pitch, uint32_t n_vals, uint32_t n_instances, cudaStream_t st);
 //     wide circuits (Program::values_wide): one grid-wide launch per level; returns the number of launches
 int launch_values_wide(const DevProgram &P, const uint32_t *lut_level_off_host, const uint8_t *wit, uint8_t *vals, cudaStream_t st);
+//     the verifier's u-plane of a wide circuit: same, for n_instances opened repetitions (grid.y)
+int launch_uvalues_wide(const DevProgram &P, const uint32_t *vlut_level_off_host, const uint8_t *leaf_vals, size_t leaf_pitch, uint32_t n_leaves,
+                        uint8_t *uvals, size_t upitch, uint32_t n_instances, cudaStream_t st);
 // K3  mask plane (XOR network over the share tensor)
 //     returns the number of kernel launches; *which (optional) names the variant: 0 VM (smem cells), 1 CTA walker, 2 per level
 //     fresh_pm: instance-major copy of the fresh masks for the VM variant ([npi][pitch] u64)

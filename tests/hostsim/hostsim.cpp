@@ -436,6 +436,12 @@ extern "C" int hs_verify(const rv_op *ops, size_t n_ops, size_t z64_cells, size_
         for (uint32_t k = 0; k < P.n_inputs; k++) uv[P.input_uid[k]] = verify_leaf_input(P.items[P.input_pos[k]], k, opens[s], proof, rows.data(), npi, s);
         for (uint32_t j = 0; j < P.n_pre; j++) uv[P.kappa_uid[j]] = verify_leaf_kappa(P.items[mul_pos[j]], recon_idx[mul_pos[j]], opens[s], proof, rows.data(), npi, s);
         for (uint32_t k = 0; k < P.rand_uid.size(); k++) uv[P.rand_uid[k]] = verify_leaf_random(P.rand_row[k], rows.data(), npi, s);
+        if (P.verify_wide)  // k_uvalues_level: one launch per level over the level-sorted list
+            for (const LutInstr &li : P.vluts) {
+                uint32_t idx = 0;
+                for (int k = 0; k < 6; k++) idx |= (uint32_t)uv[li.in[k]] << k;
+                uv[li.dst] = (uint8_t)((li.tt >> idx) & 1);
+            }
         for (uint32_t st = 0; st < P.n_vlut_steps; st++)
             for (uint32_t t = 0; t < LUT_STEP; t++) {
                 const LutInstr &li = P.vlut_steps[(size_t)st * LUT_STEP + t];
