@@ -455,3 +455,13 @@ def test_large_flat_circuit_paths(rb, default_seeds):
         assert len(p) == len(want) and p.serialize() == want
     assert p.verify(circ)
     del p
+
+
+def test_cpp_host_mirror(rb):
+    """The reference's own proof tests (src/proof/mod.rs:311-428) through the C++ host mirror include/reverie_b200.hpp."""
+    import subprocess
+
+    from tests._cppbuild import build_cpp_api_test
+
+    res = subprocess.run([build_cpp_api_test()], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "cpp host mirror ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]

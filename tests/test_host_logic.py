@@ -280,3 +280,16 @@ def test_reference_e2e_case_b2a(default_seeds):
     assert rc == 0 and rc2 == 0 and got == want
     assert hostsim.verify(ops, (4, 64), want)[0] == 1
     assert hostsim.prove(ops, gwit, (4, 64), default_seeds, wit_z64=[y + 1])[0] == N.E_WITNESS_INVALID
+
+
+def test_cpp_host_mirror_compiles():
+    """include/reverie_b200.hpp (the C++ face of the drop-in: Operation / CombineOperation / Proof::new_ / verify) builds against
+    the C ABI; its tests run on the GPU box (tests/test_gpu_parity.py::test_cpp_host_mirror)."""
+    import subprocess
+
+    from tests._cppbuild import build_cpp_api_test
+
+    exe = build_cpp_api_test()
+    assert subprocess.run([exe, "--compile-check"]).returncode == 0
+    if N.lib().rv_device_count() == 0:
+        assert subprocess.run([exe], capture_output=True).returncode == 2  # loud failure, no CPU fallback
