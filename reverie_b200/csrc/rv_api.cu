@@ -371,6 +371,7 @@ struct rv_session {
     uint8_t *h_out = nullptr;  // proof || bad(4) || comm(32); big proofs (>= PIN_THRESHOLD) skip the proof part: rv_session_fetch copies
                                // them from d_proof straight into the pinned buffer it returns
     size_t out_off = 0;        // offset of bad / comm inside h_out
+    size_t tail_off = 0;       // offset of bad / comm behind the proof bytes in d_proof
     size_t h_in_bytes = 0;
     std::vector<void *> allocs;
     bool timing = false;
@@ -484,11 +485,16 @@ extern "C" int rv_session_create(const rv_circuit *c, int first_instance, int n_
         (rc = dalloc(s, &s->d_pre, s->pitch_pre * s->nreps)) || (rc = dalloc(s, &s->d_cv_on, (size_t)s->n_chunks_on * s->nreps * 8)) ||
         (rc = dalloc(s, &s->d_cv_pre, (size_t)s->n_chunks_pre * s->nreps * 8)) || (rc = dalloc(s, &s->d_on_hash, (size_t)s->nreps * 32)) ||
         (rc = dalloc(s, &s->d_rep_hash, (size_t)s->nreps * 32)) || (rc = dalloc(s, &s->d_all_hashes, RV_TOTAL_REPS * 32)) ||
-        (rc = dalloc(s, &s->d_comm, 32)) || (rc = dalloc(s, &s->d_omit, RV_TOTAL_REPS)) || (rc = dalloc(s, &s->d_rank, RV_TOTAL_REPS)) ||
-        (rc = dalloc(s, &s->d_zconst, 16)) || (rc = dalloc(s, &s->d_bad, 1)) || (rc = dalloc(s, &s->d_proof, s->proof_len)))
+        (rc = dalloc(s, &s->d_omit, RV_TOTAL_REPS)) || (rc = dalloc(s, &s->d_rank, RV_TOTAL_REPS)) || (rc = dalloc(s, &s->d_zconst, 16)) ||
+        (rc = dalloc(s, &s->d_proof, round_up(s->proof_len, 16) + 64)))
         return bail(rc);
+    // the status flag and comm live right behind the proof bytes, so one device-to-host copy returns all three
+    s->tail_off = round_up(s->proof_len, 16);
+    s->d_bad = reinterpret_cast<int *>(s->d_proof + s->tail_off);
+    s->d_comm = s->d_proof + s->tail_off + 4;
+    if (cudaMemset(s->d_rows + (size_t)P.zero_row() * s->npi, 0, (size_t)s->npi * 8) != cudaSuccess) return bail(fail(RV_E_CUDA, "cudaMemset failed"));
     s->h_in_bytes = round_up(P.n_inputs, 16) + RV_TOTAL_REPS * 16 + 8 * (size_t)Z.n_inputs;
-    if (cudaMallocHost(&s->h_in, s->h_in_bytes) != cudaSuccess || cudaMallocHost(&s->h_out, (s->out_off = s->proof_len >= PIN_THRESHOLD ? 0 : s->proof_len) + 64) != cudaSuccess)
+    if (cudaMallocHost(&s->h_in, s->h_in_bytes) != cudaSuccess || cudaMallocHost(&s->h_out, (s->out_off = s->proof_len >= PIN_THRESHOLD ? 0 : round_up(s->proof_len, 16)) + 64) != cudaSuccess)
         return bail(fail(RV_E_NOMEM, "pinned host allocation failed"));
     uint32_t zc[16];
     memcpy(zc, c->z64_empty_hash, 32);
@@ -658,11 +664,9 @@ static int commit_body(rv_session *s) {
         launch_zvalues(DZ, s->d_zleaf, 0, s->d_zvals, 0, 1, s->d_vals, D.b2a_vrefs, s->st_val);
     }
     CU(cudaEventRecord(s->ev_vals, s->st_val));
-    CU(cudaMemsetAsync(s->d_bad, 0, sizeof(int), s->st));
-    CU(cudaMemsetAsync(s->d_rows + (size_t)P.zero_row() * s->npi, 0, (size_t)s->npi * 8, s->st));
     {
-        Scope k(s, "key_setup", 0);
-        launch_key_setup(s->d_seeds, nullptr, nullptr, nullptr, nslices, s->d_pkeys, s->d_rk_plain, s->st);
+        Scope k(s, "key_setup", 0);  // also clears the proof's "an AssertZero failed" flag
+        launch_key_setup(s->d_seeds, nullptr, nullptr, nullptr, nslices, s->d_pkeys, s->d_rk_plain, s->st, s->d_bad);
     }
     {
         Scope k(s, "mask_gen", (uint64_t)P.n_masks * s->npi * 8);
@@ -702,7 +706,7 @@ static int commit_body(rv_session *s) {
     }
     {
         // per Mul: 4 row reads + 2 stream bytes per rep (online) and 3 row reads + 1 byte per rep (pre)
-        Scope k(s, "items", ((uint64_t)P.n_and * 7 + P.n_inputs + P.n_assert) * s->npi * 8 + ((uint64_t)P.n_online + P.n_pre) * s->nreps, 2);
+        Scope k(s, "items", ((uint64_t)P.n_and * 7 + P.n_inputs + P.n_assert) * s->npi * 8 + ((uint64_t)P.n_online + P.n_pre) * s->nreps, 1);
         if (D.n_tlevels) launch_tainted(D, s->d_rows, s->npi, s->d_vals, s->d_tvals, s->st);
         launch_items(D, s->d_rows, s->npi, s->d_vals, s->d_tvals, s->d_on, s->pitch_on, s->d_pre, s->pitch_pre, s->d_bad, s->st);
     }
@@ -759,7 +763,7 @@ static int open_body(rv_session *s, const uint8_t *all_rep_hashes) {
         Scope k(s, "challenge", RV_TOTAL_REPS * 32);
         launch_challenge(hashes, s->d_comm, s->d_omit, s->d_rank, s->st);
     }
-    CU(cudaMemsetAsync(s->d_proof, 0, s->proof_len, s->st));
+    if (s->npi != RV_PACKED_REPS) CU(cudaMemsetAsync(s->d_proof, 0, s->proof_len, s->st));  // a full shard writes every byte of the proof
     {
         Scope k(s, "extract", s->proof_len);
         ExtractArgs a;
@@ -803,9 +807,8 @@ static int open_body(rv_session *s, const uint8_t *all_rep_hashes) {
         a.proof = s->d_proof;
         launch_zextract(c->zdev, a, s->st);
     }
-    if (s->out_off) CU(cudaMemcpyAsync(s->h_out, s->d_proof, s->proof_len, cudaMemcpyDeviceToHost, s->st));
-    CU(cudaMemcpyAsync(s->h_out + s->out_off, s->d_bad, 4, cudaMemcpyDeviceToHost, s->st));
-    CU(cudaMemcpyAsync(s->h_out + s->out_off + 4, s->d_comm, 32, cudaMemcpyDeviceToHost, s->st));
+    if (s->out_off) CU(cudaMemcpyAsync(s->h_out, s->d_proof, s->tail_off + 36, cudaMemcpyDeviceToHost, s->st));
+    else CU(cudaMemcpyAsync(s->h_out, s->d_proof + s->tail_off, 36, cudaMemcpyDeviceToHost, s->st));
     CU(cudaGetLastError());
     return RV_OK;
 }
@@ -1105,13 +1108,11 @@ static int verify_on_session(rv_session *s, const uint8_t *proof, size_t proof_l
     memcpy(h + o_proof, proof, proof_len);
     uint8_t *dv = s->d_vin;
     CU(cudaMemcpyAsync(dv, h, need, cudaMemcpyHostToDevice, s->st));
-    CU(cudaMemsetAsync(s->d_bad, 0, sizeof(int), s->st));
-    CU(cudaMemsetAsync(s->d_rows + (size_t)P.zero_row() * s->npi, 0, (size_t)s->npi * 8, s->st));
     const uint32_t nslices = 2 * s->npi;
     const VOpen *d_opens = reinterpret_cast<const VOpen *>(dv + o_opens);
     {
         Scope k(s, "v.key_setup", 0);
-        launch_key_setup(dv + o_seeds, dv + o_pkeys, dv + o_mode, dv + o_omit, nslices, s->d_pkeys, s->d_rk_plain, s->st);
+        launch_key_setup(dv + o_seeds, dv + o_pkeys, dv + o_mode, dv + o_omit, nslices, s->d_pkeys, s->d_rk_plain, s->st, s->d_bad);
     }
     {
         Scope k(s, "v.mask_gen", (uint64_t)P.n_masks * s->npi * 8);

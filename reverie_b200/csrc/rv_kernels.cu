@@ -18,7 +18,8 @@ namespace rv {
 // all-ones / zero "stream is active" words (the verifier's unopened player stays zero, src/generator/batch.rs:31-34).
 __global__ void __launch_bounds__(128) k_key_setup(const uint8_t *__restrict__ seeds, const uint8_t *__restrict__ pkeys_in,
                                                    const uint8_t *__restrict__ mode, const uint8_t *__restrict__ omit, uint32_t nslices,
-                                                   uint8_t *__restrict__ pkeys_out, uint32_t *__restrict__ rk_plain) {
+                                                   uint8_t *__restrict__ pkeys_out, uint32_t *__restrict__ rk_plain, int *__restrict__ bad) {
+    if (bad != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *bad = 0;  // first kernel of every proof / verification
     __shared__ uint32_t sbox32[64];  // the S-box as a byte table, built from the netlist (4 entries per thread)
     if (threadIdx.x < 64) {
         const uint32_t b = 4 * threadIdx.x;
@@ -38,8 +39,8 @@ __global__ void __launch_bounds__(128) k_key_setup(const uint8_t *__restrict__ s
 }
 
 void launch_key_setup(const uint8_t *seeds, const uint8_t *pkeys_in, const uint8_t *mode, const uint8_t *omit, uint32_t nslices,
-                      uint8_t *pkeys_out, uint32_t *rk_plain, cudaStream_t st) {
-    k_key_setup<<<(nslices + 3) / 4, 128, 0, st>>>(seeds, pkeys_in, mode, omit, nslices, pkeys_out, rk_plain);
+                      uint8_t *pkeys_out, uint32_t *rk_plain, cudaStream_t st, int *bad) {
+    k_key_setup<<<(nslices + 3) / 4, 128, 0, st>>>(seeds, pkeys_in, mode, omit, nslices, pkeys_out, rk_plain, bad);
 }
 
 // =====================================================================================================================
@@ -549,14 +550,13 @@ __global__ void __launch_bounds__(256) k_items_pre(const Item *__restrict__ item
 // of each repetition's stream.  PRE selects the preprocessing stream (one byte per Mul) instead of the online stream.
 constexpr int IT_THREADS = 256;
 template <bool PRE>
-__global__ void __launch_bounds__(IT_THREADS) k_items_tile(const Item *__restrict__ items, const uint32_t *__restrict__ mul_pos, uint32_t n,
-                                                          const uint64_t *__restrict__ rows, uint32_t npi, const uint8_t *__restrict__ vals,
-                                                          const uint64_t *__restrict__ tvals, uint8_t *__restrict__ out, size_t pitch, uint32_t T,
-                                                          int *bad) {
+__device__ __forceinline__ void items_tile_body(uint32_t tile_idx, const Item *__restrict__ items, const uint32_t *__restrict__ mul_pos, uint32_t n,
+                                                const uint64_t *__restrict__ rows, uint32_t npi, const uint8_t *__restrict__ vals,
+                                                const uint64_t *__restrict__ tvals, uint8_t *__restrict__ out, size_t pitch, uint32_t T, int *bad) {
     extern __shared__ __align__(16) uint8_t tile[];
     const uint32_t tid = threadIdx.x, pi = tid % npi, pg0 = tid / npi, pg_step = IT_THREADS / npi;
     const uint32_t tp = T + 8;  // tile pitch in bytes
-    const uint64_t T0 = (uint64_t)blockIdx.x * T;
+    const uint64_t T0 = (uint64_t)tile_idx * T;
     int flag = 0;
     for (uint32_t g = pg0; g < T / 8; g += pg_step) {
         const uint64_t t0 = T0 + 8ull * g;
@@ -582,16 +582,26 @@ __global__ void __launch_bounds__(IT_THREADS) k_items_tile(const Item *__restric
     }
 }
 
+// One launch covers both streams: CTAs [0, tiles_on) take tiles of the online stream, the rest tiles of the preprocessing
+// stream (small proofs are bound by the number of kernels in flight, not by their work).
+__global__ void __launch_bounds__(IT_THREADS) k_items(const Item *__restrict__ items, const uint32_t *__restrict__ mul_pos, uint32_t n_online,
+                                                     uint32_t n_pre, uint32_t tiles_on, const uint64_t *__restrict__ rows, uint32_t npi,
+                                                     const uint8_t *__restrict__ vals, const uint64_t *__restrict__ tvals, uint8_t *__restrict__ on,
+                                                     size_t pitch_on, uint8_t *__restrict__ pre, size_t pitch_pre, uint32_t T, int *bad) {
+    if (blockIdx.x < tiles_on) items_tile_body<false>(blockIdx.x, items, nullptr, n_online, rows, npi, vals, tvals, on, pitch_on, T, bad);
+    else items_tile_body<true>(blockIdx.x - tiles_on, items, mul_pos, n_pre, rows, npi, nullptr, nullptr, pre, pitch_pre, T, nullptr);
+}
+
 static uint32_t items_tile(uint32_t npi) { return std::max(128u, 8u * IT_THREADS / npi); }
 
 void launch_items(const DevProgram &P, const uint64_t *rows, uint32_t npi, const uint8_t *vals, const uint64_t *tvals, uint8_t *on, size_t pitch_on,
                   uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st) {
     const uint32_t T = items_tile(npi);
     const size_t smem = (size_t)8 * npi * (T + 8);
-    if (P.n_online)
-        k_items_tile<false><<<(P.n_online + T - 1) / T, IT_THREADS, smem, st>>>(P.items, nullptr, P.n_online, rows, npi, vals, tvals, on, pitch_on, T, bad);
-    if (P.n_pre)
-        k_items_tile<true><<<(P.n_pre + T - 1) / T, IT_THREADS, smem, st>>>(P.items, P.mul_pos, P.n_pre, rows, npi, nullptr, nullptr, pre, pitch_pre, T, nullptr);
+    const uint32_t tiles_on = (P.n_online + T - 1) / T, tiles_pre = (P.n_pre + T - 1) / T;
+    if (tiles_on + tiles_pre)
+        k_items<<<tiles_on + tiles_pre, IT_THREADS, smem, st>>>(P.items, P.mul_pos, P.n_online, P.n_pre, tiles_on, rows, npi, vals, tvals, on, pitch_on, pre,
+                                                                 pitch_pre, T, bad);
 }
 
 // Tainted plane: CTA = one packed instance (columns are independent), level-synchronous with CTA barriers only.

@@ -60,7 +60,7 @@ struct DevZProgram {
 //     rk_plain: [45][32 * nslices] u32 -- the 44 round-key words of every stream (stream = 8 * rep + player), then a row of
 //     all-ones / zero "stream is active" words
 void launch_key_setup(const uint8_t *seeds, const uint8_t *pkeys_in, const uint8_t *mode, const uint8_t *omit, uint32_t nslices,
-                      uint8_t *pkeys_out, uint32_t *rk_plain, cudaStream_t st);
+                      uint8_t *pkeys_out, uint32_t *rk_plain, cudaStream_t st, int *clear_flag = nullptr);
 // K2  AES-CTR mask generation straight into the share tensor (src/generator/share.rs:54-65, src/algebra/gf2/domain.rs:66-173)
 //     also writes the instance-major copy `fresh_pm` [npi][pitch_pm] (u64) that the mask VM loads from (nullptr = skip)
 void launch_mask_gen_tt(const uint32_t *rk_plain, uint32_t nslices, uint32_t n_masks, uint64_t *rows, uint64_t *fresh_pm, size_t pitch_pm, int n_sms,
