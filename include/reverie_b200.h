@@ -161,6 +161,17 @@ void rv_free(void *p);
  *   rv_proof_assemble   src/proof/mod.rs:200-221: concatenates shard blobs (any order) into the bincode `Proof`
  * ------------------------------------------------------------------------------------------------------------- */
 int rv_session_create(const rv_circuit *c, int first_instance, int n_instances, rv_session **out);
+/* A session that holds `n_proofs` independent proofs of the circuit SIDE BY SIDE (proof b owns its own columns of the share
+ * tensor, its own streams, hashes and output buffer): every phase is the same handful of kernel launches as for one proof,
+ * each launch covering all of them.  This is how many small proofs in flight keep a B200 busy -- a 22 k-gate proof alone
+ * is a few hundred CTAs per kernel.  Slots are filled with rv_session_upload_slot and read with rv_session_fetch_slot; the
+ * other session calls act on all slots.  rv_session_hashes_device / _all_hashes_device: [n_proofs][n_instances * 8 * 32] and,
+ * gathered over ranks, [rank][n_proofs][n_instances * 8 * 32] (= one plain all-gather of the former).
+ * Small GF(2) circuits only (RV_E_UNSUPPORTED otherwise: Z64 / Random / B2A, wide value planes, proofs of 4 MB and more). */
+int rv_session_create_multi(const rv_circuit *c, int first_instance, int n_instances, int n_proofs, rv_session **out);
+int rv_session_upload_slot(rv_session *s, int slot, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64, size_t n_z64,
+                           const uint8_t *seeds /* all 256 x 16 of that proof, or NULL = OS RNG */);
+int rv_session_fetch_slot(rv_session *s, int slot, uint8_t comm[RV_HASH_SIZE], uint8_t **part, size_t *part_len); /* synchronises */
 void rv_session_free(rv_session *s);
 int rv_session_upload(rv_session *s, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64, size_t n_z64,
                       const uint8_t *seeds /* all 256 x 16, or NULL = OS RNG */);

@@ -51,6 +51,9 @@ def lib() -> C.CDLL:
         "rv_free": ([vp], None),
         "rv_session_create": ([vp, i32, i32, pp], i32),
         "rv_session_free": ([vp], None),
+        "rv_session_create_multi": ([vp, i32, i32, i32, pp], i32),
+        "rv_session_upload_slot": ([vp, i32, vp, sz, vp, sz, vp], i32),
+        "rv_session_fetch_slot": ([vp, i32, vp, pp, psz], i32),
         "rv_session_upload": ([vp, vp, sz, vp, sz, vp], i32),
         "rv_session_commit": ([vp], i32),
         "rv_session_hashes": ([vp, vp], i32),
@@ -83,7 +86,7 @@ def lib() -> C.CDLL:
 
 EXPORTED = (
     "rv_last_error rv_version rv_device_count rv_set_device rv_circuit_compile rv_circuit_free rv_circuit_get_stats "
-    "rv_circuit_export rv_prove rv_verify rv_proof_new rv_proof_verify rv_free rv_session_create rv_session_free "
+    "rv_circuit_export rv_prove rv_verify rv_proof_new rv_proof_verify rv_free rv_session_create rv_session_create_multi rv_session_upload_slot rv_session_fetch_slot rv_session_free "
     "rv_session_upload rv_session_commit rv_session_hashes rv_session_hashes_device rv_session_all_hashes_device rv_session_open rv_session_prove rv_session_fetch rv_session_sync rv_session_status rv_session_proof_device "
     "rv_proof_assemble rv_batch_create rv_batch_free rv_batch_commit rv_batch_open rv_batch_prove rv_batch_stream rv_session_stream rv_session_timing rv_session_kernel_times rv_session_launch_count"
 ).split()

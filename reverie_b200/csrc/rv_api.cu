@@ -322,7 +322,10 @@ struct KTimer {
 
 struct rv_session {
     const rv_circuit *c = nullptr;
-    uint32_t first_instance = 0, npi = 0, nreps = 0, first_rep = 0;
+    uint32_t first_instance = 0, npi = 0, nreps = 0, first_rep = 0;  // npi / nreps: columns / streams of the WHOLE session
+    // several proofs side by side (rv_session_create_multi): proof b owns columns [b * npi1, (b + 1) * npi1) of the share tensor
+    uint32_t n_proofs = 1, npi1 = 0, nreps1 = 0;
+    size_t wit_pitch = 0, vals_pitch = 0, proof_pitch = 0, in_pitch = 0;
     cudaStream_t st = nullptr, st_val = nullptr;
     bool own_stream = true;
     cudaEvent_t ev_fork = nullptr, ev_vals = nullptr;
@@ -421,17 +424,28 @@ extern "C" void rv_session_free(rv_session *s) {
 }
 
 extern "C" int rv_session_create(const rv_circuit *c, int first_instance, int n_instances, rv_session **out) {
+    return rv_session_create_multi(c, first_instance, n_instances, 1, out);
+}
+
+extern "C" int rv_session_create_multi(const rv_circuit *c, int first_instance, int n_instances, int n_proofs, rv_session **out) {
     if (!c || !out) return fail(RV_E_ARG, "NULL argument");
     *out = nullptr;
     if (first_instance < 0 || n_instances <= 0 || first_instance + n_instances > RV_PACKED_REPS)
         return fail(RV_E_ARG, "shard must be a non-empty range of the 32 packed instances");
+    if (n_proofs < 1 || n_proofs > 128) return fail(RV_E_ARG, "a session holds between 1 and 128 proofs");
+    if (n_proofs > 1 && (c->prog.z.any() || c->prog.n_tvals || c->prog.values_wide ||
+                         ProofLayout{(uint32_t)(c->prog.recon_pos.size() / 8 + 1), c->prog.n_pre / 8 + 1, (uint32_t)(c->prog.n_inputs / 8 + 1)}.total() >= PIN_THRESHOLD))
+        return fail(RV_E_UNSUPPORTED, "multi-proof sessions serve small GF(2) circuits (no Z64 / Random / B2A, proofs below 4 MB): use one session per proof");
     if (c->device < 0) return fail(RV_E_CUDA, "no CUDA device: reverie-b200 has no CPU fallback");
     CU(cudaSetDevice(c->device));
     rv_session *s = new (std::nothrow) rv_session();
     if (!s) return fail(RV_E_NOMEM, "out of memory");
     s->c = c;
     s->first_instance = (uint32_t)first_instance;
-    s->npi = (uint32_t)n_instances;
+    s->n_proofs = (uint32_t)n_proofs;
+    s->npi1 = (uint32_t)n_instances;
+    s->nreps1 = 8 * s->npi1;
+    s->npi = s->npi1 * s->n_proofs;
     s->nreps = 8 * s->npi;
     s->first_rep = 8 * s->first_instance;
     const Program &P = c->prog;
@@ -478,23 +492,28 @@ extern "C" int rv_session_create(const rv_circuit *c, int first_instance, int n_
         s->pitch_fresh = round_up((size_t)P.n_masks + 128, 128);
         if ((rc = dalloc(s, &s->d_fresh_sm, s->pitch_fresh * s->npi))) return bail(rc);
     }
-    if ((rc = dalloc(s, &s->d_wit, P.n_inputs)) || (rc = dalloc(s, &s->d_seeds, (size_t)s->nreps * 16)) ||
-        (rc = dalloc(s, &s->d_pkeys, (size_t)s->nreps * 128)) || (rc = dalloc(s, &s->d_vals, round_up((size_t)P.n_vals + 1, 16))) ||
+    s->wit_pitch = round_up(std::max<size_t>(P.n_inputs, 1), 16);
+    s->vals_pitch = round_up((size_t)P.n_vals + 1, 16);
+    s->tail_off = round_up(s->proof_len, 16);
+    s->proof_pitch = s->tail_off + 64;
+    if ((rc = dalloc(s, &s->d_wit, s->wit_pitch * s->n_proofs)) || (rc = dalloc(s, &s->d_seeds, (size_t)s->nreps * 16)) ||
+        (rc = dalloc(s, &s->d_pkeys, (size_t)s->nreps * 128)) || (rc = dalloc(s, &s->d_vals, s->vals_pitch * s->n_proofs)) ||
         (rc = dalloc(s, &s->d_rk_plain, (size_t)45 * 64 * s->npi)) || (rc = dalloc(s, &s->d_tvals, (size_t)P.n_tvals * s->npi)) || 
         (rc = dalloc(s, &s->d_rows, (size_t)P.n_rows * s->npi)) || (rc = dalloc(s, &s->d_on, s->pitch_on * s->nreps)) ||
         (rc = dalloc(s, &s->d_pre, s->pitch_pre * s->nreps)) || (rc = dalloc(s, &s->d_cv_on, (size_t)s->n_chunks_on * s->nreps * 8)) ||
         (rc = dalloc(s, &s->d_cv_pre, (size_t)s->n_chunks_pre * s->nreps * 8)) || (rc = dalloc(s, &s->d_on_hash, (size_t)s->nreps * 32)) ||
-        (rc = dalloc(s, &s->d_rep_hash, (size_t)s->nreps * 32)) || (rc = dalloc(s, &s->d_all_hashes, RV_TOTAL_REPS * 32)) ||
-        (rc = dalloc(s, &s->d_omit, RV_TOTAL_REPS)) || (rc = dalloc(s, &s->d_rank, RV_TOTAL_REPS)) || (rc = dalloc(s, &s->d_zconst, 16)) ||
-        (rc = dalloc(s, &s->d_proof, round_up(s->proof_len, 16) + 64)))
+        (rc = dalloc(s, &s->d_rep_hash, (size_t)s->nreps * 32)) || (rc = dalloc(s, &s->d_all_hashes, (size_t)RV_TOTAL_REPS * 32 * s->n_proofs)) ||
+        (rc = dalloc(s, &s->d_omit, (size_t)RV_TOTAL_REPS * s->n_proofs)) || (rc = dalloc(s, &s->d_rank, (size_t)RV_TOTAL_REPS * s->n_proofs)) ||
+        (rc = dalloc(s, &s->d_zconst, 16)) || (rc = dalloc(s, &s->d_proof, s->proof_pitch * s->n_proofs)))
         return bail(rc);
     // the status flag and comm live right behind the proof bytes, so one device-to-host copy returns all three
-    s->tail_off = round_up(s->proof_len, 16);
     s->d_bad = reinterpret_cast<int *>(s->d_proof + s->tail_off);
     s->d_comm = s->d_proof + s->tail_off + 4;
     if (cudaMemset(s->d_rows + (size_t)P.zero_row() * s->npi, 0, (size_t)s->npi * 8) != cudaSuccess) return bail(fail(RV_E_CUDA, "cudaMemset failed"));
-    s->h_in_bytes = round_up(P.n_inputs, 16) + RV_TOTAL_REPS * 16 + 8 * (size_t)Z.n_inputs;
-    if (cudaMallocHost(&s->h_in, s->h_in_bytes) != cudaSuccess || cudaMallocHost(&s->h_out, (s->out_off = s->proof_len >= PIN_THRESHOLD ? 0 : round_up(s->proof_len, 16)) + 64) != cudaSuccess)
+    s->in_pitch = s->wit_pitch + RV_TOTAL_REPS * 16 + 8 * (size_t)Z.n_inputs;
+    s->h_in_bytes = s->in_pitch * s->n_proofs;
+    s->out_off = s->proof_len >= PIN_THRESHOLD ? 0 : s->tail_off;
+    if (cudaMallocHost(&s->h_in, s->h_in_bytes) != cudaSuccess || cudaMallocHost(&s->h_out, (s->out_off + 64) * s->n_proofs) != cudaSuccess)
         return bail(fail(RV_E_NOMEM, "pinned host allocation failed"));
     uint32_t zc[16];
     memcpy(zc, c->z64_empty_hash, 32);
@@ -577,16 +596,22 @@ extern "C" int rv_session_kernel_times(rv_session *s, rv_kernel_time *out, int m
 // ---- upload / commit / open / fetch ----------------------------------------------------------------------------------
 extern "C" int rv_session_upload(rv_session *s, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64, size_t n_z64,
                                  const uint8_t *seeds) {
+    return rv_session_upload_slot(s, 0, wit_gf2, n_gf2, wit_z64, n_z64, seeds);
+}
+
+extern "C" int rv_session_upload_slot(rv_session *s, int slot, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64, size_t n_z64,
+                                      const uint8_t *seeds) {
     if (!s) return fail(RV_E_ARG, "NULL session");
+    if (slot < 0 || (uint32_t)slot >= s->n_proofs) return fail(RV_E_ARG, "no such proof slot");
     const Program &P = s->c->prog;
     if (n_gf2 < P.n_inputs || n_z64 < P.z.n_inputs) return fail(RV_E_WITNESS_SHORT, "witness is too short");  // prover.rs:190
     if ((P.n_inputs && !wit_gf2) || (P.z.n_inputs && !wit_z64)) return fail(RV_E_ARG, "witness pointer is NULL");
     CU(cudaSetDevice(s->c->device));
     cudaStream_t hst = host_stream(s);
     CU(cudaStreamSynchronize(hst));  // the staging buffer may still be in flight from a previous proof
-    const size_t woff = round_up(P.n_inputs, 16);
-    if (P.n_inputs) memcpy(s->h_in, wit_gf2, P.n_inputs);
-    uint8_t *hs = s->h_in + woff;
+    uint8_t *hin = s->h_in + (size_t)slot * s->in_pitch;
+    if (P.n_inputs) memcpy(hin, wit_gf2, P.n_inputs);
+    uint8_t *hs = hin + s->wit_pitch;
     if (seeds) memcpy(hs, seeds, RV_TOTAL_REPS * 16);
     else {  // OsRng, src/proof/mod.rs:131-134
         size_t got = 0;
@@ -596,13 +621,13 @@ extern "C" int rv_session_upload(rv_session *s, const uint8_t *wit_gf2, size_t n
             got += (size_t)r;
         }
     }
-    if (P.n_inputs) CU(cudaMemcpyAsync(s->d_wit, s->h_in, P.n_inputs, cudaMemcpyHostToDevice, hst));
+    if (P.n_inputs) CU(cudaMemcpyAsync(s->d_wit + (size_t)slot * s->wit_pitch, hin, P.n_inputs, cudaMemcpyHostToDevice, hst));
     if (P.z.n_inputs) {  // the Z64 witness fills the first leaves of the value plane; the kappa leaves after it stay zero
         uint8_t *hz = hs + RV_TOTAL_REPS * 16;
         memcpy(hz, wit_z64, 8 * (size_t)P.z.n_inputs);
         CU(cudaMemcpyAsync(s->d_zleaf, hz, 8 * (size_t)P.z.n_inputs, cudaMemcpyHostToDevice, hst));
     }
-    CU(cudaMemcpyAsync(s->d_seeds, hs + (size_t)s->first_rep * 16, (size_t)s->nreps * 16, cudaMemcpyHostToDevice, hst));
+    CU(cudaMemcpyAsync(s->d_seeds + (size_t)slot * s->nreps1 * 16, hs + (size_t)s->first_rep * 16, (size_t)s->nreps1 * 16, cudaMemcpyHostToDevice, hst));
     s->committed = s->opened = false;
     return RV_OK;
 }
@@ -656,7 +681,7 @@ static int commit_body(rv_session *s) {
         launch_values_wide(D, P.lut_level_off.data(), s->d_wit, s->d_vals, s->st_val);
     } else {
         Scope k(s, "values", (uint64_t)P.lut_steps.size() * sizeof(LutInstr), 1, s->st_val);
-        launch_values(D.lut_steps, D.n_lut_steps, D.input_vid, s->d_wit, 0, D.n_inputs, s->d_vals, 0, D.n_vals, 1, s->st_val);
+        launch_values(D.lut_steps, D.n_lut_steps, D.input_vid, s->d_wit, s->wit_pitch, D.n_inputs, s->d_vals, s->vals_pitch, D.n_vals, s->n_proofs, s->st_val);
     }
     const DevZProgram &DZ = c->zdev;
     if (s->has_z) {
@@ -666,7 +691,7 @@ static int commit_body(rv_session *s) {
     CU(cudaEventRecord(s->ev_vals, s->st_val));
     {
         Scope k(s, "key_setup", 0);  // also clears the proof's "an AssertZero failed" flag
-        launch_key_setup(s->d_seeds, nullptr, nullptr, nullptr, nslices, s->d_pkeys, s->d_rk_plain, s->st, s->d_bad);
+        launch_key_setup(s->d_seeds, nullptr, nullptr, nullptr, nslices, s->d_pkeys, s->d_rk_plain, s->st, s->d_bad, s->n_proofs, s->proof_pitch);
     }
     {
         Scope k(s, "mask_gen", (uint64_t)P.n_masks * s->npi * 8);
@@ -708,7 +733,8 @@ static int commit_body(rv_session *s) {
         // per Mul: 4 row reads + 2 stream bytes per rep (online) and 3 row reads + 1 byte per rep (pre)
         Scope k(s, "items", ((uint64_t)P.n_and * 7 + P.n_inputs + P.n_assert) * s->npi * 8 + ((uint64_t)P.n_online + P.n_pre) * s->nreps, 1);
         if (D.n_tlevels) launch_tainted(D, s->d_rows, s->npi, s->d_vals, s->d_tvals, s->st);
-        launch_items(D, s->d_rows, s->npi, s->d_vals, s->d_tvals, s->d_on, s->pitch_on, s->d_pre, s->pitch_pre, s->d_bad, s->st);
+        launch_items(D, s->d_rows, s->npi1, s->d_vals, s->d_tvals, s->d_on, s->pitch_on, s->d_pre, s->pitch_pre, s->d_bad, s->st, s->n_proofs, s->vals_pitch,
+                     s->proof_pitch);
     }
     {
         Scope k(s, "chunk_cv", ((uint64_t)P.n_online + P.n_pre) * s->nreps, 1);
@@ -754,16 +780,19 @@ static int open_body(rv_session *s, const uint8_t *all_rep_hashes) {
         cudaPointerAttributes at;
         const bool on_device = cudaPointerGetAttributes(&at, all_rep_hashes) == cudaSuccess && at.type == cudaMemoryTypeDevice;
         cudaGetLastError();
-        CU(cudaMemcpyAsync(s->d_all_hashes, all_rep_hashes, RV_TOTAL_REPS * 32, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, s->st));
+        CU(cudaMemcpyAsync(s->d_all_hashes, all_rep_hashes, (size_t)RV_TOTAL_REPS * 32 * s->n_proofs, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
+                           s->st));
     } else {
-        if (s->npi != RV_PACKED_REPS) return fail(RV_E_ARG, "a partial shard needs the all-gathered repetition hashes");
+        if (s->npi1 != RV_PACKED_REPS) return fail(RV_E_ARG, "a partial shard needs the all-gathered repetition hashes");
         hashes = s->d_rep_hash;
     }
     {
-        Scope k(s, "challenge", RV_TOTAL_REPS * 32);
-        launch_challenge(hashes, s->d_comm, s->d_omit, s->d_rank, s->st);
+        // the gathered hashes are rank-major over the session's proofs: [rank][proof][this rank's repetitions x 32 bytes]
+        Scope k(s, "challenge", (uint64_t)RV_TOTAL_REPS * 32 * s->n_proofs);
+        launch_challenge(hashes, s->nreps1 * 32, s->d_comm, s->proof_pitch, s->d_omit, s->d_rank, s->n_proofs, s->st);
     }
-    if (s->npi != RV_PACKED_REPS) CU(cudaMemsetAsync(s->d_proof, 0, s->proof_len, s->st));  // a full shard writes every byte of the proof
+    if (s->npi1 != RV_PACKED_REPS)  // a full shard writes every byte of the proof
+        CU(cudaMemset2DAsync(s->d_proof, s->proof_pitch, 0, s->proof_len, s->n_proofs, s->st));
     {
         Scope k(s, "extract", s->proof_len);
         ExtractArgs a;
@@ -779,7 +808,9 @@ static int open_body(rv_session *s, const uint8_t *all_rep_hashes) {
         a.rank_of_rep = s->d_rank;
         a.z64_empty_hash = s->d_zconst;
         a.first_rep = s->first_rep;
-        a.nreps = s->nreps;
+        a.nreps = s->nreps1;
+        a.n_proofs = s->n_proofs;
+        a.proof_stride = s->proof_pitch;
         a.len_recons = s->len_recons;
         a.len_corrs = s->len_corrs;
         a.len_inputs = s->len_inputs;
@@ -807,7 +838,7 @@ static int open_body(rv_session *s, const uint8_t *all_rep_hashes) {
         a.proof = s->d_proof;
         launch_zextract(c->zdev, a, s->st);
     }
-    if (s->out_off) CU(cudaMemcpyAsync(s->h_out, s->d_proof, s->tail_off + 36, cudaMemcpyDeviceToHost, s->st));
+    if (s->out_off) CU(cudaMemcpyAsync(s->h_out, s->d_proof, s->proof_pitch * s->n_proofs, cudaMemcpyDeviceToHost, s->st));  // h_out mirrors d_proof
     else CU(cudaMemcpyAsync(s->h_out, s->d_proof + s->tail_off, 36, cudaMemcpyDeviceToHost, s->st));
     CU(cudaGetLastError());
     return RV_OK;
@@ -828,7 +859,7 @@ extern "C" int rv_session_open(rv_session *s, const uint8_t *all_rep_hashes) {
 // the device-to-host copy of the proof) is captured once and replayed as a single CUDA graph launch.
 extern "C" int rv_session_prove(rv_session *s) {
     if (!s) return fail(RV_E_ARG, "NULL session");
-    if (s->npi != RV_PACKED_REPS) return fail(RV_E_ARG, "rv_session_prove needs a full shard");
+    if (s->npi1 != RV_PACKED_REPS) return fail(RV_E_ARG, "rv_session_prove needs a full shard");
     CU(cudaSetDevice(s->c->device));
     const int rc = run_graphed(s, s->g_prove, [&] {
         const int r = commit_body(s);
@@ -896,7 +927,7 @@ static int batch_run(rv_batch *b, int kind) {
             if (!s->committed) return fail(RV_E_ARG, "rv_batch_commit has not run");
     if (kind == 2)
         for (rv_session *s : b->ss)
-            if (s->npi != RV_PACKED_REPS) return fail(RV_E_ARG, "rv_batch_prove needs full shards");
+            if (s->npi1 != RV_PACKED_REPS) return fail(RV_E_ARG, "rv_batch_prove needs full shards");
     bool timing = false;
     std::vector<uint64_t> before;
     for (rv_session *s : b->ss) {
@@ -939,18 +970,24 @@ extern "C" int rv_batch_prove(rv_batch *b) { return b ? batch_run(b, 2) : fail(R
 extern "C" void *rv_batch_stream(rv_batch *b) { return b ? (void *)b->ss[0]->st : nullptr; }
 
 extern "C" int rv_session_fetch(rv_session *s, uint8_t comm[RV_HASH_SIZE], uint8_t **part, size_t *part_len) {
+    return rv_session_fetch_slot(s, 0, comm, part, part_len);
+}
+
+extern "C" int rv_session_fetch_slot(rv_session *s, int slot, uint8_t comm[RV_HASH_SIZE], uint8_t **part, size_t *part_len) {
     if (!s || !part || !part_len) return fail(RV_E_ARG, "NULL argument");
+    if (slot < 0 || (uint32_t)slot >= s->n_proofs) return fail(RV_E_ARG, "no such proof slot");
     if (!s->opened) return fail(RV_E_ARG, "rv_session_open has not run");
     CU(cudaSetDevice(s->c->device));
     CU(cudaStreamSynchronize(host_stream(s)));
+    const uint8_t *hout = s->h_out + (size_t)slot * (s->out_off ? s->proof_pitch : 64);
     int bad;
-    memcpy(&bad, s->h_out + s->out_off, 4);
+    memcpy(&bad, hout + s->out_off, 4);
     if (bad) return fail(RV_E_WITNESS_INVALID, "witness is invalid!");  // prover.rs:223
     uint8_t *p;
     if (s->out_off) {
         p = (uint8_t *)malloc(s->proof_len);
         if (!p) return fail(RV_E_NOMEM, "out of memory");
-        memcpy(p, s->h_out, s->proof_len);
+        memcpy(p, hout, s->proof_len);
     } else {  // big proof: device -> the returned pinned buffer, no staging copy
         p = (uint8_t *)pinned_get(s->proof_len);
         if (!p) return fail(RV_E_NOMEM, "pinned host allocation failed");
@@ -961,7 +998,7 @@ extern "C" int rv_session_fetch(rv_session *s, uint8_t comm[RV_HASH_SIZE], uint8
             return fail(RV_E_CUDA, std::string("proof copy: ") + cudaGetErrorString(e));
         }
     }
-    if (comm) memcpy(comm, s->h_out + s->out_off + 4, 32);
+    if (comm) memcpy(comm, hout + s->out_off + 4, 32);
     *part = p;
     *part_len = s->proof_len;
     return RV_OK;
@@ -972,9 +1009,11 @@ extern "C" int rv_session_status(rv_session *s) {
     if (!s->opened) return fail(RV_E_ARG, "rv_session_open has not run");
     CU(cudaSetDevice(s->c->device));
     CU(cudaStreamSynchronize(host_stream(s)));
-    int bad;
-    memcpy(&bad, s->h_out + s->out_off, 4);
-    if (bad) return fail(RV_E_WITNESS_INVALID, "witness is invalid!");  // prover.rs:223
+    for (uint32_t b = 0; b < s->n_proofs; b++) {
+        int bad;
+        memcpy(&bad, s->h_out + (size_t)b * (s->out_off ? s->proof_pitch : 64) + s->out_off, 4);
+        if (bad) return fail(RV_E_WITNESS_INVALID, "witness is invalid!");  // prover.rs:223
+    }
     return RV_OK;
 }
 
@@ -1036,6 +1075,7 @@ extern "C" int rv_prove(const rv_circuit *c, const uint8_t *wit_gf2, size_t n_gf
 //  Proof::verify (src/proof/mod.rs:224-307)
 // ---------------------------------------------------------------------------------------------------------------------
 static int verify_on_session(rv_session *s, const uint8_t *proof, size_t proof_len, const PDomain &g, const PDomain &z, int *okay, int *accept) {
+    if (s->n_proofs != 1 || s->npi != RV_PACKED_REPS) return fail(RV_E_ARG, "verification runs on a single-proof, full-shard session");
     const rv_circuit *c = s->c;
     const Program &P = c->prog;
     const DevProgram &D = c->dev;

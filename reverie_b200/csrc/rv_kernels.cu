@@ -18,8 +18,10 @@ namespace rv {
 // all-ones / zero "stream is active" words (the verifier's unopened player stays zero, src/generator/batch.rs:31-34).
 __global__ void __launch_bounds__(128) k_key_setup(const uint8_t *__restrict__ seeds, const uint8_t *__restrict__ pkeys_in,
                                                    const uint8_t *__restrict__ mode, const uint8_t *__restrict__ omit, uint32_t nslices,
-                                                   uint8_t *__restrict__ pkeys_out, uint32_t *__restrict__ rk_plain, int *__restrict__ bad) {
-    if (bad != nullptr && blockIdx.x == 0 && threadIdx.x == 0) *bad = 0;  // first kernel of every proof / verification
+                                                   uint8_t *__restrict__ pkeys_out, uint32_t *__restrict__ rk_plain, int *__restrict__ bad,
+                                                   uint32_t n_flags, size_t flag_stride) {
+    // first kernel of every proof / verification: clear the "an AssertZero failed" flag of each proof of the session
+    if (bad != nullptr && blockIdx.x == 0 && threadIdx.x < n_flags) *reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(bad) + threadIdx.x * flag_stride) = 0;
     __shared__ uint32_t sbox32[64];  // the S-box as a byte table, built from the netlist (4 entries per thread)
     if (threadIdx.x < 64) {
         const uint32_t b = 4 * threadIdx.x;
@@ -39,8 +41,8 @@ __global__ void __launch_bounds__(128) k_key_setup(const uint8_t *__restrict__ s
 }
 
 void launch_key_setup(const uint8_t *seeds, const uint8_t *pkeys_in, const uint8_t *mode, const uint8_t *omit, uint32_t nslices,
-                      uint8_t *pkeys_out, uint32_t *rk_plain, cudaStream_t st, int *bad) {
-    k_key_setup<<<(nslices + 3) / 4, 128, 0, st>>>(seeds, pkeys_in, mode, omit, nslices, pkeys_out, rk_plain, bad);
+                      uint8_t *pkeys_out, uint32_t *rk_plain, cudaStream_t st, int *bad, uint32_t n_flags, size_t flag_stride) {
+    k_key_setup<<<(nslices + 3) / 4, 128, 0, st>>>(seeds, pkeys_in, mode, omit, nslices, pkeys_out, rk_plain, bad, n_flags, flag_stride);
 }
 
 // =====================================================================================================================
@@ -549,12 +551,15 @@ __global__ void __launch_bounds__(256) k_items_pre(const Item *__restrict__ item
 // pitch T + 8 bytes: 64-bit stores of consecutive instances fall into distinct banks) and leaves as whole 128-byte lines
 // of each repetition's stream.  PRE selects the preprocessing stream (one byte per Mul) instead of the online stream.
 constexpr int IT_THREADS = 256;
+// npi = packed instances of ONE proof (the tile's geometry); the session may hold several proofs side by side: col0 = first
+// column of this proof in the share tensor, row_stride = columns of the whole tensor.
 template <bool PRE>
 __device__ __forceinline__ void items_tile_body(uint32_t tile_idx, const Item *__restrict__ items, const uint32_t *__restrict__ mul_pos, uint32_t n,
-                                                const uint64_t *__restrict__ rows, uint32_t npi, const uint8_t *__restrict__ vals,
-                                                const uint64_t *__restrict__ tvals, uint8_t *__restrict__ out, size_t pitch, uint32_t T, int *bad) {
+                                                const uint64_t *__restrict__ rows, uint32_t npi, uint32_t col0, uint32_t row_stride,
+                                                const uint8_t *__restrict__ vals, const uint64_t *__restrict__ tvals, uint8_t *__restrict__ out,
+                                                size_t pitch, uint32_t T, int *bad) {
     extern __shared__ __align__(16) uint8_t tile[];
-    const uint32_t tid = threadIdx.x, pi = tid % npi, pg0 = tid / npi, pg_step = IT_THREADS / npi;
+    const uint32_t tid = threadIdx.x, pi = tid % npi, pg0 = tid / npi, pg_step = IT_THREADS / npi, col = col0 + pi;
     const uint32_t tp = T + 8;  // tile pitch in bytes
     const uint64_t T0 = (uint64_t)tile_idx * T;
     int flag = 0;
@@ -564,7 +569,8 @@ __device__ __forceinline__ void items_tile_body(uint32_t tile_idx, const Item *_
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             W[i] = 0;
-            if (t0 + i < n) W[i] = PRE ? pre_word(items[mul_pos[t0 + i]], rows, npi, pi) : prover_online_word(items[t0 + i], rows, npi, pi, vals, tvals, &flag);
+            if (t0 + i < n)
+                W[i] = PRE ? pre_word(items[mul_pos[t0 + i]], rows, row_stride, col) : prover_online_word(items[t0 + i], rows, row_stride, col, vals, tvals, &flag);
         }
         words_to_stream_bytes(W, o);
 #pragma unroll
@@ -576,7 +582,7 @@ __device__ __forceinline__ void items_tile_body(uint32_t tile_idx, const Item *_
     const uint32_t lane = tid & 31, wrp = tid >> 5, nrows = 8 * npi;
     for (uint32_t row = wrp; row < nrows; row += IT_THREADS / 32) {
         const uint32_t r = row / npi, p = row % npi;
-        uint8_t *dst = out + (size_t)(8 * p + r) * pitch + T0;
+        uint8_t *dst = out + (size_t)(8 * (col0 + p) + r) * pitch + T0;
         const uint8_t *src = tile + (size_t)row * tp;
         for (uint32_t c = 4 * lane; c < T; c += 128) *reinterpret_cast<uint32_t *>(dst + c) = *reinterpret_cast<const uint32_t *>(src + c);
     }
@@ -584,24 +590,29 @@ __device__ __forceinline__ void items_tile_body(uint32_t tile_idx, const Item *_
 
 // One launch covers both streams: CTAs [0, tiles_on) take tiles of the online stream, the rest tiles of the preprocessing
 // stream (small proofs are bound by the number of kernels in flight, not by their work).
+// grid.y = proof of the session (its witness / value plane at vals + y * vals_pitch, its flag at bad + y * flag_stride bytes).
 __global__ void __launch_bounds__(IT_THREADS) k_items(const Item *__restrict__ items, const uint32_t *__restrict__ mul_pos, uint32_t n_online,
                                                      uint32_t n_pre, uint32_t tiles_on, const uint64_t *__restrict__ rows, uint32_t npi,
-                                                     const uint8_t *__restrict__ vals, const uint64_t *__restrict__ tvals, uint8_t *__restrict__ on,
-                                                     size_t pitch_on, uint8_t *__restrict__ pre, size_t pitch_pre, uint32_t T, int *bad) {
-    if (blockIdx.x < tiles_on) items_tile_body<false>(blockIdx.x, items, nullptr, n_online, rows, npi, vals, tvals, on, pitch_on, T, bad);
-    else items_tile_body<true>(blockIdx.x - tiles_on, items, mul_pos, n_pre, rows, npi, nullptr, nullptr, pre, pitch_pre, T, nullptr);
+                                                     const uint8_t *__restrict__ vals, size_t vals_pitch, const uint64_t *__restrict__ tvals,
+                                                     uint8_t *__restrict__ on, size_t pitch_on, uint8_t *__restrict__ pre, size_t pitch_pre, uint32_t T,
+                                                     int *bad, size_t flag_stride) {
+    const uint32_t col0 = blockIdx.y * npi, row_stride = gridDim.y * npi;
+    if (blockIdx.x < tiles_on)
+        items_tile_body<false>(blockIdx.x, items, nullptr, n_online, rows, npi, col0, row_stride, vals + blockIdx.y * vals_pitch, tvals, on, pitch_on, T,
+                               reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(bad) + blockIdx.y * flag_stride));
+    else items_tile_body<true>(blockIdx.x - tiles_on, items, mul_pos, n_pre, rows, npi, col0, row_stride, nullptr, nullptr, pre, pitch_pre, T, nullptr);
 }
 
 static uint32_t items_tile(uint32_t npi) { return std::max(128u, 8u * IT_THREADS / npi); }
 
 void launch_items(const DevProgram &P, const uint64_t *rows, uint32_t npi, const uint8_t *vals, const uint64_t *tvals, uint8_t *on, size_t pitch_on,
-                  uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st) {
+                  uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st, uint32_t n_proofs, size_t vals_pitch, size_t flag_stride) {
     const uint32_t T = items_tile(npi);
     const size_t smem = (size_t)8 * npi * (T + 8);
     const uint32_t tiles_on = (P.n_online + T - 1) / T, tiles_pre = (P.n_pre + T - 1) / T;
     if (tiles_on + tiles_pre)
-        k_items<<<tiles_on + tiles_pre, IT_THREADS, smem, st>>>(P.items, P.mul_pos, P.n_online, P.n_pre, tiles_on, rows, npi, vals, tvals, on, pitch_on, pre,
-                                                                 pitch_pre, T, bad);
+        k_items<<<dim3(tiles_on + tiles_pre, n_proofs), IT_THREADS, smem, st>>>(P.items, P.mul_pos, P.n_online, P.n_pre, tiles_on, rows, npi, vals, vals_pitch,
+                                                                                 tvals, on, pitch_on, pre, pitch_pre, T, bad, flag_stride);
 }
 
 // Tainted plane: CTA = one packed instance (columns are independent), level-synchronous with CTA barriers only.
@@ -920,8 +931,13 @@ void launch_verify_items(const DevProgram &P, const VOpen *opens, const uint8_t 
 // =====================================================================================================================
 //  K6  comm + Fiat-Shamir challenge: one warp
 // =====================================================================================================================
-__global__ void __launch_bounds__(32) k_challenge(const uint8_t *__restrict__ all_hashes, uint8_t *__restrict__ comm,
-                                                  uint8_t *__restrict__ omit_of_rep, uint16_t *__restrict__ rank_of_rep) {
+// grid.x = proof of the session.  The 256 hashes of proof b arrive as n_seg segments of seg_bytes (one per rank of the
+// all-gather, rank-major over the session's proofs): segment r of proof b starts at all_hashes + (r * n_proofs + b) * seg_bytes.
+__global__ void __launch_bounds__(32) k_challenge(const uint8_t *__restrict__ all_hashes_base, uint32_t seg_bytes, uint8_t *__restrict__ comm_base,
+                                                  size_t comm_stride, uint8_t *__restrict__ omit_base, uint16_t *__restrict__ rank_base) {
+    const uint32_t pb = blockIdx.x, n_proofs = gridDim.x;
+    uint8_t *comm = comm_base + pb * comm_stride, *omit_of_rep = omit_base + pb * RV_TOTAL_REPS;
+    uint16_t *rank_of_rep = rank_base + pb * RV_TOTAL_REPS;
     __shared__ uint32_t cv[8][8];
     __shared__ uint32_t xof[32][16];
     __shared__ uint8_t omit[RV_TOTAL_REPS];
@@ -929,7 +945,8 @@ __global__ void __launch_bounds__(32) k_challenge(const uint8_t *__restrict__ al
     // combine_hashes (src/proof/mod.rs:102-108): BLAKE3 of 256 x 32 B = 8 chunks
     if (lane < 8) {
         uint32_t c[8];
-        b3_chunk_cv(reinterpret_cast<const uint32_t *>(all_hashes + 1024 * lane), 1024, lane, false, c);
+        const uint32_t byte0 = 1024 * lane, seg = byte0 / seg_bytes;  // a 1 KiB chunk (32 hashes) never straddles segments (>= 32 repetitions each)
+        b3_chunk_cv(reinterpret_cast<const uint32_t *>(all_hashes_base + ((size_t)seg * n_proofs + pb) * seg_bytes + (byte0 - seg * seg_bytes)), 1024, lane, false, c);
         for (int i = 0; i < 8; i++) cv[lane][i] = c[i];
     }
     __syncwarp();
@@ -968,8 +985,9 @@ __global__ void __launch_bounds__(32) k_challenge(const uint8_t *__restrict__ al
     }
 }
 
-void launch_challenge(const uint8_t *all_hashes, uint8_t *comm, uint8_t *omit_of_rep, uint16_t *rank_of_rep, cudaStream_t st) {
-    k_challenge<<<1, 32, 0, st>>>(all_hashes, comm, omit_of_rep, rank_of_rep);
+void launch_challenge(const uint8_t *all_hashes, uint32_t seg_bytes, uint8_t *comm, size_t comm_stride, uint8_t *omit_of_rep, uint16_t *rank_of_rep,
+                      uint32_t n_proofs, cudaStream_t st) {
+    k_challenge<<<n_proofs, 32, 0, st>>>(all_hashes, seg_bytes, comm, comm_stride, omit_of_rep, rank_of_rep);
 }
 
 // =====================================================================================================================
@@ -977,7 +995,7 @@ void launch_challenge(const uint8_t *all_hashes, uint8_t *comm, uint8_t *omit_of
 // =====================================================================================================================
 __global__ void __launch_bounds__(256) k_extract(const uint32_t *__restrict__ recon_pos, const uint32_t *__restrict__ input_pos,
                                                  uint32_t n_recon, uint32_t n_pre, uint32_t n_inputs, ExtractArgs a) {
-    const uint32_t lrep = blockIdx.x, rep = a.first_rep + lrep;
+    const uint32_t pb = blockIdx.x / a.nreps, lrep = blockIdx.x, rep = a.first_rep + blockIdx.x % a.nreps;  // lrep indexes the session's streams
     ProofLayout L{a.len_recons, a.len_corrs, a.len_inputs, a.len_zrecons, a.len_zcorrs, a.len_zinputs};
     ExtractView v;
     v.on = a.on + (size_t)lrep * a.pitch_on;
@@ -985,7 +1003,7 @@ __global__ void __launch_bounds__(256) k_extract(const uint32_t *__restrict__ re
     v.on_hash = a.on_hash + (size_t)lrep * 32;
     v.pkeys = a.pkeys + (size_t)lrep * 128;
     v.seed = a.seeds + (size_t)lrep * 16;
-    v.comm = a.comm;
+    v.comm = a.comm + pb * a.proof_stride;
     v.z64_empty_hash = a.z64_empty_hash;
     v.z_on_hash = a.z_on_hash ? a.z_on_hash + (size_t)lrep * 32 : nullptr;
     v.recon_pos = recon_pos;
@@ -994,14 +1012,16 @@ __global__ void __launch_bounds__(256) k_extract(const uint32_t *__restrict__ re
     v.n_pre = n_pre;
     v.n_inputs = n_inputs;
     // grid.y CTAs share one repetition: the packed vectors of a big circuit are megabytes per opened repetition
-    if (a.omit_of_rep[rep] >= RV_PLAYERS && blockIdx.y != 0) return;
-    extract_entry(L, v, rep, a.omit_of_rep[rep], a.rank_of_rep[rep], threadIdx.x + blockDim.x * blockIdx.y, blockDim.x * gridDim.y, a.proof);
+    const uint32_t omit = a.omit_of_rep[pb * RV_TOTAL_REPS + rep];
+    if (omit >= RV_PLAYERS && blockIdx.y != 0) return;
+    extract_entry(L, v, rep, omit, a.rank_of_rep[pb * RV_TOTAL_REPS + rep], threadIdx.x + blockDim.x * blockIdx.y, blockDim.x * gridDim.y,
+                  a.proof + pb * a.proof_stride);
 }
 
 void launch_extract(const DevProgram &P, const ExtractArgs &a, cudaStream_t st) {
     const uint32_t bytes = a.len_recons + a.len_corrs + a.len_inputs;
     const uint32_t ny = std::min(64u, std::max(1u, bytes / 4096));
-    k_extract<<<dim3(a.nreps, ny), 256, 0, st>>>(P.recon_pos, P.input_pos, P.n_recon, P.n_pre, P.n_inputs, a);
+    k_extract<<<dim3(a.nreps * a.n_proofs, ny), 256, 0, st>>>(P.recon_pos, P.input_pos, P.n_recon, P.n_pre, P.n_inputs, a);
 }
 
 }  // namespace rv

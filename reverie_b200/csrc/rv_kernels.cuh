@@ -60,7 +60,7 @@ struct DevZProgram {
 //     rk_plain: [45][32 * nslices] u32 -- the 44 round-key words of every stream (stream = 8 * rep + player), then a row of
 //     all-ones / zero "stream is active" words
 void launch_key_setup(const uint8_t *seeds, const uint8_t *pkeys_in, const uint8_t *mode, const uint8_t *omit, uint32_t nslices,
-                      uint8_t *pkeys_out, uint32_t *rk_plain, cudaStream_t st, int *clear_flag = nullptr);
+                      uint8_t *pkeys_out, uint32_t *rk_plain, cudaStream_t st, int *clear_flag = nullptr, uint32_t n_flags = 1, size_t flag_stride = 0);
 // K2  AES-CTR mask generation straight into the share tensor (src/generator/share.rs:54-65, src/algebra/gf2/domain.rs:66-173)
 //     also writes the instance-major copy `fresh_pm` [npi][pitch_pm] (u64) that the mask VM loads from (nullptr = skip)
 void launch_mask_gen_tt(const uint32_t *rk_plain, uint32_t nslices, uint32_t n_masks, uint64_t *rows, uint64_t *fresh_pm, size_t pitch_pm, int n_sms,
@@ -82,8 +82,10 @@ bool linear_uses_vm(const DevProgram &P);
 // K4  item plane: the two hash streams of every repetition
 //     tvals: tainted plane [n_tvals][npi] (launch_tainted), read by items whose operands depend on Random / B2A fresh wires
 void launch_tainted(const DevProgram &P, const uint64_t *rows, uint32_t npi, const uint8_t *vals, uint64_t *tvals, cudaStream_t st);
+//     npi = packed instances of one proof; a session holding n_proofs proofs side by side passes their count, the pitch between
+//     their value planes and the byte stride between their flags
 void launch_items(const DevProgram &P, const uint64_t *rows, uint32_t npi, const uint8_t *vals, const uint64_t *tvals, uint8_t *on, size_t pitch_on,
-                  uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st);
+                  uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st, uint32_t n_proofs = 1, size_t vals_pitch = 0, size_t flag_stride = 0);
 // K5  BLAKE3 chunk chaining values of `nreps` streams, then per-repetition tree + joins
 void launch_chunk_cv2(const uint8_t *on, size_t pitch_on, uint32_t len_on, uint32_t *cv_on, uint32_t nreps_on, const uint8_t *pre, size_t pitch_pre,
                       uint32_t len_pre, uint32_t *cv_pre, uint32_t nreps_pre, cudaStream_t st);
@@ -104,7 +106,9 @@ void launch_verify_items(const DevProgram &P, const VOpen *opens, const uint8_t 
                          cudaStream_t st);
 void launch_items_pre_range(const DevProgram &P, const uint64_t *rows, uint32_t npi, uint32_t first_pi, uint8_t *pre, size_t pitch_pre, cudaStream_t st);
 // K6  comm = H(256 rep hashes); Fiat-Shamir challenge (src/proof/mod.rs:74-108)
-void launch_challenge(const uint8_t *all_hashes, uint8_t *comm, uint8_t *omit_of_rep, uint16_t *rank_of_rep, cudaStream_t st);
+//     one warp per proof of the session; the hashes arrive as segments of seg_bytes per rank (see k_challenge)
+void launch_challenge(const uint8_t *all_hashes, uint32_t seg_bytes, uint8_t *comm, size_t comm_stride, uint8_t *omit_of_rep, uint16_t *rank_of_rep,
+                      uint32_t n_proofs, cudaStream_t st);
 // K7  openings -> bincode bytes of `Proof` (src/transcript/prover.rs:57-175, src/proof/mod.rs:40-66,200-221)
 struct ExtractArgs {
     const uint8_t *on, *pre;
@@ -112,9 +116,11 @@ struct ExtractArgs {
     const uint8_t *on_hash;      // [nreps][32]
     const uint8_t *pkeys;        // [nreps][8][16]
     const uint8_t *seeds;        // [nreps][16]
-    const uint8_t *comm;         // [32]
-    const uint8_t *omit_of_rep;  // [256]
-    const uint16_t *rank_of_rep; // [256]
+    const uint8_t *comm;         // [32], proof b at + b * proof_stride
+    const uint8_t *omit_of_rep;  // [n_proofs][256]
+    const uint16_t *rank_of_rep; // [n_proofs][256]
+    uint32_t n_proofs = 1;       // proofs held side by side by the session: streams / hashes / keys are indexed by (proof, repetition)
+    size_t proof_stride = 0;     // bytes between the proofs' output buffers
     const uint32_t *z64_empty_hash;  // B3("")
     const uint8_t *z_on_hash = nullptr;  // [nreps][32] BLAKE3 of the Z64 online streams (nullptr: no Z64 ops)
     uint32_t first_rep, nreps;

@@ -97,29 +97,31 @@ class Session:
     """One proof shard in flight (rv_session): packed instances [first, first + count) of the 32
     (src/proof/mod.rs:127-157).  Used directly for multi-GPU sharding and for device-resident timing."""
 
-    def __init__(self, circuit: Circuit, first_instance: int = 0, n_instances: int = N.PACKED_REPS):
+    def __init__(self, circuit: Circuit, first_instance: int = 0, n_instances: int = N.PACKED_REPS, n_proofs: int = 1):
+        """n_proofs > 1: the session holds that many independent proofs side by side (rv_session_create_multi); every phase is
+        the same few kernel launches covering all of them.  Fill the slots with upload(..., slot=b), read them with fetch(slot=b)."""
         self.circuit = circuit
         h = C.c_void_p()
-        N.check(N.lib().rv_session_create(circuit.handle, first_instance, n_instances, C.byref(h)))
+        N.check(N.lib().rv_session_create_multi(circuit.handle, first_instance, n_instances, n_proofs, C.byref(h)))
         self._h = h
-        self.first_instance, self.n_instances = first_instance, n_instances
+        self.first_instance, self.n_instances, self.n_proofs = first_instance, n_instances, n_proofs
 
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
             N.lib().rv_session_free(h)
 
-    def upload(self, wit_gf2, wit_z64=(), seeds=None):
+    def upload(self, wit_gf2, wit_z64=(), seeds=None, slot: int = 0):
         self._wg = np.ascontiguousarray(np.asarray(wit_gf2, dtype=np.uint8))
         self._wz = np.ascontiguousarray(np.asarray(wit_z64, dtype=np.uint64))
         self._sd = _seeds_arr(seeds)
-        N.check(N.lib().rv_session_upload(self._h, _ptr(self._wg), self._wg.size, _ptr(self._wz), self._wz.size, _ptr(self._sd)))
+        N.check(N.lib().rv_session_upload_slot(self._h, slot, _ptr(self._wg), self._wg.size, _ptr(self._wz), self._wz.size, _ptr(self._sd)))
 
     def commit(self):
         N.check(N.lib().rv_session_commit(self._h))
 
     def hashes(self) -> bytes:
-        out = np.zeros(self.n_instances * 8 * 32, dtype=np.uint8)
+        out = np.zeros(self.n_proofs * self.n_instances * 8 * 32, dtype=np.uint8)
         N.check(N.lib().rv_session_hashes(self._h, _ptr(out)))
         return out.tobytes()
 
@@ -130,7 +132,7 @@ class Session:
         ptr = int(N.lib().rv_session_hashes_device(self._h) or 0)
         if not ptr:
             raise N.ReverieError(N.E_ARG, "rv_session_commit has not run")
-        n = self.n_instances * 8 * 32
+        n = self.n_proofs * self.n_instances * 8 * 32
 
         class _Dev:
             __cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
@@ -141,9 +143,10 @@ class Session:
         """The session's own 256 x 32-byte receive buffer for the all-gather (__cuda_array_interface__); pass its address to
         open() afterwards: no copy, and the open phase replays as one CUDA graph."""
         ptr = int(N.lib().rv_session_all_hashes_device(self._h) or 0)
+        n = self.n_proofs * N.TOTAL_REPS * 32
 
         class _Dev:
-            __cuda_array_interface__ = {"shape": (N.TOTAL_REPS * 32,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "|u1", "data": (ptr, False), "version": 2}
 
         d = _Dev()
         d.ptr = ptr
@@ -157,8 +160,8 @@ class Session:
             p = C.c_void_p(all_rep_hashes)
         else:
             self._ah = np.frombuffer(bytes(all_rep_hashes), dtype=np.uint8)
-            if self._ah.size != N.TOTAL_REPS * 32:
-                raise ValueError("need 256 x 32 bytes of repetition hashes")
+            if self._ah.size != self.n_proofs * N.TOTAL_REPS * 32:
+                raise ValueError("need 256 x 32 bytes of repetition hashes per proof of the session")
             p = _ptr(self._ah)
         N.check(N.lib().rv_session_open(self._h, p))
 
@@ -166,10 +169,10 @@ class Session:
         """commit + open (own hashes) of a full shard, asynchronously; one CUDA graph launch after the first call."""
         N.check(N.lib().rv_session_prove(self._h))
 
-    def fetch(self):
+    def fetch(self, slot: int = 0):
         comm = np.zeros(32, dtype=np.uint8)
         out, n = C.c_void_p(), C.c_size_t()
-        N.check(N.lib().rv_session_fetch(self._h, _ptr(comm), C.byref(out), C.byref(n)))
+        N.check(N.lib().rv_session_fetch_slot(self._h, slot, _ptr(comm), C.byref(out), C.byref(n)))
         return comm.tobytes(), _take(out, n)
 
     def sync(self):

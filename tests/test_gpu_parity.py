@@ -465,3 +465,50 @@ def test_cpp_host_mirror(rb):
 
     res = subprocess.run([build_cpp_api_test()], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0 and "cpp host mirror ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_multi_proof_session(rb, default_seeds):
+    """rv_session_create_multi: several proofs side by side in one session, every kernel launch covering all of them; each slot's
+    bytes must be the oracle's for its own witness and seeds, across eager run, graph capture and replays; sharded too."""
+    import orc
+    from reverie_b200 import circuits as C
+
+    ops, wit, wc = C.sha256_abc_case()
+    wit2 = C.sha256_witness(C.sha256_pad_single_block(b"abc"))
+    rng = np.random.default_rng(8)
+    seeds = [default_seeds] + [rng.integers(0, 256, size=256 * 16, dtype=np.uint8).tobytes() for _ in range(4)]
+    want = [orc.prove(ops, wit, [], wc, sd)[1] for sd in seeds]
+    circ = rb.Circuit(ops, wc)
+    s = rb.Session(circ, 0, 32, n_proofs=5)
+    for rnd in range(4):
+        order = [(k + rnd) % 5 for k in range(5)]
+        for slot, k in enumerate(order):
+            s.upload(wit, (), seeds[k], slot=slot)
+        s.prove()
+        for slot, k in enumerate(order):
+            assert s.fetch(slot)[1] == want[k], (rnd, slot)
+    bad = wit.copy()
+    bad[11] ^= 1
+    s.upload(bad, (), seeds[0], slot=2)
+    s.prove()
+    assert s.fetch(0)[1] == want[order[0]]
+    with pytest.raises(rb.WitnessError):
+        s.fetch(2)
+    # sharded: two "ranks" of 16 instances, 3 proofs each; gathered layout [rank][proof][local hashes]
+    sh = [rb.Session(circ, g * 16, 16, n_proofs=3) for g in range(2)]
+    for g in range(2):
+        for b in range(3):
+            sh[g].upload(wit, (), seeds[b], slot=b)
+        sh[g].commit()
+    gathered = b"".join(x.hashes() for x in sh)
+    for x in sh:
+        x.open(gathered)
+    for b in range(3):
+        parts = [x.fetch(b) for x in sh]
+        assert rb.assemble(parts[0][0], [p for _, p in parts]) == want[b], b
+    from reverie_b200 import _native as N
+
+    with pytest.raises(rb.ReverieError) as e:  # Z64 circuits keep one proof per session
+        zops, zwc = C.flat_mul_circuit(4, domain=C.Z64)
+        rb.Session(rb.Circuit(zops, zwc), 0, 32, n_proofs=2)
+    assert e.value.code == N.E_UNSUPPORTED
