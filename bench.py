@@ -196,6 +196,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="sha256")
     ap.add_argument("--batch", type=int, default=32, help="independent proofs per step")
+    ap.add_argument("--per-session", type=int, default=8,
+                    help="proofs held side by side by one multi-proof session (small GF(2) circuits); the batch is batch/per-session such sessions")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shard", default="reps", choices=["reps", "proofs"],
                     help="N > 1: 'reps' shards the 32 packed instances of every proof over the ranks with the NCCL all-gather of repetition "
@@ -235,8 +237,23 @@ def main():
     by_proofs = world > 1 and args.shard == "proofs"
     per = 32 if by_proofs else 32 // world
     B = max(1, args.batch)
-    sessions = [rb.Session(circ, 0 if by_proofs else rank * per, per) for _ in range(B)]
+    first = 0 if by_proofs else rank * per
+    # Small GF(2) circuits: the batch is held by multi-proof sessions (P proofs side by side per session: every kernel launch
+    # covers P proofs); other circuits: one proof per session.
+    P = max(1, min(args.per_session, B))
+    try:
+        sessions = [rb.Session(circ, first, per, n_proofs=P)] if P > 1 else []
+    except rb.ReverieError:
+        P, sessions = 1, []
+    B = (B + P - 1) // P * P
+    sessions += [rb.Session(circ, first, per, n_proofs=P) for _ in range(B // P - len(sessions))]
+    sess1 = sessions[0] if B == 1 else rb.Session(circ, first, per)  # one proof alone: latency and per-kernel times
     streams = [torch.cuda.ExternalStream(x.stream) for x in sessions]
+
+    def upload_all(xs):
+        for x in xs:
+            for slot in range(x.n_proofs):
+                x.upload(wit, wz, seeds, slot=slot)
     timing_stream = torch.cuda.Stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
     recv_bufs = {}  # session -> (receive tensor over the session's own all-gather buffer, send tensor over its hashes)
@@ -251,7 +268,7 @@ def main():
     batches = {}
 
     def batch_of(sess_list):
-        key = len(sess_list)
+        key = tuple(id(x) for x in sess_list)
         if key not in batches:
             bt = rb.Batch(sess_list)
             batches[key] = (bt, torch.cuda.ExternalStream(bt.stream))
@@ -293,14 +310,13 @@ def main():
             tot += a.elapsed_time(b)
         return tot  # ms
 
-    for x in sessions:
-        x.upload(wit, wz, seeds)
-    st_proof_len = len(torch.as_tensor(sessions[0].proof_device(), device="cuda"))
+    upload_all(sessions + ([sess1] if sess1 is not sessions[0] else []))
+    st_proof_len = len(torch.as_tensor(sess1.proof_device(), device="cuda"))
     for _ in range(args.warmup):
         step_device()
     for x in sessions:
         x.sync()
-    sess = sessions[0]
+    sess = sess1
     launches0 = sum(x.launch_count for x in sessions)
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -317,12 +333,12 @@ def main():
     # single-proof device latency (B = 1), same rules
     lat_ms = None
     if world == 1:
-        keep_s, keep_st = sessions, streams
-        sessions, streams = sessions[:1], streams[:1]
+        keep_s = sessions
+        sessions = [sess1]
         for _ in range(3):  # eager run, graph capture, first replay
             step_device()
         lat_ms = timed_device(max(5, min(args.steps, 20))) / max(5, min(args.steps, 20))
-        sessions, streams = keep_s, keep_st
+        sessions = keep_s
 
     # ---- per-kernel device times -> roofline of the dominant kernel (rank 0) ----
     roofline, kernels = None, None
@@ -331,7 +347,7 @@ def main():
     if rank == 0:
         sess.timing(True)
     keep_s = sessions
-    sessions = sessions[:1]
+    sessions = [sess1]
     for _ in range(reps):  # every rank runs the steps (they contain the all-gather); only rank 0 brackets its kernels with events
         step_device()
     sessions = keep_s
@@ -358,7 +374,7 @@ def main():
 
     big = st["n_masks"] * 256 + st["z64_masks"] * 16384 > (8 << 30)  # a session of this circuit holds tens of GB: one at a time
     if big and world == 1:
-        del sess, x
+        del sess, sess1
         batches.clear()
         recv_bufs.clear()
         sessions.clear()
@@ -379,12 +395,15 @@ def main():
         def one(_):
             return rb.Proof.new(circ, wit, wz, seeds=seeds)
 
+        def step_api():  # the B queued requests of a step through the public batched call (host witnesses in, proof bytes out)
+            return rb.Proof.new_batch(circ, [wit] * B, [wz] * B, seeds=[seeds] * B)
+
         for _ in range(args.warmup):
-            proofs = list(pool.map(one, range(B)))
+            proofs = step_api()
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            proofs = list(pool.map(one, range(B)))
+            proofs = step_api()
         dt = time.perf_counter() - t0
         e2e_v = n_and * B * args.steps / dt
         proof = proofs[0]
@@ -412,11 +431,10 @@ def main():
                       "note": "Proof.verify end to end (proof bytes in host memory), B verifications in flight"}
     else:
         def step_e2e():
-            for x in sessions:
-                x.upload(wit, wz, seeds)
+            upload_all(sessions)
             step_device()
             if by_proofs:
-                outs = [x.fetch() for x in sessions]
+                outs = [x.fetch(b) for x in sessions for b in range(x.n_proofs)]
                 return outs, [p for _, p in outs]  # every rank holds its own whole proofs
             proofs = sharding.reduce_proofs(sessions)  # one NCCL reduce: rank 0 ends up with the B assembled proofs in host memory
             return [(None, proofs[0] if proofs else b"")], proofs
@@ -452,7 +470,8 @@ def main():
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak" if by_proofs else "strong", "vs_baseline": None, "dtype": "u64",
             "data": "synthetic",
             "config": {"workload": desc, "batch": B, "parallelism": (f"whole proofs per GPU, {B} proofs in flight per GPU per step, no collective" if by_proofs else
-                                                                      f"{per} packed instances (= {per * 8} repetitions) per GPU, {B} proofs in flight per step, NCCL all-gather of the repetition hashes"),
+                                                                      f"{per} packed instances (= {per * 8} repetitions) per GPU, {B} proofs in flight per step, NCCL all-gather of the repetition hashes")
+                                      + f"; {B // P} sessions x {P} proofs side by side",
                        "l2": "256 MiB memset between timed steps (outside the per-step CUDA-event pair)",
                        "timing": "one CUDA-event pair per step on a timing stream that forks to / joins the batch leader's stream (the B session streams fork from / join it inside the CUDA graph), summed over K steps"},
             "clocks": clocks, "e2e": e2e, "verify": verify, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,

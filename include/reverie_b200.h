@@ -132,6 +132,13 @@ int rv_circuit_export(const rv_circuit *c, int what, void *buf, size_t *len);
 int rv_prove(const rv_circuit *c, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64, size_t n_z64,
              const uint8_t *seeds, uint8_t **proof, size_t *proof_len);
 
+/* Proof::new for n independent witnesses of one circuit (a proving service's queue).  Arrays of n pointers / sizes; seeds may be
+ * NULL (OS RNG for all) or hold NULL entries.  proofs[i] / proof_lens[i] / statuses[i] receive each proof's result (RV_OK,
+ * RV_E_WITNESS_INVALID, RV_E_WITNESS_SHORT ...; release proofs[i] with rv_free).  The return value is RV_OK unless the call as a
+ * whole failed (CUDA / memory).  Small GF(2) circuits run side by side in multi-proof sessions; other circuits one by one. */
+int rv_prove_batch(const rv_circuit *c, int n, const uint8_t *const *wit_gf2, const size_t *n_gf2, const uint64_t *const *wit_z64,
+                   const size_t *n_z64, const uint8_t *const *seeds, uint8_t **proofs, size_t *proof_lens, int *statuses);
+
 /* Proof::verify  (src/proof/mod.rs:224-307).  Returns 1 accept / 0 reject / <0 error.
  * *okay (optional) receives the AND of the online verifiers' zero_check flags, which the reference computes
  * (src/transcript/verifier/online.rs:176-178) but never reads. */
@@ -194,6 +201,9 @@ int rv_session_status(rv_session *s);
  * rv_session_open: lets a multi-GPU caller combine the shards on the device (their non-zero bytes are disjoint, so an
  * NCCL sum-reduce of the byte buffers is the assembly of src/proof/mod.rs:200-221). */
 int rv_session_proof_device(rv_session *s, void **ptr, size_t *len);
+/* Multi-proof sessions: number of slots, and the byte distance between consecutive slots' proof buffers in device memory. */
+int rv_session_slots(const rv_session *s);
+size_t rv_session_proof_stride(const rv_session *s);
 int rv_proof_assemble(const uint8_t comm[RV_HASH_SIZE], const uint8_t *const *parts, const size_t *part_lens,
                       int n_parts, uint8_t **proof, size_t *proof_len);
 /* cudaStream_t of the session (as void*), so callers can bracket work with their own CUDA events. */

@@ -113,6 +113,7 @@ struct rv_circuit {
     // idle full-shard sessions kept for rv_prove, so that back-to-back proofs reuse their device buffers
     mutable std::mutex pool_mu;
     mutable std::vector<rv_session *> pool;
+    mutable std::vector<rv_session *> multi_pool;  // idle multi-proof sessions (rv_prove_batch), any slot counts
 };
 
 template <typename T>
@@ -132,6 +133,8 @@ extern "C" void rv_circuit_free(rv_circuit *c) {
     if (!c) return;
     for (rv_session *s : c->pool) rv_session_free(s);
     c->pool.clear();
+    for (rv_session *s : c->multi_pool) rv_session_free(s);
+    c->multi_pool.clear();
     for (void *p : c->allocs) cudaFree(p);
     delete c;
 }
@@ -1017,6 +1020,9 @@ extern "C" int rv_session_status(rv_session *s) {
     return RV_OK;
 }
 
+extern "C" size_t rv_session_proof_stride(const rv_session *s) { return s ? s->proof_pitch : 0; }
+extern "C" int rv_session_slots(const rv_session *s) { return s ? (int)s->n_proofs : 0; }
+
 extern "C" int rv_session_proof_device(rv_session *s, void **ptr, size_t *len) {
     if (!s || !ptr || !len) return fail(RV_E_ARG, "NULL argument");
     *ptr = s->d_proof;
@@ -1068,6 +1074,85 @@ extern "C" int rv_prove(const rv_circuit *c, const uint8_t *wit_gf2, size_t n_gf
     std::lock_guard<std::mutex> g(c->pool_mu);
     if (c->pool.size() < 32) c->pool.push_back(s);
     else rv_session_free(s);
+    return rc;
+}
+
+// Proof::new for n independent witnesses of one circuit, the way a proving service sees its queue: the proofs are packed side
+// by side into multi-proof sessions (RV_BATCH_SLOTS per session, each on its own stream), everything is enqueued before the
+// first synchronisation, and every session's phase is one launch per kernel for all of its proofs.
+static constexpr int RV_BATCH_SLOTS = 8;
+extern "C" int rv_prove_batch(const rv_circuit *c, int n, const uint8_t *const *wit_gf2, const size_t *n_gf2, const uint64_t *const *wit_z64,
+                              const size_t *n_z64, const uint8_t *const *seeds, uint8_t **proofs, size_t *proof_lens, int *statuses) {
+    if (!c || n <= 0 || !proofs || !proof_lens || !statuses) return fail(RV_E_ARG, "bad argument");
+    for (int i = 0; i < n; i++) {
+        proofs[i] = nullptr;
+        proof_lens[i] = 0;
+        statuses[i] = RV_OK;
+    }
+    // circuits a multi-proof session does not serve (Z64 / Random / B2A / big proofs): one rv_prove per witness
+    rv_session *probe = nullptr;
+    {
+        std::lock_guard<std::mutex> g(c->pool_mu);
+        if (!c->multi_pool.empty()) {
+            probe = c->multi_pool.back();
+            c->multi_pool.pop_back();
+        }
+    }
+    if (!probe) {
+        const int rc = rv_session_create_multi(c, 0, RV_PACKED_REPS, RV_BATCH_SLOTS, &probe);
+        if (rc == RV_E_UNSUPPORTED) {
+            int worst = RV_OK;
+            for (int i = 0; i < n; i++) {
+                statuses[i] = rv_prove(c, wit_gf2 ? wit_gf2[i] : nullptr, n_gf2 ? n_gf2[i] : 0, wit_z64 ? wit_z64[i] : nullptr, n_z64 ? n_z64[i] : 0,
+                                       seeds ? seeds[i] : nullptr, &proofs[i], &proof_lens[i]);
+                if (statuses[i] != RV_OK && worst == RV_OK) worst = statuses[i];
+            }
+            return worst == RV_E_CUDA ? worst : RV_OK;
+        }
+        if (rc != RV_OK) return rc;
+    }
+    std::vector<rv_session *> used{probe};
+    const int n_sess = (n + RV_BATCH_SLOTS - 1) / RV_BATCH_SLOTS;
+    int rc = RV_OK;
+    while ((int)used.size() < n_sess && rc == RV_OK) {
+        rv_session *s = nullptr;
+        {
+            std::lock_guard<std::mutex> g(c->pool_mu);
+            if (!c->multi_pool.empty()) {
+                s = c->multi_pool.back();
+                c->multi_pool.pop_back();
+            }
+        }
+        if (!s) rc = rv_session_create_multi(c, 0, RV_PACKED_REPS, RV_BATCH_SLOTS, &s);
+        if (s) used.push_back(s);
+    }
+    // fill the slots (unused slots of the last session re-run its first witness; their output is dropped), launch, then collect
+    for (int k = 0; k < (int)used.size() && rc == RV_OK; k++) {
+        for (int b = 0; b < RV_BATCH_SLOTS && rc == RV_OK; b++) {
+            int i = k * RV_BATCH_SLOTS + b;
+            if (i >= n) i = k * RV_BATCH_SLOTS;
+            const int r = rv_session_upload_slot(used[k], b, wit_gf2 ? wit_gf2[i] : nullptr, n_gf2 ? n_gf2[i] : 0, wit_z64 ? wit_z64[i] : nullptr,
+                                                 n_z64 ? n_z64[i] : 0, seeds ? seeds[i] : nullptr);
+            if (r == RV_E_WITNESS_SHORT || r == RV_E_ARG) {
+                if (k * RV_BATCH_SLOTS + b < n) statuses[i] = r;
+            } else if (r != RV_OK) rc = r;
+        }
+        if (rc == RV_OK) rc = rv_session_prove(used[k]);
+    }
+    for (int k = 0; k < (int)used.size() && rc == RV_OK; k++)
+        for (int b = 0; b < RV_BATCH_SLOTS; b++) {
+            const int i = k * RV_BATCH_SLOTS + b;
+            if (i >= n || statuses[i] != RV_OK) continue;
+            statuses[i] = rv_session_fetch_slot(used[k], b, nullptr, &proofs[i], &proof_lens[i]);
+            if (statuses[i] == RV_E_CUDA) rc = RV_E_CUDA;
+        }
+    {
+        std::lock_guard<std::mutex> g(c->pool_mu);
+        for (rv_session *s : used) {
+            if (rc != RV_E_CUDA && c->multi_pool.size() < 16) c->multi_pool.push_back(s);
+            else rv_session_free(s);
+        }
+    }
     return rc;
 }
 

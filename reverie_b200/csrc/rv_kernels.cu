@@ -164,6 +164,9 @@ void launch_mask_gen_tt(const uint32_t *rk_plain, uint32_t nslices, uint32_t n_m
     if (!configured) {
         cudaFuncSetAttribute(k_mask_gen_tt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM2);
         cudaFuncSetAttribute(k_mask_gen_tt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM4);
+        // ask for the full shared-memory carveout: with the default split a second CTA (of this or of another kernel) does not fit
+        cudaFuncSetAttribute(k_mask_gen_tt<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(k_mask_gen_tt<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = true;
     }
     const uint32_t n_blocks = (n_masks + 127) / 128, gy = (nslices + GT_SLICES - 1) / GT_SLICES;
@@ -512,6 +515,8 @@ int launch_linear(const DevProgram &P, const uint32_t *off_host, uint64_t *rows,
         static bool configured = false;
         if (!configured) {
             cudaFuncSetAttribute(k_mask_vm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DYN_CAP);
+            // two VM CTAs (~110 KB each for SHA-256) per SM only fit with the full shared-memory carveout
+            cudaFuncSetAttribute(k_mask_vm, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             configured = true;
         }
         if (which) *which = 0;
@@ -609,6 +614,11 @@ void launch_items(const DevProgram &P, const uint64_t *rows, uint32_t npi, const
                   uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st, uint32_t n_proofs, size_t vals_pitch, size_t flag_stride) {
     const uint32_t T = items_tile(npi);
     const size_t smem = (size_t)8 * npi * (T + 8);
+    static bool configured = false;
+    if (!configured) {  // ~35 KB tiles: the full carveout lets six CTAs share an SM
+        cudaFuncSetAttribute(k_items, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
     const uint32_t tiles_on = (P.n_online + T - 1) / T, tiles_pre = (P.n_pre + T - 1) / T;
     if (tiles_on + tiles_pre)
         k_items<<<dim3(tiles_on + tiles_pre, n_proofs), IT_THREADS, smem, st>>>(P.items, P.mul_pos, P.n_online, P.n_pre, tiles_on, rows, npi, vals, vals_pitch,

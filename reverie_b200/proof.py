@@ -182,13 +182,14 @@ class Session:
         """Synchronise and raise WitnessError if an AssertZero failed, without copying the proof."""
         N.check(N.lib().rv_session_status(self._h))
 
-    def proof_device(self):
-        """The shard's full-length proof buffer in device memory (__cuda_array_interface__, uint8)."""
+    def proof_device(self, slot: int = 0):
+        """The shard's full-length proof buffer of `slot` in device memory (__cuda_array_interface__, uint8)."""
         ptr, n = C.c_void_p(), C.c_size_t()
         N.check(N.lib().rv_session_proof_device(self._h, C.byref(ptr), C.byref(n)))
+        base = ptr.value + slot * int(N.lib().rv_session_proof_stride(self._h))
 
         class _Dev:
-            __cuda_array_interface__ = {"shape": (n.value,), "typestr": "|u1", "data": (ptr.value, False), "version": 2}
+            __cuda_array_interface__ = {"shape": (n.value,), "typestr": "|u1", "data": (base, False), "version": 2}
 
         return _Dev()
 
@@ -274,6 +275,39 @@ class Proof:
         out, n = C.c_void_p(), C.c_size_t()
         N.check(N.lib().rv_prove(c.handle, _ptr(wg), wg.size, _ptr(wz), wz.size, _ptr(sd), C.byref(out), C.byref(n)))
         return Proof(_take(out, n))
+
+    @staticmethod
+    def new_batch(circuit, wits_gf2, wits_z64=None, wire_counts=None, seeds=None):
+        """Proof::new for a list of independent witnesses of one circuit (rv_prove_batch): small GF(2) circuits are proved side
+        by side, every kernel launch covering a group of them.  `seeds`: None or one 256 x 16-byte value (or None) per witness.
+        Returns a list of Proof; raises the first per-proof error (WitnessError ...) after all proofs have run."""
+        c = _as_circuit(circuit, wire_counts)
+        n = len(wits_gf2)
+        wg = [np.ascontiguousarray(np.asarray(w, dtype=np.uint8)) for w in wits_gf2]
+        wz = [np.ascontiguousarray(np.asarray(w, dtype=np.uint64)) for w in (wits_z64 if wits_z64 is not None else [()] * n)]
+        sd = [_seeds_arr(x) for x in (seeds if seeds is not None else [None] * n)]
+        vp = C.c_void_p
+        a_wg = (vp * n)(*[w.ctypes.data if w.size else None for w in wg])
+        a_wz = (vp * n)(*[w.ctypes.data if w.size else None for w in wz])
+        a_sd = (vp * n)(*[x.ctypes.data if x is not None else None for x in sd])
+        n_g = (C.c_size_t * n)(*[w.size for w in wg])
+        n_z = (C.c_size_t * n)(*[w.size for w in wz])
+        outs, lens, sts = (vp * n)(), (C.c_size_t * n)(), (C.c_int * n)()
+        N.check(N.lib().rv_prove_batch(c.handle, n, a_wg, n_g, a_wz, n_z, a_sd, outs, lens, sts))
+        proofs, first_err = [], None
+        for i in range(n):
+            if sts[i] == 0:
+                proofs.append(Proof(_take(vp(outs[i]), C.c_size_t(lens[i]))))
+            else:
+                proofs.append(None)
+                first_err = first_err if first_err is not None else sts[i]
+        if first_err is not None:
+            msg = {N.E_WITNESS_INVALID: "witness is invalid!", N.E_WITNESS_SHORT: "witness is too short"}.get(first_err, "proof failed")
+            cls = N.WitnessError if first_err in (N.E_WITNESS_INVALID, N.E_WITNESS_SHORT) else N.ReverieError
+            err = cls(first_err, msg)
+            err.proofs = proofs
+            raise err
+        return proofs
 
     def verify(self, circuit, wire_counts=None) -> bool:
         """Proof::verify (src/proof/mod.rs:224-307)."""

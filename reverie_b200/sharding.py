@@ -87,7 +87,7 @@ def reduce_proofs(sessions, group=None, dst: int = 0):
 
     for s in sessions:
         s.status()
-    parts = [torch.as_tensor(s.proof_device(), device="cuda") for s in sessions]
+    parts = [torch.as_tensor(s.proof_device(b), device="cuda") for s in sessions for b in range(getattr(s, "n_proofs", 1))]
     buf = torch.cat(parts)
     dist.reduce(buf, dst=dst, op=dist.ReduceOp.SUM, group=group)
     if dist.get_rank(group) != dst:
