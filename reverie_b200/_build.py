@@ -13,7 +13,7 @@ LIB = os.path.join(LIBDIR, "libreverie_b200.so")
 SOURCES = ["rv_api.cu", "rv_kernels.cu", "rv_z64.cu", "rv_compile.cpp"]
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC,-O3,-Wall,-Wno-unknown-pragmas",
-    "--expt-relaxed-constexpr", "-shared", "-cudart", "shared",
+    "--expt-relaxed-constexpr", "-shared", "-cudart", "shared", "-lpthread",
 ]
 
 

@@ -78,10 +78,10 @@ def _as_circuit(circuit, wire_counts) -> Circuit:
 _ZERO_COPY_FROM = 4 << 20
 
 
-def _take(out: C.c_void_p, n: C.c_size_t):
+def _take(out: C.c_void_p, n: C.c_size_t, zero_copy_from: int = 0):
     """Library-allocated bytes -> Python.  Small results are copied into `bytes`; big ones (proofs of Z64 / 10^8-gate circuits
     run to a gigabyte) stay in the library's pinned buffer, wrapped as a read-only numpy view that frees it when collected."""
-    if n.value < _ZERO_COPY_FROM:
+    if n.value < (zero_copy_from or _ZERO_COPY_FROM):
         b = C.string_at(out, n.value)
         N.lib().rv_free(out)
         return b
@@ -297,7 +297,7 @@ class Proof:
         proofs, first_err = [], None
         for i in range(n):
             if sts[i] == 0:
-                proofs.append(Proof(_take(vp(outs[i]), C.c_size_t(lens[i]))))
+                proofs.append(Proof(_take(vp(outs[i]), C.c_size_t(lens[i]), zero_copy_from=1 << 16)))  # Proof wraps the library's buffer
             else:
                 proofs.append(None)
                 first_err = first_err if first_err is not None else sts[i]

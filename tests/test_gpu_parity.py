@@ -512,3 +512,32 @@ def test_multi_proof_session(rb, default_seeds):
         zops, zwc = C.flat_mul_circuit(4, domain=C.Z64)
         rb.Session(rb.Circuit(zops, zwc), 0, 32, n_proofs=2)
     assert e.value.code == N.E_UNSUPPORTED
+
+
+def test_prove_batch_api(rb, default_seeds):
+    """rv_prove_batch / Proof.new_batch: a queue of witnesses of one circuit, proved side by side; every proof = the oracle's
+    bytes for its own witness and seeds; a bad witness fails alone; Z64 circuits fall back to one proof at a time."""
+    import orc
+    from reverie_b200 import circuits as C
+
+    ops, wit, wc = C.aes128_fips197_case()
+    circ = rb.Circuit(ops, wc)
+    rng = np.random.default_rng(12)
+    seeds = [default_seeds] + [rng.integers(0, 256, size=256 * 16, dtype=np.uint8).tobytes() for _ in range(10)]
+    want = [orc.prove(ops, wit, [], wc, sd)[1] for sd in seeds]
+    for n in (1, 8, 11):
+        proofs = rb.Proof.new_batch(circ, [wit] * n, seeds=seeds[:n])
+        assert [p.serialize() for p in proofs] == want[:n], n
+        assert all(p.verify(circ) for p in proofs[:2])
+    bad = wit.copy()
+    bad[0] ^= 1
+    with pytest.raises(rb.WitnessError) as e:
+        rb.Proof.new_batch(circ, [wit, bad, wit], seeds=seeds[:3])
+    got = e.value.proofs
+    assert got[1] is None and got[0].serialize() == want[0] and got[2].serialize() == want[2]
+    from tests._zgen import Z64_WITNESS
+
+    zops, nw = C.z64_mul_circuit(50)
+    zc = rb.Circuit(zops, (nw, 0))
+    zp = rb.Proof.new_batch(zc, [()] * 3, [Z64_WITNESS] * 3, seeds=seeds[:3])
+    assert [p.serialize() for p in zp] == [orc.prove(zops, [], Z64_WITNESS, (nw, 0), sd)[1] for sd in seeds[:3]]
