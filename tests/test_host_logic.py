@@ -293,3 +293,30 @@ def test_cpp_host_mirror_compiles():
     assert subprocess.run([exe, "--compile-check"]).returncode == 0
     if N.lib().rv_device_count() == 0:
         assert subprocess.run([exe], capture_output=True).returncode == 2  # loud failure, no CPU fallback
+
+
+def test_multi_proof_session_argument_checks():
+    """rv_session_create_multi validates before it touches the device: slot count, circuits it does not serve, then (on a CPU-only
+    box) the loud no-fallback error."""
+    import reverie_b200 as rb
+
+    ops, wc = CI.flat_mul_circuit(5)
+    circ = rb.Circuit(ops, wc)
+    for bad in (0, 129):
+        with pytest.raises(rb.ReverieError) as e:
+            rb.Session(circ, 0, 32, n_proofs=bad)
+        assert e.value.code == N.E_ARG
+    with pytest.raises(rb.ReverieError) as e:
+        rb.Session(circ, 30, 4)
+    assert e.value.code == N.E_ARG
+    zops, zwc = CI.flat_mul_circuit(5, domain=CI.Z64)
+    with pytest.raises(rb.ReverieError) as e:
+        rb.Session(rb.Circuit(zops, zwc), 0, 32, n_proofs=2)
+    assert e.value.code == N.E_UNSUPPORTED
+    if N.lib().rv_device_count() == 0:
+        with pytest.raises(rb.ReverieError) as e:
+            rb.Session(circ, 0, 32, n_proofs=4)
+        assert e.value.code == N.E_CUDA
+        with pytest.raises(rb.ReverieError) as e:
+            rb.Proof.new_batch(circ, [[1, 1]] * 3)
+        assert e.value.code == N.E_CUDA
