@@ -71,7 +71,7 @@ def default_seeds() -> bytes:
 
 
 # bench kernel label -> kernel(s) in the committed ncu capture (profiles/r1c_traffic.json; DRAM bytes per launch)
-NCU_NAMES = {"linear": ["k_mask_vm"], "mask_gen": ["k_mask_gen_tt"], "items": ["k_items_tile<0>", "k_items_tile<1>"], "chunk_cv": ["k_chunk_cv"],
+NCU_NAMES = {"linear": ["k_mask_vm"], "mask_gen": ["k_mask_gen_tt<0>", "k_mask_gen_tt<1>", "k_mask_gen_tt"], "items": ["k_items", "k_items_tile<0>", "k_items_tile<1>"], "chunk_cv": ["k_chunk_cv"],
              "values": ["k_values<1>"], "rep_hash": ["k_rep_hash"], "extract": ["k_extract"], "challenge": ["k_challenge"], "key_setup": ["k_key_setup"],
              "z.mask_gen": ["k_zmask_gen_tt"], "z.items": ["k_zitems_online"], "z.values": ["k_zvalues"], "z.extract": ["k_zextract"]}
 
@@ -82,7 +82,7 @@ def ncu_traffic(workload: str, label: str):
     try:
         with open(os.path.join(ROOT, "profiles", "r1c_traffic.json")) as f:
             w = json.load(f)["workloads"].get(workload)
-        vals = [w[k]["dram_bytes_per_launch"] for k in NCU_NAMES.get(label, [])]
+        vals = [w[k]["dram_bytes_per_launch"] for k in NCU_NAMES.get(label, []) if k in w]
         return sum(vals) / len(vals) if vals else None
     except Exception:
         return None
