@@ -461,7 +461,7 @@ extern "C" int rv_session_create_multi(const rv_circuit *c, int first_instance, 
     if (cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&s->st_val, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&s->ev_vals, cudaEventDisableTiming) != cudaSuccess)
         return bail(fail(RV_E_CUDA, "stream/event creation failed"));
-    s->pitch_on = round_up(std::max<size_t>(P.n_online, 1), 2048);  // whole tiles of the item plane (k_items_tile: T <= 2048)
+    s->pitch_on = round_up(std::max<size_t>(P.n_online, 1), 2048);  // whole tiles of the item plane (k_items: T <= 2048)
     s->pitch_pre = round_up(std::max<size_t>(P.n_pre, 1), 2048);
     s->n_chunks_on = P.n_online == 0 ? 1 : (P.n_online + 1023) / 1024;
     s->n_chunks_pre = P.n_pre == 0 ? 1 : (P.n_pre + 1023) / 1024;
