@@ -902,7 +902,13 @@ extern "C" int rv_batch_create(rv_session *const *ss, int n, rv_batch **out) {
         if (i) {
             CU(cudaStreamSynchronize(s->st));
             s->lead = ss[0];
-            if (!s->ev_bjoin && cudaEventCreateWithFlags(&s->ev_bjoin, cudaEventDisableTiming) != cudaSuccess) return fail(RV_E_CUDA, "event creation failed");
+            if (!s->ev_bjoin && cudaEventCreateWithFlags(&s->ev_bjoin, cudaEventDisableTiming) != cudaSuccess) {
+                for (rv_session *f : b->ss) f->lead = nullptr;
+                s->lead = nullptr;
+                cudaEventDestroy(b->ev_fork);
+                delete b;
+                return fail(RV_E_CUDA, "event creation failed");
+            }
         }
         b->ss.push_back(s);
     }
