@@ -1,17 +1,18 @@
-// rv_aes_bs.cuh -- AES-128 for the mask generator, bitsliced ACROSS PRG STREAMS.
+// rv_aes_bs.cuh -- AES-128 building blocks of the mask generators.
 //
 // Replaces (reference, paths relative to its root):
 //   PRG::new / PRG::gen                 src/crypto/prg.rs:13-37   (ctr::Ctr128BE<Aes128>, IV = 0, keystream only)
 //   expand_seed                         src/transcript/mod.rs:99-106
 //   BatchGen::gen + batches_to_shares   src/generator/batch.rs:30-40, src/algebra/gf2/domain.rs:66-173,293-378
 //
-// One 32-bit register holds the same state bit of 32 different PRG streams = 4 repetitions x 8 players = one half of a
-// packed instance's u64 share.  Evaluating AES on 128 such registers for counter block j therefore yields, with no
-// transpose at all, the 32-bit halves of shares 128j .. 128j+127 in exactly the reference's packed layout
-// (stream (rep r, player p) at u64 bit 63-(8r+p), src/algebra/gf2/share.rs:23-24; keystream bits MSB-first within
-// each byte, src/algebra/gf2/domain.rs:293-377).  This is what the reference's AVX2 movemask transpose computes.
-//
-// Everything here is __host__ __device__ so tests can run the same code on the CPU against FIPS-197 vectors.
+// Three forms of the same cipher live here, all __host__ __device__ so tests can run them on the CPU against FIPS-197:
+//   * tt_aes128_encrypt  -- T-table rounds, one block per thread: what the GPU generators run (k_mask_gen_tt, k_zmask_gen_tt),
+//                           with the tables replicated per shared-memory bank;
+//   * aes128_expand_key / aes128_encrypt_block -- scalar, S-box from the 113-gate Boyar-Peralta netlist on 4 packed bytes:
+//                           seed expansion and key schedules (k_key_setup);
+//   * bs_aes128_ctr_block -- bitsliced ACROSS PRG STREAMS (one u32 = the same state bit of 32 streams, so the reference's
+//                           64 x 128 bit transpose costs nothing).  This was the first GPU generator (23 G blocks/s, ALU-pipe
+//                           bound); tests/hostsim keeps it as an independent replay of the share-tensor layout.
 #pragma once
 #include <stdint.h>
 
