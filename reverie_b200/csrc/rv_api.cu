@@ -9,7 +9,6 @@
 #include <mutex>
 #include <new>
 #include <string>
-#include <thread>
 #include <vector>
 
 #include "rv_bincode.h"
@@ -1146,21 +1145,13 @@ extern "C" int rv_prove_batch(const rv_circuit *c, int n, const uint8_t *const *
         }
         if (rc == RV_OK) rc = rv_session_prove(used[k]);
     }
-    if (rc == RV_OK) {  // collect: one host thread per session, so the copies out of the pinned staging buffers overlap
-        std::vector<std::thread> workers;
-        for (int k = 0; k < (int)used.size(); k++)
-            workers.emplace_back([&, k] {
-                cudaSetDevice(c->device);
-                for (int b = 0; b < RV_BATCH_SLOTS; b++) {
-                    const int i = k * RV_BATCH_SLOTS + b;
-                    if (i >= n || statuses[i] != RV_OK) continue;
-                    statuses[i] = rv_session_fetch_slot(used[k], b, nullptr, &proofs[i], &proof_lens[i]);
-                }
-            });
-        for (std::thread &t : workers) t.join();
-        for (int i = 0; i < n; i++)
+    for (int k = 0; k < (int)used.size() && rc == RV_OK; k++)  // collect in launch order: session k's copies overlap the later sessions' tails
+        for (int b = 0; b < RV_BATCH_SLOTS; b++) {
+            const int i = k * RV_BATCH_SLOTS + b;
+            if (i >= n || statuses[i] != RV_OK) continue;
+            statuses[i] = rv_session_fetch_slot(used[k], b, nullptr, &proofs[i], &proof_lens[i]);
             if (statuses[i] == RV_E_CUDA) rc = RV_E_CUDA;
-    }
+        }
     {
         std::lock_guard<std::mutex> g(c->pool_mu);
         for (rv_session *s : used) {

@@ -297,7 +297,7 @@ class Proof:
         proofs, first_err = [], None
         for i in range(n):
             if sts[i] == 0:
-                proofs.append(Proof(_take(vp(outs[i]), C.c_size_t(lens[i]))))
+                proofs.append(Proof(_take(vp(outs[i]), C.c_size_t(lens[i]), zero_copy_from=1 << 16)))  # Proof wraps the library's buffer
             else:
                 proofs.append(None)
                 first_err = first_err if first_err is not None else sts[i]
