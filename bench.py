@@ -7,12 +7,15 @@ sharded 32/N per rank and the only exchange is the all-gather of the 256 x 32-by
 (src/proof/mod.rs:160-171) -> strong scaling (the proof is the same for every N).
 
 A step = one batch of B independent `Proof::new` calls on the workload circuit (default: SHA-256 compression, SURVEY.md
-8(d) config 2; B = --batch, default 8) issued together, the way a proving service sees concurrent requests; B = 1 gives the
-single-proof latency, which is also reported.  The CPU arm (--impl reference) proves the same B proofs per step.
-  value  device-resident: witnesses + seeds already in HBM; per step the B sessions' commit + open run on their own CUDA
-         streams, forked from / joined into one timing stream that carries the CUDA-event pair of the step
-  e2e    host buffers in, proof bytes out, through the public API (B threads calling Proof.new -> rv_prove), all
-         host<->device copies inside the timed region
+8(d) config 2; B = --batch, default 32) issued together, the way a proving service sees its queue; B = 1 gives the
+single-proof latency, which is also reported.  Small GF(2) circuits are held by multi-proof sessions (--per-session proofs
+side by side, every kernel launch covering all of them); big / Z64 circuits one proof per session (--batch 1).
+  value  device-resident: witnesses + seeds already in HBM; the step is one CUDA graph launch per phase for all sessions
+         (rv_batch) on a leader stream that carries the CUDA-event pair of the step
+  e2e    host buffers in, proof bytes out, through the public batched call (Proof.new_batch -> rv_prove_batch), all
+         host<->device copies inside the timed region; N > 1: upload, sharded step, NCCL assembly on rank 0
+  verify Proof.verify of the same proofs (host bytes in), B verifications in flight
+The CPU arm (--impl reference) proves the same B proofs per step with the C restatement of the reference's dataflow.
 """
 from __future__ import annotations
 
