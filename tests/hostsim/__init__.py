@@ -63,6 +63,14 @@ def aes128_encrypt(key: bytes, block: bytes) -> bytes:
     return out.tobytes()
 
 
+def tt_aes128_encrypt(key: bytes, block: bytes) -> bytes:
+    """AES-128 through the T-table rounds the GPU mask generators run (csrc/rv_aes_bs.cuh: tt_aes128_encrypt)."""
+    out = np.zeros(16, dtype=np.uint8)
+    lib().hs_tt_aes128_encrypt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib().hs_tt_aes128_encrypt(_p(np.frombuffer(key, dtype=np.uint8)), _p(np.frombuffer(block, dtype=np.uint8)), _p(out))
+    return out.tobytes()
+
+
 def gf2_masks(seeds8: bytes, omit, n: int) -> np.ndarray:
     out = np.zeros(n, dtype=np.uint64)
     o = np.asarray(omit, dtype=np.uint8)

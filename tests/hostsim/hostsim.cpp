@@ -60,6 +60,29 @@ extern "C" void hs_aes128_encrypt(const uint8_t key[16], const uint8_t in[16], u
     memcpy(out, o4, 16);
 }
 
+// The T-table rounds the GPU mask generators run (tt_aes128_encrypt), with the tables built exactly like the kernels build
+// them (te0_entry of the netlist S-box, rotations for Te1..Te3) but without the per-bank replication.
+extern "C" void hs_tt_aes128_encrypt(const uint8_t key[16], const uint8_t in[16], uint8_t out[16]) {
+    static uint32_t te[4][256];
+    static bool built = false;
+    if (!built) {
+        for (uint32_t x = 0; x < 256; x++) {
+            const uint32_t t0 = te0_entry(sub_word(x) & 0xff);
+            te[0][x] = t0;
+            te[1][x] = (t0 << 8) | (t0 >> 24);
+            te[2][x] = (t0 << 16) | (t0 >> 16);
+            te[3][x] = (t0 << 24) | (t0 >> 8);
+        }
+        built = true;
+    }
+    uint32_t k[4], rk[44], i4[4], o4[4];
+    memcpy(k, key, 16);
+    memcpy(i4, in, 16);
+    aes128_expand_key(k, rk);
+    tt_aes128_encrypt(rk, i4[0], i4[1], i4[2], i4[3], [](int t, uint32_t w, int b) { return te[t][(w >> (8 * b)) & 0xff]; }, o4);
+    memcpy(out, o4, 16);
+}
+
 // rows of the share tensor for `npi` packed instances starting at first_instance: the K1 + K2 kernels
 struct SimKeys {
     std::vector<uint32_t> ks, lane_mask;

@@ -28,6 +28,15 @@ def test_aes_fips197_c1_hostsim():
     assert hostsim.aes128_encrypt(FIPS_KEY, FIPS_PT) == FIPS_CT
 
 
+def test_ttable_aes_of_the_mask_generators():
+    """csrc/rv_aes_bs.cuh: tt_aes128_encrypt (what k_mask_gen_tt / k_zmask_gen_tt run) against FIPS-197 C.1 and OpenSSL."""
+    assert hostsim.tt_aes128_encrypt(FIPS_KEY, FIPS_PT) == FIPS_CT
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        key, blk = rng.integers(0, 256, 16, dtype=np.uint8).tobytes(), rng.integers(0, 256, 16, dtype=np.uint8).tobytes()
+        assert hostsim.tt_aes128_encrypt(key, blk) == Cipher(algorithms.AES(key), modes.ECB()).encryptor().update(blk)
+
+
 def test_aes_fips197_c1_via_ctr():
     # block j of the keystream is AES_k(BE128(j)); j = 0x00112233445566778899aabbccddeeff does not fit the u64 counter,
     # so check the ECB vector through OpenSSL and the CTR streams against OpenSSL below
