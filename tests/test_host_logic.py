@@ -320,3 +320,19 @@ def test_multi_proof_session_argument_checks():
         with pytest.raises(rb.ReverieError) as e:
             rb.Proof.new_batch(circ, [[1, 1]] * 3)
         assert e.value.code == N.E_CUDA
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the driver's CPU arm): one JSON line with the contract's keys; runs the C oracle only."""
+    import subprocess
+    import sys
+
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1", "--batch", "1"],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "dtype", "data", "config",
+              "cpu_baseline", "e2e"):
+        assert k in line, k
+    assert line["impl"] == "reference" and line["unit"] == "AND-gates/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
