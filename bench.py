@@ -68,9 +68,9 @@ def make_workload(name: str):
 
 
 def default_seeds() -> bytes:
-    import reverie_oracle as R
-
-    return b"".join(R.default_seeds())
+    """256 x 16 bytes of repetition seeds, fixed so that runs are comparable (the reference draws them from OsRng,
+    src/proof/mod.rs:131-134).  Both arms use the same ones."""
+    return np.random.default_rng(20261017).integers(0, 256, size=256 * 16, dtype=np.uint8).tobytes()
 
 
 # bench kernel label -> kernel(s) in the committed ncu capture (profiles/r1c_traffic.json; DRAM bytes per launch)

@@ -5,11 +5,10 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(
 import numpy as np
 import reverie_b200 as rb
 from reverie_b200 import circuits as C
-import reverie_oracle as R
 
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 32
 ops, wit, wc = C.sha256_abc_case()
-seeds = b"".join(R.default_seeds())
+seeds = np.random.default_rng(1).integers(0, 256, size=256 * 16, dtype=np.uint8).tobytes()
 circ = rb.Circuit(ops, wc)
 s = rb.Session(circ, 0, 32, n_proofs=P)
 for b in range(P):
