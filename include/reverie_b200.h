@@ -63,7 +63,7 @@ enum rv_status {
     RV_E_ARG = -4,             /* bad argument / wire index out of range for the given wire_counts */
     RV_E_CUDA = -5,            /* CUDA runtime failure or no device */
     RV_E_NOMEM = -6,
-    RV_E_UNSUPPORTED = -7      /* op not yet accelerated: Random, B2A (reported at compile time, never silently degraded) */
+    RV_E_UNSUPPORTED = -7      /* a shape the device path does not serve (reported, never silently degraded): see DESIGN.md section 8 */
 };
 
 typedef struct rv_circuit rv_circuit; /* a compiled circuit: device-resident gate tables, reusable across proofs  */
@@ -139,12 +139,18 @@ int rv_prove(const rv_circuit *c, const uint8_t *wit_gf2, size_t n_gf2, const ui
 int rv_prove_batch(const rv_circuit *c, int n, const uint8_t *const *wit_gf2, const size_t *n_gf2, const uint64_t *const *wit_z64,
                    const size_t *n_z64, const uint8_t *const *seeds, uint8_t **proofs, size_t *proof_lens, int *statuses);
 
-/* Proof::verify  (src/proof/mod.rs:224-307).  Returns 1 accept / 0 reject / <0 error.
+/* Proof::verify  (src/proof/mod.rs:224-307).  Returns 1 accept / 0 reject / <0 error: the reference's exact verdict, i.e.
+ * "the recomputed commitment equals the proof's" (src/proof/mod.rs:305-306).
  * *okay (optional) receives the AND of the online verifiers' zero_check flags, which the reference computes
- * (src/transcript/verifier/online.rs:176-178) but never reads. */
+ * (src/transcript/verifier/online.rs:176-178) but never reads: the reference leans on the PROVER's assert
+ * (src/transcript/prover.rs:221-228) for the circuit's AssertZero constraints, so a prover that skips it passes.  A caller
+ * that wants the constraints enforced accepts only when the return value is 1 AND *okay is 1; the host mirrors
+ * (reverie_b200.hpp, reverie_b200/proof.py, the CLI) and rv_proof_verify do exactly that by default. */
 int rv_verify(const rv_circuit *c, const uint8_t *proof, size_t proof_len, int *okay);
 
-/* One-shot forms with the exact argument shape of the reference API (compile + run + free). */
+/* One-shot forms with the exact argument shape of the reference API (compile + run; compiled circuits are cached by content,
+ * see rv_circuit_cache_*).  rv_proof_verify is strict: 1 only if the commitment matches and every AssertZero of the opened
+ * repetitions holds (see rv_verify). */
 int rv_proof_new(const rv_op *ops, size_t n_ops, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64,
                  size_t n_z64, size_t z64_cells, size_t gf2_cells, const uint8_t *seeds, uint8_t **proof,
                  size_t *proof_len);

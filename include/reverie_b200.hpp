@@ -133,10 +133,17 @@ class Proof {
                       std::shared_ptr<const std::vector<uint64_t>> wit_z64, std::pair<size_t, size_t> wire_counts) {
         return new_(Circuit(*circuit, wire_counts), *wit_gf2, *wit_z64);
     }
-    // Proof::verify (src/proof/mod.rs:224)
-    bool verify(const Circuit &circuit) const { return check(rv_verify(circuit.handle(), bytes_.data(), bytes_.size(), nullptr)) == 1; }
-    bool verify(std::shared_ptr<const std::vector<CombineOperation>> circuit, std::pair<size_t, size_t> wire_counts) const {
-        return verify(Circuit(*circuit, wire_counts));
+    // Proof::verify (src/proof/mod.rs:224).  strict (default): the commitment must match AND every AssertZero of the opened
+    // repetitions must hold -- the reference computes that flag (src/transcript/verifier/online.rs:176-178) and never reads it,
+    // so a prover that skips its own assert (src/transcript/prover.rs:221-228) would be accepted.  strict = false is the
+    // reference's exact verdict (commitment equality only).
+    bool verify(const Circuit &circuit, bool strict = true) const {
+        int okay = 1;
+        const bool accept = check(rv_verify(circuit.handle(), bytes_.data(), bytes_.size(), &okay)) == 1;
+        return accept && (!strict || okay != 0);
+    }
+    bool verify(std::shared_ptr<const std::vector<CombineOperation>> circuit, std::pair<size_t, size_t> wire_counts, bool strict = true) const {
+        return verify(Circuit(*circuit, wire_counts), strict);
     }
     // bincode::serialize(&proof) / bincode::deserialize::<Proof>(bytes)
     const std::vector<uint8_t> &serialize() const { return bytes_; }

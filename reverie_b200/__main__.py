@@ -46,6 +46,8 @@ def main(argv=None) -> int:
     ap.add_argument("--witness-path")
     ap.add_argument("--program-path")
     ap.add_argument("--proof-path")
+    ap.add_argument("--reference-verify", action="store_true",
+                    help="verify: the reference's exact verdict (commitment equality only); default also requires the opened repetitions' AssertZero checks to hold")
     ap.add_argument("--assert-outputs", help="Bristol programs: expected output bits (output-wire order); appends AddConst + AssertZero")
     a = ap.parse_args(argv)
     if a.operation == "version_info":
@@ -83,7 +85,7 @@ def main(argv=None) -> int:
             with open(a.proof_path, "rb") as f:
                 proof = Proof.deserialize(f.read())
             print("Verifying Proof")
-        if proof.verify(circ):
+        if proof.verify(circ, strict=not a.reference_verify):
             print("Ok(())")
             return 0
         print('Err("Unverifiable Proof")')

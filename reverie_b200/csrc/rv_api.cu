@@ -436,11 +436,18 @@ extern "C" int rv_session_create_multi(const rv_circuit *c, int first_instance, 
     if (first_instance < 0 || n_instances <= 0 || first_instance + n_instances > RV_PACKED_REPS)
         return fail(RV_E_ARG, "shard must be a non-empty range of the 32 packed instances");
     if (n_proofs < 1 || n_proofs > 128) return fail(RV_E_ARG, "a session holds between 1 and 128 proofs");
+    // the item-plane tiles and the rank-major layout of gathered hashes are built for power-of-two shards at aligned positions
+    // (32 / G instances per rank, G in {1, 2, 4, 8, 16, 32}); anything else is refused rather than silently mis-tiled
+    if ((n_instances & (n_instances - 1)) != 0 || first_instance % n_instances != 0)
+        return fail(RV_E_ARG, "a shard is 1, 2, 4, 8, 16 or 32 packed instances starting at a multiple of its size");
+    if (n_proofs > 1 && n_instances < 4)
+        return fail(RV_E_UNSUPPORTED, "multi-proof sessions need shards of at least 4 packed instances (a 1 KiB hash chunk must not straddle ranks)");
     if (n_proofs > 1 && (c->prog.z.any() || c->prog.n_tvals || c->prog.values_wide ||
                          ProofLayout{(uint32_t)(c->prog.recon_pos.size() / 8 + 1), c->prog.n_pre / 8 + 1, (uint32_t)(c->prog.n_inputs / 8 + 1)}.total() >= PIN_THRESHOLD))
         return fail(RV_E_UNSUPPORTED, "multi-proof sessions serve small GF(2) circuits (no Z64 / Random / B2A, proofs below 4 MB): use one session per proof");
     if (c->device < 0) return fail(RV_E_CUDA, "no CUDA device: reverie-b200 has no CPU fallback");
     CU(cudaSetDevice(c->device));
+    if (const int ce = configure_kernels(c->device)) return fail(RV_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString((cudaError_t)ce));
     rv_session *s = new (std::nothrow) rv_session();
     if (!s) return fail(RV_E_NOMEM, "out of memory");
     s->c = c;
@@ -1095,18 +1102,29 @@ extern "C" int rv_prove_batch(const rv_circuit *c, int n, const uint8_t *const *
         proof_lens[i] = 0;
         statuses[i] = RV_OK;
     }
-    // circuits a multi-proof session does not serve (Z64 / Random / B2A / big proofs): one rv_prove per witness
-    rv_session *probe = nullptr;
-    {
-        std::lock_guard<std::mutex> g(c->pool_mu);
-        if (!c->multi_pool.empty()) {
-            probe = c->multi_pool.back();
-            c->multi_pool.pop_back();
+    // groups of up to RV_BATCH_SLOTS witnesses, each in a multi-proof session with exactly as many slots as it has witnesses
+    // (idle sessions are pooled per slot count); circuits a multi-proof session does not serve (Z64 / Random / B2A / big
+    // proofs) take one rv_prove per witness
+    const int n_sess = (n + RV_BATCH_SLOTS - 1) / RV_BATCH_SLOTS;
+    auto slots_of = [&](int k) { return std::min(RV_BATCH_SLOTS, n - k * RV_BATCH_SLOTS); };
+    auto take = [&](int slots, rv_session **out) -> int {
+        {
+            std::lock_guard<std::mutex> g(c->pool_mu);
+            for (size_t i = 0; i < c->multi_pool.size(); i++)
+                if ((int)c->multi_pool[i]->n_proofs == slots) {
+                    *out = c->multi_pool[i];
+                    c->multi_pool.erase(c->multi_pool.begin() + i);
+                    return RV_OK;
+                }
         }
-    }
-    if (!probe) {
-        const int rc = rv_session_create_multi(c, 0, RV_PACKED_REPS, RV_BATCH_SLOTS, &probe);
-        if (rc == RV_E_UNSUPPORTED) {
+        return rv_session_create_multi(c, 0, RV_PACKED_REPS, slots, out);
+    };
+    std::vector<rv_session *> used;
+    int rc = RV_OK;
+    for (int k = 0; k < n_sess && rc == RV_OK; k++) {
+        rv_session *s = nullptr;
+        rc = take(slots_of(k), &s);
+        if (rc == RV_E_UNSUPPORTED && used.empty()) {
             int worst = RV_OK;
             for (int i = 0; i < n; i++) {
                 statuses[i] = rv_prove(c, wit_gf2 ? wit_gf2[i] : nullptr, n_gf2 ? n_gf2[i] : 0, wit_z64 ? wit_z64[i] : nullptr, n_z64 ? n_z64[i] : 0,
@@ -1115,47 +1133,30 @@ extern "C" int rv_prove_batch(const rv_circuit *c, int n, const uint8_t *const *
             }
             return worst == RV_E_CUDA ? worst : RV_OK;
         }
-        if (rc != RV_OK) return rc;
-    }
-    std::vector<rv_session *> used{probe};
-    const int n_sess = (n + RV_BATCH_SLOTS - 1) / RV_BATCH_SLOTS;
-    int rc = RV_OK;
-    while ((int)used.size() < n_sess && rc == RV_OK) {
-        rv_session *s = nullptr;
-        {
-            std::lock_guard<std::mutex> g(c->pool_mu);
-            if (!c->multi_pool.empty()) {
-                s = c->multi_pool.back();
-                c->multi_pool.pop_back();
-            }
-        }
-        if (!s) rc = rv_session_create_multi(c, 0, RV_PACKED_REPS, RV_BATCH_SLOTS, &s);
         if (s) used.push_back(s);
     }
-    // fill the slots (unused slots of the last session re-run its first witness; their output is dropped), launch, then collect
+    // fill the slots, launch, then collect
     for (int k = 0; k < (int)used.size() && rc == RV_OK; k++) {
-        for (int b = 0; b < RV_BATCH_SLOTS && rc == RV_OK; b++) {
-            int i = k * RV_BATCH_SLOTS + b;
-            if (i >= n) i = k * RV_BATCH_SLOTS;
+        for (int b = 0; b < slots_of(k) && rc == RV_OK; b++) {
+            const int i = k * RV_BATCH_SLOTS + b;
             const int r = rv_session_upload_slot(used[k], b, wit_gf2 ? wit_gf2[i] : nullptr, n_gf2 ? n_gf2[i] : 0, wit_z64 ? wit_z64[i] : nullptr,
                                                  n_z64 ? n_z64[i] : 0, seeds ? seeds[i] : nullptr);
-            if (r == RV_E_WITNESS_SHORT || r == RV_E_ARG) {
-                if (k * RV_BATCH_SLOTS + b < n) statuses[i] = r;
-            } else if (r != RV_OK) rc = r;
+            if (r == RV_E_WITNESS_SHORT || r == RV_E_ARG) statuses[i] = r;  // the slot keeps its previous (valid) inputs; its output is dropped
+            else if (r != RV_OK) rc = r;
         }
         if (rc == RV_OK) rc = rv_session_prove(used[k]);
     }
     for (int k = 0; k < (int)used.size() && rc == RV_OK; k++)  // collect in launch order: session k's copies overlap the later sessions' tails
-        for (int b = 0; b < RV_BATCH_SLOTS; b++) {
+        for (int b = 0; b < slots_of(k); b++) {
             const int i = k * RV_BATCH_SLOTS + b;
-            if (i >= n || statuses[i] != RV_OK) continue;
+            if (statuses[i] != RV_OK) continue;
             statuses[i] = rv_session_fetch_slot(used[k], b, nullptr, &proofs[i], &proof_lens[i]);
             if (statuses[i] == RV_E_CUDA) rc = RV_E_CUDA;
         }
     {
         std::lock_guard<std::mutex> g(c->pool_mu);
         for (rv_session *s : used) {
-            if (rc != RV_E_CUDA && c->multi_pool.size() < 16) c->multi_pool.push_back(s);
+            if (rc != RV_E_CUDA && c->multi_pool.size() < 24) c->multi_pool.push_back(s);
             else rv_session_free(s);
         }
     }
@@ -1179,25 +1180,37 @@ static int verify_on_session(rv_session *s, const uint8_t *proof, size_t proof_l
                  o_zseeds = o_zopens + NON * sizeof(ZOpen), o_zpkeys = o_zseeds + 256 * 16, o_zomit = o_zpkeys + 256 * 128,
                  o_proof = round_up(o_zomit + 256, 16);
     const size_t need = o_proof + round_up(proof_len, 16);
+    // every buffer is guarded on its own: a failed allocation leaves the session usable (and poolable) for the next call
     if (s->vin_bytes < need) {
+        s->vin_bytes = 0;
         if (s->h_vin) cudaFreeHost(s->h_vin);
         s->h_vin = nullptr;
-        CU(cudaMallocHost(&s->h_vin, need));
+        if (cudaMallocHost(&s->h_vin, need) != cudaSuccess) {
+            s->h_vin = nullptr;
+            cudaGetLastError();
+            return fail(RV_E_NOMEM, "pinned host allocation failed");
+        }
         int rc = dalloc(s, &s->d_vin, need);
         if (rc) return rc;
         s->vin_bytes = need;
     }
-    if (!s->d_leaf_vals) {
+    {
         s->leaf_pitch = round_up((size_t)P.n_inputs + P.n_pre + P.rand_row.size() + 16, 16);
         s->upitch = round_up((size_t)P.n_uvals + 16, 16);
         int rc;
-        if ((rc = dalloc(s, &s->d_leaf_vals, s->leaf_pitch * NON)) || (rc = dalloc(s, &s->d_uvals, s->upitch * NON))) return rc;
+        if (!s->d_leaf_vals && (rc = dalloc(s, &s->d_leaf_vals, s->leaf_pitch * NON))) return rc;
+        if (!s->d_uvals && (rc = dalloc(s, &s->d_uvals, s->upitch * NON))) return rc;
         if (s->has_z) {
             s->zleaf_pitch = P.z.leaf_ids.size() + 1;
             s->zupitch = (size_t)P.z.n_vals + 1;
-            if ((rc = dalloc(s, &s->d_zleaf_v, s->zleaf_pitch * NON)) || (rc = dalloc(s, &s->d_zuvals, s->zupitch * NON))) return rc;
+            if (!s->d_zleaf_v && (rc = dalloc(s, &s->d_zleaf_v, s->zleaf_pitch * NON))) return rc;
+            if (!s->d_zuvals && (rc = dalloc(s, &s->d_zuvals, s->zupitch * NON))) return rc;
         }
-        CU(cudaMallocHost(&s->h_vout, RV_TOTAL_REPS * 32 + 16));
+        if (!s->h_vout && cudaMallocHost(&s->h_vout, RV_TOTAL_REPS * 32 + 16) != cudaSuccess) {
+            s->h_vout = nullptr;
+            cudaGetLastError();
+            return fail(RV_E_NOMEM, "pinned host allocation failed");
+        }
     }
     CU(cudaStreamSynchronize(s->st));
     uint8_t *h = s->h_vin;
@@ -1393,7 +1406,8 @@ extern "C" int rv_proof_verify(const rv_op *ops, size_t n_ops, size_t z64_cells,
     rv_circuit *c = nullptr;
     int rc = rv_circuit_compile(ops, n_ops, z64_cells, gf2_cells, &c);
     if (rc) return rc;
-    rc = rv_verify(c, proof, proof_len, nullptr);
+    int okay = 1;
+    rc = rv_verify(c, proof, proof_len, &okay);
     rv_circuit_free(c);
-    return rc;
+    return rc == 1 ? (okay ? 1 : 0) : rc;  // strict: see the header
 }

@@ -3,6 +3,7 @@
 #include <cuda_pipeline.h>
 
 #include <algorithm>
+#include <mutex>
 
 #include "rv_kernels.cuh"
 #include "rv_planes.cuh"
@@ -58,6 +59,7 @@ void launch_key_setup(const uint8_t *seeds, const uint8_t *pkeys_in, const uint8
 constexpr int GT_SLICES = 16, GT_THREADS = 32 * GT_SLICES, GT_TILE_PITCH = GT_SLICES + 4;  // tile row = the CTA's slice words + pad (16-byte aligned rows)
 constexpr int GT_QUADS = GT_SLICES / 4;  // 16-byte pieces of a tile row
 constexpr size_t GT_TILE_BYTES = 128 * GT_TILE_PITCH * 4;
+constexpr size_t GT_SMEM2 = 2 * 256 * 32 * 4 + GT_TILE_BYTES, GT_SMEM4 = 4 * 256 * 32 * 4 + GT_TILE_BYTES;
 // FOUR = false: Te0 / Te2 in 64 KB (Te1 / Te3 by PRMT rotation): leaves room for a mask-VM CTA on the same SM -- small proofs
 // in flight.  FOUR = true: all four tables (128 KB), 72 fewer ALU instructions per block -- circuits big enough to own the chip.
 template <bool FOUR>
@@ -159,16 +161,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_mask_gen_tt(const uint32_t *_
 void launch_mask_gen_tt(const uint32_t *rk_plain, uint32_t nslices, uint32_t n_masks, uint64_t *rows, uint64_t *fresh_pm, size_t pitch_pm, int n_sms,
                         cudaStream_t st) {
     if (n_masks == 0) return;
-    constexpr size_t SMEM2 = 2 * 256 * 32 * 4 + GT_TILE_BYTES, SMEM4 = 4 * 256 * 32 * 4 + GT_TILE_BYTES;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_mask_gen_tt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM2);
-        cudaFuncSetAttribute(k_mask_gen_tt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM4);
-        // ask for the full shared-memory carveout: with the default split a second CTA (of this or of another kernel) does not fit
-        cudaFuncSetAttribute(k_mask_gen_tt<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(k_mask_gen_tt<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured = true;
-    }
+    constexpr size_t SMEM2 = GT_SMEM2, SMEM4 = GT_SMEM4;
     const uint32_t n_blocks = (n_masks + 127) / 128, gy = (nslices + GT_SLICES - 1) / GT_SLICES;
     const uint32_t want_x = std::max(1u, (uint32_t)n_sms / gy);  // about one CTA per SM for a single small proof
     const uint32_t per = std::min(64u, std::max(4u, (n_blocks + want_x - 1) / want_x));
@@ -326,12 +319,6 @@ __global__ void __launch_bounds__(VP_THREADS) k_values(const LutInstr *__restric
 size_t launch_values(const LutInstr *steps, uint32_t n_steps, const uint32_t *leaf_ids, const uint8_t *leaf_vals, size_t leaf_pitch,
                      uint32_t n_leaves, uint8_t *vals, size_t vals_pitch, uint32_t n_vals, uint32_t n_instances, cudaStream_t st) {
     const size_t cap = SMEM_DYN_CAP;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_values<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
-        cudaFuncSetAttribute(k_values<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
-        configured = true;
-    }
     const size_t want = LutStream::BYTES + (((size_t)n_vals + 1 + 15) & ~(size_t)15);
     if (want <= cap) {
         k_values<true><<<n_instances, VP_THREADS, want, st>>>(steps, n_steps, leaf_ids, leaf_vals, leaf_pitch, n_leaves, vals, vals_pitch, n_vals);
@@ -512,13 +499,6 @@ int launch_linear(const DevProgram &P, const uint32_t *off_host, uint64_t *rows,
         return (int)P.n_llevels;
     }
     if (linear_uses_vm(P) && fresh_sm) {
-        static bool configured = false;
-        if (!configured) {
-            cudaFuncSetAttribute(k_mask_vm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_DYN_CAP);
-            // two VM CTAs (~110 KB each for SHA-256) per SM only fit with the full shared-memory carveout
-            cudaFuncSetAttribute(k_mask_vm, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            configured = true;
-        }
         if (which) *which = 0;
         k_mask_vm<<<npi, VM_THREADS, vm_smem_bytes(P), st>>>(P.vm_steps, P.n_vm_steps, fresh_sm, pitch_fresh, rows, npi);
         return 1;
@@ -614,11 +594,6 @@ void launch_items(const DevProgram &P, const uint64_t *rows, uint32_t npi, const
                   uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st, uint32_t n_proofs, size_t vals_pitch, size_t flag_stride) {
     const uint32_t T = items_tile(npi);
     const size_t smem = (size_t)8 * npi * (T + 8);
-    static bool configured = false;
-    if (!configured) {  // ~35 KB tiles: the full carveout lets six CTAs share an SM
-        cudaFuncSetAttribute(k_items, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured = true;
-    }
     const uint32_t tiles_on = (P.n_online + T - 1) / T, tiles_pre = (P.n_pre + T - 1) / T;
     if (tiles_on + tiles_pre)
         k_items<<<dim3(tiles_on + tiles_pre, n_proofs), IT_THREADS, smem, st>>>(P.items, P.mul_pos, P.n_online, P.n_pre, tiles_on, rows, npi, vals, vals_pitch,
@@ -1032,6 +1007,32 @@ void launch_extract(const DevProgram &P, const ExtractArgs &a, cudaStream_t st) 
     const uint32_t bytes = a.len_recons + a.len_corrs + a.len_inputs;
     const uint32_t ny = std::min(64u, std::max(1u, bytes / 4096));
     k_extract<<<dim3(a.nreps * a.n_proofs, ny), 256, 0, st>>>(P.recon_pos, P.input_pos, P.n_recon, P.n_pre, P.n_inputs, a);
+}
+
+// Per-device kernel attributes (opt-in dynamic shared memory above 48 KB, shared-memory carveout).  The attributes belong to the
+// (function, device) pair, so rv_session_create calls this for the session's device; the first call per device does the work.
+int configure_kernels(int device) {
+    static std::mutex mu;
+    static uint64_t done[4] = {0, 0, 0, 0};
+    if (device < 0 || device >= 256) return (int)cudaErrorInvalidDevice;
+    std::lock_guard<std::mutex> g(mu);
+    if (done[device >> 6] >> (device & 63) & 1) return 0;
+    cudaError_t e = cudaSuccess;
+    auto set = [&](const void *fn, int dyn_bytes, bool carveout) {
+        if (e == cudaSuccess && dyn_bytes) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, dyn_bytes);
+        // the full shared-memory carveout: with the default split a second CTA (of this or of another kernel) does not fit
+        if (e == cudaSuccess && carveout) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    };
+    set((const void *)k_mask_gen_tt<false>, (int)GT_SMEM2, true);
+    set((const void *)k_mask_gen_tt<true>, (int)GT_SMEM4, true);
+    set((const void *)k_values<true>, (int)SMEM_DYN_CAP, false);
+    set((const void *)k_values<false>, (int)SMEM_DYN_CAP, false);
+    set((const void *)k_mask_vm, (int)SMEM_DYN_CAP, true);  // two VM CTAs (~110 KB each for SHA-256) per SM need the full carveout
+    set((const void *)k_items, 0, true);                    // ~35 KB tiles: six CTAs share an SM
+    if (e == cudaSuccess) e = (cudaError_t)configure_zkernels();
+    if (e != cudaSuccess) return (int)e;
+    done[device >> 6] |= 1ull << (device & 63);
+    return 0;
 }
 
 }  // namespace rv

@@ -56,6 +56,11 @@ struct DevZProgram {
     uint32_t on_bytes = 0, pre_bytes = 0;
 };
 
+// Opt-in shared-memory sizes / carveouts of every kernel for `device` (the current device); idempotent, thread-safe.
+// Returns 0 or a cudaError_t.
+int configure_kernels(int device);
+int configure_zkernels();
+
 // K1  seeds -> player keys -> AES round keys (src/transcript/mod.rs:99-106, src/crypto/prg.rs:16-20)
 //     rk_plain: [45][32 * nslices] u32 -- the 44 round-key words of every stream (stream = 8 * rep + player), then a row of
 //     all-ones / zero "stream is active" words

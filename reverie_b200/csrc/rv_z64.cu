@@ -70,13 +70,11 @@ __global__ void __launch_bounds__(ZT_THREADS, 1) k_zmask_gen_tt(const uint32_t *
     }
 }
 
+// called by configure_kernels (rv_kernels.cu) once per device, with that device current
+int configure_zkernels() { return (int)cudaFuncSetAttribute(k_zmask_gen_tt, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 256 * 32 * 4); }
+
 void launch_zmask_gen_tt(const uint32_t *rk_plain, uint32_t nstreams, uint32_t n_masks, uint64_t *zrows, int n_sms, cudaStream_t st) {
     if (n_masks == 0) return;
-    static bool configured = false;
-    if (!configured) {
-        cudaFuncSetAttribute(k_zmask_gen_tt, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 256 * 32 * 4);
-        configured = true;
-    }
     const uint32_t n_blocks = (n_masks + 1) / 2, n_ranges = (n_blocks + ZT_BLOCKS_PER_TASK - 1) / ZT_BLOCKS_PER_TASK;
     const uint64_t n_tasks = (uint64_t)(nstreams / 32) * n_ranges;
     const unsigned grid = (unsigned)std::min<uint64_t>((uint64_t)n_sms, (n_tasks + ZT_THREADS / 32 - 1) / (ZT_THREADS / 32));

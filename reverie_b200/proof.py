@@ -309,12 +309,22 @@ class Proof:
             raise err
         return proofs
 
-    def verify(self, circuit, wire_counts=None) -> bool:
-        """Proof::verify (src/proof/mod.rs:224-307)."""
+    def verify_detail(self, circuit, wire_counts=None) -> Tuple[bool, bool]:
+        """(accept, okay): `accept` is the reference's verdict -- the recomputed commitment equals the proof's
+        (src/proof/mod.rs:305-306); `okay` is the AND of the online verifiers' AssertZero checks, which the reference computes
+        (src/transcript/verifier/online.rs:176-178) and never reads."""
         c = _as_circuit(circuit, wire_counts)
         buf = self._buf if isinstance(self._buf, np.ndarray) else np.frombuffer(self._buf, dtype=np.uint8)
         okay = C.c_int(1)
-        return N.check(N.lib().rv_verify(c.handle, _ptr(buf), buf.size, C.byref(okay))) == 1
+        accept = N.check(N.lib().rv_verify(c.handle, _ptr(buf), buf.size, C.byref(okay))) == 1
+        return accept, bool(okay.value)
+
+    def verify(self, circuit, wire_counts=None, strict: bool = True) -> bool:
+        """Proof::verify (src/proof/mod.rs:224-307).  strict (default) also requires every AssertZero of the opened repetitions to
+        hold: the reference relies on the prover's own assert (src/transcript/prover.rs:221-228) for that, so a prover that skips
+        it is accepted by `strict=False`, which is the reference's exact verdict."""
+        accept, okay = self.verify_detail(circuit, wire_counts)
+        return accept and (okay or not strict)
 
     def serialize(self) -> bytes:
         return self.data

@@ -469,43 +469,52 @@ def test_cpp_host_mirror(rb):
 
 def test_multi_proof_session(rb, default_seeds):
     """rv_session_create_multi: several proofs side by side in one session, every kernel launch covering all of them; each slot's
-    bytes must be the oracle's for its own witness and seeds, across eager run, graph capture and replays; sharded too."""
+    bytes must be the oracle's for its OWN witness and seeds (distinct per slot: the per-slot value planes, witness and seed
+    addressing are what is under test), across eager run, graph capture and replays; sharded too."""
     import orc
     from reverie_b200 import circuits as C
 
-    ops, wit, wc = C.sha256_abc_case()
-    wit2 = C.sha256_witness(C.sha256_pad_single_block(b"abc"))
+    ops, n_wires, _ = C.sha256_compress_circuit(None)  # no output asserts: every 768-bit witness is valid
+    wc = (0, n_wires)
     rng = np.random.default_rng(8)
+    wits = [C.sha256_witness(C.sha256_pad_single_block(m)) for m in (b"abc", b"", b"slot two", b"3" * 55)] + [rng.integers(0, 2, size=768).astype(np.uint8)]
     seeds = [default_seeds] + [rng.integers(0, 256, size=256 * 16, dtype=np.uint8).tobytes() for _ in range(4)]
-    want = [orc.prove(ops, wit, [], wc, sd)[1] for sd in seeds]
+    want = [orc.prove(ops, w, [], wc, sd)[1] for w, sd in zip(wits, seeds)]
+    assert len(set(want)) == 5
     circ = rb.Circuit(ops, wc)
     s = rb.Session(circ, 0, 32, n_proofs=5)
     for rnd in range(4):
         order = [(k + rnd) % 5 for k in range(5)]
         for slot, k in enumerate(order):
-            s.upload(wit, (), seeds[k], slot=slot)
+            s.upload(wits[k], (), seeds[k], slot=slot)
         s.prove()
         for slot, k in enumerate(order):
             assert s.fetch(slot)[1] == want[k], (rnd, slot)
-    bad = wit.copy()
-    bad[11] ^= 1
-    s.upload(bad, (), seeds[0], slot=2)
-    s.prove()
-    assert s.fetch(0)[1] == want[order[0]]
-    with pytest.raises(rb.WitnessError):
-        s.fetch(2)
     # sharded: two "ranks" of 16 instances, 3 proofs each; gathered layout [rank][proof][local hashes]
     sh = [rb.Session(circ, g * 16, 16, n_proofs=3) for g in range(2)]
     for g in range(2):
         for b in range(3):
-            sh[g].upload(wit, (), seeds[b], slot=b)
+            sh[g].upload(wits[b + 1], (), seeds[b + 1], slot=b)
         sh[g].commit()
     gathered = b"".join(x.hashes() for x in sh)
     for x in sh:
         x.open(gathered)
     for b in range(3):
         parts = [x.fetch(b) for x in sh]
-        assert rb.assemble(parts[0][0], [p for _, p in parts]) == want[b], b
+        assert rb.assemble(parts[0][0], [p for _, p in parts]) == want[b + 1], b
+    # a failed AssertZero is reported for its own slot only
+    aops, awit, awc = C.sha256_abc_case()
+    acirc = rb.Circuit(aops, awc)
+    good = orc.prove(aops, awit, [], awc, seeds[1])[1]
+    bad = awit.copy()
+    bad[11] ^= 1
+    s2 = rb.Session(acirc, 0, 32, n_proofs=3)
+    for slot, w in enumerate((awit, bad, awit)):
+        s2.upload(w, (), seeds[1], slot=slot)
+    s2.prove()
+    assert s2.fetch(0)[1] == good and s2.fetch(2)[1] == good
+    with pytest.raises(rb.WitnessError):
+        s2.fetch(1)
     from reverie_b200 import _native as N
 
     with pytest.raises(rb.ReverieError) as e:  # Z64 circuits keep one proof per session
@@ -515,29 +524,94 @@ def test_multi_proof_session(rb, default_seeds):
 
 
 def test_prove_batch_api(rb, default_seeds):
-    """rv_prove_batch / Proof.new_batch: a queue of witnesses of one circuit, proved side by side; every proof = the oracle's
-    bytes for its own witness and seeds; a bad witness fails alone; Z64 circuits fall back to one proof at a time."""
+    """rv_prove_batch / Proof.new_batch: a queue of DISTINCT witnesses of one circuit, proved side by side; every proof = the
+    oracle's bytes for its own witness and seeds; a bad witness fails alone; Z64 circuits fall back to one proof at a time."""
     import orc
     from reverie_b200 import circuits as C
 
-    ops, wit, wc = C.aes128_fips197_case()
+    ops, n_wires, _ = C.aes128_circuit(None)  # no ciphertext asserts: every (key, plaintext) is a valid witness
+    wc = (0, n_wires)
     circ = rb.Circuit(ops, wc)
     rng = np.random.default_rng(12)
     seeds = [default_seeds] + [rng.integers(0, 256, size=256 * 16, dtype=np.uint8).tobytes() for _ in range(10)]
-    want = [orc.prove(ops, wit, [], wc, sd)[1] for sd in seeds]
-    for n in (1, 8, 11):
-        proofs = rb.Proof.new_batch(circ, [wit] * n, seeds=seeds[:n])
+    wits = [C.aes128_witness(rng.bytes(16), rng.bytes(16)) for _ in range(11)]
+    want = [orc.prove(ops, w, [], wc, sd)[1] for w, sd in zip(wits, seeds)]
+    assert len(set(want)) == 11
+    for n in (1, 8, 11, 3):
+        proofs = rb.Proof.new_batch(circ, wits[:n], seeds=seeds[:n])
         assert [p.serialize() for p in proofs] == want[:n], n
         assert all(p.verify(circ) for p in proofs[:2])
-    bad = wit.copy()
+    aops, awit, awc = C.aes128_fips197_case()
+    acirc = rb.Circuit(aops, awc)
+    awant = [orc.prove(aops, awit, [], awc, sd)[1] for sd in seeds[:3]]
+    bad = awit.copy()
     bad[0] ^= 1
     with pytest.raises(rb.WitnessError) as e:
-        rb.Proof.new_batch(circ, [wit, bad, wit], seeds=seeds[:3])
+        rb.Proof.new_batch(acirc, [awit, bad, awit], seeds=seeds[:3])
     got = e.value.proofs
-    assert got[1] is None and got[0].serialize() == want[0] and got[2].serialize() == want[2]
+    assert got[1] is None and got[0].serialize() == awant[0] and got[2].serialize() == awant[2]
+    with pytest.raises(rb.WitnessError) as e:  # a short witness in the queue fails alone too
+        rb.Proof.new_batch(acirc, [awit, awit[:10]], seeds=seeds[:2])
+    assert e.value.proofs[1] is None and e.value.proofs[0].serialize() == awant[0]
     from tests._zgen import Z64_WITNESS
 
     zops, nw = C.z64_mul_circuit(50)
     zc = rb.Circuit(zops, (nw, 0))
     zp = rb.Proof.new_batch(zc, [()] * 3, [Z64_WITNESS] * 3, seeds=seeds[:3])
     assert [p.serialize() for p in zp] == [orc.prove(zops, [], Z64_WITNESS, (nw, 0), sd)[1] for sd in seeds[:3]]
+
+
+def test_bristol_text_to_proof(rb, default_seeds):
+    """SURVEY.md 8(f)1 end to end on the GPU: Bristol-Fashion text -> parse_bristol_fashion -> prove == the oracle's bytes for the
+    parsed op list, verify accepts; the parsed circuit computes SHA-256 (checked against hashlib), and a wrong expected
+    digest makes the prover refuse."""
+    import hashlib
+
+    import orc
+    from reverie_b200 import circuits as C
+
+    ops0, n_wires, outs = C.sha256_compress_circuit(None)
+    b = C.Builder()
+    b.n_wires = n_wires  # Bristol-Fashion wants the outputs as the LAST wires: copy them there with EQW gates
+    tail = [b.addc(w, 0) for w in outs]
+    ops0 = np.concatenate([ops0, b.ops()])
+    text = C.to_bristol_fashion(ops0, [512, 256], tail)
+    assert text.splitlines()[0].split()[0] == str(len(ops0) - 768) and "AND" in text and "XOR" in text and "INV" in text
+    for msg in (b"abc", b"bristol fashion"):
+        digest = hashlib.sha256(msg).digest()
+        bits = np.unpackbits(np.frombuffer(digest, dtype=np.uint8)).tolist()
+        ops, nw, _ = C.parse_bristol_fashion(text, expected_outputs=bits)
+        wit = C.sha256_witness(C.sha256_pad_single_block(msg))
+        blob = _check(rb, ops, wit, (0, nw), default_seeds)
+        assert rb.Proof(blob).verify(rb.Circuit(ops, (0, nw)))
+    bits[5] ^= 1
+    ops, nw, _ = C.parse_bristol_fashion(text, expected_outputs=bits)
+    with pytest.raises(rb.WitnessError):
+        rb.Proof.new(ops, wit, (), (0, nw), seeds=default_seeds)
+
+
+def test_strict_verify_rejects_skipped_assert(rb, default_seeds):
+    """A prover that skips its own AssertZero check (src/transcript/prover.rs:221-228) produces a proof whose commitment
+    verifies: the reference accepts it (`okay` is computed at verifier/online.rs:176-178 and never read).  strict=False gives
+    that verdict, the default strict mode rejects."""
+    import orc
+    import reverie_oracle as R
+    from reverie_b200 import circuits as C
+
+    b = C.Builder()
+    x, y = b.input(), b.input()
+    b.assert_zero(b.addc(b.mul(x, y), 1))  # x & y == 1
+    ops, wc = b.ops(), (0, b.n_wires)
+    keep = R.ProverTranscript.zero_check
+    R.ProverTranscript.zero_check = lambda self, recon: None  # the cheating prover
+    try:
+        forged = R.serialize(R.prove(orc.ops_to_tuples(ops), [1, 0], [], wc, R.default_seeds()))
+    finally:
+        R.ProverTranscript.zero_check = keep
+    assert orc.verify(ops, wc, forged) == (1, False)
+    circ = rb.Circuit(ops, wc)
+    p = rb.Proof(forged)
+    assert p.verify_detail(circ) == (True, False)
+    assert p.verify(circ, strict=False) and not p.verify(circ)
+    honest = rb.Proof.new(circ, [1, 1], (), seeds=default_seeds)
+    assert honest.verify_detail(circ) == (True, True) and honest.verify(circ)

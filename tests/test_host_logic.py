@@ -309,6 +309,15 @@ def test_multi_proof_session_argument_checks():
     with pytest.raises(rb.ReverieError) as e:
         rb.Session(circ, 30, 4)
     assert e.value.code == N.E_ARG
+    # shard shapes the tiled item plane / the rank-major hash layout are not built for are refused, not mis-tiled
+    for first, count in ((0, 3), (0, 5), (0, 6), (0, 12), (0, 24), (4, 8), (2, 4), (1, 2)):
+        with pytest.raises(rb.ReverieError) as e:
+            rb.Session(circ, first, count)
+        assert e.value.code == N.E_ARG, (first, count)
+    for count in (1, 2):  # several proofs side by side need >= 4 instances per rank (a 1 KiB chunk of hashes per rank segment)
+        with pytest.raises(rb.ReverieError) as e:
+            rb.Session(circ, 0, count, n_proofs=2)
+        assert e.value.code == N.E_UNSUPPORTED
     zops, zwc = CI.flat_mul_circuit(5, domain=CI.Z64)
     with pytest.raises(rb.ReverieError) as e:
         rb.Session(rb.Circuit(zops, zwc), 0, 32, n_proofs=2)
@@ -336,3 +345,47 @@ def test_bench_reference_arm_contract():
         assert k in line, k
     assert line["impl"] == "reference" and line["unit"] == "AND-gates/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_bristol_text_to_proof_kernel_bodies(default_seeds):
+    """SURVEY.md 8(f)1 on the CPU: Bristol-Fashion text -> parse -> the kernels' bodies (hostsim) == the oracle's proof."""
+    import hashlib
+
+    ops0, n_wires, outs = CI.sha256_compress_circuit(None)
+    b = CI.Builder()
+    b.n_wires = n_wires  # Bristol-Fashion wants the outputs as the last wires
+    tail = [b.addc(w, 0) for w in outs]
+    text = CI.to_bristol_fashion(np.concatenate([ops0, b.ops()]), [512, 256], tail)
+    msg = b"bristol fashion"
+    bits = np.unpackbits(np.frombuffer(hashlib.sha256(msg).digest(), dtype=np.uint8)).tolist()
+    ops, nw, _ = CI.parse_bristol_fashion(text, expected_outputs=bits)
+    wit = CI.sha256_witness(CI.sha256_pad_single_block(msg))
+    rc, want = orc.prove(ops, wit, [], (0, nw), default_seeds)
+    assert rc == 0
+    rc, got, _ = hostsim.prove(ops, wit, (0, nw), default_seeds)
+    assert rc == 0 and got == want
+    bits[7] ^= 1
+    ops, nw, _ = CI.parse_bristol_fashion(text, expected_outputs=bits)
+    assert orc.prove(ops, wit, [], (0, nw), default_seeds)[0] == -1 and hostsim.prove(ops, wit, (0, nw), default_seeds)[0] == -1
+
+
+def test_skipped_assert_is_visible_in_okay(default_seeds):
+    """A prover that skips its AssertZero check (src/transcript/prover.rs:221-228): the commitment still verifies (the
+    reference's verdict), the `okay` flag (verifier/online.rs:176-178) is what catches it -- both restatements and the kernel
+    bodies agree on (accept, not okay)."""
+    import reverie_oracle as R
+
+    b = CI.Builder()
+    x, y = b.input(), b.input()
+    b.assert_zero(b.addc(b.mul(x, y), 1))
+    ops, wc = b.ops(), (0, b.n_wires)
+    keep = R.ProverTranscript.zero_check
+    R.ProverTranscript.zero_check = lambda self, recon: None
+    try:
+        forged = R.serialize(R.prove(orc.ops_to_tuples(ops), [1, 0], [], wc, R.default_seeds()))
+    finally:
+        R.ProverTranscript.zero_check = keep
+    assert orc.verify(ops, wc, forged) == (1, False)
+    assert hostsim.verify(ops, wc, forged)[:2] == (1, False)
+    tap = {}
+    assert R.verify(R.deserialize(forged), orc.ops_to_tuples(ops), wc, tap=tap) and tap["okay"] is False
