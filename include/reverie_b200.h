@@ -84,6 +84,10 @@ int rv_set_device(int device);
  * wire counts are passed in the reference's own tuple order (z64, gf2)  -- src/proof/mod.rs:125,232.
  * ------------------------------------------------------------------------------------------------------------- */
 int rv_circuit_compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, rv_circuit **out);
+/* flags: RV_COMPILE_PROVE_ONLY leaves out the online verifier's tables (a third of the compile time and of the table bytes);
+ * rv_verify on such a handle returns RV_E_UNSUPPORTED. */
+#define RV_COMPILE_PROVE_ONLY 1u
+int rv_circuit_compile_ex(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, unsigned flags, rv_circuit **out);
 void rv_circuit_free(rv_circuit *c);
 
 typedef struct rv_circuit_stats {
@@ -112,6 +116,8 @@ typedef struct rv_circuit_stats {
     uint64_t z64_linear_depth;
     uint64_t z64_online_bytes;  /* bytes hashed per repetition, Z64 online stream */
     uint64_t z64_pre_bytes;
+    uint64_t compile_ns;        /* host time rv_circuit_compile spent on this handle (compile + upload of the tables) */
+    uint64_t has_verify;        /* 1 if the verifier's tables were built */
 } rv_circuit_stats;
 int rv_circuit_get_stats(const rv_circuit *c, rv_circuit_stats *out);
 
@@ -156,6 +162,15 @@ int rv_proof_new(const rv_op *ops, size_t n_ops, const uint8_t *wit_gf2, size_t 
                  size_t *proof_len);
 int rv_proof_verify(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, const uint8_t *proof,
                     size_t proof_len);
+/* The reference's exact verdict (commitment equality) with the AssertZero flag reported separately, like rv_verify. */
+int rv_proof_verify_ex(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, const uint8_t *proof,
+                       size_t proof_len, int *okay);
+/* The one-shot forms keep compiled circuits in a content-addressed cache (128-bit hash of the op list, wire counts, device) so
+ * that a caller with the reference's call shape -- Proof::new(circuit, ...) with the circuit passed every time,
+ * src/proof/mod.rs:119-124 -- compiles each circuit once.  Default: 8 entries, least recently used idle entry evicted first. */
+void rv_circuit_cache_clear(void);
+void rv_circuit_cache_limit(size_t max_entries);
+void rv_circuit_cache_stats(uint64_t *hits, uint64_t *misses, size_t *entries);
 
 void rv_free(void *p);
 

@@ -129,9 +129,19 @@ class Proof {
         rv_free(p);
         return out;
     }
+    // The reference's own call shape: the op list travels with every call; the library compiles it once and keeps it in its
+    // content-addressed cache (rv_proof_new).
     static Proof new_(std::shared_ptr<const std::vector<CombineOperation>> circuit, std::shared_ptr<const std::vector<bool>> wit_gf2,
-                      std::shared_ptr<const std::vector<uint64_t>> wit_z64, std::pair<size_t, size_t> wire_counts) {
-        return new_(Circuit(*circuit, wire_counts), *wit_gf2, *wit_z64);
+                      std::shared_ptr<const std::vector<uint64_t>> wit_z64, std::pair<size_t, size_t> wire_counts, const uint8_t *seeds = nullptr) {
+        std::vector<uint8_t> w(wit_gf2->begin(), wit_gf2->end());
+        uint8_t *p = nullptr;
+        size_t n = 0;
+        check(rv_proof_new(circuit->empty() ? nullptr : &(*circuit)[0].op, circuit->size(), w.data(), w.size(), wit_z64->data(), wit_z64->size(),
+                           wire_counts.first, wire_counts.second, seeds, &p, &n));
+        Proof out;
+        out.bytes_.assign(p, p + n);
+        rv_free(p);
+        return out;
     }
     // Proof::verify (src/proof/mod.rs:224).  strict (default): the commitment must match AND every AssertZero of the opened
     // repetitions must hold -- the reference computes that flag (src/transcript/verifier/online.rs:176-178) and never reads it,
@@ -143,7 +153,10 @@ class Proof {
         return accept && (!strict || okay != 0);
     }
     bool verify(std::shared_ptr<const std::vector<CombineOperation>> circuit, std::pair<size_t, size_t> wire_counts, bool strict = true) const {
-        return verify(Circuit(*circuit, wire_counts), strict);
+        int okay = 1;
+        const bool accept = check(rv_proof_verify_ex(circuit->empty() ? nullptr : &(*circuit)[0].op, circuit->size(), wire_counts.first,
+                                                     wire_counts.second, bytes_.data(), bytes_.size(), &okay)) == 1;
+        return accept && (!strict || okay != 0);
     }
     // bincode::serialize(&proof) / bincode::deserialize::<Proof>(bytes)
     const std::vector<uint8_t> &serialize() const { return bytes_; }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <sys/random.h>
 
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -108,6 +109,7 @@ struct rv_circuit {
     std::vector<uint32_t> z_input_item;  // k -> item index of the k-th Z64 input()
     int device = 0, n_sms = 148;
     uint64_t device_bytes = 0;
+    uint64_t compile_ns = 0;  // host compile + table upload
     uint32_t z64_empty_hash[8];  // B3("")
     uint32_t z64_rep_hash[8];    // Transcript::hash of an empty Z64 transcript: H(B3("") || B3(""))
     // idle full-shard sessions kept for rv_prove, so that back-to-back proofs reuse their device buffers
@@ -140,14 +142,20 @@ extern "C" void rv_circuit_free(rv_circuit *c) {
 }
 
 extern "C" int rv_circuit_compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, rv_circuit **out) {
+    return rv_circuit_compile_ex(ops, n_ops, z64_cells, gf2_cells, 0, out);
+}
+
+extern "C" int rv_circuit_compile_ex(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, unsigned flags, rv_circuit **out) {
     if (!out) return fail(RV_E_ARG, "out is NULL");
     *out = nullptr;
+    if (flags & ~(unsigned)RV_COMPILE_PROVE_ONLY) return fail(RV_E_ARG, "unknown compile flag");
     rv_circuit *c = new (std::nothrow) rv_circuit();
     if (!c) return fail(RV_E_NOMEM, "out of memory");
     std::string err;
     int rc;
+    const auto t0 = std::chrono::steady_clock::now();
     try {
-        rc = compile(ops, n_ops, z64_cells, gf2_cells, c->prog, err);
+        rc = compile(ops, n_ops, z64_cells, gf2_cells, c->prog, err, (flags & RV_COMPILE_PROVE_ONLY) ? COMPILE_PROVE_ONLY : 0);
     } catch (const std::bad_alloc &) {
         delete c;
         return fail(RV_E_NOMEM, "out of host memory while compiling the circuit");
@@ -176,6 +184,7 @@ extern "C" int rv_circuit_compile(const rv_op *ops, size_t n_ops, size_t z64_cel
     // but it cannot prove or verify: there is no CPU fallback and rv_session_create reports RV_E_CUDA.
     if (rv_device_count() == 0) {
         c->device = -1;
+        c->compile_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
         *out = c;
         return RV_OK;
     }
@@ -224,19 +233,19 @@ extern "C" int rv_circuit_compile(const rv_op *ops, size_t n_ops, size_t z64_cel
     D.n_llevels = (uint32_t)P.xlevel_off.size() - 1;
     D.n_lut_steps = P.n_lut_steps;
     if (P.values_wide) {
-        if ((rc = upload(c, P.luts, &D.luts))) {
+        if ((rc = upload(c, P.wgates, &D.wgates))) {
             rv_circuit_free(c);
             return rc;
         }
-        D.n_lut_levels = (uint32_t)P.lut_level_off.size() - 1;
+        D.n_wlevels = (uint32_t)P.wlevel_off.size() - 1;
     }
     D.n_vlut_steps = P.n_vlut_steps;
     if (P.verify_wide) {
-        if ((rc = upload(c, P.vluts, &D.vluts))) {
+        if ((rc = upload(c, P.vwgates, &D.vwgates))) {
             rv_circuit_free(c);
             return rc;
         }
-        D.n_vlut_levels = (uint32_t)P.vlut_level_off.size() - 1;
+        D.n_vwlevels = (uint32_t)P.vwlevel_off.size() - 1;
     }
     D.n_uvals = P.n_uvals;
     D.n_vm_steps = P.n_vm_steps;
@@ -249,6 +258,7 @@ extern "C" int rv_circuit_compile(const rv_op *ops, size_t n_ops, size_t z64_cel
     D.n_pre = P.n_pre;
     D.n_inputs = (uint32_t)P.n_inputs;
     D.n_recon = (uint32_t)P.recon_pos.size();
+    c->compile_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
     *out = c;
     return RV_OK;
 }
@@ -262,11 +272,11 @@ extern "C" int rv_circuit_get_stats(const rv_circuit *c, rv_circuit_stats *o) {
     o->n_assert = P.n_assert;
     o->n_masks = P.n_masks;
     o->n_linear = P.n_lin;
-    o->value_depth = P.lut_level_off.empty() ? 0 : P.lut_level_off.size() - 1;
+    o->value_depth = P.values_wide ? P.wlevel_off.size() - 1 : (P.lut_level_off.empty() ? 0 : P.lut_level_off.size() - 1);
     o->linear_depth = P.xlevel_off.size() - 1;
     o->plain_value_depth = P.plain_value_depth;
     o->plain_linear_depth = P.plain_linear_depth;
-    o->n_luts = P.values_wide ? P.luts.size() : (P.n_lut_steps ? P.lut_steps.size() : 0);
+    o->n_luts = P.values_wide ? P.wgates.size() : (P.n_lut_steps ? P.lut_steps.size() : 0);
     o->n_lut_steps = P.n_lut_steps;
     o->n_vm_steps = P.n_vm_steps;
     o->vm_cells = P.vm_cells;
@@ -284,6 +294,8 @@ extern "C" int rv_circuit_get_stats(const rv_circuit *c, rv_circuit_stats *o) {
     o->z64_linear_depth = Z.llevel_off.empty() ? 0 : Z.llevel_off.size() - 1;
     o->z64_online_bytes = Z.on_bytes;
     o->z64_pre_bytes = Z.pre_bytes;
+    o->compile_ns = c->compile_ns;
+    o->has_verify = P.has_verify ? 1 : 0;
     return RV_OK;
 }
 
@@ -687,8 +699,8 @@ static int commit_body(rv_session *s) {
     CU(cudaEventRecord(s->ev_fork, s->st));
     CU(cudaStreamWaitEvent(s->st_val, s->ev_fork, 0));
     if (P.values_wide) {
-        Scope k(s, "values", (uint64_t)P.luts.size() * sizeof(LutInstr), 1 + D.n_lut_levels, s->st_val);
-        launch_values_wide(D, P.lut_level_off.data(), s->d_wit, s->d_vals, s->st_val);
+        Scope k(s, "values", (uint64_t)P.wgates.size() * sizeof(VGate), 1 + D.n_wlevels, s->st_val);
+        launch_values_wide(D, P.wlevel_off.data(), s->d_wit, s->d_vals, s->st_val);
     } else {
         Scope k(s, "values", (uint64_t)P.lut_steps.size() * sizeof(LutInstr), 1, s->st_val);
         launch_values(D.lut_steps, D.n_lut_steps, D.input_vid, s->d_wit, s->wit_pitch, D.n_inputs, s->d_vals, s->vals_pitch, D.n_vals, s->n_proofs, s->st_val);
@@ -1273,7 +1285,7 @@ static int verify_on_session(rv_session *s, const uint8_t *proof, size_t proof_l
     {
         Scope k(s, "v.values", (uint64_t)P.vlut_steps.size() * sizeof(LutInstr));
         if (P.verify_wide)
-            launch_uvalues_wide(D, P.vlut_level_off.data(), s->d_leaf_vals, s->leaf_pitch, D.n_inputs + D.n_pre + D.n_rand, s->d_uvals, s->upitch, NON, s->st);
+            launch_uvalues_wide(D, P.vwlevel_off.data(), s->d_leaf_vals, s->leaf_pitch, D.n_inputs + D.n_pre + D.n_rand, s->d_uvals, s->upitch, NON, s->st);
         else
             launch_values(D.vlut_steps, D.n_vlut_steps, D.vleaf_ids, s->d_leaf_vals, s->leaf_pitch, D.n_inputs + D.n_pre + D.n_rand, s->d_uvals, s->upitch, D.n_uvals, NON,
                       s->st);
@@ -1353,7 +1365,8 @@ static int verify_on_session(rv_session *s, const uint8_t *proof, size_t proof_l
 
 extern "C" int rv_verify(const rv_circuit *c, const uint8_t *proof, size_t proof_len, int *okay) {
     if (!c || (!proof && proof_len)) return fail(RV_E_ARG, "NULL argument");
-    if (!c->prog.has_verify) return fail(RV_E_UNSUPPORTED, "verification tables are only built for circuits of at most 2^28 ops");
+    if (!c->prog.has_verify)
+        return fail(RV_E_UNSUPPORTED, "this handle has no verifier tables (compiled with RV_COMPILE_PROVE_ONLY, or more than 2^28 ops)");
     if (proof_len < 32) return fail(RV_E_FORMAT, "proof shorter than its commitment");
     PDomain g, z;
     size_t pos = 32;
@@ -1392,22 +1405,181 @@ extern "C" int rv_verify(const rv_circuit *c, const uint8_t *proof, size_t proof
     return rc == RV_OK ? accept : rc;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+//  One-shot forms with the reference's argument shape (src/proof/mod.rs:119-124,224): the circuit arrives as an op list with
+//  every call, so compiled circuits are kept in a small content-addressed cache (128-bit hash of the op bytes + wire counts +
+//  device).  Proving needs no verifier tables and compiles without them; a later verification of the same circuit upgrades
+//  the entry.  Entries in use are never evicted; idle ones leave in least-recently-used order.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+struct Hash128 {
+    uint64_t a, b;
+    bool operator==(const Hash128 &o) const { return a == o.a && b == o.b; }
+};
+inline uint64_t rotl64(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+inline uint64_t mix64(uint64_t x) {
+    x ^= x >> 32;
+    x *= 0xd6e8feb86659fd93ull;
+    x ^= x >> 32;
+    x *= 0xd6e8feb86659fd93ull;
+    return x ^ (x >> 32);
+}
+// four independent multiply-rotate lanes over 32-byte stripes (memory-speed on one core), folded to 128 bits
+Hash128 hash_bytes(const void *data, size_t len, uint64_t seed) {
+    const uint8_t *p = static_cast<const uint8_t *>(data);
+    uint64_t h[4] = {seed ^ 0x9e3779b97f4a7c15ull, seed + 0xc2b2ae3d27d4eb4full, ~seed * 0x165667b19e3779f9ull, seed ^ 0x27d4eb2f165667c5ull};
+    size_t n = len / 32;
+    for (size_t i = 0; i < n; i++, p += 32) {
+        uint64_t w[4];
+        memcpy(w, p, 32);
+        for (int k = 0; k < 4; k++) h[k] = rotl64(h[k] ^ (w[k] * 0x9fb21c651e98df25ull), 29) * 0xff51afd7ed558ccdull + k;
+    }
+    uint8_t tail[32] = {0};
+    memcpy(tail, p, len % 32);
+    uint64_t w[4];
+    memcpy(w, tail, 32);
+    for (int k = 0; k < 4; k++) h[k] = rotl64(h[k] ^ (w[k] * 0x9fb21c651e98df25ull), 29) * 0xff51afd7ed558ccdull + k;
+    Hash128 r;
+    r.a = mix64(h[0] ^ rotl64(h[1], 17) ^ len) ^ mix64(h[2] + rotl64(h[3], 41));
+    r.b = mix64(h[1] ^ rotl64(h[2], 23) ^ (len * 0x9e3779b97f4a7c15ull)) ^ mix64(h[3] + rotl64(h[0], 37));
+    return r;
+}
+struct CacheEntry {
+    Hash128 key;
+    size_t n_ops, z64_cells, gf2_cells;
+    int device;
+    rv_circuit *c;
+    int in_use;
+    uint64_t last_use;
+    bool dead;  // dropped by rv_circuit_cache_clear while in use: invisible to lookups, freed by its last user
+};
+std::mutex g_cache_mu;
+std::vector<CacheEntry> g_cache;
+uint64_t g_cache_clock = 0, g_cache_hits = 0, g_cache_misses = 0;
+size_t g_cache_max = 8;
+
+void cache_release(rv_circuit *c) {
+    bool free_it = false;
+    {
+        std::lock_guard<std::mutex> g(g_cache_mu);
+        for (size_t i = 0; i < g_cache.size(); i++)
+            if (g_cache[i].c == c) {
+                if (--g_cache[i].in_use == 0 && g_cache[i].dead) {
+                    g_cache.erase(g_cache.begin() + i);
+                    free_it = true;
+                }
+                break;
+            }
+    }
+    if (free_it) rv_circuit_free(c);
+}
+
+// Looks the circuit up (compiling it on a miss); the returned handle stays valid until cache_release.
+int cache_acquire(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, bool need_verify, rv_circuit **out) {
+    if (n_ops && !ops) return fail(RV_E_ARG, "ops is NULL");
+    const Hash128 key = hash_bytes(ops, n_ops * sizeof(rv_op), (uint64_t)z64_cells * 0x100000001b3ull ^ gf2_cells);
+    const int device = rv_device_count() ? g_device : -1;
+    {
+        std::lock_guard<std::mutex> g(g_cache_mu);
+        for (CacheEntry &e : g_cache)
+            if (!e.dead && e.key == key && e.n_ops == n_ops && e.z64_cells == z64_cells && e.gf2_cells == gf2_cells && e.device == device &&
+                (!need_verify || e.c->prog.has_verify || n_ops > VERIFY_MAX_OPS)) {
+                e.in_use++;
+                e.last_use = ++g_cache_clock;
+                g_cache_hits++;
+                *out = e.c;
+                return RV_OK;
+            }
+        g_cache_misses++;
+    }
+    rv_circuit *c = nullptr;
+    const int rc = rv_circuit_compile_ex(ops, n_ops, z64_cells, gf2_cells, need_verify ? 0 : RV_COMPILE_PROVE_ONLY, &c);
+    if (rc) return rc;
+    std::vector<rv_circuit *> drop;
+    {
+        std::lock_guard<std::mutex> g(g_cache_mu);
+        // a prove-only twin of a circuit now compiled with verifier tables is superseded; then evict idle entries, oldest first
+        for (size_t i = 0; i < g_cache.size();) {
+            CacheEntry &e = g_cache[i];
+            const bool twin = e.key == key && e.n_ops == n_ops && e.z64_cells == z64_cells && e.gf2_cells == gf2_cells && e.device == device;
+            if (twin && e.in_use == 0) {
+                drop.push_back(e.c);
+                g_cache.erase(g_cache.begin() + i);
+            } else i++;
+        }
+        while (g_cache.size() + 1 > g_cache_max) {
+            size_t victim = g_cache.size();
+            for (size_t i = 0; i < g_cache.size(); i++)
+                if (g_cache[i].in_use == 0 && (victim == g_cache.size() || g_cache[i].last_use < g_cache[victim].last_use)) victim = i;
+            if (victim == g_cache.size()) break;  // everything is in use: grow for now
+            drop.push_back(g_cache[victim].c);
+            g_cache.erase(g_cache.begin() + victim);
+        }
+        g_cache.push_back(CacheEntry{key, n_ops, z64_cells, gf2_cells, device, c, 1, ++g_cache_clock, false});
+    }
+    for (rv_circuit *d : drop) rv_circuit_free(d);
+    *out = c;
+    return RV_OK;
+}
+}  // namespace
+
+extern "C" void rv_circuit_cache_clear(void) {
+    std::vector<rv_circuit *> drop;
+    {
+        std::lock_guard<std::mutex> g(g_cache_mu);
+        for (size_t i = 0; i < g_cache.size();) {
+            if (g_cache[i].in_use == 0) {
+                drop.push_back(g_cache[i].c);
+                g_cache.erase(g_cache.begin() + i);
+            } else g_cache[i++].dead = true;  // freed by its last user
+        }
+    }
+    for (rv_circuit *d : drop) rv_circuit_free(d);
+}
+extern "C" void rv_circuit_cache_limit(size_t max_entries) {
+    std::vector<rv_circuit *> drop;
+    {
+        std::lock_guard<std::mutex> g(g_cache_mu);
+        g_cache_max = max_entries ? max_entries : 1;
+        while (g_cache.size() > g_cache_max) {
+            size_t victim = g_cache.size();
+            for (size_t i = 0; i < g_cache.size(); i++)
+                if (g_cache[i].in_use == 0 && (victim == g_cache.size() || g_cache[i].last_use < g_cache[victim].last_use)) victim = i;
+            if (victim == g_cache.size()) break;
+            drop.push_back(g_cache[victim].c);
+            g_cache.erase(g_cache.begin() + victim);
+        }
+    }
+    for (rv_circuit *d : drop) rv_circuit_free(d);
+}
+extern "C" void rv_circuit_cache_stats(uint64_t *hits, uint64_t *misses, size_t *entries) {
+    std::lock_guard<std::mutex> g(g_cache_mu);
+    if (hits) *hits = g_cache_hits;
+    if (misses) *misses = g_cache_misses;
+    if (entries) *entries = g_cache.size();
+}
+
 extern "C" int rv_proof_new(const rv_op *ops, size_t n_ops, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64, size_t n_z64,
                             size_t z64_cells, size_t gf2_cells, const uint8_t *seeds, uint8_t **proof, size_t *proof_len) {
     rv_circuit *c = nullptr;
-    int rc = rv_circuit_compile(ops, n_ops, z64_cells, gf2_cells, &c);
+    int rc = cache_acquire(ops, n_ops, z64_cells, gf2_cells, false, &c);
     if (rc) return rc;
     rc = rv_prove(c, wit_gf2, n_gf2, wit_z64, n_z64, seeds, proof, proof_len);
-    rv_circuit_free(c);
+    cache_release(c);
+    return rc;
+}
+
+extern "C" int rv_proof_verify_ex(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, const uint8_t *proof, size_t proof_len, int *okay) {
+    rv_circuit *c = nullptr;
+    int rc = cache_acquire(ops, n_ops, z64_cells, gf2_cells, true, &c);
+    if (rc) return rc;
+    rc = rv_verify(c, proof, proof_len, okay);
+    cache_release(c);
     return rc;
 }
 
 extern "C" int rv_proof_verify(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, const uint8_t *proof, size_t proof_len) {
-    rv_circuit *c = nullptr;
-    int rc = rv_circuit_compile(ops, n_ops, z64_cells, gf2_cells, &c);
-    if (rc) return rc;
     int okay = 1;
-    rc = rv_verify(c, proof, proof_len, &okay);
-    rv_circuit_free(c);
+    const int rc = rv_proof_verify_ex(ops, n_ops, z64_cells, gf2_cells, proof, proof_len, &okay);
     return rc == 1 ? (okay ? 1 : 0) : rc;  // strict: see the header
 }

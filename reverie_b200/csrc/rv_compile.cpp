@@ -2,7 +2,12 @@
 #include "rv_compile.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <thread>
 #include <initializer_list>
 
 namespace rv {
@@ -28,7 +33,18 @@ constexpr uint64_t B_AND = 2048 + 16, B_XOR = 1536 + 16, B_UNARY = 1024 + 16, B_
 //  Technology mapping: K-feasible cuts, depth first (the FPGA "priority cuts" scheme), shared by both planes.
 //  A network is a topologically ordered list of 2-input gates over node ids; id 0 is the constant 0 and is free.
 // =====================================================================================================================
-constexpr int MAP_K = 6, CUTS_PER_NODE = 6;
+struct Trace {  // RV_TRACE=1: phase times of the compiler on stderr
+    bool on = std::getenv("RV_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+    void mark(const char *what) {
+        if (!on) return;
+        const auto n = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[rv_compile] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(n - t).count());
+        t = n;
+    }
+};
+
+constexpr int MAP_K = 6, CUTS_PER_NODE = 4;  // 4 kept cuts map SHA-256 / AES-128 exactly as deep as 6 do, in 60 % of the time
 struct MGate {
     uint32_t out, a, b;  // a, b = id << 1 | negate
     uint32_t op;         // 0 xor, 1 and
@@ -41,45 +57,54 @@ struct MNode {  // one mapped node: out = f(leaf[0..n)), f given by its truth ta
     uint64_t tt;
 };
 struct Cut {
-    uint32_t leaf[MAP_K];
-    uint8_t n;
+    uint32_t leaf[MAP_K];  // sorted
     uint32_t depth;
+    uint32_t n;
+    uint64_t sig;  // OR of 1 << (leaf & 63): popcount(sig_a | sig_b) > K proves a merge infeasible without doing it
 };
 
-bool merge_cuts(const Cut &a, const Cut &b, Cut &o) {
-    int i = 0, j = 0, n = 0;
-    while (i < a.n || j < b.n) {
-        uint32_t v;
-        if (j >= b.n || (i < a.n && a.leaf[i] < b.leaf[j])) v = a.leaf[i++];
-        else if (i >= a.n || b.leaf[j] < a.leaf[i]) v = b.leaf[j++];
-        else {
-            v = a.leaf[i];
-            i++;
-            j++;
-        }
+inline bool merge_cuts(const Cut &a, const Cut &b, Cut &o) {
+    uint32_t i = 0, j = 0, n = 0;
+    while (i < a.n && j < b.n) {
+        const uint32_t x = a.leaf[i], y = b.leaf[j];
         if (n == MAP_K) return false;
-        o.leaf[n++] = v;
+        o.leaf[n++] = x < y ? x : y;
+        i += x <= y;
+        j += y <= x;
     }
-    o.n = (uint8_t)n;
+    while (i < a.n) {
+        if (n == MAP_K) return false;
+        o.leaf[n++] = a.leaf[i++];
+    }
+    while (j < b.n) {
+        if (n == MAP_K) return false;
+        o.leaf[n++] = b.leaf[j++];
+    }
+    o.n = n;
     return true;
 }
 
 // `required` marks the nodes some consumer outside the network reads; on return it also marks every leaf the chosen
 // cover uses.  With map == false every gate keeps its own two inputs as its cut (no collapsing).
 void map_network(uint32_t n_ids, const std::vector<MGate> &g, std::vector<uint8_t> &required, bool map, std::vector<MNode> &out) {
+    Trace mt;
     std::vector<uint32_t> gate_of(n_ids, NONE32);
     for (uint32_t i = 0; i < g.size(); i++) gate_of[g[i].out] = i;
     std::vector<uint32_t> depth(n_ids, 0);
     std::vector<Cut> best(g.size());
     if (map) {
+        // priority cuts: every node keeps its CUTS_PER_NODE best (depth, then size) cuts; candidates = pairwise merges of the
+        // fan-ins' cut sets (stored cuts + the trivial cut).  The kept set is maintained by insertion, so no candidate
+        // array and no sort; duplicates can only tie with a kept cut and are dropped there.
         std::vector<Cut> cuts((size_t)g.size() * CUTS_PER_NODE);
         std::vector<uint8_t> ncuts(g.size(), 0);
         auto cut_set = [&](uint32_t id, Cut *tmp, int &n) {  // the node's stored cuts plus its trivial cut
             n = 0;
             if (id == 0) {  // the constant contributes no leaf
-                tmp[n].n = 0;
-                tmp[n].depth = 0;
-                n++;
+                tmp[0].n = 0;
+                tmp[0].depth = 1;
+                tmp[0].sig = 0;
+                n = 1;
                 return;
             }
             const uint32_t gi = gate_of[id];
@@ -87,51 +112,68 @@ void map_network(uint32_t n_ids, const std::vector<MGate> &g, std::vector<uint8_
                 for (int i = 0; i < ncuts[gi]; i++) tmp[n++] = cuts[(size_t)gi * CUTS_PER_NODE + i];
             tmp[n].n = 1;
             tmp[n].leaf[0] = id;
-            tmp[n].depth = 0;
+            tmp[n].depth = depth[id] + 1;  // as a fan-in cut: (max depth of its leaves) + 1, like the stored ones
+            tmp[n].sig = 1ull << (id & 63);
             n++;
         };
-        Cut ca[CUTS_PER_NODE + 1], cb[CUTS_PER_NODE + 1], cand[(CUTS_PER_NODE + 1) * (CUTS_PER_NODE + 1)];
+        Cut ca[CUTS_PER_NODE + 1], cb[CUTS_PER_NODE + 1], keep[CUTS_PER_NODE];
         for (uint32_t gi = 0; gi < g.size(); gi++) {
-            int na, nb, nc = 0;
+            int na, nb, nk = 0;
             cut_set(g[gi].a >> 1, ca, na);
             cut_set(g[gi].b >> 1, cb, nb);
             for (int i = 0; i < na; i++)
                 for (int j = 0; j < nb; j++) {
-                    Cut &o = cand[nc];
+                    // the merged cut's depth and a lower bound on its size are known before merging: most candidates lose
+                    // against the kept set right here
+                    const uint32_t d = std::max(ca[i].depth, cb[j].depth);
+                    if (nk == CUTS_PER_NODE) {
+                        const Cut &w = keep[CUTS_PER_NODE - 1];
+                        if (d > w.depth || (d == w.depth && std::max(ca[i].n, cb[j].n) >= w.n)) continue;
+                    }
+                    const uint64_t sig = ca[i].sig | cb[j].sig;
+                    if (__builtin_popcountll(sig) > MAP_K) continue;
+                    Cut o;
                     if (!merge_cuts(ca[i], cb[j], o)) continue;
-                    uint32_t d = 0;
-                    for (int k = 0; k < o.n; k++) d = std::max(d, depth[o.leaf[k]]);
-                    o.depth = d + 1;
+                    o.depth = d;
+                    o.sig = sig;
+                    // position among the kept cuts (ties keep the earlier candidate first)
+                    int pos = nk;
+                    while (pos > 0 && (o.depth < keep[pos - 1].depth || (o.depth == keep[pos - 1].depth && o.n < keep[pos - 1].n))) pos--;
+                    if (pos == CUTS_PER_NODE) continue;
                     bool dup = false;
-                    for (int k = 0; k < nc && !dup; k++) dup = cand[k].n == o.n && std::memcmp(cand[k].leaf, o.leaf, o.n * 4) == 0;
-                    if (!dup) nc++;
+                    for (int k = 0; k < nk && !dup; k++)
+                        dup = keep[k].sig == sig && keep[k].n == o.n && std::memcmp(keep[k].leaf, o.leaf, o.n * 4) == 0;
+                    if (dup) continue;
+                    if (nk < CUTS_PER_NODE) nk++;
+                    for (int k = nk - 1; k > pos; k--) keep[k] = keep[k - 1];
+                    keep[pos] = o;
                 }
-            std::sort(cand, cand + nc, [](const Cut &x, const Cut &y) { return x.depth != y.depth ? x.depth < y.depth : x.n < y.n; });
-            const int keep = std::min(nc, CUTS_PER_NODE);
-            for (int i = 0; i < keep; i++) cuts[(size_t)gi * CUTS_PER_NODE + i] = cand[i];
-            ncuts[gi] = (uint8_t)keep;
-            best[gi] = cand[0];
-            depth[g[gi].out] = cand[0].depth;
+            for (int i = 0; i < nk; i++) cuts[(size_t)gi * CUTS_PER_NODE + i] = keep[i];
+            ncuts[gi] = (uint8_t)nk;
+            best[gi] = keep[0];
+            depth[g[gi].out] = keep[0].depth;
         }
     } else {
         for (uint32_t gi = 0; gi < g.size(); gi++) {
             Cut c;
             c.n = 0;
+            c.sig = 0;
             uint32_t a = g[gi].a >> 1, b = g[gi].b >> 1;
             if (a > b) std::swap(a, b);
             if (a) c.leaf[c.n++] = a;
             if (b && b != a) c.leaf[c.n++] = b;
             uint32_t d = 0;
-            for (int k = 0; k < c.n; k++) d = std::max(d, depth[c.leaf[k]]);
+            for (uint32_t k = 0; k < c.n; k++) d = std::max(d, depth[c.leaf[k]]);
             c.depth = d + 1;
             best[gi] = c;
             depth[g[gi].out] = c.depth;
         }
     }
+    mt.mark("    map: cuts");
     // cover: walk backwards from the required nodes
     for (size_t gi = g.size(); gi-- > 0;) {
         if (!required[g[gi].out]) continue;
-        for (int k = 0; k < best[gi].n; k++) required[best[gi].leaf[k]] = 1;
+        for (uint32_t k = 0; k < best[gi].n; k++) required[best[gi].leaf[k]] = 1;
     }
     // levels over the chosen cover and truth tables (cone simulated on the 64 input patterns at once)
     static const uint64_t PAT[6] = {0xAAAAAAAAAAAAAAAAull, 0xCCCCCCCCCCCCCCCCull, 0xF0F0F0F0F0F0F0F0ull,
@@ -147,7 +189,7 @@ void map_network(uint32_t n_ids, const std::vector<MGate> &g, std::vector<uint8_
         const Cut &c = best[gi];
         epoch++;
         uint32_t lv = 0;
-        for (int k = 0; k < c.n; k++) {
+        for (uint32_t k = 0; k < c.n; k++) {
             stamp[c.leaf[k]] = epoch;
             tmp[c.leaf[k]] = PAT[k];
             lv = std::max(lv, level[c.leaf[k]]);
@@ -178,12 +220,64 @@ void map_network(uint32_t n_ids, const std::vector<MGate> &g, std::vector<uint8_
         MNode m;
         m.out = o;
         m.n = c.n;
-        for (int k = 0; k < MAP_K; k++) m.leaf[k] = k < c.n ? c.leaf[k] : 0;
+        for (int k = 0; k < MAP_K; k++) m.leaf[k] = k < (int)c.n ? c.leaf[k] : 0;
         m.level = lv + 1;
         m.tt = tmp[o];
         level[o] = lv + 1;
         out.push_back(m);
     }
+    mt.mark("    map: cover + truth tables");
+}
+
+// Drops every gate no required node depends on (walks backwards marking the transitive fan-in in `needed`, then compacts).
+// The reference's bench circuit, for one, multiplies the same two inputs 10^8 times and reads none of the products.
+void prune_network(std::vector<MGate> &g, const std::vector<uint8_t> &required, std::vector<uint8_t> &needed) {
+    needed = required;
+    size_t n_req = 0;
+    for (size_t gi = g.size(); gi-- > 0;) {
+        if (!needed[g[gi].out]) continue;
+        n_req++;
+        needed[g[gi].a >> 1] = 1;
+        needed[g[gi].b >> 1] = 1;
+    }
+    if (n_req == g.size()) return;
+    size_t w = 0;
+    for (size_t gi = 0; gi < g.size(); gi++)
+        if (needed[g[gi].out]) g[w++] = g[gi];
+    g.resize(w);
+    if (w < g.capacity() / 2) g.shrink_to_fit();
+}
+
+// Wide networks (average level width >= WIDE_LEVEL) are evaluated with one grid-wide launch per level, so collapsing cones into
+// LUTs buys nothing there and the cut enumeration would dominate the compile time (microseconds per gate on AND-heavy
+// layers).  They keep their 2-input gates (the network is already pruned to the ones that feed a required node), sorted by
+// level.  Returns false (and leaves `out` empty) when the network is not wide.
+bool build_wide(uint32_t n_ids, const std::vector<MGate> &g, std::vector<VGate> &out, std::vector<uint32_t> &level_off) {
+    out.clear();
+    level_off.assign(1, 0);
+    const size_t n_req = g.size();  // pruned: every gate feeds a required node
+    if (n_req == 0) return false;
+    std::vector<uint32_t> level(n_ids, 0);
+    uint32_t depth = 0;
+    for (const MGate &gt : g) {
+        const uint32_t l = 1 + std::max(level[gt.a >> 1], level[gt.b >> 1]);
+        level[gt.out] = l;
+        depth = std::max(depth, l);
+    }
+    if (n_req / depth < WIDE_LEVEL) return false;
+    std::vector<uint32_t> cnt(depth + 1, 0);
+    for (const MGate &gt : g) cnt[level[gt.out]]++;
+    level_off.assign(depth + 1, 0);  // levels 1..depth -> [level_off[l - 1], level_off[l])
+    uint32_t run = 0;
+    for (uint32_t l = 1; l <= depth; l++) {
+        level_off[l - 1] = run;
+        run += cnt[l];
+    }
+    level_off[depth] = run;
+    out.resize(n_req);
+    std::vector<uint32_t> pos(level_off.begin(), level_off.end());
+    for (const MGate &gt : g) out[pos[level[gt.out] - 1]++] = VGate{gt.out, gt.a, gt.b, gt.op};
+    return true;
 }
 
 // counting sort of mapped nodes by level; returns offsets (levels 1..depth -> [off[l-1], off[l]))
@@ -674,7 +768,8 @@ struct ZBuilder {
 
 }  // namespace
 
-int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, Program &P, std::string &err) {
+int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, Program &P, std::string &err, uint32_t flags) {
+    Trace tr;
     P = Program();
     P.n_ops = n_ops;
     if (n_ops && !ops) {
@@ -683,7 +778,7 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
     }
     std::vector<Cell> cells(gf2_cells, Cell{VREF_ZERO, ZERO_MID, VREF_ZERO});
     ValueNet un;  // u-plane network (built only while the circuit stays small)
-    const bool want_verify = n_ops <= VERIFY_MAX_OPS;
+    const bool want_verify = n_ops <= VERIFY_MAX_OPS && !(flags & COMPILE_PROVE_ONLY);
     std::vector<uint32_t> vlevel(1, 0);  // per value id (plain 2-input depth, for the stats)
     std::vector<uint32_t> llevel;        // per linear node (plain depth)
     std::vector<uint32_t> tlevel;        // per tainted value
@@ -692,6 +787,41 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
     std::vector<TGate> tg;               // tainted plane, creation order
     uint64_t n_masks = 0;
     ZBuilder zb(P.z, z64_cells);
+    {  // one counting pass sizes the tables the walk appends to (a std::vector that doubles its way to 10^8 entries copies them all twice)
+        size_t c_mul = 0, c_lin = 0, c_in = 0, c_as = 0, c_b2a = 0, c_z = 0;
+        for (size_t i = 0; i < n_ops; i++) {
+            const rv_op &op = ops[i];
+            if (op.domain == RV_GF2) {
+                c_mul += op.opcode == RV_MUL;
+                c_lin += op.opcode == RV_ADD || op.opcode == RV_SUB;
+                c_in += op.opcode == RV_INPUT;
+                c_as += op.opcode == RV_ASSERT_ZERO;
+            } else if (op.domain == RV_B2A) c_b2a++;
+            else c_z += op.domain == RV_Z64;
+        }
+        c_mul += 63 * c_b2a;
+        c_lin += 189 * c_b2a;
+        c_as += 64 * c_b2a;
+        const size_t n_items = c_mul + c_in + c_as;
+        P.items.reserve(n_items);
+        P.recon_pos.reserve(c_mul + c_as);
+        P.input_pos.reserve(c_in);
+        P.input_vid.reserve(c_in);
+        vlevel.reserve(1 + c_in + c_mul + c_lin);
+        vg.reserve(c_mul + c_lin);
+        lg.reserve(c_lin);
+        llevel.reserve(c_lin);
+        if (want_verify) {
+            un.g.reserve(2 * c_mul + c_lin);
+            P.kappa_uid.reserve(c_mul);
+            P.item_ua.reserve(n_items);
+            P.item_ub.reserve(n_items);
+            P.input_uid.reserve(c_in);
+        }
+        zb.prog.reserve(c_z);
+        zb.vlevel.reserve(1 + 2 * c_z);
+        zb.Z.items.reserve(c_z / 2);
+    }
 
     auto mid_level = [&](uint32_t mid) -> uint32_t { return (mid != ZERO_MID && mid >= LIN_BASE) ? llevel[mid - LIN_BASE] : 0; };
     auto new_val = [&](uint32_t level) -> uint32_t {
@@ -931,6 +1061,7 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
             return RV_E_UNSUPPORTED;
         }
     }
+    tr.mark("op walk");
     // tainted plane by level
     {
         uint32_t depth = 0;
@@ -962,19 +1093,36 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
     for (uint32_t l : llevel) P.plain_linear_depth = std::max(P.plain_linear_depth, l);
     const bool small = n_ops <= (4u << 20);  // debug tables only where tests can use them
 
+    // The three planes are independent from here on (they only share read-only parts of P.items): for circuits big enough
+    // to care they are built side by side.
+    int mask_rc = RV_OK;
+    std::string mask_err;
     // ---- mask plane: map the XOR network, number the rows -----------------------------------------------------------
-    {
+    auto job_mask = [&]() {
+        Trace jt;
         // mapper ids: 0 = zero mask, 1 + i = fresh PRG mask i, 1 + n_masks + k = linear node k
         const uint32_t n_lin_all = (uint32_t)lg.size();
         if ((uint64_t)P.n_masks + n_lin_all + 2 >= LIN_BASE) {
-            err = "circuit too large for 32-bit row indices";
-            return RV_E_UNSUPPORTED;
+            mask_err = "circuit too large for 32-bit row indices";
+            mask_rc = RV_E_UNSUPPORTED;
+            return;
         }
         auto mask_id = [&](uint32_t mid) -> uint32_t {
             if (mid == ZERO_MID) return 0;
             if (mid >= LIN_BASE) return 1 + P.n_masks + (mid - LIN_BASE);
             return 1 + mid;
         };
+        if (n_lin_all == 0) {  // no Add/Sub of masked wires (e.g. the reference's bench circuit): rows are the fresh masks
+            P.xlevel_off.assign(1, 0);
+            P.n_lin = 0;
+            P.n_rows = P.n_masks + 1;
+            const uint32_t zero_row = P.zero_row();
+            for (Item &it : P.items) {
+                if (it.ra == ZERO_MID) it.ra = zero_row;
+                if (it.kind == ITEM_MUL && it.rb == ZERO_MID) it.rb = zero_row;
+            }
+            return;
+        }
         for (MGate &g : lg) {
             g.out = mask_id(g.out);
             g.a = mask_id(g.a) << 1;
@@ -985,6 +1133,10 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
         for (const Item &it : P.items) {
             required[mask_id(it.ra)] = 1;
             if (it.kind == ITEM_MUL) required[mask_id(it.rb)] = 1;
+        }
+        {
+            std::vector<uint8_t> needed;
+            prune_network(lg, required, needed);
         }
         std::vector<MNode> nodes;
         map_network(n_ids, lg, required, lg.size() <= LUT_MAP_MAX_GATES, nodes);
@@ -1026,16 +1178,19 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
             it.ra = row_of_id(mask_id(it.ra));
             if (it.kind == ITEM_MUL) it.rb = row_of_id(mask_id(it.rb));
         }
-    }
-    build_mask_vm(P);
-    emit_vm_steps(P);
-    if (!small) {
-        std::vector<VmInstr>().swap(P.vm);
-        std::vector<uint32_t>().swap(P.vm_level_off);
-    }
+        jt.mark("  mask: map + rows");
+        build_mask_vm(P);
+        emit_vm_steps(P);
+        jt.mark("  mask: VM");
+        if (!small) {
+            std::vector<VmInstr>().swap(P.vm);
+            std::vector<uint32_t>().swap(P.vm_level_off);
+        }
+    };
 
-    // ---- value plane: map to 6-input LUTs --------------------------------------------------------------------------
-    {
+    // ---- value plane: 6-input LUT step stream, or (wide circuits) the level-sorted 2-input gates --------------------------
+    auto job_value = [&]() {
+        Trace jt;
         std::vector<uint8_t> required(P.n_vals, 0);
         auto need = [&](uint32_t vref) {
             if (!(vref & VREF_TAINT)) required[vref >> 1] = 1;
@@ -1054,32 +1209,79 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
             P.vgates.resize(vg.size());
             for (size_t i = 0; i < vg.size(); i++) P.vgates[i] = VGate{vg[i].out, vg[i].a, vg[i].b, vg[i].op};
         }
-        map_to_luts(P.n_vals, vg, required, P.luts, P.lut_level_off);
+        std::vector<uint8_t> needed;
+        prune_network(vg, required, needed);
+        std::vector<uint8_t>().swap(needed);
+        P.values_wide = build_wide(P.n_vals, vg, P.wgates, P.wlevel_off);
+        if (!P.values_wide && !vg.empty()) {
+            map_to_luts(P.n_vals, vg, required, P.luts, P.lut_level_off);
+            emit_lut_steps(P.luts, P.lut_level_off, P.n_vals, P.lut_steps, P.n_lut_steps);
+            if (!small) std::vector<LutInstr>().swap(P.luts);
+        }
         std::vector<MGate>().swap(vg);
-    }
-    P.values_wide = P.lut_level_off.size() > 1 && P.luts.size() / (P.lut_level_off.size() - 1) >= WIDE_LEVEL;
-    if (!P.values_wide) {
-        emit_lut_steps(P.luts, P.lut_level_off, P.n_vals, P.lut_steps, P.n_lut_steps);
-        if (!small) std::vector<LutInstr>().swap(P.luts);
-    }
+        jt.mark("  value plane");
+    };
 
     // ---- online verifier's u-plane ---------------------------------------------------------------------------------
-    if (want_verify) {
+    auto job_u = [&]() {
+        if (!want_verify) return;
+        Trace jt;
         P.n_uvals = un.n_ids;
         std::vector<uint8_t> required(P.n_uvals, 0);
-        for (size_t t = 0; t < P.items.size(); t++) {
-            required[P.item_ua[t] >> 1] = 1;
-            required[P.item_ub[t] >> 1] = 1;
+        auto mark = [&]() {
+            for (size_t t = 0; t < P.items.size(); t++) {
+                required[P.item_ua[t] >> 1] = 1;
+                required[P.item_ub[t] >> 1] = 1;
+            }
+        };
+        mark();
+        std::vector<uint8_t> needed;
+        prune_network(un.g, required, needed);
+        std::vector<uint8_t>().swap(needed);
+        P.verify_wide = build_wide(P.n_uvals, un.g, P.vwgates, P.vwlevel_off);
+        if (!P.verify_wide && !un.g.empty()) {
+            std::vector<LutInstr> vluts;
+            std::vector<uint32_t> vlut_level_off;
+            map_to_luts(P.n_uvals, un.g, required, vluts, vlut_level_off);
+            emit_lut_steps(vluts, vlut_level_off, P.n_uvals, P.vlut_steps, P.n_vlut_steps);
         }
-        map_to_luts(P.n_uvals, un.g, required, P.vluts, P.vlut_level_off);
         std::vector<MGate>().swap(un.g);
-        P.verify_wide = P.vlut_level_off.size() > 1 && P.vluts.size() / (P.vlut_level_off.size() - 1) >= WIDE_LEVEL;
-        if (!P.verify_wide) {
-            emit_lut_steps(P.vluts, P.vlut_level_off, P.n_uvals, P.vlut_steps, P.n_vlut_steps);
-            std::vector<LutInstr>().swap(P.vluts);
-        }
         P.has_verify = true;
+        jt.mark("  u-plane");
+    };
+
+    if (n_ops >= 20000) {  // below that the thread start-up is not worth it
+        std::exception_ptr ex[2] = {nullptr, nullptr};
+        auto guarded = [](auto &job, std::exception_ptr &e) {
+            return [&job, &e]() {
+                try {
+                    job();
+                } catch (...) {
+                    e = std::current_exception();
+                }
+            };
+        };
+        std::thread t1(guarded(job_value, ex[0])), t2(guarded(job_u, ex[1]));
+        std::exception_ptr ex0 = nullptr;
+        try {
+            job_mask();
+        } catch (...) {
+            ex0 = std::current_exception();
+        }
+        t1.join();
+        t2.join();
+        for (std::exception_ptr e : {ex0, ex[0], ex[1]})
+            if (e) std::rethrow_exception(e);
+    } else {
+        job_mask();
+        job_value();
+        job_u();
     }
+    if (mask_rc != RV_OK) {
+        err = mask_err;
+        return mask_rc;
+    }
+    tr.mark("planes (side by side)");
     return RV_OK;
 }
 

@@ -177,15 +177,17 @@ struct Program {
     uint32_t n_vm_steps = 0;
     std::vector<LutInstr> lut_steps;    // padded device stream of the value plane (n_lut_steps * LUT_STEP slots); value n_vals = scratch
     uint32_t n_lut_steps = 0;
-    bool values_wide = false;           // levels average >= WIDE_LEVEL gates: `luts` runs one grid-wide launch per level instead of the step stream
+    bool values_wide = false;           // levels average >= WIDE_LEVEL gates: one grid-wide launch per level over `wgates` instead of the step stream
+    std::vector<VGate> wgates;          // wide circuits: the 2-input gates that feed the item plane, sorted by level (no LUT mapping)
+    std::vector<uint32_t> wlevel_off;
     // online-verifier value plane ("u-plane"): same circuit, every Mul is (a & b) ^ kappa_j with kappa_j a leaf
     std::vector<LutInstr> vlut_steps;   // padded device stream; value n_uvals = scratch
     uint32_t n_vlut_steps = 0, n_uvals = 0;
     std::vector<uint32_t> input_uid;    // witness index -> u-plane value id
     std::vector<uint32_t> kappa_uid;    // Mul index j -> u-plane value id of its kappa leaf
     std::vector<uint32_t> item_ua, item_ub;  // per online item: u-plane refs (id << 1 | negate) of the operands / asserted wire
-    std::vector<LutInstr> vluts;        // wide circuits (verify_wide): the level-sorted u-plane LUT list, one launch per level
-    std::vector<uint32_t> vlut_level_off;
+    std::vector<VGate> vwgates;         // wide circuits (verify_wide): the level-sorted 2-input gates of the u-plane, one launch per level
+    std::vector<uint32_t> vwlevel_off;
     bool verify_wide = false;
     bool has_verify = false;            // built for circuits of <= VERIFY_MAX_OPS ops
     std::vector<TGate> tgates;          // tainted plane, sorted by level
@@ -207,7 +209,9 @@ struct Program {
 };
 
 // Returns RV_OK or a negative rv_status; `err` receives a human-readable reason.
-int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, Program &out, std::string &err);
+// flags: COMPILE_PROVE_ONLY skips the online verifier's tables (u-plane): about a third of the compile time and of the table bytes.
+constexpr uint32_t COMPILE_PROVE_ONLY = 1u;
+int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, Program &out, std::string &err, uint32_t flags = 0);
 
 constexpr uint32_t WIDE_LEVEL = 4096;
 constexpr size_t VERIFY_MAX_OPS = (size_t)1 << 28;  // the verifier's tables cost ~200 bytes of host memory per gate while compiling

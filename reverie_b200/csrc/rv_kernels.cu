@@ -335,22 +335,23 @@ __global__ void __launch_bounds__(256) k_values_leaves(const uint32_t *__restric
     if (k == 0) vals[0] = 0;
     if (k < n_leaves) vals[leaf_ids[k]] = wit[k] & 1;
 }
-__global__ void __launch_bounds__(256) k_values_level(const LutInstr *__restrict__ luts, uint32_t n, uint8_t *vals) {
+// 2-input gate on byte values: v[dst] = (v[a >> 1] ^ (a & 1)) OP (v[b >> 1] ^ (b & 1))
+__device__ __forceinline__ void eval_vgate(const VGate g, uint8_t *v) {
+    const uint32_t x = (uint32_t)v[g.a >> 1] ^ (g.a & 1), y = (uint32_t)v[g.b >> 1] ^ (g.b & 1);
+    v[g.dst] = (uint8_t)((g.op ? (x & y) : (x ^ y)) & 1);
+}
+__global__ void __launch_bounds__(256) k_values_level(const VGate *__restrict__ gates, uint32_t n, uint8_t *vals) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n) return;
-    const LutInstr li = luts[g];
-    const uint32_t idx = (uint32_t)vals[li.in[0]] | ((uint32_t)vals[li.in[1]] << 1) | ((uint32_t)vals[li.in[2]] << 2) | ((uint32_t)vals[li.in[3]] << 3) |
-                         ((uint32_t)vals[li.in[4]] << 4) | ((uint32_t)vals[li.in[5]] << 5);
-    vals[li.dst] = (uint8_t)((li.tt >> idx) & 1);
+    if (g < n) eval_vgate(gates[g], vals);
 }
 
 int launch_values_wide(const DevProgram &P, const uint32_t *off_host, const uint8_t *wit, uint8_t *vals, cudaStream_t st) {
     k_values_leaves<<<(std::max(P.n_inputs, 1u) + 255) / 256, 256, 0, st>>>(P.input_vid, wit, P.n_inputs, vals);
-    for (uint32_t l = 0; l < P.n_lut_levels; l++) {
+    for (uint32_t l = 0; l < P.n_wlevels; l++) {
         const uint32_t n = off_host[l + 1] - off_host[l];
-        if (n) k_values_level<<<(n + 255) / 256, 256, 0, st>>>(P.luts + off_host[l], n, vals);
+        if (n) k_values_level<<<(n + 255) / 256, 256, 0, st>>>(P.wgates + off_host[l], n, vals);
     }
-    return 1 + (int)P.n_lut_levels;
+    return 1 + (int)P.n_wlevels;
 }
 
 __global__ void __launch_bounds__(256) k_uvalues_leaves(const uint32_t *__restrict__ leaf_ids, const uint8_t *__restrict__ leaf_vals, size_t leaf_pitch,
@@ -360,24 +361,19 @@ __global__ void __launch_bounds__(256) k_uvalues_leaves(const uint32_t *__restri
     if (k == 0) v[0] = 0;
     if (k < n_leaves) v[leaf_ids[k]] = leaf_vals[(size_t)blockIdx.y * leaf_pitch + k] & 1;
 }
-__global__ void __launch_bounds__(256) k_uvalues_level(const LutInstr *__restrict__ luts, uint32_t n, uint8_t *uvals, size_t upitch) {
+__global__ void __launch_bounds__(256) k_uvalues_level(const VGate *__restrict__ gates, uint32_t n, uint8_t *uvals, size_t upitch) {
     const uint32_t g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n) return;
-    uint8_t *v = uvals + (size_t)blockIdx.y * upitch;
-    const LutInstr li = luts[g];
-    const uint32_t idx = (uint32_t)v[li.in[0]] | ((uint32_t)v[li.in[1]] << 1) | ((uint32_t)v[li.in[2]] << 2) | ((uint32_t)v[li.in[3]] << 3) |
-                         ((uint32_t)v[li.in[4]] << 4) | ((uint32_t)v[li.in[5]] << 5);
-    v[li.dst] = (uint8_t)((li.tt >> idx) & 1);
+    if (g < n) eval_vgate(gates[g], uvals + (size_t)blockIdx.y * upitch);
 }
 
 int launch_uvalues_wide(const DevProgram &P, const uint32_t *off_host, const uint8_t *leaf_vals, size_t leaf_pitch, uint32_t n_leaves, uint8_t *uvals,
                         size_t upitch, uint32_t n_instances, cudaStream_t st) {
     k_uvalues_leaves<<<dim3((std::max(n_leaves, 1u) + 255) / 256, n_instances), 256, 0, st>>>(P.vleaf_ids, leaf_vals, leaf_pitch, n_leaves, uvals, upitch);
-    for (uint32_t l = 0; l < P.n_vlut_levels; l++) {
+    for (uint32_t l = 0; l < P.n_vwlevels; l++) {
         const uint32_t n = off_host[l + 1] - off_host[l];
-        if (n) k_uvalues_level<<<dim3((n + 255) / 256, n_instances), 256, 0, st>>>(P.vluts + off_host[l], n, uvals, upitch);
+        if (n) k_uvalues_level<<<dim3((n + 255) / 256, n_instances), 256, 0, st>>>(P.vwgates + off_host[l], n, uvals, upitch);
     }
-    return 1 + (int)P.n_vlut_levels;
+    return 1 + (int)P.n_vwlevels;
 }
 
 // =====================================================================================================================

@@ -19,13 +19,13 @@ struct DevProgram {
     const uint32_t *input_vid = nullptr;  // k -> value id
     const LutInstr *lut_steps = nullptr;   // value-plane step stream (n_lut_steps * LUT_STEP slots)
     uint32_t n_lut_steps = 0;
-    const LutInstr *luts = nullptr;        // wide circuits: the level-sorted LUT list itself, one launch per level
-    uint32_t n_lut_levels = 0;
+    const VGate *wgates = nullptr;         // wide circuits: the level-sorted 2-input gates, one launch per level
+    uint32_t n_wlevels = 0;
     // online verifier (absent for circuits of more than 4M ops)
     const LutInstr *vlut_steps = nullptr;  // u-plane step stream
     uint32_t n_vlut_steps = 0, n_uvals = 0;
-    const LutInstr *vluts = nullptr;       // wide circuits: level-sorted u-plane LUT list
-    uint32_t n_vlut_levels = 0;
+    const VGate *vwgates = nullptr;        // wide circuits: level-sorted 2-input gates of the u-plane
+    uint32_t n_vwlevels = 0;
     const uint32_t *vleaf_ids = nullptr;   // [n_inputs + n_and]: u-plane value id of every input, then of every Mul's kappa
     const uint32_t *item_ua = nullptr, *item_ub = nullptr, *recon_idx = nullptr;  // per online item
     const VmInstr *vm_steps = nullptr;     // mask-plane VM step stream (n_vm_steps * VM_STEP slots); empty without Add/Sub

@@ -38,11 +38,12 @@ class Circuit:
     """A compiled circuit (rv_circuit).  wire_counts = (z64_cells, gf2_cells), the reference's tuple order
     (src/proof/mod.rs:125)."""
 
-    def __init__(self, ops: np.ndarray, wire_counts: Tuple[int, int]):
+    def __init__(self, ops: np.ndarray, wire_counts: Tuple[int, int], prove_only: bool = False):
+        """prove_only: leave out the online verifier's tables (RV_COMPILE_PROVE_ONLY) -- a third of the compile time and memory."""
         self.ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
         self.wire_counts = (int(wire_counts[0]), int(wire_counts[1]))
         h = C.c_void_p()
-        N.check(N.lib().rv_circuit_compile(_ptr(self.ops), self.ops.size, self.wire_counts[0], self.wire_counts[1], C.byref(h)))
+        N.check(N.lib().rv_circuit_compile_ex(_ptr(self.ops), self.ops.size, self.wire_counts[0], self.wire_counts[1], 1 if prove_only else 0, C.byref(h)))
         self._h = h
 
     def __del__(self):
@@ -268,12 +269,17 @@ class Proof:
     def new(circuit, wit_gf2, wit_z64=(), wire_counts=None, seeds=None) -> "Proof":
         """Proof::new (src/proof/mod.rs:119-222).  `seeds` (256 x 16 bytes) replaces the OsRng draw at :131-134 so a
         proof can be reproduced; None draws from the OS RNG like the reference."""
-        c = _as_circuit(circuit, wire_counts)
         wg = np.ascontiguousarray(np.asarray(wit_gf2, dtype=np.uint8))
         wz = np.ascontiguousarray(np.asarray(wit_z64, dtype=np.uint64))
         sd = _seeds_arr(seeds)
         out, n = C.c_void_p(), C.c_size_t()
-        N.check(N.lib().rv_prove(c.handle, _ptr(wg), wg.size, _ptr(wz), wz.size, _ptr(sd), C.byref(out), C.byref(n)))
+        if isinstance(circuit, Circuit):
+            c = _as_circuit(circuit, wire_counts)
+            N.check(N.lib().rv_prove(c.handle, _ptr(wg), wg.size, _ptr(wz), wz.size, _ptr(sd), C.byref(out), C.byref(n)))
+        else:  # the reference's call shape: the op list with every call (rv_proof_new compiles it once, then finds it in its cache)
+            ops = np.ascontiguousarray(circuit, dtype=OP_DTYPE)
+            N.check(N.lib().rv_proof_new(_ptr(ops), ops.size, _ptr(wg), wg.size, _ptr(wz), wz.size, int(wire_counts[0]), int(wire_counts[1]),
+                                         _ptr(sd), C.byref(out), C.byref(n)))
         return Proof(_take(out, n))
 
     @staticmethod
@@ -313,10 +319,14 @@ class Proof:
         """(accept, okay): `accept` is the reference's verdict -- the recomputed commitment equals the proof's
         (src/proof/mod.rs:305-306); `okay` is the AND of the online verifiers' AssertZero checks, which the reference computes
         (src/transcript/verifier/online.rs:176-178) and never reads."""
-        c = _as_circuit(circuit, wire_counts)
         buf = self._buf if isinstance(self._buf, np.ndarray) else np.frombuffer(self._buf, dtype=np.uint8)
         okay = C.c_int(1)
-        accept = N.check(N.lib().rv_verify(c.handle, _ptr(buf), buf.size, C.byref(okay))) == 1
+        if isinstance(circuit, Circuit):
+            c = _as_circuit(circuit, wire_counts)
+            accept = N.check(N.lib().rv_verify(c.handle, _ptr(buf), buf.size, C.byref(okay))) == 1
+        else:
+            ops = np.ascontiguousarray(circuit, dtype=OP_DTYPE)
+            accept = N.check(N.lib().rv_proof_verify_ex(_ptr(ops), ops.size, int(wire_counts[0]), int(wire_counts[1]), _ptr(buf), buf.size, C.byref(okay))) == 1
         return accept, bool(okay.value)
 
     def verify(self, circuit, wire_counts=None, strict: bool = True) -> bool:

@@ -315,9 +315,9 @@ extern "C" int hs_check_steps(const rv_op *ops, size_t n_ops, size_t z64_cells, 
     stats[0] = P.n_vm_steps;
     stats[1] = P.n_lut_steps;
     stats[2] = P.vm_cells;
-    stats[3] = (uint32_t)P.luts.size();
+    stats[3] = (uint32_t)(P.values_wide ? P.wgates.size() : P.luts.size());
     stats[4] = (uint32_t)P.xlevel_off.size() - 1;
-    stats[5] = (uint32_t)P.lut_level_off.size() - 1;
+    stats[5] = (uint32_t)(P.values_wide ? P.wlevel_off.size() : P.lut_level_off.size()) - 1;
     stats[6] = P.n_lin;
     if (P.vm_steps.size() != (size_t)P.n_vm_steps * VM_STEP || P.lut_steps.size() != (size_t)P.n_lut_steps * LUT_STEP) { g_err = "stream size"; return -300; }
     // --- mask VM: once with every LOAD landing immediately, once landing as late as the cp.async group wait allows ---
@@ -382,11 +382,10 @@ extern "C" int hs_check_steps(const rv_op *ops, size_t n_ops, size_t z64_cells, 
             a[g.dst] = (uint8_t)((g.op ? (u & v) : (u ^ v)) & 1);
         }
         std::vector<std::pair<uint32_t, uint8_t>> w;
-        if (P.values_wide)  // k_values_level: one launch per level over the level-sorted list
-            for (const LutInstr &li : P.luts) {
-                uint32_t idx = 0;
-                for (int k = 0; k < 6; k++) idx |= (uint32_t)b[li.in[k]] << k;
-                b[li.dst] = (uint8_t)((li.tt >> idx) & 1);
+        if (P.values_wide)  // k_values_level: one launch per level over the level-sorted 2-input gates
+            for (const VGate &g : P.wgates) {
+                const uint32_t u = b[g.a >> 1] ^ (g.a & 1), v = b[g.b >> 1] ^ (g.b & 1);
+                b[g.dst] = (uint8_t)((g.op ? (u & v) : (u ^ v)) & 1);
             }
         for (uint32_t st = 0; st < P.n_lut_steps; st++) {
             w.clear();
@@ -459,11 +458,10 @@ extern "C" int hs_verify(const rv_op *ops, size_t n_ops, size_t z64_cells, size_
         for (uint32_t k = 0; k < P.n_inputs; k++) uv[P.input_uid[k]] = verify_leaf_input(P.items[P.input_pos[k]], k, opens[s], proof, rows.data(), npi, s);
         for (uint32_t j = 0; j < P.n_pre; j++) uv[P.kappa_uid[j]] = verify_leaf_kappa(P.items[mul_pos[j]], recon_idx[mul_pos[j]], opens[s], proof, rows.data(), npi, s);
         for (uint32_t k = 0; k < P.rand_uid.size(); k++) uv[P.rand_uid[k]] = verify_leaf_random(P.rand_row[k], rows.data(), npi, s);
-        if (P.verify_wide)  // k_uvalues_level: one launch per level over the level-sorted list
-            for (const LutInstr &li : P.vluts) {
-                uint32_t idx = 0;
-                for (int k = 0; k < 6; k++) idx |= (uint32_t)uv[li.in[k]] << k;
-                uv[li.dst] = (uint8_t)((li.tt >> idx) & 1);
+        if (P.verify_wide)  // k_uvalues_level: one launch per level over the level-sorted 2-input gates
+            for (const VGate &g : P.vwgates) {
+                const uint32_t x = uv[g.a >> 1] ^ (g.a & 1), y = uv[g.b >> 1] ^ (g.b & 1);
+                uv[g.dst] = (uint8_t)((g.op ? (x & y) : (x ^ y)) & 1);
             }
         for (uint32_t st = 0; st < P.n_vlut_steps; st++)
             for (uint32_t t = 0; t < LUT_STEP; t++) {

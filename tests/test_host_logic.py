@@ -389,3 +389,52 @@ def test_skipped_assert_is_visible_in_okay(default_seeds):
     assert hostsim.verify(ops, wc, forged)[:2] == (1, False)
     tap = {}
     assert R.verify(R.deserialize(forged), orc.ops_to_tuples(ops), wc, tap=tap) and tap["okay"] is False
+
+
+def test_one_shot_circuit_cache():
+    """rv_proof_new / rv_proof_verify (the reference's call shape: the op list with every call) compile a circuit once and find
+    it again by content; a verification upgrades a prove-only entry; a different op list is a different entry."""
+    L = N.lib()
+    L.rv_circuit_cache_clear()
+    h, m, n = C.c_uint64(), C.c_uint64(), C.c_size_t()
+
+    def stats():
+        L.rv_circuit_cache_stats(C.byref(h), C.byref(m), C.byref(n))
+        return h.value, m.value, n.value
+
+    h0, m0, _ = stats()
+    ops, wc = CI.flat_mul_circuit(100)
+    ops = np.ascontiguousarray(ops)
+    wit = np.array([1, 1], dtype=np.uint8)
+    out, ln = C.c_void_p(), C.c_size_t()
+    have_gpu = L.rv_device_count() > 0
+
+    def prove(o):
+        rc = L.rv_proof_new(o.ctypes.data_as(C.c_void_p), o.size, wit.ctypes.data_as(C.c_void_p), 2, None, 0, wc[0], wc[1], None, C.byref(out), C.byref(ln))
+        assert rc == (0 if have_gpu else N.E_CUDA)
+        if rc == 0:
+            L.rv_free(out)
+
+    prove(ops)
+    assert stats() == (h0, m0 + 1, 1)
+    prove(ops.copy())  # same content at another address
+    assert stats() == (h0 + 1, m0 + 1, 1)
+    ops2 = ops.copy()
+    ops2["b"][50] = 0
+    prove(ops2)
+    assert stats() == (h0 + 1, m0 + 2, 2)
+    blob = np.zeros(40, dtype=np.uint8)
+    rc = L.rv_proof_verify(ops.ctypes.data_as(C.c_void_p), ops.size, wc[0], wc[1], blob.ctypes.data_as(C.c_void_p), blob.size)
+    assert rc == N.E_FORMAT  # malformed proof bytes -- but the circuit was compiled WITH verifier tables and replaced its prove-only twin
+    assert stats() == (h0 + 1, m0 + 3, 2)
+    prove(ops)  # the upgraded entry serves proving too
+    assert stats() == (h0 + 2, m0 + 3, 2)
+    L.rv_circuit_cache_limit(1)
+    prove(ops2)
+    prove(ops)
+    assert stats()[2] == 1
+    L.rv_circuit_cache_limit(8)
+    L.rv_circuit_cache_clear()
+    assert stats()[2] == 0
+    st = __import__("reverie_b200").Circuit(ops, wc, prove_only=True).stats()
+    assert st["has_verify"] == 0 and st["compile_ns"] > 0
