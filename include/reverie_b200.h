@@ -63,7 +63,8 @@ enum rv_status {
     RV_E_ARG = -4,             /* bad argument / wire index out of range for the given wire_counts */
     RV_E_CUDA = -5,            /* CUDA runtime failure or no device */
     RV_E_NOMEM = -6,
-    RV_E_UNSUPPORTED = -7      /* a shape the device path does not serve (reported, never silently degraded): see DESIGN.md section 8 */
+    RV_E_UNSUPPORTED = -7,     /* a shape the device path does not serve (reported, never silently degraded): see DESIGN.md section 8 */
+    RV_E_PEER = -8             /* multi-GPU: a linked session of another rank never arrived (the role SURVEY.md 8(b) gives RV_E_NCCL) */
 };
 
 typedef struct rv_circuit rv_circuit; /* a compiled circuit: device-resident gate tables, reusable across proofs  */
@@ -227,6 +228,26 @@ int rv_session_slots(const rv_session *s);
 size_t rv_session_proof_stride(const rv_session *s);
 int rv_proof_assemble(const uint8_t comm[RV_HASH_SIZE], const uint8_t *const *parts, const size_t *part_lens,
                       int n_parts, uint8_t **proof, size_t *proof_len);
+/* ---------------------------------------------------------------------------------------------------------------
+ * Multi-GPU: linking the sessions that hold the shards of one proof on different GPUs.
+ * The one exchange of the protocol -- the all-gather of the 256 x 32-byte repetition hashes, src/proof/mod.rs:160-171 -- and
+ * the assembly of the openings (src/proof/mod.rs:200-221) then run over NVLink peer memory INSIDE the open phase: each rank's
+ * challenge kernel stores its hashes into every rank's receive buffer and waits on per-rank flags; each rank's extraction
+ * writes its entries straight into the assembling rank's (rank 0) proof buffer.  A linked shard is driven like a full one:
+ * rv_session_prove / rv_batch_prove = one CUDA graph launch per rank and step, no collective library, no host hop.
+ *   rv_session_peer_handle   opaque RV_PEER_HANDLE_BYTES naming this session (exchange block + proof buffer): raw device
+ *                            pointers for sessions of the same process, CUDA IPC handles across processes
+ *   rv_session_peer_link     rank r of `world` (2..16, world * n_instances == 32, shard r = instances [32 r / world, ...)) passes
+ *                            all ranks' handles in rank order (exchanged by any host channel: MPI, torch.distributed, a pipe)
+ * Every rank must then run the same sequence of prove steps; a rank that never arrives makes the others' status RV_E_PEER
+ * after RV_PEER_TIMEOUT_MS (environment, default 60000).  rv_session_fetch on rank 0 returns the whole proof; on the other
+ * ranks it returns the status and comm with *part = NULL.
+ * ------------------------------------------------------------------------------------------------------------- */
+#define RV_PEER_HANDLE_BYTES 256
+int rv_session_peer_handle(rv_session *s, uint8_t handle[RV_PEER_HANDLE_BYTES]);
+int rv_session_peer_link(rv_session *s, int rank, int world, const uint8_t *handles /* world x RV_PEER_HANDLE_BYTES */);
+int rv_session_peer_rank(const rv_session *s, int *rank, int *world, int *assembles);
+
 /* cudaStream_t of the session (as void*), so callers can bracket work with their own CUDA events. */
 void *rv_session_stream(rv_session *s);
 

@@ -8,7 +8,8 @@ import os
 
 from . import _build
 
-RV_OK, E_WITNESS_INVALID, E_WITNESS_SHORT, E_FORMAT, E_ARG, E_CUDA, E_NOMEM, E_UNSUPPORTED = 0, -1, -2, -3, -4, -5, -6, -7
+RV_OK, E_WITNESS_INVALID, E_WITNESS_SHORT, E_FORMAT, E_ARG, E_CUDA, E_NOMEM, E_UNSUPPORTED, E_PEER = 0, -1, -2, -3, -4, -5, -6, -7, -8
+PEER_HANDLE_BYTES = 256
 TOTAL_REPS, ONLINE_REPS, PACKED_REPS, PLAYERS = 256, 40, 32, 8
 
 
@@ -32,6 +33,9 @@ def lib() -> C.CDLL:
     if _lib is not None:
         return _lib
     path = _build.LIB if os.path.exists(_build.LIB) and not _build._stale() else _build.build()
+    # one hardware work queue per stream (the default is 8, shared): the sessions of a batch run on their own streams, and the
+    # challenge kernel of a linked session waits on the device for its peers -- work of another stream must not queue up behind it
+    os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
     L = C.CDLL(path)
     vp, sz, i32 = C.c_void_p, C.c_size_t, C.c_int
     pp, psz = C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)
@@ -84,6 +88,9 @@ def lib() -> C.CDLL:
         "rv_session_timing": ([vp, i32], i32),
         "rv_session_kernel_times": ([vp, C.POINTER(KernelTime), i32, i32], i32),
         "rv_session_launch_count": ([vp], C.c_uint64),
+        "rv_session_peer_handle": ([vp, vp], i32),
+        "rv_session_peer_link": ([vp, i32, i32, vp], i32),
+        "rv_session_peer_rank": ([vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], i32),
     }
     for name, (args, res) in sigs.items():
         fn = getattr(L, name)  # AttributeError here = the library does not export what include/reverie_b200.h declares
@@ -96,7 +103,8 @@ EXPORTED = (
     "rv_last_error rv_version rv_device_count rv_set_device rv_circuit_compile rv_circuit_compile_ex rv_circuit_cache_clear rv_circuit_cache_limit rv_circuit_cache_stats rv_proof_verify_ex rv_circuit_free rv_circuit_get_stats "
     "rv_circuit_export rv_prove rv_prove_batch rv_session_slots rv_session_proof_stride rv_verify rv_proof_new rv_proof_verify rv_free rv_session_create rv_session_create_multi rv_session_upload_slot rv_session_fetch_slot rv_session_free "
     "rv_session_upload rv_session_commit rv_session_hashes rv_session_hashes_device rv_session_all_hashes_device rv_session_open rv_session_prove rv_session_fetch rv_session_sync rv_session_status rv_session_proof_device "
-    "rv_proof_assemble rv_batch_create rv_batch_free rv_batch_commit rv_batch_open rv_batch_prove rv_batch_stream rv_session_stream rv_session_timing rv_session_kernel_times rv_session_launch_count"
+    "rv_proof_assemble rv_batch_create rv_batch_free rv_batch_commit rv_batch_open rv_batch_prove rv_batch_stream rv_session_stream rv_session_timing rv_session_kernel_times rv_session_launch_count "
+    "rv_session_peer_handle rv_session_peer_link rv_session_peer_rank"
 ).split()
 
 

@@ -2,6 +2,7 @@
 // Host orchestration only; every byte of proof data is produced by the kernels in rv_kernels.cu.
 #include <cuda_runtime.h>
 #include <sys/random.h>
+#include <unistd.h>
 
 #include <chrono>
 #include <cstdio>
@@ -349,7 +350,8 @@ struct rv_session {
         cudaGraphExec_t exec = nullptr;
         int calls = 0;
         uint64_t kernels = 0;
-    } g_prove /* commit + open of a full shard */, g_commit, g_open /* open from the session's own all-gather buffer */;
+    } g_prove /* commit + open of a full shard */, g_commit, g_open /* open from the session's own all-gather buffer */,
+      g_open_x /* open of a linked shard: exchange over peer memory */;
     // device buffers
     uint8_t *d_wit = nullptr, *d_seeds = nullptr, *d_pkeys = nullptr, *d_vals = nullptr;
     uint64_t *d_tvals = nullptr;  // tainted plane [n_tvals][npi]
@@ -399,6 +401,15 @@ struct rv_session {
     // batching (rv_batch): host-initiated work of a bound session goes to the leader's stream; the phases fork from / join into it
     rv_session *lead = nullptr;
     cudaEvent_t ev_bjoin = nullptr;
+    // exchange block (flags + double-buffered receive buffers of the repetition hashes; d_all_hashes points into it) and, once
+    // rv_session_peer_link has run, the blocks of the sessions that hold the other shards of the same proofs on other GPUs
+    uint8_t *d_xchg = nullptr;
+    size_t xchg_bytes = 0, proof_alloc_bytes = 0;
+    XchgArgs x;                      // world == 1: not linked
+    uint8_t *dst_proof = nullptr;    // the assembling rank's proof buffer as mapped here (== d_proof on that rank)
+    std::vector<void *> ipc_opened;  // cudaIpcOpenMemHandle mappings to close
+    bool linked() const { return x.world > 1; }
+    bool assembles() const { return x.world == 1 || x.rank == x.dst; }
 };
 static cudaStream_t host_stream(const rv_session *s) { return s->lead ? s->lead->st : s->st; }
 
@@ -423,6 +434,7 @@ extern "C" void rv_session_free(rv_session *s) {
             cudaEventDestroy(p.first);
             cudaEventDestroy(p.second);
         }
+    for (void *p : s->ipc_opened) cudaIpcCloseMemHandle(p);
     for (void *p : s->allocs) cudaFree(p);
     if (s->h_in) cudaFreeHost(s->h_in);
     if (s->h_out) cudaFreeHost(s->h_out);
@@ -430,7 +442,7 @@ extern "C" void rv_session_free(rv_session *s) {
     if (s->h_vout) cudaFreeHost(s->h_vout);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_bjoin) cudaEventDestroy(s->ev_bjoin);
-    for (rv_session::GraphSlot *g : {&s->g_prove, &s->g_commit, &s->g_open})
+    for (rv_session::GraphSlot *g : {&s->g_prove, &s->g_commit, &s->g_open, &s->g_open_x})
         if (g->exec) cudaGraphExecDestroy(g->exec);
     if (s->ev_vals) cudaEventDestroy(s->ev_vals);
     if (s->st && s->own_stream) cudaStreamDestroy(s->st);
@@ -524,10 +536,17 @@ extern "C" int rv_session_create_multi(const rv_circuit *c, int first_instance, 
         (rc = dalloc(s, &s->d_rows, (size_t)P.n_rows * s->npi)) || (rc = dalloc(s, &s->d_on, s->pitch_on * s->nreps)) ||
         (rc = dalloc(s, &s->d_pre, s->pitch_pre * s->nreps)) || (rc = dalloc(s, &s->d_cv_on, (size_t)s->n_chunks_on * s->nreps * 8)) ||
         (rc = dalloc(s, &s->d_cv_pre, (size_t)s->n_chunks_pre * s->nreps * 8)) || (rc = dalloc(s, &s->d_on_hash, (size_t)s->nreps * 32)) ||
-        (rc = dalloc(s, &s->d_rep_hash, (size_t)s->nreps * 32)) || (rc = dalloc(s, &s->d_all_hashes, (size_t)RV_TOTAL_REPS * 32 * s->n_proofs)) ||
+        (rc = dalloc(s, &s->d_rep_hash, (size_t)s->nreps * 32)) ||
         (rc = dalloc(s, &s->d_omit, (size_t)RV_TOTAL_REPS * s->n_proofs)) || (rc = dalloc(s, &s->d_rank, (size_t)RV_TOTAL_REPS * s->n_proofs)) ||
-        (rc = dalloc(s, &s->d_zconst, 16)) || (rc = dalloc(s, &s->d_proof, s->proof_pitch * s->n_proofs)))
+        (rc = dalloc(s, &s->d_zconst, 16)))
         return bail(rc);
+    // The exchange block and the proof buffer can be mapped into other processes (rv_session_peer_handle): each is its own
+    // allocation of whole 2 MiB pages, so that an IPC mapping exposes nothing else.
+    s->xchg_bytes = round_up(XchgLayout{s->n_proofs}.total(), (size_t)2 << 20);
+    s->proof_alloc_bytes = round_up(s->proof_pitch * s->n_proofs, (size_t)2 << 20);
+    if ((rc = dalloc(s, &s->d_xchg, s->xchg_bytes)) || (rc = dalloc(s, &s->d_proof, s->proof_alloc_bytes))) return bail(rc);
+    if (cudaMemset(s->d_xchg, 0, s->xchg_bytes) != cudaSuccess) return bail(fail(RV_E_CUDA, "cudaMemset failed"));
+    s->d_all_hashes = s->d_xchg + XchgLayout{s->n_proofs}.off_hash(0);
     // the status flag and comm live right behind the proof bytes, so one device-to-host copy returns all three
     s->d_bad = reinterpret_cast<int *>(s->d_proof + s->tail_off);
     s->d_comm = s->d_proof + s->tail_off + 4;
@@ -796,7 +815,10 @@ static int open_body(rv_session *s, const uint8_t *all_rep_hashes) {
     const rv_circuit *c = s->c;
     const DevProgram &D = c->dev;
     const uint8_t *hashes = s->d_all_hashes;
-    if (all_rep_hashes == s->d_all_hashes) {
+    const bool linked = s->linked() && all_rep_hashes == nullptr;  // the exchange happens inside k_challenge, over peer memory
+    if (linked) {
+        hashes = nullptr;
+    } else if (all_rep_hashes == s->d_all_hashes) {
         // gathered in place (rv_session_all_hashes_device): nothing to copy
     } else if (all_rep_hashes) {
         cudaPointerAttributes at;
@@ -805,16 +827,17 @@ static int open_body(rv_session *s, const uint8_t *all_rep_hashes) {
         CU(cudaMemcpyAsync(s->d_all_hashes, all_rep_hashes, (size_t)RV_TOTAL_REPS * 32 * s->n_proofs, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice,
                            s->st));
     } else {
-        if (s->npi1 != RV_PACKED_REPS) return fail(RV_E_ARG, "a partial shard needs the all-gathered repetition hashes");
+        if (s->npi1 != RV_PACKED_REPS) return fail(RV_E_ARG, "a partial shard needs the all-gathered repetition hashes (or rv_session_peer_link)");
         hashes = s->d_rep_hash;
     }
     {
         // the gathered hashes are rank-major over the session's proofs: [rank][proof][this rank's repetitions x 32 bytes]
         Scope k(s, "challenge", (uint64_t)RV_TOTAL_REPS * 32 * s->n_proofs);
-        launch_challenge(hashes, s->nreps1 * 32, s->d_comm, s->proof_pitch, s->d_omit, s->d_rank, s->n_proofs, s->st);
+        launch_challenge(hashes, s->nreps1 * 32, s->d_comm, s->proof_pitch, s->d_omit, s->d_rank, s->n_proofs, s->st, linked ? &s->x : nullptr, s->d_rep_hash);
     }
-    if (s->npi1 != RV_PACKED_REPS)  // a full shard writes every byte of the proof
-        CU(cudaMemset2DAsync(s->d_proof, s->proof_pitch, 0, s->proof_len, s->n_proofs, s->st));
+    // a full shard writes every byte of the proof, and so do the linked shards together (each straight into the assembling rank's buffer)
+    if (s->npi1 != RV_PACKED_REPS && !linked) CU(cudaMemset2DAsync(s->d_proof, s->proof_pitch, 0, s->proof_len, s->n_proofs, s->st));
+    uint8_t *proof_out = linked ? s->dst_proof : s->d_proof;
     {
         Scope k(s, "extract", s->proof_len);
         ExtractArgs a;
@@ -840,7 +863,7 @@ static int open_body(rv_session *s, const uint8_t *all_rep_hashes) {
         a.len_zcorrs = s->len_zcorrs;
         a.len_zinputs = s->len_zinputs;
         a.z_on_hash = s->has_z ? s->d_zon_hash : nullptr;
-        a.proof = s->d_proof;
+        a.proof = proof_out;
         launch_extract(D, a, s->st);
     }
     if (s->has_z) {
@@ -857,11 +880,18 @@ static int open_body(rv_session *s, const uint8_t *all_rep_hashes) {
         a.nreps = s->nreps;
         a.z_base = L.z_base();
         a.sz_on_z = L.sz_on_z();
-        a.proof = s->d_proof;
+        a.proof = proof_out;
         launch_zextract(c->zdev, a, s->st);
     }
-    if (s->out_off) CU(cudaMemcpyAsync(s->h_out, s->d_proof, s->proof_pitch * s->n_proofs, cudaMemcpyDeviceToHost, s->st));  // h_out mirrors d_proof
-    else CU(cudaMemcpyAsync(s->h_out, s->d_proof + s->tail_off, 36, cudaMemcpyDeviceToHost, s->st));
+    if (linked) {
+        Scope k(s, "xfinish", 0);
+        launch_xfinish(s->x, s->n_proofs, s->d_bad, s->proof_pitch, s->st);
+    }
+    if (s->out_off && (!linked || s->assembles()))
+        CU(cudaMemcpyAsync(s->h_out, s->d_proof, s->proof_pitch * s->n_proofs, cudaMemcpyDeviceToHost, s->st));  // h_out mirrors d_proof
+    else  // status word + comm of every proof (big proofs are copied by rv_session_fetch; a non-assembling rank has no proof bytes)
+        CU(cudaMemcpy2DAsync(s->h_out + s->out_off, s->out_off ? s->proof_pitch : 64, s->d_proof + s->tail_off, s->proof_pitch, 36, s->n_proofs,
+                             cudaMemcpyDeviceToHost, s->st));
     CU(cudaGetLastError());
     return RV_OK;
 }
@@ -872,6 +902,7 @@ extern "C" int rv_session_open(rv_session *s, const uint8_t *all_rep_hashes) {
     CU(cudaSetDevice(s->c->device));
     int rc;
     if (all_rep_hashes == s->d_all_hashes) rc = run_graphed(s, s->g_open, [&] { return open_body(s, all_rep_hashes); });
+    else if (!all_rep_hashes && s->linked()) rc = run_graphed(s, s->g_open_x, [&] { return open_body(s, nullptr); });
     else rc = open_body(s, all_rep_hashes);  // caller-owned buffer: its address may change from call to call
     if (rc == RV_OK) s->opened = true;
     return rc;
@@ -881,7 +912,7 @@ extern "C" int rv_session_open(rv_session *s, const uint8_t *all_rep_hashes) {
 // the device-to-host copy of the proof) is captured once and replayed as a single CUDA graph launch.
 extern "C" int rv_session_prove(rv_session *s) {
     if (!s) return fail(RV_E_ARG, "NULL session");
-    if (s->npi1 != RV_PACKED_REPS) return fail(RV_E_ARG, "rv_session_prove needs a full shard");
+    if (s->npi1 != RV_PACKED_REPS && !s->linked()) return fail(RV_E_ARG, "rv_session_prove needs a full shard, or a shard linked to its peers (rv_session_peer_link)");
     CU(cudaSetDevice(s->c->device));
     const int rc = run_graphed(s, s->g_prove, [&] {
         const int r = commit_body(s);
@@ -955,7 +986,7 @@ static int batch_run(rv_batch *b, int kind) {
             if (!s->committed) return fail(RV_E_ARG, "rv_batch_commit has not run");
     if (kind == 2)
         for (rv_session *s : b->ss)
-            if (s->npi1 != RV_PACKED_REPS) return fail(RV_E_ARG, "rv_batch_prove needs full shards");
+            if (s->npi1 != RV_PACKED_REPS && !s->linked()) return fail(RV_E_ARG, "rv_batch_prove needs full shards, or shards linked to their peers");
     bool timing = false;
     std::vector<uint64_t> before;
     for (rv_session *s : b->ss) {
@@ -997,6 +1028,13 @@ extern "C" int rv_batch_open(rv_batch *b) { return b ? batch_run(b, 1) : fail(RV
 extern "C" int rv_batch_prove(rv_batch *b) { return b ? batch_run(b, 2) : fail(RV_E_ARG, "NULL batch"); }
 extern "C" void *rv_batch_stream(rv_batch *b) { return b ? (void *)b->ss[0]->st : nullptr; }
 
+// the status word of a proof: RV_BAD_WITNESS (an AssertZero saw a non-zero value), RV_BAD_PEER_TIMEOUT (a linked rank never arrived)
+static int status_of(int bad) {
+    if (bad & RV_BAD_PEER_TIMEOUT) return fail(RV_E_PEER, "a linked session of another rank did not arrive in time (rv_session_peer_link: every rank must run the same steps)");
+    if (bad) return fail(RV_E_WITNESS_INVALID, "witness is invalid!");  // prover.rs:223
+    return RV_OK;
+}
+
 extern "C" int rv_session_fetch(rv_session *s, uint8_t comm[RV_HASH_SIZE], uint8_t **part, size_t *part_len) {
     return rv_session_fetch_slot(s, 0, comm, part, part_len);
 }
@@ -1010,7 +1048,13 @@ extern "C" int rv_session_fetch_slot(rv_session *s, int slot, uint8_t comm[RV_HA
     const uint8_t *hout = s->h_out + (size_t)slot * (s->out_off ? s->proof_pitch : 64);
     int bad;
     memcpy(&bad, hout + s->out_off, 4);
-    if (bad) return fail(RV_E_WITNESS_INVALID, "witness is invalid!");  // prover.rs:223
+    if (const int st = status_of(bad)) return st;
+    if (s->linked() && !s->assembles()) {  // the proof bytes live on the assembling rank; this rank reports its status and comm
+        if (comm) memcpy(comm, hout + s->out_off + 4, 32);
+        *part = nullptr;
+        *part_len = 0;
+        return RV_OK;
+    }
     uint8_t *p;
     if (s->out_off) {
         p = (uint8_t *)malloc(s->proof_len);
@@ -1040,7 +1084,7 @@ extern "C" int rv_session_status(rv_session *s) {
     for (uint32_t b = 0; b < s->n_proofs; b++) {
         int bad;
         memcpy(&bad, s->h_out + (size_t)b * (s->out_off ? s->proof_pitch : 64) + s->out_off, 4);
-        if (bad) return fail(RV_E_WITNESS_INVALID, "witness is invalid!");  // prover.rs:223
+        if (const int st = status_of(bad)) return st;
     }
     return RV_OK;
 }
@@ -1052,6 +1096,125 @@ extern "C" int rv_session_proof_device(rv_session *s, void **ptr, size_t *len) {
     if (!s || !ptr || !len) return fail(RV_E_ARG, "NULL argument");
     *ptr = s->d_proof;
     *len = s->proof_len;
+    return RV_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+//  Linking the shards of one proof across GPUs (the exchange of src/proof/mod.rs:160-171 and the assembly of
+//  :200-221 over NVLink peer memory instead of a collective library + host hop).  A handle names a session's exchange block and
+//  proof buffer: raw pointers for sessions of the same process (peer access), CUDA IPC handles across processes.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+struct PeerHandle {
+    uint64_t magic;
+    int32_t pid, device;
+    uint64_t xchg_ptr, proof_ptr, xchg_bytes, proof_bytes, proof_len;
+    uint32_t n_proofs, npi1, first_instance, pad;
+    cudaIpcMemHandle_t ipc_xchg, ipc_proof;
+};
+static_assert(sizeof(PeerHandle) <= RV_PEER_HANDLE_BYTES, "handle layout");
+constexpr uint64_t PEER_MAGIC = 0x3130424b50565252ull;  // "RRVPKB01"
+}  // namespace
+
+extern "C" int rv_session_peer_handle(rv_session *s, uint8_t *out) {
+    if (!s || !out) return fail(RV_E_ARG, "NULL argument");
+    CU(cudaSetDevice(s->c->device));
+    PeerHandle h;
+    memset(&h, 0, sizeof h);
+    h.magic = PEER_MAGIC;
+    h.pid = (int32_t)getpid();
+    h.device = s->c->device;
+    h.xchg_ptr = (uint64_t)(uintptr_t)s->d_xchg;
+    h.proof_ptr = (uint64_t)(uintptr_t)s->d_proof;
+    h.xchg_bytes = s->xchg_bytes;
+    h.proof_bytes = s->proof_alloc_bytes;
+    h.proof_len = s->proof_len;
+    h.n_proofs = s->n_proofs;
+    h.npi1 = s->npi1;
+    h.first_instance = s->first_instance;
+    CU(cudaIpcGetMemHandle(&h.ipc_xchg, s->d_xchg));
+    CU(cudaIpcGetMemHandle(&h.ipc_proof, s->d_proof));
+    memset(out, 0, RV_PEER_HANDLE_BYTES);
+    memcpy(out, &h, sizeof h);
+    return RV_OK;
+}
+
+extern "C" int rv_session_peer_link(rv_session *s, int rank, int world, const uint8_t *handles) {
+    if (!s || !handles) return fail(RV_E_ARG, "NULL argument");
+    if (world < 2 || world > RV_MAX_PEERS || rank < 0 || rank >= world) return fail(RV_E_ARG, "a link joins 2..16 ranks");
+    if (s->linked()) return fail(RV_E_ARG, "session is already linked");
+    if ((uint32_t)world * s->npi1 != RV_PACKED_REPS || s->first_instance != (uint32_t)rank * s->npi1)
+        return fail(RV_E_ARG, "rank r of a link holds packed instances [32 r / world, 32 (r + 1) / world)");
+    CU(cudaSetDevice(s->c->device));
+    CU(cudaStreamSynchronize(host_stream(s)));
+    XchgArgs x;
+    x.world = (uint32_t)world;
+    x.rank = (uint32_t)rank;
+    x.dst = 0;
+    uint64_t tmo_ms = 60000;
+    if (const char *e = getenv("RV_PEER_TIMEOUT_MS")) tmo_ms = strtoull(e, nullptr, 10);
+    x.timeout_ns = tmo_ms * 1000000ull;
+    uint8_t *dst_proof = nullptr;
+    std::vector<void *> opened;
+    auto undo = [&](int code) {
+        for (void *p : opened) cudaIpcCloseMemHandle(p);
+        return code;
+    };
+    for (int r = 0; r < world; r++) {
+        PeerHandle h;
+        memcpy(&h, handles + (size_t)r * RV_PEER_HANDLE_BYTES, sizeof h);
+        if (h.magic != PEER_MAGIC) return undo(fail(RV_E_ARG, "not a peer handle"));
+        if (h.n_proofs != s->n_proofs || h.npi1 != s->npi1 || h.first_instance != (uint32_t)r * s->npi1 || h.proof_len != s->proof_len ||
+            h.xchg_bytes != s->xchg_bytes || h.proof_bytes != s->proof_alloc_bytes)
+            return undo(fail(RV_E_ARG, "the linked sessions must hold the same circuit, slot count and consecutive shards in rank order"));
+        uint8_t *xp = nullptr, *pp = nullptr;
+        if (r == rank) {
+            if (h.xchg_ptr != (uint64_t)(uintptr_t)s->d_xchg) return undo(fail(RV_E_ARG, "handles[rank] is not this session's handle"));
+            xp = s->d_xchg;
+            pp = s->d_proof;
+        } else if (h.pid == (int32_t)getpid()) {  // same process: plain pointers, peer access between the two devices
+            if (h.device != s->c->device) {
+                int can = 0;
+                CU(cudaDeviceCanAccessPeer(&can, s->c->device, h.device));
+                if (!can) return undo(fail(RV_E_UNSUPPORTED, "no peer access between the linked devices"));
+                const cudaError_t e = cudaDeviceEnablePeerAccess(h.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return undo(fail(RV_E_CUDA, std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)));
+                cudaGetLastError();
+            }
+            xp = reinterpret_cast<uint8_t *>((uintptr_t)h.xchg_ptr);
+            pp = reinterpret_cast<uint8_t *>((uintptr_t)h.proof_ptr);
+        } else {  // another process: CUDA IPC
+            void *m = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&m, h.ipc_xchg, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return undo(fail(RV_E_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)));
+            opened.push_back(m);
+            xp = reinterpret_cast<uint8_t *>(m);
+            if (r == (int)x.dst) {
+                e = cudaIpcOpenMemHandle(&m, h.ipc_proof, cudaIpcMemLazyEnablePeerAccess);
+                if (e != cudaSuccess) return undo(fail(RV_E_CUDA, std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(e)));
+                opened.push_back(m);
+                pp = reinterpret_cast<uint8_t *>(m);
+            }
+        }
+        x.peer[r] = xp;
+        if (r == (int)x.dst) dst_proof = pp;
+    }
+    s->x = x;
+    s->dst_proof = dst_proof;
+    s->ipc_opened = opened;
+    // graphs captured before the link describe the unlinked phases
+    for (rv_session::GraphSlot *g : {&s->g_prove, &s->g_open_x}) {
+        if (g->exec) cudaGraphExecDestroy(g->exec);
+        *g = rv_session::GraphSlot();
+    }
+    return RV_OK;
+}
+
+extern "C" int rv_session_peer_rank(const rv_session *s, int *rank, int *world, int *assembles) {
+    if (!s) return fail(RV_E_ARG, "NULL session");
+    if (rank) *rank = (int)s->x.rank;
+    if (world) *world = (int)s->x.world;
+    if (assembles) *assembles = s->assembles() ? 1 : 0;
     return RV_OK;
 }
 

@@ -914,20 +914,78 @@ void launch_verify_items(const DevProgram &P, const VOpen *opens, const uint8_t 
 // =====================================================================================================================
 // grid.x = proof of the session.  The 256 hashes of proof b arrive as n_seg segments of seg_bytes (one per rank of the
 // all-gather, rank-major over the session's proofs): segment r of proof b starts at all_hashes + (r * n_proofs + b) * seg_bytes.
-__global__ void __launch_bounds__(32) k_challenge(const uint8_t *__restrict__ all_hashes_base, uint32_t seg_bytes, uint8_t *__restrict__ comm_base,
-                                                  size_t comm_stride, uint8_t *__restrict__ omit_base, uint16_t *__restrict__ rank_base) {
+//
+// Linked sessions (x.world > 1; rv_session_peer_link): the all-gather of src/proof/mod.rs:160-171 happens HERE, over peer memory.
+// The warp of proof b first stores this rank's segment into every rank's receive buffer (NVLink peer stores; double-buffered by
+// the parity of the proof's step counter), publishes it with a system-scope release of the step number into each rank's flag
+// word, then waits (system-scope acquire) until the flags of all ranks carry this step: commit -> gather -> challenge is one
+// kernel, no host pacing, no collective library on the data path.
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint64_t globaltimer_ns() {
+    uint64_t t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+// Spins until *flag == want (lanes with active == false return at once); false on timeout.
+__device__ __forceinline__ bool wait_flag(const uint32_t *flag, uint32_t want, bool active, uint64_t timeout_ns) {
+    if (!active) return true;
+    const uint64_t t0 = globaltimer_ns();
+    uint32_t spins = 0;
+    while (ld_acquire_sys(flag) != want) {
+        if ((++spins & 1023u) == 0 && globaltimer_ns() - t0 > timeout_ns) return false;
+        __nanosleep(64);
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(32) k_challenge(const uint8_t *all_hashes_base, uint32_t seg_bytes, uint8_t *__restrict__ comm_base,
+                                                  size_t comm_stride, uint8_t *__restrict__ omit_base, uint16_t *__restrict__ rank_base, XchgArgs x,
+                                                  const uint8_t *__restrict__ own_hashes) {
     const uint32_t pb = blockIdx.x, n_proofs = gridDim.x;
     uint8_t *comm = comm_base + pb * comm_stride, *omit_of_rep = omit_base + pb * RV_TOTAL_REPS;
     uint16_t *rank_of_rep = rank_base + pb * RV_TOTAL_REPS;
     __shared__ uint32_t cv[8][8];
     __shared__ uint32_t xof[32][16];
     __shared__ uint8_t omit[RV_TOTAL_REPS];
+    __shared__ __align__(16) uint32_t hbuf[RV_TOTAL_REPS * 8];
     const uint32_t lane = threadIdx.x;
+    if (x.world > 1) {
+        const XchgLayout L{n_proofs};
+        uint32_t *step = reinterpret_cast<uint32_t *>(x.peer[x.rank] + L.off_step()) + pb;
+        const uint32_t e = *step + 1, par = e & 1;
+        const uint4 *src = reinterpret_cast<const uint4 *>(own_hashes + (size_t)pb * seg_bytes);
+        for (uint32_t r = 0; r < x.world; r++) {
+            uint4 *dst = reinterpret_cast<uint4 *>(x.peer[r] + L.off_hash(par) + ((size_t)x.rank * n_proofs + pb) * seg_bytes);
+            for (uint32_t i = lane; i < seg_bytes / 16; i += 32) dst[i] = src[i];
+        }
+        __threadfence_system();
+        __syncwarp();
+        if (lane < x.world) st_release_sys(reinterpret_cast<uint32_t *>(x.peer[lane] + L.off_flag(par, x.rank)) + pb, e);
+        const bool ok = wait_flag(reinterpret_cast<const uint32_t *>(x.peer[x.rank] + L.off_flag(par, lane)) + pb, e, lane < x.world, x.timeout_ns);
+        if (!__all_sync(0xffffffffu, ok) && lane == 0) atomicOr(reinterpret_cast<int *>(comm - 4), RV_BAD_PEER_TIMEOUT);  // the flag word sits right before comm
+        __threadfence_system();
+        if (lane == 0) *step = e;
+        all_hashes_base = x.peer[x.rank] + L.off_hash(par);
+    }
     // combine_hashes (src/proof/mod.rs:102-108): BLAKE3 of 256 x 32 B = 8 chunks
+    {   // the hashes may have been written by other GPUs a moment ago: fetch them with coherent (volatile) loads into shared memory
+        for (uint32_t i = lane; i < RV_TOTAL_REPS * 2; i += 32) {  // 16-byte pieces; a 1 KiB chunk (32 hashes) never straddles segments (>= 32 repetitions each)
+            const uint32_t byte0 = 16 * i, seg = byte0 / seg_bytes;
+            const uint4 *p = reinterpret_cast<const uint4 *>(all_hashes_base + ((size_t)seg * n_proofs + pb) * seg_bytes + (byte0 - seg * seg_bytes));
+            uint4 v;
+            asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+            reinterpret_cast<uint4 *>(hbuf)[i] = v;
+        }
+        __syncwarp();
+    }
     if (lane < 8) {
         uint32_t c[8];
-        const uint32_t byte0 = 1024 * lane, seg = byte0 / seg_bytes;  // a 1 KiB chunk (32 hashes) never straddles segments (>= 32 repetitions each)
-        b3_chunk_cv(reinterpret_cast<const uint32_t *>(all_hashes_base + ((size_t)seg * n_proofs + pb) * seg_bytes + (byte0 - seg * seg_bytes)), 1024, lane, false, c);
+        b3_chunk_cv(hbuf + 256 * lane, 1024, lane, false, c);
         for (int i = 0; i < 8; i++) cv[lane][i] = c[i];
     }
     __syncwarp();
@@ -967,9 +1025,32 @@ __global__ void __launch_bounds__(32) k_challenge(const uint8_t *__restrict__ al
 }
 
 void launch_challenge(const uint8_t *all_hashes, uint32_t seg_bytes, uint8_t *comm, size_t comm_stride, uint8_t *omit_of_rep, uint16_t *rank_of_rep,
-                      uint32_t n_proofs, cudaStream_t st) {
-    k_challenge<<<n_proofs, 32, 0, st>>>(all_hashes, seg_bytes, comm, comm_stride, omit_of_rep, rank_of_rep);
+                      uint32_t n_proofs, cudaStream_t st, const XchgArgs *x, const uint8_t *own_hashes) {
+    XchgArgs none;
+    k_challenge<<<n_proofs, 32, 0, st>>>(all_hashes, seg_bytes, comm, comm_stride, omit_of_rep, rank_of_rep, x ? *x : none, own_hashes);
 }
+
+// Last kernel of a linked session's open phase (one warp).  Every rank's extraction wrote its entries straight into the assembling
+// rank's proof buffer; this publishes "rank r is done with step e" there, and on the assembling rank waits for all ranks before the
+// device-to-host copy that follows in stream order: the assembly of src/proof/mod.rs:200-221 with no reduce and no host hop.
+__global__ void __launch_bounds__(32) k_xfinish(XchgArgs x, uint32_t n_proofs, int *bad, size_t flag_stride) {
+    const XchgLayout L{n_proofs};
+    const uint32_t lane = threadIdx.x;
+    uint32_t *step = reinterpret_cast<uint32_t *>(x.peer[x.rank] + L.off_done_step());
+    const uint32_t e = *step + 1;
+    __threadfence_system();
+    if (lane == 0) st_release_sys(reinterpret_cast<uint32_t *>(x.peer[x.dst] + L.off_done()) + x.rank, e);
+    if (x.rank == x.dst) {
+        const bool ok = wait_flag(reinterpret_cast<const uint32_t *>(x.peer[x.rank] + L.off_done()) + lane, e, lane < x.world, x.timeout_ns);
+        if (!__all_sync(0xffffffffu, ok))
+            for (uint32_t b = lane; b < n_proofs; b += 32) atomicOr(reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(bad) + b * flag_stride), RV_BAD_PEER_TIMEOUT);
+        __threadfence_system();
+    }
+    __syncwarp();
+    if (lane == 0) *step = e;
+}
+
+void launch_xfinish(const XchgArgs &x, uint32_t n_proofs, int *bad, size_t flag_stride, cudaStream_t st) { k_xfinish<<<1, 32, 0, st>>>(x, n_proofs, bad, flag_stride); }
 
 // =====================================================================================================================
 //  K7  extraction: CTA = one repetition of the shard; writes its entry of the bincode `Proof` in place
@@ -1026,6 +1107,31 @@ int configure_kernels(int device) {
     set((const void *)k_mask_vm, (int)SMEM_DYN_CAP, true);  // two VM CTAs (~110 KB each for SHA-256) per SM need the full carveout
     set((const void *)k_items, 0, true);                    // ~35 KB tiles: six CTAs share an SM
     if (e == cudaSuccess) e = (cudaError_t)configure_zkernels();
+    // Load every kernel now.  With CUDA's lazy module loading the first launch of a function may have to wait for the device to go
+    // idle; the challenge kernel of a linked session waits for the other ranks on the device, so a first launch issued behind it
+    // (by a host thread that drives several GPUs, or several shards on one GPU) must never be the one that loads code.
+    auto load = [&](const void *fn) {
+        cudaFuncAttributes at;
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, fn);
+    };
+    load((const void *)k_key_setup);
+    load((const void *)k_values_leaves);
+    load((const void *)k_values_level);
+    load((const void *)k_uvalues_leaves);
+    load((const void *)k_uvalues_level);
+    load((const void *)k_linear_cta);
+    load((const void *)k_linear_level);
+    load((const void *)k_items_pre);
+    load((const void *)k_tainted);
+    load((const void *)k_chunk_cv);
+    load((const void *)k_rep_hash);
+    load((const void *)k_zrep_hash);
+    load((const void *)k_verify_leaves);
+    load((const void *)k_verify_items_online);
+    load((const void *)k_verify_items_pre);
+    load((const void *)k_challenge);
+    load((const void *)k_xfinish);
+    load((const void *)k_extract);
     if (e != cudaSuccess) return (int)e;
     done[device >> 6] |= 1ull << (device & 63);
     return 0;

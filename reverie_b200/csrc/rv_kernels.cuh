@@ -6,6 +6,14 @@
 
 #include "rv_compile.h"
 
+#ifndef RV_HD
+#if defined(__CUDACC__)
+#define RV_HD __host__ __device__ __forceinline__
+#else
+#define RV_HD inline
+#endif
+#endif
+
 namespace rv {
 
 // compiled tables resident in device memory
@@ -112,8 +120,29 @@ void launch_verify_items(const DevProgram &P, const VOpen *opens, const uint8_t 
 void launch_items_pre_range(const DevProgram &P, const uint64_t *rows, uint32_t npi, uint32_t first_pi, uint8_t *pre, size_t pitch_pre, cudaStream_t st);
 // K6  comm = H(256 rep hashes); Fiat-Shamir challenge (src/proof/mod.rs:74-108)
 //     one warp per proof of the session; the hashes arrive as segments of seg_bytes per rank (see k_challenge)
+//
+//     Linked sessions (rv_session_peer_link): the sessions that hold the shards of one proof on different GPUs each own an
+//     "exchange block" in device memory, mapped into every peer (CUDA IPC across processes, peer access inside one).
+constexpr int RV_MAX_PEERS = 16;
+constexpr int RV_BAD_WITNESS = 1, RV_BAD_PEER_TIMEOUT = 2;  // bits of a proof's status word
+struct XchgLayout {  // byte offsets inside an exchange block of a session with n_proofs slots
+    uint32_t n_proofs;
+    RV_HD size_t off_flag(uint32_t parity, uint32_t src_rank) const { return ((size_t)(parity * RV_MAX_PEERS + src_rank) * n_proofs) * 4; }  // u32 [2][MAX][n_proofs]: step number of the hashes that arrived
+    RV_HD size_t off_done() const { return off_flag(2, 0); }                      // u32 [MAX]: step number each rank finished extracting (read on the assembling rank)
+    RV_HD size_t off_step() const { return off_done() + RV_MAX_PEERS * 4; }       // u32 [n_proofs]: this rank's own step counter per proof
+    RV_HD size_t off_done_step() const { return off_step() + (size_t)n_proofs * 4; }  // u32: this rank's own counter of finished steps
+    RV_HD size_t off_hash(uint32_t parity) const { return ((off_done_step() + 4 + 255) & ~(size_t)255) + (size_t)parity * n_proofs * RV_TOTAL_REPS * 32; }  // [rank][proof][seg]
+    RV_HD size_t total() const { return off_hash(2); }
+};
+struct XchgArgs {
+    uint32_t world = 1, rank = 0, dst = 0;
+    uint64_t timeout_ns = 0;
+    uint8_t *peer[RV_MAX_PEERS] = {};  // exchange block of every rank, as mapped on this device (peer[rank] = the own one)
+};
 void launch_challenge(const uint8_t *all_hashes, uint32_t seg_bytes, uint8_t *comm, size_t comm_stride, uint8_t *omit_of_rep, uint16_t *rank_of_rep,
-                      uint32_t n_proofs, cudaStream_t st);
+                      uint32_t n_proofs, cudaStream_t st, const XchgArgs *x = nullptr, const uint8_t *own_hashes = nullptr);
+//     last kernel of a linked open phase: "this rank's entries are in the assembling rank's proof buffer"; the assembling rank waits for all
+void launch_xfinish(const XchgArgs &x, uint32_t n_proofs, int *bad, size_t flag_stride, cudaStream_t st);
 // K7  openings -> bincode bytes of `Proof` (src/transcript/prover.rs:57-175, src/proof/mod.rs:40-66,200-221)
 struct ExtractArgs {
     const uint8_t *on, *pre;

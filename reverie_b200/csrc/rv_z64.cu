@@ -71,7 +71,8 @@ __global__ void __launch_bounds__(ZT_THREADS, 1) k_zmask_gen_tt(const uint32_t *
 }
 
 // called by configure_kernels (rv_kernels.cu) once per device, with that device current
-int configure_zkernels() { return (int)cudaFuncSetAttribute(k_zmask_gen_tt, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 256 * 32 * 4); }
+// defined at the end of this file (it names every Z64 kernel)
+
 
 void launch_zmask_gen_tt(const uint32_t *rk_plain, uint32_t nstreams, uint32_t n_masks, uint64_t *zrows, int n_sms, cudaStream_t st) {
     if (n_masks == 0) return;
@@ -297,6 +298,16 @@ void launch_zextract(const DevZProgram &Z, const ZExtractArgs &a, cudaStream_t s
     const uint64_t words = (uint64_t)Z.n_recon + Z.n_corr + Z.n_inputs + 3;
     if (words == 3) return;
     k_zextract<<<dim3((unsigned)((words + 255) / 256), a.nreps), 256, 0, st>>>(Z.recon_off, Z.input_off, Z.n_recon, Z.n_corr, Z.n_inputs, a);
+}
+
+// Opt-in shared memory of the Z64 mask generator, and every Z64 kernel loaded up front (see configure_kernels).
+int configure_zkernels() {
+    cudaError_t e = cudaFuncSetAttribute(k_zmask_gen_tt, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 256 * 32 * 4);
+    cudaFuncAttributes at;
+    for (const void *fn : {(const void *)k_zlinear_level, (const void *)k_zvalues, (const void *)k_zitems_online, (const void *)k_zitems_pre,
+                           (const void *)k_zverify_leaves, (const void *)k_zverify_items_online, (const void *)k_zverify_items_pre, (const void *)k_zextract})
+        if (e == cudaSuccess) e = cudaFuncGetAttributes(&at, fn);
+    return (int)e;
 }
 
 }  // namespace rv

@@ -198,6 +198,22 @@ class Session:
     def stream(self) -> int:
         return int(N.lib().rv_session_stream(self._h) or 0)
 
+    def peer_handle(self) -> bytes:
+        """Opaque handle naming this session for rv_session_peer_link (raw pointers inside one process, CUDA IPC across)."""
+        buf = np.zeros(N.PEER_HANDLE_BYTES, dtype=np.uint8)
+        N.check(N.lib().rv_session_peer_handle(self._h, _ptr(buf)))
+        return buf.tobytes()
+
+    def peer_link(self, rank: int, world: int, handles: Sequence[bytes]):
+        """Link this shard to the sessions holding the other shards of the same proofs (handles in rank order).  Afterwards
+        prove() runs commit, the exchange of repetition hashes over peer memory, the challenge and the extraction into rank 0's
+        proof buffer as one CUDA graph launch; fetch() on rank 0 returns the whole proof."""
+        blob = np.frombuffer(b"".join(handles), dtype=np.uint8)
+        if blob.size != world * N.PEER_HANDLE_BYTES:
+            raise ValueError("need one handle per rank")
+        N.check(N.lib().rv_session_peer_link(self._h, rank, world, _ptr(blob)))
+        self.linked_rank, self.linked_world = rank, world
+
     def timing(self, enable: bool):
         N.check(N.lib().rv_session_timing(self._h, int(enable)))
 

@@ -100,6 +100,42 @@ def reduce_proofs(sessions, group=None, dst: int = 0):
     return out
 
 
+def link_sessions(sessions, group=None):
+    """Link this rank's sessions (shard `rank` of the proofs they hold) to the corresponding sessions of the other ranks of
+    `group`: afterwards Session.prove() / Batch.prove() run the whole sharded step -- commit, exchange of the repetition
+    hashes over NVLink peer memory, challenge, extraction into rank 0's buffers -- as one CUDA graph launch per rank, with
+    no collective call on the data path.  The handles travel once, through the group's host channel."""
+    import torch.distributed as dist
+
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    mine = [s.peer_handle() for s in sessions]
+    everyone = [None] * world
+    dist.all_gather_object(everyone, mine, group=group)
+    for i, s in enumerate(sessions):
+        s.peer_link(rank, world, [everyone[r][i] for r in range(world)])
+
+
+def prove_linked(circuit, wit_gf2, wit_z64=(), seeds=None, group=None, session=None) -> Optional[bytes]:
+    """Proof::new over all ranks of `group` with the device-side exchange (link_sessions).  Returns the proof on rank 0, None
+    elsewhere (after checking this rank's status)."""
+    import torch.distributed as dist
+
+    from .proof import Session
+
+    if seeds is None:
+        raise ValueError("sharded proving needs the same seeds on every rank: draw them on rank 0 and broadcast")
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    first, count = shard_of(rank, world)
+    s = session
+    if s is None:
+        s = Session(circuit, first, count)
+        link_sessions([s], group)
+    s.upload(wit_gf2, wit_z64, seeds)
+    s.prove()
+    _, proof = s.fetch()
+    return proof if rank == 0 else None
+
+
 def prove_sharded(circuit, wit_gf2, wit_z64=(), seeds=None, group=None, session=None) -> Optional[bytes]:
     """Proof::new over all ranks of `group` (NCCL, one GPU per rank).  `seeds` must be the same 256 x 16 bytes on every rank
     (rank 0 may draw them and broadcast).  Returns the proof on rank 0."""

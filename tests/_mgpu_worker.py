@@ -59,6 +59,40 @@ def main():
     if rank == 0:
         print(f"mgpu ok: batch of 2 on {world} GPUs", flush=True)
     del batch
+    # device-side exchange (rv_session_peer_link, CUDA IPC between the ranks' processes): no NCCL call on the data path;
+    # multi-proof sessions driven as one graph launch per rank and step
+    if 32 // world >= 4:
+        sops, n_wires, _ = C.sha256_compress_circuit(None)
+        swc = (0, n_wires)
+        wits = [C.sha256_witness(C.sha256_pad_single_block(m)) for m in (b"abc", b"", b"slot two")]
+        sds = [seeds, seeds2, bytes(seeds[1:] + seeds[:1])]
+        scirc = rb.Circuit(sops, swc)
+        ls = [rb.Session(scirc, first, count, n_proofs=3) for _ in range(2)]
+        sharding.link_sessions(ls)
+        lb = rb.Batch(ls)
+        for rnd in range(4):
+            for i in range(2):
+                for b in range(3):
+                    k = (b + i + rnd) % 3
+                    ls[i].upload(wits[k], (), sds[k], slot=b)
+            lb.prove()
+            for i in range(2):
+                for b in range(3):
+                    k = (b + i + rnd) % 3
+                    _, got = ls[i].fetch(b)
+                    if rank == 0:
+                        assert got == orc.prove(sops, wits[k], [], swc, sds[k])[1], (rnd, i, b)
+        del lb
+    for name, ops, gwit, zwit, wc in cases:
+        circ = rb.Circuit(ops, wc)
+        s1 = rb.Session(circ, first, count)
+        sharding.link_sessions([s1])
+        for rnd in range(3):
+            proof = sharding.prove_linked(circ, gwit, zwit, seeds, session=s1)
+            if rank == 0:
+                assert proof == orc.prove(ops, gwit, zwit, wc, seeds)[1], (name, rnd)
+    if rank == 0:
+        print(f"mgpu ok: linked sessions (device-side exchange) on {world} GPUs", flush=True)
     dist.barrier()
     dist.destroy_process_group()
 
