@@ -4,22 +4,30 @@
 Contract (driver): `python bench.py --gpus N --steps K --warmup W [--impl reference]` prints ONE JSON line on rank 0.
 For N > 1 the driver launches it under torchrun, one rank per GPU; the 32 packed instances (src/proof/mod.rs:127-157) are
 sharded 32/N per rank and the only exchange is the all-gather of the 256 x 32-byte repetition hashes
-(src/proof/mod.rs:160-171) -> strong scaling (the proof is the same for every N).
+(src/proof/mod.rs:160-171) -> strong scaling (the proof is the same for every N).  By default that exchange and the
+assembly of the proof run over NVLink peer memory inside the kernels (rv_session_peer_link: one CUDA graph launch per rank
+and step, no collective library on the data path); `--exchange nccl` keeps the NCCL all-gather + reduce for comparison.
 
 A step = one batch of B independent `Proof::new` calls on the workload circuit (default: SHA-256 compression, SURVEY.md
 8(d) config 2; B = --batch, default 32) issued together, the way a proving service sees its queue; B = 1 gives the
 single-proof latency, which is also reported.  Small GF(2) circuits are held by multi-proof sessions (--per-session proofs
 side by side, every kernel launch covering all of them); big / Z64 circuits one proof per session (--batch 1).
-  value  device-resident: witnesses + seeds already in HBM; the step is one CUDA graph launch per phase for all sessions
-         (rv_batch) on a leader stream that carries the CUDA-event pair of the step
-  e2e    host buffers in, proof bytes out, through the public batched call (Proof.new_batch -> rv_prove_batch), all
-         host<->device copies inside the timed region; N > 1: upload, sharded step, NCCL assembly on rank 0
-  verify Proof.verify of the same proofs (host bytes in), B verifications in flight
+  value    device-resident: witnesses + seeds already in HBM; the step is one CUDA graph launch for all sessions
+           (rv_batch) on a leader stream that carries the CUDA-event pair of the step
+  e2e      host buffers in, proof bytes out: N = 1 through the public batched call (Proof.new_batch -> rv_prove_batch);
+           N > 1: every rank uploads witnesses + its seeds, runs the sharded step, rank 0 fetches the assembled proofs
+  parity   after the timed region the proofs of the step are hashed (SHA-256 of the bincode bytes) and compared with the digest
+           committed in tests/golden/bench_digests.json (computed by the CPU oracle: tests/golden/make_bench_digests.py)
+  roofline the kernels of the timed (batched) configuration, CUDA events around every launch: see `roofline` in the line
+  extra_workloads (default run only): BASELINE.json configs 3 and 5 -- z64mul1000000 (N = 1), flat100000000 and
+           layered100000000 sharded over the N ranks -- each with value, e2e, path fraction and parity
 The CPU arm (--impl reference) proves the same B proofs per step with the C restatement of the reference's dataflow.
 """
 from __future__ import annotations
 
 import argparse
+import gc
+import hashlib
 import json
 import os
 import subprocess
@@ -36,6 +44,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "KKW prover AND-gates/sec (GF(2), 128-bit sec)"
 UNIT = "AND-gates/s"
+EXTRAS = ("z64mul1000000", "flat100000000", "layered100000000")
 
 
 def make_workload(name: str):
@@ -73,22 +82,34 @@ def default_seeds() -> bytes:
     return np.random.default_rng(20261017).integers(0, 256, size=256 * 16, dtype=np.uint8).tobytes()
 
 
-# bench kernel label -> kernel(s) in the committed ncu capture (profiles/r1c_traffic.json; DRAM bytes per launch)
-NCU_NAMES = {"linear": ["k_mask_vm"], "mask_gen": ["k_mask_gen_tt<0>", "k_mask_gen_tt<1>", "k_mask_gen_tt"], "items": ["k_items", "k_items_tile<0>", "k_items_tile<1>"], "chunk_cv": ["k_chunk_cv"],
+def golden_digest(workload: str):
+    """SHA-256 of the oracle's proof bytes for `workload` with default_seeds() (tests/golden/bench_digests.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "tests", "golden", "bench_digests.json")) as f:
+            return json.load(f)["digests"].get(workload)
+    except Exception:
+        return None
+
+
+# bench kernel label -> kernel(s) in the committed ncu capture (profiles/r2_traffic.json; DRAM bytes per launch, pipe utilisation)
+NCU_NAMES = {"linear": ["k_mask_vm"], "mask_gen": ["k_mask_gen_tt<0>", "k_mask_gen_tt<1>", "k_mask_gen_tt"], "items": ["k_items"], "chunk_cv": ["k_chunk_cv"],
              "values": ["k_values<1>"], "rep_hash": ["k_rep_hash"], "extract": ["k_extract"], "challenge": ["k_challenge"], "key_setup": ["k_key_setup"],
              "z.mask_gen": ["k_zmask_gen_tt"], "z.items": ["k_zitems_online"], "z.values": ["k_zvalues"], "z.extract": ["k_zextract"]}
 
 
-def ncu_traffic(workload: str, label: str):
-    """DRAM bytes per launch of the kernel behind `label`, from the committed `ncu --set full` capture of the same workload
-    (None when that workload / kernel was not captured)."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1c_traffic.json")) as f:
-            w = json.load(f)["workloads"].get(workload)
-        vals = [w[k]["dram_bytes_per_launch"] for k in NCU_NAMES.get(label, []) if k in w]
-        return sum(vals) / len(vals) if vals else None
-    except Exception:
-        return None
+def ncu_record(workload: str, label: str):
+    """The committed `ncu --set full` figures of the kernel behind `label` for this workload's timed configuration
+    (profiles/r2_traffic.json, falling back to round 1's capture), or None."""
+    for fn in ("r2_traffic.json", "r1c_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", fn)) as f:
+                w = json.load(f)["workloads"].get(workload)
+            for k in NCU_NAMES.get(label, []):
+                if w and k in w:
+                    return dict(w[k], capture=fn)
+        except Exception:
+            pass
+    return None
 
 
 def load_peaks():
@@ -184,11 +205,380 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def set_metric(workload: str):
+def unit_of(workload: str):
     """The headline metric is BASELINE.json's (GF(2) AND gates); a Z64 workload reports its multiplication gates instead."""
-    global METRIC, UNIT
     if workload.startswith("z64"):
-        METRIC, UNIT = "KKW prover MUL-gates/sec (Z64, 128-bit sec)", "MUL-gates/s"
+        return "KKW prover MUL-gates/sec (Z64, 128-bit sec)", "MUL-gates/s"
+    return METRIC, UNIT
+
+
+class Env:
+    """What every workload of one bench process shares: ranks, torch handles, peaks."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+
+        from reverie_b200 import _native
+
+        self.args, self.torch, self.dist = args, torch, dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available() or _native.lib().rv_device_count() < 1:
+            raise SystemExit("bench.py needs a CUDA device: reverie_b200 has no CPU fallback")
+        torch.cuda.set_device(self.local_rank)
+        _native.check(_native.lib().rv_set_device(self.local_rank))
+        if self.world > 1:
+            import datetime
+
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank), timeout=datetime.timedelta(seconds=900))
+        if 32 % self.world:
+            raise SystemExit("world size must divide the 32 packed instances")
+        self.peak, self.peak_src = load_peaks()
+        self.timing_stream = torch.cuda.Stream()
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def all_true(self, ok: bool) -> bool:
+        if self.world == 1:
+            return ok
+        t = self.torch.tensor([1 if ok else 0], dtype=self.torch.int32, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MIN)
+        return bool(t.item())
+
+
+def run_workload(env: Env, name: str, batch: int, per_session: int, steps: int, warmup: int, full: bool) -> dict:
+    """One workload on the env's ranks.  full = the headline workload (adds latency, per-kernel roofline, verify, one-shot and
+    the CPU baseline); otherwise the compact record of an extra workload."""
+    import reverie_b200 as rb
+    from reverie_b200 import sharding
+
+    torch, dist, args = env.torch, env.dist, env.args
+    rank, world = env.rank, env.world
+    metric, unit = unit_of(name)
+    t0 = time.perf_counter()
+    ops, wit, wz, wc, desc = make_workload(name)
+    gen_s = time.perf_counter() - t0
+    seeds = default_seeds()
+    t0 = time.perf_counter()
+    n_ops = int(ops.size)
+    # proving needs no verifier tables; the headline workload also times Proof.verify, big extras only prove
+    circ = rb.Circuit(ops, wc, prove_only=not full)
+    compile_s = time.perf_counter() - t0
+    st = circ.stats()
+    n_and = st["n_and"] + st["z64_mul"]  # multiplication gates of either domain
+    by_proofs = world > 1 and args.shard == "proofs"
+    linked = world > 1 and not by_proofs and args.exchange == "p2p"
+    per = 32 if by_proofs else 32 // world
+    first = 0 if by_proofs else rank * per
+    B = max(1, batch)
+    # Small GF(2) circuits: the batch is held by multi-proof sessions (P proofs side by side per session: every kernel launch
+    # covers P proofs); other circuits: one proof per session.
+    P = max(1, min(per_session, B))
+    try:
+        sessions = [rb.Session(circ, first, per, n_proofs=P)] if P > 1 else []
+    except rb.ReverieError:
+        P, sessions = 1, []
+    B = (B + P - 1) // P * P
+    sessions += [rb.Session(circ, first, per, n_proofs=P) for _ in range(B // P - len(sessions))]
+    if linked:
+        sharding.link_sessions(sessions)
+    recv_bufs = {}  # NCCL exchange: session -> (receive tensor over the session's own all-gather buffer, send tensor over its hashes)
+    batches = {}
+
+    def upload_all(xs):
+        for x in xs:
+            for slot in range(x.n_proofs):
+                x.upload(wit, wz, seeds, slot=slot)
+
+    # The sessions of a step are driven as one rv_batch: each phase of all of them is ONE CUDA graph launch on the leader's
+    # stream; the sessions' own streams fork from it and join back inside the graph.
+    def batch_of(sess_list):
+        key = tuple(id(x) for x in sess_list)
+        if key not in batches:
+            bt = rb.Batch(sess_list)
+            batches[key] = (bt, torch.cuda.ExternalStream(bt.stream))
+        return batches[key]
+
+    def step_device(sess_list):
+        """The proofs held by sess_list: commit + exchange + open with inputs resident in HBM."""
+        bt, lead = batch_of(sess_list)
+        if world == 1 or by_proofs or linked:
+            bt.prove()  # linked shards: the exchange of repetition hashes happens inside the challenge kernel, over peer memory
+            return
+        bt.commit()
+        # --exchange nccl: all-gather of the repetition hashes device to device, ONE NCCL group launch for the proofs in flight,
+        # enqueued on the leader's stream between the two graphs
+        for x in sess_list:
+            if x not in recv_bufs:
+                recv_bufs[x] = (torch.as_tensor(x.all_hashes_device(), device="cuda"), torch.as_tensor(x.hashes_device(), device="cuda"))
+        with torch.cuda.stream(lead):
+            sharding.all_gather_hashes_batched([recv_bufs[x][0] for x in sess_list], [recv_bufs[x][1] for x in sess_list])
+        bt.open()
+
+    def timed_device(sess_list, k: int) -> float:
+        tot = 0.0
+        _, lead = batch_of(sess_list)
+        for _ in range(k):
+            with torch.cuda.stream(env.timing_stream):
+                env.flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            env.barrier()
+            a.record(env.timing_stream)
+            lead.wait_event(a)
+            step_device(sess_list)
+            e = torch.cuda.Event()
+            e.record(lead)
+            env.timing_stream.wait_event(e)
+            b.record(env.timing_stream)
+            env.barrier()
+            tot += a.elapsed_time(b)
+        return tot  # ms
+
+    def collect(sess_list):
+        """Proof bytes of every slot on the assembling rank (rank 0; every rank with --shard proofs)."""
+        if world == 1 or by_proofs or linked:
+            return [x.fetch(b)[1] for x in sess_list for b in range(x.n_proofs)]
+        out = sharding.reduce_proofs(sess_list)  # --exchange nccl: one NCCL sum-reduce of the shards' buffers
+        return out if out is not None else [b""] * sum(x.n_proofs for x in sess_list)
+
+    upload_all(sessions)
+    for _ in range(warmup):
+        step_device(sessions)
+    for x in sessions:
+        x.sync()
+    launches0 = sum(x.launch_count for x in sessions)
+    sampler = ClockSampler(env.local_rank)
+    sampler.start()
+    ms_total = timed_device(sessions, steps)
+    launches = sum(x.launch_count for x in sessions) - launches0
+    clocks = sampler.stop()
+    ms_total = env.max_over_ranks(ms_total)
+    n_jobs = B * (world if by_proofs else 1)  # proofs completed per step by the whole job
+    value = n_and * n_jobs * steps / (ms_total * 1e-3)
+    ms_per_step = ms_total / steps
+
+    # ---- parity: the proofs the timed steps left behind vs the oracle's digest (committed; no oracle code runs here) ----
+    proofs = collect(sessions)
+    want = golden_digest(name)
+    proof_len = len(proofs[0]) if proofs else 0
+    digest, parity = None, None
+    if rank == 0 or by_proofs:
+        digests = {hashlib.sha256(memoryview(p)).hexdigest() for p in proofs}
+        digest = sorted(digests)[0]
+        parity = (len(digests) == 1 and digest == want) if want else None
+    if want:
+        parity_all = env.all_true(parity is not False)
+        if not parity_all:
+            raise SystemExit(f"PARITY FAILURE: workload {name}: proof digest {digest} != oracle digest {want} (rank {rank}, {world} GPUs)")
+    del proofs
+
+    # ---- per-kernel device times of the TIMED configuration: each session of the step run alone with CUDA events around every
+    #      launch (a launch covers the P proofs of its session) -> which kernel dominates the step, its 8(d) bytes / its time ----
+    peak = env.peak
+    path_bytes = B * st["algorithmic_bytes"]
+    path = {"algorithmic_bytes_per_step": path_bytes, "achieved": path_bytes / (ms_per_step * 1e-3) / 1e9, "peak": peak * world,
+            "frac": path_bytes / (ms_per_step * 1e-3) / 1e9 / (peak * world),
+            "note": f"SURVEY.md 8(d) bytes of the {B} proofs of a step / device time per step / ({world} x HBM peak)"}
+    roofline, kernels = None, None
+    if (full or world == 1) and (world == 1 or by_proofs or linked):
+        reps = 3 if not full else max(5, min(steps, 10))
+        if rank == 0:
+            for x in sessions:
+                x.timing(True)
+        for _ in range(reps):  # timing keeps the phases eager; every rank runs them (linked sessions meet on the device)
+            for x in sessions:
+                x.prove()
+                torch.cuda.synchronize()
+        kt = {}
+        if rank == 0:
+            for x in sessions:
+                for k in x.kernel_times():
+                    a = kt.setdefault(k["name"], {"ms": 0.0, "launches": 0, "bytes": 0})
+                    a["ms"] += k["ms"]
+                    a["launches"] += k["launches"]
+                    a["bytes"] += k["algorithmic_bytes"]
+                x.timing(False)
+            kernels = {n: {"us_per_step": a["ms"] * 1e3 / reps, "launches_per_step": a["launches"] // reps, "us_per_launch": a["ms"] * 1e3 / max(a["launches"], 1),
+                           "algorithmic_bytes_per_launch": a["bytes"] // max(a["launches"], 1),
+                           "hbm_frac": (a["bytes"] / max(a["ms"], 1e-9) / 1e6) / peak} for n, a in kt.items()}
+            side = ("values", "z.values")  # plaintext value planes: a side stream, overlapped with mask generation
+            main = {n: a for n, a in kt.items() if n not in side} or kt
+            top = max(main, key=lambda n: main[n]["ms"])
+            a = kt[top]
+            us = a["ms"] * 1e3 / max(a["launches"], 1)
+            bpl = a["bytes"] / max(a["launches"], 1)
+            ach = bpl / (us * 1e-6) / 1e9 if us > 0 else 0.0
+            rec = ncu_record(name, top) or {}
+            main_sum_us = sum(v["ms"] for v in main.values()) * 1e3 / reps
+            roofline = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": rec.get("dram_bytes_per_launch"),
+                        "peak_source": env.peak_src, "us_per_launch": us, "algorithmic_bytes_per_launch": bpl, "proofs_per_launch": P,
+                        "launches_per_step": a["launches"] // reps, "share_of_step": a["ms"] * 1e3 / reps / max(main_sum_us, 1e-9),
+                        "main_stream_kernel_us_per_step": main_sum_us,
+                        "how": "CUDA events around every launch of the step's sessions, each session run alone (eager) after the timed region; "
+                               "achieved = SURVEY.md 8(d) bytes this kernel moves per launch / its time per launch",
+                        "secondary": {"bound": "alu/lds issue (AES T-table + BLAKE3 are integer work, DESIGN.md section 5)",
+                                      "ncu": {k: rec.get(k) for k in ("alu_pipe_pct", "lsu_pipe_pct", "issue_active_pct", "sm_throughput_pct", "dram_throughput_pct", "capture") if k in rec}},
+                        "path": path}
+    if roofline is None:
+        roofline = {"bound": "hbm", "path": path, "peak": peak, "unit": "GB/s", "frac": path["frac"], "achieved": path["achieved"]}
+
+    # ---- single-proof latency on the device (one proof alone in flight), headline workload at N = 1 ----
+    lat_ms = None
+    if full and world == 1:
+        sess1 = sessions[0] if (B == 1) else rb.Session(circ, first, per)
+        if sess1 is not sessions[0]:
+            sess1.upload(wit, wz, seeds)
+        for _ in range(3):  # eager run, graph capture, first replay
+            step_device([sess1])
+        nl = max(5, min(steps, 20))
+        lat_ms = timed_device([sess1], nl) / nl
+        del sess1
+
+    big = st["n_masks"] * 256 + st["z64_masks"] * 16384 > (8 << 30)  # a session of this circuit holds tens of GB: one at a time
+    x = None  # (loop variable: would keep the last session, tens of GB, alive)
+    if big and world == 1:
+        batches.clear()
+        recv_bufs.clear()
+        sessions.clear()
+        gc.collect()
+
+    # ---- end to end (host buffers in, proof bytes out, copies inside the timed region) ----
+    verify, single_latency_ms, oneshot = None, None, None
+    if world == 1:
+        def step_api():  # the B queued requests of a step through the public call (host witnesses in, proof bytes out)
+            if B == 1:
+                return [rb.Proof.new(circ, wit, wz, seeds=seeds)]
+            return rb.Proof.new_batch(circ, [wit] * B, [wz] * B, seeds=[seeds] * B)
+
+        for _ in range(warmup):
+            out = step_api()
+        env.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = step_api()
+        dt = time.perf_counter() - t0
+        e2e_v = n_and * B * steps / dt
+        proof = out[0]
+        if want and hashlib.sha256(memoryview(proof._buf if isinstance(proof._buf, np.ndarray) else proof.data)).hexdigest() != want:
+            raise SystemExit(f"PARITY FAILURE: workload {name}: the public API's proof differs from the oracle digest")
+        d2h = B * (len(proof) + 36)
+        if full:
+            for _ in range(3):  # session creation, eager run, graph capture
+                rb.Proof.new(circ, wit, wz, seeds=seeds)
+            t0 = time.perf_counter()
+            for _ in range(10):
+                rb.Proof.new(circ, wit, wz, seeds=seeds)
+            single_latency_ms = (time.perf_counter() - t0) / 10 * 1e3
+            # the reference's own call shape: Proof::new(circuit, ...) with the op list every time (src/proof/mod.rs:119-124) ->
+            # rv_proof_new: first call compiles (prove-only tables), later calls find the circuit in the content-addressed cache
+            from reverie_b200 import _native
+
+            _native.lib().rv_circuit_cache_clear()
+            t0 = time.perf_counter()
+            p1 = rb.Proof.new(ops, wit, wz, wc, seeds=seeds)
+            first_ms = (time.perf_counter() - t0) * 1e3
+            for _ in range(2):
+                rb.Proof.new(ops, wit, wz, wc, seeds=seeds)
+            t0 = time.perf_counter()
+            for _ in range(10):
+                p1 = rb.Proof.new(ops, wit, wz, wc, seeds=seeds)
+            cached_ms = (time.perf_counter() - t0) / 10 * 1e3
+            oneshot = {"first_call_ms": first_ms, "cached_call_ms": cached_ms, "value_first_call": n_and / (first_ms * 1e-3), "value_cached": n_and / (cached_ms * 1e-3),
+                       "unit": unit, "parity_checked": (hashlib.sha256(p1.data).hexdigest() == want) if want else None,
+                       "note": "rv_proof_new(ops, ...): one proof, op list passed with every call like the reference's Proof::new; first call = circuit compile + session + proof"}
+            # Proof::verify through the same API (SURVEY.md 8(d): "also reported")
+            if st["n_ops"] <= (32 << 20):
+                from concurrent.futures import ThreadPoolExecutor
+
+                pool = ThreadPoolExecutor(max_workers=B)
+
+                def vfy(_):
+                    return proof.verify(circ)
+
+                assert all(pool.map(vfy, range(B)))
+                nv = max(2, steps // 4)
+                t0 = time.perf_counter()
+                for _ in range(nv):
+                    oks = list(pool.map(vfy, range(B)))
+                dtv = time.perf_counter() - t0
+                t0 = time.perf_counter()
+                for _ in range(5):
+                    vfy(0)
+                verify = {"value": n_and * B * nv / dtv, "unit": unit, "accepted": bool(all(oks)), "single_proof_ms": (time.perf_counter() - t0) / 5 * 1e3,
+                          "note": "Proof.verify end to end (proof bytes in host memory), B verifications in flight"}
+        del out, proof
+    else:
+        def step_e2e():
+            upload_all(sessions)
+            step_device(sessions)
+            return collect(sessions)  # rank 0 (every rank with --shard proofs) ends up with the proof bytes in host memory
+
+        for _ in range(warmup):
+            step_e2e()
+        env.barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            out = step_e2e()
+        env.barrier()
+        dt = env.max_over_ranks(time.perf_counter() - t0)
+        e2e_v = n_and * n_jobs * steps / dt
+        if want and (rank == 0 or by_proofs) and hashlib.sha256(memoryview(out[0])).hexdigest() != want:
+            raise SystemExit(f"PARITY FAILURE: workload {name}: the end-to-end proof differs from the oracle digest")
+        del out
+        d2h = B * (proof_len + 36)
+    e2e = {"value": e2e_v, "unit": unit, "h2d_bytes_per_step": B * (st["n_inputs"] + 8 * st["z64_inputs"] + per * 8 * 16),
+           "d2h_bytes_per_step": d2h, "ms_per_step": dt / steps * 1e3}
+
+    cpu = None
+    if full and rank == 0 and world == 1 and not args.no_cpu_baseline:
+        c_ops, c_wit, c_wz, c_wc, c_n, c_note = ops, wit, wz, wc, n_and, "whole proofs of the same workload"
+        if n_and > 4 * 10**6:  # bounded sample: the same circuit family at a size the CPU finishes in seconds
+            small = name.rstrip("0123456789") + str(2 * 10**6 if name.startswith("z64") is False else 2 * 10**5)
+            c_ops, c_wit, c_wz, c_wc, _ = make_workload(small)
+            c_n = int((c_ops["opcode"] == 6).sum())
+            c_note = f"whole proofs of the same circuit family at {c_n} multiplication gates ({small})"
+        n, secs, cores = cpu_port_run(c_ops, c_wit, c_wz, c_wc, seeds, 10.0, 1)
+        cpu = {"value": c_n * n / secs, "unit": unit, "cores": cores, "kind": "port",
+               "sample": f"{n} {c_note} in {secs:.1f} s; C restatement of the reference's dataflow (oracle/c), threads over the 32 packed instances"}
+
+    exchange = ("none (one GPU)" if world == 1 else "none (whole proofs per GPU)" if by_proofs else
+                "device-side: repetition hashes pushed into every rank's receive buffer over NVLink peer memory inside the challenge kernel, openings written "
+                "straight into rank 0's proof buffer (rv_session_peer_link, CUDA IPC between the ranks)" if linked else "NCCL all-gather of the repetition hashes + NCCL sum-reduce of the shard buffers")
+    res = {
+        "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms_per_step,
+        "scaling": "weak" if by_proofs else "strong",
+        "config": {"workload": desc, "batch": B,
+                   "parallelism": (f"whole proofs per GPU, {B} proofs in flight per GPU per step, no collective" if by_proofs else
+                                   f"{per} packed instances (= {per * 8} repetitions) per GPU, {B} proofs in flight per step") + f"; {B // P} sessions x {P} proofs side by side",
+                   "exchange": exchange,
+                   "l2": "256 MiB memset between timed steps (outside the per-step CUDA-event pair)",
+                   "timing": "one CUDA-event pair per step on a timing stream that forks to / joins the batch leader's stream (the session streams fork from / join it inside the CUDA graph), summed over K steps"},
+        "clocks": clocks, "e2e": e2e, "parity_checked": parity, "proof_sha256": digest, "proof_bytes": proof_len,
+        "compile_s": compile_s, "circuit_gen_s": gen_s, "gpu_launches": int(launches), "roofline": roofline,
+        "circuit": {k: st[k] for k in ("n_and", "n_ops", "value_depth", "linear_depth", "z64_mul", "z64_value_depth")},
+    }
+    if full:
+        res.update({"verify": verify, "oneshot": oneshot, "cpu_baseline": cpu, "kernels": kernels,
+                    "single_proof_latency_ms": {"device": lat_ms, "e2e": single_latency_ms}})
+    batches.clear()
+    recv_bufs.clear()
+    sessions.clear()
+    del circ
+    gc.collect()
+    return res
 
 
 def main():
@@ -202,289 +592,45 @@ def main():
     ap.add_argument("--per-session", type=int, default=8,
                     help="proofs held side by side by one multi-proof session (small GF(2) circuits); the batch is batch/per-session such sessions")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--extras", default="auto", help="comma list of extra workloads reported under extra_workloads ('none' = skip; "
+                                                     "auto = BASELINE configs 3 and 5 when the headline workload is the default one)")
     ap.add_argument("--shard", default="reps", choices=["reps", "proofs"],
-                    help="N > 1: 'reps' shards the 32 packed instances of every proof over the ranks with the NCCL all-gather of repetition "
-                         "hashes (BASELINE config 4, strong scaling); 'proofs' gives every rank its own whole proofs (no collective, weak scaling)")
+                    help="N > 1: 'reps' shards the 32 packed instances of every proof over the ranks (BASELINE config 4, strong scaling); "
+                         "'proofs' gives every rank its own whole proofs (no exchange, weak scaling)")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1, --shard reps: 'p2p' = device-side exchange over peer memory inside the kernels; 'nccl' = NCCL all-gather + reduce from the host")
     args = ap.parse_args()
-    set_metric(args.workload)
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        return run_reference(args, rank, world)
+        return run_reference(args, int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")))
 
-    import torch
-    import torch.distributed as dist
-
-    import reverie_b200 as rb
-    from reverie_b200 import _native, sharding
-
-    if not torch.cuda.is_available() or _native.lib().rv_device_count() < 1:
-        raise SystemExit("bench.py needs a CUDA device: reverie_b200 has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    _native.check(_native.lib().rv_set_device(local_rank))
-    if world > 1:
-        import datetime
-
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank), timeout=datetime.timedelta(seconds=120))
-    if 32 % world:
-        raise SystemExit("world size must divide the 32 packed instances")
-
-    ops, wit, wz, wc, desc = make_workload(args.workload)
-    seeds = default_seeds()
-    circ = rb.Circuit(ops, wc)
-    st = circ.stats()
-    n_and = st["n_and"] + st["z64_mul"]  # multiplication gates of either domain
-    st_proof_len = 0
-    by_proofs = world > 1 and args.shard == "proofs"
-    per = 32 if by_proofs else 32 // world
-    B = max(1, args.batch)
-    first = 0 if by_proofs else rank * per
-    # Small GF(2) circuits: the batch is held by multi-proof sessions (P proofs side by side per session: every kernel launch
-    # covers P proofs); other circuits: one proof per session.
-    P = max(1, min(args.per_session, B))
-    try:
-        sessions = [rb.Session(circ, first, per, n_proofs=P)] if P > 1 else []
-    except rb.ReverieError:
-        P, sessions = 1, []
-    B = (B + P - 1) // P * P
-    sessions += [rb.Session(circ, first, per, n_proofs=P) for _ in range(B // P - len(sessions))]
-    sess1 = sessions[0] if B == 1 else rb.Session(circ, first, per)  # one proof alone: latency and per-kernel times
-    streams = [torch.cuda.ExternalStream(x.stream) for x in sessions]
-
-    def upload_all(xs):
-        for x in xs:
-            for slot in range(x.n_proofs):
-                x.upload(wit, wz, seeds, slot=slot)
-    timing_stream = torch.cuda.Stream()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
-    recv_bufs = {}  # session -> (receive tensor over the session's own all-gather buffer, send tensor over its hashes)
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    # The B sessions of a step are driven as one rv_batch: each phase (commit / open / prove) of all of them is ONE CUDA
-    # graph launch on the leader's stream; the sessions' own streams fork from it and join back inside the graph.
-    batches = {}
-
-    def batch_of(sess_list):
-        key = tuple(id(x) for x in sess_list)
-        if key not in batches:
-            bt = rb.Batch(sess_list)
-            batches[key] = (bt, torch.cuda.ExternalStream(bt.stream))
-        return batches[key]
-
-    def step_device():
-        """B proofs: commit + open with inputs resident in HBM; the all-gather of repetition hashes when sharded."""
-        bt, lead = batch_of(sessions)
-        if world == 1 or by_proofs:
-            bt.prove()
-            return
-        bt.commit()
-        # the one exchange of the protocol (src/proof/mod.rs:160-171): NCCL all-gather of the repetition hashes, device to
-        # device from each session's hash buffer into its own receive buffer, ONE NCCL group launch for the B proofs in
-        # flight, enqueued on the leader's stream between the two graphs -- no host round trip, no synchronisation
-        for x in sessions:
-            if x not in recv_bufs:
-                recv_bufs[x] = (torch.as_tensor(x.all_hashes_device(), device="cuda"), torch.as_tensor(x.hashes_device(), device="cuda"))
-        with torch.cuda.stream(lead):
-            sharding.all_gather_hashes_batched([recv_bufs[x][0] for x in sessions], [recv_bufs[x][1] for x in sessions])
-        bt.open()
-
-    def timed_device(k: int):
-        tot = 0.0
-        _, lead = batch_of(sessions)
-        for _ in range(k):
-            with torch.cuda.stream(timing_stream):
-                flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            barrier()
-            a.record(timing_stream)
-            lead.wait_event(a)
-            step_device()
-            e = torch.cuda.Event()
-            e.record(lead)
-            timing_stream.wait_event(e)
-            b.record(timing_stream)
-            barrier()
-            tot += a.elapsed_time(b)
-        return tot  # ms
-
-    upload_all(sessions + ([sess1] if sess1 is not sessions[0] else []))
-    st_proof_len = len(torch.as_tensor(sess1.proof_device(), device="cuda"))
-    for _ in range(args.warmup):
-        step_device()
-    for x in sessions:
-        x.sync()
-    sess = sess1
-    launches0 = sum(x.launch_count for x in sessions)
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ms_total = timed_device(args.steps)
-    launches = sum(x.launch_count for x in sessions) - launches0
-    clocks = sampler.stop()
-    if world > 1:
-        t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-    n_jobs = B * (world if by_proofs else 1)  # proofs completed per step by the whole job
-    value = n_and * n_jobs * args.steps / (ms_total * 1e-3)
-
-    # single-proof device latency (B = 1), same rules
-    lat_ms = None
-    if world == 1:
-        keep_s = sessions
-        sessions = [sess1]
-        for _ in range(3):  # eager run, graph capture, first replay
-            step_device()
-        lat_ms = timed_device(max(5, min(args.steps, 20))) / max(5, min(args.steps, 20))
-        sessions = keep_s
-
-    # ---- per-kernel device times -> roofline of the dominant kernel (rank 0) ----
-    roofline, kernels = None, None
-    peak, peak_src = load_peaks()
-    reps = max(5, min(args.steps, 20))
-    if rank == 0:
-        sess.timing(True)
-    keep_s = sessions
-    sessions = [sess1]
-    for _ in range(reps):  # every rank runs the steps (they contain the all-gather); only rank 0 brackets its kernels with events
-        step_device()
-    sessions = keep_s
-    sess.sync()
-    if rank == 0:
-        kt = sess.kernel_times()
-        sess.timing(False)
-        comm, part = sess.fetch()
-        kernels = {k["name"]: {"us_per_step": k["ms"] * 1e3 / reps, "launches_per_step": k["launches"] // reps,
-                               "algorithmic_bytes_per_step": k["algorithmic_bytes"] // reps} for k in kt}
-        # the dominant kernel of the critical stream; the plaintext value planes run on a side stream, overlapped with mask generation
-        main_stream = [k for k in kt if k["name"] not in ("values", "z.values")] or kt
-        top = max(main_stream, key=lambda k: k["ms"])
-        per_launch_s = top["ms"] * 1e-3 / max(top["launches"], 1)
-        bytes_per_launch = top["algorithmic_bytes"] / max(top["launches"], 1)
-        ach = bytes_per_launch / per_launch_s / 1e9 if per_launch_s > 0 else 0.0
-        roofline = {"bound": "hbm", "kernel": top["name"], "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                    "traffic": ncu_traffic(args.workload, top["name"]),
-                    "peak_source": peak_src, "us_per_launch": per_launch_s * 1e6,
-                    "per_kernel_frac": {k["name"]: (k["algorithmic_bytes"] / max(k["ms"], 1e-9) / 1e6) / peak for k in kt},
-                    "path": {"algorithmic_bytes_per_step": st["algorithmic_bytes"], "achieved": B * st["algorithmic_bytes"] / (ms_total / args.steps * 1e-3) / 1e9,
-                             "frac": B * st["algorithmic_bytes"] / (ms_total / args.steps * 1e-3) / 1e9 / peak,
-                             "note": "SURVEY.md 8(d) bytes of the B proofs of a step / device time per step"}}
-
-    big = st["n_masks"] * 256 + st["z64_masks"] * 16384 > (8 << 30)  # a session of this circuit holds tens of GB: one at a time
-    if big and world == 1:
-        del sess, sess1
-        batches.clear()
-        recv_bufs.clear()
-        sessions.clear()
-        streams.clear()
-        import gc
-
+    env = Env(args)
+    line = run_workload(env, args.workload, args.batch, args.per_session, args.steps, args.warmup, full=True)
+    gc.collect()
+    extras = {}
+    names = EXTRAS if (args.extras == "auto" and args.workload == "sha256" and args.shard == "reps") else () if args.extras in ("auto", "none") else tuple(args.extras.split(","))
+    for name in names:
+        if name.startswith("z64") and env.world > 1:
+            continue  # BASELINE config 3 is a 1-GPU configuration
+        try:
+            r = run_workload(env, name, 1, 1, 3, 3, full=False)
+            extras[name] = {k: r[k] for k in ("metric", "value", "unit", "ms_per_step", "steps", "warmup", "e2e", "parity_checked", "proof_sha256", "proof_bytes", "compile_s",
+                                              "circuit_gen_s", "gpu_launches", "roofline", "circuit", "config", "clocks")}
+        except SystemExit:
+            raise
+        except Exception as ex:  # an extra must not take the headline line down with it
+            extras[name] = {"error": f"{type(ex).__name__}: {ex}"}
+            ex = None
         gc.collect()
-
-    # ---- end to end through the public API (host buffers, copies inside the timed region) ----
-    e2e = None
-    verify = None
-    single_latency_ms = None
-    if world == 1:
-        from concurrent.futures import ThreadPoolExecutor
-
-        pool = ThreadPoolExecutor(max_workers=B)
-
-        def one(_):
-            return rb.Proof.new(circ, wit, wz, seeds=seeds)
-
-        def step_api():  # the B queued requests of a step through the public batched call (host witnesses in, proof bytes out)
-            return rb.Proof.new_batch(circ, [wit] * B, [wz] * B, seeds=[seeds] * B)
-
-        for _ in range(args.warmup):
-            proofs = step_api()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            proofs = step_api()
-        dt = time.perf_counter() - t0
-        e2e_v = n_and * B * args.steps / dt
-        proof = proofs[0]
-        for _ in range(3):  # session creation, eager run, graph capture
-            one(0)
-        t0 = time.perf_counter()
-        for _ in range(10):
-            one(0)
-        single_latency_ms = (time.perf_counter() - t0) / 10 * 1e3
-        d2h = B * (len(proof) + 36)
-        # Proof::verify through the same API (SURVEY.md 8(d): "also reported"); bounded to circuits whose verifier tables
-        # (kappa leaves + u-plane of 40 repetitions) fit next to a prover session
-        if st["n_ops"] <= (32 << 20):
-            def vfy(_):
-                return proof.verify(circ)
-
-            assert all(pool.map(vfy, range(B)))
-            nv = max(2, args.steps // 4)
-            t0 = time.perf_counter()
-            for _ in range(nv):
-                oks = list(pool.map(vfy, range(B)))
-            dtv = time.perf_counter() - t0
-            t0 = time.perf_counter()
-            for _ in range(5):
-                vfy(0)
-            verify = {"value": n_and * B * nv / dtv, "unit": UNIT, "accepted": bool(all(oks)), "single_proof_ms": (time.perf_counter() - t0) / 5 * 1e3,
-                      "note": "Proof.verify end to end (proof bytes in host memory), B verifications in flight"}
-    else:
-        def step_e2e():
-            upload_all(sessions)
-            step_device()
-            if by_proofs:
-                outs = [x.fetch(b) for x in sessions for b in range(x.n_proofs)]
-                return outs, [p for _, p in outs]  # every rank holds its own whole proofs
-            proofs = sharding.reduce_proofs(sessions)  # one NCCL reduce: rank 0 ends up with the B assembled proofs in host memory
-            return [(None, proofs[0] if proofs else b"")], proofs
-        for _ in range(args.warmup):
-            step_e2e()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            outs, proofs = step_e2e()
-        barrier()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_v = n_and * n_jobs * args.steps / float(t.item())
-        d2h = B * (st_proof_len + 36)
-    e2e = {"value": e2e_v, "unit": UNIT, "h2d_bytes_per_step": B * (st["n_inputs"] + 8 * st["z64_inputs"] + per * 8 * 16 + (256 * 32 if world > 1 else 0)), "d2h_bytes_per_step": d2h}
-
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        c_ops, c_wit, c_wz, c_wc, c_n, c_note = ops, wit, wz, wc, n_and, "whole proofs of the same workload"
-        if n_and > 4 * 10**6:  # bounded sample: the same circuit family at a size the CPU finishes in seconds
-            small = args.workload.rstrip("0123456789") + str(2 * 10**6 if args.workload.startswith("z64") is False else 2 * 10**5)
-            c_ops, c_wit, c_wz, c_wc, _ = make_workload(small)
-            c_n = int((c_ops["opcode"] == 6).sum())
-            c_note = f"whole proofs of the same circuit family at {c_n} multiplication gates ({small})"
-        n, secs, cores = cpu_port_run(c_ops, c_wit, c_wz, c_wc, seeds, 10.0, 1)
-        cpu = {"value": c_n * n / secs, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n} {c_note} in {secs:.1f} s; C restatement of the reference's dataflow (oracle/c), threads over the 32 packed instances"}
-
-    if rank == 0:
-        line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak" if by_proofs else "strong", "vs_baseline": None, "dtype": "u64",
-            "data": "synthetic",
-            "config": {"workload": desc, "batch": B, "parallelism": (f"whole proofs per GPU, {B} proofs in flight per GPU per step, no collective" if by_proofs else
-                                                                      f"{per} packed instances (= {per * 8} repetitions) per GPU, {B} proofs in flight per step, NCCL all-gather of the repetition hashes")
-                                      + f"; {B // P} sessions x {P} proofs side by side",
-                       "l2": "256 MiB memset between timed steps (outside the per-step CUDA-event pair)",
-                       "timing": "one CUDA-event pair per step on a timing stream that forks to / joins the batch leader's stream (the B session streams fork from / join it inside the CUDA graph), summed over K steps"},
-            "clocks": clocks, "e2e": e2e, "verify": verify, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-            "kernels": kernels, "single_proof_latency_ms": {"device": lat_ms, "e2e": single_latency_ms}, "circuit": {k: st[k] for k in ("n_and", "n_ops", "value_depth", "linear_depth", "z64_mul", "z64_value_depth")},
-        }
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if env.rank == 0:
+        out = {"metric": line["metric"], "value": line["value"], "unit": line["unit"], "n_gpus": env.world, "steps": line["steps"], "warmup": line["warmup"],
+               "ms_per_step": line["ms_per_step"], "higher_is_better": True, "scaling": line["scaling"], "vs_baseline": None, "dtype": "u64", "data": "synthetic"}
+        out.update({k: v for k, v in line.items() if k not in out})
+        if extras:
+            out["extra_workloads"] = extras
+        print(json.dumps(out), flush=True)
+    if env.world > 1:
+        env.dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -801,6 +801,7 @@ typedef struct {
     uint8_t (*hashes)[PACKED][HASH_SIZE];       /* [32][8][32] */
     uint8_t omit_of_rep[TOTAL_REPS];
     packed_out_t *pg, *pz;                      /* [32] */
+    int err_pass1;                              /* orc_prove_lowmem: first error seen by a worker */
 } prove_ctx_t;
 
 static void prove_instance(job_t *j, int i) { /* the closure at proof/mod.rs:129-156 */
@@ -883,6 +884,71 @@ int orc_prove(const orc_op *ops, size_t n_ops, const uint8_t *wit_gf2, size_t n_
     }
     for (int i = 0; i < PACKED_REPS; i++) {
         instance_drop(&c.inst[i]);
+        for (int r = 0; r < PACKED; r++) {
+            vec_free(&c.pg[i].recons[r]); vec_free(&c.pg[i].corrs[r]); vec_free(&c.pg[i].inputs[r]);
+            vec_free(&c.pz[i].recons[r]); vec_free(&c.pz[i].corrs[r]); vec_free(&c.pz[i].inputs[r]);
+        }
+    }
+    free(c.inst); free(c.hashes); free(c.pg); free(c.pz);
+    return err;
+}
+
+/* Proof::new for circuits whose recorded transcripts (O(gates) per packed instance, transcript/prover.rs:26-34) do not fit in
+ * this machine's memory at once: the same functions in two passes.  Pass 1 runs every instance for its hashes only and drops
+ * it; pass 2 (after the challenge) runs each instance again, extracts its openings (proof/mod.rs:178-196) and drops the
+ * recorded vectors, keeping the hashers that serialize_domain finalizes.  At most n_threads instances are alive at a time.
+ * The proof bytes are identical to orc_prove's (tests/test_oracle_protocol.py pins that). */
+static void prove_instance_hash_only(job_t *j, int i) {
+    prove_ctx_t *c = (prove_ctx_t *)j->ctx;
+    prove_instance(j, i);
+    instance_t *I = &c->inst[i];
+    if (I->err) c->err_pass1 = I->err; else if (I->tg.err) c->err_pass1 = I->tg.err; else if (I->tz.err) c->err_pass1 = I->tz.err;
+    instance_drop(I);
+    memset(I, 0, sizeof *I);
+}
+static void prove_instance_and_extract(job_t *j, int i) {
+    prove_ctx_t *c = (prove_ctx_t *)j->ctx;
+    uint8_t keep[PACKED][HASH_SIZE];
+    memcpy(keep, c->hashes[i], sizeof keep);
+    prove_instance(j, i);
+    if (memcmp(keep, c->hashes[i], sizeof keep) != 0) c->err_pass1 = ORC_E_ARG; /* the two passes must agree */
+    extract_instance(j, i);
+    instance_t *I = &c->inst[i];
+    vec_free(&I->tg.reconstructions); vec_free(&I->tg.corrections); vec_free(&I->tg.inputs);
+    vec_free(&I->tz.reconstructions); vec_free(&I->tz.corrections); vec_free(&I->tz.inputs);
+    free(I->gw); free(I->zw);
+    I->gw = NULL; I->zw = NULL;
+}
+
+int orc_prove_lowmem(const orc_op *ops, size_t n_ops, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64, size_t n_z64,
+                     size_t z64_cells, size_t gf2_cells, const uint8_t *seeds, int n_threads, uint8_t **proof, size_t *proof_len) {
+    prove_ctx_t c;
+    memset(&c, 0, sizeof c);
+    c.ops = ops; c.n_ops = n_ops; c.wit_gf2 = wit_gf2; c.n_gf2 = n_gf2; c.wit_z64 = wit_z64; c.n_z64 = n_z64;
+    c.z64_cells = z64_cells; c.gf2_cells = gf2_cells; c.seeds = seeds;
+    c.inst = calloc(PACKED_REPS, sizeof(instance_t));
+    c.hashes = calloc(PACKED_REPS, sizeof *c.hashes);
+    c.pg = calloc(PACKED_REPS, sizeof(packed_out_t));
+    c.pz = calloc(PACKED_REPS, sizeof(packed_out_t));
+    parallel_for(prove_instance_hash_only, PACKED_REPS, &c, n_threads);
+    int err = c.err_pass1;
+    if (!err) {
+        uint8_t comm[32];
+        orc_b3_oneshot(c.hashes, (size_t)TOTAL_REPS * HASH_SIZE, comm);
+        orc_challenge(comm, c.omit_of_rep);
+        parallel_for(prove_instance_and_extract, PACKED_REPS, &c, n_threads);
+        err = c.err_pass1;
+        if (!err) {
+            vec_t out = {0};
+            vec_push(&out, comm, 32);
+            serialize_domain(&out, &c, 0);
+            serialize_domain(&out, &c, 1);
+            *proof = out.p;
+            *proof_len = out.len;
+        }
+    }
+    for (int i = 0; i < PACKED_REPS; i++) {
+        if (c.inst[i].tg.h_on[0].buf) instance_drop(&c.inst[i]);
         for (int r = 0; r < PACKED; r++) {
             vec_free(&c.pg[i].recons[r]); vec_free(&c.pg[i].corrs[r]); vec_free(&c.pg[i].inputs[r]);
             vec_free(&c.pz[i].recons[r]); vec_free(&c.pz[i].corrs[r]); vec_free(&c.pz[i].inputs[r]);

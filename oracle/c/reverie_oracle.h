@@ -36,6 +36,12 @@ int orc_prove(const orc_op *ops, size_t n_ops, const uint8_t *wit_gf2, size_t n_
               size_t z64_cells, size_t gf2_cells, const uint8_t *seeds /*256*16*/, int n_threads, uint8_t **proof,
               size_t *proof_len, uint8_t *rep_hashes);
 
+/* The same proof in two passes for circuits whose recorded transcripts exceed this machine's memory (10^8 gates = 51 GB): hashes
+ * first, then each instance again for its openings; at most n_threads instances are alive at once.  Same bytes as orc_prove. */
+int orc_prove_lowmem(const orc_op *ops, size_t n_ops, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64, size_t n_z64,
+                     size_t z64_cells, size_t gf2_cells, const uint8_t *seeds /*256*16*/, int n_threads, uint8_t **proof,
+                     size_t *proof_len);
+
 /* Proof::verify (src/proof/mod.rs:224-307).  Returns 1 accept / 0 reject / <0 error.  *okay (optional) receives the AND
  * of the online verifiers' zero_check flags (verifier/online.rs:176-178; unused by the reference's verify).
  * rep_hashes (256*32, optional) receives the recomputed per-repetition hashes in original rep order. */

@@ -38,6 +38,8 @@ def lib():
         L.orc_prove.argtypes = [C.c_void_p, sz, C.c_void_p, sz, C.c_void_p, sz, sz, sz, C.c_void_p, C.c_int,
                                 C.POINTER(C.c_void_p), C.POINTER(sz), C.c_void_p]
         L.orc_prove.restype = C.c_int
+        L.orc_prove_lowmem.argtypes = [C.c_void_p, sz, C.c_void_p, sz, C.c_void_p, sz, sz, sz, C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(sz)]
+        L.orc_prove_lowmem.restype = C.c_int
         L.orc_verify.argtypes = [C.c_void_p, sz, sz, sz, C.c_void_p, sz, C.c_int, C.POINTER(C.c_int), C.c_void_p]
         L.orc_verify.restype = C.c_int
         L.orc_free.argtypes = [C.c_void_p]
@@ -69,6 +71,26 @@ def prove(ops: np.ndarray, wit_gf2, wit_z64, wire_counts, seeds: bytes, n_thread
         proof = C.string_at(out, n.value)
         lib().orc_free(out)
     return (rc, proof, hashes.tobytes()) if want_hashes else (rc, proof)
+
+
+def prove_digest_lowmem(ops: np.ndarray, wit_gf2, wit_z64, wire_counts, seeds: bytes, n_threads: int = 0):
+    """orc_prove_lowmem: the same proof in two passes (at most n_threads instances' transcripts alive at a time), for circuits
+    whose transcripts do not fit in memory all at once.  -> (rc, sha256 hex digest of the proof bytes, proof length)."""
+    import hashlib
+
+    ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+    wg = np.ascontiguousarray(np.asarray(wit_gf2, dtype=np.uint8))
+    wz = np.ascontiguousarray(np.asarray(wit_z64, dtype=np.uint64))
+    sd = np.frombuffer(bytes(seeds), dtype=np.uint8)
+    out, n = C.c_void_p(), C.c_size_t()
+    rc = lib().orc_prove_lowmem(_ptr(ops), ops.size, _ptr(wg), wg.size, _ptr(wz), wz.size, wire_counts[0], wire_counts[1], _ptr(sd), n_threads,
+                                C.byref(out), C.byref(n))
+    if rc != 0:
+        return rc, None, 0
+    view = (C.c_uint8 * n.value).from_address(out.value)
+    dg = hashlib.sha256(memoryview(view)).hexdigest()
+    lib().orc_free(out)
+    return rc, dg, n.value
 
 
 def verify(ops: np.ndarray, wire_counts, proof: bytes, n_threads: int = 0, want_hashes=False):

@@ -204,3 +204,22 @@ def test_sha256_proof_verifies_and_tampering_is_rejected(default_seeds):
     bad_wit[100] ^= 1
     assert orc.prove(ops, bad_wit, [], wc, default_seeds)[0] == orc.E_WITNESS_INVALID
     assert orc.prove(ops, wit[:10], [], wc, default_seeds)[0] == orc.E_WITNESS_SHORT
+
+
+def test_lowmem_two_pass_oracle_matches(default_seeds):
+    """orc_prove_lowmem (hashes first, then every instance again for its openings) produces orc_prove's bytes: GF(2) with
+    asserts, a mixed GF(2) / Z64 / B2A circuit, and a failing witness."""
+    import hashlib
+
+    from reverie_b200 import circuits as C
+    from tests._zgen import random_z_circuit
+
+    ops, wit, wc = C.sha256_abc_case()
+    rc, want = orc.prove(ops, wit, [], wc, default_seeds)
+    assert (rc, hashlib.sha256(want).hexdigest(), len(want)) == orc.prove_digest_lowmem(ops, wit, [], wc, default_seeds, n_threads=3)
+    zops, gwit, zwit, zwc = random_z_circuit(np.random.default_rng(3), 4, 200, with_gf2=True)
+    rc, want = orc.prove(zops, gwit, zwit, zwc, default_seeds)
+    assert (rc, hashlib.sha256(want).hexdigest(), len(want)) == orc.prove_digest_lowmem(zops, gwit, zwit, zwc, default_seeds, n_threads=2)
+    bad = wit.copy()
+    bad[11] ^= 1
+    assert orc.prove_digest_lowmem(ops, bad, [], wc, default_seeds)[0] == orc.prove(ops, bad, [], wc, default_seeds)[0] != 0
