@@ -287,14 +287,24 @@ def run_workload(env: Env, name: str, batch: int, per_session: int, steps: int, 
     # Small GF(2) circuits: the batch is held by multi-proof sessions (P proofs side by side per session: every kernel launch
     # covers P proofs); other circuits: one proof per session.
     P = max(1, min(per_session, B))
-    try:
-        sessions = [rb.Session(circ, first, per, n_proofs=P)] if P > 1 else []
-    except rb.ReverieError:
-        P, sessions = 1, []
-    B = (B + P - 1) // P * P
-    sessions += [rb.Session(circ, first, per, n_proofs=P) for _ in range(B // P - len(sessions))]
+    grp = None
     if linked:
-        sharding.link_sessions(sessions)
+        # the rank's part of a multi-GPU prover behind one handle (rv_group): B / P linked sessions of P proofs, launched as one graph
+        try:
+            grp = rb.Group.rank(circ, rank, world, n_sessions=(B + P - 1) // P, slots=P)
+        except rb.ReverieError:
+            P = 1
+            grp = rb.Group.rank(circ, rank, world, n_sessions=B, slots=1)
+        B = (B + P - 1) // P * P
+        grp.link_distributed()
+        sessions = list(grp.sessions)
+    else:
+        try:
+            sessions = [rb.Session(circ, first, per, n_proofs=P)] if P > 1 else []
+        except rb.ReverieError:
+            P, sessions = 1, []
+        B = (B + P - 1) // P * P
+        sessions += [rb.Session(circ, first, per, n_proofs=P) for _ in range(B // P - len(sessions))]
     recv_bufs = {}  # NCCL exchange: session -> (receive tensor over the session's own all-gather buffer, send tensor over its hashes)
     batches = {}
 
@@ -308,7 +318,7 @@ def run_workload(env: Env, name: str, batch: int, per_session: int, steps: int, 
     def batch_of(sess_list):
         key = tuple(id(x) for x in sess_list)
         if key not in batches:
-            bt = rb.Batch(sess_list)
+            bt = grp.batch if (grp is not None and grp.batch is not None and len(sess_list) == len(grp.sessions)) else rb.Batch(sess_list)
             batches[key] = (bt, torch.cuda.ExternalStream(bt.stream))
         return batches[key]
 
@@ -522,6 +532,8 @@ def run_workload(env: Env, name: str, batch: int, per_session: int, steps: int, 
         del out, proof
     else:
         def step_e2e():
+            if grp is not None:  # one C call per rank: uploads, the step's graph launch, the fetch of the assembled proofs on rank 0
+                return [p._buf if p is not None else b"" for p in grp.prove_batch([wit] * B, [wz] * B, [seeds] * B)]
             upload_all(sessions)
             step_device(sessions)
             return collect(sessions)  # rank 0 (every rank with --shard proofs) ends up with the proof bytes in host memory
@@ -576,6 +588,7 @@ def run_workload(env: Env, name: str, batch: int, per_session: int, steps: int, 
     batches.clear()
     recv_bufs.clear()
     sessions.clear()
+    grp = None
     del circ
     gc.collect()
     return res

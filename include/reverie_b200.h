@@ -69,6 +69,8 @@ enum rv_status {
 
 typedef struct rv_circuit rv_circuit; /* a compiled circuit: device-resident gate tables, reusable across proofs  */
 typedef struct rv_session rv_session; /* one in-flight prove: device buffers + stream                              */
+typedef struct rv_batch rv_batch;     /* several sessions of one circuit launched as one CUDA graph               */
+typedef struct rv_group rv_group;     /* a multi-GPU prover: linked sessions on every GPU it drives               */
 
 /* Per-thread message for the last non-OK status returned on this thread. */
 const char *rv_last_error(void);
@@ -248,6 +250,38 @@ int rv_session_peer_handle(rv_session *s, uint8_t handle[RV_PEER_HANDLE_BYTES]);
 int rv_session_peer_link(rv_session *s, int rank, int world, const uint8_t *handles /* world x RV_PEER_HANDLE_BYTES */);
 int rv_session_peer_rank(const rv_session *s, int *rank, int *world, int *assembles);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * rv_group: Proof::new on several GPUs behind one handle.  The group owns, for every GPU it drives, `n_sessions` linked
+ * sessions of `slots` proofs each (n_sessions x slots proofs per step) and launches a step as one CUDA graph per GPU.
+ *   rv_group_create_local   ONE process drives `n_devices` GPUs (1, 2, 4, 8, 16): the circuit is cloned onto each device
+ *                           (rv_circuit_clone: the host-side compile is shared), the shards are linked through peer access.
+ *                           This is the call a Rust host makes to give Proof::new all the GPUs of a box.
+ *   rv_group_create_rank    one process PER GPU (MPI / torchrun style): this process holds rank `rank` of `world`; exchange
+ *                           rv_group_handles (rv_group_handles_bytes each) over any host channel, pass all of them in rank
+ *                           order to rv_group_link.  Every rank then makes the same rv_group_prove* calls with the same
+ *                           witnesses and seeds (seeds must be given: they have to agree across ranks); rank 0 receives
+ *                           the proofs, the other ranks receive the statuses.
+ *   rv_group_prove_batch    like rv_prove_batch; rv_group_prove = one proof (create the group with 1 session x 1 slot for that).
+ *   rv_group_step           relaunch one step on the inputs already uploaded (asynchronous; device-resident timing)
+ *   rv_group_session / rv_group_batch   the underlying objects of member `member` (0 for a rank group), for callers that
+ *                           drive uploads, steps and fetches themselves through the session API; owned by the group.
+ * ------------------------------------------------------------------------------------------------------------- */
+int rv_circuit_clone(const rv_circuit *c, int device, rv_circuit **out);
+int rv_group_create_local(const rv_circuit *c, const int *devices, int n_devices, int n_sessions, int slots, rv_group **out);
+int rv_group_create_rank(const rv_circuit *c, int rank, int world, int n_sessions, int slots, rv_group **out);
+size_t rv_group_handles_bytes(const rv_group *g);
+int rv_group_handles(rv_group *g, uint8_t *handles);
+int rv_group_link(rv_group *g, const uint8_t *all_handles /* world x rv_group_handles_bytes(g), rank order */);
+int rv_group_info(const rv_group *g, int *world, int *n_members, int *n_sessions, int *slots);
+rv_session *rv_group_session(rv_group *g, int member, int index);
+rv_batch *rv_group_batch(rv_group *g, int member);
+int rv_group_step(rv_group *g);
+int rv_group_prove_batch(rv_group *g, int n, const uint8_t *const *wit_gf2, const size_t *n_gf2, const uint64_t *const *wit_z64,
+                         const size_t *n_z64, const uint8_t *const *seeds, uint8_t **proofs, size_t *proof_lens, int *statuses);
+int rv_group_prove(rv_group *g, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64, size_t n_z64, const uint8_t *seeds,
+                   uint8_t **proof, size_t *proof_len);
+void rv_group_free(rv_group *g);
+
 /* cudaStream_t of the session (as void*), so callers can bracket work with their own CUDA events. */
 void *rv_session_stream(rv_session *s);
 
@@ -259,7 +293,6 @@ void *rv_session_stream(rv_session *s);
  * ordered on the leader's stream (rv_batch_stream), which is also where the caller enqueues the all-gather between
  * rv_batch_commit and rv_batch_open.  rv_batch_open reads every session's own rv_session_all_hashes_device buffer.
  * ------------------------------------------------------------------------------------------------------------- */
-typedef struct rv_batch rv_batch;
 int rv_batch_create(rv_session *const *sessions, int n, rv_batch **out);
 void rv_batch_free(rv_batch *b);        /* unbinds the sessions; does not free them */
 int rv_batch_commit(rv_batch *b);       /* async */

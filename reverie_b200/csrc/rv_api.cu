@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <string>
@@ -88,7 +89,11 @@ extern "C" void rv_free(void *p) {
                     g_pin_free.push_back(e);
                     return;
                 }
-                p = nullptr;
+                // pool full: keep the larger buffers (a caller that moves on to bigger proofs must not re-pin a gigabyte per call)
+                size_t small = 0;
+                for (size_t k = 1; k < g_pin_free.size(); k++)
+                    if (g_pin_free[k].second < g_pin_free[small].second) small = k;
+                if (g_pin_free[small].second < e.second) std::swap(g_pin_free[small], e);
                 cudaFreeHost(e.first);
                 return;
             }
@@ -100,7 +105,10 @@ extern "C" void rv_free(void *p) {
 //  circuit
 // ---------------------------------------------------------------------------------------------------------------------
 struct rv_circuit {
-    Program prog;
+    std::shared_ptr<Program> progp;  // the compiled host tables, shared by the per-device clones of a circuit (rv_circuit_clone)
+    Program &prog;
+    rv_circuit() : progp(std::make_shared<Program>()), prog(*progp) {}
+    explicit rv_circuit(std::shared_ptr<Program> p) : progp(std::move(p)), prog(*progp) {}
     DevProgram dev;
     std::vector<void *> allocs;
     std::vector<uint32_t> mul_pos;
@@ -142,29 +150,10 @@ extern "C" void rv_circuit_free(rv_circuit *c) {
     delete c;
 }
 
-extern "C" int rv_circuit_compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, rv_circuit **out) {
-    return rv_circuit_compile_ex(ops, n_ops, z64_cells, gf2_cells, 0, out);
-}
-
-extern "C" int rv_circuit_compile_ex(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, unsigned flags, rv_circuit **out) {
-    if (!out) return fail(RV_E_ARG, "out is NULL");
-    *out = nullptr;
-    if (flags & ~(unsigned)RV_COMPILE_PROVE_ONLY) return fail(RV_E_ARG, "unknown compile flag");
-    rv_circuit *c = new (std::nothrow) rv_circuit();
-    if (!c) return fail(RV_E_NOMEM, "out of memory");
-    std::string err;
+// Derived host tables + the device-resident copy of every table on `device`.  Without a device the handle still carries the host
+// tables (stats / export for the CPU test-suite), but it cannot prove or verify: there is no CPU fallback.
+static int circuit_to_device(rv_circuit *c, int device) {
     int rc;
-    const auto t0 = std::chrono::steady_clock::now();
-    try {
-        rc = compile(ops, n_ops, z64_cells, gf2_cells, c->prog, err, (flags & RV_COMPILE_PROVE_ONLY) ? COMPILE_PROVE_ONLY : 0);
-    } catch (const std::bad_alloc &) {
-        delete c;
-        return fail(RV_E_NOMEM, "out of host memory while compiling the circuit");
-    }
-    if (rc != RV_OK) {
-        delete c;
-        return fail(rc, err);
-    }
     Program &P = c->prog;
     for (uint32_t t = 0; t < P.n_online; t++)
         if (P.items[t].kind == ITEM_MUL) c->mul_pos.push_back(t);
@@ -185,11 +174,9 @@ extern "C" int rv_circuit_compile_ex(const rv_op *ops, size_t n_ops, size_t z64_
     // but it cannot prove or verify: there is no CPU fallback and rv_session_create reports RV_E_CUDA.
     if (rv_device_count() == 0) {
         c->device = -1;
-        c->compile_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
-        *out = c;
         return RV_OK;
     }
-    c->device = g_device;
+    c->device = device;
     cudaSetDevice(c->device);
     cudaDeviceGetAttribute(&c->n_sms, cudaDevAttrMultiProcessorCount, c->device);
     DevProgram &D = c->dev;
@@ -199,7 +186,6 @@ extern "C" int rv_circuit_compile_ex(const rv_op *ops, size_t n_ops, size_t z64_
         (rc = upload(c, c->vleaf_ids, &D.vleaf_ids)) || (rc = upload(c, P.item_ua, &D.item_ua)) || (rc = upload(c, P.item_ub, &D.item_ub)) ||
         (rc = upload(c, c->recon_idx, &D.recon_idx)) || (rc = upload(c, P.tgates, &D.tgates)) || (rc = upload(c, P.tlevel_off, &D.tlevel_off)) ||
         (rc = upload(c, P.rand_row, &D.rand_row)) || (rc = upload(c, P.b2a_vrefs, &D.b2a_vrefs)) || (rc = upload(c, P.b2a_urefs, &D.b2a_urefs))) {
-        rv_circuit_free(c);
         return rc;
     }
     D.n_tlevels = P.tlevel_off.empty() ? 0 : (uint32_t)P.tlevel_off.size() - 1;
@@ -259,6 +245,57 @@ extern "C" int rv_circuit_compile_ex(const rv_op *ops, size_t n_ops, size_t z64_
     D.n_pre = P.n_pre;
     D.n_inputs = (uint32_t)P.n_inputs;
     D.n_recon = (uint32_t)P.recon_pos.size();
+    cudaSetDevice(g_device);
+    return RV_OK;
+}
+
+
+extern "C" int rv_circuit_compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, rv_circuit **out) {
+    return rv_circuit_compile_ex(ops, n_ops, z64_cells, gf2_cells, 0, out);
+}
+
+extern "C" int rv_circuit_compile_ex(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, unsigned flags, rv_circuit **out) {
+    if (!out) return fail(RV_E_ARG, "out is NULL");
+    *out = nullptr;
+    if (flags & ~(unsigned)RV_COMPILE_PROVE_ONLY) return fail(RV_E_ARG, "unknown compile flag");
+    rv_circuit *c = new (std::nothrow) rv_circuit();
+    if (!c) return fail(RV_E_NOMEM, "out of memory");
+    std::string err;
+    int rc;
+    const auto t0 = std::chrono::steady_clock::now();
+    try {
+        rc = compile(ops, n_ops, z64_cells, gf2_cells, c->prog, err, (flags & RV_COMPILE_PROVE_ONLY) ? COMPILE_PROVE_ONLY : 0);
+    } catch (const std::bad_alloc &) {
+        delete c;
+        return fail(RV_E_NOMEM, "out of host memory while compiling the circuit");
+    }
+    if (rc != RV_OK) {
+        delete c;
+        return fail(rc, err);
+    }
+    const int rc2 = circuit_to_device(c, g_device);
+    if (rc2 != RV_OK) {
+        rv_circuit_free(c);
+        return rc2;
+    }
+    c->compile_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
+    *out = c;
+    return RV_OK;
+}
+
+// The same compiled circuit resident on another device: shares the host tables, uploads its own device tables.
+extern "C" int rv_circuit_clone(const rv_circuit *src, int device, rv_circuit **out) {
+    if (!src || !out) return fail(RV_E_ARG, "NULL argument");
+    *out = nullptr;
+    if (device < 0 || device >= rv_device_count()) return fail(RV_E_CUDA, "no such CUDA device");
+    rv_circuit *c = new (std::nothrow) rv_circuit(src->progp);
+    if (!c) return fail(RV_E_NOMEM, "out of memory");
+    const auto t0 = std::chrono::steady_clock::now();
+    const int rc = circuit_to_device(c, device);
+    if (rc != RV_OK) {
+        rv_circuit_free(c);
+        return rc;
+    }
     c->compile_ns = (uint64_t)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count();
     *out = c;
     return RV_OK;
@@ -914,10 +951,21 @@ extern "C" int rv_session_prove(rv_session *s) {
     if (!s) return fail(RV_E_ARG, "NULL session");
     if (s->npi1 != RV_PACKED_REPS && !s->linked()) return fail(RV_E_ARG, "rv_session_prove needs a full shard, or a shard linked to its peers (rv_session_peer_link)");
     CU(cudaSetDevice(s->c->device));
+    // a session bound to a batch but launched on its own: its stream forks from the leader's (where its uploads were ordered) and
+    // joins back (where its fetch synchronises)
+    const bool bound = s->lead && s->lead != s;
+    if (bound) {
+        CU(cudaEventRecord(s->ev_bjoin, s->lead->st));
+        CU(cudaStreamWaitEvent(s->st, s->ev_bjoin, 0));
+    }
     const int rc = run_graphed(s, s->g_prove, [&] {
         const int r = commit_body(s);
         return r != RV_OK ? r : open_body(s, nullptr);
     });
+    if (bound) {
+        CU(cudaEventRecord(s->ev_bjoin, s->st));
+        CU(cudaStreamWaitEvent(s->lead->st, s->ev_bjoin, 0));
+    }
     if (rc == RV_OK) s->committed = s->opened = s->ever_committed = true;
     return rc;
 }
@@ -1336,6 +1384,258 @@ extern "C" int rv_prove_batch(const rv_circuit *c, int n, const uint8_t *const *
         }
     }
     return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+//  rv_group: Proof::new on several GPUs behind one handle (SURVEY.md 8(b) "one host thread drives G GPUs ... or one thread
+//  per GPU", 8(e)).  A group owns, per GPU it drives ("member"), n_sessions linked multi-proof sessions of `slots` proofs and
+//  the rv_batch that launches them as one CUDA graph.  Local groups hold all `world` members in this process (the circuit is
+//  cloned onto each device, the shards are linked by peer access); rank groups hold one member and are linked to the other
+//  processes' groups through their handles (CUDA IPC).
+// ---------------------------------------------------------------------------------------------------------------------
+struct rv_group {
+    struct Member {
+        int rank = 0;
+        const rv_circuit *c = nullptr;
+        rv_circuit *owned = nullptr;  // clone made for this member's device
+        std::vector<rv_session *> ss;
+        rv_batch *batch = nullptr;
+    };
+    std::vector<Member> members;
+    int world = 1, n_sessions = 1, slots = 1;
+    bool linked = false, local = false;
+};
+
+extern "C" void rv_group_free(rv_group *g) {
+    if (!g) return;
+    for (auto &m : g->members) {
+        if (m.batch) rv_batch_free(m.batch);
+        for (rv_session *s : m.ss) rv_session_free(s);
+        if (m.owned) rv_circuit_free(m.owned);
+    }
+    delete g;
+}
+
+static int group_add_member(rv_group *g, const rv_circuit *c, rv_circuit *owned, int rank) {
+    g->members.emplace_back();
+    rv_group::Member &m = g->members.back();
+    m.rank = rank;
+    m.c = c;
+    m.owned = owned;
+    const int per = RV_PACKED_REPS / g->world;
+    for (int i = 0; i < g->n_sessions; i++) {
+        rv_session *s = nullptr;
+        const int rc = rv_session_create_multi(c, rank * per, per, g->slots, &s);
+        if (rc) return rc;
+        m.ss.push_back(s);
+    }
+    if (g->n_sessions > 1) return rv_batch_create(m.ss.data(), g->n_sessions, &m.batch);
+    return RV_OK;
+}
+
+static int group_check_shape(int world, int n_sessions, int slots) {
+    if (world < 1 || world > RV_MAX_PEERS || RV_PACKED_REPS % world) return fail(RV_E_ARG, "the number of GPUs must divide the 32 packed instances (1, 2, 4, 8, 16)");
+    if (n_sessions < 1 || n_sessions > 64 || slots < 1 || slots > 128) return fail(RV_E_ARG, "a group holds 1..64 sessions of 1..128 proofs");
+    return RV_OK;
+}
+
+static int group_link_all(rv_group *g, const uint8_t *all, size_t stride) {  // all: [rank][session][RV_PEER_HANDLE_BYTES]
+    std::vector<uint8_t> hs((size_t)g->world * RV_PEER_HANDLE_BYTES);
+    for (auto &m : g->members)
+        for (int i = 0; i < g->n_sessions; i++) {
+            for (int r = 0; r < g->world; r++) memcpy(hs.data() + (size_t)r * RV_PEER_HANDLE_BYTES, all + (size_t)r * stride + (size_t)i * RV_PEER_HANDLE_BYTES, RV_PEER_HANDLE_BYTES);
+            const int rc = rv_session_peer_link(m.ss[i], m.rank, g->world, hs.data());
+            if (rc) return rc;
+        }
+    g->linked = true;
+    return RV_OK;
+}
+
+extern "C" int rv_group_create_local(const rv_circuit *c, const int *devices, int n_devices, int n_sessions, int slots, rv_group **out) {
+    if (!c || !out || (n_devices > 0 && !devices)) return fail(RV_E_ARG, "NULL argument");
+    *out = nullptr;
+    if (const int rc = group_check_shape(n_devices, n_sessions, slots)) return rc;
+    if (c->device < 0) return fail(RV_E_CUDA, "no CUDA device: reverie-b200 has no CPU fallback");
+    rv_group *g = new (std::nothrow) rv_group();
+    if (!g) return fail(RV_E_NOMEM, "out of memory");
+    g->world = n_devices;
+    g->n_sessions = n_sessions;
+    g->slots = slots;
+    g->local = true;
+    g->members.reserve(n_devices);
+    int rc = RV_OK;
+    for (int r = 0; r < n_devices && rc == RV_OK; r++) {
+        const rv_circuit *mc = c;
+        rv_circuit *owned = nullptr;
+        if (devices[r] != c->device) {
+            rc = rv_circuit_clone(c, devices[r], &owned);
+            mc = owned;
+        }
+        if (rc == RV_OK) rc = group_add_member(g, mc, owned, r);
+        else if (owned) rv_circuit_free(owned);
+    }
+    if (rc == RV_OK && n_devices > 1) {
+        const size_t stride = (size_t)n_sessions * RV_PEER_HANDLE_BYTES;
+        std::vector<uint8_t> all((size_t)n_devices * stride);
+        for (int r = 0; r < n_devices && rc == RV_OK; r++)
+            for (int i = 0; i < n_sessions && rc == RV_OK; i++) rc = rv_session_peer_handle(g->members[r].ss[i], all.data() + (size_t)r * stride + (size_t)i * RV_PEER_HANDLE_BYTES);
+        if (rc == RV_OK) rc = group_link_all(g, all.data(), stride);
+    }
+    if (rc != RV_OK) {
+        rv_group_free(g);
+        return rc;
+    }
+    *out = g;
+    return RV_OK;
+}
+
+extern "C" int rv_group_create_rank(const rv_circuit *c, int rank, int world, int n_sessions, int slots, rv_group **out) {
+    if (!c || !out) return fail(RV_E_ARG, "NULL argument");
+    *out = nullptr;
+    if (const int rc = group_check_shape(world, n_sessions, slots)) return rc;
+    if (rank < 0 || rank >= world) return fail(RV_E_ARG, "rank out of range");
+    if (c->device < 0) return fail(RV_E_CUDA, "no CUDA device: reverie-b200 has no CPU fallback");
+    rv_group *g = new (std::nothrow) rv_group();
+    if (!g) return fail(RV_E_NOMEM, "out of memory");
+    g->world = world;
+    g->n_sessions = n_sessions;
+    g->slots = slots;
+    g->members.reserve(1);
+    const int rc = group_add_member(g, c, nullptr, rank);
+    if (rc != RV_OK) {
+        rv_group_free(g);
+        return rc;
+    }
+    *out = g;
+    return RV_OK;
+}
+
+extern "C" size_t rv_group_handles_bytes(const rv_group *g) { return g ? (size_t)g->n_sessions * RV_PEER_HANDLE_BYTES : 0; }
+
+extern "C" int rv_group_handles(rv_group *g, uint8_t *out) {
+    if (!g || !out) return fail(RV_E_ARG, "NULL argument");
+    if (g->local) return fail(RV_E_ARG, "a local group is linked at creation");
+    for (int i = 0; i < g->n_sessions; i++)
+        if (const int rc = rv_session_peer_handle(g->members[0].ss[i], out + (size_t)i * RV_PEER_HANDLE_BYTES)) return rc;
+    return RV_OK;
+}
+
+extern "C" int rv_group_link(rv_group *g, const uint8_t *all_handles) {
+    if (!g || !all_handles) return fail(RV_E_ARG, "NULL argument");
+    if (g->local || g->linked) return fail(RV_E_ARG, "group is already linked");
+    if (g->world == 1) return RV_OK;
+    return group_link_all(g, all_handles, rv_group_handles_bytes(g));
+}
+
+extern "C" int rv_group_info(const rv_group *g, int *world, int *n_members, int *n_sessions, int *slots) {
+    if (!g) return fail(RV_E_ARG, "NULL group");
+    if (world) *world = g->world;
+    if (n_members) *n_members = (int)g->members.size();
+    if (n_sessions) *n_sessions = g->n_sessions;
+    if (slots) *slots = g->slots;
+    return RV_OK;
+}
+extern "C" rv_session *rv_group_session(rv_group *g, int member, int index) {
+    if (!g || member < 0 || member >= (int)g->members.size() || index < 0 || index >= g->n_sessions) return nullptr;
+    return g->members[member].ss[index];
+}
+extern "C" rv_batch *rv_group_batch(rv_group *g, int member) {
+    if (!g || member < 0 || member >= (int)g->members.size()) return nullptr;
+    return g->members[member].batch;
+}
+
+// Launches one step (commit + exchange + open) of the first `n_used` sessions of every member, asynchronously.
+static int group_launch(rv_group *g, int n_used) {
+    for (auto &m : g->members) {
+        int rc = RV_OK;
+        if (n_used == g->n_sessions && m.batch) rc = rv_batch_prove(m.batch);
+        else
+            for (int i = 0; i < n_used && rc == RV_OK; i++) rc = rv_session_prove(m.ss[i]);
+        if (rc) return rc;
+    }
+    return RV_OK;
+}
+
+extern "C" int rv_group_step(rv_group *g) {
+    if (!g) return fail(RV_E_ARG, "NULL group");
+    if (g->world > 1 && !g->linked) return fail(RV_E_ARG, "rv_group_link has not run");
+    return group_launch(g, g->n_sessions);
+}
+
+extern "C" int rv_group_prove_batch(rv_group *g, int n, const uint8_t *const *wit_gf2, const size_t *n_gf2, const uint64_t *const *wit_z64,
+                                    const size_t *n_z64, const uint8_t *const *seeds, uint8_t **proofs, size_t *proof_lens, int *statuses) {
+    if (!g || n <= 0 || !statuses) return fail(RV_E_ARG, "bad argument");
+    if (g->world > 1 && !g->linked) return fail(RV_E_ARG, "rv_group_link has not run");
+    const bool assembles = g->members[0].rank == 0;
+    if (assembles && (!proofs || !proof_lens)) return fail(RV_E_ARG, "the assembling rank needs the output arrays");
+    // every rank of a proof must use the same 256 seeds: a local group draws them here, a rank group needs them from the caller
+    std::vector<uint8_t> drawn;
+    if (g->world > 1) {
+        bool missing = !seeds;
+        for (int i = 0; i < n && !missing; i++) missing = !seeds[i];
+        if (missing) {
+            if (!g->local) return fail(RV_E_ARG, "a rank group needs the proofs' seeds from the caller (the same on every rank: draw them on rank 0 and broadcast)");
+            drawn.resize((size_t)n * RV_TOTAL_REPS * 16);
+            size_t got = 0;
+            while (got < drawn.size()) {
+                ssize_t r = getrandom(drawn.data() + got, drawn.size() - got, 0);
+                if (r <= 0) return fail(RV_E_ARG, "getrandom failed");
+                got += (size_t)r;
+            }
+        }
+    }
+    auto seed_of = [&](int i) -> const uint8_t * {
+        if (seeds && seeds[i]) return seeds[i];
+        return drawn.empty() ? nullptr : drawn.data() + (size_t)i * RV_TOTAL_REPS * 16;
+    };
+    for (int i = 0; i < n; i++) {
+        statuses[i] = RV_OK;
+        if (proofs) proofs[i] = nullptr;
+        if (proof_lens) proof_lens[i] = 0;
+    }
+    const int cap = g->n_sessions * g->slots;
+    int rc = RV_OK;
+    for (int base = 0; base < n && rc == RV_OK; base += cap) {  // waves of up to `cap` proofs
+        const int cnt = std::min(cap, n - base), n_used = (cnt + g->slots - 1) / g->slots;
+        for (auto &m : g->members)
+            for (int k = 0; k < cnt && rc == RV_OK; k++) {
+                const int i = base + k;
+                const int r = rv_session_upload_slot(m.ss[k / g->slots], k % g->slots, wit_gf2 ? wit_gf2[i] : nullptr, n_gf2 ? n_gf2[i] : 0, wit_z64 ? wit_z64[i] : nullptr,
+                                                     n_z64 ? n_z64[i] : 0, seed_of(i));
+                if (r == RV_E_WITNESS_SHORT || r == RV_E_ARG) statuses[i] = r;  // the slot keeps its previous inputs; its output is dropped
+                else if (r != RV_OK) rc = r;
+            }
+        if (rc == RV_OK) rc = group_launch(g, n_used);
+        for (auto &m : g->members)
+            for (int k = 0; k < cnt && rc == RV_OK; k++) {
+                const int i = base + k;
+                if (statuses[i] != RV_OK && statuses[i] != RV_E_WITNESS_INVALID) continue;
+                uint8_t *p = nullptr;
+                size_t len = 0;
+                const int r = rv_session_fetch_slot(m.ss[k / g->slots], k % g->slots, nullptr, &p, &len);
+                if (r == RV_E_CUDA || r == RV_E_PEER) rc = r;
+                if (r != RV_OK) {
+                    statuses[i] = r;
+                    if (p) rv_free(p);
+                } else if (m.rank == 0 && proofs) {
+                    proofs[i] = p;
+                    proof_lens[i] = len;
+                } else if (p) rv_free(p);
+            }
+    }
+    return rc;
+}
+
+extern "C" int rv_group_prove(rv_group *g, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64, size_t n_z64, const uint8_t *seeds,
+                              uint8_t **proof, size_t *proof_len) {
+    int status = RV_OK;
+    uint8_t *p = nullptr;
+    size_t len = 0;
+    const int rc = rv_group_prove_batch(g, 1, &wit_gf2, &n_gf2, &wit_z64, &n_z64, seeds ? &seeds : nullptr, &p, &len, &status);
+    if (proof) *proof = p;
+    else if (p) rv_free(p);
+    if (proof_len) *proof_len = len;
+    return rc != RV_OK ? rc : status;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

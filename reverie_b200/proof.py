@@ -107,9 +107,17 @@ class Session:
         self._h = h
         self.first_instance, self.n_instances, self.n_proofs = first_instance, n_instances, n_proofs
 
+    @classmethod
+    def _view(cls, circuit: Circuit, handle, first_instance: int, n_instances: int, n_proofs: int, owner) -> "Session":
+        """A Session over a handle that `owner` (a Group) frees."""
+        s = cls.__new__(cls)
+        s.circuit, s._h, s._owner = circuit, C.c_void_p(handle), owner
+        s.first_instance, s.n_instances, s.n_proofs = first_instance, n_instances, n_proofs
+        return s
+
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and getattr(self, "_owner", None) is None:
             N.lib().rv_session_free(h)
 
     def upload(self, wit_gf2, wit_z64=(), seeds=None, slot: int = 0):
@@ -239,9 +247,15 @@ class Batch:
         N.check(N.lib().rv_batch_create(arr, len(self.sessions), C.byref(h)))
         self._h = h
 
+    @classmethod
+    def _view(cls, sessions, handle, owner) -> "Batch":
+        b = cls.__new__(cls)
+        b.sessions, b._h, b._owner = list(sessions), C.c_void_p(handle), owner
+        return b
+
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h:
+        if h and getattr(self, "_owner", None) is None:
             N.lib().rv_batch_free(h)
 
     def commit(self):
@@ -256,6 +270,127 @@ class Batch:
     @property
     def stream(self) -> int:
         return int(N.lib().rv_batch_stream(self._h) or 0)
+
+
+def _batch_args(n, wits_gf2, wits_z64, seeds):
+    wg = [np.ascontiguousarray(np.asarray(w, dtype=np.uint8)) for w in wits_gf2]
+    wz = [np.ascontiguousarray(np.asarray(w, dtype=np.uint64)) for w in (wits_z64 if wits_z64 is not None else [()] * n)]
+    sd = [_seeds_arr(x) for x in (seeds if seeds is not None else [None] * n)]
+    vp = C.c_void_p
+    a_wg = (vp * n)(*[w.ctypes.data if w.size else None for w in wg])
+    a_wz = (vp * n)(*[w.ctypes.data if w.size else None for w in wz])
+    a_sd = (vp * n)(*[x.ctypes.data if x is not None else None for x in sd])
+    n_g = (C.c_size_t * n)(*[w.size for w in wg])
+    n_z = (C.c_size_t * n)(*[w.size for w in wz])
+    return (wg, wz, sd), a_wg, n_g, a_wz, n_z, a_sd
+
+
+def _batch_results(n, outs, lens, sts, want_proofs=True):
+    vp = C.c_void_p
+    proofs, first_err = [], None
+    for i in range(n):
+        if sts[i] == 0:
+            proofs.append(Proof(_take(vp(outs[i]), C.c_size_t(lens[i]), zero_copy_from=1 << 16)) if want_proofs else None)  # Proof wraps the library's buffer
+        else:
+            proofs.append(None)
+            first_err = first_err if first_err is not None else sts[i]
+    if first_err is not None:
+        msg = {N.E_WITNESS_INVALID: "witness is invalid!", N.E_WITNESS_SHORT: "witness is too short", N.E_PEER: "a linked rank did not arrive"}.get(first_err, "proof failed")
+        cls = N.WitnessError if first_err in (N.E_WITNESS_INVALID, N.E_WITNESS_SHORT) else N.ReverieError
+        err = cls(first_err, msg)
+        err.proofs = proofs
+        raise err
+    return proofs
+
+
+class Group:
+    """Proof::new on several GPUs behind one handle (rv_group).
+
+    Group.local(circuit, devices, ...)        one process drives all the GPUs (peer access between them)
+    Group.rank(circuit, rank, world, ...)     one process per GPU: exchange `handles()` over any host channel and `link()` them
+                                              (`link_distributed()` does it through torch.distributed)
+    A step proves n_sessions x slots proofs: every GPU holds its 32 / world packed instances of each of them; the exchange of
+    repetition hashes and the assembly of the proofs happen on the devices, over peer memory (no collective library)."""
+
+    def __init__(self, circuit: Circuit, handle, rank: int):
+        self.circuit, self._h, self.rank_id = circuit, handle, rank
+        w, m, ns, sl = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        N.check(N.lib().rv_group_info(handle, C.byref(w), C.byref(m), C.byref(ns), C.byref(sl)))
+        self.world, self.n_members, self.n_sessions, self.slots = w.value, m.value, ns.value, sl.value
+        per = N.PACKED_REPS // self.world
+        self.members = []
+        for mem in range(self.n_members):
+            r = rank if self.n_members == 1 else mem
+            ss = [Session._view(circuit, N.lib().rv_group_session(handle, mem, i), r * per, per, self.slots, self) for i in range(self.n_sessions)]
+            bh = N.lib().rv_group_batch(handle, mem)
+            self.members.append((ss, Batch._view(ss, bh, self) if bh else None))
+
+    @staticmethod
+    def local(circuit: Circuit, devices: Sequence[int], n_sessions: int = 1, slots: int = 1) -> "Group":
+        arr = (C.c_int * len(devices))(*devices)
+        h = C.c_void_p()
+        N.check(N.lib().rv_group_create_local(circuit.handle, arr, len(devices), n_sessions, slots, C.byref(h)))
+        return Group(circuit, h, 0)
+
+    @staticmethod
+    def rank(circuit: Circuit, rank: int, world: int, n_sessions: int = 1, slots: int = 1) -> "Group":
+        h = C.c_void_p()
+        N.check(N.lib().rv_group_create_rank(circuit.handle, rank, world, n_sessions, slots, C.byref(h)))
+        return Group(circuit, h, rank)
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            for ss, b in getattr(self, "members", []):
+                for s in ss:
+                    s._h = None
+                if b is not None:
+                    b._h = None
+            N.lib().rv_group_free(h)
+
+    @property
+    def sessions(self):
+        """This process's sessions of member 0 (the only member of a rank group)."""
+        return self.members[0][0]
+
+    @property
+    def batch(self):
+        return self.members[0][1]
+
+    def handles(self) -> bytes:
+        buf = np.zeros(int(N.lib().rv_group_handles_bytes(self._h)), dtype=np.uint8)
+        N.check(N.lib().rv_group_handles(self._h, _ptr(buf)))
+        return buf.tobytes()
+
+    def link(self, all_handles: Sequence[bytes]):
+        blob = np.frombuffer(b"".join(all_handles), dtype=np.uint8)
+        N.check(N.lib().rv_group_link(self._h, _ptr(blob)))
+
+    def link_distributed(self, group=None):
+        """Exchange the handles through torch.distributed's host channel (once) and link."""
+        import torch.distributed as dist
+
+        if self.world == 1:
+            return
+        everyone = [None] * dist.get_world_size(group)
+        dist.all_gather_object(everyone, self.handles(), group=group)
+        self.link(everyone)
+
+    def step(self):
+        """Relaunch one step on the inputs already uploaded (asynchronous)."""
+        N.check(N.lib().rv_group_step(self._h))
+
+    def prove_batch(self, wits_gf2, wits_z64=None, seeds=None):
+        """rv_group_prove_batch: returns the list of Proof on the assembling rank (rank 0 / a local group), a list of None on the
+        other ranks of a rank group; raises the first per-proof error after all proofs have run."""
+        n = len(wits_gf2)
+        keep, a_wg, n_g, a_wz, n_z, a_sd = _batch_args(n, wits_gf2, wits_z64, seeds)
+        outs, lens, sts = (C.c_void_p * n)(), (C.c_size_t * n)(), (C.c_int * n)()
+        N.check(N.lib().rv_group_prove_batch(self._h, n, a_wg, n_g, a_wz, n_z, a_sd, outs, lens, sts))
+        return _batch_results(n, outs, lens, sts, want_proofs=self.rank_id == 0)
+
+    def prove(self, wit_gf2, wit_z64=(), seeds=None):
+        return self.prove_batch([wit_gf2], [wit_z64], [seeds] if seeds is not None else None)[0]
 
 
 def assemble(comm: bytes, parts: Sequence[bytes]) -> bytes:
@@ -305,31 +440,10 @@ class Proof:
         Returns a list of Proof; raises the first per-proof error (WitnessError ...) after all proofs have run."""
         c = _as_circuit(circuit, wire_counts)
         n = len(wits_gf2)
-        wg = [np.ascontiguousarray(np.asarray(w, dtype=np.uint8)) for w in wits_gf2]
-        wz = [np.ascontiguousarray(np.asarray(w, dtype=np.uint64)) for w in (wits_z64 if wits_z64 is not None else [()] * n)]
-        sd = [_seeds_arr(x) for x in (seeds if seeds is not None else [None] * n)]
-        vp = C.c_void_p
-        a_wg = (vp * n)(*[w.ctypes.data if w.size else None for w in wg])
-        a_wz = (vp * n)(*[w.ctypes.data if w.size else None for w in wz])
-        a_sd = (vp * n)(*[x.ctypes.data if x is not None else None for x in sd])
-        n_g = (C.c_size_t * n)(*[w.size for w in wg])
-        n_z = (C.c_size_t * n)(*[w.size for w in wz])
-        outs, lens, sts = (vp * n)(), (C.c_size_t * n)(), (C.c_int * n)()
+        keep, a_wg, n_g, a_wz, n_z, a_sd = _batch_args(n, wits_gf2, wits_z64, seeds)
+        outs, lens, sts = (C.c_void_p * n)(), (C.c_size_t * n)(), (C.c_int * n)()
         N.check(N.lib().rv_prove_batch(c.handle, n, a_wg, n_g, a_wz, n_z, a_sd, outs, lens, sts))
-        proofs, first_err = [], None
-        for i in range(n):
-            if sts[i] == 0:
-                proofs.append(Proof(_take(vp(outs[i]), C.c_size_t(lens[i]), zero_copy_from=1 << 16)))  # Proof wraps the library's buffer
-            else:
-                proofs.append(None)
-                first_err = first_err if first_err is not None else sts[i]
-        if first_err is not None:
-            msg = {N.E_WITNESS_INVALID: "witness is invalid!", N.E_WITNESS_SHORT: "witness is too short"}.get(first_err, "proof failed")
-            cls = N.WitnessError if first_err in (N.E_WITNESS_INVALID, N.E_WITNESS_SHORT) else N.ReverieError
-            err = cls(first_err, msg)
-            err.proofs = proofs
-            raise err
-        return proofs
+        return _batch_results(n, outs, lens, sts)
 
     def verify_detail(self, circuit, wire_counts=None) -> Tuple[bool, bool]:
         """(accept, okay): `accept` is the reference's verdict -- the recomputed commitment equals the proof's

@@ -91,6 +91,18 @@ def main():
             proof = sharding.prove_linked(circ, gwit, zwit, seeds, session=s1)
             if rank == 0:
                 assert proof == orc.prove(ops, gwit, zwit, wc, seeds)[1], (name, rnd)
+    # the same through the one-handle API (rv_group_create_rank + handles over the host channel): waves beyond the capacity
+    if 32 // world >= 4:
+        g = rb.Group.rank(scirc, rank, world, n_sessions=2, slots=2)
+        g.link_distributed()
+        order = [0, 1, 2, 1, 0, 2, 2]
+        for rnd in range(3):
+            got = g.prove_batch([wits[k] for k in order], None, [sds[k] for k in order])
+            if rank == 0:
+                assert [p.serialize() for p in got] == [orc.prove(sops, wits[k], [], swc, sds[k])[1] for k in order], rnd
+            else:
+                assert got == [None] * len(order)
+        del g
     if rank == 0:
         print(f"mgpu ok: linked sessions (device-side exchange) on {world} GPUs", flush=True)
     dist.barrier()

@@ -238,6 +238,53 @@ def test_linked_shards_exchange_on_device(rb, default_seeds):
         ys[0].peer_link(0, 2, hs)
 
 
+def test_group_api_local(rb, default_seeds):
+    """rv_group_create_local: one handle, one host thread, `world` members (here all on device 0 -- on a multi-GPU box pass its
+    devices); prove / prove_batch return the oracle's bytes, including waves beyond the group's capacity, partially filled
+    sessions, OS-RNG seeds (drawn once for all members) and per-proof witness errors."""
+    import orc
+    from reverie_b200 import circuits as C
+    from reverie_b200 import _native as N
+
+    ndev = N.lib().rv_device_count()
+    sops, n_wires, _ = C.sha256_compress_circuit(None)
+    swc = (0, n_wires)
+    rng = np.random.default_rng(33)
+    wits = [C.sha256_witness(C.sha256_pad_single_block(bytes([65 + k]) * k)) for k in range(7)]
+    sds = [rng.integers(0, 256, size=256 * 16, dtype=np.uint8).tobytes() for _ in range(7)]
+    want = [orc.prove(sops, w, [], swc, sd)[1] for w, sd in zip(wits, sds)]
+    circ = rb.Circuit(sops, swc)
+    for world in (1, 2, 4):
+        devices = [r % ndev for r in range(world)]
+        g = rb.Group.local(circ, devices, n_sessions=2, slots=2)  # capacity 4 proofs per step: 7 proofs = a full wave + a partial one
+        for _ in range(3):
+            got = g.prove_batch(wits, None, sds)
+            assert [p.serialize() for p in got] == want, world
+        p1 = g.prove(wits[3], (), sds[3])
+        assert p1.serialize() == want[3]
+        p2 = g.prove(wits[0])  # seeds from the OS RNG, the same for every member
+        assert p2.verify(circ)
+        del g
+    # AssertZero failures are per proof; a Z64 circuit goes through a 1 x 1 group
+    aops, awit, awc = C.sha256_abc_case()
+    acirc = rb.Circuit(aops, awc)
+    bad = awit.copy()
+    bad[11] ^= 1
+    g = rb.Group.local(acirc, [0, 0], n_sessions=1, slots=3)
+    with pytest.raises(rb.WitnessError) as e:
+        g.prove_batch([awit, bad, awit], None, [default_seeds] * 3)
+    good = orc.prove(aops, awit, [], awc, default_seeds)[1]
+    assert [None if p is None else p.serialize() for p in e.value.proofs] == [good, None, good]
+    del g
+    zops, zwc = C.flat_mul_circuit(300, domain=C.Z64)
+    zw = np.array([3, 5], dtype=np.uint64)
+    zc = rb.Circuit(zops, zwc)
+    g = rb.Group.local(zc, [0, 0, 0, 0])
+    assert g.prove((), zw, default_seeds).serialize() == orc.prove(zops, [], zw, zwc, default_seeds)[1]
+    with pytest.raises(rb.ReverieError):  # multi-proof sessions do not serve Z64
+        rb.Group.local(zc, [0, 0], n_sessions=1, slots=2)
+
+
 def test_os_rng_seeds_verify(rb):
     """seeds=NULL draws from the OS RNG like the reference (src/proof/mod.rs:131-134); the oracle's verifier must accept."""
     import orc
