@@ -313,20 +313,37 @@ def run_workload(env: Env, name: str, batch: int, per_session: int, steps: int, 
             for slot in range(x.n_proofs):
                 x.upload(wit, wz, seeds, slot=slot)
 
-    # The sessions of a step are driven as one rv_batch: each phase of all of them is ONE CUDA graph launch on the leader's
-    # stream; the sessions' own streams fork from it and join back inside the graph.
+    # N = 1 (and the NCCL / whole-proof modes): the sessions of a step are driven as one rv_batch -- each phase of all of them is
+    # ONE CUDA graph launch on the leader's stream; the sessions' own streams fork from it and join back inside the graph.
+    # Linked groups (N > 1): every session is its own CUDA graph launch on its own stream (rv_group: uploads of the next session
+    # overlap the work of the previous one), so a step is B / P launches per rank.
+    ext_streams = {}
+
     def batch_of(sess_list):
         key = tuple(id(x) for x in sess_list)
         if key not in batches:
-            bt = grp.batch if (grp is not None and grp.batch is not None and len(sess_list) == len(grp.sessions)) else rb.Batch(sess_list)
+            bt = rb.Batch(sess_list)
             batches[key] = (bt, torch.cuda.ExternalStream(bt.stream))
         return batches[key]
 
+    def streams_of(sess_list):
+        """The streams a step of sess_list runs on (what the step's CUDA-event pair has to fork to and join from)."""
+        if grp is None:
+            return [batch_of(sess_list)[1]]
+        for x in sess_list:
+            if x not in ext_streams:
+                ext_streams[x] = torch.cuda.ExternalStream(x.stream)
+        return [ext_streams[x] for x in sess_list]
+
     def step_device(sess_list):
         """The proofs held by sess_list: commit + exchange + open with inputs resident in HBM."""
+        if grp is not None:
+            for x in sess_list:
+                x.prove()  # linked shards: the exchange of repetition hashes happens inside the challenge kernel, over peer memory
+            return
         bt, lead = batch_of(sess_list)
-        if world == 1 or by_proofs or linked:
-            bt.prove()  # linked shards: the exchange of repetition hashes happens inside the challenge kernel, over peer memory
+        if world == 1 or by_proofs:
+            bt.prove()
             return
         bt.commit()
         # --exchange nccl: all-gather of the repetition hashes device to device, ONE NCCL group launch for the proofs in flight,
@@ -340,18 +357,20 @@ def run_workload(env: Env, name: str, batch: int, per_session: int, steps: int, 
 
     def timed_device(sess_list, k: int) -> float:
         tot = 0.0
-        _, lead = batch_of(sess_list)
+        sts = streams_of(sess_list)
         for _ in range(k):
             with torch.cuda.stream(env.timing_stream):
                 env.flush.zero_()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             env.barrier()
             a.record(env.timing_stream)
-            lead.wait_event(a)
+            for st_ in sts:
+                st_.wait_event(a)
             step_device(sess_list)
-            e = torch.cuda.Event()
-            e.record(lead)
-            env.timing_stream.wait_event(e)
+            for st_ in sts:
+                e = torch.cuda.Event()
+                e.record(st_)
+                env.timing_stream.wait_event(e)
             b.record(env.timing_stream)
             env.barrier()
             tot += a.elapsed_time(b)
@@ -462,6 +481,7 @@ def run_workload(env: Env, name: str, batch: int, per_session: int, steps: int, 
     if big and world == 1:
         batches.clear()
         recv_bufs.clear()
+        ext_streams.clear()
         sessions.clear()
         gc.collect()
 
@@ -539,7 +559,7 @@ def run_workload(env: Env, name: str, batch: int, per_session: int, steps: int, 
             return collect(sessions)  # rank 0 (every rank with --shard proofs) ends up with the proof bytes in host memory
 
         for _ in range(warmup):
-            step_e2e()
+            out = step_e2e()  # (held like in the timed loop: big proofs come back in pooled pinned buffers, two are in rotation)
         env.barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
@@ -577,7 +597,7 @@ def run_workload(env: Env, name: str, batch: int, per_session: int, steps: int, 
                                    f"{per} packed instances (= {per * 8} repetitions) per GPU, {B} proofs in flight per step") + f"; {B // P} sessions x {P} proofs side by side",
                    "exchange": exchange,
                    "l2": "256 MiB memset between timed steps (outside the per-step CUDA-event pair)",
-                   "timing": "one CUDA-event pair per step on a timing stream that forks to / joins the batch leader's stream (the session streams fork from / join it inside the CUDA graph), summed over K steps"},
+                   "timing": "one CUDA-event pair per step on a timing stream that forks to / joins the batch leader's stream (the session streams fork from / join it inside the CUDA graph), summed over K steps (linked groups: the pair forks to / joins every session's stream)"},
         "clocks": clocks, "e2e": e2e, "parity_checked": parity, "proof_sha256": digest, "proof_bytes": proof_len,
         "compile_s": compile_s, "circuit_gen_s": gen_s, "gpu_launches": int(launches), "roofline": roofline,
         "circuit": {k: st[k] for k in ("n_and", "n_ops", "value_depth", "linear_depth", "z64_mul", "z64_value_depth")},
@@ -587,6 +607,7 @@ def run_workload(env: Env, name: str, batch: int, per_session: int, steps: int, 
                     "single_proof_latency_ms": {"device": lat_ms, "e2e": single_latency_ms}})
     batches.clear()
     recv_bufs.clear()
+    ext_streams.clear()
     sessions.clear()
     grp = None
     del circ

@@ -252,7 +252,7 @@ int rv_session_peer_rank(const rv_session *s, int *rank, int *world, int *assemb
 
 /* ---------------------------------------------------------------------------------------------------------------
  * rv_group: Proof::new on several GPUs behind one handle.  The group owns, for every GPU it drives, `n_sessions` linked
- * sessions of `slots` proofs each (n_sessions x slots proofs per step) and launches a step as one CUDA graph per GPU.
+ * sessions of `slots` proofs each (n_sessions x slots proofs per step); a session's step is one CUDA graph launch per GPU.
  *   rv_group_create_local   ONE process drives `n_devices` GPUs (1, 2, 4, 8, 16): the circuit is cloned onto each device
  *                           (rv_circuit_clone: the host-side compile is shared), the shards are linked through peer access.
  *                           This is the call a Rust host makes to give Proof::new all the GPUs of a box.
@@ -263,8 +263,8 @@ int rv_session_peer_rank(const rv_session *s, int *rank, int *world, int *assemb
  *                           the proofs, the other ranks receive the statuses.
  *   rv_group_prove_batch    like rv_prove_batch; rv_group_prove = one proof (create the group with 1 session x 1 slot for that).
  *   rv_group_step           relaunch one step on the inputs already uploaded (asynchronous; device-resident timing)
- *   rv_group_session / rv_group_batch   the underlying objects of member `member` (0 for a rank group), for callers that
- *                           drive uploads, steps and fetches themselves through the session API; owned by the group.
+ *   rv_group_session        session `index` of member `member` (0 for a rank group), for callers that drive uploads, steps and
+ *                           fetches themselves through the session API; owned by the group.  Each session has its own stream.
  * ------------------------------------------------------------------------------------------------------------- */
 int rv_circuit_clone(const rv_circuit *c, int device, rv_circuit **out);
 int rv_group_create_local(const rv_circuit *c, const int *devices, int n_devices, int n_sessions, int slots, rv_group **out);
@@ -274,7 +274,6 @@ int rv_group_handles(rv_group *g, uint8_t *handles);
 int rv_group_link(rv_group *g, const uint8_t *all_handles /* world x rv_group_handles_bytes(g), rank order */);
 int rv_group_info(const rv_group *g, int *world, int *n_members, int *n_sessions, int *slots);
 rv_session *rv_group_session(rv_group *g, int member, int index);
-rv_batch *rv_group_batch(rv_group *g, int member);
 int rv_group_step(rv_group *g);
 int rv_group_prove_batch(rv_group *g, int n, const uint8_t *const *wit_gf2, const size_t *n_gf2, const uint64_t *const *wit_z64,
                          const size_t *n_z64, const uint8_t *const *seeds, uint8_t **proofs, size_t *proof_lens, int *statuses);

@@ -615,7 +615,8 @@ struct Scope {
     KTimer *t = nullptr;
     cudaEvent_t a = nullptr, b = nullptr;
     cudaStream_t stream;
-    Scope(rv_session *s_, const char *name, uint64_t bytes, uint64_t n_launches = 1, cudaStream_t on = nullptr) : s(s_), stream(on ? on : s_->st) {
+    const char *label;
+    Scope(rv_session *s_, const char *name, uint64_t bytes, uint64_t n_launches = 1, cudaStream_t on = nullptr) : s(s_), stream(on ? on : s_->st), label(name) {
         s->launches += n_launches;
         if (!s->timing) return;
         for (auto &k : s->timers)
@@ -632,6 +633,11 @@ struct Scope {
         cudaEventRecord(a, stream);
     }
     ~Scope() {
+        static const bool debug = getenv("RV_DEBUG") != nullptr;
+        if (debug) {  // name the launch that failed (development aid; the error stays pending for the caller's check)
+            const cudaError_t e = cudaPeekAtLastError();
+            if (e != cudaSuccess) fprintf(stderr, "[reverie_b200] launch '%s' on device %d: %s\n", label, s->c->device, cudaGetErrorString(e));
+        }
         if (!t) return;
         cudaEventRecord(b, stream);
         t->pending.push_back({a, b});
@@ -1398,8 +1404,7 @@ struct rv_group {
         int rank = 0;
         const rv_circuit *c = nullptr;
         rv_circuit *owned = nullptr;  // clone made for this member's device
-        std::vector<rv_session *> ss;
-        rv_batch *batch = nullptr;
+        std::vector<rv_session *> ss;  // each on its own stream, launched one by one: uploads of the next overlap the previous one's work
     };
     std::vector<Member> members;
     int world = 1, n_sessions = 1, slots = 1;
@@ -1409,7 +1414,6 @@ struct rv_group {
 extern "C" void rv_group_free(rv_group *g) {
     if (!g) return;
     for (auto &m : g->members) {
-        if (m.batch) rv_batch_free(m.batch);
         for (rv_session *s : m.ss) rv_session_free(s);
         if (m.owned) rv_circuit_free(m.owned);
     }
@@ -1429,7 +1433,6 @@ static int group_add_member(rv_group *g, const rv_circuit *c, rv_circuit *owned,
         if (rc) return rc;
         m.ss.push_back(s);
     }
-    if (g->n_sessions > 1) return rv_batch_create(m.ss.data(), g->n_sessions, &m.batch);
     return RV_OK;
 }
 
@@ -1539,27 +1542,20 @@ extern "C" rv_session *rv_group_session(rv_group *g, int member, int index) {
     if (!g || member < 0 || member >= (int)g->members.size() || index < 0 || index >= g->n_sessions) return nullptr;
     return g->members[member].ss[index];
 }
-extern "C" rv_batch *rv_group_batch(rv_group *g, int member) {
-    if (!g || member < 0 || member >= (int)g->members.size()) return nullptr;
-    return g->members[member].batch;
-}
 
-// Launches one step (commit + exchange + open) of the first `n_used` sessions of every member, asynchronously.
-static int group_launch(rv_group *g, int n_used) {
-    for (auto &m : g->members) {
-        int rc = RV_OK;
-        if (n_used == g->n_sessions && m.batch) rc = rv_batch_prove(m.batch);
-        else
-            for (int i = 0; i < n_used && rc == RV_OK; i++) rc = rv_session_prove(m.ss[i]);
-        if (rc) return rc;
-    }
+// Launches one step (commit + exchange + open) of session `i` of every member, asynchronously: one CUDA graph launch per GPU.
+static int group_launch(rv_group *g, int i) {
+    for (auto &m : g->members)
+        if (const int rc = rv_session_prove(m.ss[i])) return rc;
     return RV_OK;
 }
 
 extern "C" int rv_group_step(rv_group *g) {
     if (!g) return fail(RV_E_ARG, "NULL group");
     if (g->world > 1 && !g->linked) return fail(RV_E_ARG, "rv_group_link has not run");
-    return group_launch(g, g->n_sessions);
+    for (int i = 0; i < g->n_sessions; i++)
+        if (const int rc = group_launch(g, i)) return rc;
+    return RV_OK;
 }
 
 extern "C" int rv_group_prove_batch(rv_group *g, int n, const uint8_t *const *wit_gf2, const size_t *n_gf2, const uint64_t *const *wit_z64,
@@ -1597,15 +1593,18 @@ extern "C" int rv_group_prove_batch(rv_group *g, int n, const uint8_t *const *wi
     int rc = RV_OK;
     for (int base = 0; base < n && rc == RV_OK; base += cap) {  // waves of up to `cap` proofs
         const int cnt = std::min(cap, n - base), n_used = (cnt + g->slots - 1) / g->slots;
-        for (auto &m : g->members)
-            for (int k = 0; k < cnt && rc == RV_OK; k++) {
-                const int i = base + k;
-                const int r = rv_session_upload_slot(m.ss[k / g->slots], k % g->slots, wit_gf2 ? wit_gf2[i] : nullptr, n_gf2 ? n_gf2[i] : 0, wit_z64 ? wit_z64[i] : nullptr,
-                                                     n_z64 ? n_z64[i] : 0, seed_of(i));
-                if (r == RV_E_WITNESS_SHORT || r == RV_E_ARG) statuses[i] = r;  // the slot keeps its previous inputs; its output is dropped
-                else if (r != RV_OK) rc = r;
-            }
-        if (rc == RV_OK) rc = group_launch(g, n_used);
+        // session by session: fill its slots on every member, launch it; the next session's uploads overlap its work
+        for (int si = 0; si < n_used && rc == RV_OK; si++) {
+            for (auto &m : g->members)
+                for (int k = si * g->slots; k < std::min(cnt, (si + 1) * g->slots) && rc == RV_OK; k++) {
+                    const int i = base + k;
+                    const int r = rv_session_upload_slot(m.ss[si], k % g->slots, wit_gf2 ? wit_gf2[i] : nullptr, n_gf2 ? n_gf2[i] : 0, wit_z64 ? wit_z64[i] : nullptr,
+                                                         n_z64 ? n_z64[i] : 0, seed_of(i));
+                    if (r == RV_E_WITNESS_SHORT || r == RV_E_ARG) statuses[i] = r;  // the slot keeps its previous inputs; its output is dropped
+                    else if (r != RV_OK) rc = r;
+                }
+            if (rc == RV_OK) rc = group_launch(g, si);
+        }
         for (auto &m : g->members)
             for (int k = 0; k < cnt && rc == RV_OK; k++) {
                 const int i = base + k;
@@ -1644,6 +1643,7 @@ extern "C" int rv_group_prove(rv_group *g, const uint8_t *wit_gf2, size_t n_gf2,
 static int verify_on_session(rv_session *s, const uint8_t *proof, size_t proof_len, const PDomain &g, const PDomain &z, int *okay, int *accept) {
     if (s->n_proofs != 1 || s->npi != RV_PACKED_REPS) return fail(RV_E_ARG, "verification runs on a single-proof, full-shard session");
     const rv_circuit *c = s->c;
+    CU(cudaSetDevice(c->device));  // the calling thread may have been left on another device (a group's last member)
     const Program &P = c->prog;
     const DevProgram &D = c->dev;
     constexpr uint32_t NON = RV_ONLINE_REPS, NPRE = RV_PREPROCESSING_REPS, NPI_ON = RV_ONLINE_REPS / 8;

@@ -247,15 +247,9 @@ class Batch:
         N.check(N.lib().rv_batch_create(arr, len(self.sessions), C.byref(h)))
         self._h = h
 
-    @classmethod
-    def _view(cls, sessions, handle, owner) -> "Batch":
-        b = cls.__new__(cls)
-        b.sessions, b._h, b._owner = list(sessions), C.c_void_p(handle), owner
-        return b
-
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
-        if h and getattr(self, "_owner", None) is None:
+        if h:
             N.lib().rv_batch_free(h)
 
     def commit(self):
@@ -322,8 +316,7 @@ class Group:
         for mem in range(self.n_members):
             r = rank if self.n_members == 1 else mem
             ss = [Session._view(circuit, N.lib().rv_group_session(handle, mem, i), r * per, per, self.slots, self) for i in range(self.n_sessions)]
-            bh = N.lib().rv_group_batch(handle, mem)
-            self.members.append((ss, Batch._view(ss, bh, self) if bh else None))
+            self.members.append(ss)
 
     @staticmethod
     def local(circuit: Circuit, devices: Sequence[int], n_sessions: int = 1, slots: int = 1) -> "Group":
@@ -341,21 +334,15 @@ class Group:
     def __del__(self):
         h, self._h = getattr(self, "_h", None), None
         if h:
-            for ss, b in getattr(self, "members", []):
+            for ss in getattr(self, "members", []):
                 for s in ss:
                     s._h = None
-                if b is not None:
-                    b._h = None
             N.lib().rv_group_free(h)
 
     @property
     def sessions(self):
-        """This process's sessions of member 0 (the only member of a rank group)."""
-        return self.members[0][0]
-
-    @property
-    def batch(self):
-        return self.members[0][1]
+        """This process's sessions of member 0 (the only member of a rank group); each has its own stream."""
+        return self.members[0]
 
     def handles(self) -> bytes:
         buf = np.zeros(int(N.lib().rv_group_handles_bytes(self._h)), dtype=np.uint8)
