@@ -378,6 +378,7 @@ struct rv_session {
     uint32_t first_instance = 0, npi = 0, nreps = 0, first_rep = 0;  // npi / nreps: columns / streams of the WHOLE session
     // several proofs side by side (rv_session_create_multi): proof b owns columns [b * npi1, (b + 1) * npi1) of the share tensor
     uint32_t n_proofs = 1, npi1 = 0, nreps1 = 0;
+    uint32_t share = 1;  // sessions that run side by side with this one (its batch / group): sizes grids that want one wave
     size_t wit_pitch = 0, vals_pitch = 0, proof_pitch = 0, in_pitch = 0;
     cudaStream_t st = nullptr, st_val = nullptr;
     bool own_stream = true;
@@ -779,7 +780,8 @@ static int commit_body(rv_session *s) {
     }
     {
         Scope k(s, "mask_gen", (uint64_t)P.n_masks * s->npi * 8);
-        launch_mask_gen_tt(s->d_rk_plain, nslices, P.n_masks, s->d_rows, s->d_fresh_sm, s->pitch_fresh, c->n_sms, s->st);
+        launch_mask_gen_tt(s->d_rk_plain, nslices, P.n_masks, s->d_rows, s->d_fresh_sm, s->pitch_fresh, c->n_sms, s->st,
+                           P.values_wide ? 0 : s->n_proofs /* k_values: one CTA (one SM) per proof, on the side stream */, s->share);
     }
     if (D.n_llevels) {
         const double avg_width = (double)D.n_xgates / D.n_llevels;
@@ -1015,6 +1017,7 @@ extern "C" int rv_batch_create(rv_session *const *ss, int n, rv_batch **out) {
         }
         b->ss.push_back(s);
     }
+    for (rv_session *s : b->ss) s->share = (uint32_t)n;
     *out = b;
     return RV_OK;
 }
@@ -1026,6 +1029,7 @@ extern "C" void rv_batch_free(rv_batch *b) {
         cudaStreamSynchronize(b->ss[0]->st);
     }
     for (size_t i = 1; i < b->ss.size(); i++) b->ss[i]->lead = nullptr;
+    for (rv_session *s : b->ss) s->share = 1;
     for (auto &g : b->g)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
@@ -1431,6 +1435,7 @@ static int group_add_member(rv_group *g, const rv_circuit *c, rv_circuit *owned,
         rv_session *s = nullptr;
         const int rc = rv_session_create_multi(c, rank * per, per, g->slots, &s);
         if (rc) return rc;
+        s->share = (uint32_t)g->n_sessions;
         m.ss.push_back(s);
     }
     return RV_OK;

@@ -159,11 +159,15 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_mask_gen_tt(const uint32_t *_
 }
 
 void launch_mask_gen_tt(const uint32_t *rk_plain, uint32_t nslices, uint32_t n_masks, uint64_t *rows, uint64_t *fresh_pm, size_t pitch_pm, int n_sms,
-                        cudaStream_t st) {
+                        cudaStream_t st, uint32_t busy_sms, uint32_t share) {
     if (n_masks == 0) return;
     constexpr size_t SMEM2 = GT_SMEM2, SMEM4 = GT_SMEM4;
     const uint32_t n_blocks = (n_masks + 127) / 128, gy = (nslices + GT_SLICES - 1) / GT_SLICES;
-    const uint32_t want_x = std::max(1u, (uint32_t)n_sms / gy);  // about one CTA per SM for a single small proof
+    // One CTA per SM (104 registers x 512 threads), so the grid is sized to finish in ONE wave over the SMs this launch can count
+    // on: the value plane's CTAs (busy_sms, one SM each for the whole mask pipeline) and the other sessions of the batch (share)
+    // take theirs -- a grid a few CTAs larger than the free SMs would run a second, almost empty wave and double the kernel.
+    const uint32_t avail = std::max(8u, ((uint32_t)n_sms > busy_sms ? (uint32_t)n_sms - busy_sms : 0u) / std::max(1u, share));
+    const uint32_t want_x = std::max(1u, avail / gy);
     const uint32_t per = std::min(64u, std::max(4u, (n_blocks + want_x - 1) / want_x));
     dim3 grid((n_blocks + per - 1) / per, gy);
     if ((uint64_t)n_blocks * gy >= 64ull * n_sms)  // enough work for many waves: the mask generator owns the chip

@@ -76,8 +76,9 @@ void launch_key_setup(const uint8_t *seeds, const uint8_t *pkeys_in, const uint8
                       uint8_t *pkeys_out, uint32_t *rk_plain, cudaStream_t st, int *clear_flag = nullptr, uint32_t n_flags = 1, size_t flag_stride = 0);
 // K2  AES-CTR mask generation straight into the share tensor (src/generator/share.rs:54-65, src/algebra/gf2/domain.rs:66-173)
 //     also writes the instance-major copy `fresh_pm` [npi][pitch_pm] (u64) that the mask VM loads from (nullptr = skip)
+//     busy_sms: SMs held by kernels that run alongside (the value plane's CTAs); share: sessions of the batch that run side by side
 void launch_mask_gen_tt(const uint32_t *rk_plain, uint32_t nslices, uint32_t n_masks, uint64_t *rows, uint64_t *fresh_pm, size_t pitch_pm, int n_sms,
-                        cudaStream_t st);
+                        cudaStream_t st, uint32_t busy_sms = 0, uint32_t share = 1);
 // K0  value plane (plaintext evaluation; one CTA, level-synchronous).  Returns the dynamic smem it asked for.
 size_t launch_values(const LutInstr *steps, uint32_t n_steps, const uint32_t *leaf_ids, const uint8_t *leaf_vals, size_t leaf_pitch,
                      uint32_t n_leaves, uint8_t *vals, size_t vals_pitch, uint32_t n_vals, uint32_t n_instances, cudaStream_t st);

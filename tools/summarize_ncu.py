@@ -1,6 +1,7 @@
 """Turns gpurun_out ncu artefacts into the small tracked summaries under profiles/.
-usage: summarize_ncu.py launches <launches.csv> <out.md>   |   summarize_ncu.py full <file.ncu-rep> <out.md>"""
-import collections, csv, subprocess, sys
+usage: summarize_ncu.py launches <launches.csv> <out.md>   |   summarize_ncu.py full <file.ncu-rep> <out.md>
+       summarize_ncu.py traffic <out.json> <workload>=<file.ncu-rep> ...   (what bench.py reads for roofline.traffic / secondary.ncu)"""
+import collections, csv, json, re, subprocess, sys
 
 METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
            "lts__t_bytes.sum", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active",
@@ -37,5 +38,42 @@ def full(src, dst):
                     f.write(f"| {m} | {r[h.index(m)]} | {units[h.index(m)]} |\n")
             f.write("\n")
 
+def traffic(dst, *pairs):
+    doc = {"source": "ncu --set full --clock-control none (one launch each, cold cache); see the matching profiles/*_full_*.md", "workloads": {}}
+    num = lambda x: float(x.replace(",", "")) if x not in ("", "n/a") else None
+    for pair in pairs:
+        wl, src = pair.split("=", 1)
+        out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(out.splitlines()))
+        h, units = rows[0], rows[1]
+        scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1, "usecond": 1, "ms": 1e3, "msecond": 1e3, "nsecond": 1e-3, "second": 1e6}
+
+        def col(r, m):  # bytes in bytes, times in microseconds, everything else as printed
+            if m not in h or num(r[h.index(m)]) is None:
+                return None
+            return num(r[h.index(m)]) * scale.get(units[h.index(m)], 1)
+        w = doc["workloads"].setdefault(wl, {})
+        for r in rows[2:]:
+            name = re.sub(r"^void ", "", r[h.index("Kernel Name")].split("(")[0]).replace("rv::", "")
+            name = re.sub(r"<\(bool\)([01])>", r"<\1>", name)
+            if name in w:
+                continue
+            w[name] = {"dram_bytes_per_launch": (col(r, "dram__bytes_read.sum") or 0) + (col(r, "dram__bytes_write.sum") or 0),
+                       "us_per_launch_under_ncu": col(r, "gpu__time_duration.sum"),
+                       "grid": r[h.index("Grid Size")], "block": r[h.index("Block Size")],
+                       "alu_pipe_pct": col(r, "sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active"),
+                       "lsu_pipe_pct": col(r, "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+                       "issue_active_pct": col(r, "smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                       "sm_throughput_pct": col(r, "sm__throughput.avg.pct_of_peak_sustained_elapsed"),
+                       "dram_throughput_pct": col(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                       "l2_bytes": col(r, "lts__t_bytes.sum")}
+    with open(dst, "w") as f:
+        json.dump(doc, f, indent=1)
+        f.write("\n")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], *sys.argv[3:])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
