@@ -121,6 +121,8 @@ typedef struct rv_circuit_stats {
     uint64_t z64_pre_bytes;
     uint64_t compile_ns;        /* host time rv_circuit_compile spent on this handle (compile + upload of the tables) */
     uint64_t has_verify;        /* 1 if the verifier's tables were built */
+    uint64_t n_vals, n_uvals;   /* value ids of the plaintext plane / of the verifier's u-plane */
+    uint64_t n_vlut_steps;      /* steps of the u-plane's LUT program */
 } rv_circuit_stats;
 int rv_circuit_get_stats(const rv_circuit *c, rv_circuit_stats *out);
 

@@ -18,7 +18,7 @@ class CircuitStats(C.Structure):
         "n_ops", "n_and", "n_inputs", "n_assert", "n_masks", "n_linear", "value_depth", "linear_depth", "plain_value_depth",
         "plain_linear_depth", "n_luts", "n_lut_steps", "n_vm_steps", "vm_cells", "online_bytes", "pre_bytes", "algorithmic_bytes",
         "device_bytes", "z64_mul", "z64_inputs", "z64_assert", "z64_masks", "z64_linear", "z64_value_depth", "z64_linear_depth",
-        "z64_online_bytes", "z64_pre_bytes", "compile_ns", "has_verify")]
+        "z64_online_bytes", "z64_pre_bytes", "compile_ns", "has_verify", "n_vals", "n_uvals", "n_vlut_steps")]
 
 
 class KernelTime(C.Structure):

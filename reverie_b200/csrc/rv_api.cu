@@ -334,6 +334,9 @@ extern "C" int rv_circuit_get_stats(const rv_circuit *c, rv_circuit_stats *o) {
     o->z64_pre_bytes = Z.pre_bytes;
     o->compile_ns = c->compile_ns;
     o->has_verify = P.has_verify ? 1 : 0;
+    o->n_vals = P.n_vals;
+    o->n_uvals = P.n_uvals;
+    o->n_vlut_steps = P.n_vlut_steps;
     return RV_OK;
 }
 
@@ -781,7 +784,7 @@ static int commit_body(rv_session *s) {
     {
         Scope k(s, "mask_gen", (uint64_t)P.n_masks * s->npi * 8);
         launch_mask_gen_tt(s->d_rk_plain, nslices, P.n_masks, s->d_rows, s->d_fresh_sm, s->pitch_fresh, c->n_sms, s->st,
-                           P.values_wide ? 0 : s->n_proofs /* k_values: one CTA (one SM) per proof, on the side stream */, s->share);
+                           P.values_wide ? 0 : s->n_proofs /* k_values: one CTA (one SM) per proof, on the side stream */, s->share, linear_vm_pairs(D, s->npi));
     }
     if (D.n_llevels) {
         const double avg_width = (double)D.n_xgates / D.n_llevels;
@@ -1740,7 +1743,7 @@ static int verify_on_session(rv_session *s, const uint8_t *proof, size_t proof_l
     }
     {
         Scope k(s, "v.mask_gen", (uint64_t)P.n_masks * s->npi * 8);
-        launch_mask_gen_tt(s->d_rk_plain, nslices, P.n_masks, s->d_rows, s->d_fresh_sm, s->pitch_fresh, c->n_sms, s->st);
+        launch_mask_gen_tt(s->d_rk_plain, nslices, P.n_masks, s->d_rows, s->d_fresh_sm, s->pitch_fresh, c->n_sms, s->st, 0, 1, linear_vm_pairs(D, s->npi));
     }
     if (D.n_llevels) {
         Scope k(s, "v.linear", (uint64_t)P.n_lin * s->npi * 8 * 3, 2);

@@ -66,7 +66,9 @@ struct LutInstr {
 //   mask VM : step = VM_STEP slots of 20 bytes
 //   LUT     : step = LUT_STEP slots of 48 bytes; `pad` = flags
 // STEP_BAR on a slot means "CTA barrier after this step" (set on every slot of the last step of a level and of a chunk).
-constexpr uint32_t VM_STEP = 512, VM_STEPS_PER_CHUNK = 2, LUT_STEP = 128, LUT_STEPS_PER_CHUNK = 8;
+// The LUT stream carries a barrier every LUT_STEPS_PER_CHUNK steps, so it can be consumed in chunks of 4 or of 8 steps: k_values takes
+// 8 when the values still fit next to the larger ring (the prover's plane), 4 otherwise (the verifier's u-plane of SHA-256).
+constexpr uint32_t VM_STEP = 512, VM_STEPS_PER_CHUNK = 2, LUT_STEP = 128, LUT_STEPS_PER_CHUNK = 4, LUT_STEPS_PER_CHUNK_MAX = 8;
 constexpr uint32_t VM_F_LOAD = 1u, VM_F_BAR = 2u, VM_F_LEVEL_END = 4u, VM_CELL_MASK = 0xFFFFu /* also "no cell yet" */,
                    VM_ROW_NONE = 0xFFFFFFFFu;
 constexpr uint32_t LUT_F_BAR = 1u;

@@ -87,7 +87,7 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, uint32_t lane) 
 template <bool FOUR>
 __global__ void __launch_bounds__(GT_THREADS, 1) k_mask_gen_tt(const uint32_t *__restrict__ rk_plain, uint32_t nslices, uint32_t n_masks,
                                                                uint32_t blocks_per_cta, uint32_t *__restrict__ rows32,
-                                                               uint64_t *__restrict__ fresh_pm, size_t pitch_pm) {
+                                                               uint64_t *__restrict__ fresh_pm, size_t pitch_pm, bool pm_pairs) {
     extern __shared__ __align__(16) uint32_t gt_smem[];
     uint32_t *te = gt_smem, *tile = gt_smem + (FOUR ? 4 : 2) * 256 * 32;
     __shared__ uint32_t sbox32[64];
@@ -145,12 +145,23 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_mask_gen_tt(const uint32_t *_
             }
         }
         if (fresh_pm != nullptr) {  // instance-major copy for the mask VM: 8 instances x 128 masks, u64 each
+            if (pm_pairs) {  // two instances interleaved ([instance pair][mask][2]): a VM CTA that runs two columns loads 16 bytes at once
 #pragma unroll
-            for (uint32_t e = tid; e < (GT_SLICES / 2) * 128; e += GT_THREADS) {
-                const uint32_t p = e >> 7, m = e & 127;
-                if (w0 + 2 * p < nslices) {
-                    const uint2 v = *reinterpret_cast<const uint2 *>(tile + m * GT_TILE_PITCH + 2 * p);
-                    fresh_pm[(size_t)((w0 >> 1) + p) * pitch_pm + (uint64_t)j * 128 + m] = ((uint64_t)v.y << 32) | v.x;
+                for (uint32_t e = tid; e < (GT_SLICES / 4) * 128; e += GT_THREADS) {
+                    const uint32_t p = e >> 7, m = e & 127;
+                    if (w0 + 4 * p < nslices) {
+                        const uint4 v = *reinterpret_cast<const uint4 *>(tile + m * GT_TILE_PITCH + 4 * p);
+                        *reinterpret_cast<uint4 *>(fresh_pm + ((size_t)((w0 >> 2) + p) * pitch_pm + (uint64_t)j * 128 + m) * 2) = v;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (uint32_t e = tid; e < (GT_SLICES / 2) * 128; e += GT_THREADS) {
+                    const uint32_t p = e >> 7, m = e & 127;
+                    if (w0 + 2 * p < nslices) {
+                        const uint2 v = *reinterpret_cast<const uint2 *>(tile + m * GT_TILE_PITCH + 2 * p);
+                        fresh_pm[(size_t)((w0 >> 1) + p) * pitch_pm + (uint64_t)j * 128 + m] = ((uint64_t)v.y << 32) | v.x;
+                    }
                 }
             }
         }
@@ -159,7 +170,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_mask_gen_tt(const uint32_t *_
 }
 
 void launch_mask_gen_tt(const uint32_t *rk_plain, uint32_t nslices, uint32_t n_masks, uint64_t *rows, uint64_t *fresh_pm, size_t pitch_pm, int n_sms,
-                        cudaStream_t st, uint32_t busy_sms, uint32_t share) {
+                        cudaStream_t st, uint32_t busy_sms, uint32_t share, bool pm_pairs) {
     if (n_masks == 0) return;
     constexpr size_t SMEM2 = GT_SMEM2, SMEM4 = GT_SMEM4;
     const uint32_t n_blocks = (n_masks + 127) / 128, gy = (nslices + GT_SLICES - 1) / GT_SLICES;
@@ -171,9 +182,9 @@ void launch_mask_gen_tt(const uint32_t *rk_plain, uint32_t nslices, uint32_t n_m
     const uint32_t per = std::min(64u, std::max(4u, (n_blocks + want_x - 1) / want_x));
     dim3 grid((n_blocks + per - 1) / per, gy);
     if ((uint64_t)n_blocks * gy >= 64ull * n_sms)  // enough work for many waves: the mask generator owns the chip
-        k_mask_gen_tt<true><<<grid, GT_THREADS, SMEM4, st>>>(rk_plain, nslices, n_masks, per, reinterpret_cast<uint32_t *>(rows), fresh_pm, pitch_pm);
+        k_mask_gen_tt<true><<<grid, GT_THREADS, SMEM4, st>>>(rk_plain, nslices, n_masks, per, reinterpret_cast<uint32_t *>(rows), fresh_pm, pitch_pm, pm_pairs);
     else
-        k_mask_gen_tt<false><<<grid, GT_THREADS, SMEM2, st>>>(rk_plain, nslices, n_masks, per, reinterpret_cast<uint32_t *>(rows), fresh_pm, pitch_pm);
+        k_mask_gen_tt<false><<<grid, GT_THREADS, SMEM2, st>>>(rk_plain, nslices, n_masks, per, reinterpret_cast<uint32_t *>(rows), fresh_pm, pitch_pm, pm_pairs);
 }
 
 // =====================================================================================================================
@@ -266,26 +277,28 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
 //      thread per step.  Values live in shared memory (or global when they do not fit).
 // =====================================================================================================================
 constexpr int VP_THREADS = LUT_STEP;
-constexpr uint32_t LUT_CHUNK_BYTES = LUT_STEPS_PER_CHUNK * LUT_STEP * (uint32_t)sizeof(LutInstr);
-using LutStream = ChunkStream<LUT_CHUNK_BYTES, 2>;
+template <int SPC>  // steps per chunk: 4 or 8 (the stream has a barrier at least every 4 steps)
+using LutStream = ChunkStream<SPC * LUT_STEP * (uint32_t)sizeof(LutInstr), 2>;
+static_assert(LUT_STEPS_PER_CHUNK_MAX % LUT_STEPS_PER_CHUNK == 0, "chunk sizes must be multiples of the barrier period");
 
 // CTA b evaluates instance b: leaves leaf_vals[b * leaf_pitch + k] -> value id leaf_ids[k]; results to vals_g + b * vals_pitch.
 // Prover: one instance, leaves = the witness bits.  Online verifier: one instance per opened repetition (u-plane).
-template <bool SMEM_VALS>
+template <bool SMEM_VALS, int SPC>
 __global__ void __launch_bounds__(VP_THREADS) k_values(const LutInstr *__restrict__ prog, uint32_t n_steps, const uint32_t *__restrict__ leaf_ids,
                                                        const uint8_t *__restrict__ leaf_vals, size_t leaf_pitch, uint32_t n_leaves,
                                                        uint8_t *__restrict__ vals_out, size_t vals_pitch, uint32_t n_vals) {
     extern __shared__ __align__(128) uint8_t smem[];
-    const uint32_t n_chunks = (n_steps + LUT_STEPS_PER_CHUNK - 1) / LUT_STEPS_PER_CHUNK;
-    LutStream stream;
-    stream.init(smem, prog, n_chunks, (n_steps - (n_chunks ? n_chunks - 1 : 0) * LUT_STEPS_PER_CHUNK) * LUT_STEP * (uint32_t)sizeof(LutInstr));
+    using Stream = LutStream<SPC>;
+    const uint32_t n_chunks = (n_steps + SPC - 1) / SPC;
+    Stream stream;
+    stream.init(smem, prog, n_chunks, (n_steps - (n_chunks ? n_chunks - 1 : 0) * SPC) * LUT_STEP * (uint32_t)sizeof(LutInstr));
     uint8_t *vals_g = vals_out + (size_t)blockIdx.x * vals_pitch;
     const uint8_t *wit = leaf_vals + (size_t)blockIdx.x * leaf_pitch;
     // values: slot n_vals is the scratch target of empty slots.  In shared memory they are addressed as smem[BYTES + id] so
     // that every access is a plain LDS/STS with an immediate offset (no generic-address arithmetic in the hot loop).
-    auto ld = [&](uint32_t id) -> uint32_t { return SMEM_VALS ? (uint32_t)smem[LutStream::BYTES + id] : (uint32_t)vals_g[id]; };
+    auto ld = [&](uint32_t id) -> uint32_t { return SMEM_VALS ? (uint32_t)smem[Stream::BYTES + id] : (uint32_t)vals_g[id]; };
     auto st = [&](uint32_t id, uint32_t v) {
-        if (SMEM_VALS) smem[LutStream::BYTES + id] = (uint8_t)v;
+        if (SMEM_VALS) smem[Stream::BYTES + id] = (uint8_t)v;
         else vals_g[id] = (uint8_t)v;
     };
     const uint32_t tid = threadIdx.x;
@@ -294,11 +307,11 @@ __global__ void __launch_bounds__(VP_THREADS) k_values(const LutInstr *__restric
     __syncthreads();
     for (uint32_t c = 0; c < n_chunks; c++) {
         const uint32_t img = stream.begin_chunk(c) + tid * (uint32_t)sizeof(LutInstr);
-        const uint32_t nst = min((uint32_t)LUT_STEPS_PER_CHUNK, n_steps - c * LUT_STEPS_PER_CHUNK);
-        uint4 u0[LUT_STEPS_PER_CHUNK], u1[LUT_STEPS_PER_CHUNK];
-        uint2 u2[LUT_STEPS_PER_CHUNK];
+        const uint32_t nst = min((uint32_t)SPC, n_steps - c * SPC);
+        uint4 u0[SPC], u1[SPC];
+        uint2 u2[SPC];
 #pragma unroll
-        for (int k = 0; k < (int)LUT_STEPS_PER_CHUNK; k++)
+        for (int k = 0; k < SPC; k++)
             if (k < (int)nst) {
                 const uint32_t p = img + k * LUT_STEP * (uint32_t)sizeof(LutInstr);
                 u0[k] = lds128(p);       // {dst, in0, in1, in2}
@@ -306,7 +319,7 @@ __global__ void __launch_bounds__(VP_THREADS) k_values(const LutInstr *__restric
                 u2[k] = lds64(p + 32);   // {tt lo, tt hi}
             }
 #pragma unroll
-        for (int k = 0; k < (int)LUT_STEPS_PER_CHUNK; k++)
+        for (int k = 0; k < SPC; k++)
             if (k < (int)nst) {
                 const uint32_t idx = ld(u0[k].y) | (ld(u0[k].z) << 1) | (ld(u0[k].w) << 2) | (ld(u1[k].x) << 3) | (ld(u1[k].y) << 4) | (ld(u1[k].z) << 5);
                 const uint64_t tt = ((uint64_t)u2[k].y << 32) | u2[k].x;
@@ -316,20 +329,24 @@ __global__ void __launch_bounds__(VP_THREADS) k_values(const LutInstr *__restric
     }
     __syncthreads();
     if (SMEM_VALS) {
-        for (uint32_t i = tid; i < n_vals; i += VP_THREADS) vals_g[i] = smem[LutStream::BYTES + i];
+        for (uint32_t i = tid; i < n_vals; i += VP_THREADS) vals_g[i] = smem[Stream::BYTES + i];
     }
 }
 
 size_t launch_values(const LutInstr *steps, uint32_t n_steps, const uint32_t *leaf_ids, const uint8_t *leaf_vals, size_t leaf_pitch,
                      uint32_t n_leaves, uint8_t *vals, size_t vals_pitch, uint32_t n_vals, uint32_t n_instances, cudaStream_t st) {
-    const size_t cap = SMEM_DYN_CAP;
-    const size_t want = LutStream::BYTES + (((size_t)n_vals + 1 + 15) & ~(size_t)15);
-    if (want <= cap) {
-        k_values<true><<<n_instances, VP_THREADS, want, st>>>(steps, n_steps, leaf_ids, leaf_vals, leaf_pitch, n_leaves, vals, vals_pitch, n_vals);
-        return want;
+    const size_t cap = SMEM_DYN_CAP, vbytes = ((size_t)n_vals + 1 + 15) & ~(size_t)15;
+    constexpr int S8 = (int)LUT_STEPS_PER_CHUNK_MAX, S4 = (int)LUT_STEPS_PER_CHUNK;
+    if (LutStream<S8>::BYTES + vbytes <= cap) {
+        k_values<true, S8><<<n_instances, VP_THREADS, LutStream<S8>::BYTES + vbytes, st>>>(steps, n_steps, leaf_ids, leaf_vals, leaf_pitch, n_leaves, vals, vals_pitch, n_vals);
+        return LutStream<S8>::BYTES + vbytes;
     }
-    k_values<false><<<n_instances, VP_THREADS, LutStream::BYTES, st>>>(steps, n_steps, leaf_ids, leaf_vals, leaf_pitch, n_leaves, vals, vals_pitch, n_vals);
-    return LutStream::BYTES;
+    if (LutStream<S4>::BYTES + vbytes <= cap) {  // a smaller instruction ring leaves room for the values (the verifier's u-plane of SHA-256)
+        k_values<true, S4><<<n_instances, VP_THREADS, LutStream<S4>::BYTES + vbytes, st>>>(steps, n_steps, leaf_ids, leaf_vals, leaf_pitch, n_leaves, vals, vals_pitch, n_vals);
+        return LutStream<S4>::BYTES + vbytes;
+    }
+    k_values<false, S8><<<n_instances, VP_THREADS, LutStream<S8>::BYTES, st>>>(steps, n_steps, leaf_ids, leaf_vals, leaf_pitch, n_leaves, vals, vals_pitch, n_vals);
+    return LutStream<S8>::BYTES;
 }
 
 // Wide circuits: thread = one LUT of the level; values in global memory (L2-resident between the per-level launches).
@@ -400,20 +417,39 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     return v;
 }
 
+// COLS = columns (packed instances) one CTA runs: 1 (u64 cells) or 2 adjacent ones (16-byte cells: the same decoded instruction
+// moves twice the payload, so the program is streamed from L2 half as often per proof and the cell traffic uses 128-bit LDS/STS).
+template <int COLS>
+struct VmCell;
+template <>
+struct VmCell<1> {
+    using T = uint64_t;
+    static __device__ __forceinline__ T zero() { return 0; }
+    static __device__ __forceinline__ T x(T a, T b) { return a ^ b; }
+};
+template <>
+struct VmCell<2> {
+    using T = ulonglong2;
+    static __device__ __forceinline__ T zero() { return make_ulonglong2(0, 0); }
+    static __device__ __forceinline__ T x(T a, T b) { return make_ulonglong2(a.x ^ b.x, a.y ^ b.y); }
+};
+
+template <int COLS>
 __global__ void __launch_bounds__(VM_THREADS) k_mask_vm(const VmInstr *__restrict__ prog, uint32_t n_steps, const uint64_t *__restrict__ fresh_pm,
                                                         size_t pitch_fresh, uint64_t *__restrict__ rows, uint32_t npi) {
+    using Cell = typename VmCell<COLS>::T;
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t n_chunks = (n_steps + VM_STEPS_PER_CHUNK - 1) / VM_STEPS_PER_CHUNK;
     VmStream stream;
     stream.init(smem, prog, n_chunks, (n_steps - (n_chunks ? n_chunks - 1 : 0) * VM_STEPS_PER_CHUNK) * VM_STEP * (uint32_t)sizeof(VmInstr));
-    uint64_t *cells = reinterpret_cast<uint64_t *>(smem + VmStream::BYTES);
-    const uint32_t tid = threadIdx.x, pi = blockIdx.x;
-    // LOADs read the instance-major copy of the fresh masks, so a warp's 32 requests (sorted by row inside a level) fall into a
-    // few 128-byte lines.  Exported rows go straight into the row-major share tensor as 8-byte stores: the tensor of a
-    // VM-sized circuit lives in L2, which merges the 32 instances' pieces of a row before the item plane reads it.
-    const uint64_t *src = fresh_pm + (size_t)pi * pitch_fresh;
-    uint64_t *dst = rows + pi;
-    if (tid == 0) cells[0] = 0;  // cell 0 is the constant zero (first read happens after the first barrier)
+    Cell *cells = reinterpret_cast<Cell *>(smem + VmStream::BYTES);
+    const uint32_t tid = threadIdx.x, q = blockIdx.x;
+    // LOADs read the instance-major copy of the fresh masks (COLS = 2: the pair-interleaved one), so a warp's 32 requests (sorted
+    // by row inside a level) fall into a few 128-byte lines.  Exported rows go straight into the row-major share tensor: the
+    // tensor of a VM-sized circuit lives in L2, which merges the instances' pieces of a row before the item plane reads it.
+    const Cell *src = reinterpret_cast<const Cell *>(fresh_pm) + (size_t)q * pitch_fresh;
+    uint64_t *dst = rows + (size_t)COLS * q;
+    if (tid == 0) cells[0] = VmCell<COLS>::zero();  // cell 0 is the constant zero (first read happens after the first barrier)
     for (uint32_t c = 0; c < n_chunks; c++) {
         const uint32_t img = stream.begin_chunk(c) + tid * (uint32_t)sizeof(VmInstr);  // 5-word stride: conflict-free LDS.32
         const uint32_t nst = min((uint32_t)VM_STEPS_PER_CHUNK, n_steps - c * VM_STEPS_PER_CHUNK);
@@ -423,19 +459,20 @@ __global__ void __launch_bounds__(VM_THREADS) k_mask_vm(const VmInstr *__restric
             if (k < (int)nst) {
                 const uint32_t p = img + k * VM_STEP * (uint32_t)sizeof(VmInstr);
 #pragma unroll
-                for (int q = 0; q < 5; q++) u[k][q] = lds32(p + 4 * q);  // {row, dst | flags << 16, in0 | in1 << 16, in2 | in3 << 16, in4 | in5 << 16}
+                for (int w = 0; w < 5; w++) u[k][w] = lds32(p + 4 * w);  // {row, dst | flags << 16, in0 | in1 << 16, in2 | in3 << 16, in4 | in5 << 16}
             }
 #pragma unroll
         for (int k = 0; k < (int)VM_STEPS_PER_CHUNK; k++)
             if (k < (int)nst) {
                 const uint32_t row = u[k][0], d = u[k][1] & 0xFFFFu, fl = u[k][1] >> 16;
                 if (fl & VM_F_LOAD) {
-                    __pipeline_memcpy_async(cells + d, src + row, 8);
+                    __pipeline_memcpy_async(cells + d, src + row, sizeof(Cell));
                 } else {
-                    const uint64_t v = cells[u[k][2] & 0xFFFFu] ^ cells[u[k][2] >> 16] ^ cells[u[k][3] & 0xFFFFu] ^ cells[u[k][3] >> 16] ^
-                                       cells[u[k][4] & 0xFFFFu] ^ cells[u[k][4] >> 16];
+                    typedef VmCell<COLS> V;
+                    const Cell v = V::x(V::x(V::x(cells[u[k][2] & 0xFFFFu], cells[u[k][2] >> 16]), V::x(cells[u[k][3] & 0xFFFFu], cells[u[k][3] >> 16])),
+                                        V::x(cells[u[k][4] & 0xFFFFu], cells[u[k][4] >> 16]));
                     cells[d] = v;
-                    if (row != VM_ROW_NONE) dst[(size_t)row * npi] = v;
+                    if (row != VM_ROW_NONE) *reinterpret_cast<Cell *>(dst + (size_t)row * npi) = v;
                 }
                 if (fl & VM_F_LEVEL_END) {  // one cp.async group per level; LOADs of level L-2 are complete before level L starts
                     __pipeline_commit();
@@ -478,11 +515,14 @@ __global__ void __launch_bounds__(256) k_linear_level(const XGate *__restrict__ 
     rows[(size_t)gt.dst * npi + pi] = xor6(rows, gt, npi, pi);
 }
 
-static size_t vm_smem_bytes(const DevProgram &P) { return VmStream::BYTES + ((size_t)P.vm_cells + 1) * 8; }
+static size_t vm_smem_bytes(const DevProgram &P, int cols = 1) { return VmStream::BYTES + ((size_t)P.vm_cells + 1) * 8 * cols; }
 bool linear_uses_vm(const DevProgram &P) {
     if (P.n_llevels == 0 || (double)P.n_xgates / P.n_llevels >= 4096.0) return false;
     return P.n_vm_steps && P.vm_cells < VM_CELL_MASK && vm_smem_bytes(P) <= SMEM_DYN_CAP;
 }
+// Two columns per VM CTA: when the wider cells still fit and the tensor has an even number of columns (a lone proof stays on one
+// column per CTA: it is latency-bound and wants all its instances on their own SMs).
+bool linear_vm_pairs(const DevProgram &P, uint32_t npi) { return linear_uses_vm(P) && npi % 2 == 0 && npi > 32 && vm_smem_bytes(P, 2) <= SMEM_DYN_CAP; }
 
 int launch_linear(const DevProgram &P, const uint32_t *off_host, uint64_t *rows, uint32_t npi, const uint64_t *fresh_sm, size_t pitch_fresh,
                   cudaStream_t st, int *which) {
@@ -500,7 +540,8 @@ int launch_linear(const DevProgram &P, const uint32_t *off_host, uint64_t *rows,
     }
     if (linear_uses_vm(P) && fresh_sm) {
         if (which) *which = 0;
-        k_mask_vm<<<npi, VM_THREADS, vm_smem_bytes(P), st>>>(P.vm_steps, P.n_vm_steps, fresh_sm, pitch_fresh, rows, npi);
+        if (linear_vm_pairs(P, npi)) k_mask_vm<2><<<npi / 2, VM_THREADS, vm_smem_bytes(P, 2), st>>>(P.vm_steps, P.n_vm_steps, fresh_sm, pitch_fresh, rows, npi);
+        else k_mask_vm<1><<<npi, VM_THREADS, vm_smem_bytes(P), st>>>(P.vm_steps, P.n_vm_steps, fresh_sm, pitch_fresh, rows, npi);
         return 1;
     }
     if (which) *which = 1;
@@ -1106,9 +1147,11 @@ int configure_kernels(int device) {
     };
     set((const void *)k_mask_gen_tt<false>, (int)GT_SMEM2, true);
     set((const void *)k_mask_gen_tt<true>, (int)GT_SMEM4, true);
-    set((const void *)k_values<true>, (int)SMEM_DYN_CAP, false);
-    set((const void *)k_values<false>, (int)SMEM_DYN_CAP, false);
-    set((const void *)k_mask_vm, (int)SMEM_DYN_CAP, true);  // two VM CTAs (~110 KB each for SHA-256) per SM need the full carveout
+    set((const void *)k_values<true, (int)LUT_STEPS_PER_CHUNK_MAX>, (int)SMEM_DYN_CAP, false);
+    set((const void *)k_values<true, (int)LUT_STEPS_PER_CHUNK>, (int)SMEM_DYN_CAP, false);
+    set((const void *)k_values<false, (int)LUT_STEPS_PER_CHUNK_MAX>, (int)SMEM_DYN_CAP, false);
+    set((const void *)k_mask_vm<1>, (int)SMEM_DYN_CAP, true);  // two VM CTAs (~110 KB each for SHA-256) per SM need the full carveout
+    set((const void *)k_mask_vm<2>, (int)SMEM_DYN_CAP, true);
     set((const void *)k_items, 0, true);                    // ~35 KB tiles: six CTAs share an SM
     if (e == cudaSuccess) e = (cudaError_t)configure_zkernels();
     // Load every kernel now.  With CUDA's lazy module loading the first launch of a function may have to wait for the device to go

@@ -78,7 +78,7 @@ void launch_key_setup(const uint8_t *seeds, const uint8_t *pkeys_in, const uint8
 //     also writes the instance-major copy `fresh_pm` [npi][pitch_pm] (u64) that the mask VM loads from (nullptr = skip)
 //     busy_sms: SMs held by kernels that run alongside (the value plane's CTAs); share: sessions of the batch that run side by side
 void launch_mask_gen_tt(const uint32_t *rk_plain, uint32_t nslices, uint32_t n_masks, uint64_t *rows, uint64_t *fresh_pm, size_t pitch_pm, int n_sms,
-                        cudaStream_t st, uint32_t busy_sms = 0, uint32_t share = 1);
+                        cudaStream_t st, uint32_t busy_sms = 0, uint32_t share = 1, bool pm_pairs = false);
 // K0  value plane (plaintext evaluation; one CTA, level-synchronous).  Returns the dynamic smem it asked for.
 size_t launch_values(const LutInstr *steps, uint32_t n_steps, const uint32_t *leaf_ids, const uint8_t *leaf_vals, size_t leaf_pitch,
                      uint32_t n_leaves, uint8_t *vals, size_t vals_pitch, uint32_t n_vals, uint32_t n_instances, cudaStream_t st);
@@ -93,6 +93,8 @@ int launch_uvalues_wide(const DevProgram &P, const uint32_t *vlut_level_off_host
 int launch_linear(const DevProgram &P, const uint32_t *llevel_off_host, uint64_t *rows, uint32_t npi, const uint64_t *fresh_pm, size_t pitch_fresh,
                   cudaStream_t st, int *which = nullptr);
 bool linear_uses_vm(const DevProgram &P);
+//     true when the VM runs two adjacent columns per CTA for a tensor of npi columns: fresh_pm must then be the pair-interleaved copy
+bool linear_vm_pairs(const DevProgram &P, uint32_t npi);
 // K4  item plane: the two hash streams of every repetition
 //     tvals: tainted plane [n_tvals][npi] (launch_tainted), read by items whose operands depend on Random / B2A fresh wires
 void launch_tainted(const DevProgram &P, const uint64_t *rows, uint32_t npi, const uint8_t *vals, uint64_t *tvals, cudaStream_t st);
