@@ -177,6 +177,15 @@ void rv_circuit_cache_clear(void);
 void rv_circuit_cache_limit(size_t max_entries);
 void rv_circuit_cache_stats(uint64_t *hits, uint64_t *misses, size_t *entries);
 
+/* Streaming Proof::new for circuits whose share tensor and transcripts do not fit in device memory (the
+ * reference's README.md:14 calls it the streaming interface -- its own prover keeps O(gates) vectors, src/transcript/prover.rs:26-34).
+ * The op list is proved in segments of `window_ops` ops (0 = a default of 4 M); wires that cross a segment boundary are carried
+ * on the device, PRG and hash streams continue, and the circuit is walked twice (hashes, then openings).  The proof bytes are
+ * identical to rv_proof_new's.  Device memory: O(window_ops) + ~45 bytes of gate tables per gate + the proof.
+ * GF(2) circuits without Random / Z64 / B2A (RV_E_UNSUPPORTED otherwise); one GPU. */
+int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, const uint8_t *wit_gf2, size_t n_gf2,
+                       const uint64_t *wit_z64, size_t n_z64, const uint8_t *seeds, size_t window_ops, uint8_t **proof, size_t *proof_len);
+
 void rv_free(void *p);
 
 /* ---------------------------------------------------------------------------------------------------------------

@@ -4,6 +4,7 @@
 #include <sys/random.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -12,6 +13,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "rv_bincode.h"
@@ -1643,6 +1645,382 @@ extern "C" int rv_group_prove(rv_group *g, const uint8_t *wit_gf2, size_t n_gf2,
     else if (p) rv_free(p);
     if (proof_len) *proof_len = len;
     return rc != RV_OK ? rc : status;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+//  Streaming Proof::new (the "streaming interface" of the reference's README.md:14): circuits whose share tensor
+//  and transcripts (~1.1 KB of device memory per gate) do not fit in HBM.  The op list is cut into segments of `window_ops` ops.
+//  Wires that cross a segment boundary are carried in a "cell file" on the device (one slot per LIVE wire: plaintext bit + mask
+//  row), PRG streams and both hash streams simply continue (random-access CTR; BLAKE3 chunk CVs are independent, a partial chunk
+//  is carried), and because the openings can only be extracted once the challenge is known -- which needs every repetition's
+//  hash -- the circuit is walked twice: pass 1 hashes, pass 2 recomputes the streams and packs the opened repetitions' bits.
+//  Device memory: O(window) buffers + the segments' gate tables (~45 bytes per gate) + 32 bytes of chunk CVs per 1024 gates and
+//  repetition + the proof.  GF(2) circuits without Random / Z64 / B2A; one GPU.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+struct Segment {
+    size_t a = 0, b = 0;               // op range in the whole circuit
+    std::vector<rv_op> ops;            // its ops with wire cells renumbered densely (dropped after compilation)
+    uint32_t n_local = 0;
+    SegmentIO io;
+    std::vector<uint32_t> import_slot, export_slot;
+    rv_circuit *c = nullptr;
+    uint64_t mask0 = 0, on0 = 0, pre0 = 0, wit0 = 0, recon0 = 0;  // what the ops before this segment drew / emitted
+    uint32_t n_on = 0, n_pre = 0, n_in = 0, n_recon = 0, n_imp = 0, n_exp = 0;
+    const uint32_t *d_leaf_ids = nullptr, *d_imp_slot = nullptr, *d_exp_slot = nullptr, *d_exp_row = nullptr, *d_exp_vref = nullptr;
+    int rc = RV_OK;
+    std::string err;
+};
+struct DevBuf {  // frees what a failed or finished streaming call allocated
+    std::vector<void *> dev, host;
+    std::vector<rv_circuit *> circuits;
+    cudaStream_t st = nullptr;
+    ~DevBuf() {
+        if (st) {
+            cudaStreamSynchronize(st);
+            cudaStreamDestroy(st);
+        }
+        for (void *p : dev) cudaFree(p);
+        for (void *p : host) cudaFreeHost(p);
+        for (rv_circuit *c : circuits) rv_circuit_free(c);
+    }
+    template <typename T>
+    int alloc(T **p, size_t count) {
+        void *d = nullptr;
+        const cudaError_t e = cudaMalloc(&d, std::max<size_t>(count, 1) * sizeof(T));
+        if (e != cudaSuccess) return fail(e == cudaErrorMemoryAllocation ? RV_E_NOMEM : RV_E_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+        dev.push_back(d);
+        *p = reinterpret_cast<T *>(d);
+        return RV_OK;
+    }
+};
+constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
+}  // namespace
+
+extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, const uint8_t *wit_gf2, size_t n_gf2,
+                                  const uint64_t *wit_z64, size_t n_z64, const uint8_t *seeds, size_t window_ops, uint8_t **proof, size_t *proof_len) {
+    (void)wit_z64;
+    (void)n_z64;
+    (void)z64_cells;
+    if (!proof || !proof_len || (n_ops && !ops)) return fail(RV_E_ARG, "NULL argument");
+    *proof = nullptr;
+    *proof_len = 0;
+    if (rv_device_count() == 0) return fail(RV_E_CUDA, "no CUDA device: reverie-b200 has no CPU fallback");
+    if (window_ops == 0) window_ops = (size_t)1 << 22;  // ~5 GB of window buffers
+    window_ops = std::max<size_t>(window_ops, 64);
+    // ---- 1. liveness + segmentation (host, one pass backwards, one forwards) ----
+    for (size_t i = 0; i < n_ops; i++) {
+        const rv_op &op = ops[i];
+        if (op.domain == RV_SIZE_HINT) {
+            gf2_cells = std::max<size_t>(gf2_cells, op.b);
+            continue;
+        }
+        if (op.domain != RV_GF2 || op.opcode == RV_RANDOM || op.opcode > RV_CONST)
+            return fail(RV_E_UNSUPPORTED, "op " + std::to_string(i) + ": streaming mode serves GF(2) circuits without Random / Z64 / B2A");
+    }
+    const size_t n_seg = std::max<size_t>(1, (n_ops + window_ops - 1) / window_ops);
+    auto reads = [](const rv_op &op, uint32_t r[2]) -> int {
+        switch (op.opcode) {
+            case RV_ADD: case RV_SUB: case RV_MUL: r[0] = op.a; r[1] = op.b; return 2;
+            case RV_ADDC: case RV_SUBC: case RV_MULC: case RV_ASSERT_ZERO: r[0] = op.a; return 1;
+            default: return 0;
+        }
+    };
+    auto writes = [](const rv_op &op) { return op.opcode != RV_ASSERT_ZERO; };
+    std::vector<uint32_t> last_read_seg, stamp, local, slot_of;
+    std::vector<uint8_t> written;
+    try {
+        last_read_seg.assign(gf2_cells, 0);  // segment index + 1 of the wire's last read (0 = never read)
+        stamp.assign(gf2_cells, 0);          // segment index + 1 in which `local` is valid
+        local.assign(gf2_cells, 0);
+        slot_of.assign(gf2_cells, NO_SLOT);
+        written.assign(gf2_cells, 0);        // written by an earlier segment
+    } catch (const std::bad_alloc &) {
+        return fail(RV_E_NOMEM, "out of host memory");
+    }
+    for (size_t i = 0; i < n_ops; i++) {
+        const rv_op &op = ops[i];
+        if (op.domain != RV_GF2) continue;
+        uint32_t r[2];
+        const int nr = reads(op, r);
+        for (int k = 0; k < nr; k++) {
+            if (r[k] >= gf2_cells) return fail(RV_E_ARG, "op " + std::to_string(i) + ": wire index out of range for the given wire_counts");
+            last_read_seg[r[k]] = (uint32_t)(i / window_ops) + 1;
+        }
+        if (writes(op) && op.dst >= gf2_cells) return fail(RV_E_ARG, "op " + std::to_string(i) + ": wire index out of range for the given wire_counts");
+    }
+    std::vector<Segment> segs(n_seg);
+    std::vector<uint32_t> free_slots;
+    uint32_t n_slots = 0;
+    uint64_t masks = 0, on = 0, pre = 0, wit = 0, recon = 0;
+    for (size_t sidx = 0; sidx < n_seg; sidx++) {
+        Segment &S = segs[sidx];
+        S.a = sidx * window_ops;
+        S.b = std::min(n_ops, S.a + window_ops);
+        S.mask0 = masks, S.on0 = on, S.pre0 = pre, S.wit0 = wit, S.recon0 = recon;
+        const uint32_t tag = (uint32_t)sidx + 1;
+        std::vector<uint32_t> touched, to_free;
+        auto local_of = [&](uint32_t c, bool is_read) -> uint32_t {
+            if (stamp[c] != tag) {
+                stamp[c] = tag;
+                local[c] = S.n_local++;
+                touched.push_back(c);
+                if (is_read && written[c]) {  // first access is a read of a wire an earlier segment wrote: carried in
+                    S.io.import_cells.push_back(local[c]);
+                    S.import_slot.push_back(slot_of[c]);
+                    if (last_read_seg[c] == tag) to_free.push_back(c);  // ... for the last time: its slot is free after this segment
+                }
+            }
+            return local[c];
+        };
+        S.ops.reserve(S.b - S.a);
+        for (size_t i = S.a; i < S.b; i++) {
+            rv_op op = ops[i];
+            if (op.domain != RV_GF2) continue;
+            uint32_t r[2];
+            const int nr = reads(op, r);
+            if (nr >= 1) op.a = local_of(r[0], true);
+            if (nr >= 2) op.b = local_of(r[1], true);
+            if (writes(op)) op.dst = local_of(op.dst, false);
+            S.ops.push_back(op);
+            switch (op.opcode) {
+                case RV_INPUT: masks += 1, on += 1, wit += 1; break;
+                case RV_MUL: masks += 2, on += 1, pre += 1, recon += 1; break;
+                case RV_ASSERT_ZERO: on += 1, recon += 1; break;
+                default: break;
+            }
+        }
+        for (uint32_t c : to_free) {
+            free_slots.push_back(slot_of[c]);
+            slot_of[c] = NO_SLOT;
+        }
+        // wires written here and read by a later segment leave through the cell file (a slot freed above may be reused at once:
+        // imports are read at the start of the segment, exports written at its end)
+        for (size_t i = S.a; i < S.b; i++) {
+            const rv_op &op = ops[i];
+            if (op.domain != RV_GF2 || !writes(op)) continue;
+            const uint32_t c = op.dst;
+            if (written[c] == 2) continue;  // already handled in this segment
+            written[c] = 2;
+            if (last_read_seg[c] > tag) {
+                if (slot_of[c] == NO_SLOT) {
+                    if (!free_slots.empty()) {
+                        slot_of[c] = free_slots.back();
+                        free_slots.pop_back();
+                    } else slot_of[c] = n_slots++;
+                }
+                S.io.export_cells.push_back(local[c]);
+                S.export_slot.push_back(slot_of[c]);
+            }
+        }
+        for (size_t i = S.a; i < S.b; i++)
+            if (ops[i].domain == RV_GF2 && writes(ops[i])) written[ops[i].dst] = 1;
+        S.n_local = std::max<uint32_t>(S.n_local, 1);
+    }
+    std::vector<uint32_t>().swap(stamp);
+    std::vector<uint32_t>().swap(local);
+    std::vector<uint32_t>().swap(last_read_seg);
+    std::vector<uint8_t>().swap(written);
+    const uint64_t tot_on = on, tot_pre = pre, tot_inputs = wit, tot_recon = recon;
+    if (n_gf2 < tot_inputs) return fail(RV_E_WITNESS_SHORT, "witness is too short");  // prover.rs:190
+    if (tot_inputs && !wit_gf2) return fail(RV_E_ARG, "witness pointer is NULL");
+    if (tot_on / 1024 >= 0xFFFFFFF0ull || masks / 128 >= 0xFFFFFFF0ull) return fail(RV_E_UNSUPPORTED, "circuit too large for the 32-bit block counters of the streaming path");
+
+    // ---- 2. compile every segment (host threads), then make its tables resident ----
+    CU(cudaSetDevice(g_device));
+    if (const int ce = configure_kernels(g_device)) return fail(RV_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString((cudaError_t)ce));
+    DevBuf B;
+    {
+        std::atomic<size_t> next{0};
+        auto worker = [&]() {
+            for (;;) {
+                const size_t k = next.fetch_add(1);
+                if (k >= n_seg) return;
+                Segment &S = segs[k];
+                S.c = new (std::nothrow) rv_circuit();
+                if (!S.c) {
+                    S.rc = RV_E_NOMEM;
+                    continue;
+                }
+                try {
+                    S.rc = compile(S.ops.data(), S.ops.size(), 0, S.n_local, S.c->prog, S.err, COMPILE_PROVE_ONLY, &S.io);
+                } catch (const std::bad_alloc &) {
+                    S.rc = RV_E_NOMEM;
+                    S.err = "out of host memory while compiling a segment";
+                }
+                std::vector<rv_op>().swap(S.ops);
+            }
+        };
+        const unsigned nt = (unsigned)std::min<size_t>(n_seg, std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
+        std::vector<std::thread> pool;
+        for (unsigned t = 1; t < nt; t++) pool.emplace_back(worker);
+        worker();
+        for (auto &t : pool) t.join();
+    }
+    for (Segment &S : segs) {
+        if (S.c) B.circuits.push_back(S.c);
+        if (S.rc != RV_OK) return fail(S.rc, "segment [" + std::to_string(S.a) + ", " + std::to_string(S.b) + "): " + S.err);
+    }
+    size_t max_rows = 1, max_vals = 1, max_leaves = 1, max_on = 1, max_pre = 1, max_masks = 1;
+    bool any_vm = false;
+    for (Segment &S : segs) {
+        rv_circuit *c = S.c;
+        Program &P = c->prog;
+        if (P.n_tvals || P.z.any()) return fail(RV_E_UNSUPPORTED, "streaming mode serves GF(2) circuits without Random / Z64 / B2A");
+        S.n_on = P.n_online, S.n_pre = P.n_pre, S.n_in = (uint32_t)P.n_inputs, S.n_recon = (uint32_t)P.recon_pos.size();
+        S.n_imp = (uint32_t)S.io.import_cells.size(), S.n_exp = (uint32_t)S.io.export_cells.size();
+        int rc = circuit_to_device(c, g_device);
+        std::vector<uint32_t> leaf_ids(P.input_vid);
+        leaf_ids.insert(leaf_ids.end(), S.io.import_vid.begin(), S.io.import_vid.end());
+        if (rc == RV_OK) rc = upload(c, leaf_ids, &S.d_leaf_ids);
+        if (rc == RV_OK) rc = upload(c, S.import_slot, &S.d_imp_slot);
+        if (rc == RV_OK) rc = upload(c, S.export_slot, &S.d_exp_slot);
+        if (rc == RV_OK) rc = upload(c, S.io.export_row, &S.d_exp_row);
+        if (rc == RV_OK) rc = upload(c, S.io.export_vref, &S.d_exp_vref);
+        if (rc != RV_OK) return rc;
+        max_rows = std::max<size_t>(max_rows, P.n_rows);
+        max_masks = std::max<size_t>(max_masks, P.n_masks);
+        max_vals = std::max<size_t>(max_vals, (size_t)P.n_vals + 1);
+        max_leaves = std::max<size_t>(max_leaves, (size_t)S.n_in + S.n_imp);
+        max_on = std::max<size_t>(max_on, (size_t)(S.on0 % 1024) + S.n_on);
+        max_pre = std::max<size_t>(max_pre, (size_t)(S.pre0 % 1024) + S.n_pre);
+        any_vm |= linear_uses_vm(c->dev);
+        // the host copies of the big tables are not needed any more (launches read the device copies and the small level offsets)
+        std::vector<Item>().swap(P.items);
+        std::vector<XGate>().swap(P.xgates);
+        std::vector<LutInstr>().swap(P.lut_steps);
+        std::vector<VmInstr>().swap(P.vm_steps);
+        std::vector<VGate>().swap(P.wgates);
+        std::vector<uint32_t>().swap(P.recon_pos);
+        std::vector<uint32_t>().swap(P.input_pos);
+        std::vector<uint32_t>().swap(P.input_vid);
+        std::vector<uint32_t>().swap(c->mul_pos);
+        std::vector<uint32_t>().swap(c->recon_idx);
+    }
+
+    // ---- 3. window buffers, cell file, hash state ----
+    constexpr uint32_t NPI = RV_PACKED_REPS, NREPS = RV_TOTAL_REPS;
+    const uint32_t nslices = 2 * NPI;
+    const size_t pitch_on = round_up(max_on, 2048), pitch_pre = round_up(max_pre, 2048), pitch_fresh = round_up(max_masks + 128, 128);
+    const uint32_t tot_chunks_on = tot_on == 0 ? 1 : (uint32_t)((tot_on + 1023) / 1024), tot_chunks_pre = tot_pre == 0 ? 1 : (uint32_t)((tot_pre + 1023) / 1024);
+    const ProofLayout L{(uint32_t)(tot_recon / 8 + 1), (uint32_t)(tot_pre / 8 + 1), (uint32_t)(tot_inputs / 8 + 1)};
+    const size_t plen = L.total(), tail_off = round_up(plen, 16);
+    uint64_t *d_rows = nullptr, *d_fresh = nullptr, *d_cell_rows = nullptr;
+    uint8_t *d_vals = nullptr, *d_leaf = nullptr, *d_on = nullptr, *d_pre = nullptr, *d_cell_vals = nullptr, *d_carry_on = nullptr, *d_carry_pre = nullptr, *d_seeds = nullptr,
+            *d_pkeys = nullptr, *d_on_hash = nullptr, *d_rep_hash = nullptr, *d_omit = nullptr, *d_proof = nullptr;
+    uint32_t *d_cv_on = nullptr, *d_cv_pre = nullptr, *d_rk = nullptr, *d_zconst = nullptr;
+    uint16_t *d_rank = nullptr;
+    int rc;
+    if ((rc = B.alloc(&d_rows, max_rows * NPI)) || (any_vm && (rc = B.alloc(&d_fresh, pitch_fresh * NPI))) || (rc = B.alloc(&d_cell_rows, (size_t)std::max(n_slots, 1u) * NPI)) ||
+        (rc = B.alloc(&d_cell_vals, std::max(n_slots, 1u))) || (rc = B.alloc(&d_vals, round_up(max_vals, 16))) || (rc = B.alloc(&d_leaf, max_leaves + 16)) ||
+        (rc = B.alloc(&d_on, pitch_on * NREPS)) || (rc = B.alloc(&d_pre, pitch_pre * NREPS)) || (rc = B.alloc(&d_carry_on, (size_t)1024 * NREPS)) ||
+        (rc = B.alloc(&d_carry_pre, (size_t)1024 * NREPS)) || (rc = B.alloc(&d_cv_on, (size_t)tot_chunks_on * NREPS * 8)) ||
+        (rc = B.alloc(&d_cv_pre, (size_t)tot_chunks_pre * NREPS * 8)) || (rc = B.alloc(&d_seeds, (size_t)NREPS * 16)) || (rc = B.alloc(&d_pkeys, (size_t)NREPS * 128)) ||
+        (rc = B.alloc(&d_rk, (size_t)45 * 64 * NPI)) || (rc = B.alloc(&d_on_hash, (size_t)NREPS * 32)) || (rc = B.alloc(&d_rep_hash, (size_t)NREPS * 32)) ||
+        (rc = B.alloc(&d_omit, NREPS)) || (rc = B.alloc(&d_rank, NREPS)) || (rc = B.alloc(&d_zconst, 16)) || (rc = B.alloc(&d_proof, tail_off + 64)))
+        return rc;
+    int *d_bad = reinterpret_cast<int *>(d_proof + tail_off);
+    uint8_t *d_comm = d_proof + tail_off + 4;
+    CU(cudaStreamCreateWithFlags(&B.st, cudaStreamNonBlocking));
+    cudaStream_t st = B.st;
+    uint8_t h_seeds[RV_TOTAL_REPS * 16];
+    if (seeds) memcpy(h_seeds, seeds, sizeof h_seeds);
+    else {  // OsRng, src/proof/mod.rs:131-134
+        size_t got = 0;
+        while (got < sizeof h_seeds) {
+            const ssize_t r = getrandom(h_seeds + got, sizeof h_seeds - got, 0);
+            if (r <= 0) return fail(RV_E_ARG, "getrandom failed");
+            got += (size_t)r;
+        }
+    }
+    {
+        uint32_t zc[16];
+        memcpy(zc, segs[0].c->z64_empty_hash, 32);
+        memcpy(zc + 8, segs[0].c->z64_rep_hash, 32);
+        CU(cudaMemcpyAsync(d_zconst, zc, 64, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_seeds, h_seeds, sizeof h_seeds, cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    launch_key_setup(d_seeds, nullptr, nullptr, nullptr, nslices, d_pkeys, d_rk, st, d_bad, 1, 0);
+
+    // ---- 4. the two passes ----
+    const int n_sms = segs[0].c->n_sms;
+    for (int pass = 1; pass <= 2; pass++) {
+        if (pass == 2) {
+            // every repetition's hash is known: comm, challenge, then the proof's headers, keys, hashes and zeroed vectors
+            launch_rep_hash(d_cv_on, tot_chunks_on, d_cv_pre, tot_chunks_pre, d_zconst, NREPS, d_on_hash, d_rep_hash, st);
+            launch_challenge(d_rep_hash, NREPS * 32, d_comm, 0, d_omit, d_rank, 1, st);
+            ExtractArgs a;
+            a.on = d_on, a.pre = d_pre, a.pitch_on = pitch_on, a.pitch_pre = pitch_pre, a.on_hash = d_on_hash, a.pkeys = d_pkeys, a.seeds = d_seeds, a.comm = d_comm;
+            a.omit_of_rep = d_omit, a.rank_of_rep = d_rank, a.z64_empty_hash = d_zconst, a.first_rep = 0, a.nreps = NREPS, a.n_proofs = 1, a.proof_stride = 0;
+            a.len_recons = L.len_recons, a.len_corrs = L.len_corrs, a.len_inputs = L.len_inputs, a.proof = d_proof;
+            launch_extract(DevProgram(), a, st);
+        }
+        for (Segment &S : segs) {
+            const rv_circuit *c = S.c;
+            const Program &P = c->prog;
+            const DevProgram &D = c->dev;
+            const uint32_t base_on = (uint32_t)(S.on0 % 1024), base_pre = (uint32_t)(S.pre0 % 1024);
+            const bool vm = linear_uses_vm(D);
+            if (S.n_in) CU(cudaMemcpyAsync(d_leaf, wit_gf2 + S.wit0, S.n_in, cudaMemcpyHostToDevice, st));
+            launch_seg_import(S.d_imp_slot, S.n_imp, d_cell_rows, d_cell_vals, NPI, P.n_prg, d_rows, vm ? d_fresh : nullptr, pitch_fresh, false, d_leaf + S.n_in, st);
+            if (P.values_wide) {
+                DevProgram Dv = D;
+                Dv.input_vid = S.d_leaf_ids;
+                Dv.n_inputs = S.n_in + S.n_imp;
+                launch_values_wide(Dv, P.wlevel_off.data(), d_leaf, d_vals, st);
+            } else {
+                launch_values(D.lut_steps, D.n_lut_steps, S.d_leaf_ids, d_leaf, 0, S.n_in + S.n_imp, d_vals, 0, D.n_vals, 1, st);
+            }
+            launch_mask_gen_tt(d_rk, nslices, P.n_prg, d_rows, vm ? d_fresh : nullptr, pitch_fresh, n_sms, st, 0, 1, false, S.mask0);
+            CU(cudaMemsetAsync(d_rows + (size_t)P.zero_row() * NPI, 0, (size_t)NPI * 8, st));
+            if (D.n_llevels) launch_linear(D, P.xlevel_off.data(), d_rows, NPI, d_fresh, pitch_fresh, st, nullptr);
+            launch_items(D, d_rows, NPI, d_vals, nullptr, d_on, pitch_on, d_pre, pitch_pre, d_bad, st, 1, 0, 0, base_on, base_pre);
+            // the bytes of the chunk this segment starts in, left behind by the previous one
+            if (base_on) CU(cudaMemcpy2DAsync(d_on, pitch_on, d_carry_on, 1024, base_on, NREPS, cudaMemcpyDeviceToDevice, st));
+            if (base_pre) CU(cudaMemcpy2DAsync(d_pre, pitch_pre, d_carry_pre, 1024, base_pre, NREPS, cudaMemcpyDeviceToDevice, st));
+            const bool last = &S == &segs.back();
+            const uint32_t len_on = base_on + S.n_on, len_pre = base_pre + S.n_pre;
+            if (pass == 1) {
+                const uint32_t nch_on = last ? (tot_on == 0 ? 1 : (len_on + 1023) / 1024) : len_on / 1024;
+                const uint32_t nch_pre = last ? (tot_pre == 0 ? 1 : (len_pre + 1023) / 1024) : len_pre / 1024;
+                launch_chunk_cv_window(d_on, pitch_on, last ? len_on : nch_on * 1024, nch_on, (uint32_t)((S.on0 - base_on) / 1024), tot_chunks_on, d_cv_on, d_pre, pitch_pre,
+                                       last ? len_pre : nch_pre * 1024, nch_pre, (uint32_t)((S.pre0 - base_pre) / 1024), tot_chunks_pre, d_cv_pre, NREPS, st);
+            } else {
+                SegExtractArgs x;
+                x.on = d_on, x.pre = d_pre, x.pitch_on = pitch_on, x.pitch_pre = pitch_pre, x.base_on = base_on, x.base_pre = base_pre;
+                x.recon_pos = D.recon_pos, x.input_pos = D.input_pos, x.n_recon = S.n_recon, x.n_corr = S.n_pre, x.n_inputs = S.n_in;
+                x.first_recon = S.recon0, x.first_corr = S.pre0, x.first_input = S.wit0, x.omit_of_rep = d_omit, x.rank_of_rep = d_rank;
+                x.len_recons = L.len_recons, x.len_corrs = L.len_corrs, x.len_inputs = L.len_inputs, x.proof = d_proof;
+                launch_seg_extract(x, NREPS, st);
+            }
+            if (!last) {
+                const uint32_t keep_on = len_on % 1024, keep_pre = len_pre % 1024;
+                if (keep_on) CU(cudaMemcpy2DAsync(d_carry_on, 1024, d_on + (len_on - keep_on), pitch_on, keep_on, NREPS, cudaMemcpyDeviceToDevice, st));
+                if (keep_pre) CU(cudaMemcpy2DAsync(d_carry_pre, 1024, d_pre + (len_pre - keep_pre), pitch_pre, keep_pre, NREPS, cudaMemcpyDeviceToDevice, st));
+                launch_seg_export(S.d_exp_slot, S.d_exp_row, S.d_exp_vref, S.n_exp, d_rows, d_vals, NPI, d_cell_rows, d_cell_vals, st);
+            }
+            CU(cudaGetLastError());
+        }
+    }
+    // ---- 5. the proof ----
+    uint8_t tail[64];
+    CU(cudaMemcpyAsync(tail, d_proof + tail_off, 36, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    int bad;
+    memcpy(&bad, tail, 4);
+    if (const int stt = status_of(bad)) return stt;
+    uint8_t *p = plen >= PIN_THRESHOLD ? (uint8_t *)pinned_get(plen) : (uint8_t *)malloc(plen);
+    if (!p) return fail(RV_E_NOMEM, "out of memory");
+    cudaError_t e = cudaMemcpyAsync(p, d_proof, plen, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        rv_free(p);
+        return fail(RV_E_CUDA, std::string("proof copy: ") + cudaGetErrorString(e));
+    }
+    *proof = p;
+    *proof_len = plen;
+    return RV_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -15,6 +15,7 @@ namespace {
 
 constexpr uint32_t ZERO_MID = 0xFFFFFFFFu;  // "the all-zero mask" until row numbers are final
 constexpr uint32_t LIN_BASE = 0x80000000u;  // provisional ids of linear nodes: LIN_BASE + creation index
+constexpr uint32_t IMP_BASE = 0x70000000u;  // provisional ids of imported mask rows (streaming segments): IMP_BASE + import index
 constexpr uint32_t VREF_ZERO = 0;           // vid 0, not negated
 constexpr uint32_t VREF_ONE = 1;            // vid 0, negated
 constexpr uint32_t NONE32 = 0xFFFFFFFFu;
@@ -325,6 +326,7 @@ void build_mask_vm(Program &P) {
         if (it.kind == ITEM_MUL) exported[it.ra] = exported[it.rb] = 1;
         else if (it.kind != ITEM_INPUT) exported[it.ra] = 1;
     }
+    for (uint32_t r : P.export_rows) exported[r] = 1;
     // VM level of an original level L (1-based) is L + VM_DELTA - 1; the LOAD of a fresh row first used at L sits at L - 1.
     struct Tmp {  // provisional instruction: rows until the scan below assigns cells
         uint32_t dst, in[6];
@@ -768,7 +770,7 @@ struct ZBuilder {
 
 }  // namespace
 
-int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, Program &P, std::string &err, uint32_t flags) {
+int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, Program &P, std::string &err, uint32_t flags, SegmentIO *io) {
     Trace tr;
     P = Program();
     P.n_ops = n_ops;
@@ -920,8 +922,26 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
         }
     };
 
+    const uint32_t n_imports = io ? (uint32_t)io->import_cells.size() : 0;
+    if (io) {  // streaming segment: the carried wires are leaves of both planes
+        io->import_vid.clear();
+        io->export_vref.clear();
+        io->export_row.clear();
+        for (uint32_t j = 0; j < n_imports; j++) {
+            const uint32_t c = io->import_cells[j];
+            if (c >= cells.size()) return bad_wire(0);
+            const uint32_t vid = new_val(0);
+            io->import_vid.push_back(vid);
+            cells[c] = Cell{vid << 1, IMP_BASE + j, 0};
+        }
+    }
+
     for (size_t i = 0; i < n_ops; i++) {
         const rv_op &op = ops[i];
+        if (io && (op.domain != RV_GF2 || op.opcode == RV_RANDOM)) {
+            err = "op " + std::to_string(i) + ": streaming mode serves GF(2) circuits without Random / Z64 / B2A";
+            return RV_E_UNSUPPORTED;
+        }
         if (op.domain == RV_SIZE_HINT) {  // src/interpreter/combine.rs:122-129
             if (cells.size() < op.b) cells.resize(op.b, Cell{VREF_ZERO, ZERO_MID, VREF_ZERO});
             if (z64_cells < op.a) z64_cells = op.a;
@@ -1056,7 +1076,7 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
                 err = "op " + std::to_string(i) + ": unknown opcode";
                 return RV_E_ARG;
         }
-        if (n_masks >= LIN_BASE - 130 || P.items.size() >= 0xFFFFFF00ull || vlevel.size() >= 0x3FFFFFF0ull || tlevel.size() >= 0x3FFFFFF0ull) {
+        if (n_masks >= IMP_BASE - 130 || P.items.size() >= 0xFFFFFF00ull || vlevel.size() >= 0x3FFFFFF0ull || tlevel.size() >= 0x3FFFFFF0ull) {
             err = "circuit too large for 32-bit table indices";
             return RV_E_UNSUPPORTED;
         }
@@ -1081,11 +1101,19 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
         for (const TGate &g : tg) P.tgates[cur[tlevel[g.dst]]++] = g;
         std::vector<TGate>().swap(tg);
     }
+    std::vector<uint32_t> export_mid;
+    if (io)
+        for (uint32_t c : io->export_cells) {
+            if (c >= cells.size()) return bad_wire(n_ops);
+            io->export_vref.push_back(cells[c].vref);
+            export_mid.push_back(cells[c].mid);
+        }
     std::vector<Cell>().swap(cells);
     zb.finish();
     P.algorithmic_bytes += zb.alg_bytes;
 
-    P.n_masks = (uint32_t)n_masks;
+    P.n_prg = (uint32_t)n_masks;
+    P.n_masks = (uint32_t)n_masks + n_imports;  // imported rows sit right behind the PRG rows and behave like fresh rows from here on
     P.n_vals = (uint32_t)vlevel.size();
     P.n_online = (uint32_t)P.items.size();
     P.n_pre = (uint32_t)P.n_and;
@@ -1110,6 +1138,7 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
         auto mask_id = [&](uint32_t mid) -> uint32_t {
             if (mid == ZERO_MID) return 0;
             if (mid >= LIN_BASE) return 1 + P.n_masks + (mid - LIN_BASE);
+            if (mid >= IMP_BASE) return 1 + P.n_prg + (mid - IMP_BASE);
             return 1 + mid;
         };
         if (n_lin_all == 0) {  // no Add/Sub of masked wires (e.g. the reference's bench circuit): rows are the fresh masks
@@ -1117,10 +1146,13 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
             P.n_lin = 0;
             P.n_rows = P.n_masks + 1;
             const uint32_t zero_row = P.zero_row();
+            auto row_of_mid = [&](uint32_t mid) -> uint32_t { return mid == ZERO_MID ? zero_row : mask_id(mid) - 1; };
             for (Item &it : P.items) {
-                if (it.ra == ZERO_MID) it.ra = zero_row;
-                if (it.kind == ITEM_MUL && it.rb == ZERO_MID) it.rb = zero_row;
+                it.ra = row_of_mid(it.ra);
+                if (it.kind == ITEM_MUL) it.rb = row_of_mid(it.rb);
             }
+            if (io)
+                for (uint32_t mid : export_mid) io->export_row.push_back(row_of_mid(mid));
             return;
         }
         for (MGate &g : lg) {
@@ -1134,6 +1166,7 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
             required[mask_id(it.ra)] = 1;
             if (it.kind == ITEM_MUL) required[mask_id(it.rb)] = 1;
         }
+        for (uint32_t mid : export_mid) required[mask_id(mid)] = 1;  // later segments read these wires' masks
         {
             std::vector<uint8_t> needed;
             prune_network(lg, required, needed);
@@ -1178,6 +1211,12 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
             it.ra = row_of_id(mask_id(it.ra));
             if (it.kind == ITEM_MUL) it.rb = row_of_id(mask_id(it.rb));
         }
+        if (io)
+            for (uint32_t mid : export_mid) {
+                const uint32_t row = row_of_id(mask_id(mid));
+                io->export_row.push_back(row);
+                if (row >= P.n_masks && row != zero_row) P.export_rows.push_back(row);
+            }
         jt.mark("  mask: map + rows");
         build_mask_vm(P);
         emit_vm_steps(P);
@@ -1205,6 +1244,8 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
                 need(g.b);
             }
         for (uint32_t r : P.b2a_vrefs) need(r);
+        if (io)
+            for (uint32_t r : io->export_vref) need(r);
         if (small) {
             P.vgates.resize(vg.size());
             for (size_t i = 0; i < vg.size(); i++) P.vgates[i] = VGate{vg[i].out, vg[i].a, vg[i].b, vg[i].op};

@@ -207,13 +207,26 @@ struct Program {
     uint64_t algorithmic_bytes = 0;
     bool uses_z64 = false;
     ZProgram z;
+    // Streaming segments (SegmentIO): rows [n_prg, n_masks) are IMPORTED mask rows (the carried state of wires written by earlier
+    // segments), not PRG output; everywhere else they behave like fresh rows.  n_prg == n_masks for a whole circuit.
+    uint32_t n_prg = 0;
+    std::vector<uint32_t> export_rows;  // rows later segments need: written back by the mask VM even if no item of this segment reads them
     uint32_t zero_row() const { return n_rows - 1; }
+};
+
+// One segment of a circuit proved in streaming mode (rv_prove_streaming): the op list [a, b) of the whole circuit with its wire
+// cells renumbered densely.  `import_cells` name the cells whose state (plaintext value + mask row) earlier segments left behind;
+// `export_cells` the cells whose final state later segments read.  GF(2) without Random / B2A only.
+struct SegmentIO {
+    std::vector<uint32_t> import_cells, export_cells;  // in: local cell ids
+    std::vector<uint32_t> import_vid;                  // out: value id of import j (a leaf of the value plane, after the witness inputs)
+    std::vector<uint32_t> export_vref, export_row;     // out: value ref (vid << 1 | negate) and mask row of export k (zero_row = the zero mask)
 };
 
 // Returns RV_OK or a negative rv_status; `err` receives a human-readable reason.
 // flags: COMPILE_PROVE_ONLY skips the online verifier's tables (u-plane): about a third of the compile time and of the table bytes.
 constexpr uint32_t COMPILE_PROVE_ONLY = 1u;
-int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, Program &out, std::string &err, uint32_t flags = 0);
+int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, Program &out, std::string &err, uint32_t flags = 0, SegmentIO *io = nullptr);
 
 constexpr uint32_t WIDE_LEVEL = 4096;
 constexpr size_t VERIFY_MAX_OPS = (size_t)1 << 28;  // the verifier's tables cost ~200 bytes of host memory per gate while compiling

@@ -84,10 +84,11 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, uint32_t lane) 
     return x;
 }
 
+// mask_base: PRG index of row 0 (streaming segments continue the streams where the previous segment stopped; 0 otherwise).
 template <bool FOUR>
 __global__ void __launch_bounds__(GT_THREADS, 1) k_mask_gen_tt(const uint32_t *__restrict__ rk_plain, uint32_t nslices, uint32_t n_masks,
                                                                uint32_t blocks_per_cta, uint32_t *__restrict__ rows32,
-                                                               uint64_t *__restrict__ fresh_pm, size_t pitch_pm, bool pm_pairs) {
+                                                               uint64_t *__restrict__ fresh_pm, size_t pitch_pm, bool pm_pairs, uint64_t mask_base) {
     extern __shared__ __align__(16) uint32_t gt_smem[];
     uint32_t *te = gt_smem, *tile = gt_smem + (FOUR ? 4 : 2) * 256 * 32;
     __shared__ uint32_t sbox32[64];
@@ -117,13 +118,15 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_mask_gen_tt(const uint32_t *_
     }
     __syncthreads();
     const SmemTe<FOUR> tab{reinterpret_cast<const uint8_t *>(te), 4 * lane};
-    const uint32_t n_blocks = (n_masks + 127) / 128;
+    const uint64_t jb0 = mask_base / 128;  // first counter block that holds a mask of this launch
+    const uint32_t n_blocks = (uint32_t)((mask_base + n_masks + 127) / 128 - jb0);
     const uint32_t j_end = min(n_blocks, (blockIdx.x + 1) * blocks_per_cta);
+    const int64_t shift = (int64_t)(jb0 * 128) - (int64_t)mask_base;  // row of mask m of local block j = j * 128 + m + shift (may be < 0: a mask of the previous segment)
 #pragma unroll 1
     for (uint32_t j = blockIdx.x * blocks_per_cta; j < j_end; j++) {
         if (live) {
             uint32_t in[4], o[4];
-            ctr_block_words(j, in);
+            ctr_block_words((uint32_t)(jb0 + j), in);
             tt_aes128_encrypt(rk, in[0], in[1], in[2], in[3], tab, o);
 #pragma unroll
             for (int g = 0; g < 4; g++) {
@@ -137,8 +140,8 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_mask_gen_tt(const uint32_t *_
         {  // row-major share tensor: thread = (mask of the block, 4 slices) -> one 16-byte store; a row's 16 slices = 64 contiguous bytes
             for (uint32_t e = tid; e < 128 * GT_QUADS; e += GT_THREADS) {
                 const uint32_t m = e / GT_QUADS, q4 = 4 * (e % GT_QUADS);
-                const uint64_t i = (uint64_t)j * 128 + m;
-                if (i < n_masks && w0 + q4 < nslices) {
+                const int64_t i = (int64_t)j * 128 + m + shift;
+                if (i >= 0 && i < (int64_t)n_masks && w0 + q4 < nslices) {
                     const uint4 v = *reinterpret_cast<const uint4 *>(tile + m * GT_TILE_PITCH + q4);
                     *reinterpret_cast<uint4 *>(rows32 + i * nslices + w0 + q4) = v;
                 }
@@ -149,18 +152,20 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_mask_gen_tt(const uint32_t *_
 #pragma unroll
                 for (uint32_t e = tid; e < (GT_SLICES / 4) * 128; e += GT_THREADS) {
                     const uint32_t p = e >> 7, m = e & 127;
-                    if (w0 + 4 * p < nslices) {
+                    const int64_t i = (int64_t)j * 128 + m + shift;
+                    if (i >= 0 && i < (int64_t)n_masks && w0 + 4 * p < nslices) {
                         const uint4 v = *reinterpret_cast<const uint4 *>(tile + m * GT_TILE_PITCH + 4 * p);
-                        *reinterpret_cast<uint4 *>(fresh_pm + ((size_t)((w0 >> 2) + p) * pitch_pm + (uint64_t)j * 128 + m) * 2) = v;
+                        *reinterpret_cast<uint4 *>(fresh_pm + ((size_t)((w0 >> 2) + p) * pitch_pm + (uint64_t)i) * 2) = v;
                     }
                 }
             } else {
 #pragma unroll
                 for (uint32_t e = tid; e < (GT_SLICES / 2) * 128; e += GT_THREADS) {
                     const uint32_t p = e >> 7, m = e & 127;
-                    if (w0 + 2 * p < nslices) {
+                    const int64_t i = (int64_t)j * 128 + m + shift;
+                    if (i >= 0 && i < (int64_t)n_masks && w0 + 2 * p < nslices) {
                         const uint2 v = *reinterpret_cast<const uint2 *>(tile + m * GT_TILE_PITCH + 2 * p);
-                        fresh_pm[(size_t)((w0 >> 1) + p) * pitch_pm + (uint64_t)j * 128 + m] = ((uint64_t)v.y << 32) | v.x;
+                        fresh_pm[(size_t)((w0 >> 1) + p) * pitch_pm + (uint64_t)i] = ((uint64_t)v.y << 32) | v.x;
                     }
                 }
             }
@@ -170,10 +175,10 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_mask_gen_tt(const uint32_t *_
 }
 
 void launch_mask_gen_tt(const uint32_t *rk_plain, uint32_t nslices, uint32_t n_masks, uint64_t *rows, uint64_t *fresh_pm, size_t pitch_pm, int n_sms,
-                        cudaStream_t st, uint32_t busy_sms, uint32_t share, bool pm_pairs) {
+                        cudaStream_t st, uint32_t busy_sms, uint32_t share, bool pm_pairs, uint64_t mask_base) {
     if (n_masks == 0) return;
     constexpr size_t SMEM2 = GT_SMEM2, SMEM4 = GT_SMEM4;
-    const uint32_t n_blocks = (n_masks + 127) / 128, gy = (nslices + GT_SLICES - 1) / GT_SLICES;
+    const uint32_t n_blocks = (uint32_t)((mask_base + n_masks + 127) / 128 - mask_base / 128), gy = (nslices + GT_SLICES - 1) / GT_SLICES;
     // One CTA per SM (104 registers x 512 threads), so the grid is sized to finish in ONE wave over the SMs this launch can count
     // on: the value plane's CTAs (busy_sms, one SM each for the whole mask pipeline) and the other sessions of the batch (share)
     // take theirs -- a grid a few CTAs larger than the free SMs would run a second, almost empty wave and double the kernel.
@@ -182,9 +187,9 @@ void launch_mask_gen_tt(const uint32_t *rk_plain, uint32_t nslices, uint32_t n_m
     const uint32_t per = std::min(64u, std::max(4u, (n_blocks + want_x - 1) / want_x));
     dim3 grid((n_blocks + per - 1) / per, gy);
     if ((uint64_t)n_blocks * gy >= 64ull * n_sms)  // enough work for many waves: the mask generator owns the chip
-        k_mask_gen_tt<true><<<grid, GT_THREADS, SMEM4, st>>>(rk_plain, nslices, n_masks, per, reinterpret_cast<uint32_t *>(rows), fresh_pm, pitch_pm, pm_pairs);
+        k_mask_gen_tt<true><<<grid, GT_THREADS, SMEM4, st>>>(rk_plain, nslices, n_masks, per, reinterpret_cast<uint32_t *>(rows), fresh_pm, pitch_pm, pm_pairs, mask_base);
     else
-        k_mask_gen_tt<false><<<grid, GT_THREADS, SMEM2, st>>>(rk_plain, nslices, n_masks, per, reinterpret_cast<uint32_t *>(rows), fresh_pm, pitch_pm, pm_pairs);
+        k_mask_gen_tt<false><<<grid, GT_THREADS, SMEM2, st>>>(rk_plain, nslices, n_masks, per, reinterpret_cast<uint32_t *>(rows), fresh_pm, pitch_pm, pm_pairs, mask_base);
 }
 
 // =====================================================================================================================
@@ -579,11 +584,13 @@ __global__ void __launch_bounds__(256) k_items_pre(const Item *__restrict__ item
 constexpr int IT_THREADS = 256;
 // npi = packed instances of ONE proof (the tile's geometry); the session may hold several proofs side by side: col0 = first
 // column of this proof in the share tensor, row_stride = columns of the whole tensor.
+// base: buffer position of item 0 (streaming segments start inside a BLAKE3 chunk whose first bytes the previous segment left
+// behind; positions below `base` are written as zero and filled in by the caller afterwards).  0 otherwise.
 template <bool PRE>
 __device__ __forceinline__ void items_tile_body(uint32_t tile_idx, const Item *__restrict__ items, const uint32_t *__restrict__ mul_pos, uint32_t n,
                                                 const uint64_t *__restrict__ rows, uint32_t npi, uint32_t col0, uint32_t row_stride,
                                                 const uint8_t *__restrict__ vals, const uint64_t *__restrict__ tvals, uint8_t *__restrict__ out,
-                                                size_t pitch, uint32_t T, int *bad) {
+                                                size_t pitch, uint32_t T, int *bad, uint32_t base) {
     extern __shared__ __align__(16) uint8_t tile[];
     const uint32_t tid = threadIdx.x, pi = tid % npi, pg0 = tid / npi, pg_step = IT_THREADS / npi, col = col0 + pi;
     const uint32_t tp = T + 8;  // tile pitch in bytes
@@ -595,8 +602,9 @@ __device__ __forceinline__ void items_tile_body(uint32_t tile_idx, const Item *_
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             W[i] = 0;
-            if (t0 + i < n)
-                W[i] = PRE ? pre_word(items[mul_pos[t0 + i]], rows, row_stride, col) : prover_online_word(items[t0 + i], rows, row_stride, col, vals, tvals, &flag);
+            const uint64_t t = t0 + i - base;  // (wraps for positions below base)
+            if (t0 + i >= base && t < n)
+                W[i] = PRE ? pre_word(items[mul_pos[t]], rows, row_stride, col) : prover_online_word(items[t], rows, row_stride, col, vals, tvals, &flag);
         }
         words_to_stream_bytes(W, o);
 #pragma unroll
@@ -621,24 +629,25 @@ __global__ void __launch_bounds__(IT_THREADS) k_items(const Item *__restrict__ i
                                                      uint32_t n_pre, uint32_t tiles_on, const uint64_t *__restrict__ rows, uint32_t npi,
                                                      const uint8_t *__restrict__ vals, size_t vals_pitch, const uint64_t *__restrict__ tvals,
                                                      uint8_t *__restrict__ on, size_t pitch_on, uint8_t *__restrict__ pre, size_t pitch_pre, uint32_t T,
-                                                     int *bad, size_t flag_stride) {
+                                                     int *bad, size_t flag_stride, uint32_t base_on, uint32_t base_pre) {
     const uint32_t col0 = blockIdx.y * npi, row_stride = gridDim.y * npi;
     if (blockIdx.x < tiles_on)
         items_tile_body<false>(blockIdx.x, items, nullptr, n_online, rows, npi, col0, row_stride, vals + blockIdx.y * vals_pitch, tvals, on, pitch_on, T,
-                               reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(bad) + blockIdx.y * flag_stride));
-    else items_tile_body<true>(blockIdx.x - tiles_on, items, mul_pos, n_pre, rows, npi, col0, row_stride, nullptr, nullptr, pre, pitch_pre, T, nullptr);
+                               reinterpret_cast<int *>(reinterpret_cast<uint8_t *>(bad) + blockIdx.y * flag_stride), base_on);
+    else items_tile_body<true>(blockIdx.x - tiles_on, items, mul_pos, n_pre, rows, npi, col0, row_stride, nullptr, nullptr, pre, pitch_pre, T, nullptr, base_pre);
 }
 
 static uint32_t items_tile(uint32_t npi) { return std::max(128u, 8u * IT_THREADS / npi); }
 
 void launch_items(const DevProgram &P, const uint64_t *rows, uint32_t npi, const uint8_t *vals, const uint64_t *tvals, uint8_t *on, size_t pitch_on,
-                  uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st, uint32_t n_proofs, size_t vals_pitch, size_t flag_stride) {
+                  uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st, uint32_t n_proofs, size_t vals_pitch, size_t flag_stride, uint32_t base_on,
+                  uint32_t base_pre) {
     const uint32_t T = items_tile(npi);
     const size_t smem = (size_t)8 * npi * (T + 8);
-    const uint32_t tiles_on = (P.n_online + T - 1) / T, tiles_pre = (P.n_pre + T - 1) / T;
+    const uint32_t tiles_on = P.n_online ? (base_on + P.n_online + T - 1) / T : 0, tiles_pre = P.n_pre ? (base_pre + P.n_pre + T - 1) / T : 0;
     if (tiles_on + tiles_pre)
         k_items<<<dim3(tiles_on + tiles_pre, n_proofs), IT_THREADS, smem, st>>>(P.items, P.mul_pos, P.n_online, P.n_pre, tiles_on, rows, npi, vals, vals_pitch,
-                                                                                 tvals, on, pitch_on, pre, pitch_pre, T, bad, flag_stride);
+                                                                                 tvals, on, pitch_on, pre, pitch_pre, T, bad, flag_stride, base_on, base_pre);
 }
 
 // Tainted plane: CTA = one packed instance (columns are independent), level-synchronous with CTA barriers only.
@@ -674,8 +683,11 @@ void launch_items_pre_range(const DevProgram &P, const uint64_t *rows, uint32_t 
 struct ChunkJob {
     const uint8_t *stream;
     size_t pitch;
-    uint32_t len, n_chunks, nreps;
+    uint32_t len, n_chunks, nreps;  // bytes / chunks of the buffer handed to this launch
     uint32_t *cvs;
+    // streaming: the buffer holds chunks [chunk0, chunk0 + n_chunks) of streams of cv_stride chunks; single = the whole stream is one chunk
+    uint32_t chunk0, cv_stride;
+    bool single;
 };
 
 __device__ __forceinline__ void load_block(const uint4 *p, uint32_t m[16]) {
@@ -693,7 +705,7 @@ __global__ void __launch_bounds__(64) k_chunk_cv(ChunkJob j0, ChunkJob j1) {
     if (rep >= J.nreps) return;
     const uint32_t off = chunk * 1024u;
     const uint32_t clen = min(1024u, J.len - off);
-    const bool root = J.n_chunks == 1;
+    const bool root = J.single;
     const uint8_t *base = J.stream + (size_t)rep * J.pitch + off;
     uint32_t cv[8];
     b3_iv(cv);
@@ -722,9 +734,9 @@ __global__ void __launch_bounds__(64) k_chunk_cv(ChunkJob j0, ChunkJob j1) {
         }
         uint32_t flags = (b == 0 ? B3_CHUNK_START : 0) | (b + 1 == n_blocks ? B3_CHUNK_END : 0);
         if (root && b + 1 == n_blocks) flags |= B3_ROOT;
-        b3_compress_cv(cv, m, chunk, blen, flags);
+        b3_compress_cv(cv, m, J.chunk0 + chunk, blen, flags);
     }
-    uint4 *dst = reinterpret_cast<uint4 *>(J.cvs + ((size_t)rep * J.n_chunks + chunk) * 8);
+    uint4 *dst = reinterpret_cast<uint4 *>(J.cvs + ((size_t)rep * J.cv_stride + J.chunk0 + chunk) * 8);
     dst[0] = make_uint4(cv[0], cv[1], cv[2], cv[3]);
     dst[1] = make_uint4(cv[4], cv[5], cv[6], cv[7]);
 }
@@ -733,11 +745,107 @@ static uint32_t n_chunks_of(uint32_t len) { return len == 0 ? 1 : (len + 1023) /
 
 void launch_chunk_cv2(const uint8_t *on, size_t pitch_on, uint32_t len_on, uint32_t *cv_on, uint32_t nreps_on, const uint8_t *pre, size_t pitch_pre,
                       uint32_t len_pre, uint32_t *cv_pre, uint32_t nreps_pre, cudaStream_t st) {
-    ChunkJob j0{on, pitch_on, len_on, n_chunks_of(len_on), nreps_on, cv_on}, j1{pre, pitch_pre, len_pre, n_chunks_of(len_pre), nreps_pre, cv_pre};
+    ChunkJob j0{on, pitch_on, len_on, n_chunks_of(len_on), nreps_on, cv_on, 0, n_chunks_of(len_on), n_chunks_of(len_on) == 1},
+        j1{pre, pitch_pre, len_pre, n_chunks_of(len_pre), nreps_pre, cv_pre, 0, n_chunks_of(len_pre), n_chunks_of(len_pre) == 1};
     const uint64_t threads = std::max((uint64_t)j0.n_chunks * nreps_on, (uint64_t)j1.n_chunks * nreps_pre);
     if (threads == 0) return;
     dim3 grid((unsigned)((threads + 63) / 64), 2);
     k_chunk_cv<<<grid, 64, 0, st>>>(j0, j1);
+}
+
+// Streaming: chunks [chunk0, chunk0 + n_chunks) of both streams from window buffers (n_chunks may be 0 for a stream); `total_*` are
+// the whole streams' chunk counts (the pitch of the CV arrays; 1 = the stream is a single, root chunk).
+void launch_chunk_cv_window(const uint8_t *on, size_t pitch_on, uint32_t len_on, uint32_t nchunks_on, uint32_t chunk0_on, uint32_t total_on, uint32_t *cv_on,
+                            const uint8_t *pre, size_t pitch_pre, uint32_t len_pre, uint32_t nchunks_pre, uint32_t chunk0_pre, uint32_t total_pre,
+                            uint32_t *cv_pre, uint32_t nreps, cudaStream_t st) {
+    ChunkJob j0{on, pitch_on, len_on, nchunks_on, nreps, cv_on, chunk0_on, total_on, total_on == 1},
+        j1{pre, pitch_pre, len_pre, nchunks_pre, nreps, cv_pre, chunk0_pre, total_pre, total_pre == 1};
+    const uint64_t threads = std::max((uint64_t)nchunks_on, (uint64_t)nchunks_pre) * nreps;
+    if (threads == 0) return;
+    dim3 grid((unsigned)((threads + 63) / 64), 2);
+    k_chunk_cv<<<grid, 64, 0, st>>>(j0, j1);
+}
+
+// =====================================================================================================================
+//  Streaming segments: carried wire state in and out, and the segment's share of the packed openings
+// =====================================================================================================================
+// Imports: row n_prg + j of the segment's share tensor <- slot[j] of the cell file (and its instance-major copy for the mask VM);
+// plaintext leaf n_inputs + j <- the cell's value.
+__global__ void __launch_bounds__(256) k_seg_import(const uint32_t *__restrict__ slot, uint32_t n_imports, const uint64_t *__restrict__ cell_rows,
+                                                    const uint8_t *__restrict__ cell_vals, uint32_t npi, uint32_t n_prg, uint64_t *__restrict__ rows,
+                                                    uint64_t *__restrict__ fresh_pm, size_t pitch_pm, bool pm_pairs, uint8_t *__restrict__ leaf_vals) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t pi = (uint32_t)(gid % npi);
+    const uint64_t j = gid / npi;
+    if (j >= n_imports) return;
+    const uint64_t v = cell_rows[(size_t)slot[j] * npi + pi];
+    rows[(size_t)(n_prg + j) * npi + pi] = v;
+    if (fresh_pm != nullptr) {
+        if (pm_pairs) fresh_pm[((size_t)(pi >> 1) * pitch_pm + n_prg + j) * 2 + (pi & 1)] = v;
+        else fresh_pm[(size_t)pi * pitch_pm + n_prg + j] = v;
+    }
+    if (pi == 0) leaf_vals[j] = cell_vals[slot[j]];
+}
+// Exports: the final state of the wires later segments read.
+__global__ void __launch_bounds__(256) k_seg_export(const uint32_t *__restrict__ slot, const uint32_t *__restrict__ row, const uint32_t *__restrict__ vref,
+                                                    uint32_t n_exports, const uint64_t *__restrict__ rows, const uint8_t *__restrict__ vals, uint32_t npi,
+                                                    uint64_t *__restrict__ cell_rows, uint8_t *__restrict__ cell_vals) {
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t pi = (uint32_t)(gid % npi);
+    const uint64_t k = gid / npi;
+    if (k >= n_exports) return;
+    cell_rows[(size_t)slot[k] * npi + pi] = rows[(size_t)row[k] * npi + pi];
+    if (pi == 0) cell_vals[slot[k]] = (uint8_t)((vals[vref[k] >> 1] ^ vref[k]) & 1);
+}
+void launch_seg_import(const uint32_t *slot, uint32_t n_imports, const uint64_t *cell_rows, const uint8_t *cell_vals, uint32_t npi, uint32_t n_prg, uint64_t *rows,
+                       uint64_t *fresh_pm, size_t pitch_pm, bool pm_pairs, uint8_t *leaf_vals, cudaStream_t st) {
+    if (!n_imports) return;
+    const uint64_t threads = (uint64_t)n_imports * npi;
+    k_seg_import<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(slot, n_imports, cell_rows, cell_vals, npi, n_prg, rows, fresh_pm, pitch_pm, pm_pairs, leaf_vals);
+}
+void launch_seg_export(const uint32_t *slot, const uint32_t *row, const uint32_t *vref, uint32_t n_exports, const uint64_t *rows, const uint8_t *vals, uint32_t npi,
+                       uint64_t *cell_rows, uint8_t *cell_vals, cudaStream_t st) {
+    if (!n_exports) return;
+    const uint64_t threads = (uint64_t)n_exports * npi;
+    k_seg_export<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(slot, row, vref, n_exports, rows, vals, npi, cell_rows, cell_vals);
+}
+
+// The segment's bits of the opened repetitions' packed vectors (src/transcript/prover.rs:57-175), OR-ed into a proof whose headers
+// and (zeroed) vectors k_extract has already written.  CTA = repetition; thread = output byte.  A byte that straddles two segments
+// is completed by the later one (segments run one after the other).
+__global__ void __launch_bounds__(256) k_seg_extract(SegExtractArgs a) {
+    const uint32_t rep = blockIdx.x, omit = a.omit_of_rep[rep];
+    if (omit >= RV_PLAYERS) return;
+    const ProofLayout L{a.len_recons, a.len_corrs, a.len_inputs, 0, 0, 0};
+    uint8_t *e = a.proof + L.g_base() + 8 + a.rank_of_rep[rep] * L.sz_on_g();
+    const uint8_t *on = a.on + (size_t)rep * a.pitch_on + a.base_on, *pre = a.pre + (size_t)rep * a.pitch_pre + a.base_pre;
+    const uint32_t tid = threadIdx.x + blockDim.x * blockIdx.y, nt = blockDim.x * gridDim.y;
+    auto gather = [&](uint8_t *dst, uint64_t first, uint32_t n, const uint8_t *stream, const uint32_t *pos, uint32_t bit) {
+        if (n == 0) return;
+        const uint64_t g0 = first / 8, g1 = (first + n - 1) / 8;
+        for (uint64_t g = g0 + tid; g <= g1; g += nt) {
+            uint32_t r = 0;
+#pragma unroll
+            for (uint32_t i = 0; i < 8; i++) {
+                const uint64_t el = 8 * g + i;  // global element; the first one of a byte is its MSB
+                uint32_t v = 0;
+                if (el >= first && el - first < n) {
+                    const uint32_t k = (uint32_t)(el - first);
+                    v = (stream[pos ? pos[k] : k] >> bit) & 1u;
+                }
+                r = (r << 1) | v;
+            }
+            dst[g] |= (uint8_t)r;
+        }
+    };
+    gather(e + 137, a.first_recon, a.n_recon, on, a.recon_pos, 7 - omit);
+    gather(e + 145 + L.len_recons, a.first_corr, a.n_corr, pre, nullptr, 0);
+    gather(e + 153 + L.len_recons + L.len_corrs, a.first_input, a.n_inputs, on, a.input_pos, 0);
+}
+void launch_seg_extract(const SegExtractArgs &a, uint32_t nreps, cudaStream_t st) {
+    const uint32_t bytes = (a.n_recon + a.n_corr + a.n_inputs) / 8 + 1;
+    const uint32_t ny = std::min(64u, std::max(1u, bytes / 4096));
+    k_seg_extract<<<dim3(nreps, ny), 256, 0, st>>>(a);
 }
 
 // BLAKE3 tree over n chunk CVs, in place: adjacent pairs merge, an odd tail is carried up unchanged (this reproduces
@@ -1179,6 +1287,9 @@ int configure_kernels(int device) {
     load((const void *)k_challenge);
     load((const void *)k_xfinish);
     load((const void *)k_extract);
+    load((const void *)k_seg_import);
+    load((const void *)k_seg_export);
+    load((const void *)k_seg_extract);
     if (e != cudaSuccess) return (int)e;
     done[device >> 6] |= 1ull << (device & 63);
     return 0;

@@ -78,7 +78,7 @@ void launch_key_setup(const uint8_t *seeds, const uint8_t *pkeys_in, const uint8
 //     also writes the instance-major copy `fresh_pm` [npi][pitch_pm] (u64) that the mask VM loads from (nullptr = skip)
 //     busy_sms: SMs held by kernels that run alongside (the value plane's CTAs); share: sessions of the batch that run side by side
 void launch_mask_gen_tt(const uint32_t *rk_plain, uint32_t nslices, uint32_t n_masks, uint64_t *rows, uint64_t *fresh_pm, size_t pitch_pm, int n_sms,
-                        cudaStream_t st, uint32_t busy_sms = 0, uint32_t share = 1, bool pm_pairs = false);
+                        cudaStream_t st, uint32_t busy_sms = 0, uint32_t share = 1, bool pm_pairs = false, uint64_t mask_base = 0);
 // K0  value plane (plaintext evaluation; one CTA, level-synchronous).  Returns the dynamic smem it asked for.
 size_t launch_values(const LutInstr *steps, uint32_t n_steps, const uint32_t *leaf_ids, const uint8_t *leaf_vals, size_t leaf_pitch,
                      uint32_t n_leaves, uint8_t *vals, size_t vals_pitch, uint32_t n_vals, uint32_t n_instances, cudaStream_t st);
@@ -101,10 +101,14 @@ void launch_tainted(const DevProgram &P, const uint64_t *rows, uint32_t npi, con
 //     npi = packed instances of one proof; a session holding n_proofs proofs side by side passes their count, the pitch between
 //     their value planes and the byte stride between their flags
 void launch_items(const DevProgram &P, const uint64_t *rows, uint32_t npi, const uint8_t *vals, const uint64_t *tvals, uint8_t *on, size_t pitch_on,
-                  uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st, uint32_t n_proofs = 1, size_t vals_pitch = 0, size_t flag_stride = 0);
+                  uint8_t *pre, size_t pitch_pre, int *bad, cudaStream_t st, uint32_t n_proofs = 1, size_t vals_pitch = 0, size_t flag_stride = 0,
+                  uint32_t base_on = 0, uint32_t base_pre = 0);
 // K5  BLAKE3 chunk chaining values of `nreps` streams, then per-repetition tree + joins
 void launch_chunk_cv2(const uint8_t *on, size_t pitch_on, uint32_t len_on, uint32_t *cv_on, uint32_t nreps_on, const uint8_t *pre, size_t pitch_pre,
                       uint32_t len_pre, uint32_t *cv_pre, uint32_t nreps_pre, cudaStream_t st);
+void launch_chunk_cv_window(const uint8_t *on, size_t pitch_on, uint32_t len_on, uint32_t nchunks_on, uint32_t chunk0_on, uint32_t total_on, uint32_t *cv_on,
+                            const uint8_t *pre, size_t pitch_pre, uint32_t len_pre, uint32_t nchunks_pre, uint32_t chunk0_pre, uint32_t total_pre,
+                            uint32_t *cv_pre, uint32_t nreps, cudaStream_t st);
 //     zconst: [0..8) B3(""), [8..16) H(B3("") || B3("")).  Verifier: repetitions >= first_pre use the proof's online hashes.
 void launch_rep_hash(uint32_t *cv_on, uint32_t n_chunks_on, uint32_t *cv_pre, uint32_t n_chunks_pre, const uint32_t *zconst, uint32_t nreps,
                      uint8_t *on_hash, uint8_t *rep_hash, cudaStream_t st, uint32_t first_pre = 0xFFFFFFFFu, const uint8_t *on_given = nullptr,
@@ -166,6 +170,25 @@ struct ExtractArgs {
     uint8_t *proof;
 };
 void launch_extract(const DevProgram &P, const ExtractArgs &a, cudaStream_t st);
+
+// ---- streaming segments (rv_prove_streaming): carried wire state, per-segment share of the openings ----
+void launch_seg_import(const uint32_t *slot, uint32_t n_imports, const uint64_t *cell_rows, const uint8_t *cell_vals, uint32_t npi, uint32_t n_prg, uint64_t *rows,
+                       uint64_t *fresh_pm, size_t pitch_pm, bool pm_pairs, uint8_t *leaf_vals, cudaStream_t st);
+void launch_seg_export(const uint32_t *slot, const uint32_t *row, const uint32_t *vref, uint32_t n_exports, const uint64_t *rows, const uint8_t *vals, uint32_t npi,
+                       uint64_t *cell_rows, uint8_t *cell_vals, cudaStream_t st);
+struct SegExtractArgs {
+    const uint8_t *on, *pre;          // the segment's stream windows [rep][pitch]
+    size_t pitch_on, pitch_pre;
+    uint32_t base_on, base_pre;       // buffer position of the segment's first online / preprocessing byte
+    const uint32_t *recon_pos, *input_pos;  // the segment's tables (positions relative to its first online byte)
+    uint32_t n_recon, n_corr, n_inputs;     // elements this segment contributes
+    uint64_t first_recon, first_corr, first_input;  // their global element indices
+    const uint8_t *omit_of_rep;
+    const uint16_t *rank_of_rep;
+    uint32_t len_recons, len_corrs, len_inputs;  // packed byte lengths of the whole proof's vectors
+    uint8_t *proof;
+};
+void launch_seg_extract(const SegExtractArgs &a, uint32_t nreps, cudaStream_t st);
 
 // ---- Z64 domain (rv_z64.cu) ------------------------------------------------------------------------------------------
 struct ZOpen;

@@ -421,6 +421,18 @@ class Proof:
         return Proof(_take(out, n))
 
     @staticmethod
+    def new_streaming(ops, wit_gf2, wire_counts, seeds=None, window_ops: int = 0) -> "Proof":
+        """Proof::new in streaming mode (rv_prove_streaming): the circuit is proved segment by segment with O(window_ops) device
+        buffers, for circuits whose share tensor and transcripts do not fit in HBM.  Same bytes as Proof.new."""
+        ops = np.ascontiguousarray(ops, dtype=OP_DTYPE)
+        wg = np.ascontiguousarray(np.asarray(wit_gf2, dtype=np.uint8))
+        sd = _seeds_arr(seeds)
+        out, n = C.c_void_p(), C.c_size_t()
+        N.check(N.lib().rv_prove_streaming(_ptr(ops), ops.size, int(wire_counts[0]), int(wire_counts[1]), _ptr(wg), wg.size, None, 0, _ptr(sd), int(window_ops),
+                                           C.byref(out), C.byref(n)))
+        return Proof(_take(out, n))
+
+    @staticmethod
     def new_batch(circuit, wits_gf2, wits_z64=None, wire_counts=None, seeds=None):
         """Proof::new for a list of independent witnesses of one circuit (rv_prove_batch): small GF(2) circuits are proved side
         by side, every kernel launch covering a group of them.  `seeds`: None or one 256 x 16-byte value (or None) per witness.

@@ -639,3 +639,49 @@ def test_strict_verify_rejects_skipped_assert(rb, default_seeds):
     assert p.verify(circ, strict=False) and not p.verify(circ)
     honest = rb.Proof.new(circ, [1, 1], (), seeds=default_seeds)
     assert honest.verify_detail(circ) == (True, True) and honest.verify(circ)
+
+
+def test_streaming_prove_matches_oracle(rb, default_seeds):
+    """rv_prove_streaming: the circuit is proved segment by segment with wires carried across the boundaries,
+    PRG / hash streams continued and two passes (hashes, then openings); the bytes must be the oracle's whatever the window.
+    Windows are forced far below the circuit sizes: random circuits with heavy cell reuse (imports, exports, slot recycling),
+    flat lengths around BLAKE3 chunk boundaries, SHA-256 (LUT value plane + mask VM inside the segments), a wide layered circuit
+    (per-level paths), failed asserts and the unsupported shapes."""
+    import orc
+    from reverie_b200 import circuits as C
+    from reverie_b200 import _native as N
+
+    def check(ops, wit, wc, windows, seeds=default_seeds):
+        rc, want = orc.prove(ops, wit, [], wc, seeds)
+        assert rc == 0
+        for w in windows:
+            got = rb.Proof.new_streaming(ops, wit, wc, seeds=seeds, window_ops=w).serialize()
+            assert len(got) == len(want), (w, len(got), len(want))
+            assert got == want, (w, next(i for i in range(len(want)) if got[i] != want[i]))
+        return want
+
+    for seed in range(4):
+        rng = np.random.default_rng(100 + seed)
+        ops, wit, wc = _random_circuit(rng, 24, 3000, n_cells=40 + 30 * seed)
+        check(ops, wit, wc, (64, 257, 1000, 10 ** 6))
+    for n_mul in (0, 1, 1021, 1022, 1023, 1024, 2047, 2048, 5000):
+        ops, wc = C.flat_mul_circuit(n_mul)
+        check(ops, np.array([1, 1], dtype=np.uint8), wc, (64, 500, 1024))
+    ops, wit, wc = C.sha256_abc_case()
+    want = check(ops, wit, wc, (7000, 40000))
+    assert rb.Proof(want).verify(rb.Circuit(ops, wc))
+    ops, nw = C.layered_and_circuit(8192, 60000)
+    wit = np.random.default_rng(0).integers(0, 2, size=8192).astype(np.uint8)
+    check(ops, wit, (0, nw), (20000,))
+    # a failed AssertZero, a witness that is too short, unsupported domains
+    aops, awit, awc = C.sha256_abc_case()
+    bad = awit.copy()
+    bad[11] ^= 1
+    with pytest.raises(rb.WitnessError):
+        rb.Proof.new_streaming(aops, bad, awc, seeds=default_seeds, window_ops=9000)
+    with pytest.raises(rb.WitnessError):
+        rb.Proof.new_streaming(aops, awit[:100], awc, seeds=default_seeds, window_ops=9000)
+    zops, zwc = C.flat_mul_circuit(10, domain=C.Z64)
+    with pytest.raises(rb.ReverieError) as e:
+        rb.Proof.new_streaming(zops, (), zwc, seeds=default_seeds, window_ops=64)
+    assert e.value.code == N.E_UNSUPPORTED
