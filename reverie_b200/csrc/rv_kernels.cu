@@ -182,7 +182,9 @@ void launch_mask_gen_tt(const uint32_t *rk_plain, uint32_t nslices, uint32_t n_m
     // One CTA per SM (104 registers x 512 threads), so the grid is sized to finish in ONE wave over the SMs this launch can count
     // on: the value plane's CTAs (busy_sms, one SM each for the whole mask pipeline) and the other sessions of the batch (share)
     // take theirs -- a grid a few CTAs larger than the free SMs would run a second, almost empty wave and double the kernel.
-    const uint32_t avail = std::max(8u, ((uint32_t)n_sms > busy_sms ? (uint32_t)n_sms - busy_sms : 0u) / std::max(1u, share));
+    share = std::max(1u, share);
+    const uint32_t busy_all = busy_sms * share;  // every session of the batch runs its own value plane
+    const uint32_t avail = std::max(8u, ((uint32_t)n_sms > busy_all ? (uint32_t)n_sms - busy_all : 0u) / share);
     const uint32_t want_x = std::max(1u, avail / gy);
     const uint32_t per = std::min(64u, std::max(4u, (n_blocks + want_x - 1) / want_x));
     dim3 grid((n_blocks + per - 1) / per, gy);

@@ -37,7 +37,8 @@ def main():
         n_mul = int((ops["opcode"] == 6).sum())
         t0 = time.perf_counter()
         if n_mul > 20_000_000 or (name.startswith("z64") and n_mul > 500_000):
-            rc, dg, n = orc.prove_digest_lowmem(ops, wit, wz, wc, seeds, n_threads=min(os.cpu_count() or 1, 8))
+            # at most `n_threads` instances' transcripts (24 bytes per gate each) are alive at a time: bound them by the machine's memory
+            rc, dg, n = orc.prove_digest_lowmem(ops, wit, wz, wc, seeds, n_threads=min(os.cpu_count() or 1, 8 if n_mul <= 150_000_000 else 4))
         else:
             rc, proof = orc.prove(ops, wit, wz, wc, seeds)
             dg, n = (hashlib.sha256(proof).hexdigest(), len(proof)) if rc == 0 else (None, 0)
