@@ -356,9 +356,12 @@ def run_workload(env: Env, name: str, batch: int, per_session: int, steps: int, 
             sharding.all_gather_hashes_batched([recv_bufs[x][0] for x in sess_list], [recv_bufs[x][1] for x in sess_list])
         bt.open()
 
+    done_ms = []  # diagnostic: when each stream of a step finished, relative to the step's start (mean over the timed steps)
+
     def timed_device(sess_list, k: int) -> float:
         tot = 0.0
         sts = streams_of(sess_list)
+        acc = [0.0] * len(sts)
         for _ in range(k):
             with torch.cuda.stream(env.timing_stream):
                 env.flush.zero_()
@@ -368,13 +371,18 @@ def run_workload(env: Env, name: str, batch: int, per_session: int, steps: int, 
             for st_ in sts:
                 st_.wait_event(a)
             step_device(sess_list)
+            ends = []
             for st_ in sts:
-                e = torch.cuda.Event()
+                e = torch.cuda.Event(enable_timing=True)
                 e.record(st_)
                 env.timing_stream.wait_event(e)
+                ends.append(e)
             b.record(env.timing_stream)
             env.barrier()
             tot += a.elapsed_time(b)
+            for i, e in enumerate(ends):
+                acc[i] += a.elapsed_time(e)
+        done_ms[:] = [x / max(k, 1) for x in acc]
         return tot  # ms
 
     def collect(sess_list):
@@ -393,6 +401,7 @@ def run_workload(env: Env, name: str, batch: int, per_session: int, steps: int, 
     sampler = ClockSampler(env.local_rank)
     sampler.start()
     ms_total = timed_device(sessions, steps)
+    stream_done_ms = list(done_ms)
     launches = sum(x.launch_count for x in sessions) - launches0
     clocks = sampler.stop()
     ms_total = env.max_over_ranks(ms_total)
@@ -599,7 +608,7 @@ def run_workload(env: Env, name: str, batch: int, per_session: int, steps: int, 
                    "exchange": exchange,
                    "l2": "256 MiB memset between timed steps (outside the per-step CUDA-event pair)",
                    "timing": "one CUDA-event pair per step on a timing stream that forks to / joins the batch leader's stream (the session streams fork from / join it inside the CUDA graph), summed over K steps (linked groups: the pair forks to / joins every session's stream)"},
-        "clocks": clocks, "e2e": e2e, "parity_checked": parity, "proof_sha256": digest, "proof_bytes": proof_len,
+        "clocks": clocks, "stream_done_ms": stream_done_ms, "e2e": e2e, "parity_checked": parity, "proof_sha256": digest, "proof_bytes": proof_len,
         "compile_s": compile_s, "circuit_gen_s": gen_s, "gpu_launches": int(launches), "roofline": roofline,
         "circuit": {k: st[k] for k in ("n_and", "n_ops", "value_depth", "linear_depth", "z64_mul", "z64_value_depth")},
     }

@@ -1705,7 +1705,6 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
     if (!proof || !proof_len || (n_ops && !ops)) return fail(RV_E_ARG, "NULL argument");
     *proof = nullptr;
     *proof_len = 0;
-    if (rv_device_count() == 0) return fail(RV_E_CUDA, "no CUDA device: reverie-b200 has no CPU fallback");
     if (window_ops == 0) window_ops = (size_t)1 << 22;  // ~5 GB of window buffers
     window_ops = std::max<size_t>(window_ops, 64);
     // ---- 1. liveness + segmentation (host, one pass backwards, one forwards) ----
@@ -1718,6 +1717,7 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
         if (op.domain != RV_GF2 || op.opcode == RV_RANDOM || op.opcode > RV_CONST)
             return fail(RV_E_UNSUPPORTED, "op " + std::to_string(i) + ": streaming mode serves GF(2) circuits without Random / Z64 / B2A");
     }
+    if (rv_device_count() == 0) return fail(RV_E_CUDA, "no CUDA device: reverie-b200 has no CPU fallback");
     const size_t n_seg = std::max<size_t>(1, (n_ops + window_ops - 1) / window_ops);
     auto reads = [](const rv_op &op, uint32_t r[2]) -> int {
         switch (op.opcode) {

@@ -56,9 +56,10 @@ void launch_key_setup(const uint8_t *seeds, const uint8_t *pkeys_in, const uint8
 //      words of the slice (what the reference's AVX2 movemask transpose produces, src/algebra/gf2/domain.rs:66-173), and a
 //      small shared-memory tile regroups the CTA's 16 slices so every mask row leaves as one 64-byte segment.
 //      Cost per block and lane: ~190 LDS/SHFL + ~380 ALU-pipe instructions, against ~640 LOP3 bitsliced.
-constexpr int GT_SLICES = 16, GT_THREADS = 32 * GT_SLICES, GT_TILE_PITCH = GT_SLICES + 4;  // tile row = the CTA's slice words + pad (16-byte aligned rows)
-constexpr int GT_QUADS = GT_SLICES / 4;  // 16-byte pieces of a tile row
-constexpr size_t GT_TILE_BYTES = 128 * GT_TILE_PITCH * 4;
+// A CTA = 16 warps = NS slices x NB counter blocks (NS * NB = 16): full shards give every warp its own slice (NS = 16); the small
+// shards of a proof spread over 8 or 16 GPUs (8 or 4 slices) let the spare warps take the next counter blocks instead of idling.
+constexpr int GT_WARPS = 16, GT_THREADS = 32 * GT_WARPS;
+constexpr size_t GT_TILE_BYTES = 512 * (4 + 4) * 4;  // the largest tile: NS = 4 -> 4 blocks x 128 masks, pitch NS + 4 words
 constexpr size_t GT_SMEM2 = 2 * 256 * 32 * 4 + GT_TILE_BYTES, GT_SMEM4 = 4 * 256 * 32 * 4 + GT_TILE_BYTES;
 // FOUR = false: Te0 / Te2 in 64 KB (Te1 / Te3 by PRMT rotation): leaves room for a mask-VM CTA on the same SM -- small proofs
 // in flight.  FOUR = true: all four tables (128 KB), 72 fewer ALU instructions per block -- circuits big enough to own the chip.
@@ -85,14 +86,18 @@ __device__ __forceinline__ uint32_t warp_transpose32(uint32_t x, uint32_t lane) 
 }
 
 // mask_base: PRG index of row 0 (streaming segments continue the streams where the previous segment stopped; 0 otherwise).
-template <bool FOUR>
+// groups_per_cta: a CTA walks that many groups of NB consecutive counter blocks.
+template <bool FOUR, int NS>
 __global__ void __launch_bounds__(GT_THREADS, 1) k_mask_gen_tt(const uint32_t *__restrict__ rk_plain, uint32_t nslices, uint32_t n_masks,
-                                                               uint32_t blocks_per_cta, uint32_t *__restrict__ rows32,
+                                                               uint32_t groups_per_cta, uint32_t *__restrict__ rows32,
                                                                uint64_t *__restrict__ fresh_pm, size_t pitch_pm, bool pm_pairs, uint64_t mask_base) {
+    constexpr int NB = GT_WARPS / NS, PITCH = NS + 4, QUADS = NS / 4, ROWS = NB * 128;  // tile row = the CTA's slice words + pad (16-byte aligned rows)
+    static_assert(NS == 16 || NS == 8 || NS == 4, "slices per CTA");
+    static_assert((size_t)ROWS * PITCH * 4 <= GT_TILE_BYTES, "tile size");
     extern __shared__ __align__(16) uint32_t gt_smem[];
     uint32_t *te = gt_smem, *tile = gt_smem + (FOUR ? 4 : 2) * 256 * 32;
     __shared__ uint32_t sbox32[64];
-    const uint32_t tid = threadIdx.x, lane = tid & 31, wv = tid >> 5;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, wv = tid >> 5, sl = wv % NS, bl = wv / NS;
     if (tid < 64) {
         const uint32_t b = 4 * tid;
         sbox32[tid] = sub_word(b | ((b + 1) << 8) | ((b + 2) << 16) | ((b + 3) << 24));
@@ -107,7 +112,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_mask_gen_tt(const uint32_t *_
             te[16384 + x * 64 + 32 + l] = (t0 << 24) | (t0 >> 8);
         }
     }
-    const uint32_t w0 = blockIdx.y * GT_SLICES, w = w0 + wv, nstreams = nslices * 32;
+    const uint32_t w0 = blockIdx.y * NS, w = w0 + sl, nstreams = nslices * 32;
     const bool live = w < nslices;
     uint32_t rk[44], act = 0;
     if (live) {
@@ -119,52 +124,53 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_mask_gen_tt(const uint32_t *_
     __syncthreads();
     const SmemTe<FOUR> tab{reinterpret_cast<const uint8_t *>(te), 4 * lane};
     const uint64_t jb0 = mask_base / 128;  // first counter block that holds a mask of this launch
-    const uint32_t n_blocks = (uint32_t)((mask_base + n_masks + 127) / 128 - jb0);
-    const uint32_t j_end = min(n_blocks, (blockIdx.x + 1) * blocks_per_cta);
+    const uint32_t n_blocks = (uint32_t)((mask_base + n_masks + 127) / 128 - jb0), n_groups = (n_blocks + NB - 1) / NB;
+    const uint32_t g_end = min(n_groups, (blockIdx.x + 1) * groups_per_cta);
     const int64_t shift = (int64_t)(jb0 * 128) - (int64_t)mask_base;  // row of mask m of local block j = j * 128 + m + shift (may be < 0: a mask of the previous segment)
 #pragma unroll 1
-    for (uint32_t j = blockIdx.x * blocks_per_cta; j < j_end; j++) {
-        if (live) {
+    for (uint32_t g = blockIdx.x * groups_per_cta; g < g_end; g++) {
+        const uint32_t j = g * NB + bl;  // this warp's counter block
+        if (live && j < n_blocks) {
             uint32_t in[4], o[4];
             ctr_block_words((uint32_t)(jb0 + j), in);
             tt_aes128_encrypt(rk, in[0], in[1], in[2], in[3], tab, o);
 #pragma unroll
-            for (int g = 0; g < 4; g++) {
-                // lane now holds plane k = 32 g + lane of the slice = keystream byte B = k / 8, bit b = k % 8 -> mask 8 B + 7 - b of the block
-                const uint32_t t = warp_transpose32(o[g] & act, lane);
-                const uint32_t k = 32 * g + lane, m = (k & ~7u) | (7 - (k & 7));
-                tile[m * GT_TILE_PITCH + wv] = t;
+            for (int q = 0; q < 4; q++) {
+                // lane now holds plane k = 32 q + lane of the slice = keystream byte B = k / 8, bit b = k % 8 -> mask 8 B + 7 - b of the block
+                const uint32_t t = warp_transpose32(o[q] & act, lane);
+                const uint32_t k = 32 * q + lane, m = (k & ~7u) | (7 - (k & 7));
+                tile[(bl * 128 + m) * PITCH + sl] = t;
             }
         }
         __syncthreads();
-        {  // row-major share tensor: thread = (mask of the block, 4 slices) -> one 16-byte store; a row's 16 slices = 64 contiguous bytes
-            for (uint32_t e = tid; e < 128 * GT_QUADS; e += GT_THREADS) {
-                const uint32_t m = e / GT_QUADS, q4 = 4 * (e % GT_QUADS);
-                const int64_t i = (int64_t)j * 128 + m + shift;
+        const int64_t i0 = (int64_t)g * ROWS + shift;  // row of tile row 0 (rows of blocks past the end fall behind n_masks)
+        {  // row-major share tensor: thread = (mask, 4 slices) -> one 16-byte store; a row's NS slices are contiguous
+            for (uint32_t e = tid; e < ROWS * QUADS; e += GT_THREADS) {
+                const uint32_t m = e / QUADS, q4 = 4 * (e % QUADS);
+                const int64_t i = i0 + m;
                 if (i >= 0 && i < (int64_t)n_masks && w0 + q4 < nslices) {
-                    const uint4 v = *reinterpret_cast<const uint4 *>(tile + m * GT_TILE_PITCH + q4);
-                    *reinterpret_cast<uint4 *>(rows32 + i * nslices + w0 + q4) = v;
+                    const uint4 v = *reinterpret_cast<const uint4 *>(tile + m * PITCH + q4);
+                    if (nslices >= 4) *reinterpret_cast<uint4 *>(rows32 + i * nslices + w0 + q4) = v;
+                    else *reinterpret_cast<uint2 *>(rows32 + i * nslices) = make_uint2(v.x, v.y);  // a shard of one packed instance: rows of 8 bytes
                 }
             }
         }
-        if (fresh_pm != nullptr) {  // instance-major copy for the mask VM: 8 instances x 128 masks, u64 each
+        if (fresh_pm != nullptr) {  // instance-major copy for the mask VM: NS / 2 instances x the group's masks, u64 each
             if (pm_pairs) {  // two instances interleaved ([instance pair][mask][2]): a VM CTA that runs two columns loads 16 bytes at once
-#pragma unroll
-                for (uint32_t e = tid; e < (GT_SLICES / 4) * 128; e += GT_THREADS) {
-                    const uint32_t p = e >> 7, m = e & 127;
-                    const int64_t i = (int64_t)j * 128 + m + shift;
+                for (uint32_t e = tid; e < (NS / 4) * ROWS; e += GT_THREADS) {
+                    const uint32_t p = e / ROWS, m = e % ROWS;
+                    const int64_t i = i0 + m;
                     if (i >= 0 && i < (int64_t)n_masks && w0 + 4 * p < nslices) {
-                        const uint4 v = *reinterpret_cast<const uint4 *>(tile + m * GT_TILE_PITCH + 4 * p);
+                        const uint4 v = *reinterpret_cast<const uint4 *>(tile + m * PITCH + 4 * p);
                         *reinterpret_cast<uint4 *>(fresh_pm + ((size_t)((w0 >> 2) + p) * pitch_pm + (uint64_t)i) * 2) = v;
                     }
                 }
             } else {
-#pragma unroll
-                for (uint32_t e = tid; e < (GT_SLICES / 2) * 128; e += GT_THREADS) {
-                    const uint32_t p = e >> 7, m = e & 127;
-                    const int64_t i = (int64_t)j * 128 + m + shift;
+                for (uint32_t e = tid; e < (NS / 2) * ROWS; e += GT_THREADS) {
+                    const uint32_t p = e / ROWS, m = e % ROWS;
+                    const int64_t i = i0 + m;
                     if (i >= 0 && i < (int64_t)n_masks && w0 + 2 * p < nslices) {
-                        const uint2 v = *reinterpret_cast<const uint2 *>(tile + m * GT_TILE_PITCH + 2 * p);
+                        const uint2 v = *reinterpret_cast<const uint2 *>(tile + m * PITCH + 2 * p);
                         fresh_pm[(size_t)((w0 >> 1) + p) * pitch_pm + (uint64_t)i] = ((uint64_t)v.y << 32) | v.x;
                     }
                 }
@@ -174,11 +180,17 @@ __global__ void __launch_bounds__(GT_THREADS, 1) k_mask_gen_tt(const uint32_t *_
     }
 }
 
+template <bool FOUR, int NS>
+static void mask_gen_launch(dim3 grid, cudaStream_t st, const uint32_t *rk_plain, uint32_t nslices, uint32_t n_masks, uint32_t per, uint32_t *rows32,
+                            uint64_t *fresh_pm, size_t pitch_pm, bool pm_pairs, uint64_t mask_base) {
+    k_mask_gen_tt<FOUR, NS><<<grid, GT_THREADS, FOUR ? GT_SMEM4 : GT_SMEM2, st>>>(rk_plain, nslices, n_masks, per, rows32, fresh_pm, pitch_pm, pm_pairs, mask_base);
+}
+
 void launch_mask_gen_tt(const uint32_t *rk_plain, uint32_t nslices, uint32_t n_masks, uint64_t *rows, uint64_t *fresh_pm, size_t pitch_pm, int n_sms,
                         cudaStream_t st, uint32_t busy_sms, uint32_t share, bool pm_pairs, uint64_t mask_base) {
     if (n_masks == 0) return;
-    constexpr size_t SMEM2 = GT_SMEM2, SMEM4 = GT_SMEM4;
-    const uint32_t n_blocks = (uint32_t)((mask_base + n_masks + 127) / 128 - mask_base / 128), gy = (nslices + GT_SLICES - 1) / GT_SLICES;
+    const uint32_t ns = nslices <= 4 ? 4 : nslices <= 8 ? 8 : 16, nb = GT_WARPS / ns;
+    const uint32_t n_blocks = (uint32_t)((mask_base + n_masks + 127) / 128 - mask_base / 128), n_groups = (n_blocks + nb - 1) / nb, gy = (nslices + ns - 1) / ns;
     // One CTA per SM (104 registers x 512 threads), so the grid is sized to finish in ONE wave over the SMs this launch can count
     // on: the value plane's CTAs (busy_sms, one SM each for the whole mask pipeline) and the other sessions of the batch (share)
     // take theirs -- a grid a few CTAs larger than the free SMs would run a second, almost empty wave and double the kernel.
@@ -186,12 +198,15 @@ void launch_mask_gen_tt(const uint32_t *rk_plain, uint32_t nslices, uint32_t n_m
     const uint32_t busy_all = busy_sms * share;  // every session of the batch runs its own value plane
     const uint32_t avail = std::max(8u, ((uint32_t)n_sms > busy_all ? (uint32_t)n_sms - busy_all : 0u) / share);
     const uint32_t want_x = std::max(1u, avail / gy);
-    const uint32_t per = std::min(64u, std::max(4u, (n_blocks + want_x - 1) / want_x));
-    dim3 grid((n_blocks + per - 1) / per, gy);
-    if ((uint64_t)n_blocks * gy >= 64ull * n_sms)  // enough work for many waves: the mask generator owns the chip
-        k_mask_gen_tt<true><<<grid, GT_THREADS, SMEM4, st>>>(rk_plain, nslices, n_masks, per, reinterpret_cast<uint32_t *>(rows), fresh_pm, pitch_pm, pm_pairs, mask_base);
-    else
-        k_mask_gen_tt<false><<<grid, GT_THREADS, SMEM2, st>>>(rk_plain, nslices, n_masks, per, reinterpret_cast<uint32_t *>(rows), fresh_pm, pitch_pm, pm_pairs, mask_base);
+    const uint32_t per = std::min(64u, std::max(4u, (n_groups + want_x - 1) / want_x));  // counter blocks per warp
+    dim3 grid((n_groups + per - 1) / per, gy);
+    uint32_t *rows32 = reinterpret_cast<uint32_t *>(rows);
+    const bool four = (uint64_t)n_blocks * gy >= 64ull * n_sms;  // enough work for many waves: the mask generator owns the chip
+#define RV_MG(F, N) mask_gen_launch<F, N>(grid, st, rk_plain, nslices, n_masks, per, rows32, fresh_pm, pitch_pm, pm_pairs, mask_base)
+    if (ns == 16) four ? RV_MG(true, 16) : RV_MG(false, 16);
+    else if (ns == 8) four ? RV_MG(true, 8) : RV_MG(false, 8);
+    else four ? RV_MG(true, 4) : RV_MG(false, 4);
+#undef RV_MG
 }
 
 // =====================================================================================================================
@@ -1255,8 +1270,12 @@ int configure_kernels(int device) {
         // the full shared-memory carveout: with the default split a second CTA (of this or of another kernel) does not fit
         if (e == cudaSuccess && carveout) e = cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     };
-    set((const void *)k_mask_gen_tt<false>, (int)GT_SMEM2, true);
-    set((const void *)k_mask_gen_tt<true>, (int)GT_SMEM4, true);
+    set((const void *)k_mask_gen_tt<false, 16>, (int)GT_SMEM2, true);
+    set((const void *)k_mask_gen_tt<true, 16>, (int)GT_SMEM4, true);
+    set((const void *)k_mask_gen_tt<false, 8>, (int)GT_SMEM2, true);
+    set((const void *)k_mask_gen_tt<true, 8>, (int)GT_SMEM4, true);
+    set((const void *)k_mask_gen_tt<false, 4>, (int)GT_SMEM2, true);
+    set((const void *)k_mask_gen_tt<true, 4>, (int)GT_SMEM4, true);
     set((const void *)k_values<true, (int)LUT_STEPS_PER_CHUNK_MAX>, (int)SMEM_DYN_CAP, false);
     set((const void *)k_values<true, (int)LUT_STEPS_PER_CHUNK>, (int)SMEM_DYN_CAP, false);
     set((const void *)k_values<false, (int)LUT_STEPS_PER_CHUNK_MAX>, (int)SMEM_DYN_CAP, false);

@@ -438,3 +438,55 @@ def test_one_shot_circuit_cache():
     assert stats()[2] == 0
     st = __import__("reverie_b200").Circuit(ops, wc, prove_only=True).stats()
     assert st["has_verify"] == 0 and st["compile_ns"] > 0
+
+
+def test_bench_digests_are_the_oracles():
+    """tests/golden/bench_digests.json (what bench.py's `parity_checked` compares the GPU proofs with) for the workloads the
+    oracle proves in a second or two; the 10^7 .. 3 x 10^8-gate entries come from the same script (make_bench_digests.py)."""
+    import hashlib
+    import json
+
+    import bench
+    import orc
+
+    with open(os.path.join(ROOT, "tests", "golden", "bench_digests.json")) as f:
+        doc = json.load(f)
+    seeds = bench.default_seeds()
+    for name in ("sha256", "flat1000000", "layered1000000", "z64mul100000"):
+        ops, wit, wz, wc, _ = bench.make_workload(name)
+        rc, proof = orc.prove(ops, wit, wz, wc, seeds)
+        assert rc == 0
+        assert hashlib.sha256(proof).hexdigest() == doc["digests"][name], name
+        assert len(proof) == doc["proof_bytes"][name]
+    for name in ("flat100000000", "layered100000000", "z64mul1000000", "flat300000000"):
+        assert len(doc["digests"][name]) == 64
+
+
+def test_multi_gpu_and_streaming_entry_points_check_their_arguments_without_a_gpu():
+    """rv_group_* / rv_prove_streaming: shapes and unsupported circuits are refused before any device work; with no device the
+    answer is RV_E_CUDA (there is no CPU fallback)."""
+    import ctypes as C
+
+    from reverie_b200 import _native as N
+    from reverie_b200 import circuits as CC
+    from reverie_b200.proof import Circuit, _ptr
+
+    L = N.lib()
+    ops, wc = CC.flat_mul_circuit(100)
+    circ = Circuit(ops, wc, prove_only=True)
+    h = C.c_void_p()
+    devs = (C.c_int * 3)(0, 0, 0)
+    assert L.rv_group_create_local(circ.handle, devs, 3, 1, 1, C.byref(h)) == N.E_ARG  # 3 does not divide the 32 packed instances
+    assert L.rv_group_create_rank(circ.handle, 2, 2, 1, 1, C.byref(h)) == N.E_ARG       # rank out of range
+    assert L.rv_group_create_rank(circ.handle, 0, 2, 0, 1, C.byref(h)) == N.E_ARG       # no sessions
+    out, n = C.c_void_p(), C.c_size_t()
+    wit = np.array([1, 1], dtype=np.uint8)
+    zops, zwc = CC.flat_mul_circuit(4, domain=CC.Z64)
+    assert L.rv_prove_streaming(_ptr(zops), zops.size, zwc[0], zwc[1], None, 0, None, 0, None, 64, C.byref(out), C.byref(n)) == N.E_UNSUPPORTED
+    bad = ops.copy()
+    bad["a"][5] = 10 ** 6
+    if L.rv_device_count() == 0:
+        assert L.rv_prove_streaming(_ptr(ops), ops.size, wc[0], wc[1], _ptr(wit), 2, None, 0, None, 64, C.byref(out), C.byref(n)) == N.E_CUDA
+        assert L.rv_group_create_rank(circ.handle, 0, 2, 1, 1, C.byref(h)) == N.E_CUDA
+    else:
+        assert L.rv_prove_streaming(_ptr(bad), bad.size, wc[0], wc[1], _ptr(wit), 2, None, 0, None, 64, C.byref(out), C.byref(n)) == N.E_ARG
