@@ -404,6 +404,7 @@ struct rv_session {
     uint8_t *d_on = nullptr, *d_pre = nullptr;
     size_t pitch_on = 0, pitch_pre = 0;
     uint32_t *d_cv_on = nullptr, *d_cv_pre = nullptr, n_chunks_on = 1, n_chunks_pre = 1;
+    uint32_t *d_cv_scratch = nullptr;  // long streams: ping-pong buffer of the grid-wide tree levels
     uint8_t *d_on_hash = nullptr, *d_rep_hash = nullptr, *d_all_hashes = nullptr, *d_comm = nullptr, *d_omit = nullptr;
     uint16_t *d_rank = nullptr;
     uint32_t *d_zconst = nullptr;  // [0..8) B3(""), [8..16) H(B3("")||B3(""))
@@ -582,6 +583,8 @@ extern "C" int rv_session_create_multi(const rv_circuit *c, int first_instance, 
         (rc = dalloc(s, &s->d_rep_hash, (size_t)s->nreps * 32)) ||
         (rc = dalloc(s, &s->d_omit, (size_t)RV_TOTAL_REPS * s->n_proofs)) || (rc = dalloc(s, &s->d_rank, (size_t)RV_TOTAL_REPS * s->n_proofs)) ||
         (rc = dalloc(s, &s->d_zconst, 16)))
+        return bail(rc);
+    if (std::max(s->n_chunks_on, s->n_chunks_pre) > 2048 && (rc = dalloc(s, &s->d_cv_scratch, (size_t)(std::max(s->n_chunks_on, s->n_chunks_pre) + 1) / 2 * s->nreps * 8)))
         return bail(rc);
     // The exchange block and the proof buffer can be mapped into other processes (rv_session_peer_handle): each is its own
     // allocation of whole 2 MiB pages, so that an IPC mapping exposes nothing else.
@@ -834,7 +837,7 @@ static int commit_body(rv_session *s) {
     {
         Scope k(s, "rep_hash", ((uint64_t)s->n_chunks_on + s->n_chunks_pre) * s->nreps * 32);
         launch_rep_hash(s->d_cv_on, s->n_chunks_on, s->d_cv_pre, s->n_chunks_pre, s->d_zconst, s->nreps, s->d_on_hash, s->d_rep_hash, s->st, 0xFFFFFFFFu,
-                        nullptr, nullptr, s->has_z ? s->d_zrep : nullptr);
+                        nullptr, nullptr, s->has_z ? s->d_zrep : nullptr, s->d_cv_scratch);
     }
     CU(cudaGetLastError());
     return RV_OK;
@@ -1908,7 +1911,7 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
     uint64_t *d_rows = nullptr, *d_fresh = nullptr, *d_cell_rows = nullptr;
     uint8_t *d_vals = nullptr, *d_leaf = nullptr, *d_on = nullptr, *d_pre = nullptr, *d_cell_vals = nullptr, *d_carry_on = nullptr, *d_carry_pre = nullptr, *d_seeds = nullptr,
             *d_pkeys = nullptr, *d_on_hash = nullptr, *d_rep_hash = nullptr, *d_omit = nullptr, *d_proof = nullptr;
-    uint32_t *d_cv_on = nullptr, *d_cv_pre = nullptr, *d_rk = nullptr, *d_zconst = nullptr;
+    uint32_t *d_cv_on = nullptr, *d_cv_pre = nullptr, *d_rk = nullptr, *d_zconst = nullptr, *d_cv_scratch = nullptr;
     uint16_t *d_rank = nullptr;
     int rc;
     if ((rc = B.alloc(&d_rows, max_rows * NPI)) || (any_vm && (rc = B.alloc(&d_fresh, pitch_fresh * NPI))) || (rc = B.alloc(&d_cell_rows, (size_t)std::max(n_slots, 1u) * NPI)) ||
@@ -1917,7 +1920,8 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
         (rc = B.alloc(&d_carry_pre, (size_t)1024 * NREPS)) || (rc = B.alloc(&d_cv_on, (size_t)tot_chunks_on * NREPS * 8)) ||
         (rc = B.alloc(&d_cv_pre, (size_t)tot_chunks_pre * NREPS * 8)) || (rc = B.alloc(&d_seeds, (size_t)NREPS * 16)) || (rc = B.alloc(&d_pkeys, (size_t)NREPS * 128)) ||
         (rc = B.alloc(&d_rk, (size_t)45 * 64 * NPI)) || (rc = B.alloc(&d_on_hash, (size_t)NREPS * 32)) || (rc = B.alloc(&d_rep_hash, (size_t)NREPS * 32)) ||
-        (rc = B.alloc(&d_omit, NREPS)) || (rc = B.alloc(&d_rank, NREPS)) || (rc = B.alloc(&d_zconst, 16)) || (rc = B.alloc(&d_proof, tail_off + 64)))
+        (rc = B.alloc(&d_omit, NREPS)) || (rc = B.alloc(&d_rank, NREPS)) || (rc = B.alloc(&d_zconst, 16)) || (rc = B.alloc(&d_proof, tail_off + 64)) ||
+        (std::max(tot_chunks_on, tot_chunks_pre) > 2048 && (rc = B.alloc(&d_cv_scratch, (size_t)(std::max(tot_chunks_on, tot_chunks_pre) + 1) / 2 * NREPS * 8))))
         return rc;
     int *d_bad = reinterpret_cast<int *>(d_proof + tail_off);
     uint8_t *d_comm = d_proof + tail_off + 4;
@@ -1948,7 +1952,7 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
     for (int pass = 1; pass <= 2; pass++) {
         if (pass == 2) {
             // every repetition's hash is known: comm, challenge, then the proof's headers, keys, hashes and zeroed vectors
-            launch_rep_hash(d_cv_on, tot_chunks_on, d_cv_pre, tot_chunks_pre, d_zconst, NREPS, d_on_hash, d_rep_hash, st);
+            launch_rep_hash(d_cv_on, tot_chunks_on, d_cv_pre, tot_chunks_pre, d_zconst, NREPS, d_on_hash, d_rep_hash, st, 0xFFFFFFFFu, nullptr, nullptr, nullptr, d_cv_scratch);
             launch_challenge(d_rep_hash, NREPS * 32, d_comm, 0, d_omit, d_rank, 1, st);
             ExtractArgs a;
             a.on = d_on, a.pre = d_pre, a.pitch_on = pitch_on, a.pitch_pre = pitch_pre, a.on_hash = d_on_hash, a.pkeys = d_pkeys, a.seeds = d_seeds, a.comm = d_comm;

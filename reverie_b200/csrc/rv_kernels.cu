@@ -841,6 +841,13 @@ __global__ void __launch_bounds__(256) k_seg_extract(SegExtractArgs a) {
         if (n == 0) return;
         const uint64_t g0 = first / 8, g1 = (first + n - 1) / 8;
         for (uint64_t g = g0 + tid; g <= g1; g += nt) {
+            if (8 * g >= first && 8 * g + 8 <= first + n) {  // the byte's 8 elements belong to this segment: 8-byte loads when they sit side by side
+                const uint32_t k0 = (uint32_t)(8 * g - first), p0 = pos ? pos[k0] : k0;
+                if (!pos || pos[k0 + 7] == p0 + 7) {
+                    dst[g] |= gather_bit_msb_first(load8_unaligned(stream + p0), bit);
+                    continue;
+                }
+            }
             uint32_t r = 0;
 #pragma unroll
             for (uint32_t i = 0; i < 8; i++) {
@@ -901,6 +908,51 @@ __device__ void tree_reduce(uint32_t *cvs, uint32_t n) {
     }
 }
 
+// Long streams (10^8 gates = 10^5 chunks per repetition and stream): the lower levels of the tree are wide enough for the whole
+// grid, and one CTA per repetition would walk them alone (3 ms whatever the shard).  One launch per level, out of place (a thread
+// writing slot p would race with the reader of slots 2p', 2p'+1 of another CTA): thread = (repetition, pair).
+__global__ void __launch_bounds__(256) k_cv_tree_level(const uint32_t *__restrict__ in, uint32_t *__restrict__ out, uint32_t n, uint32_t in_stride,
+                                                       uint32_t out_stride, uint32_t nreps) {
+    const uint32_t outn = (n + 1) / 2;
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t p = (uint32_t)(gid % outn), rep = (uint32_t)(gid / outn);
+    if (rep >= nreps) return;
+    const uint4 *src = reinterpret_cast<const uint4 *>(in + ((size_t)rep * in_stride + 2 * (size_t)p) * 8);
+    uint4 *dst = reinterpret_cast<uint4 *>(out + ((size_t)rep * out_stride + p) * 8);
+    if (2 * p + 1 < n) {
+        const uint4 a0 = src[0], a1 = src[1], b0 = src[2], b1 = src[3];
+        const uint32_t l[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w}, r[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        uint32_t res[8];
+        b3_parent_cv(l, r, false, res);  // never the root: the per-repetition kernel finishes the last levels
+        dst[0] = make_uint4(res[0], res[1], res[2], res[3]);
+        dst[1] = make_uint4(res[4], res[5], res[6], res[7]);
+    } else {  // the odd tail is carried up unchanged (the spec's left-heavy tree)
+        dst[0] = src[0];
+        dst[1] = src[1];
+    }
+}
+
+// Reduces the CV arrays [nreps][stride] of n chunks level by level while a level is still wide; returns the remaining count and
+// leaves the survivors at the front of `cvs` rows (same stride).  `scratch` holds nreps * ceil(n / 2) CVs.
+uint32_t launch_cv_tree_wide(uint32_t *cvs, uint32_t n, uint32_t stride, uint32_t nreps, uint32_t *scratch, cudaStream_t st) {
+    constexpr uint32_t NARROW = 2048;  // below this a CTA per repetition does the rest
+    if (n <= NARROW || scratch == nullptr) return n;
+    const uint32_t sstride = (n + 1) / 2;
+    uint32_t *bufs[2] = {cvs, scratch};
+    uint32_t strides[2] = {stride, sstride};
+    int cur = 0;
+    while (n > NARROW) {
+        const uint32_t outn = (n + 1) / 2;
+        const uint64_t threads = (uint64_t)outn * nreps;
+        k_cv_tree_level<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(bufs[cur], bufs[cur ^ 1], n, strides[cur], strides[cur ^ 1], nreps);
+        n = outn;
+        cur ^= 1;
+    }
+    if (cur == 1)  // survivors are in the scratch buffer: move them to the front of the rows of `cvs`
+        cudaMemcpy2DAsync(cvs, (size_t)stride * 32, scratch, (size_t)sstride * 32, (size_t)n * 32, nreps, cudaMemcpyDeviceToDevice, st);
+    return n;
+}
+
 // CTA = one repetition: roots of both streams, then the joins of Transcript::hash (src/transcript/mod.rs:77-96) and
 // CombineInstance::hash (src/interpreter/combine.rs:104-118).
 // Verifier: repetitions >= first_pre take their online hash from the proof (VerifierTranscriptPreprocess::online_hash,
@@ -908,10 +960,11 @@ __device__ void tree_reduce(uint32_t *cvs, uint32_t n) {
 __global__ void __launch_bounds__(128) k_rep_hash(uint32_t *cv_on, uint32_t n_chunks_on, uint32_t *cv_pre, uint32_t n_chunks_pre,
                                                   const uint32_t *__restrict__ zconst, uint8_t *__restrict__ on_hash,
                                                   uint8_t *__restrict__ rep_hash, uint32_t first_pre, const uint8_t *__restrict__ on_given,
-                                                  const uint8_t *__restrict__ z_on_given, const uint32_t *__restrict__ zrep) {
+                                                  const uint8_t *__restrict__ z_on_given, const uint32_t *__restrict__ zrep, uint32_t stride_on,
+                                                  uint32_t stride_pre) {
     const uint32_t rep = blockIdx.x;
     const bool given = rep >= first_pre;
-    uint32_t *on = cv_on + (size_t)rep * n_chunks_on * 8, *pre = cv_pre + (size_t)rep * n_chunks_pre * 8;
+    uint32_t *on = cv_on + (size_t)rep * stride_on * 8, *pre = cv_pre + (size_t)rep * stride_pre * 8;
     if (!given) tree_reduce(on, n_chunks_on);
     tree_reduce(pre, n_chunks_pre);
     __syncthreads();
@@ -952,8 +1005,14 @@ __global__ void __launch_bounds__(128) k_rep_hash(uint32_t *cv_on, uint32_t n_ch
 
 void launch_rep_hash(uint32_t *cv_on, uint32_t n_chunks_on, uint32_t *cv_pre, uint32_t n_chunks_pre, const uint32_t *zconst, uint32_t nreps,
                      uint8_t *on_hash, uint8_t *rep_hash, cudaStream_t st, uint32_t first_pre, const uint8_t *on_given, const uint8_t *z_on_given,
-                     const uint32_t *zrep) {
-    k_rep_hash<<<nreps, 128, 0, st>>>(cv_on, n_chunks_on, cv_pre, n_chunks_pre, zconst, on_hash, rep_hash, first_pre, on_given, z_on_given, zrep);
+                     const uint32_t *zrep, uint32_t *scratch) {
+    // prover with long streams: the wide lower levels of both trees grid-wide first (every repetition computes both roots there)
+    uint32_t n_on = n_chunks_on, n_pre = n_chunks_pre;
+    if (scratch != nullptr && first_pre == 0xFFFFFFFFu) {
+        n_on = launch_cv_tree_wide(cv_on, n_chunks_on, n_chunks_on, nreps, scratch, st);
+        n_pre = launch_cv_tree_wide(cv_pre, n_chunks_pre, n_chunks_pre, nreps, scratch, st);
+    }
+    k_rep_hash<<<nreps, 128, 0, st>>>(cv_on, n_on, cv_pre, n_pre, zconst, on_hash, rep_hash, first_pre, on_given, z_on_given, zrep, n_chunks_on, n_chunks_pre);
 }
 
 // Z64 transcript of one repetition (CTA): Transcript::hash = H(B3(pre) || B3(on)), src/transcript/mod.rs:77-96
@@ -1301,6 +1360,7 @@ int configure_kernels(int device) {
     load((const void *)k_tainted);
     load((const void *)k_chunk_cv);
     load((const void *)k_rep_hash);
+    load((const void *)k_cv_tree_level);
     load((const void *)k_zrep_hash);
     load((const void *)k_verify_leaves);
     load((const void *)k_verify_items_online);

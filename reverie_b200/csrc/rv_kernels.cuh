@@ -110,9 +110,10 @@ void launch_chunk_cv_window(const uint8_t *on, size_t pitch_on, uint32_t len_on,
                             const uint8_t *pre, size_t pitch_pre, uint32_t len_pre, uint32_t nchunks_pre, uint32_t chunk0_pre, uint32_t total_pre,
                             uint32_t *cv_pre, uint32_t nreps, cudaStream_t st);
 //     zconst: [0..8) B3(""), [8..16) H(B3("") || B3("")).  Verifier: repetitions >= first_pre use the proof's online hashes.
+//     scratch (optional, prover): nreps * ceil(max(n_chunks) / 2) CVs; with it the wide lower levels of long streams' trees run grid-wide
 void launch_rep_hash(uint32_t *cv_on, uint32_t n_chunks_on, uint32_t *cv_pre, uint32_t n_chunks_pre, const uint32_t *zconst, uint32_t nreps,
                      uint8_t *on_hash, uint8_t *rep_hash, cudaStream_t st, uint32_t first_pre = 0xFFFFFFFFu, const uint8_t *on_given = nullptr,
-                     const uint8_t *z_on_given = nullptr, const uint32_t *zrep = nullptr);
+                     const uint8_t *z_on_given = nullptr, const uint32_t *zrep = nullptr, uint32_t *scratch = nullptr);
 //     Z64 transcript of every repetition: roots of its two streams -> zon_hash[rep] (32 B) and zrep[rep] = H(B3(pre) || B3(on))
 //     (src/transcript/mod.rs:77-96); feeds launch_rep_hash's `zrep`.  Repetitions >= first_pre take the proof's online hash.
 void launch_zrep_hash(uint32_t *cv_on, uint32_t n_chunks_on, uint32_t *cv_pre, uint32_t n_chunks_pre, uint32_t nreps, uint8_t *zon_hash,

@@ -258,11 +258,30 @@ RV_HD void challenge_consume(const uint32_t xof[16], uint8_t *omit, int *distinc
 // ---- extraction (src/transcript/prover.rs:57-175) ------------------------------------------------------------------
 // Byte g of a packed bit vector whose element e is bit `bit` of stream[pos[e]] (pos == NULL: e itself); elements past n
 // are zero; first element -> MSB (src/algebra/gf2/share.rs:66-85, src/algebra/gf2/recon.rs:127-148).
+// Bit `bit` of each of the 8 bytes of w (byte 0 = lowest address) gathered into one byte, byte 0 -> MSB.
+RV_HD uint8_t gather_bit_msb_first(uint64_t w, uint32_t bit) {
+    return (uint8_t)((((w >> bit) & 0x0101010101010101ull) * 0x8040201008040201ull) >> 56);
+}
+// 8 stream bytes starting at byte address p (any alignment) as a little-endian u64, from two aligned loads.
+RV_HD uint64_t load8_unaligned(const uint8_t *p) {
+    const uintptr_t a = reinterpret_cast<uintptr_t>(p);
+    const uint64_t *q = reinterpret_cast<const uint64_t *>(a & ~(uintptr_t)7);
+    const uint32_t sh = 8 * (uint32_t)(a & 7);
+    const uint64_t lo = q[0];
+    return sh == 0 ? lo : (lo >> sh) | (q[1] << (64 - sh));
+}
 RV_HD uint8_t pack_bits_byte(const uint8_t *stream, const uint32_t *pos, uint32_t n, uint32_t g, uint32_t bit) {
+    const uint32_t e0 = 8 * g;
+    if (e0 + 8 <= n) {  // a full byte whose 8 elements sit in 8 consecutive stream bytes (always without a position table; the rule for
+                        // runs of Mul / AssertZero gates with one): one or two 8-byte loads instead of 8 single ones.  The streams are
+                        // padded to whole 2 KiB tiles, so the aligned loads stay inside the buffer.
+        const uint32_t p0 = pos ? pos[e0] : e0;
+        if (!pos || pos[e0 + 7] == p0 + 7) return gather_bit_msb_first(load8_unaligned(stream + p0), bit);
+    }
     uint32_t r = 0;
 #pragma unroll
     for (uint32_t i = 0; i < 8; i++) {
-        const uint32_t e = 8 * g + i;
+        const uint32_t e = e0 + i;
         uint32_t v = 0;
         if (e < n) v = (stream[pos ? pos[e] : e] >> bit) & 1u;
         r = (r << 1) | v;

@@ -481,6 +481,31 @@ def test_large_flat_circuit_paths(rb, default_seeds):
     del p
 
 
+def test_long_streams_wide_tree_levels_and_streaming(rb):
+    """3 x 10^6 ANDs = 2930 BLAKE3 chunks per repetition and stream: the lower tree levels run grid-wide (k_cv_tree_level, odd
+    counts carried up), resident, sharded over two linked sessions, and in streaming mode; a layered circuit with non-contiguous
+    reconstruction positions exercises both extraction paths.  Checked against the committed oracle digests (bench_digests.json:
+    flat / layered 10^6) and the oracle itself for 3 x 10^6."""
+    import hashlib
+
+    import bench
+    import orc
+
+    seeds = bench.default_seeds()
+    for name in ("flat1000000", "layered1000000"):
+        ops, wit, wz, wc, _ = bench.make_workload(name)
+        want = bench.golden_digest(name)
+        assert hashlib.sha256(rb.Proof.new(ops, wit, (), wc, seeds=seeds).serialize()).hexdigest() == want, name
+        assert hashlib.sha256(rb.Proof.new_streaming(ops, wit, wc, seeds=seeds, window_ops=300000).serialize()).hexdigest() == want, name
+    ops, wit, wz, wc, _ = bench.make_workload("flat3000000")
+    rc, proof = orc.prove(ops, wit, [], wc, seeds)
+    want = hashlib.sha256(proof).hexdigest()
+    del proof
+    circ = rb.Circuit(ops, wc, prove_only=True)
+    assert hashlib.sha256(memoryview(rb.Proof.new(circ, wit, (), seeds=seeds)._buf)).hexdigest() == want
+    assert hashlib.sha256(memoryview(rb.Proof.new_streaming(ops, wit, wc, seeds=seeds, window_ops=1 << 20)._buf)).hexdigest() == want
+
+
 def test_cpp_host_mirror(rb):
     """The reference's own proof tests (src/proof/mod.rs:311-428) through the C++ host mirror include/reverie_b200.hpp."""
     import subprocess
