@@ -564,7 +564,7 @@ def run_workload(env: Env, name: str, batch: int, per_session: int, steps: int, 
     else:
         def step_e2e():
             if grp is not None:  # one C call per rank: uploads, the step's graph launch, the fetch of the assembled proofs on rank 0
-                return [p._buf if p is not None else b"" for p in grp.prove_batch([wit] * B, [wz] * B, [seeds] * B)]
+                return grp.prove_batch([wit] * B, [wz] * B, [seeds] * B)  # Proof objects over the library's buffers on rank 0, None elsewhere
             upload_all(sessions)
             step_device(sessions)
             return collect(sessions)  # rank 0 (every rank with --shard proofs) ends up with the proof bytes in host memory
@@ -578,7 +578,7 @@ def run_workload(env: Env, name: str, batch: int, per_session: int, steps: int, 
         env.barrier()
         dt = env.max_over_ranks(time.perf_counter() - t0)
         e2e_v = n_and * n_jobs * steps / dt
-        if want and (rank == 0 or by_proofs) and hashlib.sha256(memoryview(out[0])).hexdigest() != want:
+        if want and (rank == 0 or by_proofs) and hashlib.sha256(memoryview(out[0]._buf if isinstance(out[0], rb.Proof) else out[0])).hexdigest() != want:
             raise SystemExit(f"PARITY FAILURE: workload {name}: the end-to-end proof differs from the oracle digest")
         del out
         d2h = B * (proof_len + 36)

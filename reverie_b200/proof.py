@@ -284,7 +284,7 @@ def _batch_results(n, outs, lens, sts, want_proofs=True):
     proofs, first_err = [], None
     for i in range(n):
         if sts[i] == 0:
-            proofs.append(Proof(_take(vp(outs[i]), C.c_size_t(lens[i]), zero_copy_from=1 << 16)) if want_proofs else None)  # Proof wraps the library's buffer
+            proofs.append(Proof._from_library(outs[i], lens[i]) if (want_proofs and outs[i]) else None)  # wraps the library's buffer, no copy
         else:
             proofs.append(None)
             first_err = first_err if first_err is not None else sts[i]
@@ -394,14 +394,38 @@ def assemble(comm: bytes, parts: Sequence[bytes]) -> bytes:
 class Proof:
     """The bincode bytes of the reference's `Proof` struct (src/proof/mod.rs:40-66)."""
 
+    __slots__ = ("_data", "_lib_ptr", "_lib_len", "__weakref__")
+
     def __init__(self, data):
-        self._buf = data if isinstance(data, (bytes, np.ndarray)) else bytes(data)
+        self._data = data if isinstance(data, (bytes, np.ndarray)) else bytes(data)
+        self._lib_ptr = None
+
+    @classmethod
+    def _from_library(cls, ptr: int, n: int) -> "Proof":
+        """Wraps a buffer the library allocated (rv_free'd when the Proof is collected) without touching its bytes: a batch of
+        proofs costs a few microseconds of Python each, the bytes are only materialised when somebody reads them."""
+        p = cls.__new__(cls)
+        p._data, p._lib_ptr, p._lib_len = None, ptr, n
+        return p
+
+    def __del__(self):
+        ptr, self._lib_ptr = getattr(self, "_lib_ptr", None), None
+        if ptr:
+            N.lib().rv_free(C.c_void_p(ptr))
+
+    @property
+    def _buf(self):
+        """bytes, or a read-only numpy view of the library's buffer (kept alive by this object)."""
+        if self._data is None:
+            arr = np.ctypeslib.as_array(C.cast(C.c_void_p(self._lib_ptr), C.POINTER(C.c_uint8)), shape=(self._lib_len,))
+            arr.flags.writeable = False
+            self._data = arr
+        return self._data
 
     @property
     def data(self) -> bytes:
-        if not isinstance(self._buf, bytes):
-            return self._buf.tobytes()
-        return self._buf
+        b = self._buf
+        return b if isinstance(b, bytes) else b.tobytes()
 
     @staticmethod
     def new(circuit, wit_gf2, wit_z64=(), wire_counts=None, seeds=None) -> "Proof":
@@ -477,7 +501,7 @@ class Proof:
         return bytes(self._buf[:32])
 
     def __len__(self):
-        return len(self._buf)
+        return self._lib_len if self._data is None else len(self._data)
 
     def __eq__(self, other):
         return isinstance(other, Proof) and self.data == other.data
