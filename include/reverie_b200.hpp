@@ -143,6 +143,37 @@ class Proof {
         rv_free(p);
         return out;
     }
+    // Proof::new on several GPUs of this box: one process drives them all (rv_group_create_local: the circuit is cloned onto each
+    // device, the shards exchange their repetition hashes and assemble the proof over NVLink peer memory).  The group is built per
+    // call here for brevity; keep an rv_group next to the circuit when proving repeatedly.
+    static Proof new_on(const Circuit &circuit, const std::vector<int> &devices, const std::vector<bool> &wit_gf2, const std::vector<uint64_t> &wit_z64,
+                        const uint8_t *seeds = nullptr) {
+        std::vector<uint8_t> w(wit_gf2.begin(), wit_gf2.end());
+        rv_group *g = nullptr;
+        check(rv_group_create_local(circuit.handle(), devices.data(), (int)devices.size(), 1, 1, &g));
+        uint8_t *p = nullptr;
+        size_t n = 0;
+        const int rc = rv_group_prove(g, w.data(), w.size(), wit_z64.data(), wit_z64.size(), seeds, &p, &n);
+        rv_group_free(g);
+        check(rc);
+        Proof out;
+        out.bytes_.assign(p, p + n);
+        rv_free(p);
+        return out;
+    }
+    // Proof::new for circuits larger than device memory (rv_prove_streaming): proved in segments of window_ops ops, same bytes.
+    static Proof new_streaming(const std::vector<CombineOperation> &circuit, const std::vector<bool> &wit_gf2, std::pair<size_t, size_t> wire_counts,
+                               size_t window_ops = 0, const uint8_t *seeds = nullptr) {
+        std::vector<uint8_t> w(wit_gf2.begin(), wit_gf2.end());
+        uint8_t *p = nullptr;
+        size_t n = 0;
+        check(rv_prove_streaming(circuit.empty() ? nullptr : &circuit[0].op, circuit.size(), wire_counts.first, wire_counts.second, w.data(), w.size(),
+                                 nullptr, 0, seeds, window_ops, &p, &n));
+        Proof out;
+        out.bytes_.assign(p, p + n);
+        rv_free(p);
+        return out;
+    }
     // Proof::verify (src/proof/mod.rs:224).  strict (default): the commitment must match AND every AssertZero of the opened
     // repetitions must hold -- the reference computes that flag (src/transcript/verifier/online.rs:176-178) and never reads it,
     // so a prover that skips its own assert (src/transcript/prover.rs:221-228) would be accepted.  strict = false is the

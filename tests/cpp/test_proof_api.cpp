@@ -86,6 +86,9 @@ static int test_bench_circuits() {
         CHECK(proof.serialize() == oracle_proof(circuit, wit_gf2, wit_z64, {128, 128}, seeds));
         CHECK(proof.verify(compiled));
         CHECK(Proof::deserialize(proof.serialize()).verify(compiled));
+        // the same proof in streaming mode (segments of 30 000 ops) and through a two-member group (both on device 0 here)
+        CHECK(Proof::new_streaming(circuit, wit_gf2, {128, 128}, 30000, seeds.data()).serialize() == proof.serialize());
+        CHECK(Proof::new_on(compiled, {0, 0}, wit_gf2, wit_z64, seeds.data()).serialize() == proof.serialize());
     }
     return 0;
 }

@@ -512,7 +512,11 @@ def test_cpp_host_mirror(rb):
 
     from tests._cppbuild import build_cpp_api_test
 
-    res = subprocess.run([build_cpp_api_test()], capture_output=True, text=True, timeout=600)
+    import os
+
+    # (the two-member group of the test shares one GPU: one hardware queue per stream, see tests/_linked_worker.py)
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", RV_PEER_TIMEOUT_MS="30000")
+    res = subprocess.run([build_cpp_api_test()], capture_output=True, text=True, timeout=600, env=env)
     assert res.returncode == 0 and "cpp host mirror ok" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
 
 
