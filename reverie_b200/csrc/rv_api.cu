@@ -79,8 +79,67 @@ static void *pinned_get(size_t bytes) {
     g_pin_live.push_back({p, bytes});
     return p;
 }
+// Small proofs (the common case: 264 KB for SHA-256) are handed to the caller WITHOUT a copy: a session's device-to-host copy lands
+// in a pinned "output block" (all its slots back to back, like the device buffer), rv_session_fetch returns pointers into it, and
+// the session moves on to a fresh block for its next step (the CUDA graph's memcpy node is retargeted).  A block returns to the
+// pool when the session has let go of it and every pointer handed out has been rv_free'd.
+namespace {
+struct OutBlock {
+    uint8_t *base;
+    size_t bytes;
+    int refs;  // pointers handed out + 1 while a session targets it
+};
+std::mutex g_ob_mu;
+std::vector<OutBlock> g_ob_live;
+std::vector<std::pair<uint8_t *, size_t>> g_ob_free;
+constexpr size_t OB_POOL_MAX = 48;
+
+uint8_t *outblock_get(size_t bytes) {  // refs = 1 (the session)
+    {
+        std::lock_guard<std::mutex> g(g_ob_mu);
+        for (size_t i = 0; i < g_ob_free.size(); i++)
+            if (g_ob_free[i].second == bytes) {
+                uint8_t *b = g_ob_free[i].first;
+                g_ob_free.erase(g_ob_free.begin() + i);
+                g_ob_live.push_back({b, bytes, 1});
+                return b;
+            }
+    }
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> g(g_ob_mu);
+    g_ob_live.push_back({(uint8_t *)p, bytes, 1});
+    return (uint8_t *)p;
+}
+// +1 / -1 on the block that contains p; returns false if p is not inside an output block
+bool outblock_ref(const void *p, int delta) {
+    uint8_t *to_free = nullptr;
+    {
+        std::lock_guard<std::mutex> g(g_ob_mu);
+        const uint8_t *q = (const uint8_t *)p;
+        size_t i = 0;
+        for (; i < g_ob_live.size(); i++)
+            if (q >= g_ob_live[i].base && q < g_ob_live[i].base + g_ob_live[i].bytes) break;
+        if (i == g_ob_live.size()) return false;
+        g_ob_live[i].refs += delta;
+        if (g_ob_live[i].refs <= 0) {
+            const OutBlock b = g_ob_live[i];
+            g_ob_live.erase(g_ob_live.begin() + i);
+            if (g_ob_free.size() < OB_POOL_MAX) g_ob_free.push_back({b.base, b.bytes});
+            else to_free = b.base;
+        }
+    }
+    if (to_free) cudaFreeHost(to_free);
+    return true;
+}
+}  // namespace
+
 extern "C" void rv_free(void *p) {
     if (!p) return;
+    if (outblock_ref(p, -1)) return;
     {
         std::lock_guard<std::mutex> g(g_pin_mu);
         for (size_t i = 0; i < g_pin_live.size(); i++)
@@ -393,6 +452,8 @@ struct rv_session {
         cudaGraphExec_t exec = nullptr;
         int calls = 0;
         uint64_t kernels = 0;
+        cudaGraph_t graph = nullptr;          // kept for g_prove: its device-to-host copy node is retargeted to a fresh output block
+        cudaGraphNode_t d2h_node = nullptr;
     } g_prove /* commit + open of a full shard */, g_commit, g_open /* open from the session's own all-gather buffer */,
       g_open_x /* open of a linked shard: exchange over peer memory */;
     // device buffers
@@ -435,6 +496,9 @@ struct rv_session {
     uint8_t *h_out = nullptr;  // proof || bad(4) || comm(32); big proofs (>= PIN_THRESHOLD) skip the proof part: rv_session_fetch copies
                                // them from d_proof straight into the pinned buffer it returns
     size_t out_off = 0;        // offset of bad / comm inside h_out
+    bool out_handed = false;   // a pointer into the current h_out block has been given to the caller: the next step needs a fresh block
+    bool out_direct = false;   // the last step went through rv_session_prove (its graph's copy node follows h_out): fetch may hand out pointers
+    bool in_batch = false;     // bound to an rv_batch (whose graph bakes h_out): never retargeted
     size_t tail_off = 0;       // offset of bad / comm behind the proof bytes in d_proof
     size_t h_in_bytes = 0;
     std::vector<void *> allocs;
@@ -481,13 +545,15 @@ extern "C" void rv_session_free(rv_session *s) {
     for (void *p : s->ipc_opened) cudaIpcCloseMemHandle(p);
     for (void *p : s->allocs) cudaFree(p);
     if (s->h_in) cudaFreeHost(s->h_in);
-    if (s->h_out) cudaFreeHost(s->h_out);
+    if (s->h_out) outblock_ref(s->h_out, -1);
     if (s->h_vin) cudaFreeHost(s->h_vin);
     if (s->h_vout) cudaFreeHost(s->h_vout);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_bjoin) cudaEventDestroy(s->ev_bjoin);
-    for (rv_session::GraphSlot *g : {&s->g_prove, &s->g_commit, &s->g_open, &s->g_open_x})
+    for (rv_session::GraphSlot *g : {&s->g_prove, &s->g_commit, &s->g_open, &s->g_open_x}) {
         if (g->exec) cudaGraphExecDestroy(g->exec);
+        if (g->graph) cudaGraphDestroy(g->graph);
+    }
     if (s->ev_vals) cudaEventDestroy(s->ev_vals);
     if (s->st && s->own_stream) cudaStreamDestroy(s->st);
     if (s->st_val) cudaStreamDestroy(s->st_val);
@@ -600,7 +666,7 @@ extern "C" int rv_session_create_multi(const rv_circuit *c, int first_instance, 
     s->in_pitch = s->wit_pitch + RV_TOTAL_REPS * 16 + 8 * (size_t)Z.n_inputs;
     s->h_in_bytes = s->in_pitch * s->n_proofs;
     s->out_off = s->proof_len >= PIN_THRESHOLD ? 0 : s->tail_off;
-    if (cudaMallocHost(&s->h_in, s->h_in_bytes) != cudaSuccess || cudaMallocHost(&s->h_out, (s->out_off + 64) * s->n_proofs) != cudaSuccess)
+    if (cudaMallocHost(&s->h_in, s->h_in_bytes) != cudaSuccess || (s->h_out = outblock_get((s->out_off + 64) * s->n_proofs)) == nullptr)
         return bail(fail(RV_E_NOMEM, "pinned host allocation failed"));
     uint32_t zc[16];
     memcpy(zc, c->z64_empty_hash, 32);
@@ -728,7 +794,7 @@ extern "C" int rv_session_upload_slot(rv_session *s, int slot, const uint8_t *wi
 // Runs `body` (a sequence of asynchronous launches on the session's streams) eagerly the first time and whenever per-kernel
 // timing is on; the second plain call captures it into a CUDA graph, later calls replay that graph with one launch.
 template <typename F>
-static int run_graphed(rv_session *s, rv_session::GraphSlot &g, F &&body) {
+static int run_graphed(rv_session *s, rv_session::GraphSlot &g, F &&body, bool track_d2h = false) {
     int rc;
     if (s->timing || g.calls == 0) {
         g.calls++;
@@ -750,7 +816,23 @@ static int run_graphed(rv_session *s, rv_session::GraphSlot &g, F &&body) {
             return rc != RV_OK ? rc : fail(RV_E_CUDA, std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e));
         }
         e = cudaGraphInstantiate(&g.exec, graph, 0);
-        cudaGraphDestroy(graph);
+        if (e == cudaSuccess && track_d2h) {  // the node that copies the proofs into h_out: retargeted when the caller keeps a block
+            size_t n = 0;
+            cudaGraphGetNodes(graph, nullptr, &n);
+            std::vector<cudaGraphNode_t> nodes(n);
+            if (n) cudaGraphGetNodes(graph, nodes.data(), &n);
+            for (cudaGraphNode_t nd : nodes) {
+                cudaGraphNodeType t;
+                cudaMemcpy3DParms mp;
+                if (cudaGraphNodeGetType(nd, &t) == cudaSuccess && t == cudaGraphNodeTypeMemcpy && cudaGraphMemcpyNodeGetParams(nd, &mp) == cudaSuccess &&
+                    mp.dstPtr.ptr == (void *)s->h_out)
+                    g.d2h_node = nd;
+            }
+            cudaGetLastError();
+            g.graph = graph;  // node handles belong to the graph: keep it
+        } else {
+            cudaGraphDestroy(graph);
+        }
         if (e != cudaSuccess) return fail(RV_E_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
     }
     CU(cudaGraphLaunch(g.exec, s->st));
@@ -957,6 +1039,7 @@ extern "C" int rv_session_open(rv_session *s, const uint8_t *all_rep_hashes) {
     if (all_rep_hashes == s->d_all_hashes) rc = run_graphed(s, s->g_open, [&] { return open_body(s, all_rep_hashes); });
     else if (!all_rep_hashes && s->linked()) rc = run_graphed(s, s->g_open_x, [&] { return open_body(s, nullptr); });
     else rc = open_body(s, all_rep_hashes);  // caller-owned buffer: its address may change from call to call
+    s->out_direct = false;
     if (rc == RV_OK) s->opened = true;
     return rc;
 }
@@ -974,10 +1057,34 @@ extern "C" int rv_session_prove(rv_session *s) {
         CU(cudaEventRecord(s->ev_bjoin, s->lead->st));
         CU(cudaStreamWaitEvent(s->st, s->ev_bjoin, 0));
     }
+    const bool direct = s->out_off != 0 && !s->in_batch && s->assembles();  // small proofs: the caller gets pointers into h_out
+    if (direct && s->out_handed) {  // the caller still holds the previous step's proofs: this step writes a fresh block
+        const size_t bytes = (s->out_off + 64) * s->n_proofs;
+        uint8_t *nb = outblock_get(bytes);
+        if (!nb) return fail(RV_E_NOMEM, "pinned host allocation failed");
+        if (s->g_prove.exec && s->g_prove.d2h_node &&
+            cudaGraphExecMemcpyNodeSetParams1D(s->g_prove.exec, s->g_prove.d2h_node, nb, s->d_proof, s->proof_pitch * s->n_proofs, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            cudaGetLastError();  // could not retarget: drop the graph, it is captured again with the new block
+            cudaGraphExecDestroy(s->g_prove.exec);
+            if (s->g_prove.graph) cudaGraphDestroy(s->g_prove.graph);
+            s->g_prove = rv_session::GraphSlot();
+            s->g_prove.calls = 1;
+        }
+        for (rv_session::GraphSlot *g : {&s->g_open, &s->g_open_x})  // these bake the old block's address: captured again on demand
+            if (g->exec) {
+                cudaGraphExecDestroy(g->exec);
+                *g = rv_session::GraphSlot();
+                g->calls = 1;
+            }
+        outblock_ref(s->h_out, -1);
+        s->h_out = nb;
+        s->out_handed = false;
+    }
     const int rc = run_graphed(s, s->g_prove, [&] {
         const int r = commit_body(s);
         return r != RV_OK ? r : open_body(s, nullptr);
-    });
+    }, direct);
+    s->out_direct = direct && rc == RV_OK && (s->g_prove.exec == nullptr || s->g_prove.d2h_node != nullptr);
     if (bound) {
         CU(cudaEventRecord(s->ev_bjoin, s->st));
         CU(cudaStreamWaitEvent(s->lead->st, s->ev_bjoin, 0));
@@ -1025,7 +1132,10 @@ extern "C" int rv_batch_create(rv_session *const *ss, int n, rv_batch **out) {
         }
         b->ss.push_back(s);
     }
-    for (rv_session *s : b->ss) s->share = (uint32_t)n;
+    for (rv_session *s : b->ss) {
+        s->share = (uint32_t)n;
+        s->in_batch = true;
+    }
     *out = b;
     return RV_OK;
 }
@@ -1037,7 +1147,10 @@ extern "C" void rv_batch_free(rv_batch *b) {
         cudaStreamSynchronize(b->ss[0]->st);
     }
     for (size_t i = 1; i < b->ss.size(); i++) b->ss[i]->lead = nullptr;
-    for (rv_session *s : b->ss) s->share = 1;
+    for (rv_session *s : b->ss) {
+        s->share = 1;
+        s->in_batch = false;
+    }
     for (auto &g : b->g)
         if (g.exec) cudaGraphExecDestroy(g.exec);
     if (b->ev_fork) cudaEventDestroy(b->ev_fork);
@@ -1086,6 +1199,7 @@ static int batch_run(rv_batch *b, int kind) {
         s->launches = before[i] + per;
         if (kind != 1) s->committed = s->ever_committed = true;
         if (kind != 0) s->opened = true;
+        s->out_direct = false;
     }
     return RV_OK;
 }
@@ -1122,7 +1236,11 @@ extern "C" int rv_session_fetch_slot(rv_session *s, int slot, uint8_t comm[RV_HA
         return RV_OK;
     }
     uint8_t *p;
-    if (s->out_off) {
+    if (s->out_off && s->out_direct) {  // no copy: the caller owns this slot of the output block until rv_free
+        p = const_cast<uint8_t *>(hout);
+        outblock_ref(p, +1);
+        s->out_handed = true;
+    } else if (s->out_off) {
         p = (uint8_t *)malloc(s->proof_len);
         if (!p) return fail(RV_E_NOMEM, "out of memory");
         memcpy(p, hout, s->proof_len);
@@ -1271,6 +1389,7 @@ extern "C" int rv_session_peer_link(rv_session *s, int rank, int world, const ui
     // graphs captured before the link describe the unlinked phases
     for (rv_session::GraphSlot *g : {&s->g_prove, &s->g_open_x}) {
         if (g->exec) cudaGraphExecDestroy(g->exec);
+        if (g->graph) cudaGraphDestroy(g->graph);
         *g = rv_session::GraphSlot();
     }
     return RV_OK;
