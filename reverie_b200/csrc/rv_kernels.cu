@@ -461,7 +461,7 @@ struct VmCell<2> {
 
 template <int COLS>
 __global__ void __launch_bounds__(VM_THREADS) k_mask_vm(const VmInstr *__restrict__ prog, uint32_t n_steps, const uint64_t *__restrict__ fresh_pm,
-                                                        size_t pitch_fresh, uint64_t *__restrict__ rows, uint32_t npi) {
+                                                        size_t pitch_fresh, uint64_t *__restrict__ rows, uint32_t npi, uint32_t scratch) {
     using Cell = typename VmCell<COLS>::T;
     extern __shared__ __align__(128) uint8_t smem[];
     const uint32_t n_chunks = (n_steps + VM_STEPS_PER_CHUNK - 1) / VM_STEPS_PER_CHUNK;
@@ -474,7 +474,8 @@ __global__ void __launch_bounds__(VM_THREADS) k_mask_vm(const VmInstr *__restric
     // tensor of a VM-sized circuit lives in L2, which merges the instances' pieces of a row before the item plane reads it.
     const Cell *src = reinterpret_cast<const Cell *>(fresh_pm) + (size_t)q * pitch_fresh;
     uint64_t *dst = rows + (size_t)COLS * q;
-    if (tid == 0) cells[0] = VmCell<COLS>::zero();  // cell 0 is the constant zero (first read happens after the first barrier)
+    if (tid == 0) cells[0] = VmCell<COLS>::zero();  // cell 0 is the constant zero
+    __syncthreads();                                  // (empty slots of the first steps already read it)
     for (uint32_t c = 0; c < n_chunks; c++) {
         const uint32_t img = stream.begin_chunk(c) + tid * (uint32_t)sizeof(VmInstr);  // 5-word stride: conflict-free LDS.32
         const uint32_t nst = min((uint32_t)VM_STEPS_PER_CHUNK, n_steps - c * VM_STEPS_PER_CHUNK);
@@ -496,7 +497,7 @@ __global__ void __launch_bounds__(VM_THREADS) k_mask_vm(const VmInstr *__restric
                     typedef VmCell<COLS> V;
                     const Cell v = V::x(V::x(V::x(cells[u[k][2] & 0xFFFFu], cells[u[k][2] >> 16]), V::x(cells[u[k][3] & 0xFFFFu], cells[u[k][3] >> 16])),
                                         V::x(cells[u[k][4] & 0xFFFFu], cells[u[k][4] >> 16]));
-                    cells[d] = v;
+                    if (d != scratch) cells[d] = v;  // (empty slots and export-only XORs name the scratch cell: nobody reads it)
                     if (row != VM_ROW_NONE) *reinterpret_cast<Cell *>(dst + (size_t)row * npi) = v;
                 }
                 if (fl & VM_F_LEVEL_END) {  // one cp.async group per level; LOADs of level L-2 are complete before level L starts
@@ -565,8 +566,8 @@ int launch_linear(const DevProgram &P, const uint32_t *off_host, uint64_t *rows,
     }
     if (linear_uses_vm(P) && fresh_sm) {
         if (which) *which = 0;
-        if (linear_vm_pairs(P, npi)) k_mask_vm<2><<<npi / 2, VM_THREADS, vm_smem_bytes(P, 2), st>>>(P.vm_steps, P.n_vm_steps, fresh_sm, pitch_fresh, rows, npi);
-        else k_mask_vm<1><<<npi, VM_THREADS, vm_smem_bytes(P), st>>>(P.vm_steps, P.n_vm_steps, fresh_sm, pitch_fresh, rows, npi);
+        if (linear_vm_pairs(P, npi)) k_mask_vm<2><<<npi / 2, VM_THREADS, vm_smem_bytes(P, 2), st>>>(P.vm_steps, P.n_vm_steps, fresh_sm, pitch_fresh, rows, npi, P.vm_cells);
+        else k_mask_vm<1><<<npi, VM_THREADS, vm_smem_bytes(P), st>>>(P.vm_steps, P.n_vm_steps, fresh_sm, pitch_fresh, rows, npi, P.vm_cells);
         return 1;
     }
     if (which) *which = 1;
