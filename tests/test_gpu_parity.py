@@ -497,6 +497,12 @@ def test_long_streams_wide_tree_levels_and_streaming(rb):
         want = bench.golden_digest(name)
         assert hashlib.sha256(rb.Proof.new(ops, wit, (), wc, seeds=seeds).serialize()).hexdigest() == want, name
         assert hashlib.sha256(rb.Proof.new_streaming(ops, wit, wc, seeds=seeds, window_ops=300000).serialize()).hexdigest() == want, name
+    # Z64 at 10^5 Muls against the committed oracle digest (eager run, graph capture, replay)
+    ops, wit, wz, wc, _ = bench.make_workload("z64mul100000")
+    zc = rb.Circuit(ops, wc, prove_only=True)
+    for _ in range(3):  # eager, graph capture, replay
+        assert hashlib.sha256(memoryview(rb.Proof.new(zc, wit, wz, seeds=seeds)._buf)).hexdigest() == bench.golden_digest("z64mul100000")
+    del zc
     ops, wit, wz, wc, _ = bench.make_workload("flat3000000")
     rc, proof = orc.prove(ops, wit, [], wc, seeds)
     want = hashlib.sha256(proof).hexdigest()
