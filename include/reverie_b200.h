@@ -186,6 +186,11 @@ void rv_circuit_cache_stats(uint64_t *hits, uint64_t *misses, size_t *entries);
 int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, const uint8_t *wit_gf2, size_t n_gf2,
                        const uint64_t *wit_z64, size_t n_z64, const uint8_t *seeds, size_t window_ops, uint8_t **proof, size_t *proof_len);
 
+/* Test hook (host only, no device needed): runs rv_prove_streaming's planner -- segmentation, liveness, cell-file slots -- and
+ * checks it by a symbolic simulation of the cell file.  out: segments, slots, most imports / exports of a segment, total imports,
+ * total exports. */
+int rv_stream_plan_check(const rv_op *ops, size_t n_ops, size_t gf2_cells, size_t window_ops, uint64_t out[6]);
+
 void rv_free(void *p);
 
 /* ---------------------------------------------------------------------------------------------------------------

@@ -91,6 +91,7 @@ def lib() -> C.CDLL:
         "rv_session_peer_handle": ([vp, vp], i32),
         "rv_session_peer_link": ([vp, i32, i32, vp], i32),
         "rv_session_peer_rank": ([vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], i32),
+        "rv_stream_plan_check": ([vp, sz, sz, sz, C.POINTER(C.c_uint64)], i32),
         "rv_prove_streaming": ([vp, sz, sz, sz, vp, sz, vp, sz, vp, sz, pp, psz], i32),
         "rv_circuit_clone": ([vp, i32, pp], i32),
         "rv_group_create_local": ([vp, C.POINTER(i32), i32, i32, i32, pp], i32),
@@ -117,7 +118,7 @@ EXPORTED = (
     "rv_circuit_export rv_prove rv_prove_batch rv_session_slots rv_session_proof_stride rv_verify rv_proof_new rv_proof_verify rv_free rv_session_create rv_session_create_multi rv_session_upload_slot rv_session_fetch_slot rv_session_free "
     "rv_session_upload rv_session_commit rv_session_hashes rv_session_hashes_device rv_session_all_hashes_device rv_session_open rv_session_prove rv_session_fetch rv_session_sync rv_session_status rv_session_proof_device "
     "rv_proof_assemble rv_batch_create rv_batch_free rv_batch_commit rv_batch_open rv_batch_prove rv_batch_stream rv_session_stream rv_session_timing rv_session_kernel_times rv_session_launch_count "
-    "rv_session_peer_handle rv_session_peer_link rv_session_peer_rank rv_prove_streaming rv_circuit_clone rv_group_create_local rv_group_create_rank "
+    "rv_session_peer_handle rv_session_peer_link rv_session_peer_rank rv_prove_streaming rv_stream_plan_check rv_circuit_clone rv_group_create_local rv_group_create_rank "
     "rv_group_handles_bytes rv_group_handles rv_group_link rv_group_info rv_group_session rv_group_step rv_group_prove_batch rv_group_prove rv_group_free"
 ).split()
 

@@ -1786,6 +1786,7 @@ struct Segment {
     uint32_t n_local = 0;
     SegmentIO io;
     std::vector<uint32_t> import_slot, export_slot;
+    std::vector<uint32_t> import_global, export_global;  // the same wires by their cell index in the whole circuit (consistency check)
     rv_circuit *c = nullptr;
     uint64_t mask0 = 0, on0 = 0, pre0 = 0, wit0 = 0, recon0 = 0;  // what the ops before this segment drew / emitted
     uint32_t n_on = 0, n_pre = 0, n_in = 0, n_recon = 0, n_imp = 0, n_exp = 0;
@@ -1819,16 +1820,14 @@ struct DevBuf {  // frees what a failed or finished streaming call allocated
 constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
 }  // namespace
 
-extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, const uint8_t *wit_gf2, size_t n_gf2,
-                                  const uint64_t *wit_z64, size_t n_z64, const uint8_t *seeds, size_t window_ops, uint8_t **proof, size_t *proof_len) {
-    (void)wit_z64;
-    (void)n_z64;
-    (void)z64_cells;
-    if (!proof || !proof_len || (n_ops && !ops)) return fail(RV_E_ARG, "NULL argument");
-    *proof = nullptr;
-    *proof_len = 0;
-    if (window_ops == 0) window_ops = (size_t)1 << 22;  // ~5 GB of window buffers
-    window_ops = std::max<size_t>(window_ops, 64);
+// Liveness + segmentation of a streaming proof (host only; rv_stream_plan_check exposes it to the CPU test-suite).
+struct StreamPlan {
+    std::vector<Segment> segs;
+    uint32_t n_slots = 0;
+    uint64_t masks = 0, tot_on = 0, tot_pre = 0, tot_inputs = 0, tot_recon = 0;
+    size_t gf2_cells = 0;
+};
+static int plan_stream(const rv_op *ops, size_t n_ops, size_t gf2_cells, size_t window_ops, StreamPlan &plan) {
     // ---- 1. liveness + segmentation (host, one pass backwards, one forwards) ----
     for (size_t i = 0; i < n_ops; i++) {
         const rv_op &op = ops[i];
@@ -1839,7 +1838,6 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
         if (op.domain != RV_GF2 || op.opcode == RV_RANDOM || op.opcode > RV_CONST)
             return fail(RV_E_UNSUPPORTED, "op " + std::to_string(i) + ": streaming mode serves GF(2) circuits without Random / Z64 / B2A");
     }
-    if (rv_device_count() == 0) return fail(RV_E_CUDA, "no CUDA device: reverie-b200 has no CPU fallback");
     const size_t n_seg = std::max<size_t>(1, (n_ops + window_ops - 1) / window_ops);
     auto reads = [](const rv_op &op, uint32_t r[2]) -> int {
         switch (op.opcode) {
@@ -1871,7 +1869,8 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
         }
         if (writes(op) && op.dst >= gf2_cells) return fail(RV_E_ARG, "op " + std::to_string(i) + ": wire index out of range for the given wire_counts");
     }
-    std::vector<Segment> segs(n_seg);
+    std::vector<Segment> &segs = plan.segs;
+    segs.resize(n_seg);
     std::vector<uint32_t> free_slots;
     uint32_t n_slots = 0;
     uint64_t masks = 0, on = 0, pre = 0, wit = 0, recon = 0;
@@ -1890,6 +1889,7 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
                 if (is_read && written[c]) {  // first access is a read of a wire an earlier segment wrote: carried in
                     S.io.import_cells.push_back(local[c]);
                     S.import_slot.push_back(slot_of[c]);
+                    S.import_global.push_back(c);
                     if (last_read_seg[c] == tag) to_free.push_back(c);  // ... for the last time: its slot is free after this segment
                 }
             }
@@ -1933,6 +1933,7 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
                 }
                 S.io.export_cells.push_back(local[c]);
                 S.export_slot.push_back(slot_of[c]);
+                S.export_global.push_back(c);
             }
         }
         for (size_t i = S.a; i < S.b; i++)
@@ -1943,6 +1944,93 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
     std::vector<uint32_t>().swap(local);
     std::vector<uint32_t>().swap(last_read_seg);
     std::vector<uint8_t>().swap(written);
+    plan.n_slots = n_slots;
+    plan.masks = masks, plan.tot_on = on, plan.tot_pre = pre, plan.tot_inputs = wit, plan.tot_recon = recon;
+    plan.gf2_cells = gf2_cells;
+    return RV_OK;
+}
+
+// Test hook (CPU): the streaming planner alone, checked by a symbolic simulation of the cell file -- every wire a segment reads
+// before writing it (and that an earlier segment wrote) must be imported from a slot that holds exactly the state its last
+// writer exported, however slots were recycled in between.  out: segments, slots, most imports / exports of a segment, totals.
+extern "C" int rv_stream_plan_check(const rv_op *ops, size_t n_ops, size_t gf2_cells, size_t window_ops, uint64_t out[6]) {
+    if ((n_ops && !ops) || !out) return fail(RV_E_ARG, "NULL argument");
+    window_ops = std::max<size_t>(window_ops ? window_ops : ((size_t)1 << 22), 64);
+    StreamPlan plan;
+    if (const int rc = plan_stream(ops, n_ops, gf2_cells, window_ops, plan)) return rc;
+    constexpr int64_t NEVER = -1;
+    std::vector<int64_t> last_write(plan.gf2_cells, NEVER);
+    std::vector<uint32_t> seen(plan.gf2_cells, 0);  // segment tag of the wire's first access
+    struct Held {
+        uint32_t cell;
+        int64_t version;
+    };
+    std::vector<Held> slot(plan.n_slots, Held{0xFFFFFFFFu, NEVER});
+    uint64_t max_imp = 0, max_exp = 0, tot_imp = 0, tot_exp = 0;
+    for (size_t k = 0; k < plan.segs.size(); k++) {
+        const Segment &S = plan.segs[k];
+        const uint32_t tag = (uint32_t)k + 1;
+        std::vector<uint8_t> imported;  // by cell, sparse: mark through `seen` with a second pass instead of a map
+        for (size_t j = 0; j < S.import_global.size(); j++) {
+            const uint32_t c = S.import_global[j], sl = S.import_slot[j];
+            if (sl >= plan.n_slots || slot[sl].cell != c || slot[sl].version != last_write[c] || last_write[c] == NEVER)
+                return fail(RV_E_ARG, "plan check: segment " + std::to_string(k) + " imports wire " + std::to_string(c) + " from a slot that does not hold its latest state");
+        }
+        // completeness: a wire whose first access in the segment is a read, and that has been written before, is among the imports
+        size_t n_need = 0;
+        for (size_t i = S.a; i < S.b; i++) {
+            const rv_op &op = ops[i];
+            if (op.domain != RV_GF2) continue;
+            uint32_t r[2] = {0, 0};
+            int nr = 0;
+            switch (op.opcode) {
+                case RV_ADD: case RV_SUB: case RV_MUL: r[0] = op.a, r[1] = op.b, nr = 2; break;
+                case RV_ADDC: case RV_SUBC: case RV_MULC: case RV_ASSERT_ZERO: r[0] = op.a, nr = 1; break;
+                default: break;
+            }
+            for (int q = 0; q < nr; q++)
+                if (seen[r[q]] != tag) {
+                    seen[r[q]] = tag;
+                    if (last_write[r[q]] != NEVER && last_write[r[q]] < (int64_t)S.a) n_need++;
+                }
+            if (op.opcode != RV_ASSERT_ZERO) {
+                seen[op.dst] = tag;
+                last_write[op.dst] = (int64_t)i;
+            }
+        }
+        if (n_need != S.import_global.size())
+            return fail(RV_E_ARG, "plan check: segment " + std::to_string(k) + " needs " + std::to_string(n_need) + " carried wires but imports " +
+                                      std::to_string(S.import_global.size()));
+        for (size_t j = 0; j < S.export_global.size(); j++) {
+            if (S.export_slot[j] >= plan.n_slots) return fail(RV_E_ARG, "plan check: export slot out of range");
+            slot[S.export_slot[j]] = Held{S.export_global[j], last_write[S.export_global[j]]};
+        }
+        max_imp = std::max<uint64_t>(max_imp, S.import_global.size());
+        max_exp = std::max<uint64_t>(max_exp, S.export_global.size());
+        tot_imp += S.import_global.size();
+        tot_exp += S.export_global.size();
+    }
+    out[0] = plan.segs.size(), out[1] = plan.n_slots, out[2] = max_imp, out[3] = max_exp, out[4] = tot_imp, out[5] = tot_exp;
+    return RV_OK;
+}
+
+extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, const uint8_t *wit_gf2, size_t n_gf2,
+                                  const uint64_t *wit_z64, size_t n_z64, const uint8_t *seeds, size_t window_ops, uint8_t **proof, size_t *proof_len) {
+    (void)wit_z64;
+    (void)n_z64;
+    (void)z64_cells;
+    if (!proof || !proof_len || (n_ops && !ops)) return fail(RV_E_ARG, "NULL argument");
+    *proof = nullptr;
+    *proof_len = 0;
+    if (window_ops == 0) window_ops = (size_t)1 << 22;  // ~5 GB of window buffers
+    window_ops = std::max<size_t>(window_ops, 64);
+    StreamPlan plan;
+    if (const int prc = plan_stream(ops, n_ops, gf2_cells, window_ops, plan)) return prc;
+    if (rv_device_count() == 0) return fail(RV_E_CUDA, "no CUDA device: reverie-b200 has no CPU fallback");
+    std::vector<Segment> &segs = plan.segs;
+    const size_t n_seg = segs.size();
+    const uint32_t n_slots = plan.n_slots;
+    const uint64_t masks = plan.masks, on = plan.tot_on, pre = plan.tot_pre, wit = plan.tot_inputs, recon = plan.tot_recon;
     const uint64_t tot_on = on, tot_pre = pre, tot_inputs = wit, tot_recon = recon;
     if (n_gf2 < tot_inputs) return fail(RV_E_WITNESS_SHORT, "witness is too short");  // prover.rs:190
     if (tot_inputs && !wit_gf2) return fail(RV_E_ARG, "witness pointer is NULL");

@@ -490,3 +490,47 @@ def test_multi_gpu_and_streaming_entry_points_check_their_arguments_without_a_gp
         assert L.rv_group_create_rank(circ.handle, 0, 2, 1, 1, C.byref(h)) == N.E_CUDA
     else:
         assert L.rv_prove_streaming(_ptr(bad), bad.size, wc[0], wc[1], _ptr(wit), 2, None, 0, None, 64, C.byref(out), C.byref(n)) == N.E_ARG
+
+
+def test_streaming_planner_carries_every_live_wire():
+    """rv_prove_streaming's host planner (segmentation, liveness, recycled cell-file slots), checked by the library's symbolic
+    simulation of the cell file: random circuits with heavy cell reuse and windows from 64 ops up, SSA circuits (layered), SHA-256;
+    the slot count must stay far below the cell count when wires die young."""
+    import ctypes as C
+
+    from reverie_b200 import _native as N
+    from reverie_b200 import circuits as CC
+    from reverie_b200.proof import _ptr
+
+    L = N.lib()
+
+    def plan(ops, cells, window):
+        out = (C.c_uint64 * 6)()
+        ops = np.ascontiguousarray(ops, dtype=CC.OP_DTYPE)
+        rc = L.rv_stream_plan_check(_ptr(ops), ops.size, cells, window, out)
+        assert rc == 0, (rc, L.rv_last_error())
+        return dict(zip(("segments", "slots", "max_imports", "max_exports", "imports", "exports"), [int(x) for x in out]))
+
+    rng = np.random.default_rng(11)
+    for n_cells in (8, 40, 300):
+        recs = [(CC.GF2, CC.INPUT, 0, i, 0, 0, 0) for i in range(min(n_cells, 8))]
+        for _ in range(4000):
+            kind = int(rng.choice([CC.MUL, CC.ADD, CC.SUB, CC.ADDC, CC.MULC, CC.CONST, CC.ASSERT_ZERO], p=[0.3, 0.3, 0.1, 0.1, 0.05, 0.05, 0.1]))
+            d, a, b = (int(rng.integers(0, n_cells)) for _ in range(3))
+            recs.append((CC.GF2, kind, 0, d, a, b, int(rng.integers(0, 2))))
+        ops = np.array(recs, dtype=CC.OP_DTYPE)
+        for window in (64, 65, 100, 1000, 10 ** 6):
+            st = plan(ops, n_cells, window)
+            assert st["segments"] == max(1, -(-ops.size // max(window, 64))) and st["slots"] <= n_cells
+            if window >= ops.size:
+                assert st["imports"] == st["exports"] == st["slots"] == 0
+    ops, nw = CC.layered_and_circuit(2048, 40000)  # SSA wires: every cell is written once, read within the next two layers
+    st = plan(ops, nw, 4096)
+    assert st["slots"] < 3 * 4096 < nw and st["imports"] > 0
+    ops, wit, wc = CC.sha256_abc_case()
+    st = plan(ops, wc[1], 5000)
+    assert st["segments"] == -(-ops.size // 5000) and 0 < st["slots"] < wc[1]
+    bad = ops.copy()
+    bad["a"][int(np.flatnonzero(ops["opcode"] == CC.MUL)[0])] = wc[1] + 5  # an operand outside the declared wire count
+    out = (C.c_uint64 * 6)()
+    assert L.rv_stream_plan_check(_ptr(bad), bad.size, wc[1], 5000, out) == N.E_ARG
