@@ -580,6 +580,22 @@ def run_workload(env: Env, name: str, batch: int, per_session: int, steps: int, 
         e2e_v = n_and * n_jobs * steps / dt
         if want and (rank == 0 or by_proofs) and hashlib.sha256(memoryview(out[0]._buf if isinstance(out[0], rb.Proof) else out[0])).hexdigest() != want:
             raise SystemExit(f"PARITY FAILURE: workload {name}: the end-to-end proof differs from the oracle digest")
+        if full and grp is not None and st["n_ops"] <= (32 << 20):
+            # Proof::verify of a queue of world x B proofs spread over the GPUs (rv_group_verify_batch: whole proofs per GPU -- verification
+            # has no exchange step); every rank verifies its share
+            box = [out[0].data if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            queue = [rb.Proof(box[0])] * (B * world)
+            verdicts = grp.verify_batch(queue)
+            nv = max(2, steps // 4)
+            env.barrier()
+            t0 = time.perf_counter()
+            for _ in range(nv):
+                verdicts = grp.verify_batch(queue)
+            env.barrier()
+            dtv = env.max_over_ranks(time.perf_counter() - t0)
+            verify = {"value": n_and * B * world * nv / dtv, "unit": unit, "accepted": env.all_true(all(v for v in verdicts if v is not None)),
+                      "note": f"Proof.verify of {B * world} proofs per round, whole proofs per GPU ({B} per rank, 8 in flight), proof bytes in host memory"}
         del out
         d2h = B * (proof_len + 36)
     e2e = {"value": e2e_v, "unit": unit, "h2d_bytes_per_step": B * (st["n_inputs"] + 8 * st["z64_inputs"] + per * 8 * 16),

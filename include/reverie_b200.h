@@ -295,6 +295,10 @@ int rv_group_prove_batch(rv_group *g, int n, const uint8_t *const *wit_gf2, cons
                          const size_t *n_z64, const uint8_t *const *seeds, uint8_t **proofs, size_t *proof_lens, int *statuses);
 int rv_group_prove(rv_group *g, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64, size_t n_z64, const uint8_t *seeds,
                    uint8_t **proof, size_t *proof_len);
+/* Proof::verify for n proofs spread over the group's GPUs (whole proofs per GPU: verification has no exchange step).  results[i] =
+ * 1 accept / 0 reject / < 0 error; okay[i] (optional) = the AssertZero flag, see rv_verify.  A rank group verifies the proofs
+ * with i % world == rank and leaves the other entries untouched.  The group's circuit must carry the verifier's tables. */
+int rv_group_verify_batch(rv_group *g, int n, const uint8_t *const *proofs, const size_t *lens, int *results, int *okay);
 void rv_group_free(rv_group *g);
 
 /* cudaStream_t of the session (as void*), so callers can bracket work with their own CUDA events. */

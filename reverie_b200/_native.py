@@ -104,6 +104,7 @@ def lib() -> C.CDLL:
         "rv_group_step": ([vp], i32),
         "rv_group_prove_batch": ([vp, i32, C.POINTER(vp), psz, C.POINTER(vp), psz, C.POINTER(vp), pp, psz, C.POINTER(i32)], i32),
         "rv_group_prove": ([vp, vp, sz, vp, sz, vp, pp, psz], i32),
+        "rv_group_verify_batch": ([vp, i32, C.POINTER(vp), psz, C.POINTER(i32), C.POINTER(i32)], i32),
         "rv_group_free": ([vp], None),
     }
     for name, (args, res) in sigs.items():
@@ -119,7 +120,7 @@ EXPORTED = (
     "rv_session_upload rv_session_commit rv_session_hashes rv_session_hashes_device rv_session_all_hashes_device rv_session_open rv_session_prove rv_session_fetch rv_session_sync rv_session_status rv_session_proof_device "
     "rv_proof_assemble rv_batch_create rv_batch_free rv_batch_commit rv_batch_open rv_batch_prove rv_batch_stream rv_session_stream rv_session_timing rv_session_kernel_times rv_session_launch_count "
     "rv_session_peer_handle rv_session_peer_link rv_session_peer_rank rv_prove_streaming rv_stream_plan_check rv_circuit_clone rv_group_create_local rv_group_create_rank "
-    "rv_group_handles_bytes rv_group_handles rv_group_link rv_group_info rv_group_session rv_group_step rv_group_prove_batch rv_group_prove rv_group_free"
+    "rv_group_handles_bytes rv_group_handles rv_group_link rv_group_info rv_group_session rv_group_step rv_group_prove_batch rv_group_prove rv_group_verify_batch rv_group_free"
 ).split()
 
 

@@ -1757,6 +1757,32 @@ extern "C" int rv_group_prove_batch(rv_group *g, int n, const uint8_t *const *wi
     return rc;
 }
 
+// Proof::verify for a queue of proofs, spread over the group's GPUs.  Verification has no exchange step (the 32 packs of a proof
+// are independent, src/proof/mod.rs:234-280), so whole proofs go to whole GPUs: member m takes the proofs i = m (mod members) --
+// a rank group those with i = rank (mod world), the other entries are left untouched -- with a few verifications in flight per GPU.
+extern "C" int rv_group_verify_batch(rv_group *g, int n, const uint8_t *const *proofs, const size_t *lens, int *results, int *okay) {
+    if (!g || n <= 0 || !proofs || !lens || !results) return fail(RV_E_ARG, "bad argument");
+    const int stride = g->local ? (int)g->members.size() : g->world;
+    constexpr int IN_FLIGHT = 8;
+    std::vector<std::thread> pool;
+    std::atomic<int> worst{RV_OK};
+    for (size_t mi = 0; mi < g->members.size(); mi++) {
+        const rv_circuit *c = g->members[mi].c;
+        const int first = g->local ? (int)mi : g->members[mi].rank;
+        for (int t = 0; t < IN_FLIGHT; t++)
+            pool.emplace_back([=, &worst]() {
+                for (int i = first + t * stride; i < n; i += IN_FLIGHT * stride) {
+                    int ok = 1;
+                    results[i] = rv_verify(c, proofs[i], lens[i], &ok);
+                    if (okay) okay[i] = ok;
+                    if (results[i] == RV_E_CUDA) worst = RV_E_CUDA;
+                }
+            });
+    }
+    for (auto &t : pool) t.join();
+    return worst.load();
+}
+
 extern "C" int rv_group_prove(rv_group *g, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64, size_t n_z64, const uint8_t *seeds,
                               uint8_t **proof, size_t *proof_len) {
     int status = RV_OK;

@@ -379,6 +379,24 @@ class Group:
     def prove(self, wit_gf2, wit_z64=(), seeds=None):
         return self.prove_batch([wit_gf2], [wit_z64], [seeds] if seeds is not None else None)[0]
 
+    def verify_batch(self, proofs, strict: bool = True):
+        """Proof.verify for a list of proofs spread over the group's GPUs (rv_group_verify_batch: whole proofs per GPU).  Returns a
+        list of bool; a rank group fills the entries i with i % world == rank and leaves None elsewhere."""
+        n = len(proofs)
+        bufs = [p._buf if isinstance(p, Proof) else p for p in proofs]
+        arrs = [b if isinstance(b, np.ndarray) else np.frombuffer(b, dtype=np.uint8) for b in bufs]
+        ptrs = (C.c_void_p * n)(*[a.ctypes.data for a in arrs])
+        lens = (C.c_size_t * n)(*[a.size for a in arrs])
+        res, okay = (C.c_int * n)(*([-100] * n)), (C.c_int * n)(*([1] * n))
+        N.check(N.lib().rv_group_verify_batch(self._h, n, ptrs, lens, res, okay))
+        out = []
+        for i in range(n):
+            if res[i] == -100:
+                out.append(None)
+            else:
+                out.append(N.check(res[i]) == 1 and (bool(okay[i]) or not strict))
+        return out
+
 
 def assemble(comm: bytes, parts: Sequence[bytes]) -> bytes:
     """src/proof/mod.rs:200-221 for shard blobs produced by Session.fetch()."""

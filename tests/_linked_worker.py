@@ -141,6 +141,11 @@ def group_api_local(rb, default_seeds):
         assert p1.serialize() == want[3]
         p2 = g.prove(wits[0])  # seeds from the OS RNG, the same for every member
         assert p2.verify(circ)
+        # the queue of proofs verified across the members; a tampered one is rejected where it sits
+        bad = bytearray(got[2].serialize())
+        bad[5000] ^= 1
+        verdicts = g.verify_batch(got[:2] + [rb.Proof(bytes(bad))] + got[3:] + [p2])
+        assert verdicts == [True, True, False] + [True] * (len(got) - 3) + [True], (world, verdicts)
         del g
     # AssertZero failures are per proof; a Z64 circuit goes through a 1 x 1 group
     aops, awit, awc = C.sha256_abc_case()
