@@ -455,7 +455,8 @@ struct rv_session {
         cudaGraph_t graph = nullptr;          // kept for g_prove: its device-to-host copy node is retargeted to a fresh output block
         cudaGraphNode_t d2h_node = nullptr;
     } g_prove /* commit + open of a full shard */, g_commit, g_open /* open from the session's own all-gather buffer */,
-      g_open_x /* open of a linked shard: exchange over peer memory */;
+      g_open_x /* open of a linked shard: exchange over peer memory */, g_verify /* rv_verify: upload .. repetition hashes */;
+    size_t verify_graph_need = 0;  // staging bytes the captured verify graph copies
     // device buffers
     uint8_t *d_wit = nullptr, *d_seeds = nullptr, *d_pkeys = nullptr, *d_vals = nullptr;
     uint64_t *d_tvals = nullptr;  // tainted plane [n_tvals][npi]
@@ -550,7 +551,7 @@ extern "C" void rv_session_free(rv_session *s) {
     if (s->h_vout) cudaFreeHost(s->h_vout);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_bjoin) cudaEventDestroy(s->ev_bjoin);
-    for (rv_session::GraphSlot *g : {&s->g_prove, &s->g_commit, &s->g_open, &s->g_open_x}) {
+    for (rv_session::GraphSlot *g : {&s->g_prove, &s->g_commit, &s->g_open, &s->g_open_x, &s->g_verify}) {
         if (g->exec) cudaGraphExecDestroy(g->exec);
         if (g->graph) cudaGraphDestroy(g->graph);
     }
@@ -2349,6 +2350,16 @@ static int verify_on_session(rv_session *s, const uint8_t *proof, size_t proof_l
     }
     memcpy(h + o_proof, proof, proof_len);
     uint8_t *dv = s->d_vin;
+    // Everything from the upload of the staging blob to the copy of the repetition hashes is the same sequence for every proof of
+    // this length (what differs travels inside the blob): after one eager run it is captured and replayed as one CUDA graph launch.
+    // Z64 circuits keep the eager sequence (the Z64 openings may name their own keys: a data-dependent extra launch).
+    const bool graphable = !s->has_z && (s->g_verify.exec == nullptr || s->verify_graph_need == need);
+    if (!graphable && s->g_verify.exec) {  // another proof length: the captured copy sizes do not fit
+        cudaGraphExecDestroy(s->g_verify.exec);
+        s->g_verify = rv_session::GraphSlot();
+    }
+    s->verify_graph_need = need;
+    auto body = [&]() -> int {
     CU(cudaMemcpyAsync(dv, h, need, cudaMemcpyHostToDevice, s->st));
     const uint32_t nslices = 2 * s->npi;
     const VOpen *d_opens = reinterpret_cast<const VOpen *>(dv + o_opens);
@@ -2432,6 +2443,12 @@ static int verify_on_session(rv_session *s, const uint8_t *proof, size_t proof_l
     CU(cudaMemcpyAsync(s->h_vout, s->d_rep_hash, RV_TOTAL_REPS * 32, cudaMemcpyDeviceToHost, s->st));
     CU(cudaMemcpyAsync(s->h_vout + RV_TOTAL_REPS * 32, s->d_bad, 4, cudaMemcpyDeviceToHost, s->st));
     CU(cudaGetLastError());
+    return RV_OK;
+    };
+    {
+        const int brc = s->has_z ? body() : run_graphed(s, s->g_verify, body);
+        if (brc != RV_OK) return brc;
+    }
     CU(cudaStreamSynchronize(s->st));
     s->committed = s->opened = false;
     s->ever_committed = true;
