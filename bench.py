@@ -549,7 +549,8 @@ def run_workload(env: Env, name: str, batch: int, per_session: int, steps: int, 
                 def vfy(_):
                     return proof.verify(circ)
 
-                assert all(pool.map(vfy, range(B)))
+                for _ in range(3):  # every pooled session: eager run, graph capture, first replay
+                    assert all(pool.map(vfy, range(B)))
                 nv = max(2, steps // 4)
                 t0 = time.perf_counter()
                 for _ in range(nv):
@@ -586,7 +587,8 @@ def run_workload(env: Env, name: str, batch: int, per_session: int, steps: int, 
             box = [out[0].data if rank == 0 else None]
             dist.broadcast_object_list(box, src=0)
             queue = [rb.Proof(box[0])] * (B * world)
-            verdicts = grp.verify_batch(queue)
+            for _ in range(3):
+                verdicts = grp.verify_batch(queue)
             nv = max(2, steps // 4)
             env.barrier()
             t0 = time.perf_counter()
