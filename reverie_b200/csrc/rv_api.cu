@@ -19,6 +19,7 @@
 #include "rv_bincode.h"
 #include "rv_kernels.cuh"
 #include "rv_planes.cuh"
+#include "rv_stream_plan.h"
 #include "rv_zplanes.cuh"
 
 using namespace rv;
@@ -1807,20 +1808,6 @@ extern "C" int rv_group_prove(rv_group *g, const uint8_t *wit_gf2, size_t n_gf2,
 //  repetition + the proof.  GF(2) circuits without Random / Z64 / B2A; one GPU.
 // ---------------------------------------------------------------------------------------------------------------------
 namespace {
-struct Segment {
-    size_t a = 0, b = 0;               // op range in the whole circuit
-    std::vector<rv_op> ops;            // its ops with wire cells renumbered densely (dropped after compilation)
-    uint32_t n_local = 0;
-    SegmentIO io;
-    std::vector<uint32_t> import_slot, export_slot;
-    std::vector<uint32_t> import_global, export_global;  // the same wires by their cell index in the whole circuit (consistency check)
-    rv_circuit *c = nullptr;
-    uint64_t mask0 = 0, on0 = 0, pre0 = 0, wit0 = 0, recon0 = 0;  // what the ops before this segment drew / emitted
-    uint32_t n_on = 0, n_pre = 0, n_in = 0, n_recon = 0, n_imp = 0, n_exp = 0;
-    const uint32_t *d_leaf_ids = nullptr, *d_imp_slot = nullptr, *d_exp_slot = nullptr, *d_exp_row = nullptr, *d_exp_vref = nullptr;
-    int rc = RV_OK;
-    std::string err;
-};
 struct DevBuf {  // frees what a failed or finished streaming call allocated
     std::vector<void *> dev, host;
     std::vector<rv_circuit *> circuits;
@@ -1844,138 +1831,7 @@ struct DevBuf {  // frees what a failed or finished streaming call allocated
         return RV_OK;
     }
 };
-constexpr uint32_t NO_SLOT = 0xFFFFFFFFu;
 }  // namespace
-
-// Liveness + segmentation of a streaming proof (host only; rv_stream_plan_check exposes it to the CPU test-suite).
-struct StreamPlan {
-    std::vector<Segment> segs;
-    uint32_t n_slots = 0;
-    uint64_t masks = 0, tot_on = 0, tot_pre = 0, tot_inputs = 0, tot_recon = 0;
-    size_t gf2_cells = 0;
-};
-static int plan_stream(const rv_op *ops, size_t n_ops, size_t gf2_cells, size_t window_ops, StreamPlan &plan) {
-    // ---- 1. liveness + segmentation (host, one pass backwards, one forwards) ----
-    for (size_t i = 0; i < n_ops; i++) {
-        const rv_op &op = ops[i];
-        if (op.domain == RV_SIZE_HINT) {
-            gf2_cells = std::max<size_t>(gf2_cells, op.b);
-            continue;
-        }
-        if (op.domain != RV_GF2 || op.opcode == RV_RANDOM || op.opcode > RV_CONST)
-            return fail(RV_E_UNSUPPORTED, "op " + std::to_string(i) + ": streaming mode serves GF(2) circuits without Random / Z64 / B2A");
-    }
-    const size_t n_seg = std::max<size_t>(1, (n_ops + window_ops - 1) / window_ops);
-    auto reads = [](const rv_op &op, uint32_t r[2]) -> int {
-        switch (op.opcode) {
-            case RV_ADD: case RV_SUB: case RV_MUL: r[0] = op.a; r[1] = op.b; return 2;
-            case RV_ADDC: case RV_SUBC: case RV_MULC: case RV_ASSERT_ZERO: r[0] = op.a; return 1;
-            default: return 0;
-        }
-    };
-    auto writes = [](const rv_op &op) { return op.opcode != RV_ASSERT_ZERO; };
-    std::vector<uint32_t> last_read_seg, stamp, local, slot_of;
-    std::vector<uint8_t> written;
-    try {
-        last_read_seg.assign(gf2_cells, 0);  // segment index + 1 of the wire's last read (0 = never read)
-        stamp.assign(gf2_cells, 0);          // segment index + 1 in which `local` is valid
-        local.assign(gf2_cells, 0);
-        slot_of.assign(gf2_cells, NO_SLOT);
-        written.assign(gf2_cells, 0);        // written by an earlier segment
-    } catch (const std::bad_alloc &) {
-        return fail(RV_E_NOMEM, "out of host memory");
-    }
-    for (size_t i = 0; i < n_ops; i++) {
-        const rv_op &op = ops[i];
-        if (op.domain != RV_GF2) continue;
-        uint32_t r[2];
-        const int nr = reads(op, r);
-        for (int k = 0; k < nr; k++) {
-            if (r[k] >= gf2_cells) return fail(RV_E_ARG, "op " + std::to_string(i) + ": wire index out of range for the given wire_counts");
-            last_read_seg[r[k]] = (uint32_t)(i / window_ops) + 1;
-        }
-        if (writes(op) && op.dst >= gf2_cells) return fail(RV_E_ARG, "op " + std::to_string(i) + ": wire index out of range for the given wire_counts");
-    }
-    std::vector<Segment> &segs = plan.segs;
-    segs.resize(n_seg);
-    std::vector<uint32_t> free_slots;
-    uint32_t n_slots = 0;
-    uint64_t masks = 0, on = 0, pre = 0, wit = 0, recon = 0;
-    for (size_t sidx = 0; sidx < n_seg; sidx++) {
-        Segment &S = segs[sidx];
-        S.a = sidx * window_ops;
-        S.b = std::min(n_ops, S.a + window_ops);
-        S.mask0 = masks, S.on0 = on, S.pre0 = pre, S.wit0 = wit, S.recon0 = recon;
-        const uint32_t tag = (uint32_t)sidx + 1;
-        std::vector<uint32_t> touched, to_free;
-        auto local_of = [&](uint32_t c, bool is_read) -> uint32_t {
-            if (stamp[c] != tag) {
-                stamp[c] = tag;
-                local[c] = S.n_local++;
-                touched.push_back(c);
-                if (is_read && written[c]) {  // first access is a read of a wire an earlier segment wrote: carried in
-                    S.io.import_cells.push_back(local[c]);
-                    S.import_slot.push_back(slot_of[c]);
-                    S.import_global.push_back(c);
-                    if (last_read_seg[c] == tag) to_free.push_back(c);  // ... for the last time: its slot is free after this segment
-                }
-            }
-            return local[c];
-        };
-        S.ops.reserve(S.b - S.a);
-        for (size_t i = S.a; i < S.b; i++) {
-            rv_op op = ops[i];
-            if (op.domain != RV_GF2) continue;
-            uint32_t r[2];
-            const int nr = reads(op, r);
-            if (nr >= 1) op.a = local_of(r[0], true);
-            if (nr >= 2) op.b = local_of(r[1], true);
-            if (writes(op)) op.dst = local_of(op.dst, false);
-            S.ops.push_back(op);
-            switch (op.opcode) {
-                case RV_INPUT: masks += 1, on += 1, wit += 1; break;
-                case RV_MUL: masks += 2, on += 1, pre += 1, recon += 1; break;
-                case RV_ASSERT_ZERO: on += 1, recon += 1; break;
-                default: break;
-            }
-        }
-        for (uint32_t c : to_free) {
-            free_slots.push_back(slot_of[c]);
-            slot_of[c] = NO_SLOT;
-        }
-        // wires written here and read by a later segment leave through the cell file (a slot freed above may be reused at once:
-        // imports are read at the start of the segment, exports written at its end)
-        for (size_t i = S.a; i < S.b; i++) {
-            const rv_op &op = ops[i];
-            if (op.domain != RV_GF2 || !writes(op)) continue;
-            const uint32_t c = op.dst;
-            if (written[c] == 2) continue;  // already handled in this segment
-            written[c] = 2;
-            if (last_read_seg[c] > tag) {
-                if (slot_of[c] == NO_SLOT) {
-                    if (!free_slots.empty()) {
-                        slot_of[c] = free_slots.back();
-                        free_slots.pop_back();
-                    } else slot_of[c] = n_slots++;
-                }
-                S.io.export_cells.push_back(local[c]);
-                S.export_slot.push_back(slot_of[c]);
-                S.export_global.push_back(c);
-            }
-        }
-        for (size_t i = S.a; i < S.b; i++)
-            if (ops[i].domain == RV_GF2 && writes(ops[i])) written[ops[i].dst] = 1;
-        S.n_local = std::max<uint32_t>(S.n_local, 1);
-    }
-    std::vector<uint32_t>().swap(stamp);
-    std::vector<uint32_t>().swap(local);
-    std::vector<uint32_t>().swap(last_read_seg);
-    std::vector<uint8_t>().swap(written);
-    plan.n_slots = n_slots;
-    plan.masks = masks, plan.tot_on = on, plan.tot_pre = pre, plan.tot_inputs = wit, plan.tot_recon = recon;
-    plan.gf2_cells = gf2_cells;
-    return RV_OK;
-}
 
 // Test hook (CPU): the streaming planner alone, checked by a symbolic simulation of the cell file -- every wire a segment reads
 // before writing it (and that an earlier segment wrote) must be imported from a slot that holds exactly the state its last
@@ -1984,7 +1840,8 @@ extern "C" int rv_stream_plan_check(const rv_op *ops, size_t n_ops, size_t gf2_c
     if ((n_ops && !ops) || !out) return fail(RV_E_ARG, "NULL argument");
     window_ops = std::max<size_t>(window_ops ? window_ops : ((size_t)1 << 22), 64);
     StreamPlan plan;
-    if (const int rc = plan_stream(ops, n_ops, gf2_cells, window_ops, plan)) return rc;
+    std::string perr;
+    if (const int rc = plan_stream(ops, n_ops, gf2_cells, window_ops, plan, perr)) return fail(rc, perr);
     constexpr int64_t NEVER = -1;
     std::vector<int64_t> last_write(plan.gf2_cells, NEVER);
     std::vector<uint32_t> seen(plan.gf2_cells, 0);  // segment tag of the wire's first access
@@ -2052,7 +1909,8 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
     if (window_ops == 0) window_ops = (size_t)1 << 22;  // ~5 GB of window buffers
     window_ops = std::max<size_t>(window_ops, 64);
     StreamPlan plan;
-    if (const int prc = plan_stream(ops, n_ops, gf2_cells, window_ops, plan)) return prc;
+    std::string perr;
+    if (const int prc = plan_stream(ops, n_ops, gf2_cells, window_ops, plan, perr)) return fail(prc, perr);
     if (rv_device_count() == 0) return fail(RV_E_CUDA, "no CUDA device: reverie-b200 has no CPU fallback");
     std::vector<Segment> &segs = plan.segs;
     const size_t n_seg = segs.size();

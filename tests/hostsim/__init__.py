@@ -15,13 +15,15 @@ _lib = None
 def lib():
     global _lib
     if _lib is None:
-        deps = _SRC + [os.path.join(_ROOT, "reverie_b200", "csrc", f) for f in ("rv_planes.cuh", "rv_zplanes.cuh", "rv_aes_bs.cuh", "rv_blake3.cuh", "rv_compile.h", "rv_bincode.h")]
+        deps = _SRC + [os.path.join(_ROOT, "reverie_b200", "csrc", f) for f in ("rv_planes.cuh", "rv_zplanes.cuh", "rv_aes_bs.cuh", "rv_blake3.cuh", "rv_compile.h", "rv_bincode.h", "rv_stream_plan.h")]
         if not os.path.exists(_LIB) or any(os.path.getmtime(d) > os.path.getmtime(_LIB) for d in deps):
             subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-Wno-unknown-pragmas", "-o", _LIB] + _SRC)
         L = C.CDLL(_LIB)
         sz = C.c_size_t
         L.hs_prove.argtypes = [C.c_void_p, sz, sz, sz, C.c_void_p, sz, C.c_void_p, sz, C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(sz), C.c_void_p]
         L.hs_prove.restype = C.c_int
+        L.hs_prove_streaming.argtypes = [C.c_void_p, sz, sz, C.c_void_p, sz, C.c_void_p, sz, C.POINTER(C.c_void_p), C.POINTER(sz)]
+        L.hs_prove_streaming.restype = C.c_int
         L.hs_free.argtypes = [C.c_void_p]
         L.hs_blake3.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.hs_aes128_encrypt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
@@ -48,6 +50,20 @@ def prove(ops, wit, wire_counts, seeds: bytes, wit_z64=()):
     proof = C.string_at(out, n.value)
     lib().hs_free(out)
     return 0, proof, hashes.tobytes()
+
+
+def prove_streaming(ops, wit, wire_counts, seeds: bytes, window_ops: int):
+    """CPU replay of rv_prove_streaming's planner + segment compilation + carried cell file (GF(2) only)."""
+    ops = np.ascontiguousarray(ops)
+    w = np.ascontiguousarray(np.asarray(wit, dtype=np.uint8))
+    sd = np.frombuffer(seeds, dtype=np.uint8)
+    out, n = C.c_void_p(), C.c_size_t()
+    rc = lib().hs_prove_streaming(_p(ops), ops.size, wire_counts[1], _p(w), w.size, _p(sd), window_ops, C.byref(out), C.byref(n))
+    if rc != 0:
+        return rc, None
+    proof = C.string_at(out, n.value)
+    lib().hs_free(out)
+    return 0, proof
 
 
 def blake3(data: bytes) -> bytes:

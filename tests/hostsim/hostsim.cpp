@@ -10,6 +10,7 @@
 
 #include "../../reverie_b200/csrc/rv_planes.cuh"
 #include "../../reverie_b200/csrc/rv_zplanes.cuh"
+#include "../../reverie_b200/csrc/rv_stream_plan.h"
 
 using namespace rv;
 
@@ -296,6 +297,119 @@ extern "C" int hs_prove(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t
         v.n_recon = (uint32_t)P.recon_pos.size();
         v.n_pre = P.n_pre;
         v.n_inputs = (uint32_t)P.n_inputs;
+        for (uint32_t tid = 0; tid < 4; tid++) extract_entry(L, v, r, omit[r], rank[r], tid, 4, out);
+    }
+    *proof = out;
+    *proof_len = L.total();
+    return RV_OK;
+}
+
+// Proof::new in streaming mode on the CPU: the product's planner (rv_stream_plan.h) and its compiler's segment mode (SegmentIO),
+// with the carried wires kept in a cell file exactly as rv_prove_streaming does -- imports are leaves of both planes, exports are
+// written back after the segment.  The hash streams are simply concatenated here (the chunk carry is kernel-level logic that the
+// GPU tests cover); what this pins on the CPU is segmentation, liveness, slot recycling and the compiler's import / export rows.
+extern "C" int hs_prove_streaming(const rv_op *ops, size_t n_ops, size_t gf2_cells, const uint8_t *wit, size_t n_wit, const uint8_t *seeds,
+                                  size_t window_ops, uint8_t **proof, size_t *proof_len) {
+    StreamPlan plan;
+    int rc = plan_stream(ops, n_ops, gf2_cells, std::max<size_t>(window_ops, 64), plan, g_err);
+    if (rc) return rc;
+    if (n_wit < plan.tot_inputs) return RV_E_WITNESS_SHORT;
+    const uint32_t npi = 32, nreps = 256;
+    std::vector<uint64_t> all_rows(((size_t)plan.masks + 1) * npi, 0);
+    std::vector<uint8_t> pkeys;
+    gen_masks(seeds, nullptr, nullptr, nullptr, npi, (uint32_t)plan.masks, all_rows, pkeys);
+    std::vector<uint64_t> cell_rows((size_t)std::max(plan.n_slots, 1u) * npi, 0);
+    std::vector<uint8_t> cell_vals(std::max(plan.n_slots, 1u), 0);
+    const size_t pitch_on = (std::max<size_t>(plan.tot_on, 1) + 63) / 64 * 64, pitch_pre = (std::max<size_t>(plan.tot_pre, 1) + 63) / 64 * 64;
+    std::vector<uint8_t> on(pitch_on * nreps, 0), pre(pitch_pre * nreps, 0);
+    std::vector<uint32_t> recon_pos, input_pos;
+    int bad = 0;
+    for (Segment &S : plan.segs) {
+        Program P;
+        rc = compile(S.ops.data(), S.ops.size(), 0, S.n_local, P, g_err, COMPILE_PROVE_ONLY, &S.io);
+        if (rc) return rc;
+        if (P.n_tvals || P.z.any()) return RV_E_UNSUPPORTED;
+        const uint32_t n_imp = (uint32_t)S.io.import_cells.size();
+        if (P.n_masks != P.n_prg + n_imp) { g_err = "segment rows"; return -301; }
+        std::vector<uint64_t> rows((size_t)P.n_rows * npi, 0);
+        memcpy(rows.data(), &all_rows[(size_t)S.mask0 * npi], (size_t)P.n_prg * npi * 8);                                  // k_mask_gen_tt with mask_base
+        for (uint32_t j = 0; j < n_imp; j++) memcpy(&rows[(size_t)(P.n_prg + j) * npi], &cell_rows[(size_t)S.import_slot[j] * npi], npi * 8);  // k_seg_import
+        std::vector<uint8_t> vals(P.n_vals, 0);
+        for (size_t k = 0; k < P.n_inputs; k++) vals[P.input_vid[k]] = wit[S.wit0 + k] & 1;
+        for (uint32_t j = 0; j < n_imp; j++) vals[S.io.import_vid[j]] = cell_vals[S.import_slot[j]];
+        for (const VGate &g : P.vgates) {
+            const uint32_t a = vals[g.a >> 1] ^ (g.a & 1), b = vals[g.b >> 1] ^ (g.b & 1);
+            vals[g.dst] = (uint8_t)((g.op ? (a & b) : (a ^ b)) & 1);
+        }
+        for (const XGate &g : P.xgates)
+            for (uint32_t pi = 0; pi < npi; pi++) {
+                uint64_t v = 0;
+                for (int k = 0; k < 6; k++) v ^= rows[(size_t)g.in[k] * npi + pi];
+                rows[(size_t)g.dst * npi + pi] = v;
+            }
+        uint32_t j = 0;
+        for (uint32_t t = 0; t < P.n_online; t++) {
+            const Item &it = P.items[t];
+            for (uint32_t pi = 0; pi < npi; pi++) {
+                const uint64_t w = prover_online_word(it, rows.data(), npi, pi, vals.data(), nullptr, &bad);
+                for (int r = 0; r < 8; r++) on[(size_t)(8 * pi + r) * pitch_on + S.on0 + t] = (uint8_t)(w >> (8 * (7 - r)));  // rep r = big-endian byte r
+                if (it.kind == ITEM_MUL) {
+                    const uint64_t d = pre_word(it, rows.data(), npi, pi);
+                    for (int r = 0; r < 8; r++) pre[(size_t)(8 * pi + r) * pitch_pre + S.pre0 + j] = (uint8_t)(d >> (8 * (7 - r)));
+                }
+            }
+            if (it.kind == ITEM_MUL) j++;
+        }
+        for (uint32_t k : P.recon_pos) recon_pos.push_back((uint32_t)(S.on0 + k));
+        for (uint32_t k : P.input_pos) input_pos.push_back((uint32_t)(S.on0 + k));
+        for (size_t k = 0; k < S.io.export_cells.size(); k++) {  // k_seg_export
+            memcpy(&cell_rows[(size_t)S.export_slot[k] * npi], &rows[(size_t)S.io.export_row[k] * npi], npi * 8);
+            cell_vals[S.export_slot[k]] = (uint8_t)((vals[S.io.export_vref[k] >> 1] ^ S.io.export_vref[k]) & 1);
+        }
+    }
+    if (bad) return RV_E_WITNESS_INVALID;
+    // K5 .. K7 on the concatenated streams (GF(2) only: the Z64 transcript of every repetition is the empty one)
+    uint32_t empty[8], zrep0[8];
+    b3_chunk_cv(nullptr, 0, 0, true, empty);
+    b3_hash64(empty, empty, zrep0);
+    std::vector<uint32_t> on_hash(nreps * 8), rep_hash(nreps * 8);
+    for (uint32_t r = 0; r < nreps; r++) {
+        uint32_t h_pre[8];
+        stream_hash(&on[(size_t)r * pitch_on], (uint32_t)plan.tot_on, &on_hash[r * 8]);
+        stream_hash(&pre[(size_t)r * pitch_pre], (uint32_t)plan.tot_pre, h_pre);
+        rep_join(&on_hash[r * 8], h_pre, zrep0, &rep_hash[r * 8]);
+    }
+    uint32_t comm[8], m[16];
+    stream_hash(reinterpret_cast<const uint8_t *>(rep_hash.data()), nreps * 32, comm);
+    challenge_block(comm, m);
+    uint8_t omit[256];
+    uint16_t rank[256];
+    memset(omit, RV_PLAYERS, sizeof omit);
+    int distinct = 0;
+    for (uint64_t t = 0; distinct < RV_ONLINE_REPS; t++) {
+        uint32_t o[16];
+        challenge_xof_block(m, t, o);
+        challenge_consume(o, omit, &distinct);
+    }
+    uint16_t n_on = 0, n_pre = 0;
+    for (int i = 0; i < 256; i++) rank[i] = omit[i] < RV_PLAYERS ? n_on++ : n_pre++;
+    const ProofLayout L{(uint32_t)(recon_pos.size() / 8 + 1), (uint32_t)(plan.tot_pre / 8 + 1), (uint32_t)(plan.tot_inputs / 8 + 1)};
+    uint8_t *out = (uint8_t *)calloc(L.total(), 1);
+    for (uint32_t r = 0; r < nreps; r++) {
+        ExtractView v;
+        v.on = &on[(size_t)r * pitch_on];
+        v.pre = &pre[(size_t)r * pitch_pre];
+        v.on_hash = reinterpret_cast<const uint8_t *>(&on_hash[r * 8]);
+        v.pkeys = &pkeys[(size_t)r * 128];
+        v.seed = seeds + (size_t)r * 16;
+        v.comm = reinterpret_cast<const uint8_t *>(comm);
+        v.z64_empty_hash = empty;
+        v.z_on_hash = nullptr;
+        v.recon_pos = recon_pos.data();
+        v.input_pos = input_pos.data();
+        v.n_recon = (uint32_t)recon_pos.size();
+        v.n_pre = (uint32_t)plan.tot_pre;
+        v.n_inputs = (uint32_t)plan.tot_inputs;
         for (uint32_t tid = 0; tid < 4; tid++) extract_entry(L, v, r, omit[r], rank[r], tid, 4, out);
     }
     *proof = out;

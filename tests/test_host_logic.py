@@ -534,3 +534,21 @@ def test_streaming_planner_carries_every_live_wire():
     bad["a"][int(np.flatnonzero(ops["opcode"] == CC.MUL)[0])] = wc[1] + 5  # an operand outside the declared wire count
     out = (C.c_uint64 * 6)()
     assert L.rv_stream_plan_check(_ptr(bad), bad.size, wc[1], 5000, out) == N.E_ARG
+
+
+@pytest.mark.parametrize("seed", range(3))
+def test_streaming_segments_replayed_on_the_cpu(seed, default_seeds):
+    """The product's streaming planner and the compiler's segment mode (imports as leaves of both planes, exported rows / values,
+    slot recycling), replayed on the CPU with the kernels' own item functions: the proof must be the oracle's for windows far
+    below the circuit size.  (The chunk carry and the segment-wise packing of the openings are kernel-level: GPU tests.)"""
+    import orc
+    from tests import hostsim
+    from tests.test_gpu_parity import _random_circuit
+
+    rng = np.random.default_rng(200 + seed)
+    ops, wit, wc = _random_circuit(rng, 12, 600, n_cells=20 + 25 * seed)
+    rc, want = orc.prove(ops, wit, [], wc, default_seeds)
+    assert rc == 0
+    for window in (64, 150, 10 ** 6):
+        rc, got = hostsim.prove_streaming(ops, wit, wc, default_seeds, window)
+        assert rc == 0 and got == want, (window, rc)
