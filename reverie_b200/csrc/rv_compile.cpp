@@ -994,6 +994,14 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
             return RV_E_ARG;
         }
         const size_t nc = cells.size();
+        if (i + 48 < n_ops) {  // the operands' cell records of a wide circuit are cache misses: ask for them a few ops ahead ...
+            const rv_op &f = ops[i + 48];
+            if (f.a < nc) __builtin_prefetch(&cells[f.a]);
+            if (f.b < nc) __builtin_prefetch(&cells[f.b]);
+            const rv_op &h = ops[i + 24];  // ... and, once those are here, for the depth records of their values
+            if (h.a < nc && !tainted(cells[h.a].vref)) __builtin_prefetch(&vlevel[cells[h.a].vref >> 1]);
+            if (h.b < nc && !tainted(cells[h.b].vref)) __builtin_prefetch(&vlevel[cells[h.b].vref >> 1]);
+        }
         const uint32_t c = (uint32_t)(op.imm & 1);  // bool -> Recon, src/algebra/gf2/recon.rs:274-287
         switch (op.opcode) {
             case RV_INPUT: {  // src/transcript/prover.rs:181-199
