@@ -1908,29 +1908,34 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
     *proof_len = 0;
     if (window_ops == 0) window_ops = (size_t)1 << 22;  // ~5 GB of window buffers
     window_ops = std::max<size_t>(window_ops, 64);
-    StreamPlan plan;
-    std::string perr;
-    if (const int prc = plan_stream(ops, n_ops, gf2_cells, window_ops, plan, perr)) return fail(prc, perr);
-    if (rv_device_count() == 0) return fail(RV_E_CUDA, "no CUDA device: reverie-b200 has no CPU fallback");
-    std::vector<Segment> &segs = plan.segs;
-    const size_t n_seg = segs.size();
-    const uint32_t n_slots = plan.n_slots;
-    const uint64_t masks = plan.masks, on = plan.tot_on, pre = plan.tot_pre, wit = plan.tot_inputs, recon = plan.tot_recon;
-    const uint64_t tot_on = on, tot_pre = pre, tot_inputs = wit, tot_recon = recon;
-    if (n_gf2 < tot_inputs) return fail(RV_E_WITNESS_SHORT, "witness is too short");  // prover.rs:190
-    if (tot_inputs && !wit_gf2) return fail(RV_E_ARG, "witness pointer is NULL");
-    if (tot_on / 1024 >= 0xFFFFFFF0ull || masks / 128 >= 0xFFFFFFF0ull) return fail(RV_E_UNSUPPORTED, "circuit too large for the 32-bit block counters of the streaming path");
-
-    // ---- 2. compile every segment (host threads), then make its tables resident ----
+    // ---- 1 + 2. planning (this thread) and compilation of the segments (host threads), pipelined: a segment is compiled as soon
+    //      as the planner has published it ----
+    if (rv_device_count() == 0) {  // no device: the arguments are still checked
+        StreamPlan probe;
+        std::string perr0;
+        if (const int prc = plan_stream(ops, n_ops, gf2_cells, window_ops, probe, perr0)) return fail(prc, perr0);
+        return fail(RV_E_CUDA, "no CUDA device: reverie-b200 has no CPU fallback");
+    }
     CU(cudaSetDevice(g_device));
     if (const int ce = configure_kernels(g_device)) return fail(RV_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString((cudaError_t)ce));
+    StreamPlan plan;
     DevBuf B;
+    const size_t n_seg = stream_segments(n_ops, window_ops);
+    plan.segs.resize(n_seg);
+    std::vector<Segment> &segs = plan.segs;
+    std::string perr;
+    int plan_rc = RV_OK;
     {
-        std::atomic<size_t> next{0};
+        std::atomic<size_t> planned{0}, next{0};
+        std::atomic<bool> abort{false};
         auto worker = [&]() {
             for (;;) {
                 const size_t k = next.fetch_add(1);
                 if (k >= n_seg) return;
+                while (planned.load(std::memory_order_acquire) <= k) {
+                    if (abort.load()) return;
+                    std::this_thread::sleep_for(std::chrono::microseconds(200));  // (not a spin: the planner needs its core)
+                }
                 Segment &S = segs[k];
                 S.c = new (std::nothrow) rv_circuit();
                 if (!S.c) {
@@ -1948,14 +1953,21 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
         };
         const unsigned nt = (unsigned)std::min<size_t>(n_seg, std::max(1u, std::min(16u, std::thread::hardware_concurrency())));
         std::vector<std::thread> pool;
-        for (unsigned t = 1; t < nt; t++) pool.emplace_back(worker);
-        worker();
+        for (unsigned t = 0; t < nt; t++) pool.emplace_back(worker);
+        plan_rc = plan_stream(ops, n_ops, gf2_cells, window_ops, plan, perr, &planned);
+        if (plan_rc != RV_OK) abort.store(true);
         for (auto &t : pool) t.join();
     }
-    for (Segment &S : segs) {
+    for (Segment &S : segs)
         if (S.c) B.circuits.push_back(S.c);
+    if (plan_rc != RV_OK) return fail(plan_rc, perr);
+    for (Segment &S : segs)
         if (S.rc != RV_OK) return fail(S.rc, "segment [" + std::to_string(S.a) + ", " + std::to_string(S.b) + "): " + S.err);
-    }
+    const uint32_t n_slots = plan.n_slots;
+    const uint64_t masks = plan.masks, tot_on = plan.tot_on, tot_pre = plan.tot_pre, tot_inputs = plan.tot_inputs, tot_recon = plan.tot_recon;
+    if (n_gf2 < tot_inputs) return fail(RV_E_WITNESS_SHORT, "witness is too short");  // prover.rs:190
+    if (tot_inputs && !wit_gf2) return fail(RV_E_ARG, "witness pointer is NULL");
+    if (tot_on / 1024 >= 0xFFFFFFF0ull || masks / 128 >= 0xFFFFFFF0ull) return fail(RV_E_UNSUPPORTED, "circuit too large for the 32-bit block counters of the streaming path");
     size_t max_rows = 1, max_vals = 1, max_leaves = 1, max_on = 1, max_pre = 1, max_masks = 1;
     bool any_vm = false;
     for (Segment &S : segs) {
