@@ -760,16 +760,18 @@ extern "C" int rv_session_upload(rv_session *s, const uint8_t *wit_gf2, size_t n
     return rv_session_upload_slot(s, 0, wit_gf2, n_gf2, wit_z64, n_z64, seeds);
 }
 
-extern "C" int rv_session_upload_slot(rv_session *s, int slot, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64, size_t n_z64,
-                                      const uint8_t *seeds) {
+// Host half of an upload: the slot's witness and seeds into the session's pinned staging buffer.  `first` = the caller is about to
+// refill the buffer: wait until the copies of the previous proof have left it.
+static int stage_slot(rv_session *s, int slot, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64, size_t n_z64, const uint8_t *seeds, bool first) {
     if (!s) return fail(RV_E_ARG, "NULL session");
     if (slot < 0 || (uint32_t)slot >= s->n_proofs) return fail(RV_E_ARG, "no such proof slot");
     const Program &P = s->c->prog;
     if (n_gf2 < P.n_inputs || n_z64 < P.z.n_inputs) return fail(RV_E_WITNESS_SHORT, "witness is too short");  // prover.rs:190
     if ((P.n_inputs && !wit_gf2) || (P.z.n_inputs && !wit_z64)) return fail(RV_E_ARG, "witness pointer is NULL");
-    CU(cudaSetDevice(s->c->device));
-    cudaStream_t hst = host_stream(s);
-    CU(cudaStreamSynchronize(hst));  // the staging buffer may still be in flight from a previous proof
+    if (first) {
+        CU(cudaSetDevice(s->c->device));
+        CU(cudaStreamSynchronize(host_stream(s)));  // the staging buffer may still be in flight from a previous proof
+    }
     uint8_t *hin = s->h_in + (size_t)slot * s->in_pitch;
     if (P.n_inputs) memcpy(hin, wit_gf2, P.n_inputs);
     uint8_t *hs = hin + s->wit_pitch;
@@ -782,15 +784,28 @@ extern "C" int rv_session_upload_slot(rv_session *s, int slot, const uint8_t *wi
             got += (size_t)r;
         }
     }
-    if (P.n_inputs) CU(cudaMemcpyAsync(s->d_wit + (size_t)slot * s->wit_pitch, hin, P.n_inputs, cudaMemcpyHostToDevice, hst));
-    if (P.z.n_inputs) {  // the Z64 witness fills the first leaves of the value plane; the kappa leaves after it stay zero
-        uint8_t *hz = hs + RV_TOTAL_REPS * 16;
-        memcpy(hz, wit_z64, 8 * (size_t)P.z.n_inputs);
-        CU(cudaMemcpyAsync(s->d_zleaf, hz, 8 * (size_t)P.z.n_inputs, cudaMemcpyHostToDevice, hst));
-    }
-    CU(cudaMemcpyAsync(s->d_seeds + (size_t)slot * s->nreps1 * 16, hs + (size_t)s->first_rep * 16, (size_t)s->nreps1 * 16, cudaMemcpyHostToDevice, hst));
+    if (P.z.n_inputs) memcpy(hs + RV_TOTAL_REPS * 16, wit_z64, 8 * (size_t)P.z.n_inputs);
+    return RV_OK;
+}
+// Device half: slots [slot0, slot0 + n) of the staging buffer to the device -- one strided copy for the witnesses, one for this
+// shard's seeds (instead of two small copies per slot: a 32-proof batch issues 8 copies, not 64).
+static int flush_slots(rv_session *s, int slot0, int n) {
+    const Program &P = s->c->prog;
+    cudaStream_t hst = host_stream(s);
+    const uint8_t *hin = s->h_in + (size_t)slot0 * s->in_pitch;
+    if (P.n_inputs) CU(cudaMemcpy2DAsync(s->d_wit + (size_t)slot0 * s->wit_pitch, s->wit_pitch, hin, s->in_pitch, P.n_inputs, n, cudaMemcpyHostToDevice, hst));
+    if (P.z.n_inputs)  // (Z64 circuits: one proof per session) the Z64 witness fills the first leaves of the value plane; the kappa leaves stay zero
+        CU(cudaMemcpyAsync(s->d_zleaf, hin + s->wit_pitch + RV_TOTAL_REPS * 16, 8 * (size_t)P.z.n_inputs, cudaMemcpyHostToDevice, hst));
+    CU(cudaMemcpy2DAsync(s->d_seeds + (size_t)slot0 * s->nreps1 * 16, (size_t)s->nreps1 * 16, hin + s->wit_pitch + (size_t)s->first_rep * 16, s->in_pitch,
+                         (size_t)s->nreps1 * 16, n, cudaMemcpyHostToDevice, hst));
     s->committed = s->opened = false;
     return RV_OK;
+}
+
+extern "C" int rv_session_upload_slot(rv_session *s, int slot, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64, size_t n_z64,
+                                      const uint8_t *seeds) {
+    const int rc = stage_slot(s, slot, wit_gf2, n_gf2, wit_z64, n_z64, seeds, true);
+    return rc != RV_OK ? rc : flush_slots(s, slot, 1);
 }
 
 // Runs `body` (a sequence of asynchronous launches on the session's streams) eagerly the first time and whenever per-kernel
@@ -1501,11 +1516,12 @@ extern "C" int rv_prove_batch(const rv_circuit *c, int n, const uint8_t *const *
     for (int k = 0; k < (int)used.size() && rc == RV_OK; k++) {
         for (int b = 0; b < slots_of(k) && rc == RV_OK; b++) {
             const int i = k * RV_BATCH_SLOTS + b;
-            const int r = rv_session_upload_slot(used[k], b, wit_gf2 ? wit_gf2[i] : nullptr, n_gf2 ? n_gf2[i] : 0, wit_z64 ? wit_z64[i] : nullptr,
-                                                 n_z64 ? n_z64[i] : 0, seeds ? seeds[i] : nullptr);
-            if (r == RV_E_WITNESS_SHORT || r == RV_E_ARG) statuses[i] = r;  // the slot keeps its previous (valid) inputs; its output is dropped
+            const int r = stage_slot(used[k], b, wit_gf2 ? wit_gf2[i] : nullptr, n_gf2 ? n_gf2[i] : 0, wit_z64 ? wit_z64[i] : nullptr, n_z64 ? n_z64[i] : 0,
+                                     seeds ? seeds[i] : nullptr, b == 0);
+            if (r == RV_E_WITNESS_SHORT || r == RV_E_ARG) statuses[i] = r;  // the slot keeps whatever it held (its output is dropped)
             else if (r != RV_OK) rc = r;
         }
+        if (rc == RV_OK) rc = flush_slots(used[k], 0, slots_of(k));
         if (rc == RV_OK) rc = rv_session_prove(used[k]);
     }
     for (int k = 0; k < (int)used.size() && rc == RV_OK; k++)  // collect in launch order: session k's copies overlap the later sessions' tails
@@ -1729,14 +1745,17 @@ extern "C" int rv_group_prove_batch(rv_group *g, int n, const uint8_t *const *wi
         const int cnt = std::min(cap, n - base), n_used = (cnt + g->slots - 1) / g->slots;
         // session by session: fill its slots on every member, launch it; the next session's uploads overlap its work
         for (int si = 0; si < n_used && rc == RV_OK; si++) {
-            for (auto &m : g->members)
-                for (int k = si * g->slots; k < std::min(cnt, (si + 1) * g->slots) && rc == RV_OK; k++) {
+            const int k0 = si * g->slots, k1 = std::min(cnt, (si + 1) * g->slots);
+            for (auto &m : g->members) {
+                for (int k = k0; k < k1 && rc == RV_OK; k++) {
                     const int i = base + k;
-                    const int r = rv_session_upload_slot(m.ss[si], k % g->slots, wit_gf2 ? wit_gf2[i] : nullptr, n_gf2 ? n_gf2[i] : 0, wit_z64 ? wit_z64[i] : nullptr,
-                                                         n_z64 ? n_z64[i] : 0, seed_of(i));
-                    if (r == RV_E_WITNESS_SHORT || r == RV_E_ARG) statuses[i] = r;  // the slot keeps its previous inputs; its output is dropped
+                    const int r = stage_slot(m.ss[si], k - k0, wit_gf2 ? wit_gf2[i] : nullptr, n_gf2 ? n_gf2[i] : 0, wit_z64 ? wit_z64[i] : nullptr,
+                                             n_z64 ? n_z64[i] : 0, seed_of(i), k == k0);
+                    if (r == RV_E_WITNESS_SHORT || r == RV_E_ARG) statuses[i] = r;  // the slot keeps whatever it held (its output is dropped)
                     else if (r != RV_OK) rc = r;
                 }
+                if (rc == RV_OK) rc = flush_slots(m.ss[si], 0, k1 - k0);
+            }
             if (rc == RV_OK) rc = group_launch(g, si);
         }
         for (auto &m : g->members)
