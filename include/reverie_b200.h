@@ -191,6 +191,9 @@ int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t 
  * total exports. */
 int rv_stream_plan_check(const rv_op *ops, size_t n_ops, size_t gf2_cells, size_t window_ops, uint64_t out[6]);
 
+/* Releases any buffer the library handed out.  Proof buffers are slices of pooled pinned host blocks that the device wrote directly
+ * (no copy on the way out); a block returns to the pool once every proof in it has been released, so release proofs when done
+ * rather than keeping thousands alive. */
 void rv_free(void *p);
 
 /* ---------------------------------------------------------------------------------------------------------------
