@@ -844,27 +844,7 @@ __global__ void __launch_bounds__(256) k_seg_extract(SegExtractArgs a) {
     auto gather = [&](uint8_t *dst, uint64_t first, uint32_t n, const uint8_t *stream, const uint32_t *pos, uint32_t bit) {
         if (n == 0) return;
         const uint64_t g0 = first / 8, g1 = (first + n - 1) / 8;
-        for (uint64_t g = g0 + tid; g <= g1; g += nt) {
-            if (8 * g >= first && 8 * g + 8 <= first + n) {  // the byte's 8 elements belong to this segment: 8-byte loads when they sit side by side
-                const uint32_t k0 = (uint32_t)(8 * g - first), p0 = pos ? pos[k0] : k0;
-                if (!pos || pos[k0 + 7] == p0 + 7) {
-                    dst[g] |= gather_bit_msb_first(load8_unaligned(stream + p0), bit);
-                    continue;
-                }
-            }
-            uint32_t r = 0;
-#pragma unroll
-            for (uint32_t i = 0; i < 8; i++) {
-                const uint64_t el = 8 * g + i;  // global element; the first one of a byte is its MSB
-                uint32_t v = 0;
-                if (el >= first && el - first < n) {
-                    const uint32_t k = (uint32_t)(el - first);
-                    v = (stream[pos ? pos[k] : k] >> bit) & 1u;
-                }
-                r = (r << 1) | v;
-            }
-            dst[g] |= (uint8_t)r;
-        }
+        for (uint64_t g = g0 + tid; g <= g1; g += nt) dst[g] |= seg_pack_byte(stream, pos, first, n, g, bit);
     };
     gather(e + 137, a.first_recon, a.n_recon, on, a.recon_pos, 7 - omit);
     gather(e + 145 + L.len_recons, a.first_corr, a.n_corr, pre, nullptr, 0);

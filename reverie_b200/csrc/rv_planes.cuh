@@ -289,6 +289,28 @@ RV_HD uint8_t pack_bits_byte(const uint8_t *stream, const uint32_t *pos, uint32_
     return (uint8_t)r;
 }
 
+// Streaming: byte g of a packed bit vector, restricted to the elements [first, first + n) that one segment contributes (element
+// first + k = bit `bit` of stream[pos ? pos[k] : k], positions relative to the segment's first stream byte); the other bits of the
+// byte are zero, so the segments' contributions are OR-ed together -- a byte that straddles two segments is completed by the later one.
+RV_HD uint8_t seg_pack_byte(const uint8_t *stream, const uint32_t *pos, uint64_t first, uint32_t n, uint64_t g, uint32_t bit) {
+    if (8 * g >= first && 8 * g + 8 <= first + n) {  // all 8 elements belong to this segment: 8-byte loads when they sit side by side
+        const uint32_t k0 = (uint32_t)(8 * g - first), p0 = pos ? pos[k0] : k0;
+        if (!pos || pos[k0 + 7] == p0 + 7) return gather_bit_msb_first(load8_unaligned(stream + p0), bit);
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < 8; i++) {
+        const uint64_t el = 8 * g + i;  // global element; the first one of a byte is its MSB
+        uint32_t v = 0;
+        if (el >= first && el - first < n) {
+            const uint32_t k = (uint32_t)(el - first);
+            v = (stream[pos ? pos[k] : k] >> bit) & 1u;
+        }
+        r = (r << 1) | v;
+    }
+    return (uint8_t)r;
+}
+
 // ---- bincode `Proof` layout (src/proof/mod.rs:40-66; bincode 1.3 default: LE, u64 lengths, fixed arrays inline) ----
 struct ProofLayout {
     uint32_t len_recons, len_corrs, len_inputs;

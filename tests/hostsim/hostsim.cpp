@@ -323,6 +323,7 @@ extern "C" int hs_prove_streaming(const rv_op *ops, size_t n_ops, size_t gf2_cel
     const size_t pitch_on = (std::max<size_t>(plan.tot_on, 1) + 63) / 64 * 64, pitch_pre = (std::max<size_t>(plan.tot_pre, 1) + 63) / 64 * 64;
     std::vector<uint8_t> on(pitch_on * nreps, 0), pre(pitch_pre * nreps, 0);
     std::vector<uint32_t> recon_pos, input_pos;
+    std::vector<std::vector<uint32_t>> seg_recon_pos, seg_input_pos;
     int bad = 0;
     for (Segment &S : plan.segs) {
         Program P;
@@ -362,6 +363,8 @@ extern "C" int hs_prove_streaming(const rv_op *ops, size_t n_ops, size_t gf2_cel
         }
         for (uint32_t k : P.recon_pos) recon_pos.push_back((uint32_t)(S.on0 + k));
         for (uint32_t k : P.input_pos) input_pos.push_back((uint32_t)(S.on0 + k));
+        seg_recon_pos.push_back(P.recon_pos);  // kept per segment for the segment-wise packing of the openings below
+        seg_input_pos.push_back(P.input_pos);
         for (size_t k = 0; k < S.io.export_cells.size(); k++) {  // k_seg_export
             memcpy(&cell_rows[(size_t)S.export_slot[k] * npi], &rows[(size_t)S.io.export_row[k] * npi], npi * 8);
             cell_vals[S.export_slot[k]] = (uint8_t)((vals[S.io.export_vref[k] >> 1] ^ S.io.export_vref[k]) & 1);
@@ -410,7 +413,24 @@ extern "C" int hs_prove_streaming(const rv_op *ops, size_t n_ops, size_t gf2_cel
         v.n_recon = (uint32_t)recon_pos.size();
         v.n_pre = (uint32_t)plan.tot_pre;
         v.n_inputs = (uint32_t)plan.tot_inputs;
+        // headers, keys, hashes and zeroed vectors first (k_extract with empty tables), then every segment ORs in its bits (k_seg_extract)
+        v.n_recon = v.n_pre = v.n_inputs = 0;
         for (uint32_t tid = 0; tid < 4; tid++) extract_entry(L, v, r, omit[r], rank[r], tid, 4, out);
+        if (omit[r] >= RV_PLAYERS) continue;
+        uint8_t *e = out + L.g_base() + 8 + (size_t)rank[r] * L.sz_on_g();
+        for (size_t k = 0; k < plan.segs.size(); k++) {
+            const Segment &S = plan.segs[k];
+            const uint8_t *son = &on[(size_t)r * pitch_on + S.on0], *spre = &pre[(size_t)r * pitch_pre + S.pre0];
+            const uint32_t n_rec = (uint32_t)seg_recon_pos[k].size(), n_in = (uint32_t)seg_input_pos[k].size();
+            const uint32_t n_cor = (uint32_t)((k + 1 < plan.segs.size() ? plan.segs[k + 1].pre0 : plan.tot_pre) - S.pre0);
+            auto gather = [&](uint8_t *dst, uint64_t first, uint32_t n, const uint8_t *stream, const uint32_t *pos, uint32_t bit) {
+                if (!n) return;
+                for (uint64_t g = first / 8; g <= (first + n - 1) / 8; g++) dst[g] |= seg_pack_byte(stream, pos, first, n, g, bit);
+            };
+            gather(e + 137, S.recon0, n_rec, son, seg_recon_pos[k].data(), 7 - omit[r]);
+            gather(e + 145 + L.len_recons, S.pre0, n_cor, spre, nullptr, 0);
+            gather(e + 153 + L.len_recons + L.len_corrs, S.wit0, n_in, son, seg_input_pos[k].data(), 0);
+        }
     }
     *proof = out;
     *proof_len = L.total();
