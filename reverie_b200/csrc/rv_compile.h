@@ -96,6 +96,11 @@ struct Item {
     uint32_t vb;    // MUL: value ref of operand b
     uint32_t j;     // MUL: position in the preprocessing stream; INPUT: witness index
     uint32_t pad;
+    Item() = default;
+    // emplace_back(...) builds the record in place.  push_back(Item{...}) bounces it through the stack: dword stores, then 16-byte
+    // reloads that cannot be store-forwarded and so wait for every earlier table store to drain (the hottest spot of the op walk).
+    Item(uint32_t kind_, uint32_t ra_, uint32_t rb_, uint32_t k_, uint32_t va_, uint32_t vb_, uint32_t j_, uint32_t pad_)
+        : kind(kind_), ra(ra_), rb(rb_), k(k_), va(va_), vb(vb_), j(j_), pad(pad_) {}
 };
 static_assert(sizeof(TGate) == 16 && sizeof(VGate) == 16 && sizeof(XGate) == 32 && sizeof(VmInstr) == 20 && sizeof(LutInstr) == 48 && sizeof(Item) == 32, "POD layout");
 

@@ -25,6 +25,8 @@ def lib():
         L.hs_prove_streaming.argtypes = [C.c_void_p, sz, sz, C.c_void_p, sz, C.c_void_p, sz, C.POINTER(C.c_void_p), C.POINTER(sz)]
         L.hs_prove_streaming.restype = C.c_int
         L.hs_free.argtypes = [C.c_void_p]
+        L.hs_program_digest.argtypes = [C.c_void_p, sz, sz, sz, C.c_uint32, C.POINTER(C.c_uint64)]
+        L.hs_program_digest.restype = C.c_int
         L.hs_blake3.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
         L.hs_aes128_encrypt.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.hs_gf2_masks.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32]
@@ -105,3 +107,13 @@ def verify(ops, wire_counts, proof: bytes):
     hashes = np.zeros(256 * 32, dtype=np.uint8)
     rc = L.hs_verify(_p(ops), ops.size, wire_counts[0], wire_counts[1], _p(pb), pb.size, C.byref(okay), _p(hashes))
     return rc, bool(okay.value), hashes.tobytes()
+
+
+def program_digest(ops, wire_counts, flags: int = 0) -> int:
+    """FNV-1a of every device-bound table of the compiled program."""
+    ops = np.ascontiguousarray(ops)
+    d = C.c_uint64()
+    rc = lib().hs_program_digest(_p(ops), ops.size, wire_counts[0], wire_counts[1], flags, C.byref(d))
+    if rc != 0:
+        raise RuntimeError(f"compile failed ({rc}): {lib().hs_last_error().decode()}")
+    return d.value

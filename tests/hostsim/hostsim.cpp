@@ -439,6 +439,29 @@ extern "C" int hs_prove_streaming(const rv_op *ops, size_t n_ops, size_t gf2_cel
 
 extern "C" void hs_free(void *p) { free(p); }
 
+// 64-bit FNV-1a over every table of the compiled program that reaches the device (tests: two compiles that must agree).
+extern "C" int hs_program_digest(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, uint32_t flags, uint64_t *digest) {
+    Program P;
+    int rc = compile(ops, n_ops, z64_cells, gf2_cells, P, g_err, flags);
+    if (rc) return rc;
+    uint64_t h = 1469598103934665603ull;
+    auto eat = [&](const void *p, size_t n) {
+        const uint8_t *b = (const uint8_t *)p;
+        for (size_t i = 0; i < n; i++) h = (h ^ b[i]) * 1099511628211ull;
+        h = (h ^ (n & 0xFF)) * 1099511628211ull;
+    };
+    auto vec = [&](const auto &v) { eat(v.data(), v.size() * sizeof(v[0])); };
+    vec(P.items), vec(P.recon_pos), vec(P.input_pos), vec(P.input_vid), vec(P.xgates), vec(P.xlevel_off), vec(P.vm_steps), vec(P.lut_steps);
+    vec(P.wgates), vec(P.wlevel_off), vec(P.vlut_steps), vec(P.vwgates), vec(P.vwlevel_off), vec(P.input_uid), vec(P.kappa_uid);
+    vec(P.item_ua), vec(P.item_ub), vec(P.tgates), vec(P.tlevel_off), vec(P.rand_row), vec(P.rand_uid), vec(P.b2a_vrefs), vec(P.b2a_urefs);
+    vec(P.z.vprog), vec(P.z.lin), vec(P.z.items), vec(P.z.leaf_ids), vec(P.z.recon_off), vec(P.z.input_off), vec(P.z.mul_pos);
+    const uint64_t scalars[] = {P.n_and, P.n_inputs, P.n_assert, P.n_masks, P.n_lin, P.n_rows, P.n_vals, P.n_online, P.n_uvals, P.n_vm_steps, P.n_lut_steps,
+                                P.n_vlut_steps, P.vm_cells, P.algorithmic_bytes, (uint64_t)P.values_wide, (uint64_t)P.verify_wide};
+    eat(scalars, sizeof(scalars));
+    *digest = h;
+    return RV_OK;
+}
+
 // Replays the padded device step streams of both planes (what the kernels actually execute) against the plain networks:
 // the mask VM on random fresh rows vs. the unmapped... mapped XOR gates, the LUT stream on random witnesses vs. the circuit's
 // own 2-input gates.  stats: [n_vm_steps, n_lut_steps, vm_cells, n_luts].

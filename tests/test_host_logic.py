@@ -552,3 +552,25 @@ def test_streaming_segments_replayed_on_the_cpu(seed, default_seeds):
     for window in (64, 150, 10 ** 6):
         rc, got = hostsim.prove_streaming(ops, wit, wc, default_seeds, window)
         assert rc == 0 and got == want, (window, rc)
+
+
+def test_large_circuit_compile_is_the_same_with_and_without_page_helpers(monkeypatch):
+    """Circuits of >= 2^20 ops may be compiled with helper threads that populate the tables' pages ahead of the op walk
+    (rv_compile.cpp, Prefault).  The helpers must not change a byte of the program; neither may the choice compile() makes
+    between them (flat: on, wide layers: off)."""
+    from tests import hostsim
+    from reverie_b200 import circuits as Cc
+
+    n = (1 << 20) + 12345
+    flat, wc = Cc.flat_mul_circuit(n)
+    lay, nw = Cc.layered_and_circuit(1 << 18, n)
+    nar, nw2 = Cc.layered_and_circuit(1 << 16, n)  # wide enough for the level-sorted value plane, narrow enough for the helpers
+    for ops, counts, flags in ((flat, wc, 0), (lay, (0, nw), 0), (nar, (0, nw2), 1)):
+        got = {}
+        for mode in ("0", "1", None):
+            if mode is None:
+                monkeypatch.delenv("RV_PREFAULT", raising=False)
+            else:
+                monkeypatch.setenv("RV_PREFAULT", mode)
+            got[mode] = hostsim.program_digest(ops, counts, flags)
+        assert got["0"] == got["1"] == got[None]
