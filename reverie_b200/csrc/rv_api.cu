@@ -1937,6 +1937,15 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
     }
     CU(cudaSetDevice(g_device));
     if (const int ce = configure_kernels(g_device)) return fail(RV_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString((cudaError_t)ce));
+    const bool trace = std::getenv("RV_TRACE") != nullptr;  // stage times on stderr (the GPU stages are synchronised for it)
+    auto t_last = std::chrono::steady_clock::now();
+    auto mark = [&](const char *what, cudaStream_t sync = nullptr) {
+        if (!trace) return;
+        if (sync) cudaStreamSynchronize(sync);
+        const auto n = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[rv_stream] %-34s %9.1f ms\n", what, std::chrono::duration<double, std::milli>(n - t_last).count());
+        t_last = n;
+    };
     StreamPlan plan;
     DevBuf B;
     const size_t n_seg = stream_segments(n_ops, window_ops);
@@ -1975,7 +1984,9 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
         for (unsigned t = 0; t < nt; t++) pool.emplace_back(worker);
         plan_rc = plan_stream(ops, n_ops, gf2_cells, window_ops, plan, perr, &planned);
         if (plan_rc != RV_OK) abort.store(true);
+        mark("planner");
         for (auto &t : pool) t.join();
+        mark("compile threads' tail");
     }
     for (Segment &S : segs)
         if (S.c) B.circuits.push_back(S.c);
@@ -2024,6 +2035,7 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
         std::vector<uint32_t>().swap(c->recon_idx);
     }
 
+    mark("segment tables to the device");
     // ---- 3. window buffers, cell file, hash state ----
     constexpr uint32_t NPI = RV_PACKED_REPS, NREPS = RV_TOTAL_REPS;
     const uint32_t nslices = 2 * NPI;
@@ -2070,10 +2082,12 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
     }
     launch_key_setup(d_seeds, nullptr, nullptr, nullptr, nslices, d_pkeys, d_rk, st, d_bad, 1, 0);
 
+    mark("buffers, seeds, keys", st);
     // ---- 4. the two passes ----
     const int n_sms = segs[0].c->n_sms;
     for (int pass = 1; pass <= 2; pass++) {
         if (pass == 2) {
+            mark("pass 1 (hashes)", st);
             // every repetition's hash is known: comm, challenge, then the proof's headers, keys, hashes and zeroed vectors
             launch_rep_hash(d_cv_on, tot_chunks_on, d_cv_pre, tot_chunks_pre, d_zconst, NREPS, d_on_hash, d_rep_hash, st, 0xFFFFFFFFu, nullptr, nullptr, nullptr, d_cv_scratch);
             launch_challenge(d_rep_hash, NREPS * 32, d_comm, 0, d_omit, d_rank, 1, st);
@@ -2130,6 +2144,7 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
             CU(cudaGetLastError());
         }
     }
+    mark("pass 2 (openings)", st);
     // ---- 5. the proof ----
     uint8_t tail[64];
     CU(cudaMemcpyAsync(tail, d_proof + tail_off, 36, cudaMemcpyDeviceToHost, st));
@@ -2145,6 +2160,7 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
         rv_free(p);
         return fail(RV_E_CUDA, std::string("proof copy: ") + cudaGetErrorString(e));
     }
+    mark("proof to the host");
     *proof = p;
     *proof_len = plen;
     return RV_OK;

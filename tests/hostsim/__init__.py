@@ -25,6 +25,8 @@ def lib():
         L.hs_prove_streaming.argtypes = [C.c_void_p, sz, sz, C.c_void_p, sz, C.c_void_p, sz, C.POINTER(C.c_void_p), C.POINTER(sz)]
         L.hs_prove_streaming.restype = C.c_int
         L.hs_free.argtypes = [C.c_void_p]
+        L.hs_plan_compare.argtypes = [C.c_void_p, sz, sz, sz, C.c_uint]
+        L.hs_plan_compare.restype = C.c_int
         L.hs_program_digest.argtypes = [C.c_void_p, sz, sz, sz, C.c_uint32, C.POINTER(C.c_uint64)]
         L.hs_program_digest.restype = C.c_int
         L.hs_blake3.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p]
@@ -117,3 +119,9 @@ def program_digest(ops, wire_counts, flags: int = 0) -> int:
     if rc != 0:
         raise RuntimeError(f"compile failed ({rc}): {lib().hs_last_error().decode()}")
     return d.value
+
+
+def plan_compare(ops, gf2_cells: int, window_ops: int, n_threads: int) -> str:
+    """'' if the threaded streaming planner and the serial one agree in every field (or fail alike), else what differs."""
+    ops = np.ascontiguousarray(ops)
+    return "" if lib().hs_plan_compare(_p(ops), ops.size, gf2_cells, window_ops, n_threads) == 0 else lib().hs_last_error().decode()

@@ -439,6 +439,27 @@ extern "C" int hs_prove_streaming(const rv_op *ops, size_t n_ops, size_t gf2_cel
 
 extern "C" void hs_free(void *p) { free(p); }
 
+// The threaded planner against the serial one (rv_stream_plan.h): 0 = same return code, same error text, same plan in every field.
+extern "C" int hs_plan_compare(const rv_op *ops, size_t n_ops, size_t gf2_cells, size_t window_ops, unsigned n_threads) {
+    StreamPlan A, B;
+    std::string ea, eb;
+    const int ra = plan_stream_serial(ops, n_ops, gf2_cells, window_ops, A, ea);
+    const int rb = plan_stream(ops, n_ops, gf2_cells, window_ops, B, eb, nullptr, n_threads);
+    if (ra != rb || ea != eb) { g_err = "rc / error differ: " + std::to_string(ra) + " '" + ea + "' vs " + std::to_string(rb) + " '" + eb + "'"; return 1; }
+    if (ra != RV_OK) return 0;
+    if (A.n_slots != B.n_slots || A.masks != B.masks || A.tot_on != B.tot_on || A.tot_pre != B.tot_pre || A.tot_inputs != B.tot_inputs || A.tot_recon != B.tot_recon ||
+        A.gf2_cells != B.gf2_cells || A.segs.size() != B.segs.size()) { g_err = "totals differ"; return 1; }
+    for (size_t k = 0; k < A.segs.size(); k++) {
+        const Segment &x = A.segs[k], &y = B.segs[k];
+        const bool same = x.a == y.a && x.b == y.b && x.n_local == y.n_local && x.ops.size() == y.ops.size() &&
+                          (x.ops.empty() || !memcmp(x.ops.data(), y.ops.data(), x.ops.size() * sizeof(rv_op))) && x.io.import_cells == y.io.import_cells &&
+                          x.io.export_cells == y.io.export_cells && x.import_slot == y.import_slot && x.export_slot == y.export_slot && x.import_global == y.import_global &&
+                          x.export_global == y.export_global && x.mask0 == y.mask0 && x.on0 == y.on0 && x.pre0 == y.pre0 && x.wit0 == y.wit0 && x.recon0 == y.recon0;
+        if (!same) { g_err = "segment " + std::to_string(k) + " differs"; return 1; }
+    }
+    return 0;
+}
+
 // 64-bit FNV-1a over every table of the compiled program that reaches the device (tests: two compiles that must agree).
 extern "C" int hs_program_digest(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, uint32_t flags, uint64_t *digest) {
     Program P;

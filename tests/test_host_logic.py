@@ -574,3 +574,49 @@ def test_large_circuit_compile_is_the_same_with_and_without_page_helpers(monkeyp
                 monkeypatch.setenv("RV_PREFAULT", mode)
             got[mode] = hostsim.program_digest(ops, counts, flags)
         assert got["0"] == got["1"] == got[None]
+
+
+def test_threaded_streaming_planner_equals_the_serial_one():
+    """plan_stream (threads: liveness by atomic max / min over op ranges, segments renumbered side by side, slots in sequence)
+    must reproduce plan_stream_serial field by field -- segment ops, imports, exports, slots, stream offsets -- and fail with the
+    same code and message.  Circuits with heavy wire reuse (slots recycled), SSA layers, SHA-256 repeated; windows that do and
+    do not divide the op count; 2 ... 8 threads."""
+    from tests import hostsim
+    from reverie_b200 import circuits as CC
+
+    rng = np.random.default_rng(5)
+
+    def random_ops(n, n_cells):
+        ops = np.zeros(n, dtype=CC.OP_DTYPE)
+        ops["domain"] = CC.GF2
+        ops["opcode"] = rng.choice([CC.MUL, CC.ADD, CC.SUB, CC.ADDC, CC.MULC, CC.CONST, CC.ASSERT_ZERO, CC.INPUT], size=n, p=[0.3, 0.3, 0.1, 0.1, 0.05, 0.05, 0.05, 0.05])
+        for f in ("dst", "a", "b"):
+            ops[f] = rng.integers(0, n_cells, size=n, dtype=np.uint32)
+        ops["imm"] = rng.integers(0, 2, size=n)
+        return ops
+
+    n = 70000 + 1234
+    for n_cells, window, threads in ((8, 1000, 2), (300, 4097, 3), (300, 65536, 8), (50000, 5000, 4), (50000, 9999, 8)):
+        assert hostsim.plan_compare(random_ops(n, n_cells), n_cells, window, threads) == ""
+    lay, nw = CC.layered_and_circuit(4096, 90000)
+    assert hostsim.plan_compare(lay, nw, 8192, 4) == "" and hostsim.plan_compare(lay, nw, 10 ** 6, 4) == ""
+    flat, wc = CC.flat_mul_circuit(100000)
+    assert hostsim.plan_compare(flat, wc[1], 7000, 8) == ""
+    # refusals: the same code and the same text (the first offending op), wherever the op sits
+    ops = random_ops(n, 300)
+    for where in (5, n // 2, n - 3):
+        bad = ops.copy()
+        bad["opcode"][where] = CC.MUL
+        bad["a"][where] = 300
+        assert hostsim.plan_compare(bad, 300, 4097, 4) == ""
+        bad = ops.copy()
+        bad["opcode"][where] = CC.RANDOM
+        assert hostsim.plan_compare(bad, 300, 4097, 4) == ""
+        bad = ops.copy()
+        bad["domain"][where] = CC.Z64
+        assert hostsim.plan_compare(bad, 300, 4097, 4) == ""
+    hint = ops.copy()  # a SizeHint that grows the wire file mid-way: wires above the old size are legal only after it
+    hint["domain"][n // 2] = CC.HINT
+    hint["b"][n // 2] = 400
+    hint["dst"][n // 2 + 10 :] += rng.integers(0, 2, size=n - n // 2 - 10, dtype=np.uint32) * 100
+    assert hostsim.plan_compare(hint, 300, 4097, 4) == ""
