@@ -166,6 +166,8 @@ extern "C" void rv_free(void *p) {
 // ---------------------------------------------------------------------------------------------------------------------
 //  circuit
 // ---------------------------------------------------------------------------------------------------------------------
+static size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
 struct rv_circuit {
     std::shared_ptr<Program> progp;  // the compiled host tables, shared by the per-device clones of a circuit (rv_circuit_clone)
     Program &prog;
@@ -173,6 +175,8 @@ struct rv_circuit {
     explicit rv_circuit(std::shared_ptr<Program> p) : progp(std::move(p)), prog(*progp) {}
     DevProgram dev;
     std::vector<void *> allocs;
+    uint8_t *arena = nullptr;  // optional: one device allocation the table uploads are carved from (streaming segments: 1 cudaMalloc / cudaFree instead of 25)
+    size_t arena_cap = 0, arena_off = 0;
     std::vector<uint32_t> mul_pos;
     std::vector<uint32_t> recon_idx;  // online item -> index among the reconstruct() calls (verifier)
     std::vector<uint32_t> vleaf_ids;  // u-plane value ids of the verifier's leaves: inputs then kappas
@@ -189,15 +193,64 @@ struct rv_circuit {
     mutable std::vector<rv_session *> multi_pool;  // idle multi-proof sessions (rv_prove_batch), any slot counts
 };
 
+// A thread's pinned double buffer for big table uploads.  cudaMemcpy from pageable memory moves ~3 GB/s and does not get faster
+// with more threads (one staging path inside the driver); a memcpy into pinned memory by the uploading thread followed by an
+// async copy does, thread by thread, until the link is full.  Used by the streaming prover, whose compile threads upload 12 GB of
+// segment tables for 3 x 10^8 gates.
+struct UploadStage {
+    static constexpr size_t CHUNK = 16u << 20;
+    uint8_t *buf[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaStream_t st = nullptr;
+    bool ok = false;
+    void init() {
+        ok = cudaMallocHost(&buf[0], CHUNK) == cudaSuccess && cudaMallocHost(&buf[1], CHUNK) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming) == cudaSuccess && cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming) == cudaSuccess &&
+             cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
+        if (!ok) cudaGetLastError();  // (the plain path serves)
+    }
+    cudaError_t copy(void *d, const void *h, size_t bytes) {
+        const uint8_t *src = (const uint8_t *)h;
+        uint8_t *dst = (uint8_t *)d;
+        cudaError_t e = cudaSuccess;
+        for (size_t off = 0, k = 0; off < bytes && e == cudaSuccess; off += CHUNK, k ^= 1) {
+            const size_t n = std::min(CHUNK, bytes - off);
+            if (off >= 2 * CHUNK) e = cudaEventSynchronize(ev[k]);  // the copy that last read this half has left it
+            if (e != cudaSuccess) break;
+            memcpy(buf[k], src + off, n);
+            e = cudaMemcpyAsync(dst + off, buf[k], n, cudaMemcpyHostToDevice, st);
+            if (e == cudaSuccess) e = cudaEventRecord(ev[k], st);
+        }
+        const cudaError_t e2 = cudaStreamSynchronize(st);
+        return e != cudaSuccess ? e : e2;
+    }
+    ~UploadStage() {
+        for (int k = 0; k < 2; k++) {
+            if (buf[k]) cudaFreeHost(buf[k]);
+            if (ev[k]) cudaEventDestroy(ev[k]);
+        }
+        if (st) cudaStreamDestroy(st);
+    }
+};
+static thread_local UploadStage *g_stage = nullptr;  // set by a thread that wants its uploads staged
+
 template <typename T>
 static int upload(rv_circuit *c, const std::vector<T> &v, const T **out) {
     *out = nullptr;
-    const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T), padded = round_up(bytes, 256);
     void *d = nullptr;
-    CU(cudaMalloc(&d, bytes));
-    c->allocs.push_back(d);
+    if (c->arena && c->arena_off + padded <= c->arena_cap) {
+        d = c->arena + c->arena_off;
+        c->arena_off += padded;
+    } else {
+        CU(cudaMalloc(&d, bytes));
+        c->allocs.push_back(d);
+    }
     c->device_bytes += bytes;
-    if (!v.empty()) CU(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    if (!v.empty()) {
+        if (g_stage && g_stage->ok && v.size() * sizeof(T) >= (1u << 20)) CU(g_stage->copy(d, v.data(), v.size() * sizeof(T)));
+        else CU(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    }
     *out = reinterpret_cast<const T *>(d);
     return RV_OK;
 }
@@ -217,6 +270,7 @@ extern "C" void rv_circuit_free(rv_circuit *c) {
 static int circuit_to_device(rv_circuit *c, int device) {
     int rc;
     Program &P = c->prog;
+    c->mul_pos.reserve(P.n_and);
     for (uint32_t t = 0; t < P.n_online; t++)
         if (P.items[t].kind == ITEM_MUL) c->mul_pos.push_back(t);
     c->recon_idx.assign(P.n_online, 0);
@@ -429,7 +483,6 @@ extern "C" int rv_circuit_export(const rv_circuit *c, int what, void *buf, size_
 // ---------------------------------------------------------------------------------------------------------------------
 //  session
 // ---------------------------------------------------------------------------------------------------------------------
-static size_t round_up(size_t x, size_t m) { return (x + m - 1) / m * m; }
 
 struct KTimer {
     std::string name;
@@ -1917,6 +1970,52 @@ extern "C" int rv_stream_plan_check(const rv_op *ops, size_t n_ops, size_t gf2_c
     return RV_OK;
 }
 
+// A compiled segment's tables go to the device from the thread that compiled it (the derived host tables and the pageable copies
+// of 72 segments of 4 M gates cost 3.9 s when done one after the other, more than the planner and both GPU passes together).
+static int segment_to_device(Segment &S, int device) {
+    rv_circuit *c = S.c;
+    Program &P = c->prog;
+    if (P.n_tvals || P.z.any()) return fail(RV_E_UNSUPPORTED, "streaming mode serves GF(2) circuits without Random / Z64 / B2A");
+    S.n_on = P.n_online, S.n_pre = P.n_pre, S.n_in = (uint32_t)P.n_inputs, S.n_recon = (uint32_t)P.recon_pos.size();
+    S.n_imp = (uint32_t)S.io.import_cells.size(), S.n_exp = (uint32_t)S.io.export_cells.size();
+    {  // one arena for everything this segment uploads (a table that should not fit falls back to its own allocation)
+        size_t cap = 0;
+        auto add = [&](size_t n, size_t elem) { cap += round_up(std::max<size_t>(n, 1) * elem, 256); };
+        add(P.xgates.size(), sizeof(XGate)), add(P.xlevel_off.size(), 4), add(P.items.size(), sizeof(Item)), add(P.n_and, 4), add(P.recon_pos.size(), 4);
+        add(P.input_pos.size(), 4), add(P.input_vid.size(), 4), add(P.vm_steps.size(), sizeof(VmInstr)), add(P.lut_steps.size(), sizeof(LutInstr));
+        add(P.vlut_steps.size(), sizeof(LutInstr)), add(P.input_uid.size() + P.kappa_uid.size() + P.rand_uid.size(), 4), add(P.item_ua.size(), 4), add(P.item_ub.size(), 4);
+        add(P.n_online, 4), add(P.tgates.size(), sizeof(TGate)), add(P.tlevel_off.size(), 4), add(P.rand_row.size(), 4), add(P.b2a_vrefs.size(), 4), add(P.b2a_urefs.size(), 4);
+        add(P.wgates.size(), sizeof(VGate)), add(P.vwgates.size(), sizeof(VGate));
+        add(P.input_vid.size() + S.io.import_vid.size(), 4), add(S.import_slot.size(), 4), add(S.export_slot.size(), 4), add(S.io.export_row.size(), 4), add(S.io.export_vref.size(), 4);
+        void *a = nullptr;
+        if (cudaSetDevice(device) == cudaSuccess && cudaMalloc(&a, cap) == cudaSuccess) {
+            c->allocs.push_back(a);
+            c->arena = (uint8_t *)a, c->arena_cap = cap, c->arena_off = 0;
+        } else cudaGetLastError();
+    }
+    int rc = circuit_to_device(c, device);
+    std::vector<uint32_t> leaf_ids(P.input_vid);
+    leaf_ids.insert(leaf_ids.end(), S.io.import_vid.begin(), S.io.import_vid.end());
+    if (rc == RV_OK) rc = upload(c, leaf_ids, &S.d_leaf_ids);
+    if (rc == RV_OK) rc = upload(c, S.import_slot, &S.d_imp_slot);
+    if (rc == RV_OK) rc = upload(c, S.export_slot, &S.d_exp_slot);
+    if (rc == RV_OK) rc = upload(c, S.io.export_row, &S.d_exp_row);
+    if (rc == RV_OK) rc = upload(c, S.io.export_vref, &S.d_exp_vref);
+    if (rc != RV_OK) return rc;
+    // the host copies of the big tables are not needed any more (launches read the device copies and the small level offsets)
+    std::vector<Item>().swap(P.items);
+    std::vector<XGate>().swap(P.xgates);
+    std::vector<LutInstr>().swap(P.lut_steps);
+    std::vector<VmInstr>().swap(P.vm_steps);
+    std::vector<VGate>().swap(P.wgates);
+    std::vector<uint32_t>().swap(P.recon_pos);
+    std::vector<uint32_t>().swap(P.input_pos);
+    std::vector<uint32_t>().swap(P.input_vid);
+    std::vector<uint32_t>().swap(c->mul_pos);
+    std::vector<uint32_t>().swap(c->recon_idx);
+    return RV_OK;
+}
+
 extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, const uint8_t *wit_gf2, size_t n_gf2,
                                   const uint64_t *wit_z64, size_t n_z64, const uint8_t *seeds, size_t window_ops, uint8_t **proof, size_t *proof_len) {
     (void)wit_z64;
@@ -1935,10 +2034,10 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
         if (const int prc = plan_stream(ops, n_ops, gf2_cells, window_ops, probe, perr0)) return fail(prc, perr0);
         return fail(RV_E_CUDA, "no CUDA device: reverie-b200 has no CPU fallback");
     }
-    CU(cudaSetDevice(g_device));
-    if (const int ce = configure_kernels(g_device)) return fail(RV_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString((cudaError_t)ce));
     const bool trace = std::getenv("RV_TRACE") != nullptr;  // stage times on stderr (the GPU stages are synchronised for it)
     auto t_last = std::chrono::steady_clock::now();
+    CU(cudaSetDevice(g_device));
+    if (const int ce = configure_kernels(g_device)) return fail(RV_E_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString((cudaError_t)ce));
     auto mark = [&](const char *what, cudaStream_t sync = nullptr) {
         if (!trace) return;
         if (sync) cudaStreamSynchronize(sync);
@@ -1946,24 +2045,48 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
         std::fprintf(stderr, "[rv_stream] %-34s %9.1f ms\n", what, std::chrono::duration<double, std::milli>(n - t_last).count());
         t_last = n;
     };
+    struct Teardown {  // (declared before what it times: destroyed last)
+        bool on;
+        std::chrono::steady_clock::time_point t0;
+        ~Teardown() {
+            if (on && t0.time_since_epoch().count())
+                std::fprintf(stderr, "[rv_stream] %-34s %9.1f ms\n", "teardown", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+        }
+    } teardown{trace, {}};
     StreamPlan plan;
     DevBuf B;
     const size_t n_seg = stream_segments(n_ops, window_ops);
     plan.segs.resize(n_seg);
+    mark("device, kernels");
     std::vector<Segment> &segs = plan.segs;
     std::string perr;
     int plan_rc = RV_OK;
     {
         std::atomic<size_t> planned{0}, next{0};
         std::atomic<bool> abort{false};
+        std::atomic<uint64_t> us_compile{0}, us_upload{0}, us_wait{0};  // summed over the workers (RV_TRACE)
+        auto us_since = [](std::chrono::steady_clock::time_point t) {
+            return (uint64_t)std::chrono::duration_cast<std::chrono::microseconds>(std::chrono::steady_clock::now() - t).count();
+        };
+        const int device = g_device;  // (thread_local: the workers get the caller's)
         auto worker = [&]() {
+            g_device = device;
+            cudaSetDevice(device);
+            UploadStage stage;  // (allocated while the planner works on the first segments)
+            stage.init();
+            g_stage = &stage;
+            struct Unset {
+                ~Unset() { g_stage = nullptr; }
+            } unset;
             for (;;) {
                 const size_t k = next.fetch_add(1);
                 if (k >= n_seg) return;
+                auto t0 = std::chrono::steady_clock::now();
                 while (planned.load(std::memory_order_acquire) <= k) {
                     if (abort.load()) return;
                     std::this_thread::sleep_for(std::chrono::microseconds(200));  // (not a spin: the planner needs its core)
                 }
+                us_wait += us_since(t0);
                 Segment &S = segs[k];
                 S.c = new (std::nothrow) rv_circuit();
                 if (!S.c) {
@@ -1971,7 +2094,13 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
                     continue;
                 }
                 try {
+                    t0 = std::chrono::steady_clock::now();
                     S.rc = compile(S.ops.data(), S.ops.size(), 0, S.n_local, S.c->prog, S.err, COMPILE_PROVE_ONLY, &S.io);
+                    std::vector<rv_op>().swap(S.ops);
+                    us_compile += us_since(t0);
+                    t0 = std::chrono::steady_clock::now();
+                    if (S.rc == RV_OK && (S.rc = segment_to_device(S, device)) != RV_OK) S.err = g_err;  // (this thread's g_err)
+                    us_upload += us_since(t0);
                 } catch (const std::bad_alloc &) {
                     S.rc = RV_E_NOMEM;
                     S.err = "out of host memory while compiling a segment";
@@ -1986,7 +2115,10 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
         if (plan_rc != RV_OK) abort.store(true);
         mark("planner");
         for (auto &t : pool) t.join();
-        mark("compile threads' tail");
+        mark("compile + upload threads' tail");
+        if (trace)
+            std::fprintf(stderr, "[rv_stream]   %u workers, summed: compile %.1f s, tables to the device %.1f s, waiting for the planner %.1f s\n", nt, us_compile.load() * 1e-6,
+                         us_upload.load() * 1e-6, us_wait.load() * 1e-6);
     }
     for (Segment &S : segs)
         if (S.c) B.circuits.push_back(S.c);
@@ -2001,41 +2133,16 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
     size_t max_rows = 1, max_vals = 1, max_leaves = 1, max_on = 1, max_pre = 1, max_masks = 1;
     bool any_vm = false;
     for (Segment &S : segs) {
-        rv_circuit *c = S.c;
-        Program &P = c->prog;
-        if (P.n_tvals || P.z.any()) return fail(RV_E_UNSUPPORTED, "streaming mode serves GF(2) circuits without Random / Z64 / B2A");
-        S.n_on = P.n_online, S.n_pre = P.n_pre, S.n_in = (uint32_t)P.n_inputs, S.n_recon = (uint32_t)P.recon_pos.size();
-        S.n_imp = (uint32_t)S.io.import_cells.size(), S.n_exp = (uint32_t)S.io.export_cells.size();
-        int rc = circuit_to_device(c, g_device);
-        std::vector<uint32_t> leaf_ids(P.input_vid);
-        leaf_ids.insert(leaf_ids.end(), S.io.import_vid.begin(), S.io.import_vid.end());
-        if (rc == RV_OK) rc = upload(c, leaf_ids, &S.d_leaf_ids);
-        if (rc == RV_OK) rc = upload(c, S.import_slot, &S.d_imp_slot);
-        if (rc == RV_OK) rc = upload(c, S.export_slot, &S.d_exp_slot);
-        if (rc == RV_OK) rc = upload(c, S.io.export_row, &S.d_exp_row);
-        if (rc == RV_OK) rc = upload(c, S.io.export_vref, &S.d_exp_vref);
-        if (rc != RV_OK) return rc;
+        const Program &P = S.c->prog;
         max_rows = std::max<size_t>(max_rows, P.n_rows);
         max_masks = std::max<size_t>(max_masks, P.n_masks);
         max_vals = std::max<size_t>(max_vals, (size_t)P.n_vals + 1);
         max_leaves = std::max<size_t>(max_leaves, (size_t)S.n_in + S.n_imp);
         max_on = std::max<size_t>(max_on, (size_t)(S.on0 % 1024) + S.n_on);
         max_pre = std::max<size_t>(max_pre, (size_t)(S.pre0 % 1024) + S.n_pre);
-        any_vm |= linear_uses_vm(c->dev);
-        // the host copies of the big tables are not needed any more (launches read the device copies and the small level offsets)
-        std::vector<Item>().swap(P.items);
-        std::vector<XGate>().swap(P.xgates);
-        std::vector<LutInstr>().swap(P.lut_steps);
-        std::vector<VmInstr>().swap(P.vm_steps);
-        std::vector<VGate>().swap(P.wgates);
-        std::vector<uint32_t>().swap(P.recon_pos);
-        std::vector<uint32_t>().swap(P.input_pos);
-        std::vector<uint32_t>().swap(P.input_vid);
-        std::vector<uint32_t>().swap(c->mul_pos);
-        std::vector<uint32_t>().swap(c->recon_idx);
+        any_vm |= linear_uses_vm(S.c->dev);
     }
 
-    mark("segment tables to the device");
     // ---- 3. window buffers, cell file, hash state ----
     constexpr uint32_t NPI = RV_PACKED_REPS, NREPS = RV_TOTAL_REPS;
     const uint32_t nslices = 2 * NPI;
@@ -2161,6 +2268,7 @@ extern "C" int rv_prove_streaming(const rv_op *ops, size_t n_ops, size_t z64_cel
         return fail(RV_E_CUDA, std::string("proof copy: ") + cudaGetErrorString(e));
     }
     mark("proof to the host");
+    teardown.t0 = std::chrono::steady_clock::now();
     *proof = p;
     *proof_len = plen;
     return RV_OK;
