@@ -174,6 +174,10 @@ int rv_proof_verify_ex(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t 
  * that a caller with the reference's call shape -- Proof::new(circuit, ...) with the circuit passed every time,
  * src/proof/mod.rs:119-124 -- compiles each circuit once.  Default: 8 entries, least recently used idle entry evicted first. */
 void rv_circuit_cache_clear(void);
+/* rv_proof_new on a circuit of >= n_ops ops that it has not seen before (and that streaming serves: GF(2) without Random) proves
+ * in streaming mode instead of compiling the circuit for residency first -- same bytes, several times sooner for 10^8 gates; the
+ * next call with that circuit compiles and caches it.  Default 2^24 ops; 0 = never. */
+void rv_oneshot_streaming_min(size_t n_ops);
 void rv_circuit_cache_limit(size_t max_entries);
 void rv_circuit_cache_stats(uint64_t *hits, uint64_t *misses, size_t *entries);
 

@@ -48,6 +48,7 @@ def lib() -> C.CDLL:
         "rv_circuit_compile_ex": ([vp, sz, sz, sz, C.c_uint, pp], i32),
         "rv_circuit_free": ([vp], None),
         "rv_circuit_cache_clear": ([], None),
+        "rv_oneshot_streaming_min": ([sz], None),
         "rv_circuit_cache_limit": ([sz], None),
         "rv_circuit_cache_stats": ([C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), psz], None),
         "rv_proof_verify_ex": ([vp, sz, sz, sz, vp, sz, C.POINTER(i32)], i32),
@@ -115,7 +116,7 @@ def lib() -> C.CDLL:
 
 
 EXPORTED = (
-    "rv_last_error rv_version rv_device_count rv_set_device rv_circuit_compile rv_circuit_compile_ex rv_circuit_cache_clear rv_circuit_cache_limit rv_circuit_cache_stats rv_proof_verify_ex rv_circuit_free rv_circuit_get_stats "
+    "rv_last_error rv_version rv_device_count rv_set_device rv_circuit_compile rv_circuit_compile_ex rv_circuit_cache_clear rv_oneshot_streaming_min rv_circuit_cache_limit rv_circuit_cache_stats rv_proof_verify_ex rv_circuit_free rv_circuit_get_stats "
     "rv_circuit_export rv_prove rv_prove_batch rv_session_slots rv_session_proof_stride rv_verify rv_proof_new rv_proof_verify rv_free rv_session_create rv_session_create_multi rv_session_upload_slot rv_session_fetch_slot rv_session_free "
     "rv_session_upload rv_session_commit rv_session_hashes rv_session_hashes_device rv_session_all_hashes_device rv_session_open rv_session_prove rv_session_fetch rv_session_sync rv_session_status rv_session_proof_device "
     "rv_proof_assemble rv_batch_create rv_batch_free rv_batch_commit rv_batch_open rv_batch_prove rv_batch_stream rv_session_stream rv_session_timing rv_session_kernel_times rv_session_launch_count "

@@ -2590,10 +2590,30 @@ void cache_release(rv_circuit *c) {
     if (free_it) rv_circuit_free(c);
 }
 
+// One-shot proofs of big circuits (rv_proof_new, below): keys of circuits seen once and proved in streaming mode.
+std::vector<Hash128> g_streamed_once;
+size_t g_oneshot_stream_min = (size_t)1 << 24;
+
+Hash128 circuit_key(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells) {
+    return hash_bytes(ops, n_ops * sizeof(rv_op), (uint64_t)z64_cells * 0x100000001b3ull ^ gf2_cells);
+}
+// true if this circuit is neither cached nor has been through rv_proof_new before (and remembers that it has now)
+bool first_sight(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells) {
+    const Hash128 key = circuit_key(ops, n_ops, z64_cells, gf2_cells);
+    std::lock_guard<std::mutex> g(g_cache_mu);
+    for (const CacheEntry &e : g_cache)
+        if (!e.dead && e.key == key && e.n_ops == n_ops) return false;
+    for (const Hash128 &k : g_streamed_once)
+        if (k == key) return false;
+    if (g_streamed_once.size() >= 64) g_streamed_once.erase(g_streamed_once.begin());
+    g_streamed_once.push_back(key);
+    return true;
+}
+
 // Looks the circuit up (compiling it on a miss); the returned handle stays valid until cache_release.
 int cache_acquire(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, bool need_verify, rv_circuit **out) {
     if (n_ops && !ops) return fail(RV_E_ARG, "ops is NULL");
-    const Hash128 key = hash_bytes(ops, n_ops * sizeof(rv_op), (uint64_t)z64_cells * 0x100000001b3ull ^ gf2_cells);
+    const Hash128 key = circuit_key(ops, n_ops, z64_cells, gf2_cells);
     const int device = rv_device_count() ? g_device : -1;
     {
         std::lock_guard<std::mutex> g(g_cache_mu);
@@ -2675,8 +2695,25 @@ extern "C" void rv_circuit_cache_stats(uint64_t *hits, uint64_t *misses, size_t 
     if (entries) *entries = g_cache.size();
 }
 
+extern "C" void rv_oneshot_streaming_min(size_t n_ops) {
+    std::lock_guard<std::mutex> g(g_cache_mu);
+    g_oneshot_stream_min = n_ops;
+}
+
 extern "C" int rv_proof_new(const rv_op *ops, size_t n_ops, const uint8_t *wit_gf2, size_t n_gf2, const uint64_t *wit_z64, size_t n_z64,
                             size_t z64_cells, size_t gf2_cells, const uint8_t *seeds, uint8_t **proof, size_t *proof_len) {
+    // A big circuit seen for the first time: compiling it for residency is one thread walking the whole op list (10^8 flat gates:
+    // 7 s before a 0.2 s proof), the streaming prover compiles its segments on all host cores while it plans and uploads, and
+    // the bytes are the same.  The second call with the same circuit compiles it (from then on: cache hits, resident proofs).
+    size_t stream_min;
+    {
+        std::lock_guard<std::mutex> g(g_cache_mu);
+        stream_min = g_oneshot_stream_min;
+    }
+    if (stream_min && n_ops >= stream_min && ops && proof && proof_len && rv_device_count() > 0 && first_sight(ops, n_ops, z64_cells, gf2_cells)) {
+        const int src = rv_prove_streaming(ops, n_ops, z64_cells, gf2_cells, wit_gf2, n_gf2, wit_z64, n_z64, seeds, 0, proof, proof_len);
+        if (src != RV_E_UNSUPPORTED && src != RV_E_NOMEM) return src;  // (Z64 / Random / B2A, or no room for the window: the resident path decides)
+    }
     rv_circuit *c = nullptr;
     int rc = cache_acquire(ops, n_ops, z64_cells, gf2_cells, false, &c);
     if (rc) return rc;

@@ -720,3 +720,56 @@ def test_streaming_prove_matches_oracle(rb, default_seeds):
     with pytest.raises(rb.ReverieError) as e:
         rb.Proof.new_streaming(zops, (), zwc, seeds=default_seeds, window_ops=64)
     assert e.value.code == N.E_UNSUPPORTED
+
+
+@pytest.mark.gpu
+def test_one_shot_proof_of_a_big_circuit_streams_first_then_compiles(rb, default_seeds):
+    """rv_proof_new (the reference's call shape: the op list with every call) on a circuit above rv_oneshot_streaming_min that it
+    has not seen: the first call proves in streaming mode (nothing is compiled for residency, nothing enters the cache), the
+    second compiles and caches; both return the oracle's bytes.  Circuits streaming does not serve (Z64) take the resident path
+    at once.  The threshold is lowered for the test; the 5 x 10^6-gate flat circuit spans two default windows."""
+    import ctypes as C_
+    import orc
+    from reverie_b200 import circuits as C
+    from reverie_b200 import _native as N
+
+    L = N.lib()
+
+    def cache():
+        h, m, e = C_.c_uint64(), C_.c_uint64(), C_.c_size_t()
+        L.rv_circuit_cache_stats(C_.byref(h), C_.byref(m), C_.byref(e))
+        return h.value, m.value, e.value
+
+    L.rv_oneshot_streaming_min(10000)
+    try:
+        L.rv_circuit_cache_clear()
+        ops, wit, wc = C.sha256_abc_case()
+        rc, want = orc.prove(ops, wit, [], wc, default_seeds)
+        assert rc == 0
+        h0, m0, e0 = cache()
+        assert rb.Proof.new(ops, wit, (), wc, seeds=default_seeds).serialize() == want  # streamed
+        assert cache() == (h0, m0, e0)
+        assert rb.Proof.new(ops, wit, (), wc, seeds=default_seeds).serialize() == want  # compiled + cached
+        assert cache() == (h0, m0 + 1, e0 + 1)
+        assert rb.Proof.new(ops, wit, (), wc, seeds=default_seeds).serialize() == want  # cache hit
+        assert cache() == (h0 + 1, m0 + 1, e0 + 1)
+        bad = wit.copy()
+        bad[3] ^= 1
+        L.rv_circuit_cache_clear()
+        with pytest.raises(rb.WitnessError):  # another circuit (first sight again): the streaming path reports the failed assert like the resident one
+            rb.Proof.new(np.concatenate([ops, ops[-1:]]), bad, (), wc, seeds=default_seeds)
+        big, bwc = C.flat_mul_circuit(5_000_000)
+        p1 = rb.Proof.new(big, np.array([1, 1], dtype=np.uint8), (), bwc, seeds=default_seeds)
+        p2 = rb.Proof.new(big, np.array([1, 1], dtype=np.uint8), (), bwc, seeds=default_seeds)
+        assert len(p1) == len(p2) and np.array_equal(np.frombuffer(p1._buf, dtype=np.uint8), np.frombuffer(p2._buf, dtype=np.uint8))
+        rcb, digest, nbytes = orc.prove_digest_lowmem(big, [1, 1], [], bwc, default_seeds)
+        assert rcb == 0 and nbytes == len(p1) and hashlib.sha256(memoryview(p1._buf)).hexdigest() == digest
+        zops, zwc = C.flat_mul_circuit(20000, domain=C.Z64)  # not streamable: resident at the first call
+        _, m1, _ = cache()
+        zw = np.array([3, 5], dtype=np.uint64)
+        rcz, wantz = orc.prove(zops, [], zw, zwc, default_seeds)
+        assert rcz == 0 and rb.Proof.new(zops, (), zw, zwc, seeds=default_seeds).serialize() == wantz
+        assert cache()[1] == m1 + 1
+    finally:
+        L.rv_oneshot_streaming_min(1 << 24)
+        L.rv_circuit_cache_clear()
