@@ -1211,7 +1211,7 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
     P.n_pre = (uint32_t)P.n_and;
     for (uint32_t l : vlevel) P.plain_value_depth = std::max(P.plain_value_depth, l);
     for (uint32_t l : llevel) P.plain_linear_depth = std::max(P.plain_linear_depth, l);
-    const bool small = n_ops <= (4u << 20);  // debug tables only where tests can use them
+    const bool small = n_ops <= (io ? (1u << 20) : (4u << 20));  // debug tables only where tests can use them (not for a streaming segment of the default window: 64 MB each)
 
     // The three planes are independent from here on (they only share read-only parts of P.items): for circuits big enough
     // to care they are built side by side.

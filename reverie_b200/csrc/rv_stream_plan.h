@@ -312,9 +312,7 @@ inline int plan_stream(const rv_op *ops, size_t n_ops, size_t gf2_cells, size_t 
                     }
                     return l.local & ~HI;
                 };
-                S.ops.resize(S.b - S.a);
-                rv_op *out = S.ops.data();
-                size_t n_out = 0;
+                S.ops.reserve(S.b - S.a);  // (not resize: the zero fill would write the 96 MB of a default window twice)
                 uint64_t masks = 0, on = 0, pre = 0, wit = 0, recon = 0;
                 for (size_t i = S.a; i < S.b; i++) {
                     if (i + 16 < S.b) {  // a wide circuit's records are cache misses: ask for them a few ops ahead
@@ -340,7 +338,7 @@ inline int plan_stream(const rv_op *ops, size_t n_ops, size_t gf2_cells, size_t 
                             }
                         }
                     }
-                    out[n_out++] = op;
+                    S.ops.push_back(op);
                     switch (op.opcode) {
                         case RV_INPUT: masks += 1, on += 1, wit += 1; break;
                         case RV_MUL: masks += 2, on += 1, pre += 1, recon += 1; break;
@@ -348,7 +346,6 @@ inline int plan_stream(const rv_op *ops, size_t n_ops, size_t gf2_cells, size_t 
                         default: break;
                     }
                 }
-                S.ops.resize(n_out);
                 S.n_local = std::max<uint32_t>(n_local, 1);
                 S.import_slot.resize(S.import_global.size());
                 S.export_slot.resize(S.export_global.size());
