@@ -854,7 +854,8 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
     std::vector<Cell> cells(gf2_cells, Cell{VREF_ZERO, ZERO_MID, VREF_ZERO});
     ValueNet un;  // u-plane network (built only while the circuit stays small)
     const bool want_verify = n_ops <= VERIFY_MAX_OPS && !(flags & COMPILE_PROVE_ONLY);
-    std::vector<uint32_t> vlevel(1, 0);  // per value id (plain 2-input depth, for the stats)
+    uint64_t n_vids = 1;  // value ids handed out; id 0 is the constant 0.  (Their plain 2-input depth, a statistic, is computed by the
+                          // value-plane job from the gate list: two dependent cache misses per gate that the walk can do without.)
     std::vector<uint32_t> llevel;        // per linear node (plain depth)
     std::vector<uint32_t> tlevel;        // per tainted value
     std::vector<MGate> vg;               // value network, topological; ids = value ids
@@ -886,7 +887,6 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
         P.recon_pos.reserve(c_mul + c_as);
         P.input_pos.reserve(c_in);
         P.input_vid.reserve(c_in);
-        vlevel.reserve(1 + c_in + c_mul + c_lin);
         vg.reserve(c_mul + c_lin);
         lg.reserve(c_lin);
         llevel.reserve(c_lin);
@@ -904,7 +904,7 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
         const double mean_reach = (double)reach / (double)std::max<uint64_t>(1, 2 * n_bin);
         const bool local_reads = mean_reach * sizeof(Cell) <= PREFAULT_MAX_REACH_BYTES;
         if (n_ops >= PREFAULT_MIN_OPS && (pf_env ? pf_env[0] == '1' : local_reads)) {
-            pf.add(P.items), pf.add(P.recon_pos), pf.add(vlevel), pf.add(vg), pf.add(lg), pf.add(llevel), pf.add(cells);
+            pf.add(P.items), pf.add(P.recon_pos), pf.add(vg), pf.add(lg), pf.add(llevel), pf.add(cells);
             if (want_verify) pf.add(un.g), pf.add(P.kappa_uid), pf.add(P.item_ua), pf.add(P.item_ub);
             pf.add(zb.prog), pf.add(zb.vlevel), pf.add(zb.Z.items);
             pf.start(io ? 2 : 4);  // streaming segments are compiled several at a time already
@@ -912,10 +912,7 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
     }
 
     auto mid_level = [&](uint32_t mid) -> uint32_t { return (mid != ZERO_MID && mid >= LIN_BASE) ? llevel[mid - LIN_BASE] : 0; };
-    auto new_val = [&](uint32_t level) -> uint32_t {
-        vlevel.push_back(level);
-        return (uint32_t)(vlevel.size() - 1);
-    };
+    auto new_val = [&]() -> uint32_t { return (uint32_t)n_vids++; };
     auto bad_wire = [&](size_t i) {
         err = "op " + std::to_string(i) + ": wire index out of range for the given wire_counts";
         return RV_E_ARG;
@@ -935,7 +932,7 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
         if (!tainted(b) && (b >> 1) == 0) return a ^ (b & 1);
         if ((a & ~1u) == (b & ~1u)) return neg;  // x ^ x (^1)
         if (tainted(a) || tainted(b)) return new_tval(T_XOR, a & ~1u, b & ~1u) | neg;
-        const uint32_t vid = new_val(1 + std::max(vlevel[a >> 1], vlevel[b >> 1]));
+        const uint32_t vid = new_val();
         vg.emplace_back(vid, a & ~1u, b & ~1u, 0u);
         return (vid << 1) | neg;
     };
@@ -945,7 +942,7 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
         if (a == b) return a;
         if ((a & ~1u) == (b & ~1u)) return VREF_ZERO;  // x & ~x
         if (tainted(a) || tainted(b)) return new_tval(T_AND, a, b);
-        const uint32_t vid = new_val(1 + std::max(vlevel[a >> 1], vlevel[b >> 1]));
+        const uint32_t vid = new_val();
         vg.emplace_back(vid, a, b, 1u);
         return vid << 1;
     };
@@ -1014,7 +1011,7 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
         for (uint32_t j = 0; j < n_imports; j++) {
             const uint32_t c = io->import_cells[j];
             if (c >= cells.size()) return bad_wire(0);
-            const uint32_t vid = new_val(0);
+            const uint32_t vid = new_val();
             io->import_vid.push_back(vid);
             cells[c] = Cell{vid << 1, IMP_BASE + j, 0};
         }
@@ -1078,19 +1075,16 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
             return RV_E_ARG;
         }
         const size_t nc = cells.size();
-        if (i + 48 < n_ops) {  // the operands' cell records of a wide circuit are cache misses: ask for them a few ops ahead ...
+        if (i + 48 < n_ops) {  // the operands' cell records of a wide circuit are cache misses: ask for them a few ops ahead
             const rv_op &f = ops[i + 48];
             if (f.a < nc) __builtin_prefetch(&cells[f.a]);
             if (f.b < nc) __builtin_prefetch(&cells[f.b]);
-            const rv_op &h = ops[i + 24];  // ... and, once those are here, for the depth records of their values
-            if (h.a < nc && !tainted(cells[h.a].vref)) __builtin_prefetch(&vlevel[cells[h.a].vref >> 1]);
-            if (h.b < nc && !tainted(cells[h.b].vref)) __builtin_prefetch(&vlevel[cells[h.b].vref >> 1]);
         }
         const uint32_t c = (uint32_t)(op.imm & 1);  // bool -> Recon, src/algebra/gf2/recon.rs:274-287
         switch (op.opcode) {
             case RV_INPUT: {  // src/transcript/prover.rs:181-199
                 if (op.dst >= nc) return bad_wire(i);
-                uint32_t vid = new_val(0);
+                uint32_t vid = new_val();
                 P.input_pos.push_back((uint32_t)P.items.size());
                 P.items.emplace_back((uint32_t)ITEM_INPUT, (uint32_t)n_masks, 0u, 0u, vid << 1, 0u, (uint32_t)P.input_vid.size(), 0u);
                 P.input_vid.push_back(vid);
@@ -1118,11 +1112,9 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
             case RV_ADD:
             case RV_SUB: {  // src/interpreter/single.rs:71-85: mask and correction add component-wise
                 if (op.dst >= nc || op.a >= nc || op.b >= nc) return bad_wire(i);
-                const Cell A = cells[op.a], B = cells[op.b];
-                Cell R;
-                const int rc2 = cell_xor(A, B, R);
-                if (rc2) return rc2;
-                cells[op.dst] = R;
+                const Cell A = cells[op.a], B = cells[op.b];  // (copies: dst may be one of them)
+                const int rc2 = cell_xor(A, B, cells[op.dst]);  // written in place: a Cell returned through the stack is reloaded with a
+                if (rc2) return rc2;                            // wider load than the stores that built it, a failed store-to-load forward
                 P.algorithmic_bytes += B_XOR;
                 break;
             }
@@ -1145,9 +1137,7 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
             case RV_MUL: {  // src/interpreter/single.rs:25-69
                 if (op.dst >= nc || op.a >= nc || op.b >= nc) return bad_wire(i);
                 const Cell A = cells[op.a], B = cells[op.b];
-                Cell R;
-                cell_and(A, B, R);
-                cells[op.dst] = R;
+                cell_and(A, B, cells[op.dst]);
                 break;
             }
             case RV_ASSERT_ZERO: {  // src/interpreter/single.rs:140-147
@@ -1167,7 +1157,7 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
                 err = "op " + std::to_string(i) + ": unknown opcode";
                 return RV_E_ARG;
         }
-        if (n_masks >= IMP_BASE - 130 || P.items.size() >= 0xFFFFFF00ull || vlevel.size() >= 0x3FFFFFF0ull || tlevel.size() >= 0x3FFFFFF0ull) {
+        if (n_masks >= IMP_BASE - 130 || P.items.size() >= 0xFFFFFF00ull || n_vids >= 0x3FFFFFF0ull || tlevel.size() >= 0x3FFFFFF0ull) {
             err = "circuit too large for 32-bit table indices";
             return RV_E_UNSUPPORTED;
         }
@@ -1206,10 +1196,9 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
 
     P.n_prg = (uint32_t)n_masks;
     P.n_masks = (uint32_t)n_masks + n_imports;  // imported rows sit right behind the PRG rows and behave like fresh rows from here on
-    P.n_vals = (uint32_t)vlevel.size();
+    P.n_vals = (uint32_t)n_vids;
     P.n_online = (uint32_t)P.items.size();
     P.n_pre = (uint32_t)P.n_and;
-    for (uint32_t l : vlevel) P.plain_value_depth = std::max(P.plain_value_depth, l);
     for (uint32_t l : llevel) P.plain_linear_depth = std::max(P.plain_linear_depth, l);
     const bool small = n_ops <= (io ? (1u << 20) : (4u << 20));  // debug tables only where tests can use them (not for a streaming segment of the default window: 64 MB each)
 
@@ -1338,6 +1327,12 @@ int compile(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, 
         for (uint32_t r : P.b2a_vrefs) need(r);
         if (io)
             for (uint32_t r : io->export_vref) need(r);
+        {  // the statistic the walk no longer keeps: depth of the unpruned 2-input network
+            std::vector<uint32_t> lv(P.n_vals, 0);
+            uint32_t depth = 0;
+            for (const MGate &g : vg) depth = std::max(depth, lv[g.out] = 1 + std::max(lv[g.a >> 1], lv[g.b >> 1]));
+            P.plain_value_depth = depth;
+        }
         if (small) {
             P.vgates.resize(vg.size());
             for (size_t i = 0; i < vg.size(); i++) P.vgates[i] = VGate{vg[i].out, vg[i].a, vg[i].b, vg[i].op};
