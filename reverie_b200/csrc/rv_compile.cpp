@@ -172,42 +172,46 @@ void map_network(uint32_t n_ids, const std::vector<MGate> &g, std::vector<uint8_
         // array and no sort; duplicates can only tie with a kept cut and are dropped there.
         std::vector<Cut> cuts((size_t)g.size() * CUTS_PER_NODE);
         std::vector<uint8_t> ncuts(g.size(), 0);
-        auto cut_set = [&](uint32_t id, Cut *tmp, int &n) {  // the node's stored cuts plus its trivial cut
+        // a fan-in's cut set = its stored cuts (by pointer: copying five 40-byte records per fan-in and gate was a tenth of the
+        // mapper) plus its trivial cut, built in `triv`
+        auto cut_set = [&](uint32_t id, const Cut **set, Cut &triv, int &n) {
             n = 0;
             if (id == 0) {  // the constant contributes no leaf
-                tmp[0].n = 0;
-                tmp[0].depth = 1;
-                tmp[0].sig = 0;
-                n = 1;
+                triv.n = 0;
+                triv.depth = 1;
+                triv.sig = 0;
+                set[n++] = &triv;
                 return;
             }
             const uint32_t gi = gate_of[id];
             if (gi != NONE32)
-                for (int i = 0; i < ncuts[gi]; i++) tmp[n++] = cuts[(size_t)gi * CUTS_PER_NODE + i];
-            tmp[n].n = 1;
-            tmp[n].leaf[0] = id;
-            tmp[n].depth = depth[id] + 1;  // as a fan-in cut: (max depth of its leaves) + 1, like the stored ones
-            tmp[n].sig = 1ull << (id & 63);
-            n++;
+                for (int i = 0; i < ncuts[gi]; i++) set[n++] = &cuts[(size_t)gi * CUTS_PER_NODE + i];
+            triv.n = 1;
+            triv.leaf[0] = id;
+            triv.depth = depth[id] + 1;  // as a fan-in cut: (max depth of its leaves) + 1, like the stored ones
+            triv.sig = 1ull << (id & 63);
+            set[n++] = &triv;
         };
-        Cut ca[CUTS_PER_NODE + 1], cb[CUTS_PER_NODE + 1], keep[CUTS_PER_NODE];
+        const Cut *ca[CUTS_PER_NODE + 1], *cb[CUTS_PER_NODE + 1];
+        Cut ta, tb, keep[CUTS_PER_NODE];
         for (uint32_t gi = 0; gi < g.size(); gi++) {
             int na, nb, nk = 0;
-            cut_set(g[gi].a >> 1, ca, na);
-            cut_set(g[gi].b >> 1, cb, nb);
+            cut_set(g[gi].a >> 1, ca, ta, na);
+            cut_set(g[gi].b >> 1, cb, tb, nb);
             for (int i = 0; i < na; i++)
                 for (int j = 0; j < nb; j++) {
+                    const Cut &A = *ca[i], &B = *cb[j];
                     // the merged cut's depth and a lower bound on its size are known before merging: most candidates lose
                     // against the kept set right here
-                    const uint32_t d = std::max(ca[i].depth, cb[j].depth);
+                    const uint32_t d = std::max(A.depth, B.depth);
                     if (nk == CUTS_PER_NODE) {
                         const Cut &w = keep[CUTS_PER_NODE - 1];
-                        if (d > w.depth || (d == w.depth && std::max(ca[i].n, cb[j].n) >= w.n)) continue;
+                        if (d > w.depth || (d == w.depth && std::max(A.n, B.n) >= w.n)) continue;
                     }
-                    const uint64_t sig = ca[i].sig | cb[j].sig;
+                    const uint64_t sig = A.sig | B.sig;
                     if (__builtin_popcountll(sig) > MAP_K) continue;
                     Cut o;
-                    if (!merge_cuts(ca[i], cb[j], o)) continue;
+                    if (!merge_cuts(A, B, o)) continue;
                     o.depth = d;
                     o.sig = sig;
                     // position among the kept cuts (ties keep the earlier candidate first)
