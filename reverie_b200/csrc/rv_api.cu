@@ -2590,6 +2590,23 @@ void cache_release(rv_circuit *c) {
     if (free_it) rv_circuit_free(c);
 }
 
+// Out of device memory in a one-shot call: the idle entries of the cache (compiled tables and the pooled sessions of circuits
+// nobody is using right now -- a 10^8-gate circuit keeps ~110 GB) are the first thing to give back.  Returns how many went.
+size_t cache_drop_idle() {
+    std::vector<rv_circuit *> drop;
+    {
+        std::lock_guard<std::mutex> g(g_cache_mu);
+        for (size_t i = 0; i < g_cache.size();) {
+            if (g_cache[i].in_use == 0) {
+                drop.push_back(g_cache[i].c);
+                g_cache.erase(g_cache.begin() + i);
+            } else i++;
+        }
+    }
+    for (rv_circuit *d : drop) rv_circuit_free(d);
+    return drop.size();
+}
+
 // One-shot proofs of big circuits (rv_proof_new, below): keys of circuits seen once and proved in streaming mode.
 std::vector<Hash128> g_streamed_once;
 size_t g_oneshot_stream_min = (size_t)1 << 24;
@@ -2716,8 +2733,10 @@ extern "C" int rv_proof_new(const rv_op *ops, size_t n_ops, const uint8_t *wit_g
     }
     rv_circuit *c = nullptr;
     int rc = cache_acquire(ops, n_ops, z64_cells, gf2_cells, false, &c);
+    if (rc == RV_E_NOMEM && cache_drop_idle()) rc = cache_acquire(ops, n_ops, z64_cells, gf2_cells, false, &c);
     if (rc) return rc;
     rc = rv_prove(c, wit_gf2, n_gf2, wit_z64, n_z64, seeds, proof, proof_len);
+    if (rc == RV_E_NOMEM && cache_drop_idle()) rc = rv_prove(c, wit_gf2, n_gf2, wit_z64, n_z64, seeds, proof, proof_len);  // (c itself is in use: kept)
     cache_release(c);
     return rc;
 }
@@ -2725,8 +2744,10 @@ extern "C" int rv_proof_new(const rv_op *ops, size_t n_ops, const uint8_t *wit_g
 extern "C" int rv_proof_verify_ex(const rv_op *ops, size_t n_ops, size_t z64_cells, size_t gf2_cells, const uint8_t *proof, size_t proof_len, int *okay) {
     rv_circuit *c = nullptr;
     int rc = cache_acquire(ops, n_ops, z64_cells, gf2_cells, true, &c);
+    if (rc == RV_E_NOMEM && cache_drop_idle()) rc = cache_acquire(ops, n_ops, z64_cells, gf2_cells, true, &c);
     if (rc) return rc;
     rc = rv_verify(c, proof, proof_len, okay);
+    if (rc == RV_E_NOMEM && cache_drop_idle()) rc = rv_verify(c, proof, proof_len, okay);
     cache_release(c);
     return rc;
 }
