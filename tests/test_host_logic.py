@@ -436,6 +436,21 @@ def test_one_shot_circuit_cache():
     L.rv_circuit_cache_limit(8)
     L.rv_circuit_cache_clear()
     assert stats()[2] == 0
+    # op lists above 32 MB are hashed in slices on several threads: the key must still see every byte, wherever it sits
+    big, wc = CI.flat_mul_circuit(3_000_000)  # 72 MB of ops: three slices
+    big = np.ascontiguousarray(big)
+    h1, m1, _ = stats()
+    prove(big)
+    prove(big.copy())
+    assert stats() == (h1 + 1, m1 + 1, 1)
+    for k, where in enumerate((7, 1_500_000, big.size - 1)):  # first slice, middle slice, the very last record
+        other = big.copy()
+        other["imm"][where] ^= 1 << 40  # (bits the compiler ignores for a GF(2) Mul: only the key can tell the lists apart)
+        prove(other)
+        assert stats() == (h1 + 1, m1 + 2 + k, 2 + k)
+    L.rv_circuit_cache_clear()
+    ops, wc = CI.flat_mul_circuit(100)
+    ops = np.ascontiguousarray(ops)
     st = __import__("reverie_b200").Circuit(ops, wc, prove_only=True).stats()
     assert st["has_verify"] == 0 and st["compile_ns"] > 0
 
