@@ -114,6 +114,7 @@ struct Prefault {
     }
     ~Prefault() { finish(); }
 };
+constexpr uint32_t VM_LOAD_WINDOW = 4;  // how many levels early (beyond VM_DELTA) a LOAD may be issued to balance the steps
 constexpr size_t PREFAULT_MIN_OPS = 1u << 20, PREFAULT_MAX_REACH_BYTES = 1u << 20;
 
 constexpr int MAP_K = 6, CUTS_PER_NODE = 4;  // 4 kept cuts map SHA-256 / AES-128 exactly as deep as 6 do, in 60 % of the time
@@ -383,7 +384,7 @@ std::vector<uint32_t> sort_by_level(const std::vector<MNode> &nodes, std::vector
 //  by asynchronous LOADs issued VM_DELTA levels early; only rows that the item plane reads are written back (`row`).
 //  Cells are assigned by a linear scan over levels: a cell is free again one level after its value's last use.
 // =====================================================================================================================
-void build_mask_vm(Program &P) {
+void build_mask_vm(Program &P, uint32_t load_window) {
     P.vm.clear();
     P.vm_level_off.clear();
     P.vm_cells = 0;
@@ -410,10 +411,43 @@ void build_mask_vm(Program &P) {
         bool load;
     };
     const uint32_t n_levels = depth + VM_DELTA;
+    // A LOAD must sit at least VM_DELTA levels before the row's first use; it may sit earlier.  Every level is padded to whole
+    // steps of VM_STEP slots, and the kernel's time is its number of (dependent) steps: a level that spills a few dozen
+    // instructions into one more step hands that many of its LOADs to the spare slots of the levels before it
+    // (SHA-256: 262 -> ~205 steps for +1.5 % cells; the XORs themselves sit ALAP and have next to no room to move).
+    std::vector<uint32_t> load_level(n_masks, NONE32);
     std::vector<uint32_t> cnt(n_levels + 1, 0);
-    for (uint32_t r = 0; r < n_masks; r++)
-        if (first[r] != NONE32) cnt[first[r] - 1]++;
-    for (uint32_t l = 0; l < depth; l++) cnt[l + VM_DELTA] += P.xlevel_off[l + 1] - P.xlevel_off[l];
+    {
+        std::vector<std::vector<uint32_t>> loads_at(n_levels);
+        for (uint32_t r = 0; r < n_masks; r++)
+            if (first[r] != NONE32) loads_at[first[r] - 1].push_back(r);
+        for (uint32_t l = 0; l < depth; l++) cnt[l + VM_DELTA] += P.xlevel_off[l + 1] - P.xlevel_off[l];
+        auto room_of = [&](uint32_t v) {
+            const uint32_t c = cnt[v] + (uint32_t)loads_at[v].size();
+            return std::max<uint32_t>(1, (c + VM_STEP - 1) / VM_STEP) * VM_STEP - c;
+        };
+        for (uint32_t v = n_levels; v-- > 1;) {
+            const uint32_t c = cnt[v] + (uint32_t)loads_at[v].size();
+            const uint32_t e = c % VM_STEP;
+            if (c <= VM_STEP || e == 0 || e > loads_at[v].size()) continue;
+            uint32_t have = 0;
+            for (uint32_t d = 1; d <= load_window && d <= v && have < e; d++) have += room_of(v - d);
+            if (have < e) continue;  // would only move the spill somewhere else
+            uint32_t need = e;
+            for (uint32_t d = 1; d <= load_window && d <= v && need; d++) {
+                const uint32_t take = std::min(room_of(v - d), need);
+                for (uint32_t k = 0; k < take; k++) {
+                    loads_at[v - d].push_back(loads_at[v].back());
+                    loads_at[v].pop_back();
+                }
+                need -= take;
+            }
+        }
+        for (uint32_t v = 0; v < n_levels; v++) {
+            cnt[v] += (uint32_t)loads_at[v].size();
+            for (uint32_t r : loads_at[v]) load_level[r] = v;
+        }
+    }
     P.vm_level_off.assign(n_levels + 1, 0);
     for (uint32_t l = 0; l < n_levels; l++) P.vm_level_off[l + 1] = P.vm_level_off[l] + cnt[l];
     std::vector<Tmp> tmp(P.vm_level_off[n_levels]);
@@ -423,7 +457,7 @@ void build_mask_vm(Program &P) {
             Tmp t{};
             t.load = true;
             t.in[0] = r;
-            tmp[cursor[first[r] - 1]++] = t;
+            tmp[cursor[load_level[r]]++] = t;
         }
     for (uint32_t l = 0; l < depth; l++)
         for (uint32_t gi = P.xlevel_off[l]; gi < P.xlevel_off[l + 1]; gi++) {
@@ -484,6 +518,19 @@ void build_mask_vm(Program &P) {
         }
     }
     P.vm_cells = n_cells;
+}
+
+// Balanced LOADs live a little longer; if the extra cells cost the VM a column (or the VM altogether), the plain placement wins.
+void build_mask_vm(Program &P) {
+    build_mask_vm(P, VM_LOAD_WINDOW);
+    const int cols = P.vm.empty() ? 0 : vm_columns(P.vm_cells);
+    if (cols == 2) return;
+    std::vector<VmInstr> vm = std::move(P.vm);
+    std::vector<uint32_t> off = std::move(P.vm_level_off);
+    const uint32_t cells = P.vm_cells;
+    build_mask_vm(P, 0);
+    if ((P.vm.empty() ? 0 : vm_columns(P.vm_cells)) > cols) return;
+    P.vm = std::move(vm), P.vm_level_off = std::move(off), P.vm_cells = cells;
 }
 
 // ---- step streams (see rv_compile.h) ---------------------------------------------------------------------------------

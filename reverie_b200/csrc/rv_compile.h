@@ -69,6 +69,12 @@ struct LutInstr {
 // The LUT stream carries a barrier every LUT_STEPS_PER_CHUNK steps, so it can be consumed in chunks of 4 or of 8 steps: k_values takes
 // 8 when the values still fit next to the larger ring (the prover's plane), 4 otherwise (the verifier's u-plane of SHA-256).
 constexpr uint32_t VM_STEP = 512, VM_STEPS_PER_CHUNK = 2, LUT_STEP = 128, LUT_STEPS_PER_CHUNK = 4, LUT_STEPS_PER_CHUNK_MAX = 8;
+// Shared memory of the mask VM's CTA (rv_kernels.cu asserts that these match its own): the instruction ring + 8 bytes per cell and
+// column.  vm_columns = how many tensor columns one CTA can serve at a given cell count (2 is the fast configuration, 0 = no VM).
+constexpr size_t VM_SMEM_CAP = 226 * 1024, VM_STREAM_SMEM = (size_t)2 * VM_STEPS_PER_CHUNK * VM_STEP * 20 + 64;
+inline int vm_columns(uint32_t cells) {
+    return VM_STREAM_SMEM + ((size_t)cells + 1) * 16 <= VM_SMEM_CAP ? 2 : VM_STREAM_SMEM + ((size_t)cells + 1) * 8 <= VM_SMEM_CAP ? 1 : 0;
+}
 constexpr uint32_t VM_F_LOAD = 1u, VM_F_BAR = 2u, VM_F_LEVEL_END = 4u, VM_CELL_MASK = 0xFFFFu /* also "no cell yet" */,
                    VM_ROW_NONE = 0xFFFFFFFFu;
 constexpr uint32_t LUT_F_BAR = 1u;

@@ -542,6 +542,7 @@ __global__ void __launch_bounds__(256) k_linear_level(const XGate *__restrict__ 
 }
 
 static size_t vm_smem_bytes(const DevProgram &P, int cols = 1) { return VmStream::BYTES + ((size_t)P.vm_cells + 1) * 8 * cols; }
+static_assert(VmStream::BYTES == VM_STREAM_SMEM && SMEM_DYN_CAP == VM_SMEM_CAP, "rv_compile.h mirrors the VM's shared-memory budget (vm_columns)");
 bool linear_uses_vm(const DevProgram &P) {
     if (P.n_llevels == 0 || (double)P.n_xgates / P.n_llevels >= 4096.0) return false;
     return P.n_vm_steps && P.vm_cells < VM_CELL_MASK && vm_smem_bytes(P) <= SMEM_DYN_CAP;
