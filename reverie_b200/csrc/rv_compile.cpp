@@ -592,10 +592,63 @@ void emit_lut_steps(const std::vector<LutInstr> &luts, const std::vector<uint32_
     }
 }
 
+// The value planes run as dependent steps of LUT_STEP slots, every level padded to whole steps.  Mapped nodes sit at their earliest
+// level; one with slack (all its consumers sit more than a level later; outputs are read after the plane) may sit later.  Walking
+// the levels from the last one down, a level that spills a few nodes into one more step hands them to spare slots of later levels
+// within its nodes' slack (SHA-256: 1185 -> 1056 steps for 1028 levels; the verifier's u-plane 1486 -> 1370).  Levels keep their numbers; only MNode::level changes.
+void balance_lut_levels(uint32_t n_ids, std::vector<MNode> &nodes, uint32_t step) {
+    uint32_t depth = 0;
+    for (const MNode &m : nodes) depth = std::max(depth, m.level);
+    if (depth < 2) return;
+    constexpr uint32_t WINDOW = 256;  // how far ahead a node may be pushed (bounds the search)
+    std::vector<uint32_t> cnt(depth + 2, 0), off(depth + 2, 0), prod(n_ids, NONE32), latest(nodes.size(), depth);
+    for (const MNode &m : nodes) cnt[m.level]++;
+    for (uint32_t l = 1; l <= depth; l++) off[l + 1] = off[l] + cnt[l];
+    std::vector<uint32_t> by_level(nodes.size()), cur(off.begin(), off.end());
+    for (uint32_t i = 0; i < nodes.size(); i++) {
+        by_level[cur[nodes[i].level]++] = i;
+        prod[nodes[i].out] = i;
+    }
+    auto room = [&](uint32_t l) { return cnt[l] == 0 ? 0u : (cnt[l] + step - 1) / step * step - cnt[l]; };
+    std::vector<std::pair<uint32_t, uint32_t>> plan;
+    std::vector<uint32_t> taken(depth + 2, 0);
+    for (uint32_t l = depth; l >= 1; l--) {
+        const uint32_t need = cnt[l] % step;
+        if (need && cnt[l] > need) {  // (a level that fits one step stays: emptying it would need every node to have slack)
+            plan.clear();
+            for (uint32_t k = off[l]; k < off[l + 1] && plan.size() < need; k++) {
+                const uint32_t i = by_level[k], hi = std::min(latest[i], l + WINDOW);
+                for (uint32_t L = l + 1; L <= hi; L++)
+                    if (room(L) > taken[L]) {
+                        taken[L]++;
+                        plan.emplace_back(i, L);
+                        break;
+                    }
+            }
+            for (const auto &mv : plan) taken[mv.second] = 0;
+            if (plan.size() == need)
+                for (const auto &mv : plan) {
+                    nodes[mv.first].level = mv.second;
+                    cnt[mv.second]++;
+                    cnt[l]--;
+                }
+        }
+        // the nodes that started at this level are final now: their producers must stay below them
+        for (uint32_t k = off[l]; k < off[l + 1]; k++) {
+            const MNode &m = nodes[by_level[k]];
+            for (uint32_t q = 0; q < m.n; q++) {
+                const uint32_t pi = m.leaf[q] < n_ids ? prod[m.leaf[q]] : NONE32;
+                if (pi != NONE32) latest[pi] = std::min(latest[pi], m.level - 1);
+            }
+        }
+    }
+}
+
 // network -> level-sorted LUT list + level offsets
 void map_to_luts(uint32_t n_ids, std::vector<MGate> &net, std::vector<uint8_t> &required, std::vector<LutInstr> &luts, std::vector<uint32_t> &level_off) {
     std::vector<MNode> nodes;
     map_network(n_ids, net, required, net.size() <= LUT_MAP_MAX_GATES, nodes);
+    balance_lut_levels(n_ids, nodes, LUT_STEP);
     std::vector<uint32_t> order;
     level_off = sort_by_level(nodes, order);
     luts.resize(nodes.size());
