@@ -635,3 +635,44 @@ def test_threaded_streaming_planner_equals_the_serial_one():
     hint["b"][n // 2] = 400
     hint["dst"][n // 2 + 10 :] += rng.integers(0, 2, size=n - n // 2 - 10, dtype=np.uint32) * 100
     assert hostsim.plan_compare(hint, 300, 4097, 4) == ""
+
+
+@pytest.mark.parametrize("width,layers,seed", [(700, 40, 0), (1500, 24, 1), (300, 90, 2)])
+def test_step_balancing_keeps_the_planes_right(width, layers, seed, default_seeds):
+    """The compiler pads every level of the mask VM (512 slots) and of the value plane (128 slots) to whole steps and balances the
+    padding: LOADs may be issued earlier than two levels ahead, mapped LUT nodes with slack may sit later.  Circuits whose levels
+    spill over step boundaries in both planes -- layers of random XORs / ANDs / unary ops over the previous layers, asserts
+    on wires that are zero by construction -- replayed from the padded device streams (LOADs landing at once and as late as the
+    group wait allows) and proved by the kernel bodies on the CPU against the oracle."""
+    rng = np.random.default_rng(seed)
+    n_in = width
+    recs = np.zeros(n_in + width * layers, dtype=CI.OP_DTYPE)
+    recs["domain"] = CI.GF2
+    recs["opcode"][:n_in] = CI.INPUT
+    recs["dst"][:n_in] = np.arange(n_in)
+    n = n_in
+    for l in range(layers):
+        sl = slice(n, n + width)
+        lo = max(0, n - 3 * width)
+        recs["opcode"][sl] = rng.choice([CI.ADD, CI.MUL, CI.ADDC, CI.SUB], size=width, p=[0.55, 0.25, 0.1, 0.1])
+        recs["dst"][sl] = np.arange(n, n + width)
+        recs["a"][sl] = rng.integers(lo, n, size=width)
+        recs["b"][sl] = rng.integers(lo, n, size=width)
+        recs["imm"][sl] = rng.integers(0, 2, size=width)
+        n += width
+    # x ^ x = 0 on a few late wires: AssertZero must hold, and the asserted masks are linear rows the VM has to export
+    extra = []
+    for w in rng.integers(n - width, n, size=8):
+        extra.append((CI.GF2, CI.ADD, 0, n, int(w), int(w), 0))
+        extra.append((CI.GF2, CI.ASSERT_ZERO, 0, 0, n, 0, 0))
+        n += 1
+    ops = np.concatenate([recs, np.array(extra, dtype=CI.OP_DTYPE)])
+    wit = rng.integers(0, 2, size=n_in).astype(np.uint8)
+    wc = (0, n)
+    st = _check_steps(ops, wc)
+    assert st[0] > 0 and st[1] > 0  # both step streams exist (mask VM, LUT value plane)
+    rc, want, hashes = orc.prove(ops, wit, [], wc, default_seeds, want_hashes=True)
+    rc2, got, h2 = hostsim.prove(ops, wit, wc, default_seeds)
+    assert rc == 0 and rc2 == 0 and h2 == hashes and got == want
+    vrc, okay = hostsim.verify(ops, wc, got)[:2] if hasattr(hostsim, "verify") else (1, 1)
+    assert vrc == 1 and okay
