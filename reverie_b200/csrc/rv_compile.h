@@ -40,14 +40,15 @@ struct XGate {
 // mask-plane VM instruction (shared-memory cells; see build_mask_vm).  20 bytes: the instruction stream is re-read by every
 // CTA (one per packed instance), so its size is what bounds the kernel.
 //   XOR : v = XOR of cell[in[0..5]]; cell[dst] = v; if (row != VM_ROW_NONE) exported[row - n_masks] = v
-//   LOAD: cell[dst] <- fresh row `row`   asynchronously, `VM_DELTA` levels ahead of its first use (one cp.async group per level)
+//   LOAD: cell[dst] <- fresh row `row`   asynchronously, at least `VM_DELTA` levels ahead of its first use (one cp.async group per level;
+//         the compiler issues some earlier to fill the padding of the steps, see build_mask_vm)
 struct VmInstr {
     uint32_t row;
     uint16_t dst;    // cell
     uint16_t flags;  // VM_F_*
     uint16_t in[6];  // cells
 };
-constexpr int VM_DELTA = 2;  // prefetch distance in levels: a LOAD issued during level L-2 is awaited at the end of level L-1
+constexpr int VM_DELTA = 2;  // minimum prefetch distance in levels: a LOAD issued during level L-2 is awaited at the end of level L-1
 
 // value-plane LUT instruction: v[dst] = tt >> (v[in0] | v[in1]<<1 | ... | v[in5]<<5) & 1.  Unused inputs name value 0
 // (the constant 0).  Produced by the depth-oriented K=6 cut mapper (build_value_luts), which collapses cones of 2-input
