@@ -627,7 +627,7 @@ void emit_lut_steps(const std::vector<LutInstr> &luts, const std::vector<uint32_
 // The value planes run as dependent steps of LUT_STEP slots, every level padded to whole steps.  Mapped nodes sit at their earliest
 // level; one with slack (all its consumers sit more than a level later; outputs are read after the plane) may sit later.  Walking
 // the levels from the last one down, a level that spills a few nodes into one more step hands them to spare slots of later levels
-// within its nodes' slack (SHA-256: 1185 -> 1056 steps for 1028 levels; the verifier's u-plane 1486 -> 1370).  Levels keep their numbers; only MNode::level changes.
+// within its nodes' slack (SHA-256: 1185 -> 1036 steps for 1028 levels; the verifier's u-plane 1486 -> 1356 with the area cover).  Levels keep their numbers; only MNode::level changes.
 void balance_lut_levels(uint32_t n_ids, std::vector<MNode> &nodes, uint32_t step) {
     uint32_t depth = 0;
     for (const MNode &m : nodes) depth = std::max(depth, m.level);
