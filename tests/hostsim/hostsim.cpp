@@ -513,6 +513,12 @@ extern "C" int hs_check_steps(const rv_op *ops, size_t n_ops, size_t z64_cells, 
         cells[0] = 0;
         std::vector<std::pair<uint32_t, uint32_t>> writes;
         std::vector<std::pair<uint32_t, uint32_t>> pending[2];  // [0]: issued in the current level, [1]: in the previous one
+        // The device orders the steps of one level only loosely (a barrier at the level's end and at chunk ends), and a LOAD lands
+        // any time between its issue and the group wait: inside a level no cell may be both read and written or written twice, and
+        // a cell with a LOAD in flight (this level and the next) is off limits for everybody else.  Stamps: level of the last read /
+        // write / LOAD issue of every cell (the scratch cell takes any number of writes and is never read by a real instruction).
+        std::vector<uint32_t> rd_level(P.vm_cells + 1, 0), wr_level(P.vm_cells + 1, 0), ld_level(P.vm_cells + 1, 0);
+        uint32_t level_no = 2;  // (0 = never; LOADs of level L block their cell during L and L + 1)
         for (uint32_t st = 0; st < P.n_vm_steps; st++) {
             writes.clear();
             bool bar = false, level_end = false;
@@ -524,11 +530,24 @@ extern "C" int hs_check_steps(const rv_op *ops, size_t n_ops, size_t z64_cells, 
                 if ((in.flags & VM_F_LEVEL_END) && !bar) { g_err = "level end without barrier"; return -305; }
                 if (in.dst > P.vm_cells) { g_err = "cell id out of range"; return -306; }
                 if (in.flags & VM_F_LOAD) {
+                    if (in.dst == 0 || in.dst >= P.vm_cells) { g_err = "LOAD into the zero or scratch cell"; return -307; }
+                    if (rd_level[in.dst] == level_no || wr_level[in.dst] == level_no || ld_level[in.dst] + 1 >= level_no) { g_err = "LOAD into a cell in use in its level (step " + std::to_string(st) + ")"; return -308; }
+                    ld_level[in.dst] = level_no;
                     if (late) pending[0].push_back({in.dst, rows[in.row]});
                     else writes.push_back({in.dst, rows[in.row]});
                 } else {
                     uint32_t v = 0;
-                    for (int k = 0; k < 6; k++) v ^= cells[in.in[k]];
+                    for (int k = 0; k < 6; k++) {
+                        const uint32_t c = in.in[k];
+                        if (c != 0 && (wr_level[c] == level_no || ld_level[c] + 1 >= level_no)) { g_err = "XOR reads a cell written or loaded in its own level (step " + std::to_string(st) + ")"; return -309; }
+                        rd_level[c] = level_no;
+                        v ^= cells[c];
+                    }
+                    if (in.dst != P.vm_cells) {  // (not the scratch cell)
+                        if (in.dst == 0) { g_err = "XOR writes the zero cell"; return -310; }
+                        if (rd_level[in.dst] == level_no || wr_level[in.dst] == level_no || ld_level[in.dst] + 1 >= level_no) { g_err = "XOR writes a cell in use in its level (step " + std::to_string(st) + ")"; return -311; }
+                        wr_level[in.dst] = level_no;
+                    }
                     writes.push_back({in.dst, v});
                     if (in.row != VM_ROW_NONE) rows[in.row] = v;
                 }
@@ -539,12 +558,35 @@ extern "C" int hs_check_steps(const rv_op *ops, size_t n_ops, size_t z64_cells, 
                 for (auto &w : pending[1]) cells[w.first] = w.second;
                 pending[1].swap(pending[0]);
                 pending[0].clear();
+                level_no++;
             }
         }
         for (const Item &it : P.items) {
             const uint32_t rr[2] = {it.ra, it.kind == ITEM_MUL ? it.rb : it.ra};
             for (uint32_t r : rr)
                 if (rows[r] != ref[r]) { g_err = "VM step stream: row mismatch at row " + std::to_string(r) + (late ? " (late LOADs)" : ""); return -303; }
+        }
+    }
+    // --- the verifier's u-plane stream: the same barrier discipline (its values are checked by hs_verify) ---
+    {
+        std::vector<uint32_t> wr_region(P.n_uvals + 1, 0);
+        uint32_t region = 1;
+        if (P.vlut_steps.size() != (size_t)P.n_vlut_steps * LUT_STEP) { g_err = "u-plane stream size"; return -315; }
+        for (uint32_t st = 0; st < P.n_vlut_steps; st++) {
+            bool bar = false;
+            for (uint32_t t = 0; t < LUT_STEP; t++) {
+                const LutInstr &li = P.vlut_steps[(size_t)st * LUT_STEP + t];
+                bar |= (li.pad & LUT_F_BAR) != 0;
+                for (int k = 0; k < 6; k++) {
+                    if (li.in[k] > P.n_uvals) { g_err = "u-plane stream: value id out of range"; return -316; }
+                    if (wr_region[li.in[k]] == region) { g_err = "u-plane stream: step " + std::to_string(st) + " reads a value written since the last barrier"; return -317; }
+                }
+                if (li.dst != P.n_uvals) {
+                    if (li.dst > P.n_uvals || wr_region[li.dst] == region) { g_err = "u-plane stream: value written twice between barriers"; return -318; }
+                    wr_region[li.dst] = region;
+                }
+            }
+            if (bar) region++;
         }
     }
     // --- LUT stream ---
@@ -565,14 +607,29 @@ extern "C" int hs_check_steps(const rv_op *ops, size_t n_ops, size_t z64_cells, 
                 const uint32_t u = b[g.a >> 1] ^ (g.a & 1), v = b[g.b >> 1] ^ (g.b & 1);
                 b[g.dst] = (uint8_t)((g.op ? (u & v) : (u ^ v)) & 1);
             }
+        // steps between two barriers run in no particular order on the device: a value written in such a region must not be read
+        // (or written again) inside it.  wr_region: the region (1-based) of every value's write.
+        std::vector<uint32_t> wr_region(P.n_vals + 1, 0);
+        uint32_t region = 1;
         for (uint32_t st = 0; st < P.n_lut_steps; st++) {
             w.clear();
+            bool bar = false;
             for (uint32_t t = 0; t < LUT_STEP; t++) {
                 const LutInstr &li = P.lut_steps[(size_t)st * LUT_STEP + t];
+                bar |= (li.pad & LUT_F_BAR) != 0;
                 uint32_t idx = 0;
-                for (int k = 0; k < 6; k++) idx |= (uint32_t)b[li.in[k]] << k;
+                for (int k = 0; k < 6; k++) {
+                    if (li.in[k] > P.n_vals) { g_err = "LUT step stream: value id out of range"; return -312; }
+                    if (wr_region[li.in[k]] == region) { g_err = "LUT step stream: step " + std::to_string(st) + " reads a value written since the last barrier"; return -313; }
+                    idx |= (uint32_t)b[li.in[k]] << k;
+                }
+                if (li.dst != P.n_vals) {  // (not the scratch slot of the padding)
+                    if (wr_region[li.dst] == region) { g_err = "LUT step stream: value written twice between barriers"; return -314; }
+                    wr_region[li.dst] = region;
+                }
                 w.push_back({li.dst, (uint8_t)((li.tt >> idx) & 1)});
             }
+            if (bar) region++;
             // without a barrier the next step may or may not see these writes; with the level structure it must not matter,
             // so apply them only at barriers for non-barrier steps' sake: here we apply immediately (reads of a later step
             // of the same level never touch this level's outputs)
